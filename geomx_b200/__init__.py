@@ -1,0 +1,35 @@
+"""geomx_b200 — a Blackwell-native hierarchical-parameter-server training framework with GeoMX's capabilities.
+
+``import geomx_b200 as mx`` gives the MXNet-shaped surface the reference's scripts use (``mx.nd``, ``mx.autograd``,
+``mx.gluon``, ``mx.kv``, ``mx.optimizer``, ``mx.init``, ``mx.profiler`` …; reference ``python/mxnet/__init__.py``).
+Like the reference (``python/mxnet/__init__.py:57`` → ``kvstore_server._init_kvstore_server_module``), importing the
+package in a process whose ``DMLC_ROLE`` is *server* / *scheduler* (or global scheduler) turns that process into the
+corresponding HiPS node and exits when the job finishes.
+"""
+from __future__ import annotations
+
+__version__ = "0.1.0"
+
+from . import base  # noqa: F401
+from .base import MXNetError  # noqa: F401
+from .context import Context, cpu, cpu_pinned, current_context, gpu, num_gpus  # noqa: F401
+from . import ndarray  # noqa: F401
+from . import ndarray as nd  # noqa: F401
+from . import autograd  # noqa: F401
+from . import initializer  # noqa: F401
+from . import initializer as init  # noqa: F401
+from . import lr_scheduler  # noqa: F401
+from . import optimizer  # noqa: F401
+from . import ops  # noqa: F401
+from . import kvstore  # noqa: F401
+from . import kvstore as kv  # noqa: F401
+from . import gluon  # noqa: F401
+from . import metric  # noqa: F401
+from . import model  # noqa: F401
+from . import profiler  # noqa: F401
+from . import io  # noqa: F401
+from . import utils  # noqa: F401
+from . import kvstore_server  # noqa: F401
+
+# server / scheduler bootstrap on import (no-op for workers and plain library use)
+kvstore_server._init_kvstore_server_module()

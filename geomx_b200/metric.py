@@ -1,0 +1,164 @@
+"""Evaluation metrics.  Parity: ``python/mxnet/metric.py`` (EvalMetric, Accuracy, TopKAccuracy, MAE, MSE, RMSE,
+CrossEntropy, Loss, CompositeEvalMetric, create)."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+__all__ = ["EvalMetric", "Accuracy", "TopKAccuracy", "MAE", "MSE", "RMSE", "CrossEntropy", "Loss",
+           "CompositeEvalMetric", "create"]
+
+
+def _t(x):
+    return x._t.detach() if hasattr(x, "_t") else torch.as_tensor(x)
+
+
+class EvalMetric:
+    def __init__(self, name, output_names=None, label_names=None, **kwargs):
+        self.name = str(name); self.output_names, self.label_names = output_names, label_names
+        self._kwargs = kwargs
+        self.reset()
+
+    def reset(self):
+        self.num_inst, self.sum_metric = 0, 0.0
+
+    def update(self, labels, preds):
+        raise NotImplementedError
+
+    def get(self):
+        return (self.name, float("nan")) if self.num_inst == 0 else (self.name, self.sum_metric / self.num_inst)
+
+    def get_name_value(self):
+        name, value = self.get()
+        if not isinstance(name, list):
+            name, value = [name], [value]
+        return list(zip(name, value))
+
+    def __str__(self):
+        return "EvalMetric: {}".format(dict(self.get_name_value()))
+
+
+def _lists(labels, preds):
+    if not isinstance(labels, (list, tuple)):
+        labels = [labels]
+    if not isinstance(preds, (list, tuple)):
+        preds = [preds]
+    return labels, preds
+
+
+class Accuracy(EvalMetric):
+    def __init__(self, axis=1, name="accuracy", **kw):
+        super().__init__(name, **kw); self.axis = axis
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l), _t(p)
+            if p.dim() > l.dim():
+                p = p.argmax(dim=self.axis)
+            self.sum_metric += float((p.reshape(-1).long() == l.reshape(-1).long().to(p.device)).sum())
+            self.num_inst += l.numel()
+
+
+class TopKAccuracy(EvalMetric):
+    def __init__(self, top_k=1, name="top_k_accuracy", **kw):
+        super().__init__(name + "_%d" % top_k, **kw); self.top_k = top_k
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l), _t(p)
+            top = p.topk(self.top_k, dim=1).indices
+            self.sum_metric += float((top == l.reshape(-1, 1).long().to(p.device)).any(dim=1).sum())
+            self.num_inst += l.numel()
+
+
+class MAE(EvalMetric):
+    def __init__(self, name="mae", **kw):
+        super().__init__(name, **kw)
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).float(), _t(p).float()
+            self.sum_metric += float((l.reshape(p.shape).to(p.device) - p).abs().mean()); self.num_inst += 1
+
+
+class MSE(EvalMetric):
+    def __init__(self, name="mse", **kw):
+        super().__init__(name, **kw)
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).float(), _t(p).float()
+            self.sum_metric += float((l.reshape(p.shape).to(p.device) - p).square().mean()); self.num_inst += 1
+
+
+class RMSE(MSE):
+    def __init__(self, name="rmse", **kw):
+        super().__init__(name, **kw)
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).float(), _t(p).float()
+            self.sum_metric += math.sqrt(float((l.reshape(p.shape).to(p.device) - p).square().mean())); self.num_inst += 1
+
+
+class CrossEntropy(EvalMetric):
+    def __init__(self, eps=1e-12, name="cross-entropy", **kw):
+        super().__init__(name, **kw); self.eps = eps
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).reshape(-1).long(), _t(p)
+            prob = p[torch.arange(l.numel(), device=p.device), l.to(p.device)]
+            self.sum_metric += float((-torch.log(prob + self.eps)).sum()); self.num_inst += l.numel()
+
+
+class Loss(EvalMetric):
+    def __init__(self, name="loss", **kw):
+        super().__init__(name, **kw)
+
+    def update(self, _, preds):
+        if not isinstance(preds, (list, tuple)):
+            preds = [preds]
+        for p in preds:
+            p = _t(p); self.sum_metric += float(p.sum()); self.num_inst += p.numel()
+
+
+class CompositeEvalMetric(EvalMetric):
+    def __init__(self, metrics=None, name="composite", **kw):
+        self.metrics = [create(m) for m in (metrics or [])]
+        super().__init__(name, **kw)
+
+    def add(self, metric):
+        self.metrics.append(create(metric))
+
+    def reset(self):
+        for m in getattr(self, "metrics", []):
+            m.reset()
+
+    def update(self, labels, preds):
+        for m in self.metrics:
+            m.update(labels, preds)
+
+    def get(self):
+        names, values = [], []
+        for m in self.metrics:
+            n, v = m.get(); names.append(n); values.append(v)
+        return names, values
+
+
+_REG = {"acc": Accuracy, "accuracy": Accuracy, "top_k_accuracy": TopKAccuracy, "mae": MAE, "mse": MSE, "rmse": RMSE,
+        "ce": CrossEntropy, "cross-entropy": CrossEntropy, "loss": Loss}
+
+
+def create(metric, *args, **kwargs):
+    if isinstance(metric, EvalMetric):
+        return metric
+    if callable(metric):
+        raise NotImplementedError("custom callable metrics: subclass EvalMetric")
+    if isinstance(metric, list):
+        c = CompositeEvalMetric()
+        for m in metric:
+            c.add(create(m, *args, **kwargs))
+        return c
+    return _REG[metric.lower()](*args, **kwargs)

@@ -1,0 +1,5 @@
+"""``mx.nd`` namespace."""
+from . import random  # noqa: F401
+from .ndarray import *  # noqa: F401,F403
+from .ndarray import NDArray  # noqa: F401
+from .utils import load, load_bytes, save, save_bytes  # noqa: F401

@@ -1,0 +1,3 @@
+"""``mx.optimizer`` namespace."""
+from .optimizer import *  # noqa: F401,F403
+from .optimizer import Optimizer, Updater, create, get_updater, register  # noqa: F401

@@ -1,0 +1,149 @@
+"""MXNet-shaped API on CPU: NDArray, autograd, gluon, optimizers, local kvstore (reference: python/mxnet/*)."""
+import numpy as np
+import pytest
+import torch
+
+import geomx_b200 as mx
+
+
+def _cnn():
+    net = mx.gluon.nn.Sequential()
+    net.add(mx.gluon.nn.Conv2D(channels=16, kernel_size=5, activation="relu"), mx.gluon.nn.MaxPool2D(pool_size=2, strides=2),
+            mx.gluon.nn.Conv2D(channels=32, kernel_size=5, activation="relu"), mx.gluon.nn.MaxPool2D(pool_size=2, strides=2),
+            mx.gluon.nn.Dense(256, activation="relu"), mx.gluon.nn.Dense(128, activation="relu"), mx.gluon.nn.Dense(10))
+    return net
+
+
+def test_ndarray_basics():
+    a = mx.nd.array([[1, 2], [3, 4]])
+    assert a.shape == (2, 2) and a.size == 4 and a.dtype == np.float32
+    b = (a * 2 + 1) / 2
+    np.testing.assert_allclose(b.asnumpy(), [[1.5, 2.5], [3.5, 4.5]])
+    assert a.astype("float16").dtype == np.float16
+    assert float(a.mean().asscalar()) == 2.5
+    assert a.argmax(axis=1).asnumpy().tolist() == [1.0, 1.0]
+    a[:] = 7
+    assert a.asnumpy().sum() == 28
+    c = mx.nd.zeros((3,), ctx=mx.cpu())
+    a2 = a.copyto(mx.cpu())
+    assert a2 is not a and (a2 == a).asnumpy().all()
+    assert c.context == mx.cpu()
+
+
+def test_gpu_ctx_raises_without_device():
+    if torch.cuda.is_available():
+        pytest.skip("has gpu")
+    with pytest.raises(mx.base.MXNetError):
+        mx.nd.zeros((1,), ctx=mx.gpu(0))
+
+
+def test_cnn_param_inventory():
+    net = _cnn()
+    net.initialize(force_reinit=True, ctx=mx.cpu(), init=mx.init.Xavier())
+    net(mx.nd.random.uniform(shape=(32, 1, 28, 28)))
+    params = list(net.collect_params().values())
+    sizes = [int(np.prod(p.shape)) for p in params]
+    # 10 tensors, 178 762 elements
+    assert sizes == [400, 16, 12800, 32, 131072, 256, 32768, 128, 1280, 10]
+    assert sum(sizes) == 178762
+
+
+def test_autograd_write_and_add():
+    x = mx.nd.array([1.0, 2.0, 3.0]); x.attach_grad()
+    with mx.autograd.record():
+        y = (x * x).sum()
+    y.backward()
+    np.testing.assert_allclose(x.grad.asnumpy(), [2, 4, 6])
+    with mx.autograd.record():
+        y = (x * 3).sum()
+    y.backward()
+    np.testing.assert_allclose(x.grad.asnumpy(), [3, 3, 3])  # 'write' overwrites
+    z = mx.nd.array([1.0, 1.0]); z.attach_grad("add")
+    for _ in range(2):
+        with mx.autograd.record():
+            (z * 2).sum().backward()
+    np.testing.assert_allclose(z.grad.asnumpy(), [4, 4])
+
+
+def test_train_converges_with_trainer():
+    torch.manual_seed(0)
+    net = _cnn(); net.initialize(init=mx.init.Xavier())
+    x = mx.nd.random.uniform(shape=(32, 1, 28, 28)); y = mx.nd.array(np.arange(32) % 10)
+    loss = mx.gluon.loss.SoftmaxCrossEntropyLoss()
+    tr = mx.gluon.Trainer(net.collect_params(), "adam", {"learning_rate": 0.01}, kvstore=None)
+    first = last = None
+    for i in range(30):
+        with mx.autograd.record():
+            l = loss(net(x), y)
+        l.backward(); tr.step(32)
+        v = float(l.mean().asscalar())
+        first = v if first is None else first; last = v
+    assert last < first * 0.7
+
+
+def test_local_kvstore_semantics():
+    kv = mx.kv.create("local")
+    kv.init(3, mx.nd.ones((2, 3)))
+    out = mx.nd.zeros((2, 3)); kv.pull(3, out=out)
+    assert out.asnumpy().sum() == 6
+    kv.push(3, [mx.nd.ones((2, 3)) * 2, mx.nd.ones((2, 3)) * 3])   # multi-value push sums
+    kv.pull(3, out=out)
+    np.testing.assert_allclose(out.asnumpy(), 5 * np.ones((2, 3)))   # no updater: assign merged
+    kv._set_updater(lambda k, g, w: w.__iadd__(g * 2))
+    kv.push(3, mx.nd.ones((2, 3))); kv.pull(3, out=out)
+    np.testing.assert_allclose(out.asnumpy(), 7 * np.ones((2, 3)))
+    # list keys, str keys cannot mix with int keys
+    kv2 = mx.kv.create("local"); kv2.init(["a", "b"], [mx.nd.ones((1,)), mx.nd.ones((1,))])
+    with pytest.raises(mx.base.MXNetError):
+        kv2.init(5, mx.nd.ones((1,)))
+    assert kv.type == "local" and kv.rank == 0 and kv.num_workers == 1
+
+
+def test_kvstore_optimizer_matches_trainer():
+    torch.manual_seed(1)
+    w0 = torch.randn(10)
+    g = torch.randn(10)
+    kv = mx.kv.create("local"); kv.set_optimizer(mx.optimizer.Adam(learning_rate=0.1))
+    kv.init(0, mx.nd.array(w0)); out = mx.nd.zeros((10,))
+    ref = w0.clone().requires_grad_(True); opt = torch.optim.Adam([ref], lr=0.1, eps=1e-8)
+    for _ in range(3):
+        kv.push(0, mx.nd.array(g)); kv.pull(0, out=out)
+        ref.grad = g.clone(); opt.step()
+    np.testing.assert_allclose(out.asnumpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["sgd", "adam", "dcasgd", "nag", "rmsprop", "adagrad", "adadelta", "ftrl", "adamax",
+                                  "nadam", "signum", "ftml", "sgld"])
+def test_optimizers_step(name):
+    o = mx.optimizer.create(name, learning_rate=0.01)
+    upd = mx.optimizer.get_updater(o)
+    w = mx.nd.ones((5,)); g = mx.nd.ones((5,)) * 0.5
+    before = w.asnumpy().copy()
+    upd(0, g, w); upd(0, g, w)
+    assert np.isfinite(w.asnumpy()).all() and not np.allclose(before, w.asnumpy())
+    st = upd.get_states(dump_optimizer=True)
+    upd2 = mx.optimizer.get_updater(mx.optimizer.create(name)); upd2.set_states(st)
+    assert type(upd2.optimizer).__name__.lower() == name
+
+
+def test_trainer_save_load_states(tmp_path):
+    net = mx.gluon.nn.Dense(4, in_units=3); net.initialize()
+    tr = mx.gluon.Trainer(net.collect_params(), "adam", {"learning_rate": 0.1}, kvstore=None)
+    x = mx.nd.ones((2, 3))
+    with mx.autograd.record():
+        l = net(x).sum()
+    l.backward(); tr.step(2)
+    f = str(tmp_path / "t.states"); tr.save_states(f); tr.load_states(f)
+    assert tr.optimizer.num_update == 1
+
+
+def test_dataloader_and_split_sampler():
+    ds = mx.gluon.data.vision.MNIST(root="/nonexistent", train=True)
+    assert ds.synthetic and ds[0][0].shape == (28, 28, 1)
+    tf = mx.gluon.data.vision.transforms.Compose([mx.gluon.data.vision.transforms.Resize((28, 28)),
+                                                   mx.gluon.data.vision.transforms.ToTensor()])
+    dl = mx.gluon.data.DataLoader(ds.transform_first(tf), 32, num_workers=0)
+    X, y = next(iter(dl))
+    assert X.shape == (32, 1, 28, 28) and y.shape == (32,) and float(X.max().asscalar()) <= 1.0
+    parts = mx.gluon.utils.split_and_load(X, [mx.cpu()])
+    assert parts[0].shape == (32, 1, 28, 28)
