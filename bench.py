@@ -1,0 +1,212 @@
+#!/usr/bin/env python
+"""Headline benchmark: examples/cnn.py training throughput (samples/sec, whole job) on N B200s of one node.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (N>1: launched by ``torch.distributed.run`` one rank per GPU).
+Prints ONE JSON line on rank 0.  Metric / config are BASELINE.json's: the reference demo CNN (178 762 params), per-worker batch 32
+(weak scaling), ``dist_sync`` HiPS: workers → local PS (party reduction) → global PS (Adam on the owner shard) → broadcast, synthetic
+MNIST-shaped data, random-init (Xavier) weights, fp32 storage with TF32 tensor-core multiplies and fp32 accumulation.
+
+Timed region (device-timed, max over ranks): exactly K full training steps (forward + backward + push + server optimizer + pull), each
+bracketed by its own CUDA-event pair; between timed steps a 256 MiB buffer is written to flush the 126 MB L2.  ``e2e`` re-measures the
+same K steps through the public API ``HipsCNNTrainStep.step(X_pinned, y_pinned) -> loss`` including the per-step H2D copy of the batch
+from pinned host memory and the D2H read of the loss.
+
+``--impl reference`` reports why the unmodified reference cannot run here (see DESIGN.md §Reference arm).
+``--impl oracle`` runs the same schedule with library ops only (PyTorch/cuDNN/cuBLAS + NCCL all-reduce + torch Adam, CUDA-graphed) — the
+"baseline, not the product" yard-stick of BASELINE.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "oracle"])
+    ap.add_argument("--batch-size", type=int, default=32)
+    ap.add_argument("--parties", type=int, default=0)
+    ap.add_argument("--mode", default="dist_sync", choices=["dist_sync", "dist_async"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-multicast", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm():
+    print(json.dumps({"impl": "reference", "unavailable": "INET-RC/GeoMX is MXNet 1.4 C++: /root/reference has no setup.py/pyproject at its root; "
+                      "python/setup.py needs a prebuilt libmxnet.so whose build requires ZeroMQ, protobuf, OpenBLAS, OpenCV, lapack (absent, "
+                      "no network) and its CUDA arch list stops at sm_75 (Makefile:333) — see DESIGN.md"}))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm()
+    import torch
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # convenience: self-launch under torchrun when invoked plainly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import geomx_b200 as mx
+    from geomx_b200.ops import native
+    from geomx_b200.parallel import Topology
+
+    B, K, W = args.batch_size, args.steps, max(3, args.warmup)
+    parties = args.parties or int(os.environ.get("GEOMX_NUM_PARTIES", 0)) or (2 if (world >= 2 and world % 2 == 0) else 1)
+    topo = Topology(world, rank, parties, int(os.environ.get("DMLC_NUM_GLOBAL_SERVER", 1)))
+    torch.manual_seed(1234)  # same init on every rank; rank 0's value wins anyway (kv.init semantics)
+
+    # ---- synthetic MNIST-shaped data in pinned host memory (a rotating pool so every step copies a different batch)
+    pool = 64
+    g = torch.Generator().manual_seed(100 + rank)
+    Xs = torch.rand(pool, B, 1, 28, 28, generator=g).pin_memory()
+    ys = torch.randint(0, 10, (pool, B), generator=g).float().pin_memory()
+
+    if args.impl == "oracle":
+        from geomx_b200.parallel.nccl_oracle import OracleCNNTrainStep
+        eng = OracleCNNTrainStep(batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev, use_graph=not args.no_graph)
+    else:
+        eng = mx.models.HipsCNNTrainStep(net=None, batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev,
+                                         use_graph=not args.no_graph, use_multicast=not args.no_multicast, mode=args.mode)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    # ---------------------------------------------------------------- warm-up (also captures the CUDA graph)
+    for i in range(W):
+        eng.step(Xs[i % pool], ys[i % pool])
+    barrier()
+
+    # ---------------------------------------------------------------- kernel-timed region: K steps, device-resident batch, L2 flushed between steps
+    eng.x.copy_(Xs[0], non_blocking=True); eng.label.copy_(ys[0], non_blocking=True)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local)
+    launches0 = native.launch_count
+    barrier()
+    if rank == 0:
+        sampler.start()
+    for i in range(K):
+        if flush is not None:
+            flush.fill_(float(i))
+        starts[i].record()
+        eng.run_device()
+        ends[i].record()
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    launches_per_step = eng.kernels_per_step
+    # ---------------------------------------------------------------- end-to-end region: public API, H2D from pinned + D2H loss every step
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last_loss = 0.0
+    for i in range(K):
+        last_loss = eng.step(Xs[(W + i) % pool], ys[(W + i) % pool])
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        value = world * B * K / (dev_ms / 1e3)
+        e2e_value = world * B * K / (e2e_ms / 1e3)
+        out = {
+            "metric": "cnn.py samples/sec (whole box, device-timed, max over ranks)",
+            "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(dev_ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 (fp32 storage, TF32 tcgen05 multiply, fp32 accumulate; reference is fp32 SGEMM)", "data": "synthetic",
+            "impl": args.impl,
+            "config": {"model": "examples/cnn.py MNIST CNN (Conv16k5-Pool-Conv32k5-Pool-Dense256-Dense128-Dense10, 178762 params)",
+                       "global_batch": B * world, "per_gpu_batch": B, "seq_len": None, "kvstore": args.mode,
+                       "parallelism": "hips-dp%d: %d part%s x %d worker%s, global PS on rank%s %s" % (
+                           world, topo.num_parties, "y" if topo.num_parties == 1 else "ies", topo.party_size, "" if topo.party_size == 1 else "s",
+                           "" if topo.num_gs == 1 else "s", topo.gs_ranks),
+                       "optimizer": "Adam(lr=0.01) on the global-PS shard", "cuda_graph": not args.no_graph,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush)" if flush is not None else "no flush",
+                       "fabric": getattr(getattr(eng, "fabric", None), "heap", None) and eng.fabric.heap.backend,
+                       "multicast": bool(getattr(getattr(eng, "fabric", None), "use_multicast", False))},
+            "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms / K, 5),
+                    "h2d_bytes_per_step": eng.h2d_bytes_per_step(), "d2h_bytes_per_step": eng.d2h_bytes_per_step(), "final_loss": round(last_loss, 5)},
+            "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,383 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:   D[M,N] = epilogue( alpha * A[M,K] * B[N,K]^T )
+//
+//  * operands are fp32 in global memory, multiplied on the 5th-gen tensor cores as TF32 (kind::tf32) with fp32
+//    accumulation in TMEM — the closest tensor-core analogue of the reference's cublasSgemmEx path
+//    (reference src/operator/linalg_impl.h:196-214, FullyConnected src/operator/nn/fully_connected-inl.h:71-173,
+//    Convolution im2col+GEMM src/operator/nn/convolution-inl.h:165-284).
+//  * each operand may be K-major (row-major [rows][K]) or MN-major (row-major [K][rows]) so that forward, dgrad
+//    (dY*W) and wgrad (dY^T*X) all read the tensors where they already live — no transposes are materialised.
+//  * warp-specialised, one 128 x BLOCK_N tile per CTA: warp0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B,
+//    4-stage mbarrier ring), warp1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2-5 = epilogue
+//    (tcgen05.ld 32x32b -> registers -> fused bias / ReLU / ReLU-mask / column-sum (bias gradient) / NCHW scatter /
+//    split-K atomic accumulate).
+//  * optional `wait_flag`: the producer spins on a system-scope flag before issuing the first B load — this is how
+//    the first GEMM that consumes pulled weights is fused with the parameter-server broadcast (pull_gemm).
+//
+// Tile shapes: UMMA M=128, N=BLOCK_N in {32,64,128}, K=8 per instruction (32 B of tf32), BLOCK_K = 32 fp32 = one
+// 128-byte swizzle atom per row.  Out-of-bounds rows/cols/k are zero-filled by TMA, masked in the epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gx {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;
+constexpr int UMMA_K = 8;
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB either major
+constexpr int MN_BOX_BYTES = 32 * BLOCK_K * 4;       // one 32(MN) x 32(K) box = 4 KiB
+
+struct GemmParams {
+  int M, N, K;
+  int kb_per_split;
+  float* D;
+  long long ldd;
+  const float* bias;
+  const float* mask;
+  long long ldmask;
+  float* colsum;
+  int relu, accumulate, store_mode, hw;
+  float alpha;
+  const uint32_t* wait_flag;
+  const int* wait_epoch;  // device epoch counter: proceed when *wait_flag >= *wait_epoch (graph-replay safe)
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = SmemLayout<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N;
+  const int m0 = blockIdx.y * BLOCK_M;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      if (p.wait_flag != nullptr) {
+        const uint32_t want = (uint32_t)(*reinterpret_cast<const volatile int*>(p.wait_epoch));
+        while (ld_acquire_sys(p.wait_flag) < want) { __nanosleep(32); }
+        asm volatile("fence.proxy.async;" ::: "memory");  // remote generic-proxy stores -> async-proxy (TMA) reads
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = smem + stage * L::STAGE_BYTES;
+        uint8_t* sB = sA + A_TILE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        const int k0 = kb * BLOCK_K;
+        if constexpr (!A_MN) {
+          tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sA + j * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + 32 * j, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sB + j * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + 32 * j, k0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (one thread) ================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(/*TF32*/ 2u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t sB = sA + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // K-major SW128: rows 128 B apart, 8-row groups 1024 B apart (SBO); advance 32 B per K step inside the atom.
+          // MN-major SW128: 32-wide MN atoms LBO apart (one TMA box each), 8 K-rows = 1024 B per K step.
+          const uint64_t da = A_MN ? umma_desc_sw128(sA + k * 1024, MN_BOX_BYTES, 1024) : umma_desc_sw128(sA + k * UMMA_K * 4, 16, 1024);
+          const uint64_t db = B_MN ? umma_desc_sw128(sB + k * 1024, MN_BOX_BYTES, 1024) : umma_desc_sw128(sB + k * UMMA_K * 4, 16, 1024);
+          umma_tf32(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
+    }
+  } else {
+    // ================================ epilogue (4 warps = 128 TMEM lanes) ================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool have_acc = kb_end > kb_begin;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      if (n0 + c0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c0 + j;
+        float x = have_acc ? __uint_as_float(r[j]) * p.alpha : 0.f;
+        if (p.bias != nullptr && n < p.N && blockIdx.z == 0) x += __ldg(p.bias + n);
+        if (p.relu) x = fmaxf(x, 0.f);
+        if (p.mask != nullptr && row_ok && n < p.N) x = (__ldg(p.mask + (long long)m * p.ldmask + n) > 0.f) ? x : 0.f;
+        v[j] = (row_ok && n < p.N) ? x : 0.f;
+      }
+      if (p.colsum != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = warp_sum(v[j]);
+          if (lane == 0 && n0 + c0 + j < p.N) atomicAdd(p.colsum + n0 + c0 + j, s);
+        }
+      }
+      if (row_ok) {
+        if (p.store_mode == 0) {
+          float* dst = p.D + (long long)m * p.ldd + n0 + c0;
+          const bool vec = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && (n0 + c0 + 32 <= p.N) && !p.accumulate;
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + c0 + j < p.N) {
+                if (p.accumulate) atomicAdd(dst + j, v[j]);
+                else dst[j] = v[j];
+              }
+            }
+          }
+        } else {
+          // NCHW scatter: row m = (image, pixel), column n = channel
+          const int img = m / p.hw, pix = m - img * p.hw;
+          float* dst = p.D + ((long long)img * p.N) * p.hw + pix;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.N) {
+              if (p.accumulate) atomicAdd(dst + (long long)n * p.hw, v[j]);
+              else dst[(long long)n * p.hw] = v[j];
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// inner = contiguous dimension (elements), outer = strided dimension, ld = elements between outer rows
+static int make_tmap(CUtensorMap* tm, const float* base, long long inner, long long outer, long long ld, int box_inner, int box_outer) {
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) return -2;
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N>;
+  static bool attr_set = false;
+  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  return (int)cudaGetLastError();
+}
+
+template <int BLOCK_N>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BLOCK_N, false, false>(ta, tb, p, grid, s);
+  if (!a_mn && b_mn) return launch<BLOCK_N, false, true>(ta, tb, p, grid, s);
+  if (a_mn && !b_mn) return launch<BLOCK_N, true, false>(ta, tb, p, grid, s);
+  return launch<BLOCK_N, true, true>(ta, tb, p, grid, s);
+}
+
+}  // namespace gx
+
+// A: K-major -> [M][K] with row stride lda; MN-major -> [K][M] with row stride lda.  Same for B with N.
+// returns 0 on success, -1 if the operands do not satisfy TMA alignment (caller falls back to gx_gemm_simt).
+GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
+                        long long ldd, const float* bias, const float* mask, long long ldmask, float* colsum, int relu, int accumulate,
+                        int store_mode, int hw, float alpha, int split_k, const uint32_t* wait_flag, const int* wait_epoch,
+                        cudaStream_t stream) {
+  using namespace gx;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -1;
+  int block_n;
+  const long long mt = ceil_div(M, BLOCK_M);
+  if (N <= 32) block_n = 32;
+  else if (N <= 64 || mt * ceil_div(N, 128) < 48) block_n = 64;
+  else block_n = 128;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
+  else rc = make_tmap(&ta, A, M, K, lda, 32, BLOCK_K);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K, block_n);
+  else rc = make_tmap(&tb, B, N, K, ldb, 32, BLOCK_K);
+  if (rc) return rc;
+  const int num_kb = (int)ceil_div(K, BLOCK_K);
+  if (split_k < 1) split_k = 1;
+  if (split_k > num_kb) split_k = num_kb;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.kb_per_split = (int)ceil_div(num_kb, split_k);
+  split_k = (int)ceil_div(num_kb, p.kb_per_split);
+  p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
+  p.relu = relu; p.accumulate = (accumulate || split_k > 1) ? 1 : 0; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha;
+  p.wait_flag = wait_flag; p.wait_epoch = wait_epoch;
+  dim3 grid((unsigned)ceil_div(N, block_n), (unsigned)mt, (unsigned)split_k);
+  switch (block_n) {
+    case 32: return dispatch_major<32>(a_mn, b_mn, ta, tb, p, grid, stream);
+    case 64: return dispatch_major<64>(a_mn, b_mn, ta, tb, p, grid, stream);
+    default: return dispatch_major<128>(a_mn, b_mn, ta, tb, p, grid, stream);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core fallback for operands that violate TMA alignment (odd leading dimensions, e.g. N=10 classifier heads).
+// Same contract as gx_gemm_tf32 (fp32 FMA).  64x64 tile, 16-deep smem panels.
+namespace gx {
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ A, long long lda, int a_mn, const float* __restrict__ B,
+                                                         long long ldb, int b_mn, int M, int N, int K, GemmParams p) {
+  __shared__ float sA[16][64 + 1];
+  __shared__ float sB[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i / 64, r = i % 64;
+      const int k = k0 + kk;
+      float a = 0.f, b = 0.f;
+      if (k < K && m0 + r < M) a = a_mn ? A[(long long)k * lda + m0 + r] : A[(long long)(m0 + r) * lda + k];
+      if (k < K && n0 + r < N) b = b_mn ? B[(long long)k * ldb + n0 + r] : B[(long long)(n0 + r) * ldb + k];
+      sA[kk][r] = a;
+      sB[kk][r] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (m >= M || n >= N) continue;
+      float x = acc[i][j] * p.alpha;
+      if (p.bias) x += p.bias[n];
+      if (p.relu) x = fmaxf(x, 0.f);
+      if (p.mask) x = p.mask[(long long)m * p.ldmask + n] > 0.f ? x : 0.f;
+      if (p.colsum) atomicAdd(p.colsum + n, x);
+      float* dst = p.store_mode == 0 ? p.D + (long long)m * p.ldd + n
+                                     : p.D + ((long long)(m / p.hw) * N + n) * p.hw + (m % p.hw);
+      if (p.accumulate) atomicAdd(dst, x);
+      else *dst = x;
+    }
+  }
+}
+}  // namespace gx
+
+GX_API int gx_gemm_simt(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
+                        long long ldd, const float* bias, const float* mask, long long ldmask, float* colsum, int relu, int accumulate,
+                        int store_mode, int hw, float alpha, cudaStream_t stream) {
+  using namespace gx;
+  if (M <= 0 || N <= 0) return 0;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.kb_per_split = 0; p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
+  p.relu = relu; p.accumulate = accumulate; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha; p.wait_flag = nullptr; p.wait_epoch = nullptr;
+  dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
+  gemm_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, a_mn, B, ldb, b_mn, M, N, K, p);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,378 @@
+// HiPS data plane on NVSwitch: the two communication-bound hot paths of the reference fused into in-kernel collectives.
+//
+// Reference path per key per step: worker D2H copy -> ZMQ push -> local server CPU `+=` over NumWorkers
+// (kvstore_dist_server.h:1277-1321) -> ZMQ push to the global server -> CPU sum over parties + Python optimizer on the server
+// main thread (:1298-1319, :535-559) -> ack -> local server pulls (:899-936) -> workers pull (:1705-1763) -> H2D copy.
+//
+// Here one kernel per step, launched by every rank (one process per GPU), no NCCL / host transport on the path:
+//   phase A  every rank publishes "my gradient arena is complete" to its party (system-scope release flags)
+//   phase B  LOCAL PS TIER  = tile-sharded reduction inside the party: the owner of a tile pulls the tile from all party members
+//            with `multimem.ld_reduce` (in-switch NVLS reduction) or P2P `ld.global` loads, applies the 1/num_samples scale that the
+//            scripts apply before push, and stores the party aggregate into the global-PS owner's staging slot (P2P `st.global`).
+//   phase C  GLOBAL PS TIER = the tile's global owner waits for all parties, sums the staged aggregates and runs the partitioned
+//            optimizer (SGD / Adam / DCASGD; master weights + state live in that rank's HBM), then broadcasts the new tile to every
+//            worker's parameter arena with `multimem.st` (NVLS multicast) or P2P stores and releases a per-key ready flag.
+//   phase D  workers wait for the per-key flags (or defer the wait to the first consuming GEMM: gx_gemm_tf32(wait_flag=...)).
+// MixedSync (dist_async) is one-sided: the party's tile owner takes a per-tile system-scope lock in the global owner's HBM and
+// applies its party's update there directly (reference: DataHandleAsyncDefault kvstore_dist_server.h:1519-1611).
+// HFA / party-level sync use hips_party_allreduce (local tier only).
+//
+// Flag protocol: every cross-rank flag carries the (monotonically increasing) epoch; writers do  stores -> bar.sync -> fence.sys ->
+// st.release.sys, readers spin with ld.acquire.sys.  All CTAs of the launch are co-resident (grid <= #SMs), phases are ordered
+// A < B < C < D inside every CTA and each phase only waits on flags produced by strictly earlier phases => no cyclic wait.
+#include "common.cuh"
+
+namespace gx {
+
+constexpr int MAX_RANKS = 16;
+constexpr int TILE = 1024;           // floats per tile (= 4 KiB = one 256-thread float4 sweep)
+constexpr int FAB_THREADS = 256;
+
+
+struct OptHyperF {
+  float lr, wd, rescale, clip, momentum, beta1, beta2, eps, lamda;
+  int kind;  // 0 sgd, 1 adam, 2 dcasgd, -1 none (store aggregated gradient: Bi-Sparse / local-optimizer modes)
+};
+
+struct FabricParams {
+  int world, rank, party_size, num_parties, party, local;
+  int num_gs;
+  int gs_rank[MAX_RANKS];
+  float* grad[MAX_RANKS];      // peer pointers, indexed by global rank (only own party required)
+  float* param[MAX_RANKS];     // peer pointers, all ranks
+  float* stage[MAX_RANKS];     // peer pointers: [num_parties][n] staging on (potential) global owners
+  uint32_t* flags[MAX_RANKS];  // peer pointers to flag pads
+  const float* grad_mc;        // multicast address spanning the party's grad arenas (nullptr -> P2P loads)
+  float* param_mc;             // multicast address spanning all ranks' param arenas (nullptr -> P2P stores)
+  float* w;                    // global-owner master weights (local HBM), s0/s1 optimizer state
+  float* s0;
+  float* s1;
+  float* lock_and_steps;       // unused in sync mode
+  long long n;                 // arena elements (multiple of TILE)
+  int tiles;
+  int num_keys;
+  const int* tile_key;         // [tiles]
+  const int* key_tiles;        // [num_keys] tiles per key
+  const int* tile_owner;       // [tiles] global-PS owner rank of each tile (MultiGPS sharding rules, arena.py)
+  const unsigned char* tile_active;  // [tiles] or nullptr: only keys pushed this round take part
+  const float2* tile_mult;     // per-tile (lr_mult, wd_mult) or nullptr
+  int* key_done;               // [num_keys] cumulative completion counters on this rank (global owner side)
+  int* state;                  // [0]=epoch completed, [1]=CTA completion counter, [2]=optimizer step t
+  OptHyperF h;
+  float push_scale;            // the script-level  grad / num_samples
+  int defer_pull_wait;
+  int param_ready_off;         // uint32 offset of param_ready[num_keys] in the flag pad
+  int ready_off;               // uint32 offset of grad_ready[MAX_RANKS] (per channel: every kernel family has its own epoch)
+  int arrived_off;             // uint32 offset of arrived[num_parties][tiles]
+};
+
+__device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
+  while (ld_acquire_sys(p) < v) { __nanosleep(20); }
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+__device__ __forceinline__ void opt_apply(float& w, float g, float& a, float& b, const OptHyperF& h, float lr, float wd) {
+  if (h.kind == 1) {
+    g *= h.rescale;
+    if (h.clip >= 0.f) g = fminf(fmaxf(g, -h.clip), h.clip);
+    g = fmaf(wd, w, g);
+    a = h.beta1 * a + (1.f - h.beta1) * g;
+    b = h.beta2 * b + (1.f - h.beta2) * g * g;
+    w -= lr * a / (sqrtf(b) + h.eps);
+  } else if (h.kind == 0) {
+    g *= h.rescale;
+    if (h.clip >= 0.f) g = fminf(fmaxf(g, -h.clip), h.clip);
+    g = fmaf(wd, w, g);
+    if (h.momentum != 0.f) { a = h.momentum * a - lr * g; w += a; }
+    else w -= lr * g;
+  } else if (h.kind == 2) {
+    g *= h.rescale;
+    if (h.clip >= 0.f) g = fminf(fmaxf(g, -h.clip), h.clip);
+    const float upd = g + wd * w + h.lamda * g * g * (w - b);
+    const float prev = w;
+    if (h.momentum != 0.f) { a = h.momentum * a - lr * upd; w += a; }
+    else w -= lr * upd;
+    b = prev;
+  } else {
+    w = g;  // no optimizer on the server: store the aggregate (reference ApplyUpdates without updater_, :547-550)
+  }
+}
+
+__device__ __forceinline__ float adam_lr(const OptHyperF& h, int t) {
+  if (h.kind != 1) return h.lr;
+  return h.lr * sqrtf(1.f - powf(h.beta2, (float)t)) / (1.f - powf(h.beta1, (float)t));
+}
+
+// Global-owner side of one tile: optimizer + broadcast + per-key completion/flag.  `agg` is this thread's float4 of the summed gradient.
+__device__ __forceinline__ void global_apply_tile(const FabricParams& p, int t, float4 agg, uint32_t epoch, float lr_t) {
+  const long long off = (long long)t * TILE + threadIdx.x * 4;
+  float lr = lr_t, wd = p.h.wd;
+  if (p.tile_mult) { const float2 mm = __ldg(p.tile_mult + t); lr *= mm.x; wd *= mm.y; }
+  float4 W = *reinterpret_cast<float4*>(p.w + off);
+  float4 A = p.s0 ? *reinterpret_cast<float4*>(p.s0 + off) : make_float4(0, 0, 0, 0);
+  float4 B = p.s1 ? *reinterpret_cast<float4*>(p.s1 + off) : make_float4(0, 0, 0, 0);
+  opt_apply(W.x, agg.x, A.x, B.x, p.h, lr, wd);
+  opt_apply(W.y, agg.y, A.y, B.y, p.h, lr, wd);
+  opt_apply(W.z, agg.z, A.z, B.z, p.h, lr, wd);
+  opt_apply(W.w, agg.w, A.w, B.w, p.h, lr, wd);
+  *reinterpret_cast<float4*>(p.w + off) = W;
+  if (p.s0) *reinterpret_cast<float4*>(p.s0 + off) = A;
+  if (p.s1) *reinterpret_cast<float4*>(p.s1 + off) = B;
+  // pull/broadcast: NVLS multicast store or P2P stores into every worker's parameter arena
+  if (p.param_mc != nullptr) {
+    multimem_st_f4(p.param_mc + off, W);
+  } else {
+    for (int r = 0; r < p.world; ++r) st_f4_sys(p.param[r] + off, W);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fence_sys();
+    const int key = p.tile_key[t];
+    const int c = atomicAdd(p.key_done + key, 1) + 1;
+    if (c == p.key_tiles[key]) {  // last tile of this key for this round: reset the counter, release the key
+      p.key_done[key] = 0;
+      fence_sys();
+      for (int r = 0; r < p.world; ++r) st_release_sys(p.flags[r] + p.param_ready_off + key, epoch);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const FabricParams p) {
+  const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
+  const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
+  const float lr_t = adam_lr(p.h, opt_t);
+  const int S = p.party_size, P = p.num_parties;
+  const int party_base = p.party * S;
+  uint32_t* my_flags = p.flags[p.rank];
+
+  // ---------------- phase A: publish gradient-ready to the party
+  if (blockIdx.x == 0 && threadIdx.x < S) {
+    fence_sys();
+    st_release_sys(p.flags[party_base + threadIdx.x] + p.ready_off + p.rank, epoch);
+  }
+
+  // ---------------- phase B: local PS tier (party reduction of owned tiles)
+  bool waited_party = false;
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    if (t % S != p.local) continue;
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    if (!waited_party) {
+      if (threadIdx.x < S) wait_flag_ge(my_flags + p.ready_off + party_base + threadIdx.x, epoch);
+      __syncthreads();
+      waited_party = true;
+    }
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float4 acc;
+    if (p.grad_mc != nullptr && S > 1) {
+      acc = multimem_ld_reduce_f4(p.grad_mc + off);
+    } else {
+      acc = (S == 1) ? *reinterpret_cast<const float4*>(p.grad[p.rank] + off) : ld_f4_sys(p.grad[party_base] + off);
+      for (int j = 1; j < S; ++j) acc = f4_add(acc, ld_f4_sys(p.grad[party_base + j] + off));
+    }
+    acc = f4_scale(acc, p.push_scale);
+    const int owner = p.tile_owner[t];
+    if (P == 1 && owner == p.rank) {
+      global_apply_tile(p, t, acc, epoch, lr_t);  // both tiers collapse: stay in registers
+    } else {
+      st_f4_sys(p.stage[owner] + (long long)p.party * p.n + off, acc);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        fence_sys();
+        st_release_sys(p.flags[owner] + p.arrived_off + p.party * p.tiles + t, epoch);
+      }
+    }
+  }
+
+  // ---------------- phase C: global PS tier (tiles this rank owns globally)
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    if (p.tile_owner[t] != p.rank) continue;
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    if (P == 1 && (t % S) == p.local) continue;  // already applied in phase B
+    if (threadIdx.x < P) wait_flag_ge(my_flags + p.arrived_off + threadIdx.x * p.tiles + t, epoch);
+    __syncthreads();
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float4 acc = ld_f4_sys(p.stage[p.rank] + off);
+    for (int g = 1; g < P; ++g) acc = f4_add(acc, ld_f4_sys(p.stage[p.rank] + (long long)g * p.n + off));
+    global_apply_tile(p, t, acc, epoch, lr_t);
+  }
+
+  // ---------------- phase D: wait for the broadcast (unless deferred to the consuming GEMM)
+  if (!p.defer_pull_wait && blockIdx.x == 0) {
+    for (int t = threadIdx.x; t < p.tiles; t += blockDim.x)
+      if (p.tile_active == nullptr || p.tile_active[t]) wait_flag_ge(my_flags + p.param_ready_off + p.tile_key[t], epoch);
+  }
+
+  // ---------------- epoch / optimizer step bookkeeping (last CTA to finish publishes the new epoch)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int done = atomicAdd(p.state + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      p.state[1] = 0;
+      p.state[2] = opt_t;
+      p.state[0] = (int)epoch;
+      __threadfence();
+    }
+  }
+}
+
+// One-sided MixedSync: the party's tile owner applies its aggregate directly on the global owner's HBM under a per-tile lock.
+// locks live in the global owner's flag pad at `lock_off` (uint32 per tile), per-tile optimizer step counts right after them.
+__global__ void __launch_bounds__(FAB_THREADS, 1) hips_async_step_kernel(const FabricParams p, float* const* w_peer, float* const* s0_peer,
+                                                                          float* const* s1_peer, int lock_off, int step_off) {
+  const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
+  const int S = p.party_size;
+  const int party_base = p.party * S;
+  uint32_t* my_flags = p.flags[p.rank];
+  __shared__ int s_step;
+  if (blockIdx.x == 0 && threadIdx.x < S) {
+    fence_sys();
+    st_release_sys(p.flags[party_base + threadIdx.x] + p.ready_off + p.rank, epoch);
+  }
+  bool waited_party = false;
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    if (t % S != p.local) continue;
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    if (!waited_party) {
+      if (threadIdx.x < S) wait_flag_ge(my_flags + p.ready_off + party_base + threadIdx.x, epoch);
+      __syncthreads();
+      waited_party = true;
+    }
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float4 acc;
+    if (p.grad_mc != nullptr && S > 1) acc = multimem_ld_reduce_f4(p.grad_mc + off);
+    else {
+      acc = (S == 1) ? *reinterpret_cast<const float4*>(p.grad[p.rank] + off) : ld_f4_sys(p.grad[party_base] + off);
+      for (int j = 1; j < S; ++j) acc = f4_add(acc, ld_f4_sys(p.grad[party_base + j] + off));
+    }
+    acc = f4_scale(acc, p.push_scale);
+    const int owner = p.tile_owner[t];
+    uint32_t* lock = p.flags[owner] + lock_off + t;
+    uint32_t* stepc = p.flags[owner] + step_off + t;
+    if (threadIdx.x == 0) {
+      while (atomicCAS_system(lock, 0u, 1u) != 0u) { __nanosleep(40); }
+      fence_sys();
+      s_step = (int)ld_relaxed_sys(stepc) + 1;
+    }
+    __syncthreads();
+    float lr = adam_lr(p.h, s_step), wd = p.h.wd;
+    if (p.tile_mult) { const float2 mm = __ldg(p.tile_mult + t); lr *= mm.x; wd *= mm.y; }
+    float* wp = w_peer[owner] + off;
+    float4 W = ld_f4_sys(wp);
+    float4 A = s0_peer[owner] ? ld_f4_sys(s0_peer[owner] + off) : make_float4(0, 0, 0, 0);
+    float4 B = s1_peer[owner] ? ld_f4_sys(s1_peer[owner] + off) : make_float4(0, 0, 0, 0);
+    opt_apply(W.x, acc.x, A.x, B.x, p.h, lr, wd);
+    opt_apply(W.y, acc.y, A.y, B.y, p.h, lr, wd);
+    opt_apply(W.z, acc.z, A.z, B.z, p.h, lr, wd);
+    opt_apply(W.w, acc.w, A.w, B.w, p.h, lr, wd);
+    st_f4_sys(wp, W);
+    if (s0_peer[owner]) st_f4_sys(s0_peer[owner] + off, A);
+    if (s1_peer[owner]) st_f4_sys(s1_peer[owner] + off, B);
+    // pull for the own party only (other parties see this update when they next push)
+    for (int j = 0; j < S; ++j) st_f4_sys(p.param[party_base + j] + off, W);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      fence_sys();
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(stepc), "r"((uint32_t)s_step) : "memory");
+      fence_sys();
+      st_release_sys(lock, 0u);
+      for (int j = 0; j < S; ++j) red_add_release_sys(p.flags[party_base + j] + p.param_ready_off + p.tile_key[t], 1u);
+    }
+    __syncthreads();
+  }
+  // wait until every tile of every key has been delivered to this rank by its party's owners (cumulative counters)
+  if (blockIdx.x == 0) {
+    for (int k = threadIdx.x; k < p.num_keys; k += blockDim.x) wait_flag_ge(my_flags + p.param_ready_off + k, epoch * (uint32_t)p.key_tiles[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int done = atomicAdd(p.state + 1, 1);
+    if (done == (int)gridDim.x - 1) { p.state[1] = 0; p.state[0] = (int)epoch; __threadfence(); }
+  }
+}
+
+// Local tier only: out[party members] = scale * sum_{party} src   (HFA local synchronisation, party-level all-reduce)
+//   mode 0: write the result into every party member's `dst` arena; mode 1: only into the owner's `dst` (reduce-scatter)
+__global__ void __launch_bounds__(FAB_THREADS, 1) hips_party_allreduce_kernel(const FabricParams p, float* const* src_peer, float* const* dst_peer,
+                                                                               float scale, int mode, int flag_off) {
+  const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
+  const int S = p.party_size, party_base = p.party * S;
+  uint32_t* my_flags = p.flags[p.rank];
+  if (blockIdx.x == 0 && threadIdx.x < S) {
+    fence_sys();
+    st_release_sys(p.flags[party_base + threadIdx.x] + p.ready_off + p.rank, epoch);
+  }
+  bool waited = false;
+  int mine = 0;
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    if (t % S != p.local) continue;
+    if (!waited) {
+      if (threadIdx.x < S) wait_flag_ge(my_flags + p.ready_off + party_base + threadIdx.x, epoch);
+      __syncthreads();
+      waited = true;
+    }
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float4 acc = (S == 1) ? *reinterpret_cast<const float4*>(src_peer[p.rank] + off) : ld_f4_sys(src_peer[party_base] + off);
+    for (int j = 1; j < S; ++j) acc = f4_add(acc, ld_f4_sys(src_peer[party_base + j] + off));
+    acc = f4_scale(acc, scale);
+    if (mode == 0) for (int j = 0; j < S; ++j) st_f4_sys(dst_peer[party_base + j] + off, acc);
+    else *reinterpret_cast<float4*>(dst_peer[p.rank] + off) = acc;
+    ++mine;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && mine > 0 && mode == 0) {
+    fence_sys();
+    for (int j = 0; j < S; ++j) red_add_release_sys(p.flags[party_base + j] + flag_off, (uint32_t)mine);
+  }
+  if (mode == 0 && blockIdx.x == 0 && threadIdx.x == 0) wait_flag_ge(my_flags + flag_off, epoch * (uint32_t)p.tiles);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int done = atomicAdd(p.state + 1, 1);
+    if (done == (int)gridDim.x - 1) { p.state[1] = 0; p.state[0] = (int)epoch; __threadfence(); }
+  }
+}
+
+// Whole-world flag barrier (two-tier HiPS barrier collapses to one hop on NVSwitch): counter at flag offset `off`.
+__global__ void fabric_barrier_kernel(uint32_t* const* flags, int world, int rank, int off, int* state) {
+  if (threadIdx.x == 0) {
+    const uint32_t e = (uint32_t)(*reinterpret_cast<volatile int*>(state)) + 1u;
+    fence_sys();
+    for (int r = 0; r < world; ++r) red_add_release_sys(flags[r] + off, 1u);
+    wait_flag_ge(flags[rank] + off, e * (uint32_t)world);
+    *state = (int)e;
+  }
+}
+
+}  // namespace gx
+
+using namespace gx;
+
+GX_API int gx_fabric_params_size() { return (int)sizeof(FabricParams); }
+
+// `params` is a host copy of FabricParams (assembled by geomx_b200/parallel/fabric.py through ctypes).
+GX_API int gx_hips_fsa_step(const void* params, int grid, cudaStream_t s) {
+  FabricParams p = *reinterpret_cast<const FabricParams*>(params);
+  if (grid < 1) grid = 1;
+  hips_fsa_step_kernel<<<grid, FAB_THREADS, 0, s>>>(p);
+  return GX_CHECK_LAUNCH();
+}
+GX_API int gx_hips_async_step(const void* params, float* const* w_peer, float* const* s0_peer, float* const* s1_peer, int lock_off, int step_off,
+                              int grid, cudaStream_t s) {
+  FabricParams p = *reinterpret_cast<const FabricParams*>(params);
+  hips_async_step_kernel<<<grid, FAB_THREADS, 0, s>>>(p, w_peer, s0_peer, s1_peer, lock_off, step_off);
+  return GX_CHECK_LAUNCH();
+}
+GX_API int gx_hips_party_allreduce(const void* params, float* const* src_peer, float* const* dst_peer, float scale, int mode, int flag_off, int grid,
+                                   cudaStream_t s) {
+  FabricParams p = *reinterpret_cast<const FabricParams*>(params);
+  hips_party_allreduce_kernel<<<grid, FAB_THREADS, 0, s>>>(p, src_peer, dst_peer, scale, mode, flag_off);
+  return GX_CHECK_LAUNCH();
+}
+GX_API int gx_fabric_barrier(uint32_t* const* flags_dev, int world, int rank, int off, int* state, cudaStream_t s) {
+  fabric_barrier_kernel<<<1, 32, 0, s>>>(flags_dev, world, rank, off, state);
+  return GX_CHECK_LAUNCH();
+}

@@ -1,0 +1,203 @@
+"""The reference's demo model (``examples/cnn.py:56-64``) and its B200 training engine.
+
+``build_cnn()`` returns the Gluon network exactly as the reference scripts declare it:
+``Conv2D(16,k5,relu) → MaxPool2 → Conv2D(32,k5,relu) → MaxPool2 → Dense(256,relu) → Dense(128,relu) → Dense(10)`` (178 762 parameters).
+
+``HipsCNNTrainStep`` is the flagship hot path: one *training step* = forward + backward of that network for a per-worker batch
+plus the HiPS push/pull of all 10 keys (``dist_sync``: party reduce → global reduce + optimizer → broadcast), expressed as
+17 hand-written sm_100a kernel launches + 1 memset, captured ONCE into a CUDA graph and replayed per step:
+
+  fwd  conv0+bias+ReLU+pool (direct, CUDA cores, K=25) · im2col · conv1 GEMM (tcgen05, bias+ReLU, NCHW store) · pool ·
+       dense0 GEMM (tcgen05, bias+ReLU) · dense1 GEMM (tcgen05) · head (dense2 + softmax-CE fwd **and** bwd in one CTA)
+  bwd  dW1 / dz3(+ReLU mask, +db0) / dW0 / da2 GEMMs (tcgen05, MN-major operands read in place) · pool+ReLU bwd → pixel-major rows
+       (+dbc1) · dWc1 GEMM (split-K) · dcol1 GEMM · col2im · conv0 fused pool/ReLU-bwd + wgrad
+  kv   ``gx_hips_fsa_step`` (multi-rank: in-kernel NVLS/P2P collectives + partitioned Adam on the global owner) — with one rank and
+       one party both PS tiers collapse into the fused arena optimizer inside the same kernel.
+
+The reference runs the same step as ~200 engine ops (per-image im2col+SGEMM) + 20 ZMQ round trips.
+The public API a user calls is ``step(X_host, y_host) -> loss`` (H2D of the batch from pinned memory, graph replay, D2H of the loss).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import gluon, initializer
+from ..context import Context
+from ..ndarray import NDArray
+from ..ops import native
+from ..parallel.arena import ArenaLayout
+from ..parallel.fabric import HipsFabric, Topology
+
+__all__ = ["build_cnn", "CNN_PARAM_SHAPES", "HipsCNNTrainStep"]
+
+CNN_PARAM_SHAPES = [(16, 1, 5, 5), (16,), (32, 16, 5, 5), (32,), (256, 512), (256,), (128, 256), (128,), (10, 128), (10,)]
+
+
+def build_cnn():
+    net = gluon.nn.Sequential()
+    net.add(gluon.nn.Conv2D(channels=16, kernel_size=5, activation="relu"), gluon.nn.MaxPool2D(pool_size=2, strides=2),
+            gluon.nn.Conv2D(channels=32, kernel_size=5, activation="relu"), gluon.nn.MaxPool2D(pool_size=2, strides=2),
+            gluon.nn.Dense(256, activation="relu"), gluon.nn.Dense(128, activation="relu"), gluon.nn.Dense(10))
+    return net
+
+
+class HipsCNNTrainStep:
+    """Graph-captured training step of the demo CNN on the HiPS fabric.
+
+    Parameters
+    ----------
+    net : Gluon network from :func:`build_cnn` (initialised; its parameters are re-homed into the symmetric arena so
+          ``net(x)`` / ``save_parameters`` keep working on the live weights) or ``None`` (Xavier init here).
+    batch_size : per-worker batch (reference default 32).
+    optimizer : ``mx.optimizer.Optimizer`` with a native spec (Adam / SGD / DCASGD) — runs on the global-PS shard.
+    topo : :class:`Topology` (default: from ``WORLD_SIZE`` / ``RANK`` / ``GEOMX_NUM_PARTIES`` / ``DMLC_NUM_GLOBAL_SERVER``).
+    """
+
+    def __init__(self, net=None, batch_size=32, optimizer=None, topo=None, device=None, use_graph=True, pull_fused=False,
+                 use_multicast=True, mode="dist_sync"):
+        native.require()
+        from .. import optimizer as opt
+        self.B = B = int(batch_size)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.topo = topo or Topology.from_env()
+        self.mode = mode
+        optimizer = optimizer or opt.Adam(learning_rate=0.01)
+        spec = optimizer.spec()
+        if spec is None:
+            raise ValueError("optimizer %s has no native spec; use Adam / SGD / DCASGD" % type(optimizer).__name__)
+        self.layout = ArenaLayout.build(list(enumerate(CNN_PARAM_SHAPES)))
+        self.fabric = HipsFabric(self.layout, self.topo, self.device, spec, use_multicast=use_multicast)
+        self.fabric.set_push_scale(1.0 / B)          # the script-level `grad / num_samples`, folded into the push kernel
+        f = self.fabric
+        self.P = [f.param_view(i) for i in range(10)]
+        self.G = [f.grad_view(i) for i in range(10)]
+        self._init_params(net)
+        dev, f32 = self.device, torch.float32
+        e = lambda *s, dt=f32: torch.empty(*s, dtype=dt, device=dev)
+        self.x, self.label = e(B, 1, 28, 28), e(B)
+        self.a1, self.idx1 = e(B, 16, 12, 12), e(B, 16, 12, 12, dt=torch.uint8)
+        self.col1 = e(B * 64, 400)
+        self.z2 = e(B, 32, 8, 8)
+        self.a2, self.idx2 = e(B, 32, 4, 4), e(B, 32, 4, 4, dt=torch.uint8)
+        self.a3, self.a4 = e(B, 256), e(B, 128)
+        self.loss, self.logits = e(B), e(B, 10)
+        self.dz4, self.dz3, self.da2 = e(B, 128), e(B, 256), e(B, 512)
+        self.dz2rows, self.dcol1, self.da1 = e(B * 64, 32), e(B * 64, 400), e(B, 16, 12, 12)
+        self.loss_host = torch.empty(B, dtype=f32).pin_memory()
+        self.pull_fused = bool(pull_fused) and self.topo.world >= 1
+        self.graph = None
+        self.use_graph = use_graph
+        self.steps_done = 0
+        self.kernels_per_step = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _init_params(self, net):
+        f, topo = self.fabric, self.topo
+        if net is not None:
+            params = list(net.collect_params().values())
+            assert [tuple(p.shape) for p in params] == CNN_PARAM_SHAPES, "network does not match the demo CNN"
+            for i, p in enumerate(params):
+                self.P[i].copy_(p.data()._t.detach().to(self.device))
+        else:
+            init = initializer.Xavier()
+            for i, shape in enumerate(CNN_PARAM_SHAPES):
+                host = torch.zeros(shape)
+                init(initializer.InitDesc("w%d_%s" % (i, "weight" if len(shape) > 1 else "bias")), host)
+                self.P[i].copy_(host.to(self.device))
+        if topo.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(f.param.tensor, src=0)      # `init`: rank-0 (master worker) value wins, then barrier
+            torch.cuda.synchronize()
+            dist.barrier()
+        f.load_master_from_param()
+        if net is not None:  # re-home the Gluon parameters onto the live arena (zero-copy pull)
+            for i, p in enumerate(net.collect_params().values()):
+                d = p.data()
+                d._data = f.param_view(i)
+                d._ctx_hint = Context("gpu", self.device.index or 0)
+                if p.grad_req != "null":
+                    d.attach_grad(p.grad_req)
+        self.net = net
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _body(self):
+        n = native
+        B, P, G, f = self.B, self.P, self.G, self.fabric
+        before = n.launch_count
+        wf = we = None
+        f.grad.tensor.zero_()                                                                   # memset (accumulating epilogues)
+        n.conv_relu_pool_fwd(self.x, P[0], P[1], self.a1, self.idx1)                            # 1
+        n.im2col(self.a1, 5, 5, out=self.col1)                                                  # 2
+        n.gemm(self.col1, P[2].view(32, 400), self.z2, bias=P[3], relu=True, store_nchw_hw=64)  # 3 conv1 (tcgen05)
+        n.maxpool2x2_fwd(self.z2, self.a2, self.idx2)                                           # 4
+        a2f = self.a2.view(B, 512)
+        n.gemm(a2f, P[4], self.a3, bias=P[5], relu=True)                                        # 5 dense0
+        n.gemm(self.a3, P[6], self.a4, bias=P[7], relu=True)                                    # 6 dense1
+        n.head_fwd_bwd(self.a4, P[8], P[9], self.label, self.loss, self.logits, G[8], G[9], self.dz4, G[7], True)   # 7
+        n.gemm(self.dz4, self.a3, G[6], a_mn=True, b_mn=True)                                   # 8  dW1 = dz4ᵀ·a3
+        n.gemm(self.dz4, P[6], self.dz3, b_mn=True, mask=self.a3, colsum=G[5])                  # 9  dz3 = (dz4·W1)⊙[a3>0], db0
+        n.gemm(self.dz3, a2f, G[4], a_mn=True, b_mn=True)                                       # 10 dW0
+        n.gemm(self.dz3, P[4], self.da2, b_mn=True)                                             # 11 da2
+        n.pool_relu_bwd_rows(self.da2.view(B, 32, 4, 4), self.a2, self.idx2, self.dz2rows, G[3])  # 12 (+dbc1)
+        n.gemm(self.dz2rows, self.col1, G[2].view(32, 400), a_mn=True, b_mn=True, split_k=16, accumulate=True)  # 13 dWc1
+        n.gemm(self.dz2rows, P[2].view(32, 400), self.dcol1, b_mn=True)                         # 14 dcol1
+        n.col2im(self.dcol1, (B, 16, 12, 12), 5, 5, out=self.da1)                               # 15
+        n.conv_relu_pool_wgrad(self.x, self.da1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0])   # 16
+        if self.mode == "dist_async":
+            f.async_step()                                                                      # 17 MixedSync
+        else:
+            f.fsa_step(defer_pull_wait=False)                                                   # 17 HiPS push+pull (FSA)
+        self.kernels_per_step = n.launch_count - before
+
+    def capture(self):
+        """Warm up (2 eager steps on a side stream) and capture the step into a CUDA graph."""
+        if self.graph is not None or not self.use_graph:
+            return
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body()
+                self.steps_done += 1
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if self.topo.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self.graph = g
+
+    def run_device(self):
+        """One step on whatever is currently in ``self.x`` / ``self.label`` (device-only; used by the kernel-time bench)."""
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            self._body()
+        self.steps_done += 1
+
+    def step(self, X, y):
+        """Public API: one training step.  ``X`` (B,1,28,28) and ``y`` (B,) are host tensors / NDArrays (pinned → async H2D) or device
+        tensors.  Returns the mean loss as a Python float (forces the D2H read of the per-sample loss)."""
+        X = X._t if isinstance(X, NDArray) else X
+        y = y._t if isinstance(y, NDArray) else y
+        self.x.copy_(X.reshape(self.x.shape), non_blocking=True)
+        self.label.copy_(y.reshape(self.label.shape), non_blocking=True)
+        self.run_device()
+        self.loss_host.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host.mean())
+
+    # reference semantics helpers ------------------------------------------------------------------------------------
+    def params_numpy(self):
+        return [p.detach().cpu().numpy().copy() for p in self.P]
+
+    def h2d_bytes_per_step(self):
+        return self.x.numel() * 4 + self.label.numel() * 4
+
+    def d2h_bytes_per_step(self):
+        return self.loss.numel() * 4

@@ -1,0 +1,352 @@
+"""Python wrappers over the C ABI of ``libgeomx_kernels.so``.  All functions take raw CUDA ``torch.Tensor`` s, launch on
+the current stream and return nothing (or the output tensor); shapes/dtypes are asserted here, not in the kernels."""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import native as _n
+
+_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _lib():
+    return _n.require()
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _ck(rc, what):
+    _n.launch_count += 1
+    if rc != 0:
+        raise RuntimeError("%s failed (rc=%d)" % (what, rc))
+
+
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "expected contiguous CUDA fp32 tensor"
+    return t
+
+
+# --------------------------------------------------------------------------------------------------------------- GEMM
+def gemm(A, B, D, a_mn=False, b_mn=False, bias=None, mask=None, colsum=None, relu=False, accumulate=False,
+         store_nchw_hw=0, alpha=1.0, split_k=1, M=None, N=None, K=None, lda=None, ldb=None, ldd=None,
+         wait_flag=None, wait_epoch=None, force_simt=False):
+    """D[M,N] = epi(alpha * A·Bᵀ).  A is [M,K] (K-major) or [K,M] (MN-major, ``a_mn``); B is [N,K] or [K,N] (``b_mn``)."""
+    if M is None:
+        M = A.shape[1] if a_mn else A.shape[0]
+    if K is None:
+        K = A.shape[0] if a_mn else A.shape[1]
+    if N is None:
+        N = B.shape[1] if b_mn else B.shape[0]
+    lda = A.stride(0) if lda is None else lda
+    ldb = B.stride(0) if ldb is None else ldb
+    if ldd is None:
+        ldd = D.stride(0) if (store_nchw_hw == 0 and D.dim() >= 2) else N
+    ldmask = mask.stride(0) if mask is not None else 0
+    lib = _lib()
+    rc = -1
+    if not force_simt:
+        rc = lib.gx_gemm_tf32(_p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), M, N, K, _p(D), ldd, _p(bias), _p(mask), ldmask,
+                              _p(colsum), int(relu), int(accumulate), 1 if store_nchw_hw else 0, int(store_nchw_hw), float(alpha),
+                              int(split_k), _p(wait_flag), _p(wait_epoch), _s())
+    if rc == -1:  # TMA alignment not satisfied -> CUDA-core fallback kernel (same contract)
+        rc = lib.gx_gemm_simt(_p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), M, N, K, _p(D), ldd, _p(bias), _p(mask), ldmask,
+                              _p(colsum), int(relu), int(accumulate), 1 if store_nchw_hw else 0, int(store_nchw_hw), float(alpha), _s())
+    _ck(rc, "gemm")
+    return D
+
+
+# --------------------------------------------------------------------------------------------------------------- conv / pool
+def conv_out_hw(H, W, KH, KW, sh, sw, ph, pw):
+    return (H + 2 * ph - KH) // sh + 1, (W + 2 * pw - KW) // sw + 1
+
+
+def conv_supported(x, w, stride, padding):
+    return x.dim() == 4 and w.dim() == 4 and x.shape[1] == w.shape[1]
+
+
+def im2col(x, KH, KW, stride=(1, 1), padding=(0, 0), out=None):
+    N, C, H, W = x.shape
+    OH, OW = conv_out_hw(H, W, KH, KW, stride[0], stride[1], padding[0], padding[1])
+    K = C * KH * KW
+    ldc = (K + 3) // 4 * 4
+    if out is None:
+        out = torch.empty(N * OH * OW, ldc, dtype=torch.float32, device=x.device)
+    _ck(_lib().gx_im2col(_p(_f32c(x)), _p(out), N, C, H, W, KH, KW, stride[0], stride[1], padding[0], padding[1], ldc, _s()), "im2col")
+    return out
+
+
+def col2im(dcol, x_shape, KH, KW, stride=(1, 1), padding=(0, 0), out=None):
+    N, C, H, W = x_shape
+    if out is None:
+        out = torch.empty(x_shape, dtype=torch.float32, device=dcol.device)
+    _ck(_lib().gx_col2im(_p(dcol), _p(out), N, C, H, W, KH, KW, stride[0], stride[1], padding[0], padding[1], dcol.stride(0), _s()), "col2im")
+    return out
+
+
+def nchw_to_rows(x, out=None):
+    N, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (N * C)
+    if out is None:
+        out = torch.empty(N * HW, C, dtype=torch.float32, device=x.device)
+    _ck(_lib().gx_nchw_to_rows(_p(_f32c(x)), _p(out), N, C, HW, _s()), "nchw_to_rows")
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    R, Cc = x.shape
+    if out is None:
+        out = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    _ck(_lib().gx_colsum(_p(x), _p(out), R, Cc, x.stride(0), int(accumulate), _s()), "colsum")
+    return out
+
+
+def chansum_nchw(x, out=None):
+    N, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (N * C)
+    if out is None:
+        out = torch.empty(C, dtype=torch.float32, device=x.device)
+    _ck(_lib().gx_chansum_nchw(_p(_f32c(x)), _p(out), N, C, HW, _s()), "chansum")
+    return out
+
+
+def relu_fwd(x, out=None):
+    out = torch.empty_like(x) if out is None else out
+    _ck(_lib().gx_relu_fwd(_p(_f32c(x)), _p(out), x.numel(), _s()), "relu_fwd")
+    return out
+
+
+def relu_bwd(y, dy, out=None):
+    out = torch.empty_like(dy) if out is None else out
+    _ck(_lib().gx_relu_bwd(_p(_f32c(y)), _p(_f32c(dy)), _p(out), y.numel(), _s()), "relu_bwd")
+    return out
+
+
+def maxpool2x2_fwd(x, out=None, idx=None):
+    N, C, H, W = x.shape
+    if out is None:
+        out = torch.empty(N, C, H // 2, W // 2, dtype=torch.float32, device=x.device)
+    if idx is None:
+        idx = torch.empty(N, C, H // 2, W // 2, dtype=torch.uint8, device=x.device)
+    _ck(_lib().gx_maxpool2x2_fwd(_p(_f32c(x)), _p(out), _p(idx), N * C, H, W, _s()), "maxpool_fwd")
+    return out, idx
+
+
+def maxpool2x2_bwd(dy, idx, x_shape, out=None):
+    N, C, H, W = x_shape
+    if out is None:
+        out = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
+    _ck(_lib().gx_maxpool2x2_bwd(_p(_f32c(dy)), _p(idx), _p(out), N * C, H, W, _s()), "maxpool_bwd")
+    return out
+
+
+def pool_relu_bwd_rows(dpooled, pooled, idx, dz_rows, dbias):
+    N, C, PH, PW = pooled.shape
+    _ck(_lib().gx_pool_relu_bwd_rows(_p(dpooled), _p(pooled), _p(idx), _p(dz_rows), _p(dbias), N, C, PH, PW, _s()), "pool_relu_bwd_rows")
+
+
+def conv_relu_pool_fwd(x, w, b, y, idx):
+    N, Cin, H, W = x.shape
+    Cout, _, KH, KW = w.shape
+    _ck(_lib().gx_conv_relu_pool_fwd(_p(x), _p(w), _p(b), _p(y), _p(idx), N, Cin, H, W, Cout, KH, KW, _s()), "conv_relu_pool_fwd")
+
+
+def conv_relu_pool_wgrad(x, dpooled, pooled, idx, dw, db, w_shape):
+    N, Cin, H, W = x.shape
+    Cout, _, KH, KW = w_shape
+    _ck(_lib().gx_conv_relu_pool_wgrad(_p(x), _p(dpooled), _p(pooled), _p(idx), _p(dw), _p(db), N, Cin, H, W, Cout, KH, KW, _s()),
+        "conv_relu_pool_wgrad")
+
+
+# --------------------------------------------------------------------------------------------------------------- loss / head
+def softmax_ce_fwd(logits, label, out=None):
+    R, Cc = logits.shape
+    out = torch.empty(R, dtype=torch.float32, device=logits.device) if out is None else out
+    _ck(_lib().gx_softmax_ce_fwd(_p(_f32c(logits)), _p(_f32c(label)), _p(out), R, Cc, _s()), "softmax_ce_fwd")
+    return out
+
+
+def softmax_ce_bwd(logits, label, dloss, out=None):
+    R, Cc = logits.shape
+    out = torch.empty_like(logits) if out is None else out
+    _ck(_lib().gx_softmax_ce_bwd(_p(logits), _p(label), _p(dloss), _p(out), R, Cc, _s()), "softmax_ce_bwd")
+    return out
+
+
+def head_fwd_bwd(a, W, bias, label, loss, logits, dW, db, da, dbias_prev, relu_mask=True):
+    B, K = a.shape
+    Cc = W.shape[0]
+    _ck(_lib().gx_head_fwd_bwd(_p(a), _p(W), _p(bias), _p(label), _p(loss), _p(logits), _p(dW), _p(db), _p(da), _p(dbias_prev),
+                               B, K, Cc, int(relu_mask), _s()), "head_fwd_bwd")
+
+
+# --------------------------------------------------------------------------------------------------------------- optimizers
+_KIND = {"sgd": 0, "adam": 1, "dcasgd": 2}
+
+
+def arena_opt(kind, w, g, s0, s1, n, tile_mult, lr, wd, rescale, clip, momentum, b1, b2, eps, lamda, step_state, g_zero=None):
+    _ck(_lib().gx_arena_opt(_KIND[kind], _p(w), _p(g), _p(s0), _p(s1), n, _p(tile_mult), lr, wd, rescale, clip, momentum, b1, b2, eps,
+                            lamda, _p(step_state), _p(g_zero), _s()), "arena_opt")
+
+
+def single_opt(kind, w, g, s0, s1, lr_t, wd, rescale, clip, momentum=0.0, b1=0.9, b2=0.999, eps=1e-8, lamda=0.04):
+    _ck(_lib().gx_single_opt(_KIND[kind], _p(w), _p(g), _p(s0), _p(s1), w.numel(), lr_t, wd, rescale, clip, momentum, b1, b2, eps, lamda, _s()),
+        "single_opt")
+
+
+def adam_update(w, g, m, v, lr_t, b1, b2, eps, wd, rescale, clip):
+    single_opt("adam", w, g.contiguous(), m, v, lr_t, wd, rescale, clip, 0.0, b1, b2, eps)
+
+
+class _TensorEntry(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p), ("g", ctypes.c_void_p), ("s0", ctypes.c_void_p), ("s1", ctypes.c_void_p),
+                ("n", ctypes.c_longlong), ("lr_mult", ctypes.c_float), ("wd_mult", ctypes.c_float)]
+
+
+_mt_cache = {}
+
+
+def multi_tensor_update(optimizer, updater, idxs, ws, gs):
+    """One launch for the whole parameter list (Trainer fused path).  Returns False if this optimizer has no native spec."""
+    from ..ndarray import NDArray
+    spec = optimizer.spec()
+    kind = spec["name"]
+    if kind == "sgd" and spec.get("momentum", 0.0) == 0.0:
+        need = 0
+    else:
+        need = 1 if kind == "sgd" else 2
+    for i, w in zip(idxs, ws):
+        if i not in updater.states:
+            updater.states[i] = optimizer.create_state_multi_precision(i, NDArray(w))
+            updater.states_synced[i] = True
+    optimizer._update_count(idxs)
+    t = optimizer._index_update_count[idxs[0]]
+    lr = optimizer.learning_rate
+    lr_t = lr * math.sqrt(1.0 - spec["beta2"] ** t) / (1.0 - spec["beta1"] ** t) if kind == "adam" else lr
+    key = (id(updater), tuple(w.data_ptr() for w in ws), tuple(g.data_ptr() for g in gs))
+    ent = _mt_cache.get(key)
+    if ent is None:
+        arr = (_TensorEntry * len(ws))()
+        for j, (i, w, g) in enumerate(zip(idxs, ws, gs)):
+            st = updater.states[i]
+            s0 = s1 = None
+            if need == 1:
+                s0 = st._t
+            elif need == 2:
+                s0, s1 = st[0]._t, st[1]._t
+            p = optimizer.param_dict.get(i)
+            arr[j] = _TensorEntry(w.data_ptr(), g.data_ptr(), 0 if s0 is None else s0.data_ptr(), 0 if s1 is None else s1.data_ptr(),
+                                  w.numel(), p.lr_mult if p is not None else 1.0, p.wd_mult if p is not None else 1.0)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        dev = host.to(ws[0].device)
+        ent = (dev, max(w.numel() for w in ws), len(ws))
+        if len(_mt_cache) > 64:
+            _mt_cache.clear()
+        _mt_cache[key] = ent
+    dev, max_n, cnt = ent
+    clip = -1.0 if optimizer.clip_gradient is None else float(optimizer.clip_gradient)
+    _ck(_lib().gx_multi_tensor_opt(_KIND[kind], _p(dev), cnt, max_n, lr_t, float(optimizer.wd), float(optimizer.rescale_grad), clip,
+                                   float(spec.get("momentum", 0.0)), float(spec.get("beta1", 0.9)), float(spec.get("beta2", 0.999)),
+                                   float(spec.get("epsilon", 1e-8)), float(spec.get("lamda", 0.04)), _s()), "multi_tensor_opt")
+    return True
+
+
+def nary_sum(out, parts):
+    assert 1 <= len(parts) <= 8
+    arr = (ctypes.c_void_p * len(parts))(*[p.data_ptr() for p in parts])
+    _ck(_lib().gx_nary_sum(_p(out), arr, len(parts), out.numel(), _s()), "nary_sum")
+    return out
+
+
+def scale_cast(x, out_dtype, scale=1.0, out=None):
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device) if out is None else out
+    _ck(_lib().gx_scale_cast(_p(x.contiguous()), _DT[x.dtype], _p(out), _DT[out.dtype], float(scale), x.numel(), _s()), "scale_cast")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------- compression
+def quantize_2bit(grad, residual, out, thr):
+    _ck(_lib().gx_quantize_2bit(_p(_f32c(grad)), _p(residual), _p(out), grad.numel(), thr, _s()), "quantize_2bit")
+
+
+def dequantize_2bit(packed, out, thr, accumulate=False):
+    _ck(_lib().gx_dequantize_2bit(_p(packed), _p(out), out.numel(), thr, int(accumulate), _s()), "dequantize_2bit")
+
+
+class _BscSeg(ctypes.Structure):
+    _fields_ = [("grad", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p), ("out", ctypes.c_void_p),
+                ("n", ctypes.c_longlong), ("k", ctypes.c_int), ("sample", ctypes.c_int), ("k_sample", ctypes.c_int)]
+
+
+def _segs_to_dev(segs, device):
+    arr = (_BscSeg * len(segs))(*segs)
+    assert ctypes.sizeof(_BscSeg) == _lib().gx_bsc_seg_size()
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+
+def bsc_segment(grad, u, v, out, k, sample, k_sample):
+    return _BscSeg(grad.data_ptr() if grad is not None else 0, 0 if u is None else u.data_ptr(), 0 if v is None else v.data_ptr(),
+                   out.data_ptr(), (grad if grad is not None else v).numel(), k, sample, k_sample)
+
+
+def bsc_compress_batch(seg_table_dev, num, max_sample, momentum=0.9):
+    _ck(_lib().gx_bsc_compress_batch(_p(seg_table_dev), num, max_sample, momentum, _s()), "bsc_compress")
+
+
+def bsc_compress(grad, u, v, out, k, sample, k_sample, momentum=0.9):
+    tab = _segs_to_dev([bsc_segment(_f32c(grad), u, v, out, k, sample, k_sample)], grad.device)
+    bsc_compress_batch(tab, 1, sample, momentum)
+    return out
+
+
+def bsc_pull_compress(dense, out, k):
+    tab = _segs_to_dev([_BscSeg(dense.data_ptr(), 0, 0, out.data_ptr(), dense.numel(), k, 0, 0)], dense.device)
+    _ck(_lib().gx_bsc_pull_compress_batch(_p(tab), 1, _s()), "bsc_pull_compress")
+    return out
+
+
+def bsc_decompress(zipped, out, accumulate=False):
+    _ck(_lib().gx_bsc_decompress(_p(zipped), _p(out), out.numel(), zipped.numel() // 2, int(accumulate), _s()), "bsc_decompress")
+    return out
+
+
+def fp8_block_quantize(x, residual, q, scale):
+    _ck(_lib().gx_fp8_block_quantize(_p(_f32c(x)), _p(residual), _p(q), _p(scale), x.numel(), _s()), "fp8_quantize")
+
+
+def fp8_block_dequantize(q, scale, out, accumulate=False):
+    _ck(_lib().gx_fp8_block_dequantize(_p(q), _p(scale), _p(out), out.numel(), int(accumulate), _s()), "fp8_dequantize")
+
+
+def dgt_contrib(g, contrib, block_elems, alpha, first):
+    _ck(_lib().gx_dgt_contrib(_p(g), _p(contrib), g.numel(), block_elems, alpha, int(first), _s()), "dgt_contrib")
+
+
+# --------------------------------------------------------------------------------------------------------------- batch norm
+def bn_fwd(x, gamma, beta, rm, rv, training, momentum, eps):
+    N, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (N * C)
+    y = torch.empty_like(x)
+    sm = torch.empty(C, dtype=torch.float32, device=x.device)
+    si = torch.empty(C, dtype=torch.float32, device=x.device)
+    _ck(_lib().gx_bn_fwd(_p(_f32c(x)), _p(gamma), _p(beta), _p(rm), _p(rv), _p(y), _p(sm), _p(si), N, C, HW, int(training), momentum, eps, _s()),
+        "bn_fwd")
+    return y, sm, si
+
+
+def bn_bwd(x, dy, gamma, sm, si):
+    N, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (N * C)
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, dtype=torch.float32, device=x.device)
+    dbt = torch.empty(C, dtype=torch.float32, device=x.device)
+    _ck(_lib().gx_bn_bwd(_p(x), _p(_f32c(dy)), _p(gamma), _p(sm), _p(si), _p(dx), _p(dg), _p(dbt), N, C, HW, _s()), "bn_bwd")
+    return dx, dg, dbt

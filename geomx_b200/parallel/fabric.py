@@ -1,0 +1,341 @@
+"""HiPS fabric: topology, symmetric HBM heap and the fused push/pull kernels' host side.
+
+One process per GPU (``torchrun``); ``torch.distributed`` is used ONLY for rendezvous, symmetric-memory handle exchange and init-time
+broadcasts ("plumbing").  The per-step data path is ``gx_hips_fsa_step`` / ``gx_hips_async_step`` /
+``gx_hips_party_allreduce`` (``csrc/kernels/hips_fabric.cu``): in-kernel P2P + NVLS multimem collectives, no NCCL call.
+
+Roles (reference ``3rdparty/ps-lite/src/postoffice.cc:18-58`` and scripts ``scripts/gpu/run_vanilla_hips.sh``) become rank attributes:
+party ``g`` = ranks ``[g*S, (g+1)*S)`` (S = workers per party); the *local server* of a party is the set of tile owners inside it; the
+*global servers* are ``num_gs`` ranks (default: rank 0; MultiGPS: ranks ``0, S, 2S, …`` round-robin) whose HBM holds master weights and
+optimizer state; the *master worker* role (init keys, set optimizer) is folded into rank 0; schedulers disappear.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from ..base import MXNetError, getenv_int
+from ..ops import native
+from .arena import TILE, ArenaLayout
+
+MAX_RANKS = 16
+
+
+# ------------------------------------------------------------------------------------------------------------ topology
+class Topology:
+    def __init__(self, world=1, rank=0, num_parties=1, num_gs=1):
+        if world % num_parties:
+            raise MXNetError("world size %d is not divisible by the number of parties %d" % (world, num_parties))
+        if world > MAX_RANKS:
+            raise MXNetError("fabric supports up to %d ranks per NVSwitch domain" % MAX_RANKS)
+        self.world, self.rank, self.num_parties = world, rank, num_parties
+        self.party_size = world // num_parties
+        self.party, self.local = rank // self.party_size, rank % self.party_size
+        self.num_gs = max(1, min(num_gs, world))
+        # global servers: spread over parties first (rank 0, S, 2S, ... then 1, S+1, ...)
+        order = [p * self.party_size + l for l in range(self.party_size) for p in range(num_parties)]
+        self.gs_ranks = order[:self.num_gs]
+
+    @staticmethod
+    def from_env():
+        world = getenv_int("WORLD_SIZE", 1); rank = getenv_int("RANK", 0)
+        parties = getenv_int("GEOMX_NUM_PARTIES", 0) or getenv_int("DMLC_NUM_GLOBAL_WORKER", 0) or 1
+        if world % parties:
+            parties = 1
+        return Topology(world, rank, parties, getenv_int("DMLC_NUM_GLOBAL_SERVER", 1))
+
+    @property
+    def num_workers(self): return self.party_size          # per party  (kv.num_workers)
+    @property
+    def num_all_workers(self): return self.world           # kv.num_all_workers
+    @property
+    def is_global_server(self): return self.rank in self.gs_ranks
+    def party_ranks(self, g=None):
+        g = self.party if g is None else g
+        return list(range(g * self.party_size, (g + 1) * self.party_size))
+
+
+# ------------------------------------------------------------------------------------------------------------ symmetric heap
+class SymmetricBuffer:
+    """A tensor allocated at the same size on every rank of ``group`` with peer-mapped pointers (+ multicast address if NVLS)."""
+
+    def __init__(self, tensor, peer_ptrs, multicast_ptr=0, keepalive=None):
+        self.tensor, self.peer_ptrs, self.multicast_ptr, self._keep = tensor, list(peer_ptrs), int(multicast_ptr or 0), keepalive
+
+
+class SymmetricHeap:
+    """Allocation + handle exchange.  Preferred backend: ``torch.distributed._symmetric_memory`` (CUDA VMM + fabric/posix handles,
+    multicast objects when the driver supports NVLS).  Fallback: legacy CUDA IPC handles exchanged over the store (P2P only)."""
+
+    def __init__(self, topo: Topology, device):
+        self.topo, self.device = topo, device
+        self.backend = "local" if topo.world == 1 else None
+        self._groups = {}
+
+    def _group(self, ranks):
+        import torch.distributed as dist
+        key = tuple(ranks)
+        if key == tuple(range(self.topo.world)):
+            return dist.group.WORLD
+        if key not in self._groups:
+            # new_group is collective over the world: create every party group in the same order on all ranks
+            for g in range(self.topo.num_parties):
+                pr = tuple(self.topo.party_ranks(g))
+                if pr not in self._groups:
+                    self._groups[pr] = dist.new_group(list(pr))
+        return self._groups[key]
+
+    def alloc(self, numel, dtype, ranks=None, zero=True):
+        """Collective over ``ranks`` (default: world).  Returns SymmetricBuffer whose peer_ptrs are indexed by GLOBAL rank (0 if absent)."""
+        topo = self.topo
+        if topo.world == 1:
+            t = torch.zeros(numel, dtype=dtype, device=self.device) if zero else torch.empty(numel, dtype=dtype, device=self.device)
+            return SymmetricBuffer(t, [t.data_ptr()] + [0] * (MAX_RANKS - 1))
+        import torch.distributed as dist
+        ranks = list(range(topo.world)) if ranks is None else list(ranks)
+        group = self._group(ranks)
+        ptrs = [0] * MAX_RANKS
+        if self.backend in (None, "symm_mem"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                t = symm.empty(numel, dtype=dtype, device=self.device)
+                hdl = symm.rendezvous(t, group=group)
+                if zero:
+                    t.zero_()
+                for i, r in enumerate(ranks):
+                    ptrs[r] = int(hdl.buffer_ptrs[i])
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                self.backend = "symm_mem"
+                torch.cuda.synchronize(); dist.barrier(group=group)
+                return SymmetricBuffer(t, ptrs, mc, hdl)
+            except Exception as e:  # pragma: no cover - depends on driver support
+                if self.backend == "symm_mem":
+                    raise
+                if os.environ.get("GEOMX_VERBOSE"):
+                    print("[geomx] symmetric_memory unavailable (%r); falling back to CUDA IPC" % (e,))
+                self.backend = "cuda_ipc"
+        # legacy CUDA IPC: cudaMalloc'd storage shared through torch's IPC handle
+        t = torch.zeros(numel, dtype=dtype, device=self.device)
+        handle = t.untyped_storage()._share_cuda_()
+        gathered = [None] * len(ranks)
+        dist.all_gather_object(gathered, handle, group=group)
+        keep = []
+        me = ranks.index(topo.rank)
+        for i, r in enumerate(ranks):
+            if i == me:
+                ptrs[r] = t.data_ptr()
+                continue
+            h = gathered[i]
+            st = torch.UntypedStorage._new_shared_cuda(*h)
+            peer = torch.empty(0, dtype=dtype, device=st.device).set_(st)
+            keep.append(peer)
+            ptrs[r] = peer.data_ptr() + 0
+        torch.cuda.synchronize(); dist.barrier(group=group)
+        return SymmetricBuffer(t, ptrs, 0, keep)
+
+
+# ------------------------------------------------------------------------------------------------------------ kernel parameter block
+class _OptHyperF(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ("lr", "wd", "rescale", "clip", "momentum", "beta1", "beta2", "eps", "lamda")] + [("kind", ctypes.c_int)]
+
+
+class _FabricParams(ctypes.Structure):
+    _fields_ = [
+        ("world", ctypes.c_int), ("rank", ctypes.c_int), ("party_size", ctypes.c_int), ("num_parties", ctypes.c_int),
+        ("party", ctypes.c_int), ("local", ctypes.c_int), ("num_gs", ctypes.c_int), ("gs_rank", ctypes.c_int * MAX_RANKS),
+        ("grad", ctypes.c_void_p * MAX_RANKS), ("param", ctypes.c_void_p * MAX_RANKS), ("stage", ctypes.c_void_p * MAX_RANKS),
+        ("flags", ctypes.c_void_p * MAX_RANKS),
+        ("grad_mc", ctypes.c_void_p), ("param_mc", ctypes.c_void_p), ("w", ctypes.c_void_p), ("s0", ctypes.c_void_p),
+        ("s1", ctypes.c_void_p), ("lock_and_steps", ctypes.c_void_p),
+        ("n", ctypes.c_longlong), ("tiles", ctypes.c_int), ("num_keys", ctypes.c_int),
+        ("tile_key", ctypes.c_void_p), ("key_tiles", ctypes.c_void_p), ("tile_owner", ctypes.c_void_p), ("tile_active", ctypes.c_void_p),
+        ("tile_mult", ctypes.c_void_p), ("key_done", ctypes.c_void_p), ("state", ctypes.c_void_p),
+        ("h", _OptHyperF), ("push_scale", ctypes.c_float), ("defer_pull_wait", ctypes.c_int), ("param_ready_off", ctypes.c_int),
+        ("ready_off", ctypes.c_int), ("arrived_off", ctypes.c_int),
+    ]
+
+
+_KIND = {"sgd": 0, "adam": 1, "dcasgd": 2, None: -1, "none": -1}
+
+
+class HipsFabric:
+    """Owns the symmetric arenas of one model replica and launches the fused HiPS kernels.
+
+    ``layout``: :class:`ArenaLayout`; ``opt_spec``: ``Optimizer.spec()`` dict or None (server stores aggregated gradients)."""
+
+    def __init__(self, layout: ArenaLayout, topo: Topology | None = None, device=None, opt_spec=None, use_multicast=True):
+        native.require()
+        self.layout = layout
+        self.topo = topo or Topology.from_env()
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        t = self.topo
+        self.heap = SymmetricHeap(t, self.device)
+        n, T, K, P = layout.total, layout.num_tiles, len(layout.slots), t.num_parties
+        self.n, self.tiles, self.num_keys = n, T, K
+        # --- symmetric buffers ------------------------------------------------------------------------------------
+        self.param = self.heap.alloc(n, torch.float32)                                  # world: pull target + forward operand
+        self.grad = self.heap.alloc(n, torch.float32, ranks=t.party_ranks())            # party: local-tier reduction source
+        self.stage = self.heap.alloc(P * n, torch.float32)                              # world: per-party aggregates on global owners
+        # flag pad layout (uint32 words): one region per kernel family so that each keeps its own epoch
+        off = 0
+        self.off = {}
+        for name, size in (("fsa_ready", MAX_RANKS), ("fsa_arrived", P * T), ("fsa_param_ready", K),
+                           ("async_ready", MAX_RANKS), ("async_param_ready", K), ("async_lock", T), ("async_step", T),
+                           ("par_ready", MAX_RANKS), ("par_done", 4), ("barrier", 4)):
+            self.off[name] = off
+            off += (size + 15) // 16 * 16
+        self.flags = self.heap.alloc(off, torch.int32)
+        # --- global-owner state (private HBM) ---------------------------------------------------------------------
+        self.w = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.s0 = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.s1 = torch.zeros(n, dtype=torch.float32, device=self.device)
+        dev = self.device
+        self.tile_key = torch.from_numpy(layout.tile_key()).to(dev)
+        self.key_tiles = torch.from_numpy(layout.key_tiles()).to(dev)
+        owner_idx = layout.global_owner_index(t.num_gs, getenv_int("MXNET_KVSTORE_BIGARRAY_BOUND", 1000000))
+        self.tile_owner_np = np.array([t.gs_ranks[i] for i in owner_idx], dtype=np.int32)
+        self.tile_owner = torch.from_numpy(self.tile_owner_np).to(dev)
+        self.tile_mult = torch.from_numpy(layout.tile_mult()).to(dev)
+        self.tile_active = torch.ones(T, dtype=torch.uint8, device=dev)
+        self.key_done = torch.zeros(K, dtype=torch.int32, device=dev)
+        self.state = {k: torch.zeros(4, dtype=torch.int32, device=dev) for k in ("fsa", "async", "party", "barrier")}
+        self.use_multicast = use_multicast and bool(self.param.multicast_ptr) and os.environ.get("GEOMX_NO_MULTICAST", "0") != "1"
+        self.opt_spec = None
+        self.push_scale = 1.0
+        self.grid = max(1, min(T, 132))
+        self._params_cache = {}
+        self._peer_tables = {}
+        self.set_optimizer(opt_spec)
+
+    # -- views ----------------------------------------------------------------------------------------------------------
+    def param_view(self, i): return self.layout.view(self.param.tensor, i)
+    def grad_view(self, i): return self.layout.view(self.grad.tensor, i)
+
+    def set_optimizer(self, spec):
+        self.opt_spec = spec
+        self._params_cache.clear()
+
+    def set_push_scale(self, s):
+        self.push_scale = float(s)
+        self._params_cache.clear()
+
+    def load_master_from_param(self):
+        """Global owners adopt the (already broadcast) parameter arena as master weights — the `init` handshake."""
+        self.w.copy_(self.param.tensor)
+
+    # -- parameter block ------------------------------------------------------------------------------------------------
+    def _hyper(self):
+        h = _OptHyperF()
+        s = self.opt_spec
+        if s is None:
+            h.kind = -1; h.lr = 0.0; h.clip = -1.0; h.rescale = 1.0
+            return h
+        h.kind = _KIND[s["name"]]
+        h.lr, h.wd, h.rescale, h.clip = s["lr"], s["wd"], s["rescale_grad"], s["clip_gradient"]
+        h.momentum = s.get("momentum", 0.0); h.beta1 = s.get("beta1", 0.9); h.beta2 = s.get("beta2", 0.999)
+        h.eps = s.get("epsilon", 1e-8); h.lamda = s.get("lamda", 0.04)
+        return h
+
+    def _block(self, channel, defer_pull_wait=False, masked=False):
+        key = (channel, defer_pull_wait, masked)
+        if key in self._params_cache:
+            return self._params_cache[key]
+        t = self.topo
+        p = _FabricParams()
+        p.world, p.rank, p.party_size, p.num_parties, p.party, p.local = t.world, t.rank, t.party_size, t.num_parties, t.party, t.local
+        p.num_gs = t.num_gs
+        for i, r in enumerate(t.gs_ranks):
+            p.gs_rank[i] = r
+        for r in range(MAX_RANKS):
+            p.grad[r] = self.grad.peer_ptrs[r] or None
+            p.param[r] = self.param.peer_ptrs[r] or None
+            p.stage[r] = self.stage.peer_ptrs[r] or None
+            p.flags[r] = self.flags.peer_ptrs[r] or None
+        p.grad_mc = (self.grad.multicast_ptr or None) if self.use_multicast else None
+        p.param_mc = (self.param.multicast_ptr or None) if self.use_multicast else None
+        p.w, p.s0, p.s1 = self.w.data_ptr(), self.s0.data_ptr(), self.s1.data_ptr()
+        p.n, p.tiles, p.num_keys = self.n, self.tiles, self.num_keys
+        p.tile_key, p.key_tiles, p.tile_owner = self.tile_key.data_ptr(), self.key_tiles.data_ptr(), self.tile_owner.data_ptr()
+        p.tile_active = self.tile_active.data_ptr() if masked else None
+        p.tile_mult = self.tile_mult.data_ptr()
+        p.key_done = self.key_done.data_ptr()
+        p.state = self.state[channel].data_ptr()
+        p.h = self._hyper()
+        p.push_scale = self.push_scale
+        p.defer_pull_wait = int(defer_pull_wait)
+        pre = {"fsa": "fsa", "async": "async", "party": "par"}[channel]
+        p.ready_off = self.off[pre + "_ready"]
+        p.arrived_off = self.off["fsa_arrived"]
+        p.param_ready_off = self.off.get(pre + "_param_ready", self.off["fsa_param_ready"])
+        assert ctypes.sizeof(p) == native.require().gx_fabric_params_size(), "FabricParams layout mismatch"
+        self._params_cache[key] = p
+        return p
+
+    def _peer_table(self, name, ptrs):
+        if name not in self._peer_tables:
+            arr = np.array([int(x or 0) for x in ptrs], dtype=np.int64)
+            self._peer_tables[name] = torch.from_numpy(arr).to(self.device)
+        return self._peer_tables[name]
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # -- kernels --------------------------------------------------------------------------------------------------------
+    def fsa_step(self, defer_pull_wait=False, masked=False):
+        """dist_sync: party reduce -> global reduce + optimizer -> broadcast (one launch)."""
+        p = self._block("fsa", defer_pull_wait, masked)
+        rc = native.require().gx_hips_fsa_step(ctypes.byref(p), self.grid, self._stream())
+        native.launch_count += 1
+        if rc:
+            raise RuntimeError("gx_hips_fsa_step failed rc=%d" % rc)
+
+    def async_step(self):
+        """dist_async (MixedSync): one-sided update of the global owner's HBM under per-tile locks."""
+        p = self._block("async")
+        if "w_peer" not in self._peer_tables and self.topo.world > 1:
+            self._exchange_state_peers()
+        wp = self._peer_table("w_peer", [self.w.data_ptr()] + [0] * (MAX_RANKS - 1))
+        s0 = self._peer_table("s0_peer", [self.s0.data_ptr()] + [0] * (MAX_RANKS - 1))
+        s1 = self._peer_table("s1_peer", [self.s1.data_ptr()] + [0] * (MAX_RANKS - 1))
+        rc = native.require().gx_hips_async_step(ctypes.byref(p), ctypes.c_void_p(wp.data_ptr()), ctypes.c_void_p(s0.data_ptr()),
+                                                 ctypes.c_void_p(s1.data_ptr()), self.off["async_lock"], self.off["async_step"], self.grid, self._stream())
+        native.launch_count += 1
+        if rc:
+            raise RuntimeError("gx_hips_async_step failed rc=%d" % rc)
+
+    def _exchange_state_peers(self):
+        """Async mode needs the global owners' master/state arenas peer-mapped: re-home them in symmetric memory."""
+        for name in ("w", "s0", "s1"):
+            buf = self.heap.alloc(self.n, torch.float32)
+            buf.tensor.copy_(getattr(self, name))
+            setattr(self, name, buf.tensor)
+            setattr(self, "_sym_" + name, buf)
+            self._peer_tables[name + "_peer"] = torch.from_numpy(np.array(buf.peer_ptrs, dtype=np.int64)).to(self.device)
+        self._params_cache.clear()
+
+    def party_allreduce(self, src: SymmetricBuffer, dst: SymmetricBuffer, scale=1.0, reduce_scatter=False):
+        """Local tier only (HFA local synchronisation / generic party all-reduce)."""
+        p = self._block("party")
+        sp = self._peer_table("par_src_%d" % id(src), src.peer_ptrs)
+        dp = self._peer_table("par_dst_%d" % id(dst), dst.peer_ptrs)
+        rc = native.require().gx_hips_party_allreduce(ctypes.byref(p), ctypes.c_void_p(sp.data_ptr()), ctypes.c_void_p(dp.data_ptr()), float(scale),
+                                                      1 if reduce_scatter else 0, self.off["par_done"], self.grid, self._stream())
+        native.launch_count += 1
+        if rc:
+            raise RuntimeError("gx_hips_party_allreduce failed rc=%d" % rc)
+
+    def barrier(self):
+        """Device-side whole-world flag barrier (the two-tier HiPS barrier is one NVSwitch hop)."""
+        fl = self._peer_table("flags_peer", self.flags.peer_ptrs)
+        rc = native.require().gx_fabric_barrier(ctypes.c_void_p(fl.data_ptr()), self.topo.world, self.topo.rank, self.off["barrier"],
+                                                ctypes.c_void_p(self.state["barrier"].data_ptr()), self._stream())
+        native.launch_count += 1
+        if rc:
+            raise RuntimeError("gx_fabric_barrier failed rc=%d" % rc)
+
+    def param_ready_flag_ptr(self, key_index):
+        """Device address of this rank's ready flag for key ``key_index`` (for pull-fused GEMMs)."""
+        return self.flags.tensor.data_ptr() + 4 * (self.off["fsa_param_ready"] + key_index)

@@ -1,0 +1,258 @@
+"""GPU numerics: every hand-written sm_100a kernel against the plain PyTorch fp32 definition of the same op."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import geomx_b200 as mx
+from geomx_b200.kvstore import compression as gc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from geomx_b200.ops import native
+    native.require()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return native
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-12))
+
+
+# ---------------------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(32, 256, 512), (128, 256, 32), (2048, 32, 400), (2048, 400, 32), (200, 72, 100), (256, 512, 32)])
+def test_gemm_tf32_majors(nat, a_mn, b_mn, M, N, K):
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=dev()); B = torch.randn(N, K, device=dev())
+    Am = A.t().contiguous() if a_mn else A
+    Bm = B.t().contiguous() if b_mn else B
+    D = torch.zeros(M, N, device=dev())
+    nat.gemm(Am, Bm, D, a_mn=a_mn, b_mn=b_mn)
+    ref = A @ B.t()
+    e = rel_err(D, ref)
+    assert e < 2e-3, "tf32 gemm rel err %g (a_mn=%s b_mn=%s %dx%dx%d)" % (e, a_mn, b_mn, M, N, K)
+
+
+def test_gemm_epilogues(nat):
+    torch.manual_seed(1)
+    M, N, K = 64, 96, 128
+    A = torch.randn(M, K, device=dev()); B = torch.randn(N, K, device=dev()); bias = torch.randn(N, device=dev())
+    mask = torch.randn(M, N, device=dev())
+    ref = torch.relu(A @ B.t() + bias)
+    D = torch.empty(M, N, device=dev()); nat.gemm(A, B, D, bias=bias, relu=True)
+    assert rel_err(D, ref) < 2e-3
+    cs = torch.zeros(N, device=dev()); D2 = torch.empty(M, N, device=dev())
+    nat.gemm(A, B, D2, mask=mask, colsum=cs)
+    ref2 = (A @ B.t()) * (mask > 0)
+    assert rel_err(D2, ref2) < 2e-3 and rel_err(cs, ref2.sum(0)) < 2e-3
+    # NCHW scatter: rows = (image, pixel), cols = channel
+    n_img, hw, C = 4, 16, 24
+    A3 = torch.randn(n_img * hw, K, device=dev()); B3 = torch.randn(C, K, device=dev())
+    Y = torch.empty(n_img, C, 4, 4, device=dev()); nat.gemm(A3, B3, Y, store_nchw_hw=hw)
+    ref3 = (A3 @ B3.t()).reshape(n_img, hw, C).permute(0, 2, 1).reshape(n_img, C, 4, 4)
+    assert rel_err(Y, ref3) < 2e-3
+    # split-K accumulate
+    A4 = torch.randn(32, 2048, device=dev()); B4 = torch.randn(400, 2048, device=dev())
+    D4 = torch.zeros(32, 400, device=dev()); nat.gemm(A4, B4, D4, split_k=16, accumulate=True)
+    assert rel_err(D4, A4 @ B4.t()) < 2e-3
+    # unaligned leading dimension -> CUDA-core fallback with the same contract
+    A5 = torch.randn(50, 25, device=dev()); B5 = torch.randn(16, 25, device=dev()); D5 = torch.empty(50, 16, device=dev())
+    nat.gemm(A5, B5, D5)
+    assert rel_err(D5, A5 @ B5.t()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------- ops through autograd
+def _grads(fn, *inputs):
+    ins = [i.clone().requires_grad_(True) for i in inputs]
+    out = fn(*ins)
+    g = torch.randn_like(out)
+    out.backward(g)
+    return out.detach(), [i.grad for i in ins], g
+
+
+def test_dense_fn(nat):
+    from geomx_b200.ops import functional as OF
+    torch.manual_seed(2)
+    x = torch.randn(32, 512, device=dev()); w = torch.randn(256, 512, device=dev()) * 0.05; b = torch.randn(256, device=dev())
+    for act in (None, "relu"):
+        torch.manual_seed(3)
+        y, gr, g = _grads(lambda a, c, d: OF.dense(a, c, d, act), x, w, b)
+        OF.use_native(False)
+        torch.manual_seed(3)
+        y2, gr2, _ = _grads(lambda a, c, d: OF.dense(a, c, d, act), x, w, b)
+        OF.use_native(True)
+        assert rel_err(y, y2) < 2e-3
+        for a, c in zip(gr, gr2):
+            assert rel_err(a, c) < 3e-3
+
+
+@pytest.mark.parametrize("cin,cout,k,hw,stride,pad", [(16, 32, 5, 12, 1, 0), (1, 16, 5, 28, 1, 0), (8, 16, 3, 10, 2, 1)])
+def test_conv_fn(nat, cin, cout, k, hw, stride, pad):
+    from geomx_b200.ops import functional as OF
+    torch.manual_seed(4)
+    x = torch.randn(8, cin, hw, hw, device=dev()); w = torch.randn(cout, cin, k, k, device=dev()) * 0.1; b = torch.randn(cout, device=dev())
+    f = lambda a, c, d: OF.conv2d(a, c, d, (stride, stride), (pad, pad), act="relu")
+    torch.manual_seed(5); y, gr, _ = _grads(f, x, w, b)
+    OF.use_native(False)
+    torch.manual_seed(5); y2, gr2, _ = _grads(f, x, w, b)
+    OF.use_native(True)
+    assert rel_err(y, y2) < 2e-3
+    for a, c in zip(gr, gr2):
+        assert rel_err(a, c) < 3e-3
+
+
+def test_pool_relu_softmax_bn(nat):
+    from geomx_b200.ops import functional as OF
+    torch.manual_seed(6)
+    x = torch.randn(4, 8, 12, 12, device=dev())
+    for f in (lambda a: OF.max_pool2d(a, (2, 2), (2, 2)), lambda a: OF.activation(a, "relu")):
+        torch.manual_seed(7); y, gr, _ = _grads(f, x)
+        OF.use_native(False); torch.manual_seed(7); y2, gr2, _ = _grads(f, x); OF.use_native(True)
+        assert torch.allclose(y, y2) and torch.allclose(gr[0], gr2[0])
+    logits = torch.randn(32, 10, device=dev()); lab = torch.randint(0, 10, (32,), device=dev()).float()
+    torch.manual_seed(8); y, gr, _ = _grads(lambda a: OF.softmax_cross_entropy(a, lab), logits)
+    OF.use_native(False); torch.manual_seed(8); y2, gr2, _ = _grads(lambda a: OF.softmax_cross_entropy(a, lab), logits); OF.use_native(True)
+    assert rel_err(y, y2) < 1e-5 and rel_err(gr[0], gr2[0]) < 1e-5
+    gamma = torch.rand(8, device=dev()) + 0.5; beta = torch.randn(8, device=dev())
+    rm, rv = torch.zeros(8, device=dev()), torch.ones(8, device=dev())
+    rm2, rv2 = rm.clone(), rv.clone()
+    torch.manual_seed(9); y, gr, _ = _grads(lambda a, c, d: OF.batch_norm(a, c, d, rm, rv, True), x, gamma, beta)
+    OF.use_native(False); torch.manual_seed(9); y2, gr2, _ = _grads(lambda a, c, d: OF.batch_norm(a, c, d, rm2, rv2, True), x, gamma, beta); OF.use_native(True)
+    assert rel_err(y, y2) < 1e-4 and rel_err(rm, rm2) < 1e-4
+    for a, c in zip(gr, gr2):
+        assert rel_err(a, c) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------- optimizers
+def test_adam_kernel_matches_python(nat):
+    torch.manual_seed(10)
+    w = torch.randn(5000, device=dev()); g = torch.randn(5000, device=dev())
+    o = mx.optimizer.Adam(learning_rate=0.01, wd=0.001)
+    upd = mx.optimizer.get_updater(o)
+    wn = mx.nd.array(w.clone()); wn._data = w.clone()
+    ref = w.clone().cpu(); m = torch.zeros(5000); v = torch.zeros(5000)
+    for t in range(1, 4):
+        upd(0, mx.nd.NDArray(g), wn)      # native CUDA path inside Adam.update
+        gg = g.cpu() + 0.001 * ref
+        m = 0.9 * m + 0.1 * gg; v = 0.999 * v + 0.001 * gg * gg
+        lr = 0.01 * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        ref = ref - lr * m / (v.sqrt() + 1e-8)
+    assert rel_err(wn._t.cpu(), ref) < 1e-5
+
+
+def test_trainer_multi_tensor(nat):
+    torch.manual_seed(11)
+    net = mx.models.build_cnn(); net.initialize(init=mx.init.Xavier(), ctx=mx.gpu(0))
+    x = mx.nd.array(torch.rand(32, 1, 28, 28), ctx=mx.gpu(0)); y = mx.nd.array(torch.randint(0, 10, (32,)).float(), ctx=mx.gpu(0))
+    loss = mx.gluon.loss.SoftmaxCrossEntropyLoss()
+    tr = mx.gluon.Trainer(net.collect_params(), "adam", {"learning_rate": 0.01}, kvstore=None)
+    vals = []
+    for _ in range(25):
+        with mx.autograd.record():
+            l = loss(net(x), y)
+        l.backward(); tr.step(32)
+        vals.append(float(l.mean().asscalar()))
+    assert vals[-1] < vals[0] * 0.6, vals
+
+
+# ---------------------------------------------------------------------------------------------------------------- compression
+def test_2bit_matches_cpu_oracle(nat):
+    torch.manual_seed(12)
+    g = torch.randn(1000) * 0.6; r_cpu = torch.zeros(1000); r_gpu = torch.zeros(1000, device=dev())
+    for _ in range(3):
+        q_cpu = gc.quantize_2bit(g, r_cpu, 0.5)
+        q_gpu = gc.quantize_2bit(g.to(dev()), r_gpu, 0.5)
+        assert torch.equal(q_cpu.view(torch.int32), q_gpu.cpu().view(torch.int32))
+        assert torch.allclose(r_cpu, r_gpu.cpu())
+    d = gc.dequantize_2bit(q_gpu, 1000, 0.5)
+    assert torch.equal(d.cpu(), gc.dequantize_2bit(q_cpu, 1000, 0.5))
+
+
+def test_bsc_contract(nat):
+    torch.manual_seed(13)
+    n, thr = 131072, 0.01
+    g = torch.randn(n)
+    u_c, v_c = torch.zeros(n), torch.zeros(n)
+    u_g, v_g = torch.zeros(n, device=dev()), torch.zeros(n, device=dev())
+    for _ in range(2):
+        z_c = gc.bsc_compress(g, u_c, v_c, thr)
+        z_g = gc.bsc_compress(g.to(dev()), u_g, v_g, thr)
+        assert torch.allclose(z_c, z_g.cpu(), atol=1e-5), "GPU BSC differs from the CPU oracle"
+        assert torch.allclose(v_c, v_g.cpu(), atol=1e-5) and torch.allclose(u_c, u_g.cpu(), atol=1e-5)
+    k = z_g.numel() // 2
+    dense = gc.bsc_decompress(z_g, n)
+    assert int((dense != 0).sum()) <= k
+    z2 = gc.bsc_pull_compress(dense, thr, 2)
+    assert torch.allclose(gc.bsc_decompress(z2, n), dense)
+    assert torch.allclose(z2.cpu(), gc.bsc_pull_compress(dense.cpu(), thr, 2))
+
+
+def test_fp8_block_roundtrip(nat):
+    torch.manual_seed(14)
+    x = torch.randn(1000, device=dev()) * 3
+    res = torch.zeros(1000, device=dev())
+    q, s = gc.fp8_block_quantize(x, res)
+    y = gc.fp8_block_dequantize(q, s, 1000)
+    assert rel_err(y, x) < 0.05
+    assert torch.allclose(y + res, x, atol=1e-5)      # error feedback holds the exact remainder
+    qc, sc = gc.fp8_block_quantize(x.cpu(), torch.zeros(1000))
+    assert torch.allclose(gc.fp8_block_dequantize(qc, sc, 1000), y.cpu(), atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------- flagship step
+def _torch_reference_step(P, x, y):
+    import torch.nn.functional as F
+    ps = [p.clone().requires_grad_(True) for p in P]
+    h = F.max_pool2d(torch.relu(F.conv2d(x, ps[0], ps[1])), 2)
+    h = F.max_pool2d(torch.relu(F.conv2d(h, ps[2], ps[3])), 2).flatten(1)
+    h = torch.relu(F.linear(h, ps[4], ps[5])); h = torch.relu(F.linear(h, ps[6], ps[7]))
+    logits = F.linear(h, ps[8], ps[9])
+    loss = F.cross_entropy(logits, y.long(), reduction="none")
+    loss.sum().backward()
+    return loss.detach(), [p.grad for p in ps]
+
+
+def test_fused_step_matches_torch(nat):
+    from geomx_b200.parallel import Topology
+    torch.manual_seed(15)
+    eng = mx.models.HipsCNNTrainStep(batch_size=32, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=Topology(1, 0, 1, 1), use_graph=False)
+    X = torch.rand(32, 1, 28, 28, device=dev()); y = torch.randint(0, 10, (32,), device=dev()).float()
+    P0 = [p.clone() for p in eng.P]
+    loss_ref, grads_ref = _torch_reference_step(P0, X, y)
+    eng.x.copy_(X); eng.label.copy_(y)
+    # run everything except the optimizer: call _body with lr = 0 so weights stay put, then inspect the gradient arena
+    eng.fabric.set_optimizer(dict(mx.optimizer.SGD(learning_rate=0.0).spec()))
+    eng._body(); torch.cuda.synchronize()
+    assert rel_err(eng.loss, loss_ref) < 2e-3
+    for i, (g, gr) in enumerate(zip(eng.G, grads_ref)):
+        assert rel_err(g, gr) < 5e-3, "grad %d rel err %g" % (i, rel_err(g, gr))
+    # now one real Adam step: w' = w - lr*mhat/(sqrt(vhat)+eps) with g/num_samples pushed
+    eng.fabric.set_optimizer(mx.optimizer.Adam(learning_rate=0.01).spec())
+    eng.fabric.state["fsa"][2] = 0      # optimizer step counter t restarts for the Adam run
+    eng._body(); torch.cuda.synchronize()
+    for i, (p, p0, gr) in enumerate(zip(eng.P, P0, grads_ref)):
+        gsc = gr / 32.0
+        expect = p0 - 0.01 * gsc / (gsc.abs() + 1e-8)      # first Adam step: m̂/sqrt(v̂) = g/|g|
+        mask = gsc.abs() > 1e-4                               # sign is ill-conditioned for ~0 gradients under tf32
+        assert torch.allclose(p[mask], expect[mask], atol=2e-4), "param %d" % i
+
+
+def test_fused_step_graph_trains(nat):
+    from geomx_b200.parallel import Topology
+    torch.manual_seed(16)
+    eng = mx.models.HipsCNNTrainStep(batch_size=32, topo=Topology(1, 0, 1, 1), use_graph=True)
+    X = torch.rand(32, 1, 28, 28).pin_memory(); y = torch.randint(0, 10, (32,)).float().pin_memory()
+    l0 = eng.step(X, y)
+    for _ in range(40):
+        l = eng.step(X, y)
+    assert l < 0.5 * l0, (l0, l)
