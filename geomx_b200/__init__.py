@@ -29,6 +29,8 @@ from . import model  # noqa: F401
 from . import profiler  # noqa: F401
 from . import io  # noqa: F401
 from . import utils  # noqa: F401
+from . import parallel  # noqa: F401
+from . import models  # noqa: F401
 from . import kvstore_server  # noqa: F401
 
 # server / scheduler bootstrap on import (no-op for workers and plain library use)

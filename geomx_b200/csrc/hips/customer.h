@@ -1,0 +1,48 @@
+// Customer: per-application request tracker + receive threads.
+// Parity: ps-lite include/ps/internal/customer.h + src/customer.cc:14-87 (NewRequest/WaitRequest/NumResponse/AddResponse, recv
+// thread).  GeoMX gave servers a SECOND queue+thread for pull requests so pulls never queue behind pushes (customer.h:91-101); here
+// the split is by message kind (pull request vs. everything else) instead of a hard-coded list of cmd heads.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "message.h"
+#include "threadsafe_queue.h"
+
+namespace hips {
+
+class Postoffice;
+
+class Customer {
+ public:
+  using RecvHandle = std::function<void(const Message&)>;
+  Customer(int app_id, int customer_id, const RecvHandle& handle, bool dual_queue);
+  ~Customer();
+  int app_id() const { return app_id_; }
+  int customer_id() const { return customer_id_; }
+  // expects one response from every node of `recver` group in plane p
+  int NewRequest(int recver, Plane p);
+  int NewRequestCount(int num);
+  void WaitRequest(int timestamp);
+  int NumResponse(int timestamp);
+  void AddResponse(int timestamp, int num = 1);
+  void Accept(const Message& recved);
+
+ private:
+  void Receiving(ThreadsafeQueue<Message, MessagePriority>* q);
+  int app_id_, customer_id_;
+  RecvHandle recv_handle_;
+  ThreadsafeQueue<Message, MessagePriority> recv_queue_, pull_queue_;
+  std::unique_ptr<std::thread> recv_thread_, pull_thread_;
+  std::mutex tracker_mu_;
+  std::condition_variable tracker_cond_;
+  std::vector<std::pair<int, int>> tracker_;
+};
+
+}  // namespace hips

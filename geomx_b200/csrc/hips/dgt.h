@@ -1,0 +1,215 @@
+// DGT — Differential Gradient Transmission (block contribution ranking + prioritised / lossy-tolerant channels).
+//
+// Parity: 3rdparty/ps-lite/include/ps/kv_app.h:842-1022 (InitDGT, EvalMsgContribution: EMA(alpha) of mean|g| per (key, seq) block;
+// GetChannel; block split + sort + channel assignment in KVServer::Send) and src/van.cc:290-370,707-824 (Important_scheduler /
+// Unimportant_scheduler — the unimportant queue is drained only while the important queue is empty; 4-bit encode/decode with a
+// min/max codebook; receiver-side reassembly into a zero-filled buffer, delivery when the block with seq == seq_end arrives).
+// Modes (ENABLE_DGT): 1 = unimportant blocks may be lost (the reference uses UDP sockets; here the same TCP connection carries them and
+// the receiver drops them with probability DGT_UDP_LOSS %, which exercises the identical zero-fill tolerance), 2 = reliable but
+// priority-ordered, 3 = mode 2 + 4-bit quantised unimportant blocks.  Only dense default pushes from a local server to the global
+// servers are DGT-split, as in the reference (kv_app.h:918-919).
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <random>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "env.h"
+#include "message.h"
+#include "threadsafe_queue.h"
+#include "van.h"
+
+namespace hips {
+
+struct DGTConfig {
+  int mode = 0;          // ENABLE_DGT
+  int block_bytes = 4096;
+  int channels = 3;      // DMLC_UDP_CHANNEL_NUM
+  float k = 0.5f;        // DMLC_K: fraction of blocks on the reliable channel
+  float alpha = 0.3f;    // DGT_CONTRIBUTION_ALPHA
+  int loss_pct = 0;      // DGT_UDP_LOSS (emulated datagram loss, mode 1)
+  static DGTConfig FromEnv() {
+    Environment* e = Environment::Get();
+    DGTConfig c;
+    c.mode = e->GetInt("ENABLE_DGT", 0);
+    c.block_bytes = e->GetInt("DGT_BLOCK_SIZE", 4096);
+    c.channels = std::max(1, e->GetInt("DMLC_UDP_CHANNEL_NUM", 3));
+    c.k = static_cast<float>(e->GetFloat("DMLC_K", 0.5));
+    c.alpha = static_cast<float>(e->GetFloat("DGT_CONTRIBUTION_ALPHA", 0.3));
+    c.loss_pct = e->GetInt("DGT_UDP_LOSS", 0);
+    return c;
+  }
+};
+
+// channel of the block ranked `rank` (0 = most important) out of `total`: top k fraction -> 0, the rest evenly over 1..C
+inline int DGTGetChannel(int rank, int total, float k, int channels) {
+  const int important = static_cast<int>(std::ceil(total * k));
+  if (rank < important || channels <= 0) return 0;
+  const int rest = total - important;
+  const int per = std::max(1, (rest + channels - 1) / channels);
+  return std::min(channels, 1 + (rank - important) / per);
+}
+
+// 4-bit codec: codebook of 16 uniformly spaced centroids in [min, max]
+inline void DGTEncode4(const float* src, size_t n, std::vector<char>* out, float* mn, float* mx) {
+  float lo = src[0], hi = src[0];
+  for (size_t i = 1; i < n; ++i) { lo = std::min(lo, src[i]); hi = std::max(hi, src[i]); }
+  *mn = lo; *mx = hi;
+  const float step = (hi - lo) / 15.f;
+  out->assign((n + 1) / 2, 0);
+  for (size_t i = 0; i < n; ++i) {
+    int code = step > 0 ? static_cast<int>(std::lround((src[i] - lo) / step)) : 0;
+    code = std::max(0, std::min(15, code));
+    (*out)[i / 2] |= static_cast<char>((i & 1) ? (code << 4) : code);
+  }
+}
+inline void DGTDecode4(const char* src, size_t n, float mn, float mx, float* dst) {
+  const float step = (mx - mn) / 15.f;
+  for (size_t i = 0; i < n; ++i) {
+    const int b = static_cast<unsigned char>(src[i / 2]);
+    const int code = (i & 1) ? (b >> 4) : (b & 15);
+    dst[i] = mn + step * code;
+  }
+}
+
+class DGTSender {
+ public:
+  explicit DGTSender(Van* van) : van_(van), cfg_(DGTConfig::FromEnv()) {
+    important_ = std::thread(&DGTSender::ImportantLoop, this);
+    unimportant_ = std::thread(&DGTSender::UnimportantLoop, this);
+  }
+  void Stop() {
+    if (stop_.exchange(true)) return;
+    Message t; t.meta.control.cmd = Control::TERMINATE;
+    iq_.Push(t); uq_.Push(t);
+    important_.join(); unimportant_.join();
+  }
+  const DGTConfig& config() const { return cfg_; }
+
+  // contribution EMA of one block (kv_app.h:853-876)
+  float Contribution(int key, int seq, const float* v, size_t n) {
+    double s = 0;
+    for (size_t i = 0; i < n; ++i) s += std::fabs(v[i]);
+    const float mean = n ? static_cast<float>(s / n) : 0.f;
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = contri_.find({key, seq});
+    float c = it == contri_.end() ? mean : cfg_.alpha * it->second + (1.f - cfg_.alpha) * mean;
+    contri_[{key, seq}] = c;
+    return c;
+  }
+
+  // split one dense fp32 push `base` (data = keys|vals|lens) into ranked blocks and enqueue them.  Returns #blocks sent.
+  int SendSplit(const Message& base, int key) {
+    const SArray<char>& vals = base.data[1];
+    const int total = static_cast<int>(vals.size());
+    const int bb = cfg_.block_bytes;
+    const int nblk = (total + bb - 1) / bb;
+    struct Blk { int seq; float c; };
+    std::vector<Blk> blks(nblk);
+    for (int s = 0; s < nblk; ++s) {
+      const int off = s * bb, len = std::min(bb, total - off);
+      blks[s] = {s, Contribution(key, s, reinterpret_cast<const float*>(vals.data() + off), len / sizeof(float))};
+    }
+    // sort by contribution (desc); the LAST block stays last: its arrival triggers delivery at the receiver
+    std::sort(blks.begin(), blks.end() - 1, [](const Blk& a, const Blk& b) { return a.c > b.c; });
+    int sent = 0;
+    for (int r = 0; r < nblk; ++r) {
+      const Blk& b = blks[r];
+      const bool last = b.seq == nblk - 1;
+      if (b.c == 0.f && !last) continue;  // zero-contribution blocks are dropped (kv_app.h:973-975)
+      Message m;
+      m.meta = base.meta;
+      m.meta.msg_type = 1;
+      m.meta.first_key = key;
+      m.meta.seq = b.seq; m.meta.seq_begin = 0; m.meta.seq_end = nblk - 1;
+      m.meta.total_bytes = total;
+      const int off = b.seq * bb, len = std::min(bb, total - off);
+      m.meta.val_bytes = len;
+      const int ch = last ? 0 : DGTGetChannel(r, nblk, cfg_.k, cfg_.channels);
+      m.meta.channel = ch;
+      m.meta.tos = (cfg_.channels - ch) * 32;
+      m.meta.priority = -ch;
+      m.contribution = b.c;
+      m.data.clear();
+      m.data.push_back(base.data[0]);
+      if (cfg_.mode == 3 && ch > 0) {
+        std::vector<char> enc; float mn, mx;
+        DGTEncode4(reinterpret_cast<const float*>(vals.data() + off), len / sizeof(float), &enc, &mn, &mx);
+        SArray<char> e; e.CopyFrom(enc.data(), enc.size());
+        m.data.push_back(e);
+        m.meta.bits_num = 4; m.meta.compr = {mn, mx};
+      } else {
+        m.data.push_back(vals.segment(off, off + len));
+        m.meta.bits_num = 32;
+      }
+      m.data.push_back(base.data.size() > 2 ? base.data[2] : SArray<char>());
+      (ch == 0 ? iq_ : uq_).Push(m);
+      ++sent;
+    }
+    return sent;
+  }
+
+ private:
+  void ImportantLoop() {
+    while (true) {
+      Message m; iq_.WaitAndPop(&m);
+      if (m.meta.control.cmd == Control::TERMINATE) break;
+      van_->SendNow(m);
+    }
+  }
+  void UnimportantLoop() {  // van.cc:720-728: only send while the important queue is empty
+    while (true) {
+      Message m; uq_.WaitAndPop(&m);
+      if (m.meta.control.cmd == Control::TERMINATE) break;
+      while (iq_.Size() > 0 && !stop_) std::this_thread::yield();
+      van_->SendNow(m);
+    }
+  }
+  Van* van_;
+  DGTConfig cfg_;
+  ThreadsafeQueue<Message, MessagePriority> iq_, uq_;
+  std::thread important_, unimportant_;
+  std::atomic<bool> stop_{false};
+  std::mutex mu_;
+  std::map<std::pair<int, int>, float> contri_;
+};
+
+class DGTReceiver {
+ public:
+  DGTReceiver() : cfg_(DGTConfig::FromEnv()), rng_(4242) {}
+  // returns true and fills `whole` when the final block (seq == seq_end) of a tensor arrived
+  bool Add(const Message& blk, Message* whole) {
+    const Meta& m = blk.meta;
+    if (cfg_.mode == 1 && m.channel > 0 && cfg_.loss_pct > 0 && static_cast<int>(rng_() % 100) < cfg_.loss_pct) return false;  // lost datagram
+    const auto id = std::make_tuple(m.sender, m.first_key, m.timestamp);
+    auto& st = pending_[id];
+    if (st.buf.size() == 0) { st.buf.resize(m.total_bytes, 0); st.keys = blk.data[0]; st.lens = blk.data.size() > 2 ? blk.data[2] : SArray<char>(); }
+    const int off = m.seq * cfg_.block_bytes;
+    if (m.bits_num == 4) DGTDecode4(blk.data[1].data(), m.val_bytes / sizeof(float), m.compr[0], m.compr[1], reinterpret_cast<float*>(st.buf.data() + off));
+    else memcpy(st.buf.data() + off, blk.data[1].data(), std::min<size_t>(m.val_bytes, blk.data[1].size()));
+    if (m.seq != m.seq_end) return false;
+    whole->meta = m;
+    whole->meta.msg_type = 0; whole->meta.channel = 0;
+    whole->data.clear();
+    whole->data.push_back(st.keys);
+    whole->data.push_back(st.buf);
+    SArray<char> lens; lens.resize(sizeof(int));
+    int total = m.total_bytes; memcpy(lens.data(), &total, sizeof(int));
+    whole->data.push_back(lens);
+    pending_.erase(id);
+    return true;
+  }
+
+ private:
+  struct State { SArray<char> buf, keys, lens; };
+  DGTConfig cfg_;
+  std::mt19937 rng_;
+  std::map<std::tuple<int, int, int>, State> pending_;
+};
+
+}  // namespace hips

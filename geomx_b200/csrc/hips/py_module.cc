@@ -1,0 +1,179 @@
+// pybind11 bindings of the native runtime (module geomx_b200.lib._C).
+// Plays the role of the reference's flat C API for the kvstore / profiler / IO (include/mxnet/c_api.h:1949-2327 MXKVStore*, MXInitPSEnv,
+// src/c_api/c_api_profile.cc) — as a typed Python module instead of ctypes over a C ABI.
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "../runtime/engine.h"
+#include "../runtime/io.h"
+#include "../runtime/params_io.h"
+#include "../runtime/profiler.h"
+#include "dgt.h"
+#include "gradient_compression.h"
+#include "half.h"
+#include "key_codec.h"
+#include "kvstore_dist.h"
+#include "tsengine.h"
+
+namespace py = pybind11;
+using namespace hips;
+
+static py::array_t<float> WrapFloat(float* p, size_t n) {
+  return py::array_t<float>({static_cast<py::ssize_t>(n)}, {static_cast<py::ssize_t>(sizeof(float))}, p, py::capsule(p, [](void*) {}));
+}
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "geomx_b200 native runtime: HiPS transport + servers, compression codecs, .params IO, profiler, engine, data IO";
+  py::register_exception<hips::Error>(m, "HipsError");
+
+  // ---------------------------------------------------------------------------------------------- environment / roles
+  m.def("init_ps_env", [](const std::map<std::string, std::string>& kv) { for (auto& p : kv) Environment::Get()->Set(p.first, p.second); },
+        "MXInitPSEnv: override environment variables in-process");
+  m.def("is_worker_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_worker(); });
+  m.def("is_server_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_server(); });
+  m.def("is_scheduler_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_scheduler(); });
+  m.def("is_global_server_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_global_server(); });
+  m.def("is_global_scheduler_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_global_scheduler(); });
+  m.def("is_master_worker_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_master_worker(); });
+
+  // ---------------------------------------------------------------------------------------------- protocol helpers (unit tests)
+  m.def("server_rank_to_id", [](int r, int plane) { return ServerRankToID(r, static_cast<Plane>(plane)); });
+  m.def("worker_rank_to_id", [](int r, int plane) { return WorkerRankToID(r, static_cast<Plane>(plane)); });
+  m.def("id_to_rank", [](int id, int plane) { return IDtoRank(id, static_cast<Plane>(plane)); });
+  m.def("get_command_type", [](int req, int dtype) { return GetCommandType(static_cast<RequestType>(req), dtype); });
+  m.def("depair_command_type", [](int cmd) { auto t = DepairDataHandleType(cmd); return std::make_pair(static_cast<int>(t.requestType), t.dtype); });
+  m.def("dgt_get_channel", &DGTGetChannel);
+  m.def("dgt_encode4", [](py::array_t<float, py::array::c_style> a) {
+    std::vector<char> out; float mn, mx;
+    DGTEncode4(a.data(), a.size(), &out, &mn, &mx);
+    return py::make_tuple(py::bytes(out.data(), out.size()), mn, mx);
+  });
+  m.def("dgt_decode4", [](py::bytes b, size_t n, float mn, float mx) {
+    std::string s = b; py::array_t<float> out(n);
+    DGTDecode4(s.data(), n, mn, mx, out.mutable_data());
+    return out;
+  });
+  m.def("pack_unpack_meta", [](int head, const std::string& body, int priority, int key, bool with_control) {
+    Meta a; a.head = head; a.body = body; a.priority = priority; a.key = key; a.app_id = 3; a.timestamp = 7; a.sender = 9; a.recver = 101;
+    a.request = true; a.push = true; a.compr = {0.5f, 2.f};
+    if (with_control) { a.control.cmd = Control::ADD_NODE; Node n; n.hostname = "10.0.0.1"; n.port = 1234; n.id = 100; n.rank_hint = 2; a.control.node.push_back(n); }
+    std::vector<char> buf; PackMeta(a, &buf);
+    Meta b; UnpackMeta(buf.data(), buf.size(), &b);
+    return py::make_tuple(b.head, b.body, b.priority, b.key, b.app_id, b.timestamp, b.sender, b.recver, b.request, b.push, b.compr,
+                          b.control.cmd, b.control.node.empty() ? std::string() : b.control.node[0].hostname,
+                          b.control.node.empty() ? -1 : b.control.node[0].rank_hint, buf.size());
+  });
+  m.def("ts_pick_receiver", [](int requester, std::vector<int> idle, std::map<int, long> known, float max_greed, int trials) {
+    Environment::Get()->Set("MAX_GREED_RATE_TS", std::to_string(max_greed));
+    TSScheduler s(nullptr, 8, kLocal);
+    for (auto& kv : known) s.Record(requester, kv.first, kv.second);
+    std::vector<int> picks;
+    for (int i = 0; i < trials; ++i) picks.push_back(s.PickReceiver(requester, idle));
+    return picks;
+  }, py::arg("requester"), py::arg("idle"), py::arg("known"), py::arg("max_greed"), py::arg("trials") = 1);
+  m.def("half_roundtrip", [](float f) { return py::make_tuple(HalfToFloat(FloatToHalf(f)), BF16ToFloat(FloatToBF16(f)), FloatToHalf(f)); });
+
+  // ---------------------------------------------------------------------------------------------- CPU compression codecs
+  py::class_<GradientCompression>(m, "GradientCompression")
+      .def(py::init<>())
+      .def("set_params", &GradientCompression::SetParams)
+      .def("encode_params", &GradientCompression::EncodeParams)
+      .def("decode_params", &GradientCompression::DecodeParams)
+      .def("quantize_2bit", [](GradientCompression& g, py::array_t<float, py::array::c_style> grad, py::array_t<float, py::array::c_style> residual) {
+        const int64_t n = grad.size();
+        py::array_t<uint32_t> out(GradientCompression::CompressedSize2Bit(n));
+        g.Quantize2Bit(grad.data(), residual.mutable_data(), out.mutable_data(), n);
+        return out;
+      })
+      .def("dequantize_2bit", [](GradientCompression& g, py::array_t<uint32_t, py::array::c_style> in, int64_t n) {
+        py::array_t<float> out(n);
+        g.Dequantize2Bit(in.data(), out.mutable_data(), n);
+        return out;
+      })
+      .def("bsc_compress", [](GradientCompression& g, py::array_t<float, py::array::c_style> grad, py::array_t<float, py::array::c_style> u,
+                              py::array_t<float, py::array::c_style> v) {
+        int k, s, ks; GradientCompression::BSCSizes(grad.size(), g.threshold(), &k, &s, &ks);
+        py::array_t<float> out(2 * k);
+        g.BSCompress(grad.data(), u.mutable_data(), v.mutable_data(), out.mutable_data(), grad.size());
+        return out;
+      })
+      .def("bsc_pull_compress", [](GradientCompression& g, py::array_t<float, py::array::c_style> dense, int mult) {
+        py::array_t<float> out(GradientCompression::BSCPullSize(dense.size(), g.threshold(), mult));
+        g.BSCPullCompress(dense.data(), out.mutable_data(), dense.size(), mult);
+        return out;
+      })
+      .def_static("bsc_decompress", [](py::array_t<float, py::array::c_style> z, int64_t n) {
+        py::array_t<float> out(n);
+        GradientCompression::BSCDecompress(z.data(), z.size(), out.mutable_data(), n);
+        return out;
+      });
+
+  // ---------------------------------------------------------------------------------------------- KVStoreDist
+  py::class_<KVStoreDist>(m, "KVStoreDist")
+      .def(py::init<const std::string&>(), py::call_guard<py::gil_scoped_release>())
+      .def("shutdown", &KVStoreDist::Shutdown, py::call_guard<py::gil_scoped_release>())
+      .def_property_readonly("rank", &KVStoreDist::rank)
+      .def_property_readonly("num_workers", &KVStoreDist::num_workers)
+      .def_property_readonly("num_all_workers", &KVStoreDist::num_all_workers)
+      .def_property_readonly("is_master_worker", &KVStoreDist::is_master_worker)
+      .def("num_dead_node", &KVStoreDist::num_dead_node)
+      .def("init", [](KVStoreDist& kv, int key, uintptr_t ptr, size_t elems, int dtype) { kv.Init(key, reinterpret_cast<const void*>(ptr), elems, dtype); },
+           py::call_guard<py::gil_scoped_release>())
+      .def("push", [](KVStoreDist& kv, int key, uintptr_t ptr, size_t elems, int dtype, int priority) {
+        return kv.Push(key, reinterpret_cast<const void*>(ptr), elems, dtype, priority);
+      }, py::call_guard<py::gil_scoped_release>())
+      .def("pull", [](KVStoreDist& kv, int key, uintptr_t ptr, size_t elems, int dtype, int priority) {
+        return kv.Pull(key, reinterpret_cast<void*>(ptr), elems, dtype, priority);
+      }, py::call_guard<py::gil_scoped_release>())
+      .def("wait", &KVStoreDist::Wait, py::call_guard<py::gil_scoped_release>())
+      .def("wait_all", &KVStoreDist::WaitAll, py::call_guard<py::gil_scoped_release>())
+      .def("set_gradient_compression", &KVStoreDist::SetGradientCompression, py::call_guard<py::gil_scoped_release>())
+      .def("barrier", &KVStoreDist::Barrier, py::call_guard<py::gil_scoped_release>())
+      .def("send_command_to_servers", &KVStoreDist::SendCommandToServers, py::call_guard<py::gil_scoped_release>())
+      .def("send_bytes", &KVStoreDist::send_bytes)
+      .def("recv_bytes", &KVStoreDist::recv_bytes)
+      .def("run_server", [](KVStoreDist& kv, py::object controller, py::object updater) {
+        // python objects are held through shared_ptrs whose deleter re-acquires the GIL: the std::functions are copied / destroyed
+        // by server threads that do not hold it
+        auto hold = [](py::object o) {
+          return std::shared_ptr<py::object>(new py::object(std::move(o)), [](py::object* p) { py::gil_scoped_acquire g; delete p; });
+        };
+        KVStoreDistServer::Controller c = nullptr;
+        KVStoreDistServer::Updater u = nullptr;
+        if (!controller.is_none()) {
+          auto ch = hold(controller);
+          c = [ch](int head, const std::string& body) { py::gil_scoped_acquire g; (*ch)(head, py::bytes(body)); };
+        }
+        if (!updater.is_none()) {
+          auto uh = hold(updater);
+          u = [uh](int key, const float* grad, float* weight, size_t n) {
+            py::gil_scoped_acquire g;
+            (*uh)(key, WrapFloat(const_cast<float*>(grad), n), WrapFloat(weight, n));
+          };
+        }
+        controller = py::none(); updater = py::none();
+        py::gil_scoped_release rel;
+        kv.RunServer(c, u);
+        c = nullptr; u = nullptr;
+      });
+
+  // ---------------------------------------------------------------------------------------------- profiler
+  m.def("profiler_set_config", [](const std::string& fn, bool agg, bool cont, double period) { Profiler::Get()->SetConfig(fn, agg, cont, period); });
+  m.def("profiler_set_state", [](bool run) { Profiler::Get()->SetState(run); });
+  m.def("profiler_pause", [](bool p) { Profiler::Get()->Pause(p); });
+  m.def("profiler_add_event", [](const std::string& name, const std::string& cat, const std::string& ph, double ts, double dur, int pid, int tid, double value) {
+    Profiler::Get()->Add(name, cat, ph.empty() ? 'X' : ph[0], ts, dur, pid, tid, value);
+  });
+  m.def("profiler_now_us", [] { return Profiler::NowUs(); });
+  m.def("profiler_dump", [](bool finished) { Profiler::Get()->Dump(finished); });
+  m.def("profiler_aggregate", [] { return Profiler::Get()->AggregateTable(); });
+  m.def("profiler_clear", [] { Profiler::Get()->Clear(); });
+  m.def("profiler_size", [] { return Profiler::Get()->size(); });
+
+  // ---------------------------------------------------------------------------------------------- .params IO, data IO, engine
+  gxrt::BindParamsIO(m);
+  gxrt::BindIO(m);
+  gxrt::BindEngine(m);
+}

@@ -134,13 +134,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base_offset | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (required for MN-major tf32 operands), 4 = 64B, 6 = 32B, 0 = none
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;
-  d |= 2ull << 61;
+  d |= static_cast<uint64_t>(layout_type & 7u) << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format[4,6) a_format[7,10) b_format[10,13) a_major[15] b_major[16]

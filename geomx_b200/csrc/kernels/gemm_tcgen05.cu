@@ -138,10 +138,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t sB = sA + A_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // K-major SW128: rows 128 B apart, 8-row groups 1024 B apart (SBO); advance 32 B per K step inside the atom.
-          // MN-major SW128: 32-wide MN atoms LBO apart (one TMA box each), 8 K-rows = 1024 B per K step.
-          const uint64_t da = A_MN ? umma_desc_sw128(sA + k * 1024, MN_BOX_BYTES, 1024) : umma_desc_sw128(sA + k * UMMA_K * 4, 16, 1024);
-          const uint64_t db = B_MN ? umma_desc_sw128(sB + k * 1024, MN_BOX_BYTES, 1024) : umma_desc_sw128(sB + k * UMMA_K * 4, 16, 1024);
+          // K-major : SWIZZLE_128B, rows 128 B apart, 8-row groups 1024 B apart (SBO); advance 32 B per K step inside the atom.
+          // MN-major: tf32 operands must use SWIZZLE_128B_BASE32B ("128B swizzle, 32B atomicity", Swizzle<2,5,2>): 32-wide MN atoms
+          //           LBO apart (one TMA box each), K in groups of 4 rows = 512 B (SBO); 8 K-rows = 1024 B per MMA K step.
+          const uint64_t da = A_MN ? umma_desc(sA + k * 1024, MN_BOX_BYTES, 512, 1) : umma_desc(sA + k * UMMA_K * 4, 16, 1024, 2);
+          const uint64_t db = B_MN ? umma_desc(sB + k * 1024, MN_BOX_BYTES, 512, 1) : umma_desc(sB + k * UMMA_K * 4, 16, 1024, 2);
           umma_tf32(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -238,16 +239,20 @@ static PFN_encodeTiled get_encode() {
 }
 
 // inner = contiguous dimension (elements), outer = strided dimension, ld = elements between outer rows
-static int make_tmap(CUtensorMap* tm, const float* base, long long inner, long long outer, long long ld, int box_inner, int box_outer) {
+static int make_tmap(CUtensorMap* tm, const float* base, long long inner, long long outer, long long ld, int box_inner, int box_outer, bool mn_major) {
   PFN_encodeTiled enc = get_encode();
   if (enc == nullptr) return -2;
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
+  // driver entry points need a current context on the calling thread (autograd worker threads may never have made a runtime call)
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -3;
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(1000 + (int)r);
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -290,11 +295,11 @@ GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B,
   else block_n = 128;
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
-  else rc = make_tmap(&ta, A, M, K, lda, 32, BLOCK_K);
+  if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, false);
+  else rc = make_tmap(&ta, A, M, K, lda, 32, BLOCK_K, true);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K, block_n);
-  else rc = make_tmap(&tb, B, N, K, ldb, 32, BLOCK_K);
+  if (!b_mn) rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K, block_n, false);
+  else rc = make_tmap(&tb, B, N, K, ldb, 32, BLOCK_K, true);
   if (rc) return rc;
   const int num_kb = (int)ceil_div(K, BLOCK_K);
   if (split_k < 1) split_k = 1;

@@ -8,7 +8,7 @@ from ..base import MXNetError
 
 def create_dist(name):
     fabric = os.environ.get("GEOMX_FABRIC", "auto").lower()
-    has_ps_env = "DMLC_PS_ROOT_URI" in os.environ or "DMLC_ROLE" in os.environ
+    has_ps_env = any(k in os.environ for k in ("DMLC_PS_ROOT_URI", "DMLC_ROLE", "DMLC_ROLE_GLOBAL", "DMLC_PS_GLOBAL_ROOT_URI"))
     if fabric in ("symm", "nccl") or (fabric == "auto" and not has_ps_env and "RANK" in os.environ):
         from ..parallel.fabric_kvstore import KVStoreFabric
         return KVStoreFabric(name)

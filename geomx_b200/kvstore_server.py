@@ -41,10 +41,8 @@ class KVStoreServer:
                 logging.basicConfig(level=logging.DEBUG, format=head)
                 self.init_logging = True
             if cmd_id == 0:
-                try:
-                    optimizer = pickle.loads(cmd_body)
-                except Exception:
-                    raise
+                body = cmd_body if isinstance(cmd_body, bytes) else cmd_body.encode("latin1")
+                optimizer = pickle.loads(body)
                 self.kvstore.set_optimizer(optimizer)
             else:
                 print("server %d, unknown command (%d, %s)" % (self.kvstore.rank, cmd_id, cmd_body))

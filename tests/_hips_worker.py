@@ -1,0 +1,57 @@
+"""Worker body for the multi-process HiPS tests (CPU).  Prints RESULT lines parsed by the test."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("GEOMX_SYNTHETIC_SIZE", "256")
+import numpy as np  # noqa: E402
+
+import geomx_b200 as mx  # noqa: E402
+
+mode = os.environ.get("TEST_MODE", "sgd")
+steps = int(os.environ.get("TEST_STEPS", "3"))
+gid = int(os.environ.get("TEST_WORKER_GID", "0"))       # global worker index (for deterministic gradients)
+shapes = [(4, 5), (7,), (300,), (3, 2)] if mode != "big" else [(4, 5), (2500,)]
+
+kv = mx.kv.create(os.environ.get("TEST_KV", "dist_sync"))
+master = kv.is_master_worker
+if master or (os.environ.get("TEST_STANDALONE") == "1" and kv.rank == 0):
+    if mode in ("sgd", "big", "p3", "2bit", "async", "fp16"):
+        kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, multi_precision=(mode == "fp16")))
+    elif mode == "adam_py":
+        os.environ["GEOMX_PY_UPDATER"] = "1"
+        kv.set_optimizer(mx.optimizer.Adam(learning_rate=0.01))
+    if mode == "bsc":
+        kv.set_gradient_compression({"type": "bsc", "threshold": 0.1})
+if mode == "2bit" and not master:
+    kv.set_gradient_compression({"type": "2bit", "threshold": 0.5})
+time.sleep(0.5)
+dt = "float16" if mode == "fp16" else "float32"
+params = [mx.nd.array(np.full(s, 1.0 + i, dtype=np.float32)).astype(dt) for i, s in enumerate(shapes)]
+for i, p in enumerate(params):
+    kv.init(i, p)
+    if master:
+        continue
+    kv.pull(i, p)
+mx.nd.waitall()
+if master:
+    print("RESULT master done", flush=True)
+    kv.close()
+    sys.exit(0)
+out = {"rank": kv.rank, "num_workers": kv.num_workers, "num_all_workers": kv.num_all_workers, "vals": []}
+for step in range(steps):
+    for i, p in enumerate(params):
+        if mode == "hfa":
+            local = mx.nd.array(np.full(shapes[i], float(step + 1) * (gid + 1), dtype=np.float32))
+            kv.push(i, local / kv.num_workers, priority=-i)
+        else:
+            g = mx.nd.array(np.full(shapes[i], 0.5 * (gid + 1) * (1 if mode != "2bit" else 2), dtype=np.float32)).astype(dt)
+            kv.push(i, g, priority=-i)
+        kv.pull(i, p, priority=-i)
+    mx.nd.waitall()
+    out["vals"].append([float(p.astype("float32").asnumpy().reshape(-1)[0]) for p in params])
+    out.setdefault("last", [float(p.astype("float32").asnumpy().reshape(-1)[-1]) for p in params])
+print("RESULT " + json.dumps(out), flush=True)
+kv.close()

@@ -1,0 +1,169 @@
+"""Multi-process HiPS on one box over the native TCP transport (CPU; the reference fakes multi-node the same way:
+3rdparty/ps-lite/tests/local.sh:17-35 and scripts/cpu/run_vanilla_hips.sh).  Covers BASELINE config 1 (1 local PS + 2 workers) and the
+full two-tier topology (global scheduler + global server + master worker + central scheduler + 2 x (scheduler, server, 2 workers))."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from geomx_b200 import runtime
+
+pytestmark = pytest.mark.skipif(not runtime.available(), reason="native runtime not built")
+HERE = os.path.dirname(os.path.abspath(__file__))
+WORKER = os.path.join(HERE, "_hips_worker.py")
+BOOT = "import sys; sys.path.insert(0, %r); import geomx_b200" % os.path.dirname(HERE)
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def spawn(env, worker=False, extra=None):
+    e = dict(os.environ); e.update({k: str(v) for k, v in env.items()}); e.update(extra or {})
+    e.pop("RANK", None); e.pop("WORLD_SIZE", None)
+    cmd = [sys.executable, WORKER] if worker else [sys.executable, "-c", BOOT]
+    return subprocess.Popen(cmd, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+
+def collect(procs, timeout=120):
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise AssertionError("timeout; partial output:\n" + "\n".join((q.stdout.read() if q.stdout else "") for q in procs))
+        outs.append(o)
+        assert p.returncode == 0, o
+    return outs
+
+
+def results(outs):
+    res = []
+    for o in outs:
+        for line in o.splitlines():
+            if line.startswith("RESULT {"):
+                res.append(json.loads(line[7:]))
+    return res
+
+
+def launch_single_tier(extra, workers=2):
+    port = free_port()
+    base = {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": port, "DMLC_NUM_SERVER": 1, "DMLC_NUM_WORKER": workers, "DMLC_NUM_ALL_WORKER": workers,
+            "TEST_STANDALONE": 1}
+    procs = [spawn(dict(base, DMLC_ROLE="scheduler"), extra=extra), spawn(dict(base, DMLC_ROLE="server"), extra=extra)]
+    ws = [spawn(dict(base, DMLC_ROLE="worker", TEST_WORKER_GID=i), worker=True, extra=extra) for i in range(workers)]
+    outs = collect(procs + ws)
+    return results(outs)
+
+
+def launch_hips(extra, parties=2, wpp=2, global_servers=1):
+    gport = free_port()
+    g = {"DMLC_PS_GLOBAL_ROOT_URI": "127.0.0.1", "DMLC_PS_GLOBAL_ROOT_PORT": gport, "DMLC_NUM_GLOBAL_SERVER": global_servers, "DMLC_NUM_GLOBAL_WORKER": parties}
+    allw = parties * wpp
+    procs = [spawn(dict(g, DMLC_ROLE_GLOBAL="global_scheduler"), extra=extra)]
+    cport = free_port()
+    central = {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": cport, "DMLC_NUM_SERVER": global_servers, "DMLC_NUM_WORKER": 1, "DMLC_NUM_ALL_WORKER": allw}
+    for _ in range(global_servers):
+        procs.append(spawn(dict(g, **central, DMLC_ROLE_GLOBAL="global_server", DMLC_ROLE="server", DMLC_ENABLE_CENTRAL_WORKER=0), extra=extra))
+    procs.append(spawn(dict(central, DMLC_ROLE="scheduler"), extra=extra))
+    ws = [spawn(dict(central, DMLC_ROLE="worker", DMLC_ROLE_MASTER_WORKER=1), worker=True, extra=extra)]
+    gid = 0
+    for _ in range(parties):
+        port = free_port()
+        party = {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": port, "DMLC_NUM_SERVER": 1, "DMLC_NUM_WORKER": wpp, "DMLC_NUM_ALL_WORKER": allw}
+        procs.append(spawn(dict(party, DMLC_ROLE="scheduler"), extra=extra))
+        procs.append(spawn(dict(g, **party, DMLC_ROLE="server"), extra=extra))
+        for _ in range(wpp):
+            ws.append(spawn(dict(party, DMLC_ROLE="worker", TEST_WORKER_GID=gid), worker=True, extra=extra)); gid += 1
+    outs = collect(procs + ws, timeout=180)
+    return results(outs)
+
+
+def test_single_tier_dist_sync_sgd():
+    """BASELINE config 1: 1 local PS + 2 workers.  w_t = w_0 - t * lr * sum_workers(grad)."""
+    res = launch_single_tier({"TEST_MODE": "sgd"})
+    assert len(res) == 2
+    gsum = 0.5 * 1 + 0.5 * 2
+    for r in res:
+        assert r["num_workers"] == 2
+        for t, vals in enumerate(r["vals"]):
+            for i, v in enumerate(vals):
+                assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-5
+
+
+def test_hips_two_tier_fsa():
+    """2 parties x 2 workers, global server runs SGD: every worker sees w_0 - t*lr*sum_{4 workers} grad."""
+    res = launch_hips({"TEST_MODE": "sgd"})
+    assert len(res) == 4
+    gsum = 0.5 * (1 + 2 + 3 + 4)
+    for r in res:
+        assert r["num_all_workers"] == 4 and r["num_workers"] == 2
+        for t, vals in enumerate(r["vals"]):
+            for i, v in enumerate(vals):
+                assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-4, (t, i, v)
+
+
+def test_hips_multigps_bigarray_python_updater():
+    """MultiGPS: 2 global servers, big array partitioned across them; foreign (pickled Python) Adam executed through the Executor."""
+    res = launch_hips({"TEST_MODE": "adam_py", "MXNET_KVSTORE_BIGARRAY_BOUND": "100", "TEST_STEPS": "2"}, global_servers=2)
+    assert len(res) == 4
+    # first Adam step moves every weight by exactly lr (|m/sqrt(v)| = 1), second by ~lr again
+    for r in res:
+        for i, v in enumerate(r["vals"][0]):
+            assert abs(v - ((1.0 + i) - 0.01)) < 1e-4
+        for i, v in enumerate(r["vals"][1]):
+            assert abs(v - ((1.0 + i) - 0.02)) < 2e-4
+        assert abs(r["last"][2] - r["vals"][0][2]) < 1e-6      # both halves of the partitioned 300-element key updated
+
+
+def test_hips_bsc_and_hfa():
+    res = launch_hips({"TEST_MODE": "bsc", "MXNET_KVSTORE_SIZE_LOWER_BOUND": "100", "TEST_STEPS": "2"})
+    assert len(res) == 4
+    # no optimizer on the server: pulls return the aggregated (sparsified above the size bound) gradients
+    gsum = 0.5 * (1 + 2 + 3 + 4)
+    for r in res:
+        assert abs(r["vals"][0][0] - gsum) < 1e-5 and abs(r["vals"][0][1] - gsum) < 1e-5      # small keys: dense path
+    res = launch_hips({"TEST_MODE": "hfa", "MXNET_KVSTORE_USE_HFA": "1", "MXNET_KVSTORE_HFA_K1": "1", "MXNET_KVSTORE_HFA_K2": "2", "TEST_STEPS": "2"})
+    assert len(res) == 4
+    by_rank = sorted(res, key=lambda r: r["vals"][0][0])
+    # step 1 (local sync only): each party sees its own average  (1*(g0+1)+1*(g1+1))/2 ; step 2 (global): milestone + mean of party deltas
+    firsts = sorted(r["vals"][0][0] for r in res)
+    assert firsts == pytest.approx([1.5, 1.5, 3.5, 3.5])
+    w0 = 1.0
+    expect2 = w0 + ((2 * 1.5 - w0) + (2 * 3.5 - w0)) / 2
+    for r in res:
+        assert r["vals"][1][0] == pytest.approx(expect2, abs=1e-4)
+
+
+def test_features_p3_2bit_fp16_async():
+    res = launch_hips({"TEST_MODE": "p3", "ENABLE_P3": "1", "TEST_STEPS": "2"})
+    gsum = 0.5 * (1 + 2 + 3 + 4)
+    for r in res:
+        assert abs(r["vals"][1][0] - (1.0 - 0.1 * gsum * 2)) < 1e-4
+    res = launch_single_tier({"TEST_MODE": "2bit", "TEST_STEPS": "1"})
+    for r in res:    # grads 1.0 and 2.0 with threshold 0.5 -> each worker contributes +0.5 -> w = 1 - 0.1*(0.5+0.5)
+        assert abs(r["vals"][0][0] - (1.0 - 0.1 * 1.0)) < 1e-5
+    res = launch_single_tier({"TEST_MODE": "fp16", "TEST_STEPS": "2"})
+    for r in res:
+        assert abs(r["vals"][1][0] - (1.0 - 0.1 * 1.5 * 2)) < 5e-3
+    res = launch_hips({"TEST_MODE": "async", "TEST_KV": "dist_async", "TEST_STEPS": "2"})
+    assert len(res) == 4
+    finals = [r["vals"][1][0] for r in res]
+    # MixedSync: every party's aggregate is applied once per step, in arrival order: after 2 steps all 4 updates of both steps landed
+    assert min(finals) >= 1.0 - 0.1 * gsum * 2 - 1e-4 and max(finals) <= 1.0
+
+
+def test_dgt_priority_channels_and_resend():
+    res = launch_hips({"TEST_MODE": "big", "ENABLE_DGT": "2", "DGT_BLOCK_SIZE": "1024", "DMLC_K": "0.5", "TEST_STEPS": "2"})
+    gsum = 0.5 * (1 + 2 + 3 + 4)
+    for r in res:
+        assert abs(r["vals"][1][1] - (2.0 - 0.1 * gsum * 2)) < 1e-4 and abs(r["last"][1] - r["vals"][0][1]) < 1e-6
+    res = launch_single_tier({"TEST_MODE": "sgd", "PS_RESEND": "1", "PS_RESEND_TIMEOUT": "200", "PS_DROP_MSG": "10", "TEST_STEPS": "2"})
+    for r in res:
+        assert abs(r["vals"][1][0] - (1.0 - 0.1 * 1.5 * 2)) < 1e-5
