@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(512) bn_fwd_kernel(const float* __restrict__ x
                                                       float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ y,
                                                       float* __restrict__ save_mean, float* __restrict__ save_invstd, int N, int C, int HW,
                                                       int training, float momentum, float eps) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   __shared__ float red[16];
   const int c = blockIdx.x;
   const long long cnt = (long long)N * HW;
@@ -57,6 +59,8 @@ __global__ void __launch_bounds__(512) bn_fwd_kernel(const float* __restrict__ x
 __global__ void __launch_bounds__(512) bn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                                                       const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
                                                       float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C, int HW) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   __shared__ float red[16];
   const int c = blockIdx.x;
   const long long cnt = (long long)N * HW;
@@ -89,11 +93,11 @@ using namespace gx;
 
 GX_API int gx_bn_fwd(const float* x, const float* gamma, const float* beta, float* rm, float* rv, float* y, float* save_mean, float* save_invstd,
                      int N, int C, int HW, int training, float momentum, float eps, cudaStream_t s) {
-  bn_fwd_kernel<<<C, 512, 0, s>>>(x, gamma, beta, rm, rv, y, save_mean, save_invstd, N, C, HW, training, momentum, eps);
+  launch_pdl(bn_fwd_kernel, dim3(C), dim3(512), 0, s, x, gamma, beta, rm, rv, y, save_mean, save_invstd, N, C, HW, training, momentum, eps);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_bn_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd, float* dx, float* dgamma,
                      float* dbeta, int N, int C, int HW, cudaStream_t s) {
-  bn_bwd_kernel<<<C, 512, 0, s>>>(x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, N, C, HW);
+  launch_pdl(bn_bwd_kernel, dim3(C), dim3(512), 0, s, x, dy, gamma, save_mean, save_invstd, dx, dgamma, dbeta, N, C, HW);
   return GX_CHECK_LAUNCH();
 }

@@ -11,7 +11,34 @@
 #define GX_API extern "C" __attribute__((visibility("default")))
 #define GX_CHECK_LAUNCH() (int)cudaGetLastError()
 
+#include <cstdlib>
+#include <utility>
+
 namespace gx {
+
+// ------------------------------------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel of this library begins with pdl_wait() (griddepcontrol.wait: block until the preceding grid in the stream has completed and
+// its memory is visible) and pdl_launch() (griddepcontrol.launch_dependents: let the NEXT grid start its prologue — block scheduling,
+// smem carve-up, barrier init, TMEM alloc, tensormap prefetch — while this one is still running).  Launches go through launch_pdl(), which
+// sets cudaLaunchAttributeProgrammaticStreamSerialization; in a CUDA graph the edges become programmatic dependencies.  GEOMX_PDL=0 disables.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GEOMX_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // ------------------------------------------------------------------------------------------------ misc
 __host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

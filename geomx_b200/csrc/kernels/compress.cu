@@ -18,6 +18,8 @@ namespace gx {
 // ------------------------------------------------------------------------------------------------ 2-bit
 __global__ void __launch_bounds__(256) quantize_2bit_kernel(const float* __restrict__ grad, float* __restrict__ residual, uint32_t* __restrict__ out,
                                                              long long n, float thr) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const long long words = (n + 15) / 16;
   for (long long wi = blockIdx.x * (long long)blockDim.x + threadIdx.x; wi < words; wi += (long long)gridDim.x * blockDim.x) {
     uint32_t word = 0;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256) quantize_2bit_kernel(const float* __restr
 }
 __global__ void __launch_bounds__(256) dequantize_2bit_kernel(const uint32_t* __restrict__ in, float* __restrict__ out, long long n, float thr,
                                                                int accumulate) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const uint32_t word = in[i >> 4];
     const int j = (int)(i & 15);
@@ -93,6 +97,8 @@ __device__ __forceinline__ int block_exclusive_scan(int val, int* total, int* sm
 // mode 1: BSCPullCompress (keep non-zeros in index order)
 template <int MODE>
 __global__ void __launch_bounds__(BSC_THREADS, 1) bsc_kernel(const BscSeg* __restrict__ segs, float momentum) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const BscSeg sg = segs[blockIdx.x];
   __shared__ int s_warp[33];
   __shared__ float s_boundary;
@@ -169,6 +175,8 @@ __global__ void __launch_bounds__(BSC_THREADS, 1) bsc_kernel(const BscSeg* __res
 }
 
 __global__ void __launch_bounds__(256) bsc_decompress_kernel(const float* __restrict__ zipped, float* __restrict__ out, int k) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
     const float fi = zipped[k + j];
     if (fi >= 0.f) atomicAdd(out + (long long)fi, zipped[j]);
@@ -178,6 +186,8 @@ __global__ void __launch_bounds__(256) bsc_decompress_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------ block-scaled fp8 (e4m3, 128 values / scale)
 __global__ void __launch_bounds__(128) fp8_block_quantize_kernel(const float* __restrict__ x, float* __restrict__ residual, uint8_t* __restrict__ q,
                                                                   float* __restrict__ scale, long long n) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const long long blk = blockIdx.x;
   const long long i = blk * 128 + threadIdx.x;
   float v = 0.f;
@@ -198,6 +208,8 @@ __global__ void __launch_bounds__(128) fp8_block_quantize_kernel(const float* __
 }
 __global__ void __launch_bounds__(256) fp8_block_dequantize_kernel(const uint8_t* __restrict__ q, const float* __restrict__ scale, float* __restrict__ out,
                                                                     long long n, int accumulate) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)q[i], __NV_E4M3))) * scale[i >> 7];
     out[i] = accumulate ? out[i] + v : v;
@@ -208,6 +220,8 @@ __global__ void __launch_bounds__(256) fp8_block_dequantize_kernel(const uint8_t
 // contrib[b] = alpha * contrib[b] + (1-alpha) * mean(|g| over block b)     (kv_app.h:853-876)
 __global__ void __launch_bounds__(256) dgt_contrib_kernel(const float* __restrict__ g, float* __restrict__ contrib, long long n, int block_elems,
                                                            float alpha, int first) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const long long b = blockIdx.x;
   const long long lo = b * block_elems, hi = lo + block_elems < n ? lo + block_elems : n;
   float acc = 0.f;
@@ -234,11 +248,11 @@ static inline int cgrid(long long n) {
 using namespace gx;
 
 GX_API int gx_quantize_2bit(const float* grad, float* residual, void* out, long long n, float thr, cudaStream_t s) {
-  quantize_2bit_kernel<<<cgrid((n + 15) / 16), 256, 0, s>>>(grad, residual, reinterpret_cast<uint32_t*>(out), n, thr);
+  launch_pdl(quantize_2bit_kernel, dim3(cgrid((n + 15) / 16)), dim3(256), 0, s, grad, residual, reinterpret_cast<uint32_t*>(out), n, thr);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_dequantize_2bit(const void* in, float* out, long long n, float thr, int accumulate, cudaStream_t s) {
-  dequantize_2bit_kernel<<<cgrid(n), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(in), out, n, thr, accumulate);
+  launch_pdl(dequantize_2bit_kernel, dim3(cgrid(n)), dim3(256), 0, s, reinterpret_cast<const uint32_t*>(in), out, n, thr, accumulate);
   return GX_CHECK_LAUNCH();
 }
 // segs: device array of BscSeg (see struct above), one CTA each.  max_sample: largest `sample` among them (smem sizing).
@@ -247,30 +261,30 @@ GX_API int gx_bsc_compress_batch(const void* segs, int num_segs, int max_sample,
   const size_t smem = (size_t)max_sample * sizeof(float);
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(bsc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024); set = true; }
-  bsc_kernel<0><<<num_segs, BSC_THREADS, smem, s>>>(reinterpret_cast<const BscSeg*>(segs), momentum);
+  launch_pdl(bsc_kernel<0>, dim3(num_segs), dim3(BSC_THREADS), smem, s, reinterpret_cast<const BscSeg*>(segs), momentum);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_bsc_pull_compress_batch(const void* segs, int num_segs, cudaStream_t s) {
-  bsc_kernel<1><<<num_segs, BSC_THREADS, 0, s>>>(reinterpret_cast<const BscSeg*>(segs), 0.f);
+  launch_pdl(bsc_kernel<1>, dim3(num_segs), dim3(BSC_THREADS), 0, s, reinterpret_cast<const BscSeg*>(segs), 0.f);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_bsc_decompress(const float* zipped, float* out, long long n, int k, int accumulate, cudaStream_t s) {
   if (!accumulate) cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), s);
-  if (k > 0) bsc_decompress_kernel<<<cgrid(k), 256, 0, s>>>(zipped, out, k);
+  if (k > 0) launch_pdl(bsc_decompress_kernel, dim3(cgrid(k)), dim3(256), 0, s, zipped, out, k);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_fp8_block_quantize(const float* x, float* residual, void* q, float* scale, long long n, cudaStream_t s) {
   const long long nb = (n + 127) / 128;
-  fp8_block_quantize_kernel<<<(unsigned)nb, 128, 0, s>>>(x, residual, reinterpret_cast<uint8_t*>(q), scale, n);
+  launch_pdl(fp8_block_quantize_kernel, dim3((unsigned)nb), dim3(128), 0, s, x, residual, reinterpret_cast<uint8_t*>(q), scale, n);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_fp8_block_dequantize(const void* q, const float* scale, float* out, long long n, int accumulate, cudaStream_t s) {
-  fp8_block_dequantize_kernel<<<cgrid(n), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(q), scale, out, n, accumulate);
+  launch_pdl(fp8_block_dequantize_kernel, dim3(cgrid(n)), dim3(256), 0, s, reinterpret_cast<const uint8_t*>(q), scale, out, n, accumulate);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_dgt_contrib(const float* g, float* contrib, long long n, int block_elems, float alpha, int first, cudaStream_t s) {
   const long long nb = (n + block_elems - 1) / block_elems;
-  dgt_contrib_kernel<<<(unsigned)nb, 256, 0, s>>>(g, contrib, n, block_elems, alpha, first);
+  launch_pdl(dgt_contrib_kernel, dim3((unsigned)nb), dim3(256), 0, s, g, contrib, n, block_elems, alpha, first);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_bsc_seg_size() { return (int)sizeof(BscSeg); }

@@ -14,6 +14,8 @@ namespace gx {
 // col[(n,oh,ow)][k], k = (c*KH + kh)*KW + kw, row stride ldc (>= K, multiple of 4; pad columns are zeroed)
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int C, int H, int W,
                                                       int KH, int KW, int OH, int OW, int sh, int sw, int ph, int pw, int K, int ldc) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const long long total = (long long)N * OH * OW * ldc;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % ldc);
@@ -32,6 +34,8 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
 // gather-form col2im (no atomics): dx[n,c,h,w] = sum over (kh,kw) of dcol[(n,oh,ow)][(c,kh,kw)] with oh*sh-ph+kh == h
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int N, int C, int H, int W,
                                                       int KH, int KW, int OH, int OW, int sh, int sw, int ph, int pw, int ldc) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const long long total = (long long)N * C * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int w = (int)(i % W), h = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % C), n = (int)(i / ((long long)W * H * C));
@@ -53,9 +57,62 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
   }
 }
 
+// Shared-memory tiled variants for stride-1 / pad-0 convolutions (the demo network): one CTA per (image, group of CG channels).
+// im2col: the CG input planes are staged in smem once, the CTA then writes its [OH*OW][CG*KH*KW] slab of `col` with fully coalesced stores.
+template <int CG>
+__global__ void __launch_bounds__(256) im2col_tiled_kernel(const float* __restrict__ x, float* __restrict__ col, int C, int H, int W, int KH, int KW,
+                                                            int OH, int OW, int ldc) {
+  gx::pdl_wait();
+  gx::pdl_launch();
+  extern __shared__ float sm[];
+  const int n = blockIdx.x, c0 = blockIdx.y * CG;
+  const int cg = min(CG, C - c0);
+  for (int i = threadIdx.x; i < cg * H * W; i += blockDim.x) sm[i] = x[((long long)n * C + c0) * H * W + i];
+  __syncthreads();
+  const int KK = KH * KW, span = cg * KK;
+  for (int i = threadIdx.x; i < OH * OW * span; i += blockDim.x) {
+    const int kk = i % span, row = i / span;
+    const int cl = kk / KK, t = kk - cl * KK, kh = t / KW, kw = t - kh * KW;
+    const int oh = row / OW, ow = row - oh * OW;
+    col[((long long)n * OH * OW + row) * ldc + c0 * KK + kk] = sm[cl * H * W + (oh + kh) * W + ow + kw];
+  }
+}
+// col2im: the [OH*OW][CG*KH*KW] slab of dcol is staged in smem (coalesced), every input-gradient pixel then gathers its <= KH*KW taps from smem.
+template <int CG>
+__global__ void __launch_bounds__(256) col2im_tiled_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int C, int H, int W, int KH, int KW,
+                                                            int OH, int OW, int ldc) {
+  gx::pdl_wait();
+  gx::pdl_launch();
+  extern __shared__ float sm[];
+  const int n = blockIdx.x, c0 = blockIdx.y * CG;
+  const int cg = min(CG, C - c0);
+  const int KK = KH * KW, span = cg * KK;
+  for (int i = threadIdx.x; i < OH * OW * span; i += blockDim.x) {
+    const int kk = i % span, row = i / span;
+    sm[row * span + kk] = dcol[((long long)n * OH * OW + row) * ldc + c0 * KK + kk];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cg * H * W; i += blockDim.x) {
+    const int w = i % W, h = (i / W) % H, cl = i / (W * H);
+    float acc = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int oh = h - kh;
+      if (oh < 0 || oh >= OH) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ow = w - kw;
+        if (ow < 0 || ow >= OW) continue;
+        acc += sm[(oh * OW + ow) * span + cl * KK + kh * KW + kw];
+      }
+    }
+    dx[((long long)n * C + c0) * H * W + i] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ transposes / reductions
 // y[(n,hw)][c] = x[n,c,hw]
 __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C, int HW) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -73,6 +130,8 @@ __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restri
 
 // out[c] (+)= sum_r x[r][c]   (bias gradients)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long R, int C, long long ld, int accumulate) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ty = threadIdx.x >> 5;
   __shared__ float part[8][33];
@@ -92,6 +151,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 
 // NCHW per-channel sum: out[c] = sum_{n,hw} x[n,c,hw]   (conv bias gradient on NCHW dy)
 __global__ void __launch_bounds__(256) chansum_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int C, int HW) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const int c = blockIdx.x;
   float acc = 0.f;
   for (long long i = threadIdx.x; i < (long long)N * HW; i += blockDim.x) {
@@ -111,6 +172,8 @@ __global__ void __launch_bounds__(256) chansum_nchw_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------------ ReLU
 __global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const long long i4 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
   if (i4 + 3 < n) {
     float4 v = *reinterpret_cast<const float4*>(x + i4);
@@ -121,6 +184,8 @@ __global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__
   }
 }
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const long long i4 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
   if (i4 + 3 < n) {
     const float4 a = *reinterpret_cast<const float4*>(y + i4);
@@ -135,6 +200,8 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------ 2x2/2 max-pool
 __global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx,
                                                               long long NC, int H, int W) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const int PH = H >> 1, PW = W >> 1;
   const long long total = NC * PH * PW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -153,6 +220,8 @@ __global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __rest
 }
 __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx,
                                                               long long NC, int H, int W) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const int PH = H >> 1, PW = W >> 1;
   const long long total = NC * PH * PW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -172,6 +241,8 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) pool_relu_bwd_rows_kernel(const float* __restrict__ dpooled, const float* __restrict__ pooled,
                                                                   const uint8_t* __restrict__ idx, float* __restrict__ dz_rows,
                                                                   float* __restrict__ dbias, int N, int C, int PH, int PW) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const int n = blockIdx.x / PH, ph = blockIdx.x % PH;
   const int W = 2 * PW, H = 2 * PH;
   for (int e = threadIdx.x; e < PW * C; e += blockDim.x) {
@@ -195,6 +266,8 @@ template <int CO_PER_BLOCK>
 __global__ void __launch_bounds__(256) conv_relu_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                                                   float* __restrict__ y, uint8_t* __restrict__ idx, int Cin, int H, int W, int Cout,
                                                                   int KH, int KW) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   extern __shared__ float sm[];
   const int K = Cin * KH * KW;
   float* sx = sm;                 // Cin*H*W
@@ -245,6 +318,8 @@ __global__ void __launch_bounds__(256) conv_relu_pool_wgrad_kernel(const float* 
                                                                     const float* __restrict__ pooled, const uint8_t* __restrict__ idx,
                                                                     float* __restrict__ dw, float* __restrict__ db, int N, int Cin, int H, int W,
                                                                     int Cout, int KH, int KW) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const int co = blockIdx.x;
   const int OH = H - KH + 1, OW = W - KW + 1, PH = OH >> 1, PW = OW >> 1;
   const int K = Cin * KH * KW;
@@ -302,47 +377,62 @@ GX_API int gx_im2col(const float* x, float* col, int N, int C, int H, int W, int
                      cudaStream_t s) {
   const int OH = (H + 2 * ph - KH) / sh + 1, OW = (W + 2 * pw - KW) / sw + 1;
   const long long total = (long long)N * OH * OW * ldc;
-  im2col_kernel<<<nblocks(total), 256, 0, s>>>(x, col, N, C, H, W, KH, KW, OH, OW, sh, sw, ph, pw, C * KH * KW, ldc);
+  constexpr int CG = 4;
+  if (sh == 1 && sw == 1 && ph == 0 && pw == 0 && ldc == C * KH * KW && (size_t)CG * H * W * sizeof(float) <= 96 * 1024) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(im2col_tiled_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
+    launch_pdl(im2col_tiled_kernel<CG>, dim3(N, (C + CG - 1) / CG), dim3(256), (size_t)CG * H * W * sizeof(float), s, x, col, C, H, W, KH, KW, OH, OW, ldc);
+    return GX_CHECK_LAUNCH();
+  }
+  launch_pdl(im2col_kernel, dim3(nblocks(total)), dim3(256), 0, s, x, col, N, C, H, W, KH, KW, OH, OW, sh, sw, ph, pw, C * KH * KW, ldc);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_col2im(const float* dcol, float* dx, int N, int C, int H, int W, int KH, int KW, int sh, int sw, int ph, int pw, int ldc,
                      cudaStream_t s) {
   const int OH = (H + 2 * ph - KH) / sh + 1, OW = (W + 2 * pw - KW) / sw + 1;
-  col2im_kernel<<<nblocks((long long)N * C * H * W), 256, 0, s>>>(dcol, dx, N, C, H, W, KH, KW, OH, OW, sh, sw, ph, pw, ldc);
+  constexpr int CG = 4;
+  if (sh == 1 && sw == 1 && ph == 0 && pw == 0 && (size_t)OH * OW * CG * KH * KW * sizeof(float) <= 160 * 1024) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(col2im_tiled_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); set = true; }
+    launch_pdl(col2im_tiled_kernel<CG>, dim3(N, (C + CG - 1) / CG), dim3(256), (size_t)OH * OW * CG * KH * KW * sizeof(float), s, dcol, dx, C, H, W, KH, KW,
+               OH, OW, ldc);
+    return GX_CHECK_LAUNCH();
+  }
+  launch_pdl(col2im_kernel, dim3(nblocks((long long)N * C * H * W)), dim3(256), 0, s, dcol, dx, N, C, H, W, KH, KW, OH, OW, sh, sw, ph, pw, ldc);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_nchw_to_rows(const float* x, float* y, int N, int C, int HW, cudaStream_t s) {
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
-  nchw_to_rows_kernel<<<grid, 256, 0, s>>>(x, y, N, C, HW);
+  launch_pdl(nchw_to_rows_kernel, dim3(grid), dim3(256), 0, s, x, y, N, C, HW);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_colsum(const float* x, float* out, long long R, int C, long long ld, int accumulate, cudaStream_t s) {
-  colsum_kernel<<<(C + 31) / 32, 256, 0, s>>>(x, out, R, C, ld, accumulate);
+  launch_pdl(colsum_kernel, dim3((C + 31) / 32), dim3(256), 0, s, x, out, R, C, ld, accumulate);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_chansum_nchw(const float* x, float* out, int N, int C, int HW, cudaStream_t s) {
-  chansum_nchw_kernel<<<C, 256, 0, s>>>(x, out, N, C, HW);
+  launch_pdl(chansum_nchw_kernel, dim3(C), dim3(256), 0, s, x, out, N, C, HW);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_relu_fwd(const float* x, float* y, long long n, cudaStream_t s) {
-  relu_fwd_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(x, y, n);
+  launch_pdl(relu_fwd_kernel, dim3((unsigned)((n + 1023) / 1024)), dim3(256), 0, s, x, y, n);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_relu_bwd(const float* y, const float* dy, float* dx, long long n, cudaStream_t s) {
-  relu_bwd_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(y, dy, dx, n);
+  launch_pdl(relu_bwd_kernel, dim3((unsigned)((n + 1023) / 1024)), dim3(256), 0, s, y, dy, dx, n);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_maxpool2x2_fwd(const float* x, float* y, uint8_t* idx, long long NC, int H, int W, cudaStream_t s) {
-  maxpool2x2_fwd_kernel<<<nblocks(NC * (H / 2) * (W / 2)), 256, 0, s>>>(x, y, idx, NC, H, W);
+  launch_pdl(maxpool2x2_fwd_kernel, dim3(nblocks(NC * (H / 2) * (W / 2))), dim3(256), 0, s, x, y, idx, NC, H, W);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_maxpool2x2_bwd(const float* dy, const uint8_t* idx, float* dx, long long NC, int H, int W, cudaStream_t s) {
-  maxpool2x2_bwd_kernel<<<nblocks(NC * (H / 2) * (W / 2)), 256, 0, s>>>(dy, idx, dx, NC, H, W);
+  launch_pdl(maxpool2x2_bwd_kernel, dim3(nblocks(NC * (H / 2) * (W / 2))), dim3(256), 0, s, dy, idx, dx, NC, H, W);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_pool_relu_bwd_rows(const float* dpooled, const float* pooled, const uint8_t* idx, float* dz_rows, float* dbias, int N, int C,
                                  int PH, int PW, cudaStream_t s) {
-  pool_relu_bwd_rows_kernel<<<N * PH, 256, 0, s>>>(dpooled, pooled, idx, dz_rows, dbias, N, C, PH, PW);
+  launch_pdl(pool_relu_bwd_rows_kernel, dim3(N * PH), dim3(256), 0, s, dpooled, pooled, idx, dz_rows, dbias, N, C, PH, PW);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_conv_relu_pool_fwd(const float* x, const float* w, const float* b, float* y, uint8_t* idx, int N, int Cin, int H, int W, int Cout,
@@ -353,7 +443,7 @@ GX_API int gx_conv_relu_pool_fwd(const float* x, const float* w, const float* b,
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(conv_relu_pool_fwd_kernel<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
   dim3 grid(N, (Cout + CPB - 1) / CPB);
-  conv_relu_pool_fwd_kernel<CPB><<<grid, 192, smem, s>>>(x, w, b, y, idx, Cin, H, W, Cout, KH, KW);
+  launch_pdl(conv_relu_pool_fwd_kernel<CPB>, dim3(grid), dim3(192), smem, s, x, w, b, y, idx, Cin, H, W, Cout, KH, KW);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_conv_relu_pool_wgrad(const float* x, const float* dpooled, const float* pooled, const uint8_t* idx, float* dw, float* db, int N,
@@ -364,8 +454,7 @@ GX_API int gx_conv_relu_pool_wgrad(const float* x, const float* dpooled, const f
   if (smem > 200 * 1024) return -1;
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(conv_relu_pool_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
-  const int nsplit = N < 8 ? N : 8;
-  dim3 grid(Cout, nsplit);
-  conv_relu_pool_wgrad_kernel<<<grid, 256, smem, s>>>(x, dpooled, pooled, idx, dw, db, N, Cin, H, W, Cout, KH, KW);
+  dim3 grid(Cout, N);   // one (co, image) plane per CTA: a single round of (cold) loads, 25 atomics per CTA
+  launch_pdl(conv_relu_pool_wgrad_kernel, dim3(grid), dim3(256), smem, s, x, dpooled, pooled, idx, dw, db, N, Cin, H, W, Cout, KH, KW);
   return GX_CHECK_LAUNCH();
 }

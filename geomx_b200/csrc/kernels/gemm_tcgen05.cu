@@ -24,7 +24,6 @@ namespace gx {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;
 constexpr int UMMA_K = 8;
-constexpr int STAGES = 4;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB either major
 constexpr int MN_BOX_BYTES = 32 * BLOCK_K * 4;       // one 32(MN) x 32(K) box = 4 KiB
@@ -46,6 +45,9 @@ struct GemmParams {
 
 template <int BLOCK_N>
 struct SmemLayout {
+  // deep TMA ring: the problems this framework sees are latency-bound (few CTAs, cold operands), so as many K blocks as fit are kept in
+  // flight: 8 stages for N<=64 (160/192 KiB), 6 for N=128 (192 KiB)
+  static constexpr int STAGES = BLOCK_N <= 64 ? 8 : 6;
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
@@ -58,11 +60,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using L = SmemLayout<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int STAGES = L::STAGES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  pdl_launch();  // let the next kernel begin its own prologue right away
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_N;
@@ -93,6 +97,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();    // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -265,7 +270,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, p);
   return (int)cudaGetLastError();
 }
 
@@ -325,6 +330,8 @@ GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B,
 namespace gx {
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ A, long long lda, int a_mn, const float* __restrict__ B,
                                                          long long ldb, int b_mn, int M, int N, int K, GemmParams p) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   __shared__ float sA[16][64 + 1];
   __shared__ float sB[16][64 + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -383,6 +390,6 @@ GX_API int gx_gemm_simt(const float* A, long long lda, int a_mn, const float* B,
   p.M = M; p.N = N; p.K = K; p.kb_per_split = 0; p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
   p.relu = relu; p.accumulate = accumulate; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha; p.wait_flag = nullptr; p.wait_epoch = nullptr;
   dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
-  gemm_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, a_mn, B, ldb, b_mn, M, N, K, p);
+  launch_pdl(gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, A, lda, a_mn, B, ldb, b_mn, M, N, K, p);
   return (int)cudaGetLastError();
 }

@@ -120,6 +120,10 @@ __device__ __forceinline__ void global_apply_tile(const FabricParams& p, int t, 
   *reinterpret_cast<float4*>(p.w + off) = W;
   if (p.s0) *reinterpret_cast<float4*>(p.s0 + off) = A;
   if (p.s1) *reinterpret_cast<float4*>(p.s1 + off) = B;
+  if (p.world == 1) {  // degenerate single-rank HiPS: the arena optimizer, no cross-GPU traffic, flags or fences
+    *reinterpret_cast<float4*>(p.param[0] + off) = W;
+    return;
+  }
   // pull/broadcast: NVLS multicast store or P2P stores into every worker's parameter arena
   if (p.param_mc != nullptr) {
     multimem_st_f4(p.param_mc + off, W);
@@ -140,15 +144,20 @@ __device__ __forceinline__ void global_apply_tile(const FabricParams& p, int t, 
 }
 
 __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const FabricParams p) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
   const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
-  const float lr_t = adam_lr(p.h, opt_t);
+  __shared__ float s_lr;
+  if (threadIdx.x == 0) s_lr = adam_lr(p.h, opt_t);
+  __syncthreads();
+  const float lr_t = s_lr;
   const int S = p.party_size, P = p.num_parties;
   const int party_base = p.party * S;
   uint32_t* my_flags = p.flags[p.rank];
 
   // ---------------- phase A: publish gradient-ready to the party
-  if (blockIdx.x == 0 && threadIdx.x < S) {
+  if (p.world > 1 && blockIdx.x == 0 && threadIdx.x < S) {
     fence_sys();
     st_release_sys(p.flags[party_base + threadIdx.x] + p.ready_off + p.rank, epoch);
   }
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
     if (t % S != p.local) continue;
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
-    if (!waited_party) {
+    if (!waited_party && p.world > 1) {
       if (threadIdx.x < S) wait_flag_ge(my_flags + p.ready_off + party_base + threadIdx.x, epoch);
       __syncthreads();
       waited_party = true;
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
   }
 
   // ---------------- phase D: wait for the broadcast (unless deferred to the consuming GEMM)
-  if (!p.defer_pull_wait && blockIdx.x == 0) {
+  if (p.world > 1 && !p.defer_pull_wait && blockIdx.x == 0) {
     for (int t = threadIdx.x; t < p.tiles; t += blockDim.x)
       if (p.tile_active == nullptr || p.tile_active[t]) wait_flag_ge(my_flags + p.param_ready_off + p.tile_key[t], epoch);
   }
@@ -222,6 +231,8 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
 // locks live in the global owner's flag pad at `lock_off` (uint32 per tile), per-tile optimizer step counts right after them.
 __global__ void __launch_bounds__(FAB_THREADS, 1) hips_async_step_kernel(const FabricParams p, float* const* w_peer, float* const* s0_peer,
                                                                           float* const* s1_peer, int lock_off, int step_off) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
   const int S = p.party_size;
   const int party_base = p.party * S;
@@ -298,6 +309,8 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_async_step_kernel(const F
 //   mode 0: write the result into every party member's `dst` arena; mode 1: only into the owner's `dst` (reduce-scatter)
 __global__ void __launch_bounds__(FAB_THREADS, 1) hips_party_allreduce_kernel(const FabricParams p, float* const* src_peer, float* const* dst_peer,
                                                                                float scale, int mode, int flag_off) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
   const int S = p.party_size, party_base = p.party * S;
   uint32_t* my_flags = p.flags[p.rank];
@@ -338,6 +351,8 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_party_allreduce_kernel(co
 
 // Whole-world flag barrier (two-tier HiPS barrier collapses to one hop on NVSwitch): counter at flag offset `off`.
 __global__ void fabric_barrier_kernel(uint32_t* const* flags, int world, int rank, int off, int* state) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   if (threadIdx.x == 0) {
     const uint32_t e = (uint32_t)(*reinterpret_cast<volatile int*>(state)) + 1u;
     fence_sys();
@@ -357,22 +372,22 @@ GX_API int gx_fabric_params_size() { return (int)sizeof(FabricParams); }
 GX_API int gx_hips_fsa_step(const void* params, int grid, cudaStream_t s) {
   FabricParams p = *reinterpret_cast<const FabricParams*>(params);
   if (grid < 1) grid = 1;
-  hips_fsa_step_kernel<<<grid, FAB_THREADS, 0, s>>>(p);
+  launch_pdl(hips_fsa_step_kernel, dim3(grid), dim3(FAB_THREADS), 0, s, p);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_hips_async_step(const void* params, float* const* w_peer, float* const* s0_peer, float* const* s1_peer, int lock_off, int step_off,
                               int grid, cudaStream_t s) {
   FabricParams p = *reinterpret_cast<const FabricParams*>(params);
-  hips_async_step_kernel<<<grid, FAB_THREADS, 0, s>>>(p, w_peer, s0_peer, s1_peer, lock_off, step_off);
+  launch_pdl(hips_async_step_kernel, dim3(grid), dim3(FAB_THREADS), 0, s, p, w_peer, s0_peer, s1_peer, lock_off, step_off);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_hips_party_allreduce(const void* params, float* const* src_peer, float* const* dst_peer, float scale, int mode, int flag_off, int grid,
                                    cudaStream_t s) {
   FabricParams p = *reinterpret_cast<const FabricParams*>(params);
-  hips_party_allreduce_kernel<<<grid, FAB_THREADS, 0, s>>>(p, src_peer, dst_peer, scale, mode, flag_off);
+  launch_pdl(hips_party_allreduce_kernel, dim3(grid), dim3(FAB_THREADS), 0, s, p, src_peer, dst_peer, scale, mode, flag_off);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_fabric_barrier(uint32_t* const* flags_dev, int world, int rank, int off, int* state, cudaStream_t s) {
-  fabric_barrier_kernel<<<1, 32, 0, s>>>(flags_dev, world, rank, off, state);
+  launch_pdl(fabric_barrier_kernel, dim3(1), dim3(32), 0, s, flags_dev, world, rank, off, state);
   return GX_CHECK_LAUNCH();
 }

@@ -60,6 +60,8 @@ template <int KIND>
 __global__ void __launch_bounds__(256) arena_opt_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ s0, float* __restrict__ s1,
                                                          long long n, const float2* __restrict__ tile_mult, OptHyper h, int* __restrict__ step_state,
                                                          float* __restrict__ g_zero) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const int t = step_state ? (*reinterpret_cast<volatile int*>(step_state)) + 1 : 1;
   float lr_t = h.lr;
   if (KIND == OPT_ADAM) lr_t = h.lr * sqrtf(1.f - powf(h.beta2, (float)t)) / (1.f - powf(h.beta1, (float)t));
@@ -98,6 +100,8 @@ struct TensorEntry { float* w; const float* g; float* s0; float* s1; long long n
 
 template <int KIND>
 __global__ void __launch_bounds__(256) multi_tensor_opt_kernel(const TensorEntry* __restrict__ table, OptHyper h, float lr_t) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   const TensorEntry e = table[blockIdx.y];
   const float lr = lr_t * e.lr_mult, wd = h.wd * e.wd_mult;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < e.n; i += (long long)gridDim.x * blockDim.x) {
@@ -112,6 +116,8 @@ __global__ void __launch_bounds__(256) multi_tensor_opt_kernel(const TensorEntry
 template <int KIND>
 __global__ void __launch_bounds__(256) single_opt_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ s0, float* __restrict__ s1,
                                                           long long n, OptHyper h, float lr_t) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float W = w[i], A = s0 ? s0[i] : 0.f, Bv = s1 ? s1[i] : 0.f;
     opt_elem<KIND>(W, g[i], A, Bv, h, lr_t, h.wd);
@@ -123,6 +129,8 @@ __global__ void __launch_bounds__(256) single_opt_kernel(float* __restrict__ w, 
 
 struct PtrList8 { const float* p[8]; };
 __global__ void __launch_bounds__(256) nary_sum_kernel(float* __restrict__ out, PtrList8 in, int cnt, long long n) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float acc = 0.f;
 #pragma unroll
@@ -143,6 +151,8 @@ template <> __device__ __forceinline__ float up<__nv_bfloat16>(__nv_bfloat16 v) 
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) scale_cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, float scale, long long n) {
+  gx::pdl_wait();
+  gx::pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = cvt<TO>(up<TI>(x[i]) * scale);
 }
 
@@ -169,9 +179,9 @@ GX_API int gx_arena_opt(int kind, float* w, const float* g, float* s0, float* s1
   const OptHyper h = mk(lr, wd, rescale, clip, momentum, b1, b2, eps, lamda);
   const int grid = grid_for(n, 4);
   const float2* tm = reinterpret_cast<const float2*>(tile_mult);
-  if (kind == OPT_SGD) arena_opt_kernel<OPT_SGD><<<grid, 256, 0, s>>>(w, g, s0, s1, n, tm, h, step_state, g_zero);
-  else if (kind == OPT_ADAM) arena_opt_kernel<OPT_ADAM><<<grid, 256, 0, s>>>(w, g, s0, s1, n, tm, h, step_state, g_zero);
-  else arena_opt_kernel<OPT_DCASGD><<<grid, 256, 0, s>>>(w, g, s0, s1, n, tm, h, step_state, g_zero);
+  if (kind == OPT_SGD) launch_pdl(arena_opt_kernel<OPT_SGD>, dim3(grid), dim3(256), 0, s, w, g, s0, s1, n, tm, h, step_state, g_zero);
+  else if (kind == OPT_ADAM) launch_pdl(arena_opt_kernel<OPT_ADAM>, dim3(grid), dim3(256), 0, s, w, g, s0, s1, n, tm, h, step_state, g_zero);
+  else launch_pdl(arena_opt_kernel<OPT_DCASGD>, dim3(grid), dim3(256), 0, s, w, g, s0, s1, n, tm, h, step_state, g_zero);
   return GX_CHECK_LAUNCH();
 }
 
@@ -181,9 +191,9 @@ GX_API int gx_multi_tensor_opt(int kind, const void* table, int num_tensors, lon
   int gx_ = grid_for(max_n); if (gx_ > 64) gx_ = 64;
   dim3 grid(gx_, num_tensors);
   const TensorEntry* t = reinterpret_cast<const TensorEntry*>(table);
-  if (kind == OPT_SGD) multi_tensor_opt_kernel<OPT_SGD><<<grid, 256, 0, s>>>(t, h, lr_t);
-  else if (kind == OPT_ADAM) multi_tensor_opt_kernel<OPT_ADAM><<<grid, 256, 0, s>>>(t, h, lr_t);
-  else multi_tensor_opt_kernel<OPT_DCASGD><<<grid, 256, 0, s>>>(t, h, lr_t);
+  if (kind == OPT_SGD) launch_pdl(multi_tensor_opt_kernel<OPT_SGD>, dim3(grid), dim3(256), 0, s, t, h, lr_t);
+  else if (kind == OPT_ADAM) launch_pdl(multi_tensor_opt_kernel<OPT_ADAM>, dim3(grid), dim3(256), 0, s, t, h, lr_t);
+  else launch_pdl(multi_tensor_opt_kernel<OPT_DCASGD>, dim3(grid), dim3(256), 0, s, t, h, lr_t);
   return GX_CHECK_LAUNCH();
 }
 
@@ -191,9 +201,9 @@ GX_API int gx_single_opt(int kind, float* w, const float* g, float* s0, float* s
                          float momentum, float b1, float b2, float eps, float lamda, cudaStream_t s) {
   const OptHyper h = mk(lr_t, wd, rescale, clip, momentum, b1, b2, eps, lamda);
   const int grid = grid_for(n);
-  if (kind == OPT_SGD) single_opt_kernel<OPT_SGD><<<grid, 256, 0, s>>>(w, g, s0, s1, n, h, lr_t);
-  else if (kind == OPT_ADAM) single_opt_kernel<OPT_ADAM><<<grid, 256, 0, s>>>(w, g, s0, s1, n, h, lr_t);
-  else single_opt_kernel<OPT_DCASGD><<<grid, 256, 0, s>>>(w, g, s0, s1, n, h, lr_t);
+  if (kind == OPT_SGD) launch_pdl(single_opt_kernel<OPT_SGD>, dim3(grid), dim3(256), 0, s, w, g, s0, s1, n, h, lr_t);
+  else if (kind == OPT_ADAM) launch_pdl(single_opt_kernel<OPT_ADAM>, dim3(grid), dim3(256), 0, s, w, g, s0, s1, n, h, lr_t);
+  else launch_pdl(single_opt_kernel<OPT_DCASGD>, dim3(grid), dim3(256), 0, s, w, g, s0, s1, n, h, lr_t);
   return GX_CHECK_LAUNCH();
 }
 
@@ -201,14 +211,14 @@ GX_API int gx_nary_sum(float* out, const float* const* inputs, int cnt, long lon
   if (cnt < 1 || cnt > 8) return -1;
   PtrList8 l;
   for (int i = 0; i < 8; ++i) l.p[i] = i < cnt ? inputs[i] : nullptr;
-  nary_sum_kernel<<<grid_for(n), 256, 0, s>>>(out, l, cnt, n);
+  launch_pdl(nary_sum_kernel, dim3(grid_for(n)), dim3(256), 0, s, out, l, cnt, n);
   return GX_CHECK_LAUNCH();
 }
 
 // dtype codes: 0 fp32, 1 fp16, 2 bf16
 GX_API int gx_scale_cast(const void* x, int in_dt, void* y, int out_dt, float scale, long long n, cudaStream_t s) {
   const int grid = grid_for(n);
-#define GX_SC(TI, TO) scale_cast_kernel<TI, TO><<<grid, 256, 0, s>>>(reinterpret_cast<const TI*>(x), reinterpret_cast<TO*>(y), scale, n)
+#define GX_SC(TI, TO) launch_pdl(scale_cast_kernel<TI, TO>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const TI*>(x), reinterpret_cast<TO*>(y), scale, n)
   if (in_dt == 0 && out_dt == 0) GX_SC(float, float);
   else if (in_dt == 0 && out_dt == 1) GX_SC(float, __half);
   else if (in_dt == 0 && out_dt == 2) GX_SC(float, __nv_bfloat16);

@@ -13,8 +13,31 @@ def create_dist(name):
         from ..parallel.fabric_kvstore import KVStoreFabric
         return KVStoreFabric(name)
     if fabric == "auto" and not has_ps_env:
-        # single process, no launcher: degenerate 1-party / 1-worker HiPS on the in-process fabric
-        from ..parallel.fabric_kvstore import KVStoreFabric
-        return KVStoreFabric(name)
+        import torch
+        if torch.cuda.is_available():
+            # single process, no launcher: degenerate 1-party / 1-worker HiPS on the in-process fabric
+            from ..parallel.fabric_kvstore import KVStoreFabric
+            return KVStoreFabric(name)
+        return KVStoreDistSingle(name)
     from .dist_ps import KVStoreDist
     return KVStoreDist(name)
+
+
+from .local import KVStoreLocal  # noqa: E402
+
+
+class KVStoreDistSingle(KVStoreLocal):
+    """``dist_*`` in ONE CPU process without any launcher environment: both PS tiers collapse into the local store (1 worker, the optimizer
+    runs in-process).  Lets the demo scripts run stand-alone on a machine without GPUs."""
+
+    def __init__(self, name):
+        super().__init__("local")
+        self._type = name
+
+    @property
+    def configures_servers(self):
+        return True
+
+    def _set_gradient_compression(self, params):
+        # single tier, single worker: there is no inter-tier link to compress; the setting is accepted and recorded
+        self._gc.set_params(params)

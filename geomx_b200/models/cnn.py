@@ -87,6 +87,7 @@ class HipsCNNTrainStep:
         self.loss_host = torch.empty(B, dtype=f32).pin_memory()
         self.pull_fused = bool(pull_fused) and self.topo.world >= 1
         self.graph = None
+        self._side = torch.cuda.Stream(device=self.device)
         self.use_graph = use_graph
         self.steps_done = 0
         self.kernels_per_step = 0
@@ -135,15 +136,24 @@ class HipsCNNTrainStep:
         n.gemm(a2f, P[4], self.a3, bias=P[5], relu=True)                                        # 5 dense0
         n.gemm(self.a3, P[6], self.a4, bias=P[7], relu=True)                                    # 6 dense1
         n.head_fwd_bwd(self.a4, P[8], P[9], self.label, self.loss, self.logits, G[8], G[9], self.dz4, G[7], True)   # 7
-        n.gemm(self.dz4, self.a3, G[6], a_mn=True, b_mn=True)                                   # 8  dW1 = dz4ᵀ·a3
+        # weight-gradient GEMMs leave the critical path: they run on a side stream (parallel branches of the captured graph)
+        main, side = torch.cuda.current_stream(), self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            n.gemm(self.dz4, self.a3, G[6], a_mn=True, b_mn=True)                               # 8  dW1 = dz4ᵀ·a3
         n.gemm(self.dz4, P[6], self.dz3, b_mn=True, mask=self.a3, colsum=G[5])                  # 9  dz3 = (dz4·W1)⊙[a3>0], db0
-        n.gemm(self.dz3, a2f, G[4], a_mn=True, b_mn=True)                                       # 10 dW0
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            n.gemm(self.dz3, a2f, G[4], a_mn=True, b_mn=True)                                   # 10 dW0
         n.gemm(self.dz3, P[4], self.da2, b_mn=True)                                             # 11 da2
         n.pool_relu_bwd_rows(self.da2.view(B, 32, 4, 4), self.a2, self.idx2, self.dz2rows, G[3])  # 12 (+dbc1)
-        n.gemm(self.dz2rows, self.col1, G[2].view(32, 400), a_mn=True, b_mn=True, split_k=16, accumulate=True)  # 13 dWc1
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            n.gemm(self.dz2rows, self.col1, G[2].view(32, 400), a_mn=True, b_mn=True, split_k=16, accumulate=True)  # 13 dWc1
         n.gemm(self.dz2rows, P[2].view(32, 400), self.dcol1, b_mn=True)                         # 14 dcol1
         n.col2im(self.dcol1, (B, 16, 12, 12), 5, 5, out=self.da1)                               # 15
         n.conv_relu_pool_wgrad(self.x, self.da1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0])   # 16
+        main.wait_stream(side)
         if self.mode == "dist_async":
             f.async_step()                                                                      # 17 MixedSync
         else:

@@ -1,0 +1,230 @@
+"""``mx.kv.create('dist_sync' | 'dist_async')`` on the NVSwitch fabric — the per-key KVStore API over the fused HiPS kernels.
+
+Selected by ``kvstore.dist.create_dist`` when the process was started by ``torchrun`` (``RANK``/``WORLD_SIZE``) or stand-alone without any
+``DMLC_*`` parameter-server environment.  Semantics follow ``python/mxnet/kvstore.py`` + ``src/kvstore/kvstore_dist.h``:
+
+* ``init``   — keys are registered in call order; on the first data operation the keys are laid out in ONE flat symmetric arena
+               (``parallel/arena.py``), rank 0's values win (``InitImpl`` :308-322) and fp32 arrays passed to ``init`` are re-homed onto the arena
+               so later pulls into them are zero-copy.
+* ``push``   — queues the (summed) value into the gradient arena; ``pull`` registers its targets.  Nothing is launched until a pulled
+               array is read or ``mx.nd.waitall()`` runs — then ONE ``gx_hips_fsa_step`` (or ``gx_hips_async_step``) launch serves every queued
+               key in priority order; keys that were not pushed this round are masked out (``tile_active``).
+* roles      — ``rank`` / ``num_workers`` are party-local, ``num_all_workers`` is the world size; there is no separate master-worker process:
+               ``is_master_worker`` is False everywhere and ``configures_servers`` is True on world rank 0, whose ``set_optimizer`` /
+               ``set_gradient_compression`` calls are broadcast to all ranks when the arena is finalised (the reference ships them to the servers
+               through ``kController`` / ``kSetGradientCompression``).
+* HFA        — ``MXNET_KVSTORE_USE_HFA=1``: rounds with ``local_iters % K2 != 0`` only run the party-level all-reduce
+               (``gx_hips_party_allreduce``); global rounds average the party averages (``milestone + Σ(avg_g − milestone)/P`` with identical
+               milestones) through the FSA kernel without an optimizer.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from ..base import MXNetError, getenv_int
+from ..kvstore.base import KVStoreBase
+from ..ndarray import NDArray
+from .arena import ArenaLayout
+from .fabric import HipsFabric, SymmetricBuffer, Topology
+
+
+def _ensure_process_group(device):
+    import torch.distributed as dist
+    world = getenv_int("WORLD_SIZE", 1)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if device.type == "cuda":
+            dist.init_process_group("nccl", device_id=device)
+        else:
+            dist.init_process_group("gloo")
+    return world
+
+
+class KVStoreFabric(KVStoreBase):
+    def __init__(self, kv_type="dist_sync"):
+        super().__init__(kv_type)
+        if not torch.cuda.is_available():
+            raise MXNetError("the NVSwitch fabric KVStore needs CUDA devices; use the DMLC_* environment for the TCP parameter-server path")
+        local = getenv_int("LOCAL_RANK", 0)
+        torch.cuda.set_device(local)
+        self._device = torch.device("cuda", local)
+        _ensure_process_group(self._device)
+        self._topo = Topology.from_env()
+        self._sync = "async" not in kv_type
+        self._keys, self._init_vals = [], {}
+        self._fabric = None
+        self._opt_spec = None
+        self._pushed, self._pulls = set(), []
+        self._hfa = getenv_int("MXNET_KVSTORE_USE_HFA", 0) != 0
+        self._hfa_k2 = max(1, getenv_int("MXNET_KVSTORE_HFA_K2", 1))
+        self._local_iters = 0
+        self._key_index = {}
+
+    # -- identity ---------------------------------------------------------------------------------------------------------------
+    @property
+    def rank(self): return self._topo.local
+    @property
+    def num_workers(self): return self._topo.party_size
+    @property
+    def num_all_workers(self): return self._topo.world
+    @property
+    def is_master_worker(self): return False
+    @property
+    def configures_servers(self): return self._topo.rank == 0
+    @property
+    def fabric(self):
+        self._finalize()
+        return self._fabric
+
+    # -- configuration (rank 0 decides, broadcast at finalize) ---------------------------------------------------------------------
+    def set_optimizer(self, optimizer):
+        spec = optimizer.spec()
+        if spec is None:
+            raise MXNetError("the fabric KVStore runs optimizers natively on the global-PS shard: %s has no native spec (use Adam / SGD / "
+                             "DCASGD, or update locally with a Trainer and pull aggregated gradients)" % type(optimizer).__name__)
+        self._optimizer = optimizer
+        self._opt_spec = spec
+        if self._fabric is not None:
+            self._fabric.set_optimizer(spec)
+
+    def _set_gradient_compression(self, params):
+        t = params.get("type", "none")
+        if t == "2bit":
+            raise MXNetError("2bit is a worker->server wire format of the TCP path; on NVSwitch use fp16/bf16 or block-scaled fp8 transport")
+        # 'bsc': the party aggregate is sparsified between the tiers (see parallel/fabric_bsc.py)
+
+    # -- data ---------------------------------------------------------------------------------------------------------------------
+    def _init(self, key, value):
+        if self._fabric is not None:
+            raise MXNetError("all keys must be initialised before the first push/pull on the fabric KVStore")
+        if key in self._key_index:
+            raise MXNetError("duplicate init of key %s" % key)
+        self._key_index[key] = len(self._keys)
+        self._keys.append((key, tuple(value.shape)))
+        self._init_vals[key] = value
+
+    def _finalize(self):
+        if self._fabric is not None:
+            return
+        topo = self._topo
+        if topo.world > 1:
+            import torch.distributed as dist
+            cfg = [self._opt_spec, self._compression] if topo.rank == 0 else [None, None]
+            dist.broadcast_object_list(cfg, src=0)
+            self._opt_spec, self._compression = cfg
+        layout = ArenaLayout.build(self._keys)
+        f = HipsFabric(layout, topo, self._device, self._opt_spec)
+        for i, (key, _) in enumerate(self._keys):
+            v = self._init_vals[key]
+            f.param_view(i).copy_(v._t.detach().to(self._device))
+        if topo.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(f.param.tensor, src=0)
+            torch.cuda.synchronize(); dist.barrier()
+        f.load_master_from_param()
+        for i, (key, _) in enumerate(self._keys):
+            v = self._init_vals[key]
+            if v._data.dtype == torch.float32 and v._data.is_cuda:
+                had_grad = v._grad is not None
+                v._data = f.param_view(i)                 # zero-copy pull target from now on
+                if had_grad:
+                    v._data.requires_grad_(True)
+        self._init_vals = None
+        self._fabric = f
+
+    def _push(self, key, vals, priority):
+        self._finalize()
+        i = self._key_index[key]
+        g = self._fabric.grad_view(i)
+        g.copy_(vals[0]._t.detach().reshape(g.shape))
+        for v in vals[1:]:
+            g.add_(v._t.detach().reshape(g.shape).to(g.device))
+        self._pushed.add(i)
+        self._fabric.layout.slots[i].priority = priority
+
+    def _pull(self, key, outs, priority):
+        self._finalize()
+        self._pulls.append((self._key_index[key], outs))
+        for o in outs:
+            o._pending = self.flush
+
+    def flush(self):
+        if self._fabric is None or (not self._pushed and not self._pulls):
+            return
+        f = self._fabric
+        pulls, self._pulls = self._pulls, []
+        for _, outs in pulls:
+            for o in outs:
+                o._pending = None
+        if self._pushed:
+            nkeys = len(self._keys)
+            full = len(self._pushed) == nkeys
+            if not full:
+                mask = torch.zeros(f.tiles, dtype=torch.uint8)
+                for i in self._pushed:
+                    s = f.layout.slots[i]
+                    mask[s.offset // 1024: s.offset // 1024 + s.tiles] = 1
+                f.tile_active.copy_(mask.to(f.device))
+            if self._hfa:
+                self._flush_hfa(full)
+            elif self._sync:
+                f.fsa_step(masked=not full)
+            else:
+                if not full:
+                    raise MXNetError("dist_async on the fabric needs every key pushed each round")
+                f.async_step()
+            self._pushed.clear()
+            f.grad.tensor.zero_()
+        for i, outs in pulls:
+            src = f.param_view(i)
+            for o in outs:
+                tgt = o._data
+                if tgt.data_ptr() == src.data_ptr():
+                    continue
+                (tgt.detach() if tgt.requires_grad else tgt).copy_(src.reshape(tgt.shape), non_blocking=True)
+
+    def _flush_hfa(self, full):
+        f, topo = self._fabric, self._topo
+        if not full:
+            raise MXNetError("HFA synchronisation pushes every key (examples/cnn_hfa.py)")
+        self._local_iters += 1
+        if self._local_iters % self._hfa_k2 != 0:
+            f.party_allreduce(f.grad, f.param, scale=1.0)
+        else:
+            spec, scale = f.opt_spec, f.push_scale
+            f.set_optimizer(None); f.set_push_scale(1.0 / topo.num_parties)
+            f.fsa_step()
+            f.set_optimizer(spec); f.set_push_scale(scale)
+
+    def _barrier(self):
+        self.flush()
+        if self._fabric is not None:
+            self._fabric.barrier()
+        elif self._topo.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def save_optimizer_states(self, fname, dump_optimizer=False):
+        """Global-PS shard state (master weights + optimizer moments + step) of this rank — checkpointable, unlike the reference's servers."""
+        self._finalize(); self.flush()
+        f = self._fabric
+        torch.cuda.synchronize()
+        torch.save({"w": f.w.cpu(), "s0": f.s0.cpu(), "s1": f.s1.cpu(), "state": {k: v.cpu() for k, v in f.state.items()},
+                    "spec": f.opt_spec, "local_iters": self._local_iters}, "%s.rank%d" % (fname, self._topo.rank))
+
+    def load_optimizer_states(self, fname):
+        self._finalize()
+        f = self._fabric
+        d = torch.load("%s.rank%d" % (fname, self._topo.rank), weights_only=False)
+        f.w.copy_(d["w"]); f.s0.copy_(d["s0"]); f.s1.copy_(d["s1"])
+        f.state["fsa"][2] = d["state"]["fsa"][2]          # optimizer step t (epochs keep running)
+        self._local_iters = d.get("local_iters", 0)
+        if d.get("spec") is not None:
+            f.set_optimizer(d["spec"])
+
+    def get_num_dead_node(self, node_id=0, timeout=60):
+        return 0
