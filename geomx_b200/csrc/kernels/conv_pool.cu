@@ -311,6 +311,68 @@ __global__ void __launch_bounds__(256) conv_relu_pool_fwd_kernel(const float* __
   }
 }
 
+// Same as conv_relu_pool_fwd_kernel, plus the im2col slab of the NEXT convolution (stride 1, no padding, kernel KH2 x KW2) for the
+// CO_PER_BLOCK pooled planes this CTA just produced:  col[(n,oh2,ow2)][(co*KH2+kh)*KW2+kw] = y[n,co,oh2+kh,ow2+kw].   One launch less, and
+// the pooled activations never travel through L2 between the two steps.
+template <int CO_PER_BLOCK>
+__global__ void __launch_bounds__(256) conv_relu_pool_im2col_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                                         float* __restrict__ y, uint8_t* __restrict__ idx, float* __restrict__ col, int Cin,
+                                                                         int H, int W, int Cout, int KH, int KW, int KH2, int KW2, int ldc) {
+  gx::pdl_wait();
+  gx::pdl_launch();
+  extern __shared__ float sm[];
+  const int K = Cin * KH * KW;
+  const int OH = H - KH + 1, OW = W - KW + 1, PH = OH >> 1, PW = OW >> 1;
+  float* sx = sm;                              // Cin*H*W
+  float* sw = sx + Cin * H * W;                // CO_PER_BLOCK * K
+  float* sp = sw + CO_PER_BLOCK * K;           // CO_PER_BLOCK * PH * PW pooled planes
+  const int n = blockIdx.x, co0 = blockIdx.y * CO_PER_BLOCK;
+  for (int i = threadIdx.x; i < Cin * H * W; i += blockDim.x) sx[i] = x[(long long)n * Cin * H * W + i];
+  for (int i = threadIdx.x; i < CO_PER_BLOCK * K; i += blockDim.x) {
+    const int co = co0 + i / K;
+    sw[i] = co < Cout ? w[(long long)co * K + i % K] : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < CO_PER_BLOCK * PH * PW; e += blockDim.x) {
+    const int pw = e % PW, ph = (e / PW) % PH, cl = e / (PW * PH);
+    const int co = co0 + cl;
+    float best = 0.f; int bi = 0;
+    if (co < Cout) {
+      float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+      const float* wf = sw + cl * K;
+      for (int c = 0; c < Cin; ++c) {
+        const float* xin = sx + c * H * W + (2 * ph) * W + 2 * pw;
+        for (int kh = 0; kh < KH; ++kh) {
+#pragma unroll 5
+          for (int kw = 0; kw < KW; ++kw) {
+            const float wv = wf[(c * KH + kh) * KW + kw];
+            const float* px = xin + kh * W + kw;
+            a00 = fmaf(wv, px[0], a00); a01 = fmaf(wv, px[1], a01); a10 = fmaf(wv, px[W], a10); a11 = fmaf(wv, px[W + 1], a11);
+          }
+        }
+      }
+      best = a00;
+      if (a01 > best) { best = a01; bi = 1; }
+      if (a10 > best) { best = a10; bi = 2; }
+      if (a11 > best) { best = a11; bi = 3; }
+      best = fmaxf(best + b[co], 0.f);
+      const long long o = (((long long)n * Cout + co) * PH + ph) * PW + pw;
+      y[o] = best;
+      idx[o] = (uint8_t)bi;
+    }
+    sp[e] = best;
+  }
+  __syncthreads();
+  const int OH2 = PH - KH2 + 1, OW2 = PW - KW2 + 1, KK2 = KH2 * KW2;
+  const int cg = min(CO_PER_BLOCK, Cout - co0), span = cg * KK2;
+  for (int i = threadIdx.x; i < OH2 * OW2 * span; i += blockDim.x) {
+    const int kk = i % span, row = i / span;
+    const int cl = kk / KK2, t = kk - cl * KK2, kh = t / KW2, kw = t - kh * KW2;
+    const int oh = row / OW2, ow = row - oh * OW2;
+    col[((long long)n * OH2 * OW2 + row) * ldc + co0 * KK2 + kk] = sp[cl * PH * PW + (oh + kh) * PW + ow + kw];
+  }
+}
+
 // Fused backward of the same layer (no dx needed for a first layer):
 //   g = (pooled>0) ? dpooled : 0 at the arg-max position;  dW[co][c,kh,kw] += g * x[n,c,2ph+dy+kh,2pw+dx+kw];  db[co] += g
 // grid (Cout, NSPLIT): block (co, s) reduces images n = s, s+NSPLIT, ... ; one (c,kh,kw) tap per thread-group, smem reduce, atomics.
@@ -359,6 +421,63 @@ __global__ void __launch_bounds__(256) conv_relu_pool_wgrad_kernel(const float* 
   for (int k = wid; k < K; k += nw, ++t) {
     const float s = warp_sum(acc[t]);
     if (lane == 0) atomicAdd(dw + (long long)co * K + k, s);
+  }
+  bacc = warp_sum(bacc);
+  if (lane == 0 && bacc != 0.f && db != nullptr) atomicAdd(db + co, bacc);
+}
+
+// conv_relu_pool_wgrad_kernel with the col2im of the NEXT convolution's input gradient fused in: the gradient w.r.t. this layer's pooled
+// output plane (n, co) is gathered from dcol[(n,oh2,ow2)][(co*KH2+kh)*KW2+kw] (stride-1 / valid KH2 x KW2 conv) inside the CTA.
+__global__ void __launch_bounds__(256) conv_relu_pool_wgrad_col2im_kernel(const float* __restrict__ x, const float* __restrict__ dcol,
+                                                                           const float* __restrict__ pooled, const uint8_t* __restrict__ idx,
+                                                                           float* __restrict__ dw, float* __restrict__ db, int N, int Cin, int H, int W,
+                                                                           int Cout, int KH, int KW, int KH2, int KW2, int ldc) {
+  gx::pdl_wait();
+  gx::pdl_launch();
+  const int co = blockIdx.x, n = blockIdx.y;
+  const int OH = H - KH + 1, OW = W - KW + 1, PH = OH >> 1, PW = OW >> 1;
+  const int OH2 = PH - KH2 + 1, OW2 = PW - KW2 + 1, KK2 = KH2 * KW2;
+  const int K = Cin * KH * KW;
+  extern __shared__ float sm[];
+  float* sg = sm;                                     // PH*PW
+  int* spos = reinterpret_cast<int*>(sm + PH * PW);   // PH*PW
+  float* sx = sm + 2 * PH * PW;                       // Cin*H*W
+  float* sd = sx + Cin * H * W;                       // OH2*OW2*KK2 slab of dcol
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < Cin * H * W; i += blockDim.x) sx[i] = x[(long long)n * Cin * H * W + i];
+  for (int i = threadIdx.x; i < OH2 * OW2 * KK2; i += blockDim.x) {
+    const int kk = i % KK2, row = i / KK2;
+    sd[i] = dcol[((long long)n * OH2 * OW2 + row) * ldc + co * KK2 + kk];
+  }
+  __syncthreads();
+  float bacc = 0.f;
+  for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+    const int ph = i / PW, pw = i - ph * PW;
+    float da = 0.f;
+    for (int kh = 0; kh < KH2; ++kh) {
+      const int oh = ph - kh;
+      if (oh < 0 || oh >= OH2) continue;
+      for (int kw = 0; kw < KW2; ++kw) {
+        const int ow = pw - kw;
+        if (ow < 0 || ow >= OW2) continue;
+        da += sd[(oh * OW2 + ow) * KK2 + kh * KW2 + kw];
+      }
+    }
+    const long long pi = ((long long)n * Cout + co) * PH * PW + i;
+    const float g = pooled[pi] > 0.f ? da : 0.f;
+    const int bsel = idx[pi];
+    sg[i] = g;
+    spos[i] = (2 * ph + (bsel >> 1)) * W + 2 * pw + (bsel & 1);
+    bacc += g;
+  }
+  __syncthreads();
+  for (int k = wid; k < K; k += nw) {
+    const int kw = k % KW, kh = (k / KW) % KH, c = k / (KW * KH);
+    const float* xin = sx + c * H * W + kh * W + kw;
+    float a = 0.f;
+    for (int i = lane; i < PH * PW; i += 32) a = fmaf(sg[i], xin[spos[i]], a);
+    a = warp_sum(a);
+    if (lane == 0) atomicAdd(dw + (long long)co * K + k, a);
   }
   bacc = warp_sum(bacc);
   if (lane == 0 && bacc != 0.f && db != nullptr) atomicAdd(db + co, bacc);
@@ -456,5 +575,29 @@ GX_API int gx_conv_relu_pool_wgrad(const float* x, const float* dpooled, const f
   if (!set) { cudaFuncSetAttribute(conv_relu_pool_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
   dim3 grid(Cout, N);   // one (co, image) plane per CTA: a single round of (cold) loads, 25 atomics per CTA
   launch_pdl(conv_relu_pool_wgrad_kernel, dim3(grid), dim3(256), smem, s, x, dpooled, pooled, idx, dw, db, N, Cin, H, W, Cout, KH, KW);
+  return GX_CHECK_LAUNCH();
+}
+
+GX_API int gx_conv_relu_pool_im2col_fwd(const float* x, const float* w, const float* b, float* y, uint8_t* idx, float* col, int N, int Cin, int H, int W,
+                                        int Cout, int KH, int KW, int KH2, int KW2, int ldc, cudaStream_t s) {
+  constexpr int CPB = 4;
+  const int PH = (H - KH + 1) / 2, PW = (W - KW + 1) / 2;
+  const size_t smem = ((size_t)Cin * H * W + (size_t)CPB * Cin * KH * KW + (size_t)CPB * PH * PW) * sizeof(float);
+  if (smem > 200 * 1024 || ldc != Cout * KH2 * KW2) return -1;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(conv_relu_pool_im2col_fwd_kernel<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+  launch_pdl(conv_relu_pool_im2col_fwd_kernel<CPB>, dim3(N, (Cout + CPB - 1) / CPB), dim3(256), smem, s, x, w, b, y, idx, col, Cin, H, W, Cout, KH, KW, KH2,
+             KW2, ldc);
+  return GX_CHECK_LAUNCH();
+}
+GX_API int gx_conv_relu_pool_wgrad_col2im(const float* x, const float* dcol, const float* pooled, const uint8_t* idx, float* dw, float* db, int N, int Cin,
+                                          int H, int W, int Cout, int KH, int KW, int KH2, int KW2, int ldc, cudaStream_t s) {
+  const int PH = (H - KH + 1) / 2, PW = (W - KW + 1) / 2, OH2 = PH - KH2 + 1, OW2 = PW - KW2 + 1;
+  if (Cin * KH * KW > 2048) return -1;
+  const size_t smem = ((size_t)2 * PH * PW + (size_t)Cin * H * W + (size_t)OH2 * OW2 * KH2 * KW2) * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(conv_relu_pool_wgrad_col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+  launch_pdl(conv_relu_pool_wgrad_col2im_kernel, dim3(Cout, N), dim3(256), smem, s, x, dcol, pooled, idx, dw, db, N, Cin, H, W, Cout, KH, KW, KH2, KW2, ldc);
   return GX_CHECK_LAUNCH();
 }

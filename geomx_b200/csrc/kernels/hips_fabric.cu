@@ -64,6 +64,7 @@ struct FabricParams {
   int param_ready_off;         // uint32 offset of param_ready[num_keys] in the flag pad
   int ready_off;               // uint32 offset of grad_ready[MAX_RANKS] (per channel: every kernel family has its own epoch)
   int arrived_off;             // uint32 offset of arrived[num_parties][tiles]
+  int zero_grad;               // fuse zero_grad: clear this rank's gradient arena once every reader is done with it
 };
 
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
       for (int j = 1; j < S; ++j) acc = f4_add(acc, ld_f4_sys(p.grad[party_base + j] + off));
     }
     acc = f4_scale(acc, p.push_scale);
+    if (p.zero_grad && p.world == 1) *reinterpret_cast<float4*>(p.grad[p.rank] + off) = make_float4(0.f, 0.f, 0.f, 0.f);
     const int owner = p.tile_owner[t];
     if (P == 1 && owner == p.rank) {
       global_apply_tile(p, t, acc, epoch, lr_t);  // both tiers collapse: stay in registers
@@ -211,6 +213,17 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
   if (p.world > 1 && !p.defer_pull_wait && blockIdx.x == 0) {
     for (int t = threadIdx.x; t < p.tiles; t += blockDim.x)
       if (p.tile_active == nullptr || p.tile_active[t]) wait_flag_ge(my_flags + p.param_ready_off + p.tile_key[t], epoch);
+  }
+
+  // ---------------- fused zero_grad (multi-rank): a key's ready flag implies that every tile of it was reduced by its owner, i.e. nobody
+  // will read this rank's gradients of that key again this round
+  if (p.zero_grad && p.world > 1 && !p.defer_pull_wait) {
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+      if (threadIdx.x == 0) wait_flag_ge(my_flags + p.param_ready_off + p.tile_key[t], epoch);
+      __syncthreads();
+      *reinterpret_cast<float4*>(p.grad[p.rank] + (long long)t * TILE + threadIdx.x * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 
   // ---------------- epoch / optimizer step bookkeeping (last CTA to finish publishes the new epoch)

@@ -55,13 +55,14 @@ class HipsCNNTrainStep:
     """
 
     def __init__(self, net=None, batch_size=32, optimizer=None, topo=None, device=None, use_graph=True, pull_fused=False,
-                 use_multicast=True, mode="dist_sync"):
+                 use_multicast=True, mode="dist_sync", fused_zero_grad=True):
         native.require()
         from .. import optimizer as opt
         self.B = B = int(batch_size)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.topo = topo or Topology.from_env()
         self.mode = mode
+        self.fused_zero_grad = fused_zero_grad   # False keeps the gradients readable after a step (tests / debugging): memset instead
         optimizer = optimizer or opt.Adam(learning_rate=0.01)
         spec = optimizer.spec()
         if spec is None:
@@ -127,9 +128,10 @@ class HipsCNNTrainStep:
         B, P, G, f = self.B, self.P, self.G, self.fabric
         before = n.launch_count
         wf = we = None
-        f.grad.tensor.zero_()                                                                   # memset (accumulating epilogues)
-        n.conv_relu_pool_fwd(self.x, P[0], P[1], self.a1, self.idx1)                            # 1
-        n.im2col(self.a1, 5, 5, out=self.col1)                                                  # 2
+        # the gradient arena is cleared by the previous step's HiPS kernel (fused zero_grad) unless gradients must stay readable
+        if not self.fused_zero_grad:
+            f.grad.tensor.zero_()
+        n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)     # 1+2 conv0+ReLU+pool and conv1's im2col slab
         n.gemm(self.col1, P[2].view(32, 400), self.z2, bias=P[3], relu=True, store_nchw_hw=64)  # 3 conv1 (tcgen05)
         n.maxpool2x2_fwd(self.z2, self.a2, self.idx2)                                           # 4
         a2f = self.a2.view(B, 512)
@@ -151,13 +153,14 @@ class HipsCNNTrainStep:
         with torch.cuda.stream(side):
             n.gemm(self.dz2rows, self.col1, G[2].view(32, 400), a_mn=True, b_mn=True, split_k=16, accumulate=True)  # 13 dWc1
         n.gemm(self.dz2rows, P[2].view(32, 400), self.dcol1, b_mn=True)                         # 14 dcol1
-        n.col2im(self.dcol1, (B, 16, 12, 12), 5, 5, out=self.da1)                               # 15
-        n.conv_relu_pool_wgrad(self.x, self.da1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0])   # 16
+        n.conv_relu_pool_wgrad_col2im(self.x, self.dcol1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0], 5, 5)   # 15+16 col2im fused
         main.wait_stream(side)
         if self.mode == "dist_async":
             f.async_step()                                                                      # 17 MixedSync
+            if self.fused_zero_grad:
+                f.grad.tensor.zero_()
         else:
-            f.fsa_step(defer_pull_wait=False)                                                   # 17 HiPS push+pull (FSA)
+            f.fsa_step(defer_pull_wait=False, zero_grad=self.fused_zero_grad)                                                 # 17 HiPS push+pull (FSA)
         self.kernels_per_step = n.launch_count - before
 
     def capture(self):

@@ -166,6 +166,20 @@ def conv_relu_pool_wgrad(x, dpooled, pooled, idx, dw, db, w_shape):
         "conv_relu_pool_wgrad")
 
 
+def conv_relu_pool_im2col_fwd(x, w, b, y, idx, col, KH2, KW2):
+    N, Cin, H, W = x.shape
+    Cout, _, KH, KW = w.shape
+    _ck(_lib().gx_conv_relu_pool_im2col_fwd(_p(x), _p(w), _p(b), _p(y), _p(idx), _p(col), N, Cin, H, W, Cout, KH, KW, KH2, KW2, col.stride(0), _s()),
+        "conv_relu_pool_im2col_fwd")
+
+
+def conv_relu_pool_wgrad_col2im(x, dcol, pooled, idx, dw, db, w_shape, KH2, KW2):
+    N, Cin, H, W = x.shape
+    Cout, _, KH, KW = w_shape
+    _ck(_lib().gx_conv_relu_pool_wgrad_col2im(_p(x), _p(dcol), _p(pooled), _p(idx), _p(dw), _p(db), N, Cin, H, W, Cout, KH, KW, KH2, KW2, dcol.stride(0), _s()),
+        "conv_relu_pool_wgrad_col2im")
+
+
 # --------------------------------------------------------------------------------------------------------------- loss / head
 def softmax_ce_fwd(logits, label, out=None):
     R, Cc = logits.shape

@@ -20,6 +20,8 @@ SIGS = {
     "gx_pool_relu_bwd_rows": [P, P, P, P, P, I, I, I, I, P],
     "gx_conv_relu_pool_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, P],
     "gx_conv_relu_pool_wgrad": [P, P, P, P, P, P, I, I, I, I, I, I, I, P],
+    "gx_conv_relu_pool_im2col_fwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
+    "gx_conv_relu_pool_wgrad_col2im": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
     # loss_head.cu
     "gx_softmax_ce_fwd": [P, P, P, I, I, P],
     "gx_softmax_ce_bwd": [P, P, P, P, I, I, P],

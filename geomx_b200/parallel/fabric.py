@@ -154,7 +154,7 @@ class _FabricParams(ctypes.Structure):
         ("tile_key", ctypes.c_void_p), ("key_tiles", ctypes.c_void_p), ("tile_owner", ctypes.c_void_p), ("tile_active", ctypes.c_void_p),
         ("tile_mult", ctypes.c_void_p), ("key_done", ctypes.c_void_p), ("state", ctypes.c_void_p),
         ("h", _OptHyperF), ("push_scale", ctypes.c_float), ("defer_pull_wait", ctypes.c_int), ("param_ready_off", ctypes.c_int),
-        ("ready_off", ctypes.c_int), ("arrived_off", ctypes.c_int),
+        ("ready_off", ctypes.c_int), ("arrived_off", ctypes.c_int), ("zero_grad", ctypes.c_int),
     ]
 
 
@@ -239,8 +239,8 @@ class HipsFabric:
         h.eps = s.get("epsilon", 1e-8); h.lamda = s.get("lamda", 0.04)
         return h
 
-    def _block(self, channel, defer_pull_wait=False, masked=False):
-        key = (channel, defer_pull_wait, masked)
+    def _block(self, channel, defer_pull_wait=False, masked=False, zero_grad=False):
+        key = (channel, defer_pull_wait, masked, zero_grad)
         if key in self._params_cache:
             return self._params_cache[key]
         t = self.topo
@@ -266,6 +266,7 @@ class HipsFabric:
         p.h = self._hyper()
         p.push_scale = self.push_scale
         p.defer_pull_wait = int(defer_pull_wait)
+        p.zero_grad = int(zero_grad)
         pre = {"fsa": "fsa", "async": "async", "party": "par"}[channel]
         p.ready_off = self.off[pre + "_ready"]
         p.arrived_off = self.off["fsa_arrived"]
@@ -284,9 +285,9 @@ class HipsFabric:
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # -- kernels --------------------------------------------------------------------------------------------------------
-    def fsa_step(self, defer_pull_wait=False, masked=False):
-        """dist_sync: party reduce -> global reduce + optimizer -> broadcast (one launch)."""
-        p = self._block("fsa", defer_pull_wait, masked)
+    def fsa_step(self, defer_pull_wait=False, masked=False, zero_grad=False):
+        """dist_sync: party reduce -> global reduce + optimizer -> broadcast (one launch); optionally clears the gradient arena for the next step."""
+        p = self._block("fsa", defer_pull_wait, masked, zero_grad)
         rc = native.require().gx_hips_fsa_step(ctypes.byref(p), self.grid, self._stream())
         native.launch_count += 1
         if rc:

@@ -33,7 +33,7 @@ def main():
     B = 32
     torch.manual_seed(7)
     eng = mx.models.HipsCNNTrainStep(batch_size=B, optimizer=mx.optimizer.SGD(learning_rate=0.1), topo=topo, device=dev, use_graph=False,
-                                     use_multicast=not a.no_multicast, mode=a.mode)
+                                     use_multicast=not a.no_multicast, mode=a.mode, fused_zero_grad=False)
     if rank == 0:
         print("fabric backend=%s multicast=%s parties=%d party_size=%d gs=%s" % (eng.fabric.heap.backend, eng.fabric.use_multicast, parties,
                                                                                  topo.party_size, topo.gs_ranks), flush=True)
