@@ -29,8 +29,23 @@ inline bool pdl_enabled() {
   if (v < 0) { const char* e = getenv("GEOMX_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
+// All kernels ask for the same (maximum) shared-memory carve-out: a GEMM CTA needs ~200 KB while the element-wise kernels need none, and an
+// SM cannot run two kernels with different L1/smem splits side by side — with per-kernel defaults every GEMM <-> non-GEMM boundary of the step
+// would drain and reconfigure the SMs and defeat programmatic dependent launch.  GEOMX_CARVEOUT=0 keeps the driver defaults.
+inline void unify_carveout(const void* fn) {
+  static const void* seen[256];
+  static int nseen = 0;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("GEOMX_CARVEOUT"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return;
+  for (int i = 0; i < nseen; ++i) if (seen[i] == fn) return;
+  if (nseen < 256) seen[nseen++] = fn;
+  cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 template <typename... KArgs, typename... Args>
 inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  unify_carveout(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -157,6 +172,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):

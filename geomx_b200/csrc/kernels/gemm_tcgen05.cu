@@ -40,7 +40,11 @@ struct GemmParams {
   int relu, accumulate, store_mode, hw;
   float alpha;
   const uint32_t* wait_flag;
-  const int* wait_epoch;  // device epoch counter: proceed when *wait_flag >= *wait_epoch (graph-replay safe)
+  const int* wait_epoch;
+  int a_boxes, b_boxes;    // MN-major operands: number of 32-wide TMA boxes that are (partly) in bounds for this problem
+  int tx_bytes;            // bytes that land per stage (A box(es) + B box(es)); out-of-range rows/boxes are never requested
+  int stages;              // TMA ring depth actually used (<= SmemLayout::STAGES); smaller rings need less smem -> cheaper launch
+  unsigned long long* dbg; // optional: %globaltimer stamps of CTA (0,0,0) phases (tools/gemm_phases.py)  // device epoch counter: proceed when *wait_flag >= *wait_epoch (graph-replay safe)
 };
 
 template <int BLOCK_N>
@@ -48,10 +52,11 @@ struct SmemLayout {
   // deep TMA ring: the problems this framework sees are latency-bound (few CTAs, cold operands), so as many K blocks as fit are kept in
   // flight: 8 stages for N<=64 (160/192 KiB), 6 for N=128 (192 KiB)
   static constexpr int STAGES = BLOCK_N <= 64 ? 8 : 6;
+  static_assert(BLOCK_N >= 16, "UMMA N >= 16 for M = 128");
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 512 + 1024;  // + barriers + bias tile + alignment slack
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -60,13 +65,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using L = SmemLayout<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int STAGES = L::STAGES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  const int STAGES = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * L::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + L::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   pdl_launch();  // let the next kernel begin its own prologue right away
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  auto stamp = [&](int slot) { if (dbg_on) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[slot] = t; } };
+  if (threadIdx.x == 0) stamp(0);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_N;
@@ -82,7 +90,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1) {
     if (lane == 0) {
-#pragma unroll
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
@@ -97,7 +104,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(1);
   pdl_wait();    // everything above overlapped the previous kernel's tail; from here on we touch its outputs
+  if (threadIdx.x == 0) stamp(2);
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -113,19 +122,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sA = smem + stage * L::STAGE_BYTES;
         uint8_t* sB = sA + A_TILE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
         const int k0 = kb * BLOCK_K;
         if constexpr (!A_MN) {
           tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sA + j * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + 32 * j, k0);
+          for (int j = 0; j < BLOCK_M / 32; ++j)
+            if (j < p.a_boxes) tma_load_2d(sA + j * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + 32 * j, k0);
         }
         if constexpr (!B_MN) {
           tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sB + j * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + 32 * j, k0);
+          for (int j = 0; j < BLOCK_N / 32; ++j)
+            if (j < p.b_boxes) tma_load_2d(sB + j * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + 32 * j, k0);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -138,6 +149,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
+        if (kb == kb_begin) stamp(3);
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint32_t sB = sA + A_TILE_BYTES;
@@ -154,71 +166,98 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
+      stamp(4);
     }
   } else {
     // ================================ epilogue (4 warps = 128 TMEM lanes) ================================
+    constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;   // columns per TMEM load
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = m < p.M;
+    const bool warp_has_rows = (m0 + q * 32) < p.M;   // warp-uniform
+    // stage the bias slice of this tile in smem while the main loop runs (one coalesced load instead of per-element L2 round trips)
+    float* s_bias = reinterpret_cast<float*>(smem + p.stages * L::STAGE_BYTES + 256);
+    {
+      const int et = threadIdx.x - 64;
+      for (int j = et; j < BLOCK_N; j += 128) s_bias[j] = (p.bias != nullptr && n0 + j < p.N && blockIdx.z == 0) ? __ldg(p.bias + n0 + j) : 0.f;
+      named_bar_sync(1, 128);
+    }
     mbar_wait(tmem_full_bar, 0);
+    if (warp == 2 && lane == 0) stamp(5);
     tc_fence_after();
     const bool have_acc = kb_end > kb_begin;
+    if (warp_has_rows) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      if (n0 + c0 >= p.N) break;  // warp-uniform
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
-      tmem_ld_wait();
-      float v[32];
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        if constexpr (CH == 32) tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+        else tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+        // issue the (optional) ReLU-mask row loads before waiting on TMEM so that both latencies overlap
+        float mk[CH];
+        const bool full = n0 + c0 + CH <= p.N;
+        if (p.mask != nullptr) {
+          const float* mrow = p.mask + (long long)m * p.ldmask + n0 + c0;
+          if (row_ok && full && ((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c0 + j;
-        float x = have_acc ? __uint_as_float(r[j]) * p.alpha : 0.f;
-        if (p.bias != nullptr && n < p.N && blockIdx.z == 0) x += __ldg(p.bias + n);
-        if (p.relu) x = fmaxf(x, 0.f);
-        if (p.mask != nullptr && row_ok && n < p.N) x = (__ldg(p.mask + (long long)m * p.ldmask + n) > 0.f) ? x : 0.f;
-        v[j] = (row_ok && n < p.N) ? x : 0.f;
-      }
-      if (p.colsum != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = warp_sum(v[j]);
-          if (lane == 0 && n0 + c0 + j < p.N) atomicAdd(p.colsum + n0 + c0 + j, s);
-        }
-      }
-      if (row_ok) {
-        if (p.store_mode == 0) {
-          float* dst = p.D + (long long)m * p.ldd + n0 + c0;
-          const bool vec = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && (n0 + c0 + 32 <= p.N) && !p.accumulate;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < CH; j += 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(mrow + j)); mk[j] = t.x; mk[j + 1] = t.y; mk[j + 2] = t.z; mk[j + 3] = t.w; }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n0 + c0 + j < p.N) {
-                if (p.accumulate) atomicAdd(dst + j, v[j]);
-                else dst[j] = v[j];
+            for (int j = 0; j < CH; ++j) mk[j] = (row_ok && n0 + c0 + j < p.N) ? __ldg(mrow + j) : 0.f;
+          }
+        }
+        tmem_ld_wait();
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          float x = have_acc ? __uint_as_float(r[j]) * p.alpha : 0.f;
+          x += s_bias[c0 + j];
+          if (p.relu) x = fmaxf(x, 0.f);
+          if (p.mask != nullptr) x = mk[j] > 0.f ? x : 0.f;
+          v[j] = (row_ok && n0 + c0 + j < p.N) ? x : 0.f;
+        }
+        if (p.colsum != nullptr) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const float s = warp_sum(v[j]);
+            if (lane == 0 && n0 + c0 + j < p.N) atomicAdd(p.colsum + n0 + c0 + j, s);
+          }
+        }
+        if (row_ok) {
+          if (p.store_mode == 0) {
+            float* dst = p.D + (long long)m * p.ldd + n0 + c0;
+            const bool vec = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && full && !p.accumulate;
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) {
+                if (n0 + c0 + j < p.N) {
+                  if (p.accumulate) atomicAdd(dst + j, v[j]);
+                  else dst[j] = v[j];
+                }
               }
             }
-          }
-        } else {
-          // NCHW scatter: row m = (image, pixel), column n = channel
-          const int img = m / p.hw, pix = m - img * p.hw;
-          float* dst = p.D + ((long long)img * p.N) * p.hw + pix;
+          } else {
+            // NCHW scatter: row m = (image, pixel), column n = channel
+            const int img = m / p.hw, pix = m - img * p.hw;
+            float* dst = p.D + ((long long)img * p.N) * p.hw + pix;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < p.N) {
-              if (p.accumulate) atomicAdd(dst + (long long)n * p.hw, v[j]);
-              else dst[(long long)n * p.hw] = v[j];
+            for (int j = 0; j < CH; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < p.N) {
+                if (p.accumulate) atomicAdd(dst + (long long)n * p.hw, v[j]);
+                else dst[(long long)n * p.hw] = v[j];
+              }
             }
           }
         }
       }
     }
     tc_fence_before();
+    if (warp == 2 && lane == 0) stamp(6);
   }
   __syncthreads();
   if (warp == 1) {
@@ -261,8 +300,16 @@ static int make_tmap(CUtensorMap* tm, const float* base, long long inner, long l
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, dim3 grid, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N>;
+  static int env_stages = -1;
+  if (env_stages < 0) { const char* e = getenv("GEOMX_GEMM_STAGES"); env_stages = e ? atoi(e) : 0; }
+  int stages = L::STAGES;
+  if (p.kb_per_split < stages) stages = p.kb_per_split;   // never more ring slots than K blocks
+  if (env_stages > 0 && env_stages < stages) stages = env_stages;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const int smem_bytes = stages * L::STAGE_BYTES + 256 + 512 + 1024;
   static bool attr_set = false;
   auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
   if (!attr_set) {
@@ -270,7 +317,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, p);
+  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, ta, tb, p);
   return (int)cudaGetLastError();
 }
 
@@ -284,6 +331,9 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 
 }  // namespace gx
 
+static unsigned long long* g_gemm_dbg = nullptr;
+GX_API int gx_gemm_set_debug(unsigned long long* p) { g_gemm_dbg = p; return 0; }
+
 // A: K-major -> [M][K] with row stride lda; MN-major -> [K][M] with row stride lda.  Same for B with N.
 // returns 0 on success, -1 if the operands do not satisfy TMA alignment (caller falls back to gx_gemm_simt).
 GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
@@ -293,17 +343,28 @@ GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B,
   using namespace gx;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -1;
-  int block_n;
+  // tile width: these problems are bound by how fast ONE SM can pull its operand panel out of L2 (~100 GB/s per SM, measured with
+  // tools/gemm_phases.py), so small problems are cut into narrow tiles to spread the B panel over many SMs; large ones use 128-wide tiles.
+  int block_n = 16;
   const long long mt = ceil_div(M, BLOCK_M);
-  if (N <= 32) block_n = 32;
-  else if (N <= 64 || mt * ceil_div(N, 128) < 48) block_n = 64;
-  else block_n = 128;
+  for (int bn : {128, 64, 32, 16}) {
+    if (mt * ceil_div(N, bn) >= 24 || bn == 16) { block_n = bn; break; }
+  }
+  if (mt * ceil_div(N, 128) >= 148) block_n = 128;
+  if (b_mn && block_n < 32) block_n = 32;   // an MN-major B tile is made of 32-wide TMA boxes
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, false);
+  // TMA cost is per requested row (measured: ~1.5 ns per box row, in or out of bounds), so boxes are trimmed to the rows that exist when the
+  // whole problem fits one tile in that dimension; the untouched smem rows feed accumulator lanes that the epilogue never stores.
+  const int a_rows = (mt == 1) ? (int)((M + 7) / 8 * 8) : BLOCK_M;
+  const int nt = (int)ceil_div(N, block_n);
+  const int b_rows = (nt == 1) ? (int)((N + 7) / 8 * 8 < block_n ? (N + 7) / 8 * 8 : block_n) : block_n;
+  const int a_boxes = (mt == 1) ? (int)ceil_div(M, 32) : BLOCK_M / 32;
+  const int b_boxes = (nt == 1) ? (int)ceil_div(N, 32) : block_n / 32;
+  if (!a_mn) rc = make_tmap(&ta, A, K, M, lda, BLOCK_K, a_rows, false);
   else rc = make_tmap(&ta, A, M, K, lda, 32, BLOCK_K, true);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K, block_n, false);
+  if (!b_mn) rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K, b_rows, false);
   else rc = make_tmap(&tb, B, N, K, ldb, 32, BLOCK_K, true);
   if (rc) return rc;
   const int num_kb = (int)ceil_div(K, BLOCK_K);
@@ -315,9 +376,12 @@ GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B,
   split_k = (int)ceil_div(num_kb, p.kb_per_split);
   p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
   p.relu = relu; p.accumulate = (accumulate || split_k > 1) ? 1 : 0; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha;
-  p.wait_flag = wait_flag; p.wait_epoch = wait_epoch;
+  p.wait_flag = wait_flag; p.wait_epoch = wait_epoch; p.stages = 0; p.dbg = g_gemm_dbg;
+  p.a_boxes = a_boxes < 1 ? 1 : a_boxes; p.b_boxes = b_boxes < 1 ? 1 : b_boxes;
+  p.tx_bytes = (a_mn ? p.a_boxes * MN_BOX_BYTES : a_rows * BLOCK_K * 4) + (b_mn ? p.b_boxes * MN_BOX_BYTES : b_rows * BLOCK_K * 4);
   dim3 grid((unsigned)ceil_div(N, block_n), (unsigned)mt, (unsigned)split_k);
   switch (block_n) {
+    case 16: return dispatch_major<16>(a_mn, b_mn, ta, tb, p, grid, stream);
     case 32: return dispatch_major<32>(a_mn, b_mn, ta, tb, p, grid, stream);
     case 64: return dispatch_major<64>(a_mn, b_mn, ta, tb, p, grid, stream);
     default: return dispatch_major<128>(a_mn, b_mn, ta, tb, p, grid, stream);
@@ -388,7 +452,7 @@ GX_API int gx_gemm_simt(const float* A, long long lda, int a_mn, const float* B,
   if (M <= 0 || N <= 0) return 0;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.kb_per_split = 0; p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
-  p.relu = relu; p.accumulate = accumulate; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha; p.wait_flag = nullptr; p.wait_epoch = nullptr;
+  p.relu = relu; p.accumulate = accumulate; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha; p.wait_flag = nullptr; p.wait_epoch = nullptr; p.stages = 0; p.dbg = nullptr; p.a_boxes = p.b_boxes = 0; p.tx_bytes = 0;
   dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
   launch_pdl(gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, A, lda, a_mn, B, ldb, b_mn, M, N, K, p);
   return (int)cudaGetLastError();

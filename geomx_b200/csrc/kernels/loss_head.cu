@@ -66,9 +66,13 @@ __global__ void __launch_bounds__(1024) head_fwd_bwd_kernel(const float* __restr
   float* sw = sa + B * K;       // [C][K]
   float* dl = sw + C * K;       // [B][C]
   float* sda = dl + B * C;      // [B][K] masked input gradient (for the column sums)
+  float* sbias = sda + B * K;   // [C]
+  float* slab = sbias + 32;     // [B]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int i = threadIdx.x; i < (B * K) / 4; i += blockDim.x) reinterpret_cast<float4*>(sa)[i] = reinterpret_cast<const float4*>(a)[i];
   for (int i = threadIdx.x; i < (C * K) / 4; i += blockDim.x) reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(W)[i];
+  if (threadIdx.x < C) sbias[threadIdx.x] = bias[threadIdx.x];
+  for (int i = threadIdx.x; i < B; i += blockDim.x) slab[i] = label[i];
   __syncthreads();
   for (int b = wid; b < B; b += nw) {
     const float* ab = sa + b * K;
@@ -77,14 +81,14 @@ __global__ void __launch_bounds__(1024) head_fwd_bwd_kernel(const float* __restr
       float p = 0.f;
       const float* wc = sw + c * K;
       for (int k = lane; k < K; k += 32) p = fmaf(ab[k], wc[k], p);
-      p = warp_sum(p) + bias[c];
+      p = warp_sum(p) + sbias[c];
       if (lane == c) mylogit = p;
     }
     float mx = lane < C ? mylogit : -INFINITY;
     mx = warp_max(mx);
     const float e = lane < C ? __expf(mylogit - mx) : 0.f;
     const float s = warp_sum(e);
-    const int l = (int)label[b];
+    const int l = (int)slab[b];
     if (lane < C) {
       dl[b * C + lane] = e / s - (lane == l ? 1.f : 0.f);
       if (logits_out) logits_out[(long long)b * C + lane] = mylogit;
@@ -136,7 +140,7 @@ GX_API int gx_softmax_ce_bwd(const float* x, const float* label, const float* dl
 }
 GX_API int gx_head_fwd_bwd(const float* a, const float* W, const float* bias, const float* label, float* loss, float* logits, float* dW,
                            float* db, float* da, float* dbias_prev, int B, int K, int C, int relu_mask, cudaStream_t s) {
-  const size_t smem = ((size_t)2 * B * K + (size_t)C * K + (size_t)B * C) * sizeof(float);
+  const size_t smem = ((size_t)2 * B * K + (size_t)C * K + (size_t)B * C + 32 + (size_t)B) * sizeof(float);
   if (C > 32 || (long long)B * C > 8192 || smem > 200 * 1024 || (K & 3)) return -1;
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(head_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }

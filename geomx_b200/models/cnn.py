@@ -123,45 +123,55 @@ class HipsCNNTrainStep:
         self.net = net
 
     # ------------------------------------------------------------------------------------------------------------
-    def _body(self):
+    def _steps(self):
+        """The training step as an ordered list of (name, stream, launch) — 15 kernels; `stream` is 'main' or 'side' (parallel graph branch)."""
         n = native
         B, P, G, f = self.B, self.P, self.G, self.fabric
-        before = n.launch_count
-        wf = we = None
+        a2f = self.a2.view(B, 512)
+        Wc1, Gc1 = P[2].view(32, 400), G[2].view(32, 400)
+        kv = (lambda: (f.async_step(), f.grad.tensor.zero_() if self.fused_zero_grad else None)) if self.mode == "dist_async" else \
+            (lambda: f.fsa_step(defer_pull_wait=False, zero_grad=self.fused_zero_grad))
+        return [
+            ("conv0+relu+pool+im2col", "main", lambda: n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)),
+            ("conv1 gemm (bias,relu,nchw)", "main", lambda: n.gemm(self.col1, Wc1, self.z2, bias=P[3], relu=True, store_nchw_hw=64)),
+            ("maxpool", "main", lambda: n.maxpool2x2_fwd(self.z2, self.a2, self.idx2)),
+            ("dense0 gemm", "main", lambda: n.gemm(a2f, P[4], self.a3, bias=P[5], relu=True)),
+            ("dense1 gemm", "main", lambda: n.gemm(self.a3, P[6], self.a4, bias=P[7], relu=True)),
+            ("head fwd+bwd", "main", lambda: n.head_fwd_bwd(self.a4, P[8], P[9], self.label, self.loss, self.logits, G[8], G[9], self.dz4, G[7], True)),
+            ("dW1 gemm", "side", lambda: n.gemm(self.dz4, self.a3, G[6], a_mn=True, b_mn=True)),
+            ("dz3 gemm (mask,colsum)", "main", lambda: n.gemm(self.dz4, P[6], self.dz3, b_mn=True, mask=self.a3, colsum=G[5])),
+            ("dW0 gemm", "side", lambda: n.gemm(self.dz3, a2f, G[4], a_mn=True, b_mn=True)),
+            ("da2 gemm", "main", lambda: n.gemm(self.dz3, P[4], self.da2, b_mn=True)),
+            ("pool+relu bwd -> rows", "main", lambda: n.pool_relu_bwd_rows(self.da2.view(B, 32, 4, 4), self.a2, self.idx2, self.dz2rows, G[3])),
+            ("dWc1 gemm (split-K)", "side", lambda: n.gemm(self.dz2rows, self.col1, Gc1, a_mn=True, b_mn=True, split_k=16, accumulate=True)),
+            ("dcol1 gemm", "main", lambda: n.gemm(self.dz2rows, Wc1, self.dcol1, b_mn=True)),
+            ("conv0 wgrad + col2im", "main", lambda: n.conv_relu_pool_wgrad_col2im(self.x, self.dcol1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0], 5, 5)),
+            ("hips push+opt+pull", "join", kv),
+        ]
+
+    def _body(self, stop_after=None):
+        before = native.launch_count
+        f = self.fabric
         # the gradient arena is cleared by the previous step's HiPS kernel (fused zero_grad) unless gradients must stay readable
         if not self.fused_zero_grad:
             f.grad.tensor.zero_()
-        n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)     # 1+2 conv0+ReLU+pool and conv1's im2col slab
-        n.gemm(self.col1, P[2].view(32, 400), self.z2, bias=P[3], relu=True, store_nchw_hw=64)  # 3 conv1 (tcgen05)
-        n.maxpool2x2_fwd(self.z2, self.a2, self.idx2)                                           # 4
-        a2f = self.a2.view(B, 512)
-        n.gemm(a2f, P[4], self.a3, bias=P[5], relu=True)                                        # 5 dense0
-        n.gemm(self.a3, P[6], self.a4, bias=P[7], relu=True)                                    # 6 dense1
-        n.head_fwd_bwd(self.a4, P[8], P[9], self.label, self.loss, self.logits, G[8], G[9], self.dz4, G[7], True)   # 7
-        # weight-gradient GEMMs leave the critical path: they run on a side stream (parallel branches of the captured graph)
         main, side = torch.cuda.current_stream(), self._side
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            n.gemm(self.dz4, self.a3, G[6], a_mn=True, b_mn=True)                               # 8  dW1 = dz4ᵀ·a3
-        n.gemm(self.dz4, P[6], self.dz3, b_mn=True, mask=self.a3, colsum=G[5])                  # 9  dz3 = (dz4·W1)⊙[a3>0], db0
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            n.gemm(self.dz3, a2f, G[4], a_mn=True, b_mn=True)                                   # 10 dW0
-        n.gemm(self.dz3, P[4], self.da2, b_mn=True)                                             # 11 da2
-        n.pool_relu_bwd_rows(self.da2.view(B, 32, 4, 4), self.a2, self.idx2, self.dz2rows, G[3])  # 12 (+dbc1)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            n.gemm(self.dz2rows, self.col1, G[2].view(32, 400), a_mn=True, b_mn=True, split_k=16, accumulate=True)  # 13 dWc1
-        n.gemm(self.dz2rows, P[2].view(32, 400), self.dcol1, b_mn=True)                         # 14 dcol1
-        n.conv_relu_pool_wgrad_col2im(self.x, self.dcol1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0], 5, 5)   # 15+16 col2im fused
-        main.wait_stream(side)
-        if self.mode == "dist_async":
-            f.async_step()                                                                      # 17 MixedSync
-            if self.fused_zero_grad:
-                f.grad.tensor.zero_()
-        else:
-            f.fsa_step(defer_pull_wait=False, zero_grad=self.fused_zero_grad)                                                 # 17 HiPS push+pull (FSA)
-        self.kernels_per_step = n.launch_count - before
+        forked = False
+        for i, (name, where, fn) in enumerate(self._steps()):
+            if stop_after is not None and i >= stop_after:
+                break
+            if where == "side":      # weight-gradient GEMMs leave the critical path: parallel branch of the captured graph
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    fn()
+                forked = True
+            else:
+                if where == "join" and forked:
+                    main.wait_stream(side); forked = False
+                fn()
+        if forked:
+            main.wait_stream(side)
+        self.kernels_per_step = native.launch_count - before
 
     def capture(self):
         """Warm up (2 eager steps on a side stream) and capture the step into a CUDA graph."""
