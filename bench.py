@@ -157,6 +157,8 @@ def main():
     for i in range(K):
         if flush is not None:
             flush.fill_(float(i))
+            if world > 1 and getattr(eng, "fabric", None) is not None:
+                eng.fabric.barrier()      # untimed: re-align the ranks after the (long) flush so that the timed step does not include peers' flush skew
         starts[i].record()
         eng.run_device()
         ends[i].record()

@@ -65,6 +65,11 @@ struct FabricParams {
   int ready_off;               // uint32 offset of grad_ready[MAX_RANKS] (per channel: every kernel family has its own epoch)
   int arrived_off;             // uint32 offset of arrived[num_parties][tiles]
   int zero_grad;               // fuse zero_grad: clear this rank's gradient arena once every reader is done with it
+  // ---- LL ("low latency") protocol buffers: 8-byte {value, epoch} packets, no flags and no fences on the critical path
+  float* ll_a[MAX_RANKS];      // peer pointers: [party_size][2n]  gradients pushed by party members to a tile's party owner
+  float* ll_b[MAX_RANKS];      // peer pointers: [num_parties][2n] party aggregates pushed to a tile's global owner
+  float* ll_c[MAX_RANKS];      // peer pointers: [2n]              fresh parameters pushed by the global owner to every rank
+  float* ll_c_mc;              // multicast address of ll_c (nullptr -> one P2P store per rank)
 };
 
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
@@ -147,6 +152,10 @@ __device__ __forceinline__ void global_apply_tile(const FabricParams& p, int t, 
 __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const FabricParams p) {
   gx::pdl_wait();
   gx::pdl_launch();
+  const bool dbg = p.state[3] != 0 && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(p.state + 8);
+  auto stamp = [&](int i) { if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); stamps[i] = t; } };
+  stamp(0);
   const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
   const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
   __shared__ float s_lr;
@@ -163,6 +172,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
     st_release_sys(p.flags[party_base + threadIdx.x] + p.ready_off + p.rank, epoch);
   }
 
+  stamp(1);
   // ---------------- phase B: local PS tier (party reduction of owned tiles)
   bool waited_party = false;
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
@@ -172,6 +182,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
       if (threadIdx.x < S) wait_flag_ge(my_flags + p.ready_off + party_base + threadIdx.x, epoch);
       __syncthreads();
       waited_party = true;
+      stamp(6);
     }
     const long long off = (long long)t * TILE + threadIdx.x * 4;
     float4 acc;
@@ -182,10 +193,13 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
       for (int j = 1; j < S; ++j) acc = f4_add(acc, ld_f4_sys(p.grad[party_base + j] + off));
     }
     acc = f4_scale(acc, p.push_scale);
+    if (dbg && acc.x == 123.456f) stamps[20] = 1;  // (debug) force the loads to retire before the stamp
+    stamp(7);
     if (p.zero_grad && p.world == 1) *reinterpret_cast<float4*>(p.grad[p.rank] + off) = make_float4(0.f, 0.f, 0.f, 0.f);
     const int owner = p.tile_owner[t];
     if (P == 1 && owner == p.rank) {
       global_apply_tile(p, t, acc, epoch, lr_t);  // both tiers collapse: stay in registers
+      stamp(8);
     } else {
       st_f4_sys(p.stage[owner] + (long long)p.party * p.n + off, acc);
       __syncthreads();
@@ -193,9 +207,11 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
         fence_sys();
         st_release_sys(p.flags[owner] + p.arrived_off + p.party * p.tiles + t, epoch);
       }
+      stamp(8);
     }
   }
 
+  stamp(2);
   // ---------------- phase C: global PS tier (tiles this rank owns globally)
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
     if (p.tile_owner[t] != p.rank) continue;
@@ -203,18 +219,22 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
     if (P == 1 && (t % S) == p.local) continue;  // already applied in phase B
     if (threadIdx.x < P) wait_flag_ge(my_flags + p.arrived_off + threadIdx.x * p.tiles + t, epoch);
     __syncthreads();
+    stamp(9);
     const long long off = (long long)t * TILE + threadIdx.x * 4;
     float4 acc = ld_f4_sys(p.stage[p.rank] + off);
     for (int g = 1; g < P; ++g) acc = f4_add(acc, ld_f4_sys(p.stage[p.rank] + (long long)g * p.n + off));
     global_apply_tile(p, t, acc, epoch, lr_t);
+    stamp(10);
   }
 
+  stamp(3);
   // ---------------- phase D: wait for the broadcast (unless deferred to the consuming GEMM)
   if (p.world > 1 && !p.defer_pull_wait && blockIdx.x == 0) {
     for (int t = threadIdx.x; t < p.tiles; t += blockDim.x)
       if (p.tile_active == nullptr || p.tile_active[t]) wait_flag_ge(my_flags + p.param_ready_off + p.tile_key[t], epoch);
   }
 
+  stamp(4);
   // ---------------- fused zero_grad (multi-rank): a key's ready flag implies that every tile of it was reduced by its owner, i.e. nobody
   // will read this rank's gradients of that key again this round
   if (p.zero_grad && p.world > 1 && !p.defer_pull_wait) {
@@ -226,6 +246,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
     }
   }
 
+  stamp(5);
   // ---------------- epoch / optimizer step bookkeeping (last CTA to finish publishes the new epoch)
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -238,6 +259,124 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
       __threadfence();
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------ LL protocol
+// The flag protocol above costs one fence.acq_rel.sys per hand-off and tools/fabric_probe.py measures 2.4-7 us for each of them on
+// NVSwitch (three on the critical path of a two-tier step).  For latency-bound models the LL variant below trades 2x bytes for zero
+// fences: every 16-byte store carries {v0, epoch, v1, epoch}; each 8-byte half is written atomically, so the receiver simply polls the
+// packet until both epochs match (the scheme NCCL's LL protocol relies on).  The epoch grows by one per step, packets never need clearing.
+// Data flow per tile:  every rank --push--> party owner --aggregate--> global owner --Adam + push--> every rank --unpack--> param arena.
+// A sender overwrites a packet of step e only in step e+1, which it enters after it has unpacked ALL parameters of step e, and those
+// were produced after every packet of step e had been consumed => no extra credit/ack traffic is required in dist_sync.
+__device__ __forceinline__ void ll_store(float* dst, float4 v, uint32_t epoch) {
+  const float f = __uint_as_float(epoch);
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(v.x), "f"(f), "f"(v.y), "f"(f) : "memory");
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4), "f"(v.z), "f"(f), "f"(v.w), "f"(f) : "memory");
+}
+__device__ __forceinline__ void ll_store_mc(float* mc, float4 v, uint32_t epoch) {
+  const float f = __uint_as_float(epoch);
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(f), "f"(v.y), "f"(f) : "memory");
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + 4), "f"(v.z), "f"(f), "f"(v.w), "f"(f) : "memory");
+}
+// Poll a (local) packet pair until both halves carry `epoch`.  Bounded: a protocol bug must not hang the GPU (state[5] reports it).
+__device__ __forceinline__ float4 ll_load(const float* src, uint32_t epoch, int* err) {
+  float4 a, b;
+  const float f = __uint_as_float(epoch);
+  for (long long spin = 0;; ++spin) {
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src) : "memory");
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 4) : "memory");
+    if (__float_as_uint(a.y) == epoch && __float_as_uint(a.w) == epoch && __float_as_uint(b.y) == epoch && __float_as_uint(b.w) == epoch) break;
+    if (spin > (1ll << 24)) { *err = 1; break; }
+  }
+  (void)f;
+  return make_float4(a.x, a.z, b.x, b.z);
+}
+
+__global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const FabricParams p) {
+  gx::pdl_wait();
+  gx::pdl_launch();
+  const bool dbg = p.state[3] != 0 && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(p.state + 8);
+  auto stamp = [&](int i) { if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); stamps[i] = t; } };
+  stamp(0);
+  const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
+  const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
+  const float lr_t = adam_lr(p.h, opt_t);
+  const int S = p.party_size, P = p.num_parties;
+  const int party_base = p.party * S;
+  const long long n2 = 2 * p.n;
+  int* err = p.state + 5;
+
+  // ---- phase 1: push my gradient tiles to their party owners (tiles I own myself are read in place in phase 2)
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    if (t % S == p.local) continue;
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float* g = p.grad[p.rank] + off;
+    const float4 v = *reinterpret_cast<const float4*>(g);
+    if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
+    ll_store(p.ll_a[party_base + t % S] + (long long)p.local * n2 + 2 * off, v, epoch);
+  }
+  stamp(1);
+  // ---- phase 2: LOCAL PS TIER: the party owner sums the party's gradients of its tiles and forwards the aggregate to the global owner
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    if (t % S != p.local) continue;
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float* g = p.grad[p.rank] + off;
+    float4 acc = *reinterpret_cast<const float4*>(g);
+    if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < S; ++j) {
+      if (j == p.local) continue;
+      acc = f4_add(acc, ll_load(p.ll_a[p.rank] + (long long)j * n2 + 2 * off, epoch, err));
+    }
+    acc = f4_scale(acc, p.push_scale);
+    ll_store(p.ll_b[p.tile_owner[t]] + (long long)p.party * n2 + 2 * off, acc, epoch);
+  }
+  stamp(2);
+  // ---- phase 3: GLOBAL PS TIER: the global owner sums the parties' aggregates, runs the optimizer on its shard and pushes the parameters
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    if (p.tile_owner[t] != p.rank) continue;
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float lr = lr_t, wd = p.h.wd;
+    if (p.tile_mult) { const float2 mm = __ldg(p.tile_mult + t); lr *= mm.x; wd *= mm.y; }
+    float4 W = *reinterpret_cast<float4*>(p.w + off);   // issued before the poll: the state loads overlap the wait
+    float4 A = p.s0 ? *reinterpret_cast<float4*>(p.s0 + off) : make_float4(0, 0, 0, 0);
+    float4 B = p.s1 ? *reinterpret_cast<float4*>(p.s1 + off) : make_float4(0, 0, 0, 0);
+    float4 agg = ll_load(p.ll_b[p.rank] + 2 * off, epoch, err);
+    for (int g = 1; g < P; ++g) agg = f4_add(agg, ll_load(p.ll_b[p.rank] + (long long)g * n2 + 2 * off, epoch, err));
+    opt_apply(W.x, agg.x, A.x, B.x, p.h, lr, wd);
+    opt_apply(W.y, agg.y, A.y, B.y, p.h, lr, wd);
+    opt_apply(W.z, agg.z, A.z, B.z, p.h, lr, wd);
+    opt_apply(W.w, agg.w, A.w, B.w, p.h, lr, wd);
+    if (p.ll_c_mc != nullptr) ll_store_mc(p.ll_c_mc + 2 * off, W, epoch);
+    else for (int r = 0; r < p.world; ++r) ll_store(p.ll_c[r] + 2 * off, W, epoch);
+    *reinterpret_cast<float4*>(p.w + off) = W;
+    if (p.s0) *reinterpret_cast<float4*>(p.s0 + off) = A;
+    if (p.s1) *reinterpret_cast<float4*>(p.s1 + off) = B;
+  }
+  stamp(3);
+  // ---- phase 4: pull: unpack the fresh parameters into the (plain fp32) parameter arena the forward pass reads
+  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    *reinterpret_cast<float4*>(p.param[p.rank] + off) = ll_load(p.ll_c[p.rank] + 2 * off, epoch, err);
+  }
+  stamp(4);
+  // bookkeeping: the state words are only read by the NEXT launch (kernel boundary orders them), so a relaxed counter is enough —
+  // a __threadfence here would wait for every outstanding remote store of this CTA (~2 us)
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(p.state + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      p.state[1] = 0;
+      p.state[2] = opt_t;
+      p.state[0] = (int)epoch;
+    }
+  }
+  stamp(5);
 }
 
 // One-sided MixedSync: the party's tile owner applies its aggregate directly on the global owner's HBM under a per-tile lock.
@@ -375,6 +514,53 @@ __global__ void fabric_barrier_kernel(uint32_t* const* flags, int world, int ran
   }
 }
 
+
+// Fabric micro-probe (tools/fabric_probe.py): latency of every primitive the fused kernels are built from, measured by thread 0 of
+// CTA 0 with %globaltimer (ns) while the whole grid performs the same access on its own 4 KB tile (so queueing is included).
+//   out[2k], out[2k+1] = first / second measurement of primitive k
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory"); return t; }
+__device__ __forceinline__ void consume(float v) {  // a store cannot issue before its operand arrived, and the timer read is ordered after it
+  __shared__ float sink[FAB_THREADS];
+  asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(sink + threadIdx.x)), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(FAB_THREADS, 1) fabric_probe_kernel(float* local, float* peer, float* mc, uint32_t* peer_flag,
+                                                                      unsigned long long* out, int tiles) {
+  const bool rec = blockIdx.x == 0 && threadIdx.x == 0;
+  const long long off0 = (long long)(blockIdx.x % tiles) * TILE + threadIdx.x * 4;
+  const long long off1 = (long long)((blockIdx.x + gridDim.x) % tiles) * TILE + threadIdx.x * 4;
+  unsigned long long t0;
+  float4 v;
+  for (int rep = 0; rep < 2; ++rep) {
+    const long long off = rep ? off1 : off0;
+    int k = 0;
+    auto done = [&]() { if (rec) out[2 * k + rep] = gtime() - t0; ++k; __syncthreads(); };
+    // 0 local weak load
+    t0 = gtime(); asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(local + off) : "memory"); consume(v.x); done();
+    // 1 local ld.relaxed.sys
+    t0 = gtime(); v = ld_f4_sys(local + off); consume(v.x); done();
+    // 2 peer weak load (L1-cacheable)
+    t0 = gtime(); asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(peer + off) : "memory"); consume(v.x); done();
+    // 3 peer ld.relaxed.sys
+    t0 = gtime(); v = ld_f4_sys(peer + off); consume(v.x); done();
+    // 4 multimem.ld_reduce
+    if (mc) { t0 = gtime(); v = multimem_ld_reduce_f4(mc + off); consume(v.x); } else t0 = gtime();
+    done();
+    // 5 peer store + fence.sys
+    t0 = gtime(); st_f4_sys(peer + off, v); fence_sys(); done();
+    // 6 multimem.st + fence.sys
+    t0 = gtime(); if (mc) { multimem_st_f4(mc + off, v); fence_sys(); } done();
+    // 7 fence.sys with nothing outstanding
+    t0 = gtime(); fence_sys(); done();
+    // 8 peer store, __syncthreads, ONE fence by thread 0, release flag store (the tile hand-off idiom)
+    t0 = gtime(); st_f4_sys(peer + off, v); __syncthreads(); if (threadIdx.x == 0) { fence_sys(); st_release_sys(peer_flag + blockIdx.x, 1u); } done();
+    // 9 local acquire load of a flag
+    t0 = gtime(); { uint32_t f = ld_acquire_sys(peer_flag + 4096 + blockIdx.x); consume(__uint_as_float(f)); } done();
+    // 10 local store + __threadfence
+    t0 = gtime(); *reinterpret_cast<float4*>(local + off) = v; __threadfence(); done();
+  }
+}
+
 }  // namespace gx
 
 using namespace gx;
@@ -386,6 +572,22 @@ GX_API int gx_hips_fsa_step(const void* params, int grid, cudaStream_t s) {
   FabricParams p = *reinterpret_cast<const FabricParams*>(params);
   if (grid < 1) grid = 1;
   launch_pdl(hips_fsa_step_kernel, dim3(grid), dim3(FAB_THREADS), 0, s, p);
+  return GX_CHECK_LAUNCH();
+}
+// Largest co-resident grid of the fused kernels (they spin on each other: every CTA of a launch must be resident).
+GX_API int gx_hips_max_grid() {
+  int dev = 0, sms = 0, occ_a = 0, occ_b = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, hips_fsa_ll_kernel, FAB_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, hips_fsa_step_kernel, FAB_THREADS, 0);
+  const int occ = occ_a < occ_b ? occ_a : occ_b;
+  return sms * (occ < 1 ? 1 : (occ > 2 ? 2 : occ));
+}
+GX_API int gx_hips_fsa_ll_step(const void* params, int grid, cudaStream_t s) {
+  FabricParams p = *reinterpret_cast<const FabricParams*>(params);
+  if (grid < 1) grid = 1;
+  launch_pdl(hips_fsa_ll_kernel, dim3(grid), dim3(FAB_THREADS), 0, s, p);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_hips_async_step(const void* params, float* const* w_peer, float* const* s0_peer, float* const* s1_peer, int lock_off, int step_off,
@@ -402,5 +604,10 @@ GX_API int gx_hips_party_allreduce(const void* params, float* const* src_peer, f
 }
 GX_API int gx_fabric_barrier(uint32_t* const* flags_dev, int world, int rank, int off, int* state, cudaStream_t s) {
   launch_pdl(fabric_barrier_kernel, dim3(1), dim3(32), 0, s, flags_dev, world, rank, off, state);
+  return GX_CHECK_LAUNCH();
+}
+
+GX_API int gx_fabric_probe(float* local, float* peer, float* mc, uint32_t* peer_flag, unsigned long long* out, int tiles, int grid, cudaStream_t s) {
+  fabric_probe_kernel<<<grid, FAB_THREADS, 0, s>>>(local, peer, mc, peer_flag, out, tiles);
   return GX_CHECK_LAUNCH();
 }

@@ -49,9 +49,12 @@ SIGS = {
     # hips_fabric.cu
     "gx_fabric_params_size": [],
     "gx_hips_fsa_step": [P, I, P],
+    "gx_hips_fsa_ll_step": [P, I, P],
+    "gx_hips_max_grid": [],
     "gx_hips_async_step": [P, P, P, P, I, I, I, P],
     "gx_hips_party_allreduce": [P, P, P, F, I, I, I, P],
     "gx_fabric_barrier": [P, I, I, I, P, P],
+    "gx_fabric_probe": [P, P, P, P, P, I, I, P],
 }
 
 

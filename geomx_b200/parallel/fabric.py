@@ -155,6 +155,8 @@ class _FabricParams(ctypes.Structure):
         ("tile_mult", ctypes.c_void_p), ("key_done", ctypes.c_void_p), ("state", ctypes.c_void_p),
         ("h", _OptHyperF), ("push_scale", ctypes.c_float), ("defer_pull_wait", ctypes.c_int), ("param_ready_off", ctypes.c_int),
         ("ready_off", ctypes.c_int), ("arrived_off", ctypes.c_int), ("zero_grad", ctypes.c_int),
+        ("ll_a", ctypes.c_void_p * MAX_RANKS), ("ll_b", ctypes.c_void_p * MAX_RANKS), ("ll_c", ctypes.c_void_p * MAX_RANKS),
+        ("ll_c_mc", ctypes.c_void_p),
     ]
 
 
@@ -188,6 +190,17 @@ class HipsFabric:
             self.off[name] = off
             off += (size + 15) // 16 * 16
         self.flags = self.heap.alloc(off, torch.int32)
+        # LL protocol (latency-bound arenas): {value, epoch} packet buffers — 2x the arena per sender slot, no fences on the critical path.
+        # Bandwidth-bound arenas (> GEOMX_LL_MAX_BYTES) keep the flag ("bulk") protocol whose fences amortise over many tiles per CTA.
+        ll_max = getenv_int("GEOMX_LL_MAX_BYTES", 64 << 20)
+        proto = os.environ.get("GEOMX_FABRIC_PROTOCOL", "auto")
+        self.protocol = "bulk" if (t.world == 1 or proto == "bulk" or (proto == "auto" and 4 * n > ll_max)) else "ll"
+        if self.protocol == "ll":
+            self.ll_a = self.heap.alloc(t.party_size * 2 * n, torch.float32)
+            self.ll_b = self.heap.alloc(P * 2 * n, torch.float32)
+            self.ll_c = self.heap.alloc(2 * n, torch.float32)
+        else:
+            self.ll_a = self.ll_b = self.ll_c = None
         # --- global-owner state (private HBM) ---------------------------------------------------------------------
         self.w = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.s0 = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -201,11 +214,13 @@ class HipsFabric:
         self.tile_mult = torch.from_numpy(layout.tile_mult()).to(dev)
         self.tile_active = torch.ones(T, dtype=torch.uint8, device=dev)
         self.key_done = torch.zeros(K, dtype=torch.int32, device=dev)
-        self.state = {k: torch.zeros(4, dtype=torch.int32, device=dev) for k in ("fsa", "async", "party", "barrier")}
+        self.state = {k: torch.zeros(64, dtype=torch.int32, device=dev) for k in ("fsa", "async", "party", "barrier")}
         self.use_multicast = use_multicast and bool(self.param.multicast_ptr) and os.environ.get("GEOMX_NO_MULTICAST", "0") != "1"
         self.opt_spec = None
         self.push_scale = 1.0
-        self.grid = max(1, min(T, 132))
+        # one CTA per tile while the launch stays co-resident (the kernels spin on each other); grid-stride beyond that.  The LL kernel's
+        # phases are one round each when grid >= tiles; the bulk protocol keeps <= 132 CTAs (its per-tile fences contend at higher counts)
+        self.grid = max(1, min(T, int(native.require().gx_hips_max_grid()) if self.protocol == "ll" else 132))
         self._params_cache = {}
         self._peer_tables = {}
         self.set_optimizer(opt_spec)
@@ -254,6 +269,11 @@ class HipsFabric:
             p.param[r] = self.param.peer_ptrs[r] or None
             p.stage[r] = self.stage.peer_ptrs[r] or None
             p.flags[r] = self.flags.peer_ptrs[r] or None
+            if self.ll_a is not None:
+                p.ll_a[r] = self.ll_a.peer_ptrs[r] or None
+                p.ll_b[r] = self.ll_b.peer_ptrs[r] or None
+                p.ll_c[r] = self.ll_c.peer_ptrs[r] or None
+        p.ll_c_mc = (self.ll_c.multicast_ptr or None) if (self.ll_a is not None and self.use_multicast and os.environ.get("GEOMX_LL_MULTICAST", "0") == "1") else None
         p.grad_mc = (self.grad.multicast_ptr or None) if self.use_multicast else None
         p.param_mc = (self.param.multicast_ptr or None) if self.use_multicast else None
         p.w, p.s0, p.s1 = self.w.data_ptr(), self.s0.data_ptr(), self.s1.data_ptr()
@@ -288,10 +308,18 @@ class HipsFabric:
     def fsa_step(self, defer_pull_wait=False, masked=False, zero_grad=False):
         """dist_sync: party reduce -> global reduce + optimizer -> broadcast (one launch); optionally clears the gradient arena for the next step."""
         p = self._block("fsa", defer_pull_wait, masked, zero_grad)
-        rc = native.require().gx_hips_fsa_step(ctypes.byref(p), self.grid, self._stream())
+        lib = native.require()
+        if self.protocol == "ll" and not defer_pull_wait:
+            rc = lib.gx_hips_fsa_ll_step(ctypes.byref(p), self.grid, self._stream())
+        else:
+            rc = lib.gx_hips_fsa_step(ctypes.byref(p), self.grid, self._stream())
         native.launch_count += 1
         if rc:
             raise RuntimeError("gx_hips_fsa_step failed rc=%d" % rc)
+
+    def check_protocol_errors(self):
+        """True if a bounded LL poll ever gave up (a protocol bug or a dead peer) — state word 5 of the dist_sync channel."""
+        return bool(int(self.state["fsa"][5].item()))
 
     def async_step(self):
         """dist_async (MixedSync): one-sided update of the global owner's HBM under per-tile locks."""

@@ -35,8 +35,8 @@ def main():
     eng = mx.models.HipsCNNTrainStep(batch_size=B, optimizer=mx.optimizer.SGD(learning_rate=0.1), topo=topo, device=dev, use_graph=False,
                                      use_multicast=not a.no_multicast, mode=a.mode, fused_zero_grad=False)
     if rank == 0:
-        print("fabric backend=%s multicast=%s parties=%d party_size=%d gs=%s" % (eng.fabric.heap.backend, eng.fabric.use_multicast, parties,
-                                                                                 topo.party_size, topo.gs_ranks), flush=True)
+        print("fabric backend=%s protocol=%s multicast=%s parties=%d party_size=%d gs=%s" % (eng.fabric.heap.backend, eng.fabric.protocol, eng.fabric.use_multicast,
+                                                                                          parties, topo.party_size, topo.gs_ranks), flush=True)
     g = torch.Generator().manual_seed(100 + rank)
     X = torch.rand(B, 1, 28, 28, generator=g).to(dev); y = torch.randint(0, 10, (B,), generator=g).float().to(dev)
     eng.x.copy_(X); eng.label.copy_(y)
@@ -69,7 +69,7 @@ def main():
     ref = eng2.fabric.param.tensor.clone(); dist.broadcast(ref, src=0)
     same = bool(torch.equal(ref, eng2.fabric.param.tensor))
     print("rank %d graph: loss %.4f -> %.4f identical=%s" % (rank, l0, l, same), flush=True)
-    ok = ok and l < l0 and (same or a.mode == "dist_async")
+    ok = ok and l < l0 and (same or a.mode == "dist_async") and not eng.fabric.check_protocol_errors() and not eng2.fabric.check_protocol_errors()
     t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("FABRIC_CHECK", "PASS" if int(t) == 1 else "FAIL", flush=True)
