@@ -198,7 +198,8 @@ def main():
                        "optimizer": "Adam(lr=0.01) on the global-PS shard", "cuda_graph": not args.no_graph,
                        "l2": "256 MiB buffer written between timed steps (L2 flush)" if flush is not None else "no flush",
                        "fabric": getattr(getattr(eng, "fabric", None), "heap", None) and eng.fabric.heap.backend,
-                       "multicast": bool(getattr(getattr(eng, "fabric", None), "use_multicast", False))},
+                       "multicast": bool(getattr(getattr(eng, "fabric", None), "use_multicast", False)),
+                       "protocol": getattr(getattr(eng, "fabric", None), "protocol", None)},
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms / K, 5),
                     "h2d_bytes_per_step": eng.h2d_bytes_per_step(), "d2h_bytes_per_step": eng.d2h_bytes_per_step(), "final_loss": round(last_loss, 5)},
             "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),

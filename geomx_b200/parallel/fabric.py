@@ -273,7 +273,7 @@ class HipsFabric:
                 p.ll_a[r] = self.ll_a.peer_ptrs[r] or None
                 p.ll_b[r] = self.ll_b.peer_ptrs[r] or None
                 p.ll_c[r] = self.ll_c.peer_ptrs[r] or None
-        p.ll_c_mc = (self.ll_c.multicast_ptr or None) if (self.ll_a is not None and self.use_multicast and os.environ.get("GEOMX_LL_MULTICAST", "0") == "1") else None
+        p.ll_c_mc = (self.ll_c.multicast_ptr or None) if (self.ll_a is not None and self.use_multicast and os.environ.get("GEOMX_LL_MULTICAST", "1") == "1") else None
         p.grad_mc = (self.grad.multicast_ptr or None) if self.use_multicast else None
         p.param_mc = (self.param.multicast_ptr or None) if self.use_multicast else None
         p.w, p.s0, p.s1 = self.w.data_ptr(), self.s0.data_ptr(), self.s1.data_ptr()

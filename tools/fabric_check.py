@@ -69,7 +69,8 @@ def main():
     ref = eng2.fabric.param.tensor.clone(); dist.broadcast(ref, src=0)
     same = bool(torch.equal(ref, eng2.fabric.param.tensor))
     print("rank %d graph: loss %.4f -> %.4f identical=%s" % (rank, l0, l, same), flush=True)
-    ok = ok and l < l0 and (same or a.mode == "dist_async") and not eng.fabric.check_protocol_errors() and not eng2.fabric.check_protocol_errors()
+    lm = torch.tensor([l0, l], device=dev); dist.all_reduce(lm)   # every rank trains on its own random batch: judge the job-wide loss
+    ok = ok and float(lm[1]) < float(lm[0]) and (same or a.mode == "dist_async") and not eng.fabric.check_protocol_errors() and not eng2.fabric.check_protocol_errors()
     t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("FABRIC_CHECK", "PASS" if int(t) == 1 else "FAIL", flush=True)

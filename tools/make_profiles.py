@@ -46,11 +46,12 @@ def sass_census():
 
 def copy_logs():
     for name in ("breakdown.log", "breakdown_carve.log", "breakdown_noflush.log", "gemm_phases.log", "gemm_phases3.log", "fab2.log", "fab2b.log",
-                 "fab4.log", "fab8.log"):
+                 "fab4.log", "fab8.log", "fab2_ll_p1.log", "fab2_ll_p2.log", "fab4_ll.log", "fab4_ll_gs2.log", "fab8_ll.log", "fabric_probe.log",
+                 "fabphase_1.log", "fabphase_2.log", "fabphase_ll_1.log", "fabphase_ll_2.log", "fabphase_ll4.log", "fabphase_ll8.log"):
         p = os.path.join(GO, name)
         if os.path.exists(p):
             txt = open(p).read()
-            txt = "\n".join(l for l in txt.splitlines() if not l.startswith("frame #"))
+            txt = "\n".join(l for l in txt.splitlines() if not l.startswith("frame #") and "OMP_NUM_THREADS" not in l and not l.startswith("*****"))
             open(os.path.join(OUT, name.replace(".log", ".txt")), "w").write(txt[-12000:])
     rows = []
     for p in sorted(glob.glob(os.path.join(GO, "bench*.log"))):
