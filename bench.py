@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-multicast", action="store_true")
+    ap.add_argument("--wire-dtype", default="fp32", choices=["fp32", "fp16", "mpq"], help="transport format of the fused HiPS step (FP16 / MPQ accelerators)")
     return ap.parse_args()
 
 
@@ -130,7 +131,7 @@ def main():
         eng = OracleCNNTrainStep(batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev, use_graph=not args.no_graph)
     else:
         eng = mx.models.HipsCNNTrainStep(net=None, batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev,
-                                         use_graph=not args.no_graph, use_multicast=not args.no_multicast, mode=args.mode)
+                                         use_graph=not args.no_graph, use_multicast=not args.no_multicast, mode=args.mode, wire_dtype=args.wire_dtype)
 
     def barrier():
         torch.cuda.synchronize()
@@ -199,7 +200,7 @@ def main():
                        "l2": "256 MiB buffer written between timed steps (L2 flush)" if flush is not None else "no flush",
                        "fabric": getattr(getattr(eng, "fabric", None), "heap", None) and eng.fabric.heap.backend,
                        "multicast": bool(getattr(getattr(eng, "fabric", None), "use_multicast", False)),
-                       "protocol": getattr(getattr(eng, "fabric", None), "protocol", None)},
+                       "protocol": getattr(getattr(eng, "fabric", None), "protocol", None), "wire_dtype": args.wire_dtype},
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms / K, 5),
                     "h2d_bytes_per_step": eng.h2d_bytes_per_step(), "d2h_bytes_per_step": eng.d2h_bytes_per_step(), "final_loss": round(last_loss, 5)},
             "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),

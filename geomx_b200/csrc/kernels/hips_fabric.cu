@@ -20,6 +20,7 @@
 // Flag protocol: every cross-rank flag carries the (monotonically increasing) epoch; writers do  stores -> bar.sync -> fence.sys ->
 // st.release.sys, readers spin with ld.acquire.sys.  All CTAs of the launch are co-resident (grid <= #SMs), phases are ordered
 // A < B < C < D inside every CTA and each phase only waits on flags produced by strictly earlier phases => no cyclic wait.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace gx {
@@ -70,6 +71,10 @@ struct FabricParams {
   float* ll_b[MAX_RANKS];      // peer pointers: [num_parties][2n] party aggregates pushed to a tile's global owner
   float* ll_c[MAX_RANKS];      // peer pointers: [2n]              fresh parameters pushed by the global owner to every rank
   float* ll_c_mc;              // multicast address of ll_c (nullptr -> one P2P store per rank)
+  const unsigned char* tile_fmt;  // [tiles] wire format per tile (0 fp32, 1 fp16, 2 Bi-Sparse between the tiers) or nullptr = fp32
+  float* bsc_u;                // Bi-Sparse momentum / accumulation state of the party owner (arena-sized, local HBM)
+  float* bsc_v;
+  int bsc_k;                   // packets per tile and party  (= floor(1024 * threshold), >= 1)
 };
 
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
@@ -294,6 +299,96 @@ __device__ __forceinline__ float4 ll_load(const float* src, uint32_t epoch, int*
   return make_float4(a.x, a.z, b.x, b.z);
 }
 
+// single 16-byte packet {a, epoch, b, epoch}
+__device__ __forceinline__ void ll_store1(float* dst, float a, float b, uint32_t epoch) {
+  const float f = __uint_as_float(epoch);
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(a), "f"(f), "f"(b), "f"(f) : "memory");
+}
+__device__ __forceinline__ void ll_store1_mc(float* mc, float a, float b, uint32_t epoch) {
+  const float f = __uint_as_float(epoch);
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(a), "f"(f), "f"(b), "f"(f) : "memory");
+}
+__device__ __forceinline__ float2 ll_load1(const float* src, uint32_t epoch, int* err) {
+  float4 a;
+  for (long long spin = 0;; ++spin) {
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src) : "memory");
+    if (__float_as_uint(a.y) == epoch && __float_as_uint(a.w) == epoch) break;
+    if (spin > (1ll << 24)) { *err = 1; break; }
+  }
+  return make_float2(a.x, a.z);
+}
+__device__ __forceinline__ float pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+}
+__device__ __forceinline__ float2 unpack_h2(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+// Wire formats of a tile (FabricParams::tile_fmt): the reference's FP16 / MPQ accelerators cast at script level and Bi-Sparse runs on the
+// local server's CPU; here the cast / top-k / scale are fused into the collective kernel itself.
+constexpr int FMT_F32 = 0;   // {v0,e,v1,e}{v2,e,v3,e}
+constexpr int FMT_F16 = 1;   // {h0h1,e,h2h3,e}: half the bytes on every hop (gradients and parameters), fp32 master weights on the owner
+constexpr int FMT_BSC = 2;   // Bi-Sparse between the tiers: k {value, e, index, e} packets per tile instead of 1024 values
+
+// dense value of one thread (4 floats) -> its 32-byte packet region
+__device__ __forceinline__ void ll_send_dense(float* dst, float4 v, int fmt, uint32_t epoch) {
+  if (fmt == FMT_F16) ll_store1(dst, pack_h2(v.x, v.y), pack_h2(v.z, v.w), epoch);
+  else ll_store(dst, v, epoch);
+}
+__device__ __forceinline__ void ll_send_dense_mc(float* mc, float4 v, int fmt, uint32_t epoch) {
+  if (fmt == FMT_F16) ll_store1_mc(mc, pack_h2(v.x, v.y), pack_h2(v.z, v.w), epoch);
+  else ll_store_mc(mc, v, epoch);
+}
+__device__ __forceinline__ float4 ll_recv_dense(const float* src, int fmt, uint32_t epoch, int* err) {
+  if (fmt == FMT_F16) {
+    const float2 pk = ll_load1(src, epoch, err);
+    const float2 a = unpack_h2(pk.x), b = unpack_h2(pk.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return ll_load(src, epoch, err);
+}
+
+// exclusive block scan of one int per thread (FAB_THREADS threads); s_w: >= 8 ints of scratch
+__device__ __forceinline__ int block_excl_scan(int c, int* s_w, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += n; }
+  __syncthreads();
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  int base = 0; total = 0;
+#pragma unroll
+  for (int i = 0; i < FAB_THREADS / 32; ++i) { const int x = s_w[i]; if (i < w) base += x; total += x; }
+  return base + incl - c;
+}
+
+// k-th largest of the 1024 keys of a tile (4 per thread), 8-bit radix select, 4 passes.  Returns the key; `ties` = how many keys equal to
+// it belong to the top-k (they are taken in index order).  s_hist: 256 ints, s_w: 10 ints.
+__device__ __forceinline__ uint32_t block_kth_largest(const uint32_t (&a)[4], int k, int* s_hist, int* s_w, int& ties) {
+  uint32_t prefix = 0, mask = 0;
+  int remaining = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    __syncthreads();
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if ((a[i] & mask) == prefix) atomicAdd(&s_hist[(a[i] >> shift) & 255u], 1);
+    __syncthreads();
+    const int h = s_hist[255 - threadIdx.x];      // thread i owns bin 255-i: the exclusive scan counts the candidates in higher bins
+    int tot;
+    const int above = block_excl_scan(h, s_w, tot);
+    if (above < remaining && above + h >= remaining) { s_w[8] = 255 - (int)threadIdx.x; s_w[9] = remaining - above; }
+    __syncthreads();
+    prefix |= (uint32_t)s_w[8] << shift;
+    mask |= 255u << shift;
+    remaining = s_w[9];
+  }
+  ties = remaining;
+  return prefix;
+}
+
 __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const FabricParams p) {
   gx::pdl_wait();
   gx::pdl_launch();
@@ -301,15 +396,21 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   unsigned long long* stamps = reinterpret_cast<unsigned long long*>(p.state + 8);
   auto stamp = [&](int i) { if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); stamps[i] = t; } };
   stamp(0);
+  __shared__ float s_tile[TILE];
+  __shared__ int s_hist[FAB_THREADS];
+  __shared__ int s_w[16];
   const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
   const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
   const float lr_t = adam_lr(p.h, opt_t);
   const int S = p.party_size, P = p.num_parties;
   const int party_base = p.party * S;
   const long long n2 = 2 * p.n;
+  const int K = p.bsc_k;
   int* err = p.state + 5;
+  auto fmt_of = [&](int t) -> int { return p.tile_fmt ? (int)p.tile_fmt[t] : FMT_F32; };
 
-  // ---- phase 1: push my gradient tiles to their party owners (tiles I own myself are read in place in phase 2)
+  // ---- phase 1: push my gradient tiles to their party owners (tiles I own myself are read in place in phase 2).  Inside a party the
+  //      transport is dense (reference: worker -> local server is never sparsified), fp16 tiles travel as halves.
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
     if (t % S == p.local) continue;
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
@@ -317,53 +418,145 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
     float* g = p.grad[p.rank] + off;
     const float4 v = *reinterpret_cast<const float4*>(g);
     if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
-    ll_store(p.ll_a[party_base + t % S] + (long long)p.local * n2 + 2 * off, v, epoch);
+    ll_send_dense(p.ll_a[party_base + t % S] + (long long)p.local * n2 + 2 * off, v, fmt_of(t) == FMT_F16 ? FMT_F16 : FMT_F32, epoch);
   }
   stamp(1);
   // ---- phase 2: LOCAL PS TIER: the party owner sums the party's gradients of its tiles and forwards the aggregate to the global owner
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
     if (t % S != p.local) continue;
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    const int fmt = fmt_of(t);
     const long long off = (long long)t * TILE + threadIdx.x * 4;
     float* g = p.grad[p.rank] + off;
     float4 acc = *reinterpret_cast<const float4*>(g);
     if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < S; ++j) {
       if (j == p.local) continue;
-      acc = f4_add(acc, ll_load(p.ll_a[p.rank] + (long long)j * n2 + 2 * off, epoch, err));
+      acc = f4_add(acc, ll_recv_dense(p.ll_a[p.rank] + (long long)j * n2 + 2 * off, fmt == FMT_F16 ? FMT_F16 : FMT_F32, epoch, err));
     }
     acc = f4_scale(acc, p.push_scale);
-    ll_store(p.ll_b[p.tile_owner[t]] + (long long)p.party * n2 + 2 * off, acc, epoch);
+    float* dst = p.ll_b[p.tile_owner[t]] + (long long)p.party * n2;
+    if (fmt != FMT_BSC) {
+      ll_send_dense(dst + 2 * off, acc, fmt, epoch);
+      continue;
+    }
+    // Bi-Sparse (gradient_compression.cc:191-269 BSCompress, re-designed per 1024-value tile): momentum correction u = 0.9u + g, v += u;
+    // the k largest |v| of the tile are sent as (value, index) packets in index order and their residual state is cleared.
+    float4 U = *reinterpret_cast<float4*>(p.bsc_u + off), V = *reinterpret_cast<float4*>(p.bsc_v + off);
+    U = f4_add(f4_scale(U, 0.9f), acc);
+    V = f4_add(V, U);
+    float vv[4] = {V.x, V.y, V.z, V.w}, uu[4] = {U.x, U.y, U.z, U.w};
+    uint32_t a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __float_as_uint(fabsf(vv[i]));
+    int ties;
+    const uint32_t T = block_kth_largest(a, K, s_hist, s_w, ties);
+    int c_eq = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c_eq += (a[i] == T);
+    int tot;
+    int eq_rank = block_excl_scan(c_eq, s_w, tot);
+    bool take[4];
+    int c_take = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      take[i] = a[i] > T;
+      if (a[i] == T) { take[i] = eq_rank < ties; ++eq_rank; }
+      c_take += take[i];
+    }
+    int pos = block_excl_scan(c_take, s_w, tot);   // tot == K
+    float* pk = dst + 2 * (long long)t * TILE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (take[i]) {
+        ll_store1(pk + 4 * pos, vv[i], (float)(threadIdx.x * 4 + i), epoch);
+        ++pos; vv[i] = 0.f; uu[i] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(p.bsc_u + off) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+    *reinterpret_cast<float4*>(p.bsc_v + off) = make_float4(vv[0], vv[1], vv[2], vv[3]);
   }
   stamp(2);
-  // ---- phase 3: GLOBAL PS TIER: the global owner sums the parties' aggregates, runs the optimizer on its shard and pushes the parameters
+  // ---- phase 3: GLOBAL PS TIER: the global owner sums the parties' aggregates, runs the optimizer on its shard and pushes the result
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
     if (p.tile_owner[t] != p.rank) continue;
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    const int fmt = fmt_of(t);
     const long long off = (long long)t * TILE + threadIdx.x * 4;
     float lr = lr_t, wd = p.h.wd;
     if (p.tile_mult) { const float2 mm = __ldg(p.tile_mult + t); lr *= mm.x; wd *= mm.y; }
     float4 W = *reinterpret_cast<float4*>(p.w + off);   // issued before the poll: the state loads overlap the wait
     float4 A = p.s0 ? *reinterpret_cast<float4*>(p.s0 + off) : make_float4(0, 0, 0, 0);
     float4 B = p.s1 ? *reinterpret_cast<float4*>(p.s1 + off) : make_float4(0, 0, 0, 0);
-    float4 agg = ll_load(p.ll_b[p.rank] + 2 * off, epoch, err);
-    for (int g = 1; g < P; ++g) agg = f4_add(agg, ll_load(p.ll_b[p.rank] + (long long)g * n2 + 2 * off, epoch, err));
+    float4 agg;
+    if (fmt != FMT_BSC) {
+      agg = ll_recv_dense(p.ll_b[p.rank] + 2 * off, fmt, epoch, err);
+      for (int g = 1; g < P; ++g) agg = f4_add(agg, ll_recv_dense(p.ll_b[p.rank] + (long long)g * n2 + 2 * off, fmt, epoch, err));
+    } else {  // BSCDecompress (:310-336) of every party's packets + sum, in shared memory
+      __syncthreads();
+      *reinterpret_cast<float4*>(s_tile + threadIdx.x * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+      for (int g = 0; g < P; ++g)
+        for (int j = threadIdx.x; j < K; j += FAB_THREADS) {
+          const float2 e = ll_load1(p.ll_b[p.rank] + (long long)g * n2 + 2 * (long long)t * TILE + 4 * j, epoch, err);
+          const int idx = (int)e.y;
+          if (idx >= 0 && idx < TILE) atomicAdd(s_tile + idx, e.x);
+        }
+      __syncthreads();
+      agg = *reinterpret_cast<const float4*>(s_tile + threadIdx.x * 4);
+    }
     opt_apply(W.x, agg.x, A.x, B.x, p.h, lr, wd);
     opt_apply(W.y, agg.y, A.y, B.y, p.h, lr, wd);
     opt_apply(W.z, agg.z, A.z, B.z, p.h, lr, wd);
     opt_apply(W.w, agg.w, A.w, B.w, p.h, lr, wd);
-    if (p.ll_c_mc != nullptr) ll_store_mc(p.ll_c_mc + 2 * off, W, epoch);
-    else for (int r = 0; r < p.world; ++r) ll_store(p.ll_c[r] + 2 * off, W, epoch);
     *reinterpret_cast<float4*>(p.w + off) = W;
     if (p.s0) *reinterpret_cast<float4*>(p.s0 + off) = A;
     if (p.s1) *reinterpret_cast<float4*>(p.s1 + off) = B;
+    if (fmt == FMT_BSC && p.h.kind < 0) {
+      // BSCPullCompress (:271-308): the aggregated gradient goes back sparse — its non-zeros in index order, at most P*K of them
+      const float ww[4] = {W.x, W.y, W.z, W.w};
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c += (ww[i] != 0.f);
+      int tot;
+      int pos = block_excl_scan(c, s_w, tot);
+      const long long base = 2 * (long long)t * TILE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (ww[i] != 0.f) {
+          if (p.ll_c_mc != nullptr) ll_store1_mc(p.ll_c_mc + base + 4 * pos, ww[i], (float)(threadIdx.x * 4 + i), epoch);
+          else for (int r = 0; r < p.world; ++r) ll_store1(p.ll_c[r] + base + 4 * pos, ww[i], (float)(threadIdx.x * 4 + i), epoch);
+          ++pos;
+        }
+      }
+      for (int j = tot + threadIdx.x; j < P * K; j += FAB_THREADS) {   // padding packets: index -1
+        if (p.ll_c_mc != nullptr) ll_store1_mc(p.ll_c_mc + base + 4 * j, 0.f, -1.f, epoch);
+        else for (int r = 0; r < p.world; ++r) ll_store1(p.ll_c[r] + base + 4 * j, 0.f, -1.f, epoch);
+      }
+    } else {
+      const int bf = fmt == FMT_F16 ? FMT_F16 : FMT_F32;
+      if (p.ll_c_mc != nullptr) ll_send_dense_mc(p.ll_c_mc + 2 * off, W, bf, epoch);
+      else for (int r = 0; r < p.world; ++r) ll_send_dense(p.ll_c[r] + 2 * off, W, bf, epoch);
+    }
   }
   stamp(3);
   // ---- phase 4: pull: unpack the fresh parameters into the (plain fp32) parameter arena the forward pass reads
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    const int fmt = fmt_of(t);
     const long long off = (long long)t * TILE + threadIdx.x * 4;
-    *reinterpret_cast<float4*>(p.param[p.rank] + off) = ll_load(p.ll_c[p.rank] + 2 * off, epoch, err);
+    if (fmt == FMT_BSC && p.h.kind < 0) {   // BSCDecompress on the worker side: zero + scatter
+      __syncthreads();
+      *reinterpret_cast<float4*>(p.param[p.rank] + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+      for (int j = threadIdx.x; j < P * K; j += FAB_THREADS) {
+        const float2 e = ll_load1(p.ll_c[p.rank] + 2 * (long long)t * TILE + 4 * j, epoch, err);
+        const int idx = (int)e.y;
+        if (idx >= 0 && idx < TILE) p.param[p.rank][(long long)t * TILE + idx] = e.x;
+      }
+    } else {
+      *reinterpret_cast<float4*>(p.param[p.rank] + off) = ll_recv_dense(p.ll_c[p.rank] + 2 * off, fmt == FMT_F16 ? FMT_F16 : FMT_F32, epoch, err);
+    }
   }
   stamp(4);
   // bookkeeping: the state words are only read by the NEXT launch (kernel boundary orders them), so a relaxed counter is enough —

@@ -55,7 +55,7 @@ class HipsCNNTrainStep:
     """
 
     def __init__(self, net=None, batch_size=32, optimizer=None, topo=None, device=None, use_graph=True, pull_fused=False,
-                 use_multicast=True, mode="dist_sync", fused_zero_grad=True):
+                 use_multicast=True, mode="dist_sync", fused_zero_grad=True, wire_dtype="fp32"):
         native.require()
         from .. import optimizer as opt
         self.B = B = int(batch_size)
@@ -70,6 +70,11 @@ class HipsCNNTrainStep:
         self.layout = ArenaLayout.build(list(enumerate(CNN_PARAM_SHAPES)))
         self.fabric = HipsFabric(self.layout, self.topo, self.device, spec, use_multicast=use_multicast)
         self.fabric.set_push_scale(1.0 / B)          # the script-level `grad / num_samples`, folded into the push kernel
+        if wire_dtype in ("fp16", "mpq") and self.fabric.protocol == "ll":
+            # FP16: every key as halves on the wire (examples/cnn_fp16.py); MPQ: only the keys above MXNET_KVSTORE_SIZE_LOWER_BOUND (cnn_mpq.py:52)
+            from ..base import getenv_int
+            bound = 0 if wire_dtype == "fp16" else getenv_int("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000)
+            self.fabric.set_wire_formats({i: "fp16" for i, sl in enumerate(self.layout.slots) if sl.numel >= bound})
         f = self.fabric
         self.P = [f.param_view(i) for i in range(10)]
         self.G = [f.grad_view(i) for i in range(10)]

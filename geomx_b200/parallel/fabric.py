@@ -96,6 +96,11 @@ class SymmetricHeap:
             return SymmetricBuffer(t, [t.data_ptr()] + [0] * (MAX_RANKS - 1))
         import torch.distributed as dist
         ranks = list(range(topo.world)) if ranks is None else list(ranks)
+        if ranks == [topo.rank]:      # a party of one: nothing to map (and symmetric-memory multicast cannot be exported for one rank)
+            t = torch.zeros(numel, dtype=dtype, device=self.device)
+            ptrs = [0] * MAX_RANKS
+            ptrs[topo.rank] = t.data_ptr()
+            return SymmetricBuffer(t, ptrs)
         group = self._group(ranks)
         ptrs = [0] * MAX_RANKS
         if self.backend in (None, "symm_mem"):
@@ -157,6 +162,7 @@ class _FabricParams(ctypes.Structure):
         ("ready_off", ctypes.c_int), ("arrived_off", ctypes.c_int), ("zero_grad", ctypes.c_int),
         ("ll_a", ctypes.c_void_p * MAX_RANKS), ("ll_b", ctypes.c_void_p * MAX_RANKS), ("ll_c", ctypes.c_void_p * MAX_RANKS),
         ("ll_c_mc", ctypes.c_void_p),
+        ("tile_fmt", ctypes.c_void_p), ("bsc_u", ctypes.c_void_p), ("bsc_v", ctypes.c_void_p), ("bsc_k", ctypes.c_int),
     ]
 
 
@@ -218,6 +224,9 @@ class HipsFabric:
         self.use_multicast = use_multicast and bool(self.param.multicast_ptr) and os.environ.get("GEOMX_NO_MULTICAST", "0") != "1"
         self.opt_spec = None
         self.push_scale = 1.0
+        self.tile_fmt = None            # per-tile wire format (LL protocol): 0 fp32, 1 fp16, 2 Bi-Sparse between the tiers
+        self.bsc_u = self.bsc_v = None
+        self.bsc_k = 0
         # one CTA per tile while the launch stays co-resident (the kernels spin on each other); grid-stride beyond that.  The LL kernel's
         # phases are one round each when grid >= tiles; the bulk protocol keeps <= 132 CTAs (its per-tile fences contend at higher counts)
         self.grid = max(1, min(T, int(native.require().gx_hips_max_grid()) if self.protocol == "ll" else 132))
@@ -232,6 +241,37 @@ class HipsFabric:
     def set_optimizer(self, spec):
         self.opt_spec = spec
         self._params_cache.clear()
+
+    FMT_F32, FMT_F16, FMT_BSC = 0, 1, 2
+
+    def set_wire_formats(self, key_formats=None, bsc_threshold=0.01):
+        """Per-key wire format of the fused step: ``{key_index: 'fp32'|'fp16'|'bsc'}`` (missing keys: fp32), or None for all-fp32.
+
+        fp16 = the reference's FP16 / MPQ transports (script-level ``astype('float16')``, examples/cnn_fp16.py:115, cnn_mpq.py:122) fused
+        into the push kernel: gradients and parameters cross NVLink as halves, master weights stay fp32 on the global owner.
+        bsc  = Bi-Sparse between the tiers (gradient_compression.cc:191-336), re-designed per 1024-value tile: the party owner keeps the
+        momentum-corrected residual, sends the ``k = floor(1024*threshold)`` largest entries as (value, index) packets; without a server
+        optimizer the aggregate returns sparse as well (BSCPullCompress)."""
+        self._params_cache.clear()
+        if not key_formats:
+            self.tile_fmt = None
+            return
+        if self.protocol != "ll":
+            raise RuntimeError("wire formats need the LL protocol (world > 1 and arena <= GEOMX_LL_MAX_BYTES)")
+        code = {"fp32": 0, "fp16": 1, "bsc": 2}
+        fmt = np.zeros(self.tiles, dtype=np.uint8)
+        for i, f in key_formats.items():
+            sl = self.layout.slots[i]
+            fmt[sl.offset // 1024: sl.offset // 1024 + sl.tiles] = code[f]
+        if (fmt == 2).any():
+            k = max(1, int(1024 * float(bsc_threshold)))
+            if k * self.topo.num_parties > 512:
+                raise RuntimeError("Bi-Sparse threshold too large for the packet buffers: floor(1024*thr)*num_parties must be <= 512")
+            self.bsc_k = k
+            if self.bsc_u is None:
+                self.bsc_u = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+                self.bsc_v = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.tile_fmt = torch.from_numpy(fmt).to(self.device)
 
     def set_push_scale(self, s):
         self.push_scale = float(s)
@@ -274,6 +314,10 @@ class HipsFabric:
                 p.ll_b[r] = self.ll_b.peer_ptrs[r] or None
                 p.ll_c[r] = self.ll_c.peer_ptrs[r] or None
         p.ll_c_mc = (self.ll_c.multicast_ptr or None) if (self.ll_a is not None and self.use_multicast and os.environ.get("GEOMX_LL_MULTICAST", "1") == "1") else None
+        p.tile_fmt = self.tile_fmt.data_ptr() if self.tile_fmt is not None else None
+        p.bsc_u = self.bsc_u.data_ptr() if self.bsc_u is not None else None
+        p.bsc_v = self.bsc_v.data_ptr() if self.bsc_v is not None else None
+        p.bsc_k = int(self.bsc_k)
         p.grad_mc = (self.grad.multicast_ptr or None) if self.use_multicast else None
         p.param_mc = (self.param.multicast_ptr or None) if self.use_multicast else None
         p.w, p.s0, p.s1 = self.w.data_ptr(), self.s0.data_ptr(), self.s1.data_ptr()

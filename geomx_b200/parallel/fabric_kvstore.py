@@ -63,6 +63,7 @@ class KVStoreFabric(KVStoreBase):
         self._hfa_k2 = max(1, getenv_int("MXNET_KVSTORE_HFA_K2", 1))
         self._local_iters = 0
         self._key_index = {}
+        self._fp16_keys, self._wire_formats = set(), {}
 
     # -- identity ---------------------------------------------------------------------------------------------------------------
     @property
@@ -95,7 +96,29 @@ class KVStoreFabric(KVStoreBase):
         t = params.get("type", "none")
         if t == "2bit":
             raise MXNetError("2bit is a worker->server wire format of the TCP path; on NVSwitch use fp16/bf16 or block-scaled fp8 transport")
-        # 'bsc': the party aggregate is sparsified between the tiers (see parallel/fabric_bsc.py)
+        # 'bsc': the party aggregate is sparsified between the tiers inside the fused kernel (HipsFabric.set_wire_formats)
+        if self._fabric is not None:
+            self._apply_wire_formats()
+
+    def _apply_wire_formats(self):
+        """Map the reference's accelerators onto per-key wire formats of the fused step: Bi-Sparse for keys >= MXNET_KVSTORE_SIZE_LOWER_BOUND
+        when ``set_gradient_compression({'type':'bsc'})`` was issued (kvstore_dist_server.h:841-878), fp16 for keys the script pushes as
+        float16 (examples/cnn_fp16.py, cnn_mpq.py)."""
+        f = self._fabric
+        if f is None or f.protocol != "ll":
+            return
+        comp = self._compression or {}
+        fmts = {}
+        if comp.get("type") == "bsc":
+            bound = getenv_int("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000)
+            for i, (_, shape) in enumerate(self._keys):
+                if int(np.prod(shape)) >= bound:
+                    fmts[i] = "bsc"
+        for i in self._fp16_keys:
+            fmts.setdefault(i, "fp16")
+        if fmts != self._wire_formats:
+            f.set_wire_formats(fmts, float(comp.get("threshold", 0.01)))
+            self._wire_formats = fmts
 
     # -- data ---------------------------------------------------------------------------------------------------------------------
     def _init(self, key, value):
@@ -135,11 +158,15 @@ class KVStoreFabric(KVStoreBase):
                     v._data.requires_grad_(True)
         self._init_vals = None
         self._fabric = f
+        self._apply_wire_formats()
 
     def _push(self, key, vals, priority):
         self._finalize()
         i = self._key_index[key]
         g = self._fabric.grad_view(i)
+        if vals[0]._t.dtype == torch.float16 and i not in self._fp16_keys:
+            self._fp16_keys.add(i)                    # the script casts this key to fp16 (FP16 / MPQ): halves on the wire from now on
+            self._apply_wire_formats()
         g.copy_(vals[0]._t.detach().reshape(g.shape))
         for v in vals[1:]:
             g.add_(v._t.detach().reshape(g.shape).to(g.device))

@@ -1,0 +1,49 @@
+"""Multi-GPU checks of the fused HiPS kernels (skipped on boxes with < 2 GPUs): each test launches one rank per GPU with torchrun and
+runs a tool from tools/ that compares the in-kernel collectives with NCCL / plain PyTorch fp32 oracles."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _ngpus():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _torchrun(n, script, *args, port=29611, env=None):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", script)] + list(args)
+    e = dict(os.environ); e.update(env or {})
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    return r.returncode, r.stdout
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("parties", [1, 2])
+def test_fused_step_matches_nccl_allreduce(parties):
+    rc, out = _torchrun(2, "fabric_check.py", "--parties", str(parties), port=29611 + parties)
+    assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_fused_step_flag_protocol():
+    rc, out = _torchrun(2, "fabric_check.py", "--parties", "2", port=29621, env={"GEOMX_FABRIC_PROTOCOL": "bulk"})
+    assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("parties", [1, 2])
+def test_wire_formats_fp16_and_bisparse(parties):
+    rc, out = _torchrun(2, "fabric_formats_check.py", str(parties), port=29631 + parties)
+    assert rc == 0 and "FORMATS_CHECK PASS" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_ngpus() < 4, reason="needs >= 4 GPUs")
+def test_two_parties_two_global_servers():
+    rc, out = _torchrun(4, "fabric_check.py", "--parties", "2", "--gs", "2", port=29641)
+    assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]

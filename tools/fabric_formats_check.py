@@ -1,0 +1,93 @@
+"""Wire formats of the fused HiPS step on real GPUs (torchrun, >= 2 ranks): fp16 transport and Bi-Sparse between the tiers, checked
+against a plain PyTorch fp32 oracle assembled from all-gathered gradients.  Server optimizer: none (the aggregate is what workers pull —
+the cnn_bsc.py / cnn_fp16.py flow with a local Trainer)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import geomx_b200 as mx  # noqa: E402,F401
+from geomx_b200.parallel import Topology  # noqa: E402
+from geomx_b200.parallel.arena import ArenaLayout  # noqa: E402
+from geomx_b200.parallel.fabric import HipsFabric  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    parties = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    topo = Topology(world, rank, parties, 1)
+    S, P = topo.party_size, topo.num_parties
+    layout = ArenaLayout.build([(0, (300,)), (1, (64, 100)), (2, (5000,)), (3, (7,)), (4, (40, 128))])
+    f = HipsFabric(layout, topo, dev, None)
+    f.set_push_scale(0.5)
+    ok = True
+    thr = 0.02
+    K = int(1024 * thr)
+    f.set_wire_formats({1: "bsc", 2: "fp16", 4: "bsc"}, thr)
+    n = f.n
+    u = torch.zeros(P, n, device=dev); v = torch.zeros(P, n, device=dev)       # oracle copies of every party's residual state
+    tile_fmt = f.tile_fmt.cpu().numpy()
+    for step in range(3):
+        g = torch.Generator(device="cpu").manual_seed(1000 * step + rank)
+        grad = torch.randn(n, generator=g).to(dev)
+        if step == 2:
+            grad = grad * (torch.rand(n, generator=g).to(dev) < 0.05)          # very sparse gradients: residuals dominate
+        f.grad.tensor.copy_(grad)
+        allg = [torch.empty_like(grad) for _ in range(world)]
+        dist.all_gather(allg, grad)
+        f.fsa_step(zero_grad=True)
+        torch.cuda.synchronize()
+        # ---------------- oracle
+        expect = torch.zeros(n, device=dev)
+        tol = torch.zeros(n, device=dev)
+        for t in range(f.tiles):
+            sl = slice(t * 1024, (t + 1) * 1024)
+            fmt = int(tile_fmt[t])
+            agg_parties = []
+            for gp in range(P):
+                owner_local = t % S
+                acc = allg[gp * S + owner_local][sl].clone()
+                for j in range(S):
+                    if j != owner_local:
+                        x = allg[gp * S + j][sl]
+                        acc += x.half().float() if fmt == 1 else x
+                agg_parties.append(acc * 0.5)
+            if fmt == 0:
+                expect[sl] = sum(agg_parties)
+            elif fmt == 1:
+                w = sum(a.half().float() for a in agg_parties)
+                expect[sl] = w.half().float()
+                tol[sl] = 2e-3 * w.abs().max() + 1e-6                            # summation-order / double-rounding slack
+            else:
+                out = torch.zeros(1024, device=dev)
+                for gp in range(P):
+                    uu = 0.9 * u[gp, sl] + agg_parties[gp]
+                    vv = v[gp, sl] + uu
+                    idx = torch.topk(vv.abs(), K).indices
+                    out[idx] += vv[idx]
+                    uu[idx] = 0; vv[idx] = 0
+                    u[gp, sl] = uu; v[gp, sl] = vv
+                expect[sl] = out
+                tol[sl] = 1e-6
+        got = f.param.tensor
+        bad = ((got - expect).abs() > tol + 1e-6 * expect.abs()).sum().item()
+        nz = int((got[torch.from_numpy(np.repeat(tile_fmt, 1024) == 2).to(dev)] != 0).sum())
+        zeroed = bool((f.grad.tensor == 0).all())
+        print("rank %d step %d: mismatches=%d  bsc non-zeros pulled=%d (<= %d)  grads cleared=%s  protocol_err=%s" % (
+            rank, step, bad, nz, int((tile_fmt == 2).sum()) * P * K, zeroed, f.check_protocol_errors()), flush=True)
+        ok = ok and bad == 0 and zeroed and not f.check_protocol_errors()
+        dist.barrier()
+    t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("FORMATS_CHECK", "PASS" if int(t) == 1 else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(t) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
