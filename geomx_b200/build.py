@@ -91,7 +91,9 @@ def build_runtime(force=False, verbose=False):
             if verbose and o.strip():
                 print(o)
     if jobs or not os.path.exists(out):
-        _run([CXX, "-shared", "-o", out] + objs + ["-pthread"])
+        # link the SHARED libstdc++ explicitly: some toolchains (e.g. a relocated g++ that only ships libstdc++.a) would otherwise embed a
+        # second, static copy next to the one torch already loaded — two iostream/locale runtimes in one process crash on first use
+        _run([CXX, "-shared", "-o", out] + objs + ["-pthread", "-l:libstdc++.so.6"])
     return out
 
 

@@ -48,9 +48,9 @@ class Error : public std::runtime_error {
 };
 
 #define HIPS_CHECK(cond)                                                                         \
-  if (!(cond)) throw ::hips::Error(std::string("Check failed: " #cond " at ") + __FILE__ + ":" + std::to_string(__LINE__))
+  do { if (!(cond)) throw ::hips::Error(std::string("Check failed: " #cond " at ") + __FILE__ + ":" + std::to_string(__LINE__)); } while (0)
 #define HIPS_CHECK_MSG(cond, msg)                                                                \
-  if (!(cond)) throw ::hips::Error(std::string("Check failed: " #cond " (") + (msg) + ") at " + __FILE__ + ":" + std::to_string(__LINE__))
+  do { if (!(cond)) throw ::hips::Error(std::string("Check failed: " #cond " (") + (msg) + ") at " + __FILE__ + ":" + std::to_string(__LINE__)); } while (0)
 
 int Verbose();  // PS_VERBOSE
 #define HIPS_VLOG(level, ...)                      \

@@ -15,6 +15,7 @@
 #include "customer.h"
 #include "dgt.h"
 #include "postoffice.h"
+#include "ts_node.h"
 
 namespace hips {
 
@@ -34,6 +35,7 @@ struct KVMeta {
   int key = 0, version = 0, num_merge = 1;
   int plane = kLocal;
   int app_id = 0;
+  std::string body;   // TSEngine: origins of a merged push (ts_node.h EncodeOrigins)
 };
 
 struct SimpleData {
@@ -156,15 +158,26 @@ class KVWorker : public SimpleApp {
  public:
   using Callback = std::function<void()>;
   KVWorker(int app_id, int customer_id) : SimpleApp() {
+    // intra-party TSEngine: pushes are merged peer-to-peer and fresh parameters arrive through the relay (ts_node.h)
+    if (Environment::Get()->GetInt("ENABLE_INTRA_TS", 0) != 0 && Postoffice::Get()->num_workers() > 1 &&
+        Environment::Get()->GetInt("ENABLE_P3", 0) == 0)
+      ts_.reset(new TSNode(kLocal, app_id, customer_id));
     obj_.reset(new Customer(app_id, customer_id, [this](const Message& m) { Process(m); }, false));
   }
+  TSNode* ts() { return ts_.get(); }
   ~KVWorker() override { obj_.reset(); }
 
   // zero-copy push: the caller keeps keys/vals/lens alive until the callback / Wait returns
   int ZPush(const SArray<Key>& keys, const SArray<char>& vals, const SArray<int>& lens, int cmd = 0, const Callback& cb = nullptr,
-            int priority = 0, int int_key = 0) {
+            int priority = 0, int int_key = 0, bool allow_ts = false) {
     const int ts = obj_->NewRequest(kServerGroup, kLocal);
     AddCallback(ts, cb);
+    if (ts_ && allow_ts && keys.size() == 1 && Postoffice::Get()->num_servers() == 1) {
+      // the server acknowledges THIS request (origin) once the round completes, wherever the gradient was merged on its way
+      ts_->Offer(int_key, cmd, keys[0], vals.data(), vals.size(),
+                 TSOrigin{Postoffice::Get()->van(kLocal)->my_node().id, ts, obj_->customer_id()});
+      return ts;
+    }
     KVPairs kvs; kvs.keys = keys; kvs.vals = vals; kvs.lens = lens;
     Send(ts, true, cmd, kvs, priority, int_key, nullptr);
     return ts;
@@ -232,8 +245,9 @@ class KVWorker : public SimpleApp {
     }
   }
   void Process(const Message& msg) override {
+    if (ts_ && ts_->Handle(msg)) return;
     if (msg.meta.simple_app) { ProcessSimple(msg); return; }
-    if (msg.meta.request) return;  // workers do not serve requests (TS relays are handled in kvstore_dist)
+    if (msg.meta.request) return;  // workers do not serve requests
     const int ts = msg.meta.timestamp;
     KVPairs kvs;
     ExtractKVPairs(msg, &kvs);
@@ -284,6 +298,7 @@ class KVWorker : public SimpleApp {
   std::unordered_map<int, Callback> callbacks_;
   std::unordered_map<int, PullTarget> pull_targets_;
   std::unordered_map<int, SArray<char>> p3_targets_;
+  std::unique_ptr<TSNode> ts_;
 };
 
 // ------------------------------------------------------------------------------------------------ KVServer
@@ -297,7 +312,14 @@ class KVServer : public SimpleApp {
     enable_inter_ts = e->GetInt("ENABLE_INTER_TS", 0) != 0;
     enable_intra_ts = e->GetInt("ENABLE_INTRA_TS", 0) != 0;
     enable_dgt = e->GetInt("ENABLE_DGT", 0);
+    Postoffice* po = Postoffice::Get();
+    // TS overlays this server takes part in: as the final receiver / first relay sender of a plane, and (local servers, global plane)
+    // as a merging peer.  Compressed and P3 transports bypass the overlay.
+    if (enable_intra_ts && !enable_p3 && po->num_workers() > 1 && po->num_servers() == 1) ts_local_.reset(new TSNode(kLocal, app_id, app_id));
+    if (enable_inter_ts && !enable_p3 && po->num_global_workers() > 1 && po->num_global_servers() == 1 && po->has_plane(kGlobal))
+      ts_global_.reset(new TSNode(kGlobal, app_id, app_id));
   }
+  TSNode* ts(Plane p) { return p == kLocal ? ts_local_.get() : ts_global_.get(); }
   ~KVServer() override { obj_.reset(); }
   void set_request_handle(const ReqHandle& h) { request_handle_kv_ = h; }       // requests from workers (local) / local servers (global)
   void set_response_handle(const ReqHandle& h) { response_handle_kv_ = h; }     // responses to OUR global-plane requests
@@ -318,8 +340,13 @@ class KVServer : public SimpleApp {
 
   // ---- client side on the GLOBAL plane (local server -> global servers) ----------------------------------------------
   int Push(const SArray<Key>& keys, const SArray<char>& vals, const SArray<int>& lens, int cmd, int priority = 0, int int_key = 0,
-           bool allow_dgt = false) {
+           bool allow_dgt = false, bool allow_ts = false) {
     const int ts = obj_->NewRequest(kServerGroup, kGlobal);
+    if (ts_global_ && allow_ts && keys.size() == 1) {   // inter-party TSEngine: merge with other local servers on the way to the global server
+      ts_global_->Offer(int_key, cmd, keys[0], vals.data(), vals.size(),
+                        TSOrigin{Postoffice::Get()->van(kGlobal)->my_node().id, ts, obj_->customer_id()});
+      return ts;
+    }
     KVPairs kvs; kvs.keys = keys; kvs.vals = vals; kvs.lens = lens;
     SendGlobal(ts, true, cmd, kvs, priority, int_key, allow_dgt);
     return ts;
@@ -368,8 +395,11 @@ class KVServer : public SimpleApp {
     }
   }
   void Process(const Message& msg) override {
+    TSNode* t = ts(static_cast<Plane>(msg.meta.plane));
+    if (t && t->Handle(msg)) return;
     if (msg.meta.simple_app) { ProcessSimple(msg); return; }
     KVMeta meta;
+    meta.body = msg.meta.body;
     meta.cmd = msg.meta.head; meta.push = msg.meta.push; meta.sender = msg.meta.sender; meta.timestamp = msg.meta.timestamp;
     meta.customer_id = msg.meta.customer_id; meta.priority = msg.meta.priority; meta.key = msg.meta.key; meta.version = msg.meta.version;
     meta.num_merge = msg.meta.iters > 0 ? msg.meta.iters : 1; meta.plane = msg.meta.plane; meta.app_id = msg.meta.app_id;
@@ -383,6 +413,7 @@ class KVServer : public SimpleApp {
     }
   }
   ReqHandle request_handle_kv_, response_handle_kv_;
+  std::unique_ptr<TSNode> ts_local_, ts_global_;
 };
 
 }  // namespace hips

@@ -109,6 +109,20 @@ class KVStoreDist {
       if (it != last_push_.end()) { pending = it->second; last_push_.erase(it); }
     }
     if (pending >= 0) Wait(pending);
+    if (TSNode* t = ps_worker_->ts()) {
+      // intra-party TSEngine: after the first synchronisation round the parameters arrive through the relay broadcast — wait (in Wait())
+      // for the version that contains this worker's latest push instead of sending a pull request
+      int version = 0;
+      { std::lock_guard<std::mutex> lk(mu_); auto it = ts_push_count_.find(key); if (it != ts_push_count_.end()) version = it->second; }
+      if (version > 0) {
+        (void)t;
+        std::lock_guard<std::mutex> lk(mu_);
+        const int h = next_handle_++;
+        handles_[h] = {};
+        relay_waits_[h] = RelayWait{key, version, out, elems * static_cast<size_t>(DTypeSize(dtype))};
+        return h;
+      }
+    }
     if (enable_p3_) {  // P3: the push response already carried the parameters (filled by the push callback before Wait returned)
       std::lock_guard<std::mutex> lk(mu_);
       auto pt = p3_buf_.find(key);
@@ -134,14 +148,23 @@ class KVStoreDist {
 
   void Wait(int handle) {
     std::vector<int> tss;
+    RelayWait rw;
     {
       std::lock_guard<std::mutex> lk(mu_);
       auto it = handles_.find(handle);
       if (it == handles_.end()) return;
       tss = it->second;
       handles_.erase(it);
+      auto rt = relay_waits_.find(handle);
+      if (rt != relay_waits_.end()) { rw = rt->second; relay_waits_.erase(rt); }
     }
     for (int ts : tss) ps_worker_->Wait(ts);
+    if (rw.out != nullptr) ps_worker_->ts()->WaitRelayed(rw.key, rw.version, rw.out, rw.nbytes);
+  }
+  // (peer merges received, relay transfers sent) by this worker's TSEngine node — 0,0 when the overlay is off
+  std::pair<long, long> ts_stats() {
+    TSNode* t = ps_worker_ ? ps_worker_->ts() : nullptr;
+    return t ? std::make_pair(t->merges_received(), t->relays_sent()) : std::make_pair(0L, 0L);
   }
   void WaitAll() {
     std::vector<int> hs;
@@ -164,6 +187,7 @@ class KVStoreDist {
 
  private:
   struct KeyInfo { size_t elems; int dtype; };
+  struct RelayWait { int key = 0, version = 0; void* out = nullptr; size_t nbytes = 0; };
   int Track(const std::vector<int>& tss) {
     std::lock_guard<std::mutex> lk(mu_);
     const int h = next_handle_++;
@@ -202,7 +226,9 @@ class KVStoreDist {
       SArray<int> lens; for (int l : plan.lens) lens.push_back(l);
       SArray<char> vals(static_cast<char*>(const_cast<void*>(data)), elems * bytes, false);
       const int cmd = GetCommandType(RequestType::kDefaultPushPull, dtype);
-      tss.push_back(ps_worker_->ZPush(keys, vals, lens, cmd, nullptr, priority, key));
+      const bool via_ts = allow_compress && ps_worker_->ts() != nullptr && keys.size() == 1;
+      tss.push_back(ps_worker_->ZPush(keys, vals, lens, cmd, nullptr, priority, key, via_ts));
+      if (via_ts) { std::lock_guard<std::mutex> lk(mu_); ++ts_push_count_[key]; }
     }
     const int h = Track(tss);
     { std::lock_guard<std::mutex> lk(mu_); last_push_[key] = h; }
@@ -217,6 +243,8 @@ class KVStoreDist {
   std::unordered_map<int, KeyInfo> info_;
   std::unordered_map<int, std::vector<int>> handles_;
   std::unordered_map<int, int> last_push_;
+  std::unordered_map<int, int> ts_push_count_;            // TSEngine: rounds this worker contributed to, per key (= expected relay version)
+  std::unordered_map<int, RelayWait> relay_waits_;
   std::unordered_map<int, std::vector<float>> residual_;
   std::unordered_map<int, std::vector<char>> p3_buf_;
   int next_handle_ = 1;

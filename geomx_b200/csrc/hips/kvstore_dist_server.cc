@@ -21,6 +21,8 @@ KVStoreDistServer::KVStoreDistServer() {
   ps_server_->SimpleApp::set_request_handle([this](const SimpleData& d, SimpleApp* app) { CommandHandle(d, app); });
   ps_server_->set_request_handle([this](const KVMeta& m, const KVPairs& d, KVServer* s) { DataHandleEx(m, d, s); });
   ps_server_->set_response_handle([this](const KVMeta& m, const KVPairs& d, KVServer* s) { ResponseHandle(m, d, s); });
+  if (has_global_ && ps_server_->ts(kGlobal) != nullptr)   // local server: fresh values of TS rounds arrive through the relay
+    ps_server_->ts(kGlobal)->set_on_relayed([this](int key, int version, int cmd, const std::vector<char>& bytes) { OnRelayedFromGlobal(key, version, cmd, bytes); });
 }
 
 KVStoreDistServer::~KVStoreDistServer() { ps_server_.reset(); }
@@ -202,7 +204,9 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
     }
     respond(req);
     if (is_global_ || standalone_) { initialized_[key] = true; init_cv_.notify_all(); }
-    else if (has_global_) { lk.unlock(); PullFromGlobal(key, type); }
+    else if (has_global_) { lk.unlock(); PullFromGlobal(key, type); AskTS(key); return; }
+    lk.unlock();
+    AskTS(key);      // TSEngine: open the first round of this key
     return;
   }
   // ---- decode the contribution to fp32
@@ -223,32 +227,45 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   if (!sync) {
     // ---- MixedSync / async: apply this contribution immediately (reference :1582-1609)
     ApplyUpdate(key, &e, incoming.data(), n);
-    respond(req);
+    const std::vector<KVMeta> who = ExpandOrigins(req);
+    for (size_t i = 0; i < who.size(); ++i) {
+      if (i > 0 && who[i].sender == who[i - 1].sender && who[i].timestamp == who[i - 1].timestamp) continue;
+      respond(who[i]);
+    }
+    lk.unlock();
+    AskTS(key);
     return;
   }
   UpdateBuf& ub = update_buf_[key];
   if (ub.request.empty()) ub.merged = incoming;
   else for (size_t i = 0; i < n; ++i) ub.merged[i] += incoming[i];
-  for (int i = 0; i < std::max(1, req.num_merge); ++i) ub.request.push_back(req);
+  for (const KVMeta& r : ExpandOrigins(req)) ub.request.push_back(r);
   size_t expected;
   if (is_global_) expected = po->num_global_workers() + (po->enable_central_workers() ? po->num_workers() : 0);
   else expected = po->num_workers();
-  if (ub.request.size() < expected) return;
+  if (ub.request.size() < expected) {
+    lk.unlock();
+    AskTS(key);      // TSEngine: a partial delivery — this server is free to receive the next (merged) contribution
+    return;
+  }
   if (is_global_ || standalone_) {
     ApplyUpdate(key, &e, ub.merged.data(), n);
     std::vector<KVMeta> reqs; reqs.swap(ub.request);
-    KVMeta last = reqs.back();
     for (size_t i = 0; i < reqs.size(); ++i) {
       if (i > 0 && reqs[i].sender == reqs[i - 1].sender && reqs[i].timestamp == reqs[i - 1].timestamp) continue;  // merged duplicates (TS)
       respond(reqs[i]);
     }
+    lk.unlock();
+    RoundCompleted(key);
     return;
   }
-  FinishLocalAggregation(key, type, &ub);
+  const bool local_round_done = FinishLocalAggregation(key, type, &ub);
+  lk.unlock();
+  if (local_round_done) RoundCompleted(key);
 }
 
 // local server: all workers of the party have pushed `key`
-void KVStoreDistServer::FinishLocalAggregation(int key, const DataHandleType& type, UpdateBuf* ub) {
+bool KVStoreDistServer::FinishLocalAggregation(int key, const DataHandleType& type, UpdateBuf* ub) {
   Entry& e = store_[key];
   const size_t n = e.elems;
   float* w = e.has_master ? e.master.data() : reinterpret_cast<float*>(e.data.data());
@@ -267,7 +284,7 @@ void KVStoreDistServer::FinishLocalAggregation(int key, const DataHandleType& ty
   };
   if (use_hfa_ && (local_iters_ % hfa_k2_ != 0)) {   // local synchronisation only
     ack_all(&ub->request);
-    return;
+    return true;
   }
   if (use_hfa_) {                                    // push the party's progress since the last global sync
     auto& ms = milestone_[key];
@@ -279,6 +296,7 @@ void KVStoreDistServer::FinishLocalAggregation(int key, const DataHandleType& ty
   GlobalRound& r = rounds_[key];
   r.waiting.swap(ub->request);
   PushToGlobal(key, type);
+  return false;
 }
 
 void KVStoreDistServer::PushToGlobal(int key, const DataHandleType& type) {
@@ -319,7 +337,9 @@ void KVStoreDistServer::PushToGlobal(int key, const DataHandleType& type) {
   }
   r.cmd = cmd;
   const bool allow_dgt = ps_server_->enable_dgt != 0 && cmd == GetCommandType(RequestType::kDefaultPushPull, kFloat32);
-  r.push_ts = ps_server_->Push(keys, vals, lens, cmd, -key, key, allow_dgt);
+  // inter-party TSEngine: dense pushes are merged with other parties' aggregates on their way; the fresh value comes back by relay
+  r.via_ts = ps_server_->ts(kGlobal) != nullptr && !allow_dgt && keys.size() == 1 && DepairDataHandleType(cmd).requestType == RequestType::kDefaultPushPull;
+  r.push_ts = ps_server_->Push(keys, vals, lens, cmd, -key, key, allow_dgt, r.via_ts);
   ts_key_[r.push_ts] = key;
 }
 
@@ -363,6 +383,7 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
     // push ack: once every global server acknowledged, fetch the fresh value (reference :941-957)
     if (server->NumResponse(res.timestamp) != Postoffice::Get()->num_global_servers() - 1) return;
     ts_key_.erase(it);
+    if (r.via_ts) return;   // TSEngine: the global server relays the fresh value (OnRelayedFromGlobal)
     const DataHandleType type = DepairDataHandleType(r.cmd);
     lk.unlock();
     PullFromGlobal(key, type);
@@ -387,6 +408,19 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
     HIPS_CHECK_MSG(whole.size() == n * DTypeSize(e.dtype), "pull response size mismatch for key " + std::to_string(key));
     ToFloat(whole.data(), e.dtype, n, recved.data());
   }
+  r.parts.clear();
+  const bool was_round = r.push_ts >= 0;
+  ApplyFreshFromGlobal(key, &recved);
+  lk.unlock();
+  if (was_round) RoundCompleted(key); else AskTS(key);
+}
+
+// the value of `key` after a global round (or the initial value) reached this local server: HFA algebra, store, release the workers
+void KVStoreDistServer::ApplyFreshFromGlobal(int key, std::vector<float>* recved_p) {
+  std::vector<float>& recved = *recved_p;
+  Entry& e = store_[key];
+  GlobalRound& r = rounds_[key];
+  const size_t n = e.elems;
   float* w = e.has_master ? e.master.data() : reinterpret_cast<float*>(e.data.data());
   if (use_hfa_) {
     // HandleHFAAccumulate (reference :959-972): the first pulled value becomes the milestone, afterwards stored = milestone + sum(deltas)
@@ -397,11 +431,11 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
     memcpy(w, recved.data(), n * sizeof(float));
   }
   if (e.has_master) StoreFromFloat(&e, w, n);
-  r.parts.clear();
   initialized_[key] = true;
   init_cv_.notify_all();
   std::vector<KVMeta> waiting; waiting.swap(r.waiting);
   r.push_ts = r.pull_ts = -1;
+  r.via_ts = false;
   for (size_t i = 0; i < waiting.size(); ++i) {
     if (i > 0 && waiting[i].sender == waiting[i - 1].sender && waiting[i].timestamp == waiting[i - 1].timestamp) continue;
     if (ps_server_->enable_p3) {
@@ -409,6 +443,65 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
       ps_server_->Response(waiting[i], out);
     } else ps_server_->Response(waiting[i]);
   }
+}
+
+// inter-party TSEngine: the global server's relay delivered the fresh value of a round this local server pushed through the overlay
+void KVStoreDistServer::OnRelayedFromGlobal(int key, int version, int cmd, const std::vector<char>& bytes) {
+  std::unique_lock<std::mutex> lk(mu_);
+  auto it = store_.find(key);
+  if (it == store_.end()) return;
+  Entry& e = it->second;
+  GlobalRound& r = rounds_[key];
+  if (!r.via_ts) return;            // not waiting for a relayed round (e.g. a duplicate)
+  const size_t n = e.elems;
+  if (bytes.size() != n * DTypeSize(e.dtype)) return;
+  std::vector<float> recved(n);
+  ToFloat(bytes.data(), e.dtype, n, recved.data());
+  ApplyFreshFromGlobal(key, &recved);
+  lk.unlock();
+  RoundCompleted(key);
+}
+
+// ------------------------------------------------------------------------------------------------ TSEngine hooks
+std::vector<KVMeta> KVStoreDistServer::ExpandOrigins(const KVMeta& req) {
+  std::vector<KVMeta> out;
+  const std::vector<TSOrigin> origins = DecodeOrigins(req.body);
+  if (origins.empty()) {
+    for (int i = 0; i < std::max(1, req.num_merge); ++i) out.push_back(req);
+    return out;
+  }
+  for (const TSOrigin& o : origins) {
+    KVMeta r = req;
+    r.sender = o.sender; r.timestamp = o.timestamp; r.customer_id = o.customer; r.num_merge = 1; r.body.clear();
+    out.push_back(r);
+  }
+  return out;
+}
+
+// this server is ready to receive (more) contributions of `key`: join the scheduler's pairing queue on the planes it serves
+void KVStoreDistServer::AskTS(int key) {
+  Postoffice* po = Postoffice::Get();
+  if (TSNode* t = ps_server_->ts(kLocal)) { if (!is_global_ || po->enable_central_workers()) t->AskAsServer(key); }
+  if (is_global_) if (TSNode* t = ps_server_->ts(kGlobal)) t->AskAsServer(key);
+}
+
+// a synchronisation round of `key` finished on this server: bump the version, start the relay broadcast, open the next round
+void KVStoreDistServer::RoundCompleted(int key) {
+  std::vector<char> bytes;
+  int version, cmd;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    version = ++round_version_[key];
+    Entry& e = store_[key];
+    bytes = e.data;
+    cmd = GetCommandType(RequestType::kDefaultPushPull, e.dtype);
+  }
+  Postoffice* po = Postoffice::Get();
+  if (TSNode* t = ps_server_->ts(kLocal)) {
+    if (!is_global_ || po->enable_central_workers()) t->Relay(key, version, cmd, static_cast<Key>(key), bytes.data(), bytes.size());
+  }
+  if (is_global_) if (TSNode* t = ps_server_->ts(kGlobal)) t->Relay(key, version, cmd, static_cast<Key>(key), bytes.data(), bytes.size());
+  AskTS(key);
 }
 
 void KVStoreDistServer::HandlePull(const DataHandleType& type, const KVMeta& req, const KVPairs& data) {

@@ -126,6 +126,7 @@ class KVStoreDistServer {
     std::vector<KVMeta> waiting; // worker push requests to ack when the round completes
     int push_ts = -1, pull_ts = -1;
     int parts_expected = 0;
+    bool via_ts = false;         // pushed through the inter-party TSEngine overlay: the fresh value arrives by relay, not by pull
     std::vector<std::pair<Key, std::vector<char>>> parts;
     int cmd = 0;
   };
@@ -136,13 +137,19 @@ class KVStoreDistServer {
   void ResponseHandle(const KVMeta& res, const KVPairs& data, KVServer* server);
   void HandlePush(const DataHandleType& type, const KVMeta& req, const KVPairs& data);
   void HandlePull(const DataHandleType& type, const KVMeta& req, const KVPairs& data);
-  void FinishLocalAggregation(int key, const DataHandleType& type, UpdateBuf* ub);
+  bool FinishLocalAggregation(int key, const DataHandleType& type, UpdateBuf* ub);   // true: the round ended locally (HFA local sync)
   void PushToGlobal(int key, const DataHandleType& type);
   void PullFromGlobal(int key, const DataHandleType& type);
   void ApplyUpdate(int key, Entry* e, const float* grad, size_t n);
   void StoreFromFloat(Entry* e, const float* src, size_t n);
   void ToFloat(const char* src, int dtype, size_t n, float* dst);
   void RespondStored(const KVMeta& req, int key, Key ps_key, const DataHandleType& type);
+  // TSEngine (ts_node.h): a merged push stands for several requests; servers take part in the pairing and start the relay
+  std::vector<KVMeta> ExpandOrigins(const KVMeta& req);
+  void AskTS(int key);
+  void RoundCompleted(int key);
+  void ApplyFreshFromGlobal(int key, std::vector<float>* recved);   // mu_ held
+  void OnRelayedFromGlobal(int key, int version, int cmd, const std::vector<char>& bytes);
   // key codecs
   int DecodeKey(Key ps_key, Plane plane);
   struct PSKV { std::vector<Key> keys; std::vector<int> lens; size_t size = 0; };
@@ -164,6 +171,7 @@ class KVStoreDistServer {
   std::unordered_map<int, int> ts_key_;                  // global-plane timestamp -> key
   std::unordered_map<int, std::vector<float>> milestone_, bsc_u_, bsc_v_, residual_2bit_;
   std::unordered_map<int, bool> initialized_;
+  std::unordered_map<int, int> round_version_;           // completed synchronisation rounds per key (TSEngine relay version)
   std::unordered_map<int, PSKV> ps_kv_;
   bool sync_mode_ = false, sync_global_mode_ = false, multi_precision_ = false;
   bool is_global_ = false, has_global_ = false, standalone_ = false;

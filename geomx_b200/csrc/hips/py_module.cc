@@ -24,7 +24,22 @@ static py::array_t<float> WrapFloat(float* p, size_t n) {
   return py::array_t<float>({static_cast<py::ssize_t>(n)}, {static_cast<py::ssize_t>(sizeof(float))}, p, py::capsule(p, [](void*) {}));
 }
 
+// GEOMX_SEGV_TRACE=1: print the native stack of a crashing thread (addresses resolve with `addr2line -e lib/_C*.so`)
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void SegvTrace(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "[hips] fatal signal, native stack:\n";
+  ssize_t r = write(2, msg, sizeof(msg) - 1); (void)r;
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+
 PYBIND11_MODULE(_C, m) {
+  if (const char* t = getenv("GEOMX_SEGV_TRACE")) { if (t[0] == '1') { signal(SIGSEGV, SegvTrace); signal(SIGABRT, SegvTrace); } }
   m.doc() = "geomx_b200 native runtime: HiPS transport + servers, compression codecs, .params IO, profiler, engine, data IO";
   py::register_exception<hips::Error>(m, "HipsError");
 
@@ -134,6 +149,7 @@ PYBIND11_MODULE(_C, m) {
       .def("send_command_to_servers", &KVStoreDist::SendCommandToServers, py::call_guard<py::gil_scoped_release>())
       .def("send_bytes", &KVStoreDist::send_bytes)
       .def("recv_bytes", &KVStoreDist::recv_bytes)
+      .def("ts_stats", &KVStoreDist::ts_stats)
       .def("run_server", [](KVStoreDist& kv, py::object controller, py::object updater) {
         // python objects are held through shared_ptrs whose deleter re-acquires the GIL: the std::functions are copied / destroyed
         // by server threads that do not hold it

@@ -88,15 +88,18 @@ class TSScheduler {
     const int req = msg.meta.sender, key = msg.meta.key, version = msg.meta.version;
     if (msg.meta.app_id != -1 && msg.meta.customer_id >= 0) A_[req][msg.meta.customer_id] = msg.meta.app_id;  // report of the last transfer
     auto& st = pull_[key];
-    if (st.version != version) { st.version = version; st.served.clear(); }
-    st.served.insert(req);  // a node holding the version never needs it again
-    std::vector<int> idle;
-    for (int r = 0; r < num_workers_; ++r) {
-      const int id = WorkerRankToID(r, plane_);
-      if (!st.served.count(id)) idle.push_back(id);
+    int recv = -1;
+    if (version >= st.version) {   // a straggler still relaying an older version is simply told that everybody is served
+      if (version > st.version) { st.version = version; st.served.clear(); }
+      st.served.insert(req);  // a node holding the version never needs it again
+      std::vector<int> idle;
+      for (int r = 0; r < num_workers_; ++r) {
+        const int id = WorkerRankToID(r, plane_);
+        if (!st.served.count(id)) idle.push_back(id);
+      }
+      recv = PickReceiver(req, idle);
+      if (recv >= 0) st.served.insert(recv);
     }
-    const int recv = PickReceiver(req, idle);
-    if (recv >= 0) st.served.insert(recv);
     lk.unlock();
     Message reply;
     reply.meta.recver = req;

@@ -212,6 +212,15 @@ void Van::Start(int customer_id) {
     std::lock_guard<std::mutex> lk(nodes_mu_);
     nodes_[kScheduler] = scheduler_;
   }
+  // everything the receive thread consults must exist BEFORE it starts: a peer's first barrier request can arrive the moment this node
+  // turns ready, i.e. before Start() returns (a resender created later would neither ACK nor de-duplicate that first message)
+  if (env->GetInt("PS_RESEND", 0) != 0) resender_.reset(new Resender(env->GetInt("PS_RESEND_TIMEOUT", 1000), 100, this));
+  const bool ts_on = plane_ == kLocal ? env->GetInt("ENABLE_INTRA_TS", 0) != 0 : env->GetInt("ENABLE_INTER_TS", 0) != 0;
+  if (is_scheduler_ && ts_on) ts_sched_.reset(new TSScheduler(this, po_->num_workers_in(plane_), plane_));
+  if (plane_ == kGlobal && env->GetInt("ENABLE_DGT", 0) != 0) {
+    dgt_sender_.reset(new DGTSender(this));
+    dgt_receiver_.reset(new DGTReceiver());
+  }
   accept_thread_.reset(new std::thread(&Van::Accepting, this));
   recv_thread_.reset(new std::thread(&Van::Receiving, this));
   if (enable_p3_) prio_thread_.reset(new std::thread(&Van::PrioritySending, this));
@@ -226,16 +235,7 @@ void Van::Start(int customer_id) {
   }
   while (!ready_.load() && !stop_.load()) std::this_thread::sleep_for(std::chrono::milliseconds(5));
 
-  if (env->GetInt("PS_RESEND", 0) != 0) {
-    resender_.reset(new Resender(env->GetInt("PS_RESEND_TIMEOUT", 1000), 100, this));
-  }
   if (!is_scheduler_ && env->GetInt("PS_HEARTBEAT_INTERVAL", 0) > 0) heartbeat_thread_.reset(new std::thread(&Van::Heartbeat, this));
-  const bool ts_on = plane_ == kLocal ? env->GetInt("ENABLE_INTRA_TS", 0) != 0 : env->GetInt("ENABLE_INTER_TS", 0) != 0;
-  if (is_scheduler_ && ts_on) ts_sched_.reset(new TSScheduler(this, po_->num_workers_in(plane_), plane_));
-  if (plane_ == kGlobal && env->GetInt("ENABLE_DGT", 0) != 0) {
-    dgt_sender_.reset(new DGTSender(this));
-    dgt_receiver_.reset(new DGTReceiver());
-  }
 }
 
 void Van::Stop() {
@@ -321,7 +321,7 @@ int Van::SendNow(const Message& msg) {
   }
   if (n >= 0) {
     send_bytes_ += n;
-    if (resender_ && out.meta.control.cmd != Control::ACK) resender_->AddOutgoing(out);
+    if (resender_ && ready_.load() && out.meta.control.cmd != Control::ACK && out.meta.control.cmd != Control::ADD_NODE) resender_->AddOutgoing(out);
     if (Verbose() >= 2) HIPS_VLOG(2, "plane %d SEND %d -> %d cmd=%d req=%d push=%d ts=%d bytes=%d", plane_, out.meta.sender, id, out.meta.control.cmd,
                                    out.meta.request, out.meta.push, out.meta.timestamp, n);
   }
@@ -378,7 +378,9 @@ void Van::Receiving() {
         HIPS_VLOG(1, "plane %d drop message from %d", plane_, msg.meta.sender);
         continue;
       }
-      if (resender_ && resender_->AddIncoming(msg)) continue;
+      // registration traffic (before either side is ready) is not covered by the ACK protocol, exactly like the reference, which starts
+      // its resender only once the node table is known
+      if (resender_ && ready_.load() && msg.meta.control.cmd != Control::ADD_NODE && resender_->AddIncoming(msg)) continue;
       const Control& ctrl = msg.meta.control;
       if (!ctrl.empty()) {
         if (ctrl.cmd == Control::TERMINATE) { stop_ = true; break; }

@@ -42,6 +42,25 @@ def build_cnn():
     return net
 
 
+class LossHandle:
+    """Result of ``HipsCNNTrainStep.step_async``: the per-sample losses of one step in pinned host memory + the event that guards them."""
+
+    __slots__ = ("_host", "_event")
+
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def wait(self):
+        self._event.synchronize()
+        return self._host
+
+    def item(self):
+        self._event.synchronize()
+        return float(self._host.sum()) / self._host.numel()
+
+    asscalar = item
+
+
 class HipsCNNTrainStep:
     """Graph-captured training step of the demo CNN on the HiPS fabric.
 
@@ -208,17 +227,27 @@ class HipsCNNTrainStep:
             self._body()
         self.steps_done += 1
 
-    def step(self, X, y):
-        """Public API: one training step.  ``X`` (B,1,28,28) and ``y`` (B,) are host tensors / NDArrays (pinned → async H2D) or device
-        tensors.  Returns the mean loss as a Python float (forces the D2H read of the per-sample loss)."""
+    def step_async(self, X, y):
+        """Public API: enqueue one training step and return a :class:`LossHandle` without waiting for the GPU (the MXNet engine's contract:
+        an op returns at once, ``asscalar()`` synchronises).  ``X`` (B,1,28,28) and ``y`` (B,) are host tensors / NDArrays (pinned → async
+        H2D) or device tensors.  The per-sample loss is copied to a pinned ring slot behind the step; ``handle.item()`` waits for exactly that
+        copy, so a training loop can launch step i+1 before it reads the loss of step i."""
         X = X._t if isinstance(X, NDArray) else X
         y = y._t if isinstance(y, NDArray) else y
         self.x.copy_(X.reshape(self.x.shape), non_blocking=True)
         self.label.copy_(y.reshape(self.label.shape), non_blocking=True)
         self.run_device()
-        self.loss_host.copy_(self.loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(self.loss_host.mean())
+        i = self._ring_i = (getattr(self, "_ring_i", -1) + 1) % 4
+        if not hasattr(self, "_ring"):
+            self._ring = [(torch.empty_like(self.loss, device="cpu").pin_memory(), torch.cuda.Event()) for _ in range(4)]
+        host, ev = self._ring[i]
+        host.copy_(self.loss, non_blocking=True)
+        ev.record()
+        return LossHandle(host, ev)
+
+    def step(self, X, y):
+        """Public API: one training step; returns the mean loss as a Python float (forces the D2H read of the per-sample loss)."""
+        return self.step_async(X, y).item()
 
     # reference semantics helpers ------------------------------------------------------------------------------------
     def params_numpy(self):

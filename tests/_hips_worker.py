@@ -53,5 +53,7 @@ for step in range(steps):
     mx.nd.waitall()
     out["vals"].append([float(p.astype("float32").asnumpy().reshape(-1)[0]) for p in params])
     out.setdefault("last", [float(p.astype("float32").asnumpy().reshape(-1)[-1]) for p in params])
+if hasattr(getattr(kv, "_kv", None), "ts_stats"):
+    out["ts_stats"] = list(kv._kv.ts_stats())
 print("RESULT " + json.dumps(out), flush=True)
 kv.close()
