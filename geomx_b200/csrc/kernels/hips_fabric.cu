@@ -171,6 +171,37 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
   const int party_base = p.party * S;
   uint32_t* my_flags = p.flags[p.rank];
 
+  if (p.world == 1) {
+    // ---------------- single rank: both tiers collapse into the fused arena optimizer.  No peer ever spins on this launch, so the grid
+    // may exceed what is co-resident (one tile per CTA); all four operand loads are issued before the first use => ONE memory round trip.
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+      const long long off = (long long)t * TILE + threadIdx.x * 4;
+      float* g = p.grad[0] + off;
+      const float4 G = *reinterpret_cast<const float4*>(g);
+      float4 W = *reinterpret_cast<float4*>(p.w + off);
+      float4 A = p.s0 ? *reinterpret_cast<float4*>(p.s0 + off) : make_float4(0, 0, 0, 0);
+      float4 B = p.s1 ? *reinterpret_cast<float4*>(p.s1 + off) : make_float4(0, 0, 0, 0);
+      float lr = lr_t, wd = p.h.wd;
+      if (p.tile_mult) { const float2 mm = __ldg(p.tile_mult + t); lr *= mm.x; wd *= mm.y; }
+      const float4 agg = f4_scale(G, p.push_scale);
+      opt_apply(W.x, agg.x, A.x, B.x, p.h, lr, wd);
+      opt_apply(W.y, agg.y, A.y, B.y, p.h, lr, wd);
+      opt_apply(W.z, agg.z, A.z, B.z, p.h, lr, wd);
+      opt_apply(W.w, agg.w, A.w, B.w, p.h, lr, wd);
+      if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(p.w + off) = W;
+      if (p.s0) *reinterpret_cast<float4*>(p.s0 + off) = A;
+      if (p.s1) *reinterpret_cast<float4*>(p.s1 + off) = B;
+      *reinterpret_cast<float4*>(p.param[0] + off) = W;
+    }
+    if (threadIdx.x == 0) {
+      const int done = atomicAdd(p.state + 1, 1);
+      if (done == (int)gridDim.x - 1) { p.state[1] = 0; p.state[2] = opt_t; p.state[0] = (int)epoch; }
+    }
+    return;
+  }
+
   // ---------------- phase A: publish gradient-ready to the party
   if (p.world > 1 && blockIdx.x == 0 && threadIdx.x < S) {
     fence_sys();

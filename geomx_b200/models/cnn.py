@@ -100,7 +100,9 @@ class HipsCNNTrainStep:
         self._init_params(net)
         dev, f32 = self.device, torch.float32
         e = lambda *s, dt=f32: torch.empty(*s, dtype=dt, device=dev)
-        self.x, self.label = e(B, 1, 28, 28), e(B)
+        # the batch lives in ONE device buffer [x | label] so that the per-step staging -> compute hand-over is a single D2D copy
+        self.xin = e(B * 28 * 28 + B)
+        self.x, self.label = self.xin[:B * 784].view(B, 1, 28, 28), self.xin[B * 784:]
         self.a1, self.idx1 = e(B, 16, 12, 12), e(B, 16, 12, 12, dt=torch.uint8)
         self.col1 = e(B * 64, 400)
         self.z2 = e(B, 32, 8, 8)
@@ -227,22 +229,57 @@ class HipsCNNTrainStep:
             self._body()
         self.steps_done += 1
 
+    def _pipeline(self):
+        if not hasattr(self, "_pl"):
+            dev, B = self.device, self.B
+            stage = [torch.empty_like(self.xin) for _ in range(2)]
+            self._pl = {
+                "h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev), "stage": stage,
+                "sx": [s[:B * 784].view(B, 1, 28, 28) for s in stage], "sy": [s[B * 784:] for s in stage],
+                "ready": [torch.cuda.Event() for _ in range(2)], "done": [torch.cuda.Event() for _ in range(2)],
+                "ring": [(torch.empty_like(self.loss, device="cpu").pin_memory(), torch.cuda.Event()) for _ in range(4)], "n": 0, "last_loss": None,
+            }
+        return self._pl
+
     def step_async(self, X, y):
         """Public API: enqueue one training step and return a :class:`LossHandle` without waiting for the GPU (the MXNet engine's contract:
         an op returns at once, ``asscalar()`` synchronises).  ``X`` (B,1,28,28) and ``y`` (B,) are host tensors / NDArrays (pinned → async
-        H2D) or device tensors.  The per-sample loss is copied to a pinned ring slot behind the step; ``handle.item()`` waits for exactly that
-        copy, so a training loop can launch step i+1 before it reads the loss of step i."""
+        H2D) or device tensors.
+
+        Three streams: the batch is copied host→device on a copy stream into one of two staging buffers (overlapping the previous step's
+        compute), the compute stream takes it over with ONE device-to-device copy and replays the step graph, and the per-sample loss goes
+        device→host on a third stream into a pinned ring slot; ``handle.item()`` waits for exactly that copy.  A training loop therefore
+        launches step i+1 before it reads the loss of step i."""
         X = X._t if isinstance(X, NDArray) else X
         y = y._t if isinstance(y, NDArray) else y
-        self.x.copy_(X.reshape(self.x.shape), non_blocking=True)
-        self.label.copy_(y.reshape(self.label.shape), non_blocking=True)
+        pl = self._pipeline()
+        i = pl["n"]; b = i % 2
+        pl["n"] = i + 1
+        main = torch.cuda.current_stream()
+        if X.is_cuda:
+            self.x.copy_(X.reshape(self.x.shape), non_blocking=True)
+            self.label.copy_(y.reshape(self.label.shape), non_blocking=True)
+        else:
+            h2d = pl["h2d"]
+            if i >= 2:
+                h2d.wait_event(pl["done"][b])              # staging buffer b was handed over by step i-2
+            with torch.cuda.stream(h2d):
+                pl["sx"][b].copy_(X.reshape(self.x.shape), non_blocking=True)
+                pl["sy"][b].copy_(y.reshape(self.label.shape), non_blocking=True)
+                pl["ready"][b].record(h2d)
+            main.wait_event(pl["ready"][b])
+            self.xin.copy_(pl["stage"][b], non_blocking=True)
+        if pl["last_loss"] is not None:
+            main.wait_event(pl["last_loss"])                # the loss buffer of the previous step has been read out
         self.run_device()
-        i = self._ring_i = (getattr(self, "_ring_i", -1) + 1) % 4
-        if not hasattr(self, "_ring"):
-            self._ring = [(torch.empty_like(self.loss, device="cpu").pin_memory(), torch.cuda.Event()) for _ in range(4)]
-        host, ev = self._ring[i]
-        host.copy_(self.loss, non_blocking=True)
-        ev.record()
+        pl["done"][b].record(main)
+        host, ev = pl["ring"][i % 4]
+        d2h = pl["d2h"]
+        d2h.wait_event(pl["done"][b])
+        with torch.cuda.stream(d2h):
+            host.copy_(self.loss, non_blocking=True)
+            ev.record(d2h)
+        pl["last_loss"] = ev
         return LossHandle(host, ev)
 
     def step(self, X, y):

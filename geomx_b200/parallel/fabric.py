@@ -230,6 +230,8 @@ class HipsFabric:
         # one CTA per tile while the launch stays co-resident (the kernels spin on each other); grid-stride beyond that.  The LL kernel's
         # phases are one round each when grid >= tiles; the bulk protocol keeps <= 132 CTAs (its per-tile fences contend at higher counts)
         self.grid = max(1, min(T, int(native.require().gx_hips_max_grid()) if self.protocol == "ll" else 132))
+        if t.world == 1:
+            self.grid = max(1, min(T, 4096))     # nothing spins on a single rank: one tile per CTA, no co-residency requirement
         self._params_cache = {}
         self._peer_tables = {}
         self.set_optimizer(opt_spec)
