@@ -191,12 +191,14 @@ class KVWorker : public SimpleApp {
     Send(ts, true, cmd, kvs, priority, int_key, nullptr);
     return ts;
   }
+  // `request_payload` (optional) travels with the pull request — row_sparse pulls send the wanted row ids this way
   int ZPull(const SArray<Key>& keys, SArray<char>* vals, SArray<int>* lens = nullptr, int cmd = 0, const Callback& cb = nullptr, int priority = 0,
-            int int_key = 0) {
+            int int_key = 0, const SArray<char>* request_payload = nullptr) {
     const int ts = obj_->NewRequest(kServerGroup, kLocal);
     { std::lock_guard<std::mutex> lk(mu_); pull_targets_[ts] = PullTarget{keys, vals, lens}; }
     AddCallback(ts, cb);
     KVPairs kvs; kvs.keys = keys;
+    if (request_payload != nullptr && keys.size() == 1) { kvs.vals = *request_payload; kvs.lens.push_back(static_cast<int>(request_payload->size())); }
     Send(ts, false, cmd, kvs, priority, int_key, nullptr);
     return ts;
   }

@@ -146,6 +146,39 @@ class KVStoreDist {
     return Track({ts});
   }
 
+  // ---- row_sparse (reference PushRowSparse :628-657, PullRowSparse_ :660-702): only the listed rows travel.  Payload layout:
+  //      int64 nrows, int64 row_len, int64 ids[nrows], then (push only) float rows[nrows][row_len]
+  int PushRows(int key, const int64_t* ids, size_t nrows, const float* rows, size_t row_len, int priority) {
+    auto buf = std::make_shared<std::vector<char>>((2 + nrows) * sizeof(int64_t) + nrows * row_len * sizeof(float));
+    int64_t* hdr = reinterpret_cast<int64_t*>(buf->data());
+    hdr[0] = static_cast<int64_t>(nrows); hdr[1] = static_cast<int64_t>(row_len);
+    if (nrows) { memcpy(hdr + 2, ids, nrows * sizeof(int64_t)); memcpy(hdr + 2 + nrows, rows, nrows * row_len * sizeof(float)); }
+    const auto& krs = Postoffice::Get()->GetServerKeyRanges(kLocal);
+    SArray<Key> keys; keys.push_back(krs[(key * 9973) % krs.size()].begin() + static_cast<Key>(key));
+    SArray<char> vals(buf->data(), buf->size(), false);
+    SArray<int> lens; lens.push_back(static_cast<int>(buf->size()));
+    const int cmd = GetCommandType(RequestType::kRowSparsePushPull, kFloat32);
+    const int h = Track({ps_worker_->ZPush(keys, vals, lens, cmd, [buf]() {}, priority, key)});
+    { std::lock_guard<std::mutex> lk(mu_); last_push_[key] = h; }
+    return h;
+  }
+  int PullRows(int key, const int64_t* ids, size_t nrows, float* out, size_t row_len, int priority) {
+    int pending = -1;
+    { std::lock_guard<std::mutex> lk(mu_); auto it = last_push_.find(key); if (it != last_push_.end()) { pending = it->second; last_push_.erase(it); } }
+    if (pending >= 0) Wait(pending);
+    auto req = std::make_shared<std::vector<char>>((2 + nrows) * sizeof(int64_t));
+    int64_t* hdr = reinterpret_cast<int64_t*>(req->data());
+    hdr[0] = static_cast<int64_t>(nrows); hdr[1] = static_cast<int64_t>(row_len);
+    if (nrows) memcpy(hdr + 2, ids, nrows * sizeof(int64_t));
+    const auto& krs = Postoffice::Get()->GetServerKeyRanges(kLocal);
+    SArray<Key> keys; keys.push_back(krs[(key * 9973) % krs.size()].begin() + static_cast<Key>(key));
+    auto vals = std::make_shared<SArray<char>>(reinterpret_cast<char*>(out), nrows * row_len * sizeof(float), false);
+    auto lens = std::make_shared<SArray<int>>();
+    SArray<char> payload(req->data(), req->size(), false);
+    const int cmd = GetCommandType(RequestType::kRowSparsePushPull, kFloat32);
+    return Track({ps_worker_->ZPull(keys, vals.get(), lens.get(), cmd, [vals, lens, req]() {}, priority, key, &payload)});
+  }
+
   void Wait(int handle) {
     std::vector<int> tss;
     RelayWait rw;

@@ -162,7 +162,6 @@ void KVStoreDistServer::CommandHandle(const SimpleData& recved, SimpleApp* app) 
 // ------------------------------------------------------------------------------------------------ data
 void KVStoreDistServer::DataHandleEx(const KVMeta& req, const KVPairs& data, KVServer* server) {
   const DataHandleType type = DepairDataHandleType(req.cmd);
-  HIPS_CHECK_MSG(type.requestType != RequestType::kRowSparsePushPull, "row_sparse push/pull is served by dense storage on this server");
   ProfileScope ps(req.push ? "KVStoreDistServerPush" : "KVStoreDistServerPull");
   if (req.push) HandlePush(type, req, data);
   else HandlePull(type, req, data);
@@ -215,6 +214,21 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   if (type.requestType == RequestType::kDefaultPushPull) {
     HIPS_CHECK_MSG(data.vals.size() == n * DTypeSize(type.dtype), "push size mismatch for key " + std::to_string(key));
     ToFloat(data.vals.data(), type.dtype, n, incoming.data());
+  } else if (type.requestType == RequestType::kRowSparsePushPull) {
+    // row_sparse gradient (reference DataHandleRowSparse :561-756): scatter-add the listed rows into a dense contribution — the
+    // aggregation / tier logic below is storage-agnostic
+    HIPS_CHECK_MSG(e.dtype == kFloat32 && data.vals.size() >= 2 * sizeof(int64_t), "row_sparse push needs an fp32 key");
+    const int64_t* hdr = reinterpret_cast<const int64_t*>(data.vals.data());
+    const size_t nrows = static_cast<size_t>(hdr[0]), row_len = static_cast<size_t>(hdr[1]);
+    HIPS_CHECK_MSG(data.vals.size() == (2 + nrows) * sizeof(int64_t) + nrows * row_len * sizeof(float), "row_sparse push size mismatch");
+    const int64_t* ids = hdr + 2;
+    const float* rows = reinterpret_cast<const float*>(ids + nrows);
+    std::fill(incoming.begin(), incoming.end(), 0.f);
+    for (size_t r = 0; r < nrows; ++r) {
+      const size_t base = static_cast<size_t>(ids[r]) * row_len;
+      HIPS_CHECK_MSG(ids[r] >= 0 && base + row_len <= n, "row id out of range in row_sparse push");
+      for (size_t j = 0; j < row_len; ++j) incoming[base + j] += rows[r * row_len + j];
+    }
   } else if (type.requestType == RequestType::kCompressedPushPull) {
     gc_.Dequantize2Bit(reinterpret_cast<const uint32_t*>(data.vals.data()), incoming.data(), static_cast<int64_t>(n));
   } else {
@@ -512,7 +526,22 @@ void KVStoreDistServer::HandlePull(const DataHandleType& type, const KVMeta& req
   Entry& e = store_[key];
   KVPairs res;
   res.keys = data.keys;
-  if (type.requestType == RequestType::kBSCompressedPushPull) {
+  if (type.requestType == RequestType::kRowSparsePushPull) {
+    // row_sparse pull: only the requested rows travel back (reference DataHandleRowSparse pull branch :700-756)
+    HIPS_CHECK_MSG(data.vals.size() >= 2 * sizeof(int64_t), "row_sparse pull without row ids");
+    const int64_t* hdr = reinterpret_cast<const int64_t*>(data.vals.data());
+    const size_t nrows = static_cast<size_t>(hdr[0]), row_len = static_cast<size_t>(hdr[1]);
+    const int64_t* ids = hdr + 2;
+    std::vector<float> full(e.elems);
+    if (e.has_master) full = e.master; else ToFloat(e.data.data(), e.dtype, e.elems, full.data());
+    std::vector<float> out(nrows * row_len);
+    for (size_t r = 0; r < nrows; ++r) {
+      const size_t base = static_cast<size_t>(ids[r]) * row_len;
+      HIPS_CHECK_MSG(ids[r] >= 0 && base + row_len <= e.elems, "row id out of range in row_sparse pull");
+      memcpy(out.data() + r * row_len, full.data() + base, row_len * sizeof(float));
+    }
+    res.vals.CopyFrom(reinterpret_cast<const char*>(out.data()), out.size() * sizeof(float));
+  } else if (type.requestType == RequestType::kBSCompressedPushPull) {
     // Bi-Sparse pull: re-sparsify the aggregate, capacity k * num_parties (reference :1190-1206)
     const int mult = std::max(1, Postoffice::Get()->num_global_workers());
     const float* w = e.has_master ? e.master.data() : reinterpret_cast<const float*>(e.data.data());

@@ -150,6 +150,12 @@ PYBIND11_MODULE(_C, m) {
       .def("send_bytes", &KVStoreDist::send_bytes)
       .def("recv_bytes", &KVStoreDist::recv_bytes)
       .def("ts_stats", &KVStoreDist::ts_stats)
+      .def("push_rows", [](KVStoreDist& kv, int key, uintptr_t ids, size_t nrows, uintptr_t rows, size_t row_len, int priority) {
+        return kv.PushRows(key, reinterpret_cast<const int64_t*>(ids), nrows, reinterpret_cast<const float*>(rows), row_len, priority);
+      }, py::call_guard<py::gil_scoped_release>())
+      .def("pull_rows", [](KVStoreDist& kv, int key, uintptr_t ids, size_t nrows, uintptr_t out, size_t row_len, int priority) {
+        return kv.PullRows(key, reinterpret_cast<const int64_t*>(ids), nrows, reinterpret_cast<float*>(out), row_len, priority);
+      }, py::call_guard<py::gil_scoped_release>())
       .def("run_server", [](KVStoreDist& kv, py::object controller, py::object updater) {
         // python objects are held through shared_ptrs whose deleter re-acquires the GIL: the std::functions are copied / destroyed
         // by server threads that do not hold it

@@ -13,6 +13,7 @@ import weakref
 
 from ..base import MXNetError
 from ..ndarray import NDArray
+from ..ndarray.sparse import RowSparseNDArray
 
 __all__ = ["KVStoreBase", "create", "flush_all", "register_flushable"]
 
@@ -37,10 +38,10 @@ def _ctype_key_value(keys, vals):
         for k, v in zip(keys, vals):
             out.extend(_ctype_key_value(k, v))
         return out
-    if isinstance(vals, NDArray):
+    if isinstance(vals, (NDArray, RowSparseNDArray)):
         return [(keys, [vals])]
     for v in vals:
-        assert isinstance(v, NDArray), "value must be NDArray or list of NDArray"
+        assert isinstance(v, (NDArray, RowSparseNDArray)), "value must be NDArray or list of NDArray"
     return [(keys, list(vals))]
 
 
@@ -65,7 +66,14 @@ class KVStoreBase:
 
     def push(self, key, value, priority=0):
         for k, vals in _ctype_key_value(key, value):
-            self._push(self._key(k), vals, priority)
+            if any(isinstance(v, RowSparseNDArray) for v in vals):
+                # row_sparse gradients (kvstore_dist.h PushRowSparse :628-657): stores with a sparse wire get the rows, the rest the dense view
+                self._push_row_sparse(self._key(k), vals, priority)
+            else:
+                self._push(self._key(k), vals, priority)
+
+    def _push_row_sparse(self, key, vals, priority):
+        self._push(key, [v.tostype("default") if isinstance(v, RowSparseNDArray) else v for v in vals], priority)
 
     def pull(self, key, out=None, priority=0, ignore_sparse=True):
         assert out is not None
@@ -77,6 +85,8 @@ class KVStoreBase:
         pairs = _ctype_key_value(key, out)
         if isinstance(row_ids, NDArray):
             row_ids = [row_ids] * sum(len(o) for _, o in pairs)
+        elif len(pairs) > 1 and len(row_ids) == len(pairs) and any(len(o) != 1 for _, o in pairs):
+            row_ids = [r for r, (_, o) in zip(row_ids, pairs) for _ in o]
         flat_ids = list(row_ids)
         i = 0
         for k, outs in pairs:

@@ -46,6 +46,7 @@ class KVStoreDist(KVStoreBase):
         self._is_worker = self._C.is_worker_node()
         self._send_buf, self._recv_buf, self._push_handle = {}, {}, {}
         self._pulls = []
+        self._rows_keep = {}
         self._key_type = None
         self._next_str_key = 0
         self._closed = False
@@ -129,13 +130,47 @@ class KVStoreDist(KVStoreBase):
                 tgt = o._data
                 (tgt.detach() if tgt.requires_grad else tgt).copy_(buf.view(tgt.shape), non_blocking=True)
 
+    def _push_row_sparse(self, key, vals, priority):
+        """Only the non-zero rows travel (kvstore_dist.h PushRowSparse :628-657); several device copies are summed first."""
+        from ..ndarray import sparse
+        acc = None
+        for v in vals:
+            v = v if isinstance(v, sparse.RowSparseNDArray) else sparse.cast_storage(v, "row_sparse")
+            acc = v if acc is None else sparse.add(acc, v)
+        ids = acc.indices._t.long().cpu().contiguous()
+        rows = acc.data._t.float().cpu().contiguous()
+        row_len = 1
+        for d in acc.shape[1:]:
+            row_len *= int(d)
+        h = self._push_handle.pop(key, None)
+        if h is not None:
+            self._kv.wait(h)
+        self._rows_keep[key] = (ids, rows)
+        self._push_handle[key] = self._kv.push_rows(key, ids.data_ptr(), ids.numel(), rows.data_ptr(), row_len, int(priority))
+
     def _row_sparse_pull(self, key, outs, row_ids, priority):
+        """Sends the unique row ids, receives exactly those rows (kvstore_dist.h PullRowSparse_ :660-702)."""
+        from ..ndarray.sparse import RowSparseNDArray
         from .utils import unique_rows
-        dense = [NDArray(torch.empty_like(o._data)) for o in outs]
-        self._pull(key, dense, priority); self.flush()
-        for o, d, ids in zip(outs, dense, row_ids):
-            rows = unique_rows(ids._t)
-            o._data.zero_(); o._data[rows] = d._data[rows]
+        self.flush()
+        for o, ids in zip(outs, row_ids):
+            rows = unique_rows(ids._t).cpu().contiguous()
+            shape = o.shape
+            row_len = 1
+            for d in shape[1:]:
+                row_len *= int(d)
+            buf = _pinned(max(1, rows.numel() * row_len), torch.float32)
+            h = self._kv.pull_rows(key, rows.data_ptr(), rows.numel(), buf.data_ptr(), row_len, int(priority))
+            self._push_handle.pop(key, None)
+            self._kv.wait(h)
+            picked = buf[:rows.numel() * row_len].view((rows.numel(),) + tuple(shape[1:]))
+            if isinstance(o, RowSparseNDArray):
+                dev = o.data._t.device
+                o._set_rows(picked.to(dev).clone(), rows.to(dev))
+            else:
+                tgt = o._data
+                tgt.zero_()
+                tgt[rows.to(tgt.device)] = picked.to(tgt.device).to(tgt.dtype)
 
     # -- configuration ----------------------------------------------------------------------------------------------------------
     def set_optimizer(self, optimizer):

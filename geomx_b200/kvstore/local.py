@@ -134,13 +134,22 @@ class KVStoreLocal(KVStoreBase):
         self._comm.broadcast(key, self._store[key]._t, outs)
 
     def _row_sparse_pull(self, key, outs, row_ids, priority):
+        """``out`` may be a RowSparseNDArray (receives exactly the unique requested rows) or a dense NDArray (other rows zeroed) —
+        kvstore_local.h:357-417 PullRowSparseImpl."""
+        from ..ndarray.sparse import RowSparseNDArray, _gather
+        from .utils import unique_rows
         src = self._store[key]._t
         for o, ids in zip(outs, row_ids):
-            from .utils import unique_rows
-            rows = unique_rows(ids._t)
-            tgt = o._t
-            tgt.zero_()
-            tgt[rows] = src[rows.to(src.device)].to(tgt.device)
+            rows = unique_rows(ids._t.to(src.device))
+            picked = _gather(src.contiguous(), rows)
+            if isinstance(o, RowSparseNDArray):
+                dev = o.data._t.device
+                o._set_rows(picked.to(dev), rows.to(dev))
+                o._shape = tuple(src.shape)
+            else:
+                tgt = o._t
+                tgt.zero_()
+                tgt[rows.to(tgt.device)] = picked.to(tgt.device)
 
     def _set_gradient_compression(self, params):
         if "device" not in self._type:

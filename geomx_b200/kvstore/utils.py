@@ -1,8 +1,14 @@
 """Row-id dedup for row_sparse pulls.  Parity: ``src/kvstore/kvstore_utils.{cc,cu}`` ``UniqueImpl`` (CUB radix sort
-+ ``DeviceSelect::Unique``; blocking D2H of the count).  Here: ``torch.unique`` (CCCL radix sort + unique underneath on
-CUDA) — kept as a library call because row_sparse is off every GeoMX config path."""
++ ``DeviceSelect::Unique``; blocking D2H of the count).  CUDA ids go through the native ``gx_unique_i64`` (csrc/kernels/sparse_ops.cu,
+the same CUB pair), host ids through ``torch.unique``."""
 import torch
 
 
 def unique_rows(ids: torch.Tensor) -> torch.Tensor:
-    return torch.unique(ids.reshape(-1).long(), sorted=True)
+    ids = ids.reshape(-1).long()
+    if ids.is_cuda:
+        from ..ops import native
+        if native.available():
+            from ..ops import _native_api
+            return _native_api.unique_i64(ids)
+    return torch.unique(ids, sorted=True)

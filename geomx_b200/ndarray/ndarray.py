@@ -243,8 +243,11 @@ class NDArray:
         return NDArray(self._t.expand(*shape))
 
     def tostype(self, stype):
+        if stype == "row_sparse":
+            from . import sparse
+            return sparse.cast_storage(self, "row_sparse")
         if stype != "default":
-            raise MXNetError("only dense storage is materialised; use kv.row_sparse_pull for row_sparse")
+            raise MXNetError("storage type %s is not supported (default / row_sparse)" % stype)
         return self
 
     # ---- autograd -------------------------------------------------------------------------

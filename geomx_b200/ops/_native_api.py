@@ -344,6 +344,34 @@ def dgt_contrib(g, contrib, block_elems, alpha, first):
     _ck(_lib().gx_dgt_contrib(_p(g), _p(contrib), g.numel(), block_elems, alpha, int(first), _s()), "dgt_contrib")
 
 
+# --------------------------------------------------------------------------------------------------------------- row-sparse helpers
+def unique_i64(ids):
+    """Sorted unique of a CUDA int64 vector (CUB radix sort + select; the count is read back, as UniqueImplGPU does)."""
+    ids = ids.reshape(-1).contiguous()
+    n = ids.numel()
+    if n == 0:
+        return ids
+    lib = _lib()
+    ws = torch.empty(int(lib.gx_unique_i64_workspace(n)) + 16, dtype=torch.uint8, device=ids.device)
+    tmp, out = torch.empty_like(ids), torch.empty_like(ids)
+    cnt = torch.zeros(1, dtype=torch.int32, device=ids.device)
+    _ck(lib.gx_unique_i64(_p(ids), n, _p(tmp), _p(out), _p(cnt), _p(ws), ws.numel(), _s()), "unique_i64")
+    return out[:int(cnt.item())]
+
+
+def gather_rows(src, ids, out=None):
+    L = src.numel() // src.shape[0]
+    out = torch.empty((ids.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device) if out is None else out
+    _ck(_lib().gx_gather_rows(_p(_f32c(src)), _p(ids.contiguous()), _p(out), ids.numel(), L, _s()), "gather_rows")
+    return out
+
+
+def scatter_rows(dst, ids, rows, add=False):
+    L = dst.numel() // dst.shape[0]
+    _ck(_lib().gx_scatter_rows(_p(_f32c(dst)), _p(ids.contiguous()), _p(_f32c(rows)), ids.numel(), L, int(add), _s()), "scatter_rows")
+    return dst
+
+
 # --------------------------------------------------------------------------------------------------------------- batch norm
 def bn_fwd(x, gamma, beta, rm, rv, training, momentum, eps):
     N, C = x.shape[0], x.shape[1]

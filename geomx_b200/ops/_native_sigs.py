@@ -55,6 +55,9 @@ SIGS = {
     "gx_hips_party_allreduce": [P, P, P, F, I, I, I, P],
     "gx_fabric_barrier": [P, I, I, I, P, P],
     "gx_fabric_probe": [P, P, P, P, P, I, I, P],
+    "gx_unique_i64": [P, I, P, P, P, P, C.c_longlong, P],
+    "gx_gather_rows": [P, P, P, I, I, P],
+    "gx_scatter_rows": [P, P, P, I, I, I, P],
 }
 
 
@@ -63,3 +66,5 @@ def declare(lib):
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.gx_unique_i64_workspace.argtypes = [C.c_int]
+    lib.gx_unique_i64_workspace.restype = C.c_longlong

@@ -18,7 +18,7 @@ shapes = [(4, 5), (7,), (300,), (3, 2)] if mode != "big" else [(4, 5), (2500,)]
 kv = mx.kv.create(os.environ.get("TEST_KV", "dist_sync"))
 master = kv.is_master_worker
 if master or (os.environ.get("TEST_STANDALONE") == "1" and kv.rank == 0):
-    if mode in ("sgd", "big", "p3", "2bit", "async", "fp16"):
+    if mode in ("sgd", "big", "p3", "2bit", "async", "fp16", "rowsparse"):
         kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, multi_precision=(mode == "fp16")))
     elif mode == "adam_py":
         os.environ["GEOMX_PY_UPDATER"] = "1"
@@ -41,6 +41,20 @@ if master:
     kv.close()
     sys.exit(0)
 out = {"rank": kv.rank, "num_workers": kv.num_workers, "num_all_workers": kv.num_all_workers, "vals": []}
+if mode == "rowsparse":
+    # embedding-style key: every worker pushes two rows (one shared, one private), then pulls a few rows back through the sparse wire
+    emb = mx.nd.array(np.zeros((10, 4), dtype=np.float32))
+    kv.init(100, emb)
+    kv.pull(100, emb); mx.nd.waitall()
+    for step in range(steps):
+        g = mx.nd.sparse.row_sparse_array((np.full((2, 4), 1.0 + gid, dtype=np.float32), [3, 5 + gid]), shape=(10, 4))
+        kv.push(100, g)
+        got = mx.nd.sparse.zeros("row_sparse", (10, 4))
+        kv.row_sparse_pull(100, out=got, row_ids=mx.nd.array([5, 3, 6, 3], dtype="int64"))
+        out["vals"].append({"ids": got.indices.asnumpy().tolist(), "rows": got.data.asnumpy()[:, 0].tolist()})
+    print("RESULT " + json.dumps(out), flush=True)
+    kv.close()
+    sys.exit(0)
 for step in range(steps):
     for i, p in enumerate(params):
         if mode == "hfa":

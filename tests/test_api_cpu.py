@@ -147,3 +147,32 @@ def test_dataloader_and_split_sampler():
     assert X.shape == (32, 1, 28, 28) and y.shape == (32,) and float(X.max().asscalar()) <= 1.0
     parts = mx.gluon.utils.split_and_load(X, [mx.cpu()])
     assert parts[0].shape == (32, 1, 28, 28)
+
+
+def test_row_sparse_ndarray_and_local_kvstore():
+    """row_sparse storage + kv.row_sparse_pull / sparse push on the local store (python/mxnet/ndarray/sparse.py, kvstore_local.h:357-417)."""
+    import numpy as np
+    dense = np.zeros((6, 3), dtype=np.float32); dense[1] = 1.0; dense[4] = [1, 2, 3]
+    rs = mx.nd.array(dense).tostype("row_sparse")
+    assert rs.stype == "row_sparse" and rs.indices.asnumpy().tolist() == [1, 4] and rs.data.shape == (2, 3)
+    assert np.array_equal(rs.tostype("default").asnumpy(), dense)
+    rs2 = mx.nd.sparse.row_sparse_array((np.ones((2, 3), dtype=np.float32), [4, 0]), shape=(6, 3))
+    assert rs2.indices.asnumpy().tolist() == [0, 4]
+    s = mx.nd.sparse.add(rs, rs2)
+    assert s.indices.asnumpy().tolist() == [0, 1, 4] and np.allclose(s.tostype("default").asnumpy()[4], [2, 3, 4])
+    assert rs.retain(mx.nd.array([4, 5], dtype="int64")).indices.asnumpy().tolist() == [4]
+    z = mx.nd.sparse.zeros("row_sparse", (6, 3))
+    assert z.data.shape == (0, 3) and z.tostype("default").asnumpy().sum() == 0
+
+    kv = mx.kv.create("local")
+    w = mx.nd.array(np.arange(18, dtype=np.float32).reshape(6, 3))
+    kv.init("emb", w)
+    out = mx.nd.sparse.zeros("row_sparse", (6, 3))
+    kv.row_sparse_pull("emb", out=out, row_ids=mx.nd.array([4, 1, 4], dtype="int64"))
+    assert out.indices.asnumpy().tolist() == [1, 4] and np.array_equal(out.data.asnumpy(), w.asnumpy()[[1, 4]])
+    dense_out = mx.nd.zeros((6, 3))
+    kv.row_sparse_pull("emb", out=dense_out, row_ids=mx.nd.array([2], dtype="int64"))
+    assert np.array_equal(dense_out.asnumpy()[2], w.asnumpy()[2]) and dense_out.asnumpy()[[0, 1, 3, 4, 5]].sum() == 0
+    kv.push("emb", rs)                      # without an updater the store takes the pushed value (densified)
+    chk = mx.nd.zeros((6, 3)); kv.pull("emb", out=chk)
+    assert np.array_equal(chk.asnumpy(), dense)

@@ -201,3 +201,15 @@ def test_tsengine_two_tier_intra_and_inter():
         for t, vals in enumerate(r["vals"]):
             for i, v in enumerate(vals):
                 assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-4, (t, i, v)
+
+
+def test_row_sparse_push_pull_over_the_wire():
+    """row_sparse gradients / row_sparse_pull through the native server (kvstore_dist.h PushRowSparse / PullRowSparse_): 2 workers, SGD lr 0.1.
+    Row 3 receives both workers' rows, rows 5 / 6 one each; only the requested rows travel back."""
+    res = launch_single_tier({"TEST_MODE": "rowsparse", "TEST_STEPS": "2"})
+    assert len(res) == 2
+    for r in res:
+        for t, v in enumerate(r["vals"]):
+            assert v["ids"] == [3, 5, 6]
+            exp = [-0.1 * (1 + 2) * (t + 1), -0.1 * 1 * (t + 1), -0.1 * 2 * (t + 1)]
+            assert all(abs(a - b) < 1e-5 for a, b in zip(v["rows"], exp)), (v, exp)

@@ -287,3 +287,31 @@ def test_direct_conv_kernels_exact(nat):
     back = nat.col2im(c, tuple(x2.shape), 5, 5)
     ref_back = F.fold(c[:, :400].reshape(4, 64, 400).transpose(1, 2), (12, 12), 5)
     assert torch.allclose(back, ref_back, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_unique_gather_scatter_rows():
+    """Row-sparse support kernels (sparse_ops.cu: CUB sort+unique, row gather / scatter-add) against torch."""
+    from geomx_b200.ops import _native_api as n
+    torch.manual_seed(0)
+    ids = torch.randint(0, 500, (4000,), device="cuda", dtype=torch.int64)
+    u = n.unique_i64(ids)
+    assert torch.equal(u, torch.unique(ids, sorted=True))
+    src = torch.randn(500, 24, device="cuda")
+    g = n.gather_rows(src, u)
+    assert torch.equal(g, src[u])
+    src3 = torch.randn(500, 5, device="cuda")                 # row length not a multiple of 4: scalar path
+    assert torch.equal(n.gather_rows(src3, u), src3[u])
+    dst = torch.zeros(500, 24, device="cuda")
+    rows = torch.randn(ids.numel(), 24, device="cuda")
+    n.scatter_rows(dst, ids, rows, add=True)
+    ref = torch.zeros(500, 24, device="cuda").index_add_(0, ids, rows)
+    assert torch.allclose(dst, ref, atol=1e-4)
+    # through the public API: dense -> row_sparse -> kv.row_sparse_pull on the GPU
+    import geomx_b200 as mx
+    w = mx.nd.array(src.cpu().numpy(), ctx=mx.gpu(0))
+    kv = mx.kv.create("device")
+    kv.init(7, w)
+    out = mx.nd.sparse.zeros("row_sparse", (500, 24), ctx=mx.gpu(0))
+    kv.row_sparse_pull(7, out=out, row_ids=mx.nd.array(ids.cpu().numpy(), ctx=mx.gpu(0), dtype="int64"))
+    assert torch.equal(out.indices._t, u) and torch.equal(out.data._t, src[u])
