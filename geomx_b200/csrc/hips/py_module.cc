@@ -7,6 +7,7 @@
 #include <pybind11/stl.h>
 
 #include "../runtime/engine.h"
+#include "../runtime/gpu_topology.h"
 #include "../runtime/io.h"
 #include "../runtime/params_io.h"
 #include "../runtime/profiler.h"
@@ -124,6 +125,20 @@ PYBIND11_MODULE(_C, m) {
         GradientCompression::BSCDecompress(z.data(), z.size(), out.mutable_data(), n);
         return out;
       });
+
+  // ---------------------------------------------------------------------------------------------- GPU topology solver
+  m.def("topology_tree", [](std::vector<float> W, int n, int root) {
+    HIPS_CHECK_MSG(static_cast<int>(W.size()) == n * n && root >= 0 && root < n, "topology_tree: W must be n*n and 0 <= root < n");
+    gx_rt::TopologySolver solver(W, n);
+    gx_rt::TopoTree t = solver.BuildTree(root);
+    return py::make_tuple(t.parent, t.round, t.depth);
+  }, "binary reduction tree over a link-weight matrix: (parent[], round[], depth)");
+  m.def("topology_bisect", [](std::vector<float> W, int n, std::vector<int> set, int pin) {
+    gx_rt::TopologySolver solver(W, n);
+    std::vector<int> A, B;
+    solver.Bisect(set, pin, &A, &B);
+    return py::make_tuple(A, B);
+  }, "Kernighan-Lin balanced bisection of a device set (the half containing `pin` first)");
 
   // ---------------------------------------------------------------------------------------------- KVStoreDist
   py::class_<KVStoreDist>(m, "KVStoreDist")

@@ -88,7 +88,11 @@ class KVStoreLocal(KVStoreBase):
     def __init__(self, kv_type="local"):
         super().__init__(kv_type)
         use_dev = "device" in kv_type
-        self._comm = CommDevice() if use_dev else CommCPU()
+        if use_dev and getenv_int("MXNET_KVSTORE_USETREE", 0):
+            from .comm_tree import CommDeviceTree              # kvstore_local.h:76-86
+            self._comm = CommDeviceTree()
+        else:
+            self._comm = CommDevice() if use_dev else CommCPU()
         self._store = {}
         self._key_type = None
         self._next_str_key = 0

@@ -176,3 +176,50 @@ def test_fp8_block_codec_cpu():
     assert q.numel() == 384 and s.numel() == 3
     y = gc.fp8_block_dequantize(q, s, 300)
     assert torch.allclose(y + res, x, atol=1e-5) and float((y - x).abs().max()) < 0.07 * float(x.abs().max())
+
+
+def test_topology_solver_and_tree_comm():
+    """gpu_topology.h: Kernighan-Lin bisection keeps strongly linked devices together; the reduction tree is a spanning binary-depth tree
+    whose first-round edges are the heavy links; CommDeviceTree reduces/broadcasts exactly (CPU tensors stand in for devices)."""
+    import numpy as np
+    import torch
+    import geomx_b200 as mx
+    from geomx_b200 import runtime
+    from geomx_b200.kvstore import comm_tree
+    if not runtime.available():
+        pytest.skip("native runtime not built")
+    n = 8
+    W = np.ones((n, n), dtype=np.float32); np.fill_diagonal(W, 0)
+    for a, b in ((0, 1), (2, 3), (4, 5), (6, 7)):                # NVLink pairs
+        W[a, b] = W[b, a] = 10
+    for a, b in ((0, 2), (1, 3), (4, 6), (5, 7)):                # quads
+        W[a, b] = W[b, a] = 4
+    A, B = runtime.C().topology_bisect(W.reshape(-1).tolist(), n, list(range(n)), 0)
+    assert sorted(A) == [0, 1, 2, 3] and sorted(B) == [4, 5, 6, 7]
+    parent, rnd, depth = comm_tree.compute_tree(W.tolist(), 0)
+    assert depth == 3 and parent[0] == -1 and sum(p == -1 for p in parent) == 1
+    for d in range(n):                                            # spanning: every device reaches the root
+        seen, x = set(), d
+        while parent[x] != -1:
+            assert x not in seen; seen.add(x); x = parent[x]
+        assert x == 0
+    first = sorted((d, parent[d]) for d in range(n) if rnd[d] == 0)
+    assert all(W[d, p] == 10 for d, p in first) and len(first) == 4      # round 0 uses the four NVLink pairs
+    # exact reduce / broadcast
+    comm = comm_tree.CommDeviceTree()
+    vals = [mx.nd.array(np.full((5, 3), float(i + 1), dtype=np.float32)) for i in range(n)]
+    comm._devices = None
+    import os
+    os.environ["GEOMX_LINK_MATRIX"] = ";".join(",".join(str(x) for x in row) for row in W.tolist())
+    try:
+        comm.init(3, vals[0])
+        out = comm.reduce(3, vals)
+        assert torch.equal(out, torch.full((5, 3), float(sum(range(1, n + 1)))))
+        comm.array_bound = 4                                      # force the sliced (reduce-scatter) path
+        out = comm.reduce(3, vals)
+        assert torch.equal(out, torch.full((5, 3), float(sum(range(1, n + 1)))))
+        outs = [mx.nd.zeros((5, 3)) for _ in range(n)]
+        comm.broadcast(3, out, outs)
+        assert all(torch.equal(o._t, out) for o in outs)
+    finally:
+        os.environ.pop("GEOMX_LINK_MATRIX", None)
