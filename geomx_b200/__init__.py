@@ -28,6 +28,7 @@ from . import metric  # noqa: F401
 from . import model  # noqa: F401
 from . import profiler  # noqa: F401
 from . import io  # noqa: F401
+from . import recordio  # noqa: F401
 from . import utils  # noqa: F401
 from . import parallel  # noqa: F401
 from . import models  # noqa: F401

@@ -12,7 +12,7 @@ import geomx_b200 as mx  # noqa: E402
 
 mode = os.environ.get("TEST_MODE", "sgd")
 steps = int(os.environ.get("TEST_STEPS", "3"))
-gid = int(os.environ.get("TEST_WORKER_GID", "0"))       # global worker index (for deterministic gradients)
+gid = int(os.environ.get("TEST_WORKER_GID", os.environ.get("GEOMX_WORKER_INDEX", "0")))       # global worker index (for deterministic gradients)
 shapes = [(4, 5), (7,), (300,), (3, 2)] if mode != "big" else [(4, 5), (2500,)]
 
 kv = mx.kv.create(os.environ.get("TEST_KV", "dist_sync"))

@@ -176,3 +176,30 @@ def test_row_sparse_ndarray_and_local_kvstore():
     kv.push("emb", rs)                      # without an updater the store takes the pushed value (densified)
     chk = mx.nd.zeros((6, 3)); kv.pull("emb", out=chk)
     assert np.array_equal(chk.asnumpy(), dense)
+
+
+def test_recordio_roundtrip(tmp_path):
+    """mx.recordio: sequential + indexed files, payloads containing the magic word, image records (python/mxnet/recordio.py)."""
+    import struct
+    import numpy as np
+    from geomx_b200 import recordio
+    p = str(tmp_path / "a.rec")
+    w = recordio.MXRecordIO(p, "w")
+    payloads = [b"hello", b"", struct.pack("<I", 0xced7230a) * 2 + b"xyz", bytes(range(256)) * 3]
+    for b in payloads:
+        w.write(b)
+    w.close()
+    r = recordio.MXRecordIO(p, "r")
+    assert [r.read() for _ in payloads] == payloads and r.read() is None
+    wi = recordio.MXIndexedRecordIO(str(tmp_path / "b.idx"), str(tmp_path / "b.rec"), "w")
+    img = (np.arange(8 * 8 * 3) % 255).astype(np.uint8).reshape(8, 8, 3)
+    for i in range(5):
+        wi.write_idx(i, recordio.pack_img(recordio.IRHeader(0, float(i), i, 0), img, img_fmt=".png"))
+    wi.write_idx(7, recordio.pack(recordio.IRHeader(0, [1.0, 2.0, 3.0], 7, 0), b"raw"))
+    wi.close()
+    ri = recordio.MXIndexedRecordIO(str(tmp_path / "b.idx"), str(tmp_path / "b.rec"), "r")
+    assert ri.keys == [0, 1, 2, 3, 4, 7]
+    h, dec = recordio.unpack_img(ri.read_idx(3))
+    assert h.label == 3.0 and h.id == 3 and np.array_equal(dec, img)
+    h, raw = recordio.unpack(ri.read_idx(7))
+    assert list(h.label) == [1.0, 2.0, 3.0] and raw == b"raw"

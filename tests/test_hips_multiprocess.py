@@ -213,3 +213,19 @@ def test_row_sparse_push_pull_over_the_wire():
             assert v["ids"] == [3, 5, 6]
             exp = [-0.1 * (1 + 2) * (t + 1), -0.1 * 1 * (t + 1), -0.1 * 2 * (t + 1)]
             assert all(abs(a - b) < 1e-5 for a, b in zip(v["rows"], exp)), (v, exp)
+
+
+def test_tracker_launcher_single_tier_and_layout(tmp_path):
+    """geomx_b200.tracker: the two-tier layout is the reference's 12 processes, and a locally launched single-tier job trains correctly."""
+    from geomx_b200.tracker import HipsJob, launch
+    names = [p.name for p in HipsJob(2, 1, parties=2).processes()]
+    assert len(names) == 12 and names[:4] == ["global_scheduler", "global_server0", "central_scheduler", "master_worker"]
+    plan = launch(HipsJob(2, 1, parties=2, hosts=["10.0.0.1", "10.0.0.2", "10.0.0.3"]), ["python", "train.py"], launcher="ssh", dry_run=True)
+    assert plan[0][1][0] == "ssh" and "10.0.0.1" in plan[0][1] and any("10.0.0.3" in c for _, c, _ in plan)
+    env = {"TEST_MODE": "sgd", "TEST_STANDALONE": "1", "TEST_STEPS": "2", "PYTHONPATH": os.path.dirname(HERE)}
+    job = HipsJob(2, 1, base_port=free_port(), extra_env=env)
+    rc = launch(job, [sys.executable, WORKER], log_dir=str(tmp_path), timeout=120)
+    assert rc == 0
+    outs = [open(os.path.join(str(tmp_path), "worker%d.log" % i)).read() for i in range(2)]
+    res = results(outs)
+    assert len(res) == 2 and all(abs(r["vals"][1][0] - (1.0 - 0.1 * 1.5 * 2)) < 1e-5 for r in res)
