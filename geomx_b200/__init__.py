@@ -26,6 +26,10 @@ from . import kvstore as kv  # noqa: F401
 from . import gluon  # noqa: F401
 from . import metric  # noqa: F401
 from . import model  # noqa: F401
+from . import symbol  # noqa: F401
+from . import symbol as sym  # noqa: F401
+from . import module  # noqa: F401
+from . import module as mod  # noqa: F401
 from . import profiler  # noqa: F401
 from . import io  # noqa: F401
 from . import recordio  # noqa: F401

@@ -1,0 +1,302 @@
+"""``mx.mod.Module`` — the symbolic training front end (bind → init_params → init_optimizer → fit / forward / backward / update).
+
+Parity: ``python/mxnet/module/module.py`` (``bind`` :363-470, ``init_params`` :265-340, ``init_optimizer`` :472-560 incl. the kvstore setup
+:501-543, ``forward``/``backward``/``update`` :588-668, ``save_checkpoint`` / ``load``), ``module/base_module.py`` (``fit`` :376-560, ``score``,
+``predict``) and ``module/executor_group.py`` (``DataParallelExecutorGroup``: one executor per context, the batch split along axis 0).
+The kvstore glue is ``model.py``'s (``_create_kvstore`` / ``_initialize_kvstore`` / ``_update_params(_on_kvstore)``), i.e. a Module trains
+through the same KVStore implementations — local, device, the TCP HiPS client or the NVSwitch fabric — as the Gluon scripts do."""
+from __future__ import annotations
+
+import logging
+import time
+
+from . import initializer as init_mod
+from . import metric as metric_mod
+from . import ndarray as nd
+from . import optimizer as opt
+from .base import MXNetError
+from .context import cpu
+from .io import DataBatch, DataDesc
+from .model import BatchEndParam, _create_kvstore, _initialize_kvstore, _update_params, _update_params_on_kvstore, load_checkpoint, save_checkpoint
+from .ndarray import NDArray
+
+__all__ = ["Module", "BaseModule"]
+
+
+def _as_desc(shapes):
+    out = []
+    for s in shapes or []:
+        out.append(s if isinstance(s, DataDesc) else DataDesc(s[0], tuple(s[1])))
+    return out
+
+
+class BaseModule:
+    def __init__(self, logger=logging):
+        self.logger = logger
+        self.binded = self.for_training = self.params_initialized = self.optimizer_initialized = False
+
+    # ---- high level API shared by every module type
+    def forward_backward(self, data_batch):
+        self.forward(data_batch, is_train=True)
+        self.backward()
+
+    def score(self, eval_data, eval_metric, num_batch=None, reset=True, epoch=0):
+        assert self.binded and self.params_initialized
+        if reset:
+            eval_data.reset()
+        eval_metric = metric_mod.create(eval_metric) if not isinstance(eval_metric, metric_mod.EvalMetric) else eval_metric
+        eval_metric.reset()
+        for nbatch, batch in enumerate(eval_data):
+            if num_batch is not None and nbatch == num_batch:
+                break
+            self.forward(batch, is_train=False)
+            self.update_metric(eval_metric, batch.label)
+        return eval_metric.get_name_value()
+
+    def predict(self, eval_data, num_batch=None, merge_batches=True, reset=True):
+        assert self.binded and self.params_initialized
+        if reset:
+            eval_data.reset()
+        outs = []
+        for nbatch, batch in enumerate(eval_data):
+            if num_batch is not None and nbatch == num_batch:
+                break
+            self.forward(batch, is_train=False)
+            pad = batch.pad or 0
+            outs.append([o[0:o.shape[0] - pad].copy() for o in self.get_outputs()])
+        if not outs:
+            return outs
+        if merge_batches:
+            merged = [nd.concat(*[b[i] for b in outs], dim=0) for i in range(len(outs[0]))]
+            return merged[0] if len(merged) == 1 else merged
+        return outs
+
+    def fit(self, train_data, eval_data=None, eval_metric="acc", epoch_end_callback=None, batch_end_callback=None, kvstore="local",
+            optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), eval_end_callback=None, initializer=None, arg_params=None,
+            aux_params=None, allow_missing=False, force_rebind=False, force_init=False, begin_epoch=0, num_epoch=None, validation_metric=None):
+        assert num_epoch is not None, "please specify number of epochs"
+        self.bind(data_shapes=train_data.provide_data, label_shapes=train_data.provide_label, for_training=True, force_rebind=force_rebind)
+        self.init_params(initializer=initializer or init_mod.Uniform(0.01), arg_params=arg_params, aux_params=aux_params,
+                         allow_missing=allow_missing, force_init=force_init)
+        self.init_optimizer(kvstore=kvstore, optimizer=optimizer, optimizer_params=optimizer_params)
+        eval_metric = metric_mod.create(eval_metric) if not isinstance(eval_metric, metric_mod.EvalMetric) else eval_metric
+        validation_metric = validation_metric or eval_metric
+        for epoch in range(begin_epoch, num_epoch):
+            tic = time.time()
+            eval_metric.reset()
+            train_data.reset()
+            for nbatch, batch in enumerate(train_data):
+                self.forward_backward(batch)
+                self.update()
+                self.update_metric(eval_metric, batch.label)
+                if batch_end_callback is not None:
+                    p = BatchEndParam(epoch=epoch, nbatch=nbatch, eval_metric=eval_metric, locals=locals())
+                    for cb in (batch_end_callback if isinstance(batch_end_callback, (list, tuple)) else [batch_end_callback]):
+                        cb(p)
+            for name, val in eval_metric.get_name_value():
+                self.logger.info("Epoch[%d] Train-%s=%f", epoch, name, val)
+            self.logger.info("Epoch[%d] Time cost=%.3f", epoch, time.time() - tic)
+            if epoch_end_callback is not None:
+                arg, aux = self.get_params()
+                for cb in (epoch_end_callback if isinstance(epoch_end_callback, (list, tuple)) else [epoch_end_callback]):
+                    cb(epoch, self.symbol, arg, aux)
+            if eval_data is not None:
+                for name, val in self.score(eval_data, validation_metric, epoch=epoch):
+                    self.logger.info("Epoch[%d] Validation-%s=%f", epoch, name, val)
+
+
+class Module(BaseModule):
+    def __init__(self, symbol, data_names=("data",), label_names=("softmax_label",), logger=logging, context=None, fixed_param_names=None):
+        super().__init__(logger)
+        self._symbol = symbol
+        ctx = context if context is not None else cpu()
+        self._context = list(ctx) if isinstance(ctx, (list, tuple)) else [ctx]
+        self._data_names, self._label_names = list(data_names or []), list(label_names or [])
+        args = symbol.list_arguments()
+        self._param_names = [a for a in args if a not in self._data_names + self._label_names]
+        self._fixed = set(fixed_param_names or [])
+        self._aux_names = symbol.list_auxiliary_states()
+        self._execs, self._arg_params, self._aux_params = [], None, None
+        self._kvstore, self._update_on_kvstore, self._updater, self._optimizer = None, False, None, None
+        self._slices = []
+
+    symbol = property(lambda self: self._symbol)
+    data_names = property(lambda self: self._data_names)
+    output_names = property(lambda self: self._symbol.list_outputs())
+
+    # ---- bind: one executor per context, batch split along axis 0 (DataParallelExecutorGroup.decide_slices)
+    def bind(self, data_shapes, label_shapes=None, for_training=True, inputs_need_grad=False, force_rebind=False, shared_module=None, grad_req="write"):
+        if self.binded and not force_rebind:
+            return
+        self.for_training, self._inputs_need_grad = for_training, inputs_need_grad
+        self._data_shapes, self._label_shapes = _as_desc(data_shapes), _as_desc(label_shapes)
+        batch = self._data_shapes[0].shape[0]
+        n = len(self._context)
+        bounds = [(batch * i) // n for i in range(n + 1)]
+        self._slices = [slice(bounds[i], bounds[i + 1]) for i in range(n)]
+        self._execs = []
+        for ctx, sl in zip(self._context, self._slices):
+            shapes = {d.name: (sl.stop - sl.start,) + tuple(d.shape[1:]) for d in self._data_shapes + self._label_shapes}
+            req = {}
+            for a in self._symbol.list_arguments():
+                if a in self._param_names:
+                    req[a] = "null" if (not for_training or a in self._fixed) else grad_req
+                elif a in self._data_names:
+                    req[a] = grad_req if inputs_need_grad else "null"
+                else:
+                    req[a] = "null"
+            self._execs.append(self._symbol.simple_bind(ctx, grad_req=req, **shapes))
+        self.binded = True
+        if self._arg_params is not None:
+            self._sync_params_to_devices()
+
+    # ---- parameters
+    def init_params(self, initializer=None, arg_params=None, aux_params=None, allow_missing=False, force_init=False, allow_extra=False):
+        assert self.binded, "call bind before initializing the parameters"
+        if self.params_initialized and not force_init:
+            return
+        initializer = initializer or init_mod.Uniform(0.01)
+        ex0 = self._execs[0]
+        self._arg_params = {n: nd.zeros(ex0.arg_dict[n].shape) for n in self._param_names}
+        self._aux_params = {n: nd.zeros(ex0.aux_dict[n].shape) for n in self._aux_names}
+        for name, arr in list(self._arg_params.items()) + list(self._aux_params.items()):
+            given = (arg_params or {}).get(name) if name in self._arg_params else (aux_params or {}).get(name)
+            if given is not None:
+                arr[:] = given
+            elif (arg_params is not None or aux_params is not None) and not allow_missing and name in self._arg_params and arg_params is not None:
+                raise MXNetError("%s is not presented" % name)
+            else:
+                initializer(init_mod.InitDesc(name), arr)
+        self.params_initialized = True
+        self._sync_params_to_devices()
+
+    def _sync_params_to_devices(self):
+        for ex in self._execs:
+            ex.copy_params_from(self._arg_params, self._aux_params, allow_extra_params=True)
+
+    def get_params(self):
+        assert self.binded and self.params_initialized
+        ex0 = self._execs[0]                      # replicas are identical after update()
+        for n in self._param_names:
+            self._arg_params[n][:] = ex0.arg_dict[n].as_in_context(cpu())
+        for n in self._aux_names:
+            self._aux_params[n][:] = ex0.aux_dict[n].as_in_context(cpu())
+        return self._arg_params, self._aux_params
+
+    def set_params(self, arg_params, aux_params, allow_missing=False, force_init=True, allow_extra=False):
+        self.init_params(None, arg_params, aux_params, allow_missing, force_init, allow_extra)
+
+    # ---- optimizer + kvstore (module.py:472-560)
+    def init_optimizer(self, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), force_init=False):
+        assert self.binded and self.params_initialized
+        if self.optimizer_initialized and not force_init:
+            return
+        kv, update_on_kvstore = _create_kvstore(kvstore, len(self._context), self._arg_params)
+        batch_size = self._data_shapes[0].shape[0]
+        if kv is not None and "dist" in kv.type and "_sync" in kv.type:
+            batch_size *= kv.num_workers
+        if isinstance(optimizer, str):
+            params = dict(optimizer_params)
+            params.setdefault("rescale_grad", 1.0 / batch_size)
+            idx2name = {i: n for i, n in enumerate(self._param_names)} if update_on_kvstore else \
+                {i * len(self._context) + k: n for i, n in enumerate(self._param_names) for k in range(len(self._context))}
+            optimizer = opt.create(optimizer, param_idx2name=idx2name, **params)
+        self._optimizer, self._kvstore, self._update_on_kvstore, self._updater = optimizer, kv, update_on_kvstore, None
+        if kv is not None:
+            _initialize_kvstore(kv, self._param_arrays(), self._arg_params, self._param_names, update_on_kvstore)
+            if update_on_kvstore:
+                kv.set_optimizer(optimizer)
+        if not update_on_kvstore:
+            self._updater = opt.get_updater(optimizer)
+        self.optimizer_initialized = True
+
+    def _param_arrays(self):
+        return [[ex.arg_dict[n] for ex in self._execs] for n in self._param_names]
+
+    def _grad_arrays(self):
+        return [[ex.grad_dict.get(n) for ex in self._execs] for n in self._param_names]
+
+    # ---- computation
+    def forward(self, data_batch, is_train=None):
+        assert self.binded and self.params_initialized
+        is_train = self.for_training if is_train is None else is_train
+        data = data_batch.data if isinstance(data_batch, DataBatch) or hasattr(data_batch, "data") else data_batch
+        label = getattr(data_batch, "label", None)
+        for ex, sl in zip(self._execs, self._slices):
+            for name, arr in zip(self._data_names, data):
+                ex.arg_dict[name][:] = arr[sl].as_in_context(ex._ctx)
+            if label is not None:
+                for name, arr in zip(self._label_names, label):
+                    if name in ex.arg_dict:
+                        ex.arg_dict[name][:] = arr[sl].as_in_context(ex._ctx)
+            ex.forward(is_train=is_train)
+
+    def backward(self, out_grads=None):
+        assert self.binded and self.params_initialized and self.for_training
+        for ex, sl in zip(self._execs, self._slices):
+            g = None if out_grads is None else [o[sl] for o in (out_grads if isinstance(out_grads, (list, tuple)) else [out_grads])]
+            ex.backward(g)
+
+    def update(self):
+        assert self.optimizer_initialized
+        if self._update_on_kvstore:
+            _update_params_on_kvstore(self._param_arrays(), self._grad_arrays(), self._kvstore, self._param_names)
+        else:
+            _update_params(self._param_arrays(), self._grad_arrays(), self._updater, len(self._context), self._kvstore, self._param_names)
+
+    def get_outputs(self, merge_multi_context=True):
+        outs = [ex.outputs for ex in self._execs]
+        if not merge_multi_context:
+            return outs
+        if len(outs) == 1:
+            return outs[0]
+        return [nd.concat(*[o[i].as_in_context(outs[0][i].context) for o in outs], dim=0) for i in range(len(outs[0]))]
+
+    def get_input_grads(self, merge_multi_context=True):
+        assert self._inputs_need_grad
+        gs = [[ex.grad_dict[n] for n in self._data_names] for ex in self._execs]
+        if not merge_multi_context or len(gs) == 1:
+            return gs[0] if len(gs) == 1 else gs
+        return [nd.concat(*[g[i].as_in_context(gs[0][i].context) for g in gs], dim=0) for i in range(len(gs[0]))]
+
+    def update_metric(self, eval_metric, labels):
+        eval_metric.update(labels, self.get_outputs())
+
+    # ---- checkpoints (module.py:161-203)
+    def save_checkpoint(self, prefix, epoch, save_optimizer_states=False):
+        arg, aux = self.get_params()
+        save_checkpoint(prefix, epoch, self._symbol.tojson(), arg, aux)
+        if save_optimizer_states:
+            self.save_optimizer_states("%s-%04d.states" % (prefix, epoch))
+
+    def save_optimizer_states(self, fname):
+        assert self.optimizer_initialized
+        if self._update_on_kvstore:
+            self._kvstore.save_optimizer_states(fname)
+        else:
+            with open(fname, "wb") as f:
+                f.write(self._updater.get_states())
+
+    def load_optimizer_states(self, fname):
+        assert self.optimizer_initialized
+        if self._update_on_kvstore:
+            self._kvstore.load_optimizer_states(fname)
+        else:
+            with open(fname, "rb") as f:
+                self._updater.set_states(f.read())
+
+    @staticmethod
+    def load(prefix, epoch, load_optimizer_states=False, **kwargs):
+        from . import symbol as sym
+        js, arg, aux = load_checkpoint(prefix, epoch)
+        mod = Module(sym.load_json(js), **kwargs)
+        mod._arg_params, mod._aux_params, mod._preloaded = arg, aux, True
+        mod._loaded = (arg, aux)
+        orig_init = mod.init_params
+
+        def init_params(initializer=None, arg_params=None, aux_params=None, **kw):
+            return orig_init(initializer, arg_params or arg, aux_params or aux, **kw)
+        mod.init_params = init_params
+        if load_optimizer_states:
+            mod._preload_opt_states = "%s-%04d.states" % (prefix, epoch)
+        return mod

@@ -1,0 +1,460 @@
+"""``mx.sym`` — a small symbolic graph API with shape inference and an executor, enough for the Module training path.
+
+Parity: ``python/mxnet/symbol/symbol.py`` (``Variable``, composition, ``list_arguments`` / ``list_auxiliary_states`` / ``list_outputs``,
+``infer_shape``, ``simple_bind`` / ``bind``, ``tojson`` / ``load_json``) and ``src/executor/graph_executor.cc`` (forward / backward over
+a topologically sorted graph, gradient accumulation by ``grad_req``).  The graph is a DAG of :class:`Symbol` nodes; the executor evaluates
+it with the same dispatch the imperative API uses (``ops.functional``: native sm_100a kernels on CUDA, PyTorch on CPU) and obtains the
+gradients from the autograd tape instead of building a separate backward graph (``src/nnvm/gradient.cc``) — one code path for both front
+ends.  Argument naming follows the reference (``<name>_weight``, ``<name>_bias``, ``<name>_gamma``/``_beta``, aux ``_moving_mean``/``_var``,
+``softmax_label``)."""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import torch
+
+from .base import MXNetError
+from .ndarray import NDArray
+from .ops import functional as F
+
+__all__ = ["Symbol", "Variable", "var", "Group", "load_json", "FullyConnected", "Convolution", "Activation", "Pooling", "Flatten",
+           "BatchNorm", "Dropout", "SoftmaxOutput", "LinearRegressionOutput", "Concat", "elemwise_add", "relu", "softmax", "log_softmax",
+           "reshape", "Executor"]
+
+_counter = {}
+
+
+def _auto_name(op, name):
+    if name:
+        return name
+    i = _counter.get(op, 0)
+    _counter[op] = i + 1
+    return "%s%d" % (op.lower(), i)
+
+
+def _pair(v, default=None):
+    if v is None:
+        return default
+    return (int(v), int(v)) if np.isscalar(v) else tuple(int(x) for x in v)
+
+
+class Symbol:
+    def __init__(self, op, name, inputs=(), attrs=None, aux=()):
+        self.op, self.name, self.inputs, self.attrs, self.aux = op, name, list(inputs), dict(attrs or {}), list(aux)
+
+    # ---- composition sugar
+    def __add__(self, o): return _binary("_plus", self, o)
+    __radd__ = __add__
+    def __sub__(self, o): return _binary("_minus", self, o)
+    def __mul__(self, o): return _binary("_mul", self, o)
+    __rmul__ = __mul__
+    def __truediv__(self, o): return _binary("_div", self, o)
+    def __getitem__(self, i):
+        if self.op != "_group":
+            if i in (0, self.list_outputs()[0]):
+                return self
+            raise IndexError(i)
+        return self.inputs[i] if isinstance(i, int) else next(s for s in self.inputs if s.list_outputs()[0] == i)
+
+    # ---- graph walks
+    def _topo(self):
+        order, seen = [], set()
+
+        def visit(s):
+            if id(s) in seen:
+                return
+            seen.add(id(s))
+            for i in s.inputs + s.aux:
+                visit(i)
+            order.append(s)
+        visit(self)
+        return order
+
+    def list_arguments(self):
+        aux = {id(a) for s in self._topo() for a in s.aux}
+        return [s.name for s in self._topo() if s.op == "null" and id(s) not in aux]
+
+    def list_auxiliary_states(self):
+        out, seen = [], set()
+        for s in self._topo():
+            for a in s.aux:
+                if id(a) not in seen:
+                    seen.add(id(a)); out.append(a.name)
+        return out
+
+    def list_outputs(self):
+        if self.op == "_group":
+            return [o for s in self.inputs for o in s.list_outputs()]
+        return [self.name if self.op == "null" else self.name + "_output"]
+
+    def list_inputs(self):
+        return self.list_arguments() + self.list_auxiliary_states()
+
+    def get_internals(self):
+        return Group([s for s in self._topo() if s.op != "_group"])
+
+    def attr(self, key):
+        return self.attrs.get(key)
+
+    # ---- shape inference: run the graph once on zero tensors of the given shapes (meta-free but exact)
+    def infer_shape(self, **shapes):
+        args, auxs = self.list_arguments(), self.list_auxiliary_states()
+        known = {k: tuple(v) for k, v in shapes.items()}
+        vals = _ShapeRun(self, known).run()
+        arg_shapes = [vals.shapes.get(a) for a in args]
+        aux_shapes = [vals.shapes.get(a) for a in auxs]
+        outs = [tuple(o.shape) for o in vals.outputs]
+        return arg_shapes, outs, aux_shapes
+
+    def infer_type(self, **types):
+        args = self.list_arguments()
+        return [np.float32] * len(args), [np.float32] * len(self.list_outputs()), [np.float32] * len(self.list_auxiliary_states())
+
+    # ---- binding
+    def simple_bind(self, ctx, grad_req="write", **shapes):
+        from . import ndarray as nd
+        arg_shapes, _, aux_shapes = self.infer_shape(**shapes)
+        names = self.list_arguments()
+        if any(s is None for s in arg_shapes):
+            raise MXNetError("cannot infer shapes of %s" % [n for n, s in zip(names, arg_shapes) if s is None])
+        args = {n: nd.zeros(s, ctx=ctx) for n, s in zip(names, arg_shapes)}
+        req = grad_req if isinstance(grad_req, dict) else {n: grad_req for n in names}
+        grads = {n: nd.zeros(s, ctx=ctx) for n, s in zip(names, arg_shapes) if req.get(n, "null") != "null"}
+        aux = {n: nd.zeros(s, ctx=ctx) for n, s in zip(self.list_auxiliary_states(), aux_shapes)}
+        for n, a in aux.items():
+            if n.endswith("_moving_var"):
+                a[:] = 1.0
+        return Executor(self, ctx, args, grads, req, aux)
+
+    def bind(self, ctx, args, args_grad=None, grad_req="write", aux_states=None):
+        names = self.list_arguments()
+        if isinstance(args, (list, tuple)):
+            args = dict(zip(names, args))
+        if isinstance(args_grad, (list, tuple)):
+            args_grad = dict(zip(names, args_grad))
+        auxn = self.list_auxiliary_states()
+        if isinstance(aux_states, (list, tuple)):
+            aux_states = dict(zip(auxn, aux_states))
+        req = grad_req if isinstance(grad_req, dict) else {n: (grad_req if args_grad and n in args_grad else "null") for n in names}
+        return Executor(self, ctx, dict(args), dict(args_grad or {}), req, dict(aux_states or {}))
+
+    # ---- (de)serialisation: a flat node list in topological order
+    def tojson(self):
+        order = self._topo()
+        index = {id(s): i for i, s in enumerate(order)}
+        nodes = [{"op": s.op, "name": s.name, "attrs": {k: (list(v) if isinstance(v, tuple) else v) for k, v in s.attrs.items()},
+                  "inputs": [index[id(i)] for i in s.inputs], "aux": [index[id(a)] for a in s.aux]} for s in order]
+        return json.dumps({"nodes": nodes, "heads": [index[id(self)]], "format": "geomx_b200-symbol-1"}, indent=1)
+
+    def save(self, fname):
+        with open(fname, "w") as f:
+            f.write(self.tojson())
+
+    def __repr__(self):
+        return "<Symbol %s>" % (self.name if self.op != "_group" else "group [%s]" % ", ".join(self.list_outputs()))
+
+
+def load_json(s):
+    d = json.loads(s)
+    built = []
+    for n in d["nodes"]:
+        attrs = {k: (tuple(v) if isinstance(v, list) else v) for k, v in n["attrs"].items()}
+        built.append(Symbol(n["op"], n["name"], [built[i] for i in n["inputs"]], attrs, [built[i] for i in n.get("aux", [])]))
+    return built[d["heads"][0]]
+
+
+def load(fname):
+    with open(fname) as f:
+        return load_json(f.read())
+
+
+def Variable(name, shape=None, **kw):
+    return Symbol("null", name, attrs={"__shape__": tuple(shape)} if shape else None)
+
+
+var = Variable
+
+
+def Group(symbols):
+    return Symbol("_group", "group", list(symbols))
+
+
+def _binary(op, a, b):
+    if not isinstance(b, Symbol):
+        return Symbol(op + "_scalar", _auto_name(op, None), [a], {"scalar": float(b)})
+    return Symbol(op, _auto_name(op, None), [a, b])
+
+
+def _wb(name, no_bias):
+    w = Variable(name + "_weight")
+    return [w] if no_bias else [w, Variable(name + "_bias")]
+
+
+def FullyConnected(data, num_hidden, weight=None, bias=None, no_bias=False, flatten=True, name=None):
+    name = _auto_name("FullyConnected", name)
+    ins = [data, weight or Variable(name + "_weight")] + ([] if no_bias else [bias or Variable(name + "_bias")])
+    return Symbol("FullyConnected", name, ins, {"num_hidden": int(num_hidden), "no_bias": bool(no_bias), "flatten": bool(flatten)})
+
+
+def Convolution(data, kernel, num_filter, stride=None, pad=None, dilate=None, num_group=1, weight=None, bias=None, no_bias=False, name=None):
+    name = _auto_name("Convolution", name)
+    ins = [data, weight or Variable(name + "_weight")] + ([] if no_bias else [bias or Variable(name + "_bias")])
+    return Symbol("Convolution", name, ins, {"kernel": _pair(kernel), "num_filter": int(num_filter), "stride": _pair(stride, (1, 1)),
+                                             "pad": _pair(pad, (0, 0)), "dilate": _pair(dilate, (1, 1)), "num_group": int(num_group),
+                                             "no_bias": bool(no_bias)})
+
+
+def Activation(data, act_type="relu", name=None):
+    return Symbol("Activation", _auto_name("Activation", name), [data], {"act_type": act_type})
+
+
+def relu(data, name=None):
+    return Activation(data, "relu", name)
+
+
+def Pooling(data, kernel=(2, 2), pool_type="max", stride=None, pad=None, global_pool=False, name=None):
+    return Symbol("Pooling", _auto_name("Pooling", name), [data], {"kernel": _pair(kernel), "pool_type": pool_type, "stride": _pair(stride),
+                                                                   "pad": _pair(pad, (0, 0)), "global_pool": bool(global_pool)})
+
+
+def Flatten(data, name=None):
+    return Symbol("Flatten", _auto_name("Flatten", name), [data])
+
+
+def reshape(data, shape, name=None):
+    return Symbol("Reshape", _auto_name("Reshape", name), [data], {"shape": tuple(shape)})
+
+
+def BatchNorm(data, gamma=None, beta=None, eps=1e-5, momentum=0.9, fix_gamma=False, use_global_stats=False, axis=1, name=None):
+    name = _auto_name("BatchNorm", name)
+    aux = [Variable(name + "_moving_mean"), Variable(name + "_moving_var")]
+    return Symbol("BatchNorm", name, [data, gamma or Variable(name + "_gamma"), beta or Variable(name + "_beta")],
+                  {"eps": float(eps), "momentum": float(momentum), "fix_gamma": bool(fix_gamma), "use_global_stats": bool(use_global_stats),
+                   "axis": int(axis)}, aux)
+
+
+def Dropout(data, p=0.5, name=None):
+    return Symbol("Dropout", _auto_name("Dropout", name), [data], {"p": float(p)})
+
+
+def Concat(*data, dim=1, name=None):
+    return Symbol("Concat", _auto_name("Concat", name), list(data), {"dim": int(dim)})
+
+
+def elemwise_add(a, b, name=None):
+    return Symbol("_plus", _auto_name("_plus", name), [a, b])
+
+
+def softmax(data, axis=-1, name=None):
+    return Symbol("softmax", _auto_name("softmax", name), [data], {"axis": int(axis)})
+
+
+def log_softmax(data, axis=-1, name=None):
+    return Symbol("log_softmax", _auto_name("log_softmax", name), [data], {"axis": int(axis)})
+
+
+def SoftmaxOutput(data, label=None, grad_scale=1.0, normalization="null", name=None):
+    """Forward: softmax(data).  Backward: (softmax - onehot(label)) * grad_scale, ignoring the head gradient (src/operator/softmax_output-inl.h)."""
+    name = _auto_name("SoftmaxOutput", name)
+    return Symbol("SoftmaxOutput", name, [data, label or Variable(name + "_label")], {"grad_scale": float(grad_scale), "normalization": normalization})
+
+
+def LinearRegressionOutput(data, label=None, grad_scale=1.0, name=None):
+    name = _auto_name("LinearRegressionOutput", name)
+    return Symbol("LinearRegressionOutput", name, [data, label or Variable(name + "_label")], {"grad_scale": float(grad_scale)})
+
+
+# ------------------------------------------------------------------------------------------------------------------ evaluation
+class _SoftmaxOutputFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, label, scale, normalization):
+        p = torch.softmax(x, dim=1)
+        ctx.save_for_backward(p, label)
+        ctx.scale, ctx.norm = scale, normalization
+        return p
+
+    @staticmethod
+    def backward(ctx, _gy):
+        p, label = ctx.saved_tensors
+        g = p.clone()
+        g.scatter_add_(1, label.long().view(-1, 1), -torch.ones_like(p[:, :1]))
+        s = ctx.scale / (p.shape[0] if ctx.norm == "batch" else 1.0)
+        return g * s, None, None, None
+
+
+class _LinRegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, label, scale):
+        ctx.save_for_backward(x, label); ctx.scale = scale
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, _gy):
+        x, label = ctx.saved_tensors
+        return (x - label.view_as(x)) * ctx.scale, None, None
+
+
+def _eval_node(s, ins, aux, training):
+    a = s.attrs
+    op = s.op
+    if op == "FullyConnected":
+        return F.dense(ins[0], ins[1], None if a["no_bias"] else ins[2], None, a.get("flatten", True))
+    if op == "Convolution":
+        return F.conv2d(ins[0], ins[1], None if a["no_bias"] else ins[2], a["stride"], a["pad"], a["dilate"], a["num_group"])
+    if op == "Activation":
+        return F.activation(ins[0], a["act_type"])
+    if op == "Pooling":
+        x = ins[0]
+        k = tuple(x.shape[2:]) if a["global_pool"] else a["kernel"]
+        st = a["stride"] or k
+        return F.max_pool2d(x, k, st, a["pad"]) if a["pool_type"] == "max" else F.avg_pool2d(x, k, st, a["pad"])
+    if op == "Flatten":
+        return F.flatten(ins[0])
+    if op == "Reshape":
+        return ins[0].reshape(a["shape"])
+    if op == "BatchNorm":
+        g = torch.ones_like(ins[1]) if a["fix_gamma"] else ins[1]
+        return F.batch_norm(ins[0], g, ins[2], aux[0], aux[1], training and not a["use_global_stats"], a["momentum"], a["eps"], a["axis"])
+    if op == "Dropout":
+        return F.dropout(ins[0], a["p"], training)
+    if op == "Concat":
+        return torch.cat(ins, dim=a["dim"])
+    if op == "softmax":
+        return F.softmax(ins[0], a["axis"])
+    if op == "log_softmax":
+        return F.log_softmax(ins[0], a["axis"])
+    if op == "SoftmaxOutput":
+        return _SoftmaxOutputFn.apply(ins[0], ins[1], a["grad_scale"], a["normalization"])
+    if op == "LinearRegressionOutput":
+        return _LinRegFn.apply(ins[0], ins[1], a["grad_scale"])
+    if op in ("_plus", "_minus", "_mul", "_div"):
+        return {"_plus": torch.add, "_minus": torch.sub, "_mul": torch.mul, "_div": torch.div}[op](ins[0], ins[1])
+    if op.endswith("_scalar"):
+        return {"_plus": torch.add, "_minus": torch.sub, "_mul": torch.mul, "_div": torch.div}[op[:-7]](ins[0], a["scalar"])
+    raise MXNetError("symbol op %s is not implemented" % op)
+
+
+def _param_shape(s, idx, in_shape):
+    """Shape of the idx-th input (a parameter Variable) of node ``s`` given its data shape — the per-op rules of nnvm's InferShape."""
+    a = s.attrs
+    if s.op == "FullyConnected":
+        k = int(np.prod(in_shape[1:])) if a.get("flatten", True) else in_shape[-1]
+        return (a["num_hidden"], k) if idx == 1 else (a["num_hidden"],)
+    if s.op == "Convolution":
+        return (a["num_filter"], in_shape[1] // a["num_group"]) + tuple(a["kernel"]) if idx == 1 else (a["num_filter"],)
+    if s.op == "BatchNorm":
+        return (in_shape[a["axis"]],)
+    if s.op in ("SoftmaxOutput",):
+        return (in_shape[0],)
+    if s.op == "LinearRegressionOutput":
+        return tuple(in_shape)
+    return None
+
+
+class _ShapeRun:
+    def __init__(self, sym, known):
+        self.sym, self.shapes, self.outputs = sym, dict(known), []
+
+    def run(self):
+        vals = {}
+        for s in self.sym._topo():
+            if s.op == "null":
+                shp = self.shapes.get(s.name) or s.attrs.get("__shape__")
+                if shp is not None:
+                    self.shapes[s.name] = tuple(shp)
+                    vals[id(s)] = torch.zeros(tuple(shp))
+                continue
+            if s.op == "_group":
+                continue
+            data = vals.get(id(s.inputs[0]))
+            if data is None:
+                raise MXNetError("cannot infer the input shape of %s: provide the shape of %s" % (s.name, s.inputs[0].name))
+            for i, inp in enumerate(s.inputs[1:], 1):
+                if id(inp) not in vals:
+                    shp = _param_shape(s, i, tuple(data.shape))
+                    if shp is None:
+                        raise MXNetError("cannot infer the shape of %s" % inp.name)
+                    self.shapes[inp.name] = shp
+                    vals[id(inp)] = torch.zeros(shp)
+            for ax in s.aux:
+                if id(ax) not in vals:
+                    shp = _param_shape(s, 1, tuple(data.shape))
+                    self.shapes[ax.name] = shp
+                    vals[id(ax)] = torch.ones(shp) if ax.name.endswith("_var") else torch.zeros(shp)
+            with torch.no_grad():
+                F.use_native(False)
+                try:
+                    vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(x)].clone() for x in s.aux], False)
+                finally:
+                    F.use_native(True)
+        heads = self.sym.inputs if self.sym.op == "_group" else [self.sym]
+        self.outputs = [vals[id(h)] for h in heads]
+        return self
+
+
+class Executor:
+    """Bound graph: ``forward(is_train)`` / ``backward(out_grads)`` with ``arg_dict`` / ``grad_dict`` / ``aux_dict`` / ``outputs``."""
+
+    def __init__(self, symbol, ctx, args, grads, grad_req, aux):
+        self._symbol, self._ctx = symbol, ctx
+        self.arg_dict, self.grad_dict, self.aux_dict, self._req = args, grads, aux, grad_req
+        self.arg_arrays = [args[n] for n in symbol.list_arguments()]
+        self.grad_arrays = [grads.get(n) for n in symbol.list_arguments()]
+        self.aux_arrays = [aux[n] for n in symbol.list_auxiliary_states()]
+        self.outputs = []
+        self._heads, self._leaves = None, None
+
+    def forward(self, is_train=False, **kwargs):
+        for k, v in kwargs.items():
+            self.arg_dict[k][:] = v
+        vals, leaves = {}, {}
+        order = self._symbol._topo()
+        aux_ids = {id(a) for s in order for a in s.aux}
+        with torch.enable_grad() if is_train else torch.no_grad():
+            for s in order:
+                if s.op == "null":
+                    if id(s) in aux_ids:
+                        vals[id(s)] = self.aux_dict[s.name]._t
+                    else:
+                        t = self.arg_dict[s.name]._t.detach()
+                        if is_train and self._req.get(s.name, "null") != "null":
+                            t = t.requires_grad_(True)
+                            leaves[s.name] = t
+                        vals[id(s)] = t
+                elif s.op != "_group":
+                    vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], is_train)
+        heads = self._symbol.inputs if self._symbol.op == "_group" else [self._symbol]
+        self._heads, self._leaves = [vals[id(h)] for h in heads], leaves
+        self.outputs = [NDArray(h.detach()) for h in self._heads]
+        return self.outputs
+
+    def backward(self, out_grads=None):
+        if not self._leaves:
+            raise MXNetError("backward needs forward(is_train=True) and at least one argument with grad_req != 'null'")
+        heads = [h for h in self._heads if h.requires_grad]
+        if out_grads is None:
+            gs = [torch.ones_like(h) for h in heads]
+        else:
+            out_grads = out_grads if isinstance(out_grads, (list, tuple)) else [out_grads]
+            gs = [g._t if isinstance(g, NDArray) else g for g in out_grads]
+        names = list(self._leaves)
+        grads = torch.autograd.grad(heads, [self._leaves[n] for n in names], gs, allow_unused=True)
+        for n, g in zip(names, grads):
+            if g is None:
+                continue
+            tgt = self.grad_dict[n]._t
+            if self._req.get(n) == "add":
+                tgt.add_(g)
+            else:
+                tgt.copy_(g)
+
+    def copy_params_from(self, arg_params, aux_params=None, allow_extra_params=False):
+        for k, v in arg_params.items():
+            if k in self.arg_dict:
+                self.arg_dict[k][:] = v
+            elif not allow_extra_params:
+                raise MXNetError("unknown argument %s" % k)
+        for k, v in (aux_params or {}).items():
+            if k in self.aux_dict:
+                self.aux_dict[k][:] = v

@@ -203,3 +203,39 @@ def test_recordio_roundtrip(tmp_path):
     assert h.label == 3.0 and h.id == 3 and np.array_equal(dec, img)
     h, raw = recordio.unpack(ri.read_idx(7))
     assert list(h.label) == [1.0, 2.0, 3.0] and raw == b"raw"
+
+
+def test_symbol_and_module_fit(tmp_path):
+    """mx.sym graph + mx.mod.Module (bind / init_params / init_optimizer(kvstore) / fit / score / predict / checkpoint) on a separable toy task,
+    single context and two (CPU) contexts with a 'local' kvstore (module.py:363-668, executor_group.py)."""
+    import numpy as np
+    rng = np.random.RandomState(0)
+    X = rng.randn(256, 1, 8, 8).astype(np.float32)
+    y = (X.reshape(256, -1)[:, :32].sum(1) > X.reshape(256, -1)[:, 32:].sum(1)).astype(np.float32)
+    data = mx.sym.Variable("data")
+    net = mx.sym.Convolution(data, kernel=(3, 3), num_filter=4, name="c0")
+    net = mx.sym.Activation(net, "relu")
+    net = mx.sym.Pooling(net, kernel=(2, 2), stride=(2, 2), pool_type="max")
+    net = mx.sym.Flatten(net)
+    net = mx.sym.FullyConnected(net, num_hidden=16, name="fc0")
+    net = mx.sym.Activation(net, "relu")
+    net = mx.sym.FullyConnected(net, num_hidden=2, name="fc1")
+    net = mx.sym.SoftmaxOutput(net, name="softmax")
+    assert net.list_arguments() == ["data", "c0_weight", "c0_bias", "fc0_weight", "fc0_bias", "fc1_weight", "fc1_bias", "softmax_label"]
+    args, outs, _ = net.infer_shape(data=(32, 1, 8, 8))
+    assert outs == [(32, 2)] and args[3] == (16, 36)
+    for ctxs, kvs in (([mx.cpu()], None), ([mx.cpu(0), mx.cpu(1)], "local")):
+        it = mx.io.NDArrayIter(X, y, batch_size=32, shuffle=False)
+        mod = mx.mod.Module(net, context=ctxs)
+        mod.fit(it, num_epoch=12, optimizer="adam", optimizer_params={"learning_rate": 0.01}, kvstore=kvs, initializer=mx.init.Xavier())
+        acc = dict(mod.score(mx.io.NDArrayIter(X, y, batch_size=32), "acc"))["accuracy"]
+        assert acc > 0.9, acc
+        pred = mod.predict(mx.io.NDArrayIter(X, y, batch_size=32))
+        assert pred.shape == (256, 2)
+    prefix = str(tmp_path / "toy")
+    mod.save_checkpoint(prefix, 3)
+    mod2 = mx.mod.Module.load(prefix, 3)
+    mod2.bind(data_shapes=[("data", (32, 1, 8, 8))], label_shapes=[("softmax_label", (32,))], for_training=False)
+    mod2.init_params()
+    acc2 = dict(mod2.score(mx.io.NDArrayIter(X, y, batch_size=32), "acc"))["accuracy"]
+    assert abs(acc2 - acc) < 1e-6
