@@ -8,6 +8,7 @@
 
 #include "../runtime/engine.h"
 #include "../runtime/gpu_topology.h"
+#include "../runtime/text_io.h"
 #include "../runtime/io.h"
 #include "../runtime/params_io.h"
 #include "../runtime/profiler.h"
@@ -125,6 +126,21 @@ PYBIND11_MODULE(_C, m) {
         GradientCompression::BSCDecompress(z.data(), z.size(), out.mutable_data(), n);
         return out;
       });
+
+  // ---------------------------------------------------------------------------------------------- text data readers
+  m.def("parse_csv", [](const std::string& path) {
+    gx_rt::CSVData d;
+    { py::gil_scoped_release nogil; d = gx_rt::ParseCSV(path); }
+    py::array_t<float> a({static_cast<py::ssize_t>(d.rows), static_cast<py::ssize_t>(d.cols)});
+    if (!d.values.empty()) memcpy(a.mutable_data(), d.values.data(), d.values.size() * sizeof(float));
+    return a;
+  }, "dense float matrix of a CSV file");
+  m.def("parse_libsvm", [](const std::string& path) {
+    gx_rt::LibSVMData d;
+    { py::gil_scoped_release nogil; d = gx_rt::ParseLibSVM(path); }
+    return py::make_tuple(py::array_t<float>(d.labels.size(), d.labels.data()), py::array_t<float>(d.values.size(), d.values.data()),
+                          py::array_t<long>(d.indices.size(), d.indices.data()), py::array_t<long>(d.indptr.size(), d.indptr.data()), d.max_index);
+  }, "(labels, values, indices, indptr, max_index) of a LibSVM file");
 
   // ---------------------------------------------------------------------------------------------- GPU topology solver
   m.def("topology_tree", [](std::vector<float> W, int n, int root) {

@@ -239,3 +239,33 @@ def test_symbol_and_module_fit(tmp_path):
     mod2.init_params()
     acc2 = dict(mod2.score(mx.io.NDArrayIter(X, y, batch_size=32), "acc"))["accuracy"]
     assert abs(acc2 - acc) < 1e-6
+
+
+def test_text_and_record_iterators(tmp_path):
+    """mx.io.CSVIter / LibSVMIter (native parsers, csrc/runtime/text_io.h), ImageRecordIter over a RecordIO file, PrefetchingIter."""
+    import numpy as np
+    from geomx_b200 import recordio
+    d = np.arange(40, dtype=np.float32).reshape(10, 4) / 7
+    np.savetxt(tmp_path / "d.csv", d, delimiter=",", fmt="%.6f")
+    np.savetxt(tmp_path / "l.csv", np.arange(10), fmt="%d")
+    it = mx.io.CSVIter(data_csv=str(tmp_path / "d.csv"), data_shape=(4,), label_csv=str(tmp_path / "l.csv"), batch_size=5)
+    b = next(iter(it))
+    assert b.data[0].shape == (5, 4) and np.allclose(b.data[0].asnumpy(), d[:5], atol=1e-5) and b.label[0].asnumpy().tolist() == [0, 1, 2, 3, 4]
+    (tmp_path / "s.libsvm").write_text("1 0:1.5 3:2\n0 2:-1\n# comment\n1 1:4 2:5 3:6\n")
+    it = mx.io.LibSVMIter(data_libsvm=str(tmp_path / "s.libsvm"), data_shape=(4,), batch_size=3)
+    b = next(iter(it))
+    assert np.array_equal(b.data[0].asnumpy(), np.array([[1.5, 0, 0, 2], [0, 0, -1, 0], [0, 4, 5, 6]], dtype=np.float32))
+    assert b.label[0].asnumpy().tolist() == [1, 0, 1]
+    w = recordio.MXIndexedRecordIO(str(tmp_path / "i.idx"), str(tmp_path / "i.rec"), "w")
+    for i in range(6):
+        img = np.full((12, 12, 3), 10 * i, dtype=np.uint8)
+        w.write_idx(i, recordio.pack_img(recordio.IRHeader(0, float(i % 2), i, 0), img, img_fmt=".png"))
+    w.close()
+    it = mx.io.ImageRecordIter(path_imgrec=str(tmp_path / "i.rec"), path_imgidx=str(tmp_path / "i.idx"), data_shape=(3, 8, 8), batch_size=4,
+                               rand_crop=True, rand_mirror=True, scale=1 / 255.0)
+    pf = mx.io.PrefetchingIter(it)
+    batches = list(pf)
+    assert len(batches) == 2 and batches[0].data[0].shape == (4, 3, 8, 8) and batches[1].pad == 2
+    assert np.allclose(batches[0].data[0].asnumpy()[1], 10 / 255.0) and batches[0].label[0].asnumpy().tolist() == [0, 1, 0, 1]
+    pf.reset()
+    assert len(list(pf)) == 2
