@@ -1,0 +1,38 @@
+"""gloo worker for test_sync_batchnorm: each rank normalises its half of a batch with SyncBatchNorm; rank 0 compares with BatchNorm on the whole."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import geomx_b200 as mx  # noqa: E402
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.RandomState(0)
+X = rng.randn(8, 3, 4, 4).astype(np.float32) * 2 + 1
+W = rng.randn(8, 3, 4, 4).astype(np.float32)
+part = slice(rank * 8 // world, (rank + 1) * 8 // world)
+
+
+def run(layer, xs, ws):
+    layer.initialize()
+    x = mx.nd.array(xs); x.attach_grad()
+    with mx.autograd.record():
+        y = layer(x)
+        loss = (y * mx.nd.array(ws)).sum()
+    loss.backward()
+    return y.asnumpy(), x.grad.asnumpy(), layer.gamma.grad().asnumpy(), layer.running_var.data().asnumpy()
+
+
+y, dx, dg, rv = run(mx.gluon.contrib.nn.SyncBatchNorm(in_channels=3), X[part], W[part])
+dgt = torch.from_numpy(dg.copy()); dist.all_reduce(dgt)
+if rank == 0:
+    y0, dx0, dg0, rv0 = run(mx.gluon.nn.BatchNorm(in_channels=3), X, W)
+    ok = np.allclose(y, y0[part], atol=1e-5) and np.allclose(dx, dx0[part], atol=1e-5) and np.allclose(dgt.numpy(), dg0, atol=1e-4) \
+        and np.allclose(rv, rv0, atol=1e-5)
+    print("SYNCBN", "PASS" if ok else "FAIL", float(np.abs(y - y0[part]).max()), float(np.abs(dx - dx0[part]).max()))
+dist.barrier()
+dist.destroy_process_group()

@@ -269,3 +269,16 @@ def test_text_and_record_iterators(tmp_path):
     assert np.allclose(batches[0].data[0].asnumpy()[1], 10 / 255.0) and batches[0].label[0].asnumpy().tolist() == [0, 1, 0, 1]
     pf.reset()
     assert len(list(pf)) == 2
+
+
+def test_sync_batchnorm_two_ranks():
+    """SyncBatchNorm over 2 gloo ranks == BatchNorm over the concatenated batch (forward, input grad, gamma grad, running stats)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ); env.pop("RANK", None); env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29877", os.path.join(here, "_syncbn_worker.py")], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert "SYNCBN PASS" in r.stdout, r.stdout[-2000:]
