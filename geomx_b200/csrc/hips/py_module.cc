@@ -8,6 +8,7 @@
 
 #include "../runtime/engine.h"
 #include "../runtime/gpu_topology.h"
+#include "../runtime/storage.h"
 #include "../runtime/text_io.h"
 #include "../runtime/io.h"
 #include "../runtime/params_io.h"
@@ -126,6 +127,32 @@ PYBIND11_MODULE(_C, m) {
         GradientCompression::BSCDecompress(z.data(), z.size(), out.mutable_data(), n);
         return out;
       });
+
+  // ---------------------------------------------------------------------------------------------- storage pools / resources
+  py::class_<gx_rt::PooledHostStorage>(m, "PooledHostStorage")
+      .def(py::init<size_t, size_t>(), py::arg("page") = 4096, py::arg("max_pooled") = size_t(4) << 30)
+      .def("round_size", &gx_rt::PooledHostStorage::RoundSize)
+      .def("alloc", [](gx_rt::PooledHostStorage& s, size_t n) { bool hit = false; void* p = s.Alloc(n, &hit); return py::make_tuple(reinterpret_cast<uintptr_t>(p), hit); })
+      .def("free", [](gx_rt::PooledHostStorage& s, uintptr_t p) { return s.Free(reinterpret_cast<void*>(p)); })
+      .def("size_of", [](gx_rt::PooledHostStorage& s, uintptr_t p) { return s.SizeOf(reinterpret_cast<void*>(p)); })
+      .def("release_all", [](gx_rt::PooledHostStorage& s) {
+        std::vector<std::pair<uintptr_t, size_t>> out;
+        for (auto& kv : s.ReleaseAll()) out.emplace_back(reinterpret_cast<uintptr_t>(kv.first), kv.second);
+        return out;
+      })
+      .def("stats", [](gx_rt::PooledHostStorage& s) {
+        auto st = s.stats();
+        py::dict d; d["used_bytes"] = st.used_bytes; d["pooled_bytes"] = st.pooled_bytes; d["num_alloc"] = st.num_alloc;
+        d["num_pool_hits"] = st.num_pool_hits; d["num_system_alloc"] = st.num_system_alloc;
+        return d;
+      });
+  py::class_<gx_rt::ResourceManager>(m, "ResourceManager")
+      .def(py::init<>())
+      .def("temp_space", [](gx_rt::ResourceManager& r, int dev, int slot, size_t n, gx_rt::PooledHostStorage& pool) {
+        return reinterpret_cast<uintptr_t>(r.TempSpace(dev, slot, n, &pool));
+      })
+      .def("seed", &gx_rt::ResourceManager::SeedAll)
+      .def("next_seed", &gx_rt::ResourceManager::NextSeed);
 
   // ---------------------------------------------------------------------------------------------- text data readers
   m.def("parse_csv", [](const std::string& path) {

@@ -25,6 +25,12 @@ CMD_CONTROLLER, CMD_MULTI_PRECISION, CMD_STOP, CMD_SYNC, CMD_SYNC_GLOBAL, CMD_CO
 
 
 def _pinned(numel, dtype):
+    """Staging buffer of the PS client: a block of the native host pool (page-locked when CUDA is present; csrc/runtime/storage.h)."""
+    try:
+        from ..storage import pinned_empty
+        return pinned_empty(numel, dtype)
+    except Exception:
+        pass
     t = torch.empty(numel, dtype=dtype)
     if torch.cuda.is_available():
         try:

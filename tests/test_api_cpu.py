@@ -282,3 +282,34 @@ def test_sync_batchnorm_two_ranks():
                         "--master-port", "29877", os.path.join(here, "_syncbn_worker.py")], env=env, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=180)
     assert "SYNCBN PASS" in r.stdout, r.stdout[-2000:]
+
+
+def test_host_storage_pool_and_resources():
+    """mx.storage: size-bucketed host pool (reuse, rounding, release) and reproducible per-device seed streams (storage.cc / resource.cc)."""
+    import gc
+    import torch
+    from geomx_b200 import runtime, storage
+    if not runtime.available():
+        pytest.skip("native runtime not built")
+    pool = storage.HostPool(pin=False)
+    a = pool.empty(1000, torch.float32)
+    a.fill_(3.0)
+    assert a.numel() == 1000 and float(a.sum()) == 3000.0
+    p0 = a.data_ptr()
+    st = pool.stats()
+    assert st["used_bytes"] == 4096 and st["num_system_alloc"] == 1
+    view = a[10:20]
+    del a; gc.collect()
+    assert pool.stats()["used_bytes"] == 4096                   # a view keeps the block alive
+    del view; gc.collect()
+    b = pool.empty(900, torch.float32)                         # same bucket: served from the pool
+    assert b.data_ptr() == p0 and pool.stats()["num_pool_hits"] == 1
+    big = pool.empty((3 << 20) // 4 + 1, torch.float32)        # > 1 MiB: power-of-two bucket
+    assert pool.stats()["used_bytes"] == 4096 + (4 << 20)
+    del b, big; gc.collect()
+    assert pool.stats()["used_bytes"] == 0 and pool.stats()["pooled_bytes"] == 4096 + (4 << 20)
+    pool.release_all()
+    assert pool.stats()["pooled_bytes"] == 0
+    pool.seed(42); s1 = [pool.next_seed(0), pool.next_seed(0), pool.next_seed(1)]
+    pool.seed(42); s2 = [pool.next_seed(0), pool.next_seed(0), pool.next_seed(1)]
+    assert s1 == s2 and len(set(s1)) == 3
