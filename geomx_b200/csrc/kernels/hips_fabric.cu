@@ -75,6 +75,8 @@ struct FabricParams {
   float* bsc_u;                // Bi-Sparse momentum / accumulation state of the party owner (arena-sized, local HBM)
   float* bsc_v;
   int bsc_k;                   // packets per tile and party  (= floor(1024 * threshold), >= 1)
+  int ll_party_mode;           // 1: the party is the whole universe of this launch (HFA local round): the tile's party owner is also its
+                               //    "global" owner, results go to the party members only, no optimizer
 };
 
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
@@ -433,8 +435,12 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
   const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
   const float lr_t = adam_lr(p.h, opt_t);
-  const int S = p.party_size, P = p.num_parties;
+  const int S = p.party_size, P = p.ll_party_mode ? 1 : p.num_parties;
   const int party_base = p.party * S;
+  const int slot = p.ll_party_mode ? 0 : p.party;                       // this party's packet slot on a global owner
+  const int bc_lo = p.ll_party_mode ? party_base : 0, bc_n = p.ll_party_mode ? S : p.world;   // who receives the result
+  float* const bc_mc = p.ll_party_mode ? nullptr : p.ll_c_mc;
+  auto owner_of = [&](int t) -> int { return p.ll_party_mode ? party_base + t % S : p.tile_owner[t]; };
   const long long n2 = 2 * p.n;
   const int K = p.bsc_k;
   int* err = p.state + 5;
@@ -466,7 +472,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
       acc = f4_add(acc, ll_recv_dense(p.ll_a[p.rank] + (long long)j * n2 + 2 * off, fmt == FMT_F16 ? FMT_F16 : FMT_F32, epoch, err));
     }
     acc = f4_scale(acc, p.push_scale);
-    float* dst = p.ll_b[p.tile_owner[t]] + (long long)p.party * n2;
+    float* dst = p.ll_b[owner_of(t)] + (long long)slot * n2;
     if (fmt != FMT_BSC) {
       ll_send_dense(dst + 2 * off, acc, fmt, epoch);
       continue;
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   stamp(2);
   // ---- phase 3: GLOBAL PS TIER: the global owner sums the parties' aggregates, runs the optimizer on its shard and pushes the result
   for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-    if (p.tile_owner[t] != p.rank) continue;
+    if (owner_of(t) != p.rank) continue;
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
     const int fmt = fmt_of(t);
     const long long off = (long long)t * TILE + threadIdx.x * 4;
@@ -555,19 +561,19 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (ww[i] != 0.f) {
-          if (p.ll_c_mc != nullptr) ll_store1_mc(p.ll_c_mc + base + 4 * pos, ww[i], (float)(threadIdx.x * 4 + i), epoch);
-          else for (int r = 0; r < p.world; ++r) ll_store1(p.ll_c[r] + base + 4 * pos, ww[i], (float)(threadIdx.x * 4 + i), epoch);
+          if (bc_mc != nullptr) ll_store1_mc(bc_mc + base + 4 * pos, ww[i], (float)(threadIdx.x * 4 + i), epoch);
+          else for (int r = bc_lo; r < bc_lo + bc_n; ++r) ll_store1(p.ll_c[r] + base + 4 * pos, ww[i], (float)(threadIdx.x * 4 + i), epoch);
           ++pos;
         }
       }
       for (int j = tot + threadIdx.x; j < P * K; j += FAB_THREADS) {   // padding packets: index -1
-        if (p.ll_c_mc != nullptr) ll_store1_mc(p.ll_c_mc + base + 4 * j, 0.f, -1.f, epoch);
-        else for (int r = 0; r < p.world; ++r) ll_store1(p.ll_c[r] + base + 4 * j, 0.f, -1.f, epoch);
+        if (bc_mc != nullptr) ll_store1_mc(bc_mc + base + 4 * j, 0.f, -1.f, epoch);
+        else for (int r = bc_lo; r < bc_lo + bc_n; ++r) ll_store1(p.ll_c[r] + base + 4 * j, 0.f, -1.f, epoch);
       }
     } else {
       const int bf = fmt == FMT_F16 ? FMT_F16 : FMT_F32;
-      if (p.ll_c_mc != nullptr) ll_send_dense_mc(p.ll_c_mc + 2 * off, W, bf, epoch);
-      else for (int r = 0; r < p.world; ++r) ll_send_dense(p.ll_c[r] + 2 * off, W, bf, epoch);
+      if (bc_mc != nullptr) ll_send_dense_mc(bc_mc + 2 * off, W, bf, epoch);
+      else for (int r = bc_lo; r < bc_lo + bc_n; ++r) ll_send_dense(p.ll_c[r] + 2 * off, W, bf, epoch);
     }
   }
   stamp(3);

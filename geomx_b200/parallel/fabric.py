@@ -163,6 +163,7 @@ class _FabricParams(ctypes.Structure):
         ("ll_a", ctypes.c_void_p * MAX_RANKS), ("ll_b", ctypes.c_void_p * MAX_RANKS), ("ll_c", ctypes.c_void_p * MAX_RANKS),
         ("ll_c_mc", ctypes.c_void_p),
         ("tile_fmt", ctypes.c_void_p), ("bsc_u", ctypes.c_void_p), ("bsc_v", ctypes.c_void_p), ("bsc_k", ctypes.c_int),
+        ("ll_party_mode", ctypes.c_int),
     ]
 
 
@@ -393,6 +394,24 @@ class HipsFabric:
 
     def party_allreduce(self, src: SymmetricBuffer, dst: SymmetricBuffer, scale=1.0, reduce_scatter=False):
         """Local tier only (HFA local synchronisation / generic party all-reduce)."""
+        if self.protocol == "ll" and src is self.grad and dst is self.param and not reduce_scatter:
+            # latency-bound arenas: the LL kernel in party mode (push to the tile's party owner, sum, push to the party) — two one-way hops,
+            # no fences; it shares the packet buffers and therefore the epoch counter of the dist_sync channel
+            key = ("fsa-party", float(scale))
+            p = self._params_cache.get(key)
+            if p is None:
+                base = self._block("fsa", False, False, False)
+                p = _FabricParams.from_buffer_copy(base)
+                p.ll_party_mode = 1
+                p.h.kind = -1
+                p.push_scale = float(scale)
+                p.tile_fmt = None
+                self._params_cache[key] = p
+            rc = native.require().gx_hips_fsa_ll_step(ctypes.byref(p), self.grid, self._stream())
+            native.launch_count += 1
+            if rc:
+                raise RuntimeError("gx_hips_fsa_ll_step (party mode) failed rc=%d" % rc)
+            return
         p = self._block("party")
         sp = self._peer_table("par_src_%d" % id(src), src.peer_ptrs)
         dp = self._peer_table("par_dst_%d" % id(dst), dst.peer_ptrs)
