@@ -4,8 +4,8 @@
 // GetChannel; block split + sort + channel assignment in KVServer::Send) and src/van.cc:290-370,707-824 (Important_scheduler /
 // Unimportant_scheduler — the unimportant queue is drained only while the important queue is empty; 4-bit encode/decode with a
 // min/max codebook; receiver-side reassembly into a zero-filled buffer, delivery when the block with seq == seq_end arrives).
-// Modes (ENABLE_DGT): 1 = unimportant blocks may be lost (the reference uses UDP sockets; here the same TCP connection carries them and
-// the receiver drops them with probability DGT_UDP_LOSS %, which exercises the identical zero-fill tolerance), 2 = reliable but
+// Modes (ENABLE_DGT): 1 = unimportant blocks travel as UDP datagrams with per-message IP_TOS (Van::SendUDP) and may be lost — the receiver
+// zero-fills; DGT_UDP_LOSS % additionally drops received unimportant blocks to exercise that tolerance on a loss-free loopback, 2 = reliable but
 // priority-ordered, 3 = mode 2 + 4-bit quantised unimportant blocks.  Only dense default pushes from a local server to the global
 // servers are DGT-split, as in the reference (kv_app.h:918-919).
 #pragma once
@@ -167,7 +167,8 @@ class DGTSender {
       Message m; uq_.WaitAndPop(&m);
       if (m.meta.control.cmd == Control::TERMINATE) break;
       while (iq_.Size() > 0 && !stop_) std::this_thread::yield();
-      van_->SendNow(m);
+      if (cfg_.mode == 1 && m.meta.channel > 0) van_->SendUDP(m);   // lossy datagram channel with the block's TOS
+      else van_->SendNow(m);
     }
   }
   Van* van_;

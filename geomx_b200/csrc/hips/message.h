@@ -21,6 +21,7 @@ struct Node {
   int port = kEmpty;
   bool is_recovery = false;
   int customer_id = 0;
+  int udp_port = -1;    // DGT mode 1: datagram endpoint for unimportant blocks (reference: udp_port[] per channel, zmq_van.h:95-305)
   int rank_hint = -1;   // a server that already owns a rank in the other plane asks for the same rank (MultiGPS key sharding consistency)
   std::string DebugString() const {
     std::stringstream ss;
@@ -111,7 +112,7 @@ inline void PackMeta(const Meta& m, std::vector<char>* out) {
     w.Put<uint32_t>(static_cast<uint32_t>(m.control.node.size()));
     for (const auto& n : m.control.node) {
       w.Put<int32_t>(n.role); w.Put<int32_t>(n.id); w.PutStr(n.hostname); w.Put<int32_t>(n.port);
-      w.Put<uint8_t>(n.is_recovery); w.Put<int32_t>(n.customer_id); w.Put<int32_t>(n.rank_hint);
+      w.Put<uint8_t>(n.is_recovery); w.Put<int32_t>(n.customer_id); w.Put<int32_t>(n.rank_hint); w.Put<int32_t>(n.udp_port);
     }
   }
   out->swap(w.buf());
@@ -139,7 +140,7 @@ inline void UnpackMeta(const char* buf, size_t n, Meta* m) {
     for (uint32_t i = 0; i < nn; ++i) {
       Node nd;
       nd.role = r.Get<int32_t>(); nd.id = r.Get<int32_t>(); nd.hostname = r.GetStr(); nd.port = r.Get<int32_t>();
-      nd.is_recovery = r.Get<uint8_t>(); nd.customer_id = r.Get<int32_t>(); nd.rank_hint = r.Get<int32_t>();
+      nd.is_recovery = r.Get<uint8_t>(); nd.customer_id = r.Get<int32_t>(); nd.rank_hint = r.Get<int32_t>(); nd.udp_port = r.Get<int32_t>();
       m->control.node.push_back(nd);
     }
   }

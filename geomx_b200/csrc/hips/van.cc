@@ -144,6 +144,45 @@ int Van::SendFrame(int fd, const Message& msg) {
   return static_cast<int>(bytes + meta.size());
 }
 
+// one self-contained datagram: same layout as a TCP frame (magic | meta len | #data | data lens | meta | data...)
+static void PackDatagram(const Message& msg, std::vector<char>* out) {
+  std::vector<char> meta;
+  PackMeta(msg.meta, &meta);
+  const uint32_t nd = static_cast<uint32_t>(msg.data.size());
+  size_t total = 12 + 8 * nd + meta.size();
+  for (uint32_t i = 0; i < nd; ++i) total += msg.data[i].size();
+  out->resize(total);
+  char* p = out->data();
+  uint32_t m = kMagic, ml = static_cast<uint32_t>(meta.size());
+  memcpy(p, &m, 4); memcpy(p + 4, &ml, 4); memcpy(p + 8, &nd, 4); p += 12;
+  for (uint32_t i = 0; i < nd; ++i) { uint64_t l = msg.data[i].size(); memcpy(p, &l, 8); p += 8; }
+  memcpy(p, meta.data(), meta.size()); p += meta.size();
+  for (uint32_t i = 0; i < nd; ++i) if (msg.data[i].size()) { memcpy(p, msg.data[i].data(), msg.data[i].size()); p += msg.data[i].size(); }
+}
+static bool UnpackDatagram(const char* buf, size_t n, Message* msg) {
+  if (n < 12) return false;
+  uint32_t h[3];
+  memcpy(h, buf, 12);
+  if (h[0] != kMagic) return false;
+  const uint32_t ml = h[1], nd = h[2];
+  size_t pos = 12;
+  if (n < pos + 8ull * nd + ml) return false;
+  std::vector<uint64_t> lens(nd);
+  if (nd) memcpy(lens.data(), buf + pos, 8 * nd);
+  pos += 8ull * nd;
+  UnpackMeta(buf + pos, ml, &msg->meta);
+  pos += ml;
+  msg->data.clear();
+  for (uint32_t i = 0; i < nd; ++i) {
+    if (n < pos + lens[i]) return false;
+    SArray<char> d;
+    if (lens[i]) d.CopyFrom(buf + pos, lens[i]);
+    msg->data.push_back(d);
+    pos += lens[i];
+  }
+  return true;
+}
+
 bool Van::RecvFrame(int fd, Message* msg) {
   uint32_t h[3];
   if (!ReadAll(fd, h, 12)) return false;
@@ -204,6 +243,19 @@ void Van::Start(int customer_id) {
     my_node_.customer_id = customer_id;
     my_node_.rank_hint = rank_hint_;
   }
+  if (plane_ == kGlobal && env->GetInt("ENABLE_DGT", 0) == 1 && !is_scheduler_) {
+    // DGT mode 1: unimportant gradient blocks travel as datagrams (lossy by design), one socket, per-message IP_TOS
+    udp_fd_ = ::socket(AF_INET, SOCK_DGRAM, 0);
+    if (udp_fd_ >= 0) {
+      sockaddr_in a; memset(&a, 0, sizeof(a));
+      a.sin_family = AF_INET; a.sin_addr.s_addr = htonl(INADDR_ANY); a.sin_port = 0;
+      int rcvbuf = 8 << 20; ::setsockopt(udp_fd_, SOL_SOCKET, SO_RCVBUF, &rcvbuf, sizeof(rcvbuf));
+      socklen_t al = sizeof(a);
+      if (::bind(udp_fd_, reinterpret_cast<sockaddr*>(&a), sizeof(a)) == 0 && ::getsockname(udp_fd_, reinterpret_cast<sockaddr*>(&a), &al) == 0) {
+        my_node_.udp_port = ntohs(a.sin_port);
+      } else { ::close(udp_fd_); udp_fd_ = -1; }
+    }
+  }
   my_node_.port = Bind(&my_node_, is_scheduler_ ? 0 : 40);
   HIPS_CHECK_MSG(my_node_.port > 0, "bind failed");
   HIPS_VLOG(1, "plane %d bind to %s", plane_, my_node_.DebugString().c_str());
@@ -223,6 +275,7 @@ void Van::Start(int customer_id) {
   }
   accept_thread_.reset(new std::thread(&Van::Accepting, this));
   recv_thread_.reset(new std::thread(&Van::Receiving, this));
+  if (udp_fd_ >= 0) udp_thread_.reset(new std::thread(&Van::ReceivingUDP, this));
   if (enable_p3_) prio_thread_.reset(new std::thread(&Van::PrioritySending, this));
 
   if (!is_scheduler_) {
@@ -254,6 +307,12 @@ void Van::Stop() {
   if (listen_fd_ >= 0) { ::shutdown(listen_fd_, SHUT_RDWR); ::close(listen_fd_); listen_fd_ = -1; }
   if (accept_thread_) accept_thread_->join();
   if (recv_thread_) recv_thread_->join();
+  if (udp_thread_) { udp_thread_->join(); ::close(udp_fd_); udp_fd_ = -1; }
+  if (Environment::Get()->GetInt("GEOMX_NET_STATS", 0) != 0) {   // one machine-readable line per plane (tests, capacity planning)
+    fprintf(stdout, "RESULT {\"net_stats\": {\"plane\": %d, \"node\": %d, \"sent_bytes\": %zu, \"recv_bytes\": %zu, \"udp_sent\": %zu, \"udp_received\": %zu}}\n",
+            static_cast<int>(plane_), my_node_.id, send_bytes_.load(), recv_bytes_.load(), udp_sent_.load(), udp_received_.load());
+    fflush(stdout);
+  }
   {
     std::lock_guard<std::mutex> lk(senders_mu_);
     for (auto& s : senders_) if (s.second->fd >= 0) ::close(s.second->fd);
@@ -393,15 +452,63 @@ void Van::Receiving() {
         }
       } else {
         if (dgt_receiver_ && msg.meta.msg_type == 1) {  // DGT block: reassemble, deliver when the last block arrives
-          Message whole;
-          if (!dgt_receiver_->Add(msg, &whole)) continue;
-          ProcessData(&whole);
+          DeliverDGT(&msg);
         } else {
           ProcessData(&msg);
         }
       }
     }
   }
+}
+
+void Van::DeliverDGT(Message* msg) {
+  Message whole;
+  {
+    std::lock_guard<std::mutex> lk(deliver_mu_);      // blocks of one tensor arrive on two threads (TCP: important, UDP: the rest)
+    if (!dgt_receiver_->Add(*msg, &whole)) return;
+  }
+  ProcessData(&whole);
+}
+
+void Van::ReceivingUDP() {
+  std::vector<char> buf(65536);
+  while (!stop_.load()) {
+    struct pollfd pfd; pfd.fd = udp_fd_; pfd.events = POLLIN;
+    if (::poll(&pfd, 1, 200) <= 0) continue;
+    const ssize_t n = ::recvfrom(udp_fd_, buf.data(), buf.size(), 0, nullptr, nullptr);
+    if (n <= 0) continue;
+    Message msg;
+    if (!UnpackDatagram(buf.data(), static_cast<size_t>(n), &msg)) continue;   // truncated / foreign datagram: drop, like a lost one
+    ++udp_received_;
+    recv_bytes_ += static_cast<size_t>(n);
+    msg.meta.plane = plane_;
+    if (dgt_receiver_ && msg.meta.msg_type == 1) DeliverDGT(&msg);
+  }
+}
+
+int Van::SendUDP(const Message& msg) {
+  Node peer;
+  {
+    std::lock_guard<std::mutex> nl(nodes_mu_);
+    auto it = nodes_.find(msg.meta.recver);
+    if (it != nodes_.end()) peer = it->second;
+  }
+  std::vector<char> pkt;
+  Message out = msg;
+  if (out.meta.sender == Meta::kEmpty) out.meta.sender = my_node_.id;
+  PackDatagram(out, &pkt);
+  if (udp_fd_ < 0 || peer.udp_port <= 0 || pkt.size() > 60000) return SendNow(msg);   // no datagram endpoint (or too large): reliable path
+  sockaddr_in a; memset(&a, 0, sizeof(a));
+  a.sin_family = AF_INET; a.sin_port = htons(static_cast<uint16_t>(peer.udp_port));
+  if (::inet_pton(AF_INET, peer.hostname.c_str(), &a.sin_addr) != 1) return SendNow(msg);
+  std::lock_guard<std::mutex> lk(udp_mu_);
+  int tos = out.meta.tos & 0xFC;                                     // DSCP in the upper six bits (reference: ZMQ_TOS / iptables DSCP classes)
+  ::setsockopt(udp_fd_, IPPROTO_IP, IP_TOS, &tos, sizeof(tos));
+  const ssize_t n = ::sendto(udp_fd_, pkt.data(), pkt.size(), 0, reinterpret_cast<sockaddr*>(&a), sizeof(a));
+  if (n < 0) return -1;
+  ++udp_sent_;
+  send_bytes_ += static_cast<size_t>(n);
+  return static_cast<int>(n);
 }
 
 void Van::ProcessData(Message* msg) {

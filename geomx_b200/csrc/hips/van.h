@@ -50,6 +50,10 @@ class Van {
   DGTSender* dgt_sender() { return dgt_sender_.get(); }
   // direct (unqueued) transmit used by the priority sender thread, the resender and the DGT channel schedulers
   int SendNow(const Message& msg);
+  // lossy datagram path (DGT mode 1): one UDP packet per message with the message's TOS/DSCP; falls back to TCP when no endpoint is known
+  int SendUDP(const Message& msg);
+  size_t udp_sent() const { return udp_sent_.load(); }
+  size_t udp_received() const { return udp_received_.load(); }
 
  private:
   int Bind(Node* node, int max_retry);
@@ -59,6 +63,8 @@ class Van {
   void Accepting();
   void Receiving();
   void PrioritySending();
+  void ReceivingUDP();
+  void DeliverDGT(Message* msg);   // reassembly + delivery of a DGT block (called from the TCP and the UDP receive threads)
   void Heartbeat();
   void ProcessAddNodeAtScheduler(Message* msg, std::vector<Node>* nodes, std::vector<Node>* recovery_nodes);
   void ProcessAddNode(Message* msg, std::vector<Node>* nodes, std::vector<Node>* recovery_nodes);
@@ -72,7 +78,9 @@ class Van {
   Node scheduler_, my_node_;
   bool is_scheduler_ = false;
   std::atomic<bool> ready_{false}, stop_{false};
-  std::atomic<size_t> send_bytes_{0}, recv_bytes_{0};
+  std::atomic<size_t> send_bytes_{0}, recv_bytes_{0}, udp_sent_{0}, udp_received_{0};
+  int udp_fd_ = -1;
+  std::mutex udp_mu_, deliver_mu_;
   std::atomic<int> timestamp_{0};
   int listen_fd_ = -1;
   int wake_pipe_[2] = {-1, -1};
@@ -89,7 +97,7 @@ class Van {
   std::mutex fds_mu_;
   std::vector<int> recv_fds_;
 
-  std::unique_ptr<std::thread> accept_thread_, recv_thread_, heartbeat_thread_, prio_thread_;
+  std::unique_ptr<std::thread> accept_thread_, recv_thread_, heartbeat_thread_, prio_thread_, udp_thread_;
   ThreadsafeQueue<Message, MessagePriority> send_queue_;  // P3
   bool enable_p3_ = false;
   int drop_rate_ = 0;
