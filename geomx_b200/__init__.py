@@ -30,6 +30,9 @@ from . import symbol  # noqa: F401
 from . import symbol as sym  # noqa: F401
 from . import module  # noqa: F401
 from . import module as mod  # noqa: F401
+from . import callback  # noqa: F401
+from . import monitor  # noqa: F401
+from . import test_utils  # noqa: F401
 from . import profiler  # noqa: F401
 from . import io  # noqa: F401
 from . import recordio  # noqa: F401

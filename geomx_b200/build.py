@@ -27,6 +27,13 @@ CXX = os.environ.get("CXX", "g++")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread", "-fvisibility=hidden"]
+# GEOMX_SANITIZE=address|thread|undefined builds an instrumented runtime (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so) etc.);
+# GEOMX_DEBUG=1 adds -g -O0.  (reference: CMake USE_ASAN, Makefile DEBUG=1)
+_SAN = os.environ.get("GEOMX_SANITIZE", "")
+if _SAN:
+    CXX_FLAGS = [f for f in CXX_FLAGS if f != "-O2"] + ["-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=" + _SAN]
+if os.environ.get("GEOMX_DEBUG", "0") == "1":
+    CXX_FLAGS = [f for f in CXX_FLAGS if not f.startswith("-O")] + ["-O0", "-g"]
 
 
 def _newer(src, dst, extra=()):
@@ -93,7 +100,7 @@ def build_runtime(force=False, verbose=False):
     if jobs or not os.path.exists(out):
         # link the SHARED libstdc++ explicitly: some toolchains (e.g. a relocated g++ that only ships libstdc++.a) would otherwise embed a
         # second, static copy next to the one torch already loaded — two iostream/locale runtimes in one process crash on first use
-        _run([CXX, "-shared", "-o", out] + objs + ["-pthread", "-l:libstdc++.so.6"])
+        _run([CXX, "-shared", "-o", out] + objs + ["-pthread", "-l:libstdc++.so.6"] + (["-fsanitize=" + _SAN] if _SAN else []))
     return out
 
 

@@ -313,3 +313,23 @@ def test_host_storage_pool_and_resources():
     pool.seed(42); s1 = [pool.next_seed(0), pool.next_seed(0), pool.next_seed(1)]
     pool.seed(42); s2 = [pool.next_seed(0), pool.next_seed(0), pool.next_seed(1)]
     assert s1 == s2 and len(set(s1)) == 3
+
+
+def test_callbacks_monitor_and_test_utils(caplog):
+    """mx.callback.Speedometer / mx.monitor.Monitor on a Module, mx.test_utils numeric-gradient check against autograd."""
+    import logging
+    import numpy as np
+    X = np.random.RandomState(1).randn(64, 6).astype(np.float32); y = (X[:, 0] > 0).astype(np.float32)
+    net = mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=2, name="fc"), name="softmax")
+    mod = mx.mod.Module(net)
+    speed = mx.callback.Speedometer(16, frequent=2)
+    with caplog.at_level(logging.INFO):
+        mod.fit(mx.io.NDArrayIter(X, y, batch_size=16), num_epoch=2, optimizer_params={"learning_rate": 0.1}, batch_end_callback=speed)
+    assert speed.last_speed is not None and any("samples/sec" in r.getMessage() for r in caplog.records)
+    mon = mx.monitor.Monitor(1, pattern="fc_.*")
+    mon.install(mod._execs[0]); mon.tic()
+    mod.forward_backward(next(iter(mx.io.NDArrayIter(X, y, batch_size=16))))
+    names = [k for _, k, _ in mon.toc()]
+    assert "fc_weight" in names and "fc_weight_grad" in names
+    mx.test_utils.check_numeric_gradient(lambda a, w: mx.nd.dot(a, w).tanh() * 2.0, [np.random.randn(3, 4), np.random.randn(4, 2)])
+    mx.test_utils.assert_almost_equal(mx.nd.array([1.0, 2.0]), np.array([1.0, 2.0 + 1e-7]))
