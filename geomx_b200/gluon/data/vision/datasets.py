@@ -31,10 +31,11 @@ def _read_idx(path):
     return np.frombuffer(buf, dtype=np.uint8, offset=4 + 4 * ndim).reshape(dims)
 
 
-def _synthetic(n, shape, num_classes, seed):
-    """Class-conditional images: fixed random prototype per class + noise (learnable, deterministic)."""
-    rng = np.random.RandomState(seed)
-    protos = rng.randint(0, 200, size=(num_classes,) + shape).astype(np.float32)
+def _synthetic(n, shape, num_classes, seed, split=0):
+    """Class-conditional images: fixed random prototype per class + noise (learnable, deterministic).  The prototypes depend on the dataset
+    seed only, so the train and the test split of one dataset describe the same classes; labels / noise differ per split."""
+    protos = np.random.RandomState(seed).randint(0, 200, size=(num_classes,) + shape).astype(np.float32)
+    rng = np.random.RandomState(seed * 1000 + 17 + split)
     labels = (np.arange(n) * 7 + rng.randint(0, num_classes)) % num_classes
     noise = rng.randint(0, 56, size=(n,) + shape).astype(np.float32)
     data = np.clip(protos[labels] * 0.8 + noise, 0, 255).astype(np.uint8)
@@ -82,7 +83,7 @@ class MNIST(_ImgDataset):
             n = getenv_int("GEOMX_SYNTHETIC_SIZE", 0) or self._sizes[train]
             if not train:
                 n = max(1, n // 6)
-            data, label = _synthetic(n, (28, 28, 1), 10, self._seed + (0 if train else 1))
+            data, label = _synthetic(n, (28, 28, 1), 10, self._seed, 0 if train else 1)
         super().__init__(data, label, transform)
 
 
@@ -105,6 +106,6 @@ class CIFAR10(_ImgDataset):
             self.synthetic = False
         else:
             n = getenv_int("GEOMX_SYNTHETIC_SIZE", 0) or (50000 if train else 10000)
-            data, label = _synthetic(n, (32, 32, 3), 10, 44 + (0 if train else 1))
+            data, label = _synthetic(n, (32, 32, 3), 10, 44, 0 if train else 1)
             self.synthetic = True
         super().__init__(data, label, transform)
