@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-multicast", action="store_true")
-    ap.add_argument("--wire-dtype", default="fp32", choices=["fp32", "fp16", "mpq"], help="transport format of the fused HiPS step (FP16 / MPQ accelerators)")
+    ap.add_argument("--wire-dtype", default="fp32", choices=["fp32", "fp16", "mpq", "fp8"], help="transport format of the fused HiPS step (FP16 / MPQ accelerators)")
     return ap.parse_args()
 
 

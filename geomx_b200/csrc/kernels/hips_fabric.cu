@@ -21,6 +21,7 @@
 // st.release.sys, readers spin with ld.acquire.sys.  All CTAs of the launch are co-resident (grid <= #SMs), phases are ordered
 // A < B < C < D inside every CTA and each phase only waits on flags produced by strictly earlier phases => no cyclic wait.
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "common.cuh"
 
 namespace gx {
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 1) hips_fsa_step_kernel(const Fab
       const int done = atomicAdd(p.state + 1, 1);
       if (done == (int)gridDim.x - 1) { p.state[1] = 0; p.state[2] = opt_t; p.state[0] = (int)epoch; }
     }
+    stamp(5);
     return;
   }
 
@@ -363,17 +365,57 @@ __device__ __forceinline__ float2 unpack_h2(float f) {
 constexpr int FMT_F32 = 0;   // {v0,e,v1,e}{v2,e,v3,e}
 constexpr int FMT_F16 = 1;   // {h0h1,e,h2h3,e}: half the bytes on every hop (gradients and parameters), fp32 master weights on the owner
 constexpr int FMT_BSC = 2;   // Bi-Sparse between the tiers: k {value, e, index, e} packets per tile instead of 1024 values
+constexpr int FMT_F8 = 3;    // block-scaled fp8 gradients: e4m3 with one fp32 scale per 128 values (a warp), 8 values per packet => 1/4 of the
+                             // fp32 bytes on the two gradient hops; parameters of such tiles return as fp16
+
+// ---- block-scaled fp8 (warp-collective: all 32 lanes of a warp call these together; a lane owns 4 consecutive values)
+__device__ __forceinline__ uint32_t pack_f8x4(float4 v, float inv) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(v.x * inv, v.y * inv), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(v.z * inv, v.w * inv), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+__device__ __forceinline__ float4 unpack_f8x4(uint32_t q, float scale) {
+  const __half2_raw a = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(q & 0xffffu), __NV_E4M3);
+  const __half2_raw b = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(q >> 16), __NV_E4M3);
+  const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a)), fb = __half22float2(*reinterpret_cast<const __half2*>(&b));
+  return make_float4(fa.x * scale, fa.y * scale, fb.x * scale, fb.y * scale);
+}
+// even lanes write {own 4 values, neighbour's 4 values} as one packet into their slot, lane 1 writes the warp's scale into its (otherwise
+// unused) slot; `mc` selects the multicast store
+__device__ __forceinline__ void ll_send_f8(float* dst, bool mc, float4 v, uint32_t epoch) {
+  float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+  const float scale = fmaxf(amax, 1e-30f) * (1.f / 448.f);
+  const uint32_t q = pack_f8x4(v, 1.f / scale);
+  const uint32_t qn = __shfl_down_sync(0xffffffffu, q, 1);
+  const int lane = threadIdx.x & 31;
+  if ((lane & 1) == 0) { if (mc) ll_store1_mc(dst, __uint_as_float(q), __uint_as_float(qn), epoch); else ll_store1(dst, __uint_as_float(q), __uint_as_float(qn), epoch); }
+  else if (lane == 1) { if (mc) ll_store1_mc(dst, scale, 0.f, epoch); else ll_store1(dst, scale, 0.f, epoch); }
+}
+__device__ __forceinline__ float4 ll_recv_f8(const float* src, uint32_t epoch, int* err) {
+  const int lane = threadIdx.x & 31;
+  float2 pk = make_float2(0.f, 0.f);
+  if ((lane & 1) == 0 || lane == 1) pk = ll_load1(src, epoch, err);
+  const float scale = __shfl_sync(0xffffffffu, pk.x, 1);
+  const uint32_t from_prev = __shfl_up_sync(0xffffffffu, __float_as_uint(pk.y), 1);
+  const uint32_t q = (lane & 1) == 0 ? __float_as_uint(pk.x) : from_prev;
+  return unpack_f8x4(q, scale);
+}
 
 // dense value of one thread (4 floats) -> its 32-byte packet region
 __device__ __forceinline__ void ll_send_dense(float* dst, float4 v, int fmt, uint32_t epoch) {
-  if (fmt == FMT_F16) ll_store1(dst, pack_h2(v.x, v.y), pack_h2(v.z, v.w), epoch);
+  if (fmt == FMT_F8) ll_send_f8(dst, false, v, epoch);
+  else if (fmt == FMT_F16) ll_store1(dst, pack_h2(v.x, v.y), pack_h2(v.z, v.w), epoch);
   else ll_store(dst, v, epoch);
 }
 __device__ __forceinline__ void ll_send_dense_mc(float* mc, float4 v, int fmt, uint32_t epoch) {
-  if (fmt == FMT_F16) ll_store1_mc(mc, pack_h2(v.x, v.y), pack_h2(v.z, v.w), epoch);
+  if (fmt == FMT_F8) ll_send_f8(mc, true, v, epoch);
+  else if (fmt == FMT_F16) ll_store1_mc(mc, pack_h2(v.x, v.y), pack_h2(v.z, v.w), epoch);
   else ll_store_mc(mc, v, epoch);
 }
 __device__ __forceinline__ float4 ll_recv_dense(const float* src, int fmt, uint32_t epoch, int* err) {
+  if (fmt == FMT_F8) return ll_recv_f8(src, epoch, err);
   if (fmt == FMT_F16) {
     const float2 pk = ll_load1(src, epoch, err);
     const float2 a = unpack_h2(pk.x), b = unpack_h2(pk.y);
@@ -445,6 +487,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   const int K = p.bsc_k;
   int* err = p.state + 5;
   auto fmt_of = [&](int t) -> int { return p.tile_fmt ? (int)p.tile_fmt[t] : FMT_F32; };
+  auto grad_fmt = [](int f) -> int { return (f == FMT_F16 || f == FMT_F8) ? f : FMT_F32; };     // Bi-Sparse tiles travel dense inside a party
 
   // ---- phase 1: push my gradient tiles to their party owners (tiles I own myself are read in place in phase 2).  Inside a party the
   //      transport is dense (reference: worker -> local server is never sparsified), fp16 tiles travel as halves.
@@ -455,7 +498,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
     float* g = p.grad[p.rank] + off;
     const float4 v = *reinterpret_cast<const float4*>(g);
     if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
-    ll_send_dense(p.ll_a[party_base + t % S] + (long long)p.local * n2 + 2 * off, v, fmt_of(t) == FMT_F16 ? FMT_F16 : FMT_F32, epoch);
+    ll_send_dense(p.ll_a[party_base + t % S] + (long long)p.local * n2 + 2 * off, v, grad_fmt(fmt_of(t)), epoch);
   }
   stamp(1);
   // ---- phase 2: LOCAL PS TIER: the party owner sums the party's gradients of its tiles and forwards the aggregate to the global owner
@@ -469,7 +512,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
     if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < S; ++j) {
       if (j == p.local) continue;
-      acc = f4_add(acc, ll_recv_dense(p.ll_a[p.rank] + (long long)j * n2 + 2 * off, fmt == FMT_F16 ? FMT_F16 : FMT_F32, epoch, err));
+      acc = f4_add(acc, ll_recv_dense(p.ll_a[p.rank] + (long long)j * n2 + 2 * off, grad_fmt(fmt), epoch, err));
     }
     acc = f4_scale(acc, p.push_scale);
     float* dst = p.ll_b[owner_of(t)] + (long long)slot * n2;
@@ -571,7 +614,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
         else for (int r = bc_lo; r < bc_lo + bc_n; ++r) ll_store1(p.ll_c[r] + base + 4 * j, 0.f, -1.f, epoch);
       }
     } else {
-      const int bf = fmt == FMT_F16 ? FMT_F16 : FMT_F32;
+      const int bf = (fmt == FMT_F16 || fmt == FMT_F8) ? FMT_F16 : FMT_F32;   // parameters of fp8 tiles return as fp16
       if (bc_mc != nullptr) ll_send_dense_mc(bc_mc + 2 * off, W, bf, epoch);
       else for (int r = bc_lo; r < bc_lo + bc_n; ++r) ll_send_dense(p.ll_c[r] + 2 * off, W, bf, epoch);
     }
@@ -592,7 +635,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
         if (idx >= 0 && idx < TILE) p.param[p.rank][(long long)t * TILE + idx] = e.x;
       }
     } else {
-      *reinterpret_cast<float4*>(p.param[p.rank] + off) = ll_recv_dense(p.ll_c[p.rank] + 2 * off, fmt == FMT_F16 ? FMT_F16 : FMT_F32, epoch, err);
+      *reinterpret_cast<float4*>(p.param[p.rank] + off) = ll_recv_dense(p.ll_c[p.rank] + 2 * off, (fmt == FMT_F16 || fmt == FMT_F8) ? FMT_F16 : FMT_F32, epoch, err);
     }
   }
   stamp(4);

@@ -89,11 +89,11 @@ class HipsCNNTrainStep:
         self.layout = ArenaLayout.build(list(enumerate(CNN_PARAM_SHAPES)))
         self.fabric = HipsFabric(self.layout, self.topo, self.device, spec, use_multicast=use_multicast)
         self.fabric.set_push_scale(1.0 / B)          # the script-level `grad / num_samples`, folded into the push kernel
-        if wire_dtype in ("fp16", "mpq") and self.fabric.protocol == "ll":
+        if wire_dtype in ("fp16", "mpq", "fp8") and self.fabric.protocol == "ll":
             # FP16: every key as halves on the wire (examples/cnn_fp16.py); MPQ: only the keys above MXNET_KVSTORE_SIZE_LOWER_BOUND (cnn_mpq.py:52)
             from ..base import getenv_int
-            bound = 0 if wire_dtype == "fp16" else getenv_int("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000)
-            self.fabric.set_wire_formats({i: "fp16" for i, sl in enumerate(self.layout.slots) if sl.numel >= bound})
+            bound = getenv_int("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000) if wire_dtype == "mpq" else 0
+            self.fabric.set_wire_formats({i: ("fp8" if wire_dtype == "fp8" else "fp16") for i, sl in enumerate(self.layout.slots) if sl.numel >= bound})
         f = self.fabric
         self.P = [f.param_view(i) for i in range(10)]
         self.G = [f.grad_view(i) for i in range(10)]

@@ -245,13 +245,15 @@ class HipsFabric:
         self.opt_spec = spec
         self._params_cache.clear()
 
-    FMT_F32, FMT_F16, FMT_BSC = 0, 1, 2
+    FMT_F32, FMT_F16, FMT_BSC, FMT_F8 = 0, 1, 2, 3
 
     def set_wire_formats(self, key_formats=None, bsc_threshold=0.01):
         """Per-key wire format of the fused step: ``{key_index: 'fp32'|'fp16'|'bsc'}`` (missing keys: fp32), or None for all-fp32.
 
         fp16 = the reference's FP16 / MPQ transports (script-level ``astype('float16')``, examples/cnn_fp16.py:115, cnn_mpq.py:122) fused
         into the push kernel: gradients and parameters cross NVLink as halves, master weights stay fp32 on the global owner.
+        fp8  = block-scaled fp8 gradients (e4m3, one fp32 scale per 128 values, 8 values per packet) on both gradient hops; the parameters of
+        such keys return as fp16.
         bsc  = Bi-Sparse between the tiers (gradient_compression.cc:191-336), re-designed per 1024-value tile: the party owner keeps the
         momentum-corrected residual, sends the ``k = floor(1024*threshold)`` largest entries as (value, index) packets; without a server
         optimizer the aggregate returns sparse as well (BSCPullCompress)."""
@@ -261,7 +263,7 @@ class HipsFabric:
             return
         if self.protocol != "ll":
             raise RuntimeError("wire formats need the LL protocol (world > 1 and arena <= GEOMX_LL_MAX_BYTES)")
-        code = {"fp32": 0, "fp16": 1, "bsc": 2}
+        code = {"fp32": 0, "fp16": 1, "bsc": 2, "fp8": 3}
         fmt = np.zeros(self.tiles, dtype=np.uint8)
         for i, f in key_formats.items():
             sl = self.layout.slots[i]

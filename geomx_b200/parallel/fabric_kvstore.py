@@ -114,8 +114,9 @@ class KVStoreFabric(KVStoreBase):
             for i, (_, shape) in enumerate(self._keys):
                 if int(np.prod(shape)) >= bound:
                     fmts[i] = "bsc"
+        low = "fp8" if getenv_int("GEOMX_WIRE_FP8", 0) else "fp16"      # GEOMX_WIRE_FP8=1: block-scaled fp8 gradients for the keys pushed as float16
         for i in self._fp16_keys:
-            fmts.setdefault(i, "fp16")
+            fmts.setdefault(i, low)
         if fmts != self._wire_formats:
             f.set_wire_formats(fmts, float(comp.get("threshold", 0.01)))
             self._wire_formats = fmts

@@ -22,16 +22,21 @@ def main():
     parties = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     topo = Topology(world, rank, parties, 1)
     S, P = topo.party_size, topo.num_parties
-    layout = ArenaLayout.build([(0, (300,)), (1, (64, 100)), (2, (5000,)), (3, (7,)), (4, (40, 128))])
+    layout = ArenaLayout.build([(0, (300,)), (1, (64, 100)), (2, (5000,)), (3, (7,)), (4, (40, 128)), (5, (3000,))])
     f = HipsFabric(layout, topo, dev, None)
     f.set_push_scale(0.5)
     ok = True
     thr = 0.02
     K = int(1024 * thr)
-    f.set_wire_formats({1: "bsc", 2: "fp16", 4: "bsc"}, thr)
+    f.set_wire_formats({1: "bsc", 2: "fp16", 4: "bsc", 5: "fp8"}, thr)
     n = f.n
     u = torch.zeros(P, n, device=dev); v = torch.zeros(P, n, device=dev)       # oracle copies of every party's residual state
     tile_fmt = f.tile_fmt.cpu().numpy()
+    def q8(x):                      # block-scaled e4m3: one scale per 128 values (a warp's share of a tile)
+        b = x.view(-1, 128)
+        scale = b.abs().amax(1, keepdim=True).clamp_min(1e-30) * (1.0 / 448.0)
+        return ((b / scale).to(torch.float8_e4m3fn).float() * scale).view(-1)
+
     for step in range(3):
         g = torch.Generator(device="cpu").manual_seed(1000 * step + rank)
         grad = torch.randn(n, generator=g).to(dev)
@@ -55,10 +60,14 @@ def main():
                 for j in range(S):
                     if j != owner_local:
                         x = allg[gp * S + j][sl]
-                        acc += x.half().float() if fmt == 1 else x
+                        acc += x.half().float() if fmt == 1 else (q8(x) if fmt == 3 else x)
                 agg_parties.append(acc * 0.5)
             if fmt == 0:
                 expect[sl] = sum(agg_parties)
+            elif fmt == 3:
+                w = sum(q8(a) for a in agg_parties)
+                expect[sl] = w.half().float()
+                tol[sl] = 0.07 * w.abs().max() + 1e-6                            # at most one e4m3 rounding step of difference per hop
             elif fmt == 1:
                 w = sum(a.half().float() for a in agg_parties)
                 expect[sl] = w.half().float()
