@@ -186,10 +186,27 @@ def main():
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    # ---------------------------------------------------------------- exposed push+pull: duration of the fused HiPS kernel inside the step
+    # (%globaltimer stamps of CTA 0, first instruction -> last phase; untimed extra steps; nothing of it overlaps compute, so all of it is exposed)
+    comm_us = None
+    fab = getattr(eng, "fabric", None)
+    if fab is not None and args.mode == "dist_sync":
+        fab.state["fsa"][3] = 1
+        samples = []
+        for i in range(9):
+            if world > 1:
+                fab.barrier()
+            eng.run_device()
+            torch.cuda.synchronize()
+            st = fab.state["fsa"][8:8 + 12].view(torch.int64).tolist()
+            if st[5] > st[0] > 0:
+                samples.append((st[5] - st[0]) / 1e3)
+        fab.state["fsa"][3] = 0
+        comm_us = statistics.median(samples[1:]) if len(samples) > 1 else None
+    t = torch.tensor([dev_ms, e2e_ms, comm_us or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, comm_us = float(t[0]), float(t[1]), (float(t[2]) or None)
     if rank == 0:
         value = world * B * K / (dev_ms / 1e3)
         e2e_value = world * B * K / (e2e_ms / 1e3)
@@ -212,6 +229,7 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms / K, 5),
                     "h2d_bytes_per_step": eng.h2d_bytes_per_step(), "d2h_bytes_per_step": eng.d2h_bytes_per_step(), "final_loss": round(last_loss, 5),
                     "api": "HipsCNNTrainStep.step_async(X_pinned, y_pinned) -> LossHandle; loss of step i read (D2H, pinned) after step i+1 was enqueued"},
+            "exposed_push_pull_ms_per_step": None if comm_us is None else round(comm_us / 1e3, 5),
             "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks,
         }
