@@ -76,6 +76,9 @@ struct FabricParams {
   float* bsc_u;                // Bi-Sparse momentum / accumulation state of the party owner (arena-sized, local HBM)
   float* bsc_v;
   int bsc_k;                   // packets per tile and party  (= floor(1024 * threshold), >= 1)
+  const int* tile_order;       // DGT on the fabric: tiles are served in contribution order (most important first); nullptr = index order
+  float* dgt_contrib;          // [tiles] EMA of mean |aggregated gradient| per tile, maintained by the tile's global owner (nullptr = off)
+  float dgt_alpha;             // EMA factor (DGT_CONTRIBUTION_ALPHA)
   int ll_party_mode;           // 1: the party is the whole universe of this launch (HFA local round): the tile's party owner is also its
                                //    "global" owner, results go to the party members only, no optimizer
 };
@@ -474,6 +477,7 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   __shared__ float s_tile[TILE];
   __shared__ int s_hist[FAB_THREADS];
   __shared__ int s_w[16];
+  __shared__ float s_red[FAB_THREADS / 32];
   const uint32_t epoch = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
   const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
   const float lr_t = adam_lr(p.h, opt_t);
@@ -491,7 +495,8 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
 
   // ---- phase 1: push my gradient tiles to their party owners (tiles I own myself are read in place in phase 2).  Inside a party the
   //      transport is dense (reference: worker -> local server is never sparsified), fp16 tiles travel as halves.
-  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+  for (int ti = blockIdx.x; ti < p.tiles; ti += gridDim.x) {
+    const int t = p.tile_order ? p.tile_order[ti] : ti;   // DGT: important tiles first
     if (t % S == p.local) continue;
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
     const long long off = (long long)t * TILE + threadIdx.x * 4;
@@ -502,7 +507,8 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   }
   stamp(1);
   // ---- phase 2: LOCAL PS TIER: the party owner sums the party's gradients of its tiles and forwards the aggregate to the global owner
-  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+  for (int ti = blockIdx.x; ti < p.tiles; ti += gridDim.x) {
+    const int t = p.tile_order ? p.tile_order[ti] : ti;   // DGT: important tiles first
     if (t % S != p.local) continue;
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
     const int fmt = fmt_of(t);
@@ -558,7 +564,8 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   }
   stamp(2);
   // ---- phase 3: GLOBAL PS TIER: the global owner sums the parties' aggregates, runs the optimizer on its shard and pushes the result
-  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+  for (int ti = blockIdx.x; ti < p.tiles; ti += gridDim.x) {
+    const int t = p.tile_order ? p.tile_order[ti] : ti;   // DGT: important tiles first
     if (owner_of(t) != p.rank) continue;
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
     const int fmt = fmt_of(t);
@@ -584,6 +591,23 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
         }
       __syncthreads();
       agg = *reinterpret_cast<const float4*>(s_tile + threadIdx.x * 4);
+    }
+    if (p.dgt_contrib != nullptr) {
+      // DGT contribution of this tile (kv_app.h:853-876 EvalMsgContribution): EMA of the mean |aggregated gradient| — ranks the tiles for the
+      // next re-ordering (important first) and decides which tiles keep full precision (HipsFabric.dgt_rerank)
+      float a = fabsf(agg.x) + fabsf(agg.y) + fabsf(agg.z) + fabsf(agg.w);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < FAB_THREADS / 32; ++i) sum += s_red[i];
+        const float mean = sum * (1.f / TILE), old = p.dgt_contrib[t];
+        p.dgt_contrib[t] = old == 0.f ? mean : p.dgt_alpha * old + (1.f - p.dgt_alpha) * mean;
+      }
     }
     opt_apply(W.x, agg.x, A.x, B.x, p.h, lr, wd);
     opt_apply(W.y, agg.y, A.y, B.y, p.h, lr, wd);
@@ -621,7 +645,8 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   }
   stamp(3);
   // ---- phase 4: pull: unpack the fresh parameters into the (plain fp32) parameter arena the forward pass reads
-  for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+  for (int ti = blockIdx.x; ti < p.tiles; ti += gridDim.x) {
+    const int t = p.tile_order ? p.tile_order[ti] : ti;   // DGT: important tiles first
     if (p.tile_active != nullptr && !p.tile_active[t]) continue;
     const int fmt = fmt_of(t);
     const long long off = (long long)t * TILE + threadIdx.x * 4;

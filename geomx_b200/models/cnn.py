@@ -74,7 +74,7 @@ class HipsCNNTrainStep:
     """
 
     def __init__(self, net=None, batch_size=32, optimizer=None, topo=None, device=None, use_graph=True, pull_fused=False,
-                 use_multicast=True, mode="dist_sync", fused_zero_grad=True, wire_dtype="fp32"):
+                 use_multicast=True, mode="dist_sync", fused_zero_grad=True, wire_dtype="fp32", dgt=False, dgt_rerank_every=32):
         native.require()
         from .. import optimizer as opt
         self.B = B = int(batch_size)
@@ -94,6 +94,10 @@ class HipsCNNTrainStep:
             from ..base import getenv_int
             bound = getenv_int("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000) if wire_dtype == "mpq" else 0
             self.fabric.set_wire_formats({i: ("fp8" if wire_dtype == "fp8" else "fp16") for i, sl in enumerate(self.layout.slots) if sl.numel >= bound})
+        self._dgt_every = 0
+        if dgt and self.fabric.protocol == "ll":
+            self.fabric.enable_dgt()
+            self._dgt_every = max(1, int(dgt_rerank_every))
         f = self.fabric
         self.P = [f.param_view(i) for i in range(10)]
         self.G = [f.grad_view(i) for i in range(10)]
@@ -221,6 +225,8 @@ class HipsCNNTrainStep:
 
     def run_device(self):
         """One step on whatever is currently in ``self.x`` / ``self.label`` (device-only; used by the kernel-time bench)."""
+        if self._dgt_every and self.steps_done and self.steps_done % self._dgt_every == 0 and self.graph is not None:
+            self.fabric.dgt_rerank()          # outside the captured graph; order / formats are updated in place
         if self.use_graph:
             if self.graph is None:
                 self.capture()

@@ -163,6 +163,7 @@ class _FabricParams(ctypes.Structure):
         ("ll_a", ctypes.c_void_p * MAX_RANKS), ("ll_b", ctypes.c_void_p * MAX_RANKS), ("ll_c", ctypes.c_void_p * MAX_RANKS),
         ("ll_c_mc", ctypes.c_void_p),
         ("tile_fmt", ctypes.c_void_p), ("bsc_u", ctypes.c_void_p), ("bsc_v", ctypes.c_void_p), ("bsc_k", ctypes.c_int),
+        ("tile_order", ctypes.c_void_p), ("dgt_contrib", ctypes.c_void_p), ("dgt_alpha", ctypes.c_float),
         ("ll_party_mode", ctypes.c_int),
     ]
 
@@ -225,7 +226,9 @@ class HipsFabric:
         self.use_multicast = use_multicast and bool(self.param.multicast_ptr) and os.environ.get("GEOMX_NO_MULTICAST", "0") != "1"
         self.opt_spec = None
         self.push_scale = 1.0
-        self.tile_fmt = None            # per-tile wire format (LL protocol): 0 fp32, 1 fp16, 2 Bi-Sparse between the tiers
+        self.tile_fmt = None            # per-tile wire format (LL protocol): 0 fp32, 1 fp16, 2 Bi-Sparse between the tiers, 3 block-scaled fp8
+        self.tile_order = self.dgt_contrib = None     # DGT on the fabric (enable_dgt)
+        self.dgt_k, self.dgt_alpha, self._dgt_base_fmt = 1.0, 0.3, None
         self.bsc_u = self.bsc_v = None
         self.bsc_k = 0
         # one CTA per tile while the launch stays co-resident (the kernels spin on each other); grid-stride beyond that.  The LL kernel's
@@ -276,7 +279,49 @@ class HipsFabric:
             if self.bsc_u is None:
                 self.bsc_u = torch.zeros(self.n, dtype=torch.float32, device=self.device)
                 self.bsc_v = torch.zeros(self.n, dtype=torch.float32, device=self.device)
-        self.tile_fmt = torch.from_numpy(fmt).to(self.device)
+        new = torch.from_numpy(fmt).to(self.device)
+        if self.tile_fmt is not None and self.tile_fmt.shape == new.shape:
+            self.tile_fmt.copy_(new)              # in place: a captured CUDA graph holds this pointer
+        else:
+            self.tile_fmt = new
+
+    # -- DGT on the fabric ---------------------------------------------------------------------------------------------------------
+    def enable_dgt(self, k=None, alpha=None):
+        """Differential gradient transmission mapped onto NVSwitch (reference: kv_app.h:842-1022, van.cc:707-824): the global owner of a
+        tile keeps the EMA of its mean |aggregated gradient| (in-kernel); ``dgt_rerank()`` turns these contributions into (a) the order in
+        which the fused kernel serves the tiles — important first — and (b) the wire precision: the top ``k`` fraction keeps its format, the
+        rest travels as block-scaled fp8 (the reference's 4-bit encode of unimportant blocks, ENABLE_DGT=3)."""
+        if self.protocol != "ll":
+            raise RuntimeError("DGT on the fabric needs the LL protocol")
+        self.dgt_k = float(os.environ.get("DMLC_K", 0.8)) if k is None else float(k)
+        self.dgt_alpha = float(os.environ.get("DGT_CONTRIBUTION_ALPHA", 0.3)) if alpha is None else float(alpha)
+        if self.dgt_contrib is None:
+            self.dgt_contrib = torch.zeros(self.tiles, dtype=torch.float32, device=self.device)
+            self.tile_order = torch.arange(self.tiles, dtype=torch.int32, device=self.device)
+        if self.tile_fmt is None:
+            self.tile_fmt = torch.zeros(self.tiles, dtype=torch.uint8, device=self.device)
+        self._dgt_base_fmt = self.tile_fmt.clone()
+        self._params_cache.clear()
+
+    def dgt_rerank(self):
+        """Collective (all ranks): gather every owner's contributions, re-rank the tiles, demote the unimportant ones to fp8.  Off the hot
+        path (call every few dozen steps); everything is updated in place so captured graphs pick the new order up."""
+        assert self.dgt_contrib is not None, "enable_dgt() first"
+        c = self.dgt_contrib.clone()
+        owned = torch.from_numpy(self.tile_owner_np == self.topo.rank).to(self.device)
+        c = torch.where(owned, c, torch.zeros_like(c))
+        if self.topo.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(c)
+        order = torch.argsort(c, descending=True, stable=True)
+        self.tile_order.copy_(order.to(torch.int32))
+        n_imp = max(1, int(round(self.dgt_k * self.tiles)))
+        fmt = self._dgt_base_fmt.clone()
+        unimportant = order[n_imp:]
+        dense = (fmt[unimportant] == 0) | (fmt[unimportant] == 1)          # Bi-Sparse tiles keep their own format
+        fmt[unimportant[dense]] = 3
+        self.tile_fmt.copy_(fmt)
+        return c
 
     def set_push_scale(self, s):
         self.push_scale = float(s)
@@ -318,6 +363,9 @@ class HipsFabric:
                 p.ll_a[r] = self.ll_a.peer_ptrs[r] or None
                 p.ll_b[r] = self.ll_b.peer_ptrs[r] or None
                 p.ll_c[r] = self.ll_c.peer_ptrs[r] or None
+        p.tile_order = self.tile_order.data_ptr() if self.tile_order is not None else None
+        p.dgt_contrib = self.dgt_contrib.data_ptr() if self.dgt_contrib is not None else None
+        p.dgt_alpha = float(self.dgt_alpha)
         p.ll_c_mc = (self.ll_c.multicast_ptr or None) if (self.ll_a is not None and self.use_multicast and os.environ.get("GEOMX_LL_MULTICAST", "1") == "1") else None
         p.tile_fmt = self.tile_fmt.data_ptr() if self.tile_fmt is not None else None
         p.bsc_u = self.bsc_u.data_ptr() if self.bsc_u is not None else None
@@ -408,6 +456,7 @@ class HipsFabric:
                 p.h.kind = -1
                 p.push_scale = float(scale)
                 p.tile_fmt = None
+                p.dgt_contrib = None
                 self._params_cache[key] = p
             rc = native.require().gx_hips_fsa_ll_step(ctypes.byref(p), self.grid, self._stream())
             native.launch_count += 1

@@ -120,6 +120,8 @@ class KVStoreFabric(KVStoreBase):
         if fmts != self._wire_formats:
             f.set_wire_formats(fmts, float(comp.get("threshold", 0.01)))
             self._wire_formats = fmts
+            if f.dgt_contrib is not None:
+                f._dgt_base_fmt = f.tile_fmt.clone() if f.tile_fmt is not None else None
 
     # -- data ---------------------------------------------------------------------------------------------------------------------
     def _init(self, key, value):
@@ -160,6 +162,10 @@ class KVStoreFabric(KVStoreBase):
         self._init_vals = None
         self._fabric = f
         self._apply_wire_formats()
+        if getenv_int("ENABLE_DGT", 0) and f.protocol == "ll":
+            # DGT on NVSwitch: contribution-ranked tile order + fp8 for the unimportant (1 - DMLC_K) fraction, re-ranked every few rounds
+            f.enable_dgt()
+            self._dgt_every, self._dgt_round = max(1, getenv_int("GEOMX_DGT_RERANK_EVERY", 16)), 0
 
     def _push(self, key, vals, priority):
         self._finalize()
@@ -201,6 +207,10 @@ class KVStoreFabric(KVStoreBase):
                 self._flush_hfa(full)
             elif self._sync:
                 f.fsa_step(masked=not full)
+                if f.dgt_contrib is not None and full:
+                    self._dgt_round += 1
+                    if self._dgt_round % self._dgt_every == 0:
+                        f.dgt_rerank()
             else:
                 if not full:
                     raise MXNetError("dist_async on the fabric needs every key pushed each round")

@@ -29,6 +29,10 @@ def main():
     thr = 0.02
     K = int(1024 * thr)
     f.set_wire_formats({1: "bsc", 2: "fp16", 4: "bsc", 5: "fp8"}, thr)
+    dgt = "--dgt" in sys.argv
+    if dgt:
+        f.enable_dgt(k=0.5, alpha=0.3)
+    ema = torch.zeros(f.tiles, device=dev)
     n = f.n
     u = torch.zeros(P, n, device=dev); v = torch.zeros(P, n, device=dev)       # oracle copies of every party's residual state
     tile_fmt = f.tile_fmt.cpu().numpy()
@@ -37,7 +41,8 @@ def main():
         scale = b.abs().amax(1, keepdim=True).clamp_min(1e-30) * (1.0 / 448.0)
         return ((b / scale).to(torch.float8_e4m3fn).float() * scale).view(-1)
 
-    for step in range(3):
+    for step in range(5 if dgt else 3):
+        tile_fmt = f.tile_fmt.cpu().numpy()
         g = torch.Generator(device="cpu").manual_seed(1000 * step + rank)
         grad = torch.randn(n, generator=g).to(dev)
         if step == 2:
@@ -64,13 +69,16 @@ def main():
                 agg_parties.append(acc * 0.5)
             if fmt == 0:
                 expect[sl] = sum(agg_parties)
+                gagg = expect[sl]
             elif fmt == 3:
                 w = sum(q8(a) for a in agg_parties)
                 expect[sl] = w.half().float()
+                gagg = w
                 tol[sl] = 0.07 * w.abs().max() + 1e-6                            # at most one e4m3 rounding step of difference per hop
             elif fmt == 1:
                 w = sum(a.half().float() for a in agg_parties)
                 expect[sl] = w.half().float()
+                gagg = w
                 tol[sl] = 2e-3 * w.abs().max() + 1e-6                            # summation-order / double-rounding slack
             else:
                 out = torch.zeros(1024, device=dev)
@@ -83,6 +91,9 @@ def main():
                     u[gp, sl] = uu; v[gp, sl] = vv
                 expect[sl] = out
                 tol[sl] = 1e-6
+                gagg = out
+            m = gagg.abs().mean()
+            ema[t] = m if float(ema[t]) == 0.0 else 0.3 * ema[t] + 0.7 * m
         got = f.param.tensor
         bad = ((got - expect).abs() > tol + 1e-6 * expect.abs()).sum().item()
         nz = int((got[torch.from_numpy(np.repeat(tile_fmt, 1024) == 2).to(dev)] != 0).sum())
@@ -90,6 +101,18 @@ def main():
         print("rank %d step %d: mismatches=%d  bsc non-zeros pulled=%d (<= %d)  grads cleared=%s  protocol_err=%s" % (
             rank, step, bad, nz, int((tile_fmt == 2).sum()) * P * K, zeroed, f.check_protocol_errors()), flush=True)
         ok = ok and bad == 0 and zeroed and not f.check_protocol_errors()
+        if dgt and step % 2 == 1:
+            c = f.dgt_rerank()
+            cerr = float(((c - ema).abs() / (ema.abs() + 1e-12)).max())
+            order = f.tile_order.long()
+            sorted_ok = bool((c[order][:-1] >= c[order][1:]).all()) and sorted(order.tolist()) == list(range(f.tiles))
+            fmt_now = f.tile_fmt.cpu().numpy()
+            n_imp = max(1, int(round(0.5 * f.tiles)))
+            demoted = [int(fmt_now[t]) for t in order[n_imp:].tolist()]
+            kept = [int(fmt_now[t]) for t in order[:n_imp].tolist()]
+            fmt_ok = all(x in (2, 3) for x in demoted) and all(x != 3 or False for x in kept if x == 3) is not None
+            print("rank %d step %d: dgt contrib max rel err %.2e  order sorted=%s  demoted fmts=%s" % (rank, step, cerr, sorted_ok, sorted(set(demoted))), flush=True)
+            ok = ok and cerr < 1e-3 and sorted_ok and all(x in (2, 3) for x in demoted)
         dist.barrier()
     t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
