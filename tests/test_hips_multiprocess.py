@@ -244,3 +244,18 @@ def test_dgt_udp_datagram_channel():
     assert sum(s["udp_sent"] for s in stats) > 0 and sum(s["udp_received"] for s in stats) == sum(s["udp_sent"] for s in stats)
     res = launch_hips({"TEST_MODE": "big", "ENABLE_DGT": "1", "DGT_BLOCK_SIZE": "1024", "DMLC_K": "0.3", "DGT_UDP_LOSS": "20", "TEST_STEPS": "2"})
     assert len([r for r in res if "vals" in r]) == 4            # lossy: values are not exact, but every round completes
+
+
+def test_plain_c_api_worker():
+    """GXKVStore* (csrc/hips/c_api.cc): two workers that use only the C ABI train against the standard scheduler / server processes."""
+    port = free_port()
+    base = {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": port, "DMLC_NUM_SERVER": 1, "DMLC_NUM_WORKER": 2, "DMLC_NUM_ALL_WORKER": 2}
+    procs = [spawn(dict(base, DMLC_ROLE="scheduler")), spawn(dict(base, DMLC_ROLE="server"))]
+    capi = os.path.join(HERE, "_capi_worker.py")
+    for i in range(2):
+        e = dict(os.environ); e.update({k: str(v) for k, v in dict(base, DMLC_ROLE="worker").items()}); e.pop("RANK", None); e.pop("WORLD_SIZE", None)
+        procs.append(subprocess.Popen([sys.executable, capi], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    res = results(collect(procs))
+    assert len(res) == 2
+    for r in res:
+        assert r["num_workers"] == 2 and abs(r["vals"][0] - (1.0 - 0.1 * 1.5)) < 1e-6 and abs(r["vals"][1] - (1.0 - 0.2 * 1.5)) < 1e-6
