@@ -68,5 +68,8 @@ def test_hfa_converges(tmp_path):
 @pytest.mark.parametrize("script", ["run_mixed_sync.sh", "run_fp16.sh", "run_mixed_precision.sh", "run_dgt.sh", "run_p3.sh", "run_tsengine.sh",
                                     "run_multi_gps.sh"])
 def test_remaining_demo_scenarios_converge(script, tmp_path):
-    accs = run_scenario(script, tmp_path, iters=41)
+    # MixedSync applies every party's (stale) aggregate on arrival: with Adam the effective step doubles, so it gets the smaller learning
+    # rate such a schedule needs (at 0.01 the outcome depends on the arrival order of the first few updates)
+    args = ("-lr", "0.003") if script == "run_mixed_sync.sh" else ()
+    accs = run_scenario(script, tmp_path, iters=41, args=args)
     assert accs[-1] > 0.4, (script, accs)
