@@ -5,3 +5,5 @@ from .parameter import Constant, Parameter, ParameterDict  # noqa: F401
 from .trainer import Trainer  # noqa: F401
 
 from . import contrib  # noqa: F401,E402
+from . import model_zoo  # noqa: F401,E402
+from . import rnn  # noqa: F401,E402
