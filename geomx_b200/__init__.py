@@ -37,6 +37,7 @@ from . import profiler  # noqa: F401
 from . import io  # noqa: F401
 from . import recordio  # noqa: F401
 from . import storage  # noqa: F401
+from . import engine  # noqa: F401
 from . import utils  # noqa: F401
 from . import parallel  # noqa: F401
 from . import models  # noqa: F401

@@ -129,8 +129,14 @@ inline void BindEngine(py::module_& m) {
       .def(py::init<int, bool>(), py::arg("num_threads") = 2, py::arg("naive") = false)
       .def("new_variable", &Engine::NewVariable)
       .def("push", [](Engine& e, py::object fn, std::vector<int> cv, std::vector<int> mv, int priority, const std::string& name) {
-        auto holder = std::make_shared<py::object>(std::move(fn));
-        e.Push([holder] { py::gil_scoped_acquire g; (*holder)(); *holder = py::none(); }, cv, mv, priority, name);
+        // the callable is released under the GIL wherever the last reference dies (a worker thread, usually)
+        std::shared_ptr<py::object> holder(new py::object(std::move(fn)), [](py::object* p) { py::gil_scoped_acquire g; delete p; });
+        py::gil_scoped_release nogil;
+        e.Push([holder] {
+          py::gil_scoped_acquire g;
+          try { (*holder)(); }
+          catch (py::error_already_set& err) { err.restore(); PyErr_WriteUnraisable(holder->ptr()); }   // a failing op must not kill the worker
+        }, cv, mv, priority, name);
       }, py::arg("fn"), py::arg("const_vars") = std::vector<int>(), py::arg("mutable_vars") = std::vector<int>(), py::arg("priority") = 0,
            py::arg("name") = "")
       .def("wait_for_var", &Engine::WaitForVar, py::call_guard<py::gil_scoped_release>())

@@ -2,7 +2,7 @@
 from . import random  # noqa: F401
 from .ndarray import *  # noqa: F401,F403
 from .ndarray import NDArray  # noqa: F401
-from .utils import load, load_bytes, save, save_bytes  # noqa: F401
+from .utils import load, load_bytes, save, save_async, save_bytes  # noqa: F401
 from . import sparse  # noqa: F401,E402
 from .sparse import RowSparseNDArray  # noqa: F401,E402
 from . import op_lib as _op_lib  # noqa: E402

@@ -475,6 +475,8 @@ def waitall():
     Parity: ``Engine::WaitForAll`` via ``mx.nd.waitall`` (``python/mxnet/ndarray/ndarray.py:156``)."""
     from ..kvstore import base as _kvb
     _kvb.flush_all()
+    from .. import engine as _engine
+    _engine.wait_all()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
 

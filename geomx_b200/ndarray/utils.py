@@ -171,6 +171,37 @@ def save(fname, data):
         f.write(save_bytes(data))
 
 
+_path_vars = {}
+
+
+def save_async(fname, data):
+    """``save`` without blocking the training loop: the arrays are snapshotted now (device -> host copy, so later in-place updates do not
+    leak into the file), serialisation + file IO run on the host dependency engine (``mx.engine``).  Writes to the same path are ordered by
+    the path's engine variable; ``mx.nd.waitall()`` (or ``mx.engine.wait_all()``) waits for them.  Falls back to a synchronous ``save``
+    when the native runtime is unavailable."""
+    from .. import engine, runtime
+    if not runtime.available():
+        return save(fname, data)
+    if isinstance(data, NDArray):
+        snap = NDArray(data._t.detach().to("cpu", copy=True))
+    elif isinstance(data, dict):
+        snap = {k: NDArray(v._t.detach().to("cpu", copy=True)) for k, v in data.items()}
+    else:
+        snap = [NDArray(v._t.detach().to("cpu", copy=True)) for v in data]
+    path = str(fname)
+    var = _path_vars.get(path)
+    if var is None:
+        var = _path_vars[path] = engine.new_variable()
+
+    def write():
+        tmp = path + ".tmp%d" % id(snap)
+        with open(tmp, "wb") as f:
+            f.write(save_bytes(snap))
+        import os
+        os.replace(tmp, path)                  # readers never observe a half-written checkpoint
+    engine.push(write, mutable_vars=[var], name="nd.save_async")
+
+
 def load(fname):
     with open(fname, "rb") as f:
         return load_bytes(f.read())

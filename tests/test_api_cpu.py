@@ -333,3 +333,37 @@ def test_callbacks_monitor_and_test_utils(caplog):
     assert "fc_weight" in names and "fc_weight_grad" in names
     mx.test_utils.check_numeric_gradient(lambda a, w: mx.nd.dot(a, w).tanh() * 2.0, [np.random.randn(3, 4), np.random.randn(4, 2)])
     mx.test_utils.assert_almost_equal(mx.nd.array([1.0, 2.0]), np.array([1.0, 2.0 + 1e-7]))
+
+
+def test_engine_ordering_and_async_save(tmp_path):
+    """mx.engine: writers are exclusive and ordered, readers run in between, priorities order ready ops; nd.save_async writes a snapshot."""
+    import threading
+    import time
+    import numpy as np
+    from geomx_b200 import engine, runtime
+    if not runtime.available():
+        pytest.skip("native runtime not built")
+    v = engine.new_variable()
+    log, lock = [], threading.Lock()
+
+    def op(tag, dt=0.0):
+        def f():
+            time.sleep(dt)
+            with lock:
+                log.append(tag)
+        return f
+    engine.push(op("w1", 0.05), mutable_vars=[v])
+    engine.push(op("r1"), const_vars=[v]); engine.push(op("r2"), const_vars=[v])
+    engine.push(op("w2"), mutable_vars=[v])
+    engine.push(op("r3"), const_vars=[v])
+    engine.wait_for_var(v)
+    assert log[0] == "w1" and set(log[1:3]) == {"r1", "r2"} and log[3] == "w2" and log[4] == "r3"
+    with pytest.raises(Exception):
+        engine.push(op("bad"), const_vars=[v], mutable_vars=[v])
+    a = mx.nd.array(np.arange(6, dtype=np.float32))
+    path = str(tmp_path / "ck.params")
+    mx.nd.save_async(path, {"w": a})
+    a[:] = -1.0                                   # later in-place updates must not leak into the checkpoint
+    mx.nd.save_async(path + "2", [a])
+    mx.nd.waitall()
+    assert mx.nd.load(path)["w"].asnumpy().tolist() == [0, 1, 2, 3, 4, 5] and mx.nd.load(path + "2")[0].asnumpy().tolist() == [-1.0] * 6
