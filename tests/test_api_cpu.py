@@ -356,8 +356,10 @@ def test_engine_ordering_and_async_save(tmp_path):
     engine.push(op("r1"), const_vars=[v]); engine.push(op("r2"), const_vars=[v])
     engine.push(op("w2"), mutable_vars=[v])
     engine.push(op("r3"), const_vars=[v])
-    engine.wait_for_var(v)
-    assert log[0] == "w1" and set(log[1:3]) == {"r1", "r2"} and log[3] == "w2" and log[4] == "r3"
+    engine.wait_for_var(v)                        # a read of v: returns once w2 is done (r3 may still be running next to it)
+    assert log[0] == "w1" and set(log[1:3]) == {"r1", "r2"} and log[3] == "w2"
+    engine.wait_all()
+    assert log[4] == "r3"
     with pytest.raises(Exception):
         engine.push(op("bad"), const_vars=[v], mutable_vars=[v])
     a = mx.nd.array(np.arange(6, dtype=np.float32))
