@@ -128,7 +128,9 @@ def main():
 
     if args.impl == "oracle":
         from geomx_b200.parallel.nccl_oracle import OracleCNNTrainStep
-        eng = OracleCNNTrainStep(batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev, use_graph=not args.no_graph)
+        # multi-rank: eager launches (an NCCL all-reduce captured inside the CUDA graph stalled on the test pod; the single-rank oracle is graphed)
+        eng = OracleCNNTrainStep(batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev,
+                                 use_graph=not args.no_graph and world == 1)
     else:
         eng = mx.models.HipsCNNTrainStep(net=None, batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev,
                                          use_graph=not args.no_graph, use_multicast=not args.no_multicast, mode=args.mode, wire_dtype=args.wire_dtype)
