@@ -42,7 +42,8 @@ def pick_context(force_cpu):
     if force_cpu:
         return mx.cpu()
     try:
-        ctx = mx.gpu(int(os.environ.get("LOCAL_RANK", 0)))
+        n = mx.context.num_gpus()
+        ctx = mx.gpu(int(os.environ.get("LOCAL_RANK", 0)) % max(1, n))      # more worker processes than GPUs: share the devices round-robin
         mx.nd.zeros((1,), ctx=ctx)
         return ctx
     except mx.base.MXNetError:
