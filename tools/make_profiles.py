@@ -53,6 +53,10 @@ def copy_logs():
             txt = open(p).read()
             txt = "\n".join(l for l in txt.splitlines() if not l.startswith("frame #") and "OMP_NUM_THREADS" not in l and not l.startswith("*****"))
             open(os.path.join(OUT, name.replace(".log", ".txt")), "w").write(txt[-12000:])
+    for sub in ("gpu_vanilla", "gpu_bsc"):        # reference-style 12-process runs with GPU workers (scripts/gpu/*.sh)
+        p = os.path.join(GO, sub, "party1_worker1.log")
+        if os.path.exists(p):
+            open(os.path.join(OUT, "demo_%s_worker.txt" % sub), "w").write(open(p).read()[-4000:])
     rows = []
     for p in sorted(glob.glob(os.path.join(GO, "bench*.log"))):
         for l in open(p):
