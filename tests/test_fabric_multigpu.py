@@ -47,3 +47,17 @@ def test_wire_formats_fp16_and_bisparse(parties):
 def test_two_parties_two_global_servers():
     rc, out = _torchrun(4, "fabric_check.py", "--parties", "2", "--gs", "2", port=29641)
     assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_mixed_sync_one_sided_kernel():
+    """dist_async on the fabric (per-tile locks in the global owner's HBM): every party applies its aggregate on arrival; the run must train
+    and stay consistent inside a party."""
+    rc, out = _torchrun(2, "fabric_check.py", "--parties", "2", "--mode", "dist_async", port=29651)
+    assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_hfa_rounds():
+    rc, out = _torchrun(2, "fabric_hfa_check.py", "1", port=29661)
+    assert rc == 0 and "HFA_CHECK PASS" in out, out[-3000:]
