@@ -326,14 +326,12 @@ __device__ __forceinline__ void ll_store_mc(float* mc, float4 v, uint32_t epoch)
 // Poll a (local) packet pair until both halves carry `epoch`.  Bounded: a protocol bug must not hang the GPU (state[5] reports it).
 __device__ __forceinline__ float4 ll_load(const float* src, uint32_t epoch, int* err) {
   float4 a, b;
-  const float f = __uint_as_float(epoch);
   for (long long spin = 0;; ++spin) {
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src) : "memory");
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 4) : "memory");
     if (__float_as_uint(a.y) == epoch && __float_as_uint(a.w) == epoch && __float_as_uint(b.y) == epoch && __float_as_uint(b.w) == epoch) break;
     if (spin > (1ll << 24)) { *err = 1; break; }
   }
-  (void)f;
   return make_float4(a.x, a.z, b.x, b.z);
 }
 

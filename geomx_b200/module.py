@@ -156,6 +156,8 @@ class Module(BaseModule):
         if self.params_initialized and not force_init:
             return
         initializer = initializer or init_mod.Uniform(0.01)
+        if arg_params is None and aux_params is None and getattr(self, "_preloaded", None) is not None:
+            arg_params, aux_params = self._preloaded
         ex0 = self._execs[0]
         self._arg_params = {n: nd.zeros(ex0.arg_dict[n].shape) for n in self._param_names}
         self._aux_params = {n: nd.zeros(ex0.aux_dict[n].shape) for n in self._aux_names}
@@ -290,13 +292,7 @@ class Module(BaseModule):
         from . import symbol as sym
         js, arg, aux = load_checkpoint(prefix, epoch)
         mod = Module(sym.load_json(js), **kwargs)
-        mod._arg_params, mod._aux_params, mod._preloaded = arg, aux, True
-        mod._loaded = (arg, aux)
-        orig_init = mod.init_params
-
-        def init_params(initializer=None, arg_params=None, aux_params=None, **kw):
-            return orig_init(initializer, arg_params or arg, aux_params or aux, **kw)
-        mod.init_params = init_params
+        mod._preloaded = (arg, aux)                # used by init_params() when no explicit values are given
         if load_optimizer_states:
             mod._preload_opt_states = "%s-%04d.states" % (prefix, epoch)
         return mod

@@ -109,8 +109,6 @@ def main():
             fmt_now = f.tile_fmt.cpu().numpy()
             n_imp = max(1, int(round(0.5 * f.tiles)))
             demoted = [int(fmt_now[t]) for t in order[n_imp:].tolist()]
-            kept = [int(fmt_now[t]) for t in order[:n_imp].tolist()]
-            fmt_ok = all(x in (2, 3) for x in demoted) and all(x != 3 or False for x in kept if x == 3) is not None
             print("rank %d step %d: dgt contrib max rel err %.2e  order sorted=%s  demoted fmts=%s" % (rank, step, cerr, sorted_ok, sorted(set(demoted))), flush=True)
             ok = ok and cerr < 1e-3 and sorted_ok and all(x in (2, 3) for x in demoted)
         dist.barrier()
