@@ -38,6 +38,8 @@ struct GemmParams {
   long long ldmask;
   float* colsum;
   int relu, accumulate, store_mode, hw;
+  int pool_w;              // store_mode 2: width of the (pre-pool) feature map; rows are (image, oh, ow)
+  unsigned char* pool_idx; // store_mode 2: arg-max position (0..3) of every pooled element, same layout as D
   float alpha;
   const uint32_t* wait_flag;
   const int* wait_epoch;
@@ -224,6 +226,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0 && n0 + c0 + j < p.N) atomicAdd(p.colsum + n0 + c0 + j, s);
           }
         }
+        if (p.store_mode == 2) {
+          // fused 2x2/2 max-pool of an NCHW feature map (ReLU already applied): row m = (image, oh, ow); the three partners of a window's
+          // top-left element sit 1, W and W+1 lanes further in the same warp (host guarantees 32 % (2W) == 0 and hw % 32 == 0).
+          // First maximum wins, like maxpool2x2_fwd_kernel; only pooled values + arg-max leave the SM.
+          const int W = p.pool_w, pix = m % p.hw, oh = pix / W, ow = pix - oh * W, img = m / p.hw;
+          const bool base = row_ok && ((oh & 1) == 0) && ((ow & 1) == 0);
+          const int PW = W >> 1, PHW = p.hw >> 2;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const float a01 = __shfl_down_sync(0xffffffffu, v[j], 1), a10 = __shfl_down_sync(0xffffffffu, v[j], W),
+                        a11 = __shfl_down_sync(0xffffffffu, v[j], W + 1);
+            const int n = n0 + c0 + j;
+            if (base && n < p.N) {
+              float best = v[j]; int bi = 0;
+              if (a01 > best) { best = a01; bi = 1; }
+              if (a10 > best) { best = a10; bi = 2; }
+              if (a11 > best) { best = a11; bi = 3; }
+              const long long o = ((long long)img * p.N + n) * PHW + (oh >> 1) * PW + (ow >> 1);
+              p.D[o] = best;
+              p.pool_idx[o] = (unsigned char)bi;
+            }
+          }
+        } else
         if (row_ok) {
           if (p.store_mode == 0) {
             float* dst = p.D + (long long)m * p.ldd + n0 + c0;
@@ -336,12 +361,16 @@ GX_API int gx_gemm_set_debug(unsigned long long* p) { g_gemm_dbg = p; return 0; 
 
 // A: K-major -> [M][K] with row stride lda; MN-major -> [K][M] with row stride lda.  Same for B with N.
 // returns 0 on success, -1 if the operands do not satisfy TMA alignment (caller falls back to gx_gemm_simt).
-GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
-                        long long ldd, const float* bias, const float* mask, long long ldmask, float* colsum, int relu, int accumulate,
-                        int store_mode, int hw, float alpha, int split_k, const uint32_t* wait_flag, const int* wait_epoch,
-                        cudaStream_t stream) {
+static int gemm_tf32_impl(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
+                          long long ldd, const float* bias, const float* mask, long long ldmask, float* colsum, int relu, int accumulate,
+                          int store_mode, int hw, float alpha, int split_k, const uint32_t* wait_flag, const int* wait_epoch,
+                          int pool_w, unsigned char* pool_idx, cudaStream_t stream) {
   using namespace gx;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (store_mode == 2) {   // fused pooling: whole windows must live inside one warp's 32 rows, no split-K / accumulate
+    if (pool_w < 2 || (pool_w & 1) || (32 % (2 * pool_w)) != 0 || hw % 32 != 0 || (hw % pool_w) != 0 || ((hw / pool_w) & 1) || M % 32 != 0 ||
+        split_k > 1 || accumulate || pool_idx == nullptr) return -1;
+  }
   if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -1;
   // tile width: these problems are bound by how fast ONE SM can pull its operand panel out of L2 (~100 GB/s per SM, measured with
   // tools/gemm_phases.py), so small problems are cut into narrow tiles to spread the B panel over many SMs; large ones use 128-wide tiles.
@@ -377,6 +406,7 @@ GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B,
   p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
   p.relu = relu; p.accumulate = (accumulate || split_k > 1) ? 1 : 0; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha;
   p.wait_flag = wait_flag; p.wait_epoch = wait_epoch; p.stages = 0; p.dbg = g_gemm_dbg;
+  p.pool_w = pool_w; p.pool_idx = pool_idx;
   p.a_boxes = a_boxes < 1 ? 1 : a_boxes; p.b_boxes = b_boxes < 1 ? 1 : b_boxes;
   p.tx_bytes = (a_mn ? p.a_boxes * MN_BOX_BYTES : a_rows * BLOCK_K * 4) + (b_mn ? p.b_boxes * MN_BOX_BYTES : b_rows * BLOCK_K * 4);
   dim3 grid((unsigned)ceil_div(N, block_n), (unsigned)mt, (unsigned)split_k);
@@ -386,6 +416,22 @@ GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B,
     case 64: return dispatch_major<64>(a_mn, b_mn, ta, tb, p, grid, stream);
     default: return dispatch_major<128>(a_mn, b_mn, ta, tb, p, grid, stream);
   }
+}
+
+GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
+                        long long ldd, const float* bias, const float* mask, long long ldmask, float* colsum, int relu, int accumulate,
+                        int store_mode, int hw, float alpha, int split_k, const uint32_t* wait_flag, const int* wait_epoch,
+                        cudaStream_t stream) {
+  return gemm_tf32_impl(A, lda, a_mn, B, ldb, b_mn, M, N, K, D, ldd, bias, mask, ldmask, colsum, relu, accumulate, store_mode == 2 ? 1 : store_mode, hw,
+                        alpha, split_k, wait_flag, wait_epoch, 0, nullptr, stream);
+}
+// Convolution-as-GEMM with the 2x2/2 max-pool fused into the epilogue: rows of A are (image, oh, ow) with ow fastest and `hw` = OH*OW,
+// `pool_w` = OW.  D receives the POOLED NCHW map [images][N][OH/2][OW/2], `pool_idx` the arg-max position of every pooled element.
+// returns -1 when the geometry does not fit the in-warp pooling (caller runs GEMM + pool kernels instead).
+GX_API int gx_gemm_tf32_pool(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
+                             const float* bias, int relu, int hw, int pool_w, unsigned char* pool_idx, float alpha, cudaStream_t stream) {
+  return gemm_tf32_impl(A, lda, a_mn, B, ldb, b_mn, M, N, K, D, N, bias, nullptr, 0, nullptr, relu, 0, 2, hw, alpha, 1, nullptr, nullptr, pool_w,
+                        pool_idx, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -161,10 +161,16 @@ class HipsCNNTrainStep:
         Wc1, Gc1 = P[2].view(32, 400), G[2].view(32, 400)
         kv = (lambda: (f.async_step(), f.grad.tensor.zero_() if self.fused_zero_grad else None)) if self.mode == "dist_async" else \
             (lambda: f.fsa_step(defer_pull_wait=False, zero_grad=self.fused_zero_grad))
+        def conv1_fwd():
+            # bias + ReLU + 2x2 max-pool in the tcgen05 epilogue (only the pooled map and its arg-max leave the SM); the two-kernel form is
+            # the fallback for geometries the in-warp pooling cannot express
+            if not n.gemm_pool(self.col1, Wc1, self.a2, self.idx2, 8, 8, bias=P[3], relu=True):
+                n.gemm(self.col1, Wc1, self.z2, bias=P[3], relu=True, store_nchw_hw=64)
+                n.maxpool2x2_fwd(self.z2, self.a2, self.idx2)
+
         return [
             ("conv0+relu+pool+im2col", "main", lambda: n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)),
-            ("conv1 gemm (bias,relu,nchw)", "main", lambda: n.gemm(self.col1, Wc1, self.z2, bias=P[3], relu=True, store_nchw_hw=64)),
-            ("maxpool", "main", lambda: n.maxpool2x2_fwd(self.z2, self.a2, self.idx2)),
+            ("conv1 gemm (bias,relu,maxpool fused)", "main", conv1_fwd),
             ("dense0 gemm", "main", lambda: n.gemm(a2f, P[4], self.a3, bias=P[5], relu=True)),
             ("dense1 gemm", "main", lambda: n.gemm(self.a3, P[6], self.a4, bias=P[7], relu=True)),
             ("head fwd+bwd", "main", lambda: n.head_fwd_bwd(self.a4, P[8], P[9], self.label, self.loss, self.logits, G[8], G[9], self.dz4, G[7], True)),

@@ -64,6 +64,21 @@ def gemm(A, B, D, a_mn=False, b_mn=False, bias=None, mask=None, colsum=None, rel
     return D
 
 
+def gemm_pool(A, B, pooled, idx, OH, OW, bias=None, relu=True, a_mn=False, b_mn=False, alpha=1.0):
+    """Convolution-as-GEMM with bias + ReLU + 2x2/2 max-pool fused into the tcgen05 epilogue.  ``A``: [images*OH*OW, K] im2col rows,
+    ``B``: [N, K] filters; writes ``pooled`` [images, N, OH/2, OW/2] and ``idx`` (uint8 arg-max).  Returns False when the geometry does not
+    fit the in-warp pooling (caller falls back to gemm + maxpool2x2_fwd)."""
+    M = A.shape[1] if a_mn else A.shape[0]
+    K = A.shape[0] if a_mn else A.shape[1]
+    N = B.shape[1] if b_mn else B.shape[0]
+    rc = _lib().gx_gemm_tf32_pool(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), M, N, K, _p(pooled), _p(bias), int(relu), OH * OW, OW,
+                                  _p(idx), float(alpha), _s())
+    if rc == -1:
+        return False
+    _ck(rc, "gemm_pool")
+    return True
+
+
 # --------------------------------------------------------------------------------------------------------------- conv / pool
 def conv_out_hw(H, W, KH, KW, sh, sw, ph, pw):
     return (H + 2 * ph - KH) // sh + 1, (W + 2 * pw - KW) // sw + 1

@@ -6,6 +6,7 @@ P, I, L, F, U = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint32
 SIGS = {
     # gemm_tcgen05.cu
     "gx_gemm_tf32": [P, L, I, P, L, I, I, I, I, P, L, P, P, L, P, I, I, I, I, F, I, P, P, P],
+    "gx_gemm_tf32_pool": [P, L, I, P, L, I, I, I, I, P, P, I, I, I, P, F, P],
     "gx_gemm_set_debug": [P],
     "gx_gemm_simt": [P, L, I, P, L, I, I, I, I, P, L, P, P, L, P, I, I, I, I, F, P],
     # conv_pool.cu

@@ -316,3 +316,28 @@ def test_unique_gather_scatter_rows():
     out = mx.nd.sparse.zeros("row_sparse", (500, 24), ctx=mx.gpu(0))
     kv.row_sparse_pull(7, out=out, row_ids=mx.nd.array(ids.cpu().numpy(), ctx=mx.gpu(0), dtype="int64"))
     assert torch.equal(out.indices._t, u) and torch.equal(out.data._t, src[u])
+
+
+@pytest.mark.gpu
+def test_gemm_with_fused_maxpool_epilogue():
+    """gx_gemm_tf32_pool: conv-as-GEMM + bias + ReLU + 2x2 max-pool in the tcgen05 epilogue == GEMM (NCHW store) followed by the pool kernel,
+    values and arg-max positions (ties resolved to the first maximum), and close to the fp32 PyTorch reference."""
+    from geomx_b200.ops import _native_api as n
+    torch.manual_seed(3)
+    for (B, C, OH, OW, K) in ((32, 32, 8, 8, 400), (4, 16, 4, 16, 72), (2, 48, 16, 8, 36)):
+        A = torch.randn(B * OH * OW, K, device="cuda")
+        Wt = torch.randn(C, K, device="cuda") * 0.1
+        bias = torch.randn(C, device="cuda")
+        z = torch.empty(B, C, OH, OW, device="cuda")
+        n.gemm(A, Wt, z, bias=bias, relu=True, store_nchw_hw=OH * OW)
+        a_ref = torch.empty(B, C, OH // 2, OW // 2, device="cuda"); i_ref = torch.empty(B, C, OH // 2, OW // 2, dtype=torch.uint8, device="cuda")
+        n.maxpool2x2_fwd(z, a_ref, i_ref)
+        a = torch.full_like(a_ref, -7.0); idx = torch.full_like(i_ref, 9)
+        assert n.gemm_pool(A, Wt, a, idx, OH, OW, bias=bias, relu=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a, a_ref) and torch.equal(idx, i_ref), (B, C, OH, OW)
+        ref = torch.nn.functional.max_pool2d(torch.relu((A @ Wt.t() + bias).view(B, OH, OW, C).permute(0, 3, 1, 2)), 2)
+        assert rel_err(a, ref) < 2e-3
+    # geometry the in-warp pooling cannot express -> clean refusal (the caller falls back)
+    A = torch.randn(2 * 6 * 6, 16, device="cuda"); Wt = torch.randn(16, 16, device="cuda")
+    assert not n.gemm_pool(A, Wt, torch.empty(2, 16, 3, 3, device="cuda"), torch.empty(2, 16, 3, 3, dtype=torch.uint8, device="cuda"), 6, 6)
