@@ -19,6 +19,8 @@ The public API a user calls is ``step(X_host, y_host) -> loss`` (H2D of the batc
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -164,7 +166,7 @@ class HipsCNNTrainStep:
         def conv1_fwd():
             # bias + ReLU + 2x2 max-pool in the tcgen05 epilogue (only the pooled map and its arg-max leave the SM); the two-kernel form is
             # the fallback for geometries the in-warp pooling cannot express
-            if not n.gemm_pool(self.col1, Wc1, self.a2, self.idx2, 8, 8, bias=P[3], relu=True):
+            if os.environ.get("GEOMX_NO_POOL_FUSION", "0") == "1" or not n.gemm_pool(self.col1, Wc1, self.a2, self.idx2, 8, 8, bias=P[3], relu=True):
                 n.gemm(self.col1, Wc1, self.z2, bias=P[3], relu=True, store_nchw_hw=64)
                 n.maxpool2x2_fwd(self.z2, self.a2, self.idx2)
 
