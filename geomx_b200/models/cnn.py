@@ -156,7 +156,7 @@ class HipsCNNTrainStep:
 
     # ------------------------------------------------------------------------------------------------------------
     def _steps(self):
-        """The training step as an ordered list of (name, stream, launch) — 15 kernels; `stream` is 'main' or 'side' (parallel graph branch)."""
+        """The training step as an ordered list of (name, stream, launch) — 14 kernels; `stream` is 'main' or 'side' (parallel graph branch)."""
         n = native
         B, P, G, f = self.B, self.P, self.G, self.fabric
         a2f = self.a2.view(B, 512)
