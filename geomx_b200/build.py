@@ -11,7 +11,6 @@ GPU box with the repo snapshot.
 from __future__ import annotations
 
 import os
-import shutil
 import subprocess
 import sys
 import sysconfig

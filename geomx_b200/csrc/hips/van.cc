@@ -591,8 +591,13 @@ void Van::ProcessAddNodeAtScheduler(Message* msg, std::vector<Node>* nodes, std:
     nodes->push_back(ctrl.node[0]);
     if (nodes->size() < num_nodes) return;
     // all registered: deterministic order, then assign ranks
+    // A strict weak order (role, requested rank, host, port): ranks are counted per role, so hinted servers come out in the order of
+    // their hints.  (Comparing hints only between hinted nodes and addresses otherwise is NOT transitive once an un-hinted worker sits
+    // between two hinted servers — std::sort then returned the servers in either order and MultiGPS key ownership diverged between planes.)
     std::sort(nodes->begin(), nodes->end(), [](const Node& a, const Node& b) {
-      if (a.rank_hint != b.rank_hint && a.rank_hint >= 0 && b.rank_hint >= 0) return a.rank_hint < b.rank_hint;  // honour requested ranks
+      if (a.role != b.role) return a.role < b.role;
+      const int ha = a.rank_hint >= 0 ? a.rank_hint : 1 << 30, hb = b.rank_hint >= 0 ? b.rank_hint : 1 << 30;
+      if (ha != hb) return ha < hb;
       return a.hostname != b.hostname ? a.hostname < b.hostname : a.port < b.port;
     });
     for (auto& node : *nodes) {

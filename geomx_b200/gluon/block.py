@@ -13,12 +13,8 @@ import re
 import threading
 from collections import OrderedDict
 
-import torch
 
-from .. import autograd
 from .. import ndarray as nd
-from ..base import MXNetError
-from ..context import Context, cpu
 from ..ndarray import NDArray
 from .parameter import DeferredInitializationError, Parameter, ParameterDict
 

@@ -2,7 +2,6 @@
 MaxPool2D :749, Conv1D/3D-free subset, Conv2DTranspose, AvgPool2D, GlobalAvgPool2D, GlobalMaxPool2D)."""
 from __future__ import annotations
 
-import torch
 import torch.nn.functional as TF
 
 from ...ndarray import NDArray

@@ -7,13 +7,12 @@ from __future__ import annotations
 
 from collections import OrderedDict
 
-import numpy as np
 import torch
 
 from .. import initializer as init_mod
 from .. import ndarray as nd
 from ..base import MXNetError
-from ..context import Context, cpu, current_context
+from ..context import Context, current_context
 from ..ndarray import NDArray
 from ..ndarray.ndarray import torch_dtype
 

@@ -15,8 +15,6 @@ from __future__ import annotations
 import torch
 
 from .. import optimizer as opt
-from ..base import MXNetError
-from ..ndarray import NDArray
 from .parameter import Parameter, ParameterDict
 
 __all__ = ["Trainer"]

@@ -8,7 +8,7 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from .ndarray import NDArray, array
+from .ndarray import NDArray
 
 __all__ = ["DataDesc", "DataBatch", "DataIter", "NDArrayIter", "MNISTIter", "ResizeIter", "CSVIter", "LibSVMIter", "ImageRecordIter", "PrefetchingIter"]
 

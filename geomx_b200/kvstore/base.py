@@ -8,7 +8,6 @@ factory ``create`` (:663-705) → ``KVStore::Create`` (``src/kvstore/kvstore.cc:
 """
 from __future__ import annotations
 
-import pickle
 import weakref
 
 from ..base import MXNetError

@@ -23,9 +23,7 @@ This module is the CPU implementation *and* the numerics oracle; on CUDA tensors
 """
 from __future__ import annotations
 
-import math
 
-import numpy as np
 import torch
 
 from ..base import MXNetError

@@ -3,7 +3,6 @@ from __future__ import annotations
 
 import os
 
-from ..base import MXNetError
 
 
 def create_dist(name):

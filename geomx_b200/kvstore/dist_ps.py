@@ -180,7 +180,6 @@ class KVStoreDist(KVStoreBase):
 
     # -- configuration ----------------------------------------------------------------------------------------------------------
     def set_optimizer(self, optimizer):
-        from .. import optimizer as opt
         if not self._is_worker:
             return super().set_optimizer(optimizer)      # on a server: install the python updater (controller path)
         if self.rank == 0:

@@ -21,7 +21,6 @@ from __future__ import annotations
 
 import os
 
-import numpy as np
 import torch
 
 from .. import gluon, initializer

@@ -18,7 +18,6 @@ from .base import MXNetError
 from .context import cpu
 from .io import DataBatch, DataDesc
 from .model import BatchEndParam, _create_kvstore, _initialize_kvstore, _update_params, _update_params_on_kvstore, load_checkpoint, save_checkpoint
-from .ndarray import NDArray
 
 __all__ = ["Module", "BaseModule"]
 

@@ -18,8 +18,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ..base import MXNetError, numeric_types
-from ..context import Context, cpu, current_context
+from ..base import MXNetError
+from ..context import Context, current_context
 
 __all__ = ["NDArray", "array", "zeros", "ones", "empty", "full", "arange", "zeros_like", "ones_like",
            "waitall", "concat", "stack", "dot", "np_dtype", "torch_dtype", "dtype_name", "from_torch",

@@ -20,7 +20,7 @@ import torch
 
 from ..base import MXNetError
 from ..context import Context, cpu
-from .ndarray import NDArray, array
+from .ndarray import NDArray
 
 __all__ = ["save", "load", "save_bytes", "load_bytes"]
 

@@ -21,7 +21,6 @@ import pickle
 import numpy as np
 import torch
 
-from ..base import MXNetError
 from ..ndarray import NDArray
 
 __all__ = ["Optimizer", "SGD", "Signum", "FTML", "LBSGD", "DCASGD", "NAG", "SGLD", "ccSGD", "Adam", "AdaGrad",

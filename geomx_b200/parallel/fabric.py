@@ -19,7 +19,7 @@ import torch
 
 from ..base import MXNetError, getenv_int
 from ..ops import native
-from .arena import TILE, ArenaLayout
+from .arena import ArenaLayout
 
 MAX_RANKS = 16
 

@@ -26,9 +26,8 @@ import torch
 
 from ..base import MXNetError, getenv_int
 from ..kvstore.base import KVStoreBase
-from ..ndarray import NDArray
 from .arena import ArenaLayout
-from .fabric import HipsFabric, SymmetricBuffer, Topology
+from .fabric import HipsFabric, Topology
 
 
 def _ensure_process_group(device):

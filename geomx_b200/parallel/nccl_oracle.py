@@ -6,7 +6,6 @@ across party leaders, then broadcast — or one world all-reduce when there is a
 same hyper-parameters on every rank, all captured in a CUDA graph.  None of the hand-written kernels is on this path."""
 from __future__ import annotations
 
-import math
 
 import torch
 import torch.nn.functional as F

@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import io as _io
 import numbers
-import os
 import struct
 from collections import namedtuple
 

@@ -1,8 +1,12 @@
 """Worker body for the multi-process HiPS tests (CPU).  Prints RESULT lines parsed by the test."""
+import faulthandler
 import json
 import os
+import signal
 import sys
 import time
+
+faulthandler.register(signal.SIGUSR1, all_threads=True)      # the test harness asks for a traceback before it kills a hung run
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("GEOMX_SYNTHETIC_SIZE", "256")

@@ -35,6 +35,12 @@ def collect(procs, timeout=120):
         try:
             o, _ = p.communicate(timeout=timeout)
         except subprocess.TimeoutExpired:
+            import signal
+            import time
+            for q in procs:                      # workers dump their Python stacks on SIGUSR1 (tests/_hips_worker.py)
+                if q.poll() is None and q.args[-1].endswith("_hips_worker.py"):
+                    q.send_signal(signal.SIGUSR1)
+            time.sleep(1.0)
             for q in procs:
                 q.kill()
             parts = []
@@ -87,7 +93,7 @@ def launch_hips(extra, parties=2, wpp=2, global_servers=1):
         procs.append(spawn(dict(g, **party, DMLC_ROLE="server"), extra=extra))
         for _ in range(wpp):
             ws.append(spawn(dict(party, DMLC_ROLE="worker", TEST_WORKER_GID=gid), worker=True, extra=extra)); gid += 1
-    outs = collect(procs + ws, timeout=180)
+    outs = collect(procs + ws, timeout=int(os.environ.get("T_TIMEOUT", "180")))
     return results(outs)
 
 
