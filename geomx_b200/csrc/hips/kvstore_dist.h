@@ -50,6 +50,7 @@ class KVStoreDist {
       WaitAll();
       Barrier();
       if (rank() == 0 && !po->is_master_worker()) SendCommandToServers(static_cast<int>(CommandType::kStopServer), "");
+      po->set_finalizing();
       ps_worker_.reset();
     }
     po->Finalize(0, true);
@@ -82,6 +83,7 @@ class KVStoreDist {
       if (on_ready) on_ready(server_.get());
       server_->Run();
     }
+    po->set_finalizing();
     po->Finalize(0, true);
     started_ = false;
     server_.reset();

@@ -128,6 +128,23 @@ Customer* Postoffice::GetCustomer(int app_id, int customer_id, int timeout_sec) 
   return nullptr;
 }
 
+bool Postoffice::DeliverTo(int app_id, int customer_id, const Message& msg, int timeout_sec) {
+  for (int i = 0; i <= timeout_sec * 1000; ++i) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = customers_.find(app_id);
+      if (it != customers_.end()) {
+        auto jt = it->second.find(customer_id);
+        Customer* c = jt != it->second.end() ? jt->second : ((!it->second.empty() && customer_id == Meta::kEmpty) ? it->second.begin()->second : nullptr);
+        if (c != nullptr) { c->Accept(msg); return true; }     // Accept only enqueues
+      }
+    }
+    if (finalizing_.load()) return false;
+    std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
+  return false;
+}
+
 void Postoffice::Barrier(int customer_id, int node_group, Plane p) {
   if (GetNodeIDs(node_group, p).size() <= 1) return;
   const int role = role_in(p);

@@ -2,6 +2,7 @@
 // Parity: ps-lite include/ps/internal/postoffice.h:18-233 + src/postoffice.cc (InitEnvironment :18-58, Start :60-111, StartGlobal
 // :113-148, Barrier :202-244, GetServerKeyRanges :246-259, GetDeadNodes :284-303).
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <ctime>
 #include <map>
@@ -35,6 +36,9 @@ class Postoffice {
   bool is_global_server() const { return is_global_server_; }
   bool is_global_scheduler() const { return is_global_scheduler_; }
   bool is_master_worker() const { return is_master_worker_; }
+  // set once the applications of this process are being torn down: late (re)transmissions for them are dropped instead of waited for
+  void set_finalizing() { finalizing_ = true; }
+  bool is_finalizing() const { return finalizing_.load(); }
   bool enable_central_workers() const { return enable_central_worker_; }
   int num_workers() const { return num_workers_; }
   int num_servers() const { return num_servers_; }
@@ -52,6 +56,9 @@ class Postoffice {
   void AddCustomer(Customer* c);
   void RemoveCustomer(Customer* c);
   Customer* GetCustomer(int app_id, int customer_id, int timeout_sec = 0);
+  // look the customer up and hand it `msg` while the registry lock is held, so that a customer being destroyed on another thread cannot be
+  // dereferenced after its removal; false = no such customer (yet / any more)
+  bool DeliverTo(int app_id, int customer_id, const Message& msg, int timeout_sec);
 
   // ---- barrier / manage ----------------------------------------------------------------------------------------------
   void Barrier(int customer_id, int node_group, Plane p);
@@ -71,6 +78,7 @@ class Postoffice {
   bool has_local_ = false, has_global_ = false, started_ = false;
   bool is_worker_ = false, is_server_ = false, is_scheduler_ = false, is_global_server_ = false, is_global_scheduler_ = false;
   bool is_master_worker_ = false, enable_central_worker_ = false;
+  std::atomic<bool> finalizing_{false};
   int num_workers_ = 0, num_servers_ = 0, num_global_workers_ = 0, num_global_servers_ = 0, num_all_workers_ = 0;
   std::unordered_map<int, std::vector<int>> node_ids_[2];
   std::vector<Range> key_ranges_[2];

@@ -515,10 +515,11 @@ void Van::ProcessData(Message* msg) {
   HIPS_CHECK(msg->meta.app_id != Meta::kEmpty);
   const int app_id = msg->meta.app_id;
   const int customer_id = po_->role_in(plane_) == Node::WORKER && plane_ == kLocal ? msg->meta.customer_id : app_id;
-  Customer* c = po_->GetCustomer(app_id, customer_id, 5);
-  HIPS_CHECK_MSG(c != nullptr, "no customer for app " + std::to_string(app_id));
   msg->meta.plane = plane_;
-  c->Accept(*msg);
+  if (!po_->DeliverTo(app_id, customer_id, *msg, po_->is_finalizing() ? 0 : 5)) {
+    // the application is gone (shutdown) — e.g. a retransmission whose original was already answered; never throw on the receive thread
+    HIPS_VLOG(1, "plane %d drop message for missing customer app=%d customer=%d from %d", plane_, app_id, customer_id, msg->meta.sender);
+  }
 }
 
 void Van::ProcessHeartbeat(Message* msg) {
