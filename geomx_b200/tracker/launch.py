@@ -125,15 +125,30 @@ def launch(job: HipsJob, worker_cmd, launcher="local", log_dir=None, dry_run=Fal
             e.update(env)
         out = open(os.path.join(log_dir, p.name + ".log"), "w") if log_dir else None
         procs.append((p, subprocess.Popen(cmd, env=e, stdout=out, stderr=subprocess.STDOUT if out else None), out))
-    rc = 0
-    for p, proc, out in procs:
-        try:
-            r = proc.wait(timeout=timeout)
-        except subprocess.TimeoutExpired:
-            for _, q, _ in procs:
+    # fail fast: a role that dies at start-up would leave every other process waiting at the rendezvous forever
+    import time
+    rc, t0 = 0, time.time()
+    alive = list(procs)
+    while alive:
+        nxt = []
+        for item in alive:
+            r = item[1].poll()
+            if r is None:
+                nxt.append(item)
+            elif r != 0 and rc == 0:
+                rc = r
+                print("process %s exited with code %d - stopping the job" % (item[0].name, r), file=sys.stderr)
+        alive = nxt
+        if alive and timeout is not None and time.time() - t0 > timeout:
+            rc = rc or 124
+        if rc != 0:
+            for _, q, _ in alive:
                 q.kill()
-            r = 124
-        rc = rc or r
+            break
+        if alive:
+            time.sleep(0.2)
+    for _, q, out in procs:
+        q.wait()
         if out:
             out.close()
     return rc

@@ -41,6 +41,29 @@ for p in $(seq 1 "$PARTIES"); do
   done
 done
 echo "launched ${#pids[@]} processes; logs in $LOG_DIR (tail -f $last)"
-rc=0; for pid in "${pids[@]}"; do wait "$pid" || rc=$?; done
+# Fail fast: a role that dies at start-up (port in use, bad environment ...) would otherwise leave every other process waiting at the
+# rendezvous forever.  Poll the children; on the first non-zero exit stop the whole job and report which log to read.
+trap 'kill "${pids[@]}" 2>/dev/null' EXIT INT TERM
+rc=0; alive=("${pids[@]}")
+while [ ${#alive[@]} -gt 0 ]; do
+  next=()
+  for pid in "${alive[@]}"; do
+    if kill -0 "$pid" 2>/dev/null; then
+      next+=("$pid")
+    else
+      r=0; wait "$pid" || r=$?
+      if [ $r -ne 0 ] && [ $rc -eq 0 ]; then rc=$r; echo "process $pid exited with code $r - stopping the job (see $LOG_DIR)" >&2; fi
+    fi
+  done
+  alive=("${next[@]}")
+  if [ $rc -ne 0 ]; then
+    for pid in "${alive[@]}"; do kill "$pid" 2>/dev/null; done
+    sleep 1
+    for pid in "${alive[@]}"; do kill -9 "$pid" 2>/dev/null; done
+    break
+  fi
+  [ ${#alive[@]} -gt 0 ] && sleep 0.3
+done
+trap - EXIT
 tail -n 3 "$last"
 exit $rc

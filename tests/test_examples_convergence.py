@@ -14,12 +14,40 @@ pytestmark = pytest.mark.skipif(not runtime.available(), reason="native runtime 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _free_base_port():
-    for _ in range(50):
+def _free_base_port(span=8):
+    """A base port whose whole block (global scheduler, central party, one per party) is currently free."""
+    for _ in range(200):
         s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
-        if p < 60000:
+        if p + span >= 60000:
+            continue
+        ok = True
+        for q in range(p, p + span):
+            t = socket.socket()
+            try:
+                t.bind(("127.0.0.1", q))
+            except OSError:
+                ok = False
+            finally:
+                t.close()
+            if not ok:
+                break
+        if ok:
             return p
     return 23456
+
+
+def _run_group(cmd, env, timeout):
+    """Run a launcher script in its own process group; on timeout the whole group (all 12+ roles) is killed, not just the shell."""
+    import signal
+    p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        out, _ = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(p.pid, signal.SIGKILL)
+        out, _ = p.communicate()
+        out = (out or "") + "\n[harness] timed out after %d s, process group killed" % timeout
+        return subprocess.CompletedProcess(cmd, 124, out)
+    return subprocess.CompletedProcess(cmd, p.returncode, out)
 
 
 def run_scenario(script, tmp_path, iters=31, extra_env=None, args=()):
@@ -28,8 +56,7 @@ def run_scenario(script, tmp_path, iters=31, extra_env=None, args=()):
     env.update({"LOG_DIR": str(tmp_path), "BASE_PORT": str(_free_base_port()), "GEOMX_SYNTHETIC_SIZE": "2048", "GEOMX_MAX_ITERS": str(iters),
                 "GEOMX_EVAL_EVERY": "10", "OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1"})
     env.update(extra_env or {})
-    r = subprocess.run(["bash", os.path.join(ROOT, "scripts", "cpu", script), "-ep", "8"] + list(args), env=env, stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True, timeout=420)
+    r = _run_group(["bash", os.path.join(ROOT, "scripts", "cpu", script), "-ep", "8"] + list(args), env, 240)
     logs = {f: open(os.path.join(str(tmp_path), f)).read() for f in os.listdir(str(tmp_path)) if f.endswith(".log")}
     assert r.returncode == 0, r.stdout[-2000:] + "\n".join("%s:\n%s" % (k, v[-600:]) for k, v in logs.items())
     accs = [float(x) for x in re.findall(r"Test Acc ([0-9.]+)", logs["party1_worker1.log"])]
@@ -57,8 +84,7 @@ def test_hfa_converges(tmp_path):
     e.update({"LOG_DIR": str(tmp_path), "BASE_PORT": str(_free_base_port()), "GEOMX_SYNTHETIC_SIZE": "2048", "GEOMX_MAX_ITERS": "41",
               "GEOMX_EVAL_EVERY": "10", "OMP_NUM_THREADS": "1", "N_GS": "1"})
     e.update(env)
-    r = subprocess.run(["bash", os.path.join(ROOT, "scripts", "hips_launch.sh"), "cpu", os.path.join(ROOT, "examples", "cnn_hfa.py"), "-ep", "8"],
-                       env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=420)
+    r = _run_group(["bash", os.path.join(ROOT, "scripts", "hips_launch.sh"), "cpu", os.path.join(ROOT, "examples", "cnn_hfa.py"), "-ep", "8"], e, 240)
     log = open(os.path.join(str(tmp_path), "party1_worker1.log")).read()
     assert r.returncode == 0, r.stdout[-1500:] + log[-1500:]
     accs = [float(x) for x in re.findall(r"Test Acc ([0-9.]+)", log)]
