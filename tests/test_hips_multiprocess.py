@@ -30,29 +30,35 @@ def spawn(env, worker=False, extra=None):
 
 
 def collect(procs, timeout=120):
-    outs = []
-    for p in procs:
+    """Wait for every process.  Fails as soon as ONE exits non-zero (the rest would wait at a rendezvous forever) or when the deadline
+    passes; in both cases the workers are asked for their Python stacks (SIGUSR1) before everything is killed."""
+    import signal
+    import time
+    deadline = time.time() + timeout
+    failed = None
+    while True:
+        states = [p.poll() for p in procs]
+        failed = next((p for p, st in zip(procs, states) if st not in (None, 0)), None)
+        if failed is not None or all(st == 0 for st in states) or time.time() > deadline:
+            break
+        time.sleep(0.1)
+    if failed is None and all(p.poll() == 0 for p in procs):
+        return [p.communicate()[0] for p in procs]
+    for q in procs:
+        if q.poll() is None and str(q.args[-1]).endswith("_hips_worker.py"):
+            q.send_signal(signal.SIGUSR1)
+    time.sleep(1.0)
+    for q in procs:
+        if q.poll() is None:
+            q.kill()
+    parts = []
+    for q in procs:
         try:
-            o, _ = p.communicate(timeout=timeout)
-        except subprocess.TimeoutExpired:
-            import signal
-            import time
-            for q in procs:                      # workers dump their Python stacks on SIGUSR1 (tests/_hips_worker.py)
-                if q.poll() is None and q.args[-1].endswith("_hips_worker.py"):
-                    q.send_signal(signal.SIGUSR1)
-            time.sleep(1.0)
-            for q in procs:
-                q.kill()
-            parts = []
-            for q in procs:
-                try:
-                    parts.append((q.communicate(timeout=5)[0] or "")[-1500:])
-                except Exception:
-                    parts.append("")
-            raise AssertionError("timeout; partial output:\n" + "\n-----\n".join(parts))
-        outs.append(o)
-        assert p.returncode == 0, o
-    return outs
+            parts.append((q.communicate(timeout=5)[0] or "")[-1500:])
+        except Exception:
+            parts.append("")
+    why = "process exited with code %s" % failed.returncode if failed is not None else "timeout after %d s" % timeout
+    raise AssertionError("%s; partial output:\n" % why + "\n-----\n".join(parts))
 
 
 def results(outs):
