@@ -44,6 +44,46 @@ def sass_census():
     open(os.path.join(OUT, "sass_census.md"), "w").write("\n".join(lines))
 
 
+def sass_listing():
+    """profiles/sass_listing.md: for the GEMM and the fabric kernels, the first few SASS lines of every tensor-core / TMA / TMEM / NVLink
+    mnemonic (address + instruction), i.e. the listing that proves which hardware paths the binaries use."""
+    import re
+    want = re.compile(r"UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UTCBAR|UTCATOMSWS|LDTM|STTM|SYNCS|ELECT|UBLKCP|MULTIMEM|MEMBAR|ST\.E\.[A-Z0-9.]*STRONG\.SYS|LD\.E\.[A-Z0-9.]*STRONG\.SYS|LDG\.E\.[A-Z0-9.]*STRONG\.SYS|STG\.E\.[A-Z0-9.]*STRONG\.SYS|RED\.E|ATOM\.E|F2FP|HMMA|CCTL")
+    out = ["# SASS listing (cuobjdump -sass of the objects under geomx_b200/build_obj, sm_100a)", "",
+           "For each kernel: up to 3 occurrences of every mnemonic of interest, with its address.  UTCHMMA = tcgen05.mma, UTMALDG = TMA tensor load,",
+           "LDTM = tcgen05.ld (TMEM), UTCBAR = tcgen05.commit -> mbarrier, SYNCS = mbarrier ops, UTCATOMSWS = TMEM alloc; `*.STRONG.SYS` loads/stores and",
+           "MULTIMEM are the NVLink peer / NVSwitch-multicast accesses of the fused HiPS kernels.", ""]
+    for obj, kernels in (("gemm_tcgen05.o", ("gemm_tf32_kernelILi128ELb0ELb0E", "gemm_tf32_kernelILi16ELb0ELb0E", "gemm_tf32_kernelILi32ELb1ELb1E")),
+                         ("hips_fabric.o", ("hips_fsa_ll_kernel", "hips_fsa_step_kernel", "hips_async_step_kernel", "hips_party_allreduce_kernel"))):
+        path = os.path.join(ROOT, "geomx_b200", "build_obj", obj)
+        if not os.path.exists(path):
+            continue
+        txt = subprocess.run(["cuobjdump", "-sass", path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+        cur, seen = None, {}
+        for line in txt.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                cur = next((k for k in kernels if k in m.group(1)), None)
+                if cur:
+                    out += ["", "## %s :: %s" % (obj, m.group(1)[:110]), "```"]
+                    seen = {}
+                continue
+            if cur is None:
+                continue
+            if ".........." in line and seen:
+                out.append("```"); cur = None
+                continue
+            mm = want.search(line)
+            if mm and "/*" in line:
+                key = mm.group(0).split(".")[0] if not mm.group(0).startswith(("ST.", "LD.", "LDG", "STG")) else mm.group(0)
+                if seen.get(key, 0) < 3:
+                    seen[key] = seen.get(key, 0) + 1
+                    out.append(line.split("/* 0x")[0].rstrip())
+        if cur is not None:
+            out.append("```")
+    open(os.path.join(OUT, "sass_listing.md"), "w").write("\n".join(out) + "\n")
+
+
 def copy_logs():
     for name in ("breakdown.log", "breakdown_carve.log", "breakdown_noflush.log", "gemm_phases.log", "gemm_phases3.log", "fab2.log", "fab2b.log",
                  "fab4.log", "fab8.log", "fab2_ll_p1.log", "fab2_ll_p2.log", "fab4_ll.log", "fab4_ll_gs2.log", "fab8_ll.log", "fabric_probe.log",
@@ -109,5 +149,5 @@ def ncu_summaries():
 
 
 if __name__ == "__main__":
-    sass_census(); copy_logs(); ncu_summaries()
+    sass_census(); sass_listing(); copy_logs(); ncu_summaries()
     print(sorted(os.listdir(OUT)))
