@@ -48,11 +48,11 @@ def sass_listing():
     """profiles/sass_listing.md: for the GEMM and the fabric kernels, the first few SASS lines of every tensor-core / TMA / TMEM / NVLink
     mnemonic (address + instruction), i.e. the listing that proves which hardware paths the binaries use."""
     import re
-    want = re.compile(r"UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UTCBAR|UTCATOMSWS|LDTM|STTM|SYNCS|ELECT|UBLKCP|MULTIMEM|MEMBAR|ST\.E\.[A-Z0-9.]*STRONG\.SYS|LD\.E\.[A-Z0-9.]*STRONG\.SYS|LDG\.E\.[A-Z0-9.]*STRONG\.SYS|STG\.E\.[A-Z0-9.]*STRONG\.SYS|RED\.E|ATOM\.E|F2FP|HMMA|CCTL")
+    want = re.compile(r"UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UTCBAR|UTCATOMSWS|LDTM|STTM|SYNCS|ELECT|UBLKCP|MULTIMEM|LDGMC|STGMC|REDGMC|MEMBAR|ST\.E\.[A-Z0-9.]*STRONG\.SYS|LD\.E\.[A-Z0-9.]*STRONG\.SYS|LDG\.E\.[A-Z0-9.]*STRONG\.SYS|STG\.E\.[A-Z0-9.]*STRONG\.SYS|RED\.E|ATOM\.E|F2FP|HMMA|CCTL")
     out = ["# SASS listing (cuobjdump -sass of the objects under geomx_b200/build_obj, sm_100a)", "",
            "For each kernel: up to 3 occurrences of every mnemonic of interest, with its address.  UTCHMMA = tcgen05.mma, UTMALDG = TMA tensor load,",
            "LDTM = tcgen05.ld (TMEM), UTCBAR = tcgen05.commit -> mbarrier, SYNCS = mbarrier ops, UTCATOMSWS = TMEM alloc; `*.STRONG.SYS` loads/stores and",
-           "MULTIMEM are the NVLink peer / NVSwitch-multicast accesses of the fused HiPS kernels.", ""]
+           "LDGMC (= multimem.ld_reduce) are the NVLink peer / NVSwitch accesses of the fused HiPS kernels (multimem.st assembles to STG...STRONG.SYS).", ""]
     for obj, kernels in (("gemm_tcgen05.o", ("gemm_tf32_kernelILi128ELb0ELb0E", "gemm_tf32_kernelILi16ELb0ELb0E", "gemm_tf32_kernelILi32ELb1ELb1E")),
                          ("hips_fabric.o", ("hips_fsa_ll_kernel", "hips_fsa_step_kernel", "hips_async_step_kernel", "hips_party_allreduce_kernel"))):
         path = os.path.join(ROOT, "geomx_b200", "build_obj", obj)
