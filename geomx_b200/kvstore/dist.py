@@ -8,6 +8,10 @@ import os
 def create_dist(name):
     fabric = os.environ.get("GEOMX_FABRIC", "auto").lower()
     has_ps_env = any(k in os.environ for k in ("DMLC_PS_ROOT_URI", "DMLC_ROLE", "DMLC_ROLE_GLOBAL", "DMLC_PS_GLOBAL_ROOT_URI"))
+    if has_ps_env and os.environ.get("DMLC_ROLE") == "worker" and int(os.environ.get("WORLD_SIZE", "1")) > 1 and fabric == "auto":
+        # torchrun inside a box + the reference's worker environment for the box: several boxes, one TCP endpoint per box (kvstore/hybrid.py)
+        from .hybrid import KVStoreHybrid
+        return KVStoreHybrid(name)
     if fabric in ("symm", "nccl") or (fabric == "auto" and not has_ps_env and "RANK" in os.environ):
         from ..parallel.fabric_kvstore import KVStoreFabric
         return KVStoreFabric(name)

@@ -273,3 +273,29 @@ def test_plain_c_api_worker():
     assert len(res) == 2
     for r in res:
         assert r["num_workers"] == 2 and abs(r["vals"][0] - (1.0 - 0.1 * 1.5)) < 1e-6 and abs(r["vals"][1] - (1.0 - 0.2 * 1.5)) < 1e-6
+
+
+def test_hybrid_two_boxes_over_tcp():
+    """KVStoreHybrid: 2 "boxes" x 2 ranks (gloo inside a box — NCCL on real GPUs), one TCP endpoint per box against scheduler + server.
+    Every rank of every box must see  w_0 - t * lr * sum over all 4 ranks of the gradients."""
+    port = free_port()
+    base = {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": port, "DMLC_NUM_SERVER": 1, "DMLC_NUM_WORKER": 2, "DMLC_NUM_ALL_WORKER": 4,
+            "TEST_STANDALONE": 1, "TEST_MODE": "sgd", "TEST_STEPS": 2}
+    procs = [spawn(dict(base, DMLC_ROLE="scheduler")), spawn(dict(base, DMLC_ROLE="server"))]
+    gid = 0
+    for box in range(2):
+        mport = free_port()
+        for r in range(2):
+            e = dict(os.environ); e.update({k: str(v) for k, v in base.items()})
+            e.update({"DMLC_ROLE": "worker", "RANK": str(r), "LOCAL_RANK": str(r), "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(mport),
+                      "TEST_WORKER_GID": str(gid), "CUDA_VISIBLE_DEVICES": ""})
+            gid += 1
+            procs.append(subprocess.Popen([sys.executable, WORKER], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    res = results(collect(procs))
+    assert len(res) == 4
+    gsum = 0.5 * (1 + 2 + 3 + 4)
+    for r in res:
+        assert r["num_workers"] == 2 and r["num_all_workers"] == 4
+        for t, vals in enumerate(r["vals"]):
+            for i, v in enumerate(vals):
+                assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-4, (t, i, v)
