@@ -128,6 +128,8 @@ class KVStoreHybrid(KVStoreBase):
             self._dist.barrier()
         if self._tcp is not None:
             self._tcp.close()
+        if self._box_size > 1 and self._dist.is_initialized():
+            self._dist.destroy_process_group()
 
     def get_num_dead_node(self, node_id=7, timeout=60):
         n = self._tcp.get_num_dead_node(node_id, timeout) if self._leader else 0
