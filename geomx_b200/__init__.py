@@ -33,6 +33,12 @@ from . import module as mod  # noqa: F401
 from . import callback  # noqa: F401
 from . import monitor  # noqa: F401
 from . import test_utils  # noqa: F401
+from . import operator  # noqa: F401
+from . import random  # noqa: F401
+from . import visualization  # noqa: F401
+from . import visualization as viz  # noqa: F401
+from . import image  # noqa: F401
+from . import image as img  # noqa: F401
 from . import profiler  # noqa: F401
 from . import io  # noqa: F401
 from . import recordio  # noqa: F401

@@ -72,3 +72,56 @@ class CenterCrop(Block):
 class RandomFlipLeftRight(Block):
     def forward(self, x):
         return NDArray(x._t.flip(1)) if torch.rand(()) < 0.5 else x
+
+
+class RandomFlipTopBottom(Block):
+    def forward(self, x):
+        import random
+        return NDArray(x._t.flip(0)) if random.random() < 0.5 else x
+
+
+class RandomResizedCrop(Block):
+    """Random area/aspect crop resized to ``size`` (transforms.py RandomResizedCrop), input HWC."""
+
+    def __init__(self, size, scale=(0.08, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), interpolation=1):
+        super().__init__()
+        self._size = (size, size) if isinstance(size, int) else tuple(size)
+        self._scale, self._ratio = scale, ratio
+
+    def forward(self, x):
+        import math
+        import random
+        import torch.nn.functional as TF
+        h, w = x.shape[0], x.shape[1]
+        for _ in range(10):
+            area = random.uniform(*self._scale) * h * w
+            ar = math.exp(random.uniform(math.log(self._ratio[0]), math.log(self._ratio[1])))
+            cw, ch = int(round(math.sqrt(area * ar))), int(round(math.sqrt(area / ar)))
+            if 0 < cw <= w and 0 < ch <= h:
+                x0, y0 = random.randint(0, w - cw), random.randint(0, h - ch)
+                break
+        else:
+            cw, ch, x0, y0 = w, h, 0, 0
+        crop = x._t[y0:y0 + ch, x0:x0 + cw].permute(2, 0, 1).unsqueeze(0).float()
+        out = TF.interpolate(crop, size=(self._size[1], self._size[0]), mode="bilinear", align_corners=False)[0].permute(1, 2, 0)
+        return NDArray(out.to(x._t.dtype) if x._t.dtype.is_floating_point else out.round().clamp(0, 255).to(x._t.dtype))
+
+
+class RandomBrightness(Block):
+    def __init__(self, brightness):
+        super().__init__(); self._b = brightness
+
+    def forward(self, x):
+        import random
+        return NDArray(x._t.float() * (1.0 + random.uniform(-self._b, self._b)))
+
+
+class RandomContrast(Block):
+    def __init__(self, contrast):
+        super().__init__(); self._c = contrast
+
+    def forward(self, x):
+        import random
+        t = x._t.float()
+        alpha = 1.0 + random.uniform(-self._c, self._c)
+        return NDArray(t * alpha + t.mean() * (1 - alpha))

@@ -1,0 +1,228 @@
+"""``mx.image`` — image decoding, resizing / cropping helpers, augmenters and ``ImageIter`` (parity: python/mxnet/image/image.py: imread :45,
+imdecode :85, scale_down, resize_short :197, fixed_crop :258, random_crop :291, center_crop :331, color_normalize :380, Augmenter classes
+:480-900, CreateAugmenter :904, ImageIter :1010-1300).  Decoding uses Pillow (the reference uses OpenCV); arrays are HWC uint8/float NDArrays
+like the reference's."""
+from __future__ import annotations
+
+import os
+import random as _pyrandom
+
+import numpy as np
+import torch
+
+from . import io as _io
+from . import ndarray as nd
+from .ndarray import NDArray
+
+__all__ = ["imread", "imdecode", "imresize", "resize_short", "fixed_crop", "center_crop", "random_crop", "color_normalize", "Augmenter",
+           "ResizeAug", "ForceResizeAug", "RandomCropAug", "CenterCropAug", "HorizontalFlipAug", "CastAug", "ColorNormalizeAug", "BrightnessJitterAug",
+           "CreateAugmenter", "ImageIter"]
+
+
+def _pil():
+    from PIL import Image
+    return Image
+
+
+def imdecode(buf, flag=1, to_rgb=1):
+    import io
+    img = _pil().open(io.BytesIO(bytes(buf)))
+    img = img.convert("RGB" if flag else "L")
+    arr = np.asarray(img)
+    if arr.ndim == 2:
+        arr = arr[:, :, None]
+    if flag and not to_rgb:
+        arr = arr[:, :, ::-1]
+    return nd.array(np.ascontiguousarray(arr), dtype="uint8")
+
+
+def imread(filename, flag=1, to_rgb=1):
+    with open(filename, "rb") as f:
+        return imdecode(f.read(), flag, to_rgb)
+
+
+def imresize(src, w, h, interp=1):
+    arr = src.asnumpy()
+    squeeze = arr.shape[2] == 1
+    img = _pil().fromarray(arr[:, :, 0] if squeeze else arr.astype(np.uint8))
+    out = np.asarray(img.resize((int(w), int(h)), _pil().BILINEAR if interp == 1 else _pil().NEAREST))
+    return nd.array(out[:, :, None] if squeeze else out, dtype=str(arr.dtype))
+
+
+def resize_short(src, size, interp=1):
+    h, w = src.shape[:2]
+    if h > w:
+        return imresize(src, size, int(h * size / w), interp)
+    return imresize(src, int(w * size / h), size, interp)
+
+
+def fixed_crop(src, x0, y0, w, h, size=None, interp=1):
+    out = NDArray(src._t[y0:y0 + h, x0:x0 + w].clone())
+    if size is not None and (w, h) != tuple(size):
+        out = imresize(out, size[0], size[1], interp)
+    return out
+
+
+def center_crop(src, size, interp=1):
+    h, w = src.shape[:2]
+    nw, nh = min(w, size[0]), min(h, size[1])
+    x0, y0 = (w - nw) // 2, (h - nh) // 2
+    return fixed_crop(src, x0, y0, nw, nh, size, interp), (x0, y0, nw, nh)
+
+
+def random_crop(src, size, interp=1):
+    h, w = src.shape[:2]
+    nw, nh = min(w, size[0]), min(h, size[1])
+    x0, y0 = _pyrandom.randint(0, w - nw), _pyrandom.randint(0, h - nh)
+    return fixed_crop(src, x0, y0, nw, nh, size, interp), (x0, y0, nw, nh)
+
+
+def color_normalize(src, mean, std=None):
+    out = src.astype("float32") - (mean if isinstance(mean, NDArray) else nd.array(np.asarray(mean, dtype=np.float32)))
+    if std is not None:
+        out = out / (std if isinstance(std, NDArray) else nd.array(np.asarray(std, dtype=np.float32)))
+    return out
+
+
+class Augmenter:
+    def __init__(self, **kwargs):
+        self._kwargs = kwargs
+
+    def dumps(self):
+        import json
+        return json.dumps([self.__class__.__name__.lower(), self._kwargs])
+
+    def __call__(self, src):
+        raise NotImplementedError
+
+
+class ResizeAug(Augmenter):
+    def __init__(self, size, interp=1): super().__init__(size=size, interp=interp); self.size, self.interp = size, interp
+    def __call__(self, src): return resize_short(src, self.size, self.interp)
+
+
+class ForceResizeAug(Augmenter):
+    def __init__(self, size, interp=1): super().__init__(size=size, interp=interp); self.size, self.interp = size, interp
+    def __call__(self, src): return imresize(src, self.size[0], self.size[1], self.interp)
+
+
+class RandomCropAug(Augmenter):
+    def __init__(self, size, interp=1): super().__init__(size=size, interp=interp); self.size, self.interp = size, interp
+    def __call__(self, src): return random_crop(src, self.size, self.interp)[0]
+
+
+class CenterCropAug(Augmenter):
+    def __init__(self, size, interp=1): super().__init__(size=size, interp=interp); self.size, self.interp = size, interp
+    def __call__(self, src): return center_crop(src, self.size, self.interp)[0]
+
+
+class HorizontalFlipAug(Augmenter):
+    def __init__(self, p): super().__init__(p=p); self.p = p
+    def __call__(self, src): return NDArray(src._t.flip(1)) if _pyrandom.random() < self.p else src
+
+
+class CastAug(Augmenter):
+    def __init__(self, typ="float32"): super().__init__(type=typ); self.typ = typ
+    def __call__(self, src): return src.astype(self.typ)
+
+
+class ColorNormalizeAug(Augmenter):
+    def __init__(self, mean, std): super().__init__(mean=list(np.ravel(mean)), std=None if std is None else list(np.ravel(std))); self.mean, self.std = mean, std
+    def __call__(self, src): return color_normalize(src, self.mean, self.std)
+
+
+class BrightnessJitterAug(Augmenter):
+    def __init__(self, brightness): super().__init__(brightness=brightness); self.brightness = brightness
+    def __call__(self, src): return src.astype("float32") * (1.0 + _pyrandom.uniform(-self.brightness, self.brightness))
+
+
+def CreateAugmenter(data_shape, resize=0, rand_crop=False, rand_resize=False, rand_mirror=False, mean=None, std=None, brightness=0, inter_method=1,
+                    **kwargs):
+    augs = []
+    if resize > 0:
+        augs.append(ResizeAug(resize, inter_method))
+    crop = (data_shape[2], data_shape[1])
+    augs.append(RandomCropAug(crop, inter_method) if rand_crop else CenterCropAug(crop, inter_method))
+    if rand_mirror:
+        augs.append(HorizontalFlipAug(0.5))
+    augs.append(CastAug())
+    if brightness:
+        augs.append(BrightnessJitterAug(brightness))
+    if mean is True:
+        mean = np.array([123.68, 116.28, 103.53])
+    if std is True:
+        std = np.array([58.395, 57.12, 57.375])
+    if mean is not None:
+        augs.append(ColorNormalizeAug(mean, std))
+    return augs
+
+
+class ImageIter(_io.DataIter):
+    """Images from a RecordIO file (``path_imgrec`` [+ ``path_imgidx``]) or an image list (``imglist`` / ``path_imglist`` + ``path_root``)
+    through a list of augmenters; yields NCHW float batches."""
+
+    def __init__(self, batch_size, data_shape, label_width=1, path_imgrec=None, path_imglist=None, path_root="", path_imgidx=None, shuffle=False,
+                 aug_list=None, imglist=None, data_name="data", label_name="softmax_label", **kwargs):
+        super().__init__(batch_size)
+        from . import recordio
+        self.data_shape, self.label_width, self.shuffle = tuple(data_shape), label_width, shuffle
+        self.data_name, self.label_name = data_name, label_name
+        self.auglist = aug_list if aug_list is not None else CreateAugmenter(data_shape, **kwargs)
+        self._rec, self._items = None, []
+        if path_imgrec:
+            if path_imgidx:
+                self._rec = recordio.MXIndexedRecordIO(path_imgidx, path_imgrec, "r")
+                self._items = list(self._rec.keys)
+            else:
+                r = recordio.MXRecordIO(path_imgrec, "r")
+                while True:
+                    raw = r.read()
+                    if raw is None:
+                        break
+                    self._items.append(raw)
+        else:
+            entries = imglist
+            if entries is None:
+                entries = []
+                for line in open(path_imglist):
+                    p = line.strip().split("\t")
+                    entries.append([float(x) for x in p[1:-1]] + [p[-1]])
+            for e in entries:
+                self._items.append((np.asarray(e[:-1], dtype=np.float32), os.path.join(path_root, e[-1])))
+        self.reset()
+
+    @property
+    def provide_data(self): return [_io.DataDesc(self.data_name, (self.batch_size,) + self.data_shape)]
+    @property
+    def provide_label(self): return [_io.DataDesc(self.label_name, (self.batch_size,) if self.label_width == 1 else (self.batch_size, self.label_width))]
+
+    def reset(self):
+        self._order = list(range(len(self._items)))
+        if self.shuffle:
+            _pyrandom.shuffle(self._order)
+        self._cur = 0
+
+    def _sample(self, i):
+        from . import recordio
+        it = self._items[i]
+        if self._rec is not None:
+            header, img = recordio.unpack_img(self._rec.read_idx(it), iscolor=1 if self.data_shape[0] == 3 else 0)
+            label, arr = header.label, nd.array(img if img.ndim == 3 else img[:, :, None], dtype="uint8")
+        elif isinstance(it, bytes):
+            header, img = recordio.unpack_img(it, iscolor=1 if self.data_shape[0] == 3 else 0)
+            label, arr = header.label, nd.array(img if img.ndim == 3 else img[:, :, None], dtype="uint8")
+        else:
+            label, arr = (it[0][0] if self.label_width == 1 else it[0]), imread(it[1], flag=1 if self.data_shape[0] == 3 else 0)
+        for aug in self.auglist:
+            arr = aug(arr)
+        return arr._t.permute(2, 0, 1).float(), label
+
+    def next(self):
+        if self._cur >= len(self._order):
+            raise StopIteration
+        idx = self._order[self._cur:self._cur + self.batch_size]
+        pad = self.batch_size - len(idx)
+        idx = idx + self._order[:pad]
+        self._cur += self.batch_size
+        xs, ys = zip(*[self._sample(i) for i in idx])
+        return _io.DataBatch([NDArray(torch.stack(xs))], [nd.array(np.asarray(ys, dtype=np.float32))], pad=pad)

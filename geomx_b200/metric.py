@@ -147,7 +147,85 @@ class CompositeEvalMetric(EvalMetric):
         return names, values
 
 
-_REG = {"acc": Accuracy, "accuracy": Accuracy, "top_k_accuracy": TopKAccuracy, "mae": MAE, "mse": MSE, "rmse": RMSE,
+class F1(EvalMetric):
+    """Binary F1 (python/mxnet/metric.py F1 :560-650): ``average='macro'`` averages the per-batch scores, ``'micro'`` pools the counts."""
+
+    def __init__(self, name="f1", average="macro", **kw):
+        self.average = average
+        super().__init__(name, **kw)
+
+    def reset(self):
+        super().reset()
+        self.tp = self.fp = self.fn = 0.0
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).reshape(-1).long(), _t(p)
+            pred = p.argmax(dim=1) if p.dim() > 1 else (p > 0.5).long()
+            l = l.to(pred.device)
+            tp, fp, fn = float(((pred == 1) & (l == 1)).sum()), float(((pred == 1) & (l == 0)).sum()), float(((pred == 0) & (l == 1)).sum())
+            if self.average == "macro":
+                prec, rec = tp / max(tp + fp, 1e-12), tp / max(tp + fn, 1e-12)
+                self.sum_metric += 2 * prec * rec / max(prec + rec, 1e-12); self.num_inst += 1
+            else:
+                self.tp += tp; self.fp += fp; self.fn += fn
+                prec, rec = self.tp / max(self.tp + self.fp, 1e-12), self.tp / max(self.tp + self.fn, 1e-12)
+                self.sum_metric, self.num_inst = 2 * prec * rec / max(prec + rec, 1e-12), 1
+
+
+class Perplexity(EvalMetric):
+    """exp(mean negative log-likelihood) with an optional ``ignore_label`` (metric.py Perplexity :760-840)."""
+
+    def __init__(self, ignore_label=None, axis=-1, name="perplexity", **kw):
+        self.ignore_label, self.axis = ignore_label, axis
+        super().__init__(name, **kw)
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).reshape(-1).long(), _t(p)
+            p = p.reshape(-1, p.shape[-1])
+            prob = p[torch.arange(l.numel(), device=p.device), l.to(p.device)]
+            if self.ignore_label is not None:
+                keep = l.to(p.device) != self.ignore_label
+                prob = prob[keep]
+            self.sum_metric += float((-torch.log(prob.clamp_min(1e-10))).sum()); self.num_inst += prob.numel()
+
+    def get(self):
+        return self.name, (float("nan") if self.num_inst == 0 else math.exp(self.sum_metric / self.num_inst))
+
+
+class PearsonCorrelation(EvalMetric):
+    def __init__(self, name="pearsonr", **kw):
+        super().__init__(name, **kw)
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).reshape(-1).double(), _t(p).reshape(-1).double()
+            self.sum_metric += float(torch.corrcoef(torch.stack([l.to(p.device), p]))[0, 1]); self.num_inst += 1
+
+
+class CustomMetric(EvalMetric):
+    """Wraps ``feval(label_numpy, pred_numpy) -> float | (sum, count)`` (metric.py CustomMetric / np)."""
+
+    def __init__(self, feval, name=None, allow_extra_outputs=False, **kw):
+        self._feval = feval
+        super().__init__(name or getattr(feval, "__name__", "custom"), **kw)
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            r = self._feval(_t(l).detach().cpu().numpy(), _t(p).detach().cpu().numpy())
+            if isinstance(r, tuple):
+                self.sum_metric += r[0]; self.num_inst += r[1]
+            else:
+                self.sum_metric += r; self.num_inst += 1
+
+
+def np(numpy_feval, name=None, allow_extra_outputs=False):
+    """Create a metric from a numpy function (``mx.metric.np``)."""
+    return CustomMetric(numpy_feval, name, allow_extra_outputs)
+
+
+_REG = {"f1": F1, "perplexity": Perplexity, "pearsonr": PearsonCorrelation, "acc": Accuracy, "accuracy": Accuracy, "top_k_accuracy": TopKAccuracy, "mae": MAE, "mse": MSE, "rmse": RMSE,
         "ce": CrossEntropy, "cross-entropy": CrossEntropy, "loss": Loss}
 
 
@@ -155,7 +233,7 @@ def create(metric, *args, **kwargs):
     if isinstance(metric, EvalMetric):
         return metric
     if callable(metric):
-        raise NotImplementedError("custom callable metrics: subclass EvalMetric")
+        return CustomMetric(metric, *args, **kwargs)
     if isinstance(metric, list):
         c = CompositeEvalMetric()
         for m in metric:

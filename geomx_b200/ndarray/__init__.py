@@ -10,3 +10,9 @@ for _n in _op_lib.__all__:
     if _n not in globals():
         globals()[_n] = getattr(_op_lib, _n)
 del _n
+
+
+def Custom(*inputs, **kwargs):
+    """``mx.nd.Custom`` — run a registered ``mx.operator.CustomOp`` (see geomx_b200/operator.py)."""
+    from ..operator import Custom as _custom
+    return _custom(*inputs, **kwargs)
