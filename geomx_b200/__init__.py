@@ -39,6 +39,7 @@ from . import visualization  # noqa: F401
 from . import visualization as viz  # noqa: F401
 from . import image  # noqa: F401
 from . import image as img  # noqa: F401
+from . import rtc  # noqa: F401
 from . import profiler  # noqa: F401
 from . import io  # noqa: F401
 from . import recordio  # noqa: F401

@@ -63,3 +63,17 @@ def test_image_pipeline(tmp_path):
     batches = list(it)
     assert len(batches) == 3 and batches[0].data[0].shape == (2, 3, 16, 16) and batches[2].pad == 1
     assert batches[0].label[0].asnumpy().tolist() == [0.0, 1.0]
+
+
+def test_rtc_compiles_for_sm100a_without_a_gpu():
+    """mx.rtc: NVRTC produces an sm_100a cubin on a GPU-less box; syntax errors surface as MXNetError with the compiler log."""
+    import pytest
+    try:
+        mod = mx.rtc.CudaModule('extern "C" __global__ void axpy(const float* x, float* y, float a, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] += a * x[i]; }')
+    except ImportError:
+        pytest.skip("cuda-python not installed")
+    assert len(mod.cubin) > 1000
+    k = mod.get_kernel("axpy", "const float *x, float *y, float a, int n")
+    assert [p[0] for p in k._params] == [True, True, False, False]
+    with pytest.raises(mx.MXNetError):
+        mx.rtc.CudaModule("this is not CUDA")

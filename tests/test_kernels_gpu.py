@@ -341,3 +341,15 @@ def test_gemm_with_fused_maxpool_epilogue():
     # geometry the in-warp pooling cannot express -> clean refusal (the caller falls back)
     A = torch.randn(2 * 6 * 6, 16, device="cuda"); Wt = torch.randn(16, 16, device="cuda")
     assert not n.gemm_pool(A, Wt, torch.empty(2, 16, 3, 3, device="cuda"), torch.empty(2, 16, 3, 3, dtype=torch.uint8, device="cuda"), 6, 6)
+
+
+@pytest.mark.gpu
+def test_rtc_launch():
+    """mx.rtc end to end: NVRTC cubin -> driver module -> launch on the current stream."""
+    import geomx_b200 as mx
+    mod = mx.rtc.CudaModule('extern "C" __global__ void axpy(const float* x, float* y, float a, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] += a * x[i]; }')
+    k = mod.get_kernel("axpy", "const float *x, float *y, float a, int n")
+    x = mx.nd.array(torch.arange(1000, dtype=torch.float32), ctx=mx.gpu(0)); y = mx.nd.ones((1000,), ctx=mx.gpu(0))
+    k.launch([x, y, 2.0, 1000], mx.gpu(0), (4, 1, 1), (256, 1, 1))
+    torch.cuda.synchronize()
+    assert torch.equal(y._t.cpu(), 1 + 2 * torch.arange(1000, dtype=torch.float32))
