@@ -216,10 +216,12 @@ def main():
             "metric": "cnn.py samples/sec (whole box, device-timed, max over ranks)",
             "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(dev_ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (fp32 storage, TF32 tcgen05 multiply, fp32 accumulate; reference is fp32 SGEMM)", "data": "synthetic",
+            "dtype": "tf32", "data": "synthetic",
             "impl": args.impl,
             "config": {"model": "examples/cnn.py MNIST CNN (Conv16k5-Pool-Conv32k5-Pool-Dense256-Dense128-Dense10, 178762 params)",
                        "global_batch": B * world, "per_gpu_batch": B, "seq_len": None, "kvstore": args.mode,
+                       "precision": "fp32 storage and accumulation, TF32 tcgen05 multiplies (10-bit mantissa: above the bf16 floor; the reference "
+                                    "is fp32 SGEMM), fp32 optimizer state and wire format",
                        "parallelism": "hips-dp%d: %d part%s x %d worker%s, global PS on rank%s %s" % (
                            world, topo.num_parties, "y" if topo.num_parties == 1 else "ies", topo.party_size, "" if topo.party_size == 1 else "s",
                            "" if topo.num_gs == 1 else "s", topo.gs_ranks),
