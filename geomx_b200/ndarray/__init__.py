@@ -4,7 +4,7 @@ from .ndarray import *  # noqa: F401,F403
 from .ndarray import NDArray  # noqa: F401
 from .utils import load, load_bytes, save, save_async, save_bytes  # noqa: F401
 from . import sparse  # noqa: F401,E402
-from .sparse import RowSparseNDArray  # noqa: F401,E402
+from .sparse import CSRNDArray, RowSparseNDArray  # noqa: F401,E402
 from . import op_lib as _op_lib  # noqa: E402
 for _n in _op_lib.__all__:
     if _n not in globals():

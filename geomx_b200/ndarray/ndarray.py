@@ -243,11 +243,11 @@ class NDArray:
         return NDArray(self._t.expand(*shape))
 
     def tostype(self, stype):
-        if stype == "row_sparse":
+        if stype in ("row_sparse", "csr"):
             from . import sparse
-            return sparse.cast_storage(self, "row_sparse")
+            return sparse.cast_storage(self, stype)
         if stype != "default":
-            raise MXNetError("storage type %s is not supported (default / row_sparse)" % stype)
+            raise MXNetError("storage type %s is not supported (default / row_sparse / csr)" % stype)
         return self
 
     # ---- autograd -------------------------------------------------------------------------

@@ -92,6 +92,73 @@ class RowSparseNDArray:
         return self.tostype("default") + other
 
 
+class CSRNDArray:
+    """Compressed sparse rows (``python/mxnet/ndarray/sparse.py`` CSRNDArray :260-560): ``data`` (nnz,), ``indices`` (nnz,) column ids,
+    ``indptr`` (rows+1,).  Enough for storage conversion, (de)serialisation, slicing by rows and ``dot(csr, dense)``."""
+    stype = "csr"
+
+    def __init__(self, data, indices, indptr, shape):
+        self.data, self.indices, self.indptr, self._shape = data, indices, indptr, tuple(int(s) for s in shape)
+
+    shape = property(lambda self: self._shape)
+    dtype = property(lambda self: self.data.dtype)
+    context = property(lambda self: self.data.context)
+    ctx = context
+
+    def __repr__(self):
+        return "<CSRNDArray %dx%d @%s nnz=%d>" % (self._shape[0], self._shape[1], self.context, self.data.shape[0])
+
+    def _torch(self):
+        return torch.sparse_csr_tensor(self.indptr._t.long(), self.indices._t.long(), self.data._t, size=self._shape, check_invariants=True)
+
+    def tostype(self, stype):
+        if stype == "csr":
+            return self
+        dense = NDArray(self._torch().to_dense())
+        return dense if stype == "default" else cast_storage(dense, stype)
+
+    todense = lambda self: self.tostype("default")
+    def asnumpy(self): return self.tostype("default").asnumpy()
+    def copy(self): return CSRNDArray(self.data.copy(), self.indices.copy(), self.indptr.copy(), self._shape)
+
+    def __getitem__(self, key):
+        if isinstance(key, int):
+            key = slice(key, key + 1)
+        start, stop, step = key.indices(self._shape[0])
+        if step != 1:
+            raise MXNetError("CSRNDArray only supports contiguous row slices")
+        ptr = self.indptr._t.long()
+        lo, hi = int(ptr[start]), int(ptr[stop])
+        return CSRNDArray(NDArray(self.data._t[lo:hi].clone()), NDArray(self.indices._t[lo:hi].clone()), NDArray(ptr[start:stop + 1] - lo),
+                          (stop - start, self._shape[1]))
+
+
+def csr_matrix(arg1, shape=None, ctx=None, dtype=None):
+    """``(data, indices, indptr)`` + shape, or a dense array-like."""
+    if isinstance(arg1, CSRNDArray):
+        return arg1.copy()
+    if isinstance(arg1, tuple) and len(arg1) == 3:
+        data, indices, indptr = arg1
+        mk = lambda x, dt: x if isinstance(x, NDArray) else _dense_array(np.asarray(x), ctx=ctx, dtype=dt)
+        if shape is None:
+            raise MXNetError("csr_matrix((data, indices, indptr)) needs shape=")
+        return CSRNDArray(mk(data, dtype or "float32"), mk(indices, "int64"), mk(indptr, "int64"), shape)
+    dense = arg1 if isinstance(arg1, NDArray) else _dense_array(arg1, ctx=ctx, dtype=dtype or "float32")
+    return cast_storage(dense, "csr")
+
+
+def dot(lhs, rhs, transpose_a=False, transpose_b=False):
+    """``dot(csr, dense)`` / ``dot(csr.T, dense)`` (src/operator/tensor/dot-inl.h sparse paths); dense operands fall through to ``nd.dot``."""
+    if isinstance(lhs, CSRNDArray):
+        a = lhs._torch()
+        r = rhs._t.t() if transpose_b else rhs._t
+        if transpose_a:
+            return NDArray(torch.matmul(a.to_dense().t(), r))
+        return NDArray(torch.matmul(a, r))
+    from . import ndarray as _nd
+    return _nd.dot(lhs, rhs, transpose_a, transpose_b)
+
+
 def row_sparse_array(arg1, shape=None, ctx=None, dtype=None):
     """``(data, indices)`` + shape, a dense array-like (rows that are entirely zero are dropped), or another RowSparseNDArray."""
     if isinstance(arg1, RowSparseNDArray):
@@ -112,8 +179,16 @@ def row_sparse_array(arg1, shape=None, ctx=None, dtype=None):
 def cast_storage(arr, stype):
     if isinstance(arr, RowSparseNDArray):
         return arr.tostype(stype)
+    if isinstance(arr, CSRNDArray):
+        return arr.tostype(stype)
     if stype == "default":
         return arr
+    if stype == "csr":
+        t = arr._t
+        if t.dim() != 2:
+            raise MXNetError("csr storage needs a 2-D array")
+        sp = t.to_sparse_csr()
+        return CSRNDArray(NDArray(sp.values().clone()), NDArray(sp.col_indices().clone()), NDArray(sp.crow_indices().clone()), t.shape)
     if stype != "row_sparse":
         raise MXNetError("cast_storage to %s is not supported" % stype)
     t = arr._t
@@ -125,6 +200,10 @@ def zeros(stype, shape, ctx=None, dtype="float32"):
     from . import ndarray as _nd
     if stype == "default":
         return _nd.zeros(shape, ctx=ctx, dtype=dtype)
+    if stype == "csr":
+        ctx = ctx or current_context()
+        return CSRNDArray(_nd.zeros((0,), ctx=ctx, dtype=dtype), _nd.zeros((0,), ctx=ctx, dtype="int64"), _nd.zeros((shape[0] + 1,), ctx=ctx, dtype="int64"),
+                          tuple(shape))
     if stype != "row_sparse":
         raise MXNetError("zeros(%s) is not supported" % stype)
     ctx = ctx or current_context()

@@ -32,7 +32,36 @@ _FLAG2NP = {0: np.float32, 1: np.float64, 2: np.float16, 3: np.uint8, 4: np.int3
 _NP2FLAG = {np.dtype(v).name: k for k, v in _FLAG2NP.items()}
 
 
-def _enc_array(a: NDArray) -> bytes:
+def _np_of(a):
+    t = a._t.detach()
+    if t.dtype == torch.bfloat16:
+        t = t.float()
+    return np.ascontiguousarray(t.cpu().numpy())
+
+
+def _enc_shape(shape):
+    return struct.pack("<I", len(shape)) + struct.pack("<%dq" % len(shape), *shape)
+
+
+def _enc_sparse(a) -> bytes:
+    """NDArray V2 record of a sparse array (ndarray.cc:1583-1651): stype, storage shape, shape, context, dtype, aux types+shapes, data, aux."""
+    from .sparse import CSRNDArray
+    csr = isinstance(a, CSRNDArray)
+    data = _np_of(a.data)
+    auxs = [_np_of(a.indptr).astype(np.int64), _np_of(a.indices).astype(np.int64)] if csr else [_np_of(a.indices).astype(np.int64)]
+    ctx = a.context
+    out = [struct.pack("<Ii", V2_MAGIC, 2 if csr else 1), _enc_shape(data.shape), _enc_shape(a.shape),
+           struct.pack("<ii", ctx.device_typeid, ctx.device_id), struct.pack("<i", _NP2FLAG[data.dtype.name])]
+    for x in auxs:
+        out.append(struct.pack("<i", 6) + _enc_shape(x.shape))
+    out.append(data.tobytes())
+    out += [x.tobytes() for x in auxs]
+    return b"".join(out)
+
+
+def _enc_array(a) -> bytes:
+    if getattr(a, "stype", "default") in ("row_sparse", "csr"):
+        return _enc_sparse(a)
     t = a._t.detach()
     if t.dtype == torch.bfloat16:
         t = t.float()
@@ -101,17 +130,13 @@ def _dec_array(r: _Reader, restore_ctx=False) -> NDArray:
         for aflag, ashape in aux:
             adt = np.dtype(_FLAG2NP[aflag]); an = int(np.prod(ashape)) if len(ashape) else 0
             auxd.append(np.frombuffer(r.raw(an * adt.itemsize), dtype=adt).reshape(ashape).copy())
-        if stype == 1:  # row_sparse -> densify
-            dense = np.zeros(shape, dtype=dt)
-            if len(auxd[0]):
-                dense[auxd[0].astype(np.int64)] = data
-            data = dense
-        elif stype == 2:  # csr: aux = (indptr, indices)
-            dense = np.zeros(shape, dtype=dt); indptr, indices = auxd
-            for row in range(shape[0]):
-                s, e = int(indptr[row]), int(indptr[row + 1])
-                dense[row, indices[s:e].astype(np.int64)] = data[s:e]
-            data = dense
+        if stype == 1:  # row_sparse: aux = (row ids,)
+            from .sparse import RowSparseNDArray
+            return RowSparseNDArray(NDArray(torch.from_numpy(data)), NDArray(torch.from_numpy(auxd[0].astype(np.int64))), shape)
+        if stype == 2:  # csr: aux = (indptr, indices)
+            from .sparse import CSRNDArray
+            return CSRNDArray(NDArray(torch.from_numpy(data)), NDArray(torch.from_numpy(auxd[1].astype(np.int64))),
+                              NDArray(torch.from_numpy(auxd[0].astype(np.int64))), shape)
     else:
         if magic == V1_MAGIC:
             shape = _dec_shape64(r)
@@ -132,14 +157,14 @@ def _dec_array(r: _Reader, restore_ctx=False) -> NDArray:
 
 
 def save_bytes(data) -> bytes:
-    if isinstance(data, NDArray):
+    if isinstance(data, NDArray) or getattr(data, "stype", None) in ("row_sparse", "csr"):
         data = [data]
     if isinstance(data, dict):
         names, arrays = list(data.keys()), list(data.values())
     else:
         names, arrays = [], list(data)
     for a in arrays:
-        if not isinstance(a, NDArray):
+        if not isinstance(a, NDArray) and getattr(a, "stype", None) not in ("row_sparse", "csr"):
             raise MXNetError("save only accepts NDArray, list of NDArray or dict of str->NDArray")
     out = [struct.pack("<QQQ", LIST_MAGIC, 0, len(arrays))]
     out += [_enc_array(a) for a in arrays]

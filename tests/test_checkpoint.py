@@ -92,3 +92,22 @@ def test_block_save_load_and_checkpoint(tmp_path):
     assert set(arg2) == set(args) and aux2 == {}
     with pytest.raises(mx.base.MXNetError):
         ndu.load_bytes(b"garbage!" * 4)
+
+
+def test_sparse_arrays_roundtrip_in_params_format(tmp_path):
+    """row_sparse and csr arrays are written as V2 sparse records (stype 1 / 2 with storage shape + aux arrays, ndarray.cc:1583-1651) and read
+    back as sparse objects; csr supports row slices and dot(csr, dense)."""
+    import numpy as np
+    import geomx_b200 as mx
+    dense = np.zeros((6, 4), dtype=np.float32); dense[1] = [1, 0, 2, 0]; dense[4] = [0, 3, 0, 4]
+    rs = mx.nd.array(dense).tostype("row_sparse"); csr = mx.nd.array(dense).tostype("csr")
+    assert csr.indptr.asnumpy().tolist() == [0, 0, 2, 2, 2, 4, 4] and csr.indices.asnumpy().tolist() == [0, 2, 1, 3]
+    f = str(tmp_path / "sparse.params")
+    mx.nd.save(f, {"rs": rs, "csr": csr, "dense": mx.nd.array(dense)})
+    back = mx.nd.load(f)
+    assert back["rs"].stype == "row_sparse" and back["rs"].indices.asnumpy().tolist() == [1, 4] and np.array_equal(back["rs"].asnumpy(), dense)
+    assert back["csr"].stype == "csr" and np.array_equal(back["csr"].asnumpy(), dense) and np.array_equal(back["dense"].asnumpy(), dense)
+    assert np.array_equal(csr[1:5].asnumpy(), dense[1:5])
+    w = np.arange(8, dtype=np.float32).reshape(4, 2)
+    assert np.allclose(mx.nd.sparse.dot(csr, mx.nd.array(w)).asnumpy(), dense @ w)
+    assert np.allclose(mx.nd.sparse.dot(csr, mx.nd.array(np.ones((6, 3), dtype=np.float32)), transpose_a=True).asnumpy(), dense.T @ np.ones((6, 3)))
