@@ -26,6 +26,9 @@ from . import kvstore as kv  # noqa: F401
 from . import gluon  # noqa: F401
 from . import metric  # noqa: F401
 from . import model  # noqa: F401
+from . import name  # noqa: F401
+from . import attribute  # noqa: F401
+from .attribute import AttrScope  # noqa: F401
 from . import symbol  # noqa: F401
 from . import symbol as sym  # noqa: F401
 from . import module  # noqa: F401

@@ -22,15 +22,9 @@ __all__ = ["Symbol", "Variable", "var", "Group", "load_json", "FullyConnected", 
            "BatchNorm", "Dropout", "SoftmaxOutput", "LinearRegressionOutput", "Concat", "elemwise_add", "relu", "softmax", "log_softmax",
            "reshape", "Executor"]
 
-_counter = {}
-
-
 def _auto_name(op, name):
-    if name:
-        return name
-    i = _counter.get(op, 0)
-    _counter[op] = i + 1
-    return "%s%d" % (op.lower(), i)
+    from .name import NameManager
+    return NameManager.current().get(name, op.lower())
 
 
 def _pair(v, default=None):
@@ -42,6 +36,16 @@ def _pair(v, default=None):
 class Symbol:
     def __init__(self, op, name, inputs=(), attrs=None, aux=()):
         self.op, self.name, self.inputs, self.attrs, self.aux = op, name, list(inputs), dict(attrs or {}), list(aux)
+        from .attribute import AttrScope
+        scope = AttrScope.current().get()
+        if scope:                                         # user annotations (ctx_group, lr_mult, ...) live under a "__attr__" sub-dict
+            self.attrs.setdefault("__attr__", {}).update(scope)
+
+    def list_attr(self):
+        return dict(self.attrs.get("__attr__", {}))
+
+    def attr_dict(self):
+        return {s.name: s.list_attr() for s in self._topo() if s.attrs.get("__attr__")}
 
     # ---- composition sugar
     def __add__(self, o): return _binary("_plus", self, o)
