@@ -180,14 +180,18 @@ class KVStoreFabric(KVStoreBase):
         self._fabric.layout.slots[i].priority = priority
 
     def _pull(self, key, outs, priority):
-        self._finalize()
+        # lazy, and NOT finalising: the reference's scripts interleave `kv.init(i, w); kv.pull(i, w)` key by key (examples/cnn.py:89-96), so
+        # the arena can only be laid out when a pulled array is first read (or pushed to) — by then every key has been initialised
+        if key not in self._key_index:
+            raise MXNetError("key %s has not been initialised" % key)
         self._pulls.append((self._key_index[key], outs))
         for o in outs:
             o._pending = self.flush
 
     def flush(self):
-        if self._fabric is None or (not self._pushed and not self._pulls):
+        if not self._pushed and not self._pulls:
             return
+        self._finalize()
         f = self._fabric
         pulls, self._pulls = self._pulls, []
         for _, outs in pulls:
