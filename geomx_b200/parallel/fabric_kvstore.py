@@ -133,8 +133,9 @@ class KVStoreFabric(KVStoreBase):
         self._init_vals[key] = value
 
     def _finalize(self):
-        if self._fabric is not None:
+        if self._fabric is not None or getattr(self, "_finalizing", False):
             return
+        self._finalizing = True
         topo = self._topo
         if topo.world > 1:
             import torch.distributed as dist
@@ -145,7 +146,7 @@ class KVStoreFabric(KVStoreBase):
         f = HipsFabric(layout, topo, self._device, self._opt_spec)
         for i, (key, _) in enumerate(self._keys):
             v = self._init_vals[key]
-            f.param_view(i).copy_(v._t.detach().to(self._device))
+            f.param_view(i).copy_(v._data.detach().to(self._device))      # raw tensor: `_t` would run the pending-pull hook (re-entrancy)
         if topo.world > 1:
             import torch.distributed as dist
             dist.broadcast(f.param.tensor, src=0)
@@ -160,6 +161,7 @@ class KVStoreFabric(KVStoreBase):
                     v._data.requires_grad_(True)
         self._init_vals = None
         self._fabric = f
+        self._finalizing = False
         self._apply_wire_formats()
         if getenv_int("ENABLE_DGT", 0) and f.protocol == "ll":
             # DGT on NVSwitch: contribution-ranked tile order + fp8 for the unimportant (1 - DMLC_K) fraction, re-ranked every few rounds
