@@ -128,6 +128,20 @@ PYBIND11_MODULE(_C, m) {
         return out;
       });
 
+  // ---------------------------------------------------------------------------------------------- TSEngine helpers (unit tests)
+  m.def("ts_merge_bytes", [](py::array dst, py::array src, int dtype) {
+    HIPS_CHECK_MSG(dst.nbytes() == src.nbytes(), "ts_merge_bytes: size mismatch");
+    hips::TSMergeBytes(static_cast<char*>(dst.mutable_data()), static_cast<const char*>(src.data()), static_cast<size_t>(dst.nbytes()), dtype);
+  }, "dst += src in the payload dtype (0 fp32, 2 fp16, 12 bf16) — the merge TSEngine nodes apply to peer contributions");
+  m.def("ts_origins_roundtrip", [](std::vector<std::tuple<int, int, int>> v) {
+    std::vector<hips::TSOrigin> o;
+    for (auto& t : v) o.push_back(hips::TSOrigin{std::get<0>(t), std::get<1>(t), std::get<2>(t)});
+    std::vector<std::tuple<int, int, int>> out;
+    for (auto& x : hips::DecodeOrigins(hips::EncodeOrigins(o))) out.emplace_back(x.sender, x.timestamp, x.customer);
+    return out;
+  });
+  m.def("ts_dtype_of_cmd", &hips::TSDTypeOfCmd);
+
   // ---------------------------------------------------------------------------------------------- storage pools / resources
   py::class_<gx_rt::PooledHostStorage>(m, "PooledHostStorage")
       .def(py::init<size_t, size_t>(), py::arg("page") = 4096, py::arg("max_pooled") = size_t(4) << 30)

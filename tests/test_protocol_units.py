@@ -223,3 +223,26 @@ def test_topology_solver_and_tree_comm():
         assert all(torch.equal(o._t, out) for o in outs)
     finally:
         os.environ.pop("GEOMX_LINK_MATRIX", None)
+
+
+def test_tsengine_node_helpers():
+    """ts_node.h: payload merges in fp32 / fp16 / bf16, origin-list codec, dtype recovered from the Cantor-paired data command."""
+    import numpy as np
+    from geomx_b200 import runtime
+    if not runtime.available():
+        pytest.skip("native runtime not built")
+    C = runtime.C()
+    a = np.arange(8, dtype=np.float32); b = np.ones(8, dtype=np.float32) * 0.5
+    C.ts_merge_bytes(a, b, 0)
+    assert np.array_equal(a, np.arange(8, dtype=np.float32) + 0.5)
+    h = np.array([1.0, 2.5, -3.0, 1000.0], dtype=np.float16); g = np.array([0.5, 0.25, 3.0, 24.0], dtype=np.float16)
+    C.ts_merge_bytes(h, g, 2)
+    assert np.array_equal(h, (np.array([1.0, 2.5, -3.0, 1000.0], dtype=np.float32) + np.array([0.5, 0.25, 3.0, 24.0], dtype=np.float32)).astype(np.float16))
+    import torch
+    x = torch.tensor([1.0, 3.0, -2.0, 100.0], dtype=torch.bfloat16); y = torch.tensor([0.5, 1.0, 2.0, 1.0], dtype=torch.bfloat16)
+    xv = x.view(torch.int16).numpy(); C.ts_merge_bytes(xv, y.view(torch.int16).numpy(), 12)
+    assert torch.equal(torch.from_numpy(xv).view(torch.bfloat16), (torch.tensor([1.0, 3.0, -2.0, 100.0]) + torch.tensor([0.5, 1.0, 2.0, 1.0])).to(torch.bfloat16))
+    origins = [(101, 7, 0), (103, 12, 0), (9, 3, 1)]
+    assert C.ts_origins_roundtrip(origins) == origins and C.ts_origins_roundtrip([]) == []
+    # Cantor pairing (request type, dtype): default/f32 = 0, default/f64 = 2, 2bit/f32 = 3, default/f16 = 5, BSC/f32 = 6
+    assert [C.ts_dtype_of_cmd(c) for c in (0, 2, 3, 5, 6)] == [0, 1, 0, 2, 0]
