@@ -45,6 +45,19 @@ if master:
     kv.close()
     sys.exit(0)
 out = {"rank": kv.rank, "num_workers": kv.num_workers, "num_all_workers": kv.num_all_workers, "vals": []}
+if mode == "heartbeat":
+    # failure detection (postoffice.cc GetDeadNodes, kvstore_dist.h:225-234): a worker's view covers the scheduler it heart-beats with.
+    # Signal readiness through a file, then wait until the (killed) scheduler is reported dead.
+    open(os.environ["TEST_READY_FILE"] + str(kv.rank), "w").write("ready")
+    alive_first = kv.get_num_dead_node(1, timeout=2)
+    dead = 0
+    for _ in range(60):
+        dead = kv.get_num_dead_node(1, timeout=2)
+        if dead:
+            break
+        time.sleep(0.5)
+    print("RESULT " + json.dumps({"rank": kv.rank, "alive_first": alive_first, "dead": dead}), flush=True)
+    os._exit(0)                                  # no orderly shutdown is possible without a scheduler
 if mode == "rowsparse":
     # embedding-style key: every worker pushes two rows (one shared, one private), then pulls a few rows back through the sparse wire
     emb = mx.nd.array(np.zeros((10, 4), dtype=np.float32))

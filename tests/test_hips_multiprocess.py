@@ -299,3 +299,31 @@ def test_hybrid_two_boxes_over_tcp():
         for t, vals in enumerate(r["vals"]):
             for i, v in enumerate(vals):
                 assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-4, (t, i, v)
+
+
+def test_heartbeat_detects_dead_scheduler(tmp_path):
+    """PS_HEARTBEAT_INTERVAL / get_num_dead_node: workers heart-beat with their scheduler; after the scheduler is killed they report it dead
+    within the timeout (reference: van.cc:242-257,1128-1140; postoffice.cc:284-303)."""
+    import time
+    port = free_port()
+    ready = str(tmp_path / "ready")
+    base = {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": port, "DMLC_NUM_SERVER": 1, "DMLC_NUM_WORKER": 2, "DMLC_NUM_ALL_WORKER": 2,
+            "TEST_STANDALONE": 1, "TEST_MODE": "heartbeat", "PS_HEARTBEAT_INTERVAL": 1, "PS_HEARTBEAT_TIMEOUT": 2, "TEST_READY_FILE": ready}
+    sched = spawn(dict(base, DMLC_ROLE="scheduler"))
+    server = spawn(dict(base, DMLC_ROLE="server"))
+    ws = [spawn(dict(base, DMLC_ROLE="worker", TEST_WORKER_GID=i), worker=True) for i in range(2)]
+    try:
+        t0 = time.time()
+        while not (os.path.exists(ready + "0") and os.path.exists(ready + "1")):
+            assert time.time() - t0 < 90, "workers never became ready"
+            assert all(w.poll() is None for w in ws), "a worker died early"
+            time.sleep(0.2)
+        time.sleep(1.5)                               # a few heart-beats while everything is alive
+        sched.kill()
+        outs = [w.communicate(timeout=60)[0] for w in ws]
+    finally:
+        for p in (sched, server, *ws):
+            if p.poll() is None:
+                p.kill()
+    res = results(outs)
+    assert len(res) == 2 and all(r["alive_first"] == 0 and r["dead"] == 1 for r in res), res
