@@ -35,7 +35,8 @@ class KVStoreDist {
       ps_worker_.reset(new KVWorker(0, 0));
       po->Start(0, true);
       started_ = true;
-      // KVStore::Create: rank-0 worker configures the party's servers
+      // KVStore::Create: rank-0 worker configures the party's servers (a recovered worker finds them configured)
+      if (po->is_recovery()) return;
       if (type.find("dist") != std::string::npos && rank() == 0) SendCommandToServers(static_cast<int>(CommandType::kSyncMode), "");
       if (type.find("_sync") != std::string::npos && po->is_master_worker()) SendCommandToServers(static_cast<int>(CommandType::kSyncGlobalMode), "");
     }
@@ -61,6 +62,7 @@ class KVStoreDist {
   int num_workers() { return Postoffice::Get()->num_workers(); }
   int num_all_workers() { return Postoffice::Get()->num_all_workers(); }
   bool is_master_worker() { return Postoffice::Get()->is_master_worker(); }
+  bool is_recovery() { return Postoffice::Get()->is_recovery(); }
   int num_dead_node(int node_id, int timeout) {
     int n = 0;
     for (int r : Postoffice::Get()->GetDeadNodes(timeout, kLocal)) if (r & node_id) ++n;
@@ -93,6 +95,7 @@ class KVStoreDist {
   // ---- data -----------------------------------------------------------------------------------------------------------
   void Init(int key, const void* data, size_t elems, int dtype) {
     { std::lock_guard<std::mutex> lk(mu_); info_[key] = KeyInfo{elems, dtype}; }
+    if (Postoffice::Get()->is_recovery()) return;   // the key already lives on the servers; the others are past this barrier (kvstore_dist.h:321)
     if (rank() == 0) {
       const int h = PushImpl(key, data, elems, dtype, 0, /*allow_compress=*/false);
       Wait(h);

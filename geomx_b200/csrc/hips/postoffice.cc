@@ -78,7 +78,7 @@ void Postoffice::Start(int customer_id, bool do_barrier) {
     init_stage_ = 2;
     started_ = true;
   }
-  if (do_barrier) {
+  if (do_barrier && !is_recovery()) {   // a recovered node joins a running job (reference: kvstore_dist.h:63 `if (!ps::Postoffice::Get()->is_recovery())`)
     if (has_local_) Barrier(customer_id, kWorkerGroup + kServerGroup + kScheduler, kLocal);
     if (has_global_) Barrier(customer_id, kWorkerGroup + kServerGroup + kScheduler, kGlobal);
   }

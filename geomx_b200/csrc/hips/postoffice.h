@@ -39,6 +39,8 @@ class Postoffice {
   // set once the applications of this process are being torn down: late (re)transmissions for them are dropped instead of waited for
   void set_finalizing() { finalizing_ = true; }
   bool is_finalizing() const { return finalizing_.load(); }
+  // this process took over the id of a dead node (van.cc recovery path): it must not wait at start-up barriers the others passed long ago
+  bool is_recovery() { return (has_local_ && van_local_ && van_local_->my_node().is_recovery) || (has_global_ && van_global_ && van_global_->my_node().is_recovery); }
   bool enable_central_workers() const { return enable_central_worker_; }
   int num_workers() const { return num_workers_; }
   int num_servers() const { return num_servers_; }

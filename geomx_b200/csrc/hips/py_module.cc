@@ -205,6 +205,7 @@ PYBIND11_MODULE(_C, m) {
       .def_property_readonly("num_workers", &KVStoreDist::num_workers)
       .def_property_readonly("num_all_workers", &KVStoreDist::num_all_workers)
       .def_property_readonly("is_master_worker", &KVStoreDist::is_master_worker)
+      .def_property_readonly("is_recovery", &KVStoreDist::is_recovery)
       .def("num_dead_node", &KVStoreDist::num_dead_node)
       .def("init", [](KVStoreDist& kv, int key, uintptr_t ptr, size_t elems, int dtype) { kv.Init(key, reinterpret_cast<const void*>(ptr), elems, dtype); },
            py::call_guard<py::gil_scoped_release>())

@@ -69,6 +69,10 @@ class KVStoreDist(KVStoreBase):
     def num_all_workers(self): return self._kv.num_all_workers
     @property
     def is_master_worker(self): return self._kv.is_master_worker
+    @property
+    def is_recovery(self):
+        """True when this worker replaced a dead one (it skipped the start-up barriers and key initialisation)."""
+        return bool(self._kv.is_recovery)
 
     def _key(self, k):
         kt = str if isinstance(k, str) else int

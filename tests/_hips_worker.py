@@ -22,7 +22,7 @@ shapes = [(4, 5), (7,), (300,), (3, 2)] if mode != "big" else [(4, 5), (2500,)]
 kv = mx.kv.create(os.environ.get("TEST_KV", "dist_sync"))
 master = kv.is_master_worker
 if master or (os.environ.get("TEST_STANDALONE") == "1" and kv.rank == 0):
-    if mode in ("sgd", "big", "p3", "2bit", "async", "fp16", "rowsparse"):
+    if mode in ("sgd", "big", "p3", "2bit", "async", "fp16", "rowsparse", "recovery") and os.environ.get("TEST_RECOVERED") != "1":
         kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, multi_precision=(mode == "fp16")))
     elif mode == "adam_py":
         os.environ["GEOMX_PY_UPDATER"] = "1"
@@ -45,6 +45,26 @@ if master:
     kv.close()
     sys.exit(0)
 out = {"rank": kv.rank, "num_workers": kv.num_workers, "num_all_workers": kv.num_all_workers, "vals": []}
+if mode == "recovery":
+    # elastic recovery (van.cc:176-192): gid 1 crashes after round 1; the harness starts a replacement (TEST_RECOVERED=1) that takes over the
+    # dead id, skips barriers / init, pulls the current parameters and takes part in round 2.
+    recovered = os.environ.get("TEST_RECOVERED") == "1"
+    w = mx.nd.array(np.full((6,), 1.0, dtype=np.float32))
+    kv.init(5, w)
+    kv.pull(5, w); mx.nd.waitall()
+    vals = [float(w.asnumpy()[0])]
+    for rnd in range(2):
+        if recovered and rnd == 0:
+            continue                               # round 1 happened before this process existed
+        kv.push(5, mx.nd.array(np.full((6,), 0.5 * (gid + 1), dtype=np.float32)))
+        kv.pull(5, w); mx.nd.waitall()
+        vals.append(float(w.asnumpy()[0]))
+        if rnd == 0 and gid == 1 and not recovered:
+            print("RESULT " + json.dumps({"gid": gid, "crashed": True, "vals": vals}), flush=True)
+            os._exit(17)                           # crash
+    print("RESULT " + json.dumps({"gid": gid, "recovered": recovered, "is_recovery": bool(kv.is_recovery), "vals": vals}), flush=True)
+    kv.close()
+    sys.exit(0)
 if mode == "heartbeat":
     # failure detection (postoffice.cc GetDeadNodes, kvstore_dist.h:225-234): a worker's view covers the scheduler it heart-beats with.
     # Signal readiness through a file, then wait until the (killed) scheduler is reported dead.

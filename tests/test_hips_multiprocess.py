@@ -327,3 +327,30 @@ def test_heartbeat_detects_dead_scheduler(tmp_path):
                 p.kill()
     res = results(outs)
     assert len(res) == 2 and all(r["alive_first"] == 0 and r["dead"] == 1 for r in res), res
+
+
+def test_dead_worker_is_replaced():
+    """Elastic recovery on the local tier: a worker crashes after round 1, heart-beats expire, a restarted worker registers, receives the dead
+    node's id (is_recovery), skips the start-up barriers / key initialisation, and round 2 completes with it (reference van.cc:90-111,176-192)."""
+    import time
+    port = free_port()
+    base = {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": port, "DMLC_NUM_SERVER": 1, "DMLC_NUM_WORKER": 2, "DMLC_NUM_ALL_WORKER": 2,
+            "TEST_STANDALONE": 1, "TEST_MODE": "recovery", "PS_HEARTBEAT_INTERVAL": 1, "PS_HEARTBEAT_TIMEOUT": 2}
+    procs = [spawn(dict(base, DMLC_ROLE="scheduler")), spawn(dict(base, DMLC_ROLE="server"))]
+    w0 = spawn(dict(base, DMLC_ROLE="worker", TEST_WORKER_GID=0), worker=True)
+    w1 = spawn(dict(base, DMLC_ROLE="worker", TEST_WORKER_GID=1), worker=True)
+    w1b = None
+    try:
+        out1, _ = w1.communicate(timeout=90)
+        assert w1.returncode == 17, out1
+        time.sleep(4.0)                                # heart-beat timeout: the scheduler now considers the crashed worker dead
+        w1b = spawn(dict(base, DMLC_ROLE="worker", TEST_WORKER_GID=1, TEST_RECOVERED=1), worker=True)
+        outs = [out1] + collect(procs + [w0, w1b], timeout=120)
+    finally:
+        for p in procs + [w0, w1] + ([w1b] if w1b else []):
+            if p.poll() is None:
+                p.kill()
+    res = {(r["gid"], bool(r.get("recovered"))): r for r in results(outs) if "gid" in r}
+    assert res[(1, False)]["crashed"] and abs(res[(1, False)]["vals"][1] - 0.85) < 1e-5
+    assert res[(1, True)]["is_recovery"] and abs(res[(1, True)]["vals"][0] - 0.85) < 1e-5 and abs(res[(1, True)]["vals"][1] - 0.70) < 1e-5
+    assert abs(res[(0, False)]["vals"][1] - 0.85) < 1e-5 and abs(res[(0, False)]["vals"][2] - 0.70) < 1e-5
