@@ -422,12 +422,12 @@ def array(source, ctx=None, dtype=None):
         t = source._t.to(ctx.torch_device, copy=True)
         return NDArray(t if dtype is None else t.to(torch_dtype(dtype)), ctx)
     if isinstance(source, torch.Tensor):
-        t = source.to(ctx.torch_device)
+        t = source.detach().to(ctx.torch_device, copy=True)          # mx.nd.array always copies (zero-copy wrapping is ``from_torch``)
         return NDArray(t if dtype is None else t.to(torch_dtype(dtype)), ctx)
     a = np.asarray(source)
     if dtype is None:
         dtype = a.dtype if isinstance(source, np.ndarray) and a.dtype != np.float64 else "float32"
-    t = torch.as_tensor(a).to(torch_dtype(dtype))
+    t = torch.tensor(a).to(torch_dtype(dtype))                       # torch.tensor copies: the NDArray never aliases the numpy buffer
     return NDArray(t.to(ctx.torch_device), ctx)
 
 

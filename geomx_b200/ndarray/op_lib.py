@@ -379,4 +379,231 @@ def ctc_loss(data, label, data_lengths=None, label_lengths=None, use_data_length
 CTCLoss = ctc_loss
 
 
+
+# ------------------------------------------------------------------------------------------------ spatial transformer family
+def GridGenerator(data, transform_type="affine", target_shape=(0, 0)):
+    """Sampling grid in [-1, 1] (``grid_generator-inl.h``): ``affine`` — ``data [B, 6]`` → ``[B, 2, H, W]`` (x, y); ``warp`` — ``data [B, 2, H, W]``
+    optical flow in pixels added to the identity grid."""
+    x = _t(data)
+    if transform_type == "affine":
+        H, W = int(target_shape[0]), int(target_shape[1])
+        g = TF.affine_grid(x.reshape(-1, 2, 3), (x.shape[0], 1, H, W), align_corners=True)     # [B, H, W, 2]
+        return _W(g.permute(0, 3, 1, 2))
+    B, _, H, W = x.shape
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=x.dtype, device=x.device), torch.arange(W, dtype=x.dtype, device=x.device), indexing="ij")
+    gx = (xs[None] + x[:, 0]) / _bi.max(W - 1, 1) * 2 - 1
+    gy = (ys[None] + x[:, 1]) / _bi.max(H - 1, 1) * 2 - 1
+    return _W(torch.stack([gx, gy], 1))
+
+
+def BilinearSampler(data, grid):
+    """Bilinear sampling of ``data [B, C, H, W]`` at ``grid [B, 2, Ho, Wo]`` (x, y in [-1, 1]); outside → 0 (``bilinear_sampler-inl.h``)."""
+    return _W(TF.grid_sample(_t(data), _t(grid).permute(0, 2, 3, 1), mode="bilinear", padding_mode="zeros", align_corners=True))
+
+
+def SpatialTransformer(data, loc, target_shape=(0, 0), transform_type="affine", sampler_type="bilinear"):
+    """Affine spatial transformer network op = GridGenerator + BilinearSampler (``spatial_transformer-inl.h``)."""
+    return BilinearSampler(data, GridGenerator(loc, "affine", target_shape))
+
+
+def Correlation(data1, data2, kernel_size=1, max_displacement=1, stride1=1, stride2=1, pad_size=0, is_multiply=True):
+    """FlowNet correlation layer (``correlation-inl.h``): for every displacement (multiples of ``stride2`` up to ``max_displacement``) the patch
+    product (or absolute difference) averaged over ``kernel_size² · C``.  Output ``[B, D², Ho, Wo]``."""
+    a = TF.pad(_t(data1), (pad_size,) * 4); b = TF.pad(_t(data2), (pad_size,) * 4)
+    B, C, H, W = a.shape
+    kr = (kernel_size - 1) // 2
+    border = max_displacement + kr
+    Ho = int(_math.ceil((H - 2 * border) / stride1)); Wo = int(_math.ceil((W - 2 * border) / stride1))
+    r = max_displacement // stride2
+    outs = []
+    for dy in range(-r, r + 1):
+        for dx in range(-r, r + 1):
+            oy, ox = dy * stride2, dx * stride2
+            pa = a[:, :, border - kr: H - border + kr, border - kr: W - border + kr]
+            pb = b[:, :, border - kr + oy: H - border + kr + oy, border - kr + ox: W - border + kr + ox]
+            prod = pa * pb if is_multiply else (pa - pb).abs()
+            s = TF.avg_pool2d(prod.sum(1, keepdim=True), kernel_size, stride=1) * (kernel_size * kernel_size) if kernel_size > 1 else prod.sum(1, keepdim=True)
+            outs.append(s[:, :, ::stride1, ::stride1][:, :, :Ho, :Wo] / (kernel_size * kernel_size * C))
+    return _W(torch.cat(outs, 1))
+
+
+def ROIPooling(data, rois, pooled_size, spatial_scale):
+    from .contrib import ROIPooling as _rp
+    return _rp(data, rois, pooled_size, spatial_scale)
+
+
+def SVMOutput(data, label=None, margin=1.0, regularization_coefficient=1.0, use_linear=False):
+    """Forward is the identity (``svm_output-inl.h``); the hinge gradient is what ``gluon.loss.HingeLoss`` / ``SquaredHingeLoss`` provide."""
+    return _W(_t(data).clone())
+
+
+def Crop(*data, offset=(0, 0), h_w=(0, 0), center_crop=False, num_args=1):
+    """Crop ``data[0]`` spatially to ``h_w`` or to the size of ``data[1]`` (``crop-inl.h``)."""
+    x = _t(data[0])
+    th, tw = (int(data[1].shape[2]), int(data[1].shape[3])) if len(data) > 1 else (int(h_w[0]), int(h_w[1]))
+    oy, ox = ((x.shape[2] - th) // 2, (x.shape[3] - tw) // 2) if center_crop else (int(offset[0]), int(offset[1]))
+    return _W(x[:, :, oy:oy + th, ox:ox + tw])
+
+
+def histogram(a, bins=10, range=None):
+    """``(counts, bin_edges)`` like numpy (``tensor/histogram-inl.h``); ``bins`` may be an edge array."""
+    x = _t(a).float().flatten()
+    if isinstance(bins, NDArray):
+        edges = _t(bins).float()
+        idx = torch.bucketize(x, edges, right=True) - 1
+        idx = torch.where(x == edges[-1], torch.full_like(idx, edges.numel() - 2), idx)
+        ok = (idx >= 0) & (idx < edges.numel() - 1)
+        return _W(torch.bincount(idx[ok], minlength=edges.numel() - 1).to(torch.int64)), _W(edges)
+    lo, hi = (float(x.min()), float(x.max())) if range is None else (float(range[0]), float(range[1]))
+    return _W(torch.histc(x, int(bins), lo, hi).to(torch.int64)), _W(torch.linspace(lo, hi, int(bins) + 1, device=x.device))
+
+
+def ravel_multi_index(data, shape):
+    idx = _t(data).long(); out = torch.zeros_like(idx[0]); mul = 1
+    for d in _bi.range(len(shape) - 1, -1, -1):
+        out = out + idx[d] * mul; mul *= int(shape[d])
+    return _W(out.to(_t(data).dtype))
+
+
+def unravel_index(data, shape):
+    idx = _t(data).long(); outs = []
+    for d in _bi.range(len(shape) - 1, -1, -1):
+        outs.append(idx % int(shape[d])); idx = idx // int(shape[d])
+    return _W(torch.stack(outs[::-1]).to(_t(data).dtype))
+
+
+def choose_element_0index(lhs, rhs):
+    from .ndarray import pick as _pick
+    return _pick(lhs, rhs, axis=1)
+
+
+def fill_element_0index(lhs, mhs, rhs):
+    out = _t(lhs).clone(); out[torch.arange(out.shape[0], device=out.device), _t(rhs).long()] = _t(mhs)
+    return _W(out)
+
+
+crop = slice
+Softmax = SoftmaxOutput
+
+
+# ------------------------------------------------------------------------------------------------ optimizer update ops (optimizer_op-inl.h)
+def _prep_grad(weight, grad, wd, rescale_grad, clip_gradient):
+    g = _t(grad) * rescale_grad
+    if clip_gradient is not None and clip_gradient >= 0:
+        g = g.clamp(-clip_gradient, clip_gradient)
+    return g + wd * _t(weight)
+
+
+def _ret(weight, new, out):
+    tgt = weight if out is None else out
+    with torch.no_grad():
+        _t(tgt).copy_(new)
+    return tgt
+
+
+def sgd_update(weight, grad, lr, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0, lazy_update=True, out=None):
+    """``w -= lr * (clip(rescale * g) + wd * w)`` (``optimizer_op-inl.h:86-103``); in place on ``weight`` unless ``out`` is given."""
+    with torch.no_grad():
+        return _ret(weight, _t(weight) - lr * _prep_grad(weight, grad, wd, rescale_grad, clip_gradient), out)
+
+
+def sgd_mom_update(weight, grad, mom, lr, momentum=0.0, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0, lazy_update=True, out=None):
+    with torch.no_grad():
+        _t(mom).mul_(momentum).sub_(lr * _prep_grad(weight, grad, wd, rescale_grad, clip_gradient))
+        return _ret(weight, _t(weight) + _t(mom), out)
+
+
+def mp_sgd_update(weight, grad, weight32, lr, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0, lazy_update=True, out=None):
+    """Multi-precision SGD: the fp32 master ``weight32`` is updated, ``weight`` receives its cast (``optimizer_op-inl.h:359-400``)."""
+    with torch.no_grad():
+        g = _t(grad).float() * rescale_grad
+        if clip_gradient is not None and clip_gradient >= 0:
+            g = g.clamp(-clip_gradient, clip_gradient)
+        _t(weight32).sub_(lr * (g + wd * _t(weight32)))
+        return _ret(weight, _t(weight32).to(_t(weight).dtype), out)
+
+
+def mp_sgd_mom_update(weight, grad, mom, weight32, lr, momentum=0.0, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0, lazy_update=True, out=None):
+    with torch.no_grad():
+        g = _t(grad).float() * rescale_grad
+        if clip_gradient is not None and clip_gradient >= 0:
+            g = g.clamp(-clip_gradient, clip_gradient)
+        _t(mom).mul_(momentum).sub_(lr * (g + wd * _t(weight32)))
+        _t(weight32).add_(_t(mom))
+        return _ret(weight, _t(weight32).to(_t(weight).dtype), out)
+
+
+def adam_update(weight, grad, mean, var, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0,
+                lazy_update=True, out=None):
+    """One Adam step WITHOUT bias correction (the Python optimizer folds it into ``lr``) (``optimizer_op-inl.h:840-873``).  On CUDA fp32
+    tensors this is the single-pass native kernel (``csrc/kernels/optim.cu``)."""
+    w, g, m, v = _t(weight), _t(grad), _t(mean), _t(var)
+    if out is None and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and g.is_contiguous():
+        from ..ops import native
+        if native.available():
+            from ..ops import _native_api as n
+            n.adam_update(w, g, m, v, lr, beta1, beta2, epsilon, wd, rescale_grad, clip_gradient if clip_gradient is not None else -1.0)
+            return weight
+    with torch.no_grad():
+        gg = _prep_grad(weight, grad, wd, rescale_grad, clip_gradient)
+        m.mul_(beta1).add_(gg * (1 - beta1)); v.mul_(beta2).add_(gg * gg * (1 - beta2))
+        return _ret(weight, w - lr * m / (v.sqrt() + epsilon), out)
+
+
+def rmsprop_update(weight, grad, n, lr, gamma1=0.95, epsilon=1e-8, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0, clip_weights=-1.0, out=None):
+    with torch.no_grad():
+        g = _prep_grad(weight, grad, wd, rescale_grad, clip_gradient)
+        _t(n).mul_(gamma1).add_(g * g * (1 - gamma1))
+        new = _t(weight) - lr * g / (_t(n) + epsilon).sqrt()
+        if clip_weights is not None and clip_weights > 0:
+            new = new.clamp(-clip_weights, clip_weights)
+        return _ret(weight, new, out)
+
+
+def rmspropalex_update(weight, grad, n, g, delta, lr, gamma1=0.95, gamma2=0.9, epsilon=1e-8, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0,
+                       clip_weights=-1.0, out=None):
+    with torch.no_grad():
+        gr = _prep_grad(weight, grad, wd, rescale_grad, clip_gradient)
+        _t(n).mul_(gamma1).add_(gr * gr * (1 - gamma1)); _t(g).mul_(gamma1).add_(gr * (1 - gamma1))
+        _t(delta).mul_(gamma2).sub_(lr * gr / (_t(n) - _t(g) ** 2 + epsilon).sqrt())
+        new = _t(weight) + _t(delta)
+        if clip_weights is not None and clip_weights > 0:
+            new = new.clamp(-clip_weights, clip_weights)
+        return _ret(weight, new, out)
+
+
+def ftrl_update(weight, grad, z, n, lr, lamda1=0.01, beta=1.0, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0, out=None):
+    with torch.no_grad():
+        g = _t(grad) * rescale_grad
+        if clip_gradient is not None and clip_gradient >= 0:
+            g = g.clamp(-clip_gradient, clip_gradient)
+        w = _t(weight)
+        _t(z).add_(g - ((_t(n) + g * g).sqrt() - _t(n).sqrt()) * w / lr)
+        _t(n).add_(g * g)
+        new = (torch.sign(_t(z)) * lamda1 - _t(z)) / ((beta + _t(n).sqrt()) / lr + wd) * (_t(z).abs() > lamda1)
+        return _ret(weight, new, out)
+
+
+def signsgd_update(weight, grad, lr, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0, out=None):
+    with torch.no_grad():
+        return _ret(weight, (1 - lr * wd) * _t(weight) - lr * torch.sign(_t(grad)), out)
+
+
+def signum_update(weight, grad, mom, lr, momentum=0.0, wd=0.0, rescale_grad=1.0, clip_gradient=-1.0, wd_lh=0.0, out=None):
+    with torch.no_grad():
+        g = _prep_grad(weight, grad, wd, rescale_grad, clip_gradient)
+        _t(mom).mul_(momentum).sub_((1 - momentum) * g)
+        return _ret(weight, (1 - lr * wd_lh) * _t(weight) + lr * torch.sign(_t(mom)), out)
+
+
+def ftml_update(weight, grad, d, v, z, lr, t, beta1=0.6, beta2=0.999, epsilon=1e-8, wd=0.0, rescale_grad=1.0, clip_grad=-1.0, out=None):
+    with torch.no_grad():
+        g = _prep_grad(weight, grad, wd, rescale_grad, clip_grad)
+        _t(v).mul_(beta2).add_(g * g * (1 - beta2))
+        d_t = (1 - beta1 ** t) / lr * ((_t(v) / (1 - beta2 ** t)).sqrt() + epsilon)
+        sigma = d_t - beta1 * _t(d)
+        _t(z).mul_(beta1).add_((1 - beta1) * g - sigma * _t(weight))
+        _t(d).copy_(d_t)
+        return _ret(weight, -_t(z) / d_t, out)
+
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in ("torch", "TF", "OF", "NDArray", "torch_dtype", "annotations")]
