@@ -12,7 +12,7 @@ from ... import autograd
 from ...ndarray import NDArray
 from ..nn.basic_layers import BatchNorm
 
-__all__ = ["SyncBatchNorm"]
+__all__ = ["SyncBatchNorm", "Concurrent", "HybridConcurrent", "Identity", "SparseEmbedding", "PixelShuffle2D"]
 
 
 def _all_reduce(t):
@@ -67,3 +67,63 @@ class SyncBatchNorm(BatchNorm):
         if not (autograd.is_training() and not self._use_global):
             return super().hybrid_forward(F, x, gamma, beta, running_mean, running_var)
         return NDArray(_SyncBNFn.apply(x._t, gamma._t, beta._t, running_mean._t, running_var._t, self._momentum, self._eps))
+
+
+from ..block import Block, HybridBlock  # noqa: E402
+from ..nn.basic_layers import HybridSequential, Sequential  # noqa: E402
+
+
+class Concurrent(Sequential):
+    """Feeds the same input to every child and concatenates the outputs along ``axis``
+    (``gluon/contrib/nn/basic_layers.py:30-60``)."""
+
+    def __init__(self, axis=-1, prefix=None, params=None):
+        super().__init__(prefix=prefix, params=params); self.axis = axis
+
+    def forward(self, x):
+        return NDArray(torch.cat([blk(x)._t for blk in self._children.values()], dim=self.axis))
+
+
+class HybridConcurrent(HybridSequential):
+    def __init__(self, axis=-1, prefix=None, params=None):
+        super().__init__(prefix=prefix, params=params); self.axis = axis
+
+    def forward(self, x):
+        return NDArray(torch.cat([blk(x)._t for blk in self._children.values()], dim=self.axis))
+
+    hybrid_forward = None
+
+
+class Identity(HybridBlock):
+    """Pass-through block, useful as a branch of ``Concurrent`` for residual structures."""
+
+    def hybrid_forward(self, F, x):
+        return x
+
+
+class SparseEmbedding(Block):
+    """Embedding whose gradient is ``row_sparse``: only the rows that were looked up travel to the parameter server
+    (``gluon/contrib/nn/basic_layers.py:115-160``; see ``kv.row_sparse_pull`` and the sparse wire of the TCP plane)."""
+
+    def __init__(self, input_dim, output_dim, dtype="float32", weight_initializer=None, **kwargs):
+        super().__init__(**kwargs)
+        with self.name_scope():
+            self.weight = self.params.get("weight", shape=(input_dim, output_dim), init=weight_initializer, dtype=dtype,
+                                          grad_stype="row_sparse", stype="row_sparse")
+
+    def forward(self, x):
+        return NDArray(torch.nn.functional.embedding(x._t.long(), self.weight.data(x.context)._t))
+
+
+class PixelShuffle2D(HybridBlock):
+    """``(N, C·f1·f2, H, W) → (N, C, H·f1, W·f2)`` sub-pixel upsampling."""
+
+    def __init__(self, factor, **kwargs):
+        super().__init__(**kwargs)
+        self._f = (factor, factor) if isinstance(factor, int) else tuple(factor)
+
+    def hybrid_forward(self, F, x):
+        f1, f2 = self._f
+        N, C, H, W = x._t.shape
+        t = x._t.reshape(N, C // (f1 * f2), f1, f2, H, W).permute(0, 1, 4, 2, 5, 3)
+        return NDArray(t.reshape(N, C // (f1 * f2), H * f1, W * f2))

@@ -1,6 +1,7 @@
 """Loss blocks.  Parity: ``python/mxnet/gluon/loss.py`` — ``_apply_weighting``, ``_reshape_like``, L2Loss, L1Loss,
 SigmoidBinaryCrossEntropyLoss, SoftmaxCrossEntropyLoss (:304-318: ``-pick(log_softmax(pred), label)`` then mean
-over non-batch axes), KLDivLoss, HuberLoss, HingeLoss, SquaredHingeLoss, LogisticLoss."""
+over non-batch axes), KLDivLoss, HuberLoss, HingeLoss, SquaredHingeLoss, LogisticLoss, CTCLoss (:437-520), TripletLoss (:640-690), PoissonNLLLoss (:700-760),
+CosineEmbeddingLoss (:770-830)."""
 from __future__ import annotations
 
 import torch
@@ -10,7 +11,8 @@ from ..ops import functional as OF
 from .block import HybridBlock
 
 __all__ = ["Loss", "L2Loss", "L1Loss", "SigmoidBinaryCrossEntropyLoss", "SigmoidBCELoss", "SoftmaxCrossEntropyLoss",
-           "SoftmaxCELoss", "KLDivLoss", "HuberLoss", "HingeLoss", "SquaredHingeLoss", "LogisticLoss"]
+           "SoftmaxCELoss", "KLDivLoss", "HuberLoss", "HingeLoss", "SquaredHingeLoss", "LogisticLoss", "CTCLoss", "TripletLoss",
+           "PoissonNLLLoss", "CosineEmbeddingLoss"]
 
 
 def _w(loss, weight, sample_weight):
@@ -135,3 +137,64 @@ class LogisticLoss(Loss):
             y = (y + 1.0) / 2.0
         l = torch.relu(pred._t) - pred._t * y + torch.nn.functional.softplus(-pred._t.abs())
         return NDArray(_mean(_w(l, self._weight, sample_weight), self._batch_axis))
+
+
+class CTCLoss(Loss):
+    """Connectionist temporal classification loss.  ``layout`` 'NTC' / 'TNC' for predictions (un-normalised activations; the blank is the
+    LAST class, as in gluon), ``label_layout`` 'NT' / 'TN'; labels are padded with -1 unless ``label_lengths`` is given."""
+
+    def __init__(self, layout="NTC", label_layout="NT", weight=None, **kwargs):
+        assert layout in ("NTC", "TNC") and label_layout in ("NT", "TN")
+        super().__init__(weight, label_layout.find("N"), **kwargs)
+        self._layout, self._label_layout = layout, label_layout
+
+    def hybrid_forward(self, F, pred, label, pred_lengths=None, label_lengths=None, sample_weight=None):
+        p = pred._t if self._layout == "TNC" else pred._t.transpose(0, 1)
+        lab = label._t if self._label_layout == "NT" else label._t.transpose(0, 1)
+        T, N, C = p.shape
+        il = pred_lengths._t.long() if pred_lengths is not None else torch.full((N,), T, dtype=torch.long)
+        ll = label_lengths._t.long() if label_lengths is not None else (lab >= 0).sum(1)
+        loss = torch.nn.functional.ctc_loss(torch.log_softmax(p.float(), -1), lab.long().clamp_min(0), il, ll, blank=C - 1, reduction="none", zero_infinity=False)
+        return NDArray(_w(loss, self._weight, sample_weight))
+
+
+class TripletLoss(Loss):
+    """``max(sum((pred - pos)^2 - (pred - neg)^2) + margin, 0)``"""
+
+    def __init__(self, margin=1, weight=None, batch_axis=0, **kwargs):
+        super().__init__(weight, batch_axis, **kwargs); self._margin = margin
+
+    def hybrid_forward(self, F, pred, positive, negative, sample_weight=None):
+        d = ((pred._t - positive._t.reshape(pred._t.shape)) ** 2 - (pred._t - negative._t.reshape(pred._t.shape)) ** 2)
+        dims = [i for i in range(d.dim()) if i != self._batch_axis]
+        loss = torch.relu(d.sum(dims) + self._margin)
+        return NDArray(_w(loss, self._weight, sample_weight))
+
+
+class PoissonNLLLoss(Loss):
+    """Poisson negative log likelihood; ``from_logits`` (default) means ``pred`` is log-rate.  Returns the MEAN over all elements."""
+
+    def __init__(self, weight=None, from_logits=True, batch_axis=0, compute_full=False, **kwargs):
+        super().__init__(weight, batch_axis, **kwargs); self._from_logits, self._full = from_logits, compute_full
+
+    def hybrid_forward(self, F, pred, target, sample_weight=None, epsilon=1e-08):
+        p, t = pred._t, target._t.reshape(pred._t.shape)
+        loss = torch.exp(p) - t * p if self._from_logits else p - t * torch.log(p + epsilon)
+        if self._full:
+            st = t * torch.log(t.clamp_min(1e-30)) - t + 0.5 * torch.log(2 * t.clamp_min(1e-30) * 3.141592653589793)
+            loss = loss + torch.where(t > 1, st, torch.zeros_like(st))
+        return NDArray(_w(loss, self._weight, sample_weight).mean())
+
+
+class CosineEmbeddingLoss(Loss):
+    """``1 - cos(a, b)`` for label 1, ``max(0, cos(a, b) - margin)`` for label -1."""
+
+    def __init__(self, weight=None, batch_axis=0, margin=0, **kwargs):
+        super().__init__(weight, batch_axis, **kwargs); self._margin = margin
+
+    def hybrid_forward(self, F, input1, input2, label, sample_weight=None):
+        a, b = input1._t, input2._t.reshape(input1._t.shape)
+        cos = (a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1)).clamp_min(1e-12)
+        lab = label._t.reshape(cos.shape)
+        loss = torch.where(lab == 1, 1 - cos, torch.relu(cos - self._margin))
+        return NDArray(_w(loss, self._weight, sample_weight))

@@ -11,7 +11,7 @@ from ...ops import functional as OF
 from ..block import Block, HybridBlock
 
 __all__ = ["Sequential", "HybridSequential", "Dense", "Dropout", "BatchNorm", "Embedding", "Flatten", "LayerNorm",
-           "Lambda", "HybridLambda", "Activation", "LeakyReLU", "ELU", "SELU", "Swish"]
+           "Lambda", "HybridLambda", "Activation", "LeakyReLU", "ELU", "SELU", "Swish", "PReLU", "GELU", "InstanceNorm"]
 
 
 class Sequential(Block):
@@ -212,3 +212,44 @@ class HybridLambda(HybridBlock):
 
     def hybrid_forward(self, F, x, *args):
         return self._func(F, x, *args)
+
+
+class PReLU(HybridBlock):
+    """``max(0, x) + alpha * min(0, x)`` with a learned ``alpha`` (one value, or one per channel with ``in_channels``)
+    (``gluon/nn/activations.py:87-125``)."""
+
+    def __init__(self, alpha_initializer=None, in_channels=1, **kwargs):
+        super().__init__(**kwargs)
+        from ... import initializer
+        with self.name_scope():
+            self.alpha = self.params.get("alpha", shape=(in_channels,), init=alpha_initializer or initializer.Constant(0.25))
+
+    def hybrid_forward(self, F, x, alpha):
+        a = alpha._t
+        if a.numel() > 1:
+            a = a.view([1, -1] + [1] * (x._t.dim() - 2))
+        return NDArray(torch.where(x._t >= 0, x._t, a * x._t))
+
+
+class GELU(HybridBlock):
+    def hybrid_forward(self, F, x):
+        return NDArray(torch.nn.functional.gelu(x._t))
+
+
+class InstanceNorm(HybridBlock):
+    """Per-sample, per-channel normalisation over the spatial axes (``gluon/nn/basic_layers.py:455-540``)."""
+
+    def __init__(self, axis=1, epsilon=1e-5, center=True, scale=False, beta_initializer="zeros", gamma_initializer="ones", in_channels=0, **kwargs):
+        super().__init__(**kwargs)
+        self._axis, self._eps = axis, epsilon
+        with self.name_scope():
+            self.gamma = self.params.get("gamma", grad_req="write" if scale else "null", shape=(in_channels,), init=_bias_init("one"), allow_deferred_init=True)
+            self.beta = self.params.get("beta", grad_req="write" if center else "null", shape=(in_channels,), init=_bias_init("zero"), allow_deferred_init=True)
+
+    def _infer(self, x, *a):
+        self.gamma.shape = self.beta.shape = (x.shape[self._axis],)
+
+    def hybrid_forward(self, F, x, gamma, beta):
+        t = x._t if self._axis == 1 else x._t.movedim(self._axis, 1)
+        y = torch.nn.functional.instance_norm(t, weight=gamma._t, bias=beta._t, eps=self._eps)
+        return NDArray(y if self._axis == 1 else y.movedim(1, self._axis))

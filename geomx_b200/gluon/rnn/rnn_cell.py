@@ -8,7 +8,8 @@ from ...ndarray import NDArray
 from ...ops import functional as OF
 from ..block import HybridBlock
 
-__all__ = ["RecurrentCell", "RNNCell", "LSTMCell", "GRUCell", "SequentialRNNCell"]
+__all__ = ["RecurrentCell", "RNNCell", "LSTMCell", "GRUCell", "SequentialRNNCell", "ModifierCell", "DropoutCell", "ZoneoutCell", "ResidualCell",
+           "BidirectionalCell"]
 
 
 class RecurrentCell(HybridBlock):
@@ -124,3 +125,102 @@ class SequentialRNNCell(RecurrentCell):
             inputs, st = c(inputs, states[pos:pos + n])
             nxt += st; pos += n
         return inputs, nxt
+
+
+class DropoutCell(RecurrentCell):
+    """Dropout on the cell input; stateless (``gluon/rnn/rnn_cell.py:700-750``)."""
+
+    def __init__(self, rate, axes=(), **kwargs):
+        HybridBlock.__init__(self, **kwargs); self._rate = rate
+
+    def state_info(self, batch_size=0):
+        return []
+
+    def forward(self, inputs, states):
+        from ... import autograd
+        if self._rate > 0 and autograd.is_training():
+            inputs = NDArray(torch.nn.functional.dropout(inputs._t, self._rate, True))
+        return inputs, states
+
+
+class ModifierCell(RecurrentCell):
+    """Base of cells that wrap another cell and share its parameters / state layout (``rnn_cell.py:760-800``)."""
+
+    def __init__(self, base_cell, **kwargs):
+        HybridBlock.__init__(self, **kwargs)
+        self.base_cell = base_cell
+        self.register_child(base_cell)
+
+    def state_info(self, batch_size=0):
+        return self.base_cell.state_info(batch_size)
+
+    def begin_state(self, batch_size=0, **kw):
+        return self.base_cell.begin_state(batch_size, **kw)
+
+
+class ZoneoutCell(ModifierCell):
+    """Zoneout: randomly keep the previous output / states (``rnn_cell.py:803-860``)."""
+
+    def __init__(self, base_cell, zoneout_outputs=0.0, zoneout_states=0.0, **kwargs):
+        super().__init__(base_cell, **kwargs)
+        self._zo, self._zs, self._prev = zoneout_outputs, zoneout_states, None
+
+    def reset(self):
+        self._prev = None
+
+    def forward(self, inputs, states):
+        from ... import autograd
+        out, nxt = self.base_cell(inputs, states)
+        if not autograd.is_training():
+            self._prev = out
+            return out, nxt
+        def mix(p, new, old):
+            if p <= 0 or old is None:
+                return new
+            keep = (torch.rand_like(new._t) < p).to(new._t.dtype)
+            return NDArray(keep * old._t + (1 - keep) * new._t)
+        prev = self._prev if self._prev is not None else NDArray(torch.zeros_like(out._t))
+        out = mix(self._zo, out, prev)
+        nxt = [mix(self._zs, n, o) for n, o in zip(nxt, states)]
+        self._prev = out
+        return out, nxt
+
+
+class ResidualCell(ModifierCell):
+    """``output = base(input) + input`` (``rnn_cell.py:863-900``)."""
+
+    def forward(self, inputs, states):
+        out, nxt = self.base_cell(inputs, states)
+        return NDArray(out._t + inputs._t), nxt
+
+
+class BidirectionalCell(RecurrentCell):
+    """Runs one cell forward and one backward over a sequence and concatenates their outputs; only ``unroll`` is defined
+    (``rnn_cell.py:903-1000``)."""
+
+    def __init__(self, l_cell, r_cell, output_prefix="bi_", **kwargs):
+        HybridBlock.__init__(self, **kwargs)
+        self._cells = [l_cell, r_cell]
+        self.register_child(l_cell); self.register_child(r_cell)
+
+    def state_info(self, batch_size=0):
+        return [s for c in self._cells for s in c.state_info(batch_size)]
+
+    def begin_state(self, batch_size=0, **kw):
+        return [s for c in self._cells for s in c.begin_state(batch_size, **kw)]
+
+    def forward(self, inputs, states):
+        raise NotImplementedError("BidirectionalCell cannot be stepped; use unroll")
+
+    def unroll(self, length, inputs, begin_state=None, layout="NTC", merge_outputs=None):
+        axis = layout.find("T")
+        seq = [NDArray(t) for t in inputs._t.unbind(axis)] if isinstance(inputs, NDArray) else list(inputs)
+        batch = seq[0].shape[0]
+        states = begin_state or self.begin_state(batch, ctx=seq[0].context)
+        nl = len(self._cells[0].state_info())
+        lo, ls = self._cells[0].unroll(length, seq, states[:nl], layout, merge_outputs=False)
+        ro, rs = self._cells[1].unroll(length, seq[::-1], states[nl:], layout, merge_outputs=False)
+        outs = [NDArray(torch.cat([a._t, b._t], dim=-1)) for a, b in zip(lo, ro[::-1])]
+        if merge_outputs or merge_outputs is None and isinstance(inputs, NDArray):
+            return NDArray(torch.stack([o._t for o in outs], dim=axis)), ls + rs
+        return outs, ls + rs

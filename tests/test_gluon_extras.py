@@ -49,3 +49,80 @@ def test_rnn_cells_match_torch_and_layers_backprop():
     cell = gluon.rnn.GRUCell(5); cell.initialize()
     merged, _ = cell.unroll(4, mx.nd.random.uniform(shape=(2, 4, 3)), layout="NTC", merge_outputs=True)
     assert merged.shape == (2, 4, 5)
+
+
+def test_nd_layers_losses_and_contrib_blocks():
+    import numpy as np
+    from geomx_b200.gluon import contrib, loss as gloss, nn, rnn
+    x3 = mx.nd.array(torch.randn(2, 3, 4, 6, 6))
+    c3 = nn.Conv3D(5, 3, padding=1); c3.initialize()
+    assert c3(x3).shape == (2, 5, 4, 6, 6) and c3.weight.shape == (5, 3, 3, 3, 3)
+    t3 = nn.Conv3DTranspose(4, 2, strides=2); t3.initialize()
+    assert t3(x3).shape == (2, 4, 8, 12, 12)
+    t1 = nn.Conv1DTranspose(4, 3, strides=2); t1.initialize()
+    assert t1(mx.nd.array(torch.randn(2, 3, 5))).shape == (2, 4, 11)
+    assert nn.MaxPool3D()(x3).shape == (2, 3, 2, 3, 3) and nn.AvgPool3D()(x3).shape == (2, 3, 2, 3, 3)
+    assert nn.GlobalAvgPool3D()(x3).shape == (2, 3, 1, 1, 1) and nn.GlobalMaxPool1D()(mx.nd.array(torch.randn(2, 3, 5))).shape == (2, 3, 1)
+    img = mx.nd.array(torch.arange(16.0).reshape(1, 1, 4, 4))
+    rp = nn.ReflectionPad2D(1)(img).asnumpy()
+    assert rp.shape == (1, 1, 6, 6) and rp[0, 0, 0, 0] == 5 and rp[0, 0, 0, 1] == 4
+    pr = nn.PReLU(); pr.initialize()
+    np.testing.assert_allclose(pr(mx.nd.array([-2.0, 3.0])).asnumpy(), [-0.5, 3.0])
+    inorm = nn.InstanceNorm(); inorm.initialize()
+    y = inorm(mx.nd.array(torch.randn(2, 3, 8, 8) * 3 + 1)).asnumpy()
+    assert abs(y.mean(axis=(2, 3))).max() < 1e-5 and abs(y.std(axis=(2, 3)) - 1).max() < 1e-2
+    assert float(abs(nn.GELU()(mx.nd.array([0.0, 10.0])).asnumpy() - [0, 10]).max()) < 1e-4
+
+    # losses
+    T, N, C = 6, 2, 5
+    pred = mx.nd.array(torch.randn(N, T, C)); lab = mx.nd.array([[1, 2, -1], [3, 3, 0]])
+    l = gloss.CTCLoss()(pred, lab).asnumpy()
+    ref = torch.nn.functional.ctc_loss(torch.log_softmax(pred._t.transpose(0, 1), -1), torch.tensor([[1, 2, 0], [3, 3, 0]]), torch.tensor([T, T]),
+                                       torch.tensor([2, 3]), blank=C - 1, reduction="none")
+    np.testing.assert_allclose(l, ref.numpy(), rtol=1e-5)
+    a, p, n_ = (mx.nd.array(torch.randn(4, 8)) for _ in range(3))
+    tl = gloss.TripletLoss(margin=0.5)(a, p, n_).asnumpy()
+    np.testing.assert_allclose(tl, np.maximum(((a._t - p._t) ** 2 - (a._t - n_._t) ** 2).sum(1).numpy() + 0.5, 0), rtol=1e-5)
+    pn = gloss.PoissonNLLLoss()(mx.nd.array([0.0, 1.0]), mx.nd.array([1.0, 2.0])).asnumpy()
+    np.testing.assert_allclose(pn, np.mean([1.0 - 0.0, np.e - 2.0]), rtol=1e-5)
+    ce = gloss.CosineEmbeddingLoss()(mx.nd.array([[1.0, 0.0], [1.0, 0.0]]), mx.nd.array([[1.0, 0.0], [1.0, 0.0]]), mx.nd.array([1, -1])).asnumpy()
+    np.testing.assert_allclose(ce, [0.0, 1.0], atol=1e-6)
+
+    # contrib blocks
+    cc = contrib.nn.HybridConcurrent(axis=1)
+    cc.add(nn.Dense(3)); cc.add(contrib.nn.Identity()); cc.initialize()
+    assert cc(mx.nd.array(torch.randn(2, 4))).shape == (2, 7)
+    assert contrib.nn.PixelShuffle2D(2)(mx.nd.array(torch.randn(1, 8, 3, 3))).shape == (1, 2, 6, 6)
+    se = contrib.nn.SparseEmbedding(10, 4); se.initialize()
+    assert se(mx.nd.array([1, 3, 3])).shape == (3, 4)
+    assert list(contrib.data.IntervalSampler(7, 3)) == [0, 3, 6, 1, 4, 2, 5] and list(contrib.data.IntervalSampler(7, 3, rollover=False)) == [0, 3, 6]
+
+    # recurrent cells
+    seq = mx.nd.array(torch.randn(2, 5, 4))
+    bi = rnn.BidirectionalCell(rnn.LSTMCell(6), rnn.GRUCell(3)); bi.initialize()
+    out, st = bi.unroll(5, seq)
+    assert out.shape == (2, 5, 9) and len(st) == 3
+    res = rnn.ResidualCell(rnn.RNNCell(4)); res.initialize()
+    o, _ = res.unroll(5, seq); assert o.shape == (2, 5, 4)
+    zc = rnn.ZoneoutCell(rnn.RNNCell(4), 0.5, 0.5); zc.initialize()
+    with mx.autograd.record():
+        o, _ = zc.unroll(5, seq)
+    assert o.shape == (2, 5, 4)
+    vd = contrib.rnn.VariationalDropoutCell(rnn.LSTMCell(4), drop_inputs=0.5, drop_outputs=0.5); vd.initialize()
+    with mx.autograd.record():
+        o, _ = vd.unroll(5, seq)
+    zero_cols = (o.asnumpy() == 0).all(axis=1)                       # the output mask is shared by every time step
+    assert zero_cols.any() and o.shape == (2, 5, 4)
+    lp = contrib.rnn.LSTMPCell(8, 3); lp.initialize()
+    o, st = lp.unroll(5, seq)
+    assert o.shape == (2, 5, 3) and st[0].shape == (2, 3) and st[1].shape == (2, 8)
+    for cls, ns in ((contrib.rnn.Conv2DRNNCell, 1), (contrib.rnn.Conv2DLSTMCell, 2), (contrib.rnn.Conv2DGRUCell, 1)):
+        cell = cls((3, 8, 8), 5, 3, 3, i2h_pad=1); cell.initialize()
+        s0 = cell.begin_state(2)
+        assert len(s0) == ns and s0[0].shape == (2, 5, 8, 8)
+        with mx.autograd.record():
+            o, s1 = cell(mx.nd.array(torch.randn(2, 3, 8, 8)), s0)
+            o2, _ = cell(mx.nd.array(torch.randn(2, 3, 8, 8)), s1)
+            L = o2.sum()
+        L.backward()
+        assert o2.shape == (2, 5, 8, 8) and float(cell.h2h_weight.grad().asnumpy().__abs__().sum()) > 0
