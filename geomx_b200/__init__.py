@@ -51,6 +51,7 @@ from . import engine  # noqa: F401
 from . import utils  # noqa: F401
 from . import parallel  # noqa: F401
 from . import models  # noqa: F401
+from . import contrib  # noqa: F401
 from . import kvstore_server  # noqa: F401
 
 # server / scheduler bootstrap on import (no-op for workers and plain library use)

@@ -80,7 +80,26 @@ def predict_mode():
 
 
 # leaves with attached grads (weak) so that backward can honour grad_req
-_leaves = weakref.WeakSet()
+class _LeafRegistry:
+    """Weak, identity-keyed set.  (A ``WeakSet`` compares the referents with ``==`` when the same array is registered twice, and NDArray's
+    ``==`` is elementwise.)"""
+
+    def __init__(self):
+        self._refs = {}
+
+    def add(self, nd):
+        key = id(nd)
+        if key not in self._refs:
+            self._refs[key] = weakref.ref(nd, lambda _r, k=key: self._refs.pop(k, None))
+
+    def __iter__(self):
+        for r in list(self._refs.values()):
+            obj = r()
+            if obj is not None:
+                yield obj
+
+
+_leaves = _LeafRegistry()
 
 
 def _register_leaf(nd):

@@ -64,6 +64,20 @@ class _BlockScope:
         _BlockScope._current.value = self._old_scope
 
 
+class _HookHandle:
+    def __init__(self, table, key):
+        self._table, self._key = table, key
+
+    def detach(self):
+        self._table.pop(self._key, None)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.detach()
+
+
 class Block:
     def __init__(self, prefix=None, params=None):
         self._empty_prefix = prefix == ""
@@ -104,10 +118,14 @@ class Block:
         self._children[name] = block
 
     def register_forward_hook(self, hook):
+        """``hook(block, inputs, output)`` after every forward; returns a handle whose ``detach()`` removes it (gluon/block.py:350-380)."""
         self._forward_hooks[id(hook)] = hook
+        return _HookHandle(self._forward_hooks, id(hook))
 
     def register_forward_pre_hook(self, hook):
+        """``hook(block, inputs)`` before every forward; a tuple returned by the hook replaces the inputs."""
         self._forward_pre_hooks[id(hook)] = hook
+        return _HookHandle(self._forward_pre_hooks, id(hook))
 
     def apply(self, fn):
         for c in self._children.values():
@@ -182,10 +200,12 @@ class Block:
         self.load_parameters(filename, ctx, allow_missing, ignore_extra)
 
     def __call__(self, *args):
-        for h in self._forward_pre_hooks.values():
-            h(self, args)
+        for h in list(self._forward_pre_hooks.values()):
+            r = h(self, args)
+            if isinstance(r, tuple):
+                args = r
         out = self.forward(*args)
-        for h in self._forward_hooks.values():
+        for h in list(self._forward_hooks.values()):
             h(self, args, out)
         return out
 

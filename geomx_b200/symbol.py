@@ -302,6 +302,13 @@ class _LinRegFn(torch.autograd.Function):
 def _eval_node(s, ins, aux, training):
     a = s.attrs
     op = s.op
+    q = a.get("__quantized__")
+    if q and op in ("FullyConnected", "Convolution"):
+        # simulated quantisation (contrib/quantization.py): the layer input is clipped+rounded at the calibrated threshold
+        from .contrib.quantization import fake_quantize
+        thr = q.get("act_threshold")
+        x = ins[0]
+        ins = [fake_quantize(x, thr if thr is not None else float(x.abs().max()), "int8" if q["dtype"] == "uint8" and float(x.min()) < 0 else q["dtype"])] + list(ins[1:])
     if op == "FullyConnected":
         return F.dense(ins[0], ins[1], None if a["no_bias"] else ins[2], None, a.get("flatten", True))
     if op == "Convolution":
@@ -336,7 +343,67 @@ def _eval_node(s, ins, aux, training):
         return {"_plus": torch.add, "_minus": torch.sub, "_mul": torch.mul, "_div": torch.div}[op](ins[0], ins[1])
     if op.endswith("_scalar"):
         return {"_plus": torch.add, "_minus": torch.sub, "_mul": torch.mul, "_div": torch.div}[op[:-7]](ins[0], a["scalar"])
+    if op == "_nd":
+        return _eval_nd(a, ins)
     raise MXNetError("symbol op %s is not implemented" % op)
+
+
+# ---- generic bridge: every imperative ``mx.nd.<fn>`` / ``mx.nd.contrib.<fn>`` that maps NDArrays to ONE NDArray is also a symbolic op.
+# The node stores the function's qualified name and its JSON-able keyword arguments; evaluation calls the imperative function on the
+# bound tensors (so gradients come from the same autograd tape).  This is how ``mx.sym.exp`` / ``broadcast_add`` / ``contrib.ROIAlign`` …
+# exist without a per-op registration table (the reference generates them from the nnvm registry: python/mxnet/symbol/register.py).
+def _resolve_nd(qual):
+    from . import ndarray as nd
+    obj = nd
+    for part in qual.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+def _eval_nd(a, ins):
+    fn = _resolve_nd(a["fn"])
+    npos = a["npos"]
+    args = [NDArray(t) for t in ins[:npos]]
+    kwargs = dict(a.get("kwargs") or {})
+    for k, t in zip(a.get("sym_kwargs") or (), ins[npos:]):
+        kwargs[k] = NDArray(t)
+    out = fn(*args, **kwargs)
+    if not isinstance(out, NDArray):
+        raise MXNetError("mx.sym.%s: the imperative function returned %s, only single-output ops can be used symbolically" % (a["fn"], type(out).__name__))
+    return out._t
+
+
+def _nd_op(qual):
+    def build(*args, name=None, **kwargs):
+        pos = [x for x in args if isinstance(x, Symbol)]
+        if len(pos) != len(args):
+            raise MXNetError("mx.sym.%s: positional arguments must be Symbols, pass attributes by keyword" % qual)
+        skw = [k for k, v in kwargs.items() if isinstance(v, Symbol)]
+        attrs = {"fn": qual, "npos": len(pos), "sym_kwargs": skw,
+                 "kwargs": {k: (list(v) if isinstance(v, tuple) else v) for k, v in kwargs.items() if k not in skw}}
+        return Symbol("_nd", _auto_name(qual.split(".")[-1].lower(), name), pos + [kwargs[k] for k in skw], attrs)
+    build.__name__ = qual.split(".")[-1]
+    build.__doc__ = "Symbolic form of ``mx.nd.%s`` (generic imperative-op bridge)." % qual
+    return build
+
+
+class _ContribNamespace:
+    def __getattr__(self, item):
+        from .ndarray import contrib as ndc
+        if item.startswith("_") or not callable(getattr(ndc, item, None)):
+            raise AttributeError("mx.sym.contrib has no operator %r" % item)
+        return _nd_op("contrib." + item)
+
+
+contrib = _ContribNamespace()
+
+
+def __getattr__(item):
+    from . import ndarray as nd
+    fn = getattr(nd, item, None)
+    if item.startswith("_") or fn is None or not callable(fn) or isinstance(fn, type):
+        raise AttributeError("module 'mx.sym' has no attribute %r" % item)
+    return _nd_op(item)
 
 
 def _param_shape(s, idx, in_shape):
