@@ -17,9 +17,9 @@ DataDesc.__new__.__defaults__ = ("float32", "NCHW")
 
 
 class DataBatch:
-    def __init__(self, data, label=None, pad=None, index=None, provide_data=None, provide_label=None):
+    def __init__(self, data, label=None, pad=None, index=None, provide_data=None, provide_label=None, bucket_key=None):
         self.data, self.label, self.pad, self.index = data, label, pad, index
-        self.provide_data, self.provide_label = provide_data, provide_label
+        self.provide_data, self.provide_label, self.bucket_key = provide_data, provide_label, bucket_key
 
 
 class DataIter:

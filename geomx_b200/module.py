@@ -19,7 +19,7 @@ from .context import cpu
 from .io import DataBatch, DataDesc
 from .model import BatchEndParam, _create_kvstore, _initialize_kvstore, _update_params, _update_params_on_kvstore, load_checkpoint, save_checkpoint
 
-__all__ = ["Module", "BaseModule"]
+__all__ = ["Module", "BaseModule", "BucketingModule", "SequentialModule"]
 
 
 def _as_desc(shapes):
@@ -146,7 +146,23 @@ class Module(BaseModule):
                     req[a] = "null"
             self._execs.append(self._symbol.simple_bind(ctx, grad_req=req, **shapes))
         self.binded = True
-        if self._arg_params is not None:
+        if shared_module is not None:
+            # bucketing: parameters, gradients and aux states are the SAME arrays as the shared module's (module.py:420-440 shares the memory pool)
+            assert shared_module.binded and shared_module.params_initialized and len(shared_module._execs) == len(self._execs)
+            for ex, sex in zip(self._execs, shared_module._execs):
+                for n in self._param_names:
+                    if n in sex.arg_dict:
+                        ex.arg_dict[n] = sex.arg_dict[n]
+                        if n in sex.grad_dict and n in ex.grad_dict:
+                            ex.grad_dict[n] = sex.grad_dict[n]
+                for n in self._aux_names:
+                    if n in sex.aux_dict:
+                        ex.aux_dict[n] = sex.aux_dict[n]
+                ex.arg_arrays = [ex.arg_dict[n] for n in self._symbol.list_arguments()]
+                ex.grad_arrays = [ex.grad_dict.get(n) for n in self._symbol.list_arguments()]
+                ex.aux_arrays = [ex.aux_dict[n] for n in self._aux_names]
+            self._arg_params, self._aux_params, self.params_initialized = shared_module._arg_params, shared_module._aux_params, True
+        elif self._arg_params is not None:
             self._sync_params_to_devices()
 
     # ---- parameters
@@ -209,6 +225,13 @@ class Module(BaseModule):
                 kv.set_optimizer(optimizer)
         if not update_on_kvstore:
             self._updater = opt.get_updater(optimizer)
+        self.optimizer_initialized = True
+
+    def borrow_optimizer(self, shared_module):
+        """Use the optimizer / updater / kvstore of ``shared_module`` (whose parameters this module shares)."""
+        assert shared_module.optimizer_initialized
+        self._optimizer, self._kvstore, self._update_on_kvstore, self._updater = (shared_module._optimizer, shared_module._kvstore,
+                                                                                  shared_module._update_on_kvstore, shared_module._updater)
         self.optimizer_initialized = True
 
     def _param_arrays(self):
@@ -295,3 +318,172 @@ class Module(BaseModule):
         if load_optimizer_states:
             mod._preload_opt_states = "%s-%04d.states" % (prefix, epoch)
         return mod
+
+
+class BucketingModule(BaseModule):
+    """One Module per bucket key (e.g. sequence length), all sharing parameters, gradients and the optimizer with the default bucket's
+    module (parity: python/mxnet/module/bucketing_module.py).  ``sym_gen(key) -> (symbol, data_names, label_names)``; a batch selects its
+    bucket through ``batch.bucket_key`` (+ ``provide_data`` / ``provide_label`` for the shapes)."""
+
+    def __init__(self, sym_gen, default_bucket_key=None, logger=logging, context=None, fixed_param_names=None):
+        super().__init__(logger)
+        assert default_bucket_key is not None
+        self._sym_gen, self._default_key, self._context, self._fixed = sym_gen, default_bucket_key, context, fixed_param_names
+        self._buckets, self._curr, self._curr_key = {}, None, None
+        sym, dn, ln = sym_gen(default_bucket_key)
+        self._data_names_, self._label_names_ = list(dn or []), list(ln or [])
+
+    data_names = property(lambda self: self._data_names_)
+    symbol = property(lambda self: self._curr.symbol)
+    output_names = property(lambda self: self._curr.output_names)
+
+    def _make(self, key):
+        sym, dn, ln = self._sym_gen(key)
+        return Module(sym, dn, ln, self.logger, self._context, self._fixed)
+
+    def bind(self, data_shapes, label_shapes=None, for_training=True, inputs_need_grad=False, force_rebind=False, shared_module=None, grad_req="write"):
+        if self.binded and not force_rebind:
+            return
+        self.for_training, self._inputs_need_grad, self._grad_req = for_training, inputs_need_grad, grad_req
+        mod = self._make(self._default_key)
+        mod.bind(data_shapes, label_shapes, for_training, inputs_need_grad, force_rebind=True, grad_req=grad_req)
+        self._buckets = {self._default_key: mod}
+        self._curr, self._curr_key, self.binded = mod, self._default_key, True
+
+    def switch_bucket(self, bucket_key, data_shapes, label_shapes=None):
+        assert self.binded, "call bind before switching bucket"
+        if bucket_key not in self._buckets:
+            mod = self._make(bucket_key)
+            mod.bind(data_shapes, label_shapes, self.for_training, self._inputs_need_grad, force_rebind=True,
+                     shared_module=self._buckets[self._default_key], grad_req=self._grad_req)
+            if self.optimizer_initialized:
+                mod.borrow_optimizer(self._buckets[self._default_key])
+            self._buckets[bucket_key] = mod
+        self._curr, self._curr_key = self._buckets[bucket_key], bucket_key
+
+    def init_params(self, *args, **kwargs):
+        self._buckets[self._default_key].init_params(*args, **kwargs)
+        self.params_initialized = True
+
+    def get_params(self):
+        return self._buckets[self._default_key].get_params()
+
+    def set_params(self, arg_params, aux_params, allow_missing=False, force_init=True, allow_extra=False):
+        self._buckets[self._default_key].set_params(arg_params, aux_params, allow_missing, force_init, allow_extra)
+        self.params_initialized = True
+
+    def init_optimizer(self, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), force_init=False):
+        if self.optimizer_initialized and not force_init:
+            return
+        base = self._buckets[self._default_key]
+        base.init_optimizer(kvstore, optimizer, optimizer_params, force_init)
+        for k, m in self._buckets.items():
+            if m is not base:
+                m.borrow_optimizer(base)
+        self.optimizer_initialized = True
+
+    def prepare(self, data_batch, sparse_row_id_fn=None):
+        key = getattr(data_batch, "bucket_key", None)
+        if key is not None:
+            self.switch_bucket(key, data_batch.provide_data, data_batch.provide_label)
+
+    def forward(self, data_batch, is_train=None):
+        self.prepare(data_batch)
+        self._curr.forward(data_batch, is_train)
+
+    def backward(self, out_grads=None):
+        self._curr.backward(out_grads)
+
+    def update(self):
+        self._curr.update()
+
+    def get_outputs(self, merge_multi_context=True):
+        return self._curr.get_outputs(merge_multi_context)
+
+    def get_input_grads(self, merge_multi_context=True):
+        return self._curr.get_input_grads(merge_multi_context)
+
+    def update_metric(self, eval_metric, labels):
+        self._curr.update_metric(eval_metric, labels)
+
+    def save_checkpoint(self, prefix, epoch, save_optimizer_states=False):
+        self._buckets[self._default_key].save_checkpoint(prefix, epoch, save_optimizer_states)
+
+
+class SequentialModule(BaseModule):
+    """A chain of modules: the outputs of module i are the data of module i+1, gradients flow back through ``get_input_grads``
+    (parity: python/mxnet/module/sequential_module.py).  ``add(module, take_labels=True, auto_wiring=True)``."""
+    META_TAKE_LABELS, META_AUTO_WIRING = "take_labels", "auto_wiring"
+
+    def __init__(self, logger=logging):
+        super().__init__(logger)
+        self._modules, self._metas = [], []
+
+    def add(self, module, **kwargs):
+        self._modules.append(module); self._metas.append(kwargs)
+        self.binded = self.params_initialized = self.optimizer_initialized = False
+        return self
+
+    data_names = property(lambda self: self._modules[0].data_names if self._modules else [])
+    output_names = property(lambda self: self._modules[-1].output_names if self._modules else [])
+
+    def bind(self, data_shapes, label_shapes=None, for_training=True, inputs_need_grad=False, force_rebind=False, shared_module=None, grad_req="write"):
+        if self.binded and not force_rebind:
+            return
+        assert self._modules, "Attempting to bind an empty SequentialModule"
+        self.for_training, self._inputs_need_grad = for_training, inputs_need_grad
+        self._label_shapes = label_shapes
+        shapes = _as_desc(data_shapes)
+        for i, (m, meta) in enumerate(zip(self._modules, self._metas)):
+            lab = label_shapes if meta.get(self.META_TAKE_LABELS) else None
+            m.bind(shapes, lab, for_training, inputs_need_grad or i > 0, force_rebind=True, grad_req=grad_req)
+            if i + 1 < len(self._modules):
+                nxt = self._modules[i + 1]
+                _, out_shapes, _ = m.symbol.infer_shape(**{d.name: d.shape for d in _as_desc(shapes) + (_as_desc(lab) if lab else [])})
+                names = nxt.data_names if self._metas[i + 1].get(self.META_AUTO_WIRING, True) else m.output_names
+                shapes = [(n, s) for n, s in zip(names, out_shapes)]
+        self.binded = True
+
+    def init_params(self, initializer=None, arg_params=None, aux_params=None, allow_missing=False, force_init=False, allow_extra=False):
+        for m in self._modules:
+            m.init_params(initializer, arg_params, aux_params, allow_missing=True, force_init=force_init, allow_extra=True)
+        self.params_initialized = True
+
+    def get_params(self):
+        arg, aux = {}, {}
+        for m in self._modules:
+            a, x = m.get_params(); arg.update(a); aux.update(x)
+        return arg, aux
+
+    def init_optimizer(self, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), force_init=False):
+        for m in self._modules:
+            m.init_optimizer(kvstore, optimizer, optimizer_params, force_init)
+        self.optimizer_initialized = True
+
+    def forward(self, data_batch, is_train=None):
+        batch = data_batch
+        for i, (m, meta) in enumerate(zip(self._modules, self._metas)):
+            m.forward(batch, is_train)
+            if i + 1 < len(self._modules):
+                batch = DataBatch(m.get_outputs(), data_batch.label if self._metas[i + 1].get(self.META_TAKE_LABELS) else None)
+
+    def backward(self, out_grads=None):
+        for i in range(len(self._modules) - 1, -1, -1):
+            self._modules[i].backward(out_grads)
+            if i > 0:
+                out_grads = self._modules[i].get_input_grads()
+
+    def update(self):
+        for m in self._modules:
+            m.update()
+
+    def get_outputs(self, merge_multi_context=True):
+        return self._modules[-1].get_outputs(merge_multi_context)
+
+    def get_input_grads(self, merge_multi_context=True):
+        return self._modules[0].get_input_grads(merge_multi_context)
+
+    def update_metric(self, eval_metric, labels):
+        for m, meta in zip(self._modules, self._metas):
+            if meta.get(self.META_TAKE_LABELS):
+                m.update_metric(eval_metric, labels)

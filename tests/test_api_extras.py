@@ -77,3 +77,86 @@ def test_rtc_compiles_for_sm100a_without_a_gpu():
     assert [p[0] for p in k._params] == [True, True, False, False]
     with pytest.raises(mx.MXNetError):
         mx.rtc.CudaModule("this is not CUDA")
+
+
+def test_bucketing_and_sequential_modules():
+    import numpy as np
+    import geomx_b200 as mx
+
+    # ---- bucketing: per-length graphs sharing one set of weights
+    def sym_gen(T):
+        d = mx.sym.Variable("data")                                   # (N, T) token ids in [0, 8)
+        emb = mx.sym.one_hot(d, depth=8)                              # (N, T, 8) via the generic nd bridge
+        h = mx.sym.mean(emb, axis=1)                                  # (N, 8): bag of words, independent of T
+        out = mx.sym.SoftmaxOutput(mx.sym.FullyConnected(h, num_hidden=2, name="fc"), name="softmax")
+        return out, ("data",), ("softmax_label",)
+
+    rs = np.random.RandomState(0)
+
+    def batch(T, n=16):
+        y = rs.randint(0, 2, n)
+        x = np.where(rs.rand(n, T) < 0.7, y[:, None] * 4 + rs.randint(0, 4, (n, T)), rs.randint(0, 8, (n, T)))   # class decides the token range
+        return mx.io.DataBatch([mx.nd.array(x.astype(np.float32))], [mx.nd.array(y.astype(np.float32))], bucket_key=T,
+                               provide_data=[mx.io.DataDesc("data", (n, T), "float32", "NT")], provide_label=[mx.io.DataDesc("softmax_label", (n,), "float32", "N")])
+
+    bm = mx.mod.BucketingModule(sym_gen, default_bucket_key=10)
+    bm.bind([("data", (16, 10))], [("softmax_label", (16,))])
+    bm.init_params(mx.init.Xavier())
+    bm.init_optimizer(optimizer="adam", optimizer_params={"learning_rate": 0.05})
+    for step in range(60):
+        b = batch([5, 10, 7][step % 3])
+        bm.forward_backward(b); bm.update()
+    assert set(bm._buckets) == {5, 7, 10}
+    w10 = bm._buckets[10]._execs[0].arg_dict["fc_weight"]; w5 = bm._buckets[5]._execs[0].arg_dict["fc_weight"]
+    assert w10 is w5                                                   # literally the same array
+    m = mx.metric.Accuracy()
+    for T in (5, 7, 10):
+        b = batch(T, 16)
+        bm.forward(b, is_train=False); bm.update_metric(m, b.label)
+    assert m.get()[1] > 0.9
+
+    # ---- sequential: two modules chained, gradients cross the boundary
+    d = mx.sym.Variable("data")
+    m1 = mx.mod.Module(mx.sym.Activation(mx.sym.FullyConnected(d, num_hidden=8, name="a"), act_type="relu"), label_names=None)
+    m2 = mx.mod.Module(mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=2, name="b"), name="softmax"))
+    seq = mx.mod.SequentialModule().add(m1).add(m2, take_labels=True, auto_wiring=True)
+    x = rs.randn(64, 4).astype(np.float32); y = (x[:, 0] + x[:, 1] > 0).astype(np.float32)
+    it = mx.io.NDArrayIter(x, y, batch_size=16)
+    seq.fit(it, num_epoch=25, optimizer="adam", optimizer_params={"learning_rate": 0.05}, initializer=mx.init.Xavier())
+    assert dict(seq.score(it, "acc"))["accuracy"] > 0.9
+    arg, _ = seq.get_params()
+    assert {"a_weight", "b_weight"} <= set(arg)
+
+
+def test_rnn_bucket_iter_registry_log_features(tmp_path):
+    import geomx_b200 as mx
+    sents = [["a", "b", "c"], ["a", "b"], ["c", "c", "c", "a", "b"], ["b", "a", "c"], ["a"], ["b", "b"]] * 4
+    enc, vocab = mx.rnn.encode_sentences(sents, invalid_label=0, start_label=1)
+    assert vocab["a"] == 1 and enc[0] == [1, 2, 3]
+    it = mx.rnn.BucketSentenceIter(enc, batch_size=4, buckets=[2, 3, 5], invalid_label=0)
+    keys = []
+    for b in it:
+        assert b.data[0].shape == (4, b.bucket_key) and b.provide_data[0].shape == (4, b.bucket_key)
+        d, l = b.data[0].asnumpy(), b.label[0].asnumpy()
+        assert (l[:, :-1] == d[:, 1:]).all() and (l[:, -1] == 0).all()
+        keys.append(b.bucket_key)
+    assert sorted(set(keys)) == [2, 3, 5] and it.default_bucket_key == 5
+
+    class Base:                                                         # registry helpers
+        pass
+    reg = mx.registry.get_register_func(Base, "thing"); alias = mx.registry.get_alias_func(Base, "thing"); create = mx.registry.get_create_func(Base, "thing")
+
+    @alias("w", "widget2")
+    @reg
+    class Widget(Base):
+        def __init__(self, size=1):
+            self.size = size
+    assert create("widget", size=3).size == 3 and create('["w", {"size": 5}]').size == 5 and isinstance(create(Widget()), Widget)
+    assert set(mx.registry.get_registry(Base)) == {"widget", "w", "widget2"}
+
+    log = mx.log.get_logger("geomx_test_log", filename=str(tmp_path / "x.log"), level=mx.log.INFO)
+    log.info("hello %d", 3)
+    assert "hello 3" in open(str(tmp_path / "x.log")).read()
+    f = mx.runtime.Features()
+    assert f.is_enabled("DIST_KVSTORE") == mx.runtime.available() and "TCGEN05" in f
+    assert mx.executor.Executor is mx.symbol.Executor and mx.libinfo.find_include_path().endswith("csrc")
