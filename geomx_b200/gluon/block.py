@@ -64,6 +64,9 @@ class _BlockScope:
         _BlockScope._current.value = self._old_scope
 
 
+from .. import profiler as _prof  # noqa: E402
+
+
 class _HookHandle:
     def __init__(self, table, key):
         self._table, self._key = table, key
@@ -204,7 +207,12 @@ class Block:
             r = h(self, args)
             if isinstance(r, tuple):
                 args = r
-        out = self.forward(*args)
+        if _prof._state["running"] and (_prof._cfg["profile_imperative"] or _prof._cfg["profile_all"]):
+            dev = bool(args) and hasattr(args[0], "_t") and args[0]._t.is_cuda
+            with _prof.scope(self.name or type(self).__name__, "block", device=dev):
+                out = self.forward(*args)
+        else:
+            out = self.forward(*args)
         for h in list(self._forward_hooks.values()):
             h(self, args, out)
         return out

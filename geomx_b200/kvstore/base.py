@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import weakref
 
+from .. import profiler as _prof
 from ..base import MXNetError
 from ..ndarray import NDArray
 from ..ndarray.sparse import RowSparseNDArray
@@ -64,6 +65,12 @@ class KVStoreBase:
             self._init(self._key(k), vals[0])
 
     def push(self, key, value, priority=0):
+        if _prof._state["running"]:
+            with _prof.scope("KVStorePush", "kvstore"):                # the reference's engine-op names (kvstore_dist.h:601, comm.h:171)
+                return self._push_all(key, value, priority)
+        return self._push_all(key, value, priority)
+
+    def _push_all(self, key, value, priority):
         for k, vals in _ctype_key_value(key, value):
             if any(isinstance(v, RowSparseNDArray) for v in vals):
                 # row_sparse gradients (kvstore_dist.h PushRowSparse :628-657): stores with a sparse wire get the rows, the rest the dense view
@@ -76,6 +83,11 @@ class KVStoreBase:
 
     def pull(self, key, out=None, priority=0, ignore_sparse=True):
         assert out is not None
+        if _prof._state["running"]:
+            with _prof.scope("KVStorePull", "kvstore"):
+                for k, outs in _ctype_key_value(key, out):
+                    self._pull(self._key(k), outs, priority)
+            return
         for k, outs in _ctype_key_value(key, out):
             self._pull(self._key(k), outs, priority)
 

@@ -42,13 +42,33 @@ def set_kvstore_handle(handle):
 
 
 def set_config(**kwargs):
-    """Accepts the reference's keys; ``profile_process='server'`` forwards to all servers via the kvstore."""
+    """Accepts the reference's keys; ``profile_process='server'`` forwards to all servers via the kvstore.  ``continuous_dump=True`` rewrites
+    the trace file every ``dump_period`` seconds while the profiler runs (profiler.cc:258-296)."""
     proc = kwargs.pop("profile_process", "worker")
     if proc == "server":
         assert _kv_handle is not None, "create a dist kvstore before configuring the server profiler"
         _kv_handle.set_server_profiler_command(0, ",".join("%s:%s" % (k, v) for k, v in kwargs.items()))
         return
     _cfg.update(kwargs)
+    if _cfg["continuous_dump"]:
+        _start_continuous_dump()
+
+
+_dump_thread = None
+
+
+def _start_continuous_dump():
+    global _dump_thread
+    if _dump_thread is not None and _dump_thread.is_alive():
+        return
+
+    def loop():
+        while _cfg["continuous_dump"]:
+            time.sleep(max(0.05, float(_cfg["dump_period"])))
+            if _state["running"]:
+                dump(finished=False)
+    _dump_thread = threading.Thread(target=loop, name="profiler-continuous-dump", daemon=True)
+    _dump_thread.start()
 
 
 profiler_set_config = set_config
@@ -104,11 +124,21 @@ def dumps(reset=False, format="table"):
         evs = list(_events) + _resolve_device_ranges()
         if reset:
             _events.clear()
-    agg = {}
+    agg, open_ = {}, {}
+
+    def add(name, dur):
+        a = agg.setdefault(name, [0, 0.0, float("inf"), 0.0])
+        a[0] += 1; a[1] += dur; a[2] = min(a[2], dur); a[3] = max(a[3], dur)
     for e in evs:
-        if e.get("ph") == "X":
-            a = agg.setdefault(e["name"], [0, 0.0, float("inf"), 0.0])
-            a[0] += 1; a[1] += e["dur"]; a[2] = min(a[2], e["dur"]); a[3] = max(a[3], e["dur"])
+        ph = e.get("ph")
+        if ph == "X":
+            add(e["name"], e["dur"])
+        elif ph == "B":                                      # Task / Frame / Event durations are begin/end pairs
+            open_.setdefault((e["name"], e.get("cat")), []).append(e["ts"])
+        elif ph == "E":
+            st = open_.get((e["name"], e.get("cat")))
+            if st:
+                add(e["name"], e["ts"] - st.pop())
     if format == "json":
         return json.dumps({k: {"count": v[0], "total_us": v[1], "min_us": v[2], "max_us": v[3]} for k, v in agg.items()})
     lines = ["%-40s %10s %14s %12s %12s %12s" % ("Name", "Count", "Total(us)", "Min(us)", "Max(us)", "Avg(us)")]
@@ -237,5 +267,10 @@ class Marker:
                    "s": {"global": "g", "process": "p", "thread": "t"}.get(scope, "p")})
 
 
+# MXNET_PROFILER_AUTOSTART=1 starts profiling at import with MXNET_PROFILER_MODE (0: symbolic only, 1: everything) — profiler.cc:80-88
 if os.environ.get("MXNET_PROFILER_AUTOSTART", "0") == "1":
+    _all = os.environ.get("MXNET_PROFILER_MODE", "0") == "1"
+    set_config(profile_all=_all, profile_symbolic=True, profile_imperative=_all, profile_api=_all, profile_memory=_all)
     set_state("run")
+    import atexit as _atexit
+    _atexit.register(lambda: dump(True) if _state["running"] else None)

@@ -480,6 +480,8 @@ class Executor:
         for k, v in kwargs.items():
             self.arg_dict[k][:] = v
         vals, leaves = {}, {}
+        from . import profiler as _prof
+        prof_on = _prof._state["running"] and (_prof._cfg["profile_symbolic"] or _prof._cfg["profile_all"])
         order = self._symbol._topo()
         aux_ids = {id(a) for s in order for a in s.aux}
         with torch.enable_grad() if is_train else torch.no_grad():
@@ -494,7 +496,11 @@ class Executor:
                             leaves[s.name] = t
                         vals[id(s)] = t
                 elif s.op != "_group":
-                    vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], is_train)
+                    if prof_on:                                        # one trace event per graph node, like ProfileOperator (threaded_engine.h:336-350)
+                        with _prof.scope(s.name, "operator", device=self.arg_arrays[0]._t.is_cuda if self.arg_arrays else False):
+                            vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], is_train)
+                    else:
+                        vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], is_train)
         heads = self._symbol.inputs if self._symbol.op == "_group" else [self._symbol]
         self._heads, self._leaves = [vals[id(h)] for h in heads], leaves
         self.outputs = [NDArray(h.detach()) for h in self._heads]

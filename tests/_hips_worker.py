@@ -92,6 +92,11 @@ if mode == "rowsparse":
     print("RESULT " + json.dumps(out), flush=True)
     kv.close()
     sys.exit(0)
+prof_path = os.environ.get("TEST_SERVER_PROFILE")
+if prof_path and kv.rank == 0:
+    # remote server profiling (profiler.py:28-33 -> kSetProfilerParams): the server prefixes the file name with rank<r>_
+    mx.profiler.set_config(profile_process="server", filename=prof_path, profile_all=True, aggregate_stats=True)
+    mx.profiler.set_state("run", profile_process="server")
 for step in range(steps):
     for i, p in enumerate(params):
         if mode == "hfa":
@@ -104,6 +109,9 @@ for step in range(steps):
     mx.nd.waitall()
     out["vals"].append([float(p.astype("float32").asnumpy().reshape(-1)[0]) for p in params])
     out.setdefault("last", [float(p.astype("float32").asnumpy().reshape(-1)[-1]) for p in params])
+if prof_path and kv.rank == 0:
+    mx.profiler.pause(profile_process="server"); mx.profiler.resume(profile_process="server")
+    mx.profiler.dump(profile_process="server")
 if hasattr(getattr(kv, "_kv", None), "ts_stats"):
     out["ts_stats"] = list(kv._kv.ts_stats())
 print("RESULT " + json.dumps(out), flush=True)

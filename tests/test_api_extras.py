@@ -160,3 +160,53 @@ def test_rnn_bucket_iter_registry_log_features(tmp_path):
     f = mx.runtime.Features()
     assert f.is_enabled("DIST_KVSTORE") == mx.runtime.available() and "TCGEN05" in f
     assert mx.executor.Executor is mx.symbol.Executor and mx.libinfo.find_include_path().endswith("csrc")
+
+
+def test_profiler_trace_objects_and_hooks(tmp_path):
+    import json
+    import time
+    import numpy as np
+    import geomx_b200 as mx
+    prof = mx.profiler
+    fn = str(tmp_path / "trace.json")
+    prof.set_config(filename=fn, profile_all=True, aggregate_stats=True)
+    prof.set_state("run")
+    net = mx.gluon.nn.Sequential()
+    net.add(mx.gluon.nn.Dense(8, activation="relu"), mx.gluon.nn.Dense(2))
+    net.initialize()
+    net(mx.nd.array(np.ones((4, 3), dtype=np.float32)))
+    kv = mx.kv.create("local")
+    kv.init(3, mx.nd.ones((2,))); kv.push(3, mx.nd.ones((2,))); out = mx.nd.zeros((2,)); kv.pull(3, out=out)
+    d = mx.sym.Variable("data")
+    ex = mx.sym.FullyConnected(d, num_hidden=2, name="fcp").simple_bind(mx.cpu(), data=(1, 3))
+    ex.forward()
+    dom = prof.Domain("app")
+    with dom.new_task("stage"):
+        time.sleep(0.002)
+    c = dom.new_counter("items", 5); c += 3; c -= 1
+    dom.new_marker("here").mark()
+    prof.pause()
+    net(mx.nd.array(np.ones((4, 3), dtype=np.float32)))                # not recorded while paused
+    prof.resume()
+    table = prof.dumps()
+    assert "KVStorePush" in table and "stage" in table
+    agg = json.loads(prof.dumps(format="json"))
+    assert agg["KVStorePush"]["count"] == 1 and agg["stage"]["total_us"] >= 1500
+    prof.dump()
+    tr = json.load(open(fn))
+    names = [e["name"] for e in tr["traceEvents"]]
+    assert {"KVStorePush", "KVStorePull", "fcp", "stage", "items", "here"} <= set(names)
+    assert sum(1 for e in tr["traceEvents"] if e.get("cat") == "block") == 3        # Sequential + two Dense, once
+    counters = [e for e in tr["traceEvents"] if e["name"] == "items"]
+    assert [list(e["args"].values())[0] for e in counters][-1] == 7
+    assert all(e["ph"] in ("X", "C", "i", "M", "B", "E") for e in tr["traceEvents"])
+    assert not prof.is_active()                                         # dump(finished=True) stops the profiler
+    # continuous dump keeps rewriting the file while running
+    fn2 = str(tmp_path / "cont.json")
+    prof.set_config(filename=fn2, continuous_dump=True, dump_period=0.05)
+    prof.set_state("run")
+    with prof.scope("tick"):
+        pass
+    time.sleep(0.3)
+    assert "tick" in open(fn2).read()
+    prof.set_config(continuous_dump=False); prof.set_state("stop")

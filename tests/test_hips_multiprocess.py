@@ -115,6 +115,16 @@ def test_single_tier_dist_sync_sgd():
                 assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-5
 
 
+def test_remote_server_profiling(tmp_path):
+    """``profile_process='server'``: worker rank 0 configures, runs and dumps the profiler of the server process over the command channel."""
+    import json
+    res = launch_single_tier({"TEST_MODE": "sgd", "TEST_SERVER_PROFILE": str(tmp_path / "srv.json")})
+    assert len(res) == 2
+    tr = json.load(open(str(tmp_path / "rank0_srv.json")))
+    names = [e["name"] for e in tr["traceEvents"]]
+    assert names.count("KVStoreDistServerPush") >= 3 * 4 * 2 - 8 and "KVStoreDistServerPull" in names      # 3 steps x 4 keys x 2 workers (minus those before 'run')
+
+
 def test_hips_two_tier_fsa():
     """2 parties x 2 workers, global server runs SGD: every worker sees w_0 - t*lr*sum_{4 workers} grad."""
     res = launch_hips({"TEST_MODE": "sgd"})
