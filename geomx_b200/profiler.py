@@ -5,9 +5,11 @@ Event / Counter / Marker; ``profile_process='server'`` routes through the kvstor
 ``src/profiler/profiler.{h,cc}`` (chrome-trace JSON ``traceEvents`` with ``ph`` codes, pid = device index :155-254;
 aggregate table ``aggregate_stats.cc``; continuous dump :258-296).
 
-B200 design: events are recorded by the native ring-buffer profiler (``csrc/runtime/profiler.cc`` via ``_C``) — host
-ranges use a monotonic clock, device ranges use CUDA events resolved lazily at dump time so recording never
-synchronises a stream.  Falls back to a pure-Python recorder when ``_C`` is absent.
+Design: two recorders with one file format.  Worker-side events (this module) are appended to an in-process list — host ranges use
+a monotonic clock, device ranges use CUDA events that are resolved lazily at dump time, so recording never synchronises a stream;
+hooks: every gluon ``Block`` call (``profile_imperative``), every symbolic graph node (``profile_symbolic``), kvstore push / pull,
+plus user ``scope`` / ``Domain`` objects.  Server processes have no Python on their hot path and record with the native profiler
+(``csrc/runtime/profiler.h``: push / pull handlers, controlled remotely through command 6, files prefixed ``rank<r>_``).
 """
 from __future__ import annotations
 
