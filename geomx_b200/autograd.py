@@ -164,3 +164,63 @@ def grad(heads, variables, head_grads=None, retain_graph=None, create_graph=Fals
     out = torch.autograd.grad(ts, [v._t for v in vs], gs, retain_graph=retain_graph, create_graph=create_graph)
     res = [NDArray(o) for o in out]
     return res[0] if single else res
+
+
+class Function:
+    """User-defined differentiable function (parity: python/mxnet/autograd.py Function :365-500)::
+
+        class sigmoid(mx.autograd.Function):
+            def forward(self, x):
+                y = 1 / (1 + mx.nd.exp(-x)); self.save_for_backward(y); return y
+            def backward(self, dy):
+                y, = self.saved_tensors; return dy * y * (1 - y)
+
+    ``forward`` runs outside the tape on NDArrays; ``backward`` receives one gradient per output and returns one per input.  An instance
+    can be called once per recorded use (it holds the saved tensors)."""
+
+    def __init__(self):
+        self._used = False
+        self.saved_tensors = ()
+
+    def save_for_backward(self, *args):
+        self.saved_tensors = args
+
+    def forward(self, *inputs):
+        raise NotImplementedError
+
+    def backward(self, *output_grads):
+        raise NotImplementedError
+
+    def __call__(self, *inputs):
+        from .ndarray import NDArray
+        assert not self._used, "Each Function instance can only be called once. Please create another instance."
+        self._used = True
+        user = self
+
+        class _Bridge(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, *ts):
+                with pause():
+                    outs = user.forward(*[NDArray(t.detach()) for t in ts])
+                ctx.single = isinstance(outs, NDArray)
+                outs = (outs,) if ctx.single else tuple(outs)
+                res = tuple(o._t.detach() for o in outs)
+                return res[0] if ctx.single else res
+
+            @staticmethod
+            def backward(ctx, *gs):
+                with pause():
+                    gi = user.backward(*[NDArray(g) for g in gs])
+                gi = (gi,) if isinstance(gi, NDArray) else tuple(gi)
+                assert len(gi) == len(inputs), "%s.backward must return exactly the same number of NDArrays as the number of NDArrays arguments to forward. " \
+                    "Expecting %d got %d" % (type(user).__name__, len(inputs), len(gi))
+                return tuple(None if g is None else g._t for g in gi)
+
+        out = _Bridge.apply(*[x._t for x in inputs])
+        return NDArray(out) if isinstance(out, torch.Tensor) else tuple(NDArray(o) for o in out)
+
+
+def get_symbol(x):
+    """The reference returns the recorded computation history as a Symbol; the tape here is PyTorch's and has no nnvm form."""
+    from .base import MXNetError
+    raise MXNetError("autograd.get_symbol is not available: the autograd tape is not an nnvm graph (build the model with mx.sym to get a Symbol)")

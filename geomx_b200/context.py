@@ -90,3 +90,12 @@ def num_gpus():
 def current_context():
     v = getattr(Context._default, "value", None)
     return v if v is not None else Context("cpu", 0)
+
+
+def gpu_memory_info(device_id=0):
+    """``(free, total)`` bytes of a GPU (context.py:260-285)."""
+    import torch
+    if not torch.cuda.is_available():
+        from .base import MXNetError
+        raise MXNetError("gpu_memory_info: no GPU is visible to this process")
+    return tuple(int(v) for v in torch.cuda.mem_get_info(device_id))

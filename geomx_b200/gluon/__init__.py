@@ -1,7 +1,7 @@
 """``mx.gluon`` namespace."""
 from . import data, loss, nn, utils  # noqa: F401
-from .block import Block, HybridBlock  # noqa: F401
-from .parameter import Constant, Parameter, ParameterDict  # noqa: F401
+from .block import Block, HybridBlock, SymbolBlock  # noqa: F401
+from .parameter import Constant, DeferredInitializationError, Parameter, ParameterDict  # noqa: F401
 from .trainer import Trainer  # noqa: F401
 
 from . import contrib  # noqa: F401,E402

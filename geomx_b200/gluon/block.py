@@ -270,8 +270,93 @@ class HybridBlock(Block):
     def hybrid_forward(self, F, x, *args, **kwargs):
         raise NotImplementedError
 
+    def infer_type(self, *args):
+        """Parameters take the dtype of the first input (layers are dtype-generic; gluon/block.py infer_type)."""
+        for p in self._reg_params.values():
+            if p._data is None:
+                p.dtype = str(args[0].dtype).replace("torch.", "") if args else p.dtype
+
     def export(self, path, epoch=0):
-        self.save_parameters("%s-%04d.params" % (path, epoch))
+        """``path-%04d.params`` (``arg:`` / ``aux:`` prefixed like ``save_checkpoint``) and, for blocks that own a graph (``SymbolBlock``),
+        ``path-symbol.json``.  Imperative HybridBlocks have no nnvm graph to serialise: reload them with ``load_parameters``."""
+        sym = getattr(self, "_symbol", None)
+        if sym is not None:
+            with open("%s-symbol.json" % path, "w") as f:
+                f.write(sym.tojson())
+            aux = set(sym.list_auxiliary_states())
+            d = {("aux:" if n in aux else "arg:") + n: p.data() for n, p in self.collect_params().items()}
+            nd.save("%s-%04d.params" % (path, epoch), d)
+        else:
+            self.save_parameters("%s-%04d.params" % (path, epoch))
 
 
 _F = _FMod()
+
+
+class SymbolBlock(HybridBlock):
+    """A block built from a Symbol: ``SymbolBlock(outputs, inputs)`` turns every free argument / auxiliary state of ``outputs`` other than
+    ``inputs`` into a Parameter (named as in the graph, no prefix) and evaluates the graph on call — differentiable, so exported models
+    can be fine-tuned (parity: python/mxnet/gluon/block.py SymbolBlock :930-1100, incl. ``SymbolBlock.imports``)."""
+
+    def __init__(self, outputs, inputs, params=None):
+        super().__init__(prefix="", params=None)
+        from .. import symbol as S
+        self._symbol = S.Group(list(outputs)) if isinstance(outputs, (list, tuple)) and len(outputs) > 1 else (outputs[0] if isinstance(outputs, (list, tuple)) else outputs)
+        ins = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        self._input_names = [i.name if isinstance(i, S.Symbol) else str(i) for i in ins]
+        aux = set(self._symbol.list_auxiliary_states())
+        self._param_names = [n for n in self._symbol.list_arguments() if n not in self._input_names]
+        self._aux_names = list(self._symbol.list_auxiliary_states())
+        for n in self._param_names + self._aux_names:
+            p = (params.get(n) if params is not None and n in params else None) or Parameter(
+                n, grad_req="null" if n in aux else "write", allow_deferred_init=True, differentiable=n not in aux)
+            if n.endswith("_moving_var") or n.endswith("running_var"):
+                from .. import initializer
+                p.init = p.init or initializer.One()
+            self._params._params[n] = p
+            self._reg_params[n] = p
+
+    @staticmethod
+    def imports(symbol_file, input_names, param_file=None, ctx=None):
+        from .. import symbol as S
+        sym = S.load(symbol_file)
+        names = [input_names] if isinstance(input_names, str) else list(input_names)
+        blk = SymbolBlock(sym, [S.Variable(n) for n in names])
+        if param_file is not None:
+            loaded = nd.load(param_file)
+            loaded = {k.split(":", 1)[1] if k.startswith(("arg:", "aux:")) else k: v for k, v in loaded.items()}
+            for n, p in blk._reg_params.items():
+                if n not in loaded:
+                    raise RuntimeError("Parameter %s is missing in file %s" % (n, param_file))
+                p.shape = tuple(loaded[n].shape)
+                p.initialize(ctx=ctx)
+                p.set_data(loaded[n])
+        return blk
+
+    def _shapes_from(self, args):
+        shapes = {n: tuple(a.shape) for n, a in zip(self._input_names, args)}
+        arg_shapes, _, aux_shapes = self._symbol.infer_shape(**shapes)
+        known = dict(zip(self._symbol.list_arguments(), arg_shapes)); known.update(zip(self._aux_names, aux_shapes))
+        for n, p in self._reg_params.items():
+            if p.shape is None or 0 in tuple(p.shape) or p._data is None:
+                p.shape = tuple(known[n])
+
+    def forward(self, *args):
+        from .. import autograd
+        from ..symbol import run_graph
+        assert len(args) == len(self._input_names), "expected %d inputs (%s)" % (len(self._input_names), self._input_names)
+        try:
+            pvals = {n: p.data(args[0].context) for n, p in self._reg_params.items()}
+        except DeferredInitializationError:
+            self._shapes_from(args)
+            for p in self._reg_params.values():
+                p._finish_deferred_init()
+            pvals = {n: p.data(args[0].context) for n, p in self._reg_params.items()}
+        feed = {n: a._t for n, a in zip(self._input_names, args)}
+        feed.update({n: v._t for n, v in pvals.items()})
+        outs = run_graph(self._symbol, feed, autograd.is_training())
+        res = [NDArray(o) for o in outs]
+        return res[0] if len(res) == 1 else res
+
+    def hybrid_forward(self, F, x, *args, **kwargs):
+        raise NotImplementedError

@@ -2,7 +2,7 @@
 ArrayDataset, _LazyTransformDataset)."""
 from __future__ import annotations
 
-__all__ = ["Dataset", "SimpleDataset", "ArrayDataset"]
+__all__ = ["Dataset", "SimpleDataset", "ArrayDataset", "RecordFileDataset"]
 
 
 class Dataset:
@@ -59,3 +59,21 @@ class ArrayDataset(Dataset):
 
     def __len__(self):
         return self._length
+
+
+
+class RecordFileDataset(Dataset):
+    """Raw records of an indexed RecordIO file (``.rec`` + ``.idx``) (dataset.py RecordFileDataset :170-200)."""
+
+    def __init__(self, filename):
+        import os
+        from ... import recordio
+        self.idx_file = os.path.splitext(filename)[0] + ".idx"
+        self.filename = filename
+        self._record = recordio.MXIndexedRecordIO(self.idx_file, self.filename, "r")
+
+    def __getitem__(self, idx):
+        return self._record.read_idx(self._record.keys[idx])
+
+    def __len__(self):
+        return len(self._record.keys)

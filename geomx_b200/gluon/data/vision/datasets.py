@@ -18,7 +18,7 @@ from ....base import getenv_int
 from ....ndarray import NDArray
 from ..dataset import Dataset
 
-__all__ = ["MNIST", "FashionMNIST", "CIFAR10", "SyntheticImageDataset"]
+__all__ = ["MNIST", "FashionMNIST", "CIFAR10", "CIFAR100", "ImageRecordDataset", "ImageFolderDataset", "SyntheticImageDataset"]
 
 
 def _read_idx(path):
@@ -109,3 +109,67 @@ class CIFAR10(_ImgDataset):
             data, label = _synthetic(n, (32, 32, 3), 10, 44, 0 if train else 1)
             self.synthetic = True
         super().__init__(data, label, transform)
+
+
+class CIFAR100(_ImgDataset):
+    """CIFAR-100 from ``train.bin`` / ``test.bin`` under ``root`` (rows: coarse label, fine label, 3072 pixels); ``fine_label`` selects
+    which of the two is returned.  Synthetic stand-in when the files are absent."""
+
+    def __init__(self, root=os.path.join("~", ".mxnet", "datasets", "cifar100"), fine_label=False, train=True, transform=None):
+        root = os.path.expanduser(root)
+        path = os.path.join(root, "train.bin" if train else "test.bin")
+        if os.path.exists(path):
+            raw = np.fromfile(path, dtype=np.uint8).reshape(-1, 3072 + 2)
+            label = raw[:, 1 if fine_label else 0].astype(np.int32)
+            data = raw[:, 2:].reshape(-1, 3, 32, 32).transpose(0, 2, 3, 1).copy()
+            self.synthetic = False
+        else:
+            n = getenv_int("GEOMX_SYNTHETIC_SIZE", 0) or (50000 if train else 10000)
+            data, label = _synthetic(n, (32, 32, 3), 100 if fine_label else 20, 45, 0 if train else 1)
+            self.synthetic = True
+        super().__init__(data, label, transform)
+
+
+class ImageRecordDataset(Dataset):
+    """Images + labels from an indexed RecordIO file packed by ``tools/im2rec.py`` (datasets.py ImageRecordDataset :230-270)."""
+
+    def __init__(self, filename, flag=1, transform=None):
+        from ..dataset import RecordFileDataset
+        self._rec, self._flag, self._transform = RecordFileDataset(filename), flag, transform
+
+    def __getitem__(self, idx):
+        from .... import image, recordio
+        header, img = recordio.unpack(self._rec[idx])
+        x = image.imdecode(img, self._flag)
+        y = header.label
+        return self._transform(x, y) if self._transform is not None else (x, y)
+
+    def __len__(self):
+        return len(self._rec)
+
+
+class ImageFolderDataset(Dataset):
+    """``root/<class name>/<image>``: classes are the sorted sub-directory names (``synsets``), items ``(image HWC uint8, class index)``."""
+
+    def __init__(self, root, flag=1, transform=None):
+        self._root, self._flag, self._transform = os.path.expanduser(root), flag, transform
+        self._exts = (".jpg", ".jpeg", ".png", ".bmp", ".ppm")
+        self.synsets, self.items = [], []
+        for folder in sorted(os.listdir(self._root)):
+            path = os.path.join(self._root, folder)
+            if not os.path.isdir(path):
+                continue
+            label = len(self.synsets)
+            self.synsets.append(folder)
+            for fn in sorted(os.listdir(path)):
+                if os.path.splitext(fn)[1].lower() in self._exts:
+                    self.items.append((os.path.join(path, fn), label))
+
+    def __getitem__(self, idx):
+        from .... import image
+        x = image.imread(self.items[idx][0], self._flag)
+        y = self.items[idx][1]
+        return self._transform(x, y) if self._transform is not None else (x, y)
+
+    def __len__(self):
+        return len(self.items)

@@ -9,7 +9,7 @@ from ....ndarray import NDArray
 from ...block import Block
 from ...nn import Sequential
 
-__all__ = ["Compose", "Cast", "ToTensor", "Normalize", "Resize", "CenterCrop", "RandomFlipLeftRight"]
+__all__ = ["Compose", "Cast", "ToTensor", "Normalize", "Resize", "CenterCrop", "RandomFlipLeftRight", "RandomSaturation", "RandomHue", "RandomColorJitter", "RandomLighting"]
 
 
 class Compose(Sequential):
@@ -125,3 +125,51 @@ class RandomContrast(Block):
         t = x._t.float()
         alpha = 1.0 + random.uniform(-self._c, self._c)
         return NDArray(t * alpha + t.mean() * (1 - alpha))
+
+
+class RandomSaturation(Block):
+    def __init__(self, saturation):
+        super().__init__(); self._s = saturation
+
+    def forward(self, x):
+        from .... import image
+        return image.SaturationJitterAug(self._s)(x)
+
+
+class RandomHue(Block):
+    def __init__(self, hue):
+        super().__init__(); self._h = hue
+
+    def forward(self, x):
+        from .... import image
+        return image.HueJitterAug(self._h)(x)
+
+
+class RandomColorJitter(Block):
+    """Brightness / contrast / saturation / hue jitter in random order (transforms.py RandomColorJitter)."""
+
+    def __init__(self, brightness=0, contrast=0, saturation=0, hue=0):
+        super().__init__()
+        from .... import image
+        self._augs = [a for a in ([image.BrightnessJitterAug(brightness)] if brightness else []) + ([image.ContrastJitterAug(contrast)] if contrast else [])
+                      + ([image.SaturationJitterAug(saturation)] if saturation else []) + ([image.HueJitterAug(hue)] if hue else [])]
+
+    def forward(self, x):
+        import random
+        order = list(self._augs); random.shuffle(order)
+        for a in order:
+            x = a(x)
+        return x
+
+
+class RandomLighting(Block):
+    """AlexNet-style PCA noise with standard deviation ``alpha``."""
+
+    def __init__(self, alpha):
+        super().__init__(); self._alpha = alpha
+
+    def forward(self, x):
+        import numpy as np
+        from .... import image
+        return image.LightingAug(self._alpha, np.array([55.46, 4.794, 1.148]),
+                                 np.array([[-0.5675, 0.7192, 0.4009], [-0.5808, -0.0045, -0.8140], [-0.5836, -0.6948, 0.4203]]))(x)

@@ -34,6 +34,7 @@ class Parameter:
         self.init = init
         self.allow_deferred_init = allow_deferred_init
         self._differentiable = differentiable
+        self._stype, self._grad_stype = stype, grad_stype
         self._data = None          # list[NDArray], one per ctx
         self._ctx_list = None
         self._deferred_init = ()
@@ -126,6 +127,24 @@ class Parameter:
 
     def data(self, ctx=None):
         return self._check_and_get(self._data, ctx)
+
+    def row_sparse_data(self, row_id):
+        """The rows ``row_id`` of a ``row_sparse`` parameter as a RowSparseNDArray on ``row_id``'s context (parameter.py:480-500; with a
+        kvstore-backed Trainer the rows are pulled from the server first)."""
+        from ..ndarray.sparse import RowSparseNDArray
+        from ..ndarray import NDArray
+        import torch
+        if self._stype != "row_sparse":
+            raise RuntimeError("Cannot return a copy of Parameter %s via row_sparse_data() because its storage type is %s. Please use data() instead." % (self.name, self._stype))
+        full = self._check_and_get(self._data, row_id.context)
+        tr = getattr(self, "_trainer", None)
+        if tr is not None and getattr(tr, "_row_sparse_pull", None) is not None:
+            tr._row_sparse_pull(self, full, row_id)
+        ids = torch.unique(row_id._t.long().reshape(-1))
+        return RowSparseNDArray(NDArray(full._t.detach()[ids]), NDArray(ids), tuple(full.shape))
+
+    def list_row_sparse_data(self, row_id):
+        return [self.row_sparse_data(row_id)]
 
     def list_data(self):
         return list(self._check_and_get(self._data, list))

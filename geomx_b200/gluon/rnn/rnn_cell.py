@@ -9,7 +9,7 @@ from ...ops import functional as OF
 from ..block import HybridBlock
 
 __all__ = ["RecurrentCell", "RNNCell", "LSTMCell", "GRUCell", "SequentialRNNCell", "ModifierCell", "DropoutCell", "ZoneoutCell", "ResidualCell",
-           "BidirectionalCell"]
+           "BidirectionalCell", "HybridRecurrentCell", "HybridSequentialRNNCell"]
 
 
 class RecurrentCell(HybridBlock):
@@ -224,3 +224,8 @@ class BidirectionalCell(RecurrentCell):
         if merge_outputs or merge_outputs is None and isinstance(inputs, NDArray):
             return NDArray(torch.stack([o._t for o in outs], dim=axis)), ls + rs
         return outs, ls + rs
+
+
+# every cell here is a HybridBlock already; the reference keeps separate names for the hybridizable bases (rnn_cell.py:300-330, :690)
+HybridRecurrentCell = RecurrentCell
+HybridSequentialRNNCell = SequentialRNNCell

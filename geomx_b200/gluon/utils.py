@@ -68,3 +68,6 @@ def check_sha1(filename, sha1_hash):
 def download(url, path=None, overwrite=False, sha1_hash=None, **kw):
     raise RuntimeError("no network egress in this environment; place files under the dataset root manually "
                        "or use synthetic=True datasets")
+
+
+from .block import _HookHandle as HookHandle  # noqa: E402,F401  (gluon/utils.py HookHandle: returned by Block.register_forward_*hook)

@@ -136,18 +136,170 @@ class BrightnessJitterAug(Augmenter):
     def __call__(self, src): return src.astype("float32") * (1.0 + _pyrandom.uniform(-self.brightness, self.brightness))
 
 
-def CreateAugmenter(data_shape, resize=0, rand_crop=False, rand_resize=False, rand_mirror=False, mean=None, std=None, brightness=0, inter_method=1,
-                    **kwargs):
+_GRAY = (0.299, 0.587, 0.114)
+
+
+def _gray(t):
+    return (t[..., 0] * _GRAY[0] + t[..., 1] * _GRAY[1] + t[..., 2] * _GRAY[2]).unsqueeze(-1)
+
+
+class ContrastJitterAug(Augmenter):
+    def __init__(self, contrast): super().__init__(contrast=contrast); self.contrast = contrast
+
+    def __call__(self, src):
+        t = src._t.float(); alpha = 1.0 + _pyrandom.uniform(-self.contrast, self.contrast)
+        return NDArray(t * alpha + _gray(t).mean() * (1.0 - alpha))
+
+
+class SaturationJitterAug(Augmenter):
+    def __init__(self, saturation): super().__init__(saturation=saturation); self.saturation = saturation
+
+    def __call__(self, src):
+        t = src._t.float(); alpha = 1.0 + _pyrandom.uniform(-self.saturation, self.saturation)
+        return NDArray(t * alpha + _gray(t) * (1.0 - alpha))
+
+
+class HueJitterAug(Augmenter):
+    """Rotate the hue by a random angle in YIQ space (image.py HueJitterAug :760-800)."""
+
+    def __init__(self, hue):
+        super().__init__(hue=hue); self.hue = hue
+        self.tyiq = np.array([[0.299, 0.587, 0.114], [0.596, -0.274, -0.321], [0.211, -0.523, 0.311]])
+        self.ityiq = np.array([[1.0, 0.956, 0.621], [1.0, -0.272, -0.647], [1.0, -1.107, 1.705]])
+
+    def __call__(self, src):
+        alpha = _pyrandom.uniform(-self.hue, self.hue)
+        u, w = np.cos(alpha * np.pi), np.sin(alpha * np.pi)
+        bt = np.array([[1.0, 0.0, 0.0], [0.0, u, -w], [0.0, w, u]])
+        m = torch.as_tensor(np.dot(np.dot(self.ityiq, bt), self.tyiq).T, dtype=torch.float32)
+        return NDArray(src._t.float() @ m.to(src._t.device))
+
+
+class ColorJitterAug(Augmenter):
+    """Brightness, contrast and saturation jitter applied in random order."""
+
+    def __init__(self, brightness, contrast, saturation):
+        super().__init__(brightness=brightness, contrast=contrast, saturation=saturation)
+        self.ts = [a for a, v in ((BrightnessJitterAug, brightness), (ContrastJitterAug, contrast), (SaturationJitterAug, saturation)) if v > 0]
+        self.ts = [a(v) for a, v in zip(self.ts, [v for v in (brightness, contrast, saturation) if v > 0])]
+
+    def __call__(self, src):
+        order = list(self.ts); _pyrandom.shuffle(order)
+        for t in order:
+            src = t(src)
+        return src
+
+
+class LightingAug(Augmenter):
+    """AlexNet-style PCA lighting noise: adds ``eigvec @ (alpha * eigval)`` with ``alpha ~ N(0, alphastd)``."""
+
+    def __init__(self, alphastd, eigval, eigvec):
+        super().__init__(alphastd=alphastd, eigval=list(np.ravel(eigval)), eigvec=[list(r) for r in np.asarray(eigvec)])
+        self.alphastd, self.eigval, self.eigvec = alphastd, np.asarray(eigval, dtype=np.float32), np.asarray(eigvec, dtype=np.float32)
+
+    def __call__(self, src):
+        alpha = np.random.normal(0, self.alphastd, size=(3,)).astype(np.float32)
+        rgb = np.dot(self.eigvec * alpha, self.eigval)
+        return NDArray(src._t.float() + torch.as_tensor(rgb, device=src._t.device))
+
+
+class RandomGrayAug(Augmenter):
+    def __init__(self, p): super().__init__(p=p); self.p = p
+
+    def __call__(self, src):
+        if _pyrandom.random() < self.p:
+            return NDArray(_gray(src._t.float()).expand(-1, -1, 3).contiguous())
+        return src
+
+
+class RandomOrderAug(Augmenter):
+    def __init__(self, ts): super().__init__(); self.ts = list(ts)
+
+    def dumps(self):
+        return [self.__class__.__name__.lower(), [t.dumps() for t in self.ts]]
+
+    def __call__(self, src):
+        order = list(self.ts); _pyrandom.shuffle(order)
+        for t in order:
+            src = t(src)
+        return src
+
+
+class SequentialAug(Augmenter):
+    def __init__(self, ts): super().__init__(); self.ts = list(ts)
+
+    def dumps(self):
+        return [self.__class__.__name__.lower(), [t.dumps() for t in self.ts]]
+
+    def __call__(self, src):
+        for t in self.ts:
+            src = t(src)
+        return src
+
+
+def scale_down(src_size, size):
+    """Shrink ``size`` (w, h) proportionally so that it fits into ``src_size`` (w, h)."""
+    w, h = size; sw, sh = src_size
+    if sh < h:
+        w, h = float(w * sh) / h, sh
+    if sw < w:
+        w, h = sw, float(h * sw) / w
+    return int(w), int(h)
+
+
+def random_size_crop(src, size, area, ratio, interp=2, **kwargs):
+    """Random crop with ``area`` fraction (float or (min, max)) and aspect ``ratio`` range, resized to ``size``; falls back to a centre
+    crop after 10 failed draws.  Returns ``(image, (x0, y0, w, h))``."""
+    import math
+    h, w = src.shape[0], src.shape[1]
+    src_area = h * w
+    if "min_area" in kwargs:
+        area = kwargs.pop("min_area")
+    if isinstance(area, (int, float)):
+        area = (area, 1.0)
+    for _ in range(10):
+        target = _pyrandom.uniform(area[0], area[1]) * src_area
+        log_ratio = (math.log(ratio[0]), math.log(ratio[1]))
+        ar = math.exp(_pyrandom.uniform(*log_ratio))
+        nw, nh = int(round(math.sqrt(target * ar))), int(round(math.sqrt(target / ar)))
+        if nw <= w and nh <= h:
+            x0, y0 = _pyrandom.randint(0, w - nw), _pyrandom.randint(0, h - nh)
+            return fixed_crop(src, x0, y0, nw, nh, size, interp), (x0, y0, nw, nh)
+    return center_crop(src, size, interp)
+
+
+class RandomSizedCropAug(Augmenter):
+    def __init__(self, size, area, ratio, interp=2, **kwargs):
+        super().__init__(size=size, area=area, ratio=ratio, interp=interp)
+        self.size, self.area, self.ratio, self.interp = size, kwargs.pop("min_area", area), ratio, interp
+
+    def __call__(self, src):
+        return random_size_crop(src, self.size, self.area, self.ratio, self.interp)[0]
+
+
+def CreateAugmenter(data_shape, resize=0, rand_crop=False, rand_resize=False, rand_mirror=False, mean=None, std=None, brightness=0, contrast=0,
+                    saturation=0, hue=0, pca_noise=0, rand_gray=0, inter_method=1, **kwargs):
     augs = []
     if resize > 0:
         augs.append(ResizeAug(resize, inter_method))
     crop = (data_shape[2], data_shape[1])
-    augs.append(RandomCropAug(crop, inter_method) if rand_crop else CenterCropAug(crop, inter_method))
+    if rand_resize:
+        assert rand_crop
+        augs.append(RandomSizedCropAug(crop, 0.08, (3.0 / 4.0, 4.0 / 3.0), inter_method))
+    else:
+        augs.append(RandomCropAug(crop, inter_method) if rand_crop else CenterCropAug(crop, inter_method))
     if rand_mirror:
         augs.append(HorizontalFlipAug(0.5))
     augs.append(CastAug())
-    if brightness:
-        augs.append(BrightnessJitterAug(brightness))
+    if brightness or contrast or saturation:
+        augs.append(ColorJitterAug(brightness, contrast, saturation))
+    if hue:
+        augs.append(HueJitterAug(hue))
+    if pca_noise > 0:
+        augs.append(LightingAug(pca_noise, np.array([55.46, 4.794, 1.148]),
+                                np.array([[-0.5675, 0.7192, 0.4009], [-0.5808, -0.0045, -0.8140], [-0.5836, -0.6948, 0.4203]])))
+    if rand_gray > 0:
+        augs.append(RandomGrayAug(rand_gray))
     if mean is True:
         mean = np.array([123.68, 116.28, 103.53])
     if std is True:

@@ -14,7 +14,7 @@ import torch
 
 from .base import MXNetError
 
-__all__ = ["Initializer", "Xavier", "Uniform", "Normal", "Constant", "Zero", "One", "Orthogonal",
+__all__ = ["Initializer", "Xavier", "Uniform", "Normal", "Constant", "Zero", "One", "Orthogonal", "LSTMBias", "FusedRNN",
            "MSRAPrelu", "Bilinear", "Mixed", "Load", "InitDesc", "register", "create"]
 
 _registry = {}
@@ -179,6 +179,61 @@ class Bilinear(Initializer):
             x = i % shape[3]; y = (i // shape[3]) % shape[2]
             w[i] = (1 - abs(x / f - c)) * (1 - abs(y / f - c))
         t.copy_(torch.from_numpy(w.reshape(shape)))
+
+
+@register
+class LSTMBias(Initializer):
+    """Bias of an LSTM: zeros, except the forget gate (second quarter in MXNet's i, f, g, o order) which is ``forget_bias``
+    (initializer.py LSTMBias :640-670)."""
+
+    def __init__(self, forget_bias=1.0):
+        super().__init__(forget_bias=forget_bias); self.forget_bias = forget_bias
+
+    def _init_weight(self, _, t):
+        t.zero_()
+        h = t.shape[0] // 4
+        t[h:2 * h] = self.forget_bias
+    _init_bias = _init_default = _init_weight
+
+
+@register
+class FusedRNN(Initializer):
+    """Initialise the flat parameter vector of a fused RNN layer: weight blocks with ``init``, biases zero, LSTM forget-gate biases
+    ``forget_bias`` (initializer.py FusedRNN :673-730).  Layout: per layer and direction ``W_i2h, W_h2h`` for all, then ``b_i2h, b_h2h``."""
+
+    def __init__(self, init, num_hidden, num_layers, mode, bidirectional=False, forget_bias=1.0):
+        if isinstance(init, str):
+            import json
+            klass, kwargs = json.loads(init)
+            init = create(klass, **kwargs)
+        super().__init__(init=init.dumps() if init is not None else None, num_hidden=num_hidden, num_layers=num_layers, mode=mode,
+                         bidirectional=bidirectional, forget_bias=forget_bias)
+        self._init, self._h, self._layers, self._mode, self._bi, self._fb = init, num_hidden, num_layers, mode, bidirectional, forget_bias
+
+    def _init_weight(self, desc, t):
+        gates = {"rnn_relu": 1, "rnn_tanh": 1, "lstm": 4, "gru": 3}[self._mode]
+        dirs, h = (2 if self._bi else 1), self._h
+        flat = t.view(-1)
+        nbias = self._layers * dirs * 2 * gates * h
+        nweight = flat.numel() - nbias
+        # input size of layer 0 follows from the total length: nweight = dirs*gates*h*(in + h) + (layers-1)*dirs*gates*h*(dirs*h + h)
+        rest = (self._layers - 1) * dirs * gates * h * (dirs * h + h)
+        in0 = (nweight - rest) // (dirs * gates * h) - h
+        pos = 0
+        for layer in range(self._layers):
+            cin = in0 if layer == 0 else dirs * h
+            for _ in range(dirs):
+                for cols in (cin, h):
+                    n = gates * h * cols
+                    block = flat[pos:pos + n].view(gates * h, cols)
+                    (self._init or Uniform(0.07))._init_weight(desc, block)
+                    pos += n
+        bias = flat[pos:]
+        bias.zero_()
+        if self._mode == "lstm":
+            for k in range(self._layers * dirs * 2):
+                bias[k * 4 * h + h: k * 4 * h + 2 * h] = self._fb
+    _init_default = _init_weight
 
 
 class Mixed:

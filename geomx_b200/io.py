@@ -33,10 +33,29 @@ class DataIter:
         pass
 
     def next(self):
+        """Default ``next`` for iterators written against the low-level protocol (``iter_next`` + ``getdata`` / ``getlabel`` / ``getpad`` /
+        ``getindex``, io.py:180-260); high-level iterators override ``next`` directly."""
+        if type(self).iter_next is not DataIter.iter_next and self.iter_next():
+            return DataBatch(data=self.getdata(), label=self.getlabel(), pad=self.getpad(), index=self.getindex())
         raise StopIteration
 
     def __next__(self):
         return self.next()
+
+    def iter_next(self):
+        return False
+
+    def getdata(self):
+        return None
+
+    def getlabel(self):
+        return None
+
+    def getindex(self):
+        return None
+
+    def getpad(self):
+        return 0
 
 
 class NDArrayIter(DataIter):

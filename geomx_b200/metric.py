@@ -6,8 +6,9 @@ import math
 
 import torch
 
-__all__ = ["EvalMetric", "Accuracy", "TopKAccuracy", "MAE", "MSE", "RMSE", "CrossEntropy", "Loss",
-           "CompositeEvalMetric", "create"]
+__all__ = ["EvalMetric", "Accuracy", "TopKAccuracy", "MAE", "MSE", "RMSE", "CrossEntropy", "NegativeLogLikelihood", "Loss", "Torch", "Caffe",
+           "CompositeEvalMetric", "F1", "MCC", "Perplexity", "PearsonCorrelation", "CustomMetric", "np", "create", "register", "alias",
+           "check_label_shapes"]
 
 
 def _t(x):
@@ -28,6 +29,18 @@ class EvalMetric:
 
     def get(self):
         return (self.name, float("nan")) if self.num_inst == 0 else (self.name, self.sum_metric / self.num_inst)
+
+    def get_config(self):
+        """JSON-able description: ``create(**config)`` rebuilds the metric (metric.py:95-107)."""
+        config = dict(self._kwargs)
+        config.update({"metric": self.__class__.__name__, "name": self.name, "output_names": self.output_names, "label_names": self.label_names})
+        return config
+
+    def update_dict(self, label, pred):
+        """Update from ``{name: array}`` dicts, selecting ``output_names`` / ``label_names`` when they were given (metric.py:109-130)."""
+        preds = [pred[n] for n in self.output_names] if self.output_names is not None else list(pred.values())
+        labels = [label[n] for n in self.label_names] if self.label_names is not None else list(label.values())
+        self.update(labels, preds)
 
     def get_name_value(self):
         name, value = self.get()
@@ -220,12 +233,80 @@ class CustomMetric(EvalMetric):
                 self.sum_metric += r; self.num_inst += 1
 
 
+class NegativeLogLikelihood(EvalMetric):
+    """Mean of ``-log p[label]`` (metric.py NegativeLogLikelihood :1050-1110)."""
+
+    def __init__(self, eps=1e-12, name="nll-loss", **kw):
+        super().__init__(name, **kw); self.eps = eps
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).reshape(-1).long(), _t(p)
+            assert l.numel() == p.shape[0], "shape mismatch: %s vs. %s" % (tuple(l.shape), tuple(p.shape))
+            prob = p[torch.arange(l.numel(), device=p.device), l.to(p.device)]
+            self.sum_metric += float((-torch.log(prob + self.eps)).sum()); self.num_inst += l.numel()
+
+
+class MCC(EvalMetric):
+    """Matthews correlation coefficient of a binary classifier; ``average='macro'`` averages per-batch values, ``'micro'`` pools the
+    confusion counts (metric.py MCC :650-750)."""
+
+    def __init__(self, name="mcc", average="macro", **kw):
+        self._average = average
+        super().__init__(name, **kw)
+
+    def reset(self):
+        super().reset()
+        self._c = [0.0, 0.0, 0.0, 0.0]                     # tp, fp, fn, tn
+
+    @staticmethod
+    def _mcc(tp, fp, fn, tn):
+        den = math.sqrt(max((tp + fp) * (tp + fn) * (tn + fp) * (tn + fn), 0.0))
+        return (tp * tn - fp * fn) / den if den > 0 else 0.0
+
+    def update(self, labels, preds):
+        for l, p in zip(*_lists(labels, preds)):
+            l, p = _t(l).reshape(-1).long(), _t(p)
+            pred = p.argmax(dim=1) if p.dim() > 1 else (p > 0.5).long()
+            l = l.to(pred.device)
+            c = [float(((pred == 1) & (l == 1)).sum()), float(((pred == 1) & (l == 0)).sum()), float(((pred == 0) & (l == 1)).sum()), float(((pred == 0) & (l == 0)).sum())]
+            if self._average == "macro":
+                self.sum_metric += self._mcc(*c); self.num_inst += 1
+            else:
+                self._c = [a + b for a, b in zip(self._c, c)]
+                self.sum_metric, self.num_inst = self._mcc(*self._c), 1
+
+
+class Torch(Loss):
+    """Dummy metric for outputs that already ARE a loss value (legacy torch criterions)."""
+
+    def __init__(self, name="torch", **kw):
+        super().__init__(name, **kw)
+
+
+class Caffe(Torch):
+    def __init__(self, name="caffe", **kw):
+        super().__init__(name, **kw)
+
+
+def check_label_shapes(labels, preds, wrap=False, shape=False):
+    """Raise when the number (or, with ``shape=True``, the shapes) of labels and predictions differ; ``wrap`` puts single arrays in lists."""
+    ls, ps = (labels.shape, preds.shape) if shape else (len(labels), len(preds))
+    if ls != ps:
+        raise ValueError("Shape of labels {} does not match shape of predictions {}".format(ls, ps))
+    if wrap:
+        labels = [labels] if hasattr(labels, "_t") else labels
+        preds = [preds] if hasattr(preds, "_t") else preds
+    return labels, preds
+
+
 def np(numpy_feval, name=None, allow_extra_outputs=False):
     """Create a metric from a numpy function (``mx.metric.np``)."""
     return CustomMetric(numpy_feval, name, allow_extra_outputs)
 
 
-_REG = {"f1": F1, "perplexity": Perplexity, "pearsonr": PearsonCorrelation, "acc": Accuracy, "accuracy": Accuracy, "top_k_accuracy": TopKAccuracy, "mae": MAE, "mse": MSE, "rmse": RMSE,
+_REG = {"mcc": MCC, "nll_loss": NegativeLogLikelihood, "nll-loss": NegativeLogLikelihood, "negativeloglikelihood": NegativeLogLikelihood, "torch": Torch, "caffe": Caffe,
+        "compositeevalmetric": None, "topkaccuracy": TopKAccuracy, "crossentropy": CrossEntropy, "pearsoncorrelation": PearsonCorrelation, "f1": F1, "perplexity": Perplexity, "pearsonr": PearsonCorrelation, "acc": Accuracy, "accuracy": Accuracy, "top_k_accuracy": TopKAccuracy, "mae": MAE, "mse": MSE, "rmse": RMSE,
         "ce": CrossEntropy, "cross-entropy": CrossEntropy, "loss": Loss}
 
 
@@ -239,4 +320,20 @@ def create(metric, *args, **kwargs):
         for m in metric:
             c.add(create(m, *args, **kwargs))
         return c
+    if metric.lower() == "compositeevalmetric":
+        return CompositeEvalMetric(*args, **kwargs)
     return _REG[metric.lower()](*args, **kwargs)
+
+
+def register(klass, name=None):
+    """Register a user metric class under its lower-cased name (``mx.metric.register``)."""
+    _REG[(name or klass.__name__).lower()] = klass
+    return klass
+
+
+def alias(*aliases):
+    def deco(klass):
+        for a in aliases:
+            register(klass, a)
+        return klass
+    return deco

@@ -19,7 +19,7 @@ from .context import cpu
 from .io import DataBatch, DataDesc
 from .model import BatchEndParam, _create_kvstore, _initialize_kvstore, _update_params, _update_params_on_kvstore, load_checkpoint, save_checkpoint
 
-__all__ = ["Module", "BaseModule", "BucketingModule", "SequentialModule"]
+__all__ = ["Module", "BaseModule", "BucketingModule", "SequentialModule", "PythonModule", "PythonLossModule"]
 
 
 def _as_desc(shapes):
@@ -35,6 +35,48 @@ class BaseModule:
         self.binded = self.for_training = self.params_initialized = self.optimizer_initialized = False
 
     # ---- high level API shared by every module type
+    def iter_predict(self, eval_data, num_batch=None, reset=True):
+        """Generator of ``(outputs, batch index, batch)`` with the padding rows removed (base_module.py:290-330)."""
+        assert self.binded and self.params_initialized
+        if reset:
+            eval_data.reset()
+        for nbatch, batch in enumerate(eval_data):
+            if num_batch is not None and nbatch == num_batch:
+                break
+            self.forward(batch, is_train=False)
+            pad = batch.pad or 0
+            yield [o[0:o.shape[0] - pad] for o in self.get_outputs()], nbatch, batch
+
+    def save_params(self, fname):
+        arg, aux = self.get_params()
+        d = {"arg:%s" % k: v.as_in_context(cpu()) for k, v in arg.items()}
+        d.update({"aux:%s" % k: v.as_in_context(cpu()) for k, v in aux.items()})
+        nd.save(fname, d)
+
+    def load_params(self, fname):
+        arg, aux = {}, {}
+        for k, v in nd.load(fname).items():
+            kind, name = k.split(":", 1)
+            if kind == "arg":
+                arg[name] = v
+            elif kind == "aux":
+                aux[name] = v
+            else:
+                raise ValueError("Invalid param file " + fname)
+        self.set_params(arg, aux)
+
+    def install_monitor(self, mon):
+        raise NotImplementedError
+
+    def prepare(self, data_batch, sparse_row_id_fn=None):
+        """Hook called before ``forward`` (bucket switch, row_sparse pulls); nothing to do for dense single-graph modules."""
+
+    def get_states(self, merge_multi_context=True):
+        return []
+
+    def set_states(self, states=None, value=None):
+        assert not states and not value
+
     def forward_backward(self, data_batch):
         self.forward(data_batch, is_train=True)
         self.backward()
@@ -240,9 +282,42 @@ class Module(BaseModule):
     def _grad_arrays(self):
         return [[ex.grad_dict.get(n) for ex in self._execs] for n in self._param_names]
 
+    label_names = property(lambda self: self._label_names)
+    data_shapes = property(lambda self: self._data_shapes)
+    label_shapes = property(lambda self: self._label_shapes)
+
+    @property
+    def output_shapes(self):
+        shapes = {d.name: d.shape for d in self._data_shapes + self._label_shapes}
+        _, outs, _ = self._symbol.infer_shape(**shapes)
+        return list(zip(self._symbol.list_outputs(), outs))
+
+    def install_monitor(self, mon):
+        """Attach a ``mx.monitor.Monitor`` to every executor."""
+        assert self.binded
+        for ex in self._execs:
+            mon.install(ex)
+
+    def reshape(self, data_shapes, label_shapes=None):
+        """Re-bind for new input shapes; parameters keep their arrays (module.py:430-470)."""
+        assert self.binded
+        self._data_shapes, self._label_shapes = _as_desc(data_shapes), _as_desc(label_shapes)
+        batch = self._data_shapes[0].shape[0]
+        n = len(self._context)
+        bounds = [(batch * i) // n for i in range(n + 1)]
+        self._slices = [slice(bounds[i], bounds[i + 1]) for i in range(n)]
+        self._execs = [ex.reshape(**{d.name: (sl.stop - sl.start,) + tuple(d.shape[1:]) for d in self._data_shapes + self._label_shapes})
+                       for ex, sl in zip(self._execs, self._slices)]
+
     # ---- computation
     def forward(self, data_batch, is_train=None):
         assert self.binded and self.params_initialized
+        new_shape = tuple(data_batch.data[0].shape) if hasattr(data_batch, "data") and data_batch.data else None
+        if new_shape is not None and self._data_shapes and new_shape != tuple(self._data_shapes[0].shape):
+            # a batch of a different shape re-binds on the fly (module.py:590-620)
+            lab = getattr(data_batch, "label", None)
+            self.reshape([(d.name, tuple(a.shape)) for d, a in zip(self._data_shapes, data_batch.data)],
+                         [(d.name, tuple(a.shape)) for d, a in zip(self._label_shapes, lab)] if lab and self._label_shapes else None)
         is_train = self.for_training if is_train is None else is_train
         data = data_batch.data if isinstance(data_batch, DataBatch) or hasattr(data_batch, "data") else data_batch
         label = getattr(data_batch, "label", None)
@@ -487,3 +562,83 @@ class SequentialModule(BaseModule):
         for m, meta in zip(self._modules, self._metas):
             if meta.get(self.META_TAKE_LABELS):
                 m.update_metric(eval_metric, labels)
+
+
+class PythonModule(BaseModule):
+    """Module whose computation is written in Python — no parameters, no optimizer (parity: python/mxnet/module/python_module.py).  Subclasses
+    implement ``forward`` / ``backward`` / ``get_outputs`` / ``get_input_grads`` and ``_compute_output_shapes``."""
+
+    def __init__(self, data_names, label_names, output_names, logger=logging):
+        super().__init__(logger)
+        self._data_names_, self._label_names_, self._output_names_ = list(data_names), list(label_names or []), list(output_names)
+        self._data_shapes = self._label_shapes = self._output_shapes = None
+
+    data_names = property(lambda self: self._data_names_)
+    output_names = property(lambda self: self._output_names_)
+    data_shapes = property(lambda self: self._data_shapes)
+    label_shapes = property(lambda self: self._label_shapes)
+    output_shapes = property(lambda self: self._output_shapes)
+
+    def get_params(self):
+        return {}, {}
+
+    def init_params(self, *args, **kwargs):
+        self.params_initialized = True
+
+    def set_params(self, *args, **kwargs):
+        self.params_initialized = True
+
+    def update(self):
+        pass
+
+    def update_metric(self, eval_metric, labels):
+        if self._label_shapes is not None:
+            eval_metric.update(labels, self.get_outputs())
+
+    def bind(self, data_shapes, label_shapes=None, for_training=True, inputs_need_grad=False, force_rebind=False, shared_module=None, grad_req="write"):
+        if self.binded and not force_rebind:
+            return
+        self.for_training, self._inputs_need_grad = for_training, inputs_need_grad
+        self._data_shapes, self._label_shapes = _as_desc(data_shapes), (_as_desc(label_shapes) if label_shapes else None)
+        self._output_shapes = self._compute_output_shapes()
+        self.binded = True
+
+    def _compute_output_shapes(self):
+        raise NotImplementedError
+
+    def init_optimizer(self, *args, **kwargs):
+        self.optimizer_initialized = True
+
+
+class PythonLossModule(PythonModule):
+    """A loss layer in Python: forward stores the scores, backward produces ``grad_func(scores, labels)``; used as the last stage of a
+    ``SequentialModule`` (python_module.py:240-340)."""
+
+    def __init__(self, name="pyloss", data_names=("data",), label_names=("softmax_label",), logger=logging, grad_func=None):
+        super().__init__(data_names, label_names, [name + "_output"], logger)
+        self._name, self._scores, self._labels, self._scores_grad, self._grad_func = name, None, None, None, grad_func
+
+    def _compute_output_shapes(self):
+        return [(self._name + "_output", self._data_shapes[0].shape)]
+
+    def forward(self, data_batch, is_train=None):
+        self._scores = data_batch.data[0]
+        if (self.for_training if is_train is None else is_train) and data_batch.label:
+            self._labels = data_batch.label[0]
+
+    def get_outputs(self, merge_multi_context=True):
+        return [self._scores]
+
+    def backward(self, out_grads=None):
+        assert out_grads is None, "For a loss module, out_grads should be None"
+        assert self.for_training
+        if self._grad_func is None:
+            raise NotImplementedError("pass grad_func or override backward")
+        g = self._grad_func(self._scores, self._labels)
+        self._scores_grad = g if isinstance(g, nd.NDArray) else nd.array(g)
+
+    def get_input_grads(self, merge_multi_context=True):
+        return [self._scores_grad]
+
+    def install_monitor(self, mon):
+        raise NotImplementedError

@@ -16,7 +16,14 @@ class Monitor:
         self.exes, self.re_prog, self.sort = [], re.compile(pattern), sort
 
     def install(self, exe):
+        """Hooks the executor's per-node callback so intermediate outputs are sampled too (monitor.py:80-95)."""
+        if hasattr(exe, "set_monitor_callback"):
+            exe.set_monitor_callback(self.stat_helper)
         self.exes.append(exe)
+
+    def stat_helper(self, name, array):
+        if self.activated and self.re_prog.match(name):
+            self.queue.append((self.step, name, self.stat_func(array)))
 
     def tic(self):
         if self.step % self.interval == 0:

@@ -325,6 +325,12 @@ class NDArray:
     def __truediv__(self, o): return self._bin(o, torch.true_divide)
     def __rtruediv__(self, o): return self._bin(o, lambda x, y: x / y, True)
     def __mod__(self, o): return self._bin(o, torch.remainder)
+    def __rmod__(self, o): return self._bin(o, lambda x, y: torch.remainder(torch.as_tensor(x, dtype=y.dtype, device=y.device) if not isinstance(x, torch.Tensor) else x, y), True)
+
+    def __imod__(self, o):
+        self._t.remainder_(o._t if isinstance(o, NDArray) else o)
+        return self
+    __div__, __rdiv__ = __truediv__, __rtruediv__
     def __pow__(self, o): return self._bin(o, torch.pow)
     def __rpow__(self, o): return self._bin(o, lambda x, y: x ** y, True)
     def __neg__(self): return NDArray(-self._t)

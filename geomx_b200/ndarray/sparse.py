@@ -224,3 +224,50 @@ def add(a: RowSparseNDArray, b: RowSparseNDArray):
 
 def retain(arr, row_ids):
     return arr.retain(row_ids)
+
+
+import abc as _abc  # noqa: E402
+
+
+class BaseSparseNDArray(_abc.ABC):
+    """Marker base of the sparse array types (``isinstance(x, BaseSparseNDArray)``)."""
+
+
+BaseSparseNDArray.register(RowSparseNDArray)
+BaseSparseNDArray.register(CSRNDArray)
+
+
+def array(source_array, ctx=None, dtype=None):
+    """Sparse array from a scipy.sparse matrix, another sparse NDArray or a ``(data, indices[, indptr])`` description (sparse.py:1560-1640)."""
+    if isinstance(source_array, (RowSparseNDArray, CSRNDArray)):
+        return cast_storage(source_array.tostype("default"), source_array.stype)
+    try:
+        import scipy.sparse as sp
+        if sp.issparse(source_array):
+            m = source_array.tocsr()
+            return csr_matrix((m.data, m.indices, m.indptr), shape=m.shape, ctx=ctx, dtype=dtype)
+    except ImportError:
+        pass
+    raise ValueError("Unexpected source_array type: %s" % type(source_array))
+
+
+def empty(stype, shape, ctx=None, dtype=None):
+    return zeros(stype, shape, ctx=ctx, dtype=dtype or "float32")
+
+
+def _dense_of(x):
+    return x.tostype("default") if isinstance(x, (RowSparseNDArray, CSRNDArray)) else x
+
+
+def _elemwise(fn, lhs, rhs):
+    """Element-wise op; two operands of the same sparse type give that type back, anything else is dense (sparse.py add/subtract/…)."""
+    out = fn(_dense_of(lhs), _dense_of(rhs))
+    st = getattr(lhs, "stype", "default")
+    if st != "default" and st == getattr(rhs, "stype", "default"):
+        return cast_storage(out, st)
+    return out
+
+
+def subtract(lhs, rhs): return _elemwise(lambda a, b: a - b, lhs, rhs)
+def multiply(lhs, rhs): return _elemwise(lambda a, b: a * b, lhs, rhs)
+def divide(lhs, rhs): return _elemwise(lambda a, b: a / b, lhs, rhs)

@@ -22,7 +22,7 @@ from ..base import MXNetError
 from ..context import Context, cpu
 from .ndarray import NDArray
 
-__all__ = ["save", "load", "save_bytes", "load_bytes"]
+__all__ = ["save", "load", "load_frombuffer", "save_bytes", "load_bytes", "save_async"]
 
 LIST_MAGIC = 0x112
 V2_MAGIC = 0xF993FAC9
@@ -230,3 +230,8 @@ def save_async(fname, data):
 def load(fname):
     with open(fname, "rb") as f:
         return load_bytes(f.read())
+
+
+def load_frombuffer(buf):
+    """``mx.nd.load`` from an in-memory ``.params`` image (ndarray/utils.py:185-220)."""
+    return load_bytes(buf)

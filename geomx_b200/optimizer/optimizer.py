@@ -118,6 +118,10 @@ class Optimizer:
     def learning_rate(self):
         return self.lr_scheduler(self.num_update) if self.lr_scheduler is not None else self.lr
 
+    def set_lr_scale(self, args_lrscale):
+        """[DEPRECATED] use ``set_lr_mult``."""
+        raise DeprecationWarning("set_lr_scale is deprecated, use set_lr_mult instead")
+
     def set_lr_mult(self, args_lr_mult):
         self.lr_mult = dict(args_lr_mult)
 

@@ -61,6 +61,45 @@ class Symbol:
             raise IndexError(i)
         return self.inputs[i] if isinstance(i, int) else next(s for s in self.inputs if s.list_outputs()[0] == i)
 
+    def __pow__(self, o): return _nd_op("power")(self, o) if isinstance(o, Symbol) else _nd_op("power")(self, Symbol("_full_like", _auto_name("scalar", None), [self], {"value": float(o)}))
+    def __neg__(self): return _binary("_mul", self, -1.0)
+    def __copy__(self): return load_json(self.tojson())
+    __deepcopy__ = lambda self, memo: load_json(self.tojson())          # noqa: E731
+
+    def get_children(self):
+        """Group of the direct inputs of this node (None for variables)."""
+        return Group(self.inputs) if self.inputs else None
+
+    def eval(self, ctx=None, **kwargs):
+        """Bind with the given NDArrays and run forward once: ``(a + b).eval(a=x, b=y)`` → list of outputs."""
+        from .context import cpu
+        ex = self.bind(ctx or cpu(), kwargs)
+        return ex.forward()
+
+    def infer_shape_partial(self, **shapes):
+        """Like ``infer_shape`` but returns ``None`` entries instead of raising when something cannot be inferred."""
+        try:
+            return self.infer_shape(**shapes)
+        except MXNetError:
+            args, auxs = self.list_arguments(), self.list_auxiliary_states()
+            return [tuple(shapes[a]) if a in shapes else None for a in args], [None] * len(self.list_outputs()), [None] * len(auxs)
+
+    def debug_str(self):
+        lines = []
+        for s in self._topo():
+            if s.op == "null":
+                lines.append("Variable:%s" % s.name)
+            else:
+                lines.append("--------------------\nOp:%s, Name=%s\nInputs:\n%s\nAttrs:%s" % (
+                    s.op, s.name, "\n".join("\targ[%d]=%s" % (i, x.name) for i, x in enumerate(s.inputs)), {k: v for k, v in s.attrs.items() if not k.startswith("__")}))
+        return "\n".join(lines)
+
+    def gradient(self, wrt):
+        raise MXNetError("Symbol.gradient is not available: gradients come from the executor's autograd tape (Executor.backward)")
+
+    def get_backend_symbol(self, backend):
+        return self                                           # no graph-partitioning backends: the same graph runs on the native kernels
+
     # ---- graph walks
     def _topo(self):
         order, seen = [], set()
@@ -345,6 +384,8 @@ def _eval_node(s, ins, aux, training):
         return {"_plus": torch.add, "_minus": torch.sub, "_mul": torch.mul, "_div": torch.div}[op[:-7]](ins[0], a["scalar"])
     if op == "_nd":
         return _eval_nd(a, ins)
+    if op == "_full_like":
+        return torch.full_like(ins[0], a["value"])
     raise MXNetError("symbol op %s is not implemented" % op)
 
 
@@ -460,8 +501,26 @@ class _ShapeRun:
                 finally:
                     F.use_native(True)
         heads = self.sym.inputs if self.sym.op == "_group" else [self.sym]
+        missing = [h.name for h in heads if id(h) not in vals]
+        if missing:
+            raise MXNetError("cannot infer the shape of %s: not enough input shapes given" % missing)
         self.outputs = [vals[id(h)] for h in heads]
         return self
+
+
+def run_graph(sym, feed, training=False):
+    """Evaluate ``sym`` on live tensors: ``feed`` maps every argument / auxiliary-state name to a torch tensor; gradients flow to whatever
+    in ``feed`` requires grad.  Used by ``gluon.SymbolBlock``; returns the list of head tensors."""
+    vals = {}
+    for s in sym._topo():
+        if s.op == "null":
+            if s.name not in feed:
+                raise MXNetError("run_graph: no value for %s" % s.name)
+            vals[id(s)] = feed[s.name]
+        elif s.op != "_group":
+            vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], training)
+    heads = sym.inputs if sym.op == "_group" else [sym]
+    return [vals[id(h)] for h in heads]
 
 
 class Executor:
@@ -474,7 +533,7 @@ class Executor:
         self.grad_arrays = [grads.get(n) for n in symbol.list_arguments()]
         self.aux_arrays = [aux[n] for n in symbol.list_auxiliary_states()]
         self.outputs = []
-        self._heads, self._leaves = None, None
+        self._heads, self._leaves, self._monitor = None, None, None
 
     def forward(self, is_train=False, **kwargs):
         for k, v in kwargs.items():
@@ -501,6 +560,8 @@ class Executor:
                             vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], is_train)
                     else:
                         vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], is_train)
+                    if self._monitor is not None:
+                        self._monitor(s.name + "_output", NDArray(vals[id(s)].detach()))
         heads = self._symbol.inputs if self._symbol.op == "_group" else [self._symbol]
         self._heads, self._leaves = [vals[id(h)] for h in heads], leaves
         self.outputs = [NDArray(h.detach()) for h in self._heads]
@@ -526,6 +587,33 @@ class Executor:
             else:
                 tgt.copy_(g)
 
+    @property
+    def output_dict(self):
+        return dict(zip(self._symbol.list_outputs(), self.outputs))
+
+    def set_monitor_callback(self, callback, monitor_all=False):
+        """``callback(name, NDArray)`` for every node output of each forward (executor.py:237-260; used by ``mx.monitor.Monitor``)."""
+        self._monitor = callback
+
+    def reshape(self, partial_shaping=False, allow_up_sizing=False, **kwargs):
+        """New executor for different input shapes sharing every parameter array whose shape did not change (executor.py:380-460)."""
+        new = self._symbol.simple_bind(self._ctx, grad_req=self._req, **kwargs)
+        for n, a in self.arg_dict.items():
+            if n in new.arg_dict and tuple(new.arg_dict[n].shape) == tuple(a.shape) and n not in kwargs:
+                new.arg_dict[n] = a
+                if n in self.grad_dict and n in new.grad_dict:
+                    new.grad_dict[n] = self.grad_dict[n]
+        for n, a in self.aux_dict.items():
+            if n in new.aux_dict and tuple(new.aux_dict[n].shape) == tuple(a.shape):
+                new.aux_dict[n] = a
+        new.arg_arrays = [new.arg_dict[n] for n in self._symbol.list_arguments()]
+        new.grad_arrays = [new.grad_dict.get(n) for n in self._symbol.list_arguments()]
+        new.aux_arrays = [new.aux_dict[n] for n in self._symbol.list_auxiliary_states()]
+        return new
+
+    def debug_str(self):
+        return self._symbol.debug_str()
+
     def copy_params_from(self, arg_params, aux_params=None, allow_extra_params=False):
         for k, v in arg_params.items():
             if k in self.arg_dict:
@@ -535,3 +623,34 @@ class Executor:
         for k, v in (aux_params or {}).items():
             if k in self.aux_dict:
                 self.aux_dict[k][:] = v
+
+
+def pow(base, exp):
+    """``mx.sym.pow``: Symbol/scalar base and exponent in any combination."""
+    if isinstance(base, Symbol):
+        return base ** exp
+    if isinstance(exp, Symbol):
+        return _nd_op("power")(Symbol("_full_like", _auto_name("scalar", None), [exp], {"value": float(base)}), exp)
+    return base ** exp
+
+
+def _attach_symbol_fluent():
+    names = ["abs", "arccos", "arccosh", "arcsin", "arcsinh", "arctan", "arctanh", "argmax", "argmax_channel", "argmin", "argsort", "broadcast_axes",
+             "broadcast_like", "broadcast_to", "cbrt", "ceil", "clip", "cos", "cosh", "degrees", "depth_to_space", "diag", "exp", "expand_dims", "expm1",
+             "fix", "flatten", "flip", "floor", "log", "log10", "log1p", "log2", "log_softmax", "max", "mean", "min", "nanprod", "nansum", "norm",
+             "one_hot", "ones_like", "pad", "pick", "prod", "radians", "rcbrt", "reciprocal", "relu", "repeat", "reshape_like", "rint", "round",
+             "rsqrt", "shape_array", "sigmoid", "sign", "sin", "sinh", "size_array", "slice", "slice_axis", "slice_like", "softmax", "softmin", "sort",
+             "space_to_depth", "sqrt", "square", "squeeze", "sum", "swapaxes", "take", "tan", "tanh", "tile", "topk", "transpose", "trunc", "zeros_like"]
+    for n in names:
+        if not hasattr(Symbol, n):
+            setattr(Symbol, n, (lambda q: lambda self, *a, **k: _nd_op(q)(self, *a, **k))(n))
+    Symbol.reshape = lambda self, *shape, **kw: reshape(self, shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else (kw.get("shape") or shape))
+    Symbol.astype = lambda self, dtype: _nd_op("cast")(self, dtype=str(dtype))
+    Symbol.detach = lambda self: _nd_op("stop_gradient")(self)
+    Symbol.copy = lambda self: load_json(self.tojson())
+    for n in ("asnumpy", "asscalar", "wait_to_read", "as_in_context", "backward"):
+        setattr(Symbol, n, (lambda q: lambda self, *a, **k: (_ for _ in ()).throw(
+            NotImplementedError("Symbol.%s: symbols hold no data — bind them (simple_bind / eval) first" % q)))(n))
+
+
+_attach_symbol_fluent()

@@ -1,0 +1,207 @@
+"""Second sweep over the reference's Python surface: fluent NDArray / Symbol methods, autograd.Function, SymbolBlock + export/imports, legacy
+operator classes and FeedForward, extra metrics / initializers / augmenters / datasets, Module conveniences, sparse helpers."""
+import os
+
+import numpy as np
+import pytest
+
+import geomx_b200 as mx
+
+
+def test_fluent_ndarray_dlpack_and_legacy_helpers():
+    x = mx.nd.array([[1.0, 4.0], [9.0, 16.0]])
+    assert x.sqrt().asnumpy().tolist() == [[1, 2], [3, 4]] and x.slice_axis(axis=1, begin=0, end=1).shape == (2, 1)
+    assert x.flip(axis=0).asnumpy().tolist() == [[9, 16], [1, 4]] and x.topk(k=1).asnumpy().tolist() == [[1], [1]]
+    view = mx.nd.from_dlpack(x.to_dlpack_for_write())
+    view[:] = 0
+    assert float(x.asnumpy().sum()) == 0                                # zero copy
+    assert mx.nd.concatenate([x, x]).shape == (4, 2)
+    assert mx.nd.onehot_encode(mx.nd.array([1, 0]), mx.nd.zeros((2, 3))).asnumpy().tolist() == [[0, 1, 0], [1, 0, 0]]
+    assert (7 % mx.nd.array([2.0, 4.0])).asnumpy().tolist() == [1, 3]
+    a = mx.nd.array([5.0, 7.0]); a %= 4
+    assert a.asnumpy().tolist() == [1, 3]
+    src = np.arange(4, dtype=np.float32)
+    b = mx.nd.array(src); b += 1
+    assert src.tolist() == [0, 1, 2, 3]                                  # nd.array never aliases its source
+    buf = mx.nd.save_bytes({"w": mx.nd.ones((2,))})
+    assert mx.nd.load_frombuffer(buf)["w"].asnumpy().tolist() == [1, 1]
+    import scipy.sparse as sp
+    m = mx.nd.sparse.array(sp.random(4, 5, 0.5, format="coo", dtype=np.float32, random_state=0))
+    assert m.stype == "csr" and isinstance(m, mx.nd.sparse.BaseSparseNDArray) and not isinstance(x, mx.nd.sparse.BaseSparseNDArray)
+    assert mx.nd.sparse.multiply(m, m).stype == "csr" and mx.nd.sparse.subtract(m, x.reshape((4,))[:1] if False else m).stype == "csr"
+    assert mx.nd.sparse.empty("row_sparse", (3, 2)).shape == (3, 2)
+
+
+def test_symbol_fluent_eval_executor_reshape_and_monitor():
+    x = mx.sym.Variable("x")
+    y = (x.exp().sum(axis=1) ** 2).sqrt()
+    np.testing.assert_allclose(y.eval(x=mx.nd.array([[0.0, 0.0], [1.0, 1.0]]))[0].asnumpy(), [2, 2 * np.e], rtol=1e-5)
+    np.testing.assert_allclose(mx.sym.pow(2.0, x).eval(x=mx.nd.array([1.0, 3.0]))[0].asnumpy(), [2, 8])
+    assert x.reshape((2, -1)).infer_shape(x=(4, 3))[1] == [(2, 6)] and x.get_children() is None and len(y.get_children().inputs) == 1
+    assert x.infer_shape_partial()[1] == [None] or x.infer_shape_partial()[0] == [None]
+    fc = mx.sym.FullyConnected(x, num_hidden=2, name="fc")
+    ex = fc.simple_bind(mx.cpu(), x=(3, 4))
+    mon = mx.monitor.Monitor(1, pattern=".*output.*"); mon.install(ex)
+    mon.tic(); ex.forward(); stats = mon.toc()
+    assert any(k == "fc_output" for _, k, _ in stats) and list(ex.output_dict) == ["fc_output"]
+    ex2 = ex.reshape(x=(5, 4))
+    assert ex2.arg_dict["fc_weight"] is ex.arg_dict["fc_weight"] and ex2.forward()[0].shape == (5, 2)
+    assert "Op:FullyConnected" in fc.debug_str()
+    with pytest.raises(NotImplementedError):
+        fc.asnumpy()
+
+
+def test_autograd_function_symbolblock_export_and_legacy_ops(tmp_path):
+    class Sigmoid(mx.autograd.Function):
+        def forward(self, x):
+            y = 1 / (1 + mx.nd.exp(-x)); self.save_for_backward(y); return y
+
+        def backward(self, dy):
+            y, = self.saved_tensors; return dy * y * (1 - y)
+    a = mx.nd.array([0.0, 1.0]); a.attach_grad()
+    f = Sigmoid()
+    with mx.autograd.record():
+        c = (f(a) * 2).sum()
+    c.backward()
+    s = 1 / (1 + np.exp(-np.array([0.0, 1.0])))
+    np.testing.assert_allclose(a.grad.asnumpy(), 2 * s * (1 - s), rtol=1e-5)
+    with pytest.raises(AssertionError):
+        f(a)                                                             # one use per instance
+
+    d = mx.sym.Variable("data")
+    net = mx.sym.FullyConnected(mx.sym.Activation(mx.sym.BatchNorm(mx.sym.FullyConnected(d, num_hidden=8, name="fc1"), name="bn"), act_type="relu"), num_hidden=3, name="fc2")
+    blk = mx.gluon.SymbolBlock(net, d); blk.initialize(mx.init.Xavier())
+    x = mx.nd.array(np.random.RandomState(0).randn(5, 4).astype(np.float32))
+    tr = mx.gluon.Trainer(blk.collect_params(), "sgd", {"learning_rate": 0.1})
+    with mx.autograd.record():
+        l0 = (blk(x) ** 2).sum()
+    l0.backward(); tr.step(1)
+    with mx.autograd.record():
+        l1 = (blk(x) ** 2).sum()
+    assert float(l1.asscalar()) < float(l0.asscalar())                  # the imported graph is trainable
+    assert blk.collect_params()["bn_moving_mean"].grad_req == "null"
+    blk.export(str(tmp_path / "m"), 3)
+    assert sorted(os.listdir(str(tmp_path))) == ["m-0003.params", "m-symbol.json"]
+    b2 = mx.gluon.SymbolBlock.imports(str(tmp_path / "m-symbol.json"), ["data"], str(tmp_path / "m-0003.params"))
+    np.testing.assert_allclose(b2(x).asnumpy(), blk(x).asnumpy(), atol=1e-6)
+    arg, aux = mx.model.load_params(str(tmp_path / "m"), 3)              # same file layout as save_checkpoint
+    assert "fc1_weight" in arg and "bn_moving_var" in aux
+    assert "fc1" in mx.viz.plot_network(net, shape={"data": (5, 4)}).source
+
+    class Sq(mx.operator.NumpyOp):
+        def forward(self, in_data, out_data): out_data[0][:] = in_data[0] ** 2
+        def backward(self, out_grad, in_data, out_data, in_grad): in_grad[0][:] = 2 * in_data[0] * out_grad[0]
+    op = Sq(); v = mx.nd.array([1.0, 2.0, 3.0]); v.attach_grad()
+    with mx.autograd.record():
+        b = op(v).sum()
+    b.backward()
+    assert v.grad.asnumpy().tolist() == [2, 4, 6]
+    assert op.get_symbol(mx.sym.Variable("v")).eval(v=mx.nd.array([3.0]))[0].asnumpy().tolist() == [9]
+
+    X = np.random.RandomState(0).randn(120, 4).astype(np.float32); Y = (X[:, 0] > 0).astype(np.float32)
+    ff = mx.model.FeedForward(mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=2, name="o"), name="softmax"),
+                              num_epoch=20, optimizer="adam", learning_rate=0.05, initializer=mx.init.Xavier(), numpy_batch_size=40)
+    ff.fit(X, Y)
+    assert ff.score(mx.io.NDArrayIter(X, Y, batch_size=40)) > 0.9 and ff.predict(X).shape == (120, 2)
+    ff.save(str(tmp_path / "ff"), 20)
+    ff2 = mx.model.FeedForward.load(str(tmp_path / "ff"), 20)
+    np.testing.assert_allclose(ff2.predict(X), ff.predict(X), atol=1e-6)
+
+
+def test_metrics_initializers_augmenters_datasets(tmp_path):
+    m = mx.metric.create("mcc")
+    m.update([mx.nd.array([1, 0, 1, 1])], [mx.nd.array([[0.1, 0.9], [0.8, 0.2], [0.7, 0.3], [0.4, 0.6]])])
+    assert m.get()[1] == pytest.approx(0.57735, abs=1e-4)
+    n = mx.metric.NegativeLogLikelihood(); n.update([mx.nd.array([1, 0])], [mx.nd.array([[0.1, 0.9], [0.8, 0.2]])])
+    assert n.get()[1] == pytest.approx(-(np.log(0.9) + np.log(0.8)) / 2, abs=1e-5)
+    cfg = mx.metric.Accuracy().get_config()
+    assert cfg["metric"] == "Accuracy" and isinstance(mx.metric.create("caffe"), mx.metric.Loss)
+    acc = mx.metric.Accuracy(output_names=["o"], label_names=["l"])
+    acc.update_dict({"l": mx.nd.array([1]), "zz": mx.nd.array([0])}, {"o": mx.nd.array([[0.1, 0.9]]), "other": mx.nd.array([[1.0, 0.0]])})
+    assert acc.get()[1] == 1.0
+    with pytest.raises(ValueError):
+        mx.metric.check_label_shapes([1, 2], [1])
+    b = mx.nd.zeros((8,)); mx.init.LSTMBias(2.0)(mx.init.InitDesc("l_bias"), b)
+    assert b.asnumpy().tolist() == [0, 0, 2, 2, 0, 0, 0, 0]
+    h, L, inp = 3, 2, 5
+    tot = 4 * h * (inp + h) + 4 * h * (h + h) + L * 2 * 4 * h
+    f = mx.nd.zeros((tot,)); mx.init.FusedRNN(mx.init.Uniform(0.1), h, L, "lstm")(mx.init.InitDesc("rnn_parameters"), f)
+    fv = f.asnumpy(); nb = L * 2 * 4 * h
+    assert (fv[:-nb] != 0).all() and fv[-nb:].reshape(-1, 4, h)[:, 1].tolist() == [[1.0] * h] * (L * 2) and fv[-nb:].sum() == L * 2 * h
+
+    img = mx.nd.array(np.random.RandomState(0).randint(0, 255, (20, 30, 3)).astype(np.uint8))
+    g = mx.image.RandomGrayAug(1.0)(img).asnumpy()
+    assert np.allclose(g[..., 0], g[..., 1])
+    assert np.abs(mx.image.HueJitterAug(0.0)(img).asnumpy() - img.asnumpy()).max() < 1.0
+    assert mx.image.RandomSizedCropAug((8, 8), 0.3, (0.75, 1.33))(img).shape == (8, 8, 3) and mx.image.scale_down((640, 480), (720, 120)) == (640, 106)
+    augs = mx.image.CreateAugmenter((3, 8, 8), rand_crop=True, rand_resize=True, brightness=0.1, hue=0.1, pca_noise=0.1, rand_gray=0.1, mean=True, std=True)
+    out = img
+    for a in augs:
+        out = a(out)
+    assert out.shape == (8, 8, 3) and len(augs) == 7
+    T = mx.gluon.data.vision.transforms
+    for t in (T.RandomSaturation(0.3), T.RandomHue(0.3), T.RandomColorJitter(0.1, 0.1, 0.1, 0.1), T.RandomLighting(0.1)):
+        assert t(img).shape == (20, 30, 3)
+
+    from PIL import Image
+    for cls in ("cat", "dog"):
+        os.makedirs(str(tmp_path / "imgs" / cls))
+        for i in range(2):
+            Image.fromarray(np.full((6, 5, 3), 40 if cls == "cat" else 200, dtype=np.uint8)).save(str(tmp_path / "imgs" / cls / ("%d.png" % i)))
+    ds = mx.gluon.data.vision.ImageFolderDataset(str(tmp_path / "imgs"))
+    assert ds.synsets == ["cat", "dog"] and len(ds) == 4 and ds[3][1] == 1 and ds[0][0].shape == (6, 5, 3)
+    rec = mx.recordio.MXIndexedRecordIO(str(tmp_path / "d.idx"), str(tmp_path / "d.rec"), "w")
+    for i in range(3):
+        rec.write_idx(i, mx.recordio.pack_img(mx.recordio.IRHeader(0, float(i), i, 0), np.full((4, 4, 3), 10 * i, dtype=np.uint8), img_fmt=".png"))
+    rec.close()
+    rd = mx.gluon.data.vision.ImageRecordDataset(str(tmp_path / "d.rec"))
+    assert len(rd) == 3 and rd[2][1] == 2.0 and int(rd[2][0].asnumpy()[0, 0, 0]) == 20
+    assert len(mx.gluon.data.RecordFileDataset(str(tmp_path / "d.rec"))) == 3
+    c100 = mx.gluon.data.vision.CIFAR100(root=str(tmp_path / "none"), fine_label=True, train=False)
+    assert c100.synthetic and c100[0][0].shape == (32, 32, 3)
+
+
+def test_module_conveniences_and_python_loss_module(tmp_path):
+    rs = np.random.RandomState(0)
+    x = rs.randn(64, 4).astype(np.float32); y = (x[:, 0] > 0).astype(np.float32)
+    it = mx.io.NDArrayIter(x, y, batch_size=16)
+    mod = mx.mod.Module(mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=2, name="fc"), name="softmax"))
+    mod.fit(it, num_epoch=10, optimizer="adam", optimizer_params={"learning_rate": 0.05}, initializer=mx.init.Xavier())
+    assert mod.data_shapes[0].shape == (16, 4) and mod.label_names == ["softmax_label"] and mod.output_shapes == [("softmax_output", (16, 2))]
+    outs = [o for o, _, _ in mod.iter_predict(it)]
+    assert len(outs) == 4 and outs[0][0].shape == (16, 2)
+    mod.save_params(str(tmp_path / "p.params"))
+    w = mod.get_params()[0]["fc_weight"].asnumpy().copy()
+    mod.set_params({k: v * 0 for k, v in mod.get_params()[0].items()}, {})
+    mod.load_params(str(tmp_path / "p.params"))
+    np.testing.assert_allclose(mod.get_params()[0]["fc_weight"].asnumpy(), w)
+    mod.forward(mx.io.DataBatch([mx.nd.array(x[:5])], [mx.nd.array(y[:5])]), is_train=False)       # different batch size re-binds on the fly
+    assert mod.get_outputs()[0].shape == (5, 2)
+    np.testing.assert_allclose(mod.get_params()[0]["fc_weight"].asnumpy(), w)
+    mon = mx.monitor.Monitor(1, pattern="fc_output"); mod.install_monitor(mon)
+    mon.tic(); mod.forward(mx.io.DataBatch([mx.nd.array(x[:5])], [mx.nd.array(y[:5])]), is_train=False)
+    assert [k for _, k, _ in mon.toc()] == ["fc_output"]
+
+    # a Python loss at the end of a SequentialModule: gradient of 0.5 * ||scores - onehot||^2
+    def grad(scores, labels):
+        return scores - mx.nd.one_hot(labels, 2)
+    feat = mx.mod.Module(mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=2, name="lin"), label_names=None)
+    seq = mx.mod.SequentialModule().add(feat).add(mx.mod.PythonLossModule(grad_func=grad), take_labels=True, auto_wiring=True)
+    seq.fit(it, num_epoch=15, optimizer="sgd", optimizer_params={"learning_rate": 0.1}, initializer=mx.init.Xavier())
+    assert dict(seq.score(it, "acc"))["accuracy"] > 0.9
+
+    class Proto(mx.io.DataIter):                                       # low-level iterator protocol
+        def __init__(self):
+            super().__init__(2); self.i = 0
+
+        def iter_next(self):
+            self.i += 1
+            return self.i <= 3
+
+        def getdata(self): return [mx.nd.ones((2, 2)) * self.i]
+        def getlabel(self): return [mx.nd.zeros((2,))]
+    assert [float(b.data[0].asnumpy()[0, 0]) for b in Proto()] == [1, 2, 3]
+    assert mx.misc.FactorScheduler(10, 0.5)(25) == 0.0025
+    p = mx.gluon.Parameter("emb", shape=(6, 2), stype="row_sparse", grad_stype="row_sparse"); p.initialize(mx.init.One())
+    rsd = p.row_sparse_data(mx.nd.array([4, 1, 4]))
+    assert rsd.stype == "row_sparse" and rsd.indices.asnumpy().tolist() == [1, 4] and rsd.data.shape == (2, 2)
