@@ -109,7 +109,11 @@ class CSRNDArray:
         return "<CSRNDArray %dx%d @%s nnz=%d>" % (self._shape[0], self._shape[1], self.context, self.data.shape[0])
 
     def _torch(self):
-        return torch.sparse_csr_tensor(self.indptr._t.long(), self.indices._t.long(), self.data._t, size=self._shape, check_invariants=True)
+        """torch CSR view; column indices are sorted per row first (MXNet allows unsorted rows, torch's kernels do not)."""
+        ptr, idx, val = self.indptr._t.long(), self.indices._t.long(), self.data._t
+        rows = torch.repeat_interleave(torch.arange(self._shape[0], device=ptr.device), ptr[1:] - ptr[:-1])
+        order = torch.argsort(rows * self._shape[1] + idx, stable=True)
+        return torch.sparse_csr_tensor(ptr, idx[order], val[order], size=self._shape, check_invariants=False)
 
     def tostype(self, stype):
         if stype == "csr":

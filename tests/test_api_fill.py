@@ -205,3 +205,53 @@ def test_module_conveniences_and_python_loss_module(tmp_path):
     p = mx.gluon.Parameter("emb", shape=(6, 2), stype="row_sparse", grad_stype="row_sparse"); p.initialize(mx.init.One())
     rsd = p.row_sparse_data(mx.nd.array([4, 1, 4]))
     assert rsd.stype == "row_sparse" and rsd.indices.asnumpy().tolist() == [1, 4] and rsd.data.shape == (2, 2)
+
+
+def test_test_utils_helpers():
+    tu = mx.test_utils
+    x = mx.sym.Variable("x"); y = mx.sym.Variable("y")
+    s = mx.sym.broadcast_mul(x, y)
+    a = np.random.RandomState(0).randn(3, 4).astype(np.float32); b = np.random.RandomState(1).randn(3, 4).astype(np.float32)
+    tu.check_symbolic_forward(s, [a, b], [a * b])
+    tu.check_symbolic_backward(s, {"x": a, "y": b}, [np.ones((3, 4), np.float32)], {"x": b, "y": a})
+    with pytest.raises(AssertionError):
+        tu.check_symbolic_forward(s, [a, b], [a * b + 1])
+    assert tu.simple_forward(s, x=a, y=b).shape == (3, 4) and tu.check_speed(s, location={"x": a, "y": b}, N=3) > 0
+    arr, (vals, idx) = tu.rand_sparse_ndarray((6, 3), "row_sparse", density=0.5)
+    assert arr.stype == "row_sparse" and vals.shape == (len(idx), 3)
+    csr, (indptr, indices, data) = tu.rand_sparse_ndarray((5, 7), "csr", density=0.4, shuffle_csr_indices=True)
+    import scipy.sparse as sp
+    np.testing.assert_allclose(csr.tostype("default").asnumpy(), sp.csr_matrix((data, indices, indptr), shape=(5, 7)).toarray(), rtol=1e-6)
+    assert tu.create_sparse_array_zd((4, 2), "row_sparse", 0.0).tostype("default").asnumpy().sum() == 0
+    v = mx.nd.ones((3,)); assert tu.same_array(v, v) and not tu.same_array(v, v.copy())
+    assert tu.almost_equal_ignore_nan(np.array([1.0, np.nan]), np.array([1.0, 2.0]))
+    tu.assert_exception(lambda: 1 / 0, ZeroDivisionError)
+    assert tu.np_reduce(np.ones((2, 3, 4)), (0, 2), True, np.sum).shape == (1, 3, 1) and tu.np_reduce(np.ones((2, 3)), None, False, np.sum) == 6
+    tu.compare_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9), mx.optimizer.SGD(learning_rate=0.1, momentum=0.9), (4, 3), np.float32)
+    import scipy.stats as ss
+    buckets, probs = tu.gen_buckets_probs_with_ppf(lambda q: ss.norm.ppf(q, 0, 1), 5)
+    tu.verify_generator(lambda n: mx.nd.random.normal(0, 1, shape=(n,)).asnumpy(), buckets, probs, nsamples=20000, nrepeat=3)
+    with pytest.raises(AssertionError):
+        tu.verify_generator(lambda n: mx.nd.random.uniform(-1, 1, shape=(n,)).asnumpy(), buckets, probs, nsamples=20000, nrepeat=3)
+    assert tu.mean_check(lambda n: np.random.normal(2, 1, n), 2, 1, 20000) and tu.var_check(lambda n: np.random.normal(2, 1, n), 1, 20000)
+    with tu.EnvManager("GEOMX_TMP_VAR", "7"):
+        assert os.environ["GEOMX_TMP_VAR"] == "7"
+    assert "GEOMX_TMP_VAR" not in os.environ
+    with pytest.raises(IOError):
+        tu.download("http://example.invalid/x.bin", dirname="/nonexistent")
+    os.environ["GEOMX_SYNTHETIC_SIZE"] = "64"
+    try:
+        d = tu.get_mnist("/nonexistent")
+        tr, va = tu.get_mnist_iterator(8, (1, 28, 28), num_parts=2, part_index=1, path="/nonexistent")
+    finally:
+        os.environ.pop("GEOMX_SYNTHETIC_SIZE")
+    assert d["train_data"].shape == (64, 1, 28, 28) and d["train_data"].max() <= 1.0 and tr.provide_data[0].shape == (8, 1, 28, 28)
+    it = tu.DummyIter(va); b1 = next(it); b2 = next(it)
+    assert b1 is b2 and tu.get_im2rec_path().endswith("im2rec.py")
+    calls = []
+
+    @tu.retry(3)
+    def flaky():
+        calls.append(1)
+        assert len(calls) >= 2
+    flaky(); assert len(calls) == 2
