@@ -70,9 +70,10 @@ def test_autograd_function_symbolblock_export_and_legacy_ops(tmp_path):
 
     d = mx.sym.Variable("data")
     net = mx.sym.FullyConnected(mx.sym.Activation(mx.sym.BatchNorm(mx.sym.FullyConnected(d, num_hidden=8, name="fc1"), name="bn"), act_type="relu"), num_hidden=3, name="fc2")
+    mx.random.seed(3)
     blk = mx.gluon.SymbolBlock(net, d); blk.initialize(mx.init.Xavier())
     x = mx.nd.array(np.random.RandomState(0).randn(5, 4).astype(np.float32))
-    tr = mx.gluon.Trainer(blk.collect_params(), "sgd", {"learning_rate": 0.1})
+    tr = mx.gluon.Trainer(blk.collect_params(), "sgd", {"learning_rate": 0.005})
     with mx.autograd.record():
         l0 = (blk(x) ** 2).sum()
     l0.backward(); tr.step(1)
