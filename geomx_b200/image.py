@@ -378,3 +378,6 @@ class ImageIter(_io.DataIter):
         self._cur += self.batch_size
         xs, ys = zip(*[self._sample(i) for i in idx])
         return _io.DataBatch([NDArray(torch.stack(xs))], [nd.array(np.asarray(ys, dtype=np.float32))], pad=pad)
+
+
+from .image_detection import *  # noqa: E402,F401,F403  (mx.image.ImageDetIter, Det*Aug, CreateDetAugmenter)

@@ -256,3 +256,50 @@ def test_test_utils_helpers():
         calls.append(1)
         assert len(calls) >= 2
     flaky(); assert len(calls) == 2
+
+
+def test_detection_augmenters_and_iterator(tmp_path):
+    from PIL import Image
+    rs = np.random.RandomState(0)
+    entries = []
+    for i in range(5):
+        Image.fromarray(rs.randint(0, 255, (40, 60, 3)).astype(np.uint8)).save(str(tmp_path / ("%d.png" % i)))
+        objs = [[i % 3, 0.1, 0.2, 0.5, 0.7], [1, 0.4, 0.4, 0.9, 0.95]][:1 + i % 2]
+        entries.append([2, 5] + [v for o in objs for v in o] + ["%d.png" % i])
+    it = mx.image.ImageDetIter(2, (3, 32, 32), imglist=entries, path_root=str(tmp_path), rand_crop=0.5, rand_pad=0.5, rand_mirror=True,
+                               mean=True, std=True, brightness=0.1)
+    assert it.provide_label[0].shape == (2, 2, 5)
+    nb = 0
+    for b in it:
+        nb += 1
+        lab = b.label[0].asnumpy()
+        assert b.data[0].shape == (2, 3, 32, 32)
+        v = lab[lab[:, :, 0] >= 0]
+        assert len(v) >= 2 and (v[:, 1:5] >= -1e-6).all() and (v[:, 1:5] <= 1 + 1e-6).all() and (v[:, 3] > v[:, 1]).all() and (v[:, 4] > v[:, 2]).all()
+    assert nb == 3
+    lab = np.array([[0, 0.1, 0.2, 0.5, 0.7]], dtype=np.float32)
+    img = mx.nd.array(rs.randint(0, 255, (40, 60, 3)).astype(np.uint8))
+    fi, fl = mx.image.DetHorizontalFlipAug(1.0)(img, lab)
+    np.testing.assert_allclose(fl, [[0, 0.5, 0.2, 0.9, 0.7]], atol=1e-6)
+    assert np.array_equal(fi.asnumpy(), img.asnumpy()[:, ::-1])
+    pi, pl = mx.image.DetRandomPadAug(area_range=(1.5, 2.0))(img, lab)
+    H, W = pi.shape[:2]
+    assert H >= 40 and W >= 60 and H * W >= 1.4 * 40 * 60
+    # the padded image still shows the object at the moved box: compare the box size in pixels
+    assert abs((pl[0, 3] - pl[0, 1]) * W - 0.4 * 60) < 1e-3 and abs((pl[0, 4] - pl[0, 2]) * H - 0.5 * 40) < 1e-3
+    ci, cl = mx.image.DetRandomCropAug(min_object_covered=0.5, area_range=(0.3, 0.9))(img, lab)
+    assert ci.shape[0] <= 40 and ci.shape[1] <= 60 and (cl[:, 1:5] >= 0).all() and (cl[:, 1:5] <= 1).all()
+    sel = mx.image.CreateMultiRandCropAugmenter(min_object_covered=[0.1, 0.5], area_range=[(0.1, 1.0), (0.3, 0.9)])
+    assert len(sel.aug_list) == 2 and isinstance(json_ok(sel.dumps()), list)
+    it.reset()
+    assert next(it.draw_next(mean=np.array([123.68, 116.28, 103.53]), std=np.array([58.395, 57.12, 57.375]))).shape == (32, 32, 3)
+    val = mx.image.ImageDetIter(2, (3, 32, 32), imglist=entries[:1], path_root=str(tmp_path))
+    assert val.label_shape == (1, 5) and it.sync_label_shape(val).label_shape == (2, 5)
+    with pytest.raises(RuntimeError):
+        mx.image.ImageDetIter._parse_label([2, 5, 0, 0.5, 0.5, 0.4, 0.4])          # xmax < xmin: no valid object
+
+
+def json_ok(x):
+    import json
+    json.dumps(x)
+    return x
