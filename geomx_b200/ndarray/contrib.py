@@ -506,4 +506,129 @@ def cond(pred, then_func, else_func):
     return then_func() if bool(_t(pred).reshape(-1)[0] != 0) else else_func()
 
 
+
+# ------------------------------------------------------------------------------------------------ remaining contrib registrations
+def SparseEmbedding(data, weight, input_dim=None, output_dim=None, dtype="float32", deterministic=False):
+    """Embedding lookup whose weight gradient is row-sparse in the reference; the lookup itself is identical."""
+    return _W(TF.embedding(_t(data).long(), _t(weight)))
+
+
+def group_adagrad_update(weight, grad, history, lr, rescale_grad=1.0, clip_gradient=-1.0, epsilon=1e-5, out=None):
+    """AdaGrad with ONE accumulator per row (``contrib/optimizer_op-inl.h``): ``history += mean(g^2, axis=1)``;
+    ``w -= lr * g / sqrt(history + eps)``.  In place on ``weight`` / ``history``."""
+    with torch.no_grad():
+        g = _t(grad) * rescale_grad
+        if clip_gradient is not None and clip_gradient >= 0:
+            g = g.clamp(-clip_gradient, clip_gradient)
+        h = _t(history)
+        h.add_((g * g).mean(dim=tuple(range(1, g.dim())), keepdim=True).reshape(h.shape))
+        new = _t(weight) - lr * g / torch.sqrt(h.reshape([-1] + [1] * (g.dim() - 1)) + epsilon)
+        tgt = weight if out is None else out
+        _t(tgt).copy_(new)
+        return tgt
+
+
+def _q2f(data, lo, hi):
+    return _t(dequantize(data, lo, hi))
+
+
+def _requant_out(real, out_type="int8"):
+    r = float(real.abs().max()) if real.numel() else 0.0
+    return quantize(_W(real), _W(torch.tensor(-r)), _W(torch.tensor(r)), out_type)
+
+
+def quantized_fully_connected(data, weight, bias, min_data, max_data, min_weight, max_weight, min_bias=None, max_bias=None, num_hidden=None,
+                              no_bias=False, flatten=True):
+    """int8 FullyConnected, simulated: operands are dequantised, multiplied in fp32 and the result returned as int32-range accumulators
+    ``(out, min_out, max_out)`` like ``quantized_fully_connected.cc`` (the float value of an accumulator unit is
+    ``scale_data * scale_weight``)."""
+    x, w = _t(data).float(), _t(weight).float()
+    sd = float(torch.maximum(_t(min_data).abs().max(), _t(max_data).abs().max())) / 127.0
+    sw = float(torch.maximum(_t(min_weight).abs().max(), _t(max_weight).abs().max())) / 127.0
+    acc = TF.linear(x.flatten(1) if flatten else x, w)
+    if not no_bias and bias is not None:
+        sb = float(torch.maximum(_t(min_bias).abs().max(), _t(max_bias).abs().max())) / 127.0
+        acc = acc + torch.round(_t(bias).float() * sb / (sd * sw))
+    rng = 2147483647.0 * sd * sw
+    return _W(acc.to(torch.int32)), _W(torch.tensor([-rng])), _W(torch.tensor([rng]))
+
+
+def quantized_conv(data, weight, bias, min_data, max_data, min_weight, max_weight, min_bias=None, max_bias=None, kernel=None, stride=(1, 1),
+                   pad=(0, 0), dilate=(1, 1), num_filter=None, num_group=1, no_bias=True, layout=None):
+    x, w = _t(data).float(), _t(weight).float()
+    sd = float(torch.maximum(_t(min_data).abs().max(), _t(max_data).abs().max())) / 127.0
+    sw = float(torch.maximum(_t(min_weight).abs().max(), _t(max_weight).abs().max())) / 127.0
+    acc = TF.conv2d(x, w, None, tuple(stride), tuple(pad), tuple(dilate), num_group)
+    if not no_bias and bias is not None:
+        sb = float(torch.maximum(_t(min_bias).abs().max(), _t(max_bias).abs().max())) / 127.0
+        acc = acc + torch.round(_t(bias).float() * sb / (sd * sw)).view(1, -1, 1, 1)
+    rng = 2147483647.0 * sd * sw
+    return _W(acc.to(torch.int32)), _W(torch.tensor([-rng])), _W(torch.tensor([rng]))
+
+
+def quantized_pooling(data, min_data, max_data, kernel=(2, 2), pool_type="max", stride=None, pad=(0, 0), global_pool=False, **kw):
+    """Pooling directly on the int8 codes (max / avg commute with the affine map); ranges pass through."""
+    x = _t(data)
+    k = tuple(x.shape[2:]) if global_pool else tuple(kernel)
+    st = tuple(stride) if stride else k
+    y = TF.max_pool2d(x.float(), k, st, tuple(pad)) if pool_type == "max" else torch.round(TF.avg_pool2d(x.float(), k, st, tuple(pad)))
+    return _W(y.to(x.dtype)), min_data, max_data
+
+
+def quantized_flatten(data, min_data, max_data):
+    return _W(_t(data).flatten(1)), min_data, max_data
+
+
+def quantized_concat(*args, dim=1, num_args=None):
+    """``quantized_concat(d0, d1, …, min0, max0, min1, max1, …)``: inputs are re-scaled to the widest range, then concatenated."""
+    n = num_args or len(args) // 3
+    datas, ranges = args[:n], args[n:]
+    rs = [float(torch.maximum(_t(ranges[2 * i]).abs().max(), _t(ranges[2 * i + 1]).abs().max())) for i in range(n)]
+    top = max(rs)
+    parts = [torch.round(_t(d).float() * (r / top)).clamp(-127, 127).to(_t(d).dtype) for d, r in zip(datas, rs)]
+    return _W(torch.cat(parts, dim=dim)), _W(torch.tensor([-top])), _W(torch.tensor([top]))
+
+
+# ---- DGL graph helpers on CSR adjacency matrices whose stored values are edge ids (contrib/dgl_graph.cc)
+def edge_id(data, u, v):
+    """Edge id ``data[u[i], v[i]]`` or -1 when the edge does not exist."""
+    ptr, idx, val = data.indptr._t.long(), data.indices._t.long(), data.data._t
+    out = torch.full((_t(u).numel(),), -1.0, dtype=val.dtype if val.is_floating_point() else torch.float32)
+    for i, (a, b) in enumerate(zip(_t(u).long().tolist(), _t(v).long().tolist())):
+        cols = idx[ptr[a]:ptr[a + 1]]
+        hit = torch.nonzero(cols == b)
+        if hit.numel():
+            out[i] = val[ptr[a] + hit[0, 0]]
+    return _W(out)
+
+
+def dgl_adjacency(data):
+    """Same sparsity pattern with every stored value replaced by 1.0."""
+    from .sparse import CSRNDArray
+    return CSRNDArray(_W(torch.ones(data.data._t.shape, dtype=torch.float32)), data.indices.copy(), data.indptr.copy(), data.shape)
+
+
+def dgl_subgraph(graph, *vertex_sets, return_mapping=False, num_args=None):
+    """Vertex-induced subgraphs: for every id list ``v`` the CSR of ``graph[v][:, v]`` with edges renumbered from 0 (and, with
+    ``return_mapping``, a second CSR of the same pattern holding the ORIGINAL edge ids)."""
+    from .sparse import CSRNDArray
+    ptr, idx, val = graph.indptr._t.long(), graph.indices._t.long(), graph.data._t
+    subs, maps = [], []
+    for vs in vertex_sets:
+        ids = _t(vs).long().tolist()
+        remap = {v: i for i, v in enumerate(ids)}
+        nptr, nidx, orig = [0], [], []
+        for v in ids:
+            for j in range(int(ptr[v]), int(ptr[v + 1])):
+                c = int(idx[j])
+                if c in remap:
+                    nidx.append(remap[c]); orig.append(float(val[j]))
+            nptr.append(len(nidx))
+        shape = (len(ids), len(ids))
+        mk = lambda d: CSRNDArray(_W(torch.tensor(d, dtype=torch.float32)), _W(torch.tensor(nidx, dtype=torch.int64)),  # noqa: E731
+                                  _W(torch.tensor(nptr, dtype=torch.int64)), shape)
+        subs.append(mk(list(range(len(nidx))))); maps.append(mk(orig))
+    res = subs + (maps if return_mapping else [])
+    return res[0] if len(res) == 1 else res
+
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in ("torch", "TF", "NDArray", "annotations")]

@@ -606,4 +606,113 @@ def ftml_update(weight, grad, d, v, z, lr, t, beta1=0.6, beta2=0.999, epsilon=1e
         _t(d).copy_(d_t)
         return _ret(weight, -_t(z) / d_t, out)
 
+
+# ------------------------------------------------------------------------------------------------ fused RNN op, versioned aliases, misc
+def RNN(data, parameters, state, state_cell=None, state_size=None, num_layers=1, bidirectional=False, mode="lstm", p=0.0, state_outputs=False,
+        projection_size=None, **kw):
+    """The fused multi-layer RNN operator (``src/operator/rnn-inl.h``): ``data [T, N, C]``, ``parameters`` = ONE flat vector holding, layer by
+    layer and direction by direction, all ``W_i2h, W_h2h`` blocks and then all ``b_i2h, b_h2h`` blocks (gate order LSTM i,f,g,o; GRU r,z,n),
+    ``state`` / ``state_cell`` ``[L*D, N, H]``.  Returns the output sequence, plus the final states with ``state_outputs=True``."""
+    x, flat = _t(data), _t(parameters).reshape(-1)
+    H, L, D = int(state_size), int(num_layers), (2 if bidirectional else 1)
+    G = {"rnn_relu": 1, "rnn_tanh": 1, "lstm": 4, "gru": 3}[mode]
+    T, N, C = x.shape
+    w_shapes = []
+    for layer in _bi.range(L):
+        cin = C if layer == 0 else D * H
+        for _ in _bi.range(D):
+            w_shapes += [(G * H, cin), (G * H, H)]
+    pos, weights = 0, []
+    for shp in w_shapes:
+        n = shp[0] * shp[1]
+        weights.append(flat[pos:pos + n].view(shp)); pos += n
+    biases = []
+    for _ in w_shapes:
+        biases.append(flat[pos:pos + G * H]); pos += G * H
+    if pos != flat.numel():
+        raise ValueError("RNN: parameter vector has %d elements, the configuration needs %d" % (flat.numel(), pos))
+    h0 = _t(state); c0 = _t(state_cell) if state_cell is not None else None
+    seq, hN, cN = x, [], []
+    for layer in _bi.range(L):
+        outs_dir = []
+        for d in _bi.range(D):
+            k = layer * D + d
+            wi, wh, bi, bh = weights[2 * k], weights[2 * k + 1], biases[2 * k], biases[2 * k + 1]
+            h = h0[k]; c = c0[k] if c0 is not None else None
+            steps = _bi.range(T) if d == 0 else _bi.range(T - 1, -1, -1)
+            outs = [None] * T
+            xi_all = TF.linear(seq, wi, bi)                                    # input projections of every step in one GEMM
+            for t in steps:
+                gh = TF.linear(h, wh, bh)
+                if mode == "lstm":
+                    i, f, g, o = (xi_all[t] + gh).chunk(4, dim=-1)
+                    c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+                    h = torch.sigmoid(o) * torch.tanh(c)
+                elif mode == "gru":
+                    xr, xz, xn = xi_all[t].chunk(3, dim=-1); hr, hz, hn = gh.chunk(3, dim=-1)
+                    r = torch.sigmoid(xr + hr); z = torch.sigmoid(xz + hz)
+                    n_ = torch.tanh(xn + r * hn)
+                    h = (1 - z) * n_ + z * h
+                else:
+                    h = (torch.relu if mode == "rnn_relu" else torch.tanh)(xi_all[t] + gh)
+                outs[t] = h
+            outs_dir.append(torch.stack(outs, 0)); hN.append(h)
+            if c is not None:
+                cN.append(c)
+        seq = torch.cat(outs_dir, dim=-1) if D == 2 else outs_dir[0]
+        if p > 0 and layer + 1 < L:
+            from .. import autograd as _ag
+            seq = TF.dropout(seq, p, _ag.is_training())
+    if not state_outputs:
+        return _W(seq)
+    res = [_W(seq), _W(torch.stack(hN, 0))]
+    if mode == "lstm":
+        res.append(_W(torch.stack(cN, 0)))
+    return res
+
+
+def BatchNorm_v1(*a, **k): return BatchNorm(*a, **k)
+def CuDNNBatchNorm(*a, **k): return BatchNorm(*a, **k)
+def Convolution_v1(*a, **k): return Convolution(*a, **k)
+def Pooling_v1(*a, **k): return Pooling(*a, **k)
+
+
+def IdentityAttachKLSparseReg(data, sparseness_target=0.1, penalty=0.001, momentum=0.9):
+    """Identity in the forward pass; the reference attaches a KL sparsity penalty to the gradient of sigmoid activations
+    (``identity_attach_KL_sparse_reg-inl.h``): ``grad += penalty * (-rho/rho_hat + (1-rho)/(1-rho_hat))`` with ``rho_hat`` the batch mean."""
+    x = _t(data)
+
+    class _F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            ctx.save_for_backward(t)
+            return t.view_as(t)
+
+        @staticmethod
+        def backward(ctx, g):
+            (t,) = ctx.saved_tensors
+            rho_hat = t.mean(0, keepdim=True).clamp(1e-6, 1 - 1e-6)
+            return g + penalty * (-sparseness_target / rho_hat + (1 - sparseness_target) / (1 - rho_hat))
+    return _W(_F.apply(x))
+
+
+def cast_storage(data, stype):
+    from .sparse import cast_storage as _cs
+    return _cs(data, stype)
+
+
+def linalg_gelqf(A):
+    """LQ factorisation ``A = L Q`` with ``Q`` having orthonormal rows (``la_op.h`` gelqf); returns ``(Q, L)`` like the reference."""
+    q, r = torch.linalg.qr(_t(A).transpose(-1, -2), mode="reduced")
+    # make the diagonal of L non-negative (LAPACK convention used by the reference's tests)
+    sgn = torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)); sgn = torch.where(sgn == 0, torch.ones_like(sgn), sgn)
+    q = q * sgn.unsqueeze(-2); r = r * sgn.unsqueeze(-1)
+    return _W(q.transpose(-1, -2)), _W(r.transpose(-1, -2))
+
+
+def linalg_syevd(A):
+    """Symmetric eigendecomposition ``A = U^T diag(L) U`` (rows of ``U`` are eigenvectors, eigenvalues ascending); returns ``(U, L)``."""
+    w, v = torch.linalg.eigh(_t(A))
+    return _W(v.transpose(-1, -2)), _W(w)
+
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in ("torch", "TF", "OF", "NDArray", "torch_dtype", "annotations")]

@@ -10,7 +10,8 @@ import torch
 from .ndarray import NDArray, _ctx_of, _shape, torch_dtype
 
 __all__ = ["uniform", "normal", "randn", "randint", "shuffle", "seed", "exponential", "gamma", "poisson", "negative_binomial",
-           "generalized_negative_binomial", "multinomial"]
+           "generalized_negative_binomial", "multinomial", "uniform_like", "normal_like", "exponential_like", "gamma_like", "poisson_like",
+           "negative_binomial_like", "generalized_negative_binomial_like", "unique_zipfian"]
 
 _gens = {}
 
@@ -117,3 +118,40 @@ def multinomial(data, shape=None, get_prob=False, out=None, dtype="int32", **kw)
         logp = torch.log(p.reshape(-1, p.shape[-1]).gather(1, idx.reshape(-1, n))).reshape(idx.shape)
         return res, NDArray(logp)
     return res
+
+
+def _like(fn):
+    def f(data, *args, **kwargs):
+        kwargs.pop("shape", None)
+        return fn(*args, shape=tuple(data.shape), dtype=str(data._t.dtype).replace("torch.", ""), ctx=data.context, **kwargs)
+    f.__doc__ = "Samples with the shape / dtype / context of ``data`` (``_random_*_like``)."
+    return f
+
+
+uniform_like, normal_like, exponential_like, gamma_like = _like(uniform), _like(normal), _like(exponential), _like(gamma)
+poisson_like, negative_binomial_like, generalized_negative_binomial_like = _like(poisson), _like(negative_binomial), _like(generalized_negative_binomial)
+
+
+def unique_zipfian(range_max, shape=None, ctx=None, **kw):
+    """``shape = (batch, n)`` rows of ``n`` DISTINCT classes drawn from an approximately Zipfian (log-uniform) distribution over
+    ``[0, range_max)`` — the candidate sampler of sampled softmax (``_sample_unique_zipfian``).  Returns ``(samples, number of trials per row)``;
+    the trial counts let the caller compute expected counts."""
+    import math
+    shp = _shape(shape)
+    batch, n = (1, shp[0]) if len(shp) == 1 else shp
+    assert n <= range_max, "cannot draw %d unique classes out of %d" % (n, range_max)
+    out = torch.empty((batch, n), dtype=torch.int64); trials = torch.zeros(batch, dtype=torch.int64)
+    log_range = math.log(range_max + 1)
+    for b in range(batch):
+        seen, k = {}, 0
+        while len(seen) < n:
+            draw = (torch.exp(torch.rand(2 * n) * log_range).long() - 1) % range_max
+            for v in draw.tolist():
+                k += 1
+                if v not in seen:
+                    seen[v] = len(seen)
+                    if len(seen) == n:
+                        break
+        out[b] = torch.tensor(list(seen.keys())); trials[b] = k
+    res = out if len(shp) == 2 else out[0]
+    return NDArray(res), NDArray(trials)

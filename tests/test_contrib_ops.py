@@ -189,3 +189,68 @@ def test_sampling_families_have_the_right_moments():
     assert abs(idx.asnumpy()[0].mean() - 0.8) < 0.03 and (idx.asnumpy()[1] == 0).all()
     assert np.allclose(np.exp(logp.asnumpy()[1]), 1.0)
     assert nd.sample_multinomial(nd.array([0.5, 0.5])).shape in ((), (1,))
+
+
+def test_fused_rnn_op_linalg_factorisations_and_graph_helpers():
+    T, N, C, H, L = 5, 3, 4, 6, 2
+    torch.manual_seed(0)
+    lstm = torch.nn.LSTM(C, H, L, bidirectional=True)
+    ws, bs = [], []
+    for l in range(L):
+        for sfx in ("", "_reverse"):
+            ws += [getattr(lstm, "weight_ih_l%d%s" % (l, sfx)).detach().reshape(-1), getattr(lstm, "weight_hh_l%d%s" % (l, sfx)).detach().reshape(-1)]
+            bs += [getattr(lstm, "bias_ih_l%d%s" % (l, sfx)).detach(), getattr(lstm, "bias_hh_l%d%s" % (l, sfx)).detach()]
+    flat = torch.cat(ws + bs)
+    x = torch.randn(T, N, C); h0 = torch.randn(L * 2, N, H); c0 = torch.randn(L * 2, N, H)
+    with torch.no_grad():
+        ref, (hn, cn) = lstm(x, (h0, c0))
+    out, h, c = nd.RNN(nd.array(x), nd.array(flat), nd.array(h0), nd.array(c0), state_size=H, num_layers=L, bidirectional=True, mode="lstm", state_outputs=True)
+    for a, b in ((out, ref), (h, hn), (c, cn)):
+        np.testing.assert_allclose(a.asnumpy(), b.numpy(), atol=1e-5)
+    gru = torch.nn.GRU(C, H, 1)
+    gflat = torch.cat([gru.weight_ih_l0.detach().reshape(-1), gru.weight_hh_l0.detach().reshape(-1), gru.bias_ih_l0.detach(), gru.bias_hh_l0.detach()])
+    with torch.no_grad():
+        gref = gru(x, h0[:1])[0]
+    np.testing.assert_allclose(nd.RNN(nd.array(x), nd.array(gflat), nd.array(h0[:1]), state_size=H, mode="gru").asnumpy(), gref.numpy(), atol=1e-5)
+    # the flat vector produced by the FusedRNN initializer has exactly the size this operator expects
+    f = nd.zeros((int(flat.numel()),)); mx.init.FusedRNN(mx.init.Uniform(0.1), H, L, "lstm", bidirectional=True)(mx.init.InitDesc("p"), f)
+    assert nd.RNN(nd.array(x), f, nd.array(h0), nd.array(c0), state_size=H, num_layers=L, bidirectional=True, mode="lstm").shape == (T, N, 2 * H)
+    try:
+        nd.RNN(nd.array(x), f[:-1], nd.array(h0), nd.array(c0), state_size=H, num_layers=L, bidirectional=True, mode="lstm")
+        raise AssertionError("a short parameter vector must be rejected")
+    except ValueError:
+        pass
+
+    A = torch.randn(3, 5)
+    q, l = nd.linalg_gelqf(nd.array(A))
+    np.testing.assert_allclose((l._t @ q._t).numpy(), A.numpy(), atol=1e-5)
+    np.testing.assert_allclose((q._t @ q._t.T).numpy(), np.eye(3), atol=1e-5)
+    assert (np.diag(l.asnumpy()) >= 0).all() and np.allclose(np.triu(l.asnumpy(), 1), 0)
+    S = torch.randn(4, 4); S = S + S.T
+    u, w = nd.linalg_syevd(nd.array(S))
+    np.testing.assert_allclose((u._t.T @ torch.diag(w._t) @ u._t).numpy(), S.numpy(), atol=1e-4)
+    assert (np.diff(w.asnumpy()) >= 0).all()
+
+    assert nd.random.normal_like(nd.zeros((2, 3))).shape == (2, 3) and nd.BatchNorm_v1 is not None and nd.cast_storage(nd.ones((2, 2)), "csr").stype == "csr"
+    samp, trials = nd.random.unique_zipfian(50, shape=(2, 8))
+    s = samp.asnumpy()
+    assert s.shape == (2, 8) and all(len(set(r)) == 8 for r in s) and s.min() >= 0 and s.max() < 50 and (trials.asnumpy() >= 8).all()
+
+    g = nd.sparse.csr_matrix((np.arange(1, 6, dtype=np.float32), np.array([1, 2, 0, 2, 0]), np.array([0, 2, 4, 5])), shape=(3, 3))
+    assert nd.contrib.edge_id(g, nd.array([0, 1, 2]), nd.array([2, 1, 0])).asnumpy().tolist() == [2, -1, 5]
+    assert nd.contrib.dgl_adjacency(g).asnumpy().tolist() == [[0, 1, 1], [1, 0, 1], [1, 0, 0]]
+    sg, mp = nd.contrib.dgl_subgraph(g, nd.array([0, 2]), return_mapping=True)
+    assert sg.asnumpy().tolist() == [[0, 0], [1, 0]] and mp.asnumpy().tolist() == [[0, 2], [5, 0]]
+    w_ = nd.ones((3, 2)); hist = nd.zeros((3,))
+    nd.contrib.group_adagrad_update(w_, nd.array([[1.0, 1.0], [2.0, 2.0], [0.0, 0.0]]), hist, lr=0.1)
+    assert hist.asnumpy().tolist() == [1, 4, 0] and np.allclose(w_.asnumpy()[:2], 0.9, atol=1e-4) and w_.asnumpy()[2].tolist() == [1, 1]
+
+    # simulated int8 FC: accumulators times (scale_data * scale_weight) reproduce the float product
+    xd = torch.randn(4, 6); wd = torch.randn(3, 6)
+    qx, lox, hix = nd.contrib.quantize(nd.array(xd), nd.array([float(xd.min())]), nd.array([float(xd.max())]), "int8")
+    qw, low, hiw = nd.contrib.quantize(nd.array(wd), nd.array([float(wd.min())]), nd.array([float(wd.max())]), "int8")
+    acc, lo, hi = nd.contrib.quantized_fully_connected(qx, qw, None, lox, hix, low, hiw, no_bias=True)
+    real = nd.contrib.dequantize(acc, lo, hi).asnumpy()
+    assert np.abs(real - (xd @ wd.T).numpy()).max() < 0.15
+    p, plo, phi = nd.contrib.quantized_pooling(nd.array(torch.randint(-100, 100, (1, 2, 4, 4)).to(torch.int8)), lox, hix, kernel=(2, 2), pool_type="max")
+    assert p.shape == (1, 2, 2, 2) and p.dtype == np.int8
