@@ -113,7 +113,10 @@ class CSRNDArray:
         ptr, idx, val = self.indptr._t.long(), self.indices._t.long(), self.data._t
         rows = torch.repeat_interleave(torch.arange(self._shape[0], device=ptr.device), ptr[1:] - ptr[:-1])
         order = torch.argsort(rows * self._shape[1] + idx, stable=True)
-        return torch.sparse_csr_tensor(ptr, idx[order], val[order], size=self._shape, check_invariants=False)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)      # "Sparse CSR tensor support is in beta state"
+            return torch.sparse_csr_tensor(ptr, idx[order], val[order], size=self._shape, check_invariants=False)
 
     def tostype(self, stype):
         if stype == "csr":
