@@ -55,6 +55,10 @@ class Symbol:
     __rmul__ = __mul__
     def __truediv__(self, o): return _binary("_div", self, o)
     def __getitem__(self, i):
+        if self.op == "_nd" and isinstance(i, int) and (i > 0 or self.attrs.get("kwargs", {}).get("num_outputs", 1) > 1 or self.attrs.get("multi")):
+            # i-th output of a multi-output imperative op (split / SliceChannel / topk(ret_typ='both') / RNN(state_outputs=True) …)
+            self.attrs["multi"] = True
+            return Symbol("_item", "%s_output%d" % (self.name, i), [self], {"index": int(i)})
         if self.op != "_group":
             if i in (0, self.list_outputs()[0]):
                 return self
@@ -384,6 +388,10 @@ def _eval_node(s, ins, aux, training):
         return {"_plus": torch.add, "_minus": torch.sub, "_mul": torch.mul, "_div": torch.div}[op[:-7]](ins[0], a["scalar"])
     if op == "_nd":
         return _eval_nd(a, ins)
+    if op == "_item":
+        if not isinstance(ins[0], tuple):
+            raise MXNetError("%s: the producer has a single output" % s.name)
+        return ins[0][a["index"]]
     if op == "_full_like":
         return torch.full_like(ins[0], a["value"])
     raise MXNetError("symbol op %s is not implemented" % op)
@@ -409,8 +417,10 @@ def _eval_nd(a, ins):
     for k, t in zip(a.get("sym_kwargs") or (), ins[npos:]):
         kwargs[k] = NDArray(t)
     out = fn(*args, **kwargs)
+    if isinstance(out, (list, tuple)) and a.get("multi"):
+        return tuple(o._t for o in out)
     if not isinstance(out, NDArray):
-        raise MXNetError("mx.sym.%s: the imperative function returned %s, only single-output ops can be used symbolically" % (a["fn"], type(out).__name__))
+        raise MXNetError("mx.sym.%s: the imperative function returned %s, index the symbol (``sym[i]``) to use one output of a multi-output op" % (a["fn"], type(out).__name__))
     return out._t
 
 
@@ -479,7 +489,7 @@ class _ShapeRun:
                 continue
             if s.op == "_group":
                 continue
-            data = vals.get(id(s.inputs[0]))
+            data = vals.get(id(s.inputs[0])) if s.inputs else torch.zeros(())          # creation ops (zeros / ones / arange …) have no inputs
             if data is None:
                 raise MXNetError("cannot infer the input shape of %s: provide the shape of %s" % (s.name, s.inputs[0].name))
             for i, inp in enumerate(s.inputs[1:], 1):

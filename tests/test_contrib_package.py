@@ -177,3 +177,19 @@ def test_generic_symbol_bridge_matches_imperative():
     assert contrib.symbol.box_iou(mx.sym.Variable("a"), mx.sym.Variable("b")).infer_shape(a=(2, 4), b=(3, 4))[1] == [(2, 3)]
     with pytest.raises(AttributeError):
         mx.sym.no_such_operator
+
+
+def test_symbol_bridge_creation_and_multi_output_ops():
+    x = mx.sym.Variable("x")
+    assert (mx.sym.zeros(shape=(2, 3)) + x).infer_shape(x=(2, 3))[1] == [(2, 3)]
+    out = mx.sym.maximum(x, mx.sym.ones(shape=(2, 3))).eval(x=mx.nd.array([[0.0, 2.0, 0.5]] * 2))[0].asnumpy()
+    assert out.tolist() == [[1, 2, 1]] * 2
+    rng = mx.sym.load_json((mx.sym.arange(start=0, stop=6).reshape((2, 3)) * x).tojson()).eval(x=mx.nd.ones((2, 3)))[0].asnumpy()
+    assert rng.tolist() == [[0, 1, 2], [3, 4, 5]]
+    parts = mx.sym.split(x, num_outputs=2, axis=1)
+    y = mx.sym.load_json((parts[0] * 2 + parts[1]).tojson())
+    ex = y.simple_bind(mx.cpu(), x=(2, 4))
+    ex.arg_dict["x"][:] = mx.nd.array(np.arange(8, dtype=np.float32).reshape(2, 4))
+    assert ex.forward(is_train=True)[0].asnumpy().tolist() == [[2, 5], [14, 17]]
+    ex.backward()
+    assert ex.grad_dict["x"].asnumpy().tolist() == [[2, 2, 1, 1]] * 2
