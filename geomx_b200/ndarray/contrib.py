@@ -631,4 +631,51 @@ def dgl_subgraph(graph, *vertex_sets, return_mapping=False, num_args=None):
     res = subs + (maps if return_mapping else [])
     return res[0] if len(res) == 1 else res
 
+
+def DeformablePSROIPooling(data, rois, trans=None, spatial_scale=1.0, output_dim=None, group_size=None, pooled_size=None, part_size=0,
+                           sample_per_part=1, trans_std=0.0, no_trans=False):
+    """Deformable position-sensitive RoI pooling (``contrib/deformable_psroi_pooling.cu``): every output bin ``(c, ph, pw)`` averages
+    ``sample_per_part²`` bilinear samples of the position-sensitive channel ``(c·G + gh)·G + gw``, the bin being shifted by the learned,
+    RoI-size-normalised offset ``trans[r, 2·class (+1), part_h, part_w] · trans_std``.  ``data [N, output_dim·G², H, W]``, ``rois [R, 5]``."""
+    x, r = _t(data).float(), _t(rois).float()
+    N, C, H, W = x.shape
+    P, G, S = int(pooled_size), int(group_size), int(sample_per_part)
+    part = int(part_size) if part_size else P
+    R = r.shape[0]
+    out = x.new_zeros((R, int(output_dim), P, P))
+    tr = None if (no_trans or trans is None) else _t(trans).float()
+    ncls = 1 if tr is None else tr.shape[1] // 2
+    ch_per_cls = int(output_dim) // ncls
+    ph = torch.arange(P, device=x.device).view(1, P, 1, 1, 1).float(); pw = torch.arange(P, device=x.device).view(1, 1, P, 1, 1).float()
+    ih = torch.arange(S, device=x.device).view(1, 1, 1, S, 1).float(); iw = torch.arange(S, device=x.device).view(1, 1, 1, 1, S).float()
+    ctop = torch.arange(int(output_dim), device=x.device).view(-1, 1, 1, 1, 1)
+    gh = torch.clamp(torch.floor(ph * G / P), 0, G - 1).long(); gw = torch.clamp(torch.floor(pw * G / P), 0, G - 1).long()
+    chan = ((ctop * G + gh) * G + gw).expand(-1, P, P, S, S)                              # [D, P, P, S, S]
+    part_h = torch.floor(ph / P * part).long().clamp(0, part - 1); part_w = torch.floor(pw / P * part).long().clamp(0, part - 1)
+    cls = (ctop // ch_per_cls).clamp(0, ncls - 1)
+    for i in range(R):
+        b = int(r[i, 0])
+        sw = torch.round(r[i, 1]) * spatial_scale - 0.5; sh = torch.round(r[i, 2]) * spatial_scale - 0.5
+        ew = (torch.round(r[i, 3]) + 1.0) * spatial_scale - 0.5; eh = (torch.round(r[i, 4]) + 1.0) * spatial_scale - 0.5
+        rw = torch.clamp(ew - sw, min=0.1); rh = torch.clamp(eh - sh, min=0.1)
+        bw, bh = rw / P, rh / P
+        if tr is None:
+            tx = ty = x.new_zeros(())
+        else:
+            tx = tr[i][cls * 2, part_h, part_w] * trans_std                               # broadcast to [D, P, P, 1, 1]
+            ty = tr[i][cls * 2 + 1, part_h, part_w] * trans_std
+        ws = pw * bw + sw + tx * rw + iw * (bw / S)
+        hs = ph * bh + sh + ty * rh + ih * (bh / S)
+        ws, hs = ws.expand(int(output_dim), P, P, S, S), hs.expand(int(output_dim), P, P, S, S)
+        ok = (ws >= -0.5) & (ws <= W - 0.5) & (hs >= -0.5) & (hs <= H - 0.5)
+        wc, hc = ws.clamp(0, W - 1), hs.clamp(0, H - 1)
+        x0, y0 = torch.floor(wc).long(), torch.floor(hc).long()
+        x1, y1 = (x0 + 1).clamp(max=W - 1), (y0 + 1).clamp(max=H - 1)
+        fx, fy = wc - x0, hc - y0
+        img = x[b]
+        v = (img[chan, y0, x0] * (1 - fx) * (1 - fy) + img[chan, y0, x1] * fx * (1 - fy) + img[chan, y1, x0] * (1 - fx) * fy + img[chan, y1, x1] * fx * fy)
+        cnt = ok.sum(dim=(-1, -2)).clamp_min(1)
+        out[i] = (v * ok).sum(dim=(-1, -2)) / cnt
+    return _W(out)
+
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in ("torch", "TF", "NDArray", "annotations")]

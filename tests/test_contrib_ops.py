@@ -254,3 +254,18 @@ def test_fused_rnn_op_linalg_factorisations_and_graph_helpers():
     assert np.abs(real - (xd @ wd.T).numpy()).max() < 0.15
     p, plo, phi = nd.contrib.quantized_pooling(nd.array(torch.randint(-100, 100, (1, 2, 4, 4)).to(torch.int8)), lox, hix, kernel=(2, 2), pool_type="max")
     assert p.shape == (1, 2, 2, 2) and p.dtype == np.int8
+
+
+def test_deformable_psroi_pooling():
+    G = P = 2; D = 3
+    rois = nd.array([[0, 1.0, 1.0, 6.0, 6.0]])
+    xc = torch.arange(D * G * G).float().view(1, -1, 1, 1).expand(1, D * G * G, 8, 8).contiguous()
+    oc = nd.contrib.DeformablePSROIPooling(nd.array(xc), rois, spatial_scale=1.0, output_dim=D, group_size=G, pooled_size=P, sample_per_part=2, no_trans=True).asnumpy()
+    assert oc[0].reshape(-1).tolist() == list(range(12))               # bin (c, gh, gw) reads channel (c*G + gh)*G + gw
+    ramp = torch.arange(8.0).view(1, 1, 1, 8).expand(1, D * G * G, 8, 8).contiguous()
+    kw = dict(spatial_scale=1.0, output_dim=D, group_size=G, pooled_size=P, sample_per_part=2, trans_std=0.1)
+    t0 = nd.contrib.DeformablePSROIPooling(nd.array(ramp), rois, nd.zeros((1, 2, P, P)), **kw).asnumpy()
+    shift = nd.array(torch.cat([torch.ones(1, 1, P, P), torch.zeros(1, 1, P, P)], 1))
+    t1 = nd.contrib.DeformablePSROIPooling(nd.array(ramp), rois, shift, **kw).asnumpy()
+    np.testing.assert_allclose(t0[0, 0], [[1.25, 4.25]] * 2, atol=1e-5)
+    np.testing.assert_allclose(t1 - t0, 0.1 * 6.0, atol=1e-5)          # offset = trans * trans_std * roi width, in pixels of a unit ramp
