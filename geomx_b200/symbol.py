@@ -424,8 +424,35 @@ def _eval_nd(a, ins):
     return out._t
 
 
+# parameter inputs that are created automatically (as ``<name>_<param>`` variables) when the caller does not pass them, and whose shapes
+# follow from the attributes / data shape — the bridged counterparts of the reference ops' FListInputNames + FInferShape
+_AUTO_PARAMS = {"Embedding": ("weight",), "Deconvolution": ("weight", "bias"), "LayerNorm": ("gamma", "beta"), "InstanceNorm": ("gamma", "beta")}
+
+
+def _nd_param_shape(a, pname, in_shape):
+    fn, kw = a["fn"], a.get("kwargs") or {}
+    if fn == "Embedding" and pname == "weight":
+        return (int(kw["input_dim"]), int(kw["output_dim"]))
+    if fn == "Deconvolution":
+        k = tuple(kw["kernel"])
+        return (in_shape[1], int(kw["num_filter"]) // int(kw.get("num_group", 1))) + k if pname == "weight" else (int(kw["num_filter"]),)
+    if fn == "LayerNorm":
+        return (in_shape[int(kw.get("axis", -1))],)
+    if fn == "InstanceNorm":
+        return (in_shape[1],)
+    return None
+
+
 def _nd_op(qual):
     def build(*args, name=None, **kwargs):
+        auto = _AUTO_PARAMS.get(qual)
+        if auto and len(args) == 1:
+            name = _auto_name(qual.lower(), name)
+            for pn in auto:
+                if pn == "bias" and kwargs.get("no_bias", qual == "Deconvolution"):
+                    continue
+                if kwargs.get(pn) is None:
+                    kwargs[pn] = Variable("%s_%s" % (name, pn))
         pos = [x for x in args if isinstance(x, Symbol)]
         if len(pos) != len(args):
             raise MXNetError("mx.sym.%s: positional arguments must be Symbols, pass attributes by keyword" % qual)
@@ -494,7 +521,11 @@ class _ShapeRun:
                 raise MXNetError("cannot infer the input shape of %s: provide the shape of %s" % (s.name, s.inputs[0].name))
             for i, inp in enumerate(s.inputs[1:], 1):
                 if id(inp) not in vals:
-                    shp = _param_shape(s, i, tuple(data.shape))
+                    if s.op == "_nd":
+                        k = i - s.attrs["npos"]
+                        shp = _nd_param_shape(s.attrs, s.attrs["sym_kwargs"][k], tuple(data.shape)) if 0 <= k < len(s.attrs["sym_kwargs"]) else None
+                    else:
+                        shp = _param_shape(s, i, tuple(data.shape))
                     if shp is None:
                         raise MXNetError("cannot infer the shape of %s" % inp.name)
                     self.shapes[inp.name] = shp

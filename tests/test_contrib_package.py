@@ -193,3 +193,20 @@ def test_symbol_bridge_creation_and_multi_output_ops():
     assert ex.forward(is_train=True)[0].asnumpy().tolist() == [[2, 5], [14, 17]]
     ex.backward()
     assert ex.grad_dict["x"].asnumpy().tolist() == [[2, 2, 1, 1]] * 2
+
+
+def test_symbol_bridge_auto_parameters_train_an_embedding_model():
+    d = mx.sym.Variable("data")
+    n = mx.sym.LayerNorm(mx.sym.Embedding(d, input_dim=10, output_dim=4, name="emb"), name="ln")
+    net = mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.mean(n, axis=1), num_hidden=2, name="fc"), name="softmax")
+    assert net.list_arguments() == ["data", "emb_weight", "ln_gamma", "ln_beta", "fc_weight", "fc_bias", "softmax_label"]
+    assert net.infer_shape(data=(8, 5))[0][1:4] == [(10, 4), (4,), (4,)]
+    rs = np.random.RandomState(0)
+    y = rs.randint(0, 2, 64)
+    x = np.where(rs.rand(64, 5) < 0.8, y[:, None] * 5 + rs.randint(0, 5, (64, 5)), rs.randint(0, 10, (64, 5)))
+    it = mx.io.NDArrayIter(x.astype(np.float32), y.astype(np.float32), batch_size=8)
+    mod = mx.mod.Module(net)
+    mod.fit(it, num_epoch=8, optimizer="adam", optimizer_params={"learning_rate": 0.05}, initializer=mx.init.Xavier())
+    assert dict(mod.score(it, "acc"))["accuracy"] > 0.9
+    dc = mx.sym.Deconvolution(mx.sym.Variable("x"), kernel=(2, 2), stride=(2, 2), num_filter=3, name="up")
+    assert dc.list_arguments() == ["x", "up_weight"] and dc.infer_shape(x=(1, 4, 5, 5))[1] == [(1, 3, 10, 10)]
