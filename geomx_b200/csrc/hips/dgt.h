@@ -33,6 +33,8 @@ struct DGTConfig {
   float k = 0.5f;        // DMLC_K: fraction of blocks on the reliable channel
   float alpha = 0.3f;    // DGT_CONTRIBUTION_ALPHA
   int loss_pct = 0;      // DGT_UDP_LOSS (emulated datagram loss, mode 1)
+  bool adaptive_k = false;  // ADAPTIVE_K_FLAG: k is a share of the contribution mass (see DGTEffectiveK)
+  float k_min = 0.2f;       // DMLC_K_MIN: lower bound of the important fraction in adaptive mode
   static DGTConfig FromEnv() {
     Environment* e = Environment::Get();
     DGTConfig c;
@@ -42,6 +44,8 @@ struct DGTConfig {
     c.k = static_cast<float>(e->GetFloat("DMLC_K", 0.5));
     c.alpha = static_cast<float>(e->GetFloat("DGT_CONTRIBUTION_ALPHA", 0.3));
     c.loss_pct = e->GetInt("DGT_UDP_LOSS", 0);
+    c.adaptive_k = e->GetInt("ADAPTIVE_K_FLAG", 0) != 0;
+    c.k_min = static_cast<float>(e->GetFloat("DMLC_K_MIN", 0.2));
     return c;
   }
 };
@@ -53,6 +57,24 @@ inline int DGTGetChannel(int rank, int total, float k, int channels) {
   const int rest = total - important;
   const int per = std::max(1, (rest + channels - 1) / channels);
   return std::min(channels, 1 + (rank - important) / per);
+}
+
+// ADAPTIVE_K_FLAG / DMLC_K_MIN are parsed but never used by the reference (kv_app.h:844-848).  Here: with the flag set, the important set of
+// one push is the shortest prefix of the contribution ranking that carries `k` of the total contribution, at least `k_min` of the blocks —
+// returned as the equivalent block fraction so DGTGetChannel stays the single place that maps rank -> channel.
+inline float DGTEffectiveK(const std::vector<float>& sorted_desc, float k, bool adaptive, float k_min) {
+  const int n = static_cast<int>(sorted_desc.size());
+  if (!adaptive || n == 0) return k;
+  double total = 0;
+  for (float c : sorted_desc) total += c;
+  int need = static_cast<int>(std::lround(k_min * n));
+  if (total > 0) {
+    double cum = 0; int i = 0;
+    for (; i < n; ++i) { cum += sorted_desc[i]; if (cum / total >= k - 1e-12) break; }
+    need = std::max(need, std::min(n, i + 1));
+  }
+  need = std::max(1, std::min(n, need));
+  return static_cast<float>(need) / static_cast<float>(n);
 }
 
 // 4-bit codec: codebook of 16 uniformly spaced centroids in [min, max]
@@ -117,6 +139,13 @@ class DGTSender {
     }
     // sort by contribution (desc); the LAST block stays last: its arrival triggers delivery at the receiver
     std::sort(blks.begin(), blks.end() - 1, [](const Blk& a, const Blk& b) { return a.c > b.c; });
+    float k_eff = cfg_.k;
+    if (cfg_.adaptive_k) {
+      std::vector<float> cs(nblk);
+      for (int r = 0; r < nblk; ++r) cs[r] = blks[r].c;
+      k_eff = DGTEffectiveK(cs, cfg_.k, true, cfg_.k_min);
+    }
+    last_k_eff_ = k_eff;
     int sent = 0;
     for (int r = 0; r < nblk; ++r) {
       const Blk& b = blks[r];
@@ -130,7 +159,7 @@ class DGTSender {
       m.meta.total_bytes = total;
       const int off = b.seq * bb, len = std::min(bb, total - off);
       m.meta.val_bytes = len;
-      const int ch = last ? 0 : DGTGetChannel(r, nblk, cfg_.k, cfg_.channels);
+      const int ch = last ? 0 : DGTGetChannel(r, nblk, k_eff, cfg_.channels);
       m.meta.channel = ch;
       m.meta.tos = (cfg_.channels - ch) * 32;
       m.meta.priority = -ch;
@@ -154,7 +183,10 @@ class DGTSender {
     return sent;
   }
 
+  float last_effective_k() const { return last_k_eff_; }
+
  private:
+  float last_k_eff_ = 0.f;
   void ImportantLoop() {
     while (true) {
       Message m; iq_.WaitAndPop(&m);

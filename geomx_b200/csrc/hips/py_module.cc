@@ -63,6 +63,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("get_command_type", [](int req, int dtype) { return GetCommandType(static_cast<RequestType>(req), dtype); });
   m.def("depair_command_type", [](int cmd) { auto t = DepairDataHandleType(cmd); return std::make_pair(static_cast<int>(t.requestType), t.dtype); });
   m.def("dgt_get_channel", &DGTGetChannel);
+  m.def("dgt_effective_k", &DGTEffectiveK, "important block fraction of one push; adaptive mode = share of the contribution mass");
   m.def("dgt_encode4", [](py::array_t<float, py::array::c_style> a) {
     std::vector<char> out; float mn, mx;
     DGTEncode4(a.data(), a.size(), &out, &mn, &mx);

@@ -171,6 +171,23 @@ class _FabricParams(ctypes.Structure):
 _KIND = {"sgd": 0, "adam": 1, "dcasgd": 2, None: -1, "none": -1}
 
 
+def dgt_num_important(sorted_contrib, k, adaptive=False, k_min=0.2):
+    """Size of the important set given the contributions in DESCENDING order.  Fixed mode: ``round(k * n)`` tiles (reference semantics of
+    ``DMLC_K``, kv_app.h:987-994).  Adaptive mode: the shortest prefix whose contributions sum to ``k`` of the total, at least
+    ``k_min * n`` tiles."""
+    n = int(sorted_contrib.numel())
+    if n == 0:
+        return 0
+    if not adaptive:
+        return max(1, int(round(k * n)))
+    total = float(sorted_contrib.sum())
+    if total <= 0.0:
+        return max(1, int(round(k_min * n)))
+    cum = torch.cumsum(sorted_contrib.double(), 0) / total
+    need = int(torch.searchsorted(cum, torch.tensor([k - 1e-12], dtype=cum.dtype, device=cum.device))[0]) + 1
+    return max(1, min(n, max(need, int(round(k_min * n)))))
+
+
 class HipsFabric:
     """Owns the symmetric arenas of one model replica and launches the fused HiPS kernels.
 
@@ -294,6 +311,11 @@ class HipsFabric:
         if self.protocol != "ll":
             raise RuntimeError("DGT on the fabric needs the LL protocol")
         self.dgt_k = float(os.environ.get("DMLC_K", 0.8)) if k is None else float(k)
+        # ADAPTIVE_K_FLAG=1 (parsed but unused by the reference, kv_app.h:844-848): K is read as a share of the total CONTRIBUTION instead of
+        # a share of the tiles — the important set is the shortest prefix of the ranking that carries K of the contribution mass, never
+        # smaller than DMLC_K_MIN of the tiles.  Concentrated gradients then send few tiles at full precision, flat ones many.
+        self.dgt_adaptive = bool(int(os.environ.get("ADAPTIVE_K_FLAG", 0)))
+        self.dgt_k_min = float(os.environ.get("DMLC_K_MIN", 0.2))
         self.dgt_alpha = float(os.environ.get("DGT_CONTRIBUTION_ALPHA", 0.3)) if alpha is None else float(alpha)
         if self.dgt_contrib is None:
             self.dgt_contrib = torch.zeros(self.tiles, dtype=torch.float32, device=self.device)
@@ -315,7 +337,8 @@ class HipsFabric:
             dist.all_reduce(c)
         order = torch.argsort(c, descending=True, stable=True)
         self.tile_order.copy_(order.to(torch.int32))
-        n_imp = max(1, int(round(self.dgt_k * self.tiles)))
+        n_imp = dgt_num_important(c[order], self.dgt_k, getattr(self, "dgt_adaptive", False), getattr(self, "dgt_k_min", 0.2))
+        self.dgt_num_important = n_imp
         fmt = self._dgt_base_fmt.clone()
         unimportant = order[n_imp:]
         dense = (fmt[unimportant] == 0) | (fmt[unimportant] == 1)          # Bi-Sparse tiles keep their own format

@@ -2,7 +2,7 @@
 
 Parity: ``docs/source/env-var-summary.rst:4-142`` and the ``dmlc::GetEnv`` / ``ps::Environment::find`` call sites
 enumerated in SURVEY §5.6.  ``describe()`` prints the table; ``get(name)`` returns the typed value.  Flags marked
-``honoured=False`` are parsed-but-unused in the reference too (``ADAPTIVE_K_FLAG``, ``DMLC_K_MIN``, ``DGT_INFO``)."""
+``honoured=False`` are parsed-but-unused in the reference too (``DGT_INFO``); ``ADAPTIVE_K_FLAG`` / ``DMLC_K_MIN`` are unused there but given a meaning here."""
 from __future__ import annotations
 
 import os
@@ -63,8 +63,8 @@ _reg("ENABLE_P3", 0, int, "priority-based parameter propagation")
 _reg("ENABLE_DGT", 0, int, "1 lossy channels | 2 prioritised reliable | 3 + 4-bit encode")
 _reg("DMLC_UDP_CHANNEL_NUM", 3, int, "number of low-priority channels")
 _reg("DMLC_K", 0.5, float, "fraction of blocks on the reliable channel")
-_reg("DMLC_K_MIN", 0.2, float, "", False)
-_reg("ADAPTIVE_K_FLAG", 0, int, "", False)
+_reg("DMLC_K_MIN", 0.2, float, "lower bound of the important fraction when ADAPTIVE_K_FLAG=1 (fabric DGT)", True)
+_reg("ADAPTIVE_K_FLAG", 0, int, "fabric DGT: DMLC_K is a share of the contribution mass instead of a share of the tiles", True)
 _reg("DGT_CONTRIBUTION_ALPHA", 0.3, float, "EMA factor of block contribution")
 _reg("DGT_BLOCK_SIZE", 4096, int, "bytes per block")
 _reg("DGT_INFO", 0, int, "", False)

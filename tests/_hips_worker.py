@@ -27,7 +27,9 @@ if master or (os.environ.get("TEST_STANDALONE") == "1" and kv.rank == 0):
     elif mode == "adam_py":
         os.environ["GEOMX_PY_UPDATER"] = "1"
         kv.set_optimizer(mx.optimizer.Adam(learning_rate=0.01))
-    if mode == "bsc":
+    if mode == "bsc_async":
+        kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1))
+    if mode in ("bsc", "bsc_async"):
         kv.set_gradient_compression({"type": "bsc", "threshold": 0.1})
 if mode == "2bit" and not master:
     kv.set_gradient_compression({"type": "2bit", "threshold": 0.5})

@@ -169,6 +169,21 @@ def test_hips_bsc_and_hfa():
         assert r["vals"][1][0] == pytest.approx(expect2, abs=1e-4)
 
 
+def test_async_global_tier_with_bisparse():
+    """MixedSync + Bi-Sparse: the reference leaves ``DataHandleAsyncBSCompressed`` empty (kvstore_dist_server.h:1700-1703); here every party's
+    sparsified aggregate is applied by the global optimizer on arrival.  Constant gradients: dense keys move by exactly lr * party sum per
+    arrival; the big key moves in the same direction (top-k of an all-equal tensor sends k entries per round, the rest accumulates)."""
+    res = launch_hips({"TEST_MODE": "bsc_async", "TEST_KV": "dist_async", "MXNET_KVSTORE_SIZE_LOWER_BOUND": "100", "TEST_STEPS": "3"})
+    assert len(res) == 4
+    for r in res:
+        last = r["vals"][-1]
+        assert all(v == v and abs(v) < 1e3 for v in last)                            # finite
+        assert last[0] < 1.0 and last[1] < 2.0                                         # dense keys descended
+        # after 3 rounds both parties delivered at least twice: w0 <= 1 - 0.1 * 2 * min(party sums = 1.5, 3.5)
+        assert last[0] <= 1.0 - 0.1 * 2 * 1.5 + 1e-4
+        assert r["last"][2] <= 3.0 + 1e-6                                              # sparse key never moves against the gradient
+
+
 def test_features_p3_2bit_fp16_async():
     res = launch_hips({"TEST_MODE": "p3", "ENABLE_P3": "1", "TEST_STEPS": "2"})
     gsum = 0.5 * (1 + 2 + 3 + 4)

@@ -246,3 +246,25 @@ def test_tsengine_node_helpers():
     assert C.ts_origins_roundtrip(origins) == origins and C.ts_origins_roundtrip([]) == []
     # Cantor pairing (request type, dtype): default/f32 = 0, default/f64 = 2, 2bit/f32 = 3, default/f16 = 5, BSC/f32 = 6
     assert [C.ts_dtype_of_cmd(c) for c in (0, 2, 3, 5, 6)] == [0, 1, 0, 2, 0]
+
+
+def test_dgt_adaptive_k():
+    """ADAPTIVE_K_FLAG / DMLC_K_MIN (parsed but unused by the reference): K as a share of the contribution mass, python (fabric) and native
+    (TCP plane) implementations agree."""
+    import torch
+    from geomx_b200 import runtime
+    from geomx_b200.parallel.fabric import dgt_num_important
+    c = [10.0, 5.0, 2.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0]
+    t = torch.tensor(c)
+    cases = [((0.5, False, 0.2), 5), ((0.5, True, 0.1), 1), ((0.8, True, 0.1), 3), ((0.8, True, 0.5), 5), ((1.0, True, 0.1), 6)]
+    for (k, ad, kmin), want in cases:
+        assert dgt_num_important(t, k, ad, kmin) == want
+        if runtime.available():
+            frac = runtime.C().dgt_effective_k(c, k, ad, kmin)
+            assert (round(frac * len(c)) == want) if ad else (frac == pytest.approx(k))
+    assert dgt_num_important(torch.zeros(10), 0.8, True, 0.2) == 2
+    if runtime.available():
+        C = runtime.C()
+        # with the effective fraction, ranks below the prefix go to the reliable channel, the rest to the low-priority ones
+        frac = C.dgt_effective_k(c, 0.8, True, 0.1)
+        assert [C.dgt_get_channel(r, 10, frac, 3) for r in range(4)] == [0, 0, 0, 1]
