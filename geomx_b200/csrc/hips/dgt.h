@@ -35,6 +35,7 @@ struct DGTConfig {
   int loss_pct = 0;      // DGT_UDP_LOSS (emulated datagram loss, mode 1)
   bool adaptive_k = false;  // ADAPTIVE_K_FLAG: k is a share of the contribution mass (see DGTEffectiveK)
   float k_min = 0.2f;       // DMLC_K_MIN: lower bound of the important fraction in adaptive mode
+  int info = 0;             // DGT_INFO: log one line per split push (key, blocks, effective k, blocks sent)
   static DGTConfig FromEnv() {
     Environment* e = Environment::Get();
     DGTConfig c;
@@ -46,6 +47,7 @@ struct DGTConfig {
     c.loss_pct = e->GetInt("DGT_UDP_LOSS", 0);
     c.adaptive_k = e->GetInt("ADAPTIVE_K_FLAG", 0) != 0;
     c.k_min = static_cast<float>(e->GetFloat("DMLC_K_MIN", 0.2));
+    c.info = e->GetInt("DGT_INFO", 0);
     return c;
   }
 };
@@ -180,6 +182,7 @@ class DGTSender {
       (ch == 0 ? iq_ : uq_).Push(m);
       ++sent;
     }
+    if (cfg_.info) fprintf(stderr, "[DGT] key=%d blocks=%d k_eff=%.3f sent=%d mode=%d\n", key, nblk, k_eff, sent, cfg_.mode);
     return sent;
   }
 

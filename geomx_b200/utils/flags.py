@@ -2,7 +2,7 @@
 
 Parity: ``docs/source/env-var-summary.rst:4-142`` and the ``dmlc::GetEnv`` / ``ps::Environment::find`` call sites
 enumerated in SURVEY §5.6.  ``describe()`` prints the table; ``get(name)`` returns the typed value.  Flags marked
-``honoured=False`` are parsed-but-unused in the reference too (``DGT_INFO``); ``ADAPTIVE_K_FLAG`` / ``DMLC_K_MIN`` are unused there but given a meaning here."""
+``ADAPTIVE_K_FLAG`` / ``DMLC_K_MIN`` / ``DGT_INFO`` are parsed but unused by the reference; they are given a meaning here."""
 from __future__ import annotations
 
 import os
@@ -67,7 +67,7 @@ _reg("DMLC_K_MIN", 0.2, float, "lower bound of the important fraction when ADAPT
 _reg("ADAPTIVE_K_FLAG", 0, int, "fabric DGT: DMLC_K is a share of the contribution mass instead of a share of the tiles", True)
 _reg("DGT_CONTRIBUTION_ALPHA", 0.3, float, "EMA factor of block contribution")
 _reg("DGT_BLOCK_SIZE", 4096, int, "bytes per block")
-_reg("DGT_INFO", 0, int, "", False)
+_reg("DGT_INFO", 0, int, "log one line per DGT-split push (key, blocks, effective k, blocks sent)", True)
 _reg("ENABLE_INTER_TS", 0, int, "TSEngine between parties")
 _reg("ENABLE_INTRA_TS", 0, int, "TSEngine inside a party")
 _reg("MAX_GREED_RATE_TS", 0.9, float, "ε-greedy cap")
