@@ -17,6 +17,9 @@ KVStoreDistServer::KVStoreDistServer() {
   hfa_k2_ = std::max(1, env->GetInt("MXNET_KVSTORE_HFA_K2", 1));
   bigarray_bound_ = static_cast<size_t>(env->GetFloat("MXNET_KVSTORE_BIGARRAY_BOUND", 1000000));
   size_lower_bound_ = static_cast<size_t>(env->GetFloat("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000));
+  ckpt_prefix_ = env->GetStr("GEOMX_SERVER_CKPT_PREFIX", "");
+  ckpt_every_ = ckpt_prefix_.empty() ? 0 : std::max(0, env->GetInt("GEOMX_SERVER_CKPT_EVERY", 0));
+  resume_wanted_ = !ckpt_prefix_.empty() && env->GetInt("GEOMX_SERVER_RESUME", 0) != 0 && (is_global_ || standalone_);
   ps_server_.reset(new KVServer(0));
   ps_server_->SimpleApp::set_request_handle([this](const SimpleData& d, SimpleApp* app) { CommandHandle(d, app); });
   ps_server_->set_request_handle([this](const KVMeta& m, const KVPairs& d, KVServer* s) { DataHandleEx(m, d, s); });
@@ -116,6 +119,8 @@ void KVStoreDistServer::CommandHandle(const SimpleData& recved, SimpleApp* app) 
       OptSpec s = OptSpec::Parse(recved.body);
       HIPS_CHECK_MSG(s.valid(), "unknown native optimizer spec: " + recved.body);
       native_opt_.reset(new NativeOptimizer(s));
+      for (auto& kv : resumed_opt_) native_opt_->states()[kv.first] = kv.second;   // state checkpointed by a previous incarnation
+      resumed_opt_.clear();
       break;
     }
     case CommandType::kSetProfilerParams: {
@@ -162,6 +167,8 @@ void KVStoreDistServer::CommandHandle(const SimpleData& recved, SimpleApp* app) 
 // ------------------------------------------------------------------------------------------------ data
 void KVStoreDistServer::DataHandleEx(const KVMeta& req, const KVPairs& data, KVServer* server) {
   const DataHandleType type = DepairDataHandleType(req.cmd);
+  // the server object exists before the node has registered (its rank names the checkpoint file), so the resume happens on first traffic
+  if (resume_wanted_) std::call_once(resume_once_, [this] { TryResume(); });
   ProfileScope ps(req.push ? "KVStoreDistServerPush" : "KVStoreDistServerPull");
   if (req.push) HandlePush(type, req, data);
   else HandlePull(type, req, data);
@@ -191,6 +198,19 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
       ps_server_->Response(r, res);
     } else ps_server_->Response(r);
   };
+  if (e.elems != 0 && !skip_init_push_.empty() && (standalone_ || req.plane == kLocal)) {
+    // ---- resumed server: the restarted job initialises its keys again (kv.init); the checkpointed value wins, the push is only acknowledged.
+    // On a global server the init comes from the master worker over the LOCAL plane of the central party — the parties may already be
+    // training by then (their pulls found the restored keys initialised), so their pushes on the global plane must not be mistaken for it.
+    auto sk = skip_init_push_.find(key);
+    if (sk != skip_init_push_.end() && sk->second) {
+      sk->second = false;
+      respond(req);
+      lk.unlock();
+      AskTS(key);
+      return;
+    }
+  }
   if (e.elems == 0) {
     // ---- initialisation: the first push of a key defines it (reference :1237-1269)
     HIPS_CHECK(type.requestType == RequestType::kDefaultPushPull);
@@ -503,13 +523,22 @@ void KVStoreDistServer::AskTS(int key) {
 void KVStoreDistServer::RoundCompleted(int key) {
   std::vector<char> bytes;
   int version, cmd;
+  bool do_ckpt = false;
   {
     std::lock_guard<std::mutex> lk(mu_);
     version = ++round_version_[key];
     Entry& e = store_[key];
     bytes = e.data;
     cmd = GetCommandType(RequestType::kDefaultPushPull, e.dtype);
+    if (ckpt_every_ > 0) {
+      // a snapshot is taken when the SLOWEST key finishes round N: at that instant every key holds exactly its round-N value (a worker
+      // cannot start round N+1 of any key before it has finished round N of all of them)
+      int slowest = version;
+      for (auto& kv : store_) { auto it = round_version_.find(kv.first); slowest = std::min(slowest, it == round_version_.end() ? 0 : it->second); }
+      if (slowest > ckpt_key_ && slowest % ckpt_every_ == 0) { ckpt_key_ = slowest; do_ckpt = true; }
+    }
   }
+  if (do_ckpt) SaveStates(ckpt_prefix_);
   Postoffice* po = Postoffice::Get();
   if (TSNode* t = ps_server_->ts(kLocal)) {
     if (!is_global_ || po->enable_central_workers()) t->Relay(key, version, cmd, static_cast<Key>(key), bytes.data(), bytes.size());
@@ -560,10 +589,19 @@ void KVStoreDistServer::HandlePull(const DataHandleType& type, const KVMeta& req
 static void WriteVec(std::ofstream& f, const std::vector<float>& v) { uint64_t n = v.size(); f.write(reinterpret_cast<const char*>(&n), 8); if (n) f.write(reinterpret_cast<const char*>(v.data()), n * 4); }
 static void ReadVec(std::ifstream& f, std::vector<float>* v) { uint64_t n = 0; f.read(reinterpret_cast<char*>(&n), 8); v->resize(n); if (n) f.read(reinterpret_cast<char*>(v->data()), n * 4); }
 
+// <prefix>.server<r>g for global servers, <prefix>.server<r>l for local / stand-alone ones.  A local server of a two-tier job is named by
+// its rank on the GLOBAL plane (= its party): every party's only server has local rank 0.
+std::string KVStoreDistServer::StatePath(const std::string& prefix) const {
+  Postoffice* po = Postoffice::Get();
+  const int r = po->my_rank((is_global_ || has_global_) ? kGlobal : kLocal);
+  return prefix + ".server" + std::to_string(r) + (is_global_ ? "g" : "l");
+}
+
 void KVStoreDistServer::SaveStates(const std::string& prefix) {
   std::lock_guard<std::mutex> lk(mu_);
-  const std::string path = prefix + ".server" + std::to_string(Postoffice::Get()->my_rank(is_global_ ? kGlobal : kLocal)) + (is_global_ ? "g" : "l");
-  std::ofstream f(path, std::ios::binary);
+  const std::string path = StatePath(prefix);
+  const std::string tmp = path + ".tmp";
+  std::ofstream f(tmp, std::ios::binary);
   const uint64_t magic = 0x4869505353544154ull;  // "HiPSSTAT"
   f.write(reinterpret_cast<const char*>(&magic), 8);
   uint64_t nk = store_.size(); f.write(reinterpret_cast<const char*>(&nk), 8);
@@ -582,11 +620,26 @@ void KVStoreDistServer::SaveStates(const std::string& prefix) {
     WriteVec(f, st.a); WriteVec(f, st.b);
   }
   int64_t li = local_iters_; f.write(reinterpret_cast<const char*>(&li), 8);
+  f.close();
+  HIPS_CHECK_MSG(std::rename(tmp.c_str(), path.c_str()) == 0, "cannot move " + tmp + " to " + path);   // readers never see a torn file
+}
+
+// GEOMX_SERVER_RESUME=1: a (re)started global / stand-alone server adopts the last periodic checkpoint if there is one.  The job's scripts
+// still call kv.init for every key; those pushes are acknowledged without touching the restored values (skip_init_push_).
+void KVStoreDistServer::TryResume() {
+  const std::string path = StatePath(ckpt_prefix_);
+  std::ifstream probe(path, std::ios::binary);
+  if (!probe.good()) return;
+  probe.close();
+  LoadStates(ckpt_prefix_);
+  std::lock_guard<std::mutex> lk(mu_);
+  for (auto& kv : store_) skip_init_push_[kv.first] = true;
+  fprintf(stderr, "[hips] server resumed %zu keys from %s\n", store_.size(), path.c_str());
 }
 
 void KVStoreDistServer::LoadStates(const std::string& prefix) {
   std::lock_guard<std::mutex> lk(mu_);
-  const std::string path = prefix + ".server" + std::to_string(Postoffice::Get()->my_rank(is_global_ ? kGlobal : kLocal)) + (is_global_ ? "g" : "l");
+  const std::string path = StatePath(prefix);
   std::ifstream f(path, std::ios::binary);
   HIPS_CHECK_MSG(f.good(), "cannot open " + path);
   uint64_t magic = 0, nk = 0;
@@ -606,7 +659,10 @@ void KVStoreDistServer::LoadStates(const std::string& prefix) {
     ReadVec(f, &v); if (!v.empty()) residual_2bit_[key] = v;
     int32_t t; f.read(reinterpret_cast<char*>(&t), 4);
     NativeOptimizer::State st; st.t = t; ReadVec(f, &st.a); ReadVec(f, &st.b);
-    if (native_opt_ && !st.a.empty()) native_opt_->states()[key] = st;
+    if (!st.a.empty() || st.t != 0) {
+      if (native_opt_) native_opt_->states()[key] = st;
+      else resumed_opt_[key] = st;                     // the optimizer spec arrives later (set_optimizer command)
+    }
     initialized_[key] = true;
   }
   int64_t li = 0; f.read(reinterpret_cast<char*>(&li), 8); local_iters_ = li;

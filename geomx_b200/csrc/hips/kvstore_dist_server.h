@@ -181,6 +181,15 @@ class KVStoreDistServer {
   size_t bigarray_bound_ = 1000000, size_lower_bound_ = 200000;
   int stop_votes_ = 0;
   std::atomic<long> num_pushes_{0};
+  // periodic server-state checkpoints + resume (GEOMX_SERVER_CKPT_PREFIX / _EVERY / GEOMX_SERVER_RESUME), see RoundCompleted / TryResume
+  std::string ckpt_prefix_;
+  int ckpt_every_ = 0, ckpt_key_ = 0;                  // ckpt_key_: round number of the last snapshot
+  std::unordered_map<int, bool> skip_init_push_;         // resumed keys: the next init push of the (re)started job must not overwrite them
+  std::map<int, NativeOptimizer::State> resumed_opt_;     // optimizer state read before the optimizer was configured
+  bool resume_wanted_ = false;
+  std::once_flag resume_once_;
+  void TryResume();
+  std::string StatePath(const std::string& prefix) const;
 };
 
 }  // namespace hips

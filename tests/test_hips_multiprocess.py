@@ -169,6 +169,32 @@ def test_hips_bsc_and_hfa():
         assert r["vals"][1][0] == pytest.approx(expect2, abs=1e-4)
 
 
+def test_periodic_server_checkpoint_and_resume(tmp_path):
+    """``GEOMX_SERVER_CKPT_PREFIX`` + ``GEOMX_SERVER_CKPT_EVERY``: the server writes its state (weights, optimizer moments, compression
+    residuals) every N rounds; a restarted job with ``GEOMX_SERVER_RESUME=1`` continues from it although its scripts call ``kv.init`` again.
+    Single tier, then the two-tier topology (checkpoint taken by the global server)."""
+    gsum = 0.5 * 1 + 0.5 * 2
+    ck = {"TEST_MODE": "sgd", "GEOMX_SERVER_CKPT_PREFIX": str(tmp_path / "ck"), "GEOMX_SERVER_CKPT_EVERY": "1"}
+    res = launch_single_tier(dict(ck, TEST_STEPS="3"))
+    assert abs(res[0]["vals"][-1][0] - (1.0 - 0.1 * gsum * 3)) < 1e-5 and (tmp_path / "ck.server0l").exists()
+    res = launch_single_tier(dict(ck, TEST_STEPS="2", GEOMX_SERVER_RESUME="1"))
+    for r in res:
+        for t, vals in enumerate(r["vals"]):
+            for i, v in enumerate(vals):
+                assert abs(v - ((1.0 + i) - 0.1 * gsum * (3 + t + 1))) < 1e-5, (t, i, v)
+    # without the resume flag the same prefix is ignored: a fresh job starts from its own kv.init values
+    res = launch_single_tier(dict(ck, TEST_STEPS="1"))
+    assert abs(res[0]["vals"][0][0] - (1.0 - 0.1 * gsum)) < 1e-5
+    g4 = 0.5 * (1 + 2 + 3 + 4)
+    ck2 = {"TEST_MODE": "sgd", "GEOMX_SERVER_CKPT_PREFIX": str(tmp_path / "hips"), "GEOMX_SERVER_CKPT_EVERY": "2"}
+    launch_hips(dict(ck2, TEST_STEPS="2"))
+    assert (tmp_path / "hips.server0g").exists()
+    res = launch_hips(dict(ck2, TEST_STEPS="1", GEOMX_SERVER_RESUME="1"))
+    assert len(res) == 4
+    for r in res:
+        assert abs(r["vals"][0][0] - (1.0 - 0.1 * g4 * 3)) < 1e-4
+
+
 def test_async_global_tier_with_bisparse():
     """MixedSync + Bi-Sparse: the reference leaves ``DataHandleAsyncBSCompressed`` empty (kvstore_dist_server.h:1700-1703); here every party's
     sparsified aggregate is applied by the global optimizer on arrival.  Constant gradients: dense keys move by exactly lr * party sum per
