@@ -4,7 +4,7 @@ The optimizer runs on the global parameter server; workers push ``grad / batch``
 import os
 import time
 
-from common import Progress, accuracy, build_net, configures_servers, make_loaders, make_parser, mx, pick_context, worker_slice
+from common import checkpointing, Progress, accuracy, build_net, configures_servers, make_loaders, make_parser, mx, pick_context, worker_slice
 
 
 def main():
@@ -12,8 +12,11 @@ def main():
     ctx = pick_context(args.cpu)
     ts_on = int(os.getenv("ENABLE_INTER_TS", 0)) or int(os.getenv("ENABLE_INTRA_TS", 0))
     net = build_net(ctx, args.batch_size)
+    bind_kv = checkpointing(net, args)
 
     kv = mx.kv.create("dist_async" if (args.mixed_sync or args.dcasgd) else "dist_sync")
+
+    bind_kv(kv)
     if configures_servers(kv):
         opt = mx.optimizer.DCASGD(learning_rate=args.learning_rate) if args.dcasgd else mx.optimizer.Adam(learning_rate=args.learning_rate)
         kv.set_optimizer(opt)

@@ -3,7 +3,7 @@
 and apply Adam locally (``Trainer.step(num_all_workers)``)."""
 import time
 
-from common import Progress, accuracy, build_net, configures_servers, make_loaders, make_parser, mx, pick_context, worker_slice
+from common import checkpointing, Progress, accuracy, build_net, configures_servers, make_loaders, make_parser, mx, pick_context, worker_slice
 
 
 def main():
@@ -11,7 +11,9 @@ def main():
     assert 0 < args.bisparse_compression_ratio < 1, "bisparse_compression_ratio is not properly set"
     ctx = pick_context(args.cpu)
     net = build_net(ctx, args.batch_size)
+    bind_kv = checkpointing(net, args)
     kv = mx.kv.create("dist_sync")
+    bind_kv(kv)
     if configures_servers(kv):
         kv.set_gradient_compression({"type": "bsc", "threshold": args.bisparse_compression_ratio})
     time.sleep(1)

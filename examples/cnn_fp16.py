@@ -2,13 +2,15 @@
 """FP16 transport: every tensor crosses the parameter-server tiers as float16 (half the traffic); the update is a local fp32 Adam."""
 import time
 
-from common import Progress, accuracy, build_net, make_loaders, make_parser, mx, pick_context, worker_slice
+from common import checkpointing, Progress, accuracy, build_net, make_loaders, make_parser, mx, pick_context, worker_slice
 
 
 def run(args, low_precision_for):
     ctx = pick_context(args.cpu)
     net = build_net(ctx, args.batch_size)
+    bind_kv = checkpointing(net, args)
     kv = mx.kv.create("dist_sync")
+    bind_kv(kv)
     if getattr(args, "bisparse_compression_ratio", None) and (kv.is_master_worker or getattr(kv, "configures_servers", False)):
         kv.set_gradient_compression({"type": "bsc", "threshold": args.bisparse_compression_ratio})
     time.sleep(1)

@@ -3,7 +3,7 @@
 every K2-th round the parties' progress is merged globally (MXNET_KVSTORE_USE_HFA=1, MXNET_KVSTORE_HFA_K1, MXNET_KVSTORE_HFA_K2)."""
 import os
 
-from common import Progress, accuracy, build_net, make_loaders, make_parser, mx, pick_context, worker_slice
+from common import checkpointing, Progress, accuracy, build_net, make_loaders, make_parser, mx, pick_context, worker_slice
 
 
 def main():
@@ -13,7 +13,9 @@ def main():
     ts_on = int(os.getenv("ENABLE_INTER_TS", 0)) or int(os.getenv("ENABLE_INTRA_TS", 0))
     ctx = pick_context(args.cpu)
     net = build_net(ctx, args.batch_size)
+    bind_kv = checkpointing(net, args)
     kv = mx.kv.create("dist_sync")
+    bind_kv(kv)
     trainer = mx.gluon.Trainer(net.collect_params(), optimizer=mx.optimizer.Adam(learning_rate=args.learning_rate), kvstore=None, update_on_kvstore=False)
     loss_fn = mx.gluon.loss.SoftmaxCrossEntropyLoss()
     params = list(net.collect_params().values())

@@ -30,6 +30,9 @@ def make_parser(extra=()):
     p.add_argument("--data-dir", default=os.environ.get("GEOMX_DATA_DIR", "/root/data"))
     p.add_argument("--max-iters", type=int, default=int(os.environ.get("GEOMX_MAX_ITERS", "0")), help="stop after this many iterations (0 = all)")
     p.add_argument("--eval-every", type=int, default=int(os.environ.get("GEOMX_EVAL_EVERY", "1")))
+    p.add_argument("--load-params", default=os.environ.get("GEOMX_LOAD_PARAMS", ""), help="resume: .params file loaded into the net before kv.init "
+                   "(the master worker re-initialises the global server from it)")
+    p.add_argument("--save-params", default=os.environ.get("GEOMX_SAVE_PARAMS", ""), help="write the final parameters here (first training worker only)")
     if "mixed" in extra:
         p.add_argument("-ms", "--mixed-sync", action="store_true")
         p.add_argument("-dc", "--dcasgd", action="store_true")
@@ -55,6 +58,26 @@ def build_net(ctx, batch_size):
     net.initialize(force_reinit=True, ctx=ctx, init=mx.init.Xavier())
     net(mx.nd.random.uniform(shape=(batch_size, 1, 28, 28), ctx=ctx))     # materialise deferred shapes
     return net
+
+
+def checkpointing(net, args, kv=None):
+    """Resume / save hooks shared by the demo scripts (the reference has none: "Resume in HiPS = master worker re-inits the global server from
+    loaded params via kv.init").  Call right after ``build_net`` (``kv`` may be given later through the returned ``bind``): loads
+    ``--load-params`` now, and writes ``--save-params`` at interpreter exit on the first training worker."""
+    import atexit
+    if args.load_params:
+        net.load_parameters(args.load_params)
+    state = {"kv": kv}
+
+    def save():
+        k = state["kv"]
+        if not args.save_params or k is None or k.is_master_worker:
+            return
+        if worker_slice(args, k) == 0:                     # the worker that trains on data slice 0 (scripts pass -ds <global index>)
+            mx.nd.waitall()
+            net.save_parameters(args.save_params)
+    atexit.register(save)
+    return lambda k: state.__setitem__("kv", k)
 
 
 def configures_servers(kv):

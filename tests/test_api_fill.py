@@ -303,3 +303,30 @@ def json_ok(x):
     import json
     json.dumps(x)
     return x
+
+
+def test_demo_script_saves_and_loads_params(tmp_path):
+    """``--save-params`` / ``--load-params`` of the demo scripts (stand-alone CPU run): the saved file reproduces the trained accuracy."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GEOMX_SYNTHETIC_SIZE="512")
+    for k in ("DMLC_ROLE", "DMLC_PS_ROOT_URI", "RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = str(tmp_path / "cnn.params")
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "cnn.py"), "--cpu", "--max-iters", "30", "--eval-every", "30", "--save-params", out],
+                       env=env, capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    acc = float(r.stdout.strip().splitlines()[-1].split("Test Acc")[1])
+    assert acc > 0.9 and os.path.exists(out)
+    sys.path.insert(0, os.path.join(root, "examples"))
+    try:
+        import common
+        os.environ["GEOMX_SYNTHETIC_SIZE"] = "512"
+        net = common.build_net(mx.cpu(), 32)
+        _, test = common.make_loaders(32, 1, 0, "/nonexistent", False)
+        before = common.accuracy(test, net, mx.cpu())
+        net.load_parameters(out)
+        assert common.accuracy(test, net, mx.cpu()) > 0.9 > before
+    finally:
+        sys.path.pop(0); os.environ.pop("GEOMX_SYNTHETIC_SIZE", None)
