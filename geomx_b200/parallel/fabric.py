@@ -42,7 +42,8 @@ class Topology:
     @staticmethod
     def from_env():
         world = getenv_int("WORLD_SIZE", 1); rank = getenv_int("RANK", 0)
-        parties = getenv_int("GEOMX_NUM_PARTIES", 0) or getenv_int("DMLC_NUM_GLOBAL_WORKER", 0) or 1
+        # default: the two-tier layout of the reference's demo (2 parties) whenever the world splits evenly
+        parties = getenv_int("GEOMX_NUM_PARTIES", 0) or getenv_int("DMLC_NUM_GLOBAL_WORKER", 0) or (2 if (world >= 2 and world % 2 == 0) else 1)
         if world % parties:
             parties = 1
         return Topology(world, rank, parties, getenv_int("DMLC_NUM_GLOBAL_SERVER", 1))
