@@ -269,3 +269,42 @@ def test_deformable_psroi_pooling():
     t1 = nd.contrib.DeformablePSROIPooling(nd.array(ramp), rois, shift, **kw).asnumpy()
     np.testing.assert_allclose(t0[0, 0], [[1.25, 4.25]] * 2, atol=1e-5)
     np.testing.assert_allclose(t1 - t0, 0.1 * 6.0, atol=1e-5)          # offset = trans * trans_std * roi width, in pixels of a unit ramp
+
+
+def test_smoke_of_rarely_used_ops():
+    """One call each, against a closed form where there is a cheap one."""
+    x = nd.array(torch.randn(2, 8, 6, 6))
+    rois = nd.array([[0, 0.0, 0.0, 4.0, 4.0], [1, 1.0, 1.0, 5.0, 5.0]])
+    assert nd.contrib.PSROIPooling(x, rois, spatial_scale=1.0, output_dim=2, pooled_size=2).shape == (2, 2, 2, 2)
+    w = nd.array(torch.randn(4, 8, 3, 3)); off = nd.zeros((2, 18, 6, 6))
+    dc = nd.contrib.DeformableConvolution(x, off, w, kernel=(3, 3), pad=(1, 1), num_filter=4, no_bias=True)
+    np.testing.assert_allclose(dc.asnumpy(), torch.nn.functional.conv2d(x._t, w._t, padding=1).numpy(), atol=1e-4)    # zero offsets = plain conv
+    outs, st = nd.contrib.foreach(lambda xs, s: ([xs[0] + xs[1], xs[0] * s], s + 1), [nd.ones((3, 2)), nd.ones((3, 2)) * 2], nd.zeros((2,)))
+    assert outs[0].shape == (3, 2) and outs[1].asnumpy()[2].tolist() == [2, 2] and st.asnumpy().tolist() == [3, 3]
+    assert nd.SVMOutput(nd.ones((2, 3))).shape == (2, 3) and nd.Crop(x, h_w=(4, 4), center_crop=True).shape == (2, 8, 4, 4)
+    assert nd.Crop(x, nd.zeros((1, 1, 3, 5)), num_args=2).shape == (2, 8, 3, 5)
+    f = nd.fill_element_0index(nd.zeros((2, 3)), nd.array([5.0, 6.0]), nd.array([2, 0])).asnumpy()
+    assert f.tolist() == [[0, 0, 5], [6, 0, 0]] and nd.choose_element_0index(nd.array(f), nd.array([2, 0])).asnumpy().tolist() == [5, 6]
+    w0 = np.random.RandomState(0).randn(6).astype(np.float32); g = np.random.RandomState(1).randn(6).astype(np.float32)
+    for fn, states in ((nd.rmspropalex_update, 3), (nd.ftml_update, 3)):
+        wv = nd.array(w0); sts = [nd.zeros((6,)) for _ in range(states)]
+        kw = {"t": 1} if fn is nd.ftml_update else {}
+        fn(wv, nd.array(g), *sts, lr=0.01, **kw)
+        assert np.isfinite(wv.asnumpy()).all() and not np.allclose(wv.asnumpy(), w0)
+    w16 = nd.array(w0).astype("float16"); w32 = nd.array(w0); mom = nd.zeros((6,))
+    nd.mp_sgd_mom_update(w16, nd.array(g).astype("float16"), mom, w32, lr=0.1, momentum=0.9)
+    np.testing.assert_allclose(w32.asnumpy(), w0 - 0.1 * g.astype(np.float16).astype(np.float32), atol=1e-5)
+    q = nd.array(torch.randint(-100, 100, (1, 2, 4, 4)).to(torch.int8)); lo, hi = nd.array([-1.0]), nd.array([1.0])
+    assert nd.contrib.quantized_flatten(q, lo, hi)[0].shape == (1, 32)
+    cat, clo, chi = nd.contrib.quantized_concat(q, q, lo, hi, nd.array([-2.0]), nd.array([2.0]), dim=1)
+    assert cat.shape == (1, 4, 4, 4) and float(chi.asnumpy()[0]) == 2.0
+    np.testing.assert_allclose(cat.asnumpy()[:, 2:], q.asnumpy())                               # the wider-range input is unchanged
+    np.testing.assert_allclose(cat.asnumpy()[:, :2], np.round(q.asnumpy() / 2.0).clip(-127, 127))   # the narrower one re-scaled to it
+    xd = torch.randn(1, 3, 5, 5); wd = torch.randn(2, 3, 3, 3)
+    qx, lox, hix = nd.contrib.quantize(nd.array(xd), nd.array([float(xd.min())]), nd.array([float(xd.max())]), "int8")
+    qw, low, hiw = nd.contrib.quantize(nd.array(wd), nd.array([float(wd.min())]), nd.array([float(wd.max())]), "int8")
+    acc, alo, ahi = nd.contrib.quantized_conv(qx, qw, None, lox, hix, low, hiw, kernel=(3, 3), num_filter=2, no_bias=True)
+    assert np.abs(nd.contrib.dequantize(acc, alo, ahi).asnumpy() - torch.nn.functional.conv2d(xd, wd).numpy()).max() < 0.3
+    reg = nd.IdentityAttachKLSparseReg(nd.array([[0.2, 0.8]]))
+    assert reg.asnumpy().tolist() == [[np.float32(0.2), np.float32(0.8)]]
+    assert nd.getnnz if hasattr(nd, "getnnz") else nd.contrib.getnnz(nd.array([[0.0, 1.0], [2.0, 0.0]])).asnumpy().tolist() == [2]
