@@ -12,7 +12,15 @@ def create_dist(name):
         # torchrun inside a box + the reference's worker environment for the box: several boxes, one TCP endpoint per box (kvstore/hybrid.py)
         from .hybrid import KVStoreHybrid
         return KVStoreHybrid(name)
+    if fabric == "gloo":
+        from .collective import KVStoreCollective
+        return KVStoreCollective(name)
     if fabric in ("symm", "nccl") or (fabric == "auto" and not has_ps_env and "RANK" in os.environ):
+        import torch
+        if fabric == "auto" and not torch.cuda.is_available():
+            # torchrun on a machine without GPUs: same semantics over gloo collectives (kvstore/collective.py)
+            from .collective import KVStoreCollective
+            return KVStoreCollective(name)
         from ..parallel.fabric_kvstore import KVStoreFabric
         return KVStoreFabric(name)
     if fabric == "auto" and not has_ps_env:

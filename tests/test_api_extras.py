@@ -210,3 +210,45 @@ def test_profiler_trace_objects_and_hooks(tmp_path):
     time.sleep(0.3)
     assert "tick" in open(fn2).read()
     prof.set_config(continuous_dump=False); prof.set_state("stop")
+
+
+def _torchrun_cpu(nproc, env, timeout=240):
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    e = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    for k in ("DMLC_ROLE", "DMLC_PS_ROOT_URI", "DMLC_ROLE_GLOBAL", "DMLC_PS_GLOBAL_ROOT_URI", "RANK", "WORLD_SIZE"):
+        e.pop(k, None)
+    e.update(env)
+    import tempfile
+    outdir = tempfile.mkdtemp()
+    e["TEST_OUT_DIR"] = outdir
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(here, "_collective_worker.py")], env=e, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    res = [json.load(open(os.path.join(outdir, f))) for f in sorted(os.listdir(outdir))]
+    assert len(res) == nproc, (r.stdout + r.stderr)[-2000:]
+    return sorted(res, key=lambda d: d["rank"])
+
+
+def test_collective_kvstore_under_torchrun_on_cpu():
+    """torchrun without GPUs: ``mx.kv.create('dist_sync')`` is the gloo collective store with the fabric store's two-tier semantics."""
+    import pytest
+    res = _torchrun_cpu(4, {"TEST_MODE": "sgd", "GEOMX_NUM_PARTIES": "2"})
+    gsum = 0.5 * (1 + 2 + 3 + 4)
+    for r in res:
+        assert r["type"] == "KVStoreCollective" and r["num_workers"] == 2 and r["num_all_workers"] == 4 and r["party_rank"] == r["rank"] % 2
+        assert r["init"] == [1.0, 2.0]                                            # world rank 0's values win
+        for t, vals in enumerate(r["vals"]):
+            assert vals == pytest.approx([1.0 - 0.1 * gsum * (t + 1), 2.0 - 0.1 * gsum * (t + 1)], abs=1e-5)
+    # HFA, K2 = 2: round 1 stops at the party tier (party sums of value/num_workers), round 2 is the mean over parties of the party values
+    res = _torchrun_cpu(4, {"TEST_MODE": "hfa", "GEOMX_NUM_PARTIES": "2", "MXNET_KVSTORE_USE_HFA": "1", "MXNET_KVSTORE_HFA_K2": "2"})
+    assert [r["vals"][0][0] for r in res] == pytest.approx([1.5, 1.5, 3.5, 3.5])
+    assert all(r["vals"][1][0] == pytest.approx((2 * 1.5 + 2 * 3.5) / 2) for r in res)
+    # MixedSync: SGD is linear, so applying the party aggregates one after the other equals the synchronous result
+    res = _torchrun_cpu(4, {"TEST_MODE": "async", "GEOMX_NUM_PARTIES": "2", "TEST_STEPS": "1"})
+    assert all(r["vals"][0][0] == pytest.approx(1.0 - 0.1 * gsum, abs=1e-5) for r in res)
