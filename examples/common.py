@@ -54,6 +54,8 @@ def pick_context(force_cpu):
 
 
 def build_net(ctx, batch_size):
+    if os.environ.get("GEOMX_SEED"):                    # reproducible initial weights (the reference never seeds; tests do)
+        mx.random.seed(int(os.environ["GEOMX_SEED"]))
     net = mx.models.build_cnn()
     net.initialize(force_reinit=True, ctx=ctx, init=mx.init.Xavier())
     net(mx.nd.random.uniform(shape=(batch_size, 1, 28, 28), ctx=ctx))     # materialise deferred shapes

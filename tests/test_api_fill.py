@@ -310,7 +310,7 @@ def test_demo_script_saves_and_loads_params(tmp_path):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, GEOMX_SYNTHETIC_SIZE="512")
+    env = dict(os.environ, GEOMX_SYNTHETIC_SIZE="512", GEOMX_SEED="1")
     for k in ("DMLC_ROLE", "DMLC_PS_ROOT_URI", "RANK", "WORLD_SIZE"):
         env.pop(k, None)
     out = str(tmp_path / "cnn.params")

@@ -54,7 +54,7 @@ def run_scenario(script, tmp_path, iters=31, extra_env=None, args=()):
     env = dict(os.environ)
     env.pop("RANK", None); env.pop("WORLD_SIZE", None)
     env.update({"LOG_DIR": str(tmp_path), "BASE_PORT": str(_free_base_port()), "GEOMX_SYNTHETIC_SIZE": "2048", "GEOMX_MAX_ITERS": str(iters),
-                "GEOMX_EVAL_EVERY": "10", "OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1"})
+                "GEOMX_EVAL_EVERY": "10", "OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1", "GEOMX_SEED": "11"})
     env.update(extra_env or {})
     r = _run_group(["bash", os.path.join(ROOT, "scripts", "cpu", script), "-ep", "8"] + list(args), env, 240)
     logs = {f: open(os.path.join(str(tmp_path), f)).read() for f in os.listdir(str(tmp_path)) if f.endswith(".log")}
@@ -82,7 +82,7 @@ def test_hfa_converges(tmp_path):
     # the scenario script hard-codes K1=20/K2=10 (the reference's values); call the launcher directly with short periods
     e = dict(os.environ); e.pop("RANK", None); e.pop("WORLD_SIZE", None)
     e.update({"LOG_DIR": str(tmp_path), "BASE_PORT": str(_free_base_port()), "GEOMX_SYNTHETIC_SIZE": "2048", "GEOMX_MAX_ITERS": "41",
-              "GEOMX_EVAL_EVERY": "10", "OMP_NUM_THREADS": "1", "N_GS": "1"})
+              "GEOMX_EVAL_EVERY": "10", "OMP_NUM_THREADS": "1", "N_GS": "1", "GEOMX_SEED": "11"})
     e.update(env)
     r = _run_group(["bash", os.path.join(ROOT, "scripts", "hips_launch.sh"), "cpu", os.path.join(ROOT, "examples", "cnn_hfa.py"), "-ep", "8"], e, 240)
     log = open(os.path.join(str(tmp_path), "party1_worker1.log")).read()
