@@ -1,11 +1,13 @@
-"""Multi-layer (bi)directional recurrent layers composed of the cells (the reference dispatches to cuDNN's fused RNN; here the time loop is
-explicit and every step's GEMMs go through ``ops.functional.dense``)."""
+"""Multi-layer (bi)directional recurrent layers over the cells' parameters (the reference dispatches to cuDNN's fused RNN).  Per layer and
+direction the input projections of all time steps are ONE GEMM (``T*N`` rows — large enough for the tcgen05 path on CUDA); the time loop
+only carries the hidden-to-hidden GEMM and the gate arithmetic."""
 from __future__ import annotations
 
 import torch
 
 from ... import ndarray as nd
 from ...ndarray import NDArray
+from ...ops import functional as OF
 from ..block import HybridBlock
 from .rnn_cell import GRUCell, LSTMCell, RNNCell
 
@@ -53,9 +55,28 @@ class _RNNLayer(HybridBlock):
                 st = [NDArray(s._t[idx]) for s in states]
                 steps = range(T) if d == 0 else range(T - 1, -1, -1)
                 outs = [None] * T
+                # the input projections of ALL time steps are one GEMM (T*N rows); the recurrence only carries the h2h GEMM
+                cell._deferred_infer(NDArray(seq[0]))
+                ctx = inputs.context
+                wi, wh, bi, bh = (p.data(ctx)._t for p in (cell.i2h_weight, cell.h2h_weight, cell.i2h_bias, cell.h2h_bias))
+                xi_all = OF.dense(seq.reshape(T * N, -1), wi, bi, None, False).reshape(T, N, -1)
+                h = st[0]._t
+                c = st[1]._t if len(st) > 1 else None
+                kind = type(self)._cell.__name__
                 for t in steps:
-                    o, st = cell(NDArray(seq[t]), st)
-                    outs[t] = o._t
+                    gh = OF.dense(h, wh, bh, None, False)
+                    if kind == "LSTMCell":
+                        i, f, g, o = (xi_all[t] + gh).chunk(4, dim=-1)
+                        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+                        h = torch.sigmoid(o) * torch.tanh(c)
+                    elif kind == "GRUCell":
+                        xr, xz, xn = xi_all[t].chunk(3, dim=-1); hr, hz, hn = gh.chunk(3, dim=-1)
+                        r = torch.sigmoid(xr + hr); z = torch.sigmoid(xz + hz)
+                        h = (1 - z) * torch.tanh(xn + r * hn) + z * h
+                    else:
+                        h = OF.activation(xi_all[t] + gh, cell._activation)
+                    outs[t] = h
+                st = [NDArray(h)] + ([NDArray(c)] if c is not None else [])
                 outs_dir.append(torch.stack(outs, 0))
                 for k in range(n_state):
                     finals[k].append(st[k]._t)

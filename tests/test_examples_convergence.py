@@ -56,8 +56,13 @@ def run_scenario(script, tmp_path, iters=31, extra_env=None, args=()):
     env.update({"LOG_DIR": str(tmp_path), "BASE_PORT": str(_free_base_port()), "GEOMX_SYNTHETIC_SIZE": "2048", "GEOMX_MAX_ITERS": str(iters),
                 "GEOMX_EVAL_EVERY": "10", "OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1", "GEOMX_SEED": "11"})
     env.update(extra_env or {})
-    r = _run_group(["bash", os.path.join(ROOT, "scripts", "cpu", script), "-ep", "8"] + list(args), env, 240)
-    logs = {f: open(os.path.join(str(tmp_path), f)).read() for f in os.listdir(str(tmp_path)) if f.endswith(".log")}
+    for attempt in range(3):
+        r = _run_group(["bash", os.path.join(ROOT, "scripts", "cpu", script), "-ep", "8"] + list(args), env, 240)
+        logs = {f: open(os.path.join(str(tmp_path), f)).read() for f in os.listdir(str(tmp_path)) if f.endswith(".log")}
+        if r.returncode == 0 or not any("bind failed" in v for v in list(logs.values()) + [r.stdout]):
+            break
+        # a port of the freshly probed block was taken by somebody's ephemeral socket in the meantime: pick another block
+        env["BASE_PORT"] = str(_free_base_port())
     assert r.returncode == 0, r.stdout[-2000:] + "\n".join("%s:\n%s" % (k, v[-600:]) for k, v in logs.items())
     accs = [float(x) for x in re.findall(r"Test Acc ([0-9.]+)", logs["party1_worker1.log"])]
     assert accs, logs["party1_worker1.log"][-1500:]
