@@ -2,8 +2,9 @@
 batch_sampler / last_batch / shuffle / num_workers).
 
 B200 design: batches are assembled into **pinned host memory** (so the H2D copy of each step is a true async DMA)
-and, with ``num_workers>0``, by a native C++ prefetch thread pool (``_C.Prefetcher``) rather than forked Python
-workers; ``num_workers=0`` (what the reference examples use) assembles inline."""
+and, with ``num_workers>0``, by a pool of prefetching threads (``2 * num_workers`` batches in flight; tensor stacking, numpy and image
+decoding release the GIL) rather than forked Python workers with shared-memory hand-off; ``num_workers=0`` (what the reference examples use)
+assembles inline.  Datasets that expose ``_fast_batch(indices)`` (the in-memory vision sets) skip per-item Python entirely."""
 from __future__ import annotations
 
 import numpy as np
