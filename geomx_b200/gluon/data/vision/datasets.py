@@ -22,6 +22,11 @@ __all__ = ["MNIST", "FashionMNIST", "CIFAR10", "CIFAR100", "ImageRecordDataset",
 
 
 def _read_idx(path):
+    if not path.endswith(".gz"):
+        from .... import runtime
+        if runtime.available():                      # native parser (csrc/runtime/io.h): one read, no Python-level copies of the payload
+            dims, raw = runtime.C().read_idx(path)
+            return np.frombuffer(raw, dtype=np.uint8).reshape(dims)
     opener = gzip.open if path.endswith(".gz") else open
     with opener(path, "rb") as f:
         buf = f.read()
