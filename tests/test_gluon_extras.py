@@ -126,3 +126,32 @@ def test_nd_layers_losses_and_contrib_blocks():
             L = o2.sum()
         L.backward()
         assert o2.shape == (2, 5, 8, 8) and float(cell.h2h_weight.grad().asnumpy().__abs__().sum()) > 0
+
+
+def test_model_zoo_covers_the_reference_table_with_the_published_sizes():
+    from geomx_b200.gluon.model_zoo import vision
+    names = set(vision._models)
+    want = {"resnet%d_v%d" % (n, v) for n in (18, 34, 50, 101, 152) for v in (1, 2)} | {"vgg%d%s" % (n, s) for n in (11, 13, 16, 19) for s in ("", "_bn")} | \
+        {"alexnet", "densenet121", "densenet161", "densenet169", "densenet201", "squeezenet1.0", "squeezenet1.1", "inceptionv3", "mobilenet1.0",
+         "mobilenet0.75", "mobilenet0.5", "mobilenet0.25", "mobilenetv2_1.0", "mobilenetv2_0.75", "mobilenetv2_0.5", "mobilenetv2_0.25"}
+    assert want <= names, sorted(want - names)
+
+    def count(net):
+        return sum(int(np.prod(p.shape)) for p in net.collect_params().values() if p.grad_req != "null")
+    # learnable-parameter counts of the ImageNet configurations (the numbers every framework reports for these architectures)
+    published = {"resnet50_v1": 25557032, "resnet18_v1": 11689512, "densenet121": 7978856, "squeezenet1.0": 1248424, "squeezenet1.1": 1235496,
+                 "inceptionv3": 23834568, "mobilenet1.0": 4231976, "alexnet": 61100840}
+    for name, n in published.items():
+        net = vision.get_model(name); net.initialize()
+        hw = 299 if name == "inceptionv3" else 224
+        y = net(mx.nd.random.uniform(shape=(1, 3, hw, hw)))
+        assert y.shape == (1, 1000) and count(net) == n, (name, count(net))
+    for name in ("resnet50_v2", "mobilenetv2_0.5", "resnet18_v2"):          # pre-activation / inverted-residual families: forward + backward
+        net = vision.get_model(name, classes=7); net.initialize()
+        x = mx.nd.random.uniform(shape=(2, 3, 64, 64))
+        with mx.autograd.record():
+            loss = net(x).sum()
+        loss.backward()
+        conv_w = next(p for n, p in net.collect_params().items() if n.endswith("weight") and p.grad_req != "null")
+        assert net(x).shape == (2, 7) and float(conv_w.grad().asnumpy().__abs__().sum()) > 0
+    assert vision.get_resnet(2, 34, classes=3, thumbnail=True) is not None and vision.get_vgg(19, batch_norm=True) is not None
