@@ -52,7 +52,7 @@ from . import utils  # noqa: F401
 from . import parallel  # noqa: F401
 from . import models  # noqa: F401
 from . import contrib  # noqa: F401
-from . import executor, libinfo, log, misc, registry, rnn, util  # noqa: F401
+from . import executor, executor_manager, libinfo, log, misc, notebook, registry, rnn, util  # noqa: F401
 from . import kvstore_server  # noqa: F401
 
 # server / scheduler bootstrap on import (no-op for workers and plain library use)

@@ -330,3 +330,34 @@ def test_demo_script_saves_and_loads_params(tmp_path):
         assert common.accuracy(test, net, mx.cpu()) > 0.9 > before
     finally:
         sys.path.pop(0); os.environ.pop("GEOMX_SYNTHETIC_SIZE", None)
+
+
+def test_executor_manager_and_notebook_logger():
+    from geomx_b200 import executor_manager as em
+    rs = np.random.RandomState(0)
+    x = rs.randn(32, 4).astype(np.float32); y = (x[:, 0] > 0).astype(np.float32)
+    it = mx.io.NDArrayIter(x, y, batch_size=8)
+    sym = mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=2, name="fc"), name="softmax")
+    m = em.DataParallelExecutorManager(sym, mx.cpu(), it)
+    m.set_params({"fc_weight": mx.nd.array(rs.randn(2, 4).astype(np.float32)), "fc_bias": mx.nd.zeros((2,))}, {})
+    upd = mx.optimizer.get_updater(mx.optimizer.SGD(learning_rate=0.5, rescale_grad=1 / 8))
+    acc = mx.metric.Accuracy()
+    for _ in range(10):
+        it.reset(); acc.reset()
+        for b in it:
+            m.load_data_batch(b); m.forward(is_train=True); m.backward()
+            for i, (ws, gs) in enumerate(zip(m.param_arrays, m.grad_arrays)):
+                upd(i, gs[0], ws[0])
+            m.update_metric(acc, b.label)
+    assert acc.get()[1] > 0.9
+    a, b_ = {}, {}
+    m.copy_to(a, b_)
+    assert sorted(a) == ["fc_bias", "fc_weight"] and em._split_input_slice(10, [1, 1, 2]) == [slice(0, 2), slice(2, 4), slice(4, 10)]
+    with pytest.raises(ValueError):
+        em._split_input_slice(2, [1, 1, 1, 1])
+    log = mx.notebook.callback.PandasLogger(batch_size=8, frequent=2)
+    mod = mx.mod.Module(sym)
+    mod.fit(it, num_epoch=2, **log.callback_args())
+    assert len(log.train_df) == 4 and {"accuracy", "records_per_sec", "epoch", "minibatch_count"} <= set(log.train_df.columns) and len(log.epoch_df) == 2
+    with pytest.raises(ImportError):
+        mx.notebook.callback.LiveLearningCurve()
