@@ -230,10 +230,15 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   }
   // ---- decode the contribution to fp32
   const size_t n = e.elems;
-  std::vector<float> incoming(n);
+  // dense fp32 payloads (the common case) are consumed in place from the message buffer; every other format is decoded into `incoming`
+  std::vector<float> incoming;
+  const float* inc = nullptr;
+  const bool in_place = type.requestType == RequestType::kDefaultPushPull && type.dtype == kFloat32;
+  if (!in_place) { incoming.resize(n); inc = incoming.data(); }
   if (type.requestType == RequestType::kDefaultPushPull) {
     HIPS_CHECK_MSG(data.vals.size() == n * DTypeSize(type.dtype), "push size mismatch for key " + std::to_string(key));
-    ToFloat(data.vals.data(), type.dtype, n, incoming.data());
+    if (in_place) inc = reinterpret_cast<const float*>(data.vals.data());
+    else ToFloat(data.vals.data(), type.dtype, n, incoming.data());
   } else if (type.requestType == RequestType::kRowSparsePushPull) {
     // row_sparse gradient (reference DataHandleRowSparse :561-756): scatter-add the listed rows into a dense contribution — the
     // aggregation / tier logic below is storage-agnostic
@@ -260,7 +265,7 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   const bool sync = (is_global_ ? sync_global_mode_ : sync_mode_);
   if (!sync) {
     // ---- MixedSync / async: apply this contribution immediately (reference :1582-1609)
-    ApplyUpdate(key, &e, incoming.data(), n);
+    ApplyUpdate(key, &e, inc, n);
     const std::vector<KVMeta> who = ExpandOrigins(req);
     for (size_t i = 0; i < who.size(); ++i) {
       if (i > 0 && who[i].sender == who[i - 1].sender && who[i].timestamp == who[i - 1].timestamp) continue;
@@ -271,8 +276,8 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
     return;
   }
   UpdateBuf& ub = update_buf_[key];
-  if (ub.request.empty()) ub.merged = incoming;
-  else for (size_t i = 0; i < n; ++i) ub.merged[i] += incoming[i];
+  if (ub.request.empty()) ub.merged.assign(inc, inc + n);
+  else { float* m = ub.merged.data(); for (size_t i = 0; i < n; ++i) m[i] += inc[i]; }
   for (const KVMeta& r : ExpandOrigins(req)) ub.request.push_back(r);
   size_t expected;
   if (is_global_) expected = po->num_global_workers() + (po->enable_central_workers() ? po->num_workers() : 0);
