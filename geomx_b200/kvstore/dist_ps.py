@@ -128,9 +128,12 @@ class KVStoreDist(KVStoreBase):
             for o in outs:
                 o._pending = None
             t0 = outs[0]._data
-            buf = self._recv_buf.get(key)
-            if buf is None or buf.numel() != t0.numel() or buf.dtype != t0.dtype:
-                buf = _pinned(t0.numel(), t0.dtype); self._recv_buf[key] = buf
+            if len(outs) == 1 and t0.device.type == "cpu" and t0.is_contiguous() and not t0.requires_grad:
+                buf = t0                               # host target: the response is written straight into it (no staging copy)
+            else:
+                buf = self._recv_buf.get(key)
+                if buf is None or buf.numel() != t0.numel() or buf.dtype != t0.dtype:
+                    buf = _pinned(t0.numel(), t0.dtype); self._recv_buf[key] = buf
             h = self._kv.pull(key, buf.data_ptr(), buf.numel(), _DT[buf.dtype], prio)
             self._push_handle.pop(key, None)
             issued.append((h, buf, outs))
@@ -138,6 +141,8 @@ class KVStoreDist(KVStoreBase):
             self._kv.wait(h)
             for o in outs:
                 tgt = o._data
+                if tgt is buf:
+                    continue
                 (tgt.detach() if tgt.requires_grad else tgt).copy_(buf.view(tgt.shape), non_blocking=True)
 
     def _push_row_sparse(self, key, vals, priority):
