@@ -48,7 +48,22 @@ void Customer::AddResponse(int timestamp, int num) {
   tracker_cond_.notify_all();
 }
 
+void Customer::CountResponse(const Message& recv) {
+  if (!recv.meta.request && recv.meta.control.empty()) {
+    std::lock_guard<std::mutex> lk(tracker_mu_);
+    if (recv.meta.timestamp >= 0 && static_cast<size_t>(recv.meta.timestamp) < tracker_.size()) {
+      tracker_[recv.meta.timestamp].second++;
+      tracker_cond_.notify_all();
+    }
+  }
+}
+
 void Customer::Accept(const Message& recved) {
+  if (inline_responses_ && !recved.meta.request && recved.meta.control.empty()) {
+    recv_handle_(recved);
+    CountResponse(recved);
+    return;
+  }
   // pull requests get their own queue/thread on servers so that they never wait behind pushes (reference customer.h:91-101)
   const bool is_pull_request = recved.meta.request && !recved.meta.push && !recved.meta.simple_app && recved.meta.control.empty();
   if (pull_thread_ && is_pull_request) pull_queue_.Push(recved);
@@ -61,13 +76,7 @@ void Customer::Receiving(ThreadsafeQueue<Message, MessagePriority>* q) {
     q->WaitAndPop(&recv);
     if (!recv.meta.control.empty() && recv.meta.control.cmd == Control::TERMINATE) break;
     recv_handle_(recv);
-    if (!recv.meta.request && recv.meta.control.empty()) {
-      std::lock_guard<std::mutex> lk(tracker_mu_);
-      if (recv.meta.timestamp >= 0 && static_cast<size_t>(recv.meta.timestamp) < tracker_.size()) {
-        tracker_[recv.meta.timestamp].second++;
-        tracker_cond_.notify_all();
-      }
-    }
+    CountResponse(recv);
   }
 }
 

@@ -33,8 +33,14 @@ class Customer {
   int NumResponse(int timestamp);
   void AddResponse(int timestamp, int num = 1);
   void Accept(const Message& recved);
+  // responses are handled on the caller's (the Van receive) thread instead of being queued for the customer thread: saves one thread
+  // wake-up per response on the worker side, where response handlers only copy data and signal the waiter (never block, never wait for
+  // other messages).  Requests still go through the queue.
+  void set_inline_responses(bool on) { inline_responses_ = on; }
 
  private:
+  void CountResponse(const Message& recv);
+  bool inline_responses_ = false;
   void Receiving(ThreadsafeQueue<Message, MessagePriority>* q);
   int app_id_, customer_id_;
   RecvHandle recv_handle_;

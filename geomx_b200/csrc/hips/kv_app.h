@@ -163,6 +163,8 @@ class KVWorker : public SimpleApp {
         Environment::Get()->GetInt("ENABLE_P3", 0) == 0)
       ts_.reset(new TSNode(kLocal, app_id, customer_id));
     obj_.reset(new Customer(app_id, customer_id, [this](const Message& m) { Process(m); }, false));
+    // without the TSEngine overlay a worker's response handlers are copy-and-signal only: run them on the receive thread
+    if (!ts_ && Environment::Get()->GetInt("GEOMX_INLINE_RESPONSES", 1) != 0) obj_->set_inline_responses(true);
   }
   TSNode* ts() { return ts_.get(); }
   ~KVWorker() override { obj_.reset(); }
