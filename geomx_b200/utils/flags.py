@@ -84,6 +84,10 @@ _reg("MXNET_PROFILER_MODE", 0, int, "")
 _reg("MXNET_ENFORCE_DETERMINISM", 0, int, "")
 # geomx_b200 additions ---------------------------------------------------------------------------------------
 _reg("GEOMX_FABRIC", "auto", str, "auto | symm (NVSwitch symmetric memory) | nccl (oracle) | tcp")
+_reg("GEOMX_INLINE_RESPONSES", 1, int, "TCP plane: workers handle responses on the receive thread (one wake-up less per message); 0 = queue them")
+_reg("GEOMX_SERVER_CKPT_PREFIX", "", str, "servers write <prefix>.server<rank>{g,l} every GEOMX_SERVER_CKPT_EVERY rounds")
+_reg("GEOMX_SERVER_CKPT_EVERY", 0, int, "rounds between periodic server-state checkpoints (0 = off)")
+_reg("GEOMX_SERVER_RESUME", 0, int, "a (re)started global / stand-alone server adopts the checkpoint under GEOMX_SERVER_CKPT_PREFIX")
 _reg("GEOMX_NUM_PARTIES", 0, int, "fabric mode: number of parties (0 → DMLC_NUM_GLOBAL_WORKER, else 2 when the world is even, else 1)")
 _reg("GEOMX_FP8_TRANSPORT", 0, int, "block-scaled e4m3 payload on the fp16/MPQ path")
 _reg("GEOMX_SYNTHETIC_SIZE", 0, int, "shrink synthetic datasets")
