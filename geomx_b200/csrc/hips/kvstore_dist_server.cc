@@ -19,6 +19,7 @@ KVStoreDistServer::KVStoreDistServer() {
   size_lower_bound_ = static_cast<size_t>(env->GetFloat("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000));
   ckpt_prefix_ = env->GetStr("GEOMX_SERVER_CKPT_PREFIX", "");
   ckpt_every_ = ckpt_prefix_.empty() ? 0 : std::max(0, env->GetInt("GEOMX_SERVER_CKPT_EVERY", 0));
+  fused_tier_pull_ = env->GetInt("GEOMX_FUSED_TIER_PULL", 1) != 0 && env->GetInt("ENABLE_INTER_TS", 0) == 0;
   resume_wanted_ = !ckpt_prefix_.empty() && env->GetInt("GEOMX_SERVER_RESUME", 0) != 0 && (is_global_ || standalone_);
   ps_server_.reset(new KVServer(0));
   ps_server_->SimpleApp::set_request_handle([this](const SimpleData& d, SimpleApp* app) { CommandHandle(d, app); });
@@ -190,8 +191,17 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   std::unique_lock<std::mutex> lk(mu_);
   Entry& e = store_[key];
   const bool p3 = ps_server_->enable_p3;
+  // inter-tier fusion (GEOMX_FUSED_TIER_PULL, default on): a global server answers a local server's dense push with the post-update value,
+  // so the local server does not need a second round trip (push ack, then pull) over the slow link between parties
+  const bool fuse_up = is_global_ && fused_tier_pull_ && type.requestType == RequestType::kDefaultPushPull &&
+                       Postoffice::Get()->num_global_servers() == 1 && !use_hfa_;
   auto respond = [&](const KVMeta& r) {
-    if (p3 && !is_global_) {
+    if (fuse_up && r.plane == kGlobal && r.sender % 2 == 1) {
+      KVPairs res; res.keys = data.keys;
+      res.vals.CopyFrom(e.data.data(), e.data.size());
+      res.lens.push_back(static_cast<int>(e.data.size()));
+      ps_server_->Response(r, res);
+    } else if (p3 && !is_global_) {
       KVPairs res; res.keys = data.keys;
       res.vals.CopyFrom(e.data.data(), e.data.size());
       res.lens.push_back(static_cast<int>(e.data.size()));
@@ -424,6 +434,17 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
     ts_key_.erase(it);
     if (r.via_ts) return;   // TSEngine: the global server relays the fresh value (OnRelayedFromGlobal)
     const DataHandleType type = DepairDataHandleType(r.cmd);
+    Entry& e = store_[key];
+    if (data.vals.size() == e.elems * DTypeSize(e.dtype) && type.requestType == RequestType::kDefaultPushPull && data.vals.size() > 0) {
+      // fused inter-tier pull: the push response already carries the post-update value
+      std::vector<float> recved(e.elems);
+      ToFloat(data.vals.data(), e.dtype, e.elems, recved.data());
+      const bool was_round = r.push_ts >= 0;
+      ApplyFreshFromGlobal(key, &recved);
+      lk.unlock();
+      if (was_round) RoundCompleted(key); else AskTS(key);
+      return;
+    }
     lk.unlock();
     PullFromGlobal(key, type);
     return;

@@ -186,6 +186,7 @@ class KVStoreDistServer {
   int ckpt_every_ = 0, ckpt_key_ = 0;                  // ckpt_key_: round number of the last snapshot
   std::unordered_map<int, bool> skip_init_push_;         // resumed keys: the next init push of the (re)started job must not overwrite them
   std::map<int, NativeOptimizer::State> resumed_opt_;     // optimizer state read before the optimizer was configured
+  bool fused_tier_pull_ = true;                          // global server: dense push responses to local servers carry the fresh value
   bool resume_wanted_ = false;
   std::once_flag resume_once_;
   void TryResume();

@@ -137,6 +137,19 @@ def test_hips_two_tier_fsa():
                 assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-4, (t, i, v)
 
 
+def test_fused_inter_tier_pull_is_transparent():
+    """GEOMX_FUSED_TIER_PULL (default on): the global server answers a local server's dense push with the post-update value, saving the
+    separate pull over the link between parties.  Same arithmetic with the fusion off (the reference's push-ack-then-pull exchange)."""
+    gsum = 0.5 * (1 + 2 + 3 + 4)
+    for flag in ("1", "0"):
+        res = launch_hips({"TEST_MODE": "sgd", "GEOMX_FUSED_TIER_PULL": flag, "TEST_STEPS": "2"})
+        assert len(res) == 4
+        for r in res:
+            for t, vals in enumerate(r["vals"]):
+                for i, v in enumerate(vals):
+                    assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-4, (flag, t, i, v)
+
+
 def test_hips_multigps_bigarray_python_updater():
     """MultiGPS: 2 global servers, big array partitioned across them; foreign (pickled Python) Adam executed through the Executor."""
     res = launch_hips({"TEST_MODE": "adam_py", "MXNET_KVSTORE_BIGARRAY_BOUND": "100", "TEST_STEPS": "2"}, global_servers=2)
