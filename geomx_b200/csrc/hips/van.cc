@@ -277,6 +277,10 @@ void Van::Start(int customer_id) {
   recv_thread_.reset(new std::thread(&Van::Receiving, this));
   if (udp_fd_ >= 0) udp_thread_.reset(new std::thread(&Van::ReceivingUDP, this));
   if (enable_p3_) prio_thread_.reset(new std::thread(&Van::PrioritySending, this));
+  if (plane_ == kGlobal && env->GetInt("GEOMX_EMULATE_DELAY_MS", 0) > 0) {
+    emulate_delay_us_ = env->GetInt("GEOMX_EMULATE_DELAY_MS", 0) * 1000;
+    delay_thread_.reset(new std::thread(&Van::DelayedSending, this));
+  }
 
   if (!is_scheduler_) {
     Message msg;
@@ -300,6 +304,7 @@ void Van::Stop() {
     prio_thread_->join();
   }
   if (dgt_sender_) dgt_sender_->Stop();
+  if (delay_thread_) { { std::lock_guard<std::mutex> lk(delay_mu_); } delay_cv_.notify_all(); delay_thread_->join(); }
   if (heartbeat_thread_) heartbeat_thread_->join();
   resender_.reset();
   char c = 1;
@@ -345,7 +350,34 @@ void Van::PrioritySending() {
   }
 }
 
+static int64_t NowUs() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int Van::SendNow(const Message& msg) {
+  if (emulate_delay_us_ > 0 && msg.meta.control.empty() && ready_.load()) {
+    std::lock_guard<std::mutex> lk(delay_mu_);
+    delay_q_.emplace_back(NowUs() + emulate_delay_us_, msg);
+    delay_cv_.notify_one();
+    return 0;
+  }
+  return SendWire(msg);
+}
+
+void Van::DelayedSending() {
+  std::unique_lock<std::mutex> lk(delay_mu_);
+  while (true) {
+    delay_cv_.wait(lk, [this] { return stop_.load() || !delay_q_.empty(); });
+    if (delay_q_.empty()) { if (stop_.load()) return; continue; }
+    const int64_t due = delay_q_.front().first, now = NowUs();
+    if (now < due && !stop_.load()) { delay_cv_.wait_for(lk, std::chrono::microseconds(due - now)); continue; }
+    Message m = std::move(delay_q_.front().second);
+    delay_q_.pop_front();
+    lk.unlock();
+    SendWire(m);
+    lk.lock();
+  }
+}
+
+int Van::SendWire(const Message& msg) {
   const int id = msg.meta.recver;
   HIPS_CHECK(id != Meta::kEmpty);
   Sender* s = nullptr;

@@ -13,6 +13,8 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -50,6 +52,7 @@ class Van {
   DGTSender* dgt_sender() { return dgt_sender_.get(); }
   // direct (unqueued) transmit used by the priority sender thread, the resender and the DGT channel schedulers
   int SendNow(const Message& msg);
+  int SendWire(const Message& msg);   // the actual socket write (SendNow may defer to it through the latency emulator)
   // lossy datagram path (DGT mode 1): one UDP packet per message with the message's TOS/DSCP; falls back to TCP when no endpoint is known
   int SendUDP(const Message& msg);
   size_t udp_sent() const { return udp_sent_.load(); }
@@ -99,6 +102,14 @@ class Van {
 
   std::unique_ptr<std::thread> accept_thread_, recv_thread_, heartbeat_thread_, prio_thread_, udp_thread_;
   ThreadsafeQueue<Message, MessagePriority> send_queue_;  // P3
+  // WAN emulation (GEOMX_EMULATE_DELAY_MS, data messages of the global plane): sends are released by a timer thread `delay` after they
+  // were issued, in order — a one-way latency on the link between parties without blocking the issuing thread
+  int emulate_delay_us_ = 0;
+  std::unique_ptr<std::thread> delay_thread_;
+  std::mutex delay_mu_;
+  std::condition_variable delay_cv_;
+  std::deque<std::pair<int64_t, Message>> delay_q_;
+  void DelayedSending();
   bool enable_p3_ = false;
   int drop_rate_ = 0;
   int num_servers_seen_ = 0, num_workers_seen_ = 0;

@@ -84,6 +84,7 @@ _reg("MXNET_PROFILER_MODE", 0, int, "")
 _reg("MXNET_ENFORCE_DETERMINISM", 0, int, "")
 # geomx_b200 additions ---------------------------------------------------------------------------------------
 _reg("GEOMX_FABRIC", "auto", str, "auto | symm (NVSwitch symmetric memory) | nccl (oracle) | tcp")
+_reg("GEOMX_EMULATE_DELAY_MS", 0, int, "emulated one-way latency (ms) of data messages on the global plane (WAN between parties)")
 _reg("GEOMX_FUSED_TIER_PULL", 1, int, "global server answers a local server's dense push with the fresh value (one inter-party round trip per key instead of two)")
 _reg("GEOMX_INLINE_RESPONSES", 1, int, "TCP plane: workers handle responses on the receive thread (one wake-up less per message); 0 = queue them")
 _reg("GEOMX_SERVER_CKPT_PREFIX", "", str, "servers write <prefix>.server<rank>{g,l} every GEOMX_SERVER_CKPT_EVERY rounds")

@@ -150,6 +150,27 @@ def test_fused_inter_tier_pull_is_transparent():
                     assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-4, (flag, t, i, v)
 
 
+def test_fused_tier_pull_halves_the_round_time_on_a_slow_inter_party_link(tmp_path):
+    """``GEOMX_EMULATE_DELAY_MS`` delays every data message on the global plane (one-way latency between parties).  A synchronisation round
+    then costs about ONE inter-party round trip with the fused tier pull and about TWO with the reference's push-ack-then-pull exchange."""
+    import json
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "tcp_plane_bench.py")
+    med = {}
+    for flag in ("1", "0"):
+        env = dict(os.environ, GEOMX_EMULATE_DELAY_MS="15", GEOMX_FUSED_TIER_PULL=flag, BENCH_SHAPES="64;64")
+        for k in ("RANK", "WORLD_SIZE", "DMLC_ROLE"):
+            env.pop(k, None)
+        r = subprocess.run([sys.executable, tool, "--rounds", "12", "--two-tier"], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+        med[flag] = json.loads(r.stdout.strip().splitlines()[-1])["median_ms"]
+    rtt = 2 * 15.0
+    assert rtt * 0.95 < med["1"] < rtt * 1.5, med            # one round trip (+ local hops)
+    assert 2 * rtt * 0.95 < med["0"] < 2 * rtt * 1.4, med    # two round trips
+    assert med["0"] / med["1"] > 1.6, med
+
+
 def test_hips_multigps_bigarray_python_updater():
     """MultiGPS: 2 global servers, big array partitioned across them; foreign (pickled Python) Adam executed through the Executor."""
     res = launch_hips({"TEST_MODE": "adam_py", "MXNET_KVSTORE_BIGARRAY_BOUND": "100", "TEST_STEPS": "2"}, global_servers=2)
