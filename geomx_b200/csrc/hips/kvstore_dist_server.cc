@@ -193,8 +193,7 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   const bool p3 = ps_server_->enable_p3;
   // inter-tier fusion (GEOMX_FUSED_TIER_PULL, default on): a global server answers a local server's dense push with the post-update value,
   // so the local server does not need a second round trip (push ack, then pull) over the slow link between parties
-  const bool fuse_up = is_global_ && fused_tier_pull_ && type.requestType == RequestType::kDefaultPushPull &&
-                       Postoffice::Get()->num_global_servers() == 1 && !use_hfa_;
+  const bool fuse_up = is_global_ && fused_tier_pull_ && type.requestType == RequestType::kDefaultPushPull && !use_hfa_;
   auto respond = [&](const KVMeta& r) {
     if (fuse_up && r.plane == kGlobal && r.sender % 2 == 1) {
       KVPairs res; res.keys = data.keys;
@@ -429,22 +428,33 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
   const int key = it->second;
   GlobalRound& r = rounds_[key];
   if (res.push) {
-    // push ack: once every global server acknowledged, fetch the fresh value (reference :941-957)
+    // push ack: once every global server acknowledged, fetch the fresh value (reference :941-957) — unless the acks already carried it
+    // (fused inter-tier pull: every global server that owns a slice of the key answers with the post-update slice)
+    if (data.vals.size() > 0 && data.keys.size()) {
+      std::vector<char> bytes(data.vals.data(), data.vals.data() + data.vals.size());
+      r.parts.emplace_back(data.keys[0], std::move(bytes));
+    }
     if (server->NumResponse(res.timestamp) != Postoffice::Get()->num_global_servers() - 1) return;
     ts_key_.erase(it);
-    if (r.via_ts) return;   // TSEngine: the global server relays the fresh value (OnRelayedFromGlobal)
+    if (r.via_ts) { r.parts.clear(); return; }   // TSEngine: the global server relays the fresh value (OnRelayedFromGlobal)
     const DataHandleType type = DepairDataHandleType(r.cmd);
     Entry& e = store_[key];
-    if (data.vals.size() == e.elems * DTypeSize(e.dtype) && type.requestType == RequestType::kDefaultPushPull && data.vals.size() > 0) {
-      // fused inter-tier pull: the push response already carries the post-update value
+    size_t got = 0;
+    for (auto& p : r.parts) got += p.second.size();
+    if (type.requestType == RequestType::kDefaultPushPull && got > 0 && got == e.elems * DTypeSize(e.dtype)) {
+      std::sort(r.parts.begin(), r.parts.end(), [](const std::pair<Key, std::vector<char>>& a, const std::pair<Key, std::vector<char>>& b) { return a.first < b.first; });
+      std::vector<char> whole;
+      for (auto& p : r.parts) whole.insert(whole.end(), p.second.begin(), p.second.end());
+      r.parts.clear();
       std::vector<float> recved(e.elems);
-      ToFloat(data.vals.data(), e.dtype, e.elems, recved.data());
+      ToFloat(whole.data(), e.dtype, e.elems, recved.data());
       const bool was_round = r.push_ts >= 0;
       ApplyFreshFromGlobal(key, &recved);
       lk.unlock();
       if (was_round) RoundCompleted(key); else AskTS(key);
       return;
     }
+    r.parts.clear();
     lk.unlock();
     PullFromGlobal(key, type);
     return;
