@@ -193,7 +193,7 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   const bool p3 = ps_server_->enable_p3;
   // inter-tier fusion (GEOMX_FUSED_TIER_PULL, default on): a global server answers a local server's dense push with the post-update value,
   // so the local server does not need a second round trip (push ack, then pull) over the slow link between parties
-  const bool fuse_up = is_global_ && fused_tier_pull_ && type.requestType == RequestType::kDefaultPushPull && !use_hfa_;
+  const bool fuse_up = is_global_ && fused_tier_pull_ && type.requestType == RequestType::kDefaultPushPull;
   auto respond = [&](const KVMeta& r) {
     if (fuse_up && r.plane == kGlobal && r.sender % 2 == 1) {
       KVPairs res; res.keys = data.keys;
