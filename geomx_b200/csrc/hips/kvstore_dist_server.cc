@@ -194,11 +194,22 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   // inter-tier fusion (GEOMX_FUSED_TIER_PULL, default on): a global server answers a local server's dense push with the post-update value,
   // so the local server does not need a second round trip (push ack, then pull) over the slow link between parties
   const bool fuse_up = is_global_ && fused_tier_pull_ && type.requestType == RequestType::kDefaultPushPull;
+  const bool fuse_bsc = is_global_ && fused_tier_pull_ && type.requestType == RequestType::kBSCompressedPushPull && sync_global_mode_;
   auto respond = [&](const KVMeta& r) {
     if (fuse_up && r.plane == kGlobal && r.sender % 2 == 1) {
       KVPairs res; res.keys = data.keys;
       res.vals.CopyFrom(e.data.data(), e.data.size());
       res.lens.push_back(static_cast<int>(e.data.size()));
+      ps_server_->Response(r, res);
+    } else if (fuse_bsc && r.plane == kGlobal && r.sender % 2 == 1) {
+      // Bi-Sparse: the answer is the re-sparsified aggregate a pull would have returned (capacity k * parties, reference :1190-1206)
+      const int mult = std::max(1, Postoffice::Get()->num_global_workers());
+      const float* w = e.has_master ? e.master.data() : reinterpret_cast<const float*>(e.data.data());
+      std::vector<float> out(GradientCompression::BSCPullSize(static_cast<int64_t>(e.elems), gc_.threshold(), mult));
+      gc_.BSCPullCompress(w, out.data(), static_cast<int64_t>(e.elems), mult);
+      KVPairs res; res.keys = data.keys;
+      res.vals.CopyFrom(reinterpret_cast<const char*>(out.data()), out.size() * sizeof(float));
+      res.lens.push_back(static_cast<int>(res.vals.size()));
       ps_server_->Response(r, res);
     } else if (p3 && !is_global_) {
       KVPairs res; res.keys = data.keys;
@@ -441,6 +452,18 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
     Entry& e = store_[key];
     size_t got = 0;
     for (auto& p : r.parts) got += p.second.size();
+    if (type.requestType == RequestType::kBSCompressedPushPull && r.parts.size() == 1 && got > 0) {
+      // fused Bi-Sparse answer: [values | indices] of the re-sparsified aggregate
+      std::vector<float> recved(e.elems);
+      const auto& z = r.parts[0].second;
+      GradientCompression::BSCDecompress(reinterpret_cast<const float*>(z.data()), z.size() / sizeof(float), recved.data(), e.elems);
+      r.parts.clear();
+      const bool was_round = r.push_ts >= 0;
+      ApplyFreshFromGlobal(key, &recved);
+      lk.unlock();
+      if (was_round) RoundCompleted(key); else AskTS(key);
+      return;
+    }
     if (type.requestType == RequestType::kDefaultPushPull && got > 0 && got == e.elems * DTypeSize(e.dtype)) {
       std::sort(r.parts.begin(), r.parts.end(), [](const std::pair<Key, std::vector<char>>& a, const std::pair<Key, std::vector<char>>& b) { return a.first < b.first; });
       std::vector<char> whole;
