@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-multicast", action="store_true")
+    ap.add_argument("--fast", action="store_true", help="plain TF32 tensor-core products instead of the fp32-accurate 3xTF32 default")
     ap.add_argument("--wire-dtype", default="fp32", choices=["fp32", "fp16", "mpq", "fp8"], help="transport format of the fused HiPS step (FP16 / MPQ accelerators)")
     return ap.parse_args()
 
@@ -117,7 +118,9 @@ def main():
 
     B, K, W = args.batch_size, args.steps, max(3, args.warmup)
     parties = args.parties or int(os.environ.get("GEOMX_NUM_PARTIES", 0)) or (2 if (world >= 2 and world % 2 == 0) else 1)
-    topo = Topology(world, rank, parties, int(os.environ.get("DMLC_NUM_GLOBAL_SERVER", 1)))
+    # DMLC_NUM_GLOBAL_SERVER unset -> 0 = every rank is a global server, ownership sharded tile by tile (the fabric default)
+    topo = Topology(world, rank, parties, int(os.environ.get("DMLC_NUM_GLOBAL_SERVER", 0)))
+    native.set_gemm_precision("tf32" if args.fast else "3xtf32")
     torch.manual_seed(1234)  # same init on every rank; rank 0's value wins anyway (kv.init semantics)
 
     # ---- synthetic MNIST-shaped data in pinned host memory (a rotating pool so every step copies a different batch)
@@ -193,18 +196,24 @@ def main():
     comm_us = None
     fab = getattr(eng, "fabric", None)
     if fab is not None and args.mode == "dist_sync":
-        fab.state["fsa"][3] = 1
+        chans = list(fab.channels) or ["fsa"]
+        last = "conv" if "conv" in fab.channels else chans[-1]      # the exchange at the end of the step (nothing left to hide it behind)
+        for c in chans:
+            fab.state[c][3] = 1
         samples = []
         for i in range(9):
             if world > 1:
                 fab.barrier()
             eng.run_device()
             torch.cuda.synchronize()
-            st = fab.state["fsa"][8:8 + 12].view(torch.int64).tolist()
-            if st[5] > st[0] > 0:
-                samples.append((st[5] - st[0]) / 1e3)
-        fab.state["fsa"][3] = 0
+            st = {c: fab.state[c][8:8 + 12].view(torch.int64).tolist() for c in chans}
+            if st[last][5] > st[last][0] > 0:
+                end = max(v[5] for v in st.values())          # an overlapped channel that outlives the last one is exposed too
+                samples.append((end - st[last][0]) / 1e3)
+        for c in chans:
+            fab.state[c][3] = 0
         comm_us = statistics.median(samples[1:]) if len(samples) > 1 else None
+    proto_err = bool(fab.check_protocol_errors()) if fab is not None else False
     t = torch.tensor([dev_ms, e2e_ms, comm_us or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -216,15 +225,18 @@ def main():
             "metric": "cnn.py samples/sec (whole box, device-timed, max over ranks)",
             "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(dev_ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32", "data": "synthetic",
+            "dtype": "tf32" if args.fast else "fp32 (3xTF32 tensor-core products + fp32 FMA, fp32 accumulate)", "data": "synthetic",
             "impl": args.impl,
             "config": {"model": "examples/cnn.py MNIST CNN (Conv16k5-Pool-Conv32k5-Pool-Dense256-Dense128-Dense10, 178762 params)",
                        "global_batch": B * world, "per_gpu_batch": B, "seq_len": None, "kvstore": args.mode,
-                       "precision": "fp32 storage and accumulation, TF32 tcgen05 multiplies (10-bit mantissa: above the bf16 floor; the reference "
-                                    "is fp32 SGEMM), fp32 optimizer state and wire format",
-                       "parallelism": "hips-dp%d: %d part%s x %d worker%s, global PS on rank%s %s" % (
+                       "precision": ("fp32 storage and accumulation, TF32 tcgen05 multiplies (--fast)" if args.fast else
+                                     "fp32-accurate: tcgen05 GEMMs run 3xTF32 (hi/lo split, three MMAs per K step, fp32 TMEM accumulate), the M=32 "
+                                     "dense chain and conv0 run fp32 FMA; fp32 optimizer state and wire format (reference: fp32 SGEMM)"),
+                       "parallelism": "hips-dp%d: %d part%s x %d worker%s, global PS %s" % (
                            world, topo.num_parties, "y" if topo.num_parties == 1 else "ies", topo.party_size, "" if topo.party_size == 1 else "s",
-                           "" if topo.num_gs == 1 else "s", topo.gs_ranks),
+                           "sharded tile-by-tile over all ranks" if topo.tile_sharded else "on rank(s) %s" % topo.gs_ranks),
+                       "channels": {k: {"keys": v["keys"], "mode": "replicated 1-hop" if v["replicate"] else "sharded 2-hop", "tiles": v["tiles"]}
+                                    for k, v in getattr(getattr(eng, "fabric", None), "channels", {}).items()},
                        "optimizer": "Adam(lr=0.01) on the global-PS shard", "cuda_graph": not args.no_graph,
                        "l2": "256 MiB buffer written between timed steps (L2 flush)" if flush is not None else "no flush",
                        "fabric": getattr(getattr(eng, "fabric", None), "heap", None) and eng.fabric.heap.backend,
@@ -234,6 +246,7 @@ def main():
                     "h2d_bytes_per_step": eng.h2d_bytes_per_step(), "d2h_bytes_per_step": eng.d2h_bytes_per_step(), "final_loss": round(last_loss, 5),
                     "api": "HipsCNNTrainStep.step_async(X_pinned, y_pinned) -> LossHandle; loss of step i read (D2H, pinned) after step i+1 was enqueued"},
             "exposed_push_pull_ms_per_step": None if comm_us is None else round(comm_us / 1e3, 5),
+            "protocol_errors": proto_err,
             "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks,
         }

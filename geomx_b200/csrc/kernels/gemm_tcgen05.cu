@@ -13,6 +13,12 @@
 //  * optional `wait_flag`: the producer spins on a system-scope flag before issuing the first B load — this is how
 //    the first GEMM that consumes pulled weights is fused with the parameter-server broadcast (pull_gemm).
 //
+// Precision: the default is **3xTF32** (fp32-accurate): every operand tile that TMA lands in shared memory is split in place by the four
+// (otherwise idle) epilogue warps into hi = rn_tf32(x) and lo = rn_tf32(x - hi); the MMA thread then issues lo*hi + hi*lo + hi*hi into the
+// same fp32 TMEM accumulator.  The dropped lo*lo term and the rounding of lo are ~2^-22 relative per product, i.e. the result matches an
+// fp32 SGEMM (the reference's cublasSgemmEx with CUDA_R_32F, linalg_impl.h:196-214) to fp32 rounding.  `gx_gemm_set_precision(1)` /
+// GEOMX_GEMM_PRECISION=tf32 selects plain TF32 (one MMA per K step, no split stage).
+//
 // Tile shapes: UMMA M=128, N=BLOCK_N in {32,64,128}, K=8 per instruction (32 B of tf32), BLOCK_K = 32 fp32 = one
 // 128-byte swizzle atom per row.  Out-of-bounds rows/cols/k are zero-filled by TMA, masked in the epilogue.
 #include <cuda.h>
@@ -44,33 +50,56 @@ struct GemmParams {
   const uint32_t* wait_flag;
   const int* wait_epoch;
   int a_boxes, b_boxes;    // MN-major operands: number of 32-wide TMA boxes that are (partly) in bounds for this problem
+  int a_bytes, b_bytes;    // bytes of the A / B tile that TMA actually fills per stage (what the 3xTF32 split pass has to touch)
   int tx_bytes;            // bytes that land per stage (A box(es) + B box(es)); out-of-range rows/boxes are never requested
   int stages;              // TMA ring depth actually used (<= SmemLayout::STAGES); smaller rings need less smem -> cheaper launch
   unsigned long long* dbg; // optional: %globaltimer stamps of CTA (0,0,0) phases (tools/gemm_phases.py)  // device epoch counter: proceed when *wait_flag >= *wait_epoch (graph-replay safe)
 };
 
-template <int BLOCK_N>
+constexpr int MAX_STAGES = 8;
+template <int BLOCK_N, bool SPLIT>
 struct SmemLayout {
   // deep TMA ring: the problems this framework sees are latency-bound (few CTAs, cold operands), so as many K blocks as fit are kept in
-  // flight: 8 stages for N<=64 (160/192 KiB), 6 for N=128 (192 KiB)
-  static constexpr int STAGES = BLOCK_N <= 64 ? 8 : 6;
+  // flight: 8 stages for N<=64 (160/192 KiB), 6 for N=128 (192 KiB); the 3xTF32 variant keeps a lo copy of every tile => half as many
+  static constexpr int STAGES = SPLIT ? (BLOCK_N <= 64 ? 4 : 3) : (BLOCK_N <= 64 ? 8 : 6);
   static_assert(BLOCK_N >= 16, "UMMA N >= 16 for M = 128");
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int OPS_BYTES = A_TILE_BYTES + B_TILE_BYTES;          // [A | B] as landed by TMA (= the hi parts after the split pass)
+  static constexpr int STAGE_BYTES = SPLIT ? 2 * OPS_BYTES : OPS_BYTES;  // 3xTF32: [A_hi | B_hi | A_lo | B_lo]
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 512 + 1024;  // + barriers + bias tile + alignment slack
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+// hi = rn_tf32(x) (low 13 mantissa bits zero), lo = rn_tf32(x - hi): x = hi + lo up to ~2^-22 |x|
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
+}
+// 128 threads split `bytes` of a tile in place (hi) and into the lo copy `lo_off` bytes further; element-wise => layout/swizzle agnostic
+__device__ __forceinline__ void split_region(uint8_t* base, int bytes, int lo_off, int tid) {
+  for (int off = tid * 16; off < bytes; off += 128 * 16) {
+    const float4 v = *reinterpret_cast<const float4*>(base + off);
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<float4*>(base + off) = h;
+    *reinterpret_cast<float4*>(base + off + lo_off) = l;
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool SPLIT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * L::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + L::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + L::STAGES;
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* ready_bar = empty_bar + MAX_STAGES;     // 3xTF32: split pass done (128 arrivals) -> MMA may read the stage
+  uint64_t* tmem_full_bar = ready_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   pdl_launch();  // let the next kernel begin its own prologue right away
@@ -95,6 +124,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
+        mbar_init(&ready_bar[s], 128);
       }
       mbar_init(tmem_full_bar, 1);
       fence_barrier_init();
@@ -150,7 +180,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(SPLIT ? &ready_bar[stage] : &full_bar[stage], phase);
         if (kb == kb_begin) stamp(3);
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -160,9 +190,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // K-major : SWIZZLE_128B, rows 128 B apart, 8-row groups 1024 B apart (SBO); advance 32 B per K step inside the atom.
           // MN-major: tf32 operands must use SWIZZLE_128B_BASE32B ("128B swizzle, 32B atomicity", Swizzle<2,5,2>): 32-wide MN atoms
           //           LBO apart (one TMA box each), K in groups of 4 rows = 512 B (SBO); 8 K-rows = 1024 B per MMA K step.
-          const uint64_t da = A_MN ? umma_desc(sA + k * 1024, MN_BOX_BYTES, 512, 1) : umma_desc(sA + k * UMMA_K * 4, 16, 1024, 2);
-          const uint64_t db = B_MN ? umma_desc(sB + k * 1024, MN_BOX_BYTES, 512, 1) : umma_desc(sB + k * UMMA_K * 4, 16, 1024, 2);
-          umma_tf32(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          const uint32_t oa = A_MN ? k * 1024 : k * UMMA_K * 4, ob = B_MN ? k * 1024 : k * UMMA_K * 4;
+          const uint64_t da = A_MN ? umma_desc(sA + oa, MN_BOX_BYTES, 512, 1) : umma_desc(sA + oa, 16, 1024, 2);
+          const uint64_t db = B_MN ? umma_desc(sB + ob, MN_BOX_BYTES, 512, 1) : umma_desc(sB + ob, 16, 1024, 2);
+          const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
+          if constexpr (SPLIT) {
+            // small terms first: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, all into the same fp32 TMEM accumulator
+            const uint64_t da_lo = A_MN ? umma_desc(sA + L::OPS_BYTES + oa, MN_BOX_BYTES, 512, 1) : umma_desc(sA + L::OPS_BYTES + oa, 16, 1024, 2);
+            const uint64_t db_lo = B_MN ? umma_desc(sB + L::OPS_BYTES + ob, MN_BOX_BYTES, 512, 1) : umma_desc(sB + L::OPS_BYTES + ob, 16, 1024, 2);
+            umma_tf32(tmem_base, da_lo, db, idesc, acc);
+            umma_tf32(tmem_base, da, db_lo, idesc, 1u);
+            umma_tf32(tmem_base, da, db, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, da, db, idesc, acc);
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -184,6 +225,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int et = threadIdx.x - 64;
       for (int j = et; j < BLOCK_N; j += 128) s_bias[j] = (p.bias != nullptr && n0 + j < p.N && blockIdx.z == 0) ? __ldg(p.bias + n0 + j) : 0.f;
       named_bar_sync(1, 128);
+    }
+    if constexpr (SPLIT) {
+      // ---- 3xTF32 split pass: these four warps are idle until the accumulator is complete, so they turn every landed stage into hi/lo
+      const int et = threadIdx.x - 64;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* base = smem + stage * L::STAGE_BYTES;
+        split_region(base, p.a_bytes, L::OPS_BYTES, et);
+        split_region(base + A_TILE_BYTES, p.b_bytes, L::OPS_BYTES, et);
+        fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        mbar_arrive(&ready_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
     }
     mbar_wait(tmem_full_bar, 0);
     if (warp == 2 && lane == 0) stamp(5);
@@ -324,9 +380,9 @@ static int make_tmap(CUtensorMap* tm, const float* base, long long inner, long l
   return r == CUDA_SUCCESS ? 0 : -(1000 + (int)r);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool SPLIT>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, dim3 grid, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, SPLIT>;
   static int env_stages = -1;
   if (env_stages < 0) { const char* e = getenv("GEOMX_GEMM_STAGES"); env_stages = e ? atoi(e) : 0; }
   int stages = L::STAGES;
@@ -336,7 +392,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, di
   p.stages = stages;
   const int smem_bytes = stages * L::STAGE_BYTES + 256 + 512 + 1024;
   static bool attr_set = false;
-  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, SPLIT>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return (int)e;
@@ -346,17 +402,29 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, di
   return (int)cudaGetLastError();
 }
 
+template <int BLOCK_N, bool SPLIT>
+static int dispatch_major2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BLOCK_N, false, false, SPLIT>(ta, tb, p, grid, s);
+  if (!a_mn && b_mn) return launch<BLOCK_N, false, true, SPLIT>(ta, tb, p, grid, s);
+  if (a_mn && !b_mn) return launch<BLOCK_N, true, false, SPLIT>(ta, tb, p, grid, s);
+  return launch<BLOCK_N, true, true, SPLIT>(ta, tb, p, grid, s);
+}
 template <int BLOCK_N>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch<BLOCK_N, false, false>(ta, tb, p, grid, s);
-  if (!a_mn && b_mn) return launch<BLOCK_N, false, true>(ta, tb, p, grid, s);
-  if (a_mn && !b_mn) return launch<BLOCK_N, true, false>(ta, tb, p, grid, s);
-  return launch<BLOCK_N, true, true>(ta, tb, p, grid, s);
+static int dispatch_major(bool split, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t s) {
+  return split ? dispatch_major2<BLOCK_N, true>(a_mn, b_mn, ta, tb, p, grid, s) : dispatch_major2<BLOCK_N, false>(a_mn, b_mn, ta, tb, p, grid, s);
 }
 
 }  // namespace gx
 
 static unsigned long long* g_gemm_dbg = nullptr;
+// 3 = 3xTF32 (fp32-accurate, default), 1 = TF32.  Process-wide; GEOMX_GEMM_PRECISION=tf32|3xtf32 sets the initial value.
+static int g_gemm_prec = -1;
+static int gemm_precision() {
+  if (g_gemm_prec < 0) { const char* e = getenv("GEOMX_GEMM_PRECISION"); g_gemm_prec = (e && (e[0] == 't' || e[0] == '1')) ? 1 : 3; }
+  return g_gemm_prec;
+}
+GX_API int gx_gemm_set_precision(int prec) { g_gemm_prec = (prec == 1) ? 1 : 3; return g_gemm_prec; }
+GX_API int gx_gemm_get_precision() { return gemm_precision(); }
 GX_API int gx_gemm_set_debug(unsigned long long* p) { g_gemm_dbg = p; return 0; }
 
 // A: K-major -> [M][K] with row stride lda; MN-major -> [K][M] with row stride lda.  Same for B with N.
@@ -408,13 +476,16 @@ static int gemm_tf32_impl(const float* A, long long lda, int a_mn, const float* 
   p.wait_flag = wait_flag; p.wait_epoch = wait_epoch; p.stages = 0; p.dbg = g_gemm_dbg;
   p.pool_w = pool_w; p.pool_idx = pool_idx;
   p.a_boxes = a_boxes < 1 ? 1 : a_boxes; p.b_boxes = b_boxes < 1 ? 1 : b_boxes;
-  p.tx_bytes = (a_mn ? p.a_boxes * MN_BOX_BYTES : a_rows * BLOCK_K * 4) + (b_mn ? p.b_boxes * MN_BOX_BYTES : b_rows * BLOCK_K * 4);
+  p.a_bytes = a_mn ? p.a_boxes * MN_BOX_BYTES : a_rows * BLOCK_K * 4;
+  p.b_bytes = b_mn ? p.b_boxes * MN_BOX_BYTES : b_rows * BLOCK_K * 4;
+  p.tx_bytes = p.a_bytes + p.b_bytes;
+  const bool split = gemm_precision() == 3;
   dim3 grid((unsigned)ceil_div(N, block_n), (unsigned)mt, (unsigned)split_k);
   switch (block_n) {
-    case 16: return dispatch_major<16>(a_mn, b_mn, ta, tb, p, grid, stream);
-    case 32: return dispatch_major<32>(a_mn, b_mn, ta, tb, p, grid, stream);
-    case 64: return dispatch_major<64>(a_mn, b_mn, ta, tb, p, grid, stream);
-    default: return dispatch_major<128>(a_mn, b_mn, ta, tb, p, grid, stream);
+    case 16: return dispatch_major<16>(split, a_mn, b_mn, ta, tb, p, grid, stream);
+    case 32: return dispatch_major<32>(split, a_mn, b_mn, ta, tb, p, grid, stream);
+    case 64: return dispatch_major<64>(split, a_mn, b_mn, ta, tb, p, grid, stream);
+    default: return dispatch_major<128>(split, a_mn, b_mn, ta, tb, p, grid, stream);
   }
 }
 
@@ -498,7 +569,7 @@ GX_API int gx_gemm_simt(const float* A, long long lda, int a_mn, const float* B,
   if (M <= 0 || N <= 0) return 0;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.kb_per_split = 0; p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
-  p.relu = relu; p.accumulate = accumulate; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha; p.wait_flag = nullptr; p.wait_epoch = nullptr; p.stages = 0; p.dbg = nullptr; p.a_boxes = p.b_boxes = 0; p.tx_bytes = 0;
+  p.relu = relu; p.accumulate = accumulate; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha; p.wait_flag = nullptr; p.wait_epoch = nullptr; p.stages = 0; p.dbg = nullptr; p.a_boxes = p.b_boxes = 0; p.tx_bytes = 0; p.a_bytes = p.b_bytes = 0;
   dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
   launch_pdl(gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, A, lda, a_mn, B, ldb, b_mn, M, N, K, p);
   return (int)cudaGetLastError();

@@ -81,6 +81,14 @@ struct FabricParams {
   float dgt_alpha;             // EMA factor (DGT_CONTRIBUTION_ALPHA)
   int ll_party_mode;           // 1: the party is the whole universe of this launch (HFA local round): the tile's party owner is also its
                                //    "global" owner, results go to the party members only, no optimizer
+  // ---- direct protocol (hips_fsa_direct_kernel): gradients go straight to the rank(s) that apply the update
+  float* ll_d[MAX_RANKS];      // peer pointers: [world][2n]  per-sender gradient packet slots
+  float* ll_d_mc;              // multicast address of ll_d (replicated mode: one multimem.st reaches every rank)
+  float* ll_e[MAX_RANKS];      // peer pointers: [2n]         fresh parameters from the tile's owner (sharded mode)
+  float* ll_e_mc;              // multicast address of ll_e
+  int direct_replicate;        // 1: EVERY rank reduces and applies every active tile on its own replica of the server state (one hop);
+                               // 0: the tile's global owner does and pushes the result back (two hops)
+  int channel_id;              // 0..7, folded into the packet epoch so that channels can never mistake each other's packets
 };
 
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t v) {
@@ -675,6 +683,127 @@ __global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_ll_kernel(const Fabri
   stamp(5);
 }
 
+// ------------------------------------------------------------------------------------------------------------------ direct protocol
+// The LL kernel above walks the reference's hierarchy hop by hop (worker -> party owner -> global owner -> everybody: three dependent NVLink
+// hops).  On an NVSwitch every rank reaches every other rank at full bandwidth, so the two server tiers can live on the SAME rank without
+// changing what is computed: each gradient tile goes straight to the rank that applies the update, which sums it in the hierarchy's order
+// (inside each party first, `push_scale` on the party aggregate, then across parties — bit-identical on every rank that does it) and runs
+// the optimizer.  Two modes per launch ("channel"):
+//   sharded     (direct_replicate = 0): the tile's global owner (tile_owner, all ranks by default) reduces, updates its shard of the master
+//               weights / optimizer state and multicasts the fresh tile: TWO hops, 1/world of the optimizer work per rank.
+//   replicated  (direct_replicate = 1): every rank receives every gradient tile (one multimem.st per sender) and applies the update to its own
+//               replica of the server state: ONE hop, no result traffic.  Meant for the few small keys whose gradients are produced LAST in
+//               the backward pass (conv0/conv1 of the demo CNN: 13 tiles) — their exchange cannot overlap compute, so it must be short.
+// A training step launches one channel per key group as soon as that group's gradients are complete (HipsCNNTrainStep: the dense keys'
+// sharded channel runs on a side stream underneath the convolution backward pass; the conv keys' replicated channel is the only exposed
+// communication).  Reference for the ordering idea: per-key push with priority = -index (examples/cnn.py:121-125, kvstore_dist.h:565-625).
+// Every channel owns its state block (epoch, CTA counter, optimizer step) and stamps its id into the packet epoch.
+__global__ void __launch_bounds__(FAB_THREADS, 2) hips_fsa_direct_kernel(const FabricParams p) {
+  gx::pdl_wait();
+  gx::pdl_launch();
+  const bool dbg = p.state[3] != 0 && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(p.state + 8);
+  auto stamp = [&](int i) { if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); stamps[i] = t; } };
+  stamp(0);
+  __shared__ float s_red[FAB_THREADS / 32];
+  const uint32_t round = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
+  const uint32_t epoch = (round << 3) | (uint32_t)(p.channel_id & 7);
+  const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
+  const float lr_t = adam_lr(p.h, opt_t);
+  const int S = p.party_size, P = p.num_parties;
+  const long long n2 = 2 * p.n;
+  const bool rep = p.direct_replicate != 0;
+  int* err = p.state + 5;
+  auto fmt_of = [&](int t) -> int { const int f = p.tile_fmt ? (int)p.tile_fmt[t] : FMT_F32; return (f == FMT_F16 || f == FMT_F8) ? f : FMT_F32; };
+
+  // ---- phase 1: push my gradient tiles to the rank(s) that apply them (my own slot included: the reducer reads all slots the same way)
+  for (int ti = blockIdx.x; ti < p.tiles; ti += gridDim.x) {
+    const int t = p.tile_order ? p.tile_order[ti] : ti;
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float* g = p.grad[p.rank] + off;
+    const float4 v = *reinterpret_cast<const float4*>(g);
+    if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long slot = (long long)p.rank * n2 + 2 * off;
+    const int f = fmt_of(t);
+    if (!rep) ll_send_dense(p.ll_d[p.tile_owner[t]] + slot, v, f, epoch);
+    else if (p.ll_d_mc != nullptr) ll_send_dense_mc(p.ll_d_mc + slot, v, f, epoch);
+    else for (int r = 0; r < p.world; ++r) ll_send_dense(p.ll_d[r] + slot, v, f, epoch);
+  }
+  stamp(1);
+  // ---- phase 2: both server tiers on the applying rank: party sums, scale, sum over parties, optimizer
+  for (int ti = blockIdx.x; ti < p.tiles; ti += gridDim.x) {
+    const int t = p.tile_order ? p.tile_order[ti] : ti;
+    if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+    if (!rep && p.tile_owner[t] != p.rank) continue;
+    const int f = fmt_of(t);
+    const long long off = (long long)t * TILE + threadIdx.x * 4;
+    float lr = lr_t, wd = p.h.wd;
+    if (p.tile_mult) { const float2 mm = __ldg(p.tile_mult + t); lr *= mm.x; wd *= mm.y; }
+    float4 W = *reinterpret_cast<float4*>(p.w + off);   // issued before the polls: the state loads overlap the wait
+    float4 A = p.s0 ? *reinterpret_cast<float4*>(p.s0 + off) : make_float4(0, 0, 0, 0);
+    float4 B = p.s1 ? *reinterpret_cast<float4*>(p.s1 + off) : make_float4(0, 0, 0, 0);
+    const float* in = p.ll_d[p.rank] + 2 * off;
+    float4 agg = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < P; ++g) {
+      float4 ps = ll_recv_dense(in + (long long)(g * S) * n2, f, epoch, err);
+      for (int j = 1; j < S; ++j) ps = f4_add(ps, ll_recv_dense(in + (long long)(g * S + j) * n2, f, epoch, err));
+      ps = f4_scale(ps, p.push_scale);
+      agg = g == 0 ? ps : f4_add(agg, ps);
+    }
+    if (p.dgt_contrib != nullptr && (!rep || p.tile_owner[t] == p.rank)) {   // DGT contribution EMA (kv_app.h:853-876), as in the LL kernel
+      float a = fabsf(agg.x) + fabsf(agg.y) + fabsf(agg.z) + fabsf(agg.w);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < FAB_THREADS / 32; ++i) sum += s_red[i];
+        const float mean = sum * (1.f / TILE), old = p.dgt_contrib[t];
+        p.dgt_contrib[t] = old == 0.f ? mean : p.dgt_alpha * old + (1.f - p.dgt_alpha) * mean;
+      }
+    }
+    opt_apply(W.x, agg.x, A.x, B.x, p.h, lr, wd);
+    opt_apply(W.y, agg.y, A.y, B.y, p.h, lr, wd);
+    opt_apply(W.z, agg.z, A.z, B.z, p.h, lr, wd);
+    opt_apply(W.w, agg.w, A.w, B.w, p.h, lr, wd);
+    *reinterpret_cast<float4*>(p.w + off) = W;
+    if (p.s0) *reinterpret_cast<float4*>(p.s0 + off) = A;
+    if (p.s1) *reinterpret_cast<float4*>(p.s1 + off) = B;
+    if (rep) {
+      *reinterpret_cast<float4*>(p.param[p.rank] + off) = W;   // the pull is a local store: every rank holds the fresh replica
+    } else {
+      const int bf = f == FMT_F32 ? FMT_F32 : FMT_F16;          // parameters of fp16 / fp8 keys return as halves
+      if (p.ll_e_mc != nullptr) ll_send_dense_mc(p.ll_e_mc + 2 * off, W, bf, epoch);
+      else for (int r = 0; r < p.world; ++r) ll_send_dense(p.ll_e[r] + 2 * off, W, bf, epoch);
+    }
+  }
+  stamp(2);
+  // ---- phase 3 (sharded mode): pull = unpack the owners' packets into the parameter arena
+  if (!rep) {
+    for (int ti = blockIdx.x; ti < p.tiles; ti += gridDim.x) {
+      const int t = p.tile_order ? p.tile_order[ti] : ti;
+      if (p.tile_active != nullptr && !p.tile_active[t]) continue;
+      const long long off = (long long)t * TILE + threadIdx.x * 4;
+      const int bf = fmt_of(t) == FMT_F32 ? FMT_F32 : FMT_F16;
+      *reinterpret_cast<float4*>(p.param[p.rank] + off) = ll_recv_dense(p.ll_e[p.rank] + 2 * off, bf, epoch, err);
+    }
+  }
+  stamp(4);
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(p.state + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      p.state[1] = 0;
+      p.state[2] = opt_t;
+      p.state[0] = (int)round;
+    }
+  }
+  stamp(5);
+}
+
 // One-sided MixedSync: the party's tile owner applies its aggregate directly on the global owner's HBM under a per-tile lock.
 // locks live in the global owner's flag pad at `lock_off` (uint32 per tile), per-tile optimizer step counts right after them.
 __global__ void __launch_bounds__(FAB_THREADS, 1) hips_async_step_kernel(const FabricParams p, float* const* w_peer, float* const* s0_peer,
@@ -884,6 +1013,12 @@ GX_API int gx_hips_fsa_ll_step(const void* params, int grid, cudaStream_t s) {
   FabricParams p = *reinterpret_cast<const FabricParams*>(params);
   if (grid < 1) grid = 1;
   launch_pdl(hips_fsa_ll_kernel, dim3(grid), dim3(FAB_THREADS), 0, s, p);
+  return GX_CHECK_LAUNCH();
+}
+GX_API int gx_hips_fsa_direct_step(const void* params, int grid, cudaStream_t s) {
+  FabricParams p = *reinterpret_cast<const FabricParams*>(params);
+  if (grid < 1) grid = 1;
+  launch_pdl(hips_fsa_direct_kernel, dim3(grid), dim3(FAB_THREADS), 0, s, p);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_hips_async_step(const void* params, float* const* w_peer, float* const* s0_peer, float* const* s1_peer, int lock_off, int step_off,

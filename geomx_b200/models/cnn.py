@@ -100,6 +100,15 @@ class HipsCNNTrainStep:
             self.fabric.enable_dgt()
             self._dgt_every = max(1, int(dgt_rerank_every))
         f = self.fabric
+        # Key groups ("channels") of the step: the dense keys' gradients are complete long before the convolution backward pass ends, so their
+        # exchange runs underneath it on its own stream (two-hop, optimizer sharded over all ranks); the conv keys come last and use the
+        # one-hop replicated mode — the only communication left on the critical path (reference ordering: push(idx, priority=-idx),
+        # examples/cnn.py:121-125).  GEOMX_STEP_OVERLAP=0 restores the single fused exchange at the end of the step.
+        self.overlap = mode == "dist_sync" and os.environ.get("GEOMX_STEP_OVERLAP", "1") == "1" and (self.topo.world == 1 or f.ll_d is not None)
+        if self.overlap:
+            f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False)
+            f.add_channel("conv", [0, 1, 2, 3], replicate=True)
+        self.fused_mlp = B <= 32 and os.environ.get("GEOMX_FUSED_MLP", "1") == "1"
         self.P = [f.param_view(i) for i in range(10)]
         self.G = [f.grad_view(i) for i in range(10)]
         self._init_params(net)
@@ -120,6 +129,7 @@ class HipsCNNTrainStep:
         self.pull_fused = bool(pull_fused) and self.topo.world >= 1
         self.graph = None
         self._side = torch.cuda.Stream(device=self.device)
+        self._comm = torch.cuda.Stream(device=self.device)
         self.use_graph = use_graph
         self.steps_done = 0
         self.kernels_per_step = 0
@@ -162,6 +172,9 @@ class HipsCNNTrainStep:
         Wc1, Gc1 = P[2].view(32, 400), G[2].view(32, 400)
         kv = (lambda: (f.async_step(), f.grad.tensor.zero_() if self.fused_zero_grad else None)) if self.mode == "dist_async" else \
             (lambda: f.fsa_step(defer_pull_wait=False, zero_grad=self.fused_zero_grad))
+        if self.overlap:
+            kv = lambda: f.channel_step("conv", zero_grad=self.fused_zero_grad)
+        kv_dense = [("hips push+opt+pull (dense keys, overlapped)", "comm", lambda: f.channel_step("dense", zero_grad=self.fused_zero_grad))] if self.overlap else []
         def conv1_fwd():
             # bias + ReLU + 2x2 max-pool in the tcgen05 epilogue (only the pooled map and its arg-max leave the SM); the two-kernel form is
             # the fallback for geometries the in-warp pooling cannot express
@@ -169,9 +182,7 @@ class HipsCNNTrainStep:
                 n.gemm(self.col1, Wc1, self.z2, bias=P[3], relu=True, store_nchw_hw=64)
                 n.maxpool2x2_fwd(self.z2, self.a2, self.idx2)
 
-        return [
-            ("conv0+relu+pool+im2col", "main", lambda: n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)),
-            ("conv1 gemm (bias,relu,maxpool fused)", "main", conv1_fwd),
+        head = [
             ("dense0 gemm", "main", lambda: n.gemm(a2f, P[4], self.a3, bias=P[5], relu=True)),
             ("dense1 gemm", "main", lambda: n.gemm(self.a3, P[6], self.a4, bias=P[7], relu=True)),
             ("head fwd+bwd", "main", lambda: n.head_fwd_bwd(self.a4, P[8], P[9], self.label, self.loss, self.logits, G[8], G[9], self.dz4, G[7], True)),
@@ -179,6 +190,15 @@ class HipsCNNTrainStep:
             ("dz3 gemm (mask,colsum)", "main", lambda: n.gemm(self.dz4, P[6], self.dz3, b_mn=True, mask=self.a3, colsum=G[5])),
             ("dW0 gemm", "side", lambda: n.gemm(self.dz3, a2f, G[4], a_mn=True, b_mn=True)),
             ("da2 gemm", "main", lambda: n.gemm(self.dz3, P[4], self.da2, b_mn=True)),
+        ]
+        if self.fused_mlp:
+            # dense0 -> dense1 -> classifier -> softmax-CE forward and backward: ONE 8-CTA cluster launch instead of the seven above
+            head = [("mlp chain fwd+bwd (cluster)", "main", lambda: n.mlp_chain(a2f, P[4], P[5], P[6], P[7], P[8], P[9], self.label, self.loss, self.logits,
+                                                                              G[4], G[5], G[6], G[7], G[8], G[9], self.da2))]
+        return [
+            ("conv0+relu+pool+im2col", "main", lambda: n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)),
+            ("conv1 gemm (bias,relu,maxpool fused)", "main", conv1_fwd),
+        ] + head + kv_dense + [
             ("pool+relu bwd -> rows", "main", lambda: n.pool_relu_bwd_rows(self.da2.view(B, 32, 4, 4), self.a2, self.idx2, self.dz2rows, G[3])),
             ("dWc1 gemm (split-K)", "side", lambda: n.gemm(self.dz2rows, self.col1, Gc1, a_mn=True, b_mn=True, split_k=16, accumulate=True)),
             ("dcol1 gemm", "main", lambda: n.gemm(self.dz2rows, Wc1, self.dcol1, b_mn=True)),
@@ -192,8 +212,8 @@ class HipsCNNTrainStep:
         # the gradient arena is cleared by the previous step's HiPS kernel (fused zero_grad) unless gradients must stay readable
         if not self.fused_zero_grad:
             f.grad.tensor.zero_()
-        main, side = torch.cuda.current_stream(), self._side
-        forked = False
+        main, side, comm = torch.cuda.current_stream(), self._side, self._comm
+        forked = comm_forked = False
         for i, (name, where, fn) in enumerate(self._steps()):
             if stop_after is not None and i >= stop_after:
                 break
@@ -202,12 +222,20 @@ class HipsCNNTrainStep:
                 with torch.cuda.stream(side):
                     fn()
                 forked = True
+            elif where == "comm":    # a key group's exchange: third branch, after everything issued so far on main and side
+                comm.wait_stream(main)
+                comm.wait_stream(side)
+                with torch.cuda.stream(comm):
+                    fn()
+                comm_forked = True
             else:
                 if where == "join" and forked:
                     main.wait_stream(side); forked = False
                 fn()
         if forked:
             main.wait_stream(side)
+        if comm_forked:
+            main.wait_stream(comm)
         self.kernels_per_step = native.launch_count - before
 
     def capture(self):

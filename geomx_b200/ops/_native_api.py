@@ -36,6 +36,16 @@ def _f32c(t):
 
 
 # --------------------------------------------------------------------------------------------------------------- GEMM
+def set_gemm_precision(mode):
+    """Process-wide multiply precision of the tcgen05 GEMM: ``"3xtf32"`` (default; fp32-accurate: hi/lo split of both operands, three MMAs per
+    K step, fp32 TMEM accumulation — matches the reference's fp32 SGEMM, linalg_impl.h:196-214) or ``"tf32"`` (one MMA, 10-bit mantissa)."""
+    return _lib().gx_gemm_set_precision(1 if str(mode).lower() in ("tf32", "1", "fast") else 3)
+
+
+def gemm_precision():
+    return "tf32" if _lib().gx_gemm_get_precision() == 1 else "3xtf32"
+
+
 def gemm(A, B, D, a_mn=False, b_mn=False, bias=None, mask=None, colsum=None, relu=False, accumulate=False,
          store_nchw_hw=0, alpha=1.0, split_k=1, M=None, N=None, K=None, lda=None, ldb=None, ldd=None,
          wait_flag=None, wait_epoch=None, force_simt=False):
@@ -76,6 +86,19 @@ def gemm_pool(A, B, pooled, idx, OH, OW, bias=None, relu=True, a_mn=False, b_mn=
     if rc == -1:
         return False
     _ck(rc, "gemm_pool")
+    return True
+
+
+def mlp_chain(x, w0, b0, w1, b1, w2, b2, label, loss, logits, dw0, db0, dw1, db1, dw2, db2, dx):
+    """Dense(D1,relu) -> Dense(D2,relu) -> Dense(C) -> softmax-CE, forward and backward, in ONE cluster launch (csrc/kernels/mlp_chain.cu).
+    Returns False when the shapes are not the compiled 512 -> 256 -> 128 -> C<=16, batch <= 32 (callers then use the per-layer kernels)."""
+    B, D0 = x.shape
+    D1, D2, C = w0.shape[0], w1.shape[0], w2.shape[0]
+    rc = _lib().gx_mlp_chain_fwd_bwd(_p(x), _p(w0), _p(b0), _p(w1), _p(b1), _p(w2), _p(b2), _p(label), _p(loss), _p(logits), _p(dw0), _p(db0),
+                                     _p(dw1), _p(db1), _p(dw2), _p(db2), _p(dx), B, D0, D1, D2, C, _s())
+    if rc == -1:
+        return False
+    _ck(rc, "mlp_chain")
     return True
 
 

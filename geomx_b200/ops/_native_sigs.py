@@ -7,7 +7,11 @@ SIGS = {
     # gemm_tcgen05.cu
     "gx_gemm_tf32": [P, L, I, P, L, I, I, I, I, P, L, P, P, L, P, I, I, I, I, F, I, P, P, P],
     "gx_gemm_tf32_pool": [P, L, I, P, L, I, I, I, I, P, P, I, I, I, P, F, P],
+    "gx_mlp_chain_fwd_bwd": [P] * 17 + [I] * 5 + [P],
+    "gx_mlp_chain_smem_bytes": [],
     "gx_gemm_set_debug": [P],
+    "gx_gemm_set_precision": [I],
+    "gx_gemm_get_precision": [],
     "gx_gemm_simt": [P, L, I, P, L, I, I, I, I, P, L, P, P, L, P, I, I, I, I, F, P],
     # conv_pool.cu
     "gx_im2col": [P, P, I, I, I, I, I, I, I, I, I, I, I, P],
@@ -51,6 +55,7 @@ SIGS = {
     "gx_fabric_params_size": [],
     "gx_hips_fsa_step": [P, I, P],
     "gx_hips_fsa_ll_step": [P, I, P],
+    "gx_hips_fsa_direct_step": [P, I, P],
     "gx_hips_max_grid": [],
     "gx_hips_async_step": [P, P, P, P, I, I, I, P],
     "gx_hips_party_allreduce": [P, P, P, F, I, I, I, P],

@@ -34,7 +34,11 @@ class Topology:
         self.world, self.rank, self.num_parties = world, rank, num_parties
         self.party_size = world // num_parties
         self.party, self.local = rank // self.party_size, rank % self.party_size
-        self.num_gs = max(1, min(num_gs, world))
+        # num_gs = 0 ("auto", the fabric default): EVERY rank is a global server and ownership is sharded tile by tile, so the server-side
+        # optimizer work and the result traffic are spread over the whole box.  num_gs >= 1 (DMLC_NUM_GLOBAL_SERVER given explicitly) keeps the
+        # reference's placement: that many server ranks, small keys hashed / big keys partitioned (kvstore_dist_server.h:1770-1810).
+        self.tile_sharded = int(num_gs) <= 0
+        self.num_gs = world if self.tile_sharded else max(1, min(num_gs, world))
         # global servers: spread over parties first (rank 0, S, 2S, ... then 1, S+1, ...)
         order = [p * self.party_size + l for l in range(self.party_size) for p in range(num_parties)]
         self.gs_ranks = order[:self.num_gs]
@@ -46,7 +50,7 @@ class Topology:
         parties = getenv_int("GEOMX_NUM_PARTIES", 0) or getenv_int("DMLC_NUM_GLOBAL_WORKER", 0) or (2 if (world >= 2 and world % 2 == 0) else 1)
         if world % parties:
             parties = 1
-        return Topology(world, rank, parties, getenv_int("DMLC_NUM_GLOBAL_SERVER", 1))
+        return Topology(world, rank, parties, getenv_int("DMLC_NUM_GLOBAL_SERVER", 0))
 
     @property
     def num_workers(self): return self.party_size          # per party  (kv.num_workers)
@@ -166,6 +170,8 @@ class _FabricParams(ctypes.Structure):
         ("tile_fmt", ctypes.c_void_p), ("bsc_u", ctypes.c_void_p), ("bsc_v", ctypes.c_void_p), ("bsc_k", ctypes.c_int),
         ("tile_order", ctypes.c_void_p), ("dgt_contrib", ctypes.c_void_p), ("dgt_alpha", ctypes.c_float),
         ("ll_party_mode", ctypes.c_int),
+        ("ll_d", ctypes.c_void_p * MAX_RANKS), ("ll_d_mc", ctypes.c_void_p), ("ll_e", ctypes.c_void_p * MAX_RANKS), ("ll_e_mc", ctypes.c_void_p),
+        ("direct_replicate", ctypes.c_int), ("channel_id", ctypes.c_int),
     ]
 
 
@@ -227,6 +233,12 @@ class HipsFabric:
             self.ll_c = self.heap.alloc(2 * n, torch.float32)
         else:
             self.ll_a = self.ll_b = self.ll_c = None
+        # direct protocol (hips_fsa_direct_kernel): per-sender gradient slots + a result buffer; world x the arena, so only for small arenas
+        self.ll_d = self.ll_e = None
+        if self.protocol == "ll" and os.environ.get("GEOMX_FABRIC_DIRECT", "1") == "1" and 8 * n * t.world <= getenv_int("GEOMX_DIRECT_MAX_BYTES", 256 << 20):
+            self.ll_d = self.heap.alloc(t.world * 2 * n, torch.float32)
+            self.ll_e = self.heap.alloc(2 * n, torch.float32)
+        self.channels = {}            # name -> dict(id, mask, replicate, grid)
         # --- global-owner state (private HBM) ---------------------------------------------------------------------
         self.w = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.s0 = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -234,8 +246,14 @@ class HipsFabric:
         dev = self.device
         self.tile_key = torch.from_numpy(layout.tile_key()).to(dev)
         self.key_tiles = torch.from_numpy(layout.key_tiles()).to(dev)
-        owner_idx = layout.global_owner_index(t.num_gs, getenv_int("MXNET_KVSTORE_BIGARRAY_BOUND", 1000000))
-        self.tile_owner_np = np.array([t.gs_ranks[i] for i in owner_idx], dtype=np.int32)
+        if t.tile_sharded:
+            # tile ti -> rank ((ti // S) % P) * S + ti % S: balanced over all ranks, and the owner is the tile's party owner inside its own party
+            # (the 3-hop LL kernel then keeps one of the inter-tier hops local)
+            ti = np.arange(T)
+            self.tile_owner_np = (((ti // t.party_size) % t.num_parties) * t.party_size + ti % t.party_size).astype(np.int32)
+        else:
+            owner_idx = layout.global_owner_index(t.num_gs, getenv_int("MXNET_KVSTORE_BIGARRAY_BOUND", 1000000))
+            self.tile_owner_np = np.array([t.gs_ranks[i] for i in owner_idx], dtype=np.int32)
         self.tile_owner = torch.from_numpy(self.tile_owner_np).to(dev)
         self.tile_mult = torch.from_numpy(layout.tile_mult()).to(dev)
         self.tile_active = torch.ones(T, dtype=torch.uint8, device=dev)
@@ -369,6 +387,8 @@ class HipsFabric:
         return h
 
     def _block(self, channel, defer_pull_wait=False, masked=False, zero_grad=False):
+        if channel in self.channels:
+            return self._channel_block(channel, zero_grad)
         key = (channel, defer_pull_wait, masked, zero_grad)
         if key in self._params_cache:
             return self._params_cache[key]
@@ -387,9 +407,15 @@ class HipsFabric:
                 p.ll_a[r] = self.ll_a.peer_ptrs[r] or None
                 p.ll_b[r] = self.ll_b.peer_ptrs[r] or None
                 p.ll_c[r] = self.ll_c.peer_ptrs[r] or None
+            if self.ll_d is not None:
+                p.ll_d[r] = self.ll_d.peer_ptrs[r] or None
+                p.ll_e[r] = self.ll_e.peer_ptrs[r] or None
         p.tile_order = self.tile_order.data_ptr() if self.tile_order is not None else None
         p.dgt_contrib = self.dgt_contrib.data_ptr() if self.dgt_contrib is not None else None
         p.dgt_alpha = float(self.dgt_alpha)
+        mc_ok = self.use_multicast and os.environ.get("GEOMX_LL_MULTICAST", "1") == "1"
+        p.ll_d_mc = (self.ll_d.multicast_ptr or None) if (self.ll_d is not None and mc_ok) else None
+        p.ll_e_mc = (self.ll_e.multicast_ptr or None) if (self.ll_e is not None and mc_ok) else None
         p.ll_c_mc = (self.ll_c.multicast_ptr or None) if (self.ll_a is not None and self.use_multicast and os.environ.get("GEOMX_LL_MULTICAST", "1") == "1") else None
         p.tile_fmt = self.tile_fmt.data_ptr() if self.tile_fmt is not None else None
         p.bsc_u = self.bsc_u.data_ptr() if self.bsc_u is not None else None
@@ -416,6 +442,75 @@ class HipsFabric:
         self._params_cache[key] = p
         return p
 
+    # -- channels (direct protocol) ---------------------------------------------------------------------------------------------
+    def add_channel(self, name, key_indices, replicate=False, grid=None):
+        """Declare a key group that is exchanged by its own launch (``channel_step(name)``), typically as soon as the backward pass has
+        produced that group's gradients.  ``replicate=True`` selects the one-hop mode (every rank applies the update to its own replica of the
+        server state — for the small keys whose exchange cannot overlap compute); otherwise the two-hop sharded mode.  Each channel has its own
+        epoch / optimizer-step state, so channels of one step may run concurrently on different streams."""
+        if name in self.channels or name in self.state:
+            raise ValueError("channel %r exists" % name)
+        if len(self.channels) >= 7:
+            raise ValueError("at most 7 channels")
+        mask = np.zeros(self.tiles, dtype=np.uint8)
+        for i in key_indices:
+            sl = self.layout.slots[i]
+            mask[sl.offset // 1024: sl.offset // 1024 + sl.tiles] = 1
+        active = int(mask.sum())
+        self.state[name] = torch.zeros(64, dtype=torch.int32, device=self.device)
+        self.state[name][2] = int(self.state["fsa"][2].item())        # optimizer step t continues
+        self.channels[name] = {"id": len(self.channels) + 1, "mask": torch.from_numpy(mask).to(self.device), "replicate": bool(replicate),
+                               "keys": list(key_indices), "tiles": active,
+                               "grid": int(grid) if grid else max(1, min(active, int(native.require().gx_hips_max_grid()) // 2))}
+        self._params_cache.clear()
+        return self.channels[name]
+
+    def _channel_formats_direct_ok(self, ch):
+        if self.tile_fmt is None:
+            return True
+        return not bool(((self.tile_fmt == 2) & (ch["mask"] != 0)).any().item())      # Bi-Sparse needs the party aggregate: 3-hop kernel
+
+    def _channel_block(self, name, zero_grad):
+        key = ("channel", name, zero_grad)
+        if key in self._params_cache:
+            return self._params_cache[key]
+        ch = self.channels[name]
+        base = self._block("fsa", False, False, zero_grad)
+        p = _FabricParams.from_buffer_copy(base)
+        p.tile_active = ch["mask"].data_ptr()
+        p.state = self.state[name].data_ptr()
+        p.direct_replicate = int(ch["replicate"])
+        p.channel_id = ch["id"]
+        self._params_cache[key] = p
+        return p
+
+    def channel_step(self, name, zero_grad=False):
+        """Exchange one channel's keys: push -> (both server tiers on the applying rank) -> optimizer -> pull, one launch."""
+        ch = self.channels[name]
+        p = self._channel_block(name, zero_grad)
+        lib = native.require()
+        if self.topo.world == 1:
+            rc = lib.gx_hips_fsa_step(ctypes.byref(p), self.grid, self._stream())         # single rank: the fused arena optimizer on the masked tiles
+        elif self.ll_d is not None and self._channel_formats_direct_ok(ch):
+            rc = lib.gx_hips_fsa_direct_step(ctypes.byref(p), ch["grid"], self._stream())
+        elif self.protocol == "ll":
+            rc = lib.gx_hips_fsa_ll_step(ctypes.byref(p), self.grid, self._stream())      # 3-hop hierarchy walk (Bi-Sparse between the tiers)
+        else:
+            rc = lib.gx_hips_fsa_step(ctypes.byref(p), self.grid, self._stream())
+        native.launch_count += 1
+        if rc:
+            raise RuntimeError("channel_step(%s) failed rc=%d" % (name, rc))
+
+    @property
+    def opt_step(self):
+        """Optimizer step count t (identical on every channel that has run the same number of rounds)."""
+        names = list(self.channels) or ["fsa"]
+        return max(int(self.state[n][2].item()) for n in names)
+
+    def set_opt_step(self, t):
+        for n in ["fsa"] + list(self.channels):
+            self.state[n][2] = int(t)
+
     def _peer_table(self, name, ptrs):
         if name not in self._peer_tables:
             arr = np.array([int(x or 0) for x in ptrs], dtype=np.int64)
@@ -439,8 +534,8 @@ class HipsFabric:
             raise RuntimeError("gx_hips_fsa_step failed rc=%d" % rc)
 
     def check_protocol_errors(self):
-        """True if a bounded LL poll ever gave up (a protocol bug or a dead peer) — state word 5 of the dist_sync channel."""
-        return bool(int(self.state["fsa"][5].item()))
+        """True if a bounded LL poll ever gave up (a protocol bug or a dead peer) — state word 5 of every dist_sync channel."""
+        return any(bool(int(self.state[n][5].item())) for n in ["fsa"] + list(self.channels))
 
     def async_step(self):
         """dist_async (MixedSync): one-sided update of the global owner's HBM under per-tile locks."""

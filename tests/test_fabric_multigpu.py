@@ -25,8 +25,11 @@ def _torchrun(n, script, *args, port=29611, env=None):
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("parties", [1, 2])
-def test_fused_step_matches_nccl_allreduce(parties):
-    rc, out = _torchrun(2, "fabric_check.py", "--parties", str(parties), port=29611 + parties)
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_fused_step_matches_nccl_allreduce(parties, overlap):
+    """overlap=1: per-key-group channels of the direct protocol (dense keys two-hop sharded underneath the conv backward pass, conv keys one-hop
+    replicated); overlap=0: the single 3-hop LL exchange at the end of the step.  Both must equal w - lr * NCCL-all-reduce(grad)/B."""
+    rc, out = _torchrun(2, "fabric_check.py", "--parties", str(parties), port=29611 + parties + 4 * int(overlap), env={"GEOMX_STEP_OVERLAP": overlap})
     assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]
 
 
@@ -45,7 +48,13 @@ def test_wire_formats_fp16_and_bisparse(parties):
 
 @pytest.mark.skipif(_ngpus() < 4, reason="needs >= 4 GPUs")
 def test_two_parties_two_global_servers():
-    rc, out = _torchrun(4, "fabric_check.py", "--parties", "2", "--gs", "2", port=29641)
+    rc, out = _torchrun(4, "fabric_check.py", "--parties", "2", "--gs", "2", port=29641, env={"GEOMX_STEP_OVERLAP": "0"})
+    assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_ngpus() < 4, reason="needs >= 4 GPUs")
+def test_direct_channels_four_ranks():
+    rc, out = _torchrun(4, "fabric_check.py", "--parties", "2", port=29645)
     assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]
 
 

@@ -20,7 +20,7 @@ from geomx_b200.parallel import Topology  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--parties", type=int, default=0)
-    ap.add_argument("--gs", type=int, default=1)
+    ap.add_argument("--gs", type=int, default=0, help="global servers; 0 = every rank, ownership sharded tile by tile (fabric default)")
     ap.add_argument("--no-multicast", action="store_true")
     ap.add_argument("--mode", default="dist_sync")
     a = ap.parse_args()
@@ -35,8 +35,9 @@ def main():
     eng = mx.models.HipsCNNTrainStep(batch_size=B, optimizer=mx.optimizer.SGD(learning_rate=0.1), topo=topo, device=dev, use_graph=False,
                                      use_multicast=not a.no_multicast, mode=a.mode, fused_zero_grad=False)
     if rank == 0:
-        print("fabric backend=%s protocol=%s multicast=%s parties=%d party_size=%d gs=%s" % (eng.fabric.heap.backend, eng.fabric.protocol, eng.fabric.use_multicast,
-                                                                                          parties, topo.party_size, topo.gs_ranks), flush=True)
+        print("fabric backend=%s protocol=%s multicast=%s parties=%d party_size=%d gs=%s channels=%s" % (
+            eng.fabric.heap.backend, eng.fabric.protocol, eng.fabric.use_multicast, parties, topo.party_size, topo.gs_ranks,
+            {k: ("replicated" if v["replicate"] else "sharded") for k, v in eng.fabric.channels.items()}), flush=True)
     g = torch.Generator().manual_seed(100 + rank)
     X = torch.rand(B, 1, 28, 28, generator=g).to(dev); y = torch.randint(0, 10, (B,), generator=g).float().to(dev)
     eng.x.copy_(X); eng.label.copy_(y)
