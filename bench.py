@@ -11,7 +11,7 @@ bracketed by its own CUDA-event pair; between timed steps a 256 MiB buffer is wr
 same K steps through the public API ``HipsCNNTrainStep.step(X_pinned, y_pinned) -> loss`` including the per-step H2D copy of the batch
 from pinned host memory and the D2H read of the loss.
 
-``--impl reference`` reports why the unmodified reference cannot run here (see DESIGN.md §Reference arm).
+``--impl reference`` runs the unmodified reference build under baseline/_ref (baseline/ref_cnn_bench.py; DESIGN.md §Reference arm).
 ``--impl oracle`` runs the same schedule with library ops only (PyTorch/cuDNN/cuBLAS + NCCL all-reduce + torch Adam, CUDA-graphed) — the
 "baseline, not the product" yard-stick of BASELINE.md.
 """
@@ -88,10 +88,17 @@ class ClockSampler:
 
 
 def reference_arm():
-    print(json.dumps({"impl": "reference", "unavailable": "INET-RC/GeoMX is MXNet 1.4 C++: /root/reference has no setup.py/pyproject at its root; "
-                      "python/setup.py needs a prebuilt libmxnet.so whose build requires ZeroMQ, protobuf, OpenBLAS, OpenCV, lapack (absent, "
-                      "no network) and its CUDA arch list stops at sm_75 (Makefile:333) — see DESIGN.md"}))
-    return 0
+    """Run the UNMODIFIED reference (MXNet 1.4.0 / GeoMX, built from /root/reference into baseline/_ref — see baseline/README.md and
+    DESIGN.md §3) on the same metric/config through its own public API.  The script imports nothing of geomx_b200."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    script = os.path.join(here, "baseline", "ref_cnn_bench.py")
+    ref_pkg = os.path.join(here, "baseline", "_ref", "mxnet")
+    if not (os.path.exists(os.path.join(ref_pkg, "libmxnet.so")) or os.path.exists(os.path.join(ref_pkg, "libmxnet.so.xz"))):
+        if int(os.environ.get("RANK", 0)) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/mxnet/libmxnet.so(.xz) not present: run baseline/build_reference.sh "
+                              "(builds /root/reference with USE_CUDA=1 USE_NCCL=1 USE_DIST_KVSTORE=0 for sm_100, ~45 min on 8 cores)"}))
+        return 0
+    os.execv(sys.executable, [sys.executable, script] + sys.argv[1:])
 
 
 def main():

@@ -40,6 +40,18 @@ inline PSKVPlan EncodeKey(Plane plane, int key, size_t num_elems, int num_bytes,
   return p;
 }
 
+// Compressed keys are never partitioned: a Bi-Sparse / 2-bit payload describes the WHOLE tensor ([values | indices], packed 2-bit words), so
+// init, push and pull of such a key must all address the one hashed server — otherwise a server that only holds a slice would scatter
+// indices beyond it away (Bi-Sparse) or dequantise with the wrong length (2-bit).  (The reference splits 2-bit payloads per server with
+// EncodeCompressedKey, kvstore_dist.h:811-897, and keeps Bi-Sparse on one server, kvstore_dist_server.h:1849; one rule for both here.)
+inline bool CompressionPinsKey(int gc_type /*CompressionType*/, size_t num_elems, int dtype, size_t size_lower_bound) {
+  // 1 = kTwoBit (fp32 keys only, dtype 0 = kFloat32), 2 = kBiSparse (keys >= MXNET_KVSTORE_SIZE_LOWER_BOUND)
+  return (gc_type == 1 && dtype == 0) || (gc_type == 2 && num_elems >= size_lower_bound);
+}
+inline PSKVPlan EncodeKeyPlan(Plane plane, int key, size_t num_elems, int num_bytes, size_t bigarray_bound, bool pinned) {
+  return EncodeKey(plane, key, num_elems, num_bytes, pinned ? static_cast<size_t>(-1) : bigarray_bound);
+}
+
 // P3: a tensor is cut into bigarray_bound-element slices with globally increasing slice keys assigned round-robin to servers
 // (kvstore_dist.h:763-799); returns (slice_key, server, begin_elem, num_elems)
 struct P3Slice { int slice_key; int server; size_t begin, elems; };

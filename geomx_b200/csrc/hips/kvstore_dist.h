@@ -30,6 +30,7 @@ class KVStoreDist {
     po->InitEnvironment();
     Environment* env = Environment::Get();
     bigarray_bound_ = static_cast<size_t>(env->GetFloat("MXNET_KVSTORE_BIGARRAY_BOUND", 1000000));
+    size_lower_bound_ = static_cast<size_t>(env->GetFloat("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000));
     enable_p3_ = env->GetInt("ENABLE_P3", 0) != 0;
     if (po->is_worker()) {
       ps_worker_.reset(new KVWorker(0, 0));
@@ -141,7 +142,7 @@ class KVStoreDist {
       }
     }
     const int bytes = DTypeSize(dtype);
-    PSKVPlan plan = EncodeKey(kLocal, key, elems, bytes, bigarray_bound_);
+    PSKVPlan plan = EncodeKeyPlan(kLocal, key, elems, bytes, bigarray_bound_, Pinned(elems, dtype));
     SArray<Key> keys;
     for (Key k : plan.keys) keys.push_back(k);
     auto vals = std::make_shared<SArray<char>>(static_cast<char*>(out), elems * bytes, false);
@@ -211,6 +212,12 @@ class KVStoreDist {
   }
 
   void SetGradientCompression(const std::string& type, float threshold) {
+    {
+      // the key -> server plan depends on the compression type, so it has to be fixed before the first key exists (the reference makes the
+      // same demand: "Gradient compression must be set before init", kvstore.py set_gradient_compression)
+      std::lock_guard<std::mutex> lk(mu_);
+      HIPS_CHECK_MSG(info_.empty(), "set_gradient_compression must be called before the first kv.init");
+    }
     gc_.SetParams(type, threshold);
     // master worker: tell the global servers (rank 0 relays to the parties' servers); ordinary rank-0 worker: tell the local server
     if (rank() == 0 || is_master_worker()) SendCommandToServers(static_cast<int>(CommandType::kSetGradientCompression), gc_.EncodeParams());
@@ -233,6 +240,8 @@ class KVStoreDist {
     return h;
   }
   int NewDoneHandle() { return Track({}); }
+  // compressed keys live un-partitioned on their hashed server (key_codec.h CompressionPinsKey): init, push and pull agree on ONE plan
+  bool Pinned(size_t elems, int dtype) const { return CompressionPinsKey(static_cast<int>(gc_.type()), elems, dtype, size_lower_bound_); }
 
   int PushImpl(int key, const void* data, size_t elems, int dtype, int priority, bool allow_compress) {
     const int bytes = DTypeSize(dtype);
@@ -252,14 +261,14 @@ class KVStoreDist {
     } else if (enable_p3_ && allow_compress) {
       // P3: the response of the push carries the updated parameters; keep them for the following pull
       auto buf = std::make_shared<std::vector<char>>(static_cast<const char*>(data), static_cast<const char*>(data) + elems * bytes);
-      PSKVPlan plan = EncodeKey(kLocal, key, elems, bytes, bigarray_bound_);
+      PSKVPlan plan = EncodeKeyPlan(kLocal, key, elems, bytes, bigarray_bound_, Pinned(elems, dtype));
       SArray<Key> keys; for (Key k : plan.keys) keys.push_back(k);
       SArray<int> lens; for (int l : plan.lens) lens.push_back(l);
       SArray<char> vals(buf->data(), buf->size(), false);
       const int cmd = GetCommandType(RequestType::kDefaultPushPull, dtype);
       tss.push_back(ps_worker_->P3_ZPush(keys, vals, lens, cmd, [this, key, buf]() { std::lock_guard<std::mutex> lk(mu_); p3_buf_[key] = *buf; }, priority, key));
     } else {
-      PSKVPlan plan = EncodeKey(kLocal, key, elems, bytes, bigarray_bound_);
+      PSKVPlan plan = EncodeKeyPlan(kLocal, key, elems, bytes, bigarray_bound_, Pinned(elems, dtype));
       SArray<Key> keys; for (Key k : plan.keys) keys.push_back(k);
       SArray<int> lens; for (int l : plan.lens) lens.push_back(l);
       SArray<char> vals(static_cast<char*>(const_cast<void*>(data)), elems * bytes, false);
@@ -286,7 +295,7 @@ class KVStoreDist {
   std::unordered_map<int, std::vector<float>> residual_;
   std::unordered_map<int, std::vector<char>> p3_buf_;
   int next_handle_ = 1;
-  size_t bigarray_bound_ = 1000000;
+  size_t bigarray_bound_ = 1000000, size_lower_bound_ = 200000;
   bool enable_p3_ = false, started_ = false;
 };
 

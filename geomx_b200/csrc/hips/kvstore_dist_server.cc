@@ -275,8 +275,13 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
       for (size_t j = 0; j < row_len; ++j) incoming[base + j] += rows[r * row_len + j];
     }
   } else if (type.requestType == RequestType::kCompressedPushPull) {
+    HIPS_CHECK_MSG(data.vals.size() == static_cast<size_t>(GradientCompression::CompressedSize2Bit(static_cast<int64_t>(n))) * sizeof(uint32_t),
+                   "2-bit push of key " + std::to_string(key) + " does not match the stored tensor (compressed keys are not partitioned: "
+                   "set_gradient_compression before kv.init on every worker)");
     gc_.Dequantize2Bit(reinterpret_cast<const uint32_t*>(data.vals.data()), incoming.data(), static_cast<int64_t>(n));
   } else {
+    HIPS_CHECK_MSG(data.vals.size() % (2 * sizeof(float)) == 0 && data.vals.size() / (2 * sizeof(float)) <= n,
+                   "Bi-Sparse push of key " + std::to_string(key) + " is larger than the stored tensor");
     GradientCompression::BSCDecompress(reinterpret_cast<const float*>(data.vals.data()), data.vals.size() / sizeof(float), incoming.data(), n);
   }
   // central-party workers only train when DMLC_ENABLE_CENTRAL_WORKER=1 (reference :1274-1275)
@@ -388,7 +393,7 @@ void KVStoreDistServer::PushToGlobal(int key, const DataHandleType& type) {
     lens.push_back(static_cast<int>(vals.size()));
     cmd = GetCommandType(RequestType::kCompressedPushPull, kFloat32);
   } else {
-    PSKVPlan plan = EncodeKey(kGlobal, key, n, DTypeSize(e.dtype), bigarray_bound_);
+    PSKVPlan plan = EncodeKeyPlan(kGlobal, key, n, DTypeSize(e.dtype), bigarray_bound_, CompressionPinsKey(static_cast<int>(gc_.type()), n, e.dtype, size_lower_bound_));
     for (Key k : plan.keys) keys.push_back(k);
     for (int l : plan.lens) lens.push_back(l);
     vals.CopyFrom(e.data.data(), e.data.size());
@@ -420,7 +425,7 @@ void KVStoreDistServer::PullFromGlobal(int key, const DataHandleType& type) {
     cmd = GetCommandType(RequestType::kDefaultPushPull, e.dtype);
     r.parts_expected = 1;
   } else {
-    PSKVPlan plan = EncodeKey(kGlobal, key, n, DTypeSize(e.dtype), bigarray_bound_);
+    PSKVPlan plan = EncodeKeyPlan(kGlobal, key, n, DTypeSize(e.dtype), bigarray_bound_, CompressionPinsKey(static_cast<int>(gc_.type()), n, e.dtype, size_lower_bound_));
     for (Key k : plan.keys) keys.push_back(k);
     cmd = GetCommandType(RequestType::kDefaultPushPull, e.dtype);
     r.parts_expected = static_cast<int>(plan.keys.size());

@@ -393,7 +393,10 @@ GX_API int gx_mlp_chain_fwd_bwd(const float* x, const float* w0, const float* b0
   MlpChainParams p;
   p.x = x; p.w0 = w0; p.b0 = b0; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.label = label; p.loss = loss; p.logits = logits;
   p.dw0 = dw0; p.db0 = db0; p.dw1 = dw1; p.db1 = db1; p.dw2 = dw2; p.db2 = db2; p.dx = dx; p.B = B; p.C = C;
-  launch_pdl(kern, dim3(MC_CLUSTER), dim3(MC_THREADS), (size_t)L::BYTES, stream, p);
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("GEOMX_MLP_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
+  if (use_pdl) launch_pdl(kern, dim3(MC_CLUSTER), dim3(MC_THREADS), (size_t)L::BYTES, stream, p);
+  else kern<<<dim3(MC_CLUSTER), dim3(MC_THREADS), (size_t)L::BYTES, stream>>>(p);
   return GX_CHECK_LAUNCH();
 }
 GX_API int gx_mlp_chain_smem_bytes() { return MlpSmem<512, 256, 128>::BYTES; }

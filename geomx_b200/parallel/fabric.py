@@ -246,11 +246,19 @@ class HipsFabric:
         dev = self.device
         self.tile_key = torch.from_numpy(layout.tile_key()).to(dev)
         self.key_tiles = torch.from_numpy(layout.key_tiles()).to(dev)
-        if t.tile_sharded:
+        if t.tile_sharded and self.protocol == "ll":
             # tile ti -> rank ((ti // S) % P) * S + ti % S: balanced over all ranks, and the owner is the tile's party owner inside its own party
             # (the 3-hop LL kernel then keeps one of the inter-tier hops local)
             ti = np.arange(T)
             self.tile_owner_np = (((ti // t.party_size) % t.num_parties) * t.party_size + ti % t.party_size).astype(np.int32)
+        elif t.tile_sharded:
+            # flag ("bulk") protocol: its per-key ready flags need ONE owner per key -> whole keys, largest first onto the least loaded rank
+            load = np.zeros(t.world, dtype=np.int64)
+            self.tile_owner_np = np.zeros(T, dtype=np.int32)
+            for sl in sorted(layout.slots, key=lambda s: -s.tiles):
+                r = int(np.argmin(load))
+                load[r] += sl.tiles
+                self.tile_owner_np[sl.offset // 1024: sl.offset // 1024 + sl.tiles] = r
         else:
             owner_idx = layout.global_owner_index(t.num_gs, getenv_int("MXNET_KVSTORE_BIGARRAY_BOUND", 1000000))
             self.tile_owner_np = np.array([t.gs_ranks[i] for i in owner_idx], dtype=np.int32)

@@ -31,7 +31,7 @@ if master or (os.environ.get("TEST_STANDALONE") == "1" and kv.rank == 0):
         kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1))
     if mode in ("bsc", "bsc_async"):
         kv.set_gradient_compression({"type": "bsc", "threshold": 0.1})
-if mode == "2bit" and not master:
+if mode == "2bit":      # every worker (master included, it configures the global servers), as the reference scripts do
     kv.set_gradient_compression({"type": "2bit", "threshold": 0.5})
 time.sleep(0.5)
 dt = "float16" if mode == "fp16" else "float32"
@@ -105,12 +105,16 @@ for step in range(steps):
             local = mx.nd.array(np.full(shapes[i], float(step + 1) * (gid + 1), dtype=np.float32))
             kv.push(i, local / kv.num_workers, priority=-i)
         else:
-            g = mx.nd.array(np.full(shapes[i], 0.5 * (gid + 1) * (1 if mode != "2bit" else 2), dtype=np.float32)).astype(dt)
-            kv.push(i, g, priority=-i)
+            g = np.full(shapes[i], 0.5 * (gid + 1) * (1 if mode != "2bit" else 2), dtype=np.float32)
+            if os.environ.get("TEST_NONUNIFORM") == "1":          # ramp: the largest entries sit at the END of the tensor
+                n_el = int(np.prod(shapes[i]))
+                g = (g.reshape(-1) * (np.arange(n_el, dtype=np.float32) + 1.0) / n_el).reshape(shapes[i])
+            kv.push(i, mx.nd.array(g).astype(dt), priority=-i)
         kv.pull(i, p, priority=-i)
     mx.nd.waitall()
     out["vals"].append([float(p.astype("float32").asnumpy().reshape(-1)[0]) for p in params])
     out.setdefault("last", [float(p.astype("float32").asnumpy().reshape(-1)[-1]) for p in params])
+    out.setdefault("nonzeros", [int(np.count_nonzero(p.astype("float32").asnumpy())) for p in params])
 if prof_path and kv.rank == 0:
     mx.profiler.pause(profile_process="server"); mx.profiler.resume(profile_process="server")
     mx.profiler.dump(profile_process="server")

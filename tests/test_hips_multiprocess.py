@@ -184,6 +184,23 @@ def test_hips_multigps_bigarray_python_updater():
         assert abs(r["last"][2] - r["vals"][0][2]) < 1e-6      # both halves of the partitioned 300-element key updated
 
 
+def test_multigps_keeps_compressed_keys_on_one_server():
+    """2 global servers + a key above MXNET_KVSTORE_BIGARRAY_BOUND: dense keys of that size are partitioned across the servers, but a
+    Bi-Sparse / 2-bit key must live whole on its hashed server (init, push and pull use one plan) — with a ramp gradient the top-k entries
+    all lie in the second half of the tensor, which a server holding only the first slice would silently drop."""
+    env = {"MXNET_KVSTORE_BIGARRAY_BOUND": "100", "MXNET_KVSTORE_SIZE_LOWER_BOUND": "100", "TEST_STEPS": "1", "TEST_NONUNIFORM": "1"}
+    res = launch_hips(dict(env, TEST_MODE="bsc"), global_servers=2)
+    assert len(res) == 4
+    for r in res:
+        # key 2 (300 elements, threshold 0.1): every party sends its 30 largest entries = indices 270..299; the pull returns their sum
+        assert r["nonzeros"][2] == 30, r["nonzeros"]
+        assert abs(r["last"][2] - 0.5 * (1 + 2 + 3 + 4)) < 1e-5
+    res = launch_hips(dict(env, TEST_MODE="2bit", TEST_STEPS="2"), global_servers=2)
+    assert len(res) == 4                      # used to abort the local server with "pull response size mismatch"
+    for r in res:
+        assert r["nonzeros"][2] == 300
+
+
 def test_hips_bsc_and_hfa():
     res = launch_hips({"TEST_MODE": "bsc", "MXNET_KVSTORE_SIZE_LOWER_BOUND": "100", "TEST_STEPS": "2"})
     assert len(res) == 4
