@@ -51,9 +51,9 @@ class NativeOptimizer {
     const float lr = s_.name == "adam" ? s_.lr * std::sqrt(1.f - std::pow(s_.beta2, (float)st.t)) / (1.f - std::pow(s_.beta1, (float)st.t)) : s_.lr;
     for (size_t i = 0; i < n; ++i) {
       float gi = g[i] * s_.rescale;
+      if (s_.name == "adam") gi += s_.wd * w[i];      // adam_update clips grad + wd*w (optimizer_op-inl.h:840-873); sgd / dcasgd clip the raw gradient
       if (s_.clip >= 0.f) gi = std::fmin(std::fmax(gi, -s_.clip), s_.clip);
       if (s_.name == "adam") {
-        gi += s_.wd * w[i];
         st.a[i] = s_.beta1 * st.a[i] + (1.f - s_.beta1) * gi;
         st.b[i] = s_.beta2 * st.b[i] + (1.f - s_.beta2) * gi * gi;
         w[i] -= lr * st.a[i] / (std::sqrt(st.b[i]) + s_.eps);

@@ -30,7 +30,9 @@ namespace gx {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;
 constexpr int UMMA_K = 8;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 192;         // TF32 mode: warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int GEMM_THREADS_SPLIT = 320;   // 3xTF32 mode: + warps 6-9 = hi/lo split pass (warps 2-5 drain the accumulator chunks)
+constexpr int ACC_CHUNK_KB = 4;           // 3xTF32: K blocks accumulated in one TMEM buffer before it is drained into registers
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB either major
 constexpr int MN_BOX_BYTES = 32 * BLOCK_K * 4;       // one 32(MN) x 32(K) box = 4 KiB
 
@@ -90,7 +92,7 @@ __device__ __forceinline__ void split_region(uint8_t* base, int bytes, int lo_of
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool SPLIT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(SPLIT ? GEMM_THREADS_SPLIT : GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using L = SmemLayout<BLOCK_N, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
@@ -100,7 +102,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* ready_bar = empty_bar + MAX_STAGES;     // 3xTF32: split pass done (128 arrivals) -> MMA may read the stage
   uint64_t* tmem_full_bar = ready_bar + MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* acc_full_bar = tmem_full_bar + 1;       // [2] 3xTF32: chunk accumulated in TMEM buffer b -> drain warps
+  uint64_t* acc_empty_bar = acc_full_bar + 2;       // [2] buffer b drained (128 arrivals) -> MMA may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
 
   pdl_launch();  // let the next kernel begin its own prologue right away
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -113,7 +117,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
-  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  // The tensor core's fp32 accumulation is not round-to-nearest: its error is biased and grows linearly with the number of MMAs folded into
+  // one TMEM accumulator (measured: ~2e-8 relative per MMA, 2.9e-5 at K = 4096).  The 3xTF32 mode therefore accumulates at most
+  // ACC_CHUNK_KB K blocks (48 MMAs) per TMEM buffer, alternates between two buffers and lets the epilogue warps add every finished chunk
+  // into fp32 registers with IEEE adds while the tensor core works on the next one.
+  constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t TMEM_COLS = SPLIT ? 2 * ACC_COLS : ACC_COLS;
+  const int nchunks = SPLIT ? (kb_end - kb_begin + ACC_CHUNK_KB - 1) / ACC_CHUNK_KB : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -127,6 +137,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_init(&ready_bar[s], 128);
       }
       mbar_init(tmem_full_bar, 1);
+      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full_bar[b], 1); mbar_init(&acc_empty_bar[b], 128); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -180,6 +191,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
+        uint32_t tmem_d = tmem_base;
+        bool chunk_first = (kb == kb_begin), chunk_last = (kb == kb_end - 1);
+        int ci = 0;
+        if constexpr (SPLIT) {
+          ci = (kb - kb_begin) / ACC_CHUNK_KB;
+          const int within = (kb - kb_begin) - ci * ACC_CHUNK_KB;
+          chunk_first = within == 0;
+          chunk_last = within == ACC_CHUNK_KB - 1 || kb == kb_end - 1;
+          tmem_d = tmem_base + static_cast<uint32_t>(ci & 1) * ACC_COLS;
+          if (chunk_first && ci >= 2) {      // the buffer still holds chunk ci-2: wait until the drain warps have taken it
+            mbar_wait(&acc_empty_bar[ci & 1], static_cast<uint32_t>(((ci >> 1) - 1) & 1));
+            tc_fence_after();
+          }
+        }
         mbar_wait(SPLIT ? &ready_bar[stage] : &full_bar[stage], phase);
         if (kb == kb_begin) stamp(3);
         tc_fence_after();
@@ -193,23 +218,38 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t oa = A_MN ? k * 1024 : k * UMMA_K * 4, ob = B_MN ? k * 1024 : k * UMMA_K * 4;
           const uint64_t da = A_MN ? umma_desc(sA + oa, MN_BOX_BYTES, 512, 1) : umma_desc(sA + oa, 16, 1024, 2);
           const uint64_t db = B_MN ? umma_desc(sB + ob, MN_BOX_BYTES, 512, 1) : umma_desc(sB + ob, 16, 1024, 2);
-          const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
+          const uint32_t acc = (!chunk_first || k > 0) ? 1u : 0u;
           if constexpr (SPLIT) {
             // small terms first: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, all into the same fp32 TMEM accumulator
             const uint64_t da_lo = A_MN ? umma_desc(sA + L::OPS_BYTES + oa, MN_BOX_BYTES, 512, 1) : umma_desc(sA + L::OPS_BYTES + oa, 16, 1024, 2);
             const uint64_t db_lo = B_MN ? umma_desc(sB + L::OPS_BYTES + ob, MN_BOX_BYTES, 512, 1) : umma_desc(sB + L::OPS_BYTES + ob, 16, 1024, 2);
-            umma_tf32(tmem_base, da_lo, db, idesc, acc);
-            umma_tf32(tmem_base, da, db_lo, idesc, 1u);
-            umma_tf32(tmem_base, da, db, idesc, 1u);
+            umma_tf32(tmem_d, da_lo, db, idesc, acc);
+            umma_tf32(tmem_d, da, db_lo, idesc, 1u);
+            umma_tf32(tmem_d, da, db, idesc, 1u);
           } else {
-            umma_tf32(tmem_base, da, db, idesc, acc);
+            umma_tf32(tmem_d, da, db, idesc, acc);
           }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (SPLIT && chunk_last && ci < nchunks - 1) umma_commit(&acc_full_bar[ci & 1]);   // chunk complete -> drain (the last chunk goes to the epilogue)
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
       stamp(4);
+    }
+  } else if (SPLIT && warp >= 6) {
+    // ================================ 3xTF32 split pass (warps 6-9): every landed stage -> hi (in place) + lo copy ================================
+    const int et = threadIdx.x - 192;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      uint8_t* base = smem + stage * L::STAGE_BYTES;
+      split_region(base, p.a_bytes, L::OPS_BYTES, et);
+      split_region(base + A_TILE_BYTES, p.b_bytes, L::OPS_BYTES, et);
+      fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+      mbar_arrive(&ready_bar[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else {
     // ================================ epilogue (4 warps = 128 TMEM lanes) ================================
@@ -226,32 +266,40 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int j = et; j < BLOCK_N; j += 128) s_bias[j] = (p.bias != nullptr && n0 + j < p.N && blockIdx.z == 0) ? __ldg(p.bias + n0 + j) : 0.f;
       named_bar_sync(1, 128);
     }
+    // 3xTF32: running fp32 sums of the drained accumulator chunks (IEEE adds in registers)
+    float sum[SPLIT ? BLOCK_N : 1];
+#pragma unroll
+    for (int j = 0; j < (SPLIT ? BLOCK_N : 1); ++j) sum[j] = 0.f;
     if constexpr (SPLIT) {
-      // ---- 3xTF32 split pass: these four warps are idle until the accumulator is complete, so they turn every landed stage into hi/lo
-      const int et = threadIdx.x - 64;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        uint8_t* base = smem + stage * L::STAGE_BYTES;
-        split_region(base, p.a_bytes, L::OPS_BYTES, et);
-        split_region(base + A_TILE_BYTES, p.b_bytes, L::OPS_BYTES, et);
-        fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
-        mbar_arrive(&ready_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      for (int ci = 0; ci < nchunks - 1; ++ci) {
+        const int b = ci & 1;
+        mbar_wait(&acc_full_bar[b], static_cast<uint32_t>((ci >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+          uint32_t r[32];
+          const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(b) * ACC_COLS + static_cast<uint32_t>(c0);
+          if constexpr (CH == 32) tmem_ld_32x32(ta, r); else tmem_ld_32x16(ta, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) sum[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty_bar[b]);
       }
     }
     mbar_wait(tmem_full_bar, 0);
     if (warp == 2 && lane == 0) stamp(5);
     tc_fence_after();
     const bool have_acc = kb_end > kb_begin;
+    const uint32_t fin = SPLIT ? static_cast<uint32_t>((nchunks - 1) & 1) * ACC_COLS : 0u;   // TMEM buffer of the last chunk
     if (warp_has_rows) {
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
-        if constexpr (CH == 32) tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
-        else tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+        if constexpr (CH == 32) tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + fin + static_cast<uint32_t>(c0), r);
+        else tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + fin + static_cast<uint32_t>(c0), r);
         // issue the (optional) ReLU-mask row loads before waiting on TMEM so that both latencies overlap
         float mk[CH];
         const bool full = n0 + c0 + CH <= p.N;
@@ -269,7 +317,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          float x = have_acc ? __uint_as_float(r[j]) * p.alpha : 0.f;
+          float x = have_acc ? (__uint_as_float(r[j]) + (SPLIT ? sum[c0 + j] : 0.f)) * p.alpha : 0.f;
           x += s_bias[c0 + j];
           if (p.relu) x = fmaxf(x, 0.f);
           if (p.mask != nullptr) x = mk[j] > 0.f ? x : 0.f;
@@ -398,7 +446,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, di
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, ta, tb, p);
+  launch_pdl(kern, dim3(grid), dim3(SPLIT ? GEMM_THREADS_SPLIT : GEMM_THREADS), smem_bytes, stream, ta, tb, p);
   return (int)cudaGetLastError();
 }
 

@@ -100,9 +100,8 @@ __device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_floa
 
 __device__ __forceinline__ void opt_apply(float& w, float g, float& a, float& b, const OptHyperF& h, float lr, float wd) {
   if (h.kind == 1) {
-    g *= h.rescale;
+    g = fmaf(wd, w, g * h.rescale);            // adam_update: the regularised gradient is what gets clipped (optimizer_op-inl.h:840-873)
     if (h.clip >= 0.f) g = fminf(fmaxf(g, -h.clip), h.clip);
-    g = fmaf(wd, w, g);
     a = h.beta1 * a + (1.f - h.beta1) * g;
     b = h.beta2 * b + (1.f - h.beta2) * g * g;
     w -= lr * a / (sqrtf(b) + h.eps);

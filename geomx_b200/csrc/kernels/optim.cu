@@ -40,7 +40,9 @@ __device__ __forceinline__ void opt_elem(float& w, float g, float& s0, float& s1
     if (h.momentum != 0.f) { s0 = h.momentum * s0 - lr * g; w += s0; }
     else w -= lr * g;
   } else if (KIND == OPT_ADAM) {
-    g = prep_grad(g, w, h, wd);
+    // adam_update clips the REGULARISED gradient: rescale, + wd*w, then clip (src/operator/optimizer_op-inl.h:840-873)
+    g = fmaf(wd, w, g * h.rescale);
+    if (h.clip >= 0.f) g = fminf(fmaxf(g, -h.clip), h.clip);
     s0 = h.beta1 * s0 + (1.f - h.beta1) * g;
     s1 = h.beta2 * s1 + (1.f - h.beta2) * g * g;
     w -= lr * s0 / (sqrtf(s1) + h.eps);

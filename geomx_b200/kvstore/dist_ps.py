@@ -194,7 +194,9 @@ class KVStoreDist(KVStoreBase):
         if self.rank == 0:
             spec = optimizer.spec()
             import os
-            if spec is not None and os.environ.get("GEOMX_PY_UPDATER", "0") != "1":
+            # the declarative spec carries one scalar lr / wd: an lr_scheduler or per-parameter multipliers (e.g. wd_mult = 0 on biases) need the
+            # optimizer object itself on the server, which is what the reference always ships (kvstore.py:452-499)
+            if spec is not None and optimizer.spec_is_static() and os.environ.get("GEOMX_PY_UPDATER", "0") != "1":
                 self._kv.send_command_to_servers(CMD_OPT_SPEC, spec_to_string(spec))
             else:
                 self._kv.send_command_to_servers(CMD_CONTROLLER, pickle.dumps(optimizer, 0).decode("latin1"))

@@ -224,7 +224,8 @@ class HipsCNNTrainStep:
                 forked = True
             elif where == "comm":    # a key group's exchange: third branch, after everything issued so far on main and side
                 comm.wait_stream(main)
-                comm.wait_stream(side)
+                if forked:           # (a stream that has no work of this step yet must not be waited on: it is not part of a graph capture)
+                    comm.wait_stream(side)
                 with torch.cuda.stream(comm):
                     fn()
                 comm_forked = True

@@ -161,16 +161,31 @@ class Optimizer:
             wd *= self.wd_mult.get(self.idx2name[index], 1.0)
         return wd
 
-    def _prep_grad(self, grad, weight=None, wd=0.0):
+    def _prep_grad(self, grad, weight=None, wd=0.0, wd_before_clip=False):
+        """rescale -> clip -> + wd*w (sgd_update & friends), or rescale -> + wd*w -> clip when ``wd_before_clip`` (adam_update clips the
+        regularised gradient: src/operator/optimizer_op-inl.h:840-873)."""
         g = _t(grad)
         if g.dtype != torch.float32 and weight is not None and _t(weight).dtype == torch.float32:
             g = g.float()
         g = g * self.rescale_grad
+        if wd_before_clip and wd and weight is not None:
+            g = g + wd * _t(weight)
         if self.clip_gradient is not None:
             g = g.clamp(-self.clip_gradient, self.clip_gradient)
-        if wd and weight is not None:
+        if not wd_before_clip and wd and weight is not None:
             g = g + wd * _t(weight)
         return g
+
+    def spec_is_static(self):
+        """True when ``spec()`` (scalar lr / wd) describes this optimizer completely: no lr_scheduler and no per-parameter lr / wd multiplier
+        different from 1.  Servers only execute the native spec in that case; otherwise the pickled optimizer itself is shipped, as the
+        reference always does (python/mxnet/kvstore.py:452-499), so the scheduler and the multipliers run server-side."""
+        if self.lr_scheduler is not None:
+            return False
+        mults = list(self.lr_mult.values()) + [getattr(p, "lr_mult", 1.0) for p in self.param_dict.values()]
+        if self.wd != 0.0:      # weight-decay multipliers (wd_mult = 0 on biases / gamma / beta) only matter when there is weight decay
+            mults += list(self.wd_mult.values()) + [getattr(p, "wd_mult", 1.0) for p in self.param_dict.values()]
+        return all(float(m) == 1.0 for m in mults)
 
     def __getstate__(self):
         d = self.__dict__.copy()
@@ -358,7 +373,7 @@ class Adam(Optimizer):
                 native.adam_update(w, _t(grad), m, v, lr, self.beta1, self.beta2, self.epsilon, wd,
                                    self.rescale_grad, -1.0 if self.clip_gradient is None else self.clip_gradient)
                 return
-        g = self._prep_grad(grad, weight, wd)
+        g = self._prep_grad(grad, weight, wd, wd_before_clip=True)
         m.mul_(self.beta1).add_(g, alpha=1 - self.beta1)
         v.mul_(self.beta2).addcmul_(g, g, value=1 - self.beta2)
         w.addcdiv_(m, v.sqrt().add_(self.epsilon), value=-lr)

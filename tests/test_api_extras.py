@@ -252,3 +252,23 @@ def test_collective_kvstore_under_torchrun_on_cpu():
     # MixedSync: SGD is linear, so applying the party aggregates one after the other equals the synchronous result
     res = _torchrun_cpu(4, {"TEST_MODE": "async", "GEOMX_NUM_PARTIES": "2", "TEST_STEPS": "1"})
     assert all(r["vals"][0][0] == pytest.approx(1.0 - 0.1 * gsum, abs=1e-5) for r in res)
+
+
+def test_optimizer_spec_is_static_and_adam_clip_order():
+    """the native server spec is only used when it is complete (no scheduler / multipliers); Adam clips grad + wd*w like adam_update."""
+    import numpy as np
+    import geomx_b200 as mx
+    o = mx.optimizer.Adam(learning_rate=0.01)
+    assert o.spec_is_static()
+    assert not mx.optimizer.Adam(learning_rate=0.01, lr_scheduler=mx.lr_scheduler.FactorScheduler(step=10, factor=0.5)).spec_is_static()
+    o2 = mx.optimizer.SGD(learning_rate=0.1, wd=1e-4, param_idx2name={0: "fc_weight", 1: "fc_bias"})
+    assert not o2.spec_is_static()            # wd_mult = 0 on the bias
+    o3 = mx.optimizer.SGD(learning_rate=0.1, param_idx2name={0: "fc_weight", 1: "fc_bias"})
+    assert o3.spec_is_static()                # no weight decay: the multipliers are irrelevant
+    # Adam, one step, clip below |g + wd*w|: m = (1-b1)*clip(g + wd*w)
+    w = mx.nd.array(np.array([10.0, -10.0], dtype=np.float32)); g = mx.nd.array(np.array([0.5, -0.5], dtype=np.float32))
+    opt = mx.optimizer.Adam(learning_rate=0.1, wd=0.1, clip_gradient=1.0)
+    st = opt.create_state(0, w)
+    opt.update(0, w, g, st)
+    m = st[0].asnumpy()
+    assert np.allclose(m, 0.1 * np.array([1.0, -1.0]), atol=1e-6), m      # clip(0.5 + 1.0) = 1.0, not clip(0.5) + 1.0 = 1.5
