@@ -85,10 +85,12 @@ void KVStoreDistServer::CommandHandle(const SimpleData& recved, SimpleApp* app) 
         { std::lock_guard<std::mutex> lk(mu_); if (recved.plane == kGlobal) stop = (++stop_votes_ == po->num_global_workers()); }
         if (stop) exec_.Stop();
       } else {
-        if (has_global_) {  // relay to the global servers, do not wait (they stop only after all parties voted)
+        bool first;
+        { std::lock_guard<std::mutex> lk(mu_); first = !stop_requested_; stop_requested_ = true; }
+        if (first && has_global_) {  // relay to the global servers, do not wait (they stop only after all parties voted)
           ps_server_->Request(static_cast<int>(CommandType::kStopServer), "", kServerGroup, kGlobal);
         }
-        exec_.Stop();
+        exec_.Stop();          // idempotent: a second stop command is acknowledged, not queued behind a loop that has already ended
       }
       return;
     }
@@ -314,13 +316,16 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   }
   if (is_global_ || standalone_) {
     ApplyUpdate(key, &e, ub.merged.data(), n);
+    // the round counter moves (and a due periodic checkpoint is written) BEFORE any push of this round is acknowledged: once the acks are
+    // out, workers may start round N+1 of other keys, and a snapshot taken later could mix round-N and round-N+1 state
+    BumpRoundLocked(key);
     std::vector<KVMeta> reqs; reqs.swap(ub.request);
     for (size_t i = 0; i < reqs.size(); ++i) {
       if (i > 0 && reqs[i].sender == reqs[i - 1].sender && reqs[i].timestamp == reqs[i - 1].timestamp) continue;  // merged duplicates (TS)
       respond(reqs[i]);
     }
     lk.unlock();
-    RoundCompleted(key);
+    RoundCompleted(key, /*bumped=*/true);
     return;
   }
   const bool local_round_done = FinishLocalAggregation(key, type, &ub);
@@ -584,25 +589,27 @@ void KVStoreDistServer::AskTS(int key) {
 }
 
 // a synchronisation round of `key` finished on this server: bump the version, start the relay broadcast, open the next round
-void KVStoreDistServer::RoundCompleted(int key) {
+// caller holds mu_: advance the round counter of `key`; when the SLOWEST key thereby reaches a multiple of the checkpoint period, write the
+// snapshot right here — at this instant every key holds exactly its round-N value and nothing of round N has been acknowledged yet
+void KVStoreDistServer::BumpRoundLocked(int key) {
+  const int version = ++round_version_[key];
+  if (ckpt_every_ <= 0) return;
+  int slowest = version;
+  for (auto& kv : store_) { auto it = round_version_.find(kv.first); slowest = std::min(slowest, it == round_version_.end() ? 0 : it->second); }
+  if (slowest > ckpt_key_ && slowest % ckpt_every_ == 0) { ckpt_key_ = slowest; SaveStatesLocked(ckpt_prefix_); }
+}
+
+void KVStoreDistServer::RoundCompleted(int key, bool bumped) {
   std::vector<char> bytes;
   int version, cmd;
-  bool do_ckpt = false;
   {
     std::lock_guard<std::mutex> lk(mu_);
-    version = ++round_version_[key];
+    if (!bumped) BumpRoundLocked(key);
+    version = round_version_[key];
     Entry& e = store_[key];
     bytes = e.data;
     cmd = GetCommandType(RequestType::kDefaultPushPull, e.dtype);
-    if (ckpt_every_ > 0) {
-      // a snapshot is taken when the SLOWEST key finishes round N: at that instant every key holds exactly its round-N value (a worker
-      // cannot start round N+1 of any key before it has finished round N of all of them)
-      int slowest = version;
-      for (auto& kv : store_) { auto it = round_version_.find(kv.first); slowest = std::min(slowest, it == round_version_.end() ? 0 : it->second); }
-      if (slowest > ckpt_key_ && slowest % ckpt_every_ == 0) { ckpt_key_ = slowest; do_ckpt = true; }
-    }
   }
-  if (do_ckpt) SaveStates(ckpt_prefix_);
   Postoffice* po = Postoffice::Get();
   if (TSNode* t = ps_server_->ts(kLocal)) {
     if (!is_global_ || po->enable_central_workers()) t->Relay(key, version, cmd, static_cast<Key>(key), bytes.data(), bytes.size());
@@ -663,6 +670,10 @@ std::string KVStoreDistServer::StatePath(const std::string& prefix) const {
 
 void KVStoreDistServer::SaveStates(const std::string& prefix) {
   std::lock_guard<std::mutex> lk(mu_);
+  SaveStatesLocked(prefix);
+}
+
+void KVStoreDistServer::SaveStatesLocked(const std::string& prefix) {
   const std::string path = StatePath(prefix);
   const std::string tmp = path + ".tmp";
   std::ofstream f(tmp, std::ios::binary);

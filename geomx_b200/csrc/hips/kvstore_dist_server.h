@@ -77,10 +77,15 @@ class Executor {
   void Exec(const Func& func) {
     Block blk(func);
     auto fut = blk.p->get_future();
-    { std::lock_guard<std::mutex> lk(mu_); queue_.push(std::move(blk)); cond_.notify_one(); }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (stopped_) return;          // the loop has ended (or is about to): nothing will ever run this block
+      if (!func) stopped_ = true;
+      queue_.push(std::move(blk)); cond_.notify_one();
+    }
     fut.wait();
   }
-  void Stop() { Exec(Func()); }
+  void Stop() { Exec(Func()); }      // idempotent
 
  private:
   struct Block {
@@ -91,6 +96,7 @@ class Executor {
   std::queue<Block> queue_;
   std::mutex mu_;
   std::condition_variable cond_;
+  bool stopped_ = false;
 };
 
 class KVStoreDistServer {
@@ -147,7 +153,8 @@ class KVStoreDistServer {
   // TSEngine (ts_node.h): a merged push stands for several requests; servers take part in the pairing and start the relay
   std::vector<KVMeta> ExpandOrigins(const KVMeta& req);
   void AskTS(int key);
-  void RoundCompleted(int key);
+  void RoundCompleted(int key, bool bumped = false);
+  void BumpRoundLocked(int key);
   void ApplyFreshFromGlobal(int key, std::vector<float>* recved);   // mu_ held
   void OnRelayedFromGlobal(int key, int version, int cmd, const std::vector<char>& bytes);
   // key codecs
@@ -155,6 +162,7 @@ class KVStoreDistServer {
   struct PSKV { std::vector<Key> keys; std::vector<int> lens; size_t size = 0; };
   PSKV& EncodeGlobalKey(int key, size_t num_elems, int num_bytes);
   void SaveStates(const std::string& path);
+  void SaveStatesLocked(const std::string& path);
   void LoadStates(const std::string& path);
 
   std::unique_ptr<KVServer> ps_server_;
@@ -180,6 +188,7 @@ class KVStoreDistServer {
   long local_iters_ = 0;
   size_t bigarray_bound_ = 1000000, size_lower_bound_ = 200000;
   int stop_votes_ = 0;
+  bool stop_requested_ = false;
   std::atomic<long> num_pushes_{0};
   // periodic server-state checkpoints + resume (GEOMX_SERVER_CKPT_PREFIX / _EVERY / GEOMX_SERVER_RESUME), see RoundCompleted / TryResume
   std::string ckpt_prefix_;

@@ -31,6 +31,8 @@ int Verbose() {
 }
 
 static const uint32_t kMagic = 0x48695053;  // "HiPS"
+static const uint32_t kMaxMetaBytes = 16u << 20;   // node tables of a few thousand nodes fit easily; anything larger is not a HiPS frame
+static const uint32_t kMaxFrameParts = 64;         // keys | vals | lens (+ a few auxiliary parts)
 
 Van::Van(Postoffice* po, Plane plane) : po_(po), plane_(plane) {}
 Van::~Van() {}
@@ -166,11 +168,11 @@ static bool UnpackDatagram(const char* buf, size_t n, Message* msg) {
   if (h[0] != kMagic) return false;
   const uint32_t ml = h[1], nd = h[2];
   size_t pos = 12;
-  if (n < pos + 8ull * nd + ml) return false;
+  if (nd > kMaxFrameParts || n < pos + 8ull * nd + ml) return false;
   std::vector<uint64_t> lens(nd);
   if (nd) memcpy(lens.data(), buf + pos, 8 * nd);
   pos += 8ull * nd;
-  UnpackMeta(buf + pos, ml, &msg->meta);
+  try { UnpackMeta(buf + pos, ml, &msg->meta); } catch (const std::exception&) { return false; }   // foreign / corrupt datagram
   pos += ml;
   msg->data.clear();
   for (uint32_t i = 0; i < nd; ++i) {
@@ -183,22 +185,38 @@ static bool UnpackDatagram(const char* buf, size_t n, Message* msg) {
   return true;
 }
 
+// The listening socket is reachable by anything that can route to this host (port scanners, health checks, a stale process of another
+// job), so nothing read from a connection is trusted: a frame with the wrong magic, an implausible part count / length or a meta block
+// that does not parse makes RecvFrame return false, and the caller closes THAT connection and carries on (the ZeroMQ transport of the
+// reference tolerates foreign connections the same way).  Accepted sockets carry a receive timeout (PS_RECV_TIMEOUT_MS), so a peer that stalls
+// in the middle of a frame cannot hold the receive thread — and with it every other peer of the plane — forever.
 bool Van::RecvFrame(int fd, Message* msg) {
   uint32_t h[3];
   if (!ReadAll(fd, h, 12)) return false;
-  HIPS_CHECK_MSG(h[0] == kMagic, "bad frame magic");
+  if (h[0] != kMagic) { HIPS_VLOG(1, "plane %d: dropping a connection that does not speak the HiPS framing (magic %08x)", plane_, h[0]); return false; }
   const uint32_t ml = h[1], nd = h[2];
+  if (ml > kMaxMetaBytes || nd > kMaxFrameParts) { HIPS_VLOG(1, "plane %d: implausible frame header (meta %u B, %u parts)", plane_, ml, nd); return false; }
   std::vector<uint64_t> lens(nd);
   if (nd && !ReadAll(fd, lens.data(), 8 * nd)) return false;
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < nd; ++i) {
+    if (lens[i] > max_msg_bytes_ || (total += lens[i]) > max_msg_bytes_) { HIPS_VLOG(1, "plane %d: frame larger than PS_MAX_MSG_BYTES", plane_); return false; }
+  }
   std::vector<char> meta(ml);
   if (!ReadAll(fd, meta.data(), ml)) return false;
-  UnpackMeta(meta.data(), ml, &msg->meta);
+  try {
+    UnpackMeta(meta.data(), ml, &msg->meta);
+  } catch (const std::exception& e) {
+    HIPS_VLOG(1, "plane %d: unparsable message meta (%s)", plane_, e.what());
+    return false;
+  }
   msg->data.clear();
   size_t bytes = ml;
   for (uint32_t i = 0; i < nd; ++i) {
     SArray<char> d;
     if (lens[i]) {
-      char* buf = new char[lens[i]];
+      char* buf = new (std::nothrow) char[lens[i]];
+      if (buf == nullptr) return false;
       if (!ReadAll(fd, buf, lens[i])) { delete[] buf; return false; }
       d.reset(buf, lens[i], true);
     }
@@ -222,6 +240,8 @@ void Van::Start(int customer_id) {
   is_scheduler_ = role == Node::SCHEDULER;
   enable_p3_ = env->GetInt("ENABLE_P3", 0) != 0;
   drop_rate_ = env->GetInt("PS_DROP_MSG", 0);
+  max_msg_bytes_ = static_cast<uint64_t>(env->GetFloat("PS_MAX_MSG_BYTES", 17179869184.0));   // 16 GiB: above any single tensor message
+  recv_timeout_ms_ = env->GetInt("PS_RECV_TIMEOUT_MS", 60000);
   heartbeat_timeout_ = env->GetInt("PS_HEARTBEAT_TIMEOUT", 0);
   barrier_count_.assign(8, 0);
 
@@ -430,6 +450,10 @@ void Van::Accepting() {
     }
     int one = 1;
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+    if (recv_timeout_ms_ > 0) {      // bounds a read() in the middle of a frame; idle connections are only read after poll() reports data
+      struct timeval tv; tv.tv_sec = recv_timeout_ms_ / 1000; tv.tv_usec = (recv_timeout_ms_ % 1000) * 1000;
+      setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    }
     {
       std::lock_guard<std::mutex> lk(fds_mu_);
       recv_fds_.push_back(fd);
@@ -456,7 +480,9 @@ void Van::Receiving() {
     for (size_t i = 1; i < pfds.size(); ++i) {
       if (!(pfds[i].revents & (POLLIN | POLLHUP | POLLERR))) continue;
       Message msg;
-      if (!RecvFrame(pfds[i].fd, &msg)) {  // peer closed
+      bool got = false;
+      try { got = RecvFrame(pfds[i].fd, &msg); } catch (const std::exception& e) { HIPS_VLOG(1, "plane %d: receive error (%s)", plane_, e.what()); }
+      if (!got) {  // peer closed, stalled mid-frame, or not a HiPS peer at all: drop this connection only
         std::lock_guard<std::mutex> lk(fds_mu_);
         ::close(pfds[i].fd);
         recv_fds_.erase(std::remove(recv_fds_.begin(), recv_fds_.end(), pfds[i].fd), recv_fds_.end());

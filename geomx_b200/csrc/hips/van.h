@@ -112,6 +112,8 @@ class Van {
   void DelayedSending();
   bool enable_p3_ = false;
   int drop_rate_ = 0;
+  uint64_t max_msg_bytes_ = 1ull << 34;   // PS_MAX_MSG_BYTES: frames announcing more payload than this are rejected before any allocation
+  int recv_timeout_ms_ = 60000;           // PS_RECV_TIMEOUT_MS: SO_RCVTIMEO of accepted connections (0 = block forever)
   int num_servers_seen_ = 0, num_workers_seen_ = 0;
   std::vector<int> barrier_count_;
   std::unique_ptr<Resender> resender_;

@@ -70,8 +70,8 @@ def results(outs):
     return res
 
 
-def launch_single_tier(extra, workers=2):
-    port = free_port()
+def launch_single_tier(extra, workers=2, port=None):
+    port = port or free_port()
     base = {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": port, "DMLC_NUM_SERVER": 1, "DMLC_NUM_WORKER": workers, "DMLC_NUM_ALL_WORKER": workers,
             "TEST_STANDALONE": 1}
     procs = [spawn(dict(base, DMLC_ROLE="scheduler"), extra=extra), spawn(dict(base, DMLC_ROLE="server"), extra=extra)]
@@ -113,6 +113,44 @@ def test_single_tier_dist_sync_sgd():
         for t, vals in enumerate(r["vals"]):
             for i, v in enumerate(vals):
                 assert abs(v - ((1.0 + i) - 0.1 * gsum * (t + 1))) < 1e-5
+
+
+def test_foreign_connections_do_not_kill_a_node():
+    """a port scan / health check / stale client talking to a HiPS port must cost that connection only.  While a job runs, junk
+    is thrown at the scheduler's listening port: a wrong magic, a correct magic with an absurd header, a correct header with a meta block that
+    does not parse, and a connection that stalls mid-frame.  The job still finishes with the right numbers."""
+    import struct
+    import threading
+    import time
+    port = free_port()
+    stop = threading.Event()
+
+    def scanner():
+        magic = 0x48695053
+        junk = [b"GET / HTTP/1.1\r\nHost: x\r\n\r\n", struct.pack("<III", magic, 0xFFFFFFF0, 7), struct.pack("<III", magic, 8, 0) + b"\xff" * 8,
+                struct.pack("<III", magic, 64, 1)]                   # the last one announces a frame and then goes silent
+        held = []
+        while not stop.is_set():
+            for j in junk:
+                try:
+                    c = socket.create_connection(("127.0.0.1", port), timeout=0.5)
+                    c.sendall(j)
+                    held.append(c) if j is junk[-1] and len(held) < 4 else c.close()
+                except OSError:
+                    pass
+            time.sleep(0.05)
+        for c in held:
+            c.close()
+
+    t = threading.Thread(target=scanner, daemon=True); t.start()
+    try:
+        res = launch_single_tier({"TEST_MODE": "sgd", "PS_RECV_TIMEOUT_MS": "300"}, port=port)
+    finally:
+        stop.set(); t.join(timeout=5)
+    assert len(res) == 2
+    for r in res:
+        for step, vals in enumerate(r["vals"]):
+            assert abs(vals[0] - (1.0 - 0.1 * 1.5 * (step + 1))) < 1e-5
 
 
 def test_remote_server_profiling(tmp_path):
