@@ -1,0 +1,328 @@
+// Direct (fp32 FMA) convolution kernels for the small-batch regime of the reference's demo CNN
+//   Conv2D(16,k5,relu) -> MaxPool2 -> Conv2D(32,k5,relu) -> MaxPool2      (examples/cnn.py:56-60, input 1x28x28)
+// forward and backward, three launches in total:
+//   cnn_fwd_kernel    x -> a1 (+argmax) -> a2 (+argmax)            both convolutions, bias, ReLU and both max-pools; a1 stays in shared memory
+//   cnn_bwd_kernel    da2 -> da1 (in shared memory only) -> dW0, db0  conv1 data gradient + pool/ReLU backward of both layers + conv0 weight gradient
+//   cnn_wgrad1_kernel da2, a1 -> dW1, db1                           conv1 weight gradient (sparse: one non-zero per pooling window)
+//
+// Why not the tcgen05 implicit GEMM here: with a per-worker batch of 32 the conv1 products are M = 2048 x N = 32 x K = 400 — 16 tensor-core
+// tiles.  Measured on B200 (tools/kernel_times.py, profiles/): the tcgen05 path needs 8 us (TF32) / 16 us (3xTF32) for the forward GEMM alone
+// and 30-50 us for forward + dgrad + wgrad + im2col/col2im traffic, all of it launch / TMA / TMEM latency on 16 SMs, while the same 78 MFLOP
+// spread over 128 CTAs of plain FMAs finish in a few microseconds, in exact fp32 (the reference's cublasSgemmEx precision).  The max-pool makes
+// the backward pass 4x sparse (one non-zero per 2x2 window), which the weight-gradient kernel exploits.  Larger batches / other geometries use
+// the tcgen05 GEMM path (ops/functional.py conv2d).
+//
+// Reference kernels replaced: im2col_gpu_kernel / col2im_gpu_kernel (src/operator/nn/im2col.cuh:79-187), per-image cublasSgemmEx
+// (convolution-inl.h:165-284), bias broadcast, ReLU (activation-inl.h:89-121), pool_max_2d / unpool (pool.cuh:128-165, 379-432).
+#include "common.cuh"
+
+namespace gx {
+
+// geometry (compile time)
+constexpr int CD_H = 28, CD_K = 5;
+constexpr int CD_C1 = 16, CD_P1 = 12;            // conv0: 16 channels, 24x24 -> pooled 12x12
+constexpr int CD_C2 = 32, CD_P2 = 4;             // conv1: 32 channels,  8x8  -> pooled 4x4
+constexpr int CD_W1PAD = 28;                     // 25 taps padded to 28 floats (16-byte rows)
+
+// 2x2 output window of a 5x5 valid convolution from a 6x6 input patch: acc[dy*2+dx] += sum_{r,s} patch[dy+r][dx+s] * w[r*5+s]
+__device__ __forceinline__ void window_fma(const float (&pt)[6][6], const float (&w)[28], float (&acc)[4]) {
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const float wv = w[r * 5 + s];
+      acc[0] = fmaf(wv, pt[r][s], acc[0]);
+      acc[1] = fmaf(wv, pt[r][s + 1], acc[1]);
+      acc[2] = fmaf(wv, pt[r + 1][s], acc[2]);
+      acc[3] = fmaf(wv, pt[r + 1][s + 1], acc[3]);
+    }
+}
+// 6x6 patch whose top-left corner is `p` (8-byte aligned, row stride `ld` floats, ld even)
+__device__ __forceinline__ void load_patch(const float* p, int ld, float (&pt)[6][6]) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float2 v = *reinterpret_cast<const float2*>(p + r * ld + 2 * q);
+      pt[r][2 * q] = v.x; pt[r][2 * q + 1] = v.y;
+    }
+}
+__device__ __forceinline__ void load_w28(const float* p, float (&w)[28]) {
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+}
+// max-pool of a window's four pre-bias values (first maximum wins, like maxpool2x2_fwd_kernel), then bias + ReLU
+__device__ __forceinline__ float pool4(const float (&a)[4], float bias, int& bi) {
+  float best = a[0]; bi = 0;
+  if (a[1] > best) { best = a[1]; bi = 1; }
+  if (a[2] > best) { best = a[2]; bi = 2; }
+  if (a[3] > best) { best = a[3]; bi = 3; }
+  return fmaxf(best + bias, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------------------------ forward
+// grid (B, 4), 256 threads.  CTA (b, g): conv0 of image b (all 16 channels, kept in shared memory) and conv1 for output channels [8g, 8g+8).
+__global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float* __restrict__ b0,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ a1,
+                                                       unsigned char* __restrict__ idx1, float* __restrict__ a2, unsigned char* __restrict__ idx2) {
+  __shared__ __align__(16) float sx[CD_H * CD_H];
+  __shared__ __align__(16) float sw0[CD_C1 * CD_W1PAD];
+  __shared__ float sb0[CD_C1];
+  __shared__ __align__(16) float sa1[CD_C1 * CD_P1 * CD_P1];
+  __shared__ __align__(16) float sw1[8 * CD_C1 * CD_W1PAD];
+  __shared__ float sb1[8];
+  __shared__ __align__(16) float spart[4 * 64 * 8];
+  pdl_wait();
+  pdl_launch();
+  const int b = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < CD_H * CD_H / 4; i += 256) reinterpret_cast<float4*>(sx)[i] = reinterpret_cast<const float4*>(x + (long long)b * CD_H * CD_H)[i];
+  for (int i = tid; i < CD_C1 * CD_W1PAD; i += 256) { const int ch = i / CD_W1PAD, t = i % CD_W1PAD; sw0[i] = t < 25 ? w0[ch * 25 + t] : 0.f; }
+  if (tid < CD_C1) sb0[tid] = b0[tid];
+  for (int i = tid; i < 8 * CD_C1 * CD_W1PAD; i += 256) {
+    const int t = i % CD_W1PAD, oc_c = i / CD_W1PAD;            // oc_c = ol * 16 + c
+    sw1[i] = t < 25 ? w1[((long long)(8 * g) * CD_C1 + oc_c) * 25 + t] : 0.f;
+  }
+  if (tid < 8) sb1[tid] = b1[8 * g + tid];
+  __syncthreads();
+  // ---- conv0 + bias + ReLU + pool: thread -> channel tid/16, windows (tid%16) + 16 j
+  {
+    const int ch = tid >> 4, sub = tid & 15;
+    float w[28];
+    load_w28(sw0 + ch * CD_W1PAD, w);
+    const float bias = sb0[ch];
+#pragma unroll 1
+    for (int win = sub; win < CD_P1 * CD_P1; win += 16) {
+      const int ph = win / CD_P1, pw = win - ph * CD_P1;
+      float pt[6][6];
+      load_patch(sx + (2 * ph) * CD_H + 2 * pw, CD_H, pt);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      window_fma(pt, w, acc);
+      int bi;
+      const float v = pool4(acc, bias, bi);
+      sa1[ch * CD_P1 * CD_P1 + win] = v;
+      if (g == 0) {
+        const long long o = ((long long)b * CD_C1 + ch) * (CD_P1 * CD_P1) + win;
+        a1[o] = v; idx1[o] = (unsigned char)bi;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- conv1: thread -> input-channel quarter cq, output-channel pair op, pooling window win; 2 oc x 4 pixels accumulators
+  {
+    const int cq = tid >> 6, t64 = tid & 63, op = t64 >> 4, win = t64 & 15, ph = win >> 2, pw = win & 3;
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = 4 * cq + cc;
+      float pt[6][6], w[28];
+      load_patch(sa1 + c * (CD_P1 * CD_P1) + (2 * ph) * CD_P1 + 2 * pw, CD_P1, pt);
+      load_w28(sw1 + ((2 * op) * CD_C1 + c) * CD_W1PAD, w);
+      window_fma(pt, w, acc0);
+      load_w28(sw1 + ((2 * op + 1) * CD_C1 + c) * CD_W1PAD, w);
+      window_fma(pt, w, acc1);
+    }
+    float4* dst = reinterpret_cast<float4*>(spart + (cq * 64 + t64) * 8);
+    dst[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+    dst[1] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const int i64 = tid >> 1, which = tid & 1, op = i64 >> 4, win = i64 & 15, ol = 2 * op + which;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int cq = 0; cq < 4; ++cq) {
+      const float4 v = *reinterpret_cast<const float4*>(spart + (cq * 64 + i64) * 8 + which * 4);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    }
+    int bi;
+    const float v = pool4(acc, sb1[ol], bi);
+    const long long o = ((long long)b * CD_C2 + 8 * g + ol) * (CD_P2 * CD_P2) + win;
+    a2[o] = v; idx2[o] = (unsigned char)bi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------ backward (data + conv0)
+// grid (B, 4), 288 threads.  CTA (b, cg): conv1-input channels [4cg, 4cg+4) of image b.
+//   dz2 (32 x 8 x 8, one non-zero per pooling window where a2 > 0) is scattered into a zero-padded 32 x 16 x 16 plane in shared memory;
+//   da1 = full correlation with the flipped filters = the forward window routine on the padded plane; da1 never leaves shared memory:
+//   it is max-pool / ReLU routed straight into conv0's weight and bias gradient (the first layer needs no input gradient).
+struct CnnBwdSmem {
+  static constexpr int DZ = 0;                                   // [32][16][16]
+  static constexpr int WT = DZ + CD_C2 * 256;                    // [4 cl][32 oc][28] flipped filters
+  static constexpr int X = WT + 4 * CD_C2 * CD_W1PAD;            // [28][28]
+  static constexpr int A1 = X + CD_H * CD_H;                     // [4][144] pooled conv0 activations (ReLU mask)
+  static constexpr int DA1 = A1 + 4 * 144;                       // [4][144] -> routed gradient g
+  static constexpr int PART = DA1 + 4 * 144;                     // [4 ocq][72][8]
+  static constexpr int POS = PART + 4 * 72 * 8;                  // [4][144] int: top-left of the arg-max pixel in the 24x24 map (as x offset)
+  static constexpr int TOTAL = POS + 4 * 144;
+  static constexpr int BYTES = TOTAL * 4;
+};
+
+__global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ a1,
+                                                       const unsigned char* __restrict__ idx1, const float* __restrict__ a2,
+                                                       const unsigned char* __restrict__ idx2, const float* __restrict__ da2,
+                                                       float* __restrict__ dw0, float* __restrict__ db0) {
+  extern __shared__ __align__(16) float sm[];
+  using L = CnnBwdSmem;
+  float* sdz = sm + L::DZ; float* swt = sm + L::WT; float* sx = sm + L::X; float* sa1 = sm + L::A1; float* sda1 = sm + L::DA1;
+  float* spart = sm + L::PART; int* spos = reinterpret_cast<int*>(sm + L::POS);
+  pdl_wait();
+  pdl_launch();
+  const int b = blockIdx.x, cg = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < CD_C2 * 256 / 4; i += 288) reinterpret_cast<float4*>(sdz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 4 * CD_C2 * CD_W1PAD; i += 288) {
+    const int t = i % CD_W1PAD, r = i / CD_W1PAD, oc = r % CD_C2, cl = r / CD_C2;      // swt[(cl*32 + oc)*28 + t], t = flipped tap
+    float v = 0.f;
+    if (t < 25) { const int kh = 4 - t / 5, kw = 4 - t % 5; v = w1[(((long long)oc * CD_C1) + 4 * cg + cl) * 25 + kh * 5 + kw]; }
+    swt[i] = v;
+  }
+  for (int i = tid; i < CD_H * CD_H / 4; i += 288) reinterpret_cast<float4*>(sx)[i] = reinterpret_cast<const float4*>(x + (long long)b * CD_H * CD_H)[i];
+  for (int i = tid; i < 4 * 144; i += 288) {
+    const long long o = ((long long)b * CD_C1 + 4 * cg) * 144 + i;
+    sa1[i] = a1[o];
+    const int win = i % 144, id = idx1[o];
+    spos[i] = (2 * (win / CD_P1) + (id >> 1)) * CD_H + 2 * (win % CD_P1) + (id & 1);
+  }
+  __syncthreads();
+  // scatter the non-zeros of dz2 (pool + ReLU backward of conv1's output)
+  for (int e = tid; e < CD_C2 * 16; e += 288) {
+    const long long o = (long long)b * CD_C2 * 16 + e;
+    const int oc = e >> 4, win = e & 15, id = idx2[o];
+    const float gv = a2[o] > 0.f ? da2[o] : 0.f;
+    const int oh = 2 * (win >> 2) + (id >> 1), ow = 2 * (win & 3) + (id & 1);
+    sdz[oc * 256 + (oh + 4) * 16 + ow + 4] = gv;
+  }
+  __syncthreads();
+  // ---- conv1 data gradient: thread -> oc quarter, channel pair, 2x2 output window of the 12x12 map
+  {
+    const int ocq = tid / 72, t72 = tid % 72, cp = t72 / 36, win = t72 % 36, ph = win / 6, pw = win % 6;
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int o8 = 0; o8 < 8; ++o8) {
+      const int oc = 8 * ocq + o8;
+      float pt[6][6], w[28];
+      load_patch(sdz + oc * 256 + (2 * ph) * 16 + 2 * pw, 16, pt);
+      load_w28(swt + ((2 * cp) * CD_C2 + oc) * CD_W1PAD, w);
+      window_fma(pt, w, acc0);
+      load_w28(swt + ((2 * cp + 1) * CD_C2 + oc) * CD_W1PAD, w);
+      window_fma(pt, w, acc1);
+    }
+    float4* dst = reinterpret_cast<float4*>(spart + (ocq * 72 + t72) * 8);
+    dst[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+    dst[1] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+  }
+  __syncthreads();
+  if (tid < 144) {
+    const int i72 = tid >> 1, which = tid & 1, cp = i72 / 36, win = i72 % 36, ph = win / 6, pw = win % 6, cl = 2 * cp + which;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(spart + (q * 72 + i72) * 8 + which * 4);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    }
+    // route through conv0's ReLU (+ pool: the value belongs to the arg-max pixel recorded in spos)
+    float* d = sda1 + cl * 144 + (2 * ph) * CD_P1 + 2 * pw;
+    const float* m = sa1 + cl * 144 + (2 * ph) * CD_P1 + 2 * pw;
+    d[0] = m[0] > 0.f ? acc[0] : 0.f; d[1] = m[1] > 0.f ? acc[1] : 0.f;
+    d[CD_P1] = m[CD_P1] > 0.f ? acc[2] : 0.f; d[CD_P1 + 1] = m[CD_P1 + 1] > 0.f ? acc[3] : 0.f;
+  }
+  __syncthreads();
+  // ---- conv0 weight / bias gradient of this image (4 channels): dW0[ch][kh][kw] += sum_windows g * x[oh+kh][ow+kw]
+  if (tid < 100) {
+    const int cl = tid / 25, tap = tid % 25, koff = (tap / 5) * CD_H + tap % 5;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int p = 0; p < 144; ++p) acc = fmaf(sda1[cl * 144 + p], sx[spos[cl * 144 + p] + koff], acc);
+    atomicAdd(dw0 + (4 * cg + cl) * 25 + tap, acc);
+  } else if (tid >= 128 && tid < 132) {
+    const int cl = tid - 128;
+    float acc = 0.f;
+    for (int p = 0; p < 144; ++p) acc += sda1[cl * 144 + p];
+    atomicAdd(db0 + 4 * cg + cl, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------ conv1 weight gradient
+// grid (32 oc, 4 cg), 256 threads.  CTA owns dW1[oc][4cg..4cg+3][5][5] (100 outputs, written once: no atomics) and sums over all images:
+//   dW1[oc][c][kh][kw] = sum_{b, window} g[b][oc][window] * a1[b][c][oh+kh][ow+kw]     (g != 0 only at the window's arg-max where a2 > 0)
+__global__ void __launch_bounds__(256) cnn_wgrad1_kernel(const float* __restrict__ a1, const float* __restrict__ a2, const unsigned char* __restrict__ idx2,
+                                                          const float* __restrict__ da2, float* __restrict__ dw1, float* __restrict__ db1, int B) {
+  extern __shared__ __align__(16) float sm[];
+  float* sa = sm;                               // [B][4][144] the four input-channel planes of every image
+  float* sg = sa + (size_t)B * 576;             // [B*16] routed gradients of this output channel
+  int* sp = reinterpret_cast<int*>(sg + B * 16);  // [B*16] arg-max position as offset into a 12x12 plane
+  float* sacc = reinterpret_cast<float*>(sp + B * 16);   // [2][128]
+  pdl_wait();
+  pdl_launch();
+  const int oc = blockIdx.x, cg = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < B * 144; i += 256) {          // 144 float4 per image: 4 contiguous planes
+    const int bb = i / 144, r = i % 144;
+    reinterpret_cast<float4*>(sa)[i] = reinterpret_cast<const float4*>(a1 + ((long long)bb * CD_C1 + 4 * cg) * 144)[r];
+  }
+  for (int e = tid; e < B * 16; e += 256) {
+    const int bb = e >> 4, win = e & 15;
+    const long long o = ((long long)bb * CD_C2 + oc) * 16 + win;
+    const int id = idx2[o];
+    sg[e] = a2[o] > 0.f ? da2[o] : 0.f;
+    sp[e] = (2 * (win >> 2) + (id >> 1)) * CD_P1 + 2 * (win & 3) + (id & 1);
+  }
+  __syncthreads();
+  const int half = tid >> 7, t = tid & 127;
+  float acc = 0.f;
+  if (t < 100) {
+    const int cl = t / 25, tap = t % 25, koff = (tap / 5) * CD_P1 + tap % 5;
+    const int e0 = half * (B * 8), e1 = e0 + B * 8;      // images [half*B/2, (half+1)*B/2)
+#pragma unroll 4
+    for (int e = e0; e < e1; ++e) acc = fmaf(sg[e], sa[((e >> 4) * 4 + cl) * 144 + sp[e] + koff], acc);
+  }
+  sacc[half * 128 + t] = acc;
+  __syncthreads();
+  if (tid < 100) dw1[((long long)oc * CD_C1 + 4 * cg + tid / 25) * 25 + tid % 25] = sacc[tid] + sacc[128 + tid];
+  if (cg == 0 && tid < 32) {                 // db1[oc] = sum of all routed gradients of this channel
+    float s = 0.f;
+    for (int e = tid; e < B * 16; e += 32) s += sg[e];
+    s = warp_sum(s);
+    if (tid == 0) db1[oc] = s;
+  }
+}
+
+}  // namespace gx
+
+using namespace gx;
+
+// x [B,1,28,28]; w0 [16,1,5,5]; w1 [32,16,5,5]; writes a1 [B,16,12,12] + idx1, a2 [B,32,4,4] + idx2
+GX_API int gx_cnn_fwd(const float* x, const float* w0, const float* b0, const float* w1, const float* b1, float* a1, unsigned char* idx1, float* a2,
+                      unsigned char* idx2, int B, cudaStream_t s) {
+  if (B < 1) return 0;
+  launch_pdl(cnn_fwd_kernel, dim3(B, 4), dim3(256), 0, s, x, w0, b0, w1, b1, a1, idx1, a2, idx2);
+  return GX_CHECK_LAUNCH();
+}
+// accumulates into dw0 [16,25] / db0 [16] (atomics: zero them first)
+GX_API int gx_cnn_bwd(const float* x, const float* w1, const float* a1, const unsigned char* idx1, const float* a2, const unsigned char* idx2,
+                      const float* da2, float* dw0, float* db0, int B, cudaStream_t s) {
+  if (B < 1) return 0;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(cnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CnnBwdSmem::BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  launch_pdl(cnn_bwd_kernel, dim3(B, 4), dim3(288), (size_t)CnnBwdSmem::BYTES, s, x, w1, a1, idx1, a2, idx2, da2, dw0, db0);
+  return GX_CHECK_LAUNCH();
+}
+// overwrites dw1 [32,16,5,5] and db1 [32].  B even, B <= 64 (shared-memory planes of all images).
+GX_API int gx_cnn_wgrad1(const float* a1, const float* a2, const unsigned char* idx2, const float* da2, float* dw1, float* db1, int B, cudaStream_t s) {
+  if (B < 2 || (B & 1) || B > 64) return -1;
+  const size_t smem = ((size_t)B * 576 + (size_t)B * 16 * 2 + 256) * 4;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(cnn_wgrad1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  launch_pdl(cnn_wgrad1_kernel, dim3(CD_C2, 4), dim3(256), smem, s, a1, a2, idx2, da2, dw1, db1, B);
+  return GX_CHECK_LAUNCH();
+}

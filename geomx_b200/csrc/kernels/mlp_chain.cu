@@ -25,7 +25,8 @@ namespace cg = cooperative_groups;
 namespace gx {
 
 constexpr int MC_CLUSTER = 8;
-constexpr int MC_THREADS = 256;
+constexpr int MC_THREADS = 512;   // 16 warps: two warp-groups of 256 that either split K (P1) or run data- and weight-gradient side by side (P4, P5)
+constexpr int MC_HALF = 256;
 constexpr int MC_B = 32;      // batch rows held (rows >= B are zero)
 constexpr int MC_CMAX = 16;   // classes (padded)
 
@@ -40,6 +41,7 @@ struct MlpChainParams {
   float* dw0; float* db0; float* dw1; float* db1; float* dw2; float* db2;
   float* dx;            // [B][D0]   gradient w.r.t. x
   int B, C;
+  unsigned long long* dbg;   // optional %globaltimer stamps of cluster CTA 0 (tools/kernel_times.py)
 };
 
 // 16-byte chunk swizzle of a K-major [rows][K] tile: chunk (k>>2) is XORed with (row>>2)&7, so the 8 row-groups a warp touches in one
@@ -193,6 +195,9 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
   const int cr = (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = p.B, C = p.C;
+  const bool dbg_on = p.dbg != nullptr && cr == 0 && tid == 0;
+  auto stamp = [&](int slot) { if (dbg_on) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[slot] = t; } };
+  stamp(0);
 
   // ---------------- prologue: weights do not depend on the preceding kernel (they were written by the previous step's exchange, which a
   // kernel further up the stream has already waited for) -> stage them before griddepcontrol.wait
@@ -207,8 +212,10 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
   if (tid < NS2) sB1[tid] = p.b1[cr * NS2 + tid];
   if (tid < 16) sB2[tid] = tid < C ? p.b2[tid] : 0.f;
   cp_async_commit();
+  stamp(1);
   pdl_wait();
   pdl_launch();
+  stamp(2);
   // input activations (full copy per CTA) + labels
   for (int c = tid; c < MC_B * (D0 >> 2); c += MC_THREADS) {
     const int r = c / (D0 >> 2), q = c - r * (D0 >> 2);
@@ -220,36 +227,43 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
   cp_async_wait<0>();
   __syncthreads();
   cluster.sync();      // every CTA of the cluster is running (DSMEM stores below need the target CTA's shared memory to exist)
+  stamp(3);
 
   // tile coordinates shared by the 32-row products: 8 row groups x (NC/4) column groups per K split
   // ---------------- P1: a3[:, slice] = relu(x * W0[slice]^T + b0)          NC = 32, K = D0, KS = 4
   {
-    constexpr int KS = 4, PER = MC_THREADS / KS;       // 64 tiles per split
+    constexpr int KS = 8, PER = MC_THREADS / KS;       // 64 tiles per split, K split over all 16 warps
     const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
     float acc[4][4] = {};
     prod_nt<D0, KS>(sX, sW0, tb, tn, ks, acc);
-    put_partial<NS1>(sDZ4, tb, tn, ks, acc);            // scratch = dz4 buffer (unused until P3)
+    float* scratch = sA4;                                // [sA4 | sDZ4] = 32 KB contiguous, both unused until the end of P2 / P3
+    put_partial<NS1>(scratch, tb, tn, ks, acc);
     __syncthreads();
     // W0's row slice is no longer needed: start fetching the COLUMN slice W0[:, cr*KS0 ...] for the backward pass (da2) underneath P2..P4
     stage_plain_async(sW0, p.w0 + cr * KS0, D1, KS0, D0);
     cp_async_commit();
-    const int b = tid >> 3, n4 = tid & 7;               // 32 x 8 float4 outputs
-    float4 v = sum_partials<NS1, KS>(sDZ4, b, n4);
-    v.x = fmaxf(v.x + sB0[4 * n4], 0.f); v.y = fmaxf(v.y + sB0[4 * n4 + 1], 0.f);
-    v.z = fmaxf(v.z + sB0[4 * n4 + 2], 0.f); v.w = fmaxf(v.w + sB0[4 * n4 + 3], 0.f);
-    if (b >= B) v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int o = sw_off(b, cr * NS1 + 4 * n4, D1);
+    if (tid < MC_HALF) {
+      const int b = tid >> 3, n4 = tid & 7;              // 32 x 8 float4 outputs
+      float4 v = sum_partials<NS1, KS>(scratch, b, n4);
+      v.x = fmaxf(v.x + sB0[4 * n4], 0.f); v.y = fmaxf(v.y + sB0[4 * n4 + 1], 0.f);
+      v.z = fmaxf(v.z + sB0[4 * n4 + 2], 0.f); v.w = fmaxf(v.w + sB0[4 * n4 + 3], 0.f);
+      if (b >= B) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int o = sw_off(b, cr * NS1 + 4 * n4, D1);
 #pragma unroll
-    for (int r = 0; r < MC_CLUSTER; ++r) *reinterpret_cast<float4*>(cluster.map_shared_rank(sA3, r) + o) = v;
+      for (int r = 0; r < MC_CLUSTER; ++r) *reinterpret_cast<float4*>(cluster.map_shared_rank(sA3, r) + o) = v;
+    }
   }
   cluster.sync();
+  stamp(4);
   // ---------------- P2: a4[:, slice] = relu(a3 * W1[slice]^T + b1)         NC = 16, K = D1, KS = 8
   {
-    constexpr int KS = 8, PER = MC_THREADS / KS;       // 32 tiles per split
-    const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
-    float acc[4][4] = {};
-    prod_nt<D1, KS>(sA3, sW1, tb, tn, ks, acc);
-    put_partial<NS2>(sDZ4, tb, tn, ks, acc);
+    constexpr int KS = 8, PER = MC_HALF / KS;          // 32 tiles per split; this layer is small: warp-group 0 only
+    if (tid < MC_HALF) {
+      const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
+      float acc[4][4] = {};
+      prod_nt<D1, KS>(sA3, sW1, tb, tn, ks, acc);
+      put_partial<NS2>(sDZ4, tb, tn, ks, acc);
+    }
     __syncthreads();
     stage_plain_async(sW1, p.w1 + cr * NS1, D2, NS1, D1);   // W1[:, slice of D1] for dz3
     cp_async_commit();
@@ -265,17 +279,28 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
     }
   }
   cluster.sync();
+  stamp(5);
   // ---------------- P3: classifier + softmax-CE (every CTA redundantly: 32 x C logits), dz4 slice, dW2 slice, db2
   {
     for (int b = warp; b < MC_B; b += MC_THREADS / 32) {
-      float mylogit = 0.f;
-      for (int c = 0; c < C; ++c) {
-        float s = 0.f;
+      // all class dot products of this row at once: 16 independent partial sums per lane, then one butterfly over the whole vector
+      // (a shuffle reduction per class would be a chain of 5 dependent ~25-cycle shuffles, ten times over)
+      float part[MC_CMAX];
 #pragma unroll
-        for (int k = lane; k < D2; k += 32) s = fmaf(sA4[sw_off(b, k, D2)], sW2[c * D2 + k], s);
-        s = warp_sum(s) + sB2[c];
-        if (lane == c) mylogit = s;
+      for (int c = 0; c < MC_CMAX; ++c) part[c] = 0.f;
+#pragma unroll
+      for (int k = lane; k < D2; k += 32) {
+        const float av = sA4[sw_off(b, k, D2)];
+#pragma unroll
+        for (int c = 0; c < MC_CMAX; ++c) part[c] = fmaf(av, sW2[c * D2 + k], part[c]);      // rows >= C of sW2 are zero
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < MC_CMAX; ++c) part[c] += __shfl_xor_sync(0xffffffffu, part[c], o);
+      float mylogit = 0.f;
+#pragma unroll
+      for (int c = 0; c < MC_CMAX; ++c) if (lane == c) mylogit = part[c] + sB2[c];
       float mx = lane < C ? mylogit : -INFINITY;
       mx = warp_max(mx);
       const float e = lane < C ? __expf(mylogit - mx) : 0.f;
@@ -313,64 +338,76 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
     }
   }
   cluster.sync();
+  stamp(6);
   // ---------------- P4: dz3[:, slice] = relu'(a3) * (dz4 * W1[:, slice]);  dW1[slice of D2 rows] = dz4[:, rows]^T * a3;  db1
   float4 dz3v;   // this thread's float4 of the dz3 slice (kept in registers across the barrier that protects a3)
   {
     cp_async_wait<0>();          // W1 column slice (and W0 column slice) landed
     __syncthreads();
-    constexpr int KS = 4, PER = MC_THREADS / KS;       // NC = 32 -> 64 tiles per split, K = D2
-    const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
-    float acc[4][4] = {};
-    prod_nn<D2, NS1, KS>(sDZ4, sW1, tb, tn, ks, acc);
-    put_partial<NS1>(sA4, tb, tn, ks, acc);             // scratch = a4 buffer (dead after P3)
-    __syncthreads();
-    const int b = tid >> 3, n4 = tid & 7;
-    dz3v = sum_partials<NS1, KS>(sA4, b, n4);
-    const float4 a3 = *reinterpret_cast<const float4*>(sA3 + sw_off(b, cr * NS1 + 4 * n4, D1));
-    dz3v.x = a3.x > 0.f ? dz3v.x : 0.f; dz3v.y = a3.y > 0.f ? dz3v.y : 0.f; dz3v.z = a3.z > 0.f ? dz3v.z : 0.f; dz3v.w = a3.w > 0.f ? dz3v.w : 0.f;
-    // dW1 rows [cr*NS2, +NS2) : tiles of 4 rows x 4 columns, 4 x (D1/4) = 256 tiles
-    {
-      const int tnw = tid / (D1 / 4), tk = tid % (D1 / 4);
+    if (tid < MC_HALF) {
+      // warp-group 0: the data gradient dz3 (critical path)
+      constexpr int KS = 4, PER = MC_HALF / KS;        // NC = 32 -> 64 tiles per split, K = D2
+      const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
+      float acc[4][4] = {};
+      prod_nn<D2, NS1, KS>(sDZ4, sW1, tb, tn, ks, acc);
+      put_partial<NS1>(sA4, tb, tn, ks, acc);           // scratch = a4 buffer (dead after P3)
+      named_bar_sync(1, MC_HALF);
+      const int b = tid >> 3, n4 = tid & 7;
+      dz3v = sum_partials<NS1, KS>(sA4, b, n4);
+      const float4 a3 = *reinterpret_cast<const float4*>(sA3 + sw_off(b, cr * NS1 + 4 * n4, D1));
+      dz3v.x = a3.x > 0.f ? dz3v.x : 0.f; dz3v.y = a3.y > 0.f ? dz3v.y : 0.f; dz3v.z = a3.z > 0.f ? dz3v.z : 0.f; dz3v.w = a3.w > 0.f ? dz3v.w : 0.f;
+    } else {
+      // warp-group 1, concurrently: dW1 rows [cr*NS2, +NS2) as 4 x 4 tiles (4 x D1/4 = 256 of them) and the db1 slice
+      const int t = tid - MC_HALF;
+      const int tnw = t / (D1 / 4), tk = t % (D1 / 4);
       wgrad_tile<D2, D1, 4>(sDZ4, sA3, cr * NS2, 4 * tnw, tk, p.dw1 + (long long)cr * NS2 * D1);
-    }
-    if (tid < NS2) {   // db1 slice
-      float s = 0.f;
-      for (int bb = 0; bb < MC_B; ++bb) s += sDZ4[sw_off(bb, cr * NS2 + tid, D2)];
-      p.db1[cr * NS2 + tid] = s;
+      if (t < NS2) {
+        float s = 0.f;
+        for (int bb = 0; bb < MC_B; ++bb) s += sDZ4[sw_off(bb, cr * NS2 + t, D2)];
+        p.db1[cr * NS2 + t] = s;
+      }
     }
   }
+  stamp(7);
   cluster.sync();      // everybody is done reading a3 -> its buffer becomes dz3
-  {
+  if (tid < MC_HALF) {
     const int b = tid >> 3, n4 = tid & 7;
     const int o = sw_off(b, cr * NS1 + 4 * n4, D1);
 #pragma unroll
     for (int r = 0; r < MC_CLUSTER; ++r) *reinterpret_cast<float4*>(cluster.map_shared_rank(sA3, r) + o) = dz3v;
   }
   cluster.sync();
+  stamp(8);
   // ---------------- P5: dx[:, slice of D0] = dz3 * W0[:, slice];  dW0[slice of D1 rows] = dz3[:, rows]^T * x;  db0
   {
     float* sDZ3 = sA3;
-    constexpr int KS = 2, PER = MC_THREADS / KS;       // NC = 64 -> 128 tiles per split, K = D1
-    const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
-    float acc[4][4] = {};
-    prod_nn<D1, KS0, KS>(sDZ3, sW0, tb, tn, ks, acc);
-    put_partial<KS0>(sDZ4, tb, tn, ks, acc);            // scratch = dz4 buffer (dead after P4): 2 x 32 x 64 floats = 16 KB
-    __syncthreads();
-    for (int e = tid; e < MC_B * KS0 / 4; e += MC_THREADS) {
-      const int b = e / (KS0 / 4), n4 = e % (KS0 / 4);
-      if (b < B) *reinterpret_cast<float4*>(p.dx + (long long)b * D0 + cr * KS0 + 4 * n4) = sum_partials<KS0, KS>(sDZ4, b, n4);
-    }
-    // dW0 rows [cr*NS1, +NS1): tiles of 8 rows x 4 columns: 4 x (D0/4) = 512 tiles, two per thread
-    for (int t = tid; t < (NS1 / 8) * (D0 / 4); t += MC_THREADS) {
-      const int tnw = t / (D0 / 4), tk = t % (D0 / 4);
-      wgrad_tile<D1, D0, 8>(sDZ3, sX, cr * NS1, 8 * tnw, tk, p.dw0 + (long long)cr * NS1 * D0);
-    }
-    if (tid < NS1) {   // db0 slice
-      float s = 0.f;
-      for (int bb = 0; bb < MC_B; ++bb) s += sDZ3[sw_off(bb, cr * NS1 + tid, D1)];
-      p.db0[cr * NS1 + tid] = s;
+    if (tid < MC_HALF) {
+      // warp-group 0: the input gradient (what the convolution backward pass is waiting for)
+      constexpr int KS = 2, PER = MC_HALF / KS;        // NC = 64 -> 128 tiles per split, K = D1
+      const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
+      float acc[4][4] = {};
+      prod_nn<D1, KS0, KS>(sDZ3, sW0, tb, tn, ks, acc);
+      put_partial<KS0>(sDZ4, tb, tn, ks, acc);          // scratch = dz4 buffer (dead after P4): 2 x 32 x 64 floats = 16 KB
+      named_bar_sync(1, MC_HALF);
+      for (int e = tid; e < MC_B * KS0 / 4; e += MC_HALF) {
+        const int b = e / (KS0 / 4), n4 = e % (KS0 / 4);
+        if (b < B) *reinterpret_cast<float4*>(p.dx + (long long)b * D0 + cr * KS0 + 4 * n4) = sum_partials<KS0, KS>(sDZ4, b, n4);
+      }
+    } else {
+      // warp-group 1, concurrently: dW0 rows [cr*NS1, +NS1) as 8 x 4 tiles (4 x D0/4 = 512 tiles, two per thread) and the db0 slice
+      const int t0 = tid - MC_HALF;
+      for (int t = t0; t < (NS1 / 8) * (D0 / 4); t += MC_HALF) {
+        const int tnw = t / (D0 / 4), tk = t % (D0 / 4);
+        wgrad_tile<D1, D0, 8>(sDZ3, sX, cr * NS1, 8 * tnw, tk, p.dw0 + (long long)cr * NS1 * D0);
+      }
+      if (t0 < NS1) {
+        float s = 0.f;
+        for (int bb = 0; bb < MC_B; ++bb) s += sDZ3[sw_off(bb, cr * NS1 + t0, D1)];
+        p.db0[cr * NS1 + t0] = s;
+      }
     }
   }
+  stamp(9);
 }
 
 }  // namespace gx
@@ -378,6 +415,9 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
 using namespace gx;
 
 // 512 -> 256 -> 128 -> C (C <= 16), B <= 32.  Returns -1 for unsupported shapes (caller uses the per-layer kernels).
+static unsigned long long* g_mlp_dbg = nullptr;
+GX_API int gx_mlp_chain_set_debug(unsigned long long* p) { g_mlp_dbg = p; return 0; }
+
 GX_API int gx_mlp_chain_fwd_bwd(const float* x, const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
                                 const float* label, float* loss, float* logits, float* dw0, float* db0, float* dw1, float* db1, float* dw2,
                                 float* db2, float* dx, int B, int D0, int D1, int D2, int C, cudaStream_t stream) {
@@ -392,7 +432,7 @@ GX_API int gx_mlp_chain_fwd_bwd(const float* x, const float* w0, const float* b0
   }
   MlpChainParams p;
   p.x = x; p.w0 = w0; p.b0 = b0; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.label = label; p.loss = loss; p.logits = logits;
-  p.dw0 = dw0; p.db0 = db0; p.dw1 = dw1; p.db1 = db1; p.dw2 = dw2; p.db2 = db2; p.dx = dx; p.B = B; p.C = C;
+  p.dw0 = dw0; p.db0 = db0; p.dw1 = dw1; p.db1 = db1; p.dw2 = dw2; p.db2 = db2; p.dx = dx; p.B = B; p.C = C; p.dbg = g_mlp_dbg;
   static int use_pdl = -1;
   if (use_pdl < 0) { const char* e = getenv("GEOMX_MLP_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
   if (use_pdl) launch_pdl(kern, dim3(MC_CLUSTER), dim3(MC_THREADS), (size_t)L::BYTES, stream, p);

@@ -109,6 +109,9 @@ class HipsCNNTrainStep:
             f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False)
             f.add_channel("conv", [0, 1, 2, 3], replicate=True)
         self.fused_mlp = B <= 32 and os.environ.get("GEOMX_FUSED_MLP", "1") == "1"
+        # small-batch regime: both convolutions forward / backward as direct fp32-FMA kernels (3 launches, csrc/kernels/cnn_direct.cu) instead
+        # of im2col + tcgen05 GEMMs (GEOMX_DIRECT_CONV=0 selects the GEMM path; batches > 64 always use it)
+        self.direct_conv = B <= 64 and B % 2 == 0 and os.environ.get("GEOMX_DIRECT_CONV", "1") == "1"
         self.P = [f.param_view(i) for i in range(10)]
         self.G = [f.grad_view(i) for i in range(10)]
         self._init_params(net)
@@ -195,6 +198,15 @@ class HipsCNNTrainStep:
             # dense0 -> dense1 -> classifier -> softmax-CE forward and backward: ONE 8-CTA cluster launch instead of the seven above
             head = [("mlp chain fwd+bwd (cluster)", "main", lambda: n.mlp_chain(a2f, P[4], P[5], P[6], P[7], P[8], P[9], self.label, self.loss, self.logits,
                                                                               G[4], G[5], G[6], G[7], G[8], G[9], self.da2))]
+        if self.direct_conv:
+            da2v = self.da2
+            return [
+                ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2)),
+            ] + head + kv_dense + [
+                ("conv1 wgrad (direct, sparse)", "side", lambda: n.cnn_wgrad1(self.a1, self.a2, self.idx2, da2v, G[2], G[3])),
+                ("conv1 dgrad + conv0 wgrad (direct)", "main", lambda: n.cnn_bwd(self.x, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1])),
+                ("hips push+opt+pull", "join", kv),
+            ]
         return [
             ("conv0+relu+pool+im2col", "main", lambda: n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)),
             ("conv1 gemm (bias,relu,maxpool fused)", "main", conv1_fwd),

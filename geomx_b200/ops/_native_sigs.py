@@ -8,7 +8,11 @@ SIGS = {
     "gx_gemm_tf32": [P, L, I, P, L, I, I, I, I, P, L, P, P, L, P, I, I, I, I, F, I, P, P, P],
     "gx_gemm_tf32_pool": [P, L, I, P, L, I, I, I, I, P, P, I, I, I, P, F, P],
     "gx_mlp_chain_fwd_bwd": [P] * 17 + [I] * 5 + [P],
+    "gx_cnn_fwd": [P] * 9 + [I, P],
+    "gx_cnn_bwd": [P] * 9 + [I, P],
+    "gx_cnn_wgrad1": [P] * 6 + [I, P],
     "gx_mlp_chain_smem_bytes": [],
+    "gx_mlp_chain_set_debug": [P],
     "gx_gemm_set_debug": [P],
     "gx_gemm_set_precision": [I],
     "gx_gemm_get_precision": [],

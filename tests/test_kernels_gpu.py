@@ -52,6 +52,33 @@ def test_gemm_tf32_majors(nat, a_mn, b_mn, M, N, K):
     assert 1e-5 < e1 < 2e-3, "plain tf32 mode rel err %g" % e1     # the fast mode really is the 10-bit-mantissa product
 
 
+def test_cnn_direct_kernels_match_torch(nat):
+    """conv0+conv1 forward (bias, ReLU, 2x2 max-pool fused) and the two backward kernels of csrc/kernels/cnn_direct.cu vs autograd on the same ops."""
+    import torch.nn.functional as F
+    torch.manual_seed(21)
+    for B in (32, 6):
+        x = torch.rand(B, 1, 28, 28, device=dev())
+        w0 = torch.randn(16, 1, 5, 5, device=dev()) * 0.2; b0 = torch.randn(16, device=dev()) * 0.1
+        w1 = torch.randn(32, 16, 5, 5, device=dev()) * 0.05; b1 = torch.randn(32, device=dev()) * 0.1
+        ps = [t.clone().requires_grad_(True) for t in (w0, b0, w1, b1)]
+        h1 = F.max_pool2d(torch.relu(F.conv2d(x, ps[0], ps[1])), 2)
+        h2 = F.max_pool2d(torch.relu(F.conv2d(h1, ps[2], ps[3])), 2)
+        da2 = torch.randn_like(h2)
+        h2.backward(da2)
+        a1 = torch.empty(B, 16, 12, 12, device=dev()); idx1 = torch.empty(B, 16, 12, 12, dtype=torch.uint8, device=dev())
+        a2 = torch.empty(B, 32, 4, 4, device=dev()); idx2 = torch.empty(B, 32, 4, 4, dtype=torch.uint8, device=dev())
+        nat.cnn_fwd(x, w0, b0, w1, b1, a1, idx1, a2, idx2)
+        torch.cuda.synchronize()
+        assert rel_err(a1, h1.detach()) < 1e-6 and rel_err(a2, h2.detach()) < 1e-5
+        dw0 = torch.zeros(16, 1, 5, 5, device=dev()); db0 = torch.zeros(16, device=dev())
+        dw1 = torch.full((32, 16, 5, 5), float("nan"), device=dev()); db1 = torch.full((32,), float("nan"), device=dev())
+        nat.cnn_bwd(x, w1, a1, idx1, a2, idx2, da2.contiguous(), dw0, db0)
+        assert nat.cnn_wgrad1(a1, a2, idx2, da2.contiguous(), dw1, db1)
+        torch.cuda.synchronize()
+        for got, ref, name in ((dw0, ps[0].grad, "dw0"), (db0, ps[1].grad, "db0"), (dw1, ps[2].grad, "dw1"), (db1, ps[3].grad, "db1")):
+            assert rel_err(got, ref) < 2e-5, (B, name, rel_err(got, ref))
+
+
 def test_mlp_chain_matches_torch(nat):
     """dense0 -> dense1 -> classifier -> softmax-CE fwd+bwd in one cluster launch vs autograd on the same fp32 ops."""
     import torch.nn.functional as F
