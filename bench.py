@@ -39,6 +39,12 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-multicast", action="store_true")
+    ap.add_argument("--config", default="fsa", choices=["fsa", "bsc", "mpq_dgt", "hfa", "mixed_sync"],
+                    help="BASELINE.json configs: fsa = examples/cnn.py dist_sync (headline); bsc = cnn_bsc.py (Bi-Sparse, threshold 0.01, local Adam); "
+                         "mpq_dgt = cnn_mpq.py + DGT (fp16 for keys >= 1000 elements, contribution-ranked tiles, fp8 demotion); hfa = cnn_hfa.py "
+                         "(K1=20 local steps, K2=10 party rounds per global round); mixed_sync = cnn.py -ms (dist_async global tier)")
+    ap.add_argument("--script", action="store_true", help="time the loop of examples/cnn.py itself (gluon autograd + kv.push/kv.pull per key through "
+                                                            "the fabric KVStore) instead of the fused HipsCNNTrainStep engine")
     ap.add_argument("--fast", action="store_true", help="plain TF32 tensor-core products instead of the fp32-accurate 3xTF32 default")
     ap.add_argument("--wire-dtype", default="fp32", choices=["fp32", "fp16", "mpq", "fp8"], help="transport format of the fused HiPS step (FP16 / MPQ accelerators)")
     return ap.parse_args()
@@ -85,6 +91,61 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+class ScriptPathEngine:
+    """The training loop of examples/cnn.py, verbatim in structure: gluon net, ``autograd.record`` / ``backward``, then for every parameter
+    ``kv.push(idx, grad / n, priority=-idx)`` and ``kv.pull(idx, param, priority=-idx)`` through ``mx.kv.create('dist_sync')`` (the fabric
+    KVStore under torchrun, the device store on one GPU) with Adam set on the kvstore.  Same interface as HipsCNNTrainStep for the timing code."""
+
+    def __init__(self, mx, B, dev, args):
+        import torch
+        self.mx, self.torch, self.B = mx, torch, B
+        ctx = mx.gpu(dev.index or 0)
+        self.ctx = ctx
+        net = mx.models.build_cnn()
+        net.initialize(force_reinit=True, ctx=ctx, init=mx.init.Xavier())
+        net(mx.nd.random.uniform(shape=(B, 1, 28, 28), ctx=ctx))
+        self.net, self.loss_fn = net, mx.gluon.loss.SoftmaxCrossEntropyLoss()
+        self.kv = mx.kv.create("dist_async" if args.config == "mixed_sync" else "dist_sync") if int(os.environ.get("WORLD_SIZE", 1)) > 1 else mx.kv.create("device")
+        self.kv.set_optimizer(mx.optimizer.Adam(learning_rate=0.01))
+        self.params = list(net.collect_params().values())
+        for idx, p in enumerate(self.params):
+            self.kv.init(idx, p.data())
+            self.kv.pull(idx, p.data())
+        mx.nd.waitall()
+        self.x = torch.empty(B, 1, 28, 28, device=dev); self.label = torch.empty(B, device=dev)
+        self.fabric = getattr(self.kv, "fabric", None)
+        self.kernels_per_step = 0
+        self._loss = None
+
+    def _iter(self, X, y):
+        mx = self.mx
+        with mx.autograd.record():
+            l = self.loss_fn(self.net(X), y)
+        l.backward()
+        for idx, p in enumerate(self.params):
+            self.kv.push(idx, p.grad() / self.B, priority=-idx)
+            self.kv.pull(idx, p.data(), priority=-idx)
+        mx.nd.waitall()
+        return l
+
+    def run_device(self):
+        from geomx_b200.ops import native
+        before = native.launch_count
+        self._loss = self._iter(self.mx.nd.NDArray(self.x), self.mx.nd.NDArray(self.label))
+        self.kernels_per_step = native.launch_count - before
+
+    def step(self, X, y):
+        mx = self.mx
+        l = self._iter(mx.nd.array(X, ctx=self.ctx), mx.nd.array(y, ctx=self.ctx))
+        return float(l.mean().asscalar())
+
+    def h2d_bytes_per_step(self):
+        return self.B * 784 * 4 + self.B * 4
+
+    def d2h_bytes_per_step(self):
+        return 4
 
 
 def reference_arm():
@@ -141,9 +202,16 @@ def main():
         # multi-rank: eager launches (an NCCL all-reduce captured inside the CUDA graph stalled on the test pod; the single-rank oracle is graphed)
         eng = OracleCNNTrainStep(batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev,
                                  use_graph=not args.no_graph and world == 1)
+    elif args.script:
+        eng = ScriptPathEngine(mx, B, dev, args)
     else:
+        kw = {"fsa": {}, "mixed_sync": {"mode": "dist_async"},
+              "bsc": {"update": "local", "bsc_threshold": 0.01, "size_lower_bound": 1000},
+              "mpq_dgt": {"update": "local", "wire_dtype": "mpq", "size_lower_bound": 1000, "dgt": True},
+              "hfa": {"hfa": (int(os.environ.get("MXNET_KVSTORE_HFA_K1", 20)), int(os.environ.get("MXNET_KVSTORE_HFA_K2", 10)))}}[args.config]
+        kw.setdefault("mode", args.mode); kw.setdefault("wire_dtype", args.wire_dtype)
         eng = mx.models.HipsCNNTrainStep(net=None, batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev,
-                                         use_graph=not args.no_graph, use_multicast=not args.no_multicast, mode=args.mode, wire_dtype=args.wire_dtype)
+                                         use_graph=not args.no_graph, use_multicast=not args.no_multicast, **kw)
 
     def barrier():
         torch.cuda.synchronize()
@@ -202,7 +270,7 @@ def main():
     # (%globaltimer stamps of CTA 0, first instruction -> last phase; untimed extra steps; nothing of it overlaps compute, so all of it is exposed)
     comm_us = None
     fab = getattr(eng, "fabric", None)
-    if fab is not None and args.mode == "dist_sync":
+    if fab is not None and args.mode == "dist_sync" and args.config in ("fsa", "bsc", "mpq_dgt") and not args.script:
         chans = list(fab.channels) or ["fsa"]
         last = "conv" if "conv" in fab.channels else chans[-1]      # the exchange at the end of the step (nothing left to hide it behind)
         for c in chans:
@@ -233,7 +301,7 @@ def main():
             "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(dev_ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32" if args.fast else "fp32 (3xTF32 tensor-core products + fp32 FMA, fp32 accumulate)", "data": "synthetic",
-            "impl": args.impl,
+            "impl": args.impl, "baseline_config": args.config, "path": "examples/cnn.py loop (script)" if args.script else "HipsCNNTrainStep engine",
             "config": {"model": "examples/cnn.py MNIST CNN (Conv16k5-Pool-Conv32k5-Pool-Dense256-Dense128-Dense10, 178762 params)",
                        "global_batch": B * world, "per_gpu_batch": B, "seq_len": None, "kvstore": args.mode,
                        "precision": ("fp32 storage and accumulation, TF32 tcgen05 multiplies (--fast)" if args.fast else
@@ -251,7 +319,8 @@ def main():
                        "protocol": getattr(getattr(eng, "fabric", None), "protocol", None), "wire_dtype": args.wire_dtype},
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms / K, 5),
                     "h2d_bytes_per_step": eng.h2d_bytes_per_step(), "d2h_bytes_per_step": eng.d2h_bytes_per_step(), "final_loss": round(last_loss, 5),
-                    "api": "HipsCNNTrainStep.step_async(X_pinned, y_pinned) -> LossHandle; loss of step i read (D2H, pinned) after step i+1 was enqueued"},
+                    "api": ("examples/cnn.py loop: mx.nd.array(host batch) -> autograd -> kv.push/pull per key -> loss.asscalar()" if args.script else
+                            "HipsCNNTrainStep.step_async(X_pinned, y_pinned) -> LossHandle; loss of step i read (D2H, pinned) after step i+1 was enqueued")},
             "exposed_push_pull_ms_per_step": None if comm_us is None else round(comm_us / 1e3, 5),
             "protocol_errors": proto_err,
             "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),

@@ -67,7 +67,7 @@ __device__ __forceinline__ float pool4(const float (&a)[4], float bias, int& bi)
 // grid (B, 4), 256 threads.  CTA (b, g): conv0 of image b (all 16 channels, kept in shared memory) and conv1 for output channels [8g, 8g+8).
 __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float* __restrict__ b0,
                                                        const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ a1,
-                                                       unsigned char* __restrict__ idx1, float* __restrict__ a2, unsigned char* __restrict__ idx2) {
+                                                       unsigned char* __restrict__ idx1, float* __restrict__ a2, unsigned char* __restrict__ idx2, unsigned long long* dbg) {
   __shared__ __align__(16) float sx[CD_H * CD_H];
   __shared__ __align__(16) float sw0[CD_C1 * CD_W1PAD];
   __shared__ float sb0[CD_C1];
@@ -75,6 +75,9 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
   __shared__ __align__(16) float sw1[8 * CD_C1 * CD_W1PAD];
   __shared__ float sb1[8];
   __shared__ __align__(16) float spart[4 * 64 * 8];
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  auto stamp = [&](int slot) { if (dbg_on) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[slot] = t; } };
+  stamp(0);
   pdl_wait();
   pdl_launch();
   const int b = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
   }
   if (tid < 8) sb1[tid] = b1[8 * g + tid];
   __syncthreads();
+  stamp(1);
   // ---- conv0 + bias + ReLU + pool: thread -> channel tid/16, windows (tid%16) + 16 j
   {
     const int ch = tid >> 4, sub = tid & 15;
@@ -110,6 +114,7 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
     }
   }
   __syncthreads();
+  stamp(2);
   // ---- conv1: thread -> input-channel quarter cq, output-channel pair op, pooling window win; 2 oc x 4 pixels accumulators
   {
     const int cq = tid >> 6, t64 = tid & 63, op = t64 >> 4, win = t64 & 15, ph = win >> 2, pw = win & 3;
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
     dst[1] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
   }
   __syncthreads();
+  stamp(3);
   if (tid < 128) {
     const int i64 = tid >> 1, which = tid & 1, op = i64 >> 4, win = i64 & 15, ol = 2 * op + which;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -142,6 +148,7 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
     const long long o = ((long long)b * CD_C2 + 8 * g + ol) * (CD_P2 * CD_P2) + win;
     a2[o] = v; idx2[o] = (unsigned char)bi;
   }
+  stamp(4);
 }
 
 // ------------------------------------------------------------------------------------------------------------------ backward (data + conv0)
@@ -164,11 +171,14 @@ struct CnnBwdSmem {
 __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ a1,
                                                        const unsigned char* __restrict__ idx1, const float* __restrict__ a2,
                                                        const unsigned char* __restrict__ idx2, const float* __restrict__ da2,
-                                                       float* __restrict__ dw0, float* __restrict__ db0) {
+                                                       float* __restrict__ dw0, float* __restrict__ db0, unsigned long long* dbg) {
   extern __shared__ __align__(16) float sm[];
   using L = CnnBwdSmem;
   float* sdz = sm + L::DZ; float* swt = sm + L::WT; float* sx = sm + L::X; float* sa1 = sm + L::A1; float* sda1 = sm + L::DA1;
   float* spart = sm + L::PART; int* spos = reinterpret_cast<int*>(sm + L::POS);
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  auto stamp = [&](int slot) { if (dbg_on) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[slot] = t; } };
+  stamp(8);
   pdl_wait();
   pdl_launch();
   const int b = blockIdx.x, cg = blockIdx.y, tid = threadIdx.x;
@@ -187,6 +197,7 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
     spos[i] = (2 * (win / CD_P1) + (id >> 1)) * CD_H + 2 * (win % CD_P1) + (id & 1);
   }
   __syncthreads();
+  stamp(9);
   // scatter the non-zeros of dz2 (pool + ReLU backward of conv1's output)
   for (int e = tid; e < CD_C2 * 16; e += 288) {
     const long long o = (long long)b * CD_C2 * 16 + e;
@@ -196,6 +207,7 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
     sdz[oc * 256 + (oh + 4) * 16 + ow + 4] = gv;
   }
   __syncthreads();
+  stamp(10);
   // ---- conv1 data gradient: thread -> oc quarter, channel pair, 2x2 output window of the 12x12 map
   {
     const int ocq = tid / 72, t72 = tid % 72, cp = t72 / 36, win = t72 % 36, ph = win / 6, pw = win % 6;
@@ -215,6 +227,7 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
     dst[1] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
   }
   __syncthreads();
+  stamp(11);
   if (tid < 144) {
     const int i72 = tid >> 1, which = tid & 1, cp = i72 / 36, win = i72 % 36, ph = win / 6, pw = win % 6, cl = 2 * cp + which;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -230,6 +243,7 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
     d[CD_P1] = m[CD_P1] > 0.f ? acc[2] : 0.f; d[CD_P1 + 1] = m[CD_P1 + 1] > 0.f ? acc[3] : 0.f;
   }
   __syncthreads();
+  stamp(12);
   // ---- conv0 weight / bias gradient of this image (4 channels): dW0[ch][kh][kw] += sum_windows g * x[oh+kh][ow+kw]
   if (tid < 100) {
     const int cl = tid / 25, tap = tid % 25, koff = (tap / 5) * CD_H + tap % 5;
@@ -243,18 +257,22 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
     for (int p = 0; p < 144; ++p) acc += sda1[cl * 144 + p];
     atomicAdd(db0 + 4 * cg + cl, acc);
   }
+  stamp(13);
 }
 
 // ------------------------------------------------------------------------------------------------------------------ conv1 weight gradient
 // grid (32 oc, 4 cg), 256 threads.  CTA owns dW1[oc][4cg..4cg+3][5][5] (100 outputs, written once: no atomics) and sums over all images:
 //   dW1[oc][c][kh][kw] = sum_{b, window} g[b][oc][window] * a1[b][c][oh+kh][ow+kw]     (g != 0 only at the window's arg-max where a2 > 0)
 __global__ void __launch_bounds__(256) cnn_wgrad1_kernel(const float* __restrict__ a1, const float* __restrict__ a2, const unsigned char* __restrict__ idx2,
-                                                          const float* __restrict__ da2, float* __restrict__ dw1, float* __restrict__ db1, int B) {
+                                                          const float* __restrict__ da2, float* __restrict__ dw1, float* __restrict__ db1, int B, unsigned long long* dbg) {
   extern __shared__ __align__(16) float sm[];
   float* sa = sm;                               // [B][4][144] the four input-channel planes of every image
   float* sg = sa + (size_t)B * 576;             // [B*16] routed gradients of this output channel
   int* sp = reinterpret_cast<int*>(sg + B * 16);  // [B*16] arg-max position as offset into a 12x12 plane
   float* sacc = reinterpret_cast<float*>(sp + B * 16);   // [2][128]
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  auto stamp = [&](int slot) { if (dbg_on) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[slot] = t; } };
+  stamp(16);
   pdl_wait();
   pdl_launch();
   const int oc = blockIdx.x, cg = blockIdx.y, tid = threadIdx.x;
@@ -270,6 +288,7 @@ __global__ void __launch_bounds__(256) cnn_wgrad1_kernel(const float* __restrict
     sp[e] = (2 * (win >> 2) + (id >> 1)) * CD_P1 + 2 * (win & 3) + (id & 1);
   }
   __syncthreads();
+  stamp(17);
   const int half = tid >> 7, t = tid & 127;
   float acc = 0.f;
   if (t < 100) {
@@ -287,17 +306,21 @@ __global__ void __launch_bounds__(256) cnn_wgrad1_kernel(const float* __restrict
     s = warp_sum(s);
     if (tid == 0) db1[oc] = s;
   }
+  stamp(18);
 }
 
 }  // namespace gx
 
 using namespace gx;
 
+static unsigned long long* g_cnn_dbg = nullptr;      // optional %globaltimer stamps of CTA (0,0): fwd 0-4, bwd 8-13, wgrad1 16-18
+GX_API int gx_cnn_set_debug(unsigned long long* p) { g_cnn_dbg = p; return 0; }
+
 // x [B,1,28,28]; w0 [16,1,5,5]; w1 [32,16,5,5]; writes a1 [B,16,12,12] + idx1, a2 [B,32,4,4] + idx2
 GX_API int gx_cnn_fwd(const float* x, const float* w0, const float* b0, const float* w1, const float* b1, float* a1, unsigned char* idx1, float* a2,
                       unsigned char* idx2, int B, cudaStream_t s) {
   if (B < 1) return 0;
-  launch_pdl(cnn_fwd_kernel, dim3(B, 4), dim3(256), 0, s, x, w0, b0, w1, b1, a1, idx1, a2, idx2);
+  launch_pdl(cnn_fwd_kernel, dim3(B, 4), dim3(256), 0, s, x, w0, b0, w1, b1, a1, idx1, a2, idx2, g_cnn_dbg);
   return GX_CHECK_LAUNCH();
 }
 // accumulates into dw0 [16,25] / db0 [16] (atomics: zero them first)
@@ -310,7 +333,7 @@ GX_API int gx_cnn_bwd(const float* x, const float* w1, const float* a1, const un
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  launch_pdl(cnn_bwd_kernel, dim3(B, 4), dim3(288), (size_t)CnnBwdSmem::BYTES, s, x, w1, a1, idx1, a2, idx2, da2, dw0, db0);
+  launch_pdl(cnn_bwd_kernel, dim3(B, 4), dim3(288), (size_t)CnnBwdSmem::BYTES, s, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, g_cnn_dbg);
   return GX_CHECK_LAUNCH();
 }
 // overwrites dw1 [32,16,5,5] and db1 [32].  B even, B <= 64 (shared-memory planes of all images).
@@ -323,6 +346,6 @@ GX_API int gx_cnn_wgrad1(const float* a1, const float* a2, const unsigned char* 
     if (e != cudaSuccess) return (int)e;
     attr = smem;
   }
-  launch_pdl(cnn_wgrad1_kernel, dim3(CD_C2, 4), dim3(256), smem, s, a1, a2, idx2, da2, dw1, db1, B);
+  launch_pdl(cnn_wgrad1_kernel, dim3(CD_C2, 4), dim3(256), smem, s, a1, a2, idx2, da2, dw1, db1, B, g_cnn_dbg);
   return GX_CHECK_LAUNCH();
 }

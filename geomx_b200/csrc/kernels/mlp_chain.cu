@@ -236,12 +236,15 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
     const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
     float acc[4][4] = {};
     prod_nt<D0, KS>(sX, sW0, tb, tn, ks, acc);
+    stamp(10);
     float* scratch = sA4;                                // [sA4 | sDZ4] = 32 KB contiguous, both unused until the end of P2 / P3
     put_partial<NS1>(scratch, tb, tn, ks, acc);
     __syncthreads();
     // W0's row slice is no longer needed: start fetching the COLUMN slice W0[:, cr*KS0 ...] for the backward pass (da2) underneath P2..P4
+    stamp(11);
     stage_plain_async(sW0, p.w0 + cr * KS0, D1, KS0, D0);
     cp_async_commit();
+    stamp(12);
     if (tid < MC_HALF) {
       const int b = tid >> 3, n4 = tid & 7;              // 32 x 8 float4 outputs
       float4 v = sum_partials<NS1, KS>(scratch, b, n4);
@@ -252,6 +255,7 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
 #pragma unroll
       for (int r = 0; r < MC_CLUSTER; ++r) *reinterpret_cast<float4*>(cluster.map_shared_rank(sA3, r) + o) = v;
     }
+    stamp(13);
   }
   cluster.sync();
   stamp(4);
@@ -387,6 +391,7 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
       const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
       float acc[4][4] = {};
       prod_nn<D1, KS0, KS>(sDZ3, sW0, tb, tn, ks, acc);
+      stamp(14);
       put_partial<KS0>(sDZ4, tb, tn, ks, acc);          // scratch = dz4 buffer (dead after P4): 2 x 32 x 64 floats = 16 KB
       named_bar_sync(1, MC_HALF);
       for (int e = tid; e < MC_B * KS0 / 4; e += MC_HALF) {

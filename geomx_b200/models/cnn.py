@@ -75,26 +75,42 @@ class HipsCNNTrainStep:
     """
 
     def __init__(self, net=None, batch_size=32, optimizer=None, topo=None, device=None, use_graph=True, pull_fused=False,
-                 use_multicast=True, mode="dist_sync", fused_zero_grad=True, wire_dtype="fp32", dgt=False, dgt_rerank_every=32):
+                 use_multicast=True, mode="dist_sync", fused_zero_grad=True, wire_dtype="fp32", dgt=False, dgt_rerank_every=32,
+                 update="server", bsc_threshold=None, size_lower_bound=None, hfa=None):
+        """``update='server'`` (examples/cnn.py): the optimizer runs on the global-PS shard inside the exchange kernel.  ``update='local'``
+        (examples/cnn_bsc.py / cnn_fp16.py / cnn_mpq.py): the kvstore only aggregates gradients (``set_optimizer`` is not called on it), every
+        worker applies its own Adam to the pulled aggregate — one fused arena-optimizer launch.  ``bsc_threshold``: Bi-Sparse between the tiers
+        for keys >= ``size_lower_bound`` elements.  ``hfa=(K1, K2)`` (examples/cnn_hfa.py): local Adam on the own gradient every step, party
+        average of the weights every K1 steps, global average every K1*K2 steps (reference milestone algebra, kvstore_dist_server.h:959-972)."""
         native.require()
         from .. import optimizer as opt
         self.B = B = int(batch_size)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.topo = topo or Topology.from_env()
         self.mode = mode
+        self.hfa = tuple(int(v) for v in hfa) if hfa else None
+        self.update = "local" if (update == "local" or self.hfa) else "server"
         self.fused_zero_grad = fused_zero_grad   # False keeps the gradients readable after a step (tests / debugging): memset instead
         optimizer = optimizer or opt.Adam(learning_rate=0.01)
         spec = optimizer.spec()
         if spec is None:
             raise ValueError("optimizer %s has no native spec; use Adam / SGD / DCASGD" % type(optimizer).__name__)
         self.layout = ArenaLayout.build(list(enumerate(CNN_PARAM_SHAPES)))
-        self.fabric = HipsFabric(self.layout, self.topo, self.device, spec, use_multicast=use_multicast)
-        self.fabric.set_push_scale(1.0 / B)          # the script-level `grad / num_samples`, folded into the push kernel
+        self._local_spec = spec if self.update == "local" else None
+        self.fabric = HipsFabric(self.layout, self.topo, self.device, None if self.update == "local" else spec, use_multicast=use_multicast)
+        # the script-level `grad / num_samples`, folded into the push kernel; with local updates the aggregate is also averaged over the workers
+        self.fabric.set_push_scale(1.0 / B if self.update == "server" else 1.0 / (B * self.topo.world))
+        from ..base import getenv_int
+        lower = int(size_lower_bound) if size_lower_bound is not None else getenv_int("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000)
+        fmts = {}
         if wire_dtype in ("fp16", "mpq", "fp8") and self.fabric.protocol == "ll":
             # FP16: every key as halves on the wire (examples/cnn_fp16.py); MPQ: only the keys above MXNET_KVSTORE_SIZE_LOWER_BOUND (cnn_mpq.py:52)
-            from ..base import getenv_int
-            bound = getenv_int("MXNET_KVSTORE_SIZE_LOWER_BOUND", 200000) if wire_dtype == "mpq" else 0
-            self.fabric.set_wire_formats({i: ("fp8" if wire_dtype == "fp8" else "fp16") for i, sl in enumerate(self.layout.slots) if sl.numel >= bound})
+            bound = lower if wire_dtype == "mpq" else 0
+            fmts = {i: ("fp8" if wire_dtype == "fp8" else "fp16") for i, sl in enumerate(self.layout.slots) if sl.numel >= bound}
+        if bsc_threshold and self.fabric.protocol == "ll":
+            fmts.update({i: "bsc" for i, sl in enumerate(self.layout.slots) if sl.numel >= lower})
+        if fmts:
+            self.fabric.set_wire_formats(fmts, bsc_threshold=float(bsc_threshold or 0.01))
         self._dgt_every = 0
         if dgt and self.fabric.protocol == "ll":
             self.fabric.enable_dgt()
@@ -104,7 +120,7 @@ class HipsCNNTrainStep:
         # exchange runs underneath it on its own stream (two-hop, optimizer sharded over all ranks); the conv keys come last and use the
         # one-hop replicated mode — the only communication left on the critical path (reference ordering: push(idx, priority=-idx),
         # examples/cnn.py:121-125).  GEOMX_STEP_OVERLAP=0 restores the single fused exchange at the end of the step.
-        self.overlap = mode == "dist_sync" and os.environ.get("GEOMX_STEP_OVERLAP", "1") == "1" and (self.topo.world == 1 or f.ll_d is not None)
+        self.overlap = mode == "dist_sync" and not self.hfa and os.environ.get("GEOMX_STEP_OVERLAP", "1") == "1" and (self.topo.world == 1 or f.ll_d is not None)
         if self.overlap:
             f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False)
             f.add_channel("conv", [0, 1, 2, 3], replicate=True)
@@ -114,6 +130,14 @@ class HipsCNNTrainStep:
         self.direct_conv = B <= 64 and B % 2 == 0 and os.environ.get("GEOMX_DIRECT_CONV", "1") == "1"
         self.P = [f.param_view(i) for i in range(10)]
         self.G = [f.grad_view(i) for i in range(10)]
+        if self.update == "local":
+            # worker-local weights + optimizer state: the fabric's parameter arena only receives the aggregated gradient (or, with HFA, the
+            # averaged weights) in this mode
+            n_el = self.layout.total
+            self.Wl = torch.zeros(n_el, dtype=torch.float32, device=self.device)
+            self.s0l, self.s1l = torch.zeros_like(self.Wl), torch.zeros_like(self.Wl)
+            self.opt_state = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self.P = [self.layout.view(self.Wl, i) for i in range(10)]
         self._init_params(net)
         dev, f32 = self.device, torch.float32
         e = lambda *s, dt=f32: torch.empty(*s, dtype=dt, device=dev)
@@ -144,23 +168,25 @@ class HipsCNNTrainStep:
             params = list(net.collect_params().values())
             assert [tuple(p.shape) for p in params] == CNN_PARAM_SHAPES, "network does not match the demo CNN"
             for i, p in enumerate(params):
-                self.P[i].copy_(p.data()._t.detach().to(self.device))
+                f.param_view(i).copy_(p.data()._t.detach().to(self.device))
         else:
             init = initializer.Xavier()
             for i, shape in enumerate(CNN_PARAM_SHAPES):
                 host = torch.zeros(shape)
                 init(initializer.InitDesc("w%d_%s" % (i, "weight" if len(shape) > 1 else "bias")), host)
-                self.P[i].copy_(host.to(self.device))
+                f.param_view(i).copy_(host.to(self.device))
         if topo.world > 1:
             import torch.distributed as dist
             dist.broadcast(f.param.tensor, src=0)      # `init`: rank-0 (master worker) value wins, then barrier
             torch.cuda.synchronize()
             dist.barrier()
         f.load_master_from_param()
+        if self.update == "local":
+            self.Wl.copy_(f.param.tensor)
         if net is not None:  # re-home the Gluon parameters onto the live arena (zero-copy pull)
             for i, p in enumerate(net.collect_params().values()):
                 d = p.data()
-                d._data = f.param_view(i)
+                d._data = self.P[i]
                 d._ctx_hint = Context("gpu", self.device.index or 0)
                 if p.grad_req != "null":
                     d.attach_grad(p.grad_req)
@@ -178,6 +204,22 @@ class HipsCNNTrainStep:
         if self.overlap:
             kv = lambda: f.channel_step("conv", zero_grad=self.fused_zero_grad)
         kv_dense = [("hips push+opt+pull (dense keys, overlapped)", "comm", lambda: f.channel_step("dense", zero_grad=self.fused_zero_grad))] if self.overlap else []
+        self._tail = []
+        if self.update == "local":
+            sp = self._local_spec
+            clip = sp.get("clip_gradient", -1.0)
+
+            def local_opt(grad_tensor, zero=None):
+                n.arena_opt(sp["name"], self.Wl, grad_tensor, self.s0l, self.s1l, self.layout.total, f.tile_mult, sp["lr"], sp["wd"], sp["rescale_grad"],
+                            -1.0 if clip is None else clip, sp.get("momentum", 0.0), sp.get("beta1", 0.9), sp.get("beta2", 0.999), sp.get("epsilon", 1e-8),
+                            sp.get("lamda", 0.04), self.opt_state, zero)
+            if self.hfa:
+                # HFA: no exchange inside the step; the optimizer consumes (and clears) the worker's own gradient arena
+                kv_dense = []
+                kv = lambda: local_opt(f.grad.tensor, f.grad.tensor if self.fused_zero_grad else None)
+            else:
+                # the exchange delivered the aggregated gradient into the fabric's parameter arena: one fused arena-optimizer launch applies it
+                self._tail = [("local optimizer (fused arena Adam)", "main", lambda: local_opt(f.param.tensor))]
         def conv1_fwd():
             # bias + ReLU + 2x2 max-pool in the tcgen05 epilogue (only the pooled map and its arg-max leave the SM); the two-kernel form is
             # the fallback for geometries the in-warp pooling cannot express
@@ -206,7 +248,7 @@ class HipsCNNTrainStep:
                 ("conv1 wgrad (direct, sparse)", "side", lambda: n.cnn_wgrad1(self.a1, self.a2, self.idx2, da2v, G[2], G[3])),
                 ("conv1 dgrad + conv0 wgrad (direct)", "main", lambda: n.cnn_bwd(self.x, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1])),
                 ("hips push+opt+pull", "join", kv),
-            ]
+            ] + self._tail
         return [
             ("conv0+relu+pool+im2col", "main", lambda: n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)),
             ("conv1 gemm (bias,relu,maxpool fused)", "main", conv1_fwd),
@@ -216,7 +258,7 @@ class HipsCNNTrainStep:
             ("dcol1 gemm", "main", lambda: n.gemm(self.dz2rows, Wc1, self.dcol1, b_mn=True)),
             ("conv0 wgrad + col2im", "main", lambda: n.conv_relu_pool_wgrad_col2im(self.x, self.dcol1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0], 5, 5)),
             ("hips push+opt+pull", "join", kv),
-        ]
+        ] + self._tail
 
     def _body(self, stop_after=None):
         before = native.launch_count
@@ -282,6 +324,26 @@ class HipsCNNTrainStep:
         else:
             self._body()
         self.steps_done += 1
+        if self.hfa and self.steps_done % self.hfa[0] == 0:
+            self._hfa_sync(global_round=(self.steps_done // self.hfa[0]) % self.hfa[1] == 0)
+
+    def _hfa_sync(self, global_round):
+        """Average the workers' weights inside the party (every K1 steps) or over the whole job (every K1*K2 steps).  Outside the captured
+        step: the party round is ONE launch of the party all-reduce kernel, the global round one launch of the fused exchange without an
+        optimizer (push_scale 1/parties turns the sum of party means into their mean)."""
+        f, topo = self.fabric, self.topo
+        if topo.world == 1:
+            return
+        f.grad.tensor.copy_(self.Wl).mul_(1.0 / topo.party_size)
+        if global_round:
+            scale = f.push_scale
+            f.set_push_scale(1.0 / topo.num_parties)
+            f.fsa_step()
+            f.set_push_scale(scale)
+        else:
+            f.party_allreduce(f.grad, f.param, scale=1.0)
+        self.Wl.copy_(f.param.tensor)
+        f.grad.tensor.zero_()
 
     def _pipeline(self):
         if not hasattr(self, "_pl"):

@@ -305,6 +305,8 @@ class HipsFabric:
         momentum-corrected residual, sends the ``k = floor(1024*threshold)`` largest entries as (value, index) packets; without a server
         optimizer the aggregate returns sparse as well (BSCPullCompress)."""
         self._params_cache.clear()
+        for ch in self.channels.values():
+            ch.pop("direct_ok", None)
         if not key_formats:
             self.tile_fmt = None
             return
@@ -474,9 +476,11 @@ class HipsFabric:
         return self.channels[name]
 
     def _channel_formats_direct_ok(self, ch):
-        if self.tile_fmt is None:
-            return True
-        return not bool(((self.tile_fmt == 2) & (ch["mask"] != 0)).any().item())      # Bi-Sparse needs the party aggregate: 3-hop kernel
+        """Bi-Sparse needs the party aggregate (3-hop kernel).  Cached per channel: the check reads device memory, which is not allowed while a
+        CUDA graph is being captured (the first, eager warm-up step fills the cache; set_wire_formats invalidates it)."""
+        if "direct_ok" not in ch:
+            ch["direct_ok"] = self.tile_fmt is None or not bool(((self.tile_fmt == 2) & (ch["mask"] != 0)).any().item())
+        return ch["direct_ok"]
 
     def _channel_block(self, name, zero_grad):
         key = ("channel", name, zero_grad)

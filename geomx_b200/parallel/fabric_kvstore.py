@@ -8,7 +8,14 @@ Selected by ``kvstore.dist.create_dist`` when the process was started by ``torch
                so later pulls into them are zero-copy.
 * ``push``   — queues the (summed) value into the gradient arena; ``pull`` registers its targets.  Nothing is launched until a pulled
                array is read or ``mx.nd.waitall()`` runs — then ONE ``gx_hips_fsa_step`` (or ``gx_hips_async_step``) launch serves every queued
-               key in priority order; keys that were not pushed this round are masked out (``tile_active``).
+               key; keys that were not pushed this round are masked out (``tile_active``).  When the script passes priorities
+               (``priority=-idx``, examples/cnn.py:121-125) — or sets ``ENABLE_P3=1`` — the kernel walks the tiles of high-priority keys first
+               (``tile_order``), which is what P3 / the engine's priority queue achieve on the TCP path.
+* optimizers — Adam / SGD / DCASGD specs run natively on the global-PS shard inside the exchange kernel; any other ``mx.optimizer`` object
+               (or one with an lr_scheduler / per-parameter multipliers) is executed by the Python updater on the aggregated gradient, identically
+               on every rank — the same arithmetic the reference's server-side pickled optimizer performs (kvstore.py:452-499).
+* TSEngine   — ``ENABLE_INTRA_TS`` / ``ENABLE_INTER_TS`` select an overlay for heterogeneous TCP links; NVSwitch is uniform, so they are
+               rejected here instead of being silently ignored.
 * roles      — ``rank`` / ``num_workers`` are party-local, ``num_all_workers`` is the world size; there is no separate master-worker process:
                ``is_master_worker`` is False everywhere and ``configures_servers`` is True on world rank 0, whose ``set_optimizer`` /
                ``set_gradient_compression`` calls are broadcast to all ranks when the arena is finalised (the reference ships them to the servers
@@ -63,6 +70,13 @@ class KVStoreFabric(KVStoreBase):
         self._local_iters = 0
         self._key_index = {}
         self._fp16_keys, self._wire_formats = set(), {}
+        self._host_optimizer, self._host_updater, self._host_w = None, None, None
+        self._priorities_seen = getenv_int("ENABLE_P3", 0) != 0        # P3 = priority-ordered propagation: on the fabric, priority tile order
+        self._order_sig = None
+        if (getenv_int("ENABLE_INTRA_TS", 0) or getenv_int("ENABLE_INTER_TS", 0)) and not getenv_int("GEOMX_FABRIC_IGNORE_TS", 0):
+            raise MXNetError("ENABLE_INTRA_TS / ENABLE_INTER_TS (TSEngine) schedule peer-to-peer merges over heterogeneous TCP links "
+                             "(3rdparty/ps-lite/src/van.cc:1174-1504); the NVSwitch fabric is uniform and reduces in one fused kernel, so the "
+                             "overlay does not exist here.  Unset them, use the DMLC_* TCP launch for TSEngine, or set GEOMX_FABRIC_IGNORE_TS=1.")
 
     # -- identity ---------------------------------------------------------------------------------------------------------------
     @property
@@ -83,18 +97,27 @@ class KVStoreFabric(KVStoreBase):
     # -- configuration (rank 0 decides, broadcast at finalize) ---------------------------------------------------------------------
     def set_optimizer(self, optimizer):
         spec = optimizer.spec()
-        if spec is None:
-            raise MXNetError("the fabric KVStore runs optimizers natively on the global-PS shard: %s has no native spec (use Adam / SGD / "
-                             "DCASGD, or update locally with a Trainer and pull aggregated gradients)" % type(optimizer).__name__)
+        native_ok = spec is not None and optimizer.spec_is_static() and os.environ.get("GEOMX_PY_UPDATER", "0") != "1"
         self._optimizer = optimizer
-        self._opt_spec = spec
+        if native_ok:
+            self._opt_spec, self._host_optimizer = spec, None
+        else:
+            # no (complete) native spec: the fused kernel only aggregates, the optimizer object runs on the aggregate on every rank
+            if self._fabric is not None and self._host_w is None:
+                raise MXNetError("switching to a Python-executed optimizer needs set_optimizer before the first push/pull")
+            self._opt_spec, self._host_optimizer = None, optimizer
         if self._fabric is not None:
-            self._fabric.set_optimizer(spec)
+            self._fabric.set_optimizer(self._opt_spec)
+            if self._host_optimizer is not None:
+                from .. import optimizer as opt
+                self._host_updater = opt.get_updater(self._host_optimizer)
 
     def _set_gradient_compression(self, params):
         t = params.get("type", "none")
         if t == "2bit":
-            raise MXNetError("2bit is a worker->server wire format of the TCP path; on NVSwitch use fp16/bf16 or block-scaled fp8 transport")
+            # 2-bit with error feedback (gradient_compression-inl.h:40-127): quantised by the native kernel before the push; see _push
+            self._twobit_thr = float(params.get("threshold", 0.5))
+            self._twobit_res = {}
         # 'bsc': the party aggregate is sparsified between the tiers inside the fused kernel (HipsFabric.set_wire_formats)
         if self._fabric is not None:
             self._apply_wire_formats()
@@ -139,9 +162,11 @@ class KVStoreFabric(KVStoreBase):
         topo = self._topo
         if topo.world > 1:
             import torch.distributed as dist
-            cfg = [self._opt_spec, self._compression] if topo.rank == 0 else [None, None]
+            cfg = [self._opt_spec, self._compression, self._host_optimizer] if topo.rank == 0 else [None, None, None]
             dist.broadcast_object_list(cfg, src=0)
-            self._opt_spec, self._compression = cfg
+            self._opt_spec, self._compression, self._host_optimizer = cfg
+            if (self._compression or {}).get("type") == "2bit" and not hasattr(self, "_twobit_thr"):
+                self._twobit_thr, self._twobit_res = float(self._compression.get("threshold", 0.5)), {}
         layout = ArenaLayout.build(self._keys)
         f = HipsFabric(layout, topo, self._device, self._opt_spec)
         for i, (key, _) in enumerate(self._keys):
@@ -162,6 +187,10 @@ class KVStoreFabric(KVStoreBase):
         self._init_vals = None
         self._fabric = f
         self._finalizing = False
+        if self._host_optimizer is not None:
+            from .. import optimizer as opt
+            self._host_updater = opt.get_updater(self._host_optimizer)
+            self._host_w = f.param.tensor.clone()        # the weights: the fabric's parameter arena carries the aggregated gradient in this mode
         self._apply_wire_formats()
         if getenv_int("ENABLE_DGT", 0) and f.protocol == "ll":
             # DGT on NVSwitch: contribution-ranked tile order + fp8 for the unimportant (1 - DMLC_K) fraction, re-ranked every few rounds
@@ -178,7 +207,18 @@ class KVStoreFabric(KVStoreBase):
         g.copy_(vals[0]._t.detach().reshape(g.shape))
         for v in vals[1:]:
             g.add_(v._t.detach().reshape(g.shape).to(g.device))
+        if getattr(self, "_twobit_thr", None) is not None and g.dtype == torch.float32:
+            # 2-bit gradient compression: residual += grad; every element becomes +thr / -thr / 0, the remainder stays in the residual for
+            # the next round (quantize_2bit / dequantize_2bit kernels of csrc/kernels/compress.cu, bit-exact reference packing)
+            from ..ops import native
+            flat = g.reshape(-1)
+            res = self._twobit_res.setdefault(i, torch.zeros_like(flat))
+            packed = torch.empty((flat.numel() + 15) // 16, dtype=torch.int32, device=flat.device)
+            native.quantize_2bit(flat, res, packed, self._twobit_thr)
+            native.dequantize_2bit(packed, flat, self._twobit_thr)
         self._pushed.add(i)
+        if priority != 0:
+            self._priorities_seen = True
         self._fabric.layout.slots[i].priority = priority
 
     def _pull(self, key, outs, priority):
@@ -208,10 +248,14 @@ class KVStoreFabric(KVStoreBase):
                     s = f.layout.slots[i]
                     mask[s.offset // 1024: s.offset // 1024 + s.tiles] = 1
                 f.tile_active.copy_(mask.to(f.device))
+            if self._priorities_seen and f.dgt_contrib is None and f.protocol == "ll":
+                self._apply_priority_order()
             if self._hfa:
                 self._flush_hfa(full)
             elif self._sync:
                 f.fsa_step(masked=not full)
+                if self._host_updater is not None:
+                    self._run_host_optimizer()
                 if f.dgt_contrib is not None and full:
                     self._dgt_round += 1
                     if self._dgt_round % self._dgt_every == 0:
@@ -229,6 +273,61 @@ class KVStoreFabric(KVStoreBase):
                 if tgt.data_ptr() == src.data_ptr():
                     continue
                 (tgt.detach() if tgt.requires_grad else tgt).copy_(src.reshape(tgt.shape), non_blocking=True)
+
+    def _apply_priority_order(self):
+        """Tiles of high-priority keys first (the reference pushes with priority = -index so that the layers the next forward pass needs first
+        are exchanged first, examples/cnn.py:121-125 / kvstore_dist.h:565-625 / P3 van.cc:847-860).  The order lives in a device array the
+        kernels read through ``tile_order``; it is rewritten only when the priorities change."""
+        f = self._fabric
+        slots = f.layout.slots
+        sig = tuple(getattr(s, "priority", 0) for s in slots)
+        if sig == self._order_sig:
+            return
+        keys = sorted(range(len(slots)), key=lambda i: (-sig[i], i))
+        order = np.concatenate([np.arange(slots[i].offset // 1024, slots[i].offset // 1024 + slots[i].tiles) for i in keys]).astype(np.int32)
+        if order.size < f.tiles:                                   # padding tiles (if any) keep their place at the end
+            rest = np.setdiff1d(np.arange(f.tiles, dtype=np.int32), order)
+            order = np.concatenate([order, rest]).astype(np.int32)
+        if f.tile_order is None:
+            f.tile_order = torch.from_numpy(order).to(f.device)
+            f._params_cache.clear()
+        else:
+            f.tile_order.copy_(torch.from_numpy(order).to(f.device))
+        self._order_sig = sig
+
+    def _run_host_optimizer(self):
+        """Python-executed optimizer (no complete native spec): the exchange left the aggregated gradient of every pushed key in the
+        parameter arena; apply the optimizer object to the rank-local weight copy (identical on all ranks) and publish the weights."""
+        from ..ndarray import NDArray
+        f = self._fabric
+        for i in sorted(self._pushed):
+            w = f.layout.view(self._host_w, i)
+            agg = f.param_view(i)
+            self._host_updater(i, NDArray(agg.clone()), NDArray(w))
+            agg.copy_(w)
+
+    def _row_sparse_pull(self, key, outs, row_ids, priority):
+        """Rows of a key from the (already exchanged) parameter arena: unique row ids (CUB radix sort + select, csrc/kernels/sparse_ops.cu) and
+        a row gather — kvstore_dist.h PullRowSparse_ :660-702 without the wire."""
+        from ..ndarray.sparse import RowSparseNDArray, _gather
+        from ..kvstore.utils import unique_rows
+        if key not in self._key_index:
+            raise MXNetError("key %s has not been initialised" % key)
+        self.flush()
+        self._finalize()
+        src = self._fabric.param_view(self._key_index[key])
+        src2d = src.reshape(src.shape[0], -1)
+        for o, ids in zip(outs, row_ids):
+            rows = unique_rows(ids._t.to(src.device))
+            picked = _gather(src2d.contiguous(), rows).reshape((rows.numel(),) + tuple(src.shape[1:]))
+            if isinstance(o, RowSparseNDArray):
+                dev = o.data._t.device
+                o._set_rows(picked.to(dev), rows.to(dev))
+                o._shape = tuple(src.shape)
+            else:
+                tgt = o._t
+                tgt.zero_()
+                tgt[rows.to(tgt.device)] = picked.to(tgt.device)
 
     def _flush_hfa(self, full):
         f, topo = self._fabric, self._topo

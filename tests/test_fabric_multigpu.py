@@ -67,6 +67,35 @@ def test_mixed_sync_one_sided_kernel():
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("mode", ["hostopt", "sched", "2bit", "rowsparse"])
+def test_kvstore_api_surface_on_the_fabric(mode):
+    """Python-executed optimizers (no native spec / lr_scheduler), priorities, row_sparse_pull and 2-bit compression through
+    mx.kv.create('dist_sync') on the fabric."""
+    rc, out = _torchrun(2, "fabric_api_check.py", mode, port=29681 + ["hostopt", "sched", "2bit", "rowsparse"].index(mode))
+    assert rc == 0 and "API_CHECK %s PASS" % mode in out, out[-3000:]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_tsengine_flags_are_rejected_on_the_fabric():
+    rc, out = _torchrun(2, "fabric_api_check.py", "hostopt", port=29691, env={"ENABLE_INTRA_TS": "1"})
+    assert rc != 0 and "TSEngine" in out, out[-2000:]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("config", ["bsc", "mpq_dgt", "hfa", "mixed_sync"])
+def test_bench_configs_train(config):
+    """BASELINE.json configs 3-5 (+ MixedSync) through bench.py on 2 GPUs: must run, keep the protocol error flag clear and report a finite loss."""
+    import json
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "45", "--warmup", "5", "--config", config]
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and line, r.stdout[-3000:]
+    out = json.loads(line[-1])
+    assert out["baseline_config"] == config and out["value"] > 0 and not out.get("protocol_errors"), out
+    assert out["e2e"]["final_loss"] == out["e2e"]["final_loss"] and out["e2e"]["final_loss"] < 3.0, out["e2e"]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
 def test_hfa_rounds():
     rc, out = _torchrun(2, "fabric_hfa_check.py", "1", port=29661)
     assert rc == 0 and "HFA_CHECK PASS" in out, out[-3000:]

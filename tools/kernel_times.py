@@ -42,18 +42,30 @@ print("%-52s %-5s %8.2f" % ("sum", "", total))
 eng._body(); torch.cuda.synchronize()
 lib = native.require()
 if eng.fused_mlp:
-    dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(32, dtype=torch.int64, device="cuda")
     lib.gx_mlp_chain_set_debug(ctypes.c_void_p(dbg.data_ptr()))
     for rep in range(3):
         eng._body(); torch.cuda.synchronize()
         st = dbg.cpu().tolist()
         print("mlp chain phases (us since kernel start): 0 start|1 prologue issued|2 pdl wait done|3 inputs landed+sync|4 P1|5 P2|6 P3|7 P4 compute|8 dz3 bcast|9 end:",
-              ["%.2f" % ((v - st[0]) / 1e3) for v in st[:10]])
+              ["%.2f" % ((v - st[0]) / 1e3) for v in st[:10]], "| P1: 10 products done|11 partials synced|12 W0 prefetch issued|13 a3 broadcast:",
+              ["%.2f" % ((v - st[0]) / 1e3) for v in st[10:14]], "| P5: 14 da2 products done:", "%.2f" % ((st[14] - st[0]) / 1e3))
     lib.gx_mlp_chain_set_debug(ctypes.c_void_p(0))
+if eng.direct_conv:
+    dbg = torch.zeros(32, dtype=torch.int64, device="cuda")
+    lib.gx_cnn_set_debug(ctypes.c_void_p(dbg.data_ptr()))
+    for rep in range(2):
+        eng._body(); torch.cuda.synchronize()
+        st = dbg.cpu().tolist()
+        r = lambda a, b: ["%.2f" % ((v - st[a]) / 1e3) for v in st[a:b]]
+        print("cnn_fwd  (us): 0 start|1 operands staged|2 conv0 done|3 conv1 partials|4 end:", r(0, 5))
+        print("cnn_bwd  (us): 8 start|9 staged|10 dz2 scattered|11 dgrad partials|12 da1 routed|13 end:", r(8, 14))
+        print("cnn_wgrad1 (us): 16 start|17 staged|18 end:", r(16, 19))
+    lib.gx_cnn_set_debug(ctypes.c_void_p(0))
 dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
 lib.gx_gemm_set_debug(ctypes.c_void_p(dbg.data_ptr()))
-for label, fn in (("conv1 gemm+pool", eng._steps()[1][2]), ("dcol1 gemm", [s for s in eng._steps() if s[0].startswith("dcol1")][0][2]),
-                  ("dWc1 gemm", [s for s in eng._steps() if s[0].startswith("dWc1")][0][2])):
+gemm_steps = [(s[0], s[2]) for s in eng._steps() if "gemm" in s[0]]
+for label, fn in gemm_steps:
     for rep in range(2):
         fn(); torch.cuda.synchronize()
     st = dbg.cpu().tolist()
