@@ -17,6 +17,7 @@
 // One TSNode per (application, plane): workers use it on the local plane (intra-party TS), local servers on the global plane (inter-
 // party TS); servers of a plane use only the relay half plus AskAsServer().
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
@@ -307,7 +308,7 @@ class TSNode {
   std::map<int, RelayBuf> relay_;
   std::map<int, Received> received_;
   RelayedFn on_relayed_;
-  long merges_received_ = 0, relays_sent_ = 0;
+  std::atomic<long> merges_received_{0}, relays_sent_{0};   // read by the test / profiler thread while the TS threads count
 };
 
 }  // namespace hips

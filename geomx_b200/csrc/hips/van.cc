@@ -286,7 +286,7 @@ void Van::Start(int customer_id) {
   }
   // everything the receive thread consults must exist BEFORE it starts: a peer's first barrier request can arrive the moment this node
   // turns ready, i.e. before Start() returns (a resender created later would neither ACK nor de-duplicate that first message)
-  if (env->GetInt("PS_RESEND", 0) != 0) resender_.reset(new Resender(env->GetInt("PS_RESEND_TIMEOUT", 1000), 100, this));
+  if (env->GetInt("PS_RESEND", 0) != 0) std::atomic_store(&resender_, std::make_shared<Resender>(env->GetInt("PS_RESEND_TIMEOUT", 1000), 100, this));
   const bool ts_on = plane_ == kLocal ? env->GetInt("ENABLE_INTRA_TS", 0) != 0 : env->GetInt("ENABLE_INTER_TS", 0) != 0;
   if (is_scheduler_ && ts_on) ts_sched_.reset(new TSScheduler(this, po_->num_workers_in(plane_), plane_));
   if (plane_ == kGlobal && env->GetInt("ENABLE_DGT", 0) != 0) {
@@ -316,7 +316,7 @@ void Van::Start(int customer_id) {
 }
 
 void Van::Stop() {
-  if (resender_ && !stop_.load()) resender_->WaitDrained(5000);
+  if (std::shared_ptr<Resender> rs = std::atomic_load(&resender_)) { if (!stop_.load()) rs->WaitDrained(5000); }
   if (stop_.exchange(true)) return;
   if (prio_thread_) {
     Message exit; exit.meta.control.cmd = Control::TERMINATE; exit.meta.recver = my_node_.id; exit.meta.priority = -(1 << 30);
@@ -326,13 +326,18 @@ void Van::Stop() {
   if (dgt_sender_) dgt_sender_->Stop();
   if (delay_thread_) { { std::lock_guard<std::mutex> lk(delay_mu_); } delay_cv_.notify_all(); delay_thread_->join(); }
   if (heartbeat_thread_) heartbeat_thread_->join();
-  resender_.reset();
   char c = 1;
   if (wake_pipe_[1] >= 0) { ssize_t r = ::write(wake_pipe_[1], &c, 1); (void)r; }
-  if (listen_fd_ >= 0) { ::shutdown(listen_fd_, SHUT_RDWR); ::close(listen_fd_); listen_fd_ = -1; }
+  // shutdown() wakes the accept thread; the descriptor itself is closed (and the member rewritten) only after that thread has gone — it reads
+  // listen_fd_ on every iteration (found by ThreadSanitizer, profiles/tsan_hips.txt)
+  if (listen_fd_ >= 0) ::shutdown(listen_fd_, SHUT_RDWR);
   if (accept_thread_) accept_thread_->join();
   if (recv_thread_) recv_thread_->join();
   if (udp_thread_) { udp_thread_->join(); ::close(udp_fd_); udp_fd_ = -1; }
+  if (listen_fd_ >= 0) { ::close(listen_fd_); listen_fd_ = -1; }
+  // the receive threads hand every message to the resender (ACK / duplicate filter) and its timer thread sends through senders_: it goes
+  // away after the receivers and before the sender table
+  std::atomic_store(&resender_, std::shared_ptr<Resender>());
   if (Environment::Get()->GetInt("GEOMX_NET_STATS", 0) != 0) {   // one machine-readable line per plane (tests, capacity planning)
     fprintf(stdout, "RESULT {\"net_stats\": {\"plane\": %d, \"node\": %d, \"sent_bytes\": %zu, \"recv_bytes\": %zu, \"udp_sent\": %zu, \"udp_received\": %zu}}\n",
             static_cast<int>(plane_), my_node_.id, send_bytes_.load(), recv_bytes_.load(), udp_sent_.load(), udp_received_.load());
@@ -400,12 +405,13 @@ void Van::DelayedSending() {
 int Van::SendWire(const Message& msg) {
   const int id = msg.meta.recver;
   HIPS_CHECK(id != Meta::kEmpty);
-  Sender* s = nullptr;
+  if (stop_.load()) return -1;                 // the transport is going down: late application traffic (e.g. a last response) is dropped
+  std::shared_ptr<Sender> s;
   {
     std::lock_guard<std::mutex> lk(senders_mu_);
     auto it = senders_.find(id);
-    if (it == senders_.end()) it = senders_.emplace(id, std::unique_ptr<Sender>(new Sender())).first;
-    s = it->second.get();
+    if (it == senders_.end()) it = senders_.emplace(id, std::make_shared<Sender>()).first;
+    s = it->second;
   }
   Message out = msg;
   if (out.meta.sender == Meta::kEmpty) out.meta.sender = my_node_.id;
@@ -432,7 +438,9 @@ int Van::SendWire(const Message& msg) {
   }
   if (n >= 0) {
     send_bytes_ += n;
-    if (resender_ && ready_.load() && out.meta.control.cmd != Control::ACK && out.meta.control.cmd != Control::ADD_NODE) resender_->AddOutgoing(out);
+    if (ready_.load() && out.meta.control.cmd != Control::ACK && out.meta.control.cmd != Control::ADD_NODE) {
+      if (std::shared_ptr<Resender> rs = std::atomic_load(&resender_)) rs->AddOutgoing(out);
+    }
     if (Verbose() >= 2) HIPS_VLOG(2, "plane %d SEND %d -> %d cmd=%d req=%d push=%d ts=%d bytes=%d", plane_, out.meta.sender, id, out.meta.control.cmd,
                                    out.meta.request, out.meta.push, out.meta.timestamp, n);
   }
@@ -497,7 +505,10 @@ void Van::Receiving() {
       }
       // registration traffic (before either side is ready) is not covered by the ACK protocol, exactly like the reference, which starts
       // its resender only once the node table is known
-      if (resender_ && ready_.load() && msg.meta.control.cmd != Control::ADD_NODE && resender_->AddIncoming(msg)) continue;
+      if (ready_.load() && msg.meta.control.cmd != Control::ADD_NODE) {
+        std::shared_ptr<Resender> rs = std::atomic_load(&resender_);
+        if (rs && rs->AddIncoming(msg)) continue;
+      }
       const Control& ctrl = msg.meta.control;
       if (!ctrl.empty()) {
         if (ctrl.cmd == Control::TERMINATE) { stop_ = true; break; }

@@ -93,7 +93,7 @@ class Van {
   std::mutex nodes_mu_;
   std::unordered_map<int, Node> nodes_;                 // id -> address
   struct Sender { int fd = -1; std::mutex mu; };
-  std::unordered_map<int, std::unique_ptr<Sender>> senders_;   // id -> connected socket
+  std::unordered_map<int, std::shared_ptr<Sender>> senders_;   // id -> connected socket (shared: a sender in flight survives Stop())
   std::mutex senders_mu_;
   std::unordered_map<std::string, int> connected_;      // "host:port" -> node id (shared-address detection)
 
@@ -116,7 +116,7 @@ class Van {
   int recv_timeout_ms_ = 60000;           // PS_RECV_TIMEOUT_MS: SO_RCVTIMEO of accepted connections (0 = block forever)
   int num_servers_seen_ = 0, num_workers_seen_ = 0;
   std::vector<int> barrier_count_;
-  std::unique_ptr<Resender> resender_;
+  std::shared_ptr<Resender> resender_;      // read with std::atomic_load: application threads may still send while Stop() tears down
   std::unique_ptr<TSScheduler> ts_sched_;
   std::unique_ptr<DGTSender> dgt_sender_;
   std::unique_ptr<DGTReceiver> dgt_receiver_;
