@@ -24,6 +24,15 @@ constexpr int CD_C1 = 16, CD_P1 = 12;            // conv0: 16 channels, 24x24 ->
 constexpr int CD_C2 = 32, CD_P2 = 4;             // conv1: 32 channels,  8x8  -> pooled 4x4
 constexpr int CD_W1PAD = 28;                     // 25 taps padded to 28 floats (16-byte rows)
 
+// asynchronous global -> shared copies: all of a CTA's operand loads are in flight at once instead of one dependent round trip per element
+__device__ __forceinline__ void cpa4(float* sdst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpa16(float* sdst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
 // 2x2 output window of a 5x5 valid convolution from a 6x6 input patch: acc[dy*2+dx] += sum_{r,s} patch[dy+r][dx+s] * w[r*5+s]
 __device__ __forceinline__ void window_fma(const float (&pt)[6][6], const float (&w)[28], float (&acc)[4]) {
 #pragma unroll
@@ -81,14 +90,17 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
   pdl_wait();
   pdl_launch();
   const int b = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < CD_H * CD_H / 4; i += 256) reinterpret_cast<float4*>(sx)[i] = reinterpret_cast<const float4*>(x + (long long)b * CD_H * CD_H)[i];
-  for (int i = tid; i < CD_C1 * CD_W1PAD; i += 256) { const int ch = i / CD_W1PAD, t = i % CD_W1PAD; sw0[i] = t < 25 ? w0[ch * 25 + t] : 0.f; }
+  for (int i = tid; i < CD_H * CD_H / 4; i += 256) cpa16(sx + 4 * i, x + (long long)b * CD_H * CD_H + 4 * i);
+  for (int i = tid; i < CD_C1 * 25; i += 256) { const int ch = i / 25, t = i - ch * 25; cpa4(sw0 + ch * CD_W1PAD + t, w0 + i); }
+  for (int i = tid; i < CD_C1 * 3; i += 256) sw0[(i / 3) * CD_W1PAD + 25 + i % 3] = 0.f;          // pad taps 25..27
   if (tid < CD_C1) sb0[tid] = b0[tid];
-  for (int i = tid; i < 8 * CD_C1 * CD_W1PAD; i += 256) {
-    const int t = i % CD_W1PAD, oc_c = i / CD_W1PAD;            // oc_c = ol * 16 + c
-    sw1[i] = t < 25 ? w1[((long long)(8 * g) * CD_C1 + oc_c) * 25 + t] : 0.f;
+  {
+    const float* wsrc = w1 + (long long)(8 * g) * CD_C1 * 25;      // the 8 output channels of this CTA: 3200 contiguous floats
+    for (int i = tid; i < 8 * CD_C1 * 25; i += 256) { const int r = i / 25, t = i - r * 25; cpa4(sw1 + r * CD_W1PAD + t, wsrc + i); }
+    for (int i = tid; i < 8 * CD_C1 * 3; i += 256) sw1[(i / 3) * CD_W1PAD + 25 + i % 3] = 0.f;
   }
   if (tid < 8) sb1[tid] = b1[8 * g + tid];
+  cpa_wait_all();
   __syncthreads();
   stamp(1);
   // ---- conv0 + bias + ReLU + pool: thread -> channel tid/16, windows (tid%16) + 16 j
@@ -157,8 +169,11 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
 //   da1 = full correlation with the flipped filters = the forward window routine on the padded plane; da1 never leaves shared memory:
 //   it is max-pool / ReLU routed straight into conv0's weight and bias gradient (the first layer needs no input gradient).
 struct CnnBwdSmem {
-  static constexpr int DZ = 0;                                   // [32][16][16]
-  static constexpr int WT = DZ + CD_C2 * 256;                    // [4 cl][32 oc][28] flipped filters
+  static constexpr int DZLD = 22;                                 // row stride of the padded dz2 plane: 16 + 6 floats keeps the 6x6 patch loads of a
+                                                                 // warp (6 windows per row pair, rows 2*ld apart) on distinct banks
+  static constexpr int DZPL = 16 * DZLD;                         // floats per plane
+  static constexpr int DZ = 0;                                   // [32][16][DZLD]
+  static constexpr int WT = DZ + CD_C2 * DZPL;                   // [4 cl][32 oc][28] flipped filters
   static constexpr int X = WT + 4 * CD_C2 * CD_W1PAD;            // [28][28]
   static constexpr int A1 = X + CD_H * CD_H;                     // [4][144] pooled conv0 activations (ReLU mask)
   static constexpr int DA1 = A1 + 4 * 144;                       // [4][144] -> routed gradient g
@@ -182,20 +197,21 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
   pdl_wait();
   pdl_launch();
   const int b = blockIdx.x, cg = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < CD_C2 * 256 / 4; i += 288) reinterpret_cast<float4*>(sdz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = tid; i < 4 * CD_C2 * CD_W1PAD; i += 288) {
-    const int t = i % CD_W1PAD, r = i / CD_W1PAD, oc = r % CD_C2, cl = r / CD_C2;      // swt[(cl*32 + oc)*28 + t], t = flipped tap
-    float v = 0.f;
-    if (t < 25) { const int kh = 4 - t / 5, kw = 4 - t % 5; v = w1[(((long long)oc * CD_C1) + 4 * cg + cl) * 25 + kh * 5 + kw]; }
-    swt[i] = v;
+  for (int i = tid; i < CD_C2 * L::DZPL / 4; i += 288) reinterpret_cast<float4*>(sdz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 4 * CD_C2 * 25; i += 288) {
+    // swt[(cl*32 + oc)*28 + t] = W1[oc][4cg+cl][4 - t/5][4 - t%5]   (t = flipped tap); source index runs over (oc, cl, tap) = 100 floats per oc
+    const int oc = i / 100, rem = i - oc * 100, cl = rem / 25, tap = rem - cl * 25;
+    cpa4(swt + (cl * CD_C2 + oc) * CD_W1PAD + (24 - tap), w1 + ((long long)oc * CD_C1 + 4 * cg) * 25 + rem);
   }
-  for (int i = tid; i < CD_H * CD_H / 4; i += 288) reinterpret_cast<float4*>(sx)[i] = reinterpret_cast<const float4*>(x + (long long)b * CD_H * CD_H)[i];
+  for (int i = tid; i < 4 * CD_C2 * 3; i += 288) swt[(i / 3) * CD_W1PAD + 25 + i % 3] = 0.f;
+  for (int i = tid; i < CD_H * CD_H / 4; i += 288) cpa16(sx + 4 * i, x + (long long)b * CD_H * CD_H + 4 * i);
+  for (int i = tid; i < 4 * 144 / 4; i += 288) cpa16(sa1 + 4 * i, a1 + ((long long)b * CD_C1 + 4 * cg) * 144 + 4 * i);
   for (int i = tid; i < 4 * 144; i += 288) {
     const long long o = ((long long)b * CD_C1 + 4 * cg) * 144 + i;
-    sa1[i] = a1[o];
     const int win = i % 144, id = idx1[o];
     spos[i] = (2 * (win / CD_P1) + (id >> 1)) * CD_H + 2 * (win % CD_P1) + (id & 1);
   }
+  cpa_wait_all();
   __syncthreads();
   stamp(9);
   // scatter the non-zeros of dz2 (pool + ReLU backward of conv1's output)
@@ -204,7 +220,7 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
     const int oc = e >> 4, win = e & 15, id = idx2[o];
     const float gv = a2[o] > 0.f ? da2[o] : 0.f;
     const int oh = 2 * (win >> 2) + (id >> 1), ow = 2 * (win & 3) + (id & 1);
-    sdz[oc * 256 + (oh + 4) * 16 + ow + 4] = gv;
+    sdz[oc * L::DZPL + (oh + 4) * L::DZLD + ow + 4] = gv;
   }
   __syncthreads();
   stamp(10);
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
     for (int o8 = 0; o8 < 8; ++o8) {
       const int oc = 8 * ocq + o8;
       float pt[6][6], w[28];
-      load_patch(sdz + oc * 256 + (2 * ph) * 16 + 2 * pw, 16, pt);
+      load_patch(sdz + oc * L::DZPL + (2 * ph) * L::DZLD + 2 * pw, L::DZLD, pt);
       load_w28(swt + ((2 * cp) * CD_C2 + oc) * CD_W1PAD, w);
       window_fma(pt, w, acc0);
       load_w28(swt + ((2 * cp + 1) * CD_C2 + oc) * CD_W1PAD, w);

@@ -27,9 +27,13 @@ def main():
     elif mode == "2bit":
         kv.set_gradient_compression({"type": "2bit", "threshold": 0.5})
     params = [mx.nd.ones(s, ctx=ctx) for s in shapes]
+    emb = mx.nd.array(np.arange(40, dtype=np.float32).reshape(10, 4), ctx=ctx)
     for i, p in enumerate(params):
         kv.init(i, p)
         kv.pull(i, p)
+    if mode == "rowsparse":
+        kv.init(50, emb)            # the fabric lays its arena out at the first data operation: every key is initialised before that
+        kv.pull(50, emb)
     mx.nd.waitall()
     gsum = sum(range(1, world + 1))                       # rank r pushes (r + 1) * base
     if mode in ("hostopt", "sched"):
@@ -64,10 +68,7 @@ def main():
             ok = False
             print("rank %d 2bit: got %s expected [0, %.2f]" % (rank, outs, 0.5 * world), flush=True)
     elif mode == "rowsparse":
-        emb = mx.nd.array(np.arange(40, dtype=np.float32).reshape(10, 4), ctx=ctx)
         kv2 = kv
-        kv2.init(50, emb)
-        kv2.pull(50, emb); mx.nd.waitall()
         out = mx.nd.sparse.zeros("row_sparse", (10, 4), ctx=ctx)
         kv2.row_sparse_pull(50, out=out, row_ids=mx.nd.array([7, 2, 7, 5], ctx=ctx, dtype="int64"))
         ids = out.indices.asnumpy().tolist(); rows = out.data.asnumpy()
