@@ -24,7 +24,6 @@ namespace cg = cooperative_groups;
 
 namespace gx {
 
-constexpr int MC_CLUSTER = 8;
 constexpr int MC_THREADS = 512;   // 16 warps: two warp-groups of 256 that either split K (P1) or run data- and weight-gradient side by side (P4, P5)
 constexpr int MC_HALF = 256;
 constexpr int MC_B = 32;      // batch rows held (rows >= B are zero)
@@ -162,9 +161,9 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ sDZ, const 
     *reinterpret_cast<float4*>(out_row0 + (long long)(n0 + i) * KD + 4 * tk) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 }
 
-template <int D0, int D1, int D2>
+template <int D0, int D1, int D2, int CS>
 struct MlpSmem {
-  static constexpr int NS1 = D1 / MC_CLUSTER, NS2 = D2 / MC_CLUSTER, KS0 = D0 / MC_CLUSTER;
+  static constexpr int NS1 = D1 / CS, NS2 = D2 / CS, KS0 = D0 / CS;
   // float offsets
   static constexpr int X = 0;                                  // [32][D0] swizzled
   static constexpr int W0 = X + MC_B * D0;                     // fwd: [NS1][D0] swizzled;  bwd: [D1][KS0] plain
@@ -181,12 +180,16 @@ struct MlpSmem {
   static constexpr int BYTES = TOTAL * 4;
 };
 
-template <int D0, int D1, int D2>
-__global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS, 1) mlp_chain_kernel(const MlpChainParams p) {
-  using L = MlpSmem<D0, D1, D2>;
+// CS = CTAs per cluster: 8 (portable) or 16 (non-portable size, one GPC): every layer is cut into CS column slices
+template <int D0, int D1, int D2, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(MC_THREADS, 1) mlp_chain_kernel(const MlpChainParams p) {
+  using L = MlpSmem<D0, D1, D2, CS>;
   constexpr int NS1 = L::NS1, NS2 = L::NS2, KS0 = L::KS0;
+  constexpr int MC_CLUSTER = CS;
   static_assert(D0 % 64 == 0 && D1 % 64 == 0 && D2 % 64 == 0, "layer widths must be multiples of 64");
-  static_assert(NS1 == 32 && NS2 == 16 && KS0 == 64, "thread mappings below are written for 512 -> 256 -> 128");
+  static_assert(NS1 % 8 == 0 && NS2 % 4 == 0 && KS0 % 4 == 0, "slices must hold whole register tiles");
+  static_assert(MC_THREADS % (2 * NS1) == 0 && MC_HALF % (2 * NS2) == 0 && MC_HALF % (2 * NS1) == 0 && MC_HALF % (2 * KS0) == 0, "K splits");
+  static_assert(MC_THREADS / (2 * NS1) * MC_B * NS1 <= 2 * MC_B * D2 && MC_HALF / (2 * KS0) * MC_B * KS0 <= MC_B * D2, "scratch sizes");
   extern __shared__ __align__(16) float sm[];
   float* sX = sm + L::X; float* sW0 = sm + L::W0; float* sW1 = sm + L::W1; float* sA3 = sm + L::A3; float* sA4 = sm + L::A4;
   float* sDZ4 = sm + L::DZ4; float* sW2 = sm + L::W2; float* sDL = sm + L::DL;
@@ -232,7 +235,7 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
   // tile coordinates shared by the 32-row products: 8 row groups x (NC/4) column groups per K split
   // ---------------- P1: a3[:, slice] = relu(x * W0[slice]^T + b0)          NC = 32, K = D0, KS = 4
   {
-    constexpr int KS = 8, PER = MC_THREADS / KS;       // 64 tiles per split, K split over all 16 warps
+    constexpr int PER = 2 * NS1, KS = MC_THREADS / PER;  // 8 row groups x NS1/4 column groups per split; K split over all 16 warps
     const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
     float acc[4][4] = {};
     prod_nt<D0, KS>(sX, sW0, tb, tn, ks, acc);
@@ -245,8 +248,8 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
     stage_plain_async(sW0, p.w0 + cr * KS0, D1, KS0, D0);
     cp_async_commit();
     stamp(12);
-    if (tid < MC_HALF) {
-      const int b = tid >> 3, n4 = tid & 7;              // 32 x 8 float4 outputs
+    if (tid < MC_B * NS1 / 4) {
+      const int b = tid / (NS1 / 4), n4 = tid % (NS1 / 4);   // 32 x NS1/4 float4 outputs
       float4 v = sum_partials<NS1, KS>(scratch, b, n4);
       v.x = fmaxf(v.x + sB0[4 * n4], 0.f); v.y = fmaxf(v.y + sB0[4 * n4 + 1], 0.f);
       v.z = fmaxf(v.z + sB0[4 * n4 + 2], 0.f); v.w = fmaxf(v.w + sB0[4 * n4 + 3], 0.f);
@@ -261,7 +264,7 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
   stamp(4);
   // ---------------- P2: a4[:, slice] = relu(a3 * W1[slice]^T + b1)         NC = 16, K = D1, KS = 8
   {
-    constexpr int KS = 8, PER = MC_HALF / KS;          // 32 tiles per split; this layer is small: warp-group 0 only
+    constexpr int PER = 2 * NS2, KS = MC_HALF / PER;     // this layer is small: warp-group 0 only
     if (tid < MC_HALF) {
       const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
       float acc[4][4] = {};
@@ -272,7 +275,7 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
     stage_plain_async(sW1, p.w1 + cr * NS1, D2, NS1, D1);   // W1[:, slice of D1] for dz3
     cp_async_commit();
     if (tid < MC_B * NS2 / 4) {
-      const int b = tid >> 2, n4 = tid & 3;
+      const int b = tid / (NS2 / 4), n4 = tid % (NS2 / 4);
       float4 v = sum_partials<NS2, KS>(sDZ4, b, n4);
       v.x = fmaxf(v.x + sB1[4 * n4], 0.f); v.y = fmaxf(v.y + sB1[4 * n4 + 1], 0.f);
       v.z = fmaxf(v.z + sB1[4 * n4 + 2], 0.f); v.w = fmaxf(v.w + sB1[4 * n4 + 3], 0.f);
@@ -350,21 +353,25 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
     __syncthreads();
     if (tid < MC_HALF) {
       // warp-group 0: the data gradient dz3 (critical path)
-      constexpr int KS = 4, PER = MC_HALF / KS;        // NC = 32 -> 64 tiles per split, K = D2
+      constexpr int PER = 2 * NS1, KS = MC_HALF / PER;   // K = D2
       const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
       float acc[4][4] = {};
       prod_nn<D2, NS1, KS>(sDZ4, sW1, tb, tn, ks, acc);
       put_partial<NS1>(sA4, tb, tn, ks, acc);           // scratch = a4 buffer (dead after P3)
       named_bar_sync(1, MC_HALF);
-      const int b = tid >> 3, n4 = tid & 7;
-      dz3v = sum_partials<NS1, KS>(sA4, b, n4);
-      const float4 a3 = *reinterpret_cast<const float4*>(sA3 + sw_off(b, cr * NS1 + 4 * n4, D1));
-      dz3v.x = a3.x > 0.f ? dz3v.x : 0.f; dz3v.y = a3.y > 0.f ? dz3v.y : 0.f; dz3v.z = a3.z > 0.f ? dz3v.z : 0.f; dz3v.w = a3.w > 0.f ? dz3v.w : 0.f;
+      if (tid < MC_B * NS1 / 4) {
+        const int b = tid / (NS1 / 4), n4 = tid % (NS1 / 4);
+        dz3v = sum_partials<NS1, KS>(sA4, b, n4);
+        const float4 a3 = *reinterpret_cast<const float4*>(sA3 + sw_off(b, cr * NS1 + 4 * n4, D1));
+        dz3v.x = a3.x > 0.f ? dz3v.x : 0.f; dz3v.y = a3.y > 0.f ? dz3v.y : 0.f; dz3v.z = a3.z > 0.f ? dz3v.z : 0.f; dz3v.w = a3.w > 0.f ? dz3v.w : 0.f;
+      }
     } else {
       // warp-group 1, concurrently: dW1 rows [cr*NS2, +NS2) as 4 x 4 tiles (4 x D1/4 = 256 of them) and the db1 slice
       const int t = tid - MC_HALF;
-      const int tnw = t / (D1 / 4), tk = t % (D1 / 4);
-      wgrad_tile<D2, D1, 4>(sDZ4, sA3, cr * NS2, 4 * tnw, tk, p.dw1 + (long long)cr * NS2 * D1);
+      if (t < (NS2 / 4) * (D1 / 4)) {
+        const int tnw = t / (D1 / 4), tk = t % (D1 / 4);
+        wgrad_tile<D2, D1, 4>(sDZ4, sA3, cr * NS2, 4 * tnw, tk, p.dw1 + (long long)cr * NS2 * D1);
+      }
       if (t < NS2) {
         float s = 0.f;
         for (int bb = 0; bb < MC_B; ++bb) s += sDZ4[sw_off(bb, cr * NS2 + t, D2)];
@@ -374,8 +381,8 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
   }
   stamp(7);
   cluster.sync();      // everybody is done reading a3 -> its buffer becomes dz3
-  if (tid < MC_HALF) {
-    const int b = tid >> 3, n4 = tid & 7;
+  if (tid < MC_B * NS1 / 4) {
+    const int b = tid / (NS1 / 4), n4 = tid % (NS1 / 4);
     const int o = sw_off(b, cr * NS1 + 4 * n4, D1);
 #pragma unroll
     for (int r = 0; r < MC_CLUSTER; ++r) *reinterpret_cast<float4*>(cluster.map_shared_rank(sA3, r) + o) = dz3v;
@@ -387,12 +394,12 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
     float* sDZ3 = sA3;
     if (tid < MC_HALF) {
       // warp-group 0: the input gradient (what the convolution backward pass is waiting for)
-      constexpr int KS = 2, PER = MC_HALF / KS;        // NC = 64 -> 128 tiles per split, K = D1
+      constexpr int PER = 2 * KS0, KS = MC_HALF / PER;   // K = D1
       const int ks = tid / PER, tile = tid % PER, tb = tile & 7, tn = tile >> 3;
       float acc[4][4] = {};
       prod_nn<D1, KS0, KS>(sDZ3, sW0, tb, tn, ks, acc);
       stamp(14);
-      put_partial<KS0>(sDZ4, tb, tn, ks, acc);          // scratch = dz4 buffer (dead after P4): 2 x 32 x 64 floats = 16 KB
+      put_partial<KS0>(sDZ4, tb, tn, ks, acc);          // scratch = dz4 buffer (dead after P4): KS x 32 x KS0 floats = 16 KB
       named_bar_sync(1, MC_HALF);
       for (int e = tid; e < MC_B * KS0 / 4; e += MC_HALF) {
         const int b = e / (KS0 / 4), n4 = e % (KS0 / 4);
@@ -420,6 +427,33 @@ __global__ void __cluster_dims__(MC_CLUSTER, 1, 1) __launch_bounds__(MC_THREADS,
 using namespace gx;
 
 // 512 -> 256 -> 128 -> C (C <= 16), B <= 32.  Returns -1 for unsupported shapes (caller uses the per-layer kernels).
+template <int CS>
+static int mlp_launch(const MlpChainParams& p, cudaStream_t stream) {
+  using L = MlpSmem<512, 256, 128, CS>;
+  auto kern = mlp_chain_kernel<512, 256, 128, CS>;
+  static int ready = 0;      // 0 = not configured, 1 = ok, -1 = this cluster size cannot be scheduled on this device
+  if (ready == 0) {
+    ready = -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES) == cudaSuccess &&
+        (CS <= 8 || cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CS); cfg.blockDim = dim3(MC_THREADS); cfg.dynamicSmemBytes = L::BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters >= 1) ready = 1;
+    }
+    cudaGetLastError();
+  }
+  if (ready < 0) return -2;
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("GEOMX_MLP_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
+  if (use_pdl) launch_pdl(kern, dim3(CS), dim3(MC_THREADS), (size_t)L::BYTES, stream, p);
+  else kern<<<dim3(CS), dim3(MC_THREADS), (size_t)L::BYTES, stream>>>(p);
+  return GX_CHECK_LAUNCH();
+}
+
 static unsigned long long* g_mlp_dbg = nullptr;
 GX_API int gx_mlp_chain_set_debug(unsigned long long* p) { g_mlp_dbg = p; return 0; }
 
@@ -427,21 +461,17 @@ GX_API int gx_mlp_chain_fwd_bwd(const float* x, const float* w0, const float* b0
                                 const float* label, float* loss, float* logits, float* dw0, float* db0, float* dw1, float* db1, float* dw2,
                                 float* db2, float* dx, int B, int D0, int D1, int D2, int C, cudaStream_t stream) {
   if (D0 != 512 || D1 != 256 || D2 != 128 || C < 1 || C > MC_CMAX || B < 1 || B > MC_B) return -1;
-  using L = MlpSmem<512, 256, 128>;
-  auto kern = mlp_chain_kernel<512, 256, 128>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
   MlpChainParams p;
   p.x = x; p.w0 = w0; p.b0 = b0; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.label = label; p.loss = loss; p.logits = logits;
   p.dw0 = dw0; p.db0 = db0; p.dw1 = dw1; p.db1 = db1; p.dw2 = dw2; p.db2 = db2; p.dx = dx; p.B = B; p.C = C; p.dbg = g_mlp_dbg;
-  static int use_pdl = -1;
-  if (use_pdl < 0) { const char* e = getenv("GEOMX_MLP_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
-  if (use_pdl) launch_pdl(kern, dim3(MC_CLUSTER), dim3(MC_THREADS), (size_t)L::BYTES, stream, p);
-  else kern<<<dim3(MC_CLUSTER), dim3(MC_THREADS), (size_t)L::BYTES, stream>>>(p);
-  return GX_CHECK_LAUNCH();
+  // cluster of 16 CTAs (one GPC) halves every slice; fall back to the portable size 8 when the device cannot co-schedule 16
+  static int want = -1;
+  if (want < 0) { const char* e = getenv("GEOMX_MLP_CLUSTER"); want = e ? atoi(e) : 16; }
+  if (want >= 16) {
+    const int rc = mlp_launch<16>(p, stream);
+    if (rc != -2) return rc;
+    want = 8;
+  }
+  return mlp_launch<8>(p, stream);
 }
-GX_API int gx_mlp_chain_smem_bytes() { return MlpSmem<512, 256, 128>::BYTES; }
+GX_API int gx_mlp_chain_smem_bytes() { return MlpSmem<512, 256, 128, 8>::BYTES; }

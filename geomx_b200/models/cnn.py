@@ -76,7 +76,7 @@ class HipsCNNTrainStep:
 
     def __init__(self, net=None, batch_size=32, optimizer=None, topo=None, device=None, use_graph=True, pull_fused=False,
                  use_multicast=True, mode="dist_sync", fused_zero_grad=True, wire_dtype="fp32", dgt=False, dgt_rerank_every=32,
-                 update="server", bsc_threshold=None, size_lower_bound=None, hfa=None):
+                 update="server", bsc_threshold=None, size_lower_bound=None, hfa=None, loopback=False):
         """``update='server'`` (examples/cnn.py): the optimizer runs on the global-PS shard inside the exchange kernel.  ``update='local'``
         (examples/cnn_bsc.py / cnn_fp16.py / cnn_mpq.py): the kvstore only aggregates gradients (``set_optimizer`` is not called on it), every
         worker applies its own Adam to the pulled aggregate — one fused arena-optimizer launch.  ``bsc_threshold``: Bi-Sparse between the tiers
@@ -97,7 +97,8 @@ class HipsCNNTrainStep:
             raise ValueError("optimizer %s has no native spec; use Adam / SGD / DCASGD" % type(optimizer).__name__)
         self.layout = ArenaLayout.build(list(enumerate(CNN_PARAM_SHAPES)))
         self._local_spec = spec if self.update == "local" else None
-        self.fabric = HipsFabric(self.layout, self.topo, self.device, None if self.update == "local" else spec, use_multicast=use_multicast)
+        self.fabric = HipsFabric(self.layout, self.topo, self.device, None if self.update == "local" else spec, use_multicast=use_multicast,
+                                 loopback=loopback)
         # the script-level `grad / num_samples`, folded into the push kernel; with local updates the aggregate is also averaged over the workers
         self.fabric.set_push_scale(1.0 / B if self.update == "server" else 1.0 / (B * self.topo.world))
         from ..base import getenv_int

@@ -200,7 +200,9 @@ class HipsFabric:
 
     ``layout``: :class:`ArenaLayout`; ``opt_spec``: ``Optimizer.spec()`` dict or None (server stores aggregated gradients)."""
 
-    def __init__(self, layout: ArenaLayout, topo: Topology | None = None, device=None, opt_spec=None, use_multicast=True):
+    def __init__(self, layout: ArenaLayout, topo: Topology | None = None, device=None, opt_spec=None, use_multicast=True, loopback=False):
+        """``loopback``: with a single rank, still run the multi-rank packet kernels (push to the own slot, poll it back) instead of the
+        collapsed arena-optimizer path — a one-GPU exercise of exactly the code that runs between GPUs (smoke tests, launch census)."""
         native.require()
         self.layout = layout
         self.topo = topo or Topology.from_env()
@@ -226,7 +228,8 @@ class HipsFabric:
         # Bandwidth-bound arenas (> GEOMX_LL_MAX_BYTES) keep the flag ("bulk") protocol whose fences amortise over many tiles per CTA.
         ll_max = getenv_int("GEOMX_LL_MAX_BYTES", 64 << 20)
         proto = os.environ.get("GEOMX_FABRIC_PROTOCOL", "auto")
-        self.protocol = "bulk" if (t.world == 1 or proto == "bulk" or (proto == "auto" and 4 * n > ll_max)) else "ll"
+        self.loopback = bool(loopback) and t.world == 1
+        self.protocol = "bulk" if ((t.world == 1 and not self.loopback) or proto == "bulk" or (proto == "auto" and 4 * n > ll_max)) else "ll"
         if self.protocol == "ll":
             self.ll_a = self.heap.alloc(t.party_size * 2 * n, torch.float32)
             self.ll_b = self.heap.alloc(P * 2 * n, torch.float32)
@@ -278,7 +281,7 @@ class HipsFabric:
         # one CTA per tile while the launch stays co-resident (the kernels spin on each other); grid-stride beyond that.  The LL kernel's
         # phases are one round each when grid >= tiles; the bulk protocol keeps <= 132 CTAs (its per-tile fences contend at higher counts)
         self.grid = max(1, min(T, int(native.require().gx_hips_max_grid()) if self.protocol == "ll" else 132))
-        if t.world == 1:
+        if t.world == 1 and not self.loopback:
             self.grid = max(1, min(T, 4096))     # nothing spins on a single rank: one tile per CTA, no co-residency requirement
         self._params_cache = {}
         self._peer_tables = {}
@@ -501,7 +504,7 @@ class HipsFabric:
         ch = self.channels[name]
         p = self._channel_block(name, zero_grad)
         lib = native.require()
-        if self.topo.world == 1:
+        if self.topo.world == 1 and not self.loopback:
             rc = lib.gx_hips_fsa_step(ctypes.byref(p), self.grid, self._stream())         # single rank: the fused arena optimizer on the masked tiles
         elif self.ll_d is not None and self._channel_formats_direct_ok(ch):
             rc = lib.gx_hips_fsa_direct_step(ctypes.byref(p), ch["grid"], self._stream())
