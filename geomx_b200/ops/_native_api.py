@@ -122,6 +122,29 @@ def cnn_wgrad1(a1, a2, idx2, da2, dw1, db1):
     return True
 
 
+# --------------------------------------------------------------------------------------------------------------- depthwise convolution
+def depthwise_fwd(x, w, bias, y, stride, padding, relu=False):
+    N, C, H, W = x.shape
+    rc = _lib().gx_depthwise_fwd(_p(x), _p(w), _p(bias), _p(y), N, C, H, W, w.shape[2], w.shape[3], stride[0], stride[1], padding[0], padding[1],
+                                 int(relu), _s())
+    if rc == -1:
+        return False
+    _ck(rc, "depthwise_fwd")
+    return True
+
+
+def depthwise_dgrad(dy, w, dx, stride, padding):
+    N, C, H, W = dx.shape
+    _ck(_lib().gx_depthwise_dgrad(_p(dy), _p(w), _p(dx), N, C, H, W, w.shape[2], w.shape[3], stride[0], stride[1], padding[0], padding[1], _s()),
+        "depthwise_dgrad")
+
+
+def depthwise_wgrad(x, dy, dw, db, stride, padding):
+    N, C, H, W = x.shape
+    _ck(_lib().gx_depthwise_wgrad(_p(x), _p(dy), _p(dw), _p(db), N, C, H, W, dw.shape[2], dw.shape[3], stride[0], stride[1], padding[0], padding[1],
+                                  _s()), "depthwise_wgrad")
+
+
 # --------------------------------------------------------------------------------------------------------------- conv / pool
 def conv_out_hw(H, W, KH, KW, sh, sw, ph, pw):
     return (H + 2 * ph - KH) // sh + 1, (W + 2 * pw - KW) // sw + 1

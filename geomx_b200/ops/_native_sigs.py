@@ -11,6 +11,9 @@ SIGS = {
     "gx_cnn_fwd": [P] * 9 + [I, P],
     "gx_cnn_bwd": [P] * 9 + [I, P],
     "gx_cnn_wgrad1": [P] * 6 + [I, P],
+    "gx_depthwise_fwd": [P, P, P, P] + [I] * 11 + [P],
+    "gx_depthwise_dgrad": [P, P, P] + [I] * 10 + [P],
+    "gx_depthwise_wgrad": [P, P, P, P] + [I] * 10 + [P],
     "gx_cnn_set_debug": [P],
     "gx_mlp_chain_smem_bytes": [],
     "gx_mlp_chain_set_debug": [P],

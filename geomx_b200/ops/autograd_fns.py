@@ -95,6 +95,39 @@ class Conv2dFn(torch.autograd.Function):
         return dx, dw, db, None, None, None
 
 
+class DepthwiseConv2dFn(torch.autograd.Function):
+    """groups == channels convolution through csrc/kernels/depthwise_conv.cu (reference: src/operator/nn/depthwise_convolution_tf.cuh:76-754)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding, relu):
+        x = x.contiguous(); w = w.contiguous()
+        N, C, H, W = x.shape
+        OH, OW = native.conv_out_hw(H, W, w.shape[2], w.shape[3], stride[0], stride[1], padding[0], padding[1])
+        y = torch.empty(N, C, OH, OW, dtype=torch.float32, device=x.device)
+        if not native.depthwise_fwd(x, w, b, y, stride, padding, relu):
+            raise RuntimeError("depthwise plane does not fit shared memory")
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.cfg = (stride, padding, relu, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        stride, padding, relu, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        if relu:
+            dy = native.relu_bwd(y, dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            native.depthwise_dgrad(dy, w, dx, stride, padding)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            dw = torch.zeros_like(w)
+            db = torch.zeros(w.shape[0], dtype=torch.float32, device=dy.device) if has_bias else None
+            native.depthwise_wgrad(x, dy, dw, db, stride, padding)
+        return dx, dw, db, None, None, None
+
+
 class MaxPool2x2Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

@@ -1,4 +1,5 @@
-"""gloo worker for test_sync_batchnorm: each rank normalises its half of a batch with SyncBatchNorm; rank 0 compares with BatchNorm on the whole."""
+"""Worker for the SyncBatchNorm tests: each rank normalises its share of a batch with SyncBatchNorm; rank 0 compares with BatchNorm on the
+whole.  Backend: gloo on CPU (default) or NCCL with one GPU per rank (SYNCBN_DEVICE=cuda: the statistics cross NVLink)."""
 import os
 import sys
 
@@ -9,7 +10,13 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import geomx_b200 as mx  # noqa: E402
 
-dist.init_process_group("gloo")
+on_gpu = os.environ.get("SYNCBN_DEVICE", "cpu") == "cuda"
+if on_gpu:
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+else:
+    dist.init_process_group("gloo")
+ctx = mx.gpu(int(os.environ.get("LOCAL_RANK", 0))) if on_gpu else mx.cpu()
 rank, world = dist.get_rank(), dist.get_world_size()
 rng = np.random.RandomState(0)
 X = rng.randn(8, 3, 4, 4).astype(np.float32) * 2 + 1
@@ -18,17 +25,21 @@ part = slice(rank * 8 // world, (rank + 1) * 8 // world)
 
 
 def run(layer, xs, ws):
-    layer.initialize()
-    x = mx.nd.array(xs); x.attach_grad()
+    layer.initialize(ctx=ctx)
+    x = mx.nd.array(xs, ctx=ctx); x.attach_grad()
     with mx.autograd.record():
         y = layer(x)
-        loss = (y * mx.nd.array(ws)).sum()
+        loss = (y * mx.nd.array(ws, ctx=ctx)).sum()
     loss.backward()
     return y.asnumpy(), x.grad.asnumpy(), layer.gamma.grad().asnumpy(), layer.running_var.data().asnumpy()
 
 
 y, dx, dg, rv = run(mx.gluon.contrib.nn.SyncBatchNorm(in_channels=3), X[part], W[part])
-dgt = torch.from_numpy(dg.copy()); dist.all_reduce(dgt)
+dgt = torch.from_numpy(dg.copy())
+if on_gpu:
+    dgt = dgt.cuda()
+dist.all_reduce(dgt)
+dgt = dgt.cpu()
 if rank == 0:
     y0, dx0, dg0, rv0 = run(mx.gluon.nn.BatchNorm(in_channels=3), X, W)
     ok = np.allclose(y, y0[part], atol=1e-5) and np.allclose(dx, dx0[part], atol=1e-5) and np.allclose(dgt.numpy(), dg0, atol=1e-4) \

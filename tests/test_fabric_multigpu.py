@@ -76,6 +76,15 @@ def test_kvstore_api_surface_on_the_fabric(mode):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_sync_batchnorm_across_gpus():
+    """SyncBatchNorm with one GPU per rank: per-channel statistics and their gradients all-reduced over NCCL == BatchNorm on the whole batch."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29695",
+           os.path.join(ROOT, "tests", "_syncbn_worker.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, SYNCBN_DEVICE="cuda"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0 and "SYNCBN PASS" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
 def test_tsengine_flags_are_rejected_on_the_fabric():
     rc, out = _torchrun(2, "fabric_api_check.py", "hostopt", port=29691, env={"ENABLE_INTRA_TS": "1"})
     assert rc != 0 and "TSEngine" in out, out[-2000:]

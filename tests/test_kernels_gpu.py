@@ -173,6 +173,22 @@ def test_conv_fn(nat, cin, cout, k, hw, stride, pad):
         assert rel_err(a, c) < 1e-4      # fp32-accurate products; a ReLU mask can still flip on an activation that is zero to rounding
 
 
+@pytest.mark.parametrize("C,hw,k,stride,pad", [(8, 14, 3, 1, 1), (6, 9, 3, 2, 1), (4, 12, 5, 1, 0)])
+def test_depthwise_conv_fn(nat, C, hw, k, stride, pad):
+    """groups == channels convolution (csrc/kernels/depthwise_conv.cu) forward + all three gradients vs torch."""
+    from geomx_b200.ops import functional as OF
+    torch.manual_seed(8)
+    x = torch.randn(5, C, hw, hw, device=dev()); w = torch.randn(C, 1, k, k, device=dev()) * 0.3; b = torch.randn(C, device=dev())
+    f = lambda a, c, d: OF.conv2d(a, c, d, (stride, stride), (pad, pad), groups=C, act="relu")
+    torch.manual_seed(9); y, gr, _ = _grads(f, x, w, b)
+    OF.use_native(False)
+    torch.manual_seed(9); y2, gr2, _ = _grads(f, x, w, b)
+    OF.use_native(True)
+    assert rel_err(y, y2) < 1e-5
+    for a, c in zip(gr, gr2):
+        assert rel_err(a, c) < 1e-4
+
+
 def test_pool_relu_softmax_bn(nat):
     from geomx_b200.ops import functional as OF
     torch.manual_seed(6)
