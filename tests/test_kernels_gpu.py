@@ -60,24 +60,36 @@ def test_cnn_direct_kernels_match_torch(nat):
         x = torch.rand(B, 1, 28, 28, device=dev())
         w0 = torch.randn(16, 1, 5, 5, device=dev()) * 0.2; b0 = torch.randn(16, device=dev()) * 0.1
         w1 = torch.randn(32, 16, 5, 5, device=dev()) * 0.05; b1 = torch.randn(32, device=dev()) * 0.1
-        # fp64 reference: cuDNN's fp32 convolution algorithms (FFT / Winograd variants) are themselves only good to ~1e-4
-        ps = [t.double().clone().requires_grad_(True) for t in (w0, b0, w1, b1)]
-        h1 = F.max_pool2d(torch.relu(F.conv2d(x.double(), ps[0], ps[1])), 2)
-        h2 = F.max_pool2d(torch.relu(F.conv2d(h1, ps[2], ps[3])), 2)
-        da2 = torch.randn(B, 32, 4, 4, device=dev())
-        h2.backward(da2.double())
         a1 = torch.empty(B, 16, 12, 12, device=dev()); idx1 = torch.empty(B, 16, 12, 12, dtype=torch.uint8, device=dev())
         a2 = torch.empty(B, 32, 4, 4, device=dev()); idx2 = torch.empty(B, 32, 4, 4, dtype=torch.uint8, device=dev())
         nat.cnn_fwd(x, w0, b0, w1, b1, a1, idx1, a2, idx2)
         torch.cuda.synchronize()
-        assert rel_err(a1, h1.detach()) < 1e-6 and rel_err(a2, h2.detach()) < 1e-5
+        # forward values against fp64
+        xd, w0d, b0d, w1d, b1d = (t.double() for t in (x, w0, b0, w1, b1))
+        h1 = F.max_pool2d(torch.relu(F.conv2d(xd, w0d, b0d)), 2)
+        h2 = F.max_pool2d(torch.relu(F.conv2d(a1.double(), w1d, b1d)), 2)          # second layer from the kernel's own a1
+        assert rel_err(a1, h1) < 1e-6 and rel_err(a2, h2) < 1e-6
+        # backward against fp64 with the kernel's OWN routing decisions (arg-max positions and ReLU masks are discrete: a reference that takes
+        # them in another precision differs by whole pixels on near-ties; cuDNN's fp32 algorithms are only good to ~1e-4 anyway)
+        def route(g, pooled, idx):                  # pooled gradient -> pre-pool map (2x upsampled), one non-zero per window
+            gm = torch.where(pooled > 0, g, torch.zeros_like(g)).double()
+            out = torch.zeros(g.shape[0], g.shape[1], 2 * g.shape[2], 2 * g.shape[3], dtype=torch.float64, device=g.device)
+            for k in range(4):
+                out[:, :, (k >> 1)::2, (k & 1)::2] = torch.where(idx == k, gm, torch.zeros_like(gm))
+            return out
+        da2 = torch.randn(B, 32, 4, 4, device=dev())
+        dz2 = route(da2, a2, idx2)
+        da1 = F.conv_transpose2d(dz2, w1d)
+        ref_dw1 = torch.nn.grad.conv2d_weight(a1.double(), w1.shape, dz2); ref_db1 = dz2.sum((0, 2, 3))
+        dz1 = route(da1.float(), a1, idx1) if False else route(da1, a1, idx1)
+        ref_dw0 = torch.nn.grad.conv2d_weight(xd, w0.shape, dz1); ref_db0 = dz1.sum((0, 2, 3))
         dw0 = torch.zeros(16, 1, 5, 5, device=dev()); db0 = torch.zeros(16, device=dev())
         dw1 = torch.full((32, 16, 5, 5), float("nan"), device=dev()); db1 = torch.full((32,), float("nan"), device=dev())
-        nat.cnn_bwd(x, w1, a1, idx1, a2, idx2, da2.contiguous(), dw0, db0)
-        assert nat.cnn_wgrad1(a1, a2, idx2, da2.contiguous(), dw1, db1)
+        nat.cnn_bwd(x, w1, a1, idx1, a2, idx2, da2, dw0, db0)
+        assert nat.cnn_wgrad1(a1, a2, idx2, da2, dw1, db1)
         torch.cuda.synchronize()
-        for got, ref, name in ((dw0, ps[0].grad, "dw0"), (db0, ps[1].grad, "db0"), (dw1, ps[2].grad, "dw1"), (db1, ps[3].grad, "db1")):
-            assert rel_err(got, ref) < 2e-5, (B, name, rel_err(got, ref))
+        for got, ref, name in ((dw0, ref_dw0, "dw0"), (db0, ref_db0, "db0"), (dw1, ref_dw1, "dw1"), (db1, ref_db1, "db1")):
+            assert rel_err(got, ref) < 1e-5, (B, name, rel_err(got, ref))
 
 
 def test_mlp_chain_matches_torch(nat):
