@@ -306,6 +306,8 @@ class HipsCNNTrainStep:
                 self.steps_done += 1
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if self._dgt_every:
+            self.fabric.dgt_rerank()      # first ranking now: the collective's lazy communicator set-up belongs to the warm-up, not to a timed step
         if self.topo.world > 1:
             import torch.distributed as dist
             dist.barrier()

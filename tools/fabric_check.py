@@ -54,8 +54,32 @@ def main():
         dist.broadcast(ref, src=0)
         same = bool(torch.equal(ref, eng.fabric.param.tensor))
         if a.mode == "dist_async":
-            # async: each party applies its own aggregate in arrival order; only cross-rank consistency inside a party is defined
-            print("rank %d iter %d async max|w-expect|=%.3e" % (rank, it, err), flush=True)
+            # MixedSync: every party applies its own aggregate to the global owner's master weights on arrival and pulls what is there at that
+            # moment.  SGD updates commute, so after the first round each TILE this rank pulled is either  w0 - lr*g_own_party/B  (the other
+            # party had not arrived yet) or  w0 - lr*(g_own_party + g_other_parties)/B  — nothing else is a legal value.
+            if it == 0:
+                S = topo.party_size
+                gparty = eng.fabric.grad.tensor.clone()
+                pg = dist.new_group(list(range(topo.party * S, (topo.party + 1) * S))) if False else None
+                # party sum through the world all-reduce: zero the other parties' contributions
+                contrib = [torch.zeros_like(gparty) for _ in range(topo.num_parties)]
+                contrib[topo.party].copy_(gparty)
+                for c in contrib:
+                    dist.all_reduce(c)
+                own = w0 - 0.1 * contrib[topo.party] / B
+                full = w0 - 0.1 * sum(contrib) / B
+                p = eng.fabric.param.tensor
+                dev_own, dev_full = (p - own).abs(), (p - full).abs()
+                legal = torch.minimum(dev_own, dev_full)
+                if topo.num_parties > 2:        # any subset of the other parties may have arrived: bound by the envelope instead
+                    lo, hi = torch.minimum(own, full), torch.maximum(own, full)
+                    legal = torch.clamp(lo - p, min=0) + torch.clamp(p - hi, min=0)
+                worst = float(legal.max())
+                print("rank %d iter 0 async: max distance to a legal value %.3e (own-party-only tiles: %d of %d)" % (
+                    rank, worst, int((dev_own < dev_full).sum()), p.numel()), flush=True)
+                ok = ok and worst < 1e-5
+            else:
+                print("rank %d iter %d async max|w-sync expectation|=%.3e" % (rank, it, err), flush=True)
         else:
             print("rank %d iter %d max|w-expect|=%.3e identical_to_rank0=%s loss=%.4f" % (rank, it, err, same, float(eng.loss.mean())), flush=True)
             ok = ok and err < 1e-5 and same
