@@ -81,7 +81,7 @@ def test_cnn_direct_kernels_match_torch(nat):
         dz2 = route(da2, a2, idx2)
         da1 = F.conv_transpose2d(dz2, w1d)
         ref_dw1 = torch.nn.grad.conv2d_weight(a1.double(), w1.shape, dz2); ref_db1 = dz2.sum((0, 2, 3))
-        dz1 = route(da1.float(), a1, idx1) if False else route(da1, a1, idx1)
+        dz1 = route(da1, a1, idx1)
         ref_dw0 = torch.nn.grad.conv2d_weight(xd, w0.shape, dz1); ref_db0 = dz1.sum((0, 2, 3))
         dw0 = torch.zeros(16, 1, 5, 5, device=dev()); db0 = torch.zeros(16, device=dev())
         dw1 = torch.full((32, 16, 5, 5), float("nan"), device=dev()); db1 = torch.full((32,), float("nan"), device=dev())

@@ -58,9 +58,7 @@ def main():
             # moment.  SGD updates commute, so after the first round each TILE this rank pulled is either  w0 - lr*g_own_party/B  (the other
             # party had not arrived yet) or  w0 - lr*(g_own_party + g_other_parties)/B  — nothing else is a legal value.
             if it == 0:
-                S = topo.party_size
                 gparty = eng.fabric.grad.tensor.clone()
-                pg = dist.new_group(list(range(topo.party * S, (topo.party + 1) * S))) if False else None
                 # party sum through the world all-reduce: zero the other parties' contributions
                 contrib = [torch.zeros_like(gparty) for _ in range(topo.num_parties)]
                 contrib[topo.party].copy_(gparty)
