@@ -239,16 +239,94 @@ class _FMod:
         return getattr(nd, name)
 
 
+class _CachedOp:
+    """One captured (forward graph, backward graph) pair of a HybridBlock for one input signature."""
+
+    _tls = threading.local()
+
+    @classmethod
+    def inside(cls):
+        return getattr(cls._tls, "depth", 0) > 0
+
+    @classmethod
+    def lookup(cls, block, args):
+        import torch
+        from .. import autograd
+        if not args or not all(isinstance(a, NDArray) and a._t.is_cuda and a._t.dtype == torch.float32 for a in args) or _prof._state["running"]:
+            return None
+        try:
+            params = [p for p in block.collect_params().values() if p._data is not None]
+            if len(params) != len(block.collect_params()):
+                return None                                   # deferred shapes: run eagerly once, capture on a later call
+        except Exception:
+            return None
+        key = (tuple((tuple(a.shape), a._t.device.index) for a in args), autograd.is_recording(), autograd.is_training())
+        op = block._cached_ops.get(key)
+        if op is None:
+            op = block._cached_ops[key] = cls(block, args, params, autograd.is_recording(), autograd.is_training())
+        return op if op.ok else None
+
+    def __init__(self, block, args, params, recording, training):
+        import torch
+        self.ok = False
+        tensors = [t for p in params for t in [p.data(args[0].context)._t] if t.requires_grad]
+        cached = self
+
+        class Shim(torch.nn.Module):
+            def parameters(self, recurse=True):            # the Gluon parameters are the graph's differentiable inputs
+                return iter(tensors)
+
+            def forward(self, *xs):
+                cached._tls.depth = getattr(cached._tls, "depth", 0) + 1
+                try:
+                    out = Block.__call__(block, *[NDArray(x) for x in xs])
+                finally:
+                    cached._tls.depth -= 1
+                self.multi = isinstance(out, (list, tuple))
+                return tuple(o._t for o in out) if self.multi else out._t
+
+        self.shim = Shim()
+        from .. import autograd
+        try:
+            samples = tuple(a._t.detach().clone().requires_grad_(a._t.requires_grad) for a in args)
+            with autograd._Scope(recording, training):
+                self.fn = torch.cuda.make_graphed_callables(self.shim, samples, num_warmup_iters=3)
+            self.ok = True
+        except Exception as e:                                  # an op that cannot be captured: stay eager for this signature
+            import warnings
+            warnings.warn("hybridize(static_alloc=True): graph capture of %s failed (%s); running eagerly" % (block.name, e))
+
+    def __call__(self, args):
+        out = self.fn(*[a._t for a in args])
+        return [NDArray(o) for o in out] if isinstance(out, tuple) else NDArray(out)
+
+
 class HybridBlock(Block):
     """Block whose ``hybrid_forward(F, x, **params)`` receives its own parameters as kwargs."""
 
     def __init__(self, prefix=None, params=None):
         super().__init__(prefix, params)
         self._active = False
+        self._static_alloc = False
+        self._cached_ops = {}
 
-    def hybridize(self, active=True, **kwargs):
+    def hybridize(self, active=True, static_alloc=False, static_shape=False, **kwargs):
+        """``hybridize()`` marks the block as traceable.  ``hybridize(static_alloc=True)`` is the CachedOp of this framework (reference:
+        src/imperative/cached_op.cc — static memory planning + bulk execution of the cached graph): the block's forward AND backward are
+        captured into CUDA graphs (``torch.cuda.make_graphed_callables``, one pair per input signature) with statically allocated
+        activations, so a step replays two graph launches instead of one launch per operator.  Applies to the outermost block that was
+        hybridized this way, on CUDA, for fixed input shapes; anything else falls back to eager execution."""
         self._active = active
+        self._static_alloc = bool(active and static_alloc)
+        self._cached_ops = {}
         super().hybridize(active, **kwargs)
+
+    def __call__(self, *args):
+        if self._static_alloc and not _CachedOp.inside():
+            op = _CachedOp.lookup(self, args)
+            if op is not None:
+                return op(args)
+        return super().__call__(*args)
 
     def infer_shape(self, *args):
         """Layers with deferred shapes override ``_infer(x)``."""
