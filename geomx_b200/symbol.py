@@ -159,22 +159,24 @@ class Symbol:
         return [np.float32] * len(args), [np.float32] * len(self.list_outputs()), [np.float32] * len(self.list_auxiliary_states())
 
     # ---- binding
-    def simple_bind(self, ctx, grad_req="write", **shapes):
+    def simple_bind(self, ctx, grad_req="write", group2ctx=None, **shapes):
         from . import ndarray as nd
         arg_shapes, _, aux_shapes = self.infer_shape(**shapes)
         names = self.list_arguments()
         if any(s is None for s in arg_shapes):
             raise MXNetError("cannot infer shapes of %s" % [n for n, s in zip(names, arg_shapes) if s is None])
-        args = {n: nd.zeros(s, ctx=ctx) for n, s in zip(names, arg_shapes)}
+        # manual model parallelism: a variable annotated with ctx_group (AttrScope) is allocated on the device its group maps to
+        place = _placement(self, ctx, group2ctx)
+        args = {n: nd.zeros(s, ctx=place.get(n, ctx)) for n, s in zip(names, arg_shapes)}
         req = grad_req if isinstance(grad_req, dict) else {n: grad_req for n in names}
-        grads = {n: nd.zeros(s, ctx=ctx) for n, s in zip(names, arg_shapes) if req.get(n, "null") != "null"}
-        aux = {n: nd.zeros(s, ctx=ctx) for n, s in zip(self.list_auxiliary_states(), aux_shapes)}
+        grads = {n: nd.zeros(s, ctx=place.get(n, ctx)) for n, s in zip(names, arg_shapes) if req.get(n, "null") != "null"}
+        aux = {n: nd.zeros(s, ctx=place.get(n, ctx)) for n, s in zip(self.list_auxiliary_states(), aux_shapes)}
         for n, a in aux.items():
             if n.endswith("_moving_var"):
                 a[:] = 1.0
-        return Executor(self, ctx, args, grads, req, aux)
+        return Executor(self, ctx, args, grads, req, aux, group2ctx)
 
-    def bind(self, ctx, args, args_grad=None, grad_req="write", aux_states=None):
+    def bind(self, ctx, args, args_grad=None, grad_req="write", aux_states=None, group2ctx=None):
         names = self.list_arguments()
         if isinstance(args, (list, tuple)):
             args = dict(zip(names, args))
@@ -184,7 +186,7 @@ class Symbol:
         if isinstance(aux_states, (list, tuple)):
             aux_states = dict(zip(auxn, aux_states))
         req = grad_req if isinstance(grad_req, dict) else {n: (grad_req if args_grad and n in args_grad else "null") for n in names}
-        return Executor(self, ctx, dict(args), dict(args_grad or {}), req, dict(aux_states or {}))
+        return Executor(self, ctx, dict(args), dict(args_grad or {}), req, dict(aux_states or {}), group2ctx)
 
     # ---- (de)serialisation: a flat node list in topological order
     def tojson(self):
@@ -564,11 +566,29 @@ def run_graph(sym, feed, training=False):
     return [vals[id(h)] for h in heads]
 
 
-class Executor:
-    """Bound graph: ``forward(is_train)`` / ``backward(out_grads)`` with ``arg_dict`` / ``grad_dict`` / ``aux_dict`` / ``outputs``."""
+def _placement(symbol, default_ctx, group2ctx):
+    """node name -> Context for every node that carries a ``ctx_group`` annotation present in ``group2ctx`` (reference: the PlaceDevice pass
+    of src/executor/graph_executor.cc with _CrossDeviceCopy nodes, src/operator/cross_device_copy.cc)."""
+    if not group2ctx:
+        return {}
+    out = {}
+    for s in symbol._topo():
+        g = s.attrs.get("__attr__", {}).get("ctx_group")
+        if g is not None and g in group2ctx:
+            out[s.name] = group2ctx[g]
+    return out
 
-    def __init__(self, symbol, ctx, args, grads, grad_req, aux):
+
+class Executor:
+    """Bound graph: ``forward(is_train)`` / ``backward(out_grads)`` with ``arg_dict`` / ``grad_dict`` / ``aux_dict`` / ``outputs``.
+
+    ``group2ctx`` (manual model parallelism, ``mx.AttrScope(ctx_group=...)``): every operator runs on the device of its group; an input that
+    lives elsewhere is brought over by a differentiable device-to-device copy (NVLink P2P ``cudaMemcpyPeerAsync`` through torch), the
+    gradient travels back the same way — the reference inserts ``_CrossDeviceCopy`` nodes for this."""
+
+    def __init__(self, symbol, ctx, args, grads, grad_req, aux, group2ctx=None):
         self._symbol, self._ctx = symbol, ctx
+        self._place = _placement(symbol, ctx, group2ctx)
         self.arg_dict, self.grad_dict, self.aux_dict, self._req = args, grads, aux, grad_req
         self.arg_arrays = [args[n] for n in symbol.list_arguments()]
         self.grad_arrays = [grads.get(n) for n in symbol.list_arguments()]
@@ -596,11 +616,21 @@ class Executor:
                             leaves[s.name] = t
                         vals[id(s)] = t
                 elif s.op != "_group":
+                    ins = [vals[id(i)] for i in s.inputs]
+                    auxs = [vals[id(a)] for a in s.aux]
+                    if self._place:
+                        # model parallelism: the node's group decides the device (un-annotated nodes follow their first input); inputs
+                        # from another device cross over with a copy that autograd differentiates
+                        where = self._place.get(s.name)
+                        dev = where.torch_device if where is not None else (ins[0].device if ins else None)
+                        if dev is not None:
+                            ins = [t.to(dev) if (torch.is_tensor(t) and t.device != dev) else t for t in ins]
+                            auxs = [t.to(dev) if (torch.is_tensor(t) and t.device != dev) else t for t in auxs]
                     if prof_on:                                        # one trace event per graph node, like ProfileOperator (threaded_engine.h:336-350)
                         with _prof.scope(s.name, "operator", device=self.arg_arrays[0]._t.is_cuda if self.arg_arrays else False):
-                            vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], is_train)
+                            vals[id(s)] = _eval_node(s, ins, auxs, is_train)
                     else:
-                        vals[id(s)] = _eval_node(s, [vals[id(i)] for i in s.inputs], [vals[id(a)] for a in s.aux], is_train)
+                        vals[id(s)] = _eval_node(s, ins, auxs, is_train)
                     if self._monitor is not None:
                         self._monitor(s.name + "_output", NDArray(vals[id(s)].detach()))
         heads = self._symbol.inputs if self._symbol.op == "_group" else [self._symbol]

@@ -76,6 +76,31 @@ def test_kvstore_api_surface_on_the_fabric(mode):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_group2ctx_places_stages_on_two_gpus():
+    """Manual model parallelism on real devices: stage 1 on cuda:0, stage 2 on cuda:1, activations and gradients cross NVLink."""
+    import numpy as np
+    import geomx_b200 as mx
+    with mx.AttrScope(ctx_group="stage1"):
+        data = mx.sym.Variable("data")
+        act = mx.sym.Activation(mx.sym.FullyConnected(data, num_hidden=16, name="fc1"), act_type="relu", name="act1")
+    with mx.AttrScope(ctx_group="stage2"):
+        out = mx.sym.SoftmaxOutput(mx.sym.FullyConnected(act, num_hidden=4, name="fc2"), name="softmax")
+    ex = out.simple_bind(mx.gpu(0), group2ctx={"stage1": mx.gpu(0), "stage2": mx.gpu(1)}, data=(8, 10), softmax_label=(8,))
+    assert ex.arg_dict["fc1_weight"]._t.device.index == 0 and ex.arg_dict["fc2_weight"]._t.device.index == 1
+    rng = np.random.RandomState(4)
+    for n, a in ex.arg_dict.items():
+        a[:] = (rng.randint(0, 4, a.shape) if n == "softmax_label" else rng.randn(*a.shape) * 0.3).astype(np.float32)
+    ref = out.simple_bind(mx.cpu(0), data=(8, 10), softmax_label=(8,))
+    for n in ex.arg_dict:
+        ref.arg_dict[n][:] = ex.arg_dict[n].asnumpy()
+    o = ex.forward(is_train=True); ex.backward()
+    r = ref.forward(is_train=True); ref.backward()
+    assert o[0]._t.device.index == 1 and np.allclose(o[0].asnumpy(), r[0].asnumpy(), atol=1e-5)
+    assert ex.grad_dict["fc1_weight"]._t.device.index == 0
+    assert np.allclose(ex.grad_dict["fc1_weight"].asnumpy(), ref.grad_dict["fc1_weight"].asnumpy(), atol=1e-5)
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
 def test_sync_batchnorm_across_gpus():
     """SyncBatchNorm with one GPU per rank: per-channel statistics and their gradients all-reduced over NCCL == BatchNorm on the whole batch."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29695",
