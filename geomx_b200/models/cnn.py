@@ -123,7 +123,7 @@ class HipsCNNTrainStep:
         # examples/cnn.py:121-125).  GEOMX_STEP_OVERLAP=0 restores the single fused exchange at the end of the step.
         self.overlap = mode == "dist_sync" and not self.hfa and os.environ.get("GEOMX_STEP_OVERLAP", "1") == "1" and (self.topo.world == 1 or f.ll_d is not None)
         if self.overlap:
-            f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False)
+            f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False, grid=int(os.environ.get("GEOMX_DENSE_CHANNEL_GRID", 0)) or None)
             f.add_channel("conv", [0, 1, 2, 3], replicate=True)
         self.fused_mlp = B <= 32 and os.environ.get("GEOMX_FUSED_MLP", "1") == "1"
         # small-batch regime: both convolutions forward / backward as direct fp32-FMA kernels (3 launches, csrc/kernels/cnn_direct.cu) instead
@@ -157,7 +157,9 @@ class HipsCNNTrainStep:
         self.pull_fused = bool(pull_fused) and self.topo.world >= 1
         self.graph = None
         self._side = torch.cuda.Stream(device=self.device)
-        self._comm = torch.cuda.Stream(device=self.device)
+        # the exchange branch gets a high-priority stream: its (few) CTAs must become resident at once on every rank — they poll each other —
+        # instead of queueing behind the convolution-backward CTAs that are launched at the same time
+        self._comm = torch.cuda.Stream(device=self.device, priority=-1)
         self.use_graph = use_graph
         self.steps_done = 0
         self.kernels_per_step = 0

@@ -42,8 +42,10 @@ dist.all_reduce(dgt)
 dgt = dgt.cpu()
 if rank == 0:
     y0, dx0, dg0, rv0 = run(mx.gluon.nn.BatchNorm(in_channels=3), X, W)
-    ok = np.allclose(y, y0[part], atol=1e-5) and np.allclose(dx, dx0[part], atol=1e-5) and np.allclose(dgt.numpy(), dg0, atol=1e-4) \
-        and np.allclose(rv, rv0, atol=1e-5)
-    print("SYNCBN", "PASS" if ok else "FAIL", float(np.abs(y - y0[part]).max()), float(np.abs(dx - dx0[part]).max()))
+    tol = 2e-4 if on_gpu else 1e-5        # the single-device reference on a GPU is the native BatchNorm kernel (different summation order)
+    ok = np.allclose(y, y0[part], atol=tol) and np.allclose(dx, dx0[part], atol=tol) and np.allclose(dgt.numpy(), dg0, atol=10 * tol, rtol=1e-4) \
+        and np.allclose(rv, rv0, atol=tol, rtol=1e-4)
+    print("SYNCBN", "PASS" if ok else "FAIL", float(np.abs(y - y0[part]).max()), float(np.abs(dx - dx0[part]).max()),
+          float(np.abs(dgt.numpy() - dg0).max()), float(np.abs(rv - rv0).max()))
 dist.barrier()
 dist.destroy_process_group()
