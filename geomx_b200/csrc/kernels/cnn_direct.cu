@@ -76,7 +76,8 @@ __device__ __forceinline__ float pool4(const float (&a)[4], float bias, int& bi)
 // grid (B, 4), 256 threads.  CTA (b, g): conv0 of image b (all 16 channels, kept in shared memory) and conv1 for output channels [8g, 8g+8).
 __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float* __restrict__ b0,
                                                        const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ a1,
-                                                       unsigned char* __restrict__ idx1, float* __restrict__ a2, unsigned char* __restrict__ idx2, unsigned long long* dbg) {
+                                                       unsigned char* __restrict__ idx1, float* __restrict__ a2, unsigned char* __restrict__ idx2,
+                                                       const float* __restrict__ carry_src, float* __restrict__ carry_dst, int carry_n, unsigned long long* dbg) {
   __shared__ __align__(16) float sx[CD_H * CD_H];
   __shared__ __align__(16) float sw0[CD_C1 * CD_W1PAD];
   __shared__ float sb0[CD_C1];
@@ -90,6 +91,9 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
   pdl_wait();
   pdl_launch();
   const int b = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
+  // look-ahead steps: this launch is the tail of the previous batch's step; it hands the labels that arrived with its image batch over to
+  // the buffer the classifier head of the NEXT launch reads (a 128-byte side job instead of a copy node in the step graph)
+  if (carry_n > 0 && b == 0 && g == 0) for (int i = tid; i < carry_n; i += 256) carry_dst[i] = carry_src[i];
   for (int i = tid; i < CD_H * CD_H / 4; i += 256) cpa16(sx + 4 * i, x + (long long)b * CD_H * CD_H + 4 * i);
   for (int i = tid; i < CD_C1 * 25; i += 256) { const int ch = i / 25, t = i - ch * 25; cpa4(sw0 + ch * CD_W1PAD + t, w0 + i); }
   for (int i = tid; i < CD_C1 * 3; i += 256) sw0[(i / 3) * CD_W1PAD + 25 + i % 3] = 0.f;          // pad taps 25..27
@@ -183,20 +187,17 @@ struct CnnBwdSmem {
   static constexpr int BYTES = TOTAL * 4;
 };
 
-__global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ a1,
-                                                       const unsigned char* __restrict__ idx1, const float* __restrict__ a2,
-                                                       const unsigned char* __restrict__ idx2, const float* __restrict__ da2,
-                                                       float* __restrict__ dw0, float* __restrict__ db0, unsigned long long* dbg) {
-  extern __shared__ __align__(16) float sm[];
+__device__ __forceinline__ void cnn_bwd_body(float* sm, const int b, const int cg, const float* __restrict__ x, const float* __restrict__ w1,
+                                             const float* __restrict__ a1, const unsigned char* __restrict__ idx1, const float* __restrict__ a2,
+                                             const unsigned char* __restrict__ idx2, const float* __restrict__ da2, float* __restrict__ dw0,
+                                             float* __restrict__ db0, unsigned long long* dbg) {
   using L = CnnBwdSmem;
   float* sdz = sm + L::DZ; float* swt = sm + L::WT; float* sx = sm + L::X; float* sa1 = sm + L::A1; float* sda1 = sm + L::DA1;
   float* spart = sm + L::PART; int* spos = reinterpret_cast<int*>(sm + L::POS);
-  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  const bool dbg_on = dbg != nullptr && b == 0 && cg == 0 && threadIdx.x == 0;
   auto stamp = [&](int slot) { if (dbg_on) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[slot] = t; } };
   stamp(8);
-  pdl_wait();
-  pdl_launch();
-  const int b = blockIdx.x, cg = blockIdx.y, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   for (int i = tid; i < CD_C2 * L::DZPL / 4; i += 288) reinterpret_cast<float4*>(sdz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = tid; i < 4 * CD_C2 * 25; i += 288) {
     // swt[(cl*32 + oc)*28 + t] = W1[oc][4cg+cl][4 - t/5][4 - t%5]   (t = flipped tap); source index runs over (oc, cl, tap) = 100 floats per oc
@@ -279,19 +280,17 @@ __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------------------ conv1 weight gradient
 // grid (32 oc, 4 cg), 256 threads.  CTA owns dW1[oc][4cg..4cg+3][5][5] (100 outputs, written once: no atomics) and sums over all images:
 //   dW1[oc][c][kh][kw] = sum_{b, window} g[b][oc][window] * a1[b][c][oh+kh][ow+kw]     (g != 0 only at the window's arg-max where a2 > 0)
-__global__ void __launch_bounds__(256) cnn_wgrad1_kernel(const float* __restrict__ a1, const float* __restrict__ a2, const unsigned char* __restrict__ idx2,
-                                                          const float* __restrict__ da2, float* __restrict__ dw1, float* __restrict__ db1, int B, unsigned long long* dbg) {
-  extern __shared__ __align__(16) float sm[];
+__device__ __forceinline__ void cnn_wgrad1_body(float* sm, const int oc, const int cg, const float* __restrict__ a1, const float* __restrict__ a2,
+                                                const unsigned char* __restrict__ idx2, const float* __restrict__ da2, float* __restrict__ dw1,
+                                                float* __restrict__ db1, int B, unsigned long long* dbg) {
   float* sa = sm;                               // [B][4][144] the four input-channel planes of every image
   float* sg = sa + (size_t)B * 576;             // [B*16] routed gradients of this output channel
   int* sp = reinterpret_cast<int*>(sg + B * 16);  // [B*16] arg-max position as offset into a 12x12 plane
   float* sacc = reinterpret_cast<float*>(sp + B * 16);   // [2][128]
-  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  const bool dbg_on = dbg != nullptr && oc == 0 && cg == 0 && threadIdx.x == 0;
   auto stamp = [&](int slot) { if (dbg_on) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[slot] = t; } };
   stamp(16);
-  pdl_wait();
-  pdl_launch();
-  const int oc = blockIdx.x, cg = blockIdx.y, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   for (int i = tid; i < B * 144; i += 256) {          // 144 float4 per image: 4 contiguous planes
     const int bb = i / 144, r = i % 144;
     reinterpret_cast<float4*>(sa)[i] = reinterpret_cast<const float4*>(a1 + ((long long)bb * CD_C1 + 4 * cg) * 144)[r];
@@ -325,6 +324,37 @@ __global__ void __launch_bounds__(256) cnn_wgrad1_kernel(const float* __restrict
   stamp(18);
 }
 
+__global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* x, const float* w1, const float* a1, const unsigned char* idx1, const float* a2,
+                                                       const unsigned char* idx2, const float* da2, float* dw0, float* db0, unsigned long long* dbg) {
+  extern __shared__ __align__(16) float sm[];
+  pdl_wait();
+  pdl_launch();
+  cnn_bwd_body(sm, blockIdx.x, blockIdx.y, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dbg);
+}
+__global__ void __launch_bounds__(256) cnn_wgrad1_kernel(const float* a1, const float* a2, const unsigned char* idx2, const float* da2, float* dw1,
+                                                          float* db1, int B, unsigned long long* dbg) {
+  extern __shared__ __align__(16) float sm[];
+  pdl_wait();
+  pdl_launch();
+  cnn_wgrad1_body(sm, blockIdx.x, blockIdx.y, a1, a2, idx2, da2, dw1, db1, B, dbg);
+}
+// The whole convolution backward pass as ONE launch: CTAs [0, 4B) run the data-gradient / conv0 body, CTAs [4B, 4B + 128) the conv1
+// weight-gradient body (two independent jobs that read the same inputs; a single heterogeneous grid saves a stream fork / join in the step graph).
+__global__ void __launch_bounds__(288) cnn_bwd_all_kernel(const float* x, const float* w1, const float* a1, const unsigned char* idx1, const float* a2,
+                                                           const unsigned char* idx2, const float* da2, float* dw0, float* db0, float* dw1, float* db1,
+                                                           int B, unsigned long long* dbg) {
+  extern __shared__ __align__(16) float sm[];
+  pdl_wait();
+  pdl_launch();
+  const int i = blockIdx.x;
+  if (i < 4 * B) {
+    cnn_bwd_body(sm, i >> 2, i & 3, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dbg);
+  } else if (threadIdx.x < 256) {            // (no thread of this CTA takes the other branch, so its __syncthreads pair up among these 256)
+    const int j = i - 4 * B;
+    cnn_wgrad1_body(sm, j >> 2, j & 3, a1, a2, idx2, da2, dw1, db1, B, dbg);
+  }
+}
+
 }  // namespace gx
 
 using namespace gx;
@@ -334,9 +364,9 @@ GX_API int gx_cnn_set_debug(unsigned long long* p) { g_cnn_dbg = p; return 0; }
 
 // x [B,1,28,28]; w0 [16,1,5,5]; w1 [32,16,5,5]; writes a1 [B,16,12,12] + idx1, a2 [B,32,4,4] + idx2
 GX_API int gx_cnn_fwd(const float* x, const float* w0, const float* b0, const float* w1, const float* b1, float* a1, unsigned char* idx1, float* a2,
-                      unsigned char* idx2, int B, cudaStream_t s) {
+                      unsigned char* idx2, const float* carry_src, float* carry_dst, int carry_n, int B, cudaStream_t s) {
   if (B < 1) return 0;
-  launch_pdl(cnn_fwd_kernel, dim3(B, 4), dim3(256), 0, s, x, w0, b0, w1, b1, a1, idx1, a2, idx2, g_cnn_dbg);
+  launch_pdl(cnn_fwd_kernel, dim3(B, 4), dim3(256), 0, s, x, w0, b0, w1, b1, a1, idx1, a2, idx2, carry_src, carry_dst, carry_n, g_cnn_dbg);
   return GX_CHECK_LAUNCH();
 }
 // accumulates into dw0 [16,25] / db0 [16] (atomics: zero them first)
@@ -363,5 +393,21 @@ GX_API int gx_cnn_wgrad1(const float* a1, const float* a2, const unsigned char* 
     attr = smem;
   }
   launch_pdl(cnn_wgrad1_kernel, dim3(CD_C2, 4), dim3(256), smem, s, a1, a2, idx2, da2, dw1, db1, B, g_cnn_dbg);
+  return GX_CHECK_LAUNCH();
+}
+
+// conv backward in one launch (see cnn_bwd_all_kernel): accumulates dw0 / db0 (zero them first), overwrites dw1 / db1.  B even, <= 64.
+GX_API int gx_cnn_bwd_all(const float* x, const float* w1, const float* a1, const unsigned char* idx1, const float* a2, const unsigned char* idx2,
+                          const float* da2, float* dw0, float* db0, float* dw1, float* db1, int B, cudaStream_t s) {
+  if (B < 2 || (B & 1) || B > 64) return -1;
+  const size_t smem_w = ((size_t)B * 576 + (size_t)B * 16 * 2 + 256) * 4;
+  const size_t smem = smem_w > (size_t)CnnBwdSmem::BYTES ? smem_w : (size_t)CnnBwdSmem::BYTES;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(cnn_bwd_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  launch_pdl(cnn_bwd_all_kernel, dim3(4 * B + 4 * CD_C2), dim3(288), smem, s, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dw1, db1, B, g_cnn_dbg);
   return GX_CHECK_LAUNCH();
 }

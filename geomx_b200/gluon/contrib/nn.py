@@ -35,7 +35,7 @@ class _SyncBNFn(torch.autograd.Function):
         var = (stats[C:2 * C] / n - mean * mean).clamp_min_(0.0)
         with torch.no_grad():
             running_mean.mul_(momentum).add_(mean.to(running_mean.dtype), alpha=1 - momentum)
-            running_var.mul_(momentum).add_((var * n / (n - 1).clamp_min(1.0)).to(running_var.dtype), alpha=1 - momentum)
+            running_var.mul_(momentum).add_(var.to(running_var.dtype), alpha=1 - momentum)      # population variance (sync_batch_norm-inl.h:392)
         inv = torch.rsqrt(var + eps)
         shape = [1, C] + [1] * (x.dim() - 2)
         xhat = (xf - mean.view(shape)) * inv.view(shape)

@@ -52,10 +52,13 @@ class LossHandle:
         self._host, self._event = host, event
 
     def wait(self):
-        self._event.synchronize()
+        if self._event is not None:
+            self._event.synchronize()
         return self._host
 
     def item(self):
+        if self._host is None:          # look-ahead engine, first call: no step has finished yet
+            return float("nan")
         self._event.synchronize()
         return float(self._host.sum()) / self._host.numel()
 
@@ -74,14 +77,21 @@ class HipsCNNTrainStep:
     topo : :class:`Topology` (default: from ``WORLD_SIZE`` / ``RANK`` / ``GEOMX_NUM_PARTIES`` / ``DMLC_NUM_GLOBAL_SERVER``).
     """
 
-    def __init__(self, net=None, batch_size=32, optimizer=None, topo=None, device=None, use_graph=True, pull_fused=False,
+    def __init__(self, net=None, batch_size=32, optimizer=None, topo=None, device=None, use_graph=True,
                  use_multicast=True, mode="dist_sync", fused_zero_grad=True, wire_dtype="fp32", dgt=False, dgt_rerank_every=32,
-                 update="server", bsc_threshold=None, size_lower_bound=None, hfa=None, loopback=False):
+                 update="server", bsc_threshold=None, size_lower_bound=None, hfa=None, loopback=False, lookahead=False):
         """``update='server'`` (examples/cnn.py): the optimizer runs on the global-PS shard inside the exchange kernel.  ``update='local'``
         (examples/cnn_bsc.py / cnn_fp16.py / cnn_mpq.py): the kvstore only aggregates gradients (``set_optimizer`` is not called on it), every
         worker applies its own Adam to the pulled aggregate — one fused arena-optimizer launch.  ``bsc_threshold``: Bi-Sparse between the tiers
         for keys >= ``size_lower_bound`` elements.  ``hfa=(K1, K2)`` (examples/cnn_hfa.py): local Adam on the own gradient every step, party
-        average of the weights every K1 steps, global average every K1*K2 steps (reference milestone algebra, kvstore_dist_server.h:959-972)."""
+        average of the weights every K1 steps, global average every K1*K2 steps (reference milestone algebra, kvstore_dist_server.h:959-972).
+
+        ``lookahead=True`` software-pipelines consecutive steps: the launch made by ``step(X[k+1], y[k+1])`` starts at the classifier head of
+        batch k (whose convolutions already ran), exchanges the dense keys underneath the convolution backward pass, the conv-key exchange AND
+        the forward convolutions of batch k+1, and returns the loss of batch k (``nan`` on the first call; ``flush()`` trains the last batch).
+        The arithmetic and its order are unchanged — batch k+1's convolutions still read the conv weights updated by batch k, its head the
+        dense weights updated by batch k — only the place where the step is cut into launches moves, so that the two-hop exchange of the
+        660 KB dense keys has ~25 us of independent work to hide behind instead of ~9."""
         native.require()
         from .. import optimizer as opt
         self.B = B = int(batch_size)
@@ -154,7 +164,10 @@ class HipsCNNTrainStep:
         self.dz4, self.dz3, self.da2 = e(B, 128), e(B, 256), e(B, 512)
         self.dz2rows, self.dcol1, self.da1 = e(B * 64, 32), e(B * 64, 400), e(B, 16, 12, 12)
         self.loss_host = torch.empty(B, dtype=f32).pin_memory()
-        self.pull_fused = bool(pull_fused) and self.topo.world >= 1
+        self.lookahead = bool(lookahead) and mode == "dist_sync" and not self.hfa
+        # look-ahead: the head of the launch belongs to the PREVIOUS batch, whose labels must outlive the arrival of the next batch in `xin`
+        self.label_cur = torch.empty_like(self.label) if self.lookahead else self.label
+        self._primed = False
         self.graph = None
         self._side = torch.cuda.Stream(device=self.device)
         # the exchange branch gets a high-priority stream: its (few) CTAs must become resident at once on every rank — they poll each other —
@@ -233,7 +246,7 @@ class HipsCNNTrainStep:
         head = [
             ("dense0 gemm", "main", lambda: n.gemm(a2f, P[4], self.a3, bias=P[5], relu=True)),
             ("dense1 gemm", "main", lambda: n.gemm(self.a3, P[6], self.a4, bias=P[7], relu=True)),
-            ("head fwd+bwd", "main", lambda: n.head_fwd_bwd(self.a4, P[8], P[9], self.label, self.loss, self.logits, G[8], G[9], self.dz4, G[7], True)),
+            ("head fwd+bwd", "main", lambda: n.head_fwd_bwd(self.a4, P[8], P[9], self.label_cur, self.loss, self.logits, G[8], G[9], self.dz4, G[7], True)),
             ("dW1 gemm", "side", lambda: n.gemm(self.dz4, self.a3, G[6], a_mn=True, b_mn=True)),
             ("dz3 gemm (mask,colsum)", "main", lambda: n.gemm(self.dz4, P[6], self.dz3, b_mn=True, mask=self.a3, colsum=G[5])),
             ("dW0 gemm", "side", lambda: n.gemm(self.dz3, a2f, G[4], a_mn=True, b_mn=True)),
@@ -241,17 +254,32 @@ class HipsCNNTrainStep:
         ]
         if self.fused_mlp:
             # dense0 -> dense1 -> classifier -> softmax-CE forward and backward: ONE 8-CTA cluster launch instead of the seven above
-            head = [("mlp chain fwd+bwd (cluster)", "main", lambda: n.mlp_chain(a2f, P[4], P[5], P[6], P[7], P[8], P[9], self.label, self.loss, self.logits,
+            head = [("mlp chain fwd+bwd (cluster)", "main", lambda: n.mlp_chain(a2f, P[4], P[5], P[6], P[7], P[8], P[9], self.label_cur, self.loss, self.logits,
                                                                               G[4], G[5], G[6], G[7], G[8], G[9], self.da2))]
+        # number of leading steps that only need the batch and the conv weights (the part a look-ahead launch runs for the NEXT batch)
+        self._n_fwd = 1 if self.direct_conv else 2
+        carry = (self.label, self.label_cur) if self.lookahead else None
         if self.direct_conv:
             da2v = self.da2
+            if os.environ.get("GEOMX_CNN_BWD_ONE_LAUNCH", "1") == "1" and B % 2 == 0 and B <= 64:
+                # both backward jobs in one heterogeneous grid: no side-stream fork / join around the convolution backward
+                return [
+                    ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2, carry=carry)),
+                ] + head + kv_dense + [
+                    ("conv bwd: conv1 wgrad + dgrad + conv0 wgrad (direct, one grid)", "main",
+                     lambda: n.cnn_bwd_all(self.x, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1], G[2], G[3])),
+                    ("hips push+opt+pull", "join", kv),
+                ] + self._tail
             return [
-                ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2)),
+                ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2, carry=carry)),
             ] + head + kv_dense + [
                 ("conv1 wgrad (direct, sparse)", "side", lambda: n.cnn_wgrad1(self.a1, self.a2, self.idx2, da2v, G[2], G[3])),
                 ("conv1 dgrad + conv0 wgrad (direct)", "main", lambda: n.cnn_bwd(self.x, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1])),
                 ("hips push+opt+pull", "join", kv),
             ] + self._tail
+        if self.lookahead:
+            conv1 = conv1_fwd
+            conv1_fwd = lambda: (conv1(), self.label_cur.copy_(self.label))
         return [
             ("conv0+relu+pool+im2col", "main", lambda: n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)),
             ("conv1 gemm (bias,relu,maxpool fused)", "main", conv1_fwd),
@@ -263,7 +291,9 @@ class HipsCNNTrainStep:
             ("hips push+opt+pull", "join", kv),
         ] + self._tail
 
-    def _body(self, stop_after=None):
+    def _body(self, stop_after=None, part="all"):
+        """Issue the step (``part='all'``), only its forward convolutions (``'fwd'``), everything after them (``'rest'``), or the look-ahead
+        rotation ``rest(batch k) + fwd(batch k+1)`` (``'rotated'``)."""
         before = native.launch_count
         f = self.fabric
         # the gradient arena is cleared by the previous step's HiPS kernel (fused zero_grad) unless gradients must stay readable
@@ -271,7 +301,10 @@ class HipsCNNTrainStep:
             f.grad.tensor.zero_()
         main, side, comm = torch.cuda.current_stream(), self._side, self._comm
         forked = comm_forked = False
-        for i, (name, where, fn) in enumerate(self._steps()):
+        steps = self._steps()
+        nf = self._n_fwd
+        steps = {"all": steps, "fwd": steps[:nf], "rest": steps[nf:], "rotated": steps[nf:] + steps[:nf]}[part]
+        for i, (name, where, fn) in enumerate(steps):
             if stop_after is not None and i >= stop_after:
                 break
             if where == "side":      # weight-gradient GEMMs leave the critical path: parallel branch of the captured graph
@@ -294,7 +327,8 @@ class HipsCNNTrainStep:
             main.wait_stream(side)
         if comm_forked:
             main.wait_stream(comm)
-        self.kernels_per_step = native.launch_count - before
+        if part in ("all", "rotated"):
+            self.kernels_per_step = native.launch_count - before
 
     def capture(self):
         """Warm up (2 eager steps on a side stream) and capture the step into a CUDA graph."""
@@ -313,10 +347,27 @@ class HipsCNNTrainStep:
         if self.topo.world > 1:
             import torch.distributed as dist
             dist.barrier()
+        if self.lookahead:
+            self._prime()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._body()
+            self._body(part="rotated" if self.lookahead else "all")
         self.graph = g
+
+    def _prime(self):
+        """Look-ahead: run the forward convolutions of the batch in ``self.x`` so that the next launch can start at the classifier head."""
+        if not self._primed:
+            self._body(part="fwd")
+            self._primed = True
+
+    def flush(self):
+        """Look-ahead: train on the batch whose convolutions are already done (the last one enqueued) and return its mean loss."""
+        if not (self.lookahead and self._primed):
+            return None
+        self._body(part="rest")
+        self._primed = False
+        self.steps_done += 1
+        return float(self.loss.mean())
 
     def run_device(self):
         """One step on whatever is currently in ``self.x`` / ``self.label`` (device-only; used by the kernel-time bench)."""
@@ -325,7 +376,12 @@ class HipsCNNTrainStep:
         if self.use_graph:
             if self.graph is None:
                 self.capture()
+            if self.lookahead:
+                self._prime()
             self.graph.replay()
+        elif self.lookahead:
+            self._prime()
+            self._body(part="rotated")
         else:
             self._body()
         self.steps_done += 1
@@ -392,6 +448,14 @@ class HipsCNNTrainStep:
             self.xin.copy_(pl["stage"][b], non_blocking=True)
         if pl["last_loss"] is not None:
             main.wait_event(pl["last_loss"])                # the loss buffer of the previous step has been read out
+        if self.lookahead and not self._primed:
+            # first batch of a look-ahead run: only its convolutions can run yet (after the graph warm-up, which also uses this batch);
+            # there is no finished step to report
+            if self.use_graph and self.graph is None:
+                self.capture()
+            self._prime()
+            pl["done"][b].record(main)
+            return LossHandle(None, None)
         self.run_device()
         pl["done"][b].record(main)
         host, ev = pl["ring"][i % 4]

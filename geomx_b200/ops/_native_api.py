@@ -103,14 +103,23 @@ def mlp_chain(x, w0, b0, w1, b1, w2, b2, label, loss, logits, dw0, db0, dw1, db1
 
 
 # --------------------------------------------------------------------------------------------------------------- demo-CNN direct convolutions
-def cnn_fwd(x, w0, b0, w1, b1, a1, idx1, a2, idx2):
-    """Conv(16,k5)+ReLU+MaxPool2 -> Conv(32,k5)+ReLU+MaxPool2 of the demo CNN in one launch (csrc/kernels/cnn_direct.cu), fp32 FMA."""
-    _ck(_lib().gx_cnn_fwd(_p(x), _p(w0), _p(b0), _p(w1), _p(b1), _p(a1), _p(idx1), _p(a2), _p(idx2), x.shape[0], _s()), "cnn_fwd")
+def cnn_fwd(x, w0, b0, w1, b1, a1, idx1, a2, idx2, carry=None):
+    """Conv(16,k5)+ReLU+MaxPool2 -> Conv(32,k5)+ReLU+MaxPool2 of the demo CNN in one launch (csrc/kernels/cnn_direct.cu), fp32 FMA.
+    ``carry=(src, dst)``: also copy the small fp32 vector ``src`` to ``dst`` (the labels of a look-ahead step, see models/cnn.py)."""
+    src, dst = carry if carry is not None else (None, None)
+    _ck(_lib().gx_cnn_fwd(_p(x), _p(w0), _p(b0), _p(w1), _p(b1), _p(a1), _p(idx1), _p(a2), _p(idx2), _p(src), _p(dst),
+                          0 if src is None else src.numel(), x.shape[0], _s()), "cnn_fwd")
 
 
 def cnn_bwd(x, w1, a1, idx1, a2, idx2, da2, dw0, db0):
     """conv1 data gradient + pool/ReLU backward of both layers + conv0 weight / bias gradient (accumulated with atomics into dw0 / db0)."""
     _ck(_lib().gx_cnn_bwd(_p(x), _p(w1), _p(a1), _p(idx1), _p(a2), _p(idx2), _p(da2), _p(dw0), _p(db0), x.shape[0], _s()), "cnn_bwd")
+
+
+def cnn_bwd_all(x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dw1, db1):
+    """The whole convolution backward pass (``cnn_bwd`` + ``cnn_wgrad1``) as one heterogeneous-grid launch."""
+    _ck(_lib().gx_cnn_bwd_all(_p(x), _p(w1), _p(a1), _p(idx1), _p(a2), _p(idx2), _p(da2), _p(dw0), _p(db0), _p(dw1), _p(db1), x.shape[0], _s()),
+        "cnn_bwd_all")
 
 
 def cnn_wgrad1(a1, a2, idx2, da2, dw1, db1):

@@ -107,7 +107,19 @@ def batch_norm(x, gamma, beta, running_mean, running_var, training, momentum=0.9
         return BatchNormFn.apply(x, gamma, beta, running_mean, running_var, bool(training), float(momentum), float(eps))
     if axis != 1:
         x = x.transpose(1, axis)
-    y = F.batch_norm(x, running_mean, running_var, gamma, beta, training, 1.0 - momentum, eps)
+    if training:
+        # the running variance tracks the POPULATION variance of the batch, as the reference's kernels do (src/operator/nn/batch_norm.cu:355-362,
+        # contrib/sync_batch_norm-inl.h:392) — torch's own running update would use the unbiased estimate
+        with torch.no_grad():
+            dims = [0] + list(range(2, x.dim()))
+            xf = x.float()
+            mean = xf.mean(dims)
+            var = (xf * xf).mean(dims).sub_(mean * mean).clamp_min_(0.0)
+            running_mean.mul_(momentum).add_(mean.to(running_mean.dtype), alpha=1.0 - momentum)
+            running_var.mul_(momentum).add_(var.to(running_var.dtype), alpha=1.0 - momentum)
+        y = F.batch_norm(x, None, None, gamma, beta, True, 0.0, eps)
+    else:
+        y = F.batch_norm(x, running_mean, running_var, gamma, beta, False, 0.0, eps)
     return y.transpose(1, axis) if axis != 1 else y
 
 

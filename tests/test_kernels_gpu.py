@@ -90,6 +90,12 @@ def test_cnn_direct_kernels_match_torch(nat):
         torch.cuda.synchronize()
         for got, ref, name in ((dw0, ref_dw0, "dw0"), (db0, ref_db0, "db0"), (dw1, ref_dw1, "dw1"), (db1, ref_db1, "db1")):
             assert rel_err(got, ref) < 1e-5, (B, name, rel_err(got, ref))
+        # the one-launch form (heterogeneous grid) computes the same four gradients
+        dw0.zero_(); db0.zero_(); dw1.fill_(float("nan")); db1.fill_(float("nan"))
+        nat.cnn_bwd_all(x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dw1, db1)
+        torch.cuda.synchronize()
+        for got, ref, name in ((dw0, ref_dw0, "dw0"), (db0, ref_db0, "db0"), (dw1, ref_dw1, "dw1"), (db1, ref_db1, "db1")):
+            assert rel_err(got, ref) < 1e-5, (B, "one launch", name, rel_err(got, ref))
 
 
 def test_mlp_chain_matches_torch(nat):
@@ -391,6 +397,31 @@ def test_fused_step_graph_trains(nat):
     for _ in range(40):
         l = eng.step(X, y)
     assert l < 0.5 * l0, (l0, l)
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_lookahead_step_is_the_same_training(nat, use_graph):
+    """The look-ahead cut of the step (head of batch k .. forward convolutions of batch k+1 in one launch) is the same arithmetic in the same
+    order as the classic cut: identical loss sequence (reported one call late) and identical weights after flush()."""
+    from geomx_b200.parallel import Topology
+    g = torch.Generator().manual_seed(21)
+    Xs = [torch.rand(32, 1, 28, 28, generator=g).pin_memory() for _ in range(6)]
+    ys = [torch.randint(0, 10, (32,), generator=g).float().pin_memory() for _ in range(6)]
+    runs = {}
+    for look in (False, True):
+        torch.manual_seed(17)
+        eng = mx.models.HipsCNNTrainStep(batch_size=32, optimizer=mx.optimizer.SGD(learning_rate=0.05), topo=Topology(1, 0, 1, 1),
+                                         use_graph=use_graph, lookahead=look)
+        losses = [eng.step(X, y) for X, y in zip(Xs, ys)]
+        if look:
+            assert math.isnan(losses[0])
+            losses = losses[1:] + [eng.flush()]
+            assert eng.flush() is None
+        torch.cuda.synchronize()
+        runs[look] = (losses, eng.fabric.param.tensor.clone())
+    la, lb = runs[False][0], runs[True][0]
+    assert all(abs(a - b) < 1e-5 * max(1.0, abs(a)) for a, b in zip(la, lb)), (la, lb)
+    assert torch.allclose(runs[False][1], runs[True][1], atol=1e-5), float((runs[False][1] - runs[True][1]).abs().max())
 
 
 def test_direct_conv_kernels_exact(nat):
