@@ -46,8 +46,8 @@ def parse():
                          "(K1=20 local steps, K2=10 party rounds per global round); mixed_sync = cnn.py -ms (dist_async global tier)")
     ap.add_argument("--script", action="store_true", help="time the loop of examples/cnn.py itself (gluon autograd + kv.push/kv.pull per key through "
                                                             "the fabric KVStore) instead of the fused HipsCNNTrainStep engine")
-    ap.add_argument("--no-lookahead", action="store_true", help="cut the step before the forward convolutions (classic order) instead of after them; "
-                    "see HipsCNNTrainStep(lookahead=...)")
+    ap.add_argument("--lookahead", action="store_true", help="cut the step after the forward convolutions instead of before them (software "
+                    "pipelining across launches, see HipsCNNTrainStep(lookahead=...)); measured: no gain at 1-2 GPUs, so not the default")
     ap.add_argument("--fast", action="store_true", help="plain TF32 tensor-core products instead of the fp32-accurate 3xTF32 default")
     ap.add_argument("--wire-dtype", default="fp32", choices=["fp32", "fp16", "mpq", "fp8"], help="transport format of the fused HiPS step (FP16 / MPQ accelerators)")
     return ap.parse_args()
@@ -213,7 +213,7 @@ def main():
               "mpq_dgt": {"update": "local", "wire_dtype": "mpq", "size_lower_bound": 1000, "dgt": True},
               "hfa": {"hfa": (int(os.environ.get("MXNET_KVSTORE_HFA_K1", 20)), int(os.environ.get("MXNET_KVSTORE_HFA_K2", 10)))}}[args.config]
         kw.setdefault("mode", args.mode); kw.setdefault("wire_dtype", args.wire_dtype)
-        kw["lookahead"] = not args.no_lookahead
+        kw["lookahead"] = args.lookahead
         eng = mx.models.HipsCNNTrainStep(net=None, batch_size=B, optimizer=mx.optimizer.Adam(learning_rate=0.01), topo=topo, device=dev,
                                          use_graph=not args.no_graph, use_multicast=not args.no_multicast, **kw)
 

@@ -21,6 +21,8 @@ KVStoreDistServer::KVStoreDistServer() {
   ckpt_every_ = ckpt_prefix_.empty() ? 0 : std::max(0, env->GetInt("GEOMX_SERVER_CKPT_EVERY", 0));
   fused_tier_pull_ = env->GetInt("GEOMX_FUSED_TIER_PULL", 1) != 0 && env->GetInt("ENABLE_INTER_TS", 0) == 0;
   resume_wanted_ = !ckpt_prefix_.empty() && env->GetInt("GEOMX_SERVER_RESUME", 0) != 0 && (is_global_ || standalone_);
+  const int lanes = std::max(0, env->GetInt("GEOMX_SERVER_LANES", 4));   // 0: pushes are handled on the customer thread itself
+  for (int i = 0; i < lanes; ++i) lanes_.emplace_back(new Lane());
   ps_server_.reset(new KVServer(0));
   ps_server_->SimpleApp::set_request_handle([this](const SimpleData& d, SimpleApp* app) { CommandHandle(d, app); });
   ps_server_->set_request_handle([this](const KVMeta& m, const KVPairs& d, KVServer* s) { DataHandleEx(m, d, s); });
@@ -29,18 +31,61 @@ KVStoreDistServer::KVStoreDistServer() {
     ps_server_->ts(kGlobal)->set_on_relayed([this](int key, int version, int cmd, const std::vector<char>& bytes) { OnRelayedFromGlobal(key, version, cmd, bytes); });
 }
 
-KVStoreDistServer::~KVStoreDistServer() { ps_server_.reset(); }
+KVStoreDistServer::~KVStoreDistServer() {
+  lanes_.clear();          // drain and join the push lanes before the transport goes away
+  ps_server_.reset();
+}
 
 int KVStoreDistServer::rank_local() { return Postoffice::Get()->my_rank(kLocal); }
 
-std::vector<float> KVStoreDistServer::GetStored(int key) {
-  std::lock_guard<std::mutex> lk(mu_);
-  auto it = store_.find(key);
-  if (it == store_.end()) return {};
-  std::vector<float> out(it->second.elems);
-  if (it->second.has_master) out = it->second.master;
-  else ToFloat(it->second.data.data(), it->second.dtype, it->second.elems, out.data());
+// ------------------------------------------------------------------------------------------------ key registry
+KVStoreDistServer::KeyState* KVStoreDistServer::Find(int key) {
+  std::shared_lock<std::shared_mutex> lk(reg_mu_);
+  auto it = keys_.find(key);
+  return it == keys_.end() ? nullptr : it->second.get();
+}
+
+KVStoreDistServer::KeyState& KVStoreDistServer::Slot(int key) {
+  if (KeyState* ks = Find(key)) return *ks;
+  std::unique_lock<std::shared_mutex> lk(reg_mu_);
+  std::unique_ptr<KeyState>& p = keys_[key];
+  if (!p) p.reset(new KeyState());
+  return *p;
+}
+
+std::vector<std::pair<int, KVStoreDistServer::KeyState*>> KVStoreDistServer::Slots() {
+  std::shared_lock<std::shared_mutex> lk(reg_mu_);
+  std::vector<std::pair<int, KeyState*>> out;
+  out.reserve(keys_.size());
+  for (auto& kv : keys_) out.emplace_back(kv.first, kv.second.get());
   return out;
+}
+
+std::vector<float> KVStoreDistServer::GetStored(int key) {
+  KeyState* ks = Find(key);
+  if (ks == nullptr) return {};
+  std::lock_guard<std::mutex> lk(ks->mu);
+  const Entry& e = ks->entry;
+  std::vector<float> out(e.elems);
+  if (e.has_master) out = e.master;
+  else ToFloat(e.data.data(), e.dtype, e.elems, out.data());
+  return out;
+}
+
+void KVStoreDistServer::Send(std::vector<Reply>* out) {
+  for (Reply& r : *out) {
+    if (r.data.keys.size()) ps_server_->Response(r.to, r.data);
+    else ps_server_->Response(r.to);
+  }
+  out->clear();
+}
+
+KVStoreDistServer::Reply KVStoreDistServer::StoredReply(const KVMeta& to, int key, const Entry& e) const {
+  Reply r; r.to = to;
+  r.data.keys.push_back(static_cast<Key>(key));
+  r.data.vals.CopyFrom(e.data.data(), e.data.size());
+  r.data.lens.push_back(static_cast<int>(e.data.size()));
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------ dtype helpers
@@ -82,11 +127,11 @@ void KVStoreDistServer::CommandHandle(const SimpleData& recved, SimpleApp* app) 
       if (is_global_) {
         // a global server stops after every local server (global worker) voted; central workers' votes on the local plane are ignored
         bool stop = false;
-        { std::lock_guard<std::mutex> lk(mu_); if (recved.plane == kGlobal) stop = (++stop_votes_ == po->num_global_workers()); }
+        { std::lock_guard<std::mutex> lk(ctl_mu_); if (recved.plane == kGlobal) stop = (++stop_votes_ == po->num_global_workers()); }
         if (stop) exec_.Stop();
       } else {
         bool first;
-        { std::lock_guard<std::mutex> lk(mu_); first = !stop_requested_; stop_requested_ = true; }
+        { std::lock_guard<std::mutex> lk(ctl_mu_); first = !stop_requested_; stop_requested_ = true; }
         if (first && has_global_) {  // relay to the global servers, do not wait (they stop only after all parties voted)
           ps_server_->Request(static_cast<int>(CommandType::kStopServer), "", kServerGroup, kGlobal);
         }
@@ -97,11 +142,10 @@ void KVStoreDistServer::CommandHandle(const SimpleData& recved, SimpleApp* app) 
     case CommandType::kSyncMode: sync_mode_ = true; break;
     case CommandType::kSyncGlobalMode: sync_global_mode_ = true; break;
     case CommandType::kSetMultiPrecision: {
-      std::lock_guard<std::mutex> lk(mu_);
-      if (!multi_precision_) {
-        multi_precision_ = true;
-        for (auto& kv : store_) {
-          Entry& e = kv.second;
+      if (!multi_precision_.exchange(true)) {
+        for (auto& kv : Slots()) {
+          std::lock_guard<std::mutex> lk(kv.second->mu);
+          Entry& e = kv.second->entry;
           if (!e.has_master && e.dtype != kFloat32) { e.master.resize(e.elems); ToFloat(e.data.data(), e.dtype, e.elems, e.master.data()); e.has_master = true; }
         }
       }
@@ -118,12 +162,10 @@ void KVStoreDistServer::CommandHandle(const SimpleData& recved, SimpleApp* app) 
       break;
     }
     case CommandType::kSetOptimizerSpec: {
-      std::lock_guard<std::mutex> lk(mu_);
       OptSpec s = OptSpec::Parse(recved.body);
       HIPS_CHECK_MSG(s.valid(), "unknown native optimizer spec: " + recved.body);
-      native_opt_.reset(new NativeOptimizer(s));
-      for (auto& kv : resumed_opt_) native_opt_->states()[kv.first] = kv.second;   // state checkpointed by a previous incarnation
-      resumed_opt_.clear();
+      // the per-key optimizer state (moments, step count — possibly restored from a checkpoint) stays with the keys
+      std::atomic_store(&native_opt_, std::shared_ptr<const NativeOptimizer>(new NativeOptimizer(s)));
       break;
     }
     case CommandType::kSetProfilerParams: {
@@ -172,15 +214,30 @@ void KVStoreDistServer::DataHandleEx(const KVMeta& req, const KVPairs& data, KVS
   const DataHandleType type = DepairDataHandleType(req.cmd);
   // the server object exists before the node has registered (its rank names the checkpoint file), so the resume happens on first traffic
   if (resume_wanted_) std::call_once(resume_once_, [this] { TryResume(); });
-  ProfileScope ps(req.push ? "KVStoreDistServerPush" : "KVStoreDistServerPull");
-  if (req.push) HandlePush(type, req, data);
-  else HandlePull(type, req, data);
+  if (!req.push) {
+    ProfileScope ps("KVStoreDistServerPull");
+    HandlePull(type, req, data);
+    return;
+  }
+  if (lanes_.empty()) {
+    ProfileScope ps("KVStoreDistServerPush");
+    HandlePush(type, req, data);
+    return;
+  }
+  // the payload is reference counted: the lane keeps the message buffer alive
+  Lane* lane = lanes_[static_cast<size_t>(req.key < 0 ? -req.key : req.key) % lanes_.size()].get();
+  lane->Post([this, type, req, data] {
+    ProfileScope ps("KVStoreDistServerPush");
+    HandlePush(type, req, data);
+  });
 }
 
-void KVStoreDistServer::ApplyUpdate(int key, Entry* e, const float* grad, size_t n) {
+void KVStoreDistServer::ApplyUpdate(int key, KeyState* ks, const float* grad, size_t n) {
+  Entry* e = &ks->entry;
   float* w = e->has_master ? e->master.data() : reinterpret_cast<float*>(e->data.data());
-  if (native_opt_) native_opt_->Update(key, w, grad, n);
-  else if (updater_) exec_.Exec([this, key, grad, w, n]() { updater_(key, grad, w, n); });
+  const std::shared_ptr<const NativeOptimizer> opt = std::atomic_load(&native_opt_);
+  if (opt) opt->Update(&ks->opt, w, grad, n);
+  else if (updater_) exec_.Exec([this, key, grad, w, n]() { updater_(key, grad, w, n); });   // foreign updaters run one at a time on the main thread
   else memcpy(w, grad, n * sizeof(float));  // no optimizer on the server: store the aggregate (reference ApplyUpdates :547-550)
   if (e->has_master) StoreFromFloat(e, e->master.data(), n);
 }
@@ -190,8 +247,10 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   const int key = req.key;
   Postoffice* po = Postoffice::Get();
   num_pushes_++;
-  std::unique_lock<std::mutex> lk(mu_);
-  Entry& e = store_[key];
+  KeyState& ks = Slot(key);
+  std::vector<Reply> out;                 // built under the key's lock, sent after it is released
+  std::unique_lock<std::mutex> lk(ks.mu);
+  Entry& e = ks.entry;
   const bool p3 = ps_server_->enable_p3;
   // inter-tier fusion (GEOMX_FUSED_TIER_PULL, default on): a global server answers a local server's dense push with the post-update value,
   // so the local server does not need a second round trip (push ack, then pull) over the slow link between parties
@@ -199,39 +258,38 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   const bool fuse_bsc = is_global_ && fused_tier_pull_ && type.requestType == RequestType::kBSCompressedPushPull && sync_global_mode_;
   auto respond = [&](const KVMeta& r) {
     if (fuse_up && r.plane == kGlobal && r.sender % 2 == 1) {
-      KVPairs res; res.keys = data.keys;
-      res.vals.CopyFrom(e.data.data(), e.data.size());
-      res.lens.push_back(static_cast<int>(e.data.size()));
-      ps_server_->Response(r, res);
+      Reply rep = StoredReply(r, key, e);
+      rep.data.keys = data.keys;
+      out.push_back(std::move(rep));
     } else if (fuse_bsc && r.plane == kGlobal && r.sender % 2 == 1) {
       // Bi-Sparse: the answer is the re-sparsified aggregate a pull would have returned (capacity k * parties, reference :1190-1206)
       const int mult = std::max(1, Postoffice::Get()->num_global_workers());
       const float* w = e.has_master ? e.master.data() : reinterpret_cast<const float*>(e.data.data());
-      std::vector<float> out(GradientCompression::BSCPullSize(static_cast<int64_t>(e.elems), gc_.threshold(), mult));
-      gc_.BSCPullCompress(w, out.data(), static_cast<int64_t>(e.elems), mult);
-      KVPairs res; res.keys = data.keys;
-      res.vals.CopyFrom(reinterpret_cast<const char*>(out.data()), out.size() * sizeof(float));
-      res.lens.push_back(static_cast<int>(res.vals.size()));
-      ps_server_->Response(r, res);
+      std::vector<float> z(GradientCompression::BSCPullSize(static_cast<int64_t>(e.elems), gc_.threshold(), mult));
+      gc_.BSCPullCompress(w, z.data(), static_cast<int64_t>(e.elems), mult);
+      Reply rep; rep.to = r; rep.data.keys = data.keys;
+      rep.data.vals.CopyFrom(reinterpret_cast<const char*>(z.data()), z.size() * sizeof(float));
+      rep.data.lens.push_back(static_cast<int>(rep.data.vals.size()));
+      out.push_back(std::move(rep));
     } else if (p3 && !is_global_) {
-      KVPairs res; res.keys = data.keys;
-      res.vals.CopyFrom(e.data.data(), e.data.size());
-      res.lens.push_back(static_cast<int>(e.data.size()));
-      ps_server_->Response(r, res);
-    } else ps_server_->Response(r);
+      Reply rep = StoredReply(r, key, e);
+      rep.data.keys = data.keys;
+      out.push_back(std::move(rep));
+    } else {
+      Reply rep; rep.to = r;
+      out.push_back(std::move(rep));
+    }
   };
-  if (e.elems != 0 && !skip_init_push_.empty() && (standalone_ || req.plane == kLocal)) {
+  if (e.elems != 0 && any_skip_init_.load() && ks.skip_init_push && (standalone_ || req.plane == kLocal)) {
     // ---- resumed server: the restarted job initialises its keys again (kv.init); the checkpointed value wins, the push is only acknowledged.
     // On a global server the init comes from the master worker over the LOCAL plane of the central party — the parties may already be
     // training by then (their pulls found the restored keys initialised), so their pushes on the global plane must not be mistaken for it.
-    auto sk = skip_init_push_.find(key);
-    if (sk != skip_init_push_.end() && sk->second) {
-      sk->second = false;
-      respond(req);
-      lk.unlock();
-      AskTS(key);
-      return;
-    }
+    ks.skip_init_push = false;
+    respond(req);
+    lk.unlock();
+    Send(&out);
+    AskTS(key);
+    return;
   }
   if (e.elems == 0) {
     // ---- initialisation: the first push of a key defines it (reference :1237-1269)
@@ -244,10 +302,12 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
       e.master.resize(e.elems); ToFloat(e.data.data(), e.dtype, e.elems, e.master.data()); e.has_master = true;
     }
     respond(req);
-    if (is_global_ || standalone_) { initialized_[key] = true; init_cv_.notify_all(); }
-    else if (has_global_) { lk.unlock(); PullFromGlobal(key, type); AskTS(key); return; }
+    const bool fetch = !(is_global_ || standalone_) && has_global_;
+    if (is_global_ || standalone_) { ks.initialized = true; ks.ready.notify_all(); }
     lk.unlock();
-    AskTS(key);      // TSEngine: open the first round of this key
+    Send(&out);
+    if (fetch) PullFromGlobal(key, type);     // a local server adopts the global tier's value of the key
+    AskTS(key);                               // TSEngine: open the first round of this key
     return;
   }
   // ---- decode the contribution to fp32
@@ -287,22 +347,23 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
     GradientCompression::BSCDecompress(reinterpret_cast<const float*>(data.vals.data()), data.vals.size() / sizeof(float), incoming.data(), n);
   }
   // central-party workers only train when DMLC_ENABLE_CENTRAL_WORKER=1 (reference :1274-1275)
-  if (is_global_ && req.plane == kLocal && !po->enable_central_workers()) { respond(req); return; }
+  if (is_global_ && req.plane == kLocal && !po->enable_central_workers()) { respond(req); lk.unlock(); Send(&out); return; }
 
-  const bool sync = (is_global_ ? sync_global_mode_ : sync_mode_);
+  const bool sync = (is_global_ ? sync_global_mode_.load() : sync_mode_.load());
   if (!sync) {
     // ---- MixedSync / async: apply this contribution immediately (reference :1582-1609)
-    ApplyUpdate(key, &e, inc, n);
+    ApplyUpdate(key, &ks, inc, n);
     const std::vector<KVMeta> who = ExpandOrigins(req);
     for (size_t i = 0; i < who.size(); ++i) {
       if (i > 0 && who[i].sender == who[i - 1].sender && who[i].timestamp == who[i - 1].timestamp) continue;
       respond(who[i]);
     }
     lk.unlock();
+    Send(&out);
     AskTS(key);
     return;
   }
-  UpdateBuf& ub = update_buf_[key];
+  UpdateBuf& ub = ks.ub;
   if (ub.request.empty()) ub.merged.assign(inc, inc + n);
   else { float* m = ub.merged.data(); for (size_t i = 0; i < n; ++i) m[i] += inc[i]; }
   for (const KVMeta& r : ExpandOrigins(req)) ub.request.push_back(r);
@@ -315,62 +376,61 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
     return;
   }
   if (is_global_ || standalone_) {
-    ApplyUpdate(key, &e, ub.merged.data(), n);
-    // the round counter moves (and a due periodic checkpoint is written) BEFORE any push of this round is acknowledged: once the acks are
-    // out, workers may start round N+1 of other keys, and a snapshot taken later could mix round-N and round-N+1 state
-    BumpRoundLocked(key);
+    ApplyUpdate(key, &ks, ub.merged.data(), n);
+    // the round counter moves (and a due periodic checkpoint is written) BEFORE any push of this round is acknowledged: until the acks
+    // are out no worker can start round N+1 of any key, so a snapshot taken now holds exactly the round-N state of every key
+    const bool checkpoint_due = BumpRound(&ks);
     std::vector<KVMeta> reqs; reqs.swap(ub.request);
     for (size_t i = 0; i < reqs.size(); ++i) {
       if (i > 0 && reqs[i].sender == reqs[i - 1].sender && reqs[i].timestamp == reqs[i - 1].timestamp) continue;  // merged duplicates (TS)
       respond(reqs[i]);
     }
     lk.unlock();
+    if (checkpoint_due) SaveStates(ckpt_prefix_);
+    Send(&out);
     RoundCompleted(key, /*bumped=*/true);
     return;
   }
-  const bool local_round_done = FinishLocalAggregation(key, type, &ub);
+  const bool local_round_done = FinishLocalAggregation(key, &ks, type, &out);
   lk.unlock();
+  Send(&out);
   if (local_round_done) RoundCompleted(key);
 }
 
 // local server: all workers of the party have pushed `key`
-bool KVStoreDistServer::FinishLocalAggregation(int key, const DataHandleType& type, UpdateBuf* ub) {
-  Entry& e = store_[key];
+bool KVStoreDistServer::FinishLocalAggregation(int key, KeyState* ks, const DataHandleType& type, std::vector<Reply>* out) {
+  Entry& e = ks->entry;
+  UpdateBuf* ub = &ks->ub;
   const size_t n = e.elems;
   float* w = e.has_master ? e.master.data() : reinterpret_cast<float*>(e.data.data());
   memcpy(w, ub->merged.data(), n * sizeof(float));   // only aggregate (ApplyUpdates on a non-global server)
   if (e.has_master) StoreFromFloat(&e, w, n);
   if (key == 0) ++local_iters_;                      // HFA counts local rounds on key 0 (reference :1324)
-  auto ack_all = [&](std::vector<KVMeta>* reqs) {
-    for (size_t i = 0; i < reqs->size(); ++i) {
-      if (i > 0 && (*reqs)[i].sender == (*reqs)[i - 1].sender && (*reqs)[i].timestamp == (*reqs)[i - 1].timestamp) continue;
-      if (ps_server_->enable_p3) {
-        KVPairs res; res.keys.push_back(static_cast<Key>(key)); res.vals.CopyFrom(e.data.data(), e.data.size()); res.lens.push_back(static_cast<int>(e.data.size()));
-        ps_server_->Response((*reqs)[i], res);
-      } else ps_server_->Response((*reqs)[i]);
+  if (use_hfa_ && (local_iters_.load() % hfa_k2_ != 0)) {   // local synchronisation only
+    for (size_t i = 0; i < ub->request.size(); ++i) {
+      const std::vector<KVMeta>& q = ub->request;
+      if (i > 0 && q[i].sender == q[i - 1].sender && q[i].timestamp == q[i - 1].timestamp) continue;
+      if (ps_server_->enable_p3) out->push_back(StoredReply(q[i], key, e));
+      else { Reply rep; rep.to = q[i]; out->push_back(std::move(rep)); }
     }
-    reqs->clear();
-  };
-  if (use_hfa_ && (local_iters_ % hfa_k2_ != 0)) {   // local synchronisation only
-    ack_all(&ub->request);
+    ub->request.clear();
     return true;
   }
   if (use_hfa_) {                                    // push the party's progress since the last global sync
-    auto& ms = milestone_[key];
+    auto& ms = ks->milestone;
     HIPS_CHECK_MSG(ms.size() == n, "HFA milestone not initialised for key " + std::to_string(key));
     const float inv = 1.f / Postoffice::Get()->num_global_workers();
     for (size_t i = 0; i < n; ++i) w[i] = (w[i] - ms[i]) * inv;
     if (e.has_master) StoreFromFloat(&e, w, n);
   }
-  GlobalRound& r = rounds_[key];
-  r.waiting.swap(ub->request);
-  PushToGlobal(key, type);
+  ks->round.waiting.swap(ub->request);
+  PushToGlobal(key, ks, type);
   return false;
 }
 
-void KVStoreDistServer::PushToGlobal(int key, const DataHandleType& type) {
-  Entry& e = store_[key];
-  GlobalRound& r = rounds_[key];
+void KVStoreDistServer::PushToGlobal(int key, KeyState* st, const DataHandleType& type) {
+  Entry& e = st->entry;
+  GlobalRound& r = st->round;
   const size_t n = e.elems;
   const float* w = e.has_master ? e.master.data() : reinterpret_cast<const float*>(e.data.data());
   const int num_gs = Postoffice::Get()->num_global_servers();
@@ -380,7 +440,7 @@ void KVStoreDistServer::PushToGlobal(int key, const DataHandleType& type) {
   const CompressionType ct = gc_.type();
   if (ct == CompressionType::kBiSparse && n >= size_lower_bound_ ) {
     int k, sample, ks; GradientCompression::BSCSizes(static_cast<int64_t>(n), gc_.threshold(), &k, &sample, &ks);
-    auto& u = bsc_u_[key]; auto& v = bsc_v_[key];
+    auto& u = st->bsc_u; auto& v = st->bsc_v;
     if (u.size() != n) { u.assign(n, 0.f); v.assign(n, 0.f); }
     std::vector<float> out(2 * static_cast<size_t>(k));
     gc_.BSCompress(w, u.data(), v.data(), out.data(), static_cast<int64_t>(n));
@@ -389,7 +449,7 @@ void KVStoreDistServer::PushToGlobal(int key, const DataHandleType& type) {
     lens.push_back(static_cast<int>(vals.size()));
     cmd = GetCommandType(RequestType::kBSCompressedPushPull, kFloat32);
   } else if (ct == CompressionType::kTwoBit && e.dtype == kFloat32) {
-    auto& res = residual_2bit_[key];
+    auto& res = st->residual_2bit;
     if (res.size() != n) res.assign(n, 0.f);
     std::vector<uint32_t> words(GradientCompression::CompressedSize2Bit(static_cast<int64_t>(n)));
     gc_.Quantize2Bit(w, res.data(), words.data(), static_cast<int64_t>(n));
@@ -408,14 +468,16 @@ void KVStoreDistServer::PushToGlobal(int key, const DataHandleType& type) {
   const bool allow_dgt = ps_server_->enable_dgt != 0 && cmd == GetCommandType(RequestType::kDefaultPushPull, kFloat32);
   // inter-party TSEngine: dense pushes are merged with other parties' aggregates on their way; the fresh value comes back by relay
   r.via_ts = ps_server_->ts(kGlobal) != nullptr && !allow_dgt && keys.size() == 1 && DepairDataHandleType(cmd).requestType == RequestType::kDefaultPushPull;
+  // responses carry the key and the request's timestamp; they are matched against push_ts under this key's lock (held here), so an
+  // answer that arrives before Push() returns still finds the round
   r.push_ts = ps_server_->Push(keys, vals, lens, cmd, -key, key, allow_dgt, r.via_ts);
-  ts_key_[r.push_ts] = key;
 }
 
 void KVStoreDistServer::PullFromGlobal(int key, const DataHandleType& type) {
-  std::lock_guard<std::mutex> lk(mu_);
-  Entry& e = store_[key];
-  GlobalRound& r = rounds_[key];
+  KeyState& ksr = Slot(key);
+  std::lock_guard<std::mutex> lk(ksr.mu);
+  Entry& e = ksr.entry;
+  GlobalRound& r = ksr.round;
   const size_t n = e.elems;
   const int num_gs = Postoffice::Get()->num_global_servers();
   const auto& krs = Postoffice::Get()->GetServerKeyRanges(kGlobal);
@@ -438,17 +500,27 @@ void KVStoreDistServer::PullFromGlobal(int key, const DataHandleType& type) {
   r.parts.clear();
   r.cmd = cmd;
   r.pull_ts = ps_server_->Pull(keys, cmd, -key, key);
-  ts_key_[r.pull_ts] = key;
 }
 
-// responses to OUR requests on the global plane (local server side)
+// responses to OUR requests on the global plane (local server side); they carry the key and the timestamp of the request they answer
 void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, KVServer* server) {
-  std::unique_lock<std::mutex> lk(mu_);
-  auto it = ts_key_.find(res.timestamp);
-  if (it == ts_key_.end()) return;
-  const int key = it->second;
-  GlobalRound& r = rounds_[key];
+  const int key = res.key;
+  KeyState* ks = Find(key);
+  if (ks == nullptr) return;
+  std::vector<Reply> out;
+  std::unique_lock<std::mutex> lk(ks->mu);
+  GlobalRound& r = ks->round;
+  Entry& e = ks->entry;
+  auto finish = [&](std::vector<float>* fresh) {       // the key's new value is complete: store it, release the workers, open the next round
+    const bool was_round = r.push_ts >= 0;
+    ApplyFreshFromGlobal(key, ks, fresh, &out);
+    lk.unlock();
+    Send(&out);
+    if (was_round) RoundCompleted(key); else AskTS(key);
+  };
+  const auto by_key = [](const std::pair<Key, std::vector<char>>& a, const std::pair<Key, std::vector<char>>& b) { return a.first < b.first; };
   if (res.push) {
+    if (res.timestamp != r.push_ts) return;             // not the round in flight (late duplicate)
     // push ack: once every global server acknowledged, fetch the fresh value (reference :941-957) — unless the acks already carried it
     // (fused inter-tier pull: every global server that owns a slice of the key answers with the post-update slice)
     if (data.vals.size() > 0 && data.keys.size()) {
@@ -456,10 +528,8 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
       r.parts.emplace_back(data.keys[0], std::move(bytes));
     }
     if (server->NumResponse(res.timestamp) != Postoffice::Get()->num_global_servers() - 1) return;
-    ts_key_.erase(it);
     if (r.via_ts) { r.parts.clear(); return; }   // TSEngine: the global server relays the fresh value (OnRelayedFromGlobal)
     const DataHandleType type = DepairDataHandleType(r.cmd);
-    Entry& e = store_[key];
     size_t got = 0;
     for (auto& p : r.parts) got += p.second.size();
     if (type.requestType == RequestType::kBSCompressedPushPull && r.parts.size() == 1 && got > 0) {
@@ -468,23 +538,17 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
       const auto& z = r.parts[0].second;
       GradientCompression::BSCDecompress(reinterpret_cast<const float*>(z.data()), z.size() / sizeof(float), recved.data(), e.elems);
       r.parts.clear();
-      const bool was_round = r.push_ts >= 0;
-      ApplyFreshFromGlobal(key, &recved);
-      lk.unlock();
-      if (was_round) RoundCompleted(key); else AskTS(key);
+      finish(&recved);
       return;
     }
     if (type.requestType == RequestType::kDefaultPushPull && got > 0 && got == e.elems * DTypeSize(e.dtype)) {
-      std::sort(r.parts.begin(), r.parts.end(), [](const std::pair<Key, std::vector<char>>& a, const std::pair<Key, std::vector<char>>& b) { return a.first < b.first; });
+      std::sort(r.parts.begin(), r.parts.end(), by_key);
       std::vector<char> whole;
       for (auto& p : r.parts) whole.insert(whole.end(), p.second.begin(), p.second.end());
       r.parts.clear();
       std::vector<float> recved(e.elems);
       ToFloat(whole.data(), e.dtype, e.elems, recved.data());
-      const bool was_round = r.push_ts >= 0;
-      ApplyFreshFromGlobal(key, &recved);
-      lk.unlock();
-      if (was_round) RoundCompleted(key); else AskTS(key);
+      finish(&recved);
       return;
     }
     r.parts.clear();
@@ -493,12 +557,11 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
     return;
   }
   // pull response part
+  if (res.timestamp != r.pull_ts) return;
   std::vector<char> bytes(data.vals.data(), data.vals.data() + data.vals.size());
   r.parts.emplace_back(data.keys.size() ? data.keys[0] : 0, std::move(bytes));
   if (static_cast<int>(r.parts.size()) < r.parts_expected) return;
-  ts_key_.erase(it);
-  std::sort(r.parts.begin(), r.parts.end(), [](const std::pair<Key, std::vector<char>>& a, const std::pair<Key, std::vector<char>>& b) { return a.first < b.first; });
-  Entry& e = store_[key];
+  std::sort(r.parts.begin(), r.parts.end(), by_key);
   const size_t n = e.elems;
   const DataHandleType type = DepairDataHandleType(r.cmd);
   std::vector<float> recved(n);
@@ -512,56 +575,52 @@ void KVStoreDistServer::ResponseHandle(const KVMeta& res, const KVPairs& data, K
     ToFloat(whole.data(), e.dtype, n, recved.data());
   }
   r.parts.clear();
-  const bool was_round = r.push_ts >= 0;
-  ApplyFreshFromGlobal(key, &recved);
-  lk.unlock();
-  if (was_round) RoundCompleted(key); else AskTS(key);
+  finish(&recved);
 }
 
 // the value of `key` after a global round (or the initial value) reached this local server: HFA algebra, store, release the workers
-void KVStoreDistServer::ApplyFreshFromGlobal(int key, std::vector<float>* recved_p) {
+void KVStoreDistServer::ApplyFreshFromGlobal(int key, KeyState* ks, std::vector<float>* recved_p, std::vector<Reply>* out) {
   std::vector<float>& recved = *recved_p;
-  Entry& e = store_[key];
-  GlobalRound& r = rounds_[key];
+  Entry& e = ks->entry;
+  GlobalRound& r = ks->round;
   const size_t n = e.elems;
   float* w = e.has_master ? e.master.data() : reinterpret_cast<float*>(e.data.data());
   if (use_hfa_) {
     // HandleHFAAccumulate (reference :959-972): the first pulled value becomes the milestone, afterwards stored = milestone + sum(deltas)
-    auto& ms = milestone_[key];
+    auto& ms = ks->milestone;
     if (ms.size() != n) { memcpy(w, recved.data(), n * 4); ms.assign(w, w + n); }
     else { for (size_t i = 0; i < n; ++i) { w[i] = ms[i] + recved[i]; ms[i] = w[i]; } }
   } else {
     memcpy(w, recved.data(), n * sizeof(float));
   }
   if (e.has_master) StoreFromFloat(&e, w, n);
-  initialized_[key] = true;
-  init_cv_.notify_all();
+  ks->initialized = true;
+  ks->ready.notify_all();
   std::vector<KVMeta> waiting; waiting.swap(r.waiting);
   r.push_ts = r.pull_ts = -1;
   r.via_ts = false;
   for (size_t i = 0; i < waiting.size(); ++i) {
     if (i > 0 && waiting[i].sender == waiting[i - 1].sender && waiting[i].timestamp == waiting[i - 1].timestamp) continue;
-    if (ps_server_->enable_p3) {
-      KVPairs out; out.keys.push_back(static_cast<Key>(key)); out.vals.CopyFrom(e.data.data(), e.data.size()); out.lens.push_back(static_cast<int>(e.data.size()));
-      ps_server_->Response(waiting[i], out);
-    } else ps_server_->Response(waiting[i]);
+    if (ps_server_->enable_p3) out->push_back(StoredReply(waiting[i], key, e));
+    else { Reply rep; rep.to = waiting[i]; out->push_back(std::move(rep)); }
   }
 }
 
 // inter-party TSEngine: the global server's relay delivered the fresh value of a round this local server pushed through the overlay
 void KVStoreDistServer::OnRelayedFromGlobal(int key, int version, int cmd, const std::vector<char>& bytes) {
-  std::unique_lock<std::mutex> lk(mu_);
-  auto it = store_.find(key);
-  if (it == store_.end()) return;
-  Entry& e = it->second;
-  GlobalRound& r = rounds_[key];
-  if (!r.via_ts) return;            // not waiting for a relayed round (e.g. a duplicate)
+  KeyState* ks = Find(key);
+  if (ks == nullptr) return;
+  std::vector<Reply> out;
+  std::unique_lock<std::mutex> lk(ks->mu);
+  Entry& e = ks->entry;
+  if (!ks->round.via_ts) return;    // not waiting for a relayed round (e.g. a duplicate)
   const size_t n = e.elems;
   if (bytes.size() != n * DTypeSize(e.dtype)) return;
   std::vector<float> recved(n);
   ToFloat(bytes.data(), e.dtype, n, recved.data());
-  ApplyFreshFromGlobal(key, &recved);
+  ApplyFreshFromGlobal(key, ks, &recved, &out);
   lk.unlock();
+  Send(&out);
   RoundCompleted(key);
 }
 
@@ -588,28 +647,35 @@ void KVStoreDistServer::AskTS(int key) {
   if (is_global_) if (TSNode* t = ps_server_->ts(kGlobal)) t->AskAsServer(key);
 }
 
-// a synchronisation round of `key` finished on this server: bump the version, start the relay broadcast, open the next round
-// caller holds mu_: advance the round counter of `key`; when the SLOWEST key thereby reaches a multiple of the checkpoint period, write the
-// snapshot right here — at this instant every key holds exactly its round-N value and nothing of round N has been acknowledged yet
-void KVStoreDistServer::BumpRoundLocked(int key) {
-  const int version = ++round_version_[key];
-  if (ckpt_every_ <= 0) return;
+// ks->mu held: advance the round counter of the key.  Returns true when the SLOWEST key thereby reaches a multiple of the checkpoint period:
+// the caller then writes the snapshot after releasing the key and BEFORE acknowledging the round — until the acks are out no worker can start
+// round N+1 of any key, so every key holds exactly its round-N value while the snapshot is taken.
+bool KVStoreDistServer::BumpRound(KeyState* ks) {
+  const int version = ++ks->version;
+  if (ckpt_every_ <= 0) return false;
   int slowest = version;
-  for (auto& kv : store_) { auto it = round_version_.find(kv.first); slowest = std::min(slowest, it == round_version_.end() ? 0 : it->second); }
-  if (slowest > ckpt_key_ && slowest % ckpt_every_ == 0) { ckpt_key_ = slowest; SaveStatesLocked(ckpt_prefix_); }
+  for (auto& kv : Slots()) slowest = std::min(slowest, kv.second->version.load());
+  std::lock_guard<std::mutex> lk(round_mu_);
+  if (slowest > ckpt_key_ && slowest % ckpt_every_ == 0) { ckpt_key_ = slowest; return true; }
+  return false;
 }
 
+// a synchronisation round of `key` finished on this server: bump the version (unless the caller already did), start the relay broadcast,
+// open the next round
 void KVStoreDistServer::RoundCompleted(int key, bool bumped) {
   std::vector<char> bytes;
   int version, cmd;
+  bool checkpoint_due = false;
+  const bool relays = ps_server_->ts(kLocal) != nullptr || (is_global_ && ps_server_->ts(kGlobal) != nullptr);
   {
-    std::lock_guard<std::mutex> lk(mu_);
-    if (!bumped) BumpRoundLocked(key);
-    version = round_version_[key];
-    Entry& e = store_[key];
-    bytes = e.data;
-    cmd = GetCommandType(RequestType::kDefaultPushPull, e.dtype);
+    KeyState& ks = Slot(key);
+    std::lock_guard<std::mutex> lk(ks.mu);
+    if (!bumped) checkpoint_due = BumpRound(&ks);
+    version = ks.version.load();
+    if (relays) bytes = ks.entry.data;
+    cmd = GetCommandType(RequestType::kDefaultPushPull, ks.entry.dtype);
   }
+  if (checkpoint_due) SaveStates(ckpt_prefix_);
   Postoffice* po = Postoffice::Get();
   if (TSNode* t = ps_server_->ts(kLocal)) {
     if (!is_global_ || po->enable_central_workers()) t->Relay(key, version, cmd, static_cast<Key>(key), bytes.data(), bytes.size());
@@ -620,10 +686,11 @@ void KVStoreDistServer::RoundCompleted(int key, bool bumped) {
 
 void KVStoreDistServer::HandlePull(const DataHandleType& type, const KVMeta& req, const KVPairs& data) {
   const int key = req.key;
-  std::unique_lock<std::mutex> lk(mu_);
+  KeyState& ks = Slot(key);
+  std::unique_lock<std::mutex> lk(ks.mu);
   // the pull thread waits until the key has been initialised (reference spins with sleep(100ms) :1719-1724)
-  init_cv_.wait(lk, [this, key] { auto it = initialized_.find(key); return it != initialized_.end() && it->second; });
-  Entry& e = store_[key];
+  ks.ready.wait(lk, [&ks] { return ks.initialized; });
+  Entry& e = ks.entry;
   KVPairs res;
   res.keys = data.keys;
   if (type.requestType == RequestType::kRowSparsePushPull) {
@@ -668,52 +735,51 @@ std::string KVStoreDistServer::StatePath(const std::string& prefix) const {
   return prefix + ".server" + std::to_string(r) + (is_global_ ? "g" : "l");
 }
 
+// One key at a time under its own lock.  The periodic snapshot is taken at a quiescent point (see BumpRound); an explicit kSaveStates
+// command is issued by the job between rounds.
 void KVStoreDistServer::SaveStates(const std::string& prefix) {
-  std::lock_guard<std::mutex> lk(mu_);
-  SaveStatesLocked(prefix);
-}
-
-void KVStoreDistServer::SaveStatesLocked(const std::string& prefix) {
   const std::string path = StatePath(prefix);
   const std::string tmp = path + ".tmp";
   std::ofstream f(tmp, std::ios::binary);
   const uint64_t magic = 0x4869505353544154ull;  // "HiPSSTAT"
   f.write(reinterpret_cast<const char*>(&magic), 8);
-  uint64_t nk = store_.size(); f.write(reinterpret_cast<const char*>(&nk), 8);
-  for (auto& kv : store_) {
-    int32_t key = kv.first, dtype = kv.second.dtype; uint64_t elems = kv.second.elems;
+  const auto slots = Slots();
+  uint64_t nk = slots.size(); f.write(reinterpret_cast<const char*>(&nk), 8);
+  for (auto& kv : slots) {
+    KeyState& ks = *kv.second;
+    std::lock_guard<std::mutex> lk(ks.mu);
+    const Entry& e = ks.entry;
+    int32_t key = kv.first, dtype = e.dtype; uint64_t elems = e.elems;
     f.write(reinterpret_cast<const char*>(&key), 4); f.write(reinterpret_cast<const char*>(&dtype), 4); f.write(reinterpret_cast<const char*>(&elems), 8);
-    uint64_t nb = kv.second.data.size(); f.write(reinterpret_cast<const char*>(&nb), 8); f.write(kv.second.data.data(), nb);
-    WriteVec(f, kv.second.master);
-    WriteVec(f, milestone_.count(key) ? milestone_[key] : std::vector<float>());
-    WriteVec(f, bsc_u_.count(key) ? bsc_u_[key] : std::vector<float>());
-    WriteVec(f, bsc_v_.count(key) ? bsc_v_[key] : std::vector<float>());
-    WriteVec(f, residual_2bit_.count(key) ? residual_2bit_[key] : std::vector<float>());
-    NativeOptimizer::State st;
-    if (native_opt_ && native_opt_->states().count(key)) st = native_opt_->states()[key];
-    int32_t t = st.t; f.write(reinterpret_cast<const char*>(&t), 4);
-    WriteVec(f, st.a); WriteVec(f, st.b);
+    uint64_t nb = e.data.size(); f.write(reinterpret_cast<const char*>(&nb), 8); f.write(e.data.data(), nb);
+    WriteVec(f, e.master);
+    WriteVec(f, ks.milestone);
+    WriteVec(f, ks.bsc_u);
+    WriteVec(f, ks.bsc_v);
+    WriteVec(f, ks.residual_2bit);
+    int32_t t = ks.opt.t; f.write(reinterpret_cast<const char*>(&t), 4);
+    WriteVec(f, ks.opt.a); WriteVec(f, ks.opt.b);
   }
-  int64_t li = local_iters_; f.write(reinterpret_cast<const char*>(&li), 8);
+  int64_t li = local_iters_.load(); f.write(reinterpret_cast<const char*>(&li), 8);
   f.close();
   HIPS_CHECK_MSG(std::rename(tmp.c_str(), path.c_str()) == 0, "cannot move " + tmp + " to " + path);   // readers never see a torn file
 }
 
 // GEOMX_SERVER_RESUME=1: a (re)started global / stand-alone server adopts the last periodic checkpoint if there is one.  The job's scripts
-// still call kv.init for every key; those pushes are acknowledged without touching the restored values (skip_init_push_).
+// still call kv.init for every key; those pushes are acknowledged without touching the restored values (KeyState::skip_init_push).
 void KVStoreDistServer::TryResume() {
   const std::string path = StatePath(ckpt_prefix_);
   std::ifstream probe(path, std::ios::binary);
   if (!probe.good()) return;
   probe.close();
   LoadStates(ckpt_prefix_);
-  std::lock_guard<std::mutex> lk(mu_);
-  for (auto& kv : store_) skip_init_push_[kv.first] = true;
-  fprintf(stderr, "[hips] server resumed %zu keys from %s\n", store_.size(), path.c_str());
+  const auto slots = Slots();
+  for (auto& kv : slots) { std::lock_guard<std::mutex> lk(kv.second->mu); kv.second->skip_init_push = true; }
+  any_skip_init_ = !slots.empty();
+  fprintf(stderr, "[hips] server resumed %zu keys from %s\n", slots.size(), path.c_str());
 }
 
 void KVStoreDistServer::LoadStates(const std::string& prefix) {
-  std::lock_guard<std::mutex> lk(mu_);
   const std::string path = StatePath(prefix);
   std::ifstream f(path, std::ios::binary);
   HIPS_CHECK_MSG(f.good(), "cannot open " + path);
@@ -724,24 +790,21 @@ void KVStoreDistServer::LoadStates(const std::string& prefix) {
     int32_t key, dtype; uint64_t elems, nb;
     f.read(reinterpret_cast<char*>(&key), 4); f.read(reinterpret_cast<char*>(&dtype), 4); f.read(reinterpret_cast<char*>(&elems), 8);
     f.read(reinterpret_cast<char*>(&nb), 8);
-    Entry& e = store_[key];
+    KeyState& ks = Slot(key);
+    std::lock_guard<std::mutex> lk(ks.mu);
+    Entry& e = ks.entry;
     e.dtype = dtype; e.elems = elems; e.data.resize(nb); f.read(e.data.data(), nb);
     ReadVec(f, &e.master); e.has_master = !e.master.empty();
-    std::vector<float> v;
-    ReadVec(f, &v); if (!v.empty()) milestone_[key] = v;
-    ReadVec(f, &v); if (!v.empty()) bsc_u_[key] = v;
-    ReadVec(f, &v); if (!v.empty()) bsc_v_[key] = v;
-    ReadVec(f, &v); if (!v.empty()) residual_2bit_[key] = v;
+    ReadVec(f, &ks.milestone);
+    ReadVec(f, &ks.bsc_u);
+    ReadVec(f, &ks.bsc_v);
+    ReadVec(f, &ks.residual_2bit);
     int32_t t; f.read(reinterpret_cast<char*>(&t), 4);
-    NativeOptimizer::State st; st.t = t; ReadVec(f, &st.a); ReadVec(f, &st.b);
-    if (!st.a.empty() || st.t != 0) {
-      if (native_opt_) native_opt_->states()[key] = st;
-      else resumed_opt_[key] = st;                     // the optimizer spec arrives later (set_optimizer command)
-    }
-    initialized_[key] = true;
+    ks.opt.t = t; ReadVec(f, &ks.opt.a); ReadVec(f, &ks.opt.b);     // used by whichever native optimizer is (or will be) configured
+    ks.initialized = true;
+    ks.ready.notify_all();
   }
   int64_t li = 0; f.read(reinterpret_cast<char*>(&li), 8); local_iters_ = li;
-  init_cv_.notify_all();
 }
 
 }  // namespace hips

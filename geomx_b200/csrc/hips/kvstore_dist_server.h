@@ -8,6 +8,11 @@
 // multi-precision master copies (:374-407, :526-553), key sharding across global servers (MultiGPS :1765-1906), P3 push-response-with-
 // params (:1154-1164, :1257-1267), stop protocol (:315-328), initialized_ gate (:1719-1724), server profiler commands (:409-456).
 //
+// Concurrency: there is no server-wide lock.  Every key owns its state and a mutex (KeyState); a small reader/writer registry maps key ->
+// state; push requests are dispatched to GEOMX_SERVER_LANES worker threads by key (per-key FIFO order, different keys aggregate, run
+// their optimizer and talk to the global tier in parallel), pulls keep their own thread, and responses from the global tier are handled on
+// the receive thread of the connection they arrived on.  Replies are built under the key's lock and sent after it is released.
+//
 // Design differences: continuation-style state machine on raw byte buffers (no NDArray/engine on the server), native optimizers run
 // in the receiving thread (server_optim.h) and only *foreign* (pickled Python) optimizers hop to the main thread through `Executor`,
 // server-side state (optimizer moments, HFA milestones, BSC residuals) can be checkpointed (kSaveStates/kLoadStates) — the reference
@@ -23,6 +28,8 @@
 #include <memory>
 #include <mutex>
 #include <queue>
+#include <shared_mutex>
+#include <deque>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -137,64 +144,104 @@ class KVStoreDistServer {
     int cmd = 0;
   };
 
+  // everything the server knows about one key; `mu` guards all of it except `version`
+  struct KeyState {
+    std::mutex mu;
+    std::condition_variable ready;          // pulls wait here until the key holds a value
+    Entry entry;
+    UpdateBuf ub;
+    GlobalRound round;
+    std::vector<float> milestone, bsc_u, bsc_v, residual_2bit;
+    NativeOptimizer::State opt;
+    bool initialized = false;
+    bool skip_init_push = false;            // resumed key: the next init push of the (re)started job must not overwrite it
+    std::atomic<int> version{0};            // completed synchronisation rounds (TSEngine relay version, checkpoint cadence)
+  };
+  struct Reply { KVMeta to; KVPairs data; };
+  // push lanes: requests of one key always run on the same worker thread, in arrival order
+  class Lane {
+   public:
+    Lane() : th_([this] { Loop(); }) {}
+    ~Lane() {
+      { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+      cv_.notify_all();
+      th_.join();
+    }
+    void Post(std::function<void()> f) {
+      { std::lock_guard<std::mutex> lk(mu_); q_.push_back(std::move(f)); }
+      cv_.notify_one();
+    }
+   private:
+    void Loop() {
+      std::unique_lock<std::mutex> lk(mu_);
+      while (true) {
+        cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;             // stop requested and everything queued has run
+        std::function<void()> f = std::move(q_.front());
+        q_.pop_front();
+        lk.unlock();
+        f();
+        lk.lock();
+      }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    bool stop_ = false;
+    std::thread th_;                        // last member: starts after the queue exists
+  };
+
+  KeyState& Slot(int key);                                   // find or create
+  KeyState* Find(int key);
+  std::vector<std::pair<int, KeyState*>> Slots();            // snapshot of the registry, ordered by key
   // handlers
   void CommandHandle(const SimpleData& recved, SimpleApp* app);
   void DataHandleEx(const KVMeta& req, const KVPairs& data, KVServer* server);
   void ResponseHandle(const KVMeta& res, const KVPairs& data, KVServer* server);
   void HandlePush(const DataHandleType& type, const KVMeta& req, const KVPairs& data);
   void HandlePull(const DataHandleType& type, const KVMeta& req, const KVPairs& data);
-  bool FinishLocalAggregation(int key, const DataHandleType& type, UpdateBuf* ub);   // true: the round ended locally (HFA local sync)
-  void PushToGlobal(int key, const DataHandleType& type);
-  void PullFromGlobal(int key, const DataHandleType& type);
-  void ApplyUpdate(int key, Entry* e, const float* grad, size_t n);
+  // the functions below taking a KeyState expect its mutex to be held by the caller
+  bool FinishLocalAggregation(int key, KeyState* ks, const DataHandleType& type, std::vector<Reply>* out);   // true: the round ended locally (HFA)
+  void PushToGlobal(int key, KeyState* ks, const DataHandleType& type);
+  void PullFromGlobal(int key, const DataHandleType& type);                                                  // takes the key's lock itself
+  void ApplyUpdate(int key, KeyState* ks, const float* grad, size_t n);
+  void ApplyFreshFromGlobal(int key, KeyState* ks, std::vector<float>* recved, std::vector<Reply>* out);
+  bool BumpRound(KeyState* ks);                               // true: a periodic checkpoint is due (write it after releasing the key)
+  Reply StoredReply(const KVMeta& to, int key, const Entry& e) const;
+  void Send(std::vector<Reply>* out);
   void StoreFromFloat(Entry* e, const float* src, size_t n);
   void ToFloat(const char* src, int dtype, size_t n, float* dst);
-  void RespondStored(const KVMeta& req, int key, Key ps_key, const DataHandleType& type);
   // TSEngine (ts_node.h): a merged push stands for several requests; servers take part in the pairing and start the relay
   std::vector<KVMeta> ExpandOrigins(const KVMeta& req);
   void AskTS(int key);
   void RoundCompleted(int key, bool bumped = false);
-  void BumpRoundLocked(int key);
-  void ApplyFreshFromGlobal(int key, std::vector<float>* recved);   // mu_ held
   void OnRelayedFromGlobal(int key, int version, int cmd, const std::vector<char>& bytes);
-  // key codecs
-  int DecodeKey(Key ps_key, Plane plane);
-  struct PSKV { std::vector<Key> keys; std::vector<int> lens; size_t size = 0; };
-  PSKV& EncodeGlobalKey(int key, size_t num_elems, int num_bytes);
   void SaveStates(const std::string& path);
-  void SaveStatesLocked(const std::string& path);
   void LoadStates(const std::string& path);
 
   std::unique_ptr<KVServer> ps_server_;
   Executor exec_;
   Controller controller_;
   Updater updater_;
-  std::unique_ptr<NativeOptimizer> native_opt_;
+  std::shared_ptr<const NativeOptimizer> native_opt_;     // replaced as a whole by kSetOptimizerSpec (atomic_load / atomic_store)
   GradientCompression gc_;
-  std::mutex mu_;
-  std::condition_variable init_cv_;
-  std::unordered_map<int, Entry> store_;
-  std::unordered_map<int, UpdateBuf> update_buf_;
-  std::unordered_map<int, GlobalRound> rounds_;
-  std::unordered_map<int, int> ts_key_;                  // global-plane timestamp -> key
-  std::unordered_map<int, std::vector<float>> milestone_, bsc_u_, bsc_v_, residual_2bit_;
-  std::unordered_map<int, bool> initialized_;
-  std::unordered_map<int, int> round_version_;           // completed synchronisation rounds per key (TSEngine relay version)
-  std::unordered_map<int, PSKV> ps_kv_;
-  bool sync_mode_ = false, sync_global_mode_ = false, multi_precision_ = false;
+  std::shared_mutex reg_mu_;                              // the registry only: never held while a key's mutex is taken
+  std::map<int, std::unique_ptr<KeyState>> keys_;
+  std::vector<std::unique_ptr<Lane>> lanes_;
+  std::mutex ctl_mu_;                                     // stop votes
+  std::mutex round_mu_;                                   // checkpoint cadence (ckpt_key_)
+  std::atomic<bool> sync_mode_{false}, sync_global_mode_{false}, multi_precision_{false}, any_skip_init_{false};
   bool is_global_ = false, has_global_ = false, standalone_ = false;
   bool use_hfa_ = false;
   int hfa_k2_ = 1;
-  long local_iters_ = 0;
+  std::atomic<long> local_iters_{0};
   size_t bigarray_bound_ = 1000000, size_lower_bound_ = 200000;
   int stop_votes_ = 0;
   bool stop_requested_ = false;
   std::atomic<long> num_pushes_{0};
-  // periodic server-state checkpoints + resume (GEOMX_SERVER_CKPT_PREFIX / _EVERY / GEOMX_SERVER_RESUME), see RoundCompleted / TryResume
+  // periodic server-state checkpoints + resume (GEOMX_SERVER_CKPT_PREFIX / _EVERY / GEOMX_SERVER_RESUME), see BumpRound / TryResume
   std::string ckpt_prefix_;
   int ckpt_every_ = 0, ckpt_key_ = 0;                  // ckpt_key_: round number of the last snapshot
-  std::unordered_map<int, bool> skip_init_push_;         // resumed keys: the next init push of the (re)started job must not overwrite them
-  std::map<int, NativeOptimizer::State> resumed_opt_;     // optimizer state read before the optimizer was configured
   bool fused_tier_pull_ = true;                          // global server: dense push responses to local servers carry the fresh value
   bool resume_wanted_ = false;
   std::once_flag resume_once_;

@@ -43,9 +43,12 @@ class NativeOptimizer {
  public:
   explicit NativeOptimizer(const OptSpec& s) : s_(s) {}
   const OptSpec& spec() const { return s_; }
-  // weight (fp32 master) updated in place from grad; per-key state is created on first use
-  void Update(int key, float* w, const float* g, size_t n) {
-    State& st = st_[key];
+  // checkpointable server-side state of ONE key (the reference cannot save it: "Cannot save states for distributed training"); it lives with
+  // the key on the server, so updates of different keys never share a container
+  struct State { std::vector<float> a, b; int t = 0; };
+  // weight (fp32 master) updated in place from grad; the state is initialised on first use
+  void Update(State* state, float* w, const float* g, size_t n) const {
+    State& st = *state;
     if (st.a.size() != n) { st.a.assign(n, 0.f); st.b.assign(n, 0.f); st.t = 0; if (s_.name == "dcasgd") for (size_t i = 0; i < n; ++i) st.b[i] = w[i]; }
     ++st.t;
     const float lr = s_.name == "adam" ? s_.lr * std::sqrt(1.f - std::pow(s_.beta2, (float)st.t)) / (1.f - std::pow(s_.beta1, (float)st.t)) : s_.lr;
@@ -70,13 +73,9 @@ class NativeOptimizer {
       }
     }
   }
-  // checkpointable server-side state (the reference cannot save it: "Cannot save states for distributed training")
-  struct State { std::vector<float> a, b; int t = 0; };
-  std::map<int, State>& states() { return st_; }
 
  private:
   OptSpec s_;
-  std::map<int, State> st_;
 };
 
 }  // namespace hips
