@@ -280,10 +280,11 @@ def main():
         chans = list(fab.channels) or ["fsa"]
         last = "conv" if "conv" in fab.channels else chans[-1]      # the exchange at the end of the step (nothing left to hide it behind)
         look = bool(getattr(eng, "lookahead", False)) and getattr(eng, "direct_conv", False) and "conv" in fab.channels
+        fused = bool(getattr(eng, "fused_exchange", False))
         cdbg = None
-        if look:
-            # look-ahead steps end with the forward convolutions of the next batch: an overlapped channel is exposed only where it outlives
-            # THAT kernel.  Its end is taken from the kernel's own %globaltimer stamp, which needs a graph captured with stamping switched on.
+        if look or fused:
+            # the kernels' own %globaltimer stamps are needed (end of the forward convolutions of a look-ahead step; start / end of the
+            # exchange tail inside the convolution-backward launch): re-capture the graph with stamping switched on
             cdbg = torch.zeros(32, dtype=torch.int64, device=dev)
             native.require().gx_cnn_set_debug(ctypes.c_void_p(cdbg.data_ptr()))
             if eng.graph is not None:
@@ -298,10 +299,17 @@ def main():
             eng.run_device()
             torch.cuda.synchronize()
             st = {c: fab.state[c][8:8 + 12].view(torch.int64).tolist() for c in chans}
-            if st[last][5] > st[last][0] > 0:
+            cd = cdbg.tolist() if cdbg is not None else None
+            if fused:
+                # exposed = the tail of the backward launch from "whole grid finished" to "weights written" + whatever of the overlapped
+                # channel outlives it (or, look-ahead, outlives the forward convolutions that follow)
+                other_end = max([v[5] for k, v in st.items() if k != last] or [0])
+                hidden_until = max(cd[24], cd[4]) if look else cd[24]
+                if cd[24] > cd[21] > 0:
+                    samples.append(((cd[24] - cd[21]) + max(0, other_end - hidden_until)) / 1e3)
+            elif st[last][5] > st[last][0] > 0:
                 if look:
-                    fwd_end = int(cdbg[4])
-                    hidden_until = max(fwd_end, st[last][5])
+                    hidden_until = max(cd[4], st[last][5])
                     samples.append(((st[last][5] - st[last][0]) + max(0, max(v[5] for v in st.values()) - hidden_until)) / 1e3)
                 else:
                     end = max(v[5] for v in st.values())          # an overlapped channel that outlives the last one is exposed too

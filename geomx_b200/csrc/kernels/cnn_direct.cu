@@ -15,6 +15,7 @@
 // Reference kernels replaced: im2col_gpu_kernel / col2im_gpu_kernel (src/operator/nn/im2col.cuh:79-187), per-image cublasSgemmEx
 // (convolution-inl.h:165-284), bias broadcast, ReLU (activation-inl.h:89-121), pool_max_2d / unpool (pool.cuh:128-165, 379-432).
 #include "common.cuh"
+#include "hips_ll.cuh"
 
 namespace gx {
 
@@ -77,7 +78,8 @@ __device__ __forceinline__ float pool4(const float (&a)[4], float bias, int& bi)
 __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float* __restrict__ b0,
                                                        const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ a1,
                                                        unsigned char* __restrict__ idx1, float* __restrict__ a2, unsigned char* __restrict__ idx2,
-                                                       const float* __restrict__ carry_src, float* __restrict__ carry_dst, int carry_n, unsigned long long* dbg) {
+                                                       const float* __restrict__ carry_src, float* __restrict__ carry_dst, int carry_n, float* __restrict__ x_keep,
+                                                       unsigned long long* dbg) {
   __shared__ __align__(16) float sx[CD_H * CD_H];
   __shared__ __align__(16) float sw0[CD_C1 * CD_W1PAD];
   __shared__ float sb0[CD_C1];
@@ -107,6 +109,9 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const float* __restrict__ 
   cpa_wait_all();
   __syncthreads();
   stamp(1);
+  // look-ahead steps: the backward pass of this batch runs in the NEXT launch, after the following batch has overwritten x — keep a copy
+  if (x_keep != nullptr && g == 0) for (int i = tid; i < CD_H * CD_H / 4; i += 256)
+    reinterpret_cast<float4*>(x_keep + (long long)b * CD_H * CD_H)[i] = reinterpret_cast<const float4*>(sx)[i];
   // ---- conv0 + bias + ReLU + pool: thread -> channel tid/16, windows (tid%16) + 16 j
   {
     const int ch = tid >> 4, sub = tid & 15;
@@ -355,6 +360,103 @@ __global__ void __launch_bounds__(288) cnn_bwd_all_kernel(const float* x, const 
   }
 }
 
+// The convolution backward pass AND the exchange of the four conv keys (push -> both server tiers -> optimizer -> pull, the replicated one-hop
+// mode of hips_fabric.cu's direct protocol) as ONE launch.  Grid and bodies are those of cnn_bwd_all_kernel.  Every CTA takes a ticket when its
+// gradients are written; the CTAs that draw the last `n_active` tickets wait until the ticket counter shows that the whole grid has finished
+// and then each serve one 1024-float tile of the conv keys: gradient -> LL packets into every rank's slot, poll the packets of all ranks, sum
+// in the hierarchy's order (party sums, push_scale, sum over parties), optimizer on this rank's replica of the server state, fresh weights
+// into the parameter arena.  Compared with a separate exchange launch this removes the grid drain + launch between the last gradient store and
+// the first packet (4-5 us of the step's critical path on B200): the tail CTAs are already running when the last gradient lands.
+//   state words of the channel (FabricParams::state): [0] round, [1] tail completion counter, [2] optimizer step, [5] protocol error, [6] tickets.
+// All 256 CTAs are co-resident (2 per SM), so spinning on the ticket counter cannot starve the CTAs it waits for.
+__global__ void __launch_bounds__(288) cnn_bwd_exchange_kernel(const float* x, const float* w1, const float* a1, const unsigned char* idx1, const float* a2,
+                                                                const unsigned char* idx2, const float* da2, float* dw0, float* db0, float* dw1, float* db1,
+                                                                int B, unsigned long long* dbg, const __grid_constant__ FabricParams p,
+                                                                const int* __restrict__ tile_list, int n_active) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ int s_ticket;
+  pdl_wait();
+  pdl_launch();
+  // the channel's round / optimizer step: read before any CTA of this launch can have completed them
+  const uint32_t round = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
+  const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
+  const int i = blockIdx.x;
+  if (i < 4 * B) {
+    cnn_bwd_body(sm, i >> 2, i & 3, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dbg);
+  } else if (threadIdx.x < 256) {
+    const int j = i - 4 * B;
+    cnn_wgrad1_body(sm, j >> 2, j & 3, a1, a2, idx2, da2, dw1, db1, B, dbg);
+  }
+  if (threadIdx.x >= FAB_THREADS) return;                       // the exchange tail is written for 256 threads (one float4 of a tile each)
+  auto bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+  bar();                                                         // every gradient store / atomic of this CTA has been issued
+  if (threadIdx.x == 0) { __threadfence(); s_ticket = atomicAdd(p.state + 6, 1); }
+  bar();
+  const int first = (int)gridDim.x - n_active;
+  if (s_ticket < first) return;
+  const bool dbg_on = dbg != nullptr && s_ticket == first && threadIdx.x == 0;
+  auto stamp = [&](int slot) { if (dbg_on) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[slot] = t; } };
+  stamp(20);
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<volatile int*>(p.state + 6) < (int)gridDim.x) {}
+    __threadfence();
+  }
+  bar();
+  stamp(21);
+  const int t = tile_list[s_ticket - first];
+  const uint32_t epoch = (round << 3) | (uint32_t)(p.channel_id & 7);
+  const int S = p.party_size, P = p.num_parties;
+  const long long n2 = 2 * p.n;
+  int* err = p.state + 5;
+  int f = p.tile_fmt ? (int)p.tile_fmt[t] : FMT_F32;
+  if (f != FMT_F16 && f != FMT_F8) f = FMT_F32;
+  const long long off = (long long)t * TILE + threadIdx.x * 4;
+  float* g = p.grad[p.rank] + off;
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(g));  // written by other CTAs of this launch: read at L2
+  if (p.zero_grad) *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool wire = p.ll_d[p.rank] != nullptr;                   // false: single rank without loop-back — nothing to exchange
+  if (wire) {
+    const long long slot = (long long)p.rank * n2 + 2 * off;
+    if (p.ll_d_mc != nullptr) ll_send_dense_mc(p.ll_d_mc + slot, v, f, epoch);
+    else for (int r = 0; r < p.world; ++r) ll_send_dense(p.ll_d[r] + slot, v, f, epoch);
+  }
+  stamp(22);
+  float lr = adam_lr(p.h, opt_t), wd = p.h.wd;
+  if (p.tile_mult) { const float2 mm = __ldg(p.tile_mult + t); lr *= mm.x; wd *= mm.y; }
+  float4 W = *reinterpret_cast<float4*>(p.w + off);             // state loads overlap the flight of the packets
+  float4 A = p.s0 ? *reinterpret_cast<float4*>(p.s0 + off) : make_float4(0, 0, 0, 0);
+  float4 Bm = p.s1 ? *reinterpret_cast<float4*>(p.s1 + off) : make_float4(0, 0, 0, 0);
+  float4 agg = f4_scale(v, p.push_scale);
+  if (wire) {
+    const float* in = p.ll_d[p.rank] + 2 * off;
+    for (int gq = 0; gq < P; ++gq) {
+      float4 ps = ll_recv_dense(in + (long long)(gq * S) * n2, f, epoch, err);
+      for (int j = 1; j < S; ++j) ps = f4_add(ps, ll_recv_dense(in + (long long)(gq * S + j) * n2, f, epoch, err));
+      ps = f4_scale(ps, p.push_scale);
+      agg = gq == 0 ? ps : f4_add(agg, ps);
+    }
+  }
+  stamp(23);
+  opt_apply(W.x, agg.x, A.x, Bm.x, p.h, lr, wd);
+  opt_apply(W.y, agg.y, A.y, Bm.y, p.h, lr, wd);
+  opt_apply(W.z, agg.z, A.z, Bm.z, p.h, lr, wd);
+  opt_apply(W.w, agg.w, A.w, Bm.w, p.h, lr, wd);
+  *reinterpret_cast<float4*>(p.w + off) = W;
+  if (p.s0) *reinterpret_cast<float4*>(p.s0 + off) = A;
+  if (p.s1) *reinterpret_cast<float4*>(p.s1 + off) = Bm;
+  *reinterpret_cast<float4*>(p.param[p.rank] + off) = W;        // the pull is a local store: every rank holds the fresh replica
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(p.state + 1, 1);
+    if (done == n_active - 1) {                                  // every tail CTA is past the ticket spin: the counters can be re-armed
+      p.state[1] = 0;
+      p.state[6] = 0;
+      p.state[2] = opt_t;
+      p.state[0] = (int)round;
+    }
+  }
+  stamp(24);
+}
+
 }  // namespace gx
 
 using namespace gx;
@@ -364,9 +466,9 @@ GX_API int gx_cnn_set_debug(unsigned long long* p) { g_cnn_dbg = p; return 0; }
 
 // x [B,1,28,28]; w0 [16,1,5,5]; w1 [32,16,5,5]; writes a1 [B,16,12,12] + idx1, a2 [B,32,4,4] + idx2
 GX_API int gx_cnn_fwd(const float* x, const float* w0, const float* b0, const float* w1, const float* b1, float* a1, unsigned char* idx1, float* a2,
-                      unsigned char* idx2, const float* carry_src, float* carry_dst, int carry_n, int B, cudaStream_t s) {
+                      unsigned char* idx2, const float* carry_src, float* carry_dst, int carry_n, float* x_keep, int B, cudaStream_t s) {
   if (B < 1) return 0;
-  launch_pdl(cnn_fwd_kernel, dim3(B, 4), dim3(256), 0, s, x, w0, b0, w1, b1, a1, idx1, a2, idx2, carry_src, carry_dst, carry_n, g_cnn_dbg);
+  launch_pdl(cnn_fwd_kernel, dim3(B, 4), dim3(256), 0, s, x, w0, b0, w1, b1, a1, idx1, a2, idx2, carry_src, carry_dst, carry_n, x_keep, g_cnn_dbg);
   return GX_CHECK_LAUNCH();
 }
 // accumulates into dw0 [16,25] / db0 [16] (atomics: zero them first)
@@ -409,5 +511,31 @@ GX_API int gx_cnn_bwd_all(const float* x, const float* w1, const float* a1, cons
     attr = smem;
   }
   launch_pdl(cnn_bwd_all_kernel, dim3(4 * B + 4 * CD_C2), dim3(288), smem, s, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dw1, db1, B, g_cnn_dbg);
+  return GX_CHECK_LAUNCH();
+}
+
+// conv backward + exchange of the conv keys in one launch (see cnn_bwd_exchange_kernel).  `params`: FabricParams block of the channel
+// (replicated mode), `tile_list` / `n_active`: the channel's tiles.  Returns -1 for shapes the kernel does not cover.
+GX_API int gx_cnn_bwd_exchange(const float* x, const float* w1, const float* a1, const unsigned char* idx1, const float* a2, const unsigned char* idx2,
+                               const float* da2, float* dw0, float* db0, float* dw1, float* db1, int B, const void* params, const int* tile_list,
+                               int n_active, cudaStream_t s) {
+  if (B < 2 || (B & 1) || B > 64) return -1;
+  const int grid = 4 * B + 4 * CD_C2;
+  if (n_active < 1 || n_active > grid) return -1;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (grid > 2 * sms) return -1;                                  // the ticket wait needs the whole grid resident (2 CTAs per SM)
+  const size_t smem_w = ((size_t)B * 576 + (size_t)B * 16 * 2 + 256) * 4;
+  const size_t smem = smem_w > (size_t)CnnBwdSmem::BYTES ? smem_w : (size_t)CnnBwdSmem::BYTES;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(cnn_bwd_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  const FabricParams p = *reinterpret_cast<const FabricParams*>(params);
+  launch_pdl(cnn_bwd_exchange_kernel, dim3(grid), dim3(288), smem, s, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dw1, db1, B, g_cnn_dbg, p, tile_list,
+             n_active);
   return GX_CHECK_LAUNCH();
 }

@@ -10,8 +10,6 @@
 //    4-stage mbarrier ring), warp1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2-5 = epilogue
 //    (tcgen05.ld 32x32b -> registers -> fused bias / ReLU / ReLU-mask / column-sum (bias gradient) / NCHW scatter /
 //    split-K atomic accumulate).
-//  * optional `wait_flag`: the producer spins on a system-scope flag before issuing the first B load — this is how
-//    the first GEMM that consumes pulled weights is fused with the parameter-server broadcast (pull_gemm).
 //
 // Precision: the default is **3xTF32** (fp32-accurate): every operand tile that TMA lands in shared memory is split in place by the four
 // (otherwise idle) epilogue warps into hi = rn_tf32(x) and lo = rn_tf32(x - hi); the MMA thread then issues lo*hi + hi*lo + hi*hi into the
@@ -49,13 +47,11 @@ struct GemmParams {
   int pool_w;              // store_mode 2: width of the (pre-pool) feature map; rows are (image, oh, ow)
   unsigned char* pool_idx; // store_mode 2: arg-max position (0..3) of every pooled element, same layout as D
   float alpha;
-  const uint32_t* wait_flag;
-  const int* wait_epoch;
   int a_boxes, b_boxes;    // MN-major operands: number of 32-wide TMA boxes that are (partly) in bounds for this problem
   int a_bytes, b_bytes;    // bytes of the A / B tile that TMA actually fills per stage (what the 3xTF32 split pass has to touch)
   int tx_bytes;            // bytes that land per stage (A box(es) + B box(es)); out-of-range rows/boxes are never requested
   int stages;              // TMA ring depth actually used (<= SmemLayout::STAGES); smaller rings need less smem -> cheaper launch
-  unsigned long long* dbg; // optional: %globaltimer stamps of CTA (0,0,0) phases (tools/gemm_phases.py)  // device epoch counter: proceed when *wait_flag >= *wait_epoch (graph-replay safe)
+  unsigned long long* dbg; // optional: %globaltimer stamps of CTA (0,0,0) phases (tools/kernel_times.py)
 };
 
 constexpr int MAX_STAGES = 8;
@@ -154,11 +150,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      if (p.wait_flag != nullptr) {
-        const uint32_t want = (uint32_t)(*reinterpret_cast<const volatile int*>(p.wait_epoch));
-        while (ld_acquire_sys(p.wait_flag) < want) { __nanosleep(32); }
-        asm volatile("fence.proxy.async;" ::: "memory");  // remote generic-proxy stores -> async-proxy (TMA) reads
-      }
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -479,7 +470,7 @@ GX_API int gx_gemm_set_debug(unsigned long long* p) { g_gemm_dbg = p; return 0; 
 // returns 0 on success, -1 if the operands do not satisfy TMA alignment (caller falls back to gx_gemm_simt).
 static int gemm_tf32_impl(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
                           long long ldd, const float* bias, const float* mask, long long ldmask, float* colsum, int relu, int accumulate,
-                          int store_mode, int hw, float alpha, int split_k, const uint32_t* wait_flag, const int* wait_epoch,
+                          int store_mode, int hw, float alpha, int split_k,
                           int pool_w, unsigned char* pool_idx, cudaStream_t stream) {
   using namespace gx;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -521,7 +512,7 @@ static int gemm_tf32_impl(const float* A, long long lda, int a_mn, const float* 
   split_k = (int)ceil_div(num_kb, p.kb_per_split);
   p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
   p.relu = relu; p.accumulate = (accumulate || split_k > 1) ? 1 : 0; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha;
-  p.wait_flag = wait_flag; p.wait_epoch = wait_epoch; p.stages = 0; p.dbg = g_gemm_dbg;
+  p.stages = 0; p.dbg = g_gemm_dbg;
   p.pool_w = pool_w; p.pool_idx = pool_idx;
   p.a_boxes = a_boxes < 1 ? 1 : a_boxes; p.b_boxes = b_boxes < 1 ? 1 : b_boxes;
   p.a_bytes = a_mn ? p.a_boxes * MN_BOX_BYTES : a_rows * BLOCK_K * 4;
@@ -539,17 +530,16 @@ static int gemm_tf32_impl(const float* A, long long lda, int a_mn, const float* 
 
 GX_API int gx_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
                         long long ldd, const float* bias, const float* mask, long long ldmask, float* colsum, int relu, int accumulate,
-                        int store_mode, int hw, float alpha, int split_k, const uint32_t* wait_flag, const int* wait_epoch,
-                        cudaStream_t stream) {
+                        int store_mode, int hw, float alpha, int split_k, cudaStream_t stream) {
   return gemm_tf32_impl(A, lda, a_mn, B, ldb, b_mn, M, N, K, D, ldd, bias, mask, ldmask, colsum, relu, accumulate, store_mode == 2 ? 1 : store_mode, hw,
-                        alpha, split_k, wait_flag, wait_epoch, 0, nullptr, stream);
+                        alpha, split_k, 0, nullptr, stream);
 }
 // Convolution-as-GEMM with the 2x2/2 max-pool fused into the epilogue: rows of A are (image, oh, ow) with ow fastest and `hw` = OH*OW,
 // `pool_w` = OW.  D receives the POOLED NCHW map [images][N][OH/2][OW/2], `pool_idx` the arg-max position of every pooled element.
 // returns -1 when the geometry does not fit the in-warp pooling (caller runs GEMM + pool kernels instead).
 GX_API int gx_gemm_tf32_pool(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, int M, int N, int K, float* D,
                              const float* bias, int relu, int hw, int pool_w, unsigned char* pool_idx, float alpha, cudaStream_t stream) {
-  return gemm_tf32_impl(A, lda, a_mn, B, ldb, b_mn, M, N, K, D, N, bias, nullptr, 0, nullptr, relu, 0, 2, hw, alpha, 1, nullptr, nullptr, pool_w,
+  return gemm_tf32_impl(A, lda, a_mn, B, ldb, b_mn, M, N, K, D, N, bias, nullptr, 0, nullptr, relu, 0, 2, hw, alpha, 1, pool_w,
                         pool_idx, stream);
 }
 
@@ -617,7 +607,7 @@ GX_API int gx_gemm_simt(const float* A, long long lda, int a_mn, const float* B,
   if (M <= 0 || N <= 0) return 0;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.kb_per_split = 0; p.D = D; p.ldd = ldd; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.colsum = colsum;
-  p.relu = relu; p.accumulate = accumulate; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha; p.wait_flag = nullptr; p.wait_epoch = nullptr; p.stages = 0; p.dbg = nullptr; p.a_boxes = p.b_boxes = 0; p.tx_bytes = 0; p.a_bytes = p.b_bytes = 0;
+  p.relu = relu; p.accumulate = accumulate; p.store_mode = store_mode; p.hw = hw > 0 ? hw : 1; p.alpha = alpha; p.stages = 0; p.dbg = nullptr; p.a_boxes = p.b_boxes = 0; p.tx_bytes = 0; p.a_bytes = p.b_bytes = 0;
   dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
   launch_pdl(gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, A, lda, a_mn, B, ldb, b_mn, M, N, K, p);
   return (int)cudaGetLastError();

@@ -167,7 +167,9 @@ class HipsCNNTrainStep:
         self.lookahead = bool(lookahead) and mode == "dist_sync" and not self.hfa
         # look-ahead: the head of the launch belongs to the PREVIOUS batch, whose labels must outlive the arrival of the next batch in `xin`
         self.label_cur = torch.empty_like(self.label) if self.lookahead else self.label
+        self.x_cur = torch.empty_like(self.x) if self.lookahead else self.x        # ... and so must its images (conv0's weight gradient reads them)
         self._primed = False
+        self.fused_exchange = False
         self.graph = None
         self._side = torch.cuda.Stream(device=self.device)
         # the exchange branch gets a high-priority stream: its (few) CTAs must become resident at once on every rank — they poll each other —
@@ -216,7 +218,7 @@ class HipsCNNTrainStep:
         a2f = self.a2.view(B, 512)
         Wc1, Gc1 = P[2].view(32, 400), G[2].view(32, 400)
         kv = (lambda: (f.async_step(), f.grad.tensor.zero_() if self.fused_zero_grad else None)) if self.mode == "dist_async" else \
-            (lambda: f.fsa_step(defer_pull_wait=False, zero_grad=self.fused_zero_grad))
+            (lambda: f.fsa_step(zero_grad=self.fused_zero_grad))
         if self.overlap:
             kv = lambda: f.channel_step("conv", zero_grad=self.fused_zero_grad)
         kv_dense = [("hips push+opt+pull (dense keys, overlapped)", "comm", lambda: f.channel_step("dense", zero_grad=self.fused_zero_grad))] if self.overlap else []
@@ -263,23 +265,34 @@ class HipsCNNTrainStep:
             da2v = self.da2
             if os.environ.get("GEOMX_CNN_BWD_ONE_LAUNCH", "1") == "1" and B % 2 == 0 and B <= 64:
                 # both backward jobs in one heterogeneous grid: no side-stream fork / join around the convolution backward
+                fused = f.channel_fused_args("conv", zero_grad=self.fused_zero_grad) if self.overlap else None
+                self.fused_exchange = fused is not None
+                if fused is not None:
+                    # ... and the conv keys' exchange in the tail of the same launch (the CTAs that finish last serve one tile each)
+                    blk, tiles, n_act = fused
+                    return [
+                        ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2, carry=carry, x_keep=self.x_cur if self.lookahead else None)),
+                    ] + head + kv_dense + [
+                        ("conv bwd (one grid) + conv-key exchange in its tail", "main",
+                         lambda: n.cnn_bwd_exchange(self.x_cur, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1], G[2], G[3], blk, tiles, n_act)),
+                    ] + self._tail
                 return [
-                    ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2, carry=carry)),
+                    ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2, carry=carry, x_keep=self.x_cur if self.lookahead else None)),
                 ] + head + kv_dense + [
                     ("conv bwd: conv1 wgrad + dgrad + conv0 wgrad (direct, one grid)", "main",
-                     lambda: n.cnn_bwd_all(self.x, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1], G[2], G[3])),
+                     lambda: n.cnn_bwd_all(self.x_cur, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1], G[2], G[3])),
                     ("hips push+opt+pull", "join", kv),
                 ] + self._tail
             return [
-                ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2, carry=carry)),
+                ("conv0+conv1 fwd (direct, relu+pool fused)", "main", lambda: n.cnn_fwd(self.x, P[0], P[1], P[2], P[3], self.a1, self.idx1, self.a2, self.idx2, carry=carry, x_keep=self.x_cur if self.lookahead else None)),
             ] + head + kv_dense + [
                 ("conv1 wgrad (direct, sparse)", "side", lambda: n.cnn_wgrad1(self.a1, self.a2, self.idx2, da2v, G[2], G[3])),
-                ("conv1 dgrad + conv0 wgrad (direct)", "main", lambda: n.cnn_bwd(self.x, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1])),
+                ("conv1 dgrad + conv0 wgrad (direct)", "main", lambda: n.cnn_bwd(self.x_cur, P[2], self.a1, self.idx1, self.a2, self.idx2, da2v, G[0], G[1])),
                 ("hips push+opt+pull", "join", kv),
             ] + self._tail
         if self.lookahead:
             conv1 = conv1_fwd
-            conv1_fwd = lambda: (conv1(), self.label_cur.copy_(self.label))
+            conv1_fwd = lambda: (conv1(), self.label_cur.copy_(self.label), self.x_cur.copy_(self.x))
         return [
             ("conv0+relu+pool+im2col", "main", lambda: n.conv_relu_pool_im2col_fwd(self.x, P[0], P[1], self.a1, self.idx1, self.col1, 5, 5)),
             ("conv1 gemm (bias,relu,maxpool fused)", "main", conv1_fwd),
@@ -287,7 +300,7 @@ class HipsCNNTrainStep:
             ("pool+relu bwd -> rows", "main", lambda: n.pool_relu_bwd_rows(self.da2.view(B, 32, 4, 4), self.a2, self.idx2, self.dz2rows, G[3])),
             ("dWc1 gemm (split-K)", "side", lambda: n.gemm(self.dz2rows, self.col1, Gc1, a_mn=True, b_mn=True, split_k=16, accumulate=True)),
             ("dcol1 gemm", "main", lambda: n.gemm(self.dz2rows, Wc1, self.dcol1, b_mn=True)),
-            ("conv0 wgrad + col2im", "main", lambda: n.conv_relu_pool_wgrad_col2im(self.x, self.dcol1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0], 5, 5)),
+            ("conv0 wgrad + col2im", "main", lambda: n.conv_relu_pool_wgrad_col2im(self.x_cur, self.dcol1, self.a1, self.idx1, G[0], G[1], CNN_PARAM_SHAPES[0], 5, 5)),
             ("hips push+opt+pull", "join", kv),
         ] + self._tail
 

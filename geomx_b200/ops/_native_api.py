@@ -47,8 +47,7 @@ def gemm_precision():
 
 
 def gemm(A, B, D, a_mn=False, b_mn=False, bias=None, mask=None, colsum=None, relu=False, accumulate=False,
-         store_nchw_hw=0, alpha=1.0, split_k=1, M=None, N=None, K=None, lda=None, ldb=None, ldd=None,
-         wait_flag=None, wait_epoch=None, force_simt=False):
+         store_nchw_hw=0, alpha=1.0, split_k=1, M=None, N=None, K=None, lda=None, ldb=None, ldd=None, force_simt=False):
     """D[M,N] = epi(alpha * A·Bᵀ).  A is [M,K] (K-major) or [K,M] (MN-major, ``a_mn``); B is [N,K] or [K,N] (``b_mn``)."""
     if M is None:
         M = A.shape[1] if a_mn else A.shape[0]
@@ -66,7 +65,7 @@ def gemm(A, B, D, a_mn=False, b_mn=False, bias=None, mask=None, colsum=None, rel
     if not force_simt:
         rc = lib.gx_gemm_tf32(_p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), M, N, K, _p(D), ldd, _p(bias), _p(mask), ldmask,
                               _p(colsum), int(relu), int(accumulate), 1 if store_nchw_hw else 0, int(store_nchw_hw), float(alpha),
-                              int(split_k), _p(wait_flag), _p(wait_epoch), _s())
+                              int(split_k), _s())
     if rc == -1:  # TMA alignment not satisfied -> CUDA-core fallback kernel (same contract)
         rc = lib.gx_gemm_simt(_p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), M, N, K, _p(D), ldd, _p(bias), _p(mask), ldmask,
                               _p(colsum), int(relu), int(accumulate), 1 if store_nchw_hw else 0, int(store_nchw_hw), float(alpha), _s())
@@ -103,12 +102,13 @@ def mlp_chain(x, w0, b0, w1, b1, w2, b2, label, loss, logits, dw0, db0, dw1, db1
 
 
 # --------------------------------------------------------------------------------------------------------------- demo-CNN direct convolutions
-def cnn_fwd(x, w0, b0, w1, b1, a1, idx1, a2, idx2, carry=None):
+def cnn_fwd(x, w0, b0, w1, b1, a1, idx1, a2, idx2, carry=None, x_keep=None):
     """Conv(16,k5)+ReLU+MaxPool2 -> Conv(32,k5)+ReLU+MaxPool2 of the demo CNN in one launch (csrc/kernels/cnn_direct.cu), fp32 FMA.
-    ``carry=(src, dst)``: also copy the small fp32 vector ``src`` to ``dst`` (the labels of a look-ahead step, see models/cnn.py)."""
+    ``carry=(src, dst)``: also copy the small fp32 vector ``src`` to ``dst`` (the labels of a look-ahead step, see models/cnn.py);
+    ``x_keep``: also store a copy of the image batch there (its backward pass runs after the next batch has arrived in ``x``)."""
     src, dst = carry if carry is not None else (None, None)
     _ck(_lib().gx_cnn_fwd(_p(x), _p(w0), _p(b0), _p(w1), _p(b1), _p(a1), _p(idx1), _p(a2), _p(idx2), _p(src), _p(dst),
-                          0 if src is None else src.numel(), x.shape[0], _s()), "cnn_fwd")
+                          0 if src is None else src.numel(), _p(x_keep), x.shape[0], _s()), "cnn_fwd")
 
 
 def cnn_bwd(x, w1, a1, idx1, a2, idx2, da2, dw0, db0):
@@ -120,6 +120,14 @@ def cnn_bwd_all(x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dw1, db1):
     """The whole convolution backward pass (``cnn_bwd`` + ``cnn_wgrad1``) as one heterogeneous-grid launch."""
     _ck(_lib().gx_cnn_bwd_all(_p(x), _p(w1), _p(a1), _p(idx1), _p(a2), _p(idx2), _p(da2), _p(dw0), _p(db0), _p(dw1), _p(db1), x.shape[0], _s()),
         "cnn_bwd_all")
+
+
+def cnn_bwd_exchange(x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dw1, db1, params, tile_list, n_active):
+    """``cnn_bwd_all`` whose last CTAs also perform the exchange of the conv keys (``params``: the channel's FabricParams block from
+    ``HipsFabric.channel_fused_args``): convolution backward + push + server tiers + optimizer + pull in one launch."""
+    import ctypes
+    _ck(_lib().gx_cnn_bwd_exchange(_p(x), _p(w1), _p(a1), _p(idx1), _p(a2), _p(idx2), _p(da2), _p(dw0), _p(db0), _p(dw1), _p(db1), x.shape[0],
+                                   ctypes.byref(params), _p(tile_list), int(n_active), _s()), "cnn_bwd_exchange")
 
 
 def cnn_wgrad1(a1, a2, idx2, da2, dw1, db1):

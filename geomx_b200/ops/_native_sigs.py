@@ -5,13 +5,14 @@ P, I, L, F, U = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint32
 
 SIGS = {
     # gemm_tcgen05.cu
-    "gx_gemm_tf32": [P, L, I, P, L, I, I, I, I, P, L, P, P, L, P, I, I, I, I, F, I, P, P, P],
+    "gx_gemm_tf32": [P, L, I, P, L, I, I, I, I, P, L, P, P, L, P, I, I, I, I, F, I, P],
     "gx_gemm_tf32_pool": [P, L, I, P, L, I, I, I, I, P, P, I, I, I, P, F, P],
     "gx_mlp_chain_fwd_bwd": [P] * 17 + [I] * 5 + [P],
-    "gx_cnn_fwd": [P] * 11 + [I, I, P],
+    "gx_cnn_fwd": [P] * 11 + [I, P, I, P],
     "gx_cnn_bwd": [P] * 9 + [I, P],
     "gx_cnn_wgrad1": [P] * 6 + [I, P],
     "gx_cnn_bwd_all": [P] * 11 + [I, P],
+    "gx_cnn_bwd_exchange": [P] * 11 + [I, P, P, I, P],
     "gx_depthwise_fwd": [P, P, P, P] + [I] * 11 + [P],
     "gx_depthwise_dgrad": [P, P, P] + [I] * 10 + [P],
     "gx_depthwise_wgrad": [P, P, P, P] + [I] * 10 + [P],

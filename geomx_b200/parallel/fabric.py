@@ -399,10 +399,10 @@ class HipsFabric:
         h.eps = s.get("epsilon", 1e-8); h.lamda = s.get("lamda", 0.04)
         return h
 
-    def _block(self, channel, defer_pull_wait=False, masked=False, zero_grad=False):
+    def _block(self, channel, masked=False, zero_grad=False):
         if channel in self.channels:
             return self._channel_block(channel, zero_grad)
-        key = (channel, defer_pull_wait, masked, zero_grad)
+        key = (channel, masked, zero_grad)
         if key in self._params_cache:
             return self._params_cache[key]
         t = self.topo
@@ -445,7 +445,7 @@ class HipsFabric:
         p.state = self.state[channel].data_ptr()
         p.h = self._hyper()
         p.push_scale = self.push_scale
-        p.defer_pull_wait = int(defer_pull_wait)
+        p.defer_pull_wait = 0
         p.zero_grad = int(zero_grad)
         pre = {"fsa": "fsa", "async": "async", "party": "par"}[channel]
         p.ready_off = self.off[pre + "_ready"]
@@ -490,11 +490,13 @@ class HipsFabric:
         if key in self._params_cache:
             return self._params_cache[key]
         ch = self.channels[name]
-        base = self._block("fsa", False, False, zero_grad)
+        base = self._block("fsa", False, zero_grad)
         p = _FabricParams.from_buffer_copy(base)
         p.tile_active = ch["mask"].data_ptr()
         p.state = self.state[name].data_ptr()
         p.direct_replicate = int(ch["replicate"])
+        if ch["replicate"] and os.environ.get("GEOMX_REPL_MULTICAST", "1") != "1":
+            p.ll_d_mc = None      # one-hop mode with unicast stores: own packets stay local instead of making the round trip through the switch
         p.channel_id = ch["id"]
         self._params_cache[key] = p
         return p
@@ -516,6 +518,20 @@ class HipsFabric:
         if rc:
             raise RuntimeError("channel_step(%s) failed rc=%d" % (name, rc))
 
+    def channel_fused_args(self, name, zero_grad=False):
+        """For compute kernels that perform a replicated channel's exchange in their own tail (cnn_bwd_exchange_kernel): the channel's
+        parameter block, its tile list and tile count — or ``None`` when the channel needs a launch of its own (sharded mode, Bi-Sparse
+        tiles, DGT bookkeeping, or a multi-rank job without the direct-protocol buffers)."""
+        ch = self.channels[name]
+        single = self.topo.world == 1 and not self.loopback
+        if not ch["replicate"] or self.dgt_contrib is not None or os.environ.get("GEOMX_FUSED_EXCHANGE", "1") != "1":
+            return None
+        if not single and (self.ll_d is None or not self._channel_formats_direct_ok(ch)):
+            return None
+        if "list" not in ch:
+            ch["list"] = torch.nonzero(ch["mask"]).flatten().to(torch.int32)
+        return self._channel_block(name, zero_grad), ch["list"], ch["tiles"]
+
     @property
     def opt_step(self):
         """Optimizer step count t (identical on every channel that has run the same number of rounds)."""
@@ -536,11 +552,11 @@ class HipsFabric:
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # -- kernels --------------------------------------------------------------------------------------------------------
-    def fsa_step(self, defer_pull_wait=False, masked=False, zero_grad=False):
+    def fsa_step(self, masked=False, zero_grad=False):
         """dist_sync: party reduce -> global reduce + optimizer -> broadcast (one launch); optionally clears the gradient arena for the next step."""
-        p = self._block("fsa", defer_pull_wait, masked, zero_grad)
+        p = self._block("fsa", masked, zero_grad)
         lib = native.require()
-        if self.protocol == "ll" and not defer_pull_wait:
+        if self.protocol == "ll":
             rc = lib.gx_hips_fsa_ll_step(ctypes.byref(p), self.grid, self._stream())
         else:
             rc = lib.gx_hips_fsa_step(ctypes.byref(p), self.grid, self._stream())
@@ -584,7 +600,7 @@ class HipsFabric:
             key = ("fsa-party", float(scale))
             p = self._params_cache.get(key)
             if p is None:
-                base = self._block("fsa", False, False, False)
+                base = self._block("fsa", False, False)
                 p = _FabricParams.from_buffer_copy(base)
                 p.ll_party_mode = 1
                 p.h.kind = -1
@@ -615,6 +631,3 @@ class HipsFabric:
         if rc:
             raise RuntimeError("gx_fabric_barrier failed rc=%d" % rc)
 
-    def param_ready_flag_ptr(self, key_index):
-        """Device address of this rank's ready flag for key ``key_index`` (for pull-fused GEMMs)."""
-        return self.flags.tensor.data_ptr() + 4 * (self.off["fsa_param_ready"] + key_index)

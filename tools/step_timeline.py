@@ -57,9 +57,13 @@ def main():
         st = {k: fab.state[k][8:8 + 12].view(torch.int64).tolist() for k in chans}
         row = {"cnn_fwd": (c[0], c[4]), "mlp_chain": (m[0], m[9]), "cnn_bwd": (c[8], c[13]), "cnn_wgrad1": (c[16], c[18])}
         for k in chans:
-            row["chan:" + k] = (st[k][0], st[k][5])
+            if st[k][0] > 0:
+                row["chan:" + k] = (st[k][0], st[k][5])
+        if getattr(eng, "fused_exchange", False):       # exchange tail of the backward launch: 20 ticket | 21 grid done | 22 sent | 23 received | 24 end
+            row["bwd tail"] = (c[20], c[24])
+            row["_tail"] = [(v - c[20]) / 1e3 for v in c[20:25]]
         row["_ms"] = ev[0].elapsed_time(ev[1])
-        row["_ph"] = {k: [(v - st[k][0]) / 1e3 for v in st[k][:6]] for k in chans}
+        row["_ph"] = {k: [(v - st[k][0]) / 1e3 for v in st[k][:6]] for k in chans if st[k][0] > 0}
         rows.append(row)
     rows = rows[4:]
     names = [k for k in rows[0] if not k.startswith("_")]
@@ -69,7 +73,9 @@ def main():
         rel1 = [(r[k][1] - min(v[0] for kk, v in r.items() if not kk.startswith("_") and v[0] > 0)) / 1e3 for r in rows]
         lines.append("  %-12s start %7.2f  end %7.2f  (dur %6.2f us)" % (k, statistics.median(rel0), statistics.median(rel1),
                                                                         statistics.median(b - a for a, b in zip(rel0, rel1))))
-    for k in chans:
+    if "_tail" in rows[0]:
+        lines.append("  bwd tail (us since first tail ticket): ticket|grid done|sent|received|end %s" % ["%.2f" % statistics.median(r["_tail"][i] for r in rows) for i in range(5)])
+    for k in rows[0]["_ph"]:
         lines.append("  chan:%s phases since its start (us): %s" % (k, ["%.2f" % statistics.median(r["_ph"][k][i] for r in rows) for i in range(6)]))
     for r in range(world):
         if r == rank:
