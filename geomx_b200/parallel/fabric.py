@@ -524,7 +524,7 @@ class HipsFabric:
         tiles, DGT bookkeeping, or a multi-rank job without the direct-protocol buffers)."""
         ch = self.channels[name]
         single = self.topo.world == 1 and not self.loopback
-        if not ch["replicate"] or self.dgt_contrib is not None or os.environ.get("GEOMX_FUSED_EXCHANGE", "1") != "1":
+        if not ch["replicate"] or self.dgt_contrib is not None or os.environ.get("GEOMX_FUSED_EXCHANGE", "0") != "1":
             return None
         if not single and (self.ll_d is None or not self._channel_formats_direct_ok(ch)):
             return None
