@@ -285,7 +285,7 @@ def main():
         if look or fused:
             # the kernels' own %globaltimer stamps are needed (end of the forward convolutions of a look-ahead step; start / end of the
             # exchange tail inside the convolution-backward launch): re-capture the graph with stamping switched on
-            cdbg = torch.zeros(32, dtype=torch.int64, device=dev)
+            cdbg = torch.zeros(1024, dtype=torch.int64, device=dev)
             native.require().gx_cnn_set_debug(ctypes.c_void_p(cdbg.data_ptr()))
             if eng.graph is not None:
                 eng.graph = None

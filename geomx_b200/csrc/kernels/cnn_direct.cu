@@ -267,14 +267,22 @@ __device__ __forceinline__ void cnn_bwd_body(float* sm, const int b, const int c
   __syncthreads();
   stamp(12);
   // ---- conv0 weight / bias gradient of this image (4 channels): dW0[ch][kh][kw] += sum_windows g * x[oh+kh][ow+kw]
-  if (tid < 100) {
-    const int cl = tid / 25, tap = tid % 25, koff = (tap / 5) * CD_H + tap % 5;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int p = 0; p < 144; ++p) acc = fmaf(sda1[cl * 144 + p], sx[spos[cl * 144 + p] + koff], acc);
-    atomicAdd(dw0 + (4 * cg + cl) * 25 + tap, acc);
-  } else if (tid >= 128 && tid < 132) {
-    const int cl = tid - 128;
+  // 200 threads: (tap, channel) x 2 halves of the 144 windows; four independent accumulators break the FMA dependency chain
+  if (tid < 200) {
+    const int half = tid / 100, t = tid - half * 100, cl = t / 25, tap = t % 25, koff = (tap / 5) * CD_H + tap % 5;
+    const float* gp = sda1 + cl * 144 + half * 72;
+    const int* pp = spos + cl * 144 + half * 72;
+    float a0 = 0.f, a1_ = 0.f, a2_ = 0.f, a3 = 0.f;
+#pragma unroll 2
+    for (int p = 0; p < 72; p += 4) {
+      a0 = fmaf(gp[p], sx[pp[p] + koff], a0);
+      a1_ = fmaf(gp[p + 1], sx[pp[p + 1] + koff], a1_);
+      a2_ = fmaf(gp[p + 2], sx[pp[p + 2] + koff], a2_);
+      a3 = fmaf(gp[p + 3], sx[pp[p + 3] + koff], a3);
+    }
+    atomicAdd(dw0 + (4 * cg + cl) * 25 + tap, (a0 + a1_) + (a2_ + a3));
+  } else if (tid >= 224 && tid < 228) {
+    const int cl = tid - 224;
     float acc = 0.f;
     for (int p = 0; p < 144; ++p) acc += sda1[cl * 144 + p];
     atomicAdd(db0 + 4 * cg + cl, acc);
@@ -298,7 +306,7 @@ __device__ __forceinline__ void cnn_wgrad1_body(float* sm, const int oc, const i
   const int tid = threadIdx.x;
   for (int i = tid; i < B * 144; i += 256) {          // 144 float4 per image: 4 contiguous planes
     const int bb = i / 144, r = i % 144;
-    reinterpret_cast<float4*>(sa)[i] = reinterpret_cast<const float4*>(a1 + ((long long)bb * CD_C1 + 4 * cg) * 144)[r];
+    cpa16(sa + 4 * i, a1 + ((long long)bb * CD_C1 + 4 * cg) * 144 + 4 * r);
   }
   for (int e = tid; e < B * 16; e += 256) {
     const int bb = e >> 4, win = e & 15;
@@ -307,6 +315,7 @@ __device__ __forceinline__ void cnn_wgrad1_body(float* sm, const int oc, const i
     sg[e] = a2[o] > 0.f ? da2[o] : 0.f;
     sp[e] = (2 * (win >> 2) + (id >> 1)) * CD_P1 + 2 * (win & 3) + (id & 1);
   }
+  cpa_wait_all();
   __syncthreads();
   stamp(17);
   const int half = tid >> 7, t = tid & 127;
@@ -314,8 +323,18 @@ __device__ __forceinline__ void cnn_wgrad1_body(float* sm, const int oc, const i
   if (t < 100) {
     const int cl = t / 25, tap = t % 25, koff = (tap / 5) * CD_P1 + tap % 5;
     const int e0 = half * (B * 8), e1 = e0 + B * 8;      // images [half*B/2, (half+1)*B/2)
-#pragma unroll 4
-    for (int e = e0; e < e1; ++e) acc = fmaf(sg[e], sa[((e >> 4) * 4 + cl) * 144 + sp[e] + koff], acc);
+    // four independent accumulators (the chain of B*8 dependent FMAs was the critical path of this phase)
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    const float* sak = sa + cl * 144 + koff;
+#pragma unroll 2
+    for (int e = e0; e < e1; e += 4) {       // B*8 is a multiple of 16; e .. e+3 belong to the same image
+      const float* img = sak + (e >> 4) * 576;
+      c0 = fmaf(sg[e], img[sp[e]], c0);
+      c1 = fmaf(sg[e + 1], img[sp[e + 1]], c1);
+      c2 = fmaf(sg[e + 2], img[sp[e + 2]], c2);
+      c3 = fmaf(sg[e + 3], img[sp[e + 3]], c3);
+    }
+    acc = (c0 + c1) + (c2 + c3);
   }
   sacc[half * 128 + t] = acc;
   __syncthreads();
@@ -352,11 +371,20 @@ __global__ void __launch_bounds__(288) cnn_bwd_all_kernel(const float* x, const 
   pdl_wait();
   pdl_launch();
   const int i = blockIdx.x;
+  // debug: every CTA records (start, end, SM id) at dbg[64 + 3 i ..] so that tools/step_timeline.py can show how the grid packs onto the SMs
+  unsigned long long t0 = 0;
+  if (dbg != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
   if (i < 4 * B) {
     cnn_bwd_body(sm, i >> 2, i & 3, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dbg);
   } else if (threadIdx.x < 256) {            // (no thread of this CTA takes the other branch, so its __syncthreads pair up among these 256)
     const int j = i - 4 * B;
     cnn_wgrad1_body(sm, j >> 2, j & 3, a1, a2, idx2, da2, dw1, db1, B, dbg);
+  }
+  if (dbg != nullptr && threadIdx.x == 0) {
+    unsigned long long t1; unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    dbg[64 + 3 * i] = t0; dbg[65 + 3 * i] = t1; dbg[66 + 3 * i] = smid;
   }
 }
 

@@ -52,7 +52,7 @@ if eng.fused_mlp:
               ["%.2f" % ((v - st[0]) / 1e3) for v in st[10:14]], "| P5: 14 da2 products done:", "%.2f" % ((st[14] - st[0]) / 1e3))
     lib.gx_mlp_chain_set_debug(ctypes.c_void_p(0))
 if eng.direct_conv:
-    dbg = torch.zeros(32, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(1024, dtype=torch.int64, device="cuda")
     lib.gx_cnn_set_debug(ctypes.c_void_p(dbg.data_ptr()))
     for rep in range(2):
         eng._body(); torch.cuda.synchronize()

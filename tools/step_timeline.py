@@ -30,7 +30,7 @@ def main():
     topo = Topology(world, rank, parties, 0)
     native.set_gemm_precision("3xtf32")
     lib = native.require()
-    cdbg = torch.zeros(32, dtype=torch.int64, device=dev)
+    cdbg = torch.zeros(1024, dtype=torch.int64, device=dev)
     mdbg = torch.zeros(32, dtype=torch.int64, device=dev)
     lib.gx_cnn_set_debug(ctypes.c_void_p(cdbg.data_ptr()))
     lib.gx_mlp_chain_set_debug(ctypes.c_void_p(mdbg.data_ptr()))
@@ -62,6 +62,9 @@ def main():
         if getattr(eng, "fused_exchange", False):       # exchange tail of the backward launch: 20 ticket | 21 grid done | 22 sent | 23 received | 24 end
             row["bwd tail"] = (c[20], c[24])
             row["_tail"] = [(v - c[20]) / 1e3 for v in c[20:25]]
+        if not getattr(eng, "fused_exchange", False):
+            per = [(c[64 + 3 * i], c[65 + 3 * i], c[66 + 3 * i]) for i in range(256)]
+            row["_cta"] = per
         row["_ms"] = ev[0].elapsed_time(ev[1])
         row["_ph"] = {k: [(v - st[k][0]) / 1e3 for v in st[k][:6]] for k in chans if st[k][0] > 0}
         rows.append(row)
@@ -73,6 +76,26 @@ def main():
         rel1 = [(r[k][1] - min(v[0] for kk, v in r.items() if not kk.startswith("_") and v[0] > 0)) / 1e3 for r in rows]
         lines.append("  %-12s start %7.2f  end %7.2f  (dur %6.2f us)" % (k, statistics.median(rel0), statistics.median(rel1),
                                                                         statistics.median(b - a for a, b in zip(rel0, rel1))))
+    if "_cta" in rows[0]:
+        # how the 256 CTAs of the convolution-backward grid pack onto the SMs (last sampled step)
+        r = rows[-1]
+        base = min(v[0] for kk, v in r.items() if not kk.startswith("_") and v[0] > 0)
+        for name, lo, hi in (("bwd CTAs  (0..127)", 0, 128), ("wgrad CTAs (128..255)", 128, 256)):
+            st = sorted((a - base) / 1e3 for a, b, sm_ in r["_cta"][lo:hi]); en = sorted((b - base) / 1e3 for a, b, sm_ in r["_cta"][lo:hi])
+            du = sorted((b - a) / 1e3 for a, b, sm_ in r["_cta"][lo:hi])
+            lines.append("  %-22s start min/med/max %.2f %.2f %.2f | end %.2f %.2f %.2f | duration %.2f %.2f %.2f" % (
+                name, st[0], st[64], st[-1], en[0], en[64], en[-1], du[0], du[64], du[-1]))
+        sms = {}
+        for i, (a, b, sm_) in enumerate(r["_cta"]):
+            sms.setdefault(sm_, []).append(i)
+        shared = sorted(len(v) for v in sms.values())
+        lines.append("  SMs used %d; CTAs per SM: %s" % (len(sms), {k: shared.count(k) for k in sorted(set(shared))}))
+        pair = {"bwd+bwd": 0, "bwd+wgrad": 0, "wgrad+wgrad": 0}
+        for v in sms.values():
+            if len(v) == 2:
+                k = sum(1 for i in v if i >= 128)
+                pair[["bwd+bwd", "bwd+wgrad", "wgrad+wgrad"][k]] += 1
+        lines.append("  SM sharing: %s" % pair)
     if "_tail" in rows[0]:
         lines.append("  bwd tail (us since first tail ticket): ticket|grid done|sent|received|end %s" % ["%.2f" % statistics.median(r["_tail"][i] for r in rows) for i in range(5)])
     for k in rows[0]["_ph"]:
