@@ -426,6 +426,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, di
   if (env_stages < 0) { const char* e = getenv("GEOMX_GEMM_STAGES"); env_stages = e ? atoi(e) : 0; }
   int stages = L::STAGES;
   if (p.kb_per_split < stages) stages = p.kb_per_split;   // never more ring slots than K blocks
+  if (!SPLIT && BLOCK_N == 128 && stages > 3) {
+    // Throughput regime (at least two tiles per SM): a 3-deep ring is 98 KB, so TWO CTAs share an SM and one tile's epilogue (TMEM -> registers
+    // -> 64 KB of stores) overlaps the other tile's MMA main loop.  Measured at 8192 x 4096 x 4096: 473 -> 574 TFLOP/s (profiles/gemm_anchor.txt).
+    static int sms = 0;
+    if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    if ((long long)grid.x * grid.y * grid.z >= 2LL * sms) stages = 3;
+  }
   if (env_stages > 0 && env_stages < stages) stages = env_stages;
   if (stages < 1) stages = 1;
   p.stages = stages;

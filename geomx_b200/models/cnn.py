@@ -171,6 +171,8 @@ class HipsCNNTrainStep:
         self._primed = False
         self.fused_exchange = False
         self.graph = None
+        self._graph_alt = None
+        self._xbufs = [self.xin, None]
         self._side = torch.cuda.Stream(device=self.device)
         # the exchange branch gets a high-priority stream: its (few) CTAs must become resident at once on every rank — they poll each other —
         # instead of queueing behind the convolution-backward CTAs that are launched at the same time
@@ -366,6 +368,7 @@ class HipsCNNTrainStep:
         with torch.cuda.graph(g):
             self._body(part="rotated" if self.lookahead else "all")
         self.graph = g
+        self._graph_alt = None
 
     def _prime(self):
         """Look-ahead: run the forward convolutions of the batch in ``self.x`` so that the next launch can start at the classifier head."""
@@ -382,8 +385,36 @@ class HipsCNNTrainStep:
         self.steps_done += 1
         return float(self.loss.mean())
 
-    def run_device(self):
-        """One step on whatever is currently in ``self.x`` / ``self.label`` (device-only; used by the kernel-time bench)."""
+    def _bind_input(self, k):
+        """Point the step at input buffer ``k`` (0 = ``self.xin``; 1 = the second staging buffer of the host pipeline).  Only matters while
+        launches are being issued or captured: a captured graph keeps the buffer it was captured with."""
+        buf = self._xbufs[k]
+        B = self.B
+        self.xin, self.x, self.label = buf, buf[:B * 784].view(B, 1, 28, 28), buf[B * 784:]
+        if not self.lookahead:
+            self.x_cur, self.label_cur = self.x, self.label
+
+    def _alt_graph(self):
+        """The same step captured on input buffer 1: the host pipeline alternates between the two graphs, so a batch is consumed where the
+        H2D copy put it (no staging -> compute copy on the critical path of the step)."""
+        if self._graph_alt is None:
+            self._bind_input(1)
+            try:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(s):
+                    with torch.cuda.graph(g, stream=s):
+                        self._body()
+                torch.cuda.current_stream().wait_stream(s)
+            finally:
+                self._bind_input(0)
+            self._graph_alt = g
+        return self._graph_alt
+
+    def run_device(self, buf=0):
+        """One step on whatever is currently in input buffer ``buf`` (0: ``self.x`` / ``self.label``; device-only, used by the kernel-time
+        bench and by the host pipeline)."""
         if self._dgt_every and self.steps_done and self.steps_done % self._dgt_every == 0 and self.graph is not None:
             self.fabric.dgt_rerank()          # outside the captured graph; order / formats are updated in place
         if self.use_graph:
@@ -391,7 +422,13 @@ class HipsCNNTrainStep:
                 self.capture()
             if self.lookahead:
                 self._prime()
-            self.graph.replay()
+            (self._alt_graph() if buf == 1 else self.graph).replay()
+        elif buf == 1:
+            self._bind_input(1)
+            try:
+                self._body()
+            finally:
+                self._bind_input(0)
         elif self.lookahead:
             self._prime()
             self._body(part="rotated")
@@ -422,7 +459,14 @@ class HipsCNNTrainStep:
     def _pipeline(self):
         if not hasattr(self, "_pl"):
             dev, B = self.device, self.B
-            stage = [torch.empty_like(self.xin) for _ in range(2)]
+            # direct mode: the two H2D targets ARE the step's two input buffers (one captured graph each); look-ahead steps and DGT runs
+            # keep the single-graph form with a staging -> compute copy
+            self._direct_inputs = not self.lookahead and os.environ.get("GEOMX_E2E_DIRECT_INPUT", "1") == "1"
+            if self._direct_inputs:
+                self._xbufs[1] = torch.empty_like(self.xin)
+                stage = [self._xbufs[0], self._xbufs[1]]
+            else:
+                stage = [torch.empty_like(self.xin) for _ in range(2)]
             self._pl = {
                 "h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev), "stage": stage,
                 "sx": [s[:B * 784].view(B, 1, 28, 28) for s in stage], "sy": [s[B * 784:] for s in stage],
@@ -436,10 +480,11 @@ class HipsCNNTrainStep:
         an op returns at once, ``asscalar()`` synchronises).  ``X`` (B,1,28,28) and ``y`` (B,) are host tensors / NDArrays (pinned → async
         H2D) or device tensors.
 
-        Three streams: the batch is copied host→device on a copy stream into one of two staging buffers (overlapping the previous step's
-        compute), the compute stream takes it over with ONE device-to-device copy and replays the step graph, and the per-sample loss goes
-        device→host on a third stream into a pinned ring slot; ``handle.item()`` waits for exactly that copy.  A training loop therefore
-        launches step i+1 before it reads the loss of step i."""
+        Three streams: the batch is copied host→device on a copy stream into one of the step's TWO input buffers (overlapping the previous
+        step's compute); the compute stream replays the graph that was captured on that buffer (two graphs of the same step, alternating —
+        no staging→compute copy; ``GEOMX_E2E_DIRECT_INPUT=0`` and look-ahead steps use one graph plus a device-to-device copy), and the
+        per-sample loss goes device→host on a third stream into a pinned ring slot; ``handle.item()`` waits for exactly that copy.  A
+        training loop therefore launches step i+1 before it reads the loss of step i."""
         X = X._t if isinstance(X, NDArray) else X
         y = y._t if isinstance(y, NDArray) else y
         pl = self._pipeline()
@@ -458,7 +503,8 @@ class HipsCNNTrainStep:
                 pl["sy"][b].copy_(y.reshape(self.label.shape), non_blocking=True)
                 pl["ready"][b].record(h2d)
             main.wait_event(pl["ready"][b])
-            self.xin.copy_(pl["stage"][b], non_blocking=True)
+            if not self._direct_inputs:
+                self.xin.copy_(pl["stage"][b], non_blocking=True)
         if pl["last_loss"] is not None:
             main.wait_event(pl["last_loss"])                # the loss buffer of the previous step has been read out
         if self.lookahead and not self._primed:
@@ -469,7 +515,7 @@ class HipsCNNTrainStep:
             self._prime()
             pl["done"][b].record(main)
             return LossHandle(None, None)
-        self.run_device()
+        self.run_device(buf=b if (not X.is_cuda and self._direct_inputs) else 0)
         pl["done"][b].record(main)
         host, ev = pl["ring"][i % 4]
         d2h = pl["d2h"]

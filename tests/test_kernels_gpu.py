@@ -399,6 +399,24 @@ def test_fused_step_graph_trains(nat):
     assert l < 0.5 * l0, (l0, l)
 
 
+def test_host_pipeline_direct_inputs_match_staged(nat, monkeypatch):
+    """step(X_pinned, y_pinned): alternating between two graphs captured on the two H2D target buffers gives the same training as the
+    single graph fed through a staging copy."""
+    from geomx_b200.parallel import Topology
+    g = torch.Generator().manual_seed(5)
+    Xs = [torch.rand(32, 1, 28, 28, generator=g).pin_memory() for _ in range(7)]
+    ys = [torch.randint(0, 10, (32,), generator=g).float().pin_memory() for _ in range(7)]
+    out = {}
+    for direct in ("1", "0"):
+        monkeypatch.setenv("GEOMX_E2E_DIRECT_INPUT", direct)
+        torch.manual_seed(23)
+        eng = mx.models.HipsCNNTrainStep(batch_size=32, optimizer=mx.optimizer.SGD(learning_rate=0.05), topo=Topology(1, 0, 1, 1), use_graph=True)
+        out[direct] = ([eng.step(X, y) for X, y in zip(Xs, ys)], eng.fabric.param.tensor.clone())
+        assert (eng._graph_alt is not None) == (direct == "1")
+    assert all(abs(a - b) < 1e-5 * max(1.0, abs(a)) for a, b in zip(out["1"][0], out["0"][0])), (out["1"][0], out["0"][0])
+    assert torch.allclose(out["1"][1], out["0"][1], atol=1e-5)
+
+
 @pytest.mark.parametrize("use_graph", [True, False])
 def test_lookahead_step_is_the_same_training(nat, use_graph):
     """The look-ahead cut of the step (head of batch k .. forward convolutions of batch k+1 in one launch) is the same arithmetic in the same
