@@ -135,6 +135,13 @@ class HipsCNNTrainStep:
         if self.overlap:
             f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False, grid=int(os.environ.get("GEOMX_DENSE_CHANNEL_GRID", 0)) or None)
             f.add_channel("conv", [0, 1, 2, 3], replicate=True)
+        # GEOMX_STEP_OVERLAP=0: ONE exchange of all keys after the backward pass.  GEOMX_STEP_EXCHANGE picks its protocol: `ll` (three-hop
+        # hierarchy walk), `sharded` / `replicated` (direct protocol, two hops / one hop)
+        self.single = None
+        one = os.environ.get("GEOMX_STEP_EXCHANGE", "ll")
+        if not self.overlap and mode == "dist_sync" and not self.hfa and one in ("sharded", "replicated") and self.topo.world > 1 and f.ll_d is not None:
+            f.add_channel("all", list(range(10)), replicate=one == "replicated")
+            self.single = "all"
         self.fused_mlp = B <= 32 and os.environ.get("GEOMX_FUSED_MLP", "1") == "1"
         # small-batch regime: both convolutions forward / backward as direct fp32-FMA kernels (3 launches, csrc/kernels/cnn_direct.cu) instead
         # of im2col + tcgen05 GEMMs (GEOMX_DIRECT_CONV=0 selects the GEMM path; batches > 64 always use it)
@@ -223,6 +230,8 @@ class HipsCNNTrainStep:
             (lambda: f.fsa_step(zero_grad=self.fused_zero_grad))
         if self.overlap:
             kv = lambda: f.channel_step("conv", zero_grad=self.fused_zero_grad)
+        elif self.single:
+            kv = lambda: f.channel_step(self.single, zero_grad=self.fused_zero_grad)
         kv_dense = [("hips push+opt+pull (dense keys, overlapped)", "comm", lambda: f.channel_step("dense", zero_grad=self.fused_zero_grad))] if self.overlap else []
         self._tail = []
         if self.update == "local":

@@ -269,6 +269,35 @@ def test_pool_relu_softmax_bn(nat):
         assert rel_err(a, c) < 1e-3
 
 
+def test_batchnorm_split_form_matches_fp64(nat):
+    """Feature-map sized BatchNorm (statistics kernel on a (channel, slice) grid + streaming apply kernel) against an fp64 reference:
+    forward, running statistics (population variance), input / scale / shift gradients, inference mode; vector and scalar tails."""
+    from geomx_b200.ops import functional as OF
+    torch.manual_seed(31)
+    for shape in ((16, 24, 28, 28), (9, 5, 23, 23)):
+        x = (torch.randn(*shape, device=dev()) * 1.7 + 0.6).requires_grad_(True)
+        C = shape[1]
+        gamma = (torch.rand(C, device=dev()) + 0.5).requires_grad_(True); beta = torch.randn(C, device=dev()).requires_grad_(True)
+        rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+        wgt = torch.randn(*shape, device=dev())
+        for rep in range(2):                      # twice: the accumulators must re-arm themselves
+            for t in (x, gamma, beta):
+                t.grad = None
+            y = OF.batch_norm(x, gamma, beta, rm, rv, True, momentum=0.9, eps=1e-5)
+            (y * wgt).sum().backward()
+        xd = x.detach().double().requires_grad_(True); gd = gamma.detach().double().requires_grad_(True); bd = beta.detach().double().requires_grad_(True)
+        mean = xd.mean((0, 2, 3), keepdim=True); var = ((xd - mean) ** 2).mean((0, 2, 3), keepdim=True)
+        yd = (xd - mean) / torch.sqrt(var + 1e-5) * gd.view(1, C, 1, 1) + bd.view(1, C, 1, 1)
+        (yd * wgt.double()).sum().backward()
+        assert rel_err(y, yd) < 1e-5
+        assert rel_err(x.grad, xd.grad) < 1e-4 and rel_err(gamma.grad, gd.grad) < 1e-5 and rel_err(beta.grad, bd.grad) < 1e-5
+        m1, v1 = mean.flatten().float(), var.flatten().float()
+        assert torch.allclose(rm, 0.19 * m1, atol=1e-5) and torch.allclose(rv, 0.81 + 0.19 * v1, atol=1e-4)     # two updates with momentum 0.9
+        ye = OF.batch_norm(x.detach(), gamma.detach(), beta.detach(), rm, rv, False, eps=1e-5)
+        ref = (x.detach() - rm.view(1, C, 1, 1)) / torch.sqrt(rv.view(1, C, 1, 1) + 1e-5) * gamma.detach().view(1, C, 1, 1) + beta.detach().view(1, C, 1, 1)
+        assert rel_err(ye, ref) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------------------------- optimizers
 def test_adam_kernel_matches_python(nat):
     torch.manual_seed(10)
