@@ -46,6 +46,8 @@ def parse():
                          "(K1=20 local steps, K2=10 party rounds per global round); mixed_sync = cnn.py -ms (dist_async global tier)")
     ap.add_argument("--script", action="store_true", help="time the loop of examples/cnn.py itself (gluon autograd + kv.push/kv.pull per key through "
                                                             "the fabric KVStore) instead of the fused HipsCNNTrainStep engine")
+    ap.add_argument("--hybridize", action="store_true", help="--script only: net.hybridize(static_alloc=True) — forward / backward of the gluon net "
+                    "replay as CUDA graphs (the CachedOp analogue); the per-key push / pull loop stays eager Python")
     ap.add_argument("--lookahead", action="store_true", help="cut the step after the forward convolutions instead of before them (software "
                     "pipelining across launches, see HipsCNNTrainStep(lookahead=...)); measured: no gain at 1-2 GPUs, so not the default")
     ap.add_argument("--fast", action="store_true", help="plain TF32 tensor-core products instead of the fp32-accurate 3xTF32 default")
@@ -109,6 +111,8 @@ class ScriptPathEngine:
         net = mx.models.build_cnn()
         net.initialize(force_reinit=True, ctx=ctx, init=mx.init.Xavier())
         net(mx.nd.random.uniform(shape=(B, 1, 28, 28), ctx=ctx))
+        if getattr(args, "hybridize", False):
+            net.hybridize(static_alloc=True, static_shape=True)
         self.net, self.loss_fn = net, mx.gluon.loss.SoftmaxCrossEntropyLoss()
         self.kv = mx.kv.create("dist_async" if args.config == "mixed_sync" else "dist_sync") if int(os.environ.get("WORLD_SIZE", 1)) > 1 else mx.kv.create("device")
         self.kv.set_optimizer(mx.optimizer.Adam(learning_rate=0.01))
@@ -333,7 +337,7 @@ def main():
             "ms_per_step": round(dev_ms / K, 5), "ms_per_step_p10_p50_p90": [round(pct(0.1), 5), round(pct(0.5), 5), round(pct(0.9), 5)],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32" if args.fast else "fp32 (3xTF32 tensor-core products + fp32 FMA, fp32 accumulate)", "data": "synthetic",
-            "impl": args.impl, "baseline_config": args.config, "path": "examples/cnn.py loop (script)" if args.script else "HipsCNNTrainStep engine",
+            "impl": args.impl, "baseline_config": args.config, "path": ("examples/cnn.py loop (script%s)" % (", hybridize(static_alloc=True)" if args.hybridize else "")) if args.script else "HipsCNNTrainStep engine",
             "config": {"model": "examples/cnn.py MNIST CNN (Conv16k5-Pool-Conv32k5-Pool-Dense256-Dense128-Dense10, 178762 params)",
                        "global_batch": B * world, "per_gpu_batch": B, "seq_len": None, "kvstore": args.mode,
                        "precision": ("fp32 storage and accumulation, TF32 tcgen05 multiplies (--fast)" if args.fast else

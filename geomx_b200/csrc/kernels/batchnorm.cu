@@ -120,14 +120,24 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
   const int c = blockIdx.x, S = gridDim.y;
   float s = 0.f, q = 0.f;
   if ((HW & 3) == 0) {
-    const int hw4 = HW >> 2;
-    for (int n = blockIdx.y; n < N; n += S) {
-      const float4* p = reinterpret_cast<const float4*>(x + ((long long)n * C + c) * HW);
-      for (int i = threadIdx.x; i < hw4; i += 256) {
-        const float4 v = __ldg(p + i);
-        s += (v.x + v.y) + (v.z + v.w);
-        q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
-      }
+    // flattened (image, 128-bit chunk) index: all 256 threads stay busy whatever HW is, four independent loads in flight per thread
+    const int hw4 = HW >> 2, imgs = (N - (int)blockIdx.y + S - 1) / S, total = imgs * hw4;
+    const long long img_stride = (long long)S * C * HW;
+    const float* base = x + ((long long)blockIdx.y * C + c) * HW;
+    auto at = [&](int j) { const int k = j / hw4; return __ldg(reinterpret_cast<const float4*>(base + k * img_stride) + (j - k * hw4)); };
+    int j = threadIdx.x;
+    for (; j + 768 < total; j += 1024) {
+      const float4 v0 = at(j), v1 = at(j + 256), v2 = at(j + 512), v3 = at(j + 768);
+      s += ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w)) + ((v2.x + v2.y) + (v2.z + v2.w)) + ((v3.x + v3.y) + (v3.z + v3.w));
+      q = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, q))));
+      q = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, q))));
+      q = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, fmaf(v2.z, v2.z, fmaf(v2.w, v2.w, q))));
+      q = fmaf(v3.x, v3.x, fmaf(v3.y, v3.y, fmaf(v3.z, v3.z, fmaf(v3.w, v3.w, q))));
+    }
+    for (; j < total; j += 256) {
+      const float4 v = at(j);
+      s += (v.x + v.y) + (v.z + v.w);
+      q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
     }
   } else {
     for (int n = blockIdx.y; n < N; n += S) {
@@ -162,19 +172,38 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                         float eps, float* __restrict__ y, long long planes, int C, int HW) {
   gx::pdl_wait();
   gx::pdl_launch();
+  if ((HW & 3) == 0) {
+    // the tensor is one flat array of planes: grid-stride over its 128-bit chunks, two in flight per thread; a chunk never straddles a plane
+    const long long total = planes * (HW >> 2), stride = (long long)gridDim.x * 256;
+    const int hw4 = HW >> 2;
+    auto coef = [&](long long i, float& a, float& off) {
+      const int c = (int)((i / hw4) % C);
+      const float invstd = is_var ? rsqrtf(__ldg(var_or_invstd + c) + eps) : __ldg(var_or_invstd + c);
+      a = (gamma ? __ldg(gamma + c) : 1.f) * invstd;
+      off = (beta ? __ldg(beta + c) : 0.f) - __ldg(mean_src + c) * a;
+    };
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    for (; i + stride < total; i += 2 * stride) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(x) + i), v1 = __ldg(reinterpret_cast<const float4*>(x) + i + stride);
+      float a0, o0, a1, o1;
+      coef(i, a0, o0); coef(i + stride, a1, o1);
+      reinterpret_cast<float4*>(y)[i] = make_float4(fmaf(v0.x, a0, o0), fmaf(v0.y, a0, o0), fmaf(v0.z, a0, o0), fmaf(v0.w, a0, o0));
+      reinterpret_cast<float4*>(y)[i + stride] = make_float4(fmaf(v1.x, a1, o1), fmaf(v1.y, a1, o1), fmaf(v1.z, a1, o1), fmaf(v1.w, a1, o1));
+    }
+    for (; i < total; i += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      float a, o;
+      coef(i, a, o);
+      reinterpret_cast<float4*>(y)[i] = make_float4(fmaf(v.x, a, o), fmaf(v.y, a, o), fmaf(v.z, a, o), fmaf(v.w, a, o));
+    }
+    return;
+  }
   for (long long pl = blockIdx.x; pl < planes; pl += gridDim.x) {
     const int c = (int)(pl % C);
     const float invstd = is_var ? rsqrtf(var_or_invstd[c] + eps) : var_or_invstd[c];
     const float a = (gamma ? gamma[c] : 1.f) * invstd, off = (beta ? beta[c] : 0.f) - mean_src[c] * a;
     const float* px = x + pl * HW; float* py = y + pl * HW;
-    if ((HW & 3) == 0) {
-      for (int i = threadIdx.x; i < (HW >> 2); i += 256) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(px) + i);
-        reinterpret_cast<float4*>(py)[i] = make_float4(fmaf(v.x, a, off), fmaf(v.y, a, off), fmaf(v.z, a, off), fmaf(v.w, a, off));
-      }
-    } else {
-      for (int i = threadIdx.x; i < HW; i += 256) py[i] = fmaf(__ldg(px + i), a, off);
-    }
+    for (int i = threadIdx.x; i < HW; i += 256) py[i] = fmaf(__ldg(px + i), a, off);
   }
 }
 
@@ -188,15 +217,23 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restri
   const float mean = save_mean[c], invstd = save_invstd[c];
   float sdy = 0.f, sdyx = 0.f;
   if ((HW & 3) == 0) {
-    const int hw4 = HW >> 2;
-    for (int n = blockIdx.y; n < N; n += S) {
-      const long long o = ((long long)n * C + c) * HW;
-      const float4* px = reinterpret_cast<const float4*>(x + o); const float4* pg = reinterpret_cast<const float4*>(dy + o);
-      for (int i = threadIdx.x; i < hw4; i += 256) {
-        const float4 v = __ldg(px + i), g = __ldg(pg + i);
-        sdy += (g.x + g.y) + (g.z + g.w);
-        sdyx = fmaf(g.x, v.x - mean, fmaf(g.y, v.y - mean, fmaf(g.z, v.z - mean, fmaf(g.w, v.w - mean, sdyx))));
-      }
+    const int hw4 = HW >> 2, imgs = (N - (int)blockIdx.y + S - 1) / S, total = imgs * hw4;
+    const long long img_stride = (long long)S * C * HW, o0 = ((long long)blockIdx.y * C + c) * HW;
+    auto off = [&](int j) { const int k = j / hw4; return o0 + k * img_stride + 4LL * (j - k * hw4); };
+    int j = threadIdx.x;
+    for (; j + 256 < total; j += 512) {
+      const long long oa = off(j), ob = off(j + 256);
+      const float4 va = __ldg(reinterpret_cast<const float4*>(x + oa)), ga = __ldg(reinterpret_cast<const float4*>(dy + oa));
+      const float4 vb = __ldg(reinterpret_cast<const float4*>(x + ob)), gb = __ldg(reinterpret_cast<const float4*>(dy + ob));
+      sdy += ((ga.x + ga.y) + (ga.z + ga.w)) + ((gb.x + gb.y) + (gb.z + gb.w));
+      sdyx = fmaf(ga.x, va.x - mean, fmaf(ga.y, va.y - mean, fmaf(ga.z, va.z - mean, fmaf(ga.w, va.w - mean, sdyx))));
+      sdyx = fmaf(gb.x, vb.x - mean, fmaf(gb.y, vb.y - mean, fmaf(gb.z, vb.z - mean, fmaf(gb.w, vb.w - mean, sdyx))));
+    }
+    for (; j < total; j += 256) {
+      const long long oa = off(j);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + oa)), g = __ldg(reinterpret_cast<const float4*>(dy + oa));
+      sdy += (g.x + g.y) + (g.z + g.w);
+      sdyx = fmaf(g.x, v.x - mean, fmaf(g.y, v.y - mean, fmaf(g.z, v.z - mean, fmaf(g.w, v.w - mean, sdyx))));
     }
   } else {
     for (int n = blockIdx.y; n < N; n += S) {
@@ -226,23 +263,29 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                             const float* __restrict__ sums, float* __restrict__ dx, long long planes, int C, int HW, float inv_cnt) {
   gx::pdl_wait();
   gx::pdl_launch();
+  if ((HW & 3) == 0) {
+    const long long total = planes * (HW >> 2), stride = (long long)gridDim.x * 256;
+    const int hw4 = HW >> 2;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+      const int c = (int)((i / hw4) % C);
+      const float mean = __ldg(save_mean + c), invstd = __ldg(save_invstd + c);
+      const float k = (gamma ? __ldg(gamma + c) : 1.f) * invstd;
+      const float m_dy = __ldg(sums + 2 * c) * inv_cnt, m_dyx = __ldg(sums + 2 * c + 1) * inv_cnt * invstd;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i), g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+      float4 o;
+      o.x = k * (g.x - m_dy - (v.x - mean) * m_dyx); o.y = k * (g.y - m_dy - (v.y - mean) * m_dyx);
+      o.z = k * (g.z - m_dy - (v.z - mean) * m_dyx); o.w = k * (g.w - m_dy - (v.w - mean) * m_dyx);
+      reinterpret_cast<float4*>(dx)[i] = o;
+    }
+    return;
+  }
   for (long long pl = blockIdx.x; pl < planes; pl += gridDim.x) {
     const int c = (int)(pl % C);
     const float mean = save_mean[c], invstd = save_invstd[c];
     const float k = (gamma ? gamma[c] : 1.f) * invstd;
     const float m_dy = sums[2 * c] * inv_cnt, m_dyx = sums[2 * c + 1] * inv_cnt * invstd;   // dx = k * (dy - mean(dy) - xhat * mean(dy*xhat))
     const float* px = x + pl * HW; const float* pg = dy + pl * HW; float* pd = dx + pl * HW;
-    if ((HW & 3) == 0) {
-      for (int i = threadIdx.x; i < (HW >> 2); i += 256) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(px) + i), g = __ldg(reinterpret_cast<const float4*>(pg) + i);
-        float4 o;
-        o.x = k * (g.x - m_dy - (v.x - mean) * m_dyx); o.y = k * (g.y - m_dy - (v.y - mean) * m_dyx);
-        o.z = k * (g.z - m_dy - (v.z - mean) * m_dyx); o.w = k * (g.w - m_dy - (v.w - mean) * m_dyx);
-        reinterpret_cast<float4*>(pd)[i] = o;
-      }
-    } else {
-      for (int i = threadIdx.x; i < HW; i += 256) pd[i] = k * (__ldg(pg + i) - m_dy - (__ldg(px + i) - mean) * m_dyx);
-    }
+    for (int i = threadIdx.x; i < HW; i += 256) pd[i] = k * (__ldg(pg + i) - m_dy - (__ldg(px + i) - mean) * m_dyx);
   }
 }
 

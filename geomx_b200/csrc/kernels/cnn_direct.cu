@@ -220,6 +220,11 @@ __device__ __forceinline__ void cnn_bwd_body(float* sm, const int b, const int c
   cpa_wait_all();
   __syncthreads();
   stamp(9);
+  // Everything staged so far was produced by the forward kernel (complete long ago); da2 comes from the kernel right before this one.
+  // The grid dependency is resolved HERE, so that with programmatic dependent launch these CTAs become resident on the SMs the 16-CTA
+  // dense-chain cluster leaves idle and finish their staging while it is still running.
+  pdl_wait();
+  pdl_launch();
   // scatter the non-zeros of dz2 (pool + ReLU backward of conv1's output)
   for (int e = tid; e < CD_C2 * 16; e += 288) {
     const long long o = (long long)b * CD_C2 * 16 + e;
@@ -310,10 +315,14 @@ __device__ __forceinline__ void cnn_wgrad1_body(float* sm, const int oc, const i
   }
   for (int e = tid; e < B * 16; e += 256) {
     const int bb = e >> 4, win = e & 15;
-    const long long o = ((long long)bb * CD_C2 + oc) * 16 + win;
-    const int id = idx2[o];
-    sg[e] = a2[o] > 0.f ? da2[o] : 0.f;
+    const int id = idx2[((long long)bb * CD_C2 + oc) * 16 + win];
     sp[e] = (2 * (win >> 2) + (id >> 1)) * CD_P1 + 2 * (win & 3) + (id & 1);
+  }
+  pdl_wait();            // (see cnn_bwd_body: only da2 depends on the preceding kernel)
+  pdl_launch();
+  for (int e = tid; e < B * 16; e += 256) {
+    const long long o = ((long long)(e >> 4) * CD_C2 + oc) * 16 + (e & 15);
+    sg[e] = a2[o] > 0.f ? da2[o] : 0.f;
   }
   cpa_wait_all();
   __syncthreads();
@@ -351,15 +360,11 @@ __device__ __forceinline__ void cnn_wgrad1_body(float* sm, const int oc, const i
 __global__ void __launch_bounds__(288) cnn_bwd_kernel(const float* x, const float* w1, const float* a1, const unsigned char* idx1, const float* a2,
                                                        const unsigned char* idx2, const float* da2, float* dw0, float* db0, unsigned long long* dbg) {
   extern __shared__ __align__(16) float sm[];
-  pdl_wait();
-  pdl_launch();
   cnn_bwd_body(sm, blockIdx.x, blockIdx.y, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dbg);
 }
 __global__ void __launch_bounds__(256) cnn_wgrad1_kernel(const float* a1, const float* a2, const unsigned char* idx2, const float* da2, float* dw1,
                                                           float* db1, int B, unsigned long long* dbg) {
   extern __shared__ __align__(16) float sm[];
-  pdl_wait();
-  pdl_launch();
   cnn_wgrad1_body(sm, blockIdx.x, blockIdx.y, a1, a2, idx2, da2, dw1, db1, B, dbg);
 }
 // The whole convolution backward pass as ONE launch: CTAs [0, 4B) run the data-gradient / conv0 body, CTAs [4B, 4B + 128) the conv1
@@ -368,9 +373,7 @@ __global__ void __launch_bounds__(288) cnn_bwd_all_kernel(const float* x, const 
                                                            const unsigned char* idx2, const float* da2, float* dw0, float* db0, float* dw1, float* db1,
                                                            int B, unsigned long long* dbg) {
   extern __shared__ __align__(16) float sm[];
-  pdl_wait();
-  pdl_launch();
-  const int i = blockIdx.x;
+  const int i = blockIdx.x;      // (the grid dependency is resolved inside the bodies, after their independent staging)
   // debug: every CTA records (start, end, SM id) at dbg[64 + 3 i ..] so that tools/step_timeline.py can show how the grid packs onto the SMs
   unsigned long long t0 = 0;
   if (dbg != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -403,11 +406,6 @@ __global__ void __launch_bounds__(288) cnn_bwd_exchange_kernel(const float* x, c
                                                                 const int* __restrict__ tile_list, int n_active) {
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_ticket;
-  pdl_wait();
-  pdl_launch();
-  // the channel's round / optimizer step: read before any CTA of this launch can have completed them
-  const uint32_t round = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
-  const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
   const int i = blockIdx.x;
   if (i < 4 * B) {
     cnn_bwd_body(sm, i >> 2, i & 3, x, w1, a1, idx1, a2, idx2, da2, dw0, db0, dbg);
@@ -416,6 +414,9 @@ __global__ void __launch_bounds__(288) cnn_bwd_exchange_kernel(const float* x, c
     cnn_wgrad1_body(sm, j >> 2, j & 3, a1, a2, idx2, da2, dw1, db1, B, dbg);
   }
   if (threadIdx.x >= FAB_THREADS) return;                       // the exchange tail is written for 256 threads (one float4 of a tile each)
+  // the channel's round / optimizer step (they can only advance after every CTA of this launch has drawn its ticket below)
+  const uint32_t round = (uint32_t)(*reinterpret_cast<volatile int*>(p.state)) + 1u;
+  const int opt_t = (*reinterpret_cast<volatile int*>(p.state + 2)) + 1;
   auto bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
   bar();                                                         // every gradient store / atomic of this CTA has been issued
   if (threadIdx.x == 0) { __threadfence(); s_ticket = atomicAdd(p.state + 6, 1); }

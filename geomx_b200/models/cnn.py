@@ -133,7 +133,7 @@ class HipsCNNTrainStep:
         # examples/cnn.py:121-125).  GEOMX_STEP_OVERLAP=0 restores the single fused exchange at the end of the step.
         self.overlap = mode == "dist_sync" and not self.hfa and os.environ.get("GEOMX_STEP_OVERLAP", "1") == "1" and (self.topo.world == 1 or f.ll_d is not None)
         if self.overlap:
-            f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False, grid=int(os.environ.get("GEOMX_DENSE_CHANNEL_GRID", 0)) or None)
+            f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False, grid=int(os.environ.get("GEOMX_DENSE_CHANNEL_GRID", 40)) or None)
             f.add_channel("conv", [0, 1, 2, 3], replicate=True)
         # GEOMX_STEP_OVERLAP=0: ONE exchange of all keys after the backward pass.  GEOMX_STEP_EXCHANGE picks its protocol: `ll` (three-hop
         # hierarchy walk), `sharded` / `replicated` (direct protocol, two hops / one hop)
