@@ -348,6 +348,10 @@ def main():
                            "sharded tile-by-tile over all ranks" if topo.tile_sharded else "on rank(s) %s" % topo.gs_ranks),
                        "channels": {k: {"keys": v["keys"], "mode": "replicated 1-hop" if v["replicate"] else "sharded 2-hop", "tiles": v["tiles"]}
                                     for k, v in getattr(getattr(eng, "fabric", None), "channels", {}).items()},
+                       "exchange": ("key-group channels: dense keys' two-hop exchange underneath the conv backward, conv keys one-hop after it"
+                                    if getattr(eng, "overlap", False) else
+                                    ("one fused exchange of all keys after the backward pass (%s protocol)" % (getattr(eng, "single", None) and "direct" or
+                                     getattr(getattr(eng, "fabric", None), "protocol", None))) if hasattr(eng, "overlap") else None),
                        "step_cut": ("look-ahead: each launch = head+backward+exchange of batch k, then forward convolutions of batch k+1 (same "
                                     "arithmetic, loss reported one call late)" if getattr(eng, "lookahead", False) else "classic: forward..exchange of one batch per launch"),
                        "optimizer": "Adam(lr=0.01) on the global-PS shard", "cuda_graph": not args.no_graph,

@@ -130,8 +130,12 @@ class HipsCNNTrainStep:
         # Key groups ("channels") of the step: the dense keys' gradients are complete long before the convolution backward pass ends, so their
         # exchange runs underneath it on its own stream (two-hop, optimizer sharded over all ranks); the conv keys come last and use the
         # one-hop replicated mode — the only communication left on the critical path (reference ordering: push(idx, priority=-idx),
-        # examples/cnn.py:121-125).  GEOMX_STEP_OVERLAP=0 restores the single fused exchange at the end of the step.
-        self.overlap = mode == "dist_sync" and not self.hfa and os.environ.get("GEOMX_STEP_OVERLAP", "1") == "1" and (self.topo.world == 1 or f.ll_d is not None)
+        # examples/cnn.py:121-125).  GEOMX_STEP_OVERLAP=0 selects the single fused exchange at the end of the step, =1 the channels.
+        # Measured on B200 (profiles/bench_history.md): one rank -> channels (their exchange is local arithmetic); 2 ranks -> a tie; 4 and 8 ranks
+        # -> the single LL exchange after the backward pass wins (0.0631 vs 0.0662 ms at 4, 0.0653 vs 0.0764 ms at 8: at 8 ranks the overlapped
+        # two-hop channel takes 26-36 us underneath a 12 us backward pass and its polling slows that pass down).  Hence the default by world size.
+        want_overlap = os.environ.get("GEOMX_STEP_OVERLAP", "1" if self.topo.world == 1 else "0") == "1"
+        self.overlap = mode == "dist_sync" and not self.hfa and want_overlap and (self.topo.world == 1 or f.ll_d is not None)
         if self.overlap:
             f.add_channel("dense", [4, 5, 6, 7, 8, 9], replicate=False, grid=int(os.environ.get("GEOMX_DENSE_CHANNEL_GRID", 40)) or None)
             f.add_channel("conv", [0, 1, 2, 3], replicate=True)

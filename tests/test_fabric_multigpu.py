@@ -54,7 +54,7 @@ def test_two_parties_two_global_servers():
 
 @pytest.mark.skipif(_ngpus() < 4, reason="needs >= 4 GPUs")
 def test_direct_channels_four_ranks():
-    rc, out = _torchrun(4, "fabric_check.py", "--parties", "2", port=29645)
+    rc, out = _torchrun(4, "fabric_check.py", "--parties", "2", port=29645, env={"GEOMX_STEP_OVERLAP": "1"})
     assert rc == 0 and "FABRIC_CHECK PASS" in out, out[-3000:]
 
 
