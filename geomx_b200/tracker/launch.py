@@ -8,6 +8,13 @@ Roles and variables follow ``3rdparty/ps-lite/src/postoffice.cc:18-58`` (``DMLC_
 GLOBAL_WORKER,GLOBAL_SERVER,ALL_WORKER}``, ``DMLC_ROLE_MASTER_WORKER``, ``DMLC_ENABLE_CENTRAL_WORKER``, ``DMLC_PS_ROOT_{URI,PORT}``,
 ``DMLC_PS_GLOBAL_ROOT_{URI,PORT}``).  With ``--launcher ssh`` parties are placed on consecutive hosts of the host file (central party on
 the first one), which is the multi-datacentre layout HiPS exists for; ``mpi`` prints/executes one ``mpirun`` per process group.
+
+Cluster schedulers (capability parity with the reference's dmlc-core tracker back-ends ``mpi / sge / slurm / kubernetes``,
+3rdparty/dmlc-core/tracker/dmlc_tracker/{mpi,sge,slurm,kubernetes}.py; yarn / mesos are Hadoop-era and not rebuilt): every back-end is a
+function ``(Proc, argv, env, cwd) -> command`` over the same process table, so a HiPS job has the identical layout whatever starts it:
+``slurm`` = one ``srun`` step per process pinned to the process's host, ``sge`` = one ``qsub`` of a generated job script per process,
+``kubernetes`` = ``--dry-run`` prints (and a real run ``kubectl apply``s) one manifest with a headless Service + Pod per process, the
+rendezvous addresses rewritten to the Services' DNS names.
 """
 from __future__ import annotations
 
@@ -101,6 +108,58 @@ def _mpi_line(host, argv, env):
     return ["mpirun", "-n", "1", "--host", host] + xs + list(argv)
 
 
+def _slurm_line(p, argv, env, cwd):
+    exports = ",".join(["ALL"] + ["%s=%s" % kv for kv in env.items()])
+    host = [] if p.host in ("127.0.0.1", "localhost") else ["--nodelist", p.host]
+    return ["srun", "--nodes=1", "--ntasks=1", "--job-name", "hips-" + p.name, "--chdir", cwd, "--export", exports] + host + list(argv)
+
+
+def _sge_script(p, argv, env, cwd):
+    """Job script of one role for Sun Grid Engine (submitted with ``qsub -sync y`` so that the launcher sees the exit code)."""
+    lines = ["#!/bin/bash", "#$ -S /bin/bash", "#$ -N hips-" + p.name, "#$ -cwd", "#$ -j y"]
+    if p.host not in ("127.0.0.1", "localhost"):
+        lines.append("#$ -l hostname=" + p.host)
+    lines += ["export %s=%s" % (k, shlex.quote(v)) for k, v in env.items()]
+    lines += ["cd " + shlex.quote(cwd), "exec " + " ".join(shlex.quote(a) for a in argv), ""]
+    return "\n".join(lines)
+
+
+def kubernetes_manifest(job: HipsJob, worker_cmd, image="geomx-b200:latest", namespace="default", python="python"):
+    """One YAML document per process: a headless Service (stable DNS name for the rendezvous) and a Pod.  Scheduler / root addresses are
+    rewritten from host names to Service names, so nothing in the job depends on Pod IPs."""
+    lines_ = job.command_lines(worker_cmd, python=python)
+    svc = {}                                              # rendezvous host -> Service name of the process that listens there
+    for p, argv, env in lines_:
+        name = "hips-" + p.name.replace("_", "-")
+        if p.name == "global_scheduler":
+            svc[("g", p.host, env["DMLC_PS_GLOBAL_ROOT_PORT"])] = name
+        elif p.name.endswith("scheduler"):
+            svc[("l", p.host, env["DMLC_PS_ROOT_PORT"])] = name
+    docs = []
+    for p, argv, env in lines_:
+        name = "hips-" + p.name.replace("_", "-")
+        e = dict(env)
+        gk = ("g", e.get("DMLC_PS_GLOBAL_ROOT_URI"), e.get("DMLC_PS_GLOBAL_ROOT_PORT"))
+        lk = ("l", e.get("DMLC_PS_ROOT_URI"), e.get("DMLC_PS_ROOT_PORT"))
+        if gk in svc:
+            e["DMLC_PS_GLOBAL_ROOT_URI"] = svc[gk]
+        if lk in svc:
+            e["DMLC_PS_ROOT_URI"] = svc[lk]
+        e["DMLC_NODE_HOST"] = name
+        envs = "\n".join("        - {name: %s, value: %s}" % (k, _yq(v)) for k, v in sorted(e.items()))
+        cmd = ", ".join(_yq(a) for a in argv)
+        docs.append(("apiVersion: v1\nkind: Service\nmetadata: {name: %s, namespace: %s}\nspec:\n  clusterIP: None\n  selector: {hips-role: %s}\n"
+                     "  ports: [{name: ps, port: 9000}]\n---\napiVersion: v1\nkind: Pod\nmetadata:\n  name: %s\n  namespace: %s\n  labels: {hips-role: %s, "
+                     "hips-job: hips}\nspec:\n  restartPolicy: Never\n  hostname: %s\n  containers:\n    - name: main\n      image: %s\n"
+                     "      command: [%s]\n      env:\n%s\n") % (name, namespace, name, name, namespace, name, name, image, cmd, envs)
+                    + ("      resources: {limits: {nvidia.com/gpu: 1}}\n" if p.is_worker else ""))
+    return "---\n".join(docs)
+
+
+def _yq(v):
+    return '"%s"' % str(v).replace("\\", "\\\\").replace('"', '\\"')
+
+
 def launch(job: HipsJob, worker_cmd, launcher="local", log_dir=None, dry_run=False, timeout=None):
     """Start every process of ``job``; returns the worst exit code (``dry_run``: the command lines instead)."""
     lines = job.command_lines(worker_cmd)
@@ -111,8 +170,23 @@ def launch(job: HipsJob, worker_cmd, launcher="local", log_dir=None, dry_run=Fal
             plan.append((p, _ssh_line(p.host, argv, env, cwd), None))
         elif launcher == "mpi":
             plan.append((p, _mpi_line(p.host, argv, env), None))
+        elif launcher == "slurm":
+            plan.append((p, _slurm_line(p, argv, env, cwd), None))
+        elif launcher == "sge":
+            script_dir = log_dir or os.path.join(cwd, ".hips_sge")
+            path = os.path.join(script_dir, p.name + ".sh")
+            if not dry_run:
+                os.makedirs(script_dir, exist_ok=True)
+                with open(path, "w") as f:
+                    f.write(_sge_script(p, argv, env, cwd))
+            plan.append((p, ["qsub", "-sync", "y", path], None))
         else:
             plan.append((p, argv, env))
+    if launcher == "kubernetes":
+        manifest = kubernetes_manifest(job, worker_cmd)
+        if dry_run:
+            return [("manifest", ["kubectl", "apply", "-f", "-"], {"MANIFEST": manifest})]
+        return subprocess.run(["kubectl", "apply", "-f", "-"], input=manifest.encode()).returncode
     if dry_run:
         return [(p.name, cmd, env) for p, cmd, env in plan]
     if log_dir:
@@ -161,7 +235,7 @@ def main(argv=None):
     ap.add_argument("--parties", type=int, default=0, help="number of participating parties (0: single tier)")
     ap.add_argument("--global-servers", type=int, default=1)
     ap.add_argument("--central-worker", action="store_true")
-    ap.add_argument("--launcher", default="local", choices=["local", "ssh", "mpi"])
+    ap.add_argument("--launcher", default="local", choices=["local", "ssh", "mpi", "slurm", "sge", "kubernetes"])
     ap.add_argument("-H", "--hostfile")
     ap.add_argument("--base-port", type=int, default=9092)
     ap.add_argument("--log-dir")
@@ -176,6 +250,9 @@ def main(argv=None):
     if not cmd:
         ap.error("missing worker command")
     res = launch(job, cmd, a.launcher, a.log_dir, a.dry_run)
+    if a.dry_run and a.launcher == "kubernetes":
+        print(res[0][2]["MANIFEST"])
+        return 0
     if a.dry_run:
         for name, c, env in res:
             print(name, ":", " ".join(shlex.quote(x) for x in c), "| env:", " ".join("%s=%s" % kv for kv in sorted((env or {}).items())))

@@ -375,6 +375,28 @@ def test_row_sparse_push_pull_over_the_wire():
             assert all(abs(a - b) < 1e-5 for a, b in zip(v["rows"], exp)), (v, exp)
 
 
+def test_tracker_cluster_backends_dry_run(tmp_path):
+    """slurm / sge / kubernetes back-ends describe the same 12-process two-tier job (3rdparty/dmlc-core/tracker/dmlc_tracker/{slurm,sge,kubernetes}.py)."""
+    from geomx_b200.tracker.launch import HipsJob, launch, kubernetes_manifest, _sge_script
+    job = HipsJob(2, 1, 2, 1, 9092, ["c0", "h1", "h2"], {"ENABLE_P3": "1"})
+    sl = launch(job, ["python", "examples/cnn.py"], "slurm", dry_run=True)
+    assert len(sl) == 12 and all(c[0] == "srun" for _, c, _ in sl)
+    w = [c for n, c, _ in sl if n == "party1_worker1"][0]
+    assert w[-2:] == ["python", "examples/cnn.py"] and "h2" in w and any("DMLC_ROLE=worker" in a and "ENABLE_P3=1" in a for a in w)
+    sg = launch(job, ["python", "examples/cnn.py"], "sge", log_dir=str(tmp_path), dry_run=True)
+    assert len(sg) == 12 and sg[0][1][:3] == ["qsub", "-sync", "y"]
+    procs = {p.name: (p, a, e) for p, a, e in job.command_lines(["python", "examples/cnn.py"])}
+    script = _sge_script(*procs["party0_server"], "/work")
+    assert "#$ -l hostname=h1" in script and "export DMLC_ROLE=server" in script and "export DMLC_PS_GLOBAL_ROOT_URI=c0" in script and "import geomx_b200" in script
+    m = kubernetes_manifest(job, ["python", "examples/cnn.py"])
+    assert m.count("kind: Pod") == 12 and m.count("kind: Service") == 12
+    pod = m[m.index("name: hips-party0-server\n  namespace"):]
+    pod = pod[:pod.index("---")]
+    # rendezvous addresses point at the schedulers' Services, not at host names
+    assert 'DMLC_PS_GLOBAL_ROOT_URI, value: "hips-global-scheduler"' in pod and 'DMLC_PS_ROOT_URI, value: "hips-party0-scheduler"' in pod
+    assert "nvidia.com/gpu" not in pod and "nvidia.com/gpu" in m[m.index("name: hips-party1-worker0\n  namespace"):][:1500]
+
+
 def test_tracker_launcher_single_tier_and_layout(tmp_path):
     """geomx_b200.tracker: the two-tier layout is the reference's 12 processes, and a locally launched single-tier job trains correctly."""
     from geomx_b200.tracker import HipsJob, launch
