@@ -405,8 +405,12 @@ bool KVStoreDistServer::FinishLocalAggregation(int key, KeyState* ks, const Data
   float* w = e.has_master ? e.master.data() : reinterpret_cast<float*>(e.data.data());
   memcpy(w, ub->merged.data(), n * sizeof(float));   // only aggregate (ApplyUpdates on a non-global server)
   if (e.has_master) StoreFromFloat(&e, w, n);
-  if (key == 0) ++local_iters_;                      // HFA counts local rounds on key 0 (reference :1324)
-  if (use_hfa_ && (local_iters_.load() % hfa_k2_ != 0)) {   // local synchronisation only
+  // HFA: every K2-th local round of a key goes to the global tier.  The reference counts local rounds on key 0 (:1324) and relies on one
+  // thread serving the keys in arrival order; keys are served by concurrent lanes here, so every key counts its OWN rounds — all keys are
+  // pushed once per iteration, hence the counters agree and the decision cannot depend on which lane ran first.
+  ++ks->local_rounds;
+  if (key == 0) local_iters_ = ks->local_rounds;
+  if (use_hfa_ && (ks->local_rounds % hfa_k2_ != 0)) {   // local synchronisation only
     for (size_t i = 0; i < ub->request.size(); ++i) {
       const std::vector<KVMeta>& q = ub->request;
       if (i > 0 && q[i].sender == q[i - 1].sender && q[i].timestamp == q[i - 1].timestamp) continue;
@@ -805,6 +809,7 @@ void KVStoreDistServer::LoadStates(const std::string& prefix) {
     ks.ready.notify_all();
   }
   int64_t li = 0; f.read(reinterpret_cast<char*>(&li), 8); local_iters_ = li;
+  for (auto& kv : Slots()) { std::lock_guard<std::mutex> lk(kv.second->mu); kv.second->local_rounds = li; }
 }
 
 }  // namespace hips

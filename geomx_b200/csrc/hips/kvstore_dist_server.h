@@ -154,6 +154,7 @@ class KVStoreDistServer {
     std::vector<float> milestone, bsc_u, bsc_v, residual_2bit;
     NativeOptimizer::State opt;
     bool initialized = false;
+    long local_rounds = 0;                  // completed local aggregation rounds (HFA: every K2-th one goes to the global tier)
     bool skip_init_push = false;            // resumed key: the next init push of the (re)started job must not overwrite it
     std::atomic<int> version{0};            // completed synchronisation rounds (TSEngine relay version, checkpoint cadence)
   };
