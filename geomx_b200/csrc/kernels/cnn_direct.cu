@@ -1,9 +1,13 @@
 // Direct (fp32 FMA) convolution kernels for the small-batch regime of the reference's demo CNN
 //   Conv2D(16,k5,relu) -> MaxPool2 -> Conv2D(32,k5,relu) -> MaxPool2      (examples/cnn.py:56-60, input 1x28x28)
-// forward and backward, three launches in total:
-//   cnn_fwd_kernel    x -> a1 (+argmax) -> a2 (+argmax)            both convolutions, bias, ReLU and both max-pools; a1 stays in shared memory
-//   cnn_bwd_kernel    da2 -> da1 (in shared memory only) -> dW0, db0  conv1 data gradient + pool/ReLU backward of both layers + conv0 weight gradient
-//   cnn_wgrad1_kernel da2, a1 -> dW1, db1                           conv1 weight gradient (sparse: one non-zero per pooling window)
+// forward and backward, TWO launches in total:
+//   cnn_fwd_kernel      x -> a1 (+argmax) -> a2 (+argmax)          both convolutions, bias, ReLU and both max-pools; a1 stays in shared memory
+//   cnn_bwd_all_kernel  one heterogeneous grid: CTAs [0, 4B)  da2 -> da1 (shared memory only) -> dW0, db0   (conv1 data gradient + pool/ReLU
+//                       backward of both layers + conv0 weight gradient), CTAs [4B, 4B+128)  da2, a1 -> dW1, db1  (conv1 weight gradient,
+//                       sparse: one non-zero per pooling window).  Both bodies resolve the programmatic grid dependency only AFTER the staging
+//                       that does not depend on the preceding kernel, so the CTAs become resident and stage while that kernel still runs.
+//                       (cnn_bwd_kernel / cnn_wgrad1_kernel: the same bodies as separate launches; cnn_bwd_exchange_kernel: the same grid
+//                       whose last CTAs also perform the conv keys' exchange — measured, no gain, opt-in.)
 //
 // Why not the tcgen05 implicit GEMM here: with a per-worker batch of 32 the conv1 products are M = 2048 x N = 32 x K = 400 — 16 tensor-core
 // tiles.  Measured on B200 (tools/kernel_times.py, profiles/): the tcgen05 path needs 8 us (TF32) / 16 us (3xTF32) for the forward GEMM alone

@@ -5,15 +5,19 @@
 // pick broadcast_reduce_op_index.cu:39-45): 3 forward GEMMs + 6 backward GEMMs + bias / activation / softmax kernels, each a separate engine op.
 //
 // With a per-worker batch of 32 every one of those GEMMs has M = 32: a tcgen05 tile would be 3/4 padding and each launch is pure latency
-// (profiles/prof_step_ncu_raw.md: tensor pipe 1-5 %, 6-10 us per launch).  Here the whole chain is one kernel on a cluster of 8 CTAs:
-//   * every CTA owns a 1/8 column slice of each layer; weights are staged in shared memory ONCE (cp.async, issued before griddepcontrol.wait
+// (profiles/round1/prof_step_ncu_raw.md: tensor pipe 1-5 %, 6-10 us per launch).  Here the whole chain is one kernel on a cluster of CS CTAs
+// (16 — a non-portable cluster size, opted into at launch — or 8 when the device cannot co-schedule 16; GEOMX_MLP_CLUSTER):
+//   * every CTA owns a 1/CS column slice of each layer; weights are staged in shared memory ONCE (cp.async, issued before griddepcontrol.wait
 //     so the 150 KB of weight traffic overlaps the tail of the convolution kernels) and reused by forward and backward;
 //   * products run on the fp32 FMA pipes (exact fp32, like the reference's SGEMM): 4x4 register tiles, K split over warps, operands read with
 //     conflict-free 128-bit shared loads from XOR-swizzled tiles, partial sums reduced through shared memory;
-//   * layer outputs are broadcast to all 8 CTAs with distributed-shared-memory stores (st.shared::cluster through
+//   * layer outputs are broadcast to all CTAs of the cluster with distributed-shared-memory stores (st.shared::cluster through
 //     cluster.map_shared_rank) followed by one hardware cluster barrier — no global round trip between layers;
 //   * epilogues fused: bias, ReLU, ReLU masks of the backward pass, softmax / loss / dlogits, bias gradients (column sums).
-// Five cluster barriers replace what used to be seven kernel launches (dense0, dense1, head, dW1, dz3, dW0, da2).
+//   * 512 threads: the two warp-groups split K in the wide forward layer and run data-gradient and weight-gradient products side by side
+//     in the backward phases.
+// A handful of cluster barriers replace what used to be seven kernel launches (dense0, dense1, head, dW1, dz3, dW0, da2); measured 24.5 us
+// for the whole chain forward + backward on B200 (profiles/kernel_times.txt, with per-phase %globaltimer stamps).
 //
 // Shapes are compile-time (D0 -> D1 -> D2 -> C<=16, batch <= 32): the demo CNN's 512 -> 256 -> 128 -> 10.  Other shapes use the tcgen05 GEMMs.
 #include <cooperative_groups.h>

@@ -4,15 +4,19 @@
 ``Conv2D(16,k5,relu) → MaxPool2 → Conv2D(32,k5,relu) → MaxPool2 → Dense(256,relu) → Dense(128,relu) → Dense(10)`` (178 762 parameters).
 
 ``HipsCNNTrainStep`` is the flagship hot path: one *training step* = forward + backward of that network for a per-worker batch
-plus the HiPS push/pull of all 10 keys (``dist_sync``: party reduce → global reduce + optimizer → broadcast), expressed as
-17 hand-written sm_100a kernel launches + 1 memset, captured ONCE into a CUDA graph and replayed per step:
+plus the HiPS push/pull of all 10 keys (``dist_sync``: party aggregation → global aggregation + optimizer → broadcast), captured ONCE
+into a CUDA graph and replayed per step.  At the reference's batch size (32 per worker) the step is 4-5 hand-written sm_100a launches:
 
-  fwd  conv0+bias+ReLU+pool (direct, CUDA cores, K=25) · im2col · conv1 GEMM (tcgen05, bias+ReLU, NCHW store) · pool ·
-       dense0 GEMM (tcgen05, bias+ReLU) · dense1 GEMM (tcgen05) · head (dense2 + softmax-CE fwd **and** bwd in one CTA)
-  bwd  dW1 / dz3(+ReLU mask, +db0) / dW0 / da2 GEMMs (tcgen05, MN-major operands read in place) · pool+ReLU bwd → pixel-major rows
-       (+dbc1) · dWc1 GEMM (split-K) · dcol1 GEMM · col2im · conv0 fused pool/ReLU-bwd + wgrad
-  kv   ``gx_hips_fsa_step`` (multi-rank: in-kernel NVLS/P2P collectives + partitioned Adam on the global owner) — with one rank and
-       one party both PS tiers collapse into the fused arena optimizer inside the same kernel.
+  cnn_fwd      conv0+bias+ReLU+pool → conv1+bias+ReLU+pool, fp32 FMA, the conv0 map never leaves shared memory      (csrc/kernels/cnn_direct.cu)
+  mlp_chain    dense0 → dense1 → classifier → softmax-CE forward AND backward in one 16-CTA cluster                  (csrc/kernels/mlp_chain.cu)
+  cnn_bwd_all  conv1 data gradient + pool/ReLU routing + conv0 weight gradient ‖ conv1 weight gradient, one grid      (csrc/kernels/cnn_direct.cu)
+  exchange     one LL kernel for all keys after the backward pass (several ranks), or key-group channels: the dense keys' exchange on
+               a high-priority stream underneath cnn_bwd_all, the conv keys' one-hop exchange after it (one rank / GEOMX_STEP_OVERLAP=1)
+                                                                                                                      (csrc/kernels/hips_fabric.cu)
+
+Larger batches (and ``GEOMX_DIRECT_CONV=0`` / ``GEOMX_FUSED_MLP=0``) use the generic kernels: direct conv0 + im2col, tcgen05 GEMMs with fused
+bias / ReLU / max-pool / mask / column-sum epilogues (3xTF32 = fp32-accurate by default), weight-gradient GEMMs on a parallel graph branch.
+With one rank and one party both PS tiers collapse into the arena optimizer inside the exchange kernels.
 
 The reference runs the same step as ~200 engine ops (per-image im2col+SGEMM) + 20 ZMQ round trips.
 The public API a user calls is ``step(X_host, y_host) -> loss`` (H2D of the batch from pinned memory, graph replay, D2H of the loss).
@@ -225,7 +229,8 @@ class HipsCNNTrainStep:
 
     # ------------------------------------------------------------------------------------------------------------
     def _steps(self):
-        """The training step as an ordered list of (name, stream, launch) — 14 kernels; `stream` is 'main' or 'side' (parallel graph branch)."""
+        """The training step as an ordered list of (name, stream, launch); `stream` is 'main', 'side' (parallel graph branch for weight
+        gradients), 'comm' (a key group's exchange on the high-priority stream) or 'join' (main, after the side branch)."""
         n = native
         B, P, G, f = self.B, self.P, self.G, self.fabric
         a2f = self.a2.view(B, 512)
