@@ -164,4 +164,13 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        rc = main()
+    except SystemExit:
+        raise
+    except BaseException as e:  # pragma: no cover - depends on the box (e.g. a kvstore type the build cannot serve at this N)
+        import traceback
+        traceback.print_exc()
+        print(json.dumps({"impl": "reference", "unavailable": "reference run failed: %r" % (e,)}))
+        rc = 0
+    sys.exit(rc)
