@@ -163,6 +163,15 @@ GX_CAPI int GXEnginePushAsync(GXEngineFn fn, void* arg, const int* const_vars, i
                 priority, name ? name : "c_api_op");
   });
 }
+// same, on the worker pool of `device` (-1: CPU) chosen by `prop` (0 normal / compute, 1 copy, 2 priority) — engine.h FnProperty + exec_ctx
+GX_CAPI int GXEnginePushAsyncEx(GXEngineFn fn, void* arg, const int* const_vars, int num_const, const int* mutable_vars, int num_mutable, int priority,
+                                const char* name, int device, int prop) {
+  return Guard([&] {
+    Eng()->Push([fn, arg] { fn(arg); }, std::vector<int>(const_vars, const_vars + num_const), std::vector<int>(mutable_vars, mutable_vars + num_mutable),
+                priority, name ? name : "c_api_op", device, static_cast<gxrt::FnProperty>(prop < 0 || prop > 2 ? 0 : prop));
+  });
+}
+GX_CAPI int GXEngineDeleteVariable(int var) { return Guard([&] { Eng()->DeleteVariable(var); }); }
 GX_CAPI int GXEngineWaitForVar(int var) { return Guard([&] { Eng()->WaitForVar(var); }); }
 GX_CAPI int GXEngineWaitAll() { return Guard([&] { Eng()->WaitForAll(); }); }
 

@@ -335,6 +335,62 @@ def test_callbacks_monitor_and_test_utils(caplog):
     mx.test_utils.assert_almost_equal(mx.nd.array([1.0, 2.0]), np.array([1.0, 2.0 + 1e-7]))
 
 
+def test_engine_device_pools_exceptions_and_delete():
+    """mx.engine: per-device worker pools (compute / copy per GPU, normal / priority on the CPU; threaded_engine_perdevice.cc), exceptions
+    surface at the wait points (threaded_engine.h OnComplete / var exception), DeleteVariable after pending ops."""
+    import threading
+    import time
+    from geomx_b200 import engine, runtime
+    if not runtime.available():
+        pytest.skip("native runtime not built")
+    engine.wait_all()
+    before = engine.stats()
+    seen, lock = {}, threading.Lock()
+
+    def tag(name, dt=0.0):
+        def f():
+            time.sleep(dt)
+            with lock:
+                seen.setdefault(name, threading.current_thread().ident)
+        return f
+    v0, v1 = engine.new_variable(), engine.new_variable()
+    # a slow op on GPU 0's compute pool must not delay GPU 1's pool nor the copy pool of GPU 0
+    t0 = time.time()
+    for _ in range(4):
+        engine.push(tag("g0", 0.15), mutable_vars=[], ctx=mx.gpu(0))          # 4 x 0.15 s on 2 threads = 0.3 s of queueing in that pool
+    engine.push(tag("g1"), mutable_vars=[v1], ctx=mx.gpu(1))
+    engine.push(tag("c0"), mutable_vars=[v0], ctx=0, prop=engine.COPY)
+    engine.wait_for_var(v1); engine.wait_for_var(v0)
+    assert time.time() - t0 < 0.14, "independent pools were blocked behind gpu0's queue"
+    engine.push(tag("prio"), prop=engine.PRIORITY); engine.push(tag("cpu"))
+    engine.wait_all()
+    after = engine.stats()
+    delta = {k: after.get(k, 0) - before.get(k, 0) for k in after}
+    assert delta["gpu0"] == 4 and delta["gpu1"] == 1 and delta["gpu0/copy"] == 1 and delta["cpu"] >= 1 and delta["priority"] >= 1
+    assert len({seen["g0"], seen["g1"], seen["c0"]}) == 3                       # three different worker threads
+    # exceptions: remembered on the written variable, raised by the next wait on it; later ops still run
+    def boom():
+        raise ValueError("op failed")
+    ran = []
+    engine.push(boom, mutable_vars=[v0])
+    engine.push(lambda: ran.append(1), mutable_vars=[v0])
+    with pytest.raises(Exception, match="op failed"):
+        engine.wait_for_var(v0)
+    assert ran == [1]
+    engine.wait_for_var(v0)                                                      # reported once
+    engine.push(boom, mutable_vars=[v1])
+    with pytest.raises(Exception, match="op failed"):
+        engine.wait_all()
+    engine.wait_all()
+    # DeleteVariable: after the ops already pushed on it
+    n = engine.get().num_variables()
+    v2 = engine.new_variable()
+    engine.push(tag("last", 0.02), mutable_vars=[v2])
+    engine.delete_variable(v2)
+    engine.wait_all()
+    assert "last" in seen and engine.get().num_variables() == n
+
+
 def test_engine_ordering_and_async_save(tmp_path):
     """mx.engine: writers are exclusive and ordered, readers run in between, priorities order ready ops; nd.save_async writes a snapshot."""
     import threading

@@ -44,6 +44,11 @@ def test_runtime_c_api(tmp_path):
         ck(lib.GXEnginePushAsync(cb, None, None, 0, mv, 1, 0, b"w"))
     ck(lib.GXEngineWaitForVar(v.value)); ck(lib.GXEngineWaitAll())
     assert log == [0, 1, 2, 3, 4]
+    # ... also on a device's copy pool (GXEnginePushAsyncEx: exec device + FnProperty), then the variable is deleted
+    cb2 = FN(lambda a: log.append("copy"))
+    ck(lib.GXEnginePushAsyncEx(cb2, None, None, 0, mv, 1, 0, b"c", 3, 1))
+    ck(lib.GXEngineDeleteVariable(v.value)); ck(lib.GXEngineWaitAll())
+    assert log[-1] == "copy"
     # profiler
     prof = str(tmp_path / "prof.json").encode()
     ck(lib.GXSetProfilerConfig(1, (ctypes.c_char_p * 1)(b"filename"), (ctypes.c_char_p * 1)(prof)))
