@@ -443,8 +443,8 @@ def test_host_pipeline_direct_inputs_match_staged(nat, monkeypatch):
         eng = mx.models.HipsCNNTrainStep(batch_size=32, optimizer=mx.optimizer.SGD(learning_rate=0.002), topo=Topology(1, 0, 1, 1), use_graph=True)
         out[direct] = ([eng.step(X, y) for X, y in zip(Xs, ys)], eng.fabric.param.tensor.clone())
         assert (eng._graph_alt is not None) == (direct == "1")
-    assert all(abs(a - b) < 2e-5 * max(1.0, abs(a)) for a, b in zip(out["1"][0], out["0"][0])), (out["1"][0], out["0"][0])
-    assert torch.allclose(out["1"][1], out["0"][1], atol=1e-5)
+    assert all(abs(a - b) < 1e-4 * max(1.0, abs(a)) for a, b in zip(out["1"][0], out["0"][0])), (out["1"][0], out["0"][0])
+    assert torch.allclose(out["1"][1], out["0"][1], atol=1e-4)      # a batch read from the wrong buffer would show up at the 1e-2 level
 
 
 @pytest.mark.parametrize("use_graph", [True, False])
