@@ -64,6 +64,10 @@ void Customer::Accept(const Message& recved) {
     CountResponse(recved);
     return;
   }
+  if (inline_requests_.load() && recved.meta.request && !recved.meta.simple_app && recved.meta.control.empty()) {
+    recv_handle_(recved);
+    return;
+  }
   // pull requests get their own queue/thread on servers so that they never wait behind pushes (reference customer.h:91-101)
   const bool is_pull_request = recved.meta.request && !recved.meta.push && !recved.meta.simple_app && recved.meta.control.empty();
   if (pull_thread_ && is_pull_request) pull_queue_.Push(recved);

@@ -37,10 +37,14 @@ class Customer {
   // wake-up per response on the worker side, where response handlers only copy data and signal the waiter (never block, never wait for
   // other messages).  Requests still go through the queue.
   void set_inline_responses(bool on) { inline_responses_ = on; }
+  // data requests (push / pull, not commands, not control) are handled on the Van receive thread as well: for servers whose request
+  // handler only hands the message to a worker lane and never blocks
+  void set_inline_requests(bool on) { inline_requests_ = on; }
 
  private:
   void CountResponse(const Message& recv);
   bool inline_responses_ = false;
+  std::atomic<bool> inline_requests_{false};
   void Receiving(ThreadsafeQueue<Message, MessagePriority>* q);
   int app_id_, customer_id_;
   RecvHandle recv_handle_;

@@ -27,6 +27,12 @@ KVStoreDistServer::KVStoreDistServer() {
   ps_server_->SimpleApp::set_request_handle([this](const SimpleData& d, SimpleApp* app) { CommandHandle(d, app); });
   ps_server_->set_request_handle([this](const KVMeta& m, const KVPairs& d, KVServer* s) { DataHandleEx(m, d, s); });
   ps_server_->set_response_handle([this](const KVMeta& m, const KVPairs& d, KVServer* s) { ResponseHandle(m, d, s); });
+  // With lanes the customer thread would only forward data requests to them: let the transport's receive thread do that itself (one thread
+  // wake-up less per request).  Kept off where the customer queue does real work: P3 (priority order of queued requests) and TSEngine
+  // (its node logic sees every message first).
+  if (!lanes_.empty() && !ps_server_->enable_p3 && ps_server_->ts(kLocal) == nullptr && ps_server_->ts(kGlobal) == nullptr &&
+      env->GetInt("GEOMX_INLINE_REQUESTS", 1) != 0)
+    ps_server_->get_customer()->set_inline_requests(true);
   if (has_global_ && ps_server_->ts(kGlobal) != nullptr)   // local server: fresh values of TS rounds arrive through the relay
     ps_server_->ts(kGlobal)->set_on_relayed([this](int key, int version, int cmd, const std::vector<char>& bytes) { OnRelayedFromGlobal(key, version, cmd, bytes); });
 }
@@ -215,8 +221,18 @@ void KVStoreDistServer::DataHandleEx(const KVMeta& req, const KVPairs& data, KVS
   // the server object exists before the node has registered (its rank names the checkpoint file), so the resume happens on first traffic
   if (resume_wanted_) std::call_once(resume_once_, [this] { TryResume(); });
   if (!req.push) {
-    ProfileScope ps("KVStoreDistServerPull");
-    HandlePull(type, req, data);
+    // pulls never block (parked until the key has a value), so without lanes they are answered right here; with lanes they take the
+    // key's lane, which keeps them ordered behind the pushes of that key that arrived earlier
+    if (lanes_.empty()) {
+      ProfileScope ps("KVStoreDistServerPull");
+      HandlePull(type, req, data);
+    } else {
+      Lane* lane = lanes_[static_cast<size_t>(req.key < 0 ? -req.key : req.key) % lanes_.size()].get();
+      lane->Post([this, type, req, data] {
+        ProfileScope ps("KVStoreDistServerPull");
+        HandlePull(type, req, data);
+      });
+    }
     return;
   }
   if (lanes_.empty()) {
@@ -303,7 +319,7 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
     }
     respond(req);
     const bool fetch = !(is_global_ || standalone_) && has_global_;
-    if (is_global_ || standalone_) { ks.initialized = true; ks.ready.notify_all(); }
+    if (is_global_ || standalone_) { ks.initialized = true; FlushParkedPulls(&ks, &out); }
     lk.unlock();
     Send(&out);
     if (fetch) PullFromGlobal(key, type);     // a local server adopts the global tier's value of the key
@@ -599,7 +615,7 @@ void KVStoreDistServer::ApplyFreshFromGlobal(int key, KeyState* ks, std::vector<
   }
   if (e.has_master) StoreFromFloat(&e, w, n);
   ks->initialized = true;
-  ks->ready.notify_all();
+  FlushParkedPulls(ks, out);
   std::vector<KVMeta> waiting; waiting.swap(r.waiting);
   r.push_ts = r.pull_ts = -1;
   r.via_ts = false;
@@ -688,15 +704,34 @@ void KVStoreDistServer::RoundCompleted(int key, bool bumped) {
   AskTS(key);
 }
 
+// A pull never blocks a thread: while the key has no value yet (the reference spins with sleep(100ms), :1719-1724) the request is parked with
+// the key and answered by whoever initialises it.
 void KVStoreDistServer::HandlePull(const DataHandleType& type, const KVMeta& req, const KVPairs& data) {
   const int key = req.key;
   KeyState& ks = Slot(key);
-  std::unique_lock<std::mutex> lk(ks.mu);
-  // the pull thread waits until the key has been initialised (reference spins with sleep(100ms) :1719-1724)
-  ks.ready.wait(lk, [&ks] { return ks.initialized; });
-  Entry& e = ks.entry;
-  KVPairs res;
+  std::vector<Reply> out;
+  {
+    std::lock_guard<std::mutex> lk(ks.mu);
+    if (!ks.initialized) { ks.parked_pulls.push_back(ParkedPull{type, req, data}); return; }
+    out.push_back(PullReply(&ks, type, req, data));
+  }
+  Send(&out);
+}
+
+// ks->mu held: the key just received its value — answer the pulls that arrived before it
+void KVStoreDistServer::FlushParkedPulls(KeyState* ks, std::vector<Reply>* out) {
+  for (ParkedPull& p : ks->parked_pulls) out->push_back(PullReply(ks, p.type, p.req, p.data));
+  ks->parked_pulls.clear();
+}
+
+// ks->mu held
+KVStoreDistServer::Reply KVStoreDistServer::PullReply(KeyState* ks, const DataHandleType& type, const KVMeta& req, const KVPairs& data) {
+  Entry& e = ks->entry;
+  Reply rep;
+  rep.to = req;
+  KVPairs& res = rep.data;
   res.keys = data.keys;
+  if (res.keys.size() == 0) res.keys.push_back(static_cast<Key>(req.key));
   if (type.requestType == RequestType::kRowSparsePushPull) {
     // row_sparse pull: only the requested rows travel back (reference DataHandleRowSparse pull branch :700-756)
     HIPS_CHECK_MSG(data.vals.size() >= 2 * sizeof(int64_t), "row_sparse pull without row ids");
@@ -723,8 +758,7 @@ void KVStoreDistServer::HandlePull(const DataHandleType& type, const KVMeta& req
     res.vals.CopyFrom(e.data.data(), e.data.size());
   }
   res.lens.push_back(static_cast<int>(res.vals.size()));
-  lk.unlock();
-  ps_server_->Response(req, res);
+  return rep;
 }
 
 // ------------------------------------------------------------------------------------------------ server-state checkpoint
@@ -790,6 +824,7 @@ void KVStoreDistServer::LoadStates(const std::string& prefix) {
   uint64_t magic = 0, nk = 0;
   f.read(reinterpret_cast<char*>(&magic), 8); f.read(reinterpret_cast<char*>(&nk), 8);
   HIPS_CHECK(magic == 0x4869505353544154ull);
+  std::vector<Reply> late;       // pulls that were waiting for a key this file brings
   for (uint64_t i = 0; i < nk; ++i) {
     int32_t key, dtype; uint64_t elems, nb;
     f.read(reinterpret_cast<char*>(&key), 4); f.read(reinterpret_cast<char*>(&dtype), 4); f.read(reinterpret_cast<char*>(&elems), 8);
@@ -806,8 +841,11 @@ void KVStoreDistServer::LoadStates(const std::string& prefix) {
     int32_t t; f.read(reinterpret_cast<char*>(&t), 4);
     ks.opt.t = t; ReadVec(f, &ks.opt.a); ReadVec(f, &ks.opt.b);     // used by whichever native optimizer is (or will be) configured
     ks.initialized = true;
-    ks.ready.notify_all();
+    std::vector<Reply> parked;
+    FlushParkedPulls(&ks, &parked);
+    late.insert(late.end(), std::make_move_iterator(parked.begin()), std::make_move_iterator(parked.end()));
   }
+  Send(&late);
   int64_t li = 0; f.read(reinterpret_cast<char*>(&li), 8); local_iters_ = li;
   for (auto& kv : Slots()) { std::lock_guard<std::mutex> lk(kv.second->mu); kv.second->local_rounds = li; }
 }

@@ -144,10 +144,11 @@ class KVStoreDistServer {
     int cmd = 0;
   };
 
+  struct ParkedPull { DataHandleType type; KVMeta req; KVPairs data; };
   // everything the server knows about one key; `mu` guards all of it except `version`
   struct KeyState {
     std::mutex mu;
-    std::condition_variable ready;          // pulls wait here until the key holds a value
+    std::vector<ParkedPull> parked_pulls;   // pulls that arrived before the key had a value: answered by whoever initialises it
     Entry entry;
     UpdateBuf ub;
     GlobalRound round;
@@ -209,6 +210,8 @@ class KVStoreDistServer {
   void ApplyFreshFromGlobal(int key, KeyState* ks, std::vector<float>* recved, std::vector<Reply>* out);
   bool BumpRound(KeyState* ks);                               // true: a periodic checkpoint is due (write it after releasing the key)
   Reply StoredReply(const KVMeta& to, int key, const Entry& e) const;
+  Reply PullReply(KeyState* ks, const DataHandleType& type, const KVMeta& req, const KVPairs& data);
+  void FlushParkedPulls(KeyState* ks, std::vector<Reply>* out);
   void Send(std::vector<Reply>* out);
   void StoreFromFloat(Entry* e, const float* src, size_t n);
   void ToFloat(const char* src, int dtype, size_t n, float* dst);
