@@ -8,9 +8,11 @@
 // multi-precision master copies (:374-407, :526-553), key sharding across global servers (MultiGPS :1765-1906), P3 push-response-with-
 // params (:1154-1164, :1257-1267), stop protocol (:315-328), initialized_ gate (:1719-1724), server profiler commands (:409-456).
 //
-// Concurrency: there is no server-wide lock.  Every key owns its state and a mutex (KeyState); a small reader/writer registry maps key ->
-// state; push requests are dispatched to GEOMX_SERVER_LANES worker threads by key (per-key FIFO order, different keys aggregate, run
-// their optimizer and talk to the global tier in parallel), pulls keep their own thread, and responses from the global tier are handled on
+// Concurrency: there is no server-wide lock and no handler ever blocks.  Every key owns its state and a mutex (KeyState); a small
+// reader/writer registry maps key -> state; data requests (pushes AND pulls) are handed by the transport's receive thread straight to one of
+// GEOMX_SERVER_LANES worker threads chosen by key (per-key FIFO order; different keys aggregate, run their optimizer and talk to the global
+// tier in parallel; GEOMX_INLINE_REQUESTS=0 or P3 / TSEngine route them through the customer's priority queue first).  A pull that arrives
+// before its key has a value is parked with the key and answered by whoever initialises it.  Responses from the global tier are handled on
 // the receive thread of the connection they arrived on.  Replies are built under the key's lock and sent after it is released.
 //
 // Design differences: continuation-style state machine on raw byte buffers (no NDArray/engine on the server), native optimizers run
