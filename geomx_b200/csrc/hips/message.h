@@ -89,6 +89,7 @@ class Reader {
   Reader(const char* p, size_t n) : p_(p), n_(n) {}
   template <typename T> T Get() { HIPS_CHECK(o_ + sizeof(T) <= n_); T v; memcpy(&v, p_ + o_, sizeof(T)); o_ += sizeof(T); return v; }
   std::string GetStr() { uint32_t n = Get<uint32_t>(); HIPS_CHECK(o_ + n <= n_); std::string s(p_ + o_, n); o_ += n; return s; }
+  size_t remaining() const { return n_ - o_; }
  private:
   const char* p_; size_t n_, o_ = 0;
 };
@@ -130,6 +131,7 @@ inline void UnpackMeta(const char* buf, size_t n, Meta* m) {
   m->total_bytes = r.Get<int32_t>(); m->bits_num = r.Get<int32_t>(); m->tos = r.Get<int32_t>();
   m->keys_len = r.Get<int32_t>(); m->vals_len = r.Get<int32_t>(); m->lens_len = r.Get<int32_t>();
   uint32_t nc = r.Get<uint32_t>();
+  HIPS_CHECK_MSG(static_cast<size_t>(nc) * sizeof(float) <= r.remaining(), "meta: codebook length exceeds the frame");   // (never allocate from an unchecked count)
   m->compr.resize(nc);
   for (uint32_t i = 0; i < nc; ++i) m->compr[i] = r.Get<float>();
   m->control.cmd = r.Get<int32_t>();

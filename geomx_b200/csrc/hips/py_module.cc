@@ -84,6 +84,31 @@ PYBIND11_MODULE(_C, m) {
                           b.control.cmd, b.control.node.empty() ? std::string() : b.control.node[0].hostname,
                           b.control.node.empty() ? -1 : b.control.node[0].rank_hint, buf.size());
   });
+  // fuzzing hooks (tests/test_fuzz_codecs.py): arbitrary bytes must either decode or be rejected with an exception — never crash, never
+  // allocate from an unchecked length; a decoded meta re-encodes to bytes that decode to the same meta
+  m.def("fuzz_unpack_meta", [](py::bytes b) {
+    const std::string s = b;
+    Meta a;
+    try { UnpackMeta(s.data(), s.size(), &a); } catch (const std::exception&) { return py::make_tuple(false, py::bytes()); }
+    std::vector<char> again; PackMeta(a, &again);
+    Meta c; UnpackMeta(again.data(), again.size(), &c);
+    std::vector<char> third; PackMeta(c, &third);
+    if (again != third) throw std::runtime_error("meta codec is not idempotent");
+    return py::make_tuple(true, py::bytes(again.data(), again.size()));
+  });
+  m.def("pack_meta_fields", [](int head, int app, int customer, int ts, int sender, int recver, bool request, bool push, bool simple, const std::string& body,
+                               int priority, int key, std::vector<float> compr, int ctrl_cmd, std::vector<std::tuple<int, int, std::string, int>> nodes) {
+    Meta a; a.head = head; a.app_id = app; a.customer_id = customer; a.timestamp = ts; a.sender = sender; a.recver = recver; a.request = request;
+    a.push = push; a.simple_app = simple; a.body = body; a.priority = priority; a.key = key; a.compr = compr; a.control.cmd = ctrl_cmd;
+    for (auto& t : nodes) { Node n; n.role = std::get<0>(t); n.id = std::get<1>(t); n.hostname = std::get<2>(t); n.port = std::get<3>(t); a.control.node.push_back(n); }
+    std::vector<char> buf; PackMeta(a, &buf);
+    Meta b; UnpackMeta(buf.data(), buf.size(), &b);
+    std::vector<std::tuple<int, int, std::string, int>> back;
+    for (auto& n : b.control.node) back.emplace_back(n.role, n.id, n.hostname, n.port);
+    return py::make_tuple(py::bytes(buf.data(), buf.size()),
+                          py::make_tuple(b.head, b.app_id, b.customer_id, b.timestamp, b.sender, b.recver, b.request, b.push, b.simple_app, b.body, b.priority,
+                                         b.key, b.compr, b.control.cmd, back));
+  });
   m.def("ts_pick_receiver", [](int requester, std::vector<int> idle, std::map<int, long> known, float max_greed, int trials) {
     Environment::Get()->Set("MAX_GREED_RATE_TS", std::to_string(max_greed));
     TSScheduler s(nullptr, 8, kLocal);

@@ -1,0 +1,77 @@
+"""Property-based tests (hypothesis) of the wire codecs: what a node reads from a socket is untrusted, so ANY byte string must either decode
+or be rejected with an exception; valid messages round-trip exactly; the gradient codecs keep their contracts on arbitrary inputs."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from geomx_b200 import runtime
+from geomx_b200.kvstore import compression as gc
+
+pytestmark = pytest.mark.skipif(not runtime.available(), reason="native runtime not built")
+i32 = st.integers(-2**31, 2**31 - 1)
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.binary(max_size=600))
+def test_unpack_meta_never_crashes_on_garbage(blob):
+    ok, again = runtime.C().fuzz_unpack_meta(blob)
+    if ok:                                   # whatever decoded re-encodes canonically (checked natively) and decodes again
+        assert runtime.C().fuzz_unpack_meta(again)[0]
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.binary(min_size=4, max_size=200), st.integers(0, 199), st.integers(0, 255))
+def test_unpack_meta_survives_bit_flips_of_valid_messages(body, pos, val):
+    C = runtime.C()
+    good, _ = C.pack_meta_fields(1, 2, 3, 4, 9, 101, True, True, False, body.decode("latin1"), -3, 7, [0.5, 2.0], 2, [(1, 100, "10.0.0.1", 9000)])
+    bad = bytearray(good)
+    bad[pos % len(bad)] = val
+    C.fuzz_unpack_meta(bytes(bad))           # must return (True, ...) or (False, ...) — not raise, not crash
+    huge = bytearray(good)                   # a length field blown up to 4 GiB must be rejected without allocating
+    for off in range(0, len(huge) - 4, 4):
+        probe = bytearray(good); probe[off:off + 4] = b"\xff\xff\xff\xff"
+        C.fuzz_unpack_meta(bytes(probe))
+
+
+@settings(max_examples=200, deadline=None)
+@given(i32, i32, i32, i32, i32, i32, st.booleans(), st.booleans(), st.booleans(), st.text(max_size=64), i32, i32,
+       st.lists(st.floats(width=32, allow_nan=False), max_size=4), st.sampled_from([0, 1, 2, 3, 4, 5]),
+       st.lists(st.tuples(st.integers(0, 7), i32, st.text(alphabet="abc.0123456789", max_size=24), st.integers(0, 65535)), max_size=4))
+def test_meta_roundtrip_is_exact(head, app, cust, ts, snd, rcv, req, push, simple, body, prio, key, compr, cmd, nodes):
+    _, back = runtime.C().pack_meta_fields(head, app, cust, ts, snd, rcv, req, push, simple, body, prio, key, compr, cmd, nodes)
+    want_nodes = nodes if cmd != 0 else []   # nodes only travel with a control command
+    assert tuple(back[:12]) == (head, app, cust, ts, snd, rcv, req, push, simple, body, prio, key)
+    assert list(back[12]) == pytest.approx(compr) and back[13] == cmd and [tuple(n) for n in back[14]] == [tuple(n) for n in want_nodes]
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(1, 300), st.floats(0.05, 4.0), st.integers(0, 2**31 - 1))
+def test_2bit_codec_contract(n, thr, seed):
+    g = torch.from_numpy(np.random.RandomState(seed).randn(n).astype(np.float32) * 2)
+    r = torch.zeros(n)
+    q = gc.quantize_2bit(g.clone(), r, thr)
+    d = gc.dequantize_2bit(q, n, thr)
+    assert set(np.unique(d.numpy())).issubset({-np.float32(thr), 0.0, np.float32(thr)})
+    assert torch.allclose(d + r, g, atol=1e-5)                        # nothing is lost: sent value + residual = gradient
+    assert float(r.abs().max()) <= max(float(g.abs().max()) - thr, thr) + 1e-5
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(64, 4000), st.floats(0.005, 0.2), st.integers(0, 2**31 - 1))
+def test_bsc_codec_contract(n, ratio, seed):
+    rs = np.random.RandomState(seed)
+    g = torch.from_numpy(rs.randn(n).astype(np.float32))
+    u, v = torch.zeros(n), torch.zeros(n)
+    out = gc.bsc_compress(g, u, v, ratio)
+    k = out.numel() // 2
+    if k == 0:                               # int(n * ratio) == 0 (the reference's truncation): nothing travels, the gradient stays in the accumulators
+        assert int(n * ratio) == 0 and torch.allclose(v, g) and torch.allclose(u, g)
+        return
+    vals, idx = out[:k], out[k:]
+    live = idx >= 0
+    ids = idx[live].long()
+    assert bool((ids[1:] > ids[:-1]).all()) and bool((ids < n).all())        # index-ordered, in range, sentinel-padded
+    dense = gc.bsc_decompress(out, n)
+    assert torch.equal(dense[ids], vals[live]) and float(dense.abs().sum()) == pytest.approx(float(vals[live].abs().sum()), rel=1e-5)
+    assert float(v[ids].abs().max()) == 0.0 if ids.numel() else True                      # error feedback cleared exactly where values were sent
