@@ -222,12 +222,25 @@ class DGTReceiver {
   bool Add(const Message& blk, Message* whole) {
     const Meta& m = blk.meta;
     if (cfg_.mode == 1 && m.channel > 0 && cfg_.loss_pct > 0 && static_cast<int>(rng_() % 100) < cfg_.loss_pct) return false;  // lost datagram
+    // A block comes off the wire (over UDP from anybody who can reach the port): every field is validated before it sizes or indexes
+    // memory; a block that does not fit the tensor it claims to belong to is dropped like a lost one.
+    if (blk.data.size() < 2 || m.total_bytes <= 0 || static_cast<size_t>(m.total_bytes) > kMaxTensorBytes) return false;
+    if (m.seq < 0 || m.seq_end < m.seq || m.val_bytes < 0 || m.val_bytes % static_cast<int>(sizeof(float)) != 0) return false;
+    const size_t off = static_cast<size_t>(m.seq) * static_cast<size_t>(cfg_.block_bytes);
+    const size_t total = static_cast<size_t>(m.total_bytes), want = static_cast<size_t>(m.val_bytes);
+    if (off > total || want > total - off) return false;
+    if (m.bits_num == 4) {
+      if (m.compr.size() < 2 || blk.data[1].size() < (want / sizeof(float) + 1) / 2) return false;
+    } else if (blk.data[1].size() < want) {
+      return false;
+    }
     const auto id = std::make_tuple(m.sender, m.first_key, m.timestamp);
+    if (pending_.size() >= kMaxPending && pending_.find(id) == pending_.end()) pending_.clear();   // partial tensors of senders that went away
     auto& st = pending_[id];
-    if (st.buf.size() == 0) { st.buf.resize(m.total_bytes, 0); st.keys = blk.data[0]; st.lens = blk.data.size() > 2 ? blk.data[2] : SArray<char>(); }
-    const int off = m.seq * cfg_.block_bytes;
-    if (m.bits_num == 4) DGTDecode4(blk.data[1].data(), m.val_bytes / sizeof(float), m.compr[0], m.compr[1], reinterpret_cast<float*>(st.buf.data() + off));
-    else memcpy(st.buf.data() + off, blk.data[1].data(), std::min<size_t>(m.val_bytes, blk.data[1].size()));
+    if (st.buf.size() == 0) { st.buf.resize(total, 0); st.keys = blk.data[0]; st.lens = blk.data.size() > 2 ? blk.data[2] : SArray<char>(); }
+    else if (st.buf.size() != total) return false;            // a block that disagrees with the first one about the tensor's size
+    if (m.bits_num == 4) DGTDecode4(blk.data[1].data(), want / sizeof(float), m.compr[0], m.compr[1], reinterpret_cast<float*>(st.buf.data() + off));
+    else memcpy(st.buf.data() + off, blk.data[1].data(), want);
     if (m.seq != m.seq_end) return false;
     whole->meta = m;
     whole->meta.msg_type = 0; whole->meta.channel = 0;
@@ -235,13 +248,15 @@ class DGTReceiver {
     whole->data.push_back(st.keys);
     whole->data.push_back(st.buf);
     SArray<char> lens; lens.resize(sizeof(int));
-    int total = m.total_bytes; memcpy(lens.data(), &total, sizeof(int));
+    int total_i = m.total_bytes; memcpy(lens.data(), &total_i, sizeof(int));
     whole->data.push_back(lens);
     pending_.erase(id);
     return true;
   }
 
  private:
+  static constexpr size_t kMaxTensorBytes = size_t(1) << 31;   // one key's tensor (2 GiB): larger claims are not honoured
+  static constexpr size_t kMaxPending = 4096;
   struct State { SArray<char> buf, keys, lens; };
   DGTConfig cfg_;
   std::mt19937 rng_;

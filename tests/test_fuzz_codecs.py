@@ -75,3 +75,20 @@ def test_bsc_codec_contract(n, ratio, seed):
     dense = gc.bsc_decompress(out, n)
     assert torch.equal(dense[ids], vals[live]) and float(dense.abs().sum()) == pytest.approx(float(vals[live].abs().sum()), rel=1e-5)
     assert float(v[ids].abs().max()) == 0.0 if ids.numel() else True                      # error feedback cleared exactly where values were sent
+
+
+@settings(max_examples=500, deadline=None)
+@given(i32, i32, i32, i32, st.sampled_from([0, 4, 32]), st.integers(0, 4), st.integers(0, 70000), st.integers(0, 3))
+def test_dgt_reassembly_rejects_inconsistent_blocks(seq, seq_end, total, val_bytes, bits, ncompr, payload, nparts):
+    """A DGT block header comes off the wire (UDP): offsets / sizes that do not fit the tensor they claim must be dropped, not written."""
+    done = runtime.C().fuzz_dgt_block(seq, seq_end, total, val_bytes, bits, ncompr, payload, nparts)
+    if done:                                          # a tensor was completed: then the block was the last one and fitted
+        assert seq == seq_end and 0 < total and 0 <= val_bytes <= total and nparts >= 2
+
+
+def test_dgt_reassembly_accepts_a_valid_tensor():
+    C = runtime.C()
+    # block size = DGT_BLOCK_SIZE (4096 bytes by default): a 2-block tensor of 6000 bytes
+    assert C.fuzz_dgt_block(0, 1, 6000, 4096, 32, 0, 4096, 2) is False
+    assert C.fuzz_dgt_block(1, 1, 6000, 1904, 32, 0, 1904, 2) is True
+    assert C.fuzz_dgt_block(1, 1, 6000, 4096, 32, 0, 4096, 2) is False      # would run past the end of the tensor
