@@ -63,6 +63,31 @@ class Topology:
         return list(range(g * self.party_size, (g + 1) * self.party_size))
 
 
+def global_tile_owners(topo, layout, protocol, bigarray_bound=1000000):
+    """World rank that plays global server for every 1024-float tile of ``layout`` (int32 array of ``layout.total // 1024`` entries).
+
+    * ``topo.tile_sharded`` (``DMLC_NUM_GLOBAL_SERVER`` unset) and a packet protocol: tile ``ti`` -> rank ``((ti // S) % P) * S + ti % S`` —
+      balanced over all ranks, and the owner is the tile's party owner inside its own party (the 3-hop LL kernel keeps one inter-tier hop local);
+    * ``tile_sharded`` with the flag ("bulk") protocol: its per-key ready flags need ONE owner per key -> whole keys, largest first onto the
+      least loaded rank;
+    * explicit ``num_gs``: the reference's placement over ``topo.gs_ranks`` (small keys hashed, big keys partitioned,
+      kvstore_dist_server.h:1770-1810)."""
+    T = layout.total // 1024
+    if topo.tile_sharded and protocol == "ll":
+        ti = np.arange(T)
+        return (((ti // topo.party_size) % topo.num_parties) * topo.party_size + ti % topo.party_size).astype(np.int32)
+    if topo.tile_sharded:
+        load = np.zeros(topo.world, dtype=np.int64)
+        owners = np.zeros(T, dtype=np.int32)
+        for sl in sorted(layout.slots, key=lambda s: -s.tiles):
+            r = int(np.argmin(load))
+            load[r] += sl.tiles
+            owners[sl.offset // 1024: sl.offset // 1024 + sl.tiles] = r
+        return owners
+    owner_idx = layout.global_owner_index(topo.num_gs, bigarray_bound)
+    return np.array([topo.gs_ranks[i] for i in owner_idx], dtype=np.int32)
+
+
 # ------------------------------------------------------------------------------------------------------------ symmetric heap
 class SymmetricBuffer:
     """A tensor allocated at the same size on every rank of ``group`` with peer-mapped pointers (+ multicast address if NVLS)."""
@@ -249,22 +274,7 @@ class HipsFabric:
         dev = self.device
         self.tile_key = torch.from_numpy(layout.tile_key()).to(dev)
         self.key_tiles = torch.from_numpy(layout.key_tiles()).to(dev)
-        if t.tile_sharded and self.protocol == "ll":
-            # tile ti -> rank ((ti // S) % P) * S + ti % S: balanced over all ranks, and the owner is the tile's party owner inside its own party
-            # (the 3-hop LL kernel then keeps one of the inter-tier hops local)
-            ti = np.arange(T)
-            self.tile_owner_np = (((ti // t.party_size) % t.num_parties) * t.party_size + ti % t.party_size).astype(np.int32)
-        elif t.tile_sharded:
-            # flag ("bulk") protocol: its per-key ready flags need ONE owner per key -> whole keys, largest first onto the least loaded rank
-            load = np.zeros(t.world, dtype=np.int64)
-            self.tile_owner_np = np.zeros(T, dtype=np.int32)
-            for sl in sorted(layout.slots, key=lambda s: -s.tiles):
-                r = int(np.argmin(load))
-                load[r] += sl.tiles
-                self.tile_owner_np[sl.offset // 1024: sl.offset // 1024 + sl.tiles] = r
-        else:
-            owner_idx = layout.global_owner_index(t.num_gs, getenv_int("MXNET_KVSTORE_BIGARRAY_BOUND", 1000000))
-            self.tile_owner_np = np.array([t.gs_ranks[i] for i in owner_idx], dtype=np.int32)
+        self.tile_owner_np = global_tile_owners(t, layout, self.protocol, getenv_int("MXNET_KVSTORE_BIGARRAY_BOUND", 1000000))
         self.tile_owner = torch.from_numpy(self.tile_owner_np).to(dev)
         self.tile_mult = torch.from_numpy(layout.tile_mult()).to(dev)
         self.tile_active = torch.ones(T, dtype=torch.uint8, device=dev)

@@ -54,6 +54,32 @@ def test_key_sharding_rules():
     assert list(lay.tile_key()) == [0, 1, 2, 2, 2, 2, 2, 3]
 
 
+def test_fabric_global_tile_ownership():
+    """Who plays global server for a tile on the fabric: sharded over ALL ranks by default (balanced; the owner is the tile's party owner
+    inside its own party), whole keys per rank for the flag protocol, the reference's hashing / partitioning when DMLC_NUM_GLOBAL_SERVER is given."""
+    import numpy as np
+    from geomx_b200.models.cnn import CNN_PARAM_SHAPES
+    from geomx_b200.parallel.fabric import Topology, global_tile_owners
+    lay = ArenaLayout.build(list(enumerate(CNN_PARAM_SHAPES)))
+    T = lay.total // TILE
+    for world, parties in ((8, 2), (8, 4), (4, 2), (2, 2), (2, 1), (1, 1)):
+        topo = Topology(world, 0, parties, 0)
+        assert topo.tile_sharded and topo.num_gs == world and sorted(topo.gs_ranks) == list(range(world))
+        own = global_tile_owners(topo, lay, "ll")
+        cnt = np.bincount(own, minlength=world)
+        assert own.shape == (T,) and cnt.max() - cnt.min() <= 1                       # balanced to within one tile
+        assert ((own % topo.party_size) == (np.arange(T) % topo.party_size)).all()    # global owner = the tile's party owner in its own party
+        bulk = global_tile_owners(topo, lay, "bulk")
+        for sl in lay.slots:                                                           # one owner per key
+            assert len(set(bulk[sl.offset // TILE: sl.offset // TILE + sl.tiles].tolist())) == 1
+        assert np.bincount(bulk, minlength=world).max() == max(s.tiles for s in lay.slots) or world == 1
+    topo = Topology(8, 3, 2, 2)                                                        # two explicit global servers: ranks 0 and 4 (one per party)
+    assert not topo.tile_sharded and topo.gs_ranks == [0, 4]
+    own = global_tile_owners(topo, lay, "ll", bigarray_bound=1000000)
+    assert set(own.tolist()) <= {0, 4}
+    assert [int(own[s.offset // TILE]) for s in lay.slots] == [topo.gs_ranks[(i * 9973) % 2] for i in range(len(lay.slots))]
+
+
 def test_2bit_bit_layout_and_residual():
     # posbits {0xc0,0x30,0x0c,0x03}: value j of a 16-value word lives in byte j>>2, bit pair 6-2*(j&3); 11=+thr 10=-thr 00=0
     g = torch.zeros(16); g[0] = 1.0; g[1] = -1.0; g[5] = 0.7; g[15] = -0.2
