@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 
 from . import base  # noqa: F401
 from .base import MXNetError  # noqa: F401
-from .context import Context, cpu, cpu_pinned, current_context, gpu, num_gpus  # noqa: F401
+from .context import Context, cpu, cpu_pinned, cpu_shared, current_context, gpu, num_gpus  # noqa: F401
 from . import ndarray  # noqa: F401
 from . import ndarray as nd  # noqa: F401
 from . import autograd  # noqa: F401

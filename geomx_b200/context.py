@@ -13,7 +13,7 @@ import torch
 
 from .base import MXNetError
 
-__all__ = ["Context", "cpu", "gpu", "cpu_pinned", "current_context", "num_gpus"]
+__all__ = ["Context", "cpu", "gpu", "cpu_pinned", "cpu_shared", "current_context", "num_gpus"]
 
 
 class Context:
@@ -38,6 +38,16 @@ class Context:
         if self.device_typeid == 2:
             return torch.device("cuda", self.device_id)
         return torch.device("cpu")
+
+    def place(self, t: torch.Tensor) -> torch.Tensor:
+        """Give ``t`` (already on ``torch_device``) the storage kind of this context: ``cpu_pinned`` = page-locked host memory (asynchronous
+        H2D / D2H copies; reference ``Context::CPUPinned``, src/storage/pinned_memory_storage.h), ``cpu_shared`` = POSIX shared memory that
+        other processes can map (reference ``Context::CPUShared``, src/storage/cpu_shared_storage_manager.h — the DataLoader hand-off)."""
+        if self.device_typeid == 3 and t.device.type == "cpu" and torch.cuda.is_available() and not t.is_pinned():
+            return t.pin_memory()
+        if self.device_typeid == 5 and t.device.type == "cpu" and not t.is_shared():
+            return t.share_memory_()
+        return t
 
     def check_available(self):
         if self.device_typeid == 2:
@@ -77,6 +87,10 @@ def cpu(device_id=0):
 
 def cpu_pinned(device_id=0):
     return Context("cpu_pinned", device_id)
+
+
+def cpu_shared(device_id=0):
+    return Context("cpu_shared", device_id)
 
 
 def gpu(device_id=0):

@@ -195,8 +195,10 @@ class NDArray:
         ctx = _ctx_of(ctx)
         ctx.check_available()
         if ctx.torch_device == self._data.device:
+            if ctx.device_typeid in (3, 5) and ctx != self.context:       # same device, other storage kind (pinned / shared host memory)
+                return NDArray(ctx.place(self._t.clone()), ctx)
             return self
-        return NDArray(self._t.to(ctx.torch_device, non_blocking=True), ctx)
+        return NDArray(ctx.place(self._t.to(ctx.torch_device, non_blocking=True)), ctx)
 
     def copyto(self, other):
         if isinstance(other, NDArray):
@@ -206,7 +208,7 @@ class NDArray:
             return other
         ctx = _ctx_of(other)
         ctx.check_available()
-        return NDArray(self._t.to(ctx.torch_device, copy=True), ctx)
+        return NDArray(ctx.place(self._t.to(ctx.torch_device, copy=True)), ctx)
 
     def copy(self):
         return NDArray(self._t.clone(), self._ctx_hint)
@@ -426,15 +428,15 @@ def array(source, ctx=None, dtype=None):
     ctx.check_available()
     if isinstance(source, NDArray):
         t = source._t.to(ctx.torch_device, copy=True)
-        return NDArray(t if dtype is None else t.to(torch_dtype(dtype)), ctx)
+        return NDArray(ctx.place(t if dtype is None else t.to(torch_dtype(dtype))), ctx)
     if isinstance(source, torch.Tensor):
         t = source.detach().to(ctx.torch_device, copy=True)          # mx.nd.array always copies (zero-copy wrapping is ``from_torch``)
-        return NDArray(t if dtype is None else t.to(torch_dtype(dtype)), ctx)
+        return NDArray(ctx.place(t if dtype is None else t.to(torch_dtype(dtype))), ctx)
     a = np.asarray(source)
     if dtype is None:
         dtype = a.dtype if isinstance(source, np.ndarray) and a.dtype != np.float64 else "float32"
     t = torch.tensor(a).to(torch_dtype(dtype))                       # torch.tensor copies: the NDArray never aliases the numpy buffer
-    return NDArray(t.to(ctx.torch_device), ctx)
+    return NDArray(ctx.place(t.to(ctx.torch_device)), ctx)
 
 
 def _shape(shape):
@@ -443,22 +445,22 @@ def _shape(shape):
 
 def zeros(shape, ctx=None, dtype=None, **kw):
     ctx = _ctx_of(ctx); ctx.check_available()
-    return NDArray(torch.zeros(_shape(shape), dtype=torch_dtype(dtype), device=ctx.torch_device), ctx)
+    return NDArray(ctx.place(torch.zeros(_shape(shape), dtype=torch_dtype(dtype), device=ctx.torch_device)), ctx)
 
 
 def ones(shape, ctx=None, dtype=None, **kw):
     ctx = _ctx_of(ctx); ctx.check_available()
-    return NDArray(torch.ones(_shape(shape), dtype=torch_dtype(dtype), device=ctx.torch_device), ctx)
+    return NDArray(ctx.place(torch.ones(_shape(shape), dtype=torch_dtype(dtype), device=ctx.torch_device)), ctx)
 
 
 def empty(shape, ctx=None, dtype=None):
     ctx = _ctx_of(ctx); ctx.check_available()
-    return NDArray(torch.empty(_shape(shape), dtype=torch_dtype(dtype), device=ctx.torch_device), ctx)
+    return NDArray(ctx.place(torch.empty(_shape(shape), dtype=torch_dtype(dtype), device=ctx.torch_device)), ctx)
 
 
 def full(shape, val, ctx=None, dtype=None):
     ctx = _ctx_of(ctx); ctx.check_available()
-    return NDArray(torch.full(_shape(shape), val, dtype=torch_dtype(dtype), device=ctx.torch_device), ctx)
+    return NDArray(ctx.place(torch.full(_shape(shape), val, dtype=torch_dtype(dtype), device=ctx.torch_device)), ctx)
 
 
 def arange(start, stop=None, step=1.0, repeat=1, ctx=None, dtype=None):

@@ -147,6 +147,12 @@ def test_dataloader_and_split_sampler():
     assert X.shape == (32, 1, 28, 28) and y.shape == (32,) and float(X.max().asscalar()) <= 1.0
     parts = mx.gluon.utils.split_and_load(X, [mx.cpu()])
     assert parts[0].shape == (32, 1, 28, 28)
+    # thread workers and process workers (batches come back through shared memory) deliver the same batches in the same order
+    small = mx.gluon.data.ArrayDataset(np.random.RandomState(0).rand(50, 3, 4).astype(np.float32), np.arange(50, dtype=np.float32))
+    ref = [(a.asnumpy(), b.asnumpy()) for a, b in mx.gluon.data.DataLoader(small, batch_size=8)]
+    for kw in ({"num_workers": 2}, {"num_workers": 2, "worker_type": "process"}, {"num_workers": 3, "worker_type": "process", "prefetch": 2}):
+        got = [(a.asnumpy(), b.asnumpy()) for a, b in mx.gluon.data.DataLoader(small, batch_size=8, **kw)]
+        assert len(got) == len(ref) == 7 and all((p[0] == q[0]).all() and (p[1] == q[1]).all() for p, q in zip(ref, got)), kw
 
 
 def test_row_sparse_ndarray_and_local_kvstore():
@@ -333,6 +339,27 @@ def test_callbacks_monitor_and_test_utils(caplog):
     assert "fc_weight" in names and "fc_weight_grad" in names
     mx.test_utils.check_numeric_gradient(lambda a, w: mx.nd.dot(a, w).tanh() * 2.0, [np.random.randn(3, 4), np.random.randn(4, 2)])
     mx.test_utils.assert_almost_equal(mx.nd.array([1.0, 2.0]), np.array([1.0, 2.0 + 1e-7]))
+
+
+def test_cpu_shared_and_pinned_contexts():
+    """mx.cpu_shared(): POSIX shared memory another process can map (CPUSharedStorageManager, the DataLoader hand-off); mx.cpu_pinned():
+    page-locked memory when a CUDA driver is present, plain host memory otherwise."""
+    import torch.multiprocessing as tmp
+    a = mx.nd.array(np.arange(6, dtype=np.float32).reshape(2, 3), ctx=mx.cpu_shared())
+    assert str(a.context) == "cpu_shared(0)" and a._t.is_shared()
+    b = mx.nd.zeros((4,), ctx=mx.cpu_shared(0))
+    ctx = tmp.get_context("spawn")
+    p = ctx.Process(target=_write_shared, args=(b._t,))
+    p.start(); p.join(60)
+    assert p.exitcode == 0 and b.asnumpy().tolist() == [1.0, 2.0, 3.0, 4.0]      # the child wrote into the same pages
+    c = mx.nd.ones((3,)).as_in_context(mx.cpu_shared())
+    assert c._t.is_shared() and str(c.context) == "cpu_shared(0)"
+    d = mx.nd.array([1, 2, 3], ctx=mx.cpu_pinned())
+    assert str(d.context) == "cpu_pinned(0)" and d._t.is_pinned() == torch.cuda.is_available()
+
+
+def _write_shared(t):
+    t.copy_(torch.tensor([1.0, 2.0, 3.0, 4.0]))
 
 
 def test_engine_device_pools_exceptions_and_delete():
