@@ -468,7 +468,12 @@ _register_families()
 
 def get_model(name, pretrained=False, **kwargs):
     if pretrained:
-        raise MXNetError("pretrained weights are not available offline; load a .params file with net.load_parameters")
+        # no download: the file must already be in the model store (model_store.get_model_file explains where it looked)
+        from .model_store import get_model_file
+        path = get_model_file(name, root=kwargs.pop("root", None))
+        net = get_model(name, pretrained=False, **{k: v for k, v in kwargs.items() if k != "ctx"})
+        net.load_parameters(path, ctx=kwargs.get("ctx"))
+        return net
     name = name.lower()
     if name not in _models:
         raise MXNetError("Model %s is not supported. Available: %s" % (name, ", ".join(sorted(_models))))

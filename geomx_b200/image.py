@@ -381,3 +381,18 @@ class ImageIter(_io.DataIter):
 
 
 from .image_detection import *  # noqa: E402,F401,F403  (mx.image.ImageDetIter, Det*Aug, CreateDetAugmenter)
+
+
+# the reference's package layout (python/mxnet/image/{image,detection}.py) as importable paths
+def _register_paths():
+    import sys
+    from ._alias import submodule
+    from . import image_detection as _det
+    g = globals()
+    own = {k: v for k, v in g.items() if not k.startswith("_") and getattr(v, "__module__", None) == __name__}
+    submodule(__name__, "image", own)
+    sys.modules[__name__ + ".detection"] = _det
+    g["detection"] = _det
+
+
+_register_paths()

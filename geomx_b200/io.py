@@ -312,3 +312,15 @@ class ImageRecordIter(DataIter):
         data = NDArray(torch.from_numpy(np.ascontiguousarray(np.stack(xs))))
         label = NDArray(torch.from_numpy(np.asarray(ys, dtype=np.float32)))
         return DataBatch([data], [label], pad=pad)
+
+
+# the reference's package layout (python/mxnet/io/{io,utils}.py) as importable paths
+def _register_paths():
+    from ._alias import submodule
+    g = globals()
+    names = [k for k, v in g.items() if isinstance(v, type) and (issubclass(v, DataIter) or k in ("DataBatch", "DataDesc"))]
+    submodule(__name__, "io", {k: g[k] for k in names})
+    submodule(__name__, "utils", {k: g[k] for k in ("_init_data", "_has_instance", "_getdata_by_idx") if k in g})
+
+
+_register_paths()

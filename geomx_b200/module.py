@@ -642,3 +642,16 @@ class PythonLossModule(PythonModule):
 
     def install_monitor(self, mon):
         raise NotImplementedError
+
+
+# the reference's package layout (python/mxnet/module/*.py) as importable paths
+def _register_paths():
+    from ._alias import submodule
+    submodule(__name__, "base_module", {"BaseModule": BaseModule})
+    submodule(__name__, "module", {"Module": Module})
+    submodule(__name__, "bucketing_module", {"BucketingModule": BucketingModule})
+    submodule(__name__, "sequential_module", {"SequentialModule": SequentialModule})
+    submodule(__name__, "python_module", {"PythonModule": PythonModule, "PythonLossModule": PythonLossModule})
+
+
+_register_paths()

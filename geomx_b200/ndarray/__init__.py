@@ -11,6 +11,7 @@ for _n in _op_lib.__all__:
         globals()[_n] = getattr(_op_lib, _n)
 del _n
 from . import contrib  # noqa: F401,E402
+from . import _internal, image, linalg, op  # noqa: F401,E402
 from .random import (exponential as random_exponential, gamma as random_gamma, generalized_negative_binomial as random_generalized_negative_binomial,  # noqa: F401,E402
                      multinomial as sample_multinomial, negative_binomial as random_negative_binomial, normal as random_normal, poisson as random_poisson,
                      randint as random_randint, uniform as random_uniform)

@@ -467,15 +467,28 @@ def _nd_op(qual):
     return build
 
 
-class _ContribNamespace:
-    def __getattr__(self, item):
-        from .ndarray import contrib as ndc
-        if item.startswith("_") or not callable(getattr(ndc, item, None)):
-            raise AttributeError("mx.sym.contrib has no operator %r" % item)
-        return _nd_op("contrib." + item)
+def _namespace(sub, target):
+    """``mx.sym.<sub>``: the symbolic forms of the operators in ``mx.nd.<target>`` (reference: python/mxnet/symbol/{contrib,linalg,random,
+    sparse,image,op,_internal}.py, generated from the operator registry).  Also importable as ``<package>.symbol.<sub>``."""
+    def lookup(item):
+        from . import ndarray as nd
+        ns = nd
+        for part in (target.split(".") if target else ()):
+            ns = getattr(ns, part)
+        if item.startswith("__") or not callable(getattr(ns, item, None)) or isinstance(getattr(ns, item), type):
+            raise AttributeError("mx.sym.%s has no operator %r" % (sub, item))
+        return _nd_op((target + "." if target else "") + item)
+    from ._alias import submodule
+    return submodule(__name__, sub, getattr_fn=lookup, doc="mx.sym.%s operator namespace" % sub)
 
 
-contrib = _ContribNamespace()
+contrib = _namespace("contrib", "contrib")
+linalg = _namespace("linalg", "linalg")
+random = _namespace("random", "random")
+sparse = _namespace("sparse", "sparse")
+image = _namespace("image", "image")
+op = _namespace("op", "")
+_internal = _namespace("_internal", "_internal")
 
 
 def __getattr__(item):
@@ -725,3 +738,14 @@ def _attach_symbol_fluent():
 
 
 _attach_symbol_fluent()
+
+
+# the reference's sub-module paths (python/mxnet/symbol/{symbol,register}.py)
+def _register_paths():
+    from ._alias import submodule
+    g = globals()
+    submodule(__name__, "symbol", {k: g[k] for k in ("Symbol", "Variable", "var", "Group", "load", "load_json") if k in g})
+    submodule(__name__, "register", {"_nd_op": _nd_op}, doc="operators are bridged from mx.nd on attribute access: nothing to generate")
+
+
+_register_paths()

@@ -1,0 +1,125 @@
+"""Operator namespaces and sub-module import paths of the reference that user code relies on: mx.nd.{linalg,image,op,_internal},
+mx.sym.{linalg,random,sparse,image,op,contrib}, mxnet.{module,io,image,symbol}.<submodule>, optimizer.contrib, gluon.nn.activations,
+gluon.model_zoo.model_store."""
+import hashlib
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import geomx_b200 as mx
+
+
+def test_reference_import_paths_exist():
+    for p in ["gluon.nn.activations", "gluon.model_zoo.model_store", "ndarray.image", "ndarray.linalg", "ndarray._internal", "ndarray.op",
+              "symbol.linalg", "symbol.contrib", "symbol.random", "symbol.sparse", "symbol.image", "symbol.op", "symbol.symbol", "symbol._internal",
+              "symbol.register", "module.base_module", "module.bucketing_module", "module.module", "module.python_module", "module.sequential_module",
+              "io.io", "io.utils", "image.detection", "image.image", "optimizer.contrib", "optimizer.optimizer", "rnn.rnn_cell", "rnn.rnn", "rnn.io"]:
+        importlib.import_module("geomx_b200." + p)
+    from geomx_b200.image.detection import ImageDetIter
+    from geomx_b200.image.image import ImageIter
+    from geomx_b200.io.io import DataIter, NDArrayIter
+    from geomx_b200.module.base_module import BaseModule
+    from geomx_b200.module.module import Module
+    from geomx_b200.symbol.symbol import Symbol
+    assert issubclass(Module, BaseModule) and issubclass(NDArrayIter, DataIter) and issubclass(ImageDetIter, ImageIter) and Symbol is mx.sym.Symbol
+    assert mx.mod.Module is Module and mx.io.NDArrayIter is NDArrayIter
+
+
+def test_nd_linalg_namespace():
+    rs = np.random.RandomState(0)
+    a = rs.rand(2, 4, 4).astype(np.float32)
+    spd = a @ a.transpose(0, 2, 1) + 4 * np.eye(4, dtype=np.float32)
+    A = mx.nd.array(spd)
+    L = mx.nd.linalg.potrf(A)
+    assert np.allclose(mx.nd.linalg.gemm2(L, L, transpose_b=True).asnumpy(), spd, atol=1e-4)
+    assert np.allclose(mx.nd.linalg.sumlogdiag(L).asnumpy() * 2, np.linalg.slogdet(spd)[1], atol=1e-4)
+    sign, logdet = mx.nd.linalg.slogdet(A)
+    assert np.allclose(sign.asnumpy(), 1.0) and np.allclose(logdet.asnumpy(), np.linalg.slogdet(spd)[1], atol=1e-4)
+    tri = mx.nd.linalg.extracttrian(A)
+    assert tri.shape == (2, 10) and np.allclose(mx.nd.linalg.maketrian(tri).asnumpy(), np.tril(spd))
+    up = mx.nd.linalg.extracttrian(A, offset=1)
+    assert up.shape == (2, 6) and np.allclose(mx.nd.linalg.maketrian(up, offset=1).asnumpy(), np.triu(spd, 1))
+    assert np.allclose(mx.nd.linalg.inverse(A).asnumpy() @ spd, np.broadcast_to(np.eye(4), (2, 4, 4)), atol=1e-3)
+
+
+def test_nd_image_namespace():
+    rs = np.random.RandomState(1)
+    img = mx.nd.array(rs.randint(0, 256, (8, 6, 3)).astype(np.uint8))
+    t = mx.nd.image.to_tensor(img)
+    assert t.shape == (3, 8, 6) and t.dtype == np.float32 and float(t.max().asscalar()) <= 1.0
+    n = mx.nd.image.normalize(t, mean=(0.5, 0.4, 0.3), std=(0.2, 0.2, 0.2))
+    assert np.allclose(n.asnumpy()[1], (t.asnumpy()[1] - 0.4) / 0.2, atol=1e-6)
+    assert np.array_equal(mx.nd.image.flip_left_right(img).asnumpy(), img.asnumpy()[:, ::-1]) and np.array_equal(mx.nd.image.flip_top_bottom(img).asnumpy(), img.asnumpy()[::-1])
+    assert mx.nd.image.resize(img, (12, 16)).shape == (16, 12, 3) and mx.nd.image.resize(img, 12, keep_ratio=True).shape == (16, 12, 3)
+    assert mx.nd.image.crop(img, 1, 2, 3, 4).shape == (4, 3, 3)
+    for fn in (lambda x: mx.nd.image.random_brightness(x, 0.5, 1.5), lambda x: mx.nd.image.random_contrast(x, 0.5, 1.5),
+               lambda x: mx.nd.image.random_saturation(x, 0.5, 1.5), lambda x: mx.nd.image.random_hue(x, -0.1, 0.1),
+               lambda x: mx.nd.image.random_color_jitter(x, 0.2, 0.2, 0.2, 0.05), lambda x: mx.nd.image.random_lighting(x, 0.1)):
+        o = fn(img)
+        assert o.shape == img.shape and o.dtype == np.uint8
+    assert np.array_equal(mx.nd.image.random_saturation(img, 1.0, 1.0).asnumpy(), img.asnumpy())       # factor 1 is the identity
+    assert np.array_equal(mx.nd.image.adjust_lighting(img, (0.0, 0.0, 0.0)).asnumpy(), img.asnumpy())
+
+
+def test_nd_op_and_internal_namespaces():
+    a = mx.nd.array([[1.0, -2.0], [3.0, 4.0]])
+    assert np.array_equal(mx.nd.op.relu(a).asnumpy(), [[1, 0], [3, 4]]) and mx.nd.op.zeros((2, 3)).shape == (2, 3)
+    I = mx.nd._internal
+    assert np.array_equal(I._plus_scalar(a, 1).asnumpy(), a.asnumpy() + 1) and np.array_equal(I._rminus_scalar(a, 1).asnumpy(), 1 - a.asnumpy())
+    assert np.array_equal(I._rdiv_scalar(a, 2).asnumpy(), 2 / a.asnumpy()) and np.array_equal(I._greater_scalar(a, 0).asnumpy(), (a.asnumpy() > 0))
+    assert np.array_equal(I._mul(a, a).asnumpy(), a.asnumpy() ** 2) and np.array_equal(I._lesser_equal(a, a).asnumpy(), np.ones((2, 2)))
+    out = mx.nd.zeros((2, 2)); I._set_value(7.0, out=out)
+    assert np.array_equal(out.asnumpy(), np.full((2, 2), 7.0)) and I._zeros((3,)).shape == (3,) and I._full((2,), 5).asnumpy().tolist() == [5, 5]
+    assert I._random_uniform(0, 1, shape=(4,)).shape == (4,) and np.array_equal(I._copyto(a, out=out).asnumpy(), a.asnumpy())
+    with pytest.raises(AttributeError):
+        I._no_such_operator
+
+
+def test_sym_namespaces():
+    a = mx.sym.Variable("a")
+    g = mx.sym.linalg.gemm2(a, a, transpose_b=True)
+    x = np.arange(6, dtype=np.float32).reshape(2, 3)
+    assert np.allclose(g.bind(mx.cpu(), {"a": mx.nd.array(x)}).forward()[0].asnumpy(), x @ x.T)
+    assert mx.sym.random.uniform(low=0, high=1, shape=(2, 3)).bind(mx.cpu(), {}).forward()[0].shape == (2, 3)
+    assert np.array_equal(mx.sym.op.relu(a).bind(mx.cpu(), {"a": mx.nd.array(x - 2)}).forward()[0].asnumpy(), np.maximum(x - 2, 0))
+    img = mx.sym.image.to_tensor(a)
+    assert img.bind(mx.cpu(), {"a": mx.nd.array(np.zeros((4, 5, 3), dtype=np.uint8))}).forward()[0].shape == (3, 4, 5)
+    assert np.array_equal(mx.sym._internal._plus_scalar(a, scalar=2.0).bind(mx.cpu(), {"a": mx.nd.array(x)}).forward()[0].asnumpy(), x + 2)
+    with pytest.raises(AttributeError):
+        mx.sym.linalg.no_such_op
+
+
+def test_group_adagrad_and_model_store(tmp_path):
+    o = mx.optimizer.create("groupadagrad", learning_rate=0.1)
+    assert isinstance(o, mx.optimizer.contrib.GroupAdaGrad)
+    w, g = mx.nd.ones((4, 3)), mx.nd.array(np.arange(12, dtype=np.float32).reshape(4, 3))
+    st = o.create_state(0, w)
+    o.update(0, w, g, st)
+    h = (g.asnumpy() ** 2).mean(1, keepdims=True)
+    assert np.allclose(st.asnumpy(), h) and np.allclose(w.asnumpy(), 1 - 0.1 * g.asnumpy() / np.sqrt(h + 1e-5), atol=1e-6)
+    with pytest.raises(Exception):
+        mx.optimizer.contrib.GroupAdaGrad(wd=0.1).update(0, w, g, st)
+    # model store: resolves files that are already there (hash-tagged names are verified), explains itself otherwise
+    store = mx.gluon.model_zoo.model_store
+    net = mx.gluon.model_zoo.vision.get_model("squeezenet1.1", classes=10)
+    net.initialize(); net(mx.nd.zeros((1, 3, 64, 64)))
+    f = str(tmp_path / "squeezenet1.1.params")
+    net.save_parameters(f)
+    assert store.get_model_file("squeezenet1.1", root=str(tmp_path)) == f
+    tag = hashlib.sha1(open(f, "rb").read()).hexdigest()[:8]
+    tagged = str(tmp_path / ("squeezenet1.1-%s.params" % tag))
+    os.rename(f, tagged)
+    assert store.get_model_file("squeezenet1.1", root=str(tmp_path)) == tagged and store.short_hash("squeezenet1.1", str(tmp_path)) == tag
+    net2 = mx.gluon.model_zoo.vision.get_model("squeezenet1.1", pretrained=True, root=str(tmp_path), classes=10)
+    x = mx.nd.array(np.random.RandomState(0).rand(1, 3, 64, 64).astype(np.float32))
+    assert np.allclose(net2(x).asnumpy(), net(x).asnumpy(), atol=1e-5)
+    with open(tagged, "ab") as fh:
+        fh.write(b"x")
+    with pytest.raises(mx.MXNetError, match="does not match the hash"):
+        store.get_model_file("squeezenet1.1", root=str(tmp_path))
+    with pytest.raises(mx.MXNetError, match="no parameter file"):
+        store.get_model_file("resnet18_v1", root=str(tmp_path))
+    store.purge(str(tmp_path))
+    assert not os.listdir(str(tmp_path))
