@@ -56,6 +56,14 @@ class Initializer:
         name = str(desc)
         t = arr._t if hasattr(arr, "_t") else arr
         t = t.detach()
+        own = getattr(desc, "attrs", None) and desc.attrs.get("__init__")
+        if own:                                   # the variable names its own initializer (mx.sym.Variable(..., init=...)): it wins
+            import json
+            klass, kwargs = json.loads(own)
+            if getattr(desc, "global_init", None) is None and isinstance(desc, InitDesc):
+                desc.global_init = self          # composite initializers (FusedRNN) fill their blocks with the caller's initializer
+            create(klass, **kwargs)._init_weight(desc, t)
+            return
         if name.endswith("weight"):
             self._init_weight(name, t)
         elif name.endswith("bias"):
@@ -226,7 +234,7 @@ class FusedRNN(Initializer):
                 for cols in (cin, h):
                     n = gates * h * cols
                     block = flat[pos:pos + n].view(gates * h, cols)
-                    (self._init or Uniform(0.07))._init_weight(desc, block)
+                    (self._init or getattr(desc, "global_init", None) or Uniform(0.07))._init_weight(str(desc).replace("parameters", "weight"), block)
                     pos += n
         bias = flat[pos:]
         bias.zero_()

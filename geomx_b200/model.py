@@ -74,7 +74,7 @@ def _update_params(param_arrays, grad_arrays, updater, num_device, kvstore=None,
 def save_checkpoint(prefix, epoch, symbol, arg_params, aux_params):
     if symbol is not None:
         with open("%s-symbol.json" % prefix, "w") as f:
-            f.write(symbol if isinstance(symbol, str) else json.dumps(symbol))
+            f.write(symbol if isinstance(symbol, str) else symbol.tojson() if hasattr(symbol, "tojson") else json.dumps(symbol))
     save_dict = {("arg:%s" % k): v for k, v in arg_params.items()}
     save_dict.update({("aux:%s" % k): v for k, v in (aux_params or {}).items()})
     param_name = "%s-%04d.params" % (prefix, epoch)

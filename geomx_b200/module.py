@@ -218,6 +218,7 @@ class Module(BaseModule):
         ex0 = self._execs[0]
         self._arg_params = {n: nd.zeros(ex0.arg_dict[n].shape) for n in self._param_names}
         self._aux_params = {n: nd.zeros(ex0.aux_dict[n].shape) for n in self._aux_names}
+        attrs = self._symbol.attr_dict() if hasattr(self._symbol, "attr_dict") else {}
         for name, arr in list(self._arg_params.items()) + list(self._aux_params.items()):
             given = (arg_params or {}).get(name) if name in self._arg_params else (aux_params or {}).get(name)
             if given is not None:
@@ -225,7 +226,7 @@ class Module(BaseModule):
             elif (arg_params is not None or aux_params is not None) and not allow_missing and name in self._arg_params and arg_params is not None:
                 raise MXNetError("%s is not presented" % name)
             else:
-                initializer(init_mod.InitDesc(name), arr)
+                initializer(init_mod.InitDesc(name, attrs.get(name)), arr)
         self.params_initialized = True
         self._sync_params_to_devices()
 

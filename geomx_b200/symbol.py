@@ -54,6 +54,8 @@ class Symbol:
     def __mul__(self, o): return _binary("_mul", self, o)
     __rmul__ = __mul__
     def __truediv__(self, o): return _binary("_div", self, o)
+    def __rsub__(self, o): return _binary("_plus", -self, o)                      # scalar - symbol
+    def __rtruediv__(self, o): return _binary("_mul", _nd_op("reciprocal")(self), o)   # scalar / symbol
     def __getitem__(self, i):
         if self.op == "_nd" and isinstance(i, int) and (i > 0 or self.attrs.get("kwargs", {}).get("num_outputs", 1) > 1 or self.attrs.get("multi")):
             # i-th output of a multi-output imperative op (split / SliceChannel / topk(ret_typ='both') / RNN(state_outputs=True) …)
@@ -218,8 +220,25 @@ def load(fname):
         return load_json(f.read())
 
 
-def Variable(name, shape=None, **kw):
-    return Symbol("null", name, attrs={"__shape__": tuple(shape)} if shape else None)
+def Variable(name, shape=None, init=None, lr_mult=None, wd_mult=None, dtype=None, attr=None, **kw):
+    """A named input of the graph.  ``init`` (the Initializer ``Module.init_params`` uses for this variable instead of the global one),
+    ``lr_mult`` / ``wd_mult``, ``dtype`` and free-form ``attr`` become node attributes (``__init__``, ``__lr_mult__`` ... as in
+    python/mxnet/symbol/symbol.py:var), visible through ``list_attr()`` / ``attr_dict()``."""
+    user = {str(k): str(v) for k, v in (attr or {}).items()}
+    if init is not None:
+        user["__init__"] = init if isinstance(init, str) else init.dumps()
+    if lr_mult is not None:
+        user["__lr_mult__"] = str(lr_mult)
+    if wd_mult is not None:
+        user["__wd_mult__"] = str(wd_mult)
+    if dtype is not None:
+        user["__dtype__"] = str(dtype)
+    attrs = {}
+    if shape:
+        attrs["__shape__"] = tuple(shape)
+    if user:
+        attrs["__attr__"] = user
+    return Symbol("null", name, attrs=attrs or None)
 
 
 var = Variable
@@ -442,6 +461,17 @@ def _nd_param_shape(a, pname, in_shape):
         return (in_shape[int(kw.get("axis", -1))],)
     if fn == "InstanceNorm":
         return (in_shape[1],)
+    if fn == "RNN" and pname == "parameters":
+        # one flat vector: per layer and direction W_i2h [G*H, C_in] and W_h2h [G*H, H], then as many bias pairs (src/operator/rnn-inl.h)
+        H, L, D = int(kw["state_size"]), int(kw.get("num_layers", 1)), 2 if kw.get("bidirectional") else 1
+        G = {"rnn_relu": 1, "rnn_tanh": 1, "lstm": 4, "gru": 3}[kw.get("mode", "lstm")]
+        total = 0
+        for layer in range(L):
+            cin = in_shape[2] if layer == 0 else D * H
+            total += D * (G * H * (cin + H) + 2 * G * H)
+        return (total,)
+    if fn == "RNN" and pname in ("state", "state_cell"):
+        return ((int(kw.get("num_layers", 1)) * (2 if kw.get("bidirectional") else 1)), in_shape[1], int(kw["state_size"]))
     return None
 
 
