@@ -16,6 +16,7 @@ from ..context import Context, current_context
 from ..ndarray import NDArray
 from ..ndarray.ndarray import torch_dtype
 
+tensor_types = None      # set below: the array types a Parameter accepts (python/mxnet/gluon/parameter.py:37)
 __all__ = ["Parameter", "Constant", "ParameterDict", "DeferredInitializationError"]
 
 
@@ -329,3 +330,8 @@ class ParameterDict:
                 p.shape = tuple(v.shape)
                 p.initialize(ctx=ctx)
             p.set_data(v)
+
+
+from ..ndarray import NDArray as _NDArray  # noqa: E402
+from ..symbol import Symbol as _Symbol  # noqa: E402
+tensor_types = (_Symbol, _NDArray)

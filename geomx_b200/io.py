@@ -314,6 +314,24 @@ class ImageRecordIter(DataIter):
         return DataBatch([data], [label], pad=pad)
 
 
+import abc as _abc  # noqa: E402
+
+
+class MXDataIter(DataIter, metaclass=_abc.ABCMeta):
+    """In the reference this wraps an iterator implemented in C++ (``MXDataIterCreateIter``).  The native iterators of this framework
+    (``MNISTIter``, ``CSVIter``, ``LibSVMIter``, ``ImageRecordIter`` over ``csrc/runtime/{io,text_io}.h``) are ordinary ``DataIter`` classes, so
+    this name is kept as the (virtual) base they are recognised by: ``isinstance(it, MXDataIter)`` is true for exactly those."""
+
+    @_abc.abstractmethod
+    def next(self):
+        raise NotImplementedError
+
+
+for _cls in (MNISTIter, CSVIter, LibSVMIter, ImageRecordIter):
+    MXDataIter.register(_cls)
+del _cls
+
+
 # the reference's package layout (python/mxnet/io/{io,utils}.py) as importable paths
 def _register_paths():
     from ._alias import submodule

@@ -534,6 +534,40 @@ def get_mnist_iterator(batch_size, input_shape, num_parts=1, part_index=0, path=
             io.NDArrayIter(va, d["test_label"].astype(np.float32), batch_size))
 
 
+def get_zip_data(data_dir, url, data_origin_name):
+    """Extract ``data_origin_name`` (a .zip that must already be under ``data_dir``: nothing is downloaded) unless it has been extracted."""
+    import os
+    import zipfile
+    os.makedirs(data_dir, exist_ok=True)
+    path = download(url, fname=data_origin_name, dirname=data_dir)
+    marker = os.path.join(data_dir, "." + data_origin_name + ".extracted")
+    if not os.path.exists(marker):
+        with zipfile.ZipFile(path) as z:
+            z.extractall(data_dir)
+        open(marker, "w").close()
+
+
+def get_bz2_data(data_dir, data_name, url, data_origin_name):
+    """Decompress ``data_origin_name`` (.bz2, already under ``data_dir``) to ``data_name`` unless that exists."""
+    import bz2
+    import os
+    os.makedirs(data_dir, exist_ok=True)
+    target = os.path.join(data_dir, data_name)
+    if os.path.exists(target):
+        return
+    src = download(url, fname=data_origin_name, dirname=data_dir)
+    with bz2.BZ2File(src) as fi, open(target, "wb") as fo:
+        for chunk in iter(lambda: fi.read(1 << 20), b""):
+            fo.write(chunk)
+
+
+def get_mnist_pkl(path="data"):
+    """The ``mnist.pkl.gz`` fixture of the reference's tests must be present locally (no network)."""
+    import os
+    if not os.path.exists(os.path.join(path, "mnist.pkl.gz")):
+        raise IOError("get_mnist_pkl: %s/mnist.pkl.gz is missing and there is no network access; use get_mnist() for the synthetic stand-in" % path)
+
+
 def get_cifar10(path="data"):
     from .gluon.data.vision import CIFAR10
     return CIFAR10(root=path, train=True), CIFAR10(root=path, train=False)
