@@ -74,6 +74,11 @@ class Context:
     def __exit__(self, *a):
         Context._default.value = self._old
 
+    @property
+    def default_ctx(self):
+        """The context entered with ``with ctx:`` in this thread, if any (python/mxnet/context.py: Context._default_ctx.value)."""
+        return getattr(Context._default, "value", None) or Context("cpu", 0)
+
     @staticmethod
     def from_torch(dev: torch.device) -> "Context":
         if dev.type == "cuda":

@@ -33,6 +33,15 @@ class RecurrentCell(HybridBlock):
     def state_info(self, batch_size=0):
         return [{"shape": (batch_size, self._hidden_size), "__layout__": "NC"}]
 
+    def reset(self):
+        """Forget the per-sequence bookkeeping (step counters used to name states) of this cell and its children; call between sequences
+        when cells are stepped by hand (rnn_cell.py RecurrentCell.reset)."""
+        self._init_counter = -1
+        self._counter = -1
+        for c in self._children.values():
+            if hasattr(c, "reset"):
+                c.reset()
+
     def begin_state(self, batch_size=0, func=None, ctx=None, **kwargs):
         func = func or nd.zeros
         return [func(info["shape"], ctx=ctx) for info in self.state_info(batch_size)]

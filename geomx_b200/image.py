@@ -354,20 +354,62 @@ class ImageIter(_io.DataIter):
             _pyrandom.shuffle(self._order)
         self._cur = 0
 
-    def _sample(self, i):
+    # ---- the per-sample pipeline as overridable steps (python/mxnet/image/image.py ImageIter: next_sample / imdecode / check_valid_image /
+    # augmentation_transform / postprocess_data), so that sub-classes such as ImageDetIter change one stage only
+    def hard_reset(self):
+        """Reset ignoring any roll-over state (this iterator keeps none)."""
+        self.reset()
+
+    def _fetch(self, i):
+        """``(label, raw)`` of item ``i``: ``raw`` is the encoded image (bytes) or, for image lists, the file path."""
         from . import recordio
         it = self._items[i]
-        if self._rec is not None:
-            header, img = recordio.unpack_img(self._rec.read_idx(it), iscolor=1 if self.data_shape[0] == 3 else 0)
-            label, arr = header.label, nd.array(img if img.ndim == 3 else img[:, :, None], dtype="uint8")
-        elif isinstance(it, bytes):
-            header, img = recordio.unpack_img(it, iscolor=1 if self.data_shape[0] == 3 else 0)
-            label, arr = header.label, nd.array(img if img.ndim == 3 else img[:, :, None], dtype="uint8")
-        else:
-            label, arr = (it[0][0] if self.label_width == 1 else it[0]), imread(it[1], flag=1 if self.data_shape[0] == 3 else 0)
+        if self._rec is not None or isinstance(it, bytes):
+            header, img = recordio.unpack(self._rec.read_idx(it) if self._rec is not None else it)
+            return header.label, img
+        return (it[0][0] if self.label_width == 1 else it[0]), it[1]
+
+    def next_sample(self):
+        """``(label, raw)`` of the next sample in iteration order (raises StopIteration at the end of the epoch)."""
+        if self._cur >= len(self._order):
+            raise StopIteration
+        self._cur += 1
+        return self._fetch(self._order[self._cur - 1])
+
+    def read_image(self, fname):
+        with open(fname, "rb") as f:
+            return f.read()
+
+    def imdecode(self, s):
+        """Decode raw bytes (or read + decode a path) into an HWC uint8 NDArray."""
+        if isinstance(s, str):
+            s = self.read_image(s)
+        return imdecode(s, flag=1 if self.data_shape[0] == 3 else 0)
+
+    def check_valid_image(self, data):
+        if len(data[0].shape) == 0:
+            raise RuntimeError("Data shape is wrong")
+
+    def check_data_shape(self, data_shape):
+        if not len(data_shape) == 3:
+            raise ValueError("data_shape should have length 3, with dimensions CxHxW")
+        if not data_shape[0] in (1, 3):
+            raise ValueError("This iterator expects inputs to have 1 or 3 channels.")
+
+    def augmentation_transform(self, data):
         for aug in self.auglist:
-            arr = aug(arr)
-        return arr._t.permute(2, 0, 1).float(), label
+            data = aug(data)
+        return data
+
+    def postprocess_data(self, datum):
+        """HWC -> CHW float tensor of the batch."""
+        return datum._t.permute(2, 0, 1).float()
+
+    def _sample(self, i):
+        label, raw = self._fetch(i)
+        arr = self.imdecode(raw)
+        self.check_valid_image([arr])
+        return self.postprocess_data(self.augmentation_transform(arr)), label
 
     def next(self):
         if self._cur >= len(self._order):

@@ -52,6 +52,17 @@ class Initializer:
         import json
         return json.dumps([self.__class__.__name__.lower(), self._kwargs])
 
+    def set_verbosity(self, verbose=False, print_func=None):
+        """Log a statistic of every array right after it was initialised (``print_func(array) -> str``; default: its L2 norm / sqrt(size))."""
+        self._verbose = bool(verbose)
+        self._print_func = print_func or (lambda x: str(float(x.norm()) / max(1.0, float(x.numel()) ** 0.5)))
+        return self
+
+    def _verbose_print(self, desc, init, arr):
+        if getattr(self, "_verbose", False):
+            import logging
+            logging.info("Initialized %s as %s: %s", desc, init, self._print_func(arr))
+
     def __call__(self, desc, arr):
         name = str(desc)
         t = arr._t if hasattr(arr, "_t") else arr
@@ -80,6 +91,7 @@ class Initializer:
             t.zero_()
         else:
             self._init_default(name, t)
+        self._verbose_print(name, type(self).__name__, t)
 
     def _init_bias(self, _, t): t.zero_()
     def _init_gamma(self, _, t): t.fill_(1.0)

@@ -12,8 +12,28 @@ from .ndarray import NDArray
 
 __all__ = ["DataDesc", "DataBatch", "DataIter", "NDArrayIter", "MNISTIter", "ResizeIter", "CSVIter", "LibSVMIter", "ImageRecordIter", "PrefetchingIter"]
 
-DataDesc = namedtuple("DataDesc", ["name", "shape", "dtype", "layout"])
-DataDesc.__new__.__defaults__ = ("float32", "NCHW")
+class DataDesc(namedtuple("DataDesc", ["name", "shape", "dtype", "layout"])):
+    """Name, shape, dtype and layout of one input (``python/mxnet/io/io.py`` DataDesc)."""
+    __slots__ = ()
+
+    def __new__(cls, name, shape, dtype="float32", layout="NCHW"):
+        return super().__new__(cls, name, tuple(shape), dtype, layout)
+
+    def __repr__(self):
+        return "DataDesc[%s,%s,%s,%s]" % (self.name, self.shape, self.dtype, self.layout)
+
+    @staticmethod
+    def get_batch_axis(layout):
+        """Index of the batch dimension ``N`` in ``layout`` (0 when the layout is unknown)."""
+        return 0 if layout is None else layout.find("N")
+
+    @staticmethod
+    def get_list(shapes, types):
+        """``[(name, shape), ...]`` (+ ``[(name, dtype), ...]``) -> list of DataDesc."""
+        if types is not None:
+            tdict = dict(types)
+            return [DataDesc(n, s, tdict[n]) for n, s in shapes]
+        return [DataDesc(n, s) for n, s in shapes]
 
 
 class DataBatch:

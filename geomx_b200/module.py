@@ -34,6 +34,51 @@ class BaseModule:
         self.logger = logger
         self.binded = self.for_training = self.params_initialized = self.optimizer_initialized = False
 
+    # ---- what a concrete module provides (base_module.py:840-1050: the computation / parameter / optimizer interface)
+    def _abstract(self, what):
+        raise NotImplementedError("%s must be implemented by %s" % (what, type(self).__name__))
+
+    data_names = property(lambda self: self._abstract("data_names"))
+    output_names = property(lambda self: self._abstract("output_names"))
+    data_shapes = property(lambda self: self._abstract("data_shapes"))
+    label_shapes = property(lambda self: self._abstract("label_shapes"))
+    output_shapes = property(lambda self: self._abstract("output_shapes"))
+    symbol = property(lambda self: self._abstract("symbol"))
+
+    def bind(self, data_shapes, label_shapes=None, for_training=True, inputs_need_grad=False, force_rebind=False, shared_module=None, grad_req="write"):
+        self._abstract("bind")
+
+    def init_params(self, initializer=None, arg_params=None, aux_params=None, allow_missing=False, force_init=False, allow_extra=False):
+        self._abstract("init_params")
+
+    def get_params(self):
+        self._abstract("get_params")
+
+    def set_params(self, arg_params, aux_params, allow_missing=False, force_init=True, allow_extra=False):
+        self.init_params(initializer=None, arg_params=arg_params, aux_params=aux_params, allow_missing=allow_missing, force_init=force_init,
+                         allow_extra=allow_extra)
+
+    def init_optimizer(self, kvstore="local", optimizer="sgd", optimizer_params=(("learning_rate", 0.01),), force_init=False):
+        self._abstract("init_optimizer")
+
+    def forward(self, data_batch, is_train=None):
+        self._abstract("forward")
+
+    def backward(self, out_grads=None):
+        self._abstract("backward")
+
+    def update(self):
+        self._abstract("update")
+
+    def get_outputs(self, merge_multi_context=True):
+        self._abstract("get_outputs")
+
+    def get_input_grads(self, merge_multi_context=True):
+        self._abstract("get_input_grads")
+
+    def update_metric(self, eval_metric, labels, pre_sliced=False):
+        self._abstract("update_metric")
+
     # ---- high level API shared by every module type
     def iter_predict(self, eval_data, num_batch=None, reset=True):
         """Generator of ``(outputs, batch index, batch)`` with the padding rows removed (base_module.py:290-330)."""
@@ -412,6 +457,9 @@ class BucketingModule(BaseModule):
     data_names = property(lambda self: self._data_names_)
     symbol = property(lambda self: self._curr.symbol)
     output_names = property(lambda self: self._curr.output_names)
+    data_shapes = property(lambda self: self._curr.data_shapes)          # of the bucket that is currently switched in
+    label_shapes = property(lambda self: self._curr.label_shapes)
+    output_shapes = property(lambda self: self._curr.output_shapes)
 
     def _make(self, key):
         sym, dn, ln = self._sym_gen(key)

@@ -24,7 +24,50 @@ def _gather(src, ids):
     return src.index_select(0, ids.to(src.device))
 
 
-class RowSparseNDArray:
+class BaseSparseNDArray:
+    """What the two sparse storage types share (python/mxnet/ndarray/sparse.py BaseSparseNDArray :100-250): size / ndim, dtype casts,
+    copies to other arrays or contexts, format validation.  Element-wise maths densifies (``tostype('default')``) unless a sparse kernel exists."""
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape))
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def astype(self, dtype, copy=True):
+        return self._rebuild(self.data.astype(dtype))
+
+    def as_in_context(self, ctx):
+        return self._rebuild(self.data.as_in_context(ctx), move=ctx)
+
+    def copyto(self, other):
+        """Into another array of the same storage type (in place), into a dense NDArray, or onto a Context (a new sparse array there)."""
+        from ..context import Context
+        if isinstance(other, Context):
+            return self.as_in_context(other)
+        if isinstance(other, NDArray):
+            other._t.copy_(self.tostype("default")._t)
+            return other
+        if type(other) is not type(self):
+            raise TypeError("copyto does not support type %s" % type(other))
+        fresh = self.copy()
+        other.__dict__.update(fresh.__dict__)
+        return other
+
+    def reshape(self, *a, **k):
+        raise NotImplementedError("reshape is not supported for sparse arrays: convert with tostype('default') first")
+
+    def wait_to_read(self):
+        self.data.wait_to_read()
+
+    def check_format(self, full_check=True):
+        """Raise if the auxiliary arrays do not describe a valid array of this storage type (sorted, in range, consistent lengths)."""
+        self._check(full_check)
+
+
+class RowSparseNDArray(BaseSparseNDArray):
     stype = "row_sparse"
 
     def __init__(self, data: NDArray, indices: NDArray, shape):
@@ -72,6 +115,17 @@ class RowSparseNDArray:
             return other
         return self.as_in_context(other)
 
+    def _rebuild(self, data, move=None):
+        return RowSparseNDArray(data, self.indices.as_in_context(move) if move is not None else self.indices.copy(), self._shape)
+
+    def _check(self, full):
+        idx = self.indices._t.long()
+        if idx.numel() != self.data._t.shape[0] or tuple(self.data._t.shape[1:]) != tuple(self._shape[1:]):
+            raise MXNetError("row_sparse: data has %s rows of shape %s for %d indices into an array of shape %s"
+                             % (self.data._t.shape[0], tuple(self.data._t.shape[1:]), idx.numel(), self._shape))
+        if full and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self._shape[0] or bool((idx[1:] <= idx[:-1]).any())):
+            raise MXNetError("row_sparse: indices must be strictly increasing and within [0, %d)" % self._shape[0])
+
     def retain(self, row_ids):
         """sparse_retain: keep only the listed rows (ids need not be present)."""
         ids = row_ids._t.reshape(-1).long() if isinstance(row_ids, NDArray) else torch.as_tensor(row_ids, dtype=torch.int64)
@@ -92,7 +146,7 @@ class RowSparseNDArray:
         return self.tostype("default") + other
 
 
-class CSRNDArray:
+class CSRNDArray(BaseSparseNDArray):
     """Compressed sparse rows (``python/mxnet/ndarray/sparse.py`` CSRNDArray :260-560): ``data`` (nnz,), ``indices`` (nnz,) column ids,
     ``indptr`` (rows+1,).  Enough for storage conversion, (de)serialisation, slicing by rows and ``dot(csr, dense)``."""
     stype = "csr"
@@ -127,6 +181,22 @@ class CSRNDArray:
     todense = lambda self: self.tostype("default")
     def asnumpy(self): return self.tostype("default").asnumpy()
     def copy(self): return CSRNDArray(self.data.copy(), self.indices.copy(), self.indptr.copy(), self._shape)
+
+    def _rebuild(self, data, move=None):
+        mv = (lambda x: x.as_in_context(move)) if move is not None else (lambda x: x.copy())
+        return CSRNDArray(data, mv(self.indices), mv(self.indptr), self._shape)
+
+    def _check(self, full):
+        ptr, idx = self.indptr._t.long(), self.indices._t.long()
+        if ptr.numel() != self._shape[0] + 1 or int(ptr[0]) != 0 or int(ptr[-1]) != idx.numel() or idx.numel() != self.data._t.shape[0]:
+            raise MXNetError("csr: indptr / indices / data lengths are inconsistent")
+        if full and (bool((ptr[1:] < ptr[:-1]).any()) or (idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self._shape[1]))):
+            raise MXNetError("csr: indptr must be non-decreasing and column ids within [0, %d)" % self._shape[1])
+
+    def asscipy(self):
+        """``scipy.sparse.csr_matrix`` sharing nothing with this array."""
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.data.asnumpy(), self.indices.asnumpy(), self.indptr.asnumpy()), shape=self._shape)
 
     def __getitem__(self, key):
         if isinstance(key, int):

@@ -754,7 +754,7 @@ def _attach_symbol_fluent():
              "fix", "flatten", "flip", "floor", "log", "log10", "log1p", "log2", "log_softmax", "max", "mean", "min", "nanprod", "nansum", "norm",
              "one_hot", "ones_like", "pad", "pick", "prod", "radians", "rcbrt", "reciprocal", "relu", "repeat", "reshape_like", "rint", "round",
              "rsqrt", "shape_array", "sigmoid", "sign", "sin", "sinh", "size_array", "slice", "slice_axis", "slice_like", "softmax", "softmin", "sort",
-             "space_to_depth", "sqrt", "square", "squeeze", "sum", "swapaxes", "take", "tan", "tanh", "tile", "topk", "transpose", "trunc", "zeros_like"]
+             "space_to_depth", "split", "sqrt", "square", "squeeze", "sum", "swapaxes", "take", "tan", "tanh", "tile", "topk", "transpose", "trunc", "zeros_like"]
     for n in names:
         if not hasattr(Symbol, n):
             setattr(Symbol, n, (lambda q: lambda self, *a, **k: _nd_op(q)(self, *a, **k))(n))

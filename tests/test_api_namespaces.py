@@ -123,3 +123,41 @@ def test_group_adagrad_and_model_store(tmp_path):
         store.get_model_file("resnet18_v1", root=str(tmp_path))
     store.purge(str(tmp_path))
     assert not os.listdir(str(tmp_path))
+
+
+def test_class_level_members_of_the_reference_front_end():
+    """Members the reference's classes have and user code touches: sparse array utilities, DataDesc helpers, ImageIter pipeline hooks,
+    BaseModule interface, Context.default_ctx, Initializer.set_verbosity, RecurrentCell.reset, Symbol.split."""
+    csr = mx.nd.array(np.array([[0, 1, 0], [2, 0, 3], [0, 0, 0]], dtype=np.float32)).tostype("csr")
+    csr.check_format()
+    assert (csr.size, csr.ndim) == (9, 2) and csr.astype("float64").dtype == np.float64
+    assert np.array_equal(csr.asscipy().toarray(), csr.asnumpy()) and np.array_equal(csr.copyto(mx.nd.zeros((3, 3))).asnumpy(), csr.asnumpy())
+    assert isinstance(csr, mx.nd.sparse.BaseSparseNDArray) and isinstance(csr.copyto(mx.cpu()), mx.nd.sparse.CSRNDArray)
+    rs = mx.nd.sparse.row_sparse_array((np.ones((2, 2), dtype=np.float32), [3, 1]), shape=(4, 2))
+    rs.check_format()
+    with pytest.raises(mx.MXNetError):
+        mx.nd.sparse.RowSparseNDArray(mx.nd.ones((2, 2)), mx.nd.array([1, 1], dtype="int64"), (4, 2)).check_format()
+    with pytest.raises(NotImplementedError):
+        rs.reshape((2, 4))
+    d = mx.io.DataDesc("data", [2, 3])
+    assert d.shape == (2, 3) and d.dtype == "float32" and mx.io.DataDesc.get_batch_axis("TNC") == 1 and mx.io.DataDesc.get_batch_axis(None) == 0
+    assert mx.io.DataDesc.get_list([("a", (1, 2))], [("a", "float16")])[0].dtype == "float16"
+    for m in ("hard_reset", "next_sample", "read_image", "imdecode", "check_valid_image", "check_data_shape", "augmentation_transform", "postprocess_data"):
+        assert callable(getattr(mx.image.ImageIter, m))
+    with pytest.raises(NotImplementedError):
+        mx.mod.BaseModule().forward(None)
+    assert issubclass(mx.io.MNISTIter, mx.io.MXDataIter) and not issubclass(mx.io.NDArrayIter, mx.io.MXDataIter)
+    with mx.cpu(0):
+        assert str(mx.cpu(3).default_ctx) == "cpu(0)"
+    a = mx.sym.Variable("a")
+    halves = a.split(num_outputs=2, axis=1)
+    x = np.arange(8, dtype=np.float32).reshape(2, 4)
+    assert np.array_equal(halves[1].bind(mx.cpu(), {"a": mx.nd.array(x)}).forward()[0].asnumpy(), x[:, 2:])
+    assert np.array_equal((1.0 - a).bind(mx.cpu(), {"a": mx.nd.array(x)}).forward()[0].asnumpy(), 1 - x)
+    assert np.allclose((2.0 / (a + 1)).bind(mx.cpu(), {"a": mx.nd.array(x)}).forward()[0].asnumpy(), 2 / (x + 1))
+    w = mx.nd.zeros((3, 3))
+    mx.init.Xavier().set_verbosity(True)(mx.init.InitDesc("w_weight"), w)
+    assert float(w.abs().sum().asscalar()) > 0
+    c = mx.gluon.rnn.LSTMCell(4, input_size=3)
+    c.initialize(); c(mx.nd.ones((2, 3)), c.begin_state(2)); c.reset()
+    assert c._counter == -1
