@@ -54,6 +54,11 @@ from . import models  # noqa: F401
 from . import contrib  # noqa: F401
 from . import executor, executor_manager, libinfo, log, misc, notebook, registry, rnn, util  # noqa: F401
 from . import kvstore_server  # noqa: F401
+from . import monitor as mon  # noqa: F401
+from . import random as rnd  # noqa: F401
+from . import ndarray_doc, symbol_doc  # noqa: F401
+from . import torch  # noqa: F401
+from . import torch as th  # noqa: F401
 
 # server / scheduler bootstrap on import (no-op for workers and plain library use)
 kvstore_server._init_kvstore_server_module()

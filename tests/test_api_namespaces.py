@@ -161,3 +161,20 @@ def test_class_level_members_of_the_reference_front_end():
     c = mx.gluon.rnn.LSTMCell(4, input_size=3)
     c.initialize(); c(mx.nd.ones((2, 3)), c.begin_state(2)); c.reset()
     assert c._counter == -1
+
+
+def test_top_level_aliases_and_torch_bridge():
+    """mx.th / mx.torch (torch functions on NDArrays, zero copy), mx.rnd, mx.mon, mx.ndarray_doc / mx.symbol_doc."""
+    a = mx.nd.array([[1.0, 2.0], [3.0, 4.0]])
+    assert np.array_equal(mx.th.mm(a, a).asnumpy(), a.asnumpy() @ a.asnumpy()) and isinstance(mx.th.svd(a)[0], mx.nd.NDArray)
+    t = mx.th.to_torch(a)
+    t[0, 0] = 9.0
+    assert float(a[0, 0].asscalar()) == 9.0 and mx.th.from_torch(t)._t is t and mx.torch is mx.th
+    with pytest.raises(AttributeError):
+        mx.th.no_such_function
+    assert mx.rnd is mx.random and mx.mon is mx.monitor
+    doc = mx.ndarray_doc._build_doc("relu", "Rectifier.", ["data", "num_args"], ["NDArray", "int"], ["the   input\\n array", "count"], key_var_num_args="num_args",
+                                    ret_type="NDArray")
+    assert "Parameters\\n----------\\ndata : NDArray\\n    the input array" in doc and "num_args" not in doc and "Returns" in doc
+    fc = mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=3, name="fc")
+    assert mx.symbol_doc.SymbolDoc.get_output_shape(fc, data=(2, 5)) == {"fc_output": (2, 3)}
