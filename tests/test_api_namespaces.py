@@ -173,8 +173,8 @@ def test_top_level_aliases_and_torch_bridge():
     with pytest.raises(AttributeError):
         mx.th.no_such_function
     assert mx.rnd is mx.random and mx.mon is mx.monitor
-    doc = mx.ndarray_doc._build_doc("relu", "Rectifier.", ["data", "num_args"], ["NDArray", "int"], ["the   input\\n array", "count"], key_var_num_args="num_args",
+    doc = mx.ndarray_doc._build_doc("relu", "Rectifier.", ["data", "num_args"], ["NDArray", "int"], ["the   input\n array", "count"], key_var_num_args="num_args",
                                     ret_type="NDArray")
-    assert "Parameters\\n----------\\ndata : NDArray\\n    the input array" in doc and "num_args" not in doc and "Returns" in doc
+    assert "Parameters\n----------\ndata : NDArray\n    the input array" in doc and "num_args" not in doc and "Returns" in doc
     fc = mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=3, name="fc")
     assert mx.symbol_doc.SymbolDoc.get_output_shape(fc, data=(2, 5)) == {"fc_output": (2, 3)}
