@@ -693,6 +693,67 @@ class PythonLossModule(PythonModule):
         raise NotImplementedError
 
 
+class DataParallelExecutorGroup:
+    """The per-context executors of one symbol with batch slicing (``python/mxnet/module/executor_group.py``), for code that drives them
+    without a Module.  Here the Module class itself owns exactly this machinery, so the group is a view onto a bound Module with the
+    reference's constructor and method names."""
+
+    def __init__(self, symbol, contexts, workload, data_shapes, label_shapes, param_names, for_training, inputs_need_grad, shared_group=None,
+                 logger=logging, fixed_param_names=None, grad_req="write", state_names=None, group2ctxs=None):
+        name_of = lambda d: d[0] if isinstance(d, (tuple, list)) else d.name
+        self.symbol, self.contexts, self.workload = symbol, list(contexts), workload
+        self.param_names, self.for_training, self.inputs_need_grad = list(param_names), for_training, inputs_need_grad
+        self._mod = Module(symbol, data_names=[name_of(d) for d in data_shapes], label_names=[name_of(d) for d in (label_shapes or [])] or None,
+                           logger=logger, context=self.contexts, fixed_param_names=fixed_param_names)
+        self._mod.bind(data_shapes, label_shapes, for_training=for_training, inputs_need_grad=inputs_need_grad,
+                       shared_module=shared_group._mod if shared_group is not None else None, grad_req=grad_req)
+        self._mod.params_initialized = True          # parameters are whatever set_params puts there (zeros until then)
+
+    execs = property(lambda self: self._mod._execs)
+    slices = property(lambda self: self._mod._slices)
+    data_shapes = property(lambda self: self._mod.data_shapes)
+    label_shapes = property(lambda self: self._mod.label_shapes)
+    param_arrays = property(lambda self: self._mod._param_arrays())
+    grad_arrays = property(lambda self: self._mod._grad_arrays())
+    aux_arrays = property(lambda self: [[ex.aux_dict[n] for ex in self._mod._execs] for n in self._mod._aux_names])
+
+    def reshape(self, data_shapes, label_shapes):
+        self._mod.reshape(data_shapes, label_shapes)
+
+    def set_params(self, arg_params, aux_params, allow_extra=False):
+        for ex in self._mod._execs:
+            ex.copy_params_from(arg_params, aux_params, allow_extra_params=allow_extra)
+
+    def get_params(self, arg_params, aux_params):
+        """Write the current parameters (first device: replicas are identical) into the given dicts."""
+        ex0 = self._mod._execs[0]
+        for n in self.param_names:
+            arg_params[n] = ex0.arg_dict[n].as_in_context(cpu()) if n not in arg_params else arg_params[n]
+            arg_params[n][:] = ex0.arg_dict[n].as_in_context(cpu())
+        for n in self._mod._aux_names:
+            aux_params[n] = ex0.aux_dict[n].as_in_context(cpu()) if n not in aux_params else aux_params[n]
+            aux_params[n][:] = ex0.aux_dict[n].as_in_context(cpu())
+
+    def forward(self, data_batch, is_train=None):
+        self._mod.forward(data_batch, is_train=is_train)
+
+    def backward(self, out_grads=None):
+        self._mod.backward(out_grads)
+
+    def get_outputs(self, merge_multi_context=True, begin=0, end=None):
+        outs = self._mod.get_outputs(merge_multi_context)
+        return outs[begin:end]
+
+    def get_input_grads(self, merge_multi_context=True):
+        return self._mod.get_input_grads(merge_multi_context)
+
+    def update_metric(self, eval_metric, labels, pre_sliced=False):
+        self._mod.update_metric(eval_metric, labels)
+
+    def install_monitor(self, mon):
+        self._mod.install_monitor(mon)
+
+
 # the reference's package layout (python/mxnet/module/*.py) as importable paths
 def _register_paths():
     from ._alias import submodule
@@ -701,6 +762,7 @@ def _register_paths():
     submodule(__name__, "bucketing_module", {"BucketingModule": BucketingModule})
     submodule(__name__, "sequential_module", {"SequentialModule": SequentialModule})
     submodule(__name__, "python_module", {"PythonModule": PythonModule, "PythonLossModule": PythonLossModule})
+    submodule(__name__, "executor_group", {"DataParallelExecutorGroup": DataParallelExecutorGroup})
 
 
 _register_paths()

@@ -15,7 +15,7 @@ def test_reference_import_paths_exist():
     for p in ["gluon.nn.activations", "gluon.model_zoo.model_store", "ndarray.image", "ndarray.linalg", "ndarray._internal", "ndarray.op",
               "symbol.linalg", "symbol.contrib", "symbol.random", "symbol.sparse", "symbol.image", "symbol.op", "symbol.symbol", "symbol._internal",
               "symbol.register", "module.base_module", "module.bucketing_module", "module.module", "module.python_module", "module.sequential_module",
-              "io.io", "io.utils", "image.detection", "image.image", "optimizer.contrib", "optimizer.optimizer", "rnn.rnn_cell", "rnn.rnn", "rnn.io"]:
+              "module.executor_group", "io.io", "io.utils", "image.detection", "image.image", "optimizer.contrib", "optimizer.optimizer", "rnn.rnn_cell", "rnn.rnn", "rnn.io"]:
         importlib.import_module("geomx_b200." + p)
     from geomx_b200.image.detection import ImageDetIter
     from geomx_b200.image.image import ImageIter
@@ -178,3 +178,23 @@ def test_top_level_aliases_and_torch_bridge():
     assert "Parameters\n----------\ndata : NDArray\n    the input array" in doc and "num_args" not in doc and "Returns" in doc
     fc = mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=3, name="fc")
     assert mx.symbol_doc.SymbolDoc.get_output_shape(fc, data=(2, 5)) == {"fc_output": (2, 3)}
+
+
+def test_data_parallel_executor_group():
+    from geomx_b200.module.executor_group import DataParallelExecutorGroup
+    net = mx.sym.SoftmaxOutput(mx.sym.FullyConnected(mx.sym.Variable("data"), num_hidden=3, name="fc"), name="softmax")
+    g = DataParallelExecutorGroup(net, [mx.cpu(0), mx.cpu(1)], [1, 1], [("data", (8, 4))], [("softmax_label", (8,))], ["fc_weight", "fc_bias"], True, False)
+    w = np.random.RandomState(0).rand(3, 4).astype(np.float32)
+    g.set_params({"fc_weight": mx.nd.array(w), "fc_bias": mx.nd.zeros((3,))}, {})
+    x = np.random.RandomState(1).rand(8, 4).astype(np.float32)
+    g.forward(mx.io.DataBatch([mx.nd.array(x)], [mx.nd.array(np.arange(8) % 3)]), is_train=True)
+    g.backward()
+    out = g.get_outputs()[0].asnumpy()
+    e = np.exp(x @ w.T); ref = e / e.sum(1, keepdims=True)
+    assert out.shape == (8, 3) and np.allclose(out, ref, atol=1e-5)
+    assert len(g.execs) == 2 and [(s.start, s.stop) for s in g.slices] == [(0, 4), (4, 8)] and g.grad_arrays[0][0].shape == (3, 4)
+    arg, aux = {}, {}
+    g.get_params(arg, aux)
+    assert np.allclose(arg["fc_weight"].asnumpy(), w)
+    m = mx.metric.Accuracy(); g.update_metric(m, [mx.nd.array(np.arange(8) % 3)])
+    assert m.num_inst == 8
