@@ -11,6 +11,7 @@
 #include "../runtime/storage.h"
 #include "../runtime/text_io.h"
 #include "../runtime/io.h"
+#include "../runtime/recordio.h"
 #include "../runtime/params_io.h"
 #include "../runtime/profiler.h"
 #include "dgt.h"
@@ -309,5 +310,6 @@ PYBIND11_MODULE(_C, m) {
   // ---------------------------------------------------------------------------------------------- .params IO, data IO, engine
   gxrt::BindParamsIO(m);
   gxrt::BindIO(m);
+  gxrt::BindRecordIO(m);
   gxrt::BindEngine(m);
 }

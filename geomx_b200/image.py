@@ -326,12 +326,10 @@ class ImageIter(_io.DataIter):
                 self._rec = recordio.MXIndexedRecordIO(path_imgidx, path_imgrec, "r")
                 self._items = list(self._rec.keys)
             else:
-                r = recordio.MXRecordIO(path_imgrec, "r")
-                while True:
-                    raw = r.read()
-                    if raw is None:
-                        break
-                    self._items.append(raw)
+                # no index file: find the records in the memory-mapped file (native scan) and fetch payloads lazily by offset — the
+                # payloads themselves are never all resident
+                self._reader = recordio.RecordReader(path_imgrec)
+                self._items = [("@", off) for off in self._reader.offsets]
         else:
             entries = imglist
             if entries is None:
@@ -364,6 +362,8 @@ class ImageIter(_io.DataIter):
         """``(label, raw)`` of item ``i``: ``raw`` is the encoded image (bytes) or, for image lists, the file path."""
         from . import recordio
         it = self._items[i]
+        if isinstance(it, tuple) and len(it) == 2 and isinstance(it[0], str) and it[0] == "@":
+            it = self._reader.read(it[1])
         if self._rec is not None or isinstance(it, bytes):
             header, img = recordio.unpack(self._rec.read_idx(it) if self._rec is not None else it)
             return header.label, img

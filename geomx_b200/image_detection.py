@@ -311,6 +311,8 @@ class ImageDetIter(ImageIter):
         from . import recordio
         from .image import imread
         it = self._items[i]
+        if isinstance(it, tuple) and len(it) == 2 and isinstance(it[0], str) and it[0] == "@":       # lazily read record of an un-indexed .rec
+            it = self._reader.read(it[1])
         if self._rec is not None or isinstance(it, bytes):
             header, img = recordio.unpack_img(self._rec.read_idx(it) if self._rec is not None else it, iscolor=1 if self.data_shape[0] == 3 else 0)
             return header.label, nd.array(img if img.ndim == 3 else img[:, :, None], dtype="uint8")

@@ -3,8 +3,9 @@
 Parity: ``python/mxnet/recordio.py`` (``MXRecordIO`` :36-210, ``MXIndexedRecordIO`` :213-330, ``IRHeader``/``pack``/``unpack``/``pack_img``/
 ``unpack_img`` :333-480) over dmlc-core's on-disk format (``3rdparty/dmlc-core/include/dmlc/recordio.h``): every record is
 ``uint32 magic 0xced7230a | uint32 (cflag << 29 | length) | payload | pad to 4 bytes``; payloads that contain the magic word are split into
-continuation records (cflag 1 = first, 2 = middle, 3 = last), which this reader re-assembles.  Pure Python file IO — record packing is not a
-hot path of any GeoMX configuration (the examples read idx files through ``gluon.data.vision``)."""
+continuation records (cflag 1 = first, 2 = middle, 3 = last), which the readers re-assemble.  Writing is Python file IO; reading has a native
+path as well (``csrc/runtime/recordio.h``: the file is memory-mapped, ``scan_offsets`` finds the records, ``RecordReader`` fetches them by
+offset, several at a time on worker threads) which ``mx.image.ImageIter`` uses for .rec files without an index."""
 from __future__ import annotations
 
 import io as _io
@@ -14,7 +15,7 @@ from collections import namedtuple
 
 import numpy as np
 
-__all__ = ["MXRecordIO", "MXIndexedRecordIO", "IRHeader", "pack", "unpack", "pack_img", "unpack_img"]
+__all__ = ["MXRecordIO", "MXIndexedRecordIO", "IRHeader", "pack", "unpack", "pack_img", "unpack_img", "RecordReader", "scan_offsets"]
 
 _MAGIC = 0xced7230a
 _MAGIC_BYTES = struct.pack("<I", _MAGIC)
@@ -177,3 +178,59 @@ def unpack_img(s, iscolor=-1):
     elif iscolor == 1:
         img = img.convert("RGB")
     return header, np.asarray(img)
+
+
+class RecordReader:
+    """Random access to the records of a ``.rec`` file by byte offset (native, memory-mapped; falls back to ``MXRecordIO`` seeks when the
+    native runtime is not built).  ``offsets`` lists every record; ``read(off)`` / ``read_many(offs)`` return payload bytes."""
+
+    def __init__(self, uri):
+        from . import runtime
+        self.uri = str(uri)
+        self._native = runtime.C().RecordFile(self.uri) if runtime.available() and hasattr(runtime.C(), "RecordFile") else None
+        self._py = None
+        self._offsets = None
+
+    @property
+    def offsets(self):
+        if self._offsets is None:
+            self._offsets = list(self._native.scan()) if self._native is not None else _scan_python(self.uri)
+        return self._offsets
+
+    def __len__(self):
+        return len(self.offsets)
+
+    def read(self, offset):
+        if self._native is not None:
+            return self._native.read(int(offset))
+        if self._py is None:
+            self._py = MXRecordIO(self.uri, "r")
+        self._py.fp.seek(int(offset))
+        return self._py.read()
+
+    def read_many(self, offsets, threads=4):
+        if self._native is not None:
+            return list(self._native.read_many([int(o) for o in offsets], int(threads)))
+        return [self.read(o) for o in offsets]
+
+
+def _scan_python(uri):
+    out = []
+    with open(uri, "rb") as f:
+        while True:
+            pos = f.tell()
+            head = f.read(8)
+            if len(head) < 8:
+                return out
+            magic, lrec = struct.unpack("<II", head)
+            if magic != _MAGIC:
+                raise IOError("invalid RecordIO file %s (bad magic at %d)" % (uri, pos))
+            cflag, length = lrec >> 29, lrec & ((1 << 29) - 1)
+            if cflag in (0, 1):
+                out.append(pos)
+            f.seek((length + 3) & ~3, 1)
+
+
+def scan_offsets(uri):
+    """Byte offsets of all records of a ``.rec`` file (what ``tools/im2rec.py`` writes into the ``.idx`` file, recomputed from the data)."""
+    return RecordReader(uri).offsets

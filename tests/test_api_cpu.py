@@ -209,6 +209,21 @@ def test_recordio_roundtrip(tmp_path):
     assert h.label == 3.0 and h.id == 3 and np.array_equal(dec, img)
     h, raw = recordio.unpack(ri.read_idx(7))
     assert list(h.label) == [1.0, 2.0, 3.0] and raw == b"raw"
+    # native reader: memory-mapped scan + random access by offset (multi-chunk records re-assembled), several records per call
+    rd = recordio.RecordReader(p)
+    assert len(rd) == len(payloads) and rd.offsets == recordio._scan_python(p) and [rd.read(o) for o in rd.offsets] == payloads
+    assert rd.read_many(rd.offsets[::-1], threads=3) == payloads[::-1]
+    with pytest.raises(Exception):
+        rd.read(rd.offsets[-1] + 4)                       # not the start of a record
+    # the offsets are what an .idx file stores: an un-indexed .rec is iterated lazily through them by ImageIter
+    assert recordio.scan_offsets(str(tmp_path / "b.rec")) == [ri.idx[k] for k in ri.keys]
+    wc = recordio.MXRecordIO(str(tmp_path / "c.rec"), "w")
+    for i in range(5):
+        wc.write(recordio.pack_img(recordio.IRHeader(0, float(i), i, 0), np.full((8, 8, 3), 20 * i, dtype=np.uint8), img_fmt=".png"))
+    wc.close()
+    it = mx.image.ImageIter(batch_size=2, data_shape=(3, 8, 8), path_imgrec=str(tmp_path / "c.rec"), aug_list=[])
+    got = [(b.data[0].asnumpy()[:, 0, 0, 0].tolist(), b.label[0].asnumpy().tolist(), b.pad) for b in it]
+    assert got == [([0.0, 20.0], [0.0, 1.0], 0), ([40.0, 60.0], [2.0, 3.0], 0), ([80.0, 0.0], [4.0, 0.0], 1)]
 
 
 def test_symbol_and_module_fit(tmp_path):
