@@ -92,3 +92,27 @@ def test_dgt_reassembly_accepts_a_valid_tensor():
     assert C.fuzz_dgt_block(0, 1, 6000, 4096, 32, 0, 4096, 2) is False
     assert C.fuzz_dgt_block(1, 1, 6000, 1904, 32, 0, 1904, 2) is True
     assert C.fuzz_dgt_block(1, 1, 6000, 4096, 32, 0, 4096, 2) is False      # would run past the end of the tensor
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.binary(max_size=400), st.integers(0, 500))
+def test_native_record_reader_on_corrupt_files(tmp_path_factory, blob, off):
+    """A damaged / hostile .rec file: scanning and reading either work or raise — lengths in chunk headers are checked against the file size."""
+    from geomx_b200 import recordio
+    import struct
+    d = tmp_path_factory.mktemp("rec")
+    p = str(d / "x.rec")
+    good = struct.pack("<II", 0xced7230a, 5) + b"hello\x00\x00\x00"
+    with open(p, "wb") as f:
+        f.write(good + blob)
+    r = recordio.RecordReader(p)
+    try:
+        offs = r.offsets
+    except Exception:
+        offs = [0]
+    assert r.read(0) == b"hello"
+    for o in list(offs)[:4] + [off]:
+        try:
+            r.read(o)
+        except Exception:
+            pass
