@@ -59,6 +59,7 @@ from . import random as rnd  # noqa: F401
 from . import ndarray_doc, symbol_doc  # noqa: F401
 from . import torch  # noqa: F401
 from . import torch as th  # noqa: F401
+from . import predictor  # noqa: F401
 
 # server / scheduler bootstrap on import (no-op for workers and plain library use)
 kvstore_server._init_kvstore_server_module()

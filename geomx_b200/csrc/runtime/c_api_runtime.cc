@@ -55,6 +55,7 @@ gxrt::Engine* Eng() {
 }  // namespace
 
 GX_CAPI const char* GXRTGetLastError() { return rt_error.c_str(); }
+void GXRTSetLastError(const std::string& msg) { rt_error = msg; }       // for the other translation units of the C ABI (c_predict_api.cc)
 
 // ------------------------------------------------------------------------------------------------ NDArray (host)
 // dtype: mshadow flags (0 f32, 1 f64, 2 f16, 3 u8, 4 i32, 5 i8, 6 i64)

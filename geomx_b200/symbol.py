@@ -191,23 +191,177 @@ class Symbol:
         return Executor(self, ctx, dict(args), dict(args_grad or {}), req, dict(aux_states or {}), group2ctx)
 
     # ---- (de)serialisation: a flat node list in topological order
-    def tojson(self):
+    def tojson(self, nnvm=False):
+        """Graph as JSON.  ``nnvm=True`` writes the reference's dialect (python-repr string attributes, ``[node, output, version]`` input
+        triples, ``arg_nodes`` / ``node_row_ptr`` / ``heads``; src/nnvm + nnvm::pass::SaveJSON) so ``-symbol.json`` files can be read by
+        MXNet-family tools; ``load_json`` reads both dialects."""
+        if nnvm:
+            return _to_nnvm_json(self)
         order = self._topo()
         index = {id(s): i for i, s in enumerate(order)}
         nodes = [{"op": s.op, "name": s.name, "attrs": {k: (list(v) if isinstance(v, tuple) else v) for k, v in s.attrs.items()},
                   "inputs": [index[id(i)] for i in s.inputs], "aux": [index[id(a)] for a in s.aux]} for s in order]
         return json.dumps({"nodes": nodes, "heads": [index[id(self)]], "format": "geomx_b200-symbol-1"}, indent=1)
 
-    def save(self, fname):
+    def save(self, fname, nnvm=False):
         with open(fname, "w") as f:
-            f.write(self.tojson())
+            f.write(self.tojson(nnvm=nnvm))
 
     def __repr__(self):
         return "<Symbol %s>" % (self.name if self.op != "_group" else "group [%s]" % ", ".join(self.list_outputs()))
 
 
+_NNVM_BINARY = {"elemwise_add": "_plus", "_Plus": "_plus", "_plus": "_plus", "_add": "_plus", "elemwise_sub": "_minus", "_Minus": "_minus", "_minus": "_minus",
+                "_sub": "_minus", "elemwise_mul": "_mul", "_Mul": "_mul", "_mul": "_mul", "elemwise_div": "_div", "_Div": "_div", "_div": "_div"}
+_NNVM_SCALAR = {"_plus_scalar": "_plus", "_PlusScalar": "_plus", "_minus_scalar": "_minus", "_MinusScalar": "_minus", "_mul_scalar": "_mul", "_MulScalar": "_mul",
+                "_div_scalar": "_div", "_DivScalar": "_div"}
+
+
+def _lit(v):
+    """python-repr attribute string of the nnvm dialect -> value ("(5, 5)" -> (5, 5), "True" -> True, "relu" -> "relu")."""
+    if not isinstance(v, str):
+        return v
+    import ast
+    try:
+        return ast.literal_eval(v)
+    except (ValueError, SyntaxError):
+        return v
+
+
+def _from_nnvm(d):
+    """Build the graph from the reference's JSON dialect (what ``Symbol.save`` of MXNet / GeoMX writes)."""
+    built = []
+
+    def user_attrs(n, raw):
+        a = dict(n.get("attr") or {}) if ("attrs" in n or "param" in n) else {}
+        a.update({k: v for k, v in raw.items() if k.startswith("__")})
+        return a
+    for n in d["nodes"]:
+        op, name = n["op"], n["name"]
+        raw = n.get("attrs") or n.get("param") or (n.get("attr") if n["op"] != "null" and "param" not in n else None) or {}
+        if op == "null":
+            raw = n.get("attrs") or n.get("attr") or {}
+        kw = {k: _lit(v) for k, v in raw.items() if not k.startswith("__")}
+        ins = []
+        for e in n["inputs"]:
+            src = built[e[0]]
+            ins.append(src[e[1]] if e[1] else src)
+        usr = user_attrs(n, raw)
+        if op == "null":
+            sym = Symbol("null", name, attrs={"__attr__": {k: str(v) for k, v in usr.items()}} if usr else None)
+            if "__shape__" in usr:
+                sym.attrs["__shape__"] = tuple(_lit(usr["__shape__"]))
+        elif op == "FullyConnected":
+            sym = Symbol(op, name, ins, {"num_hidden": int(kw["num_hidden"]), "no_bias": bool(kw.get("no_bias", False)), "flatten": bool(kw.get("flatten", True))})
+        elif op == "Convolution" and len(tuple(kw["kernel"])) == 2:
+            sym = Symbol(op, name, ins, {"kernel": _pair(kw["kernel"]), "num_filter": int(kw["num_filter"]), "stride": _pair(kw.get("stride") or None, (1, 1)),
+                                         "pad": _pair(kw.get("pad") or None, (0, 0)), "dilate": _pair(kw.get("dilate") or None, (1, 1)),
+                                         "num_group": int(kw.get("num_group", 1)), "no_bias": bool(kw.get("no_bias", False))})
+        elif op == "Activation":
+            sym = Symbol(op, name, ins, {"act_type": kw["act_type"]})
+        elif op == "Pooling" and kw.get("pooling_convention", "valid") == "valid" and kw.get("pool_type", "max") in ("max", "avg") \
+                and (kw.get("global_pool") or len(tuple(kw.get("kernel", ()))) == 2):
+            sym = Symbol(op, name, ins, {"kernel": _pair(kw.get("kernel") or None, (1, 1)), "pool_type": kw.get("pool_type", "max"),
+                                         "stride": _pair(kw.get("stride") or None, (1, 1)), "pad": _pair(kw.get("pad") or None, (0, 0)),
+                                         "global_pool": bool(kw.get("global_pool", False))})
+        elif op in ("Flatten", "flatten"):
+            sym = Symbol("Flatten", name, ins)
+        elif op in ("Reshape", "reshape") and "shape" in kw and all(int(v) > 0 or int(v) == -1 for v in kw["shape"]):
+            sym = Symbol("Reshape", name, ins, {"shape": tuple(int(v) for v in kw["shape"])})
+        elif op == "BatchNorm":
+            sym = Symbol(op, name, ins[:3], {"eps": float(kw.get("eps", 1e-3)), "momentum": float(kw.get("momentum", 0.9)), "fix_gamma": bool(kw.get("fix_gamma", True)),
+                                             "use_global_stats": bool(kw.get("use_global_stats", False)), "axis": int(kw.get("axis", 1))}, ins[3:5])
+        elif op == "Dropout":
+            sym = Symbol(op, name, ins, {"p": float(kw.get("p", 0.5))})
+        elif op in ("Concat", "concat"):
+            sym = Symbol("Concat", name, ins, {"dim": int(kw.get("dim", 1))})
+        elif op in ("softmax", "log_softmax"):
+            sym = Symbol(op, name, ins, {"axis": int(kw.get("axis", -1))})
+        elif op in ("SoftmaxOutput", "Softmax"):
+            sym = Symbol("SoftmaxOutput", name, ins, {"grad_scale": float(kw.get("grad_scale", 1.0)), "normalization": kw.get("normalization", "null")})
+        elif op == "LinearRegressionOutput":
+            sym = Symbol(op, name, ins, {"grad_scale": float(kw.get("grad_scale", 1.0))})
+        elif op in _NNVM_BINARY:
+            sym = Symbol(_NNVM_BINARY[op], name, ins)
+        elif op in _NNVM_SCALAR:
+            sym = Symbol(_NNVM_SCALAR[op] + "_scalar", name, ins, {"scalar": float(kw["scalar"])})
+        else:                                   # everything else: the imperative operator of that name through the generic bridge
+            from . import ndarray as nd
+            if not callable(getattr(nd, op, None)):
+                raise MXNetError("symbol JSON: operator %s (node %s) is not available" % (op, name))
+            kw.pop("num_args", None)
+            sym = _nd_op(op)(*ins, name=name, **kw)
+        if usr and op != "null":
+            sym.attrs.setdefault("__attr__", {}).update({k: str(v) for k, v in usr.items()})
+        built.append(sym)
+    heads = [built[h[0]][h[1]] if h[1] else built[h[0]] for h in d["heads"]]
+    return heads[0] if len(heads) == 1 else Group(heads)
+
+
+def _repr_attr(v):
+    if isinstance(v, bool):
+        return "True" if v else "False"
+    if isinstance(v, (list, tuple)):
+        return "(" + ", ".join(_repr_attr(x) for x in v) + ("," if len(v) == 1 else "") + ")"
+    return str(v)
+
+
+_TO_NNVM_OP = {"_plus": "elemwise_add", "_minus": "elemwise_sub", "_mul": "elemwise_mul", "_div": "elemwise_div"}
+
+
+def _to_nnvm_json(sym):
+    order = [s for s in sym._topo() if s.op != "_group"]
+    index = {id(s): i for i, s in enumerate(order)}
+    nodes = []
+    for s in order:
+        if s.op == "_item":
+            continue
+        usr = dict(s.attrs.get("__attr__", {}))
+        if s.op == "null":
+            if s.attrs.get("__shape__") is not None:
+                usr["__shape__"] = _repr_attr(s.attrs["__shape__"])
+            node = {"op": "null", "name": s.name, "inputs": []}
+            if usr:
+                node["attrs"] = usr
+            nodes.append(node)
+            continue
+        if s.op == "_nd":
+            if s.attrs.get("sym_kwargs"):
+                raise MXNetError("tojson(nnvm=True): %s takes tensor keyword arguments, which have no positional order in the nnvm dialect" % s.name)
+            op, kw = s.attrs["fn"].split(".")[-1], dict(s.attrs.get("kwargs") or {})
+        elif s.op == "_full_like":
+            raise MXNetError("tojson(nnvm=True): scalar-broadcast helper nodes cannot be written in the nnvm dialect")
+        else:
+            op = _TO_NNVM_OP.get(s.op, s.op)
+            kw = {k: v for k, v in s.attrs.items() if not k.startswith("__") and v is not None}
+            if s.op == "Concat":
+                kw["num_args"] = len(s.inputs)
+            if s.op == "Pooling" and s.attrs.get("stride") is None:
+                kw["stride"] = s.attrs["kernel"]            # here an absent stride means the window; the nnvm default is 1
+        attrs = {k: _repr_attr(v) for k, v in kw.items() if v is not None}
+        attrs.update(usr)
+        ins = []
+        for i in list(s.inputs) + list(s.aux):
+            ins.append([index[id(i.inputs[0])], int(i.attrs["index"]), 0] if i.op == "_item" else [index[id(i)], 0, 0])
+        node = {"op": op, "name": s.name, "inputs": ins}
+        if attrs:
+            node["attrs"] = attrs
+        nodes.append(node)
+    # _item nodes were skipped: compact the numbering
+    keep = [i for i, s in enumerate(order) if s.op != "_item"]
+    renum = {old: new for new, old in enumerate(keep)}
+    for n in nodes:
+        n["inputs"] = [[renum[e[0]], e[1], e[2]] for e in n["inputs"]]
+    heads = sym.inputs if sym.op == "_group" else [sym]
+    head_entries = [[renum[index[id(h.inputs[0])]], int(h.attrs["index"]), 0] if h.op == "_item" else [renum[index[id(h)]], 0, 0] for h in heads]
+    return json.dumps({"nodes": nodes, "arg_nodes": [i for i, n in enumerate(nodes) if n["op"] == "null"], "node_row_ptr": list(range(len(nodes) + 1)),
+                       "heads": head_entries, "attrs": {"mxnet_version": ["int", 10400]}}, indent=2)
+
+
 def load_json(s):
     d = json.loads(s)
+    if "format" not in d and ("arg_nodes" in d or (d.get("nodes") and d["nodes"][0].get("inputs") is not None and d.get("heads") and isinstance(d["heads"][0], list))):
+        return _from_nnvm(d)
     built = []
     for n in d["nodes"]:
         attrs = {k: (tuple(v) if isinstance(v, list) else v) for k, v in n["attrs"].items()}

@@ -116,3 +116,107 @@ def test_native_record_reader_on_corrupt_files(tmp_path_factory, blob, off):
             r.read(o)
         except Exception:
             pass
+
+
+_PRED_JSON = None
+
+
+def _pred_fixture():
+    global _PRED_JSON
+    if _PRED_JSON is None:
+        import geomx_b200 as mx
+        s = mx.sym
+        d = s.Variable("data")
+        c = s.Convolution(d, kernel=(3, 3), num_filter=4, pad=(1, 1), name="c")
+        p = s.Pooling(s.Activation(s.BatchNorm(c, name="bn"), "relu"), kernel=(2, 2), pool_type="avg")
+        net = s.SoftmaxOutput(s.FullyConnected(s.Concat(s.Flatten(p), s.Flatten(p) * 2.0, dim=1), num_hidden=5, name="fc"), name="sm")
+        shapes = {"data": (2, 3, 8, 8)}
+        arg_shapes, _, aux_shapes = net.infer_shape(**shapes)
+        import numpy as np
+        import os
+        import tempfile
+        save = {"arg:" + n: mx.nd.array(np.full(sh, 0.1, np.float32)) for n, sh in zip(net.list_arguments(), arg_shapes) if n not in ("data", "sm_label")}
+        save.update({"aux:" + n: mx.nd.array(np.ones(sh, np.float32)) for n, sh in zip(net.list_auxiliary_states(), aux_shapes)})
+        f = os.path.join(tempfile.mkdtemp(), "f.params")
+        mx.nd.save(f, save)
+        _PRED_JSON = (net.tojson(nnvm=True), net.tojson(), open(f, "rb").read(), shapes)
+    return _PRED_JSON
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.data())
+def test_native_predictor_on_hostile_graphs_and_params(data):
+    """Symbol JSON and parameter files are user-supplied deployment artefacts: mutated graphs (attribute values, input references, operator
+    names), truncated / bit-flipped JSON and parameter blobs either load and run or raise MXNetError — no crash, no hang, no huge allocation."""
+    import json
+    import numpy as np
+    from geomx_b200 import predictor
+    from geomx_b200.base import MXNetError
+    nn, ours, blob, shapes = _pred_fixture()
+    mode = data.draw(st.sampled_from(["attr", "ref", "bytes", "params", "op"]))
+    text, pb = data.draw(st.sampled_from([nn, ours])), blob
+    if mode in ("attr", "ref", "op"):
+        d = json.loads(text)
+        n = data.draw(st.sampled_from([x for x in d["nodes"] if x["op"] != "null"]))
+        if mode == "attr":
+            at = n.setdefault("attrs", {})
+            key = data.draw(st.sampled_from(sorted(at) + ["kernel", "stride", "pad", "axis", "dim", "num_hidden", "shape"]))
+            at[key] = data.draw(st.one_of(st.integers(-5, 70000), st.sampled_from(["(0, 0)", "(-1, 3)", "None", "nan", "", "(99999, 99999)", "True", [0, 0], [-2, 1 << 40], None, 1e30]),
+                                          st.text(max_size=8)))
+        elif mode == "ref":
+            if n["inputs"]:
+                i = data.draw(st.integers(0, len(n["inputs"]) - 1))
+                v = data.draw(st.integers(-3, len(d["nodes"]) + 3))
+                n["inputs"][i] = [v, data.draw(st.integers(0, 2)), 0] if isinstance(n["inputs"][i], list) else v
+        else:
+            n["op"] = data.draw(st.sampled_from(["Pooling", "Convolution", "transpose", "Reshape", "Concat", "BatchNorm", "Embedding", "softmax", "_group", "_item", "x"]))
+        text = json.dumps(d)
+    elif mode == "bytes":
+        b = bytearray(text.encode())
+        for _ in range(data.draw(st.integers(1, 4))):
+            b[data.draw(st.integers(0, len(b) - 1))] = data.draw(st.integers(32, 126))
+        text = bytes(b[:data.draw(st.integers(1, len(b)))]).decode("latin-1") if data.draw(st.booleans()) else b.decode("latin-1")
+    else:
+        b = bytearray(pb)
+        for _ in range(data.draw(st.integers(1, 4))):
+            b[data.draw(st.integers(0, min(len(b) - 1, 400)))] = data.draw(st.integers(0, 255))
+        pb = bytes(b[:data.draw(st.integers(0, len(b)))]) if data.draw(st.booleans()) else bytes(b)
+    try:
+        p = predictor.Predictor(text, pb, shapes)
+        p.forward(data=np.ones(shapes["data"], np.float32))
+        for i in range(p.num_outputs):
+            if int(np.prod(p.get_output_shape(i))) < (1 << 24):
+                p.get_output(i)
+    except MXNetError:
+        pass
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.data())
+def test_native_params_parser_on_corrupt_files(data):
+    """The C++ `.params` parser (C API GXNDArrayLoad / GXNDList*, predictor parameters): dense, row_sparse and csr records with flipped bytes
+    or cut short either parse or raise — ranks, extents, dtype flags and sparse indices are validated before any allocation or copy."""
+    import numpy as np
+    import geomx_b200 as mx
+    from geomx_b200 import predictor
+    from geomx_b200.base import MXNetError
+    from geomx_b200.ndarray.utils import save_bytes
+    global _SPARSE_BLOB
+    try:
+        blob = _SPARSE_BLOB
+    except NameError:
+        dense = mx.nd.array(np.arange(12, dtype=np.float32).reshape(3, 4))
+        rsp = mx.nd.sparse.row_sparse_array((np.ones((2, 4), np.float32), np.array([0, 2])), shape=(3, 4))
+        csr = mx.nd.sparse.csr_matrix((np.array([1., 2., 3.], np.float32), np.array([0, 2, 1]), np.array([0, 1, 2, 3])), shape=(3, 4))
+        blob = _SPARSE_BLOB = save_bytes({"d": dense, "r": rsp, "c": csr})
+        got = predictor.load_ndarray_file(blob)
+        assert got["r"].tolist() == [[1] * 4, [0] * 4, [1] * 4] and got["c"].tolist() == [[1, 0, 0, 0], [0, 0, 2, 0], [0, 3, 0, 0]]
+    b = bytearray(blob)
+    for _ in range(data.draw(st.integers(1, 6))):
+        b[data.draw(st.integers(0, len(b) - 1))] = data.draw(st.integers(0, 255))
+    if data.draw(st.booleans()):
+        b = b[:data.draw(st.integers(0, len(b)))]
+    try:
+        predictor.load_ndarray_file(bytes(b))
+    except MXNetError:
+        pass
