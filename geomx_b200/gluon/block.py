@@ -336,6 +336,11 @@ class HybridBlock(Block):
         pass
 
     def forward(self, x, *args):
+        from ..symbol import Symbol
+        if isinstance(x, Symbol):                     # symbolic tracing (export): build the graph instead of computing
+            from . import _symbolic
+            return _symbolic.call(self, x, *args)
+        self._n_inputs = 1 + len(args)
         try:
             params = {k: v.data(x.context) if len(v.list_ctx()) > 1 else v.data() for k, v in self._reg_params.items()}
         except DeferredInitializationError:
@@ -354,18 +359,27 @@ class HybridBlock(Block):
             if p._data is None:
                 p.dtype = str(args[0].dtype).replace("torch.", "") if args else p.dtype
 
-    def export(self, path, epoch=0):
-        """``path-%04d.params`` (``arg:`` / ``aux:`` prefixed like ``save_checkpoint``) and, for blocks that own a graph (``SymbolBlock``),
-        ``path-symbol.json``.  Imperative HybridBlocks have no nnvm graph to serialise: reload them with ``load_parameters``."""
+    def export(self, path, epoch=0, nnvm=False):
+        """``path-symbol.json`` + ``path-%04d.params`` (``arg:`` / ``aux:`` prefixed like ``save_checkpoint``) — loadable by
+        ``SymbolBlock.imports``, ``mx.model.load_checkpoint``, ``Module`` and the C predict API.  A ``SymbolBlock`` writes the graph it
+        owns; any other HybridBlock is traced symbolically (``gluon/_symbolic.py``) with inputs named ``data`` (``data0``, ``data1`` … when
+        it was last called with several).  ``nnvm=True`` writes the JSON in the reference's dialect.  Parity: gluon/block.py:866-927."""
+        from .. import symbol as S
         sym = getattr(self, "_symbol", None)
-        if sym is not None:
-            with open("%s-symbol.json" % path, "w") as f:
-                f.write(sym.tojson())
-            aux = set(sym.list_auxiliary_states())
-            d = {("aux:" if n in aux else "arg:") + n: p.data() for n, p in self.collect_params().items()}
-            nd.save("%s-%04d.params" % (path, epoch), d)
-        else:
-            self.save_parameters("%s-%04d.params" % (path, epoch))
+        if sym is None:
+            n_in = getattr(self, "_n_inputs", 1)
+            ins = [S.Variable("data")] if n_in == 1 else [S.Variable("data%d" % i) for i in range(n_in)]
+            out = self(*ins)
+            sym = S.Group(list(out)) if isinstance(out, (list, tuple)) else out
+        with open("%s-symbol.json" % path, "w") as f:
+            f.write(sym.tojson(nnvm=nnvm))
+        aux, args = set(sym.list_auxiliary_states()), set(sym.list_arguments())
+        d = {}
+        for n, p in self.collect_params().items():
+            if n in aux or n in args:
+                d[("aux:" if n in aux else "arg:") + n] = p.data()
+        nd.save("%s-%04d.params" % (path, epoch), d)
+        return sym
 
 
 _F = _FMod()

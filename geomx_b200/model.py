@@ -95,10 +95,14 @@ def load_params(prefix, epoch):
 
 
 def load_checkpoint(prefix, epoch):
+    """``(symbol, arg_params, aux_params)`` of ``prefix-symbol.json`` + ``prefix-%04d.params`` (python/mxnet/model.py:414-450).  The symbol is
+    a ``Symbol`` (either JSON dialect); ``None`` when the file is absent or holds no graph."""
+    from . import symbol as sym
     symbol = None
     try:
         with open("%s-symbol.json" % prefix) as f:
-            symbol = f.read()
+            text = f.read()
+        symbol = sym.load_json(text) if '"nodes"' in text else None
     except FileNotFoundError:
         pass
     arg_params, aux_params = load_params(prefix, epoch)
@@ -168,8 +172,8 @@ class FeedForward:
     @staticmethod
     def load(prefix, epoch, ctx=None, **kwargs):
         from . import symbol as sym
-        js, arg, aux = load_checkpoint(prefix, epoch)
-        return FeedForward(sym.load_json(js), ctx=ctx, arg_params=arg, aux_params=aux, begin_epoch=epoch, **kwargs)
+        net, arg, aux = load_checkpoint(prefix, epoch)
+        return FeedForward(net, ctx=ctx, arg_params=arg, aux_params=aux, begin_epoch=epoch, **kwargs)
 
     @staticmethod
     def create(symbol, X, y=None, ctx=None, num_epoch=None, epoch_size=None, optimizer="sgd", initializer=None, eval_data=None, eval_metric="acc",

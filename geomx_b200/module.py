@@ -433,8 +433,8 @@ class Module(BaseModule):
     @staticmethod
     def load(prefix, epoch, load_optimizer_states=False, **kwargs):
         from . import symbol as sym
-        js, arg, aux = load_checkpoint(prefix, epoch)
-        mod = Module(sym.load_json(js), **kwargs)
+        net, arg, aux = load_checkpoint(prefix, epoch)
+        mod = Module(net, **kwargs)
         mod._preloaded = (arg, aux)                # used by init_params() when no explicit values are given
         if load_optimizer_states:
             mod._preload_opt_states = "%s-%04d.states" % (prefix, epoch)

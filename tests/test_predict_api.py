@@ -206,3 +206,63 @@ def test_ndlist_and_errors(tmp_path):
     keys = (ctypes.c_char_p * 1)(b"data"); indptr = (ctypes.c_uint32 * 2)(0, 2); shp = (ctypes.c_uint32 * 2)(2, 5)
     assert lib.GXPredCreate(net.tojson().encode(), b"", 0, 2, 0, 1, keys, indptr, shp, ctypes.byref(h)) == -1
     assert b"Python Executor" in lib.GXRTGetLastError()
+
+
+def test_hybridblock_export_traces_a_graph(tmp_path):
+    """HybridBlock.export of imperative nets: built-in layers through their symbolic rules, user blocks through hybrid_forward(F=mx.sym);
+    the files load into SymbolBlock, Module-style checkpoints and the native predictor (gluon/block.py export :866-927)."""
+    from geomx_b200 import gluon
+    from geomx_b200.gluon import nn
+    from geomx_b200.gluon.model_zoo import vision
+
+    class Gate(gluon.HybridBlock):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            with self.name_scope():
+                self.fc = nn.Dense(6, flatten=True)
+                self.scale = self.params.get("scale", shape=(6,), init=mx.init.Constant(0.5))
+
+        def hybrid_forward(self, F, x, scale):
+            h = F.tanh(self.fc(x))
+            return F.broadcast_mul(h, F.reshape(scale, shape=(1, -1))) + h
+
+    rng = np.random.RandomState(0)
+    net = nn.HybridSequential()
+    net.add(nn.Conv2D(4, 3, padding=1, activation="relu"), nn.BatchNorm(), nn.AvgPool2D(2), nn.Dropout(0.2), Gate(), nn.LeakyReLU(0.1), nn.Dense(3))
+    net.initialize(mx.init.Xavier())
+    x = mx.nd.array(rng.randn(3, 2, 8, 8).astype(np.float32))
+    with mx.autograd.predict_mode():
+        ref = net(x).asnumpy()
+    prefix = str(tmp_path / "gate")
+    graph = net.export(prefix, epoch=2)
+    assert graph.list_arguments()[0] == "data" and len(graph.list_auxiliary_states()) == 2
+    blob = open(prefix + "-0002.params", "rb").read()
+    for nnvm in (False, True):
+        if nnvm:
+            net.export(prefix, epoch=2, nnvm=True)
+        p = predictor.Predictor(open(prefix + "-symbol.json").read(), blob, {"data": x.shape})
+        p.forward(data=x.asnumpy())
+        np.testing.assert_allclose(p.get_output(0), ref, atol=2e-6)
+        blk = gluon.SymbolBlock.imports(prefix + "-symbol.json", ["data"], prefix + "-0002.params")
+        with mx.autograd.predict_mode():
+            np.testing.assert_allclose(blk(x).asnumpy(), ref, atol=1e-6)
+    s, arg_params, aux_params = mx.model.load_checkpoint(prefix, 2)
+    assert set(arg_params) | {"data"} == set(s.list_arguments()) and set(aux_params) == set(s.list_auxiliary_states())
+    # a residual network from the model zoo
+    rn = vision.get_model("resnet18_v1", classes=5)
+    rn.initialize()
+    xi = mx.nd.array(rng.randn(2, 3, 32, 32).astype(np.float32))
+    with mx.autograd.predict_mode():
+        want = rn(xi).asnumpy()
+    rn.export(str(tmp_path / "rn"))
+    p = predictor.Predictor(open(str(tmp_path / "rn-symbol.json")).read(), open(str(tmp_path / "rn-0000.params"), "rb").read(), {"data": xi.shape})
+    p.forward(data=xi.asnumpy())
+    np.testing.assert_allclose(p.get_output(0), want, atol=1e-5)
+    arena, nops = p.plan()
+    assert arena < 1 << 20 and nops > 60
+
+    class Opaque(gluon.HybridBlock):                       # computes on tensors directly: reported, not mis-exported
+        def hybrid_forward(self, F, x):
+            return mx.nd.NDArray(x._t * 2)
+    with pytest.raises(MXNetError, match="no symbolic rule"):
+        Opaque().export(str(tmp_path / "op"))
