@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "host_array.h"
 #include "params_io.h"
 #include "profiler.h"
 #include "storage.h"
@@ -31,14 +32,8 @@ int Guard(F&& f) {
   catch (const std::exception& e) { rt_error = e.what(); return -1; }
   catch (...) { rt_error = "unknown error"; return -1; }
 }
-struct HostArray {
-  gxrt::NDRec rec;
-  std::vector<uint32_t> shape32;      // GetShape hands out a pointer that stays valid until the handle is freed
-};
-HostArray* ND(void* h) {
-  if (h == nullptr) throw std::runtime_error("null NDArray handle");
-  return static_cast<HostArray*>(h);
-}
+using gxrt::capi::HostArray;
+using gxrt::capi::ND;
 // results of the last GXNDArrayLoad of this thread (the reference returns pointers into thread-local storage as well, c_api.cc MXNDArrayLoad)
 thread_local std::vector<void*> load_handles;
 thread_local std::vector<std::string> load_names;

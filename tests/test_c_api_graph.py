@@ -1,0 +1,432 @@
+"""Symbol / Executor / imperative / autograd / RecordIO / DataIter groups of the flat C ABI (csrc/runtime/c_api_graph.cc, c_api_io.cc), driven
+through ctypes only and checked against PyTorch fp32 on the CPU and against the Python front end (JSON, RecordIO interchange)."""
+import ctypes
+import struct
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as TF
+
+import _capi as C
+from _capi import ck, lib, u32, vp, cp
+
+
+def _cnn():
+    """The reference's demo CNN (examples/cnn.py:56-66) composed through GXSymbol*."""
+    x = C.var("data")
+    c0 = C.op("Convolution", "conv0", [x], kernel="(5, 5)", num_filter=16)
+    a0 = C.op("Activation", "relu0", [c0], act_type="relu")
+    p0 = C.op("Pooling", "pool0", [a0], kernel="(2, 2)", stride="(2, 2)", pool_type="max")
+    c1 = C.op("Convolution", "conv1", [p0], kernel="(5, 5)", num_filter=32)
+    a1 = C.op("Activation", "relu1", [c1], act_type="relu")
+    p1 = C.op("Pooling", "pool1", [a1], kernel="(2, 2)", stride="(2, 2)", pool_type="max")
+    f = C.op("Flatten", "flat", [p1])
+    d0 = C.op("FullyConnected", "fc0", [f], num_hidden=256)
+    r0 = C.op("Activation", "relu2", [d0], act_type="relu")
+    d1 = C.op("FullyConnected", "fc1", [r0], num_hidden=128)
+    r1 = C.op("Activation", "relu3", [d1], act_type="relu")
+    d2 = C.op("FullyConnected", "fc2", [r1], num_hidden=10)
+    return C.op("SoftmaxOutput", "softmax", kwinputs={"data": d2, "label": C.var("softmax_label")}, normalization="batch")
+
+
+def test_symbol_compose_infer_json_roundtrip(tmp_path):
+    net = _cnn()
+    args = C.list_arguments(net)
+    assert args == ["data", "conv0_weight", "conv0_bias", "conv1_weight", "conv1_bias", "fc0_weight", "fc0_bias", "fc1_weight", "fc1_bias", "fc2_weight", "fc2_bias",
+                    "softmax_label"]
+    assert C.list_outputs(net) == ["softmax_output"] and C.list_aux(net) == []
+    a, o, x, complete = C.infer_shape(net, data=(32, 1, 28, 28))
+    assert complete and o == [(32, 10)] and x == []
+    assert dict(zip(args, a))["fc0_weight"] == (256, 512) and dict(zip(args, a))["conv1_weight"] == (32, 16, 5, 5) and dict(zip(args, a))["softmax_label"] == (32,)
+    assert sum(int(np.prod(s)) for n, s in zip(args, a) if n not in ("data", "softmax_label")) == 178762     # the parameter count BASELINE.md quotes
+    # nothing known: partial inference reports incomplete, the strict form fails with the name of the first undetermined node
+    a2, _, _, complete2 = C.infer_shape(net, partial=True)
+    assert not complete2 and a2[0] == ()
+    with pytest.raises(RuntimeError, match="cannot be determined"):
+        C.infer_shape(net)
+    with pytest.raises(RuntimeError, match="expected"):
+        C.infer_shape(net, data=(32, 1, 28, 28), fc0_weight=(256, 100))
+    # JSON: native -> Python front end -> native, same graph
+    js = C.sym_json(net)
+    import geomx_b200 as mx
+    psym = mx.sym.load_json(js)
+    assert psym.list_arguments() == args
+    _, pout, _ = psym.infer_shape(data=(32, 1, 28, 28))
+    assert pout == [(32, 10)]
+    back = C.sym_from_json(psym.tojson(nnvm=True))
+    assert C.list_arguments(back) == args and C.infer_shape(back, data=(8, 1, 28, 28))[1] == [(8, 10)]
+    own = C.sym_from_json(psym.tojson())                       # this framework's own dialect loads too
+    assert C.list_arguments(own) == args
+    fname = str(tmp_path / "net-symbol.json").encode()
+    ck(lib().GXSymbolSaveToFile(net, fname))
+    h = vp(); ck(lib().GXSymbolCreateFromFile(fname, ctypes.byref(h)))
+    assert C.sym_json(h) == js
+    # internals / outputs / children / attributes / copy / print
+    internals = vp(); ck(lib().GXSymbolGetInternals(net, ctypes.byref(internals)))
+    names = C.list_outputs(internals)
+    assert "fc1_output" in names and "conv0_weight" in names and names[-1] == "softmax_output"
+    fc1 = vp(); ck(lib().GXSymbolGetOutput(internals, names.index("fc1_output"), ctypes.byref(fc1)))
+    assert C.list_outputs(fc1) == ["fc1_output"] and "fc2_weight" not in C.list_arguments(fc1)
+    kids = vp(); ck(lib().GXSymbolGetChildren(fc1, ctypes.byref(kids)))
+    assert C.list_outputs(kids) == ["relu2_output", "fc1_weight", "fc1_bias"]
+    out, ok = cp(), ctypes.c_int()
+    ck(lib().GXSymbolGetAttr(fc1, b"num_hidden", ctypes.byref(out), ctypes.byref(ok))); assert ok.value == 1 and out.value == b"128"
+    w = C.var("w"); ck(lib().GXSymbolSetAttr(w, b"__lr_mult__", b"0.1"))
+    ck(lib().GXSymbolGetAttr(w, b"lr_mult", ctypes.byref(out), ctypes.byref(ok))); assert ok.value == 1 and out.value == b"0.1"
+    ck(lib().GXSymbolGetAttr(w, b"nope", ctypes.byref(out), ctypes.byref(ok))); assert ok.value == 0
+    n = u32(); ck(lib().GXSymbolGetNumOutputs(internals, ctypes.byref(n))); assert n.value == len(names)
+    ck(lib().GXSymbolGetName(net, ctypes.byref(out), ctypes.byref(ok))); assert out.value == b"softmax"
+    cpy = vp(); ck(lib().GXSymbolCopy(net, ctypes.byref(cpy))); assert C.sym_json(cpy) == js
+    ck(lib().GXSymbolPrint(net, ctypes.byref(out))); assert b"Op:Convolution, Name=conv0" in out.value
+    grp = vp(); ck(lib().GXSymbolCreateGroup(2, C.handles([fc1, net]), ctypes.byref(grp))); assert C.list_outputs(grp) == ["fc1_output", "softmax_output"]
+    # operator table
+    ops = C.str_list(lib().GXListAllOpNames)
+    assert {"Convolution", "FullyConnected", "BatchNorm", "SoftmaxOutput", "broadcast_mul", "dot"} <= set(ops)
+    nc, creators = u32(), ctypes.POINTER(vp)()
+    ck(lib().GXSymbolListAtomicSymbolCreators(ctypes.byref(nc), ctypes.byref(creators)))
+    info = {}
+    for i in range(nc.value):
+        nm, desc, na, an, at, ad, kv, rt = cp(), cp(), u32(), ctypes.POINTER(cp)(), ctypes.POINTER(cp)(), ctypes.POINTER(cp)(), cp(), cp()
+        ck(lib().GXSymbolGetAtomicSymbolInfo(vp(creators[i]), ctypes.byref(nm), ctypes.byref(desc), ctypes.byref(na), ctypes.byref(an), ctypes.byref(at), ctypes.byref(ad),
+                                             ctypes.byref(kv), ctypes.byref(rt)))
+        info[nm.value.decode()] = ([an[j].decode() for j in range(na.value)], kv.value.decode())
+    assert info["Convolution"][0][:2] == ["kernel", "num_filter"] and info["Concat"][1] == "num_args"
+    # errors are reported, not thrown across the ABI
+    bad = vp()
+    assert lib().GXSymbolCreateAtomicSymbolByName(b"NoSuchOp", 0, None, None, ctypes.byref(bad)) == -1 and "not registered" in C.err()
+    assert lib().GXSymbolCreateFromJSON(b'{"nodes": [{"op": "null", "name": "x", "inputs": [[3, 0, 0]]}], "heads": [[0, 0, 0]]}', ctypes.byref(bad)) == -1
+    for h in (net, back, own, internals, fc1, kids, cpy, grp, w):
+        ck(lib().GXSymbolFree(h))
+
+
+def _torch_cnn(params, X, y):
+    p = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+    h = TF.max_pool2d(torch.relu(TF.conv2d(X, p["conv0_weight"], p["conv0_bias"])), 2)
+    h = TF.max_pool2d(torch.relu(TF.conv2d(h, p["conv1_weight"], p["conv1_bias"])), 2).flatten(1)
+    h = torch.relu(TF.linear(h, p["fc0_weight"], p["fc0_bias"]))
+    h = torch.relu(TF.linear(h, p["fc1_weight"], p["fc1_bias"]))
+    logits = TF.linear(h, p["fc2_weight"], p["fc2_bias"])
+    TF.cross_entropy(logits, y.long(), reduction="mean").backward()
+    return torch.softmax(logits, 1).detach().numpy(), {k: v.grad.numpy() for k, v in p.items()}
+
+
+def test_executor_cnn_matches_torch_and_trains():
+    net = _cnn()
+    B = 16
+    ex, args, grads, aux = C.simple_bind(net, {"data": (B, 1, 28, 28)}, no_grad=("data", "softmax_label"))
+    assert set(grads) == set(args) - {"data", "softmax_label"} and aux == {}
+    rng = np.random.RandomState(0)
+    params = {}
+    for k, h in args.items():
+        if k in ("data", "softmax_label"):
+            continue
+        shp = C.nd_shape(h)
+        params[k] = (rng.randn(*shp) * (0.1 if k.endswith("weight") else 0.01)).astype(np.float32)
+        C.nd_set(h, params[k])
+    X = rng.rand(B, 1, 28, 28).astype(np.float32); y = rng.randint(0, 10, B).astype(np.float32)
+    C.nd_set(args["data"], X); C.nd_set(args["softmax_label"], y)
+    prob = C.forward(ex, True)[0]
+    C.backward(ex)
+    tprob, tgrad = _torch_cnn(params, torch.tensor(X), torch.tensor(y))
+    assert np.allclose(prob, tprob, atol=1e-5)
+    for k in params:
+        g = C.nd_get(grads[k])
+        assert np.allclose(g, tgrad[k], rtol=1e-3, atol=1e-5 * max(1.0, np.abs(tgrad[k]).max())), (k, np.abs(g - tgrad[k]).max())
+    # a few SGD steps through the C ABI only: the loss goes down
+    def loss():
+        p = C.forward(ex, True)[0]
+        return float(-np.log(p[np.arange(B), y.astype(int)] + 1e-12).mean())
+    l0 = loss()
+    for _ in range(30):
+        loss(); C.backward(ex)
+        for k in params:
+            params[k] = params[k] - 0.1 * C.nd_get(grads[k]); C.nd_set(args[k], params[k])
+    assert loss() < 0.8 * l0
+    out = cp(); ck(lib().GXExecutorPrint(ex, ctypes.byref(out))); assert b"Op:Convolution, Name=conv1" in out.value
+    # grad_req add accumulates; explicit Bind with caller-owned arrays
+    x = C.var("x"); s = C.op("_mul_scalar", "twice", [x], scalar=2.0)
+    xa, ga = C.nd_create(np.ones((2, 3))), C.nd_create(np.full((2, 3), 5.0))
+    e2 = vp()
+    ck(lib().GXExecutorBind(s, 1, 0, 1, C.handles([xa]), C.handles([ga]), (u32 * 1)(3), 0, None, ctypes.byref(e2)))
+    assert np.allclose(C.forward(e2, True)[0], 2.0)
+    hg = C.nd_create(np.full((2, 3), 0.5)); C.backward(e2, [hg])
+    assert np.allclose(C.nd_get(ga), 6.0)
+    assert lib().GXExecutorBackward(e2, 1, C.handles([C.nd_create(np.ones(5))])) == -1 and "does not match" in C.err()
+    ck(lib().GXExecutorFree(e2)); ck(lib().GXExecutorFree(ex))
+
+
+def _t(a, grad=True):
+    return torch.tensor(np.asarray(a, dtype=np.float32), requires_grad=grad)
+
+
+def test_imperative_autograd_matches_torch():
+    rng = np.random.RandomState(1)
+    xn, wn, gn, bn = rng.randn(4, 3, 6, 6), rng.randn(5, 3, 3, 3) * 0.3, rng.rand(5) + 0.5, rng.randn(5) * 0.1
+    emb_idx, emb_w = np.array([[0, 2], [3, 2]], dtype=np.float32), rng.randn(4, 6)
+    x, w, g, b, ew = [C.nd_create(a) for a in (xn, wn, gn, bn, emb_w)]
+    grads = [C.nd_create(np.zeros_like(a)) for a in (xn, wn, gn, bn, emb_w)]
+    C.mark_variables([x, w, g, b, ew], grads)
+    mm, mv = C.nd_create(np.zeros(5)), C.nd_create(np.ones(5))
+    with C.record():
+        c = C.invoke("Convolution", [x, w], kernel="(3, 3)", num_filter=5, pad="(1, 1)", stride="(2, 2)", no_bias=True)      # (4, 5, 3, 3)
+        n = C.invoke("BatchNorm", [c, g, b, mm, mv], fix_gamma=False, eps=1e-5, momentum=0.9)
+        a = C.invoke("LeakyReLU", [n], act_type="leaky", slope=0.1)
+        p = C.invoke("Pooling", [a], kernel="(2, 2)", stride="(1, 1)", pad="(1, 1)", pool_type="avg")                          # (4, 5, 4, 4)
+        t = C.invoke("transpose", [p], axes="(0, 2, 3, 1)")
+        r = C.invoke("Reshape", [t], shape="(4, -1)")                                                                           # (4, 80)
+        e = C.invoke("Embedding", [C.nd_create(emb_idx), ew], input_dim=4, output_dim=6)                                         # (2, 2, 6)
+        e2 = C.invoke("Reshape", [e], shape="(4, 6)")
+        cat = C.invoke("Concat", [r, e2], dim=1)                                                                                # (4, 86)
+        sm = C.invoke("log_softmax", [cat], axis=-1)
+        m = C.invoke("mean", [sm], axis="(1,)", keepdims=True)                                                                  # (4, 1)
+        bm = C.invoke("broadcast_mul", [cat, m])
+        d = C.invoke("dot", [bm, cat], transpose_b=True)                                                                        # (4, 4)
+        out = C.invoke("sum", [C.invoke("tanh", [d])])
+    sym = vp(); ck(lib().GXAutogradGetSymbol(out, ctypes.byref(sym)))
+    assert [a_ for a_ in C.list_arguments(sym) if a_.startswith("var")] == ["var0", "var1", "var2", "var3", "var4"] and "Op:dot" in _print(sym)
+    C.ag_backward([out])
+    with pytest.raises(RuntimeError, match="already freed"):
+        C.ag_backward([out])
+    # the same computation in torch
+    tx, tw, tg, tb, tew = _t(xn), _t(wn), _t(gn), _t(bn), _t(emb_w)
+    tc = TF.conv2d(tx, tw, None, stride=2, padding=1)
+    tn = TF.batch_norm(tc, torch.zeros(5), torch.ones(5), tg, tb, training=True, momentum=0.1, eps=1e-5)
+    ta = TF.leaky_relu(tn, 0.1)
+    tp = TF.avg_pool2d(ta, 2, 1, 1, count_include_pad=True)
+    tr = tp.permute(0, 2, 3, 1).reshape(4, -1)
+    te = tew[torch.tensor(emb_idx).long()].reshape(4, 6)
+    tcat = torch.cat([tr, te], 1)
+    tm = torch.log_softmax(tcat, -1).mean(1, keepdim=True)
+    tout = torch.tanh((tcat * tm) @ tcat.t()).sum()
+    tout.backward()
+    assert np.allclose(C.nd_get(out), tout.item(), rtol=1e-4)
+    for h, tt, name in zip(grads, (tx, tw, tg, tb, tew), "x w gamma beta emb".split()):
+        got, want = C.nd_get(h), tt.grad.numpy()
+        assert np.allclose(got, want, rtol=2e-3, atol=2e-5 * max(1.0, np.abs(want).max())), (name, np.abs(got - want).max())
+    # running statistics were updated in place (momentum 0.9 towards the batch statistics)
+    assert np.allclose(C.nd_get(mm), 0.1 * tc.detach().mean((0, 2, 3)).numpy(), atol=1e-5)
+    # not recording: no history; dropout is the identity outside training mode and a mask inside
+    y = C.invoke("relu", [x])
+    with pytest.raises(RuntimeError, match="not computed while recording"):
+        C.ag_backward([y])
+    ones = C.nd_create(np.ones((64, 64)))
+    assert np.array_equal(C.nd_get(C.invoke("Dropout", [ones], p=0.5)), np.ones((64, 64)))
+    with C.record(train=True):
+        dm = C.nd_get(C.invoke("Dropout", [ones], p=0.5))
+    assert set(np.unique(dm)) == {0.0, 2.0} and 0.35 < (dm == 0).mean() < 0.65
+    # wrong input count / dtype are errors
+    with pytest.raises(RuntimeError, match="inputs given"):
+        C.invoke("dot", [x])
+    gh = vp(); ck(lib().GXNDArrayGetGrad(x, ctypes.byref(gh))); assert gh.value == grads[0].value
+    det = vp(); ck(lib().GXNDArrayDetach(out, ctypes.byref(det))); assert np.allclose(C.nd_get(det), C.nd_get(out))
+
+
+def _print(sym):
+    out = cp(); ck(lib().GXSymbolPrint(sym, ctypes.byref(out)))
+    return out.value.decode()
+
+
+@pytest.mark.parametrize("case", ["sigmoid_logistic", "maxpool_full", "softmax_ignore", "grouped_conv", "broadcast_div_max", "scalars"])
+def test_operator_gradients(case):
+    rng = np.random.RandomState(2)
+    if case == "sigmoid_logistic":
+        xn, yn = rng.randn(6, 3), rng.rand(6, 3)
+        net = C.op("LogisticRegressionOutput", "lro", kwinputs={"data": C.op("FullyConnected", "fc", [C.var("data")], num_hidden=3, no_bias=True), "label": C.var("label")},
+                   grad_scale=2.0)
+        ex, args, grads, _ = C.simple_bind(net, {"data": (6, 3)}, no_grad=("label",))
+        wn = rng.randn(3, 3)
+        C.nd_set(args["data"], xn); C.nd_set(args["fc_weight"], wn); C.nd_set(args["label"], yn)
+        C.forward(ex, True); C.backward(ex)
+        tx, tw = _t(xn), _t(wn)
+        z = tx @ tw.t()                      # the op's gradient (p - y) * grad_scale / num_output is taken w.r.t. its INPUT (regression_output-inl.h:200)
+        z.backward((torch.sigmoid(z.detach()) - torch.tensor(yn, dtype=torch.float32)) * 2.0 / 3)
+        assert np.allclose(C.nd_get(grads["data"]), tx.grad.numpy(), atol=1e-5) and np.allclose(C.nd_get(grads["fc_weight"]), tw.grad.numpy(), atol=1e-5)
+    elif case == "maxpool_full":
+        xn = rng.randn(2, 3, 7, 7)
+        net = C.op("MakeLoss", "l", [C.op("Pooling", "p", [C.var("data")], kernel="(3, 3)", stride="(2, 2)", pad="(1, 1)", pool_type="max", pooling_convention="full")])
+        ex, args, grads, _ = C.simple_bind(net, {"data": (2, 3, 7, 7)})
+        C.nd_set(args["data"], xn)
+        out = C.forward(ex, True)[0]; C.backward(ex)
+        tx = _t(xn)
+        tp = TF.max_pool2d(tx, 3, 2, 1, ceil_mode=True)
+        tp.sum().backward()
+        assert out.shape == tuple(tp.shape) and np.allclose(out, tp.detach().numpy()) and np.allclose(C.nd_get(grads["data"]), tx.grad.numpy())
+    elif case == "softmax_ignore":
+        xn = rng.randn(2, 4, 5); yn = rng.randint(0, 4, (2, 5)).astype(np.float32); yn[0, 1] = -1; yn[1, 3] = -1
+        net = C.op("SoftmaxOutput", "sm", kwinputs={"data": C.var("data"), "label": C.var("label")}, multi_output=True, use_ignore=True, ignore_label=-1,
+                   normalization="valid")
+        ex, args, grads, _ = C.simple_bind(net, {"data": (2, 4, 5)}, no_grad=("label",))
+        assert C.nd_shape(args["label"]) == (2, 5)
+        C.nd_set(args["data"], xn); C.nd_set(args["label"], yn)
+        C.forward(ex, True); C.backward(ex)
+        tx = _t(xn)
+        TF.cross_entropy(tx, torch.tensor(yn).long(), ignore_index=-1, reduction="mean").backward()
+        assert np.allclose(C.nd_get(grads["data"]), tx.grad.numpy(), atol=1e-6)
+    elif case == "grouped_conv":
+        xn, wn, bn = rng.randn(2, 4, 6, 5), rng.randn(6, 2, 3, 2), rng.randn(6)
+        net = C.op("MakeLoss", "l", [C.op("square", "sq", [C.op("Convolution", "c", [C.var("data")], kernel="(3, 2)", num_filter=6, num_group=2, dilate="(2, 1)", pad="(2, 0)")])])
+        ex, args, grads, _ = C.simple_bind(net, {"data": (2, 4, 6, 5)})
+        for k, v in (("data", xn), ("c_weight", wn), ("c_bias", bn)):
+            C.nd_set(args[k], v)
+        out = C.forward(ex, True)[0]; C.backward(ex)
+        tx, tw, tb = _t(xn), _t(wn), _t(bn)
+        to = TF.conv2d(tx, tw, tb, dilation=(2, 1), padding=(2, 0), groups=2) ** 2
+        to.sum().backward()
+        assert np.allclose(out, to.detach().numpy(), rtol=1e-4, atol=1e-5)
+        for k, t in (("data", tx), ("c_weight", tw), ("c_bias", tb)):
+            assert np.allclose(C.nd_get(grads[k]), t.grad.numpy(), rtol=1e-3, atol=1e-4), k
+    elif case == "broadcast_div_max":
+        an, bn = rng.rand(3, 1, 4) + 0.5, rng.rand(2, 1) + 0.5
+        a, b = C.var("a"), C.var("b")
+        net = C.op("MakeLoss", "l", [C.op("broadcast_maximum", "mx", [C.op("broadcast_div", "dv", [a, b]), C.op("broadcast_sub", "sb", [a, b])])])
+        ex, args, grads, _ = C.simple_bind(net, {"a": (3, 1, 4), "b": (2, 1)})
+        C.nd_set(args["a"], an); C.nd_set(args["b"], bn)
+        out = C.forward(ex, True)[0]; C.backward(ex)
+        ta, tb = _t(an), _t(bn)
+        to = torch.maximum(ta / tb, ta - tb); to.sum().backward()
+        assert out.shape == (3, 2, 4) and np.allclose(out, to.detach().numpy(), atol=1e-6)
+        assert np.allclose(C.nd_get(grads["a"]), ta.grad.numpy(), atol=1e-5) and np.allclose(C.nd_get(grads["b"]), tb.grad.numpy(), atol=1e-5)
+    else:
+        xn = rng.rand(3, 4) + 0.5
+        x = C.var("x")
+        h = C.op("_rdiv_scalar", "rd", [C.op("_power_scalar", "pw", [C.op("_rminus_scalar", "rm", [x], scalar=3.0)], scalar=1.5)], scalar=2.0)
+        h = C.op("elemwise_add", "ad", [C.op("softsign", "ss", [C.op("sqrt", "sq", [h])]), C.op("BlockGrad", "bg", [C.op("exp", "ex", [x])])])
+        net = C.op("MakeLoss", "l", [C.op("add_n", "an", [h, C.op("clip", "cl", [x], a_min=0.8, a_max=1.2), C.op("log", "lg", [x])])], grad_scale=0.5)
+        ex, args, grads, _ = C.simple_bind(net, {"x": (3, 4)})
+        C.nd_set(args["x"], xn)
+        out = C.forward(ex, True)[0]; C.backward(ex)
+        tx = _t(xn)
+        th = torch.sqrt(2.0 / (3.0 - tx) ** 1.5)
+        to = th / (1 + th.abs()) + torch.exp(tx).detach() + tx.clamp(0.8, 1.2) + torch.log(tx)
+        (0.5 * to).sum().backward()
+        assert np.allclose(out, to.detach().numpy(), rtol=1e-5) and np.allclose(C.nd_get(grads["x"]), tx.grad.numpy(), rtol=1e-4, atol=1e-6)
+    ck(lib().GXExecutorFree(ex))
+
+
+def test_batchnorm_inference_and_aux_states():
+    x = C.var("data")
+    net = C.op("BatchNorm", "bn", [x], fix_gamma=True, eps=1e-3)
+    assert C.list_arguments(net) == ["data", "bn_gamma", "bn_beta"] and C.list_aux(net) == ["bn_moving_mean", "bn_moving_var"]
+    a, o, aux, ok = C.infer_shape(net, data=(4, 3, 2, 2))
+    assert ok and a == [(4, 3, 2, 2), (3,), (3,)] and aux == [(3,), (3,)]
+    ex, args, grads, auxs = C.simple_bind(net, {"data": (4, 3, 2, 2)})
+    rng = np.random.RandomState(3)
+    xn = rng.randn(4, 3, 2, 2).astype(np.float32)
+    C.nd_set(args["data"], xn); C.nd_set(args["bn_gamma"], np.full(3, 7.0)); C.nd_set(args["bn_beta"], np.array([1.0, 2.0, 3.0]))
+    C.nd_set(auxs["bn_moving_mean"], np.array([0.5, -0.5, 0.0])); C.nd_set(auxs["bn_moving_var"], np.array([4.0, 1.0, 0.25]))
+    out = C.forward(ex, False)[0]                      # inference: running statistics, gamma fixed to 1
+    want = (xn - np.array([0.5, -0.5, 0.0]).reshape(1, 3, 1, 1)) / np.sqrt(np.array([4.0, 1.0, 0.25]).reshape(1, 3, 1, 1) + 1e-3) + np.array([1.0, 2.0, 3.0]).reshape(1, 3, 1, 1)
+    assert np.allclose(out, want, atol=1e-5)
+    assert np.allclose(C.nd_get(auxs["bn_moving_mean"]), [0.5, -0.5, 0.0])
+    out = C.forward(ex, True)[0]                       # training: batch statistics, running statistics move
+    assert np.allclose(out.mean((0, 2, 3)), [1.0, 2.0, 3.0], atol=1e-4)
+    assert np.allclose(C.nd_get(auxs["bn_moving_mean"]), 0.9 * np.array([0.5, -0.5, 0.0]) + 0.1 * xn.mean((0, 2, 3)), atol=1e-5)
+    C.backward(ex, [C.nd_create(np.ones((4, 3, 2, 2)))])
+    assert np.allclose(C.nd_get(grads["bn_gamma"]), 0.0) and np.allclose(C.nd_get(grads["bn_beta"]), 16.0)
+    ck(lib().GXExecutorFree(ex))
+
+
+def test_recordio_c_api_interchange_with_python(tmp_path):
+    import geomx_b200 as mx
+    magic = struct.pack("<I", 0xced7230a)
+    payloads = [b"hello", b"", b"x" * 1001, b"abcd" + magic + b"tail", magic + magic + b"zz", bytes(range(256)) * 3]
+    path = str(tmp_path / "c.rec")
+    w = vp(); ck(lib().GXRecordIOWriterCreate(path.encode(), ctypes.byref(w)))
+    offs = []
+    for p in payloads:
+        pos = ctypes.c_size_t(); ck(lib().GXRecordIOWriterTell(w, ctypes.byref(pos))); offs.append(pos.value)
+        ck(lib().GXRecordIOWriterWriteRecord(w, p, ctypes.c_size_t(len(p))))
+    ck(lib().GXRecordIOWriterFree(w))
+    r = mx.recordio.MXRecordIO(path, "r")              # the Python front end reads what the C API wrote
+    assert [r.read() for _ in payloads] == payloads and r.read() is None
+    r.close()
+    path2 = str(tmp_path / "py.rec")
+    pw = mx.recordio.MXRecordIO(path2, "w")
+    for p in payloads:
+        pw.write(p)
+    pw.close()
+    assert open(path, "rb").read() == open(path2, "rb").read()          # byte-identical files
+    rd = vp(); ck(lib().GXRecordIOReaderCreate(path2.encode(), ctypes.byref(rd)))
+    got = []
+    while True:
+        buf, size = ctypes.POINTER(ctypes.c_char)(), ctypes.c_size_t()
+        ck(lib().GXRecordIOReaderReadRecord(rd, ctypes.byref(buf), ctypes.byref(size)))
+        if not buf:
+            break
+        got.append(ctypes.string_at(buf, size.value))
+    assert got == payloads
+    ck(lib().GXRecordIOReaderSeek(rd, ctypes.c_size_t(offs[3])))
+    buf, size = ctypes.POINTER(ctypes.c_char)(), ctypes.c_size_t()
+    ck(lib().GXRecordIOReaderReadRecord(rd, ctypes.byref(buf), ctypes.byref(size)))
+    assert ctypes.string_at(buf, size.value) == payloads[3]
+    ck(lib().GXRecordIOReaderFree(rd))
+    # a damaged file is an error, not a crash
+    bad = str(tmp_path / "bad.rec")
+    open(bad, "wb").write(open(path, "rb").read()[:30] + b"\x00" * 7)
+    rd = vp(); ck(lib().GXRecordIOReaderCreate(bad.encode(), ctypes.byref(rd)))
+    rcs = []
+    for _ in range(4):
+        rcs.append(lib().GXRecordIOReaderReadRecord(rd, ctypes.byref(buf), ctypes.byref(size)))
+    assert -1 in rcs
+    ck(lib().GXRecordIOReaderFree(rd))
+
+
+def test_data_iterators_c_api(tmp_path):
+    rng = np.random.RandomState(4)
+    img = rng.randint(0, 256, (50, 28, 28)).astype(np.uint8); lab = rng.randint(0, 10, 50).astype(np.uint8)
+    ip, lp = str(tmp_path / "img.idx"), str(tmp_path / "lab.idx")
+    open(ip, "wb").write(struct.pack(">IIII", 0x803, 50, 28, 28) + img.tobytes())
+    open(lp, "wb").write(struct.pack(">II", 0x801, 50) + lab.tobytes())
+    n, creators = u32(), ctypes.POINTER(vp)()
+    ck(lib().GXListDataIters(ctypes.byref(n), ctypes.byref(creators)))
+    byname = {}
+    for i in range(n.value):
+        nm, desc, na, an, at, ad = cp(), cp(), u32(), ctypes.POINTER(cp)(), ctypes.POINTER(cp)(), ctypes.POINTER(cp)()
+        ck(lib().GXDataIterGetIterInfo(vp(creators[i]), ctypes.byref(nm), ctypes.byref(desc), ctypes.byref(na), ctypes.byref(an), ctypes.byref(at), ctypes.byref(ad)))
+        byname[nm.value.decode()] = vp(creators[i])
+    assert set(byname) == {"MNISTIter", "CSVIter"}
+
+    def make(name, **kw):
+        h = vp()
+        rc = lib().GXDataIterCreateIter(byname[name], len(kw), C.strs(list(kw.keys())), C.strs([str(v) for v in kw.values()]), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(C.err())
+        return h
+
+    def batches(it):
+        out = []
+        while True:
+            more = ctypes.c_int(); ck(lib().GXDataIterNext(it, ctypes.byref(more)))
+            if not more.value:
+                return out
+            d, l, pad = vp(), vp(), ctypes.c_int()
+            ck(lib().GXDataIterGetData(it, ctypes.byref(d))); ck(lib().GXDataIterGetLabel(it, ctypes.byref(l))); ck(lib().GXDataIterGetPadNum(it, ctypes.byref(pad)))
+            idx, ni = ctypes.POINTER(ctypes.c_uint64)(), ctypes.c_uint64()
+            ck(lib().GXDataIterGetIndex(it, ctypes.byref(idx), ctypes.byref(ni)))
+            out.append((C.nd_get(d), C.nd_get(l), pad.value, [idx[i] for i in range(ni.value)]))
+    it = make("MNISTIter", image=ip, label=lp, batch_size=16, shuffle=0)
+    bs = batches(it)
+    assert len(bs) == 3 and bs[0][0].shape == (16, 1, 28, 28) and bs[0][1].shape == (16,)            # 50 // 16 full batches, the partial one is dropped
+    assert np.allclose(bs[1][0][:, 0], img[16:32] / 256.0) and np.array_equal(bs[1][1], lab[16:32]) and bs[1][3] == list(range(16, 32))
+    ck(lib().GXDataIterBeforeFirst(it)); assert len(batches(it)) == 3
+    ck(lib().GXDataIterFree(it))
+    it = make("MNISTIter", image=ip, label=lp, batch_size=10, shuffle=1, seed=7, flat=1, num_parts=2, part_index=1)
+    bs = batches(it)
+    seen = sorted(i for b in bs for i in b[3])
+    assert bs[0][0].shape == (10, 784) and len(bs) == 2 and len(set(seen)) == 20 and bs[0][3] != list(range(10))
+    assert all(np.array_equal(b[1], lab[25:][b[3]]) for b in bs)
+    ck(lib().GXDataIterFree(it))
+    dn, ln = rng.randn(7, 6).astype(np.float32), rng.randint(0, 3, (7, 1)).astype(np.float32)
+    dp, lpath = str(tmp_path / "d.csv"), str(tmp_path / "l.csv")
+    np.savetxt(dp, dn, delimiter=",", fmt="%.8g"); np.savetxt(lpath, ln, delimiter=",", fmt="%g")
+    it = make("CSVIter", data_csv=dp, data_shape="(2, 3)", label_csv=lpath, batch_size=3)
+    bs = batches(it)
+    assert [b[2] for b in bs] == [0, 0, 2] and bs[0][0].shape == (3, 2, 3) and np.allclose(bs[2][0][0].ravel(), dn[6], atol=1e-6)
+    assert np.allclose(bs[2][0][1].ravel(), dn[0], atol=1e-6) and np.array_equal(bs[2][1], [ln[6, 0], ln[0, 0], ln[1, 0]])          # round_batch wraps to the start
+    ck(lib().GXDataIterFree(it))
+    with pytest.raises(RuntimeError, match="columns"):
+        make("CSVIter", data_csv=dp, data_shape="(5,)", batch_size=2)
+    with pytest.raises(RuntimeError, match="required"):
+        make("MNISTIter", image=ip)
+    v = ctypes.c_int(); ck(lib().GXGetVersion(ctypes.byref(v))); assert v.value == 10400
