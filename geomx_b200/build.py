@@ -103,9 +103,41 @@ def build_runtime(force=False, verbose=False):
     return out
 
 
+def build_capi(force=False, verbose=False):
+    """``lib/libgeomx_capi.so``: the flat C ABI (GXKVStore* / GXNDArray* / GXSymbol* / GXExecutor* / GXAutograd* / GXRecordIO* / GXDataIter* /
+    GXPred* / profiler / engine / storage) WITHOUT Python — the same sources as ``_C``, minus the pybind11 module, compiled with
+    ``-DGEOMX_NO_PYTHON`` and with neither the pybind11 nor the CPython include directory on the command line.  This is what a C / C++ /
+    other-language front end links (header: ``geomx_b200/include/geomx/c_api.h``; the role of the reference's libmxnet.so C API)."""
+    rdirs = [os.path.join(CSRC, "hips"), os.path.join(CSRC, "runtime")]
+    os.makedirs(LIB, exist_ok=True); os.makedirs(OBJ, exist_ok=True)
+    out = os.path.join(LIB, "libgeomx_capi.so")
+    hdrs, srcs = [], []
+    for d in rdirs:
+        for f in sorted(os.listdir(d)):
+            p = os.path.join(d, f)
+            if f.endswith(".cc") and f != "py_module.cc":
+                srcs.append(p)
+            elif f.endswith((".h", ".hpp")):
+                hdrs.append(p)
+    objs, jobs = [], []
+    for src in srcs:
+        obj = os.path.join(OBJ, "capi_" + os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(src, obj, tuple(hdrs)):
+            jobs.append([CXX] + CXX_FLAGS + ["-DGEOMX_NO_PYTHON", "-I", CSRC, "-c", src, "-o", obj])
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
+        for o in pool.map(_run, jobs):
+            if verbose and o.strip():
+                print(o)
+    if jobs or not os.path.exists(out):
+        _run([CXX, "-shared", "-o", out] + objs + ["-pthread", "-l:libstdc++.so.6", "-Wl,--no-undefined"] + (["-fsanitize=" + _SAN] if _SAN else []))
+    return out
+
+
 def build_all(force=False, verbose=False):
     k = build_kernels(force, verbose)
     r = build_runtime(force, verbose)
+    build_capi(force, verbose)
     return k, r
 
 
@@ -115,3 +147,4 @@ if __name__ == "__main__":
         print(build_kernels(force, True))
     if "--kernels-only" not in sys.argv:
         print(build_runtime(force, True))
+        print(build_capi(force, True))

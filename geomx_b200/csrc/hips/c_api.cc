@@ -70,5 +70,19 @@ GX_CAPI int GXKVStoreSetGradientCompression(void* h, const char* type, float thr
 }
 GX_CAPI int GXKVStoreGetNumDeadNode(void* h, int node_id, int timeout_sec, int* out) { return Guard([&] { *out = KV(h)->num_dead_node(node_id, timeout_sec); }); }
 // server / scheduler processes: blocks until the job ends.  Optimizers arrive as declarative specs (command 7) and run natively.
+GX_CAPI int GXKVStoreGetType(void* h, const char** out) { return Guard([&] { *out = KV(h)->type().c_str(); }); }
+// MXKVStoreRunServer(handle, controller, controller_handle) + MXKVStoreSetUpdater(handle, updater, updater_handle) in one call for server
+// processes: controller(head, body, arg) receives the commands workers send with SendCommmandToServers; updater(key, grad, weight, n, arg)
+// replaces the built-in optimizer when not null (fp32 host buffers, update `weight` in place).
+typedef void (*GXKVController)(int head, const char* body, void* arg);
+typedef void (*GXKVUpdater)(int key, const float* grad, float* weight, size_t n, void* arg);
+GX_CAPI int GXKVStoreRunServerEx(void* h, GXKVController controller, void* controller_arg, GXKVUpdater updater, void* updater_arg) {
+  return Guard([&] {
+    hips::KVStoreDistServer::Controller c = nullptr; hips::KVStoreDistServer::Updater u = nullptr;
+    if (controller) c = [controller, controller_arg](int head, const std::string& body) { controller(head, body.c_str(), controller_arg); };
+    if (updater) u = [updater, updater_arg](int key, const float* g, float* w, size_t n) { updater(key, g, w, n, updater_arg); };
+    KV(h)->RunServer(c, u, nullptr);
+  });
+}
 GX_CAPI int GXKVStoreRunServer(void* h) { return Guard([&] { KV(h)->RunServer(nullptr, nullptr, nullptr); }); }
 GX_CAPI int GXKVStoreShutdown(void* h) { return Guard([&] { KV(h)->Shutdown(); }); }

@@ -59,6 +59,7 @@ class KVStoreDist {
   }
 
   // ---- roles / sizes ------------------------------------------------------------------------------------------------
+  const std::string& type() const { return type_; }
   int rank() { return Postoffice::Get()->my_rank(kLocal); }
   int num_workers() { return Postoffice::Get()->num_workers(); }
   int num_all_workers() { return Postoffice::Get()->num_all_workers(); }

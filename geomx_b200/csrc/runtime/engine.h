@@ -13,9 +13,11 @@
 // per-device pool buys is that the host threads that issue launches / copies for GPU d never wait behind host work for GPU e.
 // Duplicate vars in const / mutable sets are rejected like threaded_engine.h:432.
 #pragma once
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 #include <pybind11/functional.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
+#endif
 
 #include <atomic>
 #include <condition_variable>
@@ -34,7 +36,9 @@
 #include <vector>
 
 namespace gxrt {
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 namespace py = pybind11;
+#endif
 
 enum class FnProperty : int { kNormal = 0, kCopy = 1, kPriority = 2 };
 
@@ -209,6 +213,7 @@ class Engine {
   bool stop_ = false;
 };
 
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 inline void BindEngine(py::module_& m) {
   py::class_<Engine>(m, "Engine")
       .def(py::init<int, bool>(), py::arg("num_threads") = 2, py::arg("naive") = false)
@@ -229,5 +234,6 @@ inline void BindEngine(py::module_& m) {
       .def("stats", &Engine::Stats)
       .def("num_variables", &Engine::NumVariables);
 }
+#endif
 
 }  // namespace gxrt

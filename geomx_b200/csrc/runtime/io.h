@@ -2,9 +2,11 @@
 // Parity: src/io/iter_mnist.cc:80-260 (MNISTIter: idx magic parsing, scaling to [0,1], shuffle / partition), src/io/iter_prefetcher.h
 // (background producer with a bounded queue).  Batches are written straight into caller-provided (pinned) host buffers.
 #pragma once
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -20,7 +22,9 @@
 #include <vector>
 
 namespace gxrt {
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 namespace py = pybind11;
+#endif
 
 inline uint32_t BE32(const unsigned char* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
 
@@ -36,6 +40,7 @@ inline std::pair<std::vector<int64_t>, std::string> ReadIdx(const std::string& p
   return {dims, buf.substr(4 + 4 * ndim)};
 }
 
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 // Prefetcher over an in-memory uint8 image set: worker threads build (float image batch scaled by 1/255, float label batch)
 class BatchPrefetcher {
  public:
@@ -126,5 +131,6 @@ inline void BindIO(py::module_& m) {
       .def("num_batches", &BatchPrefetcher::num_batches)
       .def("next", &BatchPrefetcher::Next, py::call_guard<py::gil_scoped_release>());
 }
+#endif
 
 }  // namespace gxrt

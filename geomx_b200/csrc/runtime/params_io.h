@@ -2,8 +2,10 @@
 // Parity: src/ndarray/ndarray.cc:1583-1811 (NDArray::Save/Load V2 magic 0xF993fac9, V1 0xF993fac8, legacy magic==ndim; list magic 0x112),
 // dmlc serializer of vector<string> names.  Dense arrays are returned as (dtype_flag, shape, bytes); row_sparse / csr are densified.
 #pragma once
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
+#endif
 
 #include <algorithm>
 #include <cstdint>
@@ -14,7 +16,9 @@
 #include <vector>
 
 namespace gxrt {
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 namespace py = pybind11;
+#endif
 
 struct NDRec {
   int dtype = 0;
@@ -137,6 +141,7 @@ inline std::string WriteList(const std::vector<NDRec>& arrays, const std::vector
   return out;
 }
 
+#ifndef GEOMX_NO_PYTHON   // the Python-free C library (lib/libgeomx_capi.so) compiles the runtime without the pybind11 bindings
 inline void BindParamsIO(py::module_& m) {
   m.def("params_load", [](py::bytes blob) {
     std::string s = blob;
@@ -160,5 +165,6 @@ inline void BindParamsIO(py::module_& m) {
     return py::bytes(WriteList(recs, names));
   });
 }
+#endif
 
 }  // namespace gxrt

@@ -430,3 +430,111 @@ def test_data_iterators_c_api(tmp_path):
     with pytest.raises(RuntimeError, match="required"):
         make("MNISTIter", image=ip)
     v = ctypes.c_int(); ck(lib().GXGetVersion(ctypes.byref(v))); assert v.value == 10400
+
+
+def test_python_free_c_library_and_c_example(tmp_path):
+    """lib/libgeomx_capi.so exports every function the public header declares, depends on neither libpython nor torch, and the pure-C
+    training example (examples/c_api/train_cnn.c) builds against it, trains the demo CNN and serves its checkpoint through GXPred*."""
+    import os
+    import re
+    import shutil
+    import subprocess
+    so = os.path.join(C.ROOT, "geomx_b200", "lib", "libgeomx_capi.so")
+    if not os.path.exists(so):
+        from geomx_b200 import build
+        build.build_capi()
+    header = open(os.path.join(C.ROOT, "geomx_b200", "include", "geomx", "c_api.h")).read()
+    declared = set(re.findall(r"\b(GX[A-Za-z0-9]+)\s*\(", header)) - {"GXEngineFn"}
+    exported = {l.split()[-1] for l in subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout.splitlines() if " T " in l}
+    assert len(declared) > 130 and not (declared - exported), sorted(declared - exported)
+    pyext = {l.split()[-1] for l in subprocess.run(["nm", "-D", "--defined-only", C.lib()._name], capture_output=True, text=True, check=True).stdout.splitlines() if " T " in l}
+    assert not (declared - pyext), sorted(declared - pyext)          # the Python extension carries the same ABI
+    needed = subprocess.run(["ldd", so], capture_output=True, text=True, check=True).stdout
+    assert "python" not in needed and "torch" not in needed, needed
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "train_cnn")
+    subprocess.run([cc, "-O2", "-Wall", "-Werror", "-std=c99", "-I", os.path.join(C.ROOT, "geomx_b200", "include"), os.path.join(C.ROOT, "examples", "c_api", "train_cnn.c"),
+                    "-L", os.path.dirname(so), "-lgeomx_capi", "-Wl,-rpath," + os.path.dirname(so), "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe, "40", str(tmp_path / "cnn")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "predictor agrees with the executor on 32/32" in r.stdout
+    # the checkpoint the C program wrote is a regular checkpoint for the Python front end
+    import geomx_b200 as mx
+    sym, arg, aux = mx.model.load_checkpoint(str(tmp_path / "cnn"), 1)
+    assert sym.list_outputs() == ["softmax_output"] and tuple(arg["fc0_weight"].shape) == (256, 512) and aux == {}
+
+
+def test_ndarray_views_raw_bytes_profile_objects_and_knobs(tmp_path):
+    a = C.nd_create(np.arange(24, dtype=np.float32).reshape(4, 3, 2))
+    s, t, r = vp(), vp(), vp()
+    ck(lib().GXNDArraySlice(a, 1, 3, ctypes.byref(s))); assert np.array_equal(C.nd_get(s), np.arange(24).reshape(4, 3, 2)[1:3])
+    ck(lib().GXNDArrayAt(a, 2, ctypes.byref(t))); assert np.array_equal(C.nd_get(t), np.arange(24).reshape(4, 3, 2)[2])
+    ck(lib().GXNDArrayReshape(a, 3, (ctypes.c_int * 3)(0, -1, 1), ctypes.byref(r))); assert C.nd_shape(r) == (4, 6, 1)
+    assert lib().GXNDArraySlice(a, 3, 9, ctypes.byref(s)) == -1 and lib().GXNDArrayReshape(a, 2, (ctypes.c_int * 2)(5, -1), ctypes.byref(r)) == -1
+    dt, di, st = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    ck(lib().GXNDArrayGetContext(a, ctypes.byref(dt), ctypes.byref(di))); ck(lib().GXNDArrayGetStorageType(a, ctypes.byref(st)))
+    assert (dt.value, di.value, st.value) == (1, 0, 0)
+    ck(lib().GXNDArrayWaitToRead(a)); ck(lib().GXNDArrayWaitToWrite(a)); ck(lib().GXNDArrayWaitAll())
+    n, buf = ctypes.c_size_t(), ctypes.POINTER(ctypes.c_char)()
+    ck(lib().GXNDArraySaveRawBytes(a, ctypes.byref(n), ctypes.byref(buf)))
+    raw = ctypes.string_at(buf, n.value)
+    b = vp(); ck(lib().GXNDArrayLoadFromRawBytes(raw, ctypes.c_size_t(len(raw)), ctypes.byref(b)))
+    assert np.array_equal(C.nd_get(b), C.nd_get(a))
+    assert lib().GXNDArrayLoadFromRawBytes(raw[:20], ctypes.c_size_t(20), ctypes.byref(b)) == -1
+    none = vp(); ck(lib().GXNDArrayCreateNone(ctypes.byref(none))); ck(lib().GXNDArrayGetStorageType(none, ctypes.byref(st))); assert st.value == -1
+    # profiler objects end up in the chrome trace
+    prof = str(tmp_path / "objs.json").encode()
+    ck(lib().GXSetProfilerConfig(1, (cp * 1)(b"filename"), (cp * 1)(prof))); ck(lib().GXSetProfilerState(1))
+    dom, task, ev, ctr = vp(), vp(), vp(), vp()
+    ck(lib().GXProfileCreateDomain(b"capi_domain", ctypes.byref(dom))); ck(lib().GXProfileCreateTask(dom, b"capi_task", ctypes.byref(task)))
+    ck(lib().GXProfileCreateEvent(b"capi_event", ctypes.byref(ev))); ck(lib().GXProfileCreateCounter(dom, b"capi_counter", ctypes.byref(ctr)))
+    assert lib().GXProfileDurationStop(task) == -1
+    for h in (task, ev):
+        ck(lib().GXProfileDurationStart(h)); ck(lib().GXProfileDurationStop(h))
+    ck(lib().GXProfileSetCounter(ctr, ctypes.c_uint64(5))); ck(lib().GXProfileAdjustCounter(ctr, ctypes.c_int64(-2)))
+    ck(lib().GXDumpProfile(1)); ck(lib().GXSetProfilerState(0))
+    trace = open(prof.decode()).read()
+    assert "capi_task" in trace and "capi_event" in trace and '"capi_counter":3' in trace.replace(" ", "")
+    for h in (dom, task, ev, ctr):
+        ck(lib().GXProfileDestroyHandle(h))
+    v, prev = ctypes.c_int(), ctypes.c_int()
+    ck(lib().GXSetNumOMPThreads(3)); ck(lib().GXGetNumOMPThreads(ctypes.byref(v))); assert v.value == 3
+    ck(lib().GXEngineSetBulkSize(4, ctypes.byref(prev))); ck(lib().GXEngineSetBulkSize(prev.value, ctypes.byref(v))); assert v.value == 4
+    ck(lib().GXGetGPUCount(ctypes.byref(v))); assert v.value >= 0
+    ck(lib().GXNotifyShutdown())
+
+
+def test_python_free_parameter_server_job(tmp_path):
+    """examples/c_api/ps_node.c: scheduler + server (optimizer = a C callback through GXKVStoreRunServerEx) + two workers, four processes of one
+    C binary linked against libgeomx_capi.so only — the HiPS TCP plane without an interpreter in any process."""
+    import os
+    import shutil
+    import socket
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    libdir = os.path.join(C.ROOT, "geomx_b200", "lib")
+    exe = str(tmp_path / "ps_node")
+    subprocess.run([cc, "-O2", "-Wall", "-Werror", "-std=c99", "-I", os.path.join(C.ROOT, "geomx_b200", "include"), os.path.join(C.ROOT, "examples", "c_api", "ps_node.c"),
+                    "-L", libdir, "-lgeomx_capi", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = {k: v for k, v in os.environ.items() if not k.startswith(("DMLC_", "PS_")) and k not in ("RANK", "WORLD_SIZE")}
+    env.update({"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(port), "DMLC_NUM_SERVER": "1", "DMLC_NUM_WORKER": "2", "DMLC_NUM_ALL_WORKER": "2"})
+    procs = [subprocess.Popen([exe], env=dict(env, DMLC_ROLE=role), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for role in ("scheduler", "server", "worker", "worker")]
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=120)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "server done: 2 updates, 1 controller commands" in outs[1]
+    for o in outs[2:]:
+        vals = [float(l.split()[-1]) for l in o.splitlines() if l.startswith("RESULT")]
+        assert len(vals) == 2 and abs(vals[0] - 0.85) < 1e-6 and abs(vals[1] - 0.70) < 1e-6, o          # 1 - 0.1 * (0.5 + 1.0) per round
