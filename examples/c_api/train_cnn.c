@@ -24,6 +24,7 @@ static SymbolHandle layer(const char* op, const char* name, SymbolHandle in, int
   SymbolHandle s;
   CK(GXSymbolCreateAtomicSymbolByName(op, (uint32_t)nattr, keys, vals, &s));
   CK(GXSymbolCompose(s, name, 1, NULL, &in));
+  CK(GXSymbolFree(in));                                   /* the composed node keeps its own reference to the input graph */
   return s;
 }
 
@@ -49,6 +50,7 @@ static SymbolHandle build(void) {
     ins[0] = h; ins[1] = label;
     CK(GXSymbolCreateAtomicSymbolByName("SoftmaxOutput", 1, k, v, &out));
     CK(GXSymbolCompose(out, "softmax", 2, in_keys, ins));
+    CK(GXSymbolFree(h)); CK(GXSymbolFree(label));
   }
   return out;
 }

@@ -38,7 +38,7 @@ def handles(items):
 def str_list(fn, *args):
     n, out = u32(), ctypes.POINTER(cp)()
     ck(fn(*args, ctypes.byref(n), ctypes.byref(out)))
-    return [out[i].decode() for i in range(n.value)]
+    return [out[i].decode(errors="replace") for i in range(n.value)]
 
 
 # ---------------------------------------------------------------------------------------------------------------- NDArray
