@@ -124,6 +124,12 @@ inline std::vector<std::string> InDataLabel(const AttrView&) { return {"data", "
 inline std::vector<std::string> InWB(const AttrView& a) { return a.Bool("no_bias", false) ? std::vector<std::string>{"data", "weight"} : std::vector<std::string>{"data", "weight", "bias"}; }
 inline std::vector<std::string> InBN(const AttrView&) { return {"data", "gamma", "beta", "moving_mean", "moving_var"}; }
 inline std::vector<std::string> InEmb(const AttrView&) { return {"data", "weight"}; }
+inline std::vector<std::string> InGB(const AttrView&) { return {"data", "gamma", "beta"}; }
+inline std::vector<std::string> InDeconv(const AttrView& a) { return a.Bool("no_bias", true) ? std::vector<std::string>{"data", "weight"} : std::vector<std::string>{"data", "weight", "bias"}; }
+inline std::vector<std::string> InTake(const AttrView&) { return {"a", "indices"}; }
+inline std::vector<std::string> InPick(const AttrView&) { return {"data", "index"}; }
+inline std::vector<std::string> InWhere(const AttrView&) { return {"condition", "x", "y"}; }
+inline std::vector<std::string> InIdx(const AttrView&) { return {"indices"}; }
 inline std::vector<std::string> InVar(const AttrView& a) {
   std::vector<std::string> v;
   const int64_t n = a.Int("num_args", 0);
@@ -192,6 +198,52 @@ inline const std::vector<OpDef>& OpTable() {
                  {{"axis", "Shape(tuple), optional, default=()", "axes (all when empty)"}, {"keepdims", "boolean, optional, default=0", "keep reduced axes"}}});
     v.push_back({"dot", InLR, 0, "", "matrix product of 2-D operands (src/operator/tensor/dot.cc)",
                  {{"transpose_a", "boolean, optional, default=0", "use lhs^T"}, {"transpose_b", "boolean, optional, default=0", "use rhs^T"}}});
+    // ---- second tier: normalisation / transposed convolution / indexing / shape manipulation / more reductions
+    v.push_back({"LayerNorm", InGB, 0, "", "normalise over one axis with learned scale and shift (src/operator/nn/layer_norm.cc)",
+                 {{"axis", "int, optional, default=-1", "axis"}, {"eps", "float, optional, default=1e-5", "variance floor"}}});
+    v.push_back({"InstanceNorm", InGB, 0, "", "normalise every (sample, channel) map (src/operator/instance_norm.cc)", {{"eps", "float, optional, default=0.001", "variance floor"}}});
+    v.push_back({"L2Normalization", InData, 0, "", "divide by the L2 norm per instance / channel / spatial position (src/operator/l2_normalization.cc)",
+                 {{"mode", "{'channel', 'instance', 'spatial'}, optional, default='instance'", "group"}, {"eps", "float, optional, default=1e-10", "floor"}}});
+    v.push_back({"LRN", InData, 0, "", "local response normalisation across channels (src/operator/nn/lrn.cc)",
+                 {{"nsize", "int, required", "window"}, {"alpha", "float, optional, default=0.0001", "scale"}, {"beta", "float, optional, default=0.75", "exponent"},
+                  {"knorm", "float, optional, default=2", "offset"}}});
+    v.push_back({"Deconvolution", InDeconv, 0, "", "2-D transposed convolution (src/operator/nn/deconvolution.cc)",
+                 {{"kernel", "Shape(tuple), required", "window"}, {"num_filter", "int, required", "output channels"}, {"stride", "Shape(tuple), optional", "stride"},
+                  {"pad", "Shape(tuple), optional", "padding"}, {"adj", "Shape(tuple), optional", "output adjustment"}, {"dilate", "Shape(tuple), optional", "dilation"},
+                  {"num_group", "int, optional, default=1", "groups"}, {"no_bias", "boolean, optional, default=1", "disable the bias"}}});
+    v.push_back({"UpSampling", InVar, 0, "num_args", "nearest-neighbour upsampling (src/operator/nn/upsampling.cc)",
+                 {{"scale", "int, required", "factor"}, {"sample_type", "{'nearest'}, required", "method"}, {"num_args", "int, required", "number of inputs (1)"}}});
+    v.push_back({"softmax_cross_entropy", InDataLabel, 0, "", "summed cross entropy of softmax(data) against integer labels (src/operator/loss_binary_op.cc)", none});
+    v.push_back({"smooth_l1", InData, 0, "", "Huber-like loss with transition at 1/sigma^2", {{"scalar", "float, required", "sigma"}}});
+    v.push_back({"slice_axis", InData, 0, "", "slice along one axis (src/operator/tensor/matrix_op.cc)",
+                 {{"axis", "int, required", "axis"}, {"begin", "int, required", "first index"}, {"end", "int or None, required", "one past the last index"}}});
+    v.push_back({"slice", InData, 0, "", "slice by per-axis begin / end (None = full range)", {{"begin", "Shape(tuple), required", "starts"}, {"end", "Shape(tuple), required", "stops"}}});
+    v.push_back({"SwapAxis", InData, 0, "", "exchange two axes", {{"dim1", "int, optional, default=0", "axis"}, {"dim2", "int, optional, default=0", "axis"}}});
+    v.push_back({"tile", InData, 0, "", "repeat the whole array", {{"reps", "Shape(tuple), required", "repetitions per axis"}}});
+    v.push_back({"repeat", InData, 0, "", "repeat elements along an axis", {{"repeats", "int, required", "count"}, {"axis", "int, required", "axis"}}});
+    v.push_back({"Pad", InData, 0, "", "pad with a constant, the edge value or a reflection (src/operator/pad.cc)",
+                 {{"mode", "{'constant', 'edge', 'reflect'}, required", "fill"}, {"pad_width", "Shape(tuple), required", "(before, after) per axis"},
+                  {"constant_value", "double, optional, default=0", "fill value"}}});
+    v.push_back({"squeeze", InData, 0, "", "drop axes of extent 1", {{"axis", "Shape(tuple), optional", "axes (all when absent)"}}});
+    v.push_back({"broadcast_to", InData, 0, "", "broadcast to a shape (0 keeps the input extent)", {{"shape", "Shape(tuple), required", "target"}}});
+    v.push_back({"broadcast_axis", InData, 0, "", "broadcast axes of extent 1", {{"axis", "Shape(tuple), required", "axes"}, {"size", "Shape(tuple), required", "extents"}}});
+    v.push_back({"reverse", InData, 0, "", "reverse along axes", {{"axis", "Shape(tuple), required", "axes"}}});
+    v.push_back({"take", InTake, 0, "", "gather slices along an axis, indices clipped (src/operator/tensor/indexing_op.cc)", {{"axis", "int, optional, default=0", "axis"}}});
+    v.push_back({"pick", InPick, 0, "", "one element per position along an axis", {{"axis", "int, optional, default=-1", "axis"}, {"keepdims", "boolean, optional, default=0", "keep the axis"}}});
+    v.push_back({"one_hot", InIdx, 0, "", "one-hot encode indices", {{"depth", "int, required", "classes"}, {"on_value", "double, optional, default=1", "hot"}, {"off_value", "double, optional, default=0", "cold"}}});
+    v.push_back({"where", InWhere, 0, "", "x where condition != 0, else y", none});
+    v.push_back({"Cast", InData, 0, "", "dtype conversion (the host executor computes in float32)", {{"dtype", "{'float32'}, required", "target dtype"}}});
+    for (const char* n : {"max", "min", "prod", "norm"})
+      v.push_back({n, InData, 0, "", "reduction over axes (norm: L2)", {{"axis", "Shape(tuple), optional, default=()", "axes (all when empty)"}, {"keepdims", "boolean, optional, default=0", "keep reduced axes"}}});
+    for (const char* n : {"argmax", "argmin"})
+      v.push_back({n, InData, 0, "", "index of the extreme value along an axis (no gradient)", {{"axis", "int, required", "axis"}, {"keepdims", "boolean, optional, default=0", "keep the axis"}}});
+    for (const char* n : {"broadcast_power", "broadcast_equal", "broadcast_not_equal", "broadcast_greater", "broadcast_greater_equal", "broadcast_lesser", "broadcast_lesser_equal"})
+      v.push_back({n, InLR, 0, "", "binary power / comparison (1.0 or 0.0) with numpy broadcasting", none});
+    for (const char* n : {"_maximum_scalar", "_minimum_scalar", "_rpower_scalar"})
+      v.push_back({n, InData, 0, "", "max / min / scalar ** x with a scalar", {{"scalar", "float, required", "the scalar"}}});
+    for (const char* n : {"sin", "cos", "tan", "arcsin", "arccos", "arctan", "sinh", "cosh", "log1p", "expm1", "log2", "log10", "rsqrt", "reciprocal", "cbrt", "erf",
+                          "floor", "ceil", "round", "sign"})
+      v.push_back({n, InData, 0, "", "elementwise function (src/operator/tensor/elemwise_unary_op_{basic,trig}.cc)", none});
     for (const char* n : {"elemwise_add", "elemwise_sub", "elemwise_mul", "elemwise_div", "broadcast_add", "broadcast_sub", "broadcast_mul", "broadcast_div",
                           "broadcast_maximum", "broadcast_minimum"})
       v.push_back({n, InLR, 0, "", "binary arithmetic with numpy broadcasting (src/operator/tensor/elemwise_binary_broadcast_op_basic.cc)", none});
@@ -212,7 +264,11 @@ inline std::string CanonicalOp(const std::string& op) {
       {"_Minus", "elemwise_sub"}, {"_sub", "elemwise_sub"}, {"_mul", "elemwise_mul"}, {"_Mul", "elemwise_mul"}, {"_div", "elemwise_div"}, {"_Div", "elemwise_div"},
       {"broadcast_plus", "broadcast_add"}, {"broadcast_minus", "broadcast_sub"}, {"_maximum", "broadcast_maximum"}, {"_minimum", "broadcast_minimum"},
       {"_PlusScalar", "_plus_scalar"}, {"_MinusScalar", "_minus_scalar"}, {"_RMinusScalar", "_rminus_scalar"}, {"_MulScalar", "_mul_scalar"},
-      {"_DivScalar", "_div_scalar"}, {"_RDivScalar", "_rdiv_scalar"}, {"_PowerScalar", "_power_scalar"}};
+      {"_DivScalar", "_div_scalar"}, {"_RDivScalar", "_rdiv_scalar"}, {"_PowerScalar", "_power_scalar"}, {"_MaximumScalar", "_maximum_scalar"},
+      {"_MinimumScalar", "_minimum_scalar"}, {"_RPowerScalar", "_rpower_scalar"}, {"_power", "broadcast_power"}, {"_Power", "broadcast_power"}, {"swapaxes", "SwapAxis"},
+      {"pad", "Pad"}, {"cast", "Cast"}, {"flip", "reverse"}, {"_equal", "broadcast_equal"}, {"_not_equal", "broadcast_not_equal"}, {"_greater", "broadcast_greater"},
+      {"_greater_equal", "broadcast_greater_equal"}, {"_lesser", "broadcast_lesser"}, {"_lesser_equal", "broadcast_lesser_equal"}, {"max_axis", "max"}, {"min_axis", "min"},
+      {"sum_axis", "sum"}};
   auto it = alias.find(op);
   return it == alias.end() ? op : it->second;
 }
@@ -521,6 +577,35 @@ inline Shape ReduceShape(const Shape& x, std::vector<int64_t> axes, bool keep, c
   if (out.empty()) out.push_back(1);
   return out;
 }
+// "(None, 2, -1)" -> {nullopt, 2, -1}: tuples whose entries may be None (slice begin / end)
+inline std::vector<std::pair<bool, int64_t>> TupleOpt(const AttrView& a, const std::string& key) {
+  std::vector<std::pair<bool, int64_t>> out;
+  const std::string* v = a.Raw(key);
+  if (!v) return out;
+  std::string tok;
+  auto flush = [&] {
+    size_t b = 0, e = tok.size();
+    while (b < e && (tok[b] == ' ' || tok[b] == '(' || tok[b] == '[')) ++b;
+    while (e > b && (tok[e - 1] == ' ' || tok[e - 1] == ')' || tok[e - 1] == ']')) --e;
+    const std::string t = tok.substr(b, e - b);
+    tok.clear();
+    if (t.empty()) return;
+    if (t == "None") { out.emplace_back(false, 0); return; }
+    try { out.emplace_back(true, std::stoll(t)); } catch (...) { throw std::runtime_error("attribute " + key + ": bad tuple entry " + t); }
+  };
+  for (char c : *v) { if (c == ',') flush(); else tok.push_back(c); }
+  flush();
+  return out;
+}
+// [begin, end) of a slice along an axis of extent n, python style (negative counts from the end, None = open)
+inline void SliceRange(bool hb, int64_t b, bool he, int64_t e, int64_t n, const std::string& who, int64_t* lo, int64_t* hi) {
+  if (!hb) b = 0;
+  if (!he) e = n;
+  if (b < 0) b += n;
+  if (e < 0) e += n;
+  if (b < 0 || e > n || b >= e) throw std::runtime_error(who + ": slice [" + std::to_string(b) + ", " + std::to_string(e) + ") is empty or outside the extent " + std::to_string(n));
+  *lo = b; *hi = e;
+}
 inline Shape ReshapeTo(const Node& n, const Shape& x) {
   const auto spec = AttrView(n.attrs).Tuple("shape", {});
   Shape out; size_t src = 0; int infer = -1;
@@ -637,8 +722,131 @@ inline bool InferNode(const Node& n, const std::vector<const Shape*>& in, const 
     const int64_t m = ta ? x[1] : x[0], k = ta ? x[0] : x[1], k2 = tb ? y[1] : y[0], nn = tb ? y[0] : y[1];
     if (k != k2) throw std::runtime_error(n.name + ": inner dimensions differ, " + ShapeStr(x) + " x " + ShapeStr(y));
     *out = {m, nn};
-  } else if (op == "sum" || op == "mean") {
+  } else if (op == "sum" || op == "mean" || op == "max" || op == "min" || op == "prod" || op == "norm") {
     *out = ReduceShape(x, a.Tuple("axis", {}), a.Bool("keepdims", false), n.name);
+  } else if (op == "argmax" || op == "argmin") {
+    if (!a.Has("axis")) throw std::runtime_error(n.name + ": axis is required");
+    *out = ReduceShape(x, {a.Int("axis", 0)}, a.Bool("keepdims", false), n.name);
+  } else if (op == "LayerNorm") {
+    const int64_t ax = AxisOf(a.Int("axis", -1), x.size(), n.name);
+    need(1, {x[ax]}); need(2, {x[ax]});
+    *out = x;
+  } else if (op == "InstanceNorm") {
+    if (x.size() < 3) throw std::runtime_error(n.name + ": InstanceNorm needs (batch, channel, spatial...)");
+    need(1, {x[1]}); need(2, {x[1]});
+    *out = x;
+  } else if (op == "LRN") {
+    if (x.size() != 4) throw std::runtime_error(n.name + ": LRN input must be NCHW");
+    const int64_t ns = a.Int("nsize", 0);
+    if (ns < 1 || ns % 2 == 0) throw std::runtime_error(n.name + ": nsize must be odd and positive");
+    *out = x;
+  } else if (op == "Deconvolution") {
+    if (x.size() != 4) throw std::runtime_error(n.name + ": deconvolution input must be NCHW, got " + ShapeStr(x));
+    const Win w = Window(n, false, x);
+    auto adj = a.Tuple("adj", {0, 0}); if (adj.empty()) adj = {0, 0}; if (adj.size() == 1) adj.push_back(adj[0]);
+    const int64_t f = a.Int("num_filter", 0), g = a.Int("num_group", 1);
+    if (f < 1 || g < 1 || x[1] % g || f % g) throw std::runtime_error(n.name + ": num_filter / num_group do not divide the channels");
+    if (adj[0] < 0 || adj[1] < 0 || adj[0] >= w.sh || adj[1] >= w.sw) throw std::runtime_error(n.name + ": adj must be in [0, stride)");
+    need(1, {x[1], f / g, w.kh, w.kw});
+    if (in.size() > 2) need(2, {f});
+    const int64_t oh = (x[2] - 1) * w.sh - 2 * w.ph + w.dh * (w.kh - 1) + 1 + adj[0], ow = (x[3] - 1) * w.sw - 2 * w.pw + w.dw * (w.kw - 1) + 1 + adj[1];
+    if (oh <= 0 || ow <= 0) throw std::runtime_error(n.name + ": padding larger than the output");
+    *out = {x[0], f, oh, ow};
+  } else if (op == "UpSampling") {
+    if (in.size() != 1 || a.Str("sample_type", "nearest") != "nearest") throw std::runtime_error(n.name + ": the native runtime has single-input nearest-neighbour UpSampling");
+    const int64_t sc = a.Int("scale", 0);
+    if (x.size() != 4 || sc < 1 || sc > 64) throw std::runtime_error(n.name + ": needs NCHW input and 1 <= scale <= 64");
+    *out = {x[0], x[1], x[2] * sc, x[3] * sc};
+  } else if (op == "softmax_cross_entropy") {
+    if (x.size() != 2) throw std::runtime_error(n.name + ": data must be (batch, classes)");
+    need(1, {x[0]});
+    *out = {1};
+  } else if (op == "slice_axis") {
+    const int64_t ax = AxisOf(a.Int("axis", 0), x.size(), n.name);
+    int64_t lo, hi; SliceRange(a.Has("begin"), a.Int("begin", 0), a.Has("end"), a.Int("end", 0), x[ax], n.name, &lo, &hi);
+    *out = x; (*out)[ax] = hi - lo;
+  } else if (op == "slice") {
+    const auto b = TupleOpt(a, "begin"), e = TupleOpt(a, "end");
+    if (b.size() != e.size() || b.size() > x.size() || b.empty()) throw std::runtime_error(n.name + ": begin / end must have the same length, at most the input rank");
+    *out = x;
+    for (size_t i = 0; i < b.size(); ++i) { int64_t lo, hi; SliceRange(b[i].first, b[i].second, e[i].first, e[i].second, x[i], n.name, &lo, &hi); (*out)[i] = hi - lo; }
+  } else if (op == "SwapAxis") {
+    *out = x; std::swap((*out)[AxisOf(a.Int("dim1", 0), x.size(), n.name)], (*out)[AxisOf(a.Int("dim2", 0), x.size(), n.name)]);
+  } else if (op == "tile") {
+    const auto reps = a.Tuple("reps", {});
+    if (reps.empty() || reps.size() > 8) throw std::runtime_error(n.name + ": reps must have 1..8 entries");
+    Shape xs = x; while (xs.size() < reps.size()) xs.insert(xs.begin(), 1);
+    *out = xs;
+    for (size_t i = 0; i < reps.size(); ++i) { const int64_t r = reps[i]; if (r < 1 || r > 4096) throw std::runtime_error(n.name + ": reps out of range"); (*out)[xs.size() - reps.size() + i] *= r; }
+  } else if (op == "repeat") {
+    if (!a.Has("axis")) throw std::runtime_error(n.name + ": the native runtime needs an explicit axis");
+    const int64_t ax = AxisOf(a.Int("axis", 0), x.size(), n.name), r = a.Int("repeats", 0);
+    if (r < 1 || r > 4096) throw std::runtime_error(n.name + ": repeats out of range");
+    *out = x; (*out)[ax] *= r;
+  } else if (op == "Pad") {
+    const auto pw = a.Tuple("pad_width", {});
+    if (pw.size() != 2 * x.size()) throw std::runtime_error(n.name + ": pad_width needs (before, after) for each of the " + std::to_string(x.size()) + " axes");
+    const std::string mode = a.Str("mode", "constant");
+    if (mode != "constant" && mode != "edge" && mode != "reflect") throw std::runtime_error(n.name + ": mode " + mode + " is not supported");
+    *out = x;
+    for (size_t i = 0; i < x.size(); ++i) {
+      if (pw[2 * i] < 0 || pw[2 * i + 1] < 0 || pw[2 * i] > 65536 || pw[2 * i + 1] > 65536) throw std::runtime_error(n.name + ": pad_width out of range");
+      if (mode == "reflect" && (pw[2 * i] >= x[i] || pw[2 * i + 1] >= x[i])) throw std::runtime_error(n.name + ": reflect padding must be smaller than the extent");
+      (*out)[i] += pw[2 * i] + pw[2 * i + 1];
+    }
+  } else if (op == "squeeze") {
+    const auto axes = a.Tuple("axis", {});
+    std::vector<char> drop(x.size(), 0);
+    if (axes.empty()) { for (size_t i = 0; i < x.size(); ++i) drop[i] = x[i] == 1; }
+    else for (auto ax : axes) { const int64_t k = AxisOf(ax, x.size(), n.name); if (x[k] != 1) throw std::runtime_error(n.name + ": cannot squeeze an axis of extent " + std::to_string(x[k])); drop[k] = 1; }
+    out->clear();
+    for (size_t i = 0; i < x.size(); ++i) if (!drop[i]) out->push_back(x[i]);
+    if (out->empty()) out->push_back(1);
+  } else if (op == "broadcast_to") {
+    const auto t = a.Tuple("shape", {});
+    if (t.size() != x.size()) throw std::runtime_error(n.name + ": shape must have the input rank");
+    *out = x;
+    for (size_t i = 0; i < x.size(); ++i) {
+      if (t[i] == 0 || t[i] == x[i]) continue;
+      if (x[i] != 1 || t[i] < 1 || t[i] > (int64_t{1} << 24)) throw std::runtime_error(n.name + ": cannot broadcast " + ShapeStr(x) + " to the requested shape");
+      (*out)[i] = t[i];
+    }
+  } else if (op == "broadcast_axis") {
+    const auto axes = a.Tuple("axis", {}), sizes = a.Tuple("size", {});
+    if (axes.size() != sizes.size() || axes.empty()) throw std::runtime_error(n.name + ": axis and size must have the same length");
+    *out = x;
+    for (size_t i = 0; i < axes.size(); ++i) {
+      const int64_t k = AxisOf(axes[i], x.size(), n.name);
+      if (x[k] != 1 || sizes[i] < 1 || sizes[i] > (int64_t{1} << 24)) throw std::runtime_error(n.name + ": only axes of extent 1 can be broadcast");
+      (*out)[k] = sizes[i];
+    }
+  } else if (op == "reverse") {
+    for (auto ax : a.Tuple("axis", {})) AxisOf(ax, x.size(), n.name);
+    *out = x;
+  } else if (op == "take") {
+    if (!in[1]) return false;
+    const int64_t ax = AxisOf(a.Int("axis", 0), x.size(), n.name);
+    out->assign(x.begin(), x.begin() + ax);
+    out->insert(out->end(), in[1]->begin(), in[1]->end());
+    out->insert(out->end(), x.begin() + ax + 1, x.end());
+  } else if (op == "pick") {
+    const int64_t ax = AxisOf(a.Int("axis", -1), x.size(), n.name);
+    Shape idx = x; idx.erase(idx.begin() + ax); if (idx.empty()) idx.push_back(1);
+    if (!in[1]) fill(1, idx);
+    else if (Numel(*in[1]) != Numel(idx)) throw std::runtime_error(n.name + ": index has " + std::to_string(Numel(*in[1])) + " elements, expected " + std::to_string(Numel(idx)));
+    *out = idx;
+    if (a.Bool("keepdims", false)) { *out = x; (*out)[ax] = 1; }
+  } else if (op == "one_hot") {
+    const int64_t d = a.Int("depth", 0);
+    if (d < 1 || d > (int64_t{1} << 24)) throw std::runtime_error(n.name + ": depth out of range");
+    *out = x; out->push_back(d);
+  } else if (op == "where") {
+    if (!in[1]) { fill(1, x); } else if (*in[1] != x) throw std::runtime_error(n.name + ": x must have the condition's shape");
+    if (!in[2]) { fill(2, x); } else if (*in[2] != x) throw std::runtime_error(n.name + ": y must have the condition's shape");
+    *out = x;
+  } else if (op == "Cast") {
+    if (a.Str("dtype", "float32") != "float32") throw std::runtime_error(n.name + ": the host executor computes in float32 only");
+    *out = x;
   } else if (in.size() == 2) {           // binary arithmetic
     if (!in[1]) { if (op.compare(0, 9, "elemwise_") == 0) { fill(1, x); *out = x; return true; } return false; }
     if (op.compare(0, 9, "elemwise_") == 0 && *in[1] != x) throw std::runtime_error(n.name + ": elementwise operands differ in shape, " + ShapeStr(x) + " vs " + ShapeStr(*in[1]));

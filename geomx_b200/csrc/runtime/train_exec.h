@@ -277,7 +277,8 @@ class Executor {
     bool is_aux = false, need_grad = false;
     std::vector<float> own, grad;
     std::vector<int32_t> idx;          // Pooling(max): winning input offset per output
-    std::vector<float> saved;          // Dropout mask / BatchNorm batch mean + inverse std
+    std::vector<float> saved;          // Dropout mask / BatchNorm batch mean + inverse std / LayerNorm statistics / LRN scale / softmax probabilities
+    std::vector<int64_t> map;          // gather-style operators: source element of every output element (-1 = constant fill)
   };
   Symbol sym_;
   std::vector<Node*> order_;
@@ -463,6 +464,102 @@ class Executor {
     } else if (op == "clip") {
       const float lo = static_cast<float>(a.Float("a_min", -std::numeric_limits<float>::infinity())), hi = static_cast<float>(a.Float("a_max", std::numeric_limits<float>::infinity()));
       for (int64_t i = 0; i < ny; ++i) y[i] = std::min(std::max(x[i], lo), hi);
+    } else if (IsGather(op)) {
+      BuildMap(s);
+      const float fill = op == "Pad" ? static_cast<float>(a.Float("constant_value", 0)) : 0.f;
+      for (int64_t i = 0; i < ny; ++i) y[i] = s.map[i] < 0 ? fill : x[s.map[i]];
+    } else if (op == "squeeze" || op == "Cast") {
+      memcpy(y, x, ny * sizeof(float));
+    } else if (op == "where") {
+      const float* t = Val(s.in[1]); const float* f = Val(s.in[2]);
+      for (int64_t i = 0; i < ny; ++i) y[i] = x[i] != 0.f ? t[i] : f[i];
+    } else if (op == "one_hot") {
+      const int64_t D = s.shape.back();
+      const float on = static_cast<float>(a.Float("on_value", 1)), off = static_cast<float>(a.Float("off_value", 0));
+      for (int64_t i = 0; i < nx; ++i) for (int64_t k = 0; k < D; ++k) y[i * D + k] = static_cast<int64_t>(x[i]) == k ? on : off;
+    } else if (op == "argmax" || op == "argmin") {
+      int64_t outer, C, inner; SplitAxis(xs, graph::detail::AxisOf(a.Int("axis", 0), xs.size(), n.name), &outer, &C, &inner);
+      const bool mx = op == "argmax";
+      for (int64_t o = 0; o < outer; ++o) for (int64_t i = 0; i < inner; ++i) {
+        const float* p = x + o * C * inner + i; int64_t best = 0;
+        for (int64_t k = 1; k < C; ++k) if (mx ? p[k * inner] > p[best * inner] : p[k * inner] < p[best * inner]) best = k;
+        y[o * inner + i] = static_cast<float>(best);
+      }
+    } else if (op == "max" || op == "min" || op == "prod" || op == "norm") {
+      const auto red = ReducedAxes(s, xs);
+      const int kind = op == "max" ? 0 : op == "min" ? 1 : op == "prod" ? 2 : 3;
+      std::vector<double> acc(static_cast<size_t>(ny), kind == 0 ? -std::numeric_limits<double>::infinity() : kind == 1 ? std::numeric_limits<double>::infinity() : kind == 2 ? 1.0 : 0.0);
+      for (int64_t f = 0; f < nx; ++f) {
+        double& v = acc[ReducedIndex(f, xs, red)];
+        if (kind == 0) v = std::max<double>(v, x[f]); else if (kind == 1) v = std::min<double>(v, x[f]); else if (kind == 2) v *= x[f]; else v += static_cast<double>(x[f]) * x[f];
+      }
+      for (int64_t i = 0; i < ny; ++i) y[i] = static_cast<float>(kind == 3 ? std::sqrt(acc[i]) : acc[i]);
+    } else if (op == "LayerNorm" || op == "InstanceNorm") {
+      int64_t outer, C, inner; NormGroups(s, xs, &outer, &C, &inner);
+      const bool layer = op == "LayerNorm";
+      const float eps = static_cast<float>(a.Float("eps", layer ? 1e-5 : 1e-3));
+      const float* gamma = Val(s.in[1]); const float* beta = Val(s.in[2]);
+      // LayerNorm: statistics over the middle axis C per (outer, inner), scale indexed by c.  InstanceNorm: statistics over inner per (n, c), scale indexed by c.
+      const int64_t groups = layer ? outer * inner : outer * C, len = layer ? C : inner;
+      s.saved.assign(static_cast<size_t>(2 * groups), 0.f);
+      for (int64_t g = 0; g < groups; ++g) {
+        const int64_t base = layer ? (g / inner) * C * inner + g % inner : g * inner, stride = layer ? inner : 1;
+        double sm = 0, sq = 0;
+        for (int64_t k = 0; k < len; ++k) sm += x[base + k * stride];
+        const float mean = static_cast<float>(sm / len);
+        for (int64_t k = 0; k < len; ++k) { const double d = x[base + k * stride] - mean; sq += d * d; }
+        const float inv = 1.f / std::sqrt(static_cast<float>(sq / len) + eps);
+        s.saved[2 * g] = mean; s.saved[2 * g + 1] = inv;
+        for (int64_t k = 0; k < len; ++k) { const int64_t c = layer ? k : g % C; y[base + k * stride] = (x[base + k * stride] - mean) * inv * gamma[c] + beta[c]; }
+      }
+    } else if (op == "L2Normalization") {
+      int64_t outer, C, inner; NormGroups(s, xs, &outer, &C, &inner);
+      const float eps = static_cast<float>(a.Float("eps", 1e-10));
+      s.saved.assign(static_cast<size_t>(outer * inner), 0.f);
+      for (int64_t o = 0; o < outer; ++o) for (int64_t i = 0; i < inner; ++i) {
+        const float* p = x + o * C * inner + i; float* q = y + o * C * inner + i;
+        double sq = 0;
+        for (int64_t k = 0; k < C; ++k) sq += static_cast<double>(p[k * inner]) * p[k * inner];
+        const float nrm = std::sqrt(static_cast<float>(sq) + eps);
+        s.saved[o * inner + i] = nrm;
+        for (int64_t k = 0; k < C; ++k) q[k * inner] = p[k * inner] / nrm;
+      }
+    } else if (op == "LRN") {
+      const int64_t N = xs[0], C = xs[1], P = xs[2] * xs[3], half = a.Int("nsize", 1) / 2;
+      const float alpha = static_cast<float>(a.Float("alpha", 1e-4)) / static_cast<float>(a.Int("nsize", 1)), beta = static_cast<float>(a.Float("beta", 0.75)), knorm = static_cast<float>(a.Float("knorm", 2));
+      s.saved.assign(static_cast<size_t>(nx), 0.f);
+      for (int64_t b = 0; b < N; ++b) for (int64_t c = 0; c < C; ++c) for (int64_t p = 0; p < P; ++p) {
+        float sq = 0;
+        for (int64_t k = std::max<int64_t>(c - half, 0); k <= std::min(c + half, C - 1); ++k) { const float v = x[(b * C + k) * P + p]; sq += v * v; }
+        const int64_t at = (b * C + c) * P + p;
+        s.saved[at] = knorm + alpha * sq;
+        y[at] = x[at] * std::pow(s.saved[at], -beta);
+      }
+    } else if (op == "Deconvolution") {
+      const Win w = WinOf(graph::detail::Window(n, false, xs));
+      const int64_t N = xs[0], C = xs[1], H = xs[2], W = xs[3], F = s.shape[1], OH = s.shape[2], OW = s.shape[3], G = a.Int("num_group", 1);
+      const int64_t Cg = C / G, Fg = F / G, K = Fg * w.kh * w.kw, P = H * W;
+      const float* wt = Val(s.in[1]); const float* b = s.in.size() > 2 ? Val(s.in[2]) : nullptr;
+      std::fill(y, y + ny, 0.f);
+      ParallelFor(N, static_cast<double>(N) * C * K * P, [&](int64_t lo, int64_t hi) {
+        std::vector<float> col(static_cast<size_t>(K * P));
+        for (int64_t i = lo; i < hi; ++i) for (int64_t g = 0; g < G; ++g) {
+          GemmSerial(true, false, K, P, Cg, wt + g * Cg * K, x + (i * C + g * Cg) * P, col.data(), false);      // col = W_g^T . x_g
+          Col2Im(col.data(), Fg, OH, OW, w, H, W, y + (i * F + g * Fg) * OH * OW);
+        }
+        if (b) for (int64_t i = lo; i < hi; ++i) for (int64_t f = 0; f < F; ++f) { float* o = y + (i * F + f) * OH * OW; for (int64_t p = 0; p < OH * OW; ++p) o[p] += b[f]; }
+      });
+    } else if (op == "smooth_l1") {
+      const float s2 = static_cast<float>(a.Float("scalar", 1)) * static_cast<float>(a.Float("scalar", 1));
+      for (int64_t i = 0; i < ny; ++i) { const float v = std::fabs(x[i]); y[i] = v < 1.f / s2 ? 0.5f * s2 * v * v : v - 0.5f / s2; }
+    } else if (op == "softmax_cross_entropy") {
+      const int64_t N = xs[0], C = xs[1];
+      const float* label = Val(s.in[1]);
+      s.saved.resize(static_cast<size_t>(nx));
+      SoftmaxFwd(x, s.saved.data(), N, C, 1, false);
+      double loss = 0;
+      for (int64_t i = 0; i < N; ++i) loss -= std::log(std::max(s.saved[i * C + std::min<int64_t>(std::max<int64_t>(static_cast<int64_t>(label[i]), 0), C - 1)], 1e-30f));
+      y[0] = static_cast<float>(loss);
     } else if (op == "sum" || op == "mean") {
       ReduceFwd(s, x, xs, y, op == "mean");
     } else if (op == "dot") {
@@ -487,26 +584,51 @@ class Executor {
   }
 
   static int BinaryKind(const std::string& op) {
-    static const char* names[] = {"add", "sub", "mul", "div", "maximum", "minimum"};
-    for (int i = 0; i < 6; ++i) if (op.find(names[i]) != std::string::npos) return i;
+    static const std::pair<const char*, int> names[] = {
+        {"elemwise_add", 0}, {"broadcast_add", 0}, {"elemwise_sub", 1}, {"broadcast_sub", 1}, {"elemwise_mul", 2}, {"broadcast_mul", 2}, {"elemwise_div", 3},
+        {"broadcast_div", 3}, {"broadcast_maximum", 4}, {"broadcast_minimum", 5}, {"broadcast_power", 6}, {"broadcast_equal", 7}, {"broadcast_not_equal", 8},
+        {"broadcast_greater", 9}, {"broadcast_greater_equal", 10}, {"broadcast_lesser", 11}, {"broadcast_lesser_equal", 12}};
+    for (auto& e : names) if (op == e.first) return e.second;
     throw std::runtime_error("operator " + op + " has no host kernel");
   }
-  static float Bin(int k, float l, float r) { switch (k) { case 0: return l + r; case 1: return l - r; case 2: return l * r; case 3: return l / r; case 4: return std::max(l, r); default: return std::min(l, r); } }
+  static float Bin(int k, float l, float r) {
+    switch (k) {
+      case 0: return l + r; case 1: return l - r; case 2: return l * r; case 3: return l / r; case 4: return std::max(l, r); case 5: return std::min(l, r);
+      case 6: return std::pow(l, r); case 7: return l == r; case 8: return l != r; case 9: return l > r; case 10: return l >= r; case 11: return l < r; default: return l <= r;
+    }
+  }
   static int ScalarKind(const std::string& op) {
-    static const char* names[] = {"_plus_scalar", "_minus_scalar", "_rminus_scalar", "_mul_scalar", "_div_scalar", "_rdiv_scalar", "_power_scalar"};
-    for (int i = 0; i < 7; ++i) if (op == names[i]) return i;
+    static const char* names[] = {"_plus_scalar", "_minus_scalar", "_rminus_scalar", "_mul_scalar", "_div_scalar", "_rdiv_scalar", "_power_scalar", "_maximum_scalar",
+                                  "_minimum_scalar", "_rpower_scalar"};
+    for (int i = 0; i < 10; ++i) if (op == names[i]) return i;
     throw std::runtime_error("operator " + op + " has no host kernel");
   }
-  static float Sc(int k, float x, float c) { switch (k) { case 0: return x + c; case 1: return x - c; case 2: return c - x; case 3: return x * c; case 4: return x / c; case 5: return c / x; default: return std::pow(x, c); } }
+  static float Sc(int k, float x, float c) {
+    switch (k) {
+      case 0: return x + c; case 1: return x - c; case 2: return c - x; case 3: return x * c; case 4: return x / c; case 5: return c / x; case 6: return std::pow(x, c);
+      case 7: return std::max(x, c); case 8: return std::min(x, c); default: return std::pow(c, x);
+    }
+  }
+  static float ScG(int k, float x, float c, float y) {
+    switch (k) {
+      case 0: case 1: return 1.f; case 2: return -1.f; case 3: return c; case 4: return 1.f / c; case 5: return -c / (x * x); case 6: return c * std::pow(x, c - 1.f);
+      case 7: return x >= c ? 1.f : 0.f; case 8: return x <= c ? 1.f : 0.f; default: return y * std::log(c);
+    }
+  }
   static int UnaryKind(const std::string& op) {
-    static const char* names[] = {"relu", "sigmoid", "tanh", "exp", "log", "sqrt", "abs", "negative", "square", "softsign"};
-    for (int i = 0; i < 10; ++i) if (op == names[i]) return i;
+    static const char* names[] = {"relu", "sigmoid", "tanh", "exp", "log", "sqrt", "abs", "negative", "square", "softsign", "sin", "cos", "tan", "arcsin", "arccos", "arctan",
+                                  "sinh", "cosh", "log1p", "expm1", "log2", "log10", "rsqrt", "reciprocal", "cbrt", "erf", "floor", "ceil", "round", "sign"};
+    for (int i = 0; i < 30; ++i) if (op == names[i]) return i;
     return -1;
   }
   static float Un(int k, float v) {
     switch (k) {
       case 0: return v > 0 ? v : 0; case 1: return 1.f / (1.f + std::exp(-v)); case 2: return std::tanh(v); case 3: return std::exp(v); case 4: return std::log(v);
-      case 5: return std::sqrt(v); case 6: return std::fabs(v); case 7: return -v; case 8: return v * v; default: return v / (1.f + std::fabs(v));
+      case 5: return std::sqrt(v); case 6: return std::fabs(v); case 7: return -v; case 8: return v * v; case 9: return v / (1.f + std::fabs(v));
+      case 10: return std::sin(v); case 11: return std::cos(v); case 12: return std::tan(v); case 13: return std::asin(v); case 14: return std::acos(v); case 15: return std::atan(v);
+      case 16: return std::sinh(v); case 17: return std::cosh(v); case 18: return std::log1p(v); case 19: return std::expm1(v); case 20: return std::log2(v);
+      case 21: return std::log10(v); case 22: return 1.f / std::sqrt(v); case 23: return 1.f / v; case 24: return std::cbrt(v); case 25: return std::erf(v);
+      case 26: return std::floor(v); case 27: return std::ceil(v); case 28: return std::round(v); default: return v > 0 ? 1.f : v < 0 ? -1.f : 0.f;
     }
   }
   // d out / d in for unary kinds, from input x and output y
@@ -514,8 +636,118 @@ class Executor {
     switch (k) {
       case 0: return x > 0 ? 1.f : 0.f; case 1: return y * (1.f - y); case 2: return 1.f - y * y; case 3: return y; case 4: return 1.f / x;
       case 5: return 0.5f / y; case 6: return x > 0 ? 1.f : x < 0 ? -1.f : 0.f; case 7: return -1.f; case 8: return 2.f * x;
-      default: { const float d = 1.f + std::fabs(x); return 1.f / (d * d); }
+      case 9: { const float d = 1.f + std::fabs(x); return 1.f / (d * d); }
+      case 10: return std::cos(x); case 11: return -std::sin(x); case 12: return 1.f + y * y; case 13: return 1.f / std::sqrt(1.f - x * x); case 14: return -1.f / std::sqrt(1.f - x * x);
+      case 15: return 1.f / (1.f + x * x); case 16: return std::cosh(x); case 17: return std::sinh(x); case 18: return 1.f / (1.f + x); case 19: return y + 1.f;
+      case 20: return 1.f / (x * 0.6931471805599453f); case 21: return 1.f / (x * 2.302585092994046f); case 22: return -0.5f * y / x; case 23: return -y * y;
+      case 24: return y / (3.f * x); case 25: return 1.1283791670955126f * std::exp(-x * x);
+      default: return 0.f;                // floor / ceil / round / sign
     }
+  }
+
+  static bool IsGather(const std::string& op) {
+    static const char* names[] = {"slice_axis", "slice", "SwapAxis", "tile", "repeat", "Pad", "reverse", "broadcast_to", "broadcast_axis", "UpSampling", "take", "pick"};
+    for (auto nme : names) if (op == nme) return true;
+    return false;
+  }
+  // source element of every output element for the gather-style operators; rebuilt every forward (take / pick depend on index values)
+  void BuildMap(Slot& s) {
+    const Node& n = *s.node;
+    const std::string& op = n.op;
+    AttrView a(n.attrs);
+    const Shape& xs = slots_[s.in[0]].shape;
+    const Shape& os = s.shape;
+    const int64_t ny = Numel(os);
+    s.map.assign(static_cast<size_t>(ny), 0);
+    if (op == "take" || op == "pick") {
+      const float* idx = Val(s.in[1]);
+      const int64_t ax = graph::detail::AxisOf(a.Int("axis", op == "take" ? 0 : -1), xs.size(), n.name);
+      int64_t outer, C, inner; SplitAxis(xs, ax, &outer, &C, &inner);
+      if (op == "take") {
+        const int64_t ni = Numel(slots_[s.in[1]].shape);
+        for (int64_t o = 0; o < outer; ++o) for (int64_t j = 0; j < ni; ++j) {
+          const int64_t r = std::min<int64_t>(std::max<int64_t>(static_cast<int64_t>(idx[j]), 0), C - 1);
+          for (int64_t i = 0; i < inner; ++i) s.map[(o * ni + j) * inner + i] = (o * C + r) * inner + i;
+        }
+      } else {
+        for (int64_t o = 0; o < outer; ++o) for (int64_t i = 0; i < inner; ++i) {
+          const int64_t r = std::min<int64_t>(std::max<int64_t>(static_cast<int64_t>(idx[o * inner + i]), 0), C - 1);
+          s.map[o * inner + i] = (o * C + r) * inner + i;
+        }
+      }
+      return;
+    }
+    // per-axis affine / modular index rules: the input may have a lower rank than the output (tile)
+    const size_t r = os.size();
+    Shape in = xs; while (in.size() < r) in.insert(in.begin(), 1);
+    std::vector<int64_t> stride(r, 1);
+    for (int i = static_cast<int>(r) - 2; i >= 0; --i) stride[i] = stride[i + 1] * in[i + 1];
+    std::vector<int64_t> off(r, 0), div(r, 1), perm(r);
+    std::vector<char> wrap(r, 0), flip(r, 0), bcast(r, 0);
+    for (size_t i = 0; i < r; ++i) perm[i] = static_cast<int64_t>(i);
+    std::vector<int64_t> before(r, 0);
+    int pad_mode = -1;
+    if (op == "slice_axis") {
+      const int64_t ax = graph::detail::AxisOf(a.Int("axis", 0), r, n.name);
+      int64_t lo, hi; graph::detail::SliceRange(a.Has("begin"), a.Int("begin", 0), a.Has("end"), a.Int("end", 0), in[ax], n.name, &lo, &hi);
+      off[ax] = lo;
+    } else if (op == "slice") {
+      const auto b = graph::detail::TupleOpt(a, "begin"), e = graph::detail::TupleOpt(a, "end");
+      for (size_t i = 0; i < b.size(); ++i) { int64_t lo, hi; graph::detail::SliceRange(b[i].first, b[i].second, e[i].first, e[i].second, in[i], n.name, &lo, &hi); off[i] = lo; }
+    } else if (op == "SwapAxis") {
+      std::swap(perm[graph::detail::AxisOf(a.Int("dim1", 0), r, n.name)], perm[graph::detail::AxisOf(a.Int("dim2", 0), r, n.name)]);
+    } else if (op == "tile") {
+      for (size_t i = 0; i < r; ++i) wrap[i] = 1;
+    } else if (op == "repeat") {
+      div[graph::detail::AxisOf(a.Int("axis", 0), r, n.name)] = a.Int("repeats", 1);
+    } else if (op == "UpSampling") {
+      div[2] = div[3] = a.Int("scale", 1);
+    } else if (op == "reverse") {
+      for (auto ax : a.Tuple("axis", {})) flip[graph::detail::AxisOf(ax, r, n.name)] = 1;
+    } else if (op == "broadcast_to" || op == "broadcast_axis") {
+      for (size_t i = 0; i < r; ++i) bcast[i] = in[i] == 1 && os[i] != 1;
+    } else if (op == "Pad") {
+      const auto pw = a.Tuple("pad_width", {});
+      for (size_t i = 0; i < r; ++i) before[i] = pw[2 * i];
+      const std::string mode = a.Str("mode", "constant");
+      pad_mode = mode == "constant" ? 0 : mode == "edge" ? 1 : 2;
+    }
+    std::vector<int64_t> idx(r);
+    for (int64_t f = 0; f < ny; ++f) {
+      int64_t rem = f;
+      for (int i = static_cast<int>(r) - 1; i >= 0; --i) { idx[i] = rem % os[i]; rem /= os[i]; }
+      int64_t src = 0; bool constant = false;
+      for (size_t i = 0; i < r; ++i) {
+        int64_t v = idx[i];
+        const size_t d = static_cast<size_t>(perm[i]);           // SwapAxis: output axis i reads input axis perm[i]
+        if (pad_mode >= 0) {
+          v -= before[i];
+          if (v < 0 || v >= in[i]) {
+            if (pad_mode == 0) { constant = true; break; }
+            v = pad_mode == 1 ? std::min(std::max<int64_t>(v, 0), in[i] - 1) : (v < 0 ? -v : 2 * (in[i] - 1) - v);
+          }
+        }
+        v = v / div[i] + off[i];
+        if (wrap[i]) v %= in[i];
+        if (flip[i]) v = in[i] - 1 - v;
+        if (bcast[i]) v = 0;
+        src += v * stride[d];
+      }
+      s.map[f] = constant ? -1 : src;
+    }
+  }
+  // (outer, C, inner) view for the normalisation operators
+  void NormGroups(const Slot& s, const Shape& xs, int64_t* outer, int64_t* C, int64_t* inner) const {
+    const Node& n = *s.node;
+    AttrView a(n.attrs);
+    if (n.op == "LayerNorm") { SplitAxis(xs, graph::detail::AxisOf(a.Int("axis", -1), xs.size(), n.name), outer, C, inner); return; }
+    if (n.op == "InstanceNorm") { *outer = xs[0]; *C = xs[1]; *inner = Numel(xs) / (xs[0] * xs[1]); return; }
+    const std::string mode = a.Str("mode", "instance");
+    const int64_t total = Numel(xs);
+    if (mode == "instance") { *outer = xs[0]; *C = total / xs[0]; *inner = 1; }
+    else if (mode == "channel") { if (xs.size() < 2) throw std::runtime_error(n.name + ": channel mode needs at least 2 axes"); *outer = xs[0]; *C = xs[1]; *inner = total / (xs[0] * xs[1]); }
+    else if (mode == "spatial") { if (xs.size() < 3) throw std::runtime_error(n.name + ": spatial mode needs at least 3 axes"); *outer = xs[0] * xs[1]; *C = total / (xs[0] * xs[1]); *inner = 1; }
+    else throw std::runtime_error(n.name + ": L2Normalization mode " + mode + " is not supported");
   }
 
   std::vector<char> ReducedAxes(const Slot& s, const Shape& xs) const {
@@ -720,6 +952,93 @@ class Executor {
       if (!dx) return;
       const float lo = static_cast<float>(a.Float("a_min", -std::numeric_limits<float>::infinity())), hi = static_cast<float>(a.Float("a_max", std::numeric_limits<float>::infinity()));
       for (int64_t i = 0; i < ny; ++i) if (x[i] >= lo && x[i] <= hi) dx[i] += dy[i];
+    } else if (IsGather(op)) {
+      if (dx) for (int64_t i = 0; i < ny; ++i) if (s.map[i] >= 0) dx[s.map[i]] += dy[i];
+    } else if (op == "squeeze" || op == "Cast") {
+      if (dx) for (int64_t i = 0; i < ny; ++i) dx[i] += dy[i];
+    } else if (op == "where") {
+      float* dt = GradOf(s.in[1]); float* df = GradOf(s.in[2]);
+      for (int64_t i = 0; i < ny; ++i) { if (x[i] != 0.f) { if (dt) dt[i] += dy[i]; } else if (df) df[i] += dy[i]; }
+    } else if (op == "one_hot" || op == "argmax" || op == "argmin") {
+    } else if (op == "max" || op == "min" || op == "prod" || op == "norm") {
+      if (!dx) return;
+      const auto red = ReducedAxes(s, xs);
+      for (int64_t f = 0; f < nx; ++f) {
+        const int64_t o = ReducedIndex(f, xs, red);
+        if (op == "prod") dx[f] += dy[o] * y[o] / x[f];
+        else if (op == "norm") dx[f] += y[o] > 0 ? dy[o] * x[f] / y[o] : 0.f;
+        else if (x[f] == y[o]) dx[f] += dy[o];
+      }
+    } else if (op == "LayerNorm" || op == "InstanceNorm") {
+      int64_t outer, C, inner; NormGroups(s, xs, &outer, &C, &inner);
+      const bool layer = op == "LayerNorm";
+      const float* gamma = Val(s.in[1]);
+      float* dg = GradOf(s.in[1]); float* db = GradOf(s.in[2]);
+      const int64_t groups = layer ? outer * inner : outer * C, len = layer ? C : inner;
+      for (int64_t g = 0; g < groups; ++g) {
+        const int64_t base = layer ? (g / inner) * C * inner + g % inner : g * inner, stride = layer ? inner : 1;
+        const float mean = s.saved[2 * g], inv = s.saved[2 * g + 1];
+        double sg = 0, sgx = 0;
+        for (int64_t k = 0; k < len; ++k) {
+          const int64_t c = layer ? k : g % C, at = base + k * stride;
+          const float xh = (x[at] - mean) * inv, gy = dy[at] * gamma[c];
+          sg += gy; sgx += gy * xh;
+          if (dg) dg[c] += dy[at] * xh;
+          if (db) db[c] += dy[at];
+        }
+        if (!dx) continue;
+        const float msg = static_cast<float>(sg / len), msgx = static_cast<float>(sgx / len);
+        for (int64_t k = 0; k < len; ++k) {
+          const int64_t c = layer ? k : g % C, at = base + k * stride;
+          dx[at] += inv * (dy[at] * gamma[c] - msg - (x[at] - mean) * inv * msgx);
+        }
+      }
+    } else if (op == "L2Normalization") {
+      if (!dx) return;
+      int64_t outer, C, inner; NormGroups(s, xs, &outer, &C, &inner);
+      for (int64_t o = 0; o < outer; ++o) for (int64_t i = 0; i < inner; ++i) {
+        const int64_t base = o * C * inner + i;
+        const float nrm = s.saved[o * inner + i];
+        double dot = 0;
+        for (int64_t k = 0; k < C; ++k) dot += static_cast<double>(dy[base + k * inner]) * y[base + k * inner];
+        for (int64_t k = 0; k < C; ++k) dx[base + k * inner] += (dy[base + k * inner] - y[base + k * inner] * static_cast<float>(dot)) / nrm;
+      }
+    } else if (op == "LRN") {
+      if (!dx) return;
+      const int64_t N = xs[0], C = xs[1], P = xs[2] * xs[3], half = a.Int("nsize", 1) / 2;
+      const float alpha = static_cast<float>(a.Float("alpha", 1e-4)) / static_cast<float>(a.Int("nsize", 1)), beta = static_cast<float>(a.Float("beta", 0.75));
+      for (int64_t b = 0; b < N; ++b) for (int64_t c = 0; c < C; ++c) for (int64_t p = 0; p < P; ++p) {
+        const int64_t at = (b * C + c) * P + p;
+        float acc = 0;
+        for (int64_t k = std::max<int64_t>(c - half, 0); k <= std::min(c + half, C - 1); ++k) { const int64_t o = (b * C + k) * P + p; acc += dy[o] * y[o] / s.saved[o]; }
+        dx[at] += dy[at] * std::pow(s.saved[at], -beta) - 2.f * alpha * beta * x[at] * acc;
+      }
+    } else if (op == "Deconvolution") {
+      const Win w = WinOf(graph::detail::Window(n, false, xs));
+      const int64_t N = xs[0], C = xs[1], H = xs[2], W = xs[3], F = s.shape[1], OH = s.shape[2], OW = s.shape[3], G = a.Int("num_group", 1);
+      const int64_t Cg = C / G, Fg = F / G, K = Fg * w.kh * w.kw, P = H * W;
+      const float* wt = Val(s.in[1]);
+      float* dw = GradOf(s.in[1]);
+      float* db = s.in.size() > 2 ? GradOf(s.in[2]) : nullptr;
+      std::vector<float> col(static_cast<size_t>(K * P));
+      for (int64_t i = 0; i < N; ++i) for (int64_t g = 0; g < G; ++g) {
+        Im2Col(dy + (i * F + g * Fg) * OH * OW, Fg, OH, OW, w, H, W, col.data());                               // col(dY): [K, H*W]
+        if (dx) GemmSerial(false, false, Cg, P, K, wt + g * Cg * K, col.data(), dx + (i * C + g * Cg) * P, true);   // dX_g += W_g . col
+        if (dw) GemmSerial(false, true, Cg, K, P, x + (i * C + g * Cg) * P, col.data(), dw + g * Cg * K, true);     // dW_g += X_g . col^T
+      }
+      if (db) for (int64_t i = 0; i < N; ++i) for (int64_t f = 0; f < F; ++f) { const float* o = dy + (i * F + f) * OH * OW; float sm = 0; for (int64_t p = 0; p < OH * OW; ++p) sm += o[p]; db[f] += sm; }
+    } else if (op == "smooth_l1") {
+      if (!dx) return;
+      const float s2 = static_cast<float>(a.Float("scalar", 1)) * static_cast<float>(a.Float("scalar", 1));
+      for (int64_t i = 0; i < ny; ++i) dx[i] += dy[i] * (std::fabs(x[i]) < 1.f / s2 ? s2 * x[i] : (x[i] > 0 ? 1.f : -1.f));
+    } else if (op == "softmax_cross_entropy") {
+      if (!dx) return;
+      const int64_t N = xs[0], C = xs[1];
+      const float* label = Val(s.in[1]);
+      for (int64_t i = 0; i < N; ++i) {
+        const int64_t cls = std::min<int64_t>(std::max<int64_t>(static_cast<int64_t>(label[i]), 0), C - 1);
+        for (int64_t k = 0; k < C; ++k) dx[i * C + k] += dy[0] * (s.saved[i * C + k] - (k == cls ? 1.f : 0.f));
+      }
     } else if (op == "sum" || op == "mean") {
       if (!dx) return;
       const auto red = ReducedAxes(s, xs);
@@ -751,7 +1070,9 @@ class Executor {
           case 2: gl = g * rv; gr = g * l; break;
           case 3: gl = g / rv; gr = -g * l / (rv * rv); break;
           case 4: gl = l >= rv ? g : 0.f; gr = l >= rv ? 0.f : g; break;
-          default: gl = l <= rv ? g : 0.f; gr = l <= rv ? 0.f : g; break;
+          case 5: gl = l <= rv ? g : 0.f; gr = l <= rv ? 0.f : g; break;
+          case 6: gl = g * rv * std::pow(l, rv - 1.f); gr = g * y[i] * std::log(l); break;
+          default: gl = 0.f; gr = 0.f; break;               // comparisons
         }
         if (dx) dx[li] += gl;
         if (dr) dr[ri] += gr;
@@ -760,11 +1081,7 @@ class Executor {
       if (!dx) return;
       const float c = static_cast<float>(a.Float("scalar", 0));
       const int k = ScalarKind(op);
-      for (int64_t i = 0; i < ny; ++i) {
-        float g;
-        switch (k) { case 0: case 1: g = 1.f; break; case 2: g = -1.f; break; case 3: g = c; break; case 4: g = 1.f / c; break; case 5: g = -c / (x[i] * x[i]); break; default: g = c * std::pow(x[i], c - 1.f); }
-        dx[i] += dy[i] * g;
-      }
+      for (int64_t i = 0; i < ny; ++i) dx[i] += dy[i] * ScG(k, x[i], c, y[i]);
     } else {
       if (!dx) return;
       const int k = UnaryKind(op);

@@ -538,3 +538,116 @@ def test_python_free_parameter_server_job(tmp_path):
     for o in outs[2:]:
         vals = [float(l.split()[-1]) for l in o.splitlines() if l.startswith("RESULT")]
         assert len(vals) == 2 and abs(vals[0] - 0.85) < 1e-6 and abs(vals[1] - 0.70) < 1e-6, o          # 1 - 0.1 * (0.5 + 1.0) per round
+
+
+def _pad_nd(t, widths, mode, value=0.0):
+    """numpy-style N-D padding for the torch reference (torch's F.pad has rank restrictions in the non-constant modes)."""
+    out = t
+    for ax, (b, a) in enumerate(widths):
+        if b == 0 and a == 0:
+            continue
+        n = out.shape[ax]
+        idx = torch.arange(-b, n + a)
+        if mode == "edge":
+            idx = idx.clamp(0, n - 1)
+        elif mode == "reflect":
+            idx = torch.where(idx < 0, -idx, idx); idx = torch.where(idx >= n, 2 * (n - 1) - idx, idx)
+        if mode == "constant":
+            shape = list(out.shape); shape[ax] = b; left = torch.full(shape, value); shape[ax] = a; right = torch.full(shape, value)
+            out = torch.cat([left, out, right], ax)
+        else:
+            out = out.index_select(ax, idx)
+    return out
+
+
+# (case id, operator, attributes, input shapes by name, torch reference over the inputs in ListArguments order, inputs without gradient)
+_RNG = np.random.RandomState(5)
+_IDX = {"take_idx": np.array([[2, 0], [9, 1]], dtype=np.float32), "pick_idx": _RNG.randint(0, 4, (3, 5)).astype(np.float32),
+        "cond": (_RNG.rand(3, 4) > 0.5).astype(np.float32), "hot": np.array([[1, 0, 3]], dtype=np.float32), "lab": np.array([2, 0, 1, 2], dtype=np.float32)}
+_TIER2 = [
+    ("layernorm", "LayerNorm", dict(axis=1, eps=1e-5), {"data": (3, 5, 2)}, lambda x, g, b: TF.layer_norm(x.transpose(1, 2), (5,), g, b, 1e-5).transpose(1, 2), ()),
+    ("instancenorm", "InstanceNorm", dict(eps=1e-3), {"data": (2, 3, 4, 2)}, lambda x, g, b: TF.instance_norm(x, weight=g, bias=b, eps=1e-3), ()),
+    ("l2norm_channel", "L2Normalization", dict(mode="channel", eps=1e-6), {"data": (2, 3, 4)}, lambda x: x / torch.sqrt((x * x).sum(1, keepdim=True) + 1e-6), ()),
+    ("l2norm_instance", "L2Normalization", dict(mode="instance", eps=1e-6), {"data": (2, 3, 4)}, lambda x: x / torch.sqrt((x * x).sum((1, 2), keepdim=True) + 1e-6), ()),
+    ("l2norm_spatial", "L2Normalization", dict(mode="spatial", eps=1e-6), {"data": (2, 3, 4)}, lambda x: x / torch.sqrt((x * x).sum(2, keepdim=True) + 1e-6), ()),
+    ("lrn", "LRN", dict(nsize=3, alpha=0.3, beta=0.75, knorm=2.0), {"data": (2, 5, 3, 2)}, lambda x: TF.local_response_norm(x, 3, alpha=0.3, beta=0.75, k=2.0), ()),
+    ("deconv", "Deconvolution", dict(kernel="(3, 2)", num_filter=4, stride="(2, 2)", pad="(1, 0)", adj="(1, 0)", num_group=2, no_bias=False), {"data": (2, 4, 3, 4)},
+     lambda x, w, b: TF.conv_transpose2d(x, w, b, stride=2, padding=(1, 0), output_padding=(1, 0), groups=2), ()),
+    ("deconv_dilated", "Deconvolution", dict(kernel="(2, 2)", num_filter=3, dilate="(2, 1)"), {"data": (1, 2, 3, 3)}, lambda x, w: TF.conv_transpose2d(x, w, None, dilation=(2, 1)), ()),
+    ("upsampling", "UpSampling", dict(scale=2, sample_type="nearest", num_args=1), {"arg0": (2, 2, 3, 2)}, lambda x: TF.interpolate(x, scale_factor=2, mode="nearest"), ()),
+    ("softmax_ce", "softmax_cross_entropy", {}, {"data": (4, 3), "label": "lab"}, lambda x, l: TF.cross_entropy(x, l.long(), reduction="sum").reshape(1), ("label",)),
+    ("smooth_l1", "smooth_l1", dict(scalar=2.0), {"data": (4, 5)}, lambda x: torch.where(x.abs() < 0.25, 2.0 * x * x, x.abs() - 0.125), ()),
+    ("slice_axis", "slice_axis", dict(axis=1, begin=-3, end="None"), {"data": (2, 5, 3)}, lambda x: x[:, -3:], ()),
+    ("slice", "slice", dict(begin="(None, 1)", end="(2, -1)"), {"data": (3, 5, 2)}, lambda x: x[:2, 1:-1], ()),
+    ("swapaxis", "SwapAxis", dict(dim1=0, dim2=2), {"data": (2, 3, 4)}, lambda x: x.transpose(0, 2), ()),
+    ("tile", "tile", dict(reps="(2, 1, 3)"), {"data": (2, 3)}, lambda x: x.repeat(2, 1, 3), ()),
+    ("repeat", "repeat", dict(repeats=3, axis=1), {"data": (2, 3, 2)}, lambda x: x.repeat_interleave(3, 1), ()),
+    ("pad_constant", "Pad", dict(mode="constant", pad_width="(0, 0, 1, 2, 2, 0)", constant_value=1.5), {"data": (2, 3, 2)}, lambda x: _pad_nd(x, [(0, 0), (1, 2), (2, 0)], "constant", 1.5), ()),
+    ("pad_edge", "Pad", dict(mode="edge", pad_width="(0, 0, 0, 0, 1, 2, 2, 1)"), {"data": (1, 2, 3, 3)}, lambda x: _pad_nd(x, [(0, 0), (0, 0), (1, 2), (2, 1)], "edge"), ()),
+    ("pad_reflect", "Pad", dict(mode="reflect", pad_width="(0, 0, 0, 0, 2, 1, 1, 2)"), {"data": (1, 2, 3, 4)}, lambda x: _pad_nd(x, [(0, 0), (0, 0), (2, 1), (1, 2)], "reflect"), ()),
+    ("squeeze", "squeeze", dict(axis="(1,)"), {"data": (3, 1, 2, 1)}, lambda x: x.squeeze(1), ()),
+    ("broadcast_to", "broadcast_to", dict(shape="(0, 4, 3)"), {"data": (2, 1, 1)}, lambda x: x.expand(2, 4, 3), ()),
+    ("broadcast_axis", "broadcast_axis", dict(axis="(0, 2)", size="(3, 2)"), {"data": (1, 4, 1)}, lambda x: x.expand(3, 4, 2), ()),
+    ("reverse", "reverse", dict(axis="(0, 2)"), {"data": (2, 3, 4)}, lambda x: x.flip(0, 2), ()),
+    ("take", "take", dict(axis=1), {"a": (3, 4, 2), "indices": "take_idx"}, lambda a, i: a[:, i.long().clamp(0, 3)], ("indices",)),
+    ("pick", "pick", dict(axis=1, keepdims=True), {"data": (3, 4, 5), "index": "pick_idx"}, lambda d, i: d.gather(1, i.long().unsqueeze(1)), ("index",)),
+    ("one_hot", "one_hot", dict(depth=4, on_value=2.0, off_value=-1.0), {"indices": "hot"}, lambda i: TF.one_hot(i.long(), 4).float() * 3.0 - 1.0, ("indices",)),
+    ("where", "where", {}, {"condition": "cond", "x": (3, 4), "y": (3, 4)}, lambda c, x, y: torch.where(c != 0, x, y), ("condition",)),
+    ("cast", "Cast", dict(dtype="float32"), {"data": (2, 3)}, lambda x: x * 1.0, ()),
+    ("max", "max", dict(axis="(1,)", keepdims=True), {"data": (3, 4, 2)}, lambda x: x.amax(1, keepdim=True), ()),
+    ("min_all", "min", {}, {"data": (3, 4)}, lambda x: x.amin().reshape(1), ()),
+    ("prod", "prod", dict(axis="(0, 2)"), {"data": (2, 3, 2)}, lambda x: x.prod(2).prod(0), ()),
+    ("norm", "norm", dict(axis="(1,)"), {"data": (3, 4)}, lambda x: x.norm(dim=1), ()),
+    ("argmax", "argmax", dict(axis=1), {"data": (3, 5, 2)}, lambda x: x.argmax(1).float(), ("data",)),
+    ("argmin_keep", "argmin", dict(axis=-1, keepdims=True), {"data": (3, 5)}, lambda x: x.argmin(-1, keepdim=True).float(), ("data",)),
+    ("power", "broadcast_power", {}, {"lhs": (3, 1, 2), "rhs": (4, 1)}, lambda l, r: l ** r, ()),
+    ("greater_equal", "broadcast_greater_equal", {}, {"lhs": (3, 4), "rhs": (1, 4)}, lambda l, r: (l >= r).float(), ("lhs", "rhs")),
+    ("not_equal", "broadcast_not_equal", {}, {"lhs": (3, 4), "rhs": (3, 4)}, lambda l, r: (l != r).float(), ("lhs", "rhs")),
+    ("max_scalar", "_maximum_scalar", dict(scalar=1.0), {"data": (3, 4)}, lambda x: x.clamp(min=1.0), ()),
+    ("min_scalar", "_minimum_scalar", dict(scalar=1.0), {"data": (3, 4)}, lambda x: x.clamp(max=1.0), ()),
+    ("rpower_scalar", "_rpower_scalar", dict(scalar=1.7), {"data": (3, 4)}, lambda x: 1.7 ** x, ()),
+] + [(u, u, {}, {"data": (3, 4)}, f, ()) for u, f in [
+    ("sin", torch.sin), ("cos", torch.cos), ("tan", torch.tan), ("arctan", torch.atan), ("sinh", torch.sinh), ("cosh", torch.cosh), ("log1p", torch.log1p), ("expm1", torch.expm1),
+    ("log2", torch.log2), ("log10", torch.log10), ("rsqrt", torch.rsqrt), ("reciprocal", torch.reciprocal), ("cbrt", lambda x: x ** (1.0 / 3)), ("erf", torch.erf),
+    ("floor", torch.floor), ("ceil", torch.ceil), ("sign", torch.sign)]] + [
+    ("arcsin", "arcsin", {}, {"data": (3, 4)}, lambda x: torch.asin(x / 2), ()), ("arccos", "arccos", {}, {"data": (3, 4)}, lambda x: torch.acos(x / 2), ())]
+
+
+@pytest.mark.parametrize("case", _TIER2, ids=[c[0] for c in _TIER2])
+def test_second_tier_operators_match_torch(case):
+    cid, opname, attrs, shapes, ref, no_grad = case
+    rng = np.random.RandomState(abs(hash(cid)) % 1000)
+    names = list(shapes.keys())
+    values = {}
+    for k, v in shapes.items():
+        values[k] = _IDX[v] if isinstance(v, str) else (rng.rand(*v) + 0.5).astype(np.float32)        # (0.5, 1.5): inside every domain used here
+    halve = cid in ("arcsin", "arccos")
+    ins = [C.var(k) for k in names]
+    if halve:
+        ins = [C.op("_mul_scalar", "half", ins, scalar=0.5)]
+    sym = C.op(opname, "n", ins, **attrs)
+    args = C.list_arguments(sym)
+    extra = [a for a in args if a not in names]                                   # learned parameters the operator declared itself (gamma, weight, ...)
+    a_, o_, _, _ = C.infer_shape(sym, partial=True, **{k: values[k].shape for k in names})
+    for a, shp in zip(args, a_):
+        if a in extra:
+            values[a] = (rng.rand(*shp) + 0.5).astype(np.float32)
+    ex, hargs, hgrads, _ = C.simple_bind(sym, {k: values[k].shape for k in names}, no_grad=tuple(no_grad))
+    for k in args:
+        C.nd_set(hargs[k], values[k])
+    out = C.forward(ex, True)[0]
+    tin = [torch.tensor(values[k], requires_grad=k not in no_grad) for k in args]
+    tout = ref(*tin)
+    assert out.shape == tuple(tout.shape), (out.shape, tuple(tout.shape))
+    assert np.allclose(out, tout.detach().numpy(), rtol=1e-4, atol=1e-5), np.abs(out - tout.detach().numpy()).max()
+    head = rng.rand(*out.shape).astype(np.float32)
+    C.backward(ex, [C.nd_create(head)])
+    if tout.requires_grad:
+        tout.backward(torch.tensor(head))
+        for k, t in zip(args, tin):
+            if k in no_grad:
+                continue
+            want = t.grad.numpy() if t.grad is not None else np.zeros_like(values[k])
+            got = C.nd_get(hgrads[k])
+            assert np.allclose(got, want, rtol=2e-3, atol=2e-5 * max(1.0, np.abs(want).max())), (k, np.abs(got - want).max())
+    ck(lib().GXExecutorFree(ex))
