@@ -47,6 +47,8 @@ from . import profiler  # noqa: F401
 from . import io  # noqa: F401
 from . import recordio  # noqa: F401
 from . import storage  # noqa: F401
+if base.getenv_str("GEOMX_GPU_MEM_POOL", "torch") == "native" and __import__("torch").cuda.is_available():       # before the first CUDA allocation
+    storage.use_native_gpu_pool()
 from . import engine  # noqa: F401
 from . import utils  # noqa: F401
 from . import parallel  # noqa: F401

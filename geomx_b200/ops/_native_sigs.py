@@ -82,5 +82,11 @@ def declare(lib):
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    # storage_gpu.cu (device memory pool): pointer / 64-bit returns
+    U64 = C.c_uint64
+    for name, args, res in (("gx_gpu_pool_create_sim", [I, U64, I, U64, I, I], I), ("gx_gpu_pool_destroy", [I], I), ("gx_gpu_pool_alloc", [I, U64, P], P),
+                            ("gx_gpu_pool_free", [I, P, P], I), ("gx_gpu_pool_release_all", [I], I), ("gx_gpu_pool_round_size", [I, U64], U64),
+                            ("gx_gpu_pool_stats", [I, C.POINTER(U64)], I)):
+        fn = getattr(lib, name); fn.argtypes = args; fn.restype = res
     lib.gx_unique_i64_workspace.argtypes = [C.c_int]
     lib.gx_unique_i64_workspace.restype = C.c_longlong

@@ -77,8 +77,11 @@ _reg("MXNET_CPU_WORKER_NTHREADS", 1, int, "")
 _reg("MXNET_CPU_PRIORITY_NTHREADS", 4, int, "")
 _reg("MXNET_GPU_WORKER_NTHREADS", 2, int, "")
 _reg("MXNET_GPU_COPY_NTHREADS", 2, int, "")
-_reg("MXNET_GPU_MEM_POOL_TYPE", "Naive", str, "handled by torch's caching allocator")
-_reg("MXNET_GPU_MEM_POOL_RESERVE", 5, int, "")
+_reg("MXNET_GPU_MEM_POOL_TYPE", "Naive", str, "Naive | Round | Unpooled: bucketing of the native device pool (storage.DevicePool, csrc/kernels/storage_gpu.cu)")
+_reg("MXNET_GPU_MEM_POOL_RESERVE", 5, int, "percent of device memory the native pool keeps free (cached blocks are released first)")
+_reg("MXNET_GPU_MEM_POOL_PAGE_SIZE", 4096, int, "bucket granularity of the native device pool")
+_reg("MXNET_GPU_MEM_POOL_ROUND_LINEAR_CUTOFF", 24, int, "log2 size above which the Round pool uses power-of-two buckets")
+_reg("GEOMX_GPU_MEM_POOL", "torch", str, "torch | native: native installs the pool as PyTorch's CUDA allocator at import")
 _reg("MXNET_PROFILER_AUTOSTART", 0, int, "")
 _reg("MXNET_PROFILER_MODE", 0, int, "")
 _reg("MXNET_ENFORCE_DETERMINISM", 0, int, "")
