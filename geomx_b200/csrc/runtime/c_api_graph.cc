@@ -34,12 +34,14 @@ namespace capi {
 struct AGNode {
   // leaf: a marked variable
   HostArray* var = nullptr;                           // nulled when the handle is freed
-  // operator: one recorded invocation (single visible output)
+  // operator: one recorded invocation
   std::unique_ptr<exec::Executor> ex;
   graph::Symbol sym;                                  // the one-node graph (inputs are variables in0, in1, ...)
   std::vector<std::vector<float>> in_copy;            // inputs as they were at invocation time (the caller may overwrite or free its arrays)
   std::vector<std::vector<float>> in_grad;
   std::vector<std::shared_ptr<AGNode>> in_node;       // history of each input (null: not tracked)
+  std::vector<int> in_out;                            // ... and which output of that producer the input is
+  int num_outputs = 1;
   std::string op;
   graph::AttrMap attrs;
   bool released = false;
@@ -146,14 +148,19 @@ void CollectTopo(const std::shared_ptr<AGNode>& n, std::set<AGNode*>* seen, std:
 void BackwardImpl(uint32_t num, void** outs, void** ograds, bool retain) {
   std::vector<std::shared_ptr<AGNode>> order;
   std::set<AGNode*> seen;
-  std::map<AGNode*, std::vector<float>> grad;
+  std::map<AGNode*, std::vector<std::vector<float>>> grad;          // per history node: one gradient buffer per output (empty = no gradient arrived)
+  auto slot = [&](AGNode* n, int out, size_t size) -> std::vector<float>& {
+    auto& v = grad[n];
+    if (v.empty()) v.resize(static_cast<size_t>(std::max(n->num_outputs, 1)));
+    if (v[out].empty()) v[out].assign(size, 0.f);
+    return v[out];
+  };
   for (uint32_t i = 0; i < num; ++i) {
     HostArray* o = ND(outs[i]);
     if (!o->ag) throw std::runtime_error("Backward: output " + std::to_string(i) + " was not computed while recording (or its graph was already freed)");
     CollectTopo(o->ag, &seen, &order);
-    auto& g = grad[o->ag.get()];
     const size_t n = o->rec.data.size() / 4;
-    if (g.empty()) g.assign(n, 0.f);
+    auto& g = slot(o->ag.get(), o->ag_out, n);
     if (ograds && ograds[i]) {
       HostArray* og = ND(ograds[i]);
       if (og->rec.data.size() != o->rec.data.size()) throw std::runtime_error("Backward: head gradient " + std::to_string(i) + " does not match its output");
@@ -166,20 +173,26 @@ void BackwardImpl(uint32_t num, void** outs, void** ograds, bool retain) {
     auto it = grad.find(n);
     if (it == grad.end()) continue;
     if (n->op.empty()) {                    // leaf
-      if (n->var && n->var->grad && n->var->grad_req != E::kNullOp) {
+      const std::vector<float>& g = it->second[0];
+      if (n->var && n->var->grad && n->var->grad_req != E::kNullOp && !g.empty()) {
         float* dst = F32(n->var->grad, "gradient buffer");
-        if (n->var->grad->rec.data.size() / 4 != it->second.size()) throw std::runtime_error("Backward: a gradient buffer does not match its variable");
-        if (n->var->grad_req == E::kAddTo) for (size_t i = 0; i < it->second.size(); ++i) dst[i] += it->second[i];
-        else memcpy(dst, it->second.data(), it->second.size() * 4);
+        if (n->var->grad->rec.data.size() / 4 != g.size()) throw std::runtime_error("Backward: a gradient buffer does not match its variable");
+        if (n->var->grad_req == E::kAddTo) for (size_t i = 0; i < g.size(); ++i) dst[i] += g[i];
+        else memcpy(dst, g.data(), g.size() * 4);
       }
       continue;
     }
     if (n->released) throw std::runtime_error("Backward: the graph was already freed by an earlier backward pass (retain_graph = 0)");
-    n->ex->Backward({it->second.data()});
+    std::vector<const float*> heads;
+    for (int o = 0; o < n->num_outputs; ++o) {           // outputs nobody differentiated through contribute zeros
+      auto& g = it->second[o];
+      if (g.empty()) g.assign(static_cast<size_t>(Numel(n->ex->OutputShape(o))), 0.f);
+      heads.push_back(g.data());
+    }
+    n->ex->Backward(heads);
     for (size_t i = 0; i < n->in_node.size(); ++i) {
       if (!n->in_node[i]) continue;
-      auto& g = grad[n->in_node[i].get()];
-      if (g.empty()) g.assign(n->in_grad[i].size(), 0.f);
+      auto& g = slot(n->in_node[i].get(), n->in_out[i], n->in_grad[i].size());
       for (size_t e = 0; e < g.size(); ++e) g[e] += n->in_grad[i][e];
     }
   }
@@ -533,6 +546,7 @@ GX_CAPI int GXImperativeInvoke(void* creator, int num_inputs, void** inputs, int
       in.push_back(a);
       node->in_copy.emplace_back(p, p + a->rec.data.size() / 4);
       node->in_node.push_back(i < n_arg && ag_recording ? a->ag : nullptr);
+      node->in_out.push_back(a->ag_out);
       if (node->in_node.back()) tracked = true;
     }
     std::vector<E::Tensor> ta, tg, tx; std::vector<int> reqs;
@@ -546,19 +560,26 @@ GX_CAPI int GXImperativeInvoke(void* creator, int num_inputs, void** inputs, int
     node->ex.reset(new E::Executor(sym, ta, tg, reqs, tx));
     node->ex->Forward(ag_training);
     for (int i = n_arg; i < num_inputs; ++i) memcpy(&in[i]->rec.data[0], node->in_copy[i].data(), in[i]->rec.data.size());      // running statistics are updated in place
-    const Shape& os = node->ex->OutputShape(0);
-    HostArray* out = nullptr;
-    if (*num_outputs > 0 && outputs && *outputs) {
-      out = ND((*outputs)[0]);
-      out->rec.dtype = 0; out->rec.shape.assign(os.begin(), os.end()); out->rec.data.assign(static_cast<size_t>(Numel(os)) * 4, '\0');
-    } else {
-      out = NewArray(os);
-      ret_inv.handles.assign(1, out);
-      *outputs = ret_inv.handles.data();
+    const int nout = static_cast<int>(node->ex->NumOutputs());
+    node->num_outputs = nout;
+    const bool given = *num_outputs > 0 && outputs && *outputs;
+    if (given && *num_outputs != nout) throw std::runtime_error(std::string(d->name) + ": " + std::to_string(*num_outputs) + " output arrays given, the operator produces " + std::to_string(nout));
+    if (!given) ret_inv.handles.clear();
+    for (int o = 0; o < nout; ++o) {
+      const Shape& os = node->ex->OutputShape(o);
+      HostArray* out = nullptr;
+      if (given) {
+        out = ND((*outputs)[o]);
+        out->rec.dtype = 0; out->rec.shape.assign(os.begin(), os.end()); out->rec.data.assign(static_cast<size_t>(Numel(os)) * 4, '\0');
+      } else {
+        out = NewArray(os);
+        ret_inv.handles.push_back(out);
+      }
+      memcpy(&out->rec.data[0], node->ex->OutputData(o), out->rec.data.size());
+      if (tracked) { out->ag = node; out->ag_out = o; } else { out->ag.reset(); out->ag_out = 0; }
     }
-    *num_outputs = 1;
-    memcpy(&out->rec.data[0], node->ex->OutputData(0), out->rec.data.size());
-    if (tracked) out->ag = node; else out->ag.reset();
+    if (!given) *outputs = ret_inv.handles.data();
+    *num_outputs = nout;
   });
 }
 GX_CAPI int GXImperativeInvokeByName(const char* op, int num_inputs, void** inputs, int* num_outputs, void*** outputs, int num_params, const char** param_keys,
@@ -590,13 +611,17 @@ GX_CAPI int GXAutogradGetSymbol(void* handle, void** out) {
       else {
         s = G::CreateAtomic(n->op, n->attrs);
         std::vector<Symbol> ins;
-        for (auto& i : n->in_node) ins.push_back(i ? build(i) : G::Variable("const" + std::to_string(nconst++)));
+        for (size_t k = 0; k < n->in_node.size(); ++k) {
+          if (!n->in_node[k]) { ins.push_back(G::Variable("const" + std::to_string(nconst++))); continue; }
+          const Symbol src = build(n->in_node[k]);
+          ins.push_back(Symbol{{src.outputs.at(static_cast<size_t>(n->in_out[k]))}});
+        }
         G::Compose(&s, n->op + std::to_string(nop++), ins, {});
       }
       built[n.get()] = s;
       return s;
     };
-    *out = new Symbol(build(a->ag));
+    *out = new Symbol(Symbol{{build(a->ag).outputs.at(static_cast<size_t>(a->ag_out))}});
   });
 }
 

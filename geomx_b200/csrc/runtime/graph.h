@@ -213,6 +213,8 @@ inline const std::vector<OpDef>& OpTable() {
                   {"num_group", "int, optional, default=1", "groups"}, {"no_bias", "boolean, optional, default=1", "disable the bias"}}});
     v.push_back({"UpSampling", InVar, 0, "num_args", "nearest-neighbour upsampling (src/operator/nn/upsampling.cc)",
                  {{"scale", "int, required", "factor"}, {"sample_type", "{'nearest'}, required", "method"}, {"num_args", "int, required", "number of inputs (1)"}}});
+    v.push_back({"SliceChannel", InData, 0, "", "split into num_outputs equal parts along an axis — the multi-output operator of the table (src/operator/slice_channel.cc)",
+                 {{"num_outputs", "int, required", "number of parts"}, {"axis", "int, optional, default=1", "axis"}, {"squeeze_axis", "boolean, optional, default=0", "drop the axis when the parts have extent 1"}}});
     v.push_back({"softmax_cross_entropy", InDataLabel, 0, "", "summed cross entropy of softmax(data) against integer labels (src/operator/loss_binary_op.cc)", none});
     v.push_back({"smooth_l1", InData, 0, "", "Huber-like loss with transition at 1/sigma^2", {{"scalar", "float, required", "sigma"}}});
     v.push_back({"slice_axis", InData, 0, "", "slice along one axis (src/operator/tensor/matrix_op.cc)",
@@ -268,7 +270,7 @@ inline std::string CanonicalOp(const std::string& op) {
       {"_MinimumScalar", "_minimum_scalar"}, {"_RPowerScalar", "_rpower_scalar"}, {"_power", "broadcast_power"}, {"_Power", "broadcast_power"}, {"swapaxes", "SwapAxis"},
       {"pad", "Pad"}, {"cast", "Cast"}, {"flip", "reverse"}, {"_equal", "broadcast_equal"}, {"_not_equal", "broadcast_not_equal"}, {"_greater", "broadcast_greater"},
       {"_greater_equal", "broadcast_greater_equal"}, {"_lesser", "broadcast_lesser"}, {"_lesser_equal", "broadcast_lesser_equal"}, {"max_axis", "max"}, {"min_axis", "min"},
-      {"sum_axis", "sum"}};
+      {"sum_axis", "sum"}, {"split", "SliceChannel"}};
   auto it = alias.find(op);
   return it == alias.end() ? op : it->second;
 }
@@ -281,6 +283,14 @@ inline const OpDef& GetOp(const std::string& op) {
   const OpDef* d = FindOp(op);
   if (!d) throw std::runtime_error("operator " + op + " is not registered in the native graph runtime");
   return *d;
+}
+
+// visible outputs of a node: 1 for every operator of the table except SliceChannel (all outputs of one node have the same shape)
+inline int NumOutputs(const Node& n) {
+  if (n.op != "SliceChannel") return 1;
+  const int64_t k = AttrView(n.attrs).Int("num_outputs", 0);
+  if (k < 1 || k > 4096) throw std::runtime_error(n.name + ": num_outputs must be in 1..4096");
+  return static_cast<int>(k);
 }
 
 // ------------------------------------------------------------------------------------------------ construction
@@ -304,7 +314,10 @@ inline Symbol CreateAtomic(const std::string& op, const AttrMap& attrs) {
   auto n = std::make_shared<Node>();
   n->op = d.name; n->attrs = attrs; n->composed = false;
   d.inputs(AttrView(n->attrs));        // validates num_args & co. early
-  return Symbol{{Entry{n, 0}}};
+  Symbol out;
+  const int k = NumOutputs(*n);
+  for (int i = 0; i < k; ++i) out.outputs.push_back(Entry{n, i});
+  return out;
 }
 
 inline Symbol Group(const std::vector<Symbol>& parts) {
@@ -316,7 +329,8 @@ inline Symbol Group(const std::vector<Symbol>& parts) {
 // Supplies the inputs of an atomic symbol: positional `args` and / or keyword `kwargs`; inputs that are not given become variables named
 // `<name>_<input>` (nnvm Symbol::Compose + the front ends' auto-variable rule, python/mxnet/symbol/symbol.py).
 inline void Compose(Symbol* s, const std::string& name, const std::vector<Symbol>& args, const std::vector<std::pair<std::string, Symbol>>& kwargs) {
-  if (s->outputs.size() != 1 || s->outputs[0].node->composed || s->outputs[0].node->op == "null") throw std::runtime_error("Compose: not an atomic symbol");
+  if (s->outputs.empty() || s->outputs[0].node->composed || s->outputs[0].node->op == "null") throw std::runtime_error("Compose: not an atomic symbol");
+  for (auto& e : s->outputs) if (e.node != s->outputs[0].node) throw std::runtime_error("Compose: not an atomic symbol");
   Node& n = *s->outputs[0].node;
   const OpDef& d = GetOp(n.op);
   n.name = name.empty() ? AutoName(n.op) : name;
@@ -343,7 +357,12 @@ inline void Compose(Symbol* s, const std::string& name, const std::vector<Symbol
 
 inline Symbol Copy(const Symbol& s) {
   Symbol c = s;
-  for (auto& e : c.outputs) if (!e.node->composed) e.node = std::make_shared<Node>(*e.node);
+  std::map<Node*, std::shared_ptr<Node>> fresh;
+  for (auto& e : c.outputs) if (!e.node->composed) {
+    auto& f = fresh[e.node.get()];
+    if (!f) f = std::make_shared<Node>(*e.node);
+    e.node = f;
+  }
   return c;
 }
 
@@ -390,7 +409,10 @@ inline std::vector<std::string> ListAuxiliaryStates(const Symbol& s) {
   for (Node* n : order) if (aux.count(n)) out.push_back(n->name);
   return out;
 }
-inline std::string OutputName(const Entry& e) { return e.node->op == "null" ? e.node->name : e.node->name + "_output"; }
+inline std::string OutputName(const Entry& e) {
+  if (e.node->op == "null") return e.node->name;
+  return NumOutputs(*e.node) > 1 ? e.node->name + "_output" + std::to_string(e.index) : e.node->name + "_output";
+}
 inline std::vector<std::string> ListOutputs(const Symbol& s) {
   std::vector<std::string> out;
   for (auto& e : s.outputs) out.push_back(OutputName(e));
@@ -401,7 +423,7 @@ inline Symbol GetInternals(const Symbol& s) {
   std::map<Node*, std::shared_ptr<Node>> owner;
   std::function<void(const Entry&)> own = [&](const Entry& e) { if (owner.emplace(e.node.get(), e.node).second) for (auto& i : e.node->inputs) own(i); };
   for (auto& h : s.outputs) own(h);
-  for (Node* n : Topo(s)) r.outputs.push_back(Entry{owner[n], 0});
+  for (Node* n : Topo(s)) for (int i = 0, k = NumOutputs(*n); i < k; ++i) r.outputs.push_back(Entry{owner[n], i});
   return r;
 }
 inline Symbol GetChildren(const Symbol& s) {
@@ -445,7 +467,7 @@ inline std::string ToJSON(const Symbol& s) {
   bool first = true;
   for (size_t i = 0; i < order.size(); ++i) if (order[i]->op == "null") { o << (first ? "" : ", ") << i; first = false; }
   o << "], \n  \"node_row_ptr\": [";
-  for (size_t i = 0; i <= order.size(); ++i) o << (i ? ", " : "") << i;
+  { size_t row = 0; o << 0; for (size_t i = 0; i < order.size(); ++i) { row += static_cast<size_t>(NumOutputs(*order[i])); o << ", " << row; } }
   o << "], \n  \"heads\": [";
   for (size_t i = 0; i < s.outputs.size(); ++i) o << (i ? ", " : "") << "[" << id[s.outputs[i].node.get()] << ", " << s.outputs[i].index << ", 0]";
   o << "], \n  \"attrs\": {\"mxnet_version\": [\"int\", 10400]}\n}";
@@ -482,8 +504,8 @@ inline Symbol FromJSON(const std::string& json) {
     else if (e.kind == JValue::kArr && !e.arr.empty() && e.arr[0].kind == JValue::kNum) { idx = static_cast<int64_t>(e.arr[0].num); en.index = e.arr.size() > 1 ? static_cast<int>(e.arr[1].num) : 0; }
     else throw std::runtime_error("symbol JSON: malformed input reference");
     if (idx < 0 || static_cast<size_t>(idx) >= limit) throw std::runtime_error("symbol JSON: node inputs must refer to earlier nodes");
-    if (en.index != 0) throw std::runtime_error("symbol JSON: secondary operator outputs are not produced by the native graph runtime");
     en.node = nodes[static_cast<size_t>(idx)];
+    if (en.index < 0 || en.index >= NumOutputs(*en.node)) throw std::runtime_error("symbol JSON: " + en.node->name + " has no output " + std::to_string(en.index));
     return en;
   };
   for (size_t i = 0; i < nodes.size(); ++i) {
@@ -757,6 +779,15 @@ inline bool InferNode(const Node& n, const std::vector<const Shape*>& in, const 
     const int64_t sc = a.Int("scale", 0);
     if (x.size() != 4 || sc < 1 || sc > 64) throw std::runtime_error(n.name + ": needs NCHW input and 1 <= scale <= 64");
     *out = {x[0], x[1], x[2] * sc, x[3] * sc};
+  } else if (op == "SliceChannel") {
+    const int64_t ax = AxisOf(a.Int("axis", 1), x.size(), n.name), k = NumOutputs(n);
+    if (x[ax] % k) throw std::runtime_error(n.name + ": extent " + std::to_string(x[ax]) + " of axis " + std::to_string(ax) + " is not divisible into " + std::to_string(k) + " parts");
+    *out = x; (*out)[ax] = x[ax] / k;
+    if (a.Bool("squeeze_axis", false)) {
+      if ((*out)[ax] != 1) throw std::runtime_error(n.name + ": squeeze_axis needs parts of extent 1");
+      out->erase(out->begin() + ax);
+      if (out->empty()) out->push_back(1);
+    }
   } else if (op == "softmax_cross_entropy") {
     if (x.size() != 2) throw std::runtime_error(n.name + ": data must be (batch, classes)");
     need(1, {x[0]});

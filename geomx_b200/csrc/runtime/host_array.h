@@ -19,6 +19,7 @@ struct HostArray {
   gxrt::NDRec rec;
   std::vector<uint32_t> shape32;        // GetShape hands out a pointer that stays valid until the handle is freed
   std::shared_ptr<AGNode> ag;           // set while the array is a marked variable or the output of a recorded operator
+  int ag_out = 0;                       // which output of that operator
   HostArray* grad = nullptr;            // marked variables: where Backward writes (not owned)
   int grad_req = 0;
   ~HostArray();

@@ -175,9 +175,13 @@ class Executor {
     for (Node* n : order_) {
       index_[n] = static_cast<int>(slots_.size());
       slots_.emplace_back();
+      slots_.back().node = n;
+      if (n->op != "null") {
+        // outputs 1.. of a multi-output node live in sibling slots right behind the node's own slot: consumers address (node, j) as slot + j
+        for (int j = 1, k = graph::NumOutputs(*n); j < k; ++j) { slots_.emplace_back(); slots_.back().node = n; slots_.back().sibling_of = index_[n]; }
+        continue;
+      }
       Slot& s = slots_.back();
-      s.node = n;
-      if (n->op != "null") continue;
       if (aux_nodes.count(n)) {
         if (xi >= aux.size()) throw std::runtime_error("Bind: " + std::to_string(aux.size()) + " auxiliary states given, the symbol has more (missing " + n->name + ")");
         s.ext = aux[xi].data; s.shape = aux[xi].shape; s.is_aux = true; ++xi;
@@ -202,15 +206,16 @@ class Executor {
     for (auto& s : slots_) {
       s.shape = sr.shape.at(s.node);
       if (s.node->op != "null") { s.own.assign(static_cast<size_t>(Numel(s.shape)), 0.f); }
-      for (auto& e : s.node->inputs) s.in.push_back(index_.at(e.node.get()));
+      if (s.sibling_of < 0) for (auto& e : s.node->inputs) s.in.push_back(index_.at(e.node.get()) + e.index);
     }
     // gradient flow: a node needs a gradient when any input does; BlockGrad cuts it
     for (auto& s : slots_) {
       if (s.node->op == "null") { s.need_grad = s.req != kNullOp; continue; }
       if (s.node->op == "BlockGrad") continue;
+      if (s.sibling_of >= 0) { s.need_grad = slots_[s.sibling_of].need_grad; continue; }
       for (int i : s.in) if (slots_[i].need_grad) s.need_grad = true;
     }
-    for (auto& h : sym_.outputs) heads_.push_back(index_.at(h.node.get()));
+    for (auto& h : sym_.outputs) heads_.push_back(index_.at(h.node.get()) + h.index);
     rng_.seed(GlobalSeed().fetch_add(1) * 2654435761u + 12345u);
   }
 
@@ -222,7 +227,7 @@ class Executor {
 
   void Forward(bool is_train) {
     is_train_ = is_train;
-    for (auto& s : slots_) if (s.node->op != "null") Run(s);
+    for (auto& s : slots_) if (s.node->op != "null" && s.sibling_of < 0) Run(s);
     forwarded_ = true;
   }
 
@@ -241,7 +246,7 @@ class Executor {
     }
     for (size_t k = slots_.size(); k-- > 0;) {
       Slot& s = slots_[k];
-      if (s.node->op == "null" || !s.need_grad) continue;
+      if (s.node->op == "null" || !s.need_grad || s.sibling_of >= 0) continue;       // a sibling's gradient is consumed by its node's own slot, visited later in this sweep
       Grad(s);
       std::vector<float>().swap(s.grad);                   // activations' gradients are dead once propagated
     }
@@ -257,6 +262,7 @@ class Executor {
     std::string o;
     int64_t act = 0;
     for (auto& s : slots_) {
+      if (s.sibling_of >= 0) continue;
       if (s.node->op == "null") { o += "Variable:" + s.node->name + " " + ShapeStr(s.shape) + (s.is_aux ? " aux" : s.req != kNullOp ? " grad" : "") + "\n"; continue; }
       o += "Op:" + s.node->op + ", Name=" + s.node->name + " -> " + ShapeStr(s.shape) + "\n";
       for (int i : s.in) o += "  arg: " + slots_[i].node->name + "\n";
@@ -275,6 +281,7 @@ class Executor {
     float* ext_grad = nullptr;
     int req = kNullOp;
     bool is_aux = false, need_grad = false;
+    int sibling_of = -1;               // >= 0: this slot is output (index - sibling_of) of the multi-output node in slot sibling_of
     std::vector<float> own, grad;
     std::vector<int32_t> idx;          // Pooling(max): winning input offset per output
     std::vector<float> saved;          // Dropout mask / BatchNorm batch mean + inverse std / LayerNorm statistics / LRN scale / softmax probabilities
@@ -464,6 +471,14 @@ class Executor {
     } else if (op == "clip") {
       const float lo = static_cast<float>(a.Float("a_min", -std::numeric_limits<float>::infinity())), hi = static_cast<float>(a.Float("a_max", std::numeric_limits<float>::infinity()));
       for (int64_t i = 0; i < ny; ++i) y[i] = std::min(std::max(x[i], lo), hi);
+    } else if (op == "SliceChannel") {
+      const int64_t k = graph::NumOutputs(n);
+      int64_t outer, C, inner; SplitAxis(xs, graph::detail::AxisOf(a.Int("axis", 1), xs.size(), n.name), &outer, &C, &inner);
+      const int64_t Ck = C / k, self = &s - slots_.data();
+      for (int64_t j = 0; j < k; ++j) {
+        float* dst = slots_[self + j].own.data();
+        for (int64_t o = 0; o < outer; ++o) memcpy(dst + o * Ck * inner, x + (o * C + j * Ck) * inner, Ck * inner * sizeof(float));
+      }
     } else if (IsGather(op)) {
       BuildMap(s);
       const float fill = op == "Pad" ? static_cast<float>(a.Float("constant_value", 0)) : 0.f;
@@ -952,6 +967,16 @@ class Executor {
       if (!dx) return;
       const float lo = static_cast<float>(a.Float("a_min", -std::numeric_limits<float>::infinity())), hi = static_cast<float>(a.Float("a_max", std::numeric_limits<float>::infinity()));
       for (int64_t i = 0; i < ny; ++i) if (x[i] >= lo && x[i] <= hi) dx[i] += dy[i];
+    } else if (op == "SliceChannel") {
+      if (!dx) return;
+      const int64_t k = graph::NumOutputs(n);
+      int64_t outer, C, inner; SplitAxis(xs, graph::detail::AxisOf(a.Int("axis", 1), xs.size(), n.name), &outer, &C, &inner);
+      const int64_t Ck = C / k, self = &s - slots_.data();
+      for (int64_t j = 0; j < k; ++j) {
+        const float* g = slots_[self + j].grad.data();
+        for (int64_t o = 0; o < outer; ++o) for (int64_t e = 0; e < Ck * inner; ++e) dx[(o * C + j * Ck) * inner + e] += g[o * Ck * inner + e];
+      }
+      for (int64_t j = 1; j < k; ++j) std::vector<float>().swap(slots_[self + j].grad);
     } else if (IsGather(op)) {
       if (dx) for (int64_t i = 0; i < ny; ++i) if (s.map[i] >= 0) dx[s.map[i]] += dy[i];
     } else if (op == "squeeze" || op == "Cast") {

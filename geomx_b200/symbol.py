@@ -135,7 +135,7 @@ class Symbol:
     def list_outputs(self):
         if self.op == "_group":
             return [o for s in self.inputs for o in s.list_outputs()]
-        return [self.name if self.op == "null" else self.name + "_output"]
+        return [self.name if self.op in ("null", "_item") else self.name + "_output"]          # an _item is already called <node>_output<i>
 
     def list_inputs(self):
         return self.list_arguments() + self.list_auxiliary_states()
@@ -231,6 +231,12 @@ def _lit(v):
 def _from_nnvm(d):
     """Build the graph from the reference's JSON dialect (what ``Symbol.save`` of MXNet / GeoMX writes)."""
     built = []
+    # nodes with several outputs: output 0 must be taken as an item too (a consumer of the bare node would receive the tuple of all outputs)
+    rows = d.get("node_row_ptr") or []
+    multi = {i for i in range(len(rows) - 1) if rows[i + 1] - rows[i] > 1}
+    for n in d["nodes"]:
+        multi.update(e[0] for e in n["inputs"] if len(e) > 1 and e[1])
+    multi.update(h[0] for h in d.get("heads", []) if len(h) > 1 and h[1])
 
     def user_attrs(n, raw):
         a = dict(n.get("attr") or {}) if ("attrs" in n or "param" in n) else {}
@@ -245,7 +251,7 @@ def _from_nnvm(d):
         ins = []
         for e in n["inputs"]:
             src = built[e[0]]
-            ins.append(src[e[1]] if e[1] else src)
+            ins.append(src[e[1]] if (e[1] or e[0] in multi) else src)
         usr = user_attrs(n, raw)
         if op == "null":
             sym = Symbol("null", name, attrs={"__attr__": {k: str(v) for k, v in usr.items()}} if usr else None)
@@ -294,7 +300,7 @@ def _from_nnvm(d):
         if usr and op != "null":
             sym.attrs.setdefault("__attr__", {}).update({k: str(v) for k, v in usr.items()})
         built.append(sym)
-    heads = [built[h[0]][h[1]] if h[1] else built[h[0]] for h in d["heads"]]
+    heads = [built[h[0]][h[1]] if (h[1] or h[0] in multi) else built[h[0]] for h in d["heads"]]
     return heads[0] if len(heads) == 1 else Group(heads)
 
 
