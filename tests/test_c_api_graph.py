@@ -711,3 +711,39 @@ def test_multi_output_operator_slice_channel():
     assert np.allclose(C.nd_get(g), want, rtol=1e-5)
     bad = vp()
     assert lib().GXSymbolCreateFromJSON(js.replace('[%d, 2, 0]' % sp, '[%d, 7, 0]' % sp).encode(), ctypes.byref(bad)) == -1 and "has no output 7" in C.err()
+
+
+def test_python_free_distributed_training(tmp_path):
+    """examples/c_api/dist_train_cnn.c: the reference's cnn.py flow (init, per-step forward / backward, push + pull of every parameter) as four C
+    processes — two workers computing with GXExecutor*, a server applying SGD natively, a scheduler.  Workers must end with identical parameters."""
+    import os
+    import re
+    import shutil
+    import socket
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    libdir = os.path.join(C.ROOT, "geomx_b200", "lib")
+    exe = str(tmp_path / "dist_train_cnn")
+    subprocess.run([cc, "-O2", "-Wall", "-Werror", "-std=c99", "-I", os.path.join(C.ROOT, "geomx_b200", "include"), os.path.join(C.ROOT, "examples", "c_api", "dist_train_cnn.c"),
+                    "-L", libdir, "-lgeomx_capi", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = {k: v for k, v in os.environ.items() if not k.startswith(("DMLC_", "PS_")) and k not in ("RANK", "WORLD_SIZE")}
+    env.update({"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(port), "DMLC_NUM_SERVER": "1", "DMLC_NUM_WORKER": "2", "DMLC_NUM_ALL_WORKER": "2"})
+    procs = [subprocess.Popen([exe, "30"], env=dict(env, DMLC_ROLE=role), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for role in ("scheduler", "server", "worker", "worker")]
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=240)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    assert all(p.returncode == 0 for p in procs), outs
+    finals = [re.search(r"FINAL rank (\d) of 2 loss ([\d.]+) -> ([\d.]+) checksum ([-\d.]+)", o) for o in outs[2:]]
+    assert all(finals), outs
+    assert sorted(m.group(1) for m in finals) == ["0", "1"]
+    assert finals[0].group(4) == finals[1].group(4)                      # the same parameters on both workers, to the last printed digit
+    assert all(float(m.group(3)) < 0.3 * float(m.group(2)) for m in finals)
