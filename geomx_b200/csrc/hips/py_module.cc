@@ -110,9 +110,12 @@ PYBIND11_MODULE(_C, m) {
                           py::make_tuple(b.head, b.app_id, b.customer_id, b.timestamp, b.sender, b.recver, b.request, b.push, b.simple_app, b.body, b.priority,
                                          b.key, b.compr, b.control.cmd, back));
   });
-  m.def("fuzz_dgt_block", [](int seq, int seq_end, int total_bytes, int val_bytes, int bits_num, int ncompr, int payload_len, int nparts) {
+  m.def("fuzz_dgt_block", [](int seq, int seq_end, int total_bytes, int val_bytes, int bits_num, int ncompr, int payload_len, int nparts, bool reset) {
     // one reassembly step of the DGT receiver on a block whose header fields are arbitrary: must be dropped or accepted, never index out of range
-    static DGTReceiver rx;
+    // (reset: start from a receiver without partial tensors — the fuzz tests deliberately leave some behind)
+    static std::unique_ptr<DGTReceiver> rxp;
+    if (reset || !rxp) rxp.reset(new DGTReceiver());
+    DGTReceiver& rx = *rxp;
     Message blk, whole;
     blk.meta.sender = 9; blk.meta.first_key = 1; blk.meta.timestamp = 3; blk.meta.seq = seq; blk.meta.seq_end = seq_end;
     blk.meta.total_bytes = total_bytes; blk.meta.val_bytes = val_bytes; blk.meta.bits_num = bits_num; blk.meta.msg_type = 1;
@@ -122,7 +125,8 @@ PYBIND11_MODULE(_C, m) {
     if (nparts >= 1) blk.data.push_back(keys);
     if (nparts >= 2) blk.data.push_back(vals);
     return rx.Add(blk, &whole);
-  });
+  }, py::arg("seq"), py::arg("seq_end"), py::arg("total_bytes"), py::arg("val_bytes"), py::arg("bits_num"), py::arg("ncompr"), py::arg("payload_len"), py::arg("nparts"),
+     py::arg("reset") = false);
   m.def("ts_pick_receiver", [](int requester, std::vector<int> idle, std::map<int, long> known, float max_greed, int trials) {
     Environment::Get()->Set("MAX_GREED_RATE_TS", std::to_string(max_greed));
     TSScheduler s(nullptr, 8, kLocal);

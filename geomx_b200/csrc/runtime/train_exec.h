@@ -813,6 +813,7 @@ class Executor {
       float* dw = GradOf(s.in[1]);
       float* db = s.in.size() > 2 ? GradOf(s.in[2]) : nullptr;
       std::mutex mu;
+      std::map<int64_t, std::pair<std::vector<float>, std::vector<float>>> parts;      // per chunk of images, keyed by its first image: summed in key order below
       ParallelFor(N, static_cast<double>(N) * F * K * P * 2, [&](int64_t lo, int64_t hi) {
         std::vector<float> col(static_cast<size_t>(K * P)), dcol(dx ? static_cast<size_t>(K * P) : 0);
         std::vector<float> dw_local(dw ? static_cast<size_t>(F * K) : 0, 0.f), db_local(db ? static_cast<size_t>(F) : 0, 0.f);
@@ -829,9 +830,13 @@ class Executor {
           }
         }
         std::lock_guard<std::mutex> lk(mu);
-        if (dw) for (size_t k = 0; k < dw_local.size(); ++k) dw[k] += dw_local[k];
-        if (db) for (size_t k = 0; k < db_local.size(); ++k) db[k] += db_local[k];
+        parts[lo] = {std::move(dw_local), std::move(db_local)};
       });
+      // a fixed summation order: the weight gradient does not depend on which thread finished first (bitwise reproducible runs)
+      for (auto& kv : parts) {
+        if (dw) for (size_t k = 0; k < kv.second.first.size(); ++k) dw[k] += kv.second.first[k];
+        if (db) for (size_t k = 0; k < kv.second.second.size(); ++k) db[k] += kv.second.second[k];
+      }
     } else if (op == "Pooling") {
       if (!dx) return;
       const Win w = WinOf(graph::detail::Window(n, true, xs));

@@ -238,6 +238,7 @@ int GXPredForward(PredictorHandle handle);
 int GXPredPartialForward(PredictorHandle handle, int step, int* step_left);
 int GXPredGetOutput(PredictorHandle handle, uint32_t index, float* data, uint32_t size);
 int GXPredGetPlan(PredictorHandle handle, uint64_t* arena_bytes, uint32_t* num_ops);
+int GXPredGetEngine(PredictorHandle handle, int* out);        /* 1 planned predictor, 2 general executor (operators outside the planned set) */
 int GXPredFree(PredictorHandle handle);
 int GXNDListCreate(const char* nd_file_bytes, int nd_file_size, NDListHandle* out, uint32_t* out_length);
 int GXNDListGet(NDListHandle handle, uint32_t index, const char** out_key, const float** out_data, const uint32_t** out_shape, uint32_t* out_ndim);

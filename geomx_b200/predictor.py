@@ -191,7 +191,7 @@ def load_ndarray_file(nd_bytes):
             shape = tuple(pshape[j] for j in range(ndim.value))
             size = int(np.prod(shape)) if shape else 0
             arrays.append(np.ctypeslib.as_array(pdata, shape=(size,)).reshape(shape).copy() if size else np.zeros(shape, np.float32))
-            names.append(key.value.decode() if key.value else "")
+            names.append(key.value.decode(errors="replace") if key.value else "")
         return dict(zip(names, arrays)) if any(names) else arrays
     finally:
         lib.GXNDListFree(h)

@@ -20,7 +20,7 @@ def lib():
 
 
 def err():
-    return lib().GXRTGetLastError().decode()
+    return lib().GXRTGetLastError().decode(errors="replace")
 
 
 def ck(rc):
@@ -95,7 +95,7 @@ def op(opname, name, inputs=(), kwinputs=None, **attrs):
 def sym_json(h):
     out = cp()
     ck(lib().GXSymbolSaveToJSON(h, ctypes.byref(out)))
-    return out.value.decode()
+    return out.value.decode(errors="replace")
 
 
 def sym_from_json(js):

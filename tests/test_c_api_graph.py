@@ -141,7 +141,7 @@ def test_executor_cnn_matches_torch_and_trains():
     for _ in range(30):
         loss(); C.backward(ex)
         for k in params:
-            params[k] = params[k] - 0.1 * C.nd_get(grads[k]); C.nd_set(args[k], params[k])
+            params[k] = params[k] - 0.05 * C.nd_get(grads[k]); C.nd_set(args[k], params[k])
     assert loss() < 0.8 * l0
     out = cp(); ck(lib().GXExecutorPrint(ex, ctypes.byref(out))); assert b"Op:Convolution, Name=conv1" in out.value
     # grad_req add accumulates; explicit Bind with caller-owned arrays
@@ -747,3 +747,78 @@ def test_python_free_distributed_training(tmp_path):
     assert sorted(m.group(1) for m in finals) == ["0", "1"]
     assert finals[0].group(4) == finals[1].group(4)                      # the same parameters on both workers, to the last printed digit
     assert all(float(m.group(3)) < 0.3 * float(m.group(2)) for m in finals)
+
+
+def test_predict_api_falls_back_to_the_general_executor(tmp_path):
+    """Graphs with operators outside the planned predictor's set (LayerNorm, SliceChannel, Deconvolution ...) are served by the general executor
+    behind the same GXPred* ABI; graphs inside the set keep the planned engine."""
+    rng = np.random.RandomState(11)
+    x = C.var("data")
+    h = C.op("Deconvolution", "up", [x], kernel="(2, 2)", stride="(2, 2)", num_filter=4)                    # (N, 4, 8, 8)
+    parts = C.op("SliceChannel", "sp", [h], num_outputs=2, axis=1)
+    a, b = vp(), vp()
+    ck(lib().GXSymbolGetOutput(parts, 0, ctypes.byref(a))); ck(lib().GXSymbolGetOutput(parts, 1, ctypes.byref(b)))
+    h = C.op("broadcast_mul", "gate", [C.op("sigmoid", "s", [a]), b])                                       # (N, 2, 8, 8)
+    h = C.op("LayerNorm", "ln", [C.op("Flatten", "f", [h])], axis=-1)
+    net = C.op("softmax", "prob", [C.op("FullyConnected", "fc", [h], num_hidden=3)])
+    args = C.list_arguments(net)
+    shapes, _, _, _ = C.infer_shape(net, data=(2, 3, 4, 4))
+    values = {n: (rng.randn(*s) * 0.5).astype(np.float32) for n, s in zip(args, shapes)}
+    fname = str(tmp_path / "m.params").encode()
+    keys = [n for n in args if n != "data"]
+    ck(lib().GXNDArraySave(fname, len(keys), C.handles([C.nd_create(values[k]) for k in keys]), C.strs(["arg:" + k for k in keys])))
+    blob = open(fname, "rb").read()
+    js = C.sym_json(net).encode()
+
+    def create(json_bytes, batch, out_keys=None):
+        p = vp()
+        ind, dims = (u32 * 2)(0, 4), (u32 * 4)(batch, 3, 4, 4)
+        if out_keys:
+            rc = lib().GXPredCreatePartialOut(json_bytes, blob, len(blob), 1, 0, 1, C.strs(["data"]), ind, dims, len(out_keys), C.strs(out_keys), ctypes.byref(p))
+        else:
+            rc = lib().GXPredCreate(json_bytes, blob, len(blob), 1, 0, 1, C.strs(["data"]), ind, dims, ctypes.byref(p))
+        if rc != 0:
+            raise RuntimeError(C.err())
+        return p
+
+    def run(p, xin, n_out):
+        ck(lib().GXPredSetInput(p, b"data", xin.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), xin.size)); ck(lib().GXPredForward(p))
+        out = np.empty(n_out, dtype=np.float32)
+        ck(lib().GXPredGetOutput(p, 0, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), out.size))
+        return out
+    p = create(js, 2)
+    eng = ctypes.c_int(); ck(lib().GXPredGetEngine(p, ctypes.byref(eng))); assert eng.value == 2
+    xin = rng.rand(2, 3, 4, 4).astype(np.float32)
+    got = run(p, xin, 6).reshape(2, 3)
+    t = {k: torch.tensor(v) for k, v in values.items()}
+    th = TF.conv_transpose2d(torch.tensor(xin), t["up_weight"], None, stride=2)
+    ta, tb = th.split(2, 1)
+    tn = TF.layer_norm((torch.sigmoid(ta) * tb).flatten(1), (128,), t["ln_gamma"], t["ln_beta"], 1e-5)
+    want = torch.softmax(TF.linear(tn, t["fc_weight"], t["fc_bias"]), -1).numpy()
+    assert np.allclose(got, want, atol=1e-5)
+    sd, nd_ = ctypes.POINTER(u32)(), u32()
+    ck(lib().GXPredGetOutputShape(p, 0, ctypes.byref(sd), ctypes.byref(nd_))); assert [sd[i] for i in range(nd_.value)] == [2, 3]
+    # reshape to another batch on the same parameters; internal output by name; plan statistics
+    p5 = vp(); ck(lib().GXPredReshape(1, C.strs(["data"]), (u32 * 2)(0, 4), (u32 * 4)(5, 3, 4, 4), p, ctypes.byref(p5)))
+    x5 = rng.rand(5, 3, 4, 4).astype(np.float32)
+    assert np.allclose(run(p5, x5, 15).reshape(5, 3)[:2], run(create(js, 5), x5, 15).reshape(5, 3)[:2])
+    pin = create(js, 2, ["sp_output1"])
+    assert np.allclose(run(pin, xin, 2 * 2 * 8 * 8).reshape(2, 2, 8, 8), tb.numpy(), atol=1e-5)
+    arena, nops = ctypes.c_uint64(), u32()
+    ck(lib().GXPredGetPlan(p, ctypes.byref(arena), ctypes.byref(nops))); assert nops.value == 8 and arena.value > 0
+    with pytest.raises(RuntimeError, match="unknown input"):
+        bad = np.zeros(3, np.float32)
+        if lib().GXPredSetInput(p, b"fc_weight", bad.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 3) != 0:
+            raise RuntimeError(C.err())
+    # a graph inside the planned set keeps engine 1
+    small = C.op("softmax", "prob", [C.op("FullyConnected", "fc", [C.op("Flatten", "f", [C.var("data")])], num_hidden=3)])
+    w = {"fc_weight": rng.randn(3, 48).astype(np.float32), "fc_bias": np.zeros(3, np.float32)}
+    ck(lib().GXNDArraySave(fname, 2, C.handles([C.nd_create(w[k]) for k in w]), C.strs(["arg:" + k for k in w])))
+    blob = open(fname, "rb").read()
+    ps = create(C.sym_json(small).encode(), 2)
+    ck(lib().GXPredGetEngine(ps, ctypes.byref(eng))); assert eng.value == 1
+    for h_ in (p, p5, pin, ps):
+        ck(lib().GXPredFree(h_))
+    # a missing parameter is reported with both engines' reasons
+    with pytest.raises(RuntimeError, match="general executor could not run the graph either"):
+        create(js, 2)
