@@ -381,7 +381,7 @@ void KVStoreDistServer::HandlePush(const DataHandleType& type, const KVMeta& req
   }
   UpdateBuf& ub = ks.ub;
   if (ub.request.empty()) ub.merged.assign(inc, inc + n);
-  else { float* m = ub.merged.data(); for (size_t i = 0; i < n; ++i) m[i] += inc[i]; }
+  else { float* m = ub.merged.data(); ParallelFor(n, size_t(1) << 18, [m, inc](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) m[i] += inc[i]; }); }
   for (const KVMeta& r : ExpandOrigins(req)) ub.request.push_back(r);
   size_t expected;
   if (is_global_) expected = po->num_global_workers() + (po->enable_central_workers() ? po->num_workers() : 0);

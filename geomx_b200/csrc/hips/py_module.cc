@@ -1,6 +1,7 @@
 // pybind11 bindings of the native runtime (module geomx_b200.lib._C).
 // Plays the role of the reference's flat C API for the kvstore / profiler / IO (include/mxnet/c_api.h:1949-2327 MXKVStore*, MXInitPSEnv,
 // src/c_api/c_api_profile.cc) — as a typed Python module instead of ctypes over a C ABI.
+#include <algorithm>
 #include <pybind11/functional.h>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
@@ -19,6 +20,7 @@
 #include "half.h"
 #include "key_codec.h"
 #include "kvstore_dist.h"
+#include "server_optim.h"
 #include "tsengine.h"
 
 namespace py = pybind11;
@@ -50,6 +52,30 @@ PYBIND11_MODULE(_C, m) {
   // ---------------------------------------------------------------------------------------------- environment / roles
   m.def("init_ps_env", [](const std::map<std::string, std::string>& kv) { for (auto& p : kv) Environment::Get()->Set(p.first, p.second); },
         "MXInitPSEnv: override environment variables in-process");
+  // message-buffer pool (block_pool.h): {cached_bytes, hits, misses, limit_bytes}; set_limit(0) disables pooling and trims the cache
+  m.def("buffer_pool_stats", [] { uint64_t st[4]; BlockPool::Get()->Stats(st);
+                                  return std::map<std::string, uint64_t>{{"cached_bytes", st[0]}, {"hits", st[1]}, {"misses", st[2]}, {"limit_bytes", st[3]}}; });
+  m.def("buffer_pool_set_limit", [](uint64_t bytes) { BlockPool::Get()->SetLimit(static_cast<size_t>(bytes)); });
+  m.def("buffer_pool_trim", [] { BlockPool::Get()->Trim(); });
+  m.def("buffer_pool_class_of", [](uint64_t n) { return static_cast<uint64_t>(BlockPool::ClassOf(static_cast<size_t>(n))); });
+  // allocate-and-drop `rounds` SArrays of `nbytes` (what a stream of received frames does): returns the distinct block addresses seen
+  m.def("buffer_pool_probe", [](uint64_t nbytes, int rounds) { std::vector<uint64_t> seen; for (int i = 0; i < rounds; ++i) { SArray<char> a; a.Allocate(nbytes); a[0] = 1; a[nbytes - 1] = 2;
+                                                               const uint64_t p = reinterpret_cast<uint64_t>(a.data()); if (std::find(seen.begin(), seen.end(), p) == seen.end()) seen.push_back(p); } return seen; });
+  // the native server-side optimizer on caller-owned arrays (unit tests: big tensors take the multi-threaded path of server_optim.h)
+  m.def("native_optimizer_run", [](const std::string& spec, py::array_t<float, py::array::c_style | py::array::forcecast> w0,
+                                   py::array_t<float, py::array::c_style | py::array::forcecast> grads) {
+    OptSpec sp = OptSpec::Parse(spec);
+    if (!sp.valid()) throw std::invalid_argument("unknown optimizer spec: " + spec);
+    const size_t n = static_cast<size_t>(w0.size());
+    if (grads.ndim() != 2 || static_cast<size_t>(grads.shape(1)) != n) throw std::invalid_argument("grads must be [steps, n]");
+    NativeOptimizer opt(sp);
+    NativeOptimizer::State st;
+    py::array_t<float> out(w0.size());
+    memcpy(out.mutable_data(), w0.data(), n * sizeof(float));
+    { py::gil_scoped_release rel; for (py::ssize_t t = 0; t < grads.shape(0); ++t) opt.Update(&st, out.mutable_data(), grads.data() + t * n, n); }
+    return out;
+  });
+  m.def("server_threads", [] { return ServerThreads(); });
   m.def("is_worker_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_worker(); });
   m.def("is_server_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_server(); });
   m.def("is_scheduler_node", [] { Postoffice::Get()->InitEnvironment(); return Postoffice::Get()->is_scheduler(); });

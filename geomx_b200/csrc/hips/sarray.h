@@ -4,7 +4,10 @@
 #include <memory>
 #include <vector>
 
+#include <type_traits>
+
 #include "base.h"
+#include "block_pool.h"
 
 namespace hips {
 
@@ -32,17 +35,34 @@ class SArray {
     if (deletable) ptr_.reset(data, [](T* p) { delete[] p; });
     else ptr_.reset(data, [](T*) {});
   }
+  // n uninitialised elements.  Large arrays (message payloads) come from the process-wide BlockPool and go back to it when the last
+  // reference dies, so that steady-state rounds reuse warm pages instead of faulting in a fresh mapping per message (block_pool.h).
+  void Allocate(size_t n) {
+    static_assert(std::is_trivially_copyable<T>::value, "SArray holds plain data");
+    const size_t bytes = n * sizeof(T);
+    if (bytes >= BlockPool::kMinPooled) {
+      size_t cap = 0;
+      char* b = BlockPool::Get()->Acquire(bytes, &cap);
+      HIPS_CHECK_MSG(b != nullptr, "out of memory: " + std::to_string(bytes) + " bytes");
+      size_ = capacity_ = n;
+      ptr_.reset(reinterpret_cast<T*>(b), [cap](T* p) { BlockPool::Get()->Release(reinterpret_cast<char*>(p), cap); });
+    } else {
+      reset(new T[n ? n : 1], n, true);
+    }
+  }
   void resize(size_t n, T val = T()) {
     if (n <= capacity_) { size_ = n; return; }
-    T* nd = new T[n];
-    if (size_) memcpy(nd, data(), size_ * sizeof(T));
-    for (size_t i = size_; i < n; ++i) nd[i] = val;
-    reset(nd, n, true);
+    SArray<T> nd;
+    nd.Allocate(n);
+    if (size_) memcpy(nd.data(), data(), size_ * sizeof(T));
+    for (size_t i = size_; i < n; ++i) nd.data()[i] = val;
+    ptr_ = nd.ptr_; size_ = capacity_ = n;
   }
   void CopyFrom(const T* src, size_t n) {
-    T* nd = new T[n ? n : 1];
-    if (n) memcpy(nd, src, n * sizeof(T));
-    reset(nd, n, true);
+    SArray<T> nd;
+    nd.Allocate(n);
+    if (n) memcpy(nd.data(), src, n * sizeof(T));
+    ptr_ = nd.ptr_; size_ = capacity_ = n;
   }
   void CopyFrom(const SArray<T>& o) { if (this != &o) CopyFrom(o.data(), o.size()); }
   SArray<T> segment(size_t begin, size_t end) const {

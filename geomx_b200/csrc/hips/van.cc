@@ -215,10 +215,8 @@ bool Van::RecvFrame(int fd, Message* msg) {
   for (uint32_t i = 0; i < nd; ++i) {
     SArray<char> d;
     if (lens[i]) {
-      char* buf = new (std::nothrow) char[lens[i]];
-      if (buf == nullptr) return false;
-      if (!ReadAll(fd, buf, lens[i])) { delete[] buf; return false; }
-      d.reset(buf, lens[i], true);
+      try { d.Allocate(lens[i]); } catch (const std::exception&) { return false; }      // pooled above 64 KiB (block_pool.h)
+      if (!ReadAll(fd, d.data(), lens[i])) return false;
     }
     msg->data.push_back(d);
     bytes += lens[i];

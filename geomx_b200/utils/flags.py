@@ -82,6 +82,8 @@ _reg("MXNET_GPU_MEM_POOL_RESERVE", 5, int, "percent of device memory the native 
 _reg("MXNET_GPU_MEM_POOL_PAGE_SIZE", 4096, int, "bucket granularity of the native device pool")
 _reg("MXNET_GPU_MEM_POOL_ROUND_LINEAR_CUTOFF", 24, int, "log2 size above which the Round pool uses power-of-two buckets")
 _reg("GEOMX_GPU_MEM_POOL", "torch", str, "torch | native: native installs the pool as PyTorch's CUDA allocator at import")
+_reg("PS_BUFFER_POOL_MB", 1024, int, "cache of released message buffers >= 64 KiB (csrc/hips/block_pool.h); 0 disables pooling")
+_reg("GEOMX_SERVER_THREADS", 0, int, "threads of a server's optimizer step / aggregation on big tensors; 0 = min(4, cores/2)")
 _reg("MXNET_PROFILER_AUTOSTART", 0, int, "")
 _reg("MXNET_PROFILER_MODE", 0, int, "")
 _reg("MXNET_ENFORCE_DETERMINISM", 0, int, "")

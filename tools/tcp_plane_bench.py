@@ -43,6 +43,23 @@ def worker_main():
     mx.nd.waitall()
     if master:
         kv.close(); return
+    if os.environ.get("BENCH_SPLIT") == "1":          # push and pull timed separately (each followed by a wait): where a round's time goes
+        tp, tq = [], []
+        for r in range(rounds + 5):
+            t0 = time.perf_counter()
+            for i, g in enumerate(grads):
+                kv.push(i, g, priority=-i)
+            mx.nd.waitall(); t1 = time.perf_counter()
+            for i, p in enumerate(params):
+                kv.pull(i, p, priority=-i)
+            mx.nd.waitall(); t2 = time.perf_counter()
+            if r >= 5:
+                tp.append((t1 - t0) * 1e3); tq.append((t2 - t1) * 1e3)
+        if os.environ.get("BENCH_REPORT") == "1":
+            tp.sort(); tq.sort()
+            print("RESULT " + json.dumps({"rounds": rounds, "push_median_ms": round(tp[len(tp) // 2], 3), "pull_median_ms": round(tq[len(tq) // 2], 3),
+                                          "payload_bytes_each_way": sum(int(np.prod(s)) for s in SHAPES) * 4}), flush=True)
+        kv.close(); return
     times = []
     for r in range(rounds + 10):
         t0 = time.perf_counter()
